@@ -1,0 +1,188 @@
+/*
+ * rg_b200.h -- C ABI of the B200-native regenie hot path (librg_b200.so).
+ *
+ * The reference (rgcgithub/regenie v4.1.2) has no FFI: its hot path is a sequence of
+ * C++ member/free functions called from Data::run_step1 / Data::test_snps_fast.  Each
+ * entry point below replaces the call(s) cited next to it; INTEGRATION.md shows the
+ * binding a maintainer would add to src/Data.cpp.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no C++/torch types; all matrices are column-major f64
+ *     exactly like Eigen::MatrixXd unless stated.
+ *   - every function returns 0 on success, non-zero on error; rg_last_error() gives the
+ *     message (the reference throws std::string, src/Regenie.cpp:67-92).
+ *   - the host owns host buffers, the library owns device buffers.  Pointers flagged
+ *     [host|device] may be either: the library inspects them with
+ *     cudaPointerGetAttributes and copies host memory itself (pinned memory is copied
+ *     asynchronously).
+ *   - one rg_handle per GPU / per host thread; calls on a handle are serialised on the
+ *     handle's CUDA stream and are asynchronous until rg_sync or a call that returns
+ *     host data.
+ *   - there is NO CPU fallback: every call fails with an error when no CUDA device
+ *     (sm_100) is usable.
+ */
+#ifndef RG_B200_H
+#define RG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rg_ctx* rg_handle;
+
+/* ------------------------------------------------------------------ library */
+const char* rg_last_error(void);
+const char* rg_version(void);
+/* number of usable CUDA devices (0 => nothing below can run) */
+int rg_device_count(void);
+
+/* ------------------------------------------------------------------ Step 1 */
+typedef struct rg_step1_config {
+  int32_t device;          /* CUDA ordinal                                               */
+  int64_t n_samples;       /* N  = params.n_samples (after --keep/--remove)              */
+  int32_t n_cov;           /* C  = params.ncov, columns of the orthonormal basis X       */
+  int32_t n_pheno;         /* P                                                          */
+  int32_t n_folds;         /* K  = params.cv_folds (ignored when loocv != 0)             */
+  int32_t n_ridge_l0;      /* R  = params.n_ridge_l0                                     */
+  int32_t n_ridge_l1;      /* R1 = params.n_ridge_l1                                     */
+  int32_t loocv;           /* params.use_loocv                                           */
+  int32_t max_block_size;  /* params.block_size                                          */
+  int32_t total_blocks;    /* params.total_n_block  (columns of W = total_blocks * R)    */
+  int64_t n_analyzed;      /* params.n_analyzed                                          */
+} rg_step1_config;
+
+/*
+ * rg_step1_create -- replaces Data::setmem / set_folds (src/Data.cpp:401-431,478-577):
+ * uploads the state every block shares.
+ *   X           [N x C]  pheno_data.new_cov   (orthonormal, zero rows outside analysis)
+ *   Y           [N x P]  pheno_data.phenotypes (residualised, scaled, masked)
+ *   mask        [N x P]  pheno_data.masked_indivs as bytes (column-major)
+ *   in_analysis [N]      filters.ind_in_analysis as bytes
+ *   fold_sizes  [K]      params.cv_sizes (contiguous folds in sample order)
+ *   lambda      [R]      params.lambda AFTER the M(1-h)/h map (src/Data.cpp:607)
+ *   neff        [P]      pheno_data.Neff
+ */
+int rg_step1_create(const rg_step1_config* cfg, const double* X, const double* Y,
+                    const uint8_t* mask, const uint8_t* in_analysis,
+                    const int64_t* fold_sizes, const double* lambda, const double* neff,
+                    rg_handle* out);
+void rg_destroy(rg_handle h);
+int rg_sync(rg_handle h);
+
+/*
+ * rg_l0_block_bed -- one level-0 block from 2-bit PLINK rows.  Replaces, for one block,
+ *   readChunkFromBedFileToG (decode + mean-impute)   src/Geno.cpp:1702-1768
+ *   Data::residualize_genotypes                      src/Data.cpp:190-228
+ *   Data::calc_cv_matrices                           src/Data.cpp:729-776
+ *   ridge_level_0 / ridge_level_0_loocv              src/Step1_Models.cpp:458-613 / 615-726
+ * and leaves the block's N x R level-0 predictors of every phenotype in the device
+ * resident W (columns block_id*R .. block_id*R+R-1).
+ *   packed      [host|device] bs rows of row_stride bytes, the .bed rows of the block
+ *   sample_idx  [host|device] N entries: index in the .bed row of sample i (handles
+ *               --keep/--remove, i.e. filters.ind_ignore); NULL = identity
+ *   ref_first   params.ref_first
+ * Error (non-zero) when a SNP has sd < 1e-6 is deferred to the next rg_sync /
+ * rg_l0_status (reference throws at src/Data.cpp:207).
+ */
+int rg_l0_block_bed(rg_handle h, const uint8_t* packed, int64_t row_stride, int32_t bs,
+                    const int32_t* sample_idx, int32_t ref_first, int32_t block_id);
+
+/* 0 = all blocks so far fine; otherwise 1 + index (block_id * max_block_size + snp) of the
+ * first low-variance SNP (src/Data.cpp:205-209).  Synchronises the stream. */
+int64_t rg_l0_status(rg_handle h);
+
+/*
+ * rg_l0_fetch_W -- copy a block's level-0 predictors of phenotype ph to the host as the
+ * N x R column-major slab the reference appends to <prefix>_l0_Y<ph+1> under --lowmem
+ * (write_l0_file, src/Step1_Models.cpp:728-733).
+ */
+int rg_l0_fetch_W(rg_handle h, int32_t block_id, int32_t ph, double* out_NxR);
+
+/*
+ * rg_l1_fit -- level-1 ridge for all phenotypes.  Replaces ridge_level_1 /
+ * ridge_level_1_loocv (src/Step1_Models.cpp:772-872 / 875-963) and the tau* choice of
+ * Data::output (src/Data.cpp:1025-1037).
+ *   tau      [P x R1] row-major: params.tau[ph] AFTER the B(1-h)/h map
+ *   cumsum   [5 x P x R1] out: l1_ests.cumsum_values[0..4] (Sx, Sy, Sx2, Sy2, Sxy)
+ *   best_idx [P] out: argmin_j (Sx2 + Sy2 - 2 Sxy)/Neff
+ */
+int rg_l1_fit(rg_handle h, const double* tau, double* cumsum, int32_t* best_idx);
+
+/*
+ * rg_loco -- per-chromosome predictions + LOCO assembly.  Replaces make_predictions /
+ * make_predictions_loocv (src/Data.cpp:1196-1343) and the arithmetic of
+ * write_predictions (src/Data.cpp:1846-1858).
+ *   chr_of_block [total_blocks]  chromosome (1..23) of each level-0 block
+ *   pred_out     [P][N x 23] column-major per phenotype: the values of `pred` written row
+ *                by row into <out>_<ph+1>.loco
+ */
+int rg_loco(rg_handle h, const int32_t* chr_of_block, double* pred_out);
+
+/* ------------------------------------------------------------------ Step 2 (QT) */
+typedef struct rg_step2_config {
+  int32_t device;
+  int64_t n_samples;       /* N                                                          */
+  int32_t n_cov;           /* C                                                          */
+  int32_t n_pheno;         /* P                                                          */
+  int32_t max_block_size;
+  int64_t n_analyzed;
+} rg_step2_config;
+
+/*
+ * rg_step2_create / rg_s2_set_chr -- upload what Data::compute_res (src/Data.cpp:2386-2404)
+ * produces for one chromosome: res = (Y - blup) o mask scaled by p_sd_yres, and YtX.
+ */
+int rg_step2_create(const rg_step2_config* cfg, const double* X, const uint8_t* mask,
+                    const uint8_t* in_analysis, rg_handle* out);
+int rg_s2_set_chr(rg_handle h, const double* res /*[N x P]*/);
+
+/* per-variant outputs of one Step-2 block (struct-of-arrays, bs entries each) */
+typedef struct rg_s2_out {
+  double* sum_g;      /* [bs]      total dosage over analysed non-missing samples          */
+  int32_t* n_nonmiss; /* [bs]      ns1: analysed & non-missing                             */
+  int32_t* ns_ph;     /* [bs x P]  per-trait non-missing counts (update_trait_counts)      */
+  double* sum_g_ph;   /* [bs x P]  per-trait dosage sums                                   */
+  int32_t* n_nonzero; /* [bs]      analysed samples with g != 0 after imputation           */
+  double* scale_fac;  /* [bs]      residualize_geno scale (dense path), src/Geno.cpp:3242  */
+  double* num;        /* [bs x P]  res^T g~        (compute_score_qt numerator, :415)      */
+  double* denum;      /* [bs x P]  mask_ph^T (g~ o g~)               (:416)                */
+  double* gtx;        /* [bs x C]  X^T g (imputed, un-residualised)                        */
+  double* sumsq_ph;   /* [bs x P]  mask_ph^T (g o g), imputed un-residualised (sparse :410)*/
+  double* gx_ph;      /* [bs x P x C] (X o mask_ph)^T g  (sparse path :410)                */
+  double* num_raw;    /* [bs x P]  res^T g (imputed, un-residualised; sparse path :404)    */
+} rg_s2_out;
+
+/*
+ * rg_s2_block_bed -- Step-2 sufficient statistics for bs variants from 2-bit PLINK rows.
+ * Replaces parseSnpfromBed + compute_mac/compute_aaf_info + residualize_geno +
+ * the N-length reductions of compute_score_qt (src/Geno.cpp:2414-2536,3077-3163,3242;
+ * src/Step2_Models.cpp:343-467).  The host finishes beta/SE/chisq/log10P per variant.
+ */
+int rg_s2_block_bed(rg_handle h, const uint8_t* packed, int64_t row_stride, int32_t bs,
+                    const int32_t* sample_idx, int32_t ref_first, const rg_s2_out* out);
+
+/* ------------------------------------------------------------------ multi-GPU */
+/* Number of level-0 predictor columns held locally; W of other ranks is attached with
+ * rg_l1_attach_W before rg_l1_fit (the exchange itself is done by the caller with NCCL). */
+int rg_W_info(rg_handle h, int32_t ph, void** dev_ptr, int64_t* ld, int64_t* ncols);
+
+/* ------------------------------------------------------------------ test / profiling hooks */
+/* Copy a named intermediate of the last level-0 block to the host (tests only).
+ * Returns the number of bytes written, or <0 on error.  See DESIGN.md for names. */
+int64_t rg_debug_fetch(rg_handle h, const char* name, void* out, int64_t max_bytes);
+/* Number of kernels launched by this handle since creation (for bench.py gpu_launches). */
+int64_t rg_launch_count(rg_handle h);
+/* CUDA stream of the handle as a void* (cudaStream_t), so callers can record events. */
+void* rg_stream(rg_handle h);
+/* Accumulated device time (ms) of the tensor-core Gram kernel, measured with CUDA events on
+ * the handle's stream when timing is enabled. */
+int rg_set_timing(rg_handle h, int32_t enable);
+int rg_get_timing(rg_handle h, const char* kernel, double* total_ms, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RG_B200_H */

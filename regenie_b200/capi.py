@@ -1,0 +1,187 @@
+"""ctypes binding of librg_b200.so -- the C ABI declared in include/rg_b200.h.
+
+This is plumbing for tests / bench.py; the product boundary is the C header.  There is no
+CPU fallback: importing works anywhere (so CPU-only checks can verify the exported symbols),
+but every compute entry point raises RgError when no sm_100 device is present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librg_b200.so")
+
+
+class RgError(RuntimeError):
+    pass
+
+
+class Step1Config(C.Structure):
+    _fields_ = [
+        ("device", C.c_int32), ("n_samples", C.c_int64), ("n_cov", C.c_int32), ("n_pheno", C.c_int32),
+        ("n_folds", C.c_int32), ("n_ridge_l0", C.c_int32), ("n_ridge_l1", C.c_int32), ("loocv", C.c_int32),
+        ("max_block_size", C.c_int32), ("total_blocks", C.c_int32), ("n_analyzed", C.c_int64),
+    ]
+
+
+class Step2Config(C.Structure):
+    _fields_ = [
+        ("device", C.c_int32), ("n_samples", C.c_int64), ("n_cov", C.c_int32), ("n_pheno", C.c_int32),
+        ("max_block_size", C.c_int32), ("n_analyzed", C.c_int64),
+    ]
+
+
+class S2Out(C.Structure):
+    _fields_ = [
+        ("sum_g", C.c_void_p), ("n_nonmiss", C.c_void_p), ("ns_ph", C.c_void_p), ("sum_g_ph", C.c_void_p),
+        ("n_nonzero", C.c_void_p), ("scale_fac", C.c_void_p), ("num", C.c_void_p), ("denum", C.c_void_p),
+        ("gtx", C.c_void_p), ("sumsq_ph", C.c_void_p), ("gx_ph", C.c_void_p), ("num_raw", C.c_void_p),
+    ]
+
+
+# every symbol include/rg_b200.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "rg_last_error", "rg_version", "rg_device_count", "rg_step1_create", "rg_destroy", "rg_sync",
+    "rg_l0_block_bed", "rg_l0_status", "rg_l0_fetch_W", "rg_l1_fit", "rg_loco", "rg_step2_create",
+    "rg_s2_set_chr", "rg_s2_block_bed", "rg_W_info", "rg_debug_fetch", "rg_launch_count", "rg_stream",
+    "rg_set_timing", "rg_get_timing",
+]
+
+_lib = None
+
+
+def lib():
+    """Load librg_b200.so (fails loudly if it was never built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RgError("librg_b200.so not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(LIB_PATH)
+        L.rg_last_error.restype = C.c_char_p
+        L.rg_version.restype = C.c_char_p
+        L.rg_l0_status.restype = C.c_int64
+        L.rg_debug_fetch.restype = C.c_int64
+        L.rg_launch_count.restype = C.c_int64
+        L.rg_stream.restype = C.c_void_p
+        L.rg_destroy.restype = None
+        for name in ("rg_destroy", "rg_sync", "rg_l0_status", "rg_launch_count", "rg_stream"):
+            getattr(L, name).argtypes = [C.c_void_p]
+        L.rg_l0_block_bed.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]
+        L.rg_l0_fetch_W.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        L.rg_debug_fetch.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]
+        L.rg_set_timing.argtypes = [C.c_void_p, C.c_int32]
+        L.rg_get_timing.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p]
+        L.rg_l1_fit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rg_loco.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rg_s2_set_chr.argtypes = [C.c_void_p, C.c_void_p]
+        L.rg_s2_block_bed.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+        L.rg_W_info.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RgError(lib().rg_last_error().decode())
+
+
+def _ptr(a):
+    """numpy array -> void* (host), int -> raw (device) pointer, None -> NULL."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a, order="F"):
+    return np.require(a, dtype=np.float64, requirements=["F" if order == "F" else "C", "A"])
+
+
+class Step1:
+    """Host-side mirror of the Step-1 call sequence of Data::run_step1 (src/Data.cpp:95-133)."""
+
+    def __init__(self, X, Y, mask, in_analysis, fold_sizes, lam, neff, n_analyzed, max_block_size,
+                 total_blocks, n_ridge_l1=5, loocv=False, device=0):
+        L = lib()
+        X = _f64(X); Y = _f64(Y)
+        mask = np.require(np.asarray(mask, dtype=np.uint8), requirements=["F", "A"])
+        ia = np.ascontiguousarray(in_analysis, dtype=np.uint8)
+        fs = np.ascontiguousarray(fold_sizes, dtype=np.int64)
+        lam = np.ascontiguousarray(lam, dtype=np.float64)
+        neff = np.ascontiguousarray(neff, dtype=np.float64)
+        self.N, self.C = X.shape
+        self.P = Y.shape[1]
+        self.R = len(lam)
+        self.R1 = n_ridge_l1
+        self.total_blocks = total_blocks
+        cfg = Step1Config(device, self.N, self.C, self.P, len(fs), self.R, n_ridge_l1, int(loocv),
+                          max_block_size, total_blocks, int(n_analyzed))
+        h = C.c_void_p()
+        check(L.rg_step1_create(C.byref(cfg), _ptr(X), _ptr(Y), _ptr(mask), _ptr(ia), _ptr(fs), _ptr(lam),
+                                _ptr(neff), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().rg_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def l0_block_bed(self, packed, bs, block_id, row_stride=None, sample_idx=None, ref_first=False):
+        """packed: uint8 ndarray [bs, stride] (host) or an int device pointer (+ row_stride)."""
+        if not isinstance(packed, int):
+            packed = np.ascontiguousarray(packed, dtype=np.uint8)
+            row_stride = packed.shape[1]
+        if sample_idx is not None and not isinstance(sample_idx, int):
+            sample_idx = np.ascontiguousarray(sample_idx, dtype=np.int32)
+            self._keep_idx = sample_idx
+        check(lib().rg_l0_block_bed(self.h, _ptr(packed), row_stride, bs, _ptr(sample_idx), int(ref_first),
+                                    block_id))
+
+    def status(self):
+        return lib().rg_l0_status(self.h)
+
+    def sync(self):
+        check(lib().rg_sync(self.h))
+
+    def fetch_W(self, block_id, ph):
+        out = np.empty((self.N, self.R), dtype=np.float64, order="F")
+        check(lib().rg_l0_fetch_W(self.h, block_id, ph, _ptr(out)))
+        return out
+
+    def l1_fit(self, tau):
+        tau = np.ascontiguousarray(tau, dtype=np.float64).reshape(self.P, self.R1)
+        cs = np.zeros((5, self.P, self.R1))
+        best = np.zeros(self.P, dtype=np.int32)
+        check(lib().rg_l1_fit(self.h, _ptr(tau), _ptr(cs), _ptr(best)))
+        return cs, best
+
+    def loco(self, chr_of_block):
+        cb = np.ascontiguousarray(chr_of_block, dtype=np.int32)
+        out = np.zeros((self.P, 23, self.N))          # [P][N x 23] column-major
+        check(lib().rg_loco(self.h, _ptr(cb), _ptr(out)))
+        return out.transpose(0, 2, 1)                 # -> [P, N, 23]
+
+    def debug(self, name, dtype, count):
+        out = np.empty(count, dtype=dtype)
+        n = lib().rg_debug_fetch(self.h, name.encode(), _ptr(out), out.nbytes)
+        if n < 0:
+            raise RgError("debug fetch failed for %s: %s" % (name, lib().rg_last_error().decode()))
+        return out[: n // out.itemsize]
+
+    def launch_count(self):
+        return lib().rg_launch_count(self.h)
+
+    def stream(self):
+        return lib().rg_stream(self.h)
+
+    def set_timing(self, on=True):
+        check(lib().rg_set_timing(self.h, int(on)))
+
+    def timing(self, name):
+        ms = C.c_double(); n = C.c_int64()
+        check(lib().rg_get_timing(self.h, name.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value

@@ -1,0 +1,70 @@
+// Per-GPU state behind an rg_handle.
+#pragma once
+#include <map>
+#include <memory>
+
+#include "../../include/rg_b200.h"
+#include "kernels.cuh"
+
+struct rg_ctx {
+  int kind = 0;  // 1 = step 1, 2 = step 2
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+
+  // ---- problem sizes
+  int64_t N = 0, Npad = 0, n_analyzed = 0;
+  int C = 0, P = 0, K = 1, R = 0, R1 = 0, loocv = 0;
+  int bs_max = 0, rows_p_max = 0, total_blocks = 0, cpp = 0;
+  int64_t B = 0;  // total_blocks * R
+
+  // ---- padded fold layout (host copies)
+  std::vector<int64_t> fold_sizes, fold_pad_start, fold_pad_len;
+  std::vector<int32_t> pad_of;   // [N]   sample -> padded slot
+  std::vector<int32_t> src_of;   // [Npad] padded slot -> sample or -1
+  std::vector<uint8_t> in_analysis;
+  std::vector<int32_t> cached_sample_idx;
+  bool file_idx_valid = false;
+  int nchunks = 0;
+
+  // ---- device state shared by all blocks
+  rg::DevBuf<double> xy;            // [Npad][cpp]  (X | Y), zero padded
+  rg::DevBuf<uint8_t> mask;         // [P][Npad]
+  rg::DevBuf<uint8_t> is_real;      // [Npad]
+  rg::DevBuf<int32_t> tile_fold;    // [Npad/128]
+  rg::DevBuf<int4> chunks;          // [nchunks] (t0, len, fold, 0)
+  rg::DevBuf<int2> fold_chunks;     // [K]
+  rg::DevBuf<int2> fold_k;          // [K] (first 128-sample K block, #blocks)
+  rg::DevBuf<double> XtX_f, XtY_f, lambda, neff;
+  rg::DevBuf<int32_t> file_idx_pad; // [Npad]
+  rg::DevBuf<unsigned long long> err_slot;
+
+  // ---- per-block scratch
+  rg::DevBuf<uint8_t> packed_dev;
+  rg::DevBuf<int32_t> sample_idx_dev;
+  rg::DevBuf<uint32_t> gp;          // [rows_p][Npad/16]
+  rg::DevBuf<uint8_t> z;            // [2 rows_p][Npad] e4m3
+  rg::DevBuf<float> zz;             // [K][2 rows_p][2 rows_p]
+  rg::DevBuf<int32_t> cnt_part, cnt_fold;
+  rg::DevBuf<double> sum_part, sum_fold;
+  rg::DevBuf<double> mu, inv_sd, Bv, Af, Qf, gty_f, rhs;
+  rg::DevBuf<double> cm;            // [nmat][n_aug][nC]
+  rg::DevBuf<double> gam, gmu, cvec, part, mean_invsd;
+  std::map<int, CUtensorMap> tmaps;                       // keyed by rows_p
+  std::map<int, std::unique_ptr<rg::DevBuf<int2>>> tile_lists;
+  std::map<int, int> tile_counts;
+
+  // ---- level-0 output
+  rg::DevBuf<double> W;             // [P][Npad x B] column-major
+  int last_bs = 0, last_rows_p = 0, last_nC = 0, last_n_aug = 0, last_nmat = 0;
+
+  // ---- timing
+  bool timing = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::map<std::string, std::pair<double, int64_t>> timers;
+  std::vector<std::tuple<std::string, cudaEvent_t, cudaEvent_t>> pending;
+};
+
+namespace rg {
+void flush_timers(rg_ctx* h);
+}

@@ -1,0 +1,89 @@
+// Kernel launchers and argument bundles shared between the .cu translation units.
+#pragma once
+#include "common.cuh"
+
+namespace rg {
+
+constexpr int kMaxFolds = 16;
+constexpr int kMaxCov = 64;
+
+// ---- bed_kernels.cu
+void launch_bed_relayout(const uint8_t* packed, int64_t row_stride, int bs, int rows_p,
+                         const int32_t* file_idx_pad, int ref_first, uint32_t* gp, int64_t npad,
+                         cudaStream_t s);
+void launch_bed_expand_fp8(const uint32_t* gp, int rows_p, uint8_t* z, int64_t npad, cudaStream_t s);
+
+// ---- l0_stats.cu
+struct SnpFinalizeArgs {
+  int bs, rows_p, C, P, K, cpp, loocv;
+  long long n_analyzed;
+  double numtol;
+  const int32_t* cnt_fold;   // [K][rows_p][4]
+  const double* sum_fold;    // [K][rows_p][2][cpp]
+  const double* XtX_f;       // [K][C][C]
+  const double* XtY_f;       // [K][C][P]
+  double *mu, *inv_sd;       // [rows_p]
+  double* Bv;                // [rows_p][C]
+  double *Af, *Qf;           // [K][rows_p][C]
+  double *gty_f, *rhs;       // [K][rows_p][P]
+  unsigned long long* err_slot;
+  long long err_base;
+};
+
+struct AssembleArgs {
+  int bs, rows_p, nC, C, K, R, loocv;
+  const float* zz;           // [K][2*rows_p][ldz] exact integer Grams
+  int64_t ldz, zz_fold_stride;
+  const double *mu, *inv_sd, *Bv, *Af, *Qf;
+  const double* lambda;      // [R]
+  double* cm;                // batched row-major lower systems
+  int64_t cm_stride;
+  int ldc;
+};
+
+void launch_l0_stats(const uint32_t* gp, int64_t npad, const double* xy, int cpp, const int4* chunks,
+                     int nchunks, int rows_p, int32_t* cnt_part, double* sum_part, cudaStream_t s);
+void launch_l0_fold_reduce(const int32_t* cnt_part, const double* sum_part, int rows_p, int cpp,
+                           const int2* fold_chunks, int K, int32_t* cnt_fold, double* sum_fold,
+                           cudaStream_t s);
+void launch_l0_snp_finalize(const SnpFinalizeArgs& a, cudaStream_t s);
+void launch_l0_assemble(const AssembleArgs& a, const double* rhs, int P, int Ppad, int nmat, cudaStream_t s);
+
+// ---- gram_tcgen05.cu
+void make_gram_tensor_map(CUtensorMap* tm, const uint8_t* z, int64_t npad, int rows2);
+size_t gram_smem_bytes();
+void gram_tile_list(int rows2, std::vector<int2>& tiles);
+void launch_gram_tcgen05(const CUtensorMap& tm, const int2* tiles, int ntiles, const int2* fold_k, int K,
+                         float* out, int ldo, int64_t fold_stride, cudaStream_t s);
+void launch_gram_reference(const uint8_t* z, int64_t npad, int rows2, int k0, int k1, float* out, int ldo,
+                           cudaStream_t s);
+
+// ---- chol.cu
+void launch_chol_factor(double* cm, int64_t stride, int nC, int n_aug, int batch,
+                        unsigned long long* err_slot, long long err_base, cudaStream_t s);
+void launch_chol_backsolve(double* cm, int64_t stride, int nC, int P, int batch, cudaStream_t s);
+int chol_num_launches(int nC);
+
+// ---- l0_predict.cu
+struct PredictArgs {
+  int bs, rows_p, C, P, R, Qp, cpp, col0;
+  int64_t npad, words_per_row, w_stride;
+  const uint32_t* gp;
+  const int32_t* tile_fold;  // [npad/128]
+  const double *gam, *gmu;   // [K][rows_p][Qp]
+  const double* cvec;        // [K][Qp][C]
+  const double* xy;          // [npad][cpp]
+  const uint8_t* mask;       // [P][npad]
+  double* W;                 // [P][w_stride], column-major npad x B per phenotype
+  double* part;              // [ntiles][Qp][2]
+};
+void launch_l0_gamma(const double* cm, int64_t cm_stride, int ldc, int nC, int R, int P, int Qp,
+                     int bs, int rows_p, int K, const double* mu, const double* inv_sd,
+                     const double* Bv, int C, double* gam, double* gmu, double* cvec, cudaStream_t s);
+void launch_l0_predict(const PredictArgs& a, int ntiles, cudaStream_t s);
+void launch_l0_standardize(const double* part, int ntiles, int Qp, int Q, int P, const double* neff,
+                           double* mean_invsd, double* W, int64_t w_stride, int64_t npad, int col0,
+                           const uint8_t* is_real, cudaStream_t s);
+int predict_qt();
+
+}  // namespace rg

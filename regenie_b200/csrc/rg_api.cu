@@ -1,0 +1,571 @@
+// C ABI of librg_b200.so (see include/rg_b200.h): handle lifetime, Step-1 level-0 block path.
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "context.cuh"
+
+namespace rg {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& m) { g_last_error = m; }
+
+bool is_device_pointer(const void* p) {
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+void copy_to_device(void* dst, const void* src, size_t bytes, cudaStream_t stream) {
+  if (bytes == 0) return;
+  RG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream));
+}
+
+struct ScopedTimer {
+  rg_ctx* h;
+  std::string name;
+  cudaEvent_t a = nullptr, b = nullptr;
+  ScopedTimer(rg_ctx* h_, const char* n) : h(h_), name(n) {
+    if (!h->timing) return;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, h->stream);
+  }
+  ~ScopedTimer() {
+    if (!h->timing) return;
+    cudaEventRecord(b, h->stream);
+    h->pending.emplace_back(name, a, b);
+  }
+};
+
+void flush_timers(rg_ctx* h) {
+  for (auto& t : h->pending) {
+    float ms = 0.f;
+    cudaEventSynchronize(std::get<2>(t));
+    cudaEventElapsedTime(&ms, std::get<1>(t), std::get<2>(t));
+    auto& acc = h->timers[std::get<0>(t)];
+    acc.first += ms;
+    acc.second += 1;
+    cudaEventDestroy(std::get<1>(t));
+    cudaEventDestroy(std::get<2>(t));
+  }
+  h->pending.clear();
+}
+
+static void require_gpu(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    throw Error{"no CUDA device available: librg_b200 has no CPU fallback"};
+  }
+  RG_CHECK(device >= 0 && device < n, "invalid CUDA device ordinal");
+  cudaDeviceProp prop;
+  RG_CUDA(cudaGetDeviceProperties(&prop, device));
+  RG_CHECK(prop.major == 10, std::string("librg_b200 is built for sm_100a only; device is sm_") +
+                                 std::to_string(prop.major) + std::to_string(prop.minor));
+}
+
+// Build the padded fold layout + all device state shared by the blocks.
+static void build_layout(rg_ctx* h, const double* X, const double* Y, const uint8_t* mask,
+                         const uint8_t* in_analysis, const int64_t* fold_sizes) {
+  const int64_t N = h->N;
+  const int K = h->K, C = h->C, P = h->P;
+  h->fold_sizes.assign(K, 0);
+  if (h->loocv) {
+    h->fold_sizes[0] = N;
+  } else {
+    int64_t tot = 0;
+    for (int f = 0; f < K; ++f) {
+      RG_CHECK(fold_sizes[f] > 0, "fold sizes must be positive");
+      h->fold_sizes[f] = fold_sizes[f];
+      tot += fold_sizes[f];
+    }
+    RG_CHECK(tot == N, "fold sizes must sum to n_samples");
+  }
+  h->fold_pad_start.assign(K, 0);
+  h->fold_pad_len.assign(K, 0);
+  int64_t off = 0;
+  for (int f = 0; f < K; ++f) {
+    h->fold_pad_start[f] = off;
+    h->fold_pad_len[f] = round_up(h->fold_sizes[f], kSamplePad);
+    off += h->fold_pad_len[f];
+  }
+  h->Npad = off;
+  RG_CHECK(h->Npad < (1ll << 31), "padded sample count must fit in int32");
+  h->pad_of.assign(N, 0);
+  h->src_of.assign(h->Npad, -1);
+  std::vector<int32_t> tile_fold(h->Npad / 128);
+  {
+    int64_t s = 0;
+    for (int f = 0; f < K; ++f) {
+      for (int64_t o = 0; o < h->fold_sizes[f]; ++o, ++s) {
+        h->pad_of[s] = (int32_t)(h->fold_pad_start[f] + o);
+        h->src_of[h->fold_pad_start[f] + o] = (int32_t)s;
+      }
+      for (int64_t t = h->fold_pad_start[f]; t < h->fold_pad_start[f] + h->fold_pad_len[f]; t += 128)
+        tile_fold[t / 128] = f;
+    }
+  }
+  h->in_analysis.assign(in_analysis, in_analysis + N);
+
+  // (X | Y) sample-major, zero padded to cpp columns
+  h->cpp = (int)round_up(C + P, 16);
+  std::vector<double> xy((size_t)h->Npad * h->cpp, 0.0);
+  std::vector<uint8_t> maskp((size_t)P * h->Npad, 0), is_real(h->Npad, 0);
+  for (int64_t s = 0; s < N; ++s) {
+    const int64_t t = h->pad_of[s];
+    is_real[t] = 1;
+    double* r = &xy[(size_t)t * h->cpp];
+    for (int c = 0; c < C; ++c) r[c] = X[(size_t)c * N + s];
+    for (int p = 0; p < P; ++p) {
+      r[C + p] = Y[(size_t)p * N + s];
+      maskp[(size_t)p * h->Npad + t] = mask[(size_t)p * N + s] ? 1 : 0;
+    }
+  }
+  // per-fold X_f^T X_f and X_f^T Y_f (Appendix B item 6 of SURVEY.md)
+  std::vector<double> XtX((size_t)K * C * C, 0.0), XtY((size_t)K * C * P, 0.0);
+  {
+    int64_t s = 0;
+    for (int f = 0; f < K; ++f)
+      for (int64_t o = 0; o < h->fold_sizes[f]; ++o, ++s)
+        for (int c = 0; c < C; ++c) {
+          const double xc = X[(size_t)c * N + s];
+          if (xc == 0.0) continue;
+          for (int c2 = 0; c2 < C; ++c2) XtX[((size_t)f * C + c) * C + c2] += xc * X[(size_t)c2 * N + s];
+          for (int p = 0; p < P; ++p) XtY[((size_t)f * C + c) * P + p] += xc * Y[(size_t)p * N + s];
+        }
+  }
+  // chunk table for the f64 reductions
+  std::vector<int4> chunks;
+  std::vector<int2> fold_chunks(K), fold_k(K);
+  for (int f = 0; f < K; ++f) {
+    fold_chunks[f].x = (int)chunks.size();
+    for (int64_t o = 0; o < h->fold_pad_len[f]; o += kStatChunk) {
+      const int len = (int)std::min<int64_t>(kStatChunk, h->fold_pad_len[f] - o);
+      chunks.push_back(make_int4((int)(h->fold_pad_start[f] + o), len, f, 0));
+    }
+    fold_chunks[f].y = (int)chunks.size();
+    fold_k[f] = make_int2((int)(h->fold_pad_start[f] / 128), (int)(h->fold_pad_len[f] / 128));
+  }
+  h->nchunks = (int)chunks.size();
+
+  cudaStream_t s = h->stream;
+  h->xy.alloc(xy.size());
+  h->mask.alloc(maskp.size());
+  h->is_real.alloc(is_real.size());
+  h->tile_fold.alloc(tile_fold.size());
+  h->chunks.alloc(chunks.size());
+  h->fold_chunks.alloc(K);
+  h->fold_k.alloc(K);
+  h->XtX_f.alloc(XtX.size());
+  h->XtY_f.alloc(XtY.size());
+  RG_CUDA(cudaMemcpyAsync(h->xy.p, xy.data(), xy.size() * 8, cudaMemcpyHostToDevice, s));
+  RG_CUDA(cudaMemcpyAsync(h->mask.p, maskp.data(), maskp.size(), cudaMemcpyHostToDevice, s));
+  RG_CUDA(cudaMemcpyAsync(h->is_real.p, is_real.data(), is_real.size(), cudaMemcpyHostToDevice, s));
+  RG_CUDA(cudaMemcpyAsync(h->tile_fold.p, tile_fold.data(), tile_fold.size() * 4, cudaMemcpyHostToDevice, s));
+  RG_CUDA(cudaMemcpyAsync(h->chunks.p, chunks.data(), chunks.size() * sizeof(int4), cudaMemcpyHostToDevice, s));
+  RG_CUDA(cudaMemcpyAsync(h->fold_chunks.p, fold_chunks.data(), K * sizeof(int2), cudaMemcpyHostToDevice, s));
+  RG_CUDA(cudaMemcpyAsync(h->fold_k.p, fold_k.data(), K * sizeof(int2), cudaMemcpyHostToDevice, s));
+  RG_CUDA(cudaMemcpyAsync(h->XtX_f.p, XtX.data(), XtX.size() * 8, cudaMemcpyHostToDevice, s));
+  RG_CUDA(cudaMemcpyAsync(h->XtY_f.p, XtY.data(), XtY.size() * 8, cudaMemcpyHostToDevice, s));
+  RG_CUDA(cudaStreamSynchronize(s));   // host vectors go out of scope
+}
+
+// file_idx_pad[t] = index of the sample in the .bed row, or -1 for layout padding and for
+// samples outside the analysis (whose genotypes the reference zeroes, src/Data.cpp:196).
+static void build_file_idx(rg_ctx* h, const int32_t* sample_idx_host) {
+  std::vector<int32_t> fi(h->Npad, -1);
+  for (int64_t t = 0; t < h->Npad; ++t) {
+    const int32_t s = h->src_of[t];
+    if (s < 0 || !h->in_analysis[s]) continue;
+    fi[t] = sample_idx_host ? sample_idx_host[s] : s;
+  }
+  h->file_idx_pad.alloc(h->Npad);
+  RG_CUDA(cudaMemcpyAsync(h->file_idx_pad.p, fi.data(), fi.size() * 4, cudaMemcpyHostToDevice, h->stream));
+  RG_CUDA(cudaStreamSynchronize(h->stream));
+  h->file_idx_valid = true;
+}
+
+static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, int bs,
+                         const int32_t* sample_idx, int ref_first, int block_id) {
+  RG_CHECK(h->kind == 1, "handle is not a Step-1 handle");
+  RG_CHECK(bs > 0 && bs <= h->bs_max, "block size out of range");
+  RG_CHECK(block_id >= 0 && block_id < h->total_blocks, "block_id out of range");
+  RG_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const int C = h->C, P = h->P, K = h->K, R = h->R;
+  const int rows_p = (int)round_up(bs, kRowPad);
+  const int nC = (int)round_up(bs, 64);
+  const int Ppad = (int)round_up(P, 64);
+  const int n_aug = nC + Ppad;
+  const int nmat = (h->loocv ? 1 : K) * R;
+  const int QT = predict_qt();
+  const int Q = R * P, Qp = (int)round_up(Q, QT);
+  const int64_t Npad = h->Npad;
+
+  // --- sample index map (cached)
+  {
+    std::vector<int32_t> host_idx;
+    const int32_t* hidx = nullptr;
+    if (sample_idx) {
+      host_idx.resize(h->N);
+      RG_CUDA(cudaMemcpy(host_idx.data(), sample_idx, h->N * 4, cudaMemcpyDefault));
+      hidx = host_idx.data();
+      if (!h->file_idx_valid || h->cached_sample_idx != host_idx) {
+        build_file_idx(h, hidx);
+        h->cached_sample_idx = host_idx;
+      }
+    } else if (!h->file_idx_valid || !h->cached_sample_idx.empty()) {
+      build_file_idx(h, nullptr);
+      h->cached_sample_idx.clear();
+    }
+  }
+
+  // --- input rows to the device
+  const uint8_t* packed_d = packed;
+  if (!is_device_pointer(packed)) {
+    h->packed_dev.alloc((size_t)h->bs_max * row_stride);
+    ScopedTimer t(h, "h2d");
+    copy_to_device(h->packed_dev.p, packed, (size_t)bs * row_stride, s);
+    packed_d = h->packed_dev.p;
+  }
+
+  // --- scratch
+  h->gp.alloc((size_t)h->rows_p_max * (Npad / 16));
+  h->z.alloc((size_t)2 * h->rows_p_max * Npad);
+  h->zz.alloc((size_t)K * 4 * h->rows_p_max * h->rows_p_max);
+  h->cnt_part.alloc((size_t)h->nchunks * h->rows_p_max * 4);
+  h->sum_part.alloc((size_t)h->nchunks * h->rows_p_max * 2 * h->cpp);
+  h->cnt_fold.alloc((size_t)K * h->rows_p_max * 4);
+  h->sum_fold.alloc((size_t)K * h->rows_p_max * 2 * h->cpp);
+  h->mu.alloc(h->rows_p_max);
+  h->inv_sd.alloc(h->rows_p_max);
+  h->Bv.alloc((size_t)h->rows_p_max * C);
+  h->Af.alloc((size_t)K * h->rows_p_max * C);
+  h->Qf.alloc((size_t)K * h->rows_p_max * C);
+  h->gty_f.alloc((size_t)K * h->rows_p_max * P);
+  h->rhs.alloc((size_t)K * h->rows_p_max * P);
+  {
+    const int nC_max = (int)round_up(h->bs_max, 64);
+    const size_t need = (size_t)nmat * (nC_max + Ppad) * nC_max;
+    if (h->cm.n < need) {
+      h->cm.alloc(need);
+      RG_CUDA(cudaMemsetAsync(h->cm.p, 0, need * 8, s));
+    }
+  }
+  const int Kg = h->loocv ? 1 : K;
+  h->gam.alloc((size_t)Kg * h->rows_p_max * Qp);
+  h->gmu.alloc((size_t)Kg * h->rows_p_max * Qp);
+  h->cvec.alloc((size_t)Kg * Qp * C);
+  const int ntiles_s = (int)(Npad / 128);
+  h->part.alloc((size_t)ntiles_s * Qp * 2);
+  h->mean_invsd.alloc((size_t)2 * Qp);
+
+  // --- 1. decode: PLINK rows -> padded 2-bit rows -> e4m3 planes
+  {
+    ScopedTimer t(h, "bed_relayout");
+    launch_bed_relayout(packed_d, row_stride, bs, rows_p, h->file_idx_pad.p, ref_first, h->gp.p, Npad, s);
+  }
+  {
+    ScopedTimer t(h, "bed_expand");
+    launch_bed_expand_fp8(h->gp.p, rows_p, h->z.p, Npad, s);
+  }
+  h->launches += 2;
+
+  // --- 2. f64 sufficient statistics
+  {
+    ScopedTimer t(h, "l0_stats");
+    launch_l0_stats(h->gp.p, Npad, h->xy.p, h->cpp, h->chunks.p, h->nchunks, rows_p, h->cnt_part.p,
+                    h->sum_part.p, s);
+    launch_l0_fold_reduce(h->cnt_part.p, h->sum_part.p, rows_p, h->cpp, h->fold_chunks.p, K,
+                          h->cnt_fold.p, h->sum_fold.p, s);
+    SnpFinalizeArgs a;
+    a.bs = bs; a.rows_p = rows_p; a.C = C; a.P = P; a.K = K; a.cpp = h->cpp; a.loocv = h->loocv;
+    a.n_analyzed = h->n_analyzed; a.numtol = 1e-6;
+    a.cnt_fold = h->cnt_fold.p; a.sum_fold = h->sum_fold.p; a.XtX_f = h->XtX_f.p; a.XtY_f = h->XtY_f.p;
+    a.mu = h->mu.p; a.inv_sd = h->inv_sd.p; a.Bv = h->Bv.p; a.Af = h->Af.p; a.Qf = h->Qf.p;
+    a.gty_f = h->gty_f.p; a.rhs = h->rhs.p; a.err_slot = h->err_slot.p;
+    a.err_base = (long long)block_id * h->bs_max;
+    launch_l0_snp_finalize(a, s);
+    h->launches += 3;
+  }
+
+  // --- 3. exact integer Grams on the tensor cores
+  {
+    if (!h->tmaps.count(rows_p)) {
+      CUtensorMap tm;
+      make_gram_tensor_map(&tm, h->z.p, Npad, 2 * rows_p);
+      h->tmaps[rows_p] = tm;
+      std::vector<int2> tiles;
+      gram_tile_list(2 * rows_p, tiles);
+      auto buf = std::make_unique<DevBuf<int2>>();
+      buf->alloc(tiles.size());
+      RG_CUDA(cudaMemcpy(buf->p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice));
+      h->tile_counts[rows_p] = (int)tiles.size();
+      h->tile_lists[rows_p] = std::move(buf);
+    }
+    ScopedTimer t(h, "gram_tcgen05");
+    launch_gram_tcgen05(h->tmaps[rows_p], h->tile_lists[rows_p]->p, h->tile_counts[rows_p], h->fold_k.p, K,
+                        h->zz.p, 2 * rows_p, (int64_t)4 * rows_p * rows_p, s);
+    h->launches += 1;
+  }
+
+  // --- 4. ridge systems
+  AssembleArgs aa;
+  aa.bs = bs; aa.rows_p = rows_p; aa.nC = nC; aa.C = C; aa.K = K; aa.R = R; aa.loocv = h->loocv;
+  aa.zz = h->zz.p; aa.ldz = 2 * rows_p; aa.zz_fold_stride = (int64_t)4 * rows_p * rows_p;
+  aa.mu = h->mu.p; aa.inv_sd = h->inv_sd.p; aa.Bv = h->Bv.p; aa.Af = h->Af.p; aa.Qf = h->Qf.p;
+  aa.lambda = h->lambda.p; aa.cm = h->cm.p; aa.cm_stride = (int64_t)n_aug * nC; aa.ldc = nC;
+  {
+    ScopedTimer t(h, "l0_assemble");
+    launch_l0_assemble(aa, h->rhs.p, P, Ppad, nmat, s);
+    h->launches += 2;
+  }
+  {
+    ScopedTimer t(h, "chol_factor");
+    launch_chol_factor(h->cm.p, aa.cm_stride, nC, n_aug, nmat, h->err_slot.p,
+                       (long long)(1ll << 40) + (long long)block_id * 1024, s);
+    h->launches += chol_num_launches(nC);
+  }
+  {
+    ScopedTimer t(h, "chol_backsolve");
+    launch_chol_backsolve(h->cm.p, aa.cm_stride, nC, P, nmat, s);
+    h->launches += 1;
+  }
+  h->last_bs = bs; h->last_rows_p = rows_p; h->last_nC = nC; h->last_n_aug = n_aug; h->last_nmat = nmat;
+
+  RG_CHECK(!h->loocv, "LOOCV level 0 is not implemented yet");
+
+  // --- 5. out-of-fold predictions, standardised into W
+  {
+    ScopedTimer t(h, "l0_predict");
+    launch_l0_gamma(h->cm.p, aa.cm_stride, nC, nC, R, P, Qp, bs, rows_p, K, h->mu.p, h->inv_sd.p, h->Bv.p, C,
+                    h->gam.p, h->gmu.p, h->cvec.p, s);
+    PredictArgs pa;
+    pa.bs = bs; pa.rows_p = rows_p; pa.C = C; pa.P = P; pa.R = R; pa.Qp = Qp; pa.cpp = h->cpp;
+    pa.col0 = block_id * R; pa.npad = Npad; pa.words_per_row = Npad / 16; pa.w_stride = Npad * h->B;
+    pa.gp = h->gp.p; pa.tile_fold = h->tile_fold.p; pa.gam = h->gam.p; pa.gmu = h->gmu.p;
+    pa.cvec = h->cvec.p; pa.xy = h->xy.p; pa.mask = h->mask.p; pa.W = h->W.p; pa.part = h->part.p;
+    launch_l0_predict(pa, ntiles_s, s);
+    launch_l0_standardize(h->part.p, ntiles_s, Qp, Q, P, h->neff.p, h->mean_invsd.p, h->W.p, pa.w_stride, Npad,
+                          pa.col0, h->is_real.p, s);
+    h->launches += 5;
+  }
+}
+
+}  // namespace rg
+
+using namespace rg;
+
+#define RG_API_BEGIN try {
+#define RG_API_END                         \
+  }                                        \
+  catch (const rg::Error& e) {             \
+    rg::set_last_error(e.msg);             \
+    return 1;                              \
+  }                                        \
+  catch (const std::exception& e) {        \
+    rg::set_last_error(e.what());          \
+    return 1;                              \
+  }                                        \
+  return 0;
+
+extern "C" {
+
+const char* rg_last_error(void) { return rg::g_last_error.c_str(); }
+const char* rg_version(void) { return "regenie_b200 0.1 (sm_100a)"; }
+
+int rg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int rg_step1_create(const rg_step1_config* cfg, const double* X, const double* Y, const uint8_t* mask,
+                    const uint8_t* in_analysis, const int64_t* fold_sizes, const double* lambda,
+                    const double* neff, rg_handle* out) {
+  RG_API_BEGIN
+  RG_CHECK(cfg && X && Y && mask && in_analysis && lambda && neff && out, "null argument");
+  require_gpu(cfg->device);
+  RG_CHECK(cfg->n_samples > 0 && cfg->n_cov > 0 && cfg->n_pheno > 0, "bad sizes");
+  RG_CHECK(cfg->n_cov <= kMaxCov, "too many covariates for this build");
+  RG_CHECK(cfg->loocv || (cfg->n_folds >= 2 && cfg->n_folds <= kMaxFolds), "n_folds out of range");
+  RG_CHECK(cfg->n_ridge_l0 >= 1 && cfg->max_block_size >= 1 && cfg->total_blocks >= 1, "bad sizes");
+  RG_CUDA(cudaSetDevice(cfg->device));
+  std::unique_ptr<rg_ctx> h(new rg_ctx());
+  h->kind = 1;
+  h->device = cfg->device;
+  RG_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->N = cfg->n_samples; h->C = cfg->n_cov; h->P = cfg->n_pheno;
+  h->loocv = cfg->loocv ? 1 : 0;
+  h->K = h->loocv ? 1 : cfg->n_folds;
+  h->R = cfg->n_ridge_l0; h->R1 = cfg->n_ridge_l1;
+  h->bs_max = cfg->max_block_size;
+  h->rows_p_max = (int)round_up(h->bs_max, kRowPad);
+  h->total_blocks = cfg->total_blocks;
+  h->B = (int64_t)h->total_blocks * h->R;
+  h->n_analyzed = cfg->n_analyzed;
+  build_layout(h.get(), X, Y, mask, in_analysis, fold_sizes);
+  h->lambda.alloc(h->R);
+  h->neff.alloc(h->P);
+  RG_CUDA(cudaMemcpy(h->lambda.p, lambda, h->R * 8, cudaMemcpyHostToDevice));
+  RG_CUDA(cudaMemcpy(h->neff.p, neff, h->P * 8, cudaMemcpyHostToDevice));
+  h->err_slot.alloc(1);
+  RG_CUDA(cudaMemset(h->err_slot.p, 0xFF, 8));
+  h->W.alloc((size_t)h->P * h->Npad * h->B);
+  RG_CUDA(cudaMemset(h->W.p, 0, (size_t)h->P * h->Npad * h->B * 8));
+  *out = h.release();
+  RG_API_END
+}
+
+void rg_destroy(rg_handle h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  rg::flush_timers(h);
+  cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int rg_sync(rg_handle h) {
+  RG_API_BEGIN
+  RG_CHECK(h, "null handle");
+  RG_CUDA(cudaSetDevice(h->device));
+  RG_CUDA(cudaStreamSynchronize(h->stream));
+  rg::flush_timers(h);
+  RG_API_END
+}
+
+int rg_l0_block_bed(rg_handle h, const uint8_t* packed, int64_t row_stride, int32_t bs,
+                    const int32_t* sample_idx, int32_t ref_first, int32_t block_id) {
+  RG_API_BEGIN
+  RG_CHECK(h && packed, "null argument");
+  l0_block_bed(h, packed, row_stride, bs, sample_idx, ref_first, block_id);
+  RG_CUDA(cudaGetLastError());
+  RG_API_END
+}
+
+int64_t rg_l0_status(rg_handle h) {
+  if (!h) return -1;
+  cudaSetDevice(h->device);
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess) {
+    rg::set_last_error(std::string("CUDA error: ") + cudaGetErrorString(cudaGetLastError()));
+    return -1;
+  }
+  rg::flush_timers(h);
+  unsigned long long v = 0;
+  cudaMemcpy(&v, h->err_slot.p, 8, cudaMemcpyDeviceToHost);
+  if (v == ~0ull) return 0;
+  if (v >= (1ull << 40)) {
+    rg::set_last_error("Cholesky pivot not positive (system id " + std::to_string(v - (1ull << 40)) + ")");
+    return (int64_t)v;
+  }
+  rg::set_last_error("SNP has low variance (index " + std::to_string(v - 1) + ")");
+  return (int64_t)v;
+}
+
+int rg_l0_fetch_W(rg_handle h, int32_t block_id, int32_t ph, double* out) {
+  RG_API_BEGIN
+  RG_CHECK(h && out, "null argument");
+  RG_CHECK(h->kind == 1 && block_id >= 0 && block_id < h->total_blocks && ph >= 0 && ph < h->P, "bad index");
+  RG_CUDA(cudaSetDevice(h->device));
+  std::vector<double> tmp((size_t)h->Npad * h->R);
+  const double* src = h->W.p + (size_t)ph * h->Npad * h->B + (size_t)block_id * h->R * h->Npad;
+  RG_CUDA(cudaMemcpyAsync(tmp.data(), src, tmp.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+  RG_CUDA(cudaStreamSynchronize(h->stream));
+  for (int r = 0; r < h->R; ++r)
+    for (int64_t s = 0; s < h->N; ++s) out[(size_t)r * h->N + s] = tmp[(size_t)r * h->Npad + h->pad_of[s]];
+  RG_API_END
+}
+
+int64_t rg_debug_fetch(rg_handle h, const char* name, void* out, int64_t max_bytes) {
+  if (!h || !name || !out) return -1;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  const std::string n(name);
+  const void* p = nullptr;
+  size_t bytes = 0;
+  const int rp = h->last_rows_p;
+  if (n == "gp") { p = h->gp.p; bytes = (size_t)rp * (h->Npad / 16) * 4; }
+  else if (n == "z") { p = h->z.p; bytes = (size_t)2 * rp * h->Npad; }
+  else if (n == "zz") { p = h->zz.p; bytes = (size_t)h->K * 4 * rp * rp * 4; }
+  else if (n == "mu") { p = h->mu.p; bytes = (size_t)rp * 8; }
+  else if (n == "inv_sd") { p = h->inv_sd.p; bytes = (size_t)rp * 8; }
+  else if (n == "Bv") { p = h->Bv.p; bytes = (size_t)rp * h->C * 8; }
+  else if (n == "gty_f") { p = h->gty_f.p; bytes = (size_t)h->K * rp * h->P * 8; }
+  else if (n == "rhs") { p = h->rhs.p; bytes = (size_t)h->K * rp * h->P * 8; }
+  else if (n == "cm") { p = h->cm.p; bytes = (size_t)h->last_nmat * h->last_n_aug * h->last_nC * 8; }
+  else if (n == "mean_invsd") { p = h->mean_invsd.p; bytes = (size_t)2 * h->R * h->P * 8; }
+  else if (n == "dims") {
+    int64_t d[8] = {h->Npad, rp, h->last_nC, h->last_n_aug, h->last_nmat, h->K, h->cpp, h->nchunks};
+    if (max_bytes < (int64_t)sizeof(d)) return -1;
+    memcpy(out, d, sizeof(d));
+    return sizeof(d);
+  } else if (n == "pad_of") {
+    if (max_bytes < (int64_t)(h->N * 4)) return -1;
+    memcpy(out, h->pad_of.data(), h->N * 4);
+    return h->N * 4;
+  } else if (n == "zz_ref") {
+    // test-only: recompute the integer Grams on CUDA cores from the e4m3 planes
+    rg::DevBuf<float> ref;
+    const size_t per = (size_t)4 * rp * rp;
+    ref.alloc(per * h->K);
+    cudaMemsetAsync(ref.p, 0, per * h->K * 4, h->stream);
+    for (int f = 0; f < h->K; ++f)
+      rg::launch_gram_reference(h->z.p, h->Npad, 2 * rp, (int)h->fold_pad_start[f],
+                                (int)(h->fold_pad_start[f] + h->fold_pad_len[f]), ref.p + per * f, 2 * rp,
+                                h->stream);
+    bytes = per * h->K * 4;
+    if ((int64_t)bytes > max_bytes) return -1;
+    if (cudaMemcpyAsync(out, ref.p, bytes, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
+    return (int64_t)bytes;
+  } else {
+    rg::set_last_error("unknown debug buffer: " + n);
+    return -1;
+  }
+  if ((int64_t)bytes > max_bytes) return -1;
+  if (cudaMemcpy(out, p, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int64_t)bytes;
+}
+
+int64_t rg_launch_count(rg_handle h) { return h ? h->launches : 0; }
+void* rg_stream(rg_handle h) { return h ? (void*)h->stream : nullptr; }
+
+int rg_set_timing(rg_handle h, int32_t enable) {
+  RG_API_BEGIN
+  RG_CHECK(h, "null handle");
+  h->timing = enable != 0;
+  RG_API_END
+}
+
+int rg_get_timing(rg_handle h, const char* kernel, double* total_ms, int64_t* launches) {
+  RG_API_BEGIN
+  RG_CHECK(h && kernel, "null argument");
+  RG_CUDA(cudaStreamSynchronize(h->stream));
+  rg::flush_timers(h);
+  auto it = h->timers.find(kernel);
+  if (total_ms) *total_ms = it == h->timers.end() ? 0.0 : it->second.first;
+  if (launches) *launches = it == h->timers.end() ? 0 : it->second.second;
+  RG_API_END
+}
+
+int rg_timing_reset(rg_handle h) {
+  RG_API_BEGIN
+  RG_CHECK(h, "null handle");
+  RG_CUDA(cudaStreamSynchronize(h->stream));
+  rg::flush_timers(h);
+  h->timers.clear();
+  RG_API_END
+}
+
+}  // extern "C"

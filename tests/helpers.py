@@ -1,0 +1,98 @@
+"""Shared builders for the parity tests: synthetic PLINK filesets + oracle-side preparation."""
+import os
+
+import numpy as np
+
+from oracle import plink, prep, step1
+from regenie_b200 import synth
+
+
+def write_fileset(d, g, Y, cov, na, n_chr=3, drop_pheno=(), drop_cov=()):
+    """Write <d>/syn.{bed,bim,fam}, pheno.txt, covar.txt.  g: [M, N] codes (3 = missing)."""
+    M, N = g.shape
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, "syn.bed"), "wb") as fh:
+        fh.write(b"\x6c\x1b\x01")
+        fh.write(synth.pack_bed(g).tobytes())
+    per = int(np.ceil(M / n_chr))
+    with open(os.path.join(d, "syn.bim"), "w") as fh:
+        for i in range(M):
+            fh.write("%d rs%d 0 %d A G\n" % (i // per + 1, i, 1000 + i))
+    with open(os.path.join(d, "syn.fam"), "w") as fh:
+        for s in range(N):
+            fh.write("F%d I%d 0 0 %d -9\n" % (s, s, 1 + s % 2))
+    with open(os.path.join(d, "pheno.txt"), "w") as fh:
+        fh.write("FID IID " + " ".join("Y%d" % (p + 1) for p in range(Y.shape[1])) + "\n")
+        for s in range(N):
+            if s in drop_pheno:
+                continue
+            fh.write("F%d I%d " % (s, s) + " ".join(
+                "NA" if na[s, p] else repr(float(Y[s, p])) for p in range(Y.shape[1])) + "\n")
+    with open(os.path.join(d, "covar.txt"), "w") as fh:
+        fh.write("FID IID " + " ".join("V%d" % (c + 1) for c in range(cov.shape[1])) + "\n")
+        for s in range(N):
+            if s in drop_cov:
+                continue
+            fh.write("F%d I%d " % (s, s) + " ".join(repr(float(v)) for v in cov[s]) + "\n")
+    return os.path.join(d, "syn")
+
+
+class Problem:
+    """Everything both sides need for a QT Step-1 run on a PLINK fileset."""
+
+    def __init__(self, prefix, pheno, covar, bsize, K=5, loocv=False, remove=None):
+        self.bim = plink.read_bim(prefix + ".bim")
+        keys_file, _ = plink.read_fam(prefix + ".fam")
+        self.n_file = len(keys_file)
+        remove = set(remove or ())
+        self.keep = np.array([k not in remove for k in keys_file])
+        self.sample_idx = np.nonzero(self.keep)[0].astype(np.int32)
+        self.keys = [k for k in keys_file if k not in remove]
+        self.prep = prep.prepare(self.keys, pheno, covar)
+        self.blocks = prep.set_blocks(self.bim.chrom, bsize)
+        self.bsize = bsize
+        self.loocv = loocv
+        self.K = K
+        self.fold_sizes = (np.array([len(self.keys)]) if loocv
+                           else prep.set_folds(self.prep.in_analysis, K))
+        self.packed = plink.read_bed_rows(prefix + ".bed", self.n_file, self.bim.offset)
+        self.M = len(self.bim.ids)
+        self.h0 = prep.set_ridge_params(5)
+        self.lam = self.M * (1 - self.h0) / self.h0
+
+    def oracle_block(self, b):
+        c, s, bs = self.blocks[b]
+        g = plink.decode_bed(self.packed[s:s + bs], self.n_file, keep=self.keep)
+        gi, mu = plink.mean_impute_block(g, self.prep.in_analysis)
+        return gi, mu
+
+    def oracle_l0(self, b):
+        gi, mu = self.oracle_block(b)
+        pr = self.prep
+        Gt, sd = step1.residualize_genotypes(gi, pr.X, pr.in_analysis, pr.n_analyzed, pr.ncov)
+        if self.loocv:
+            W = step1.level0_loocv(Gt, pr.Y, pr.mask, self.lam, pr.neff)
+        else:
+            W = step1.level0_kfold(Gt, pr.Y, pr.mask, self.fold_sizes, self.lam, pr.neff)
+        return W, mu, sd, Gt
+
+    def gpu_step1(self, device=0):
+        from regenie_b200 import capi
+        pr = self.prep
+        return capi.Step1(pr.X, pr.Y, pr.mask, pr.in_analysis, self.fold_sizes, self.lam, pr.neff,
+                          pr.n_analyzed, self.bsize, len(self.blocks), loocv=self.loocv, device=device)
+
+    def gpu_l0_block(self, st, b):
+        c, s, bs = self.blocks[b]
+        idx = None if self.keep.all() else self.sample_idx
+        st.l0_block_bed(self.packed[s:s + bs], bs, b, sample_idx=idx)
+
+
+def synthetic_problem(tmp, N=1000, M=300, P=3, C=3, bsize=128, K=5, miss=0.02, seed=7, na_frac=0.03,
+                      drop=True, loocv=False):
+    g = synth.genotypes(N, M, seed=seed, miss=miss)
+    Y, cov, na = synth.phenotypes(g, P, C, seed=seed, na_frac=na_frac)
+    drop_p = {5, 77, N - 3} if drop else ()
+    drop_c = {11, 500 % N} if drop else ()
+    prefix = write_fileset(str(tmp), g, Y, cov, na, drop_pheno=drop_p, drop_cov=drop_c)
+    return Problem(prefix, str(tmp) + "/pheno.txt", str(tmp) + "/covar.txt", bsize, K=K, loocv=loocv)
