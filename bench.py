@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- Step-1 level-0 ridge throughput (SNPs/s) on synthetic PLINK panels.
+
+  python bench.py --gpus N --steps K --warmup W            # the B200 path (C ABI)
+  python bench.py --impl reference --steps K --warmup W    # the CPU port of the reference path
+
+One "step" = one full level-0 pass (decode -> Gram -> ridge solves -> out-of-fold predictions
+-> standardised W) over ALL blocks of the workload (BASELINE.json configs[1]: N=100k samples,
+M=50k SNPs, 10 QTs, --bsize 1000, 5 folds, 5 ridge values, 3 covariates incl. intercept).
+`value` is device-resident throughput; `e2e` feeds the same pass from pinned HOST .bed rows
+through the C ABI (H2D inside the timed region) and reads the status word back.
+With --gpus N (torchrun) every rank runs the same-size workload on its own SNP panel
+(SNP blocks shard with no data-path collective): weak scaling, value = total SNPs / max time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20260924
+CFG = dict(N=100_000, M=50_000, P=10, C=3, bsize=1000, K=5, R=5, miss=0.01)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ----------------------------------------------------------------------------- synthetic data
+def gen_panel_gpu(torch, N, M, bsize, seed, device, miss):
+    """Packed PLINK rows [M, ceil(N/4)] on the device: MAF~U(0.01,0.5), Binomial(2,MAF), `miss` NA."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    stride = (N + 3) // 4
+    out = torch.empty((M, stride), dtype=torch.uint8, device=device)
+    code = torch.tensor([3, 2, 0, 1], dtype=torch.uint8, device=device)   # dosage 0,1,2,NA -> PLINK code
+    for s in range(0, M, bsize):
+        bs = min(bsize, M - s)
+        maf = torch.rand((bs, 1), generator=g, device=device) * 0.49 + 0.01
+        d = (torch.rand((bs, N), generator=g, device=device) < maf).to(torch.uint8)
+        d += (torch.rand((bs, N), generator=g, device=device) < maf).to(torch.uint8)
+        if miss > 0:
+            d[torch.rand((bs, N), generator=g, device=device) < miss] = 3
+        c = code[d.long()]
+        if N % 4:
+            c = torch.nn.functional.pad(c, (0, 4 - N % 4))
+        c = c.view(bs, stride, 4)
+        out[s:s + bs] = c[:, :, 0] | (c[:, :, 1] << 2) | (c[:, :, 2] << 4) | (c[:, :, 3] << 6)
+        del d, c
+    return out
+
+
+def gen_pheno(N, P, C, seed):
+    rng = np.random.default_rng(seed)
+    Y = rng.normal(size=(N, P))
+    cov = rng.normal(size=(N, C - 1))
+    na = rng.random(size=(N, P)) < 0.02
+    return Y, cov, na
+
+
+def blocks_of(M, bsize):
+    return [(s, min(bsize, M - s)) for s in range(0, M, bsize)]
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip().split(", "))
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        hi = [x for x in sm if mx and x > 0.3 * mx] or sm
+        return {"sm_mhz": float(np.median(hi)) if hi else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU port
+def cpu_level0_blocks(packed_rows_list, N, X, Y, mask, in_an, fsz, lam, neff):
+    """Time the oracle's level-0 (decode + impute + residualise + cv matrices + ridge) per block."""
+    from oracle import plink, step1          # the one place bench.py runs the oracle: the CPU baseline
+    t0 = time.perf_counter()
+    nsnp = 0
+    for rows in packed_rows_list:
+        g = plink.decode_bed(rows, N)
+        gi, _ = plink.mean_impute_block(g, in_an.astype(bool))
+        Gt, _ = step1.residualize_genotypes(gi, X, in_an.astype(bool), int(in_an.sum()), X.shape[1])
+        step1.level0_kfold(Gt, Y, mask.astype(bool), fsz, lam, neff)
+        nsnp += rows.shape[0]
+    return nsnp, time.perf_counter() - t0
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ----------------------------------------------------------------------------- main arms
+def run_reference(args):
+    """--impl reference: the CPU port (oracle/, numpy+OpenBLAS on all host threads), one block per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from regenie_b200 import hostprep, synth
+    c = CFG
+    N, bs = c["N"], c["bsize"]
+    Yr, cov, na = gen_pheno(N, c["P"], c["C"], SEED)
+    X, Y, mask, in_an, neff = hostprep.prepare_qt(Yr, cov, na)
+    fsz = hostprep.fold_sizes(N, c["K"])
+    lam = c["M"] * (1 - hostprep.ridge_grid(c["R"])) / hostprep.ridge_grid(c["R"])
+    n_steps = args.steps + args.warmup
+    rows = [synth.pack_bed(synth.genotypes(N, bs, seed=SEED + i, miss=c["miss"])) for i in range(min(n_steps, 2))]
+    times = []
+    for i in range(n_steps):
+        n, dt = cpu_level0_blocks([rows[i % len(rows)]], N, X, Y, mask, in_an, fsz, lam, neff)
+        if i >= args.warmup:
+            times.append(dt)
+    tot = sum(times)
+    val = bs * len(times) / tot
+    cores = host_threads()
+    line = {
+        "impl": "reference", "metric": "step1_level0_snps_per_sec", "value": val, "unit": "SNPs/s",
+        "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(),
+        "cpu_baseline": {"value": val, "unit": "SNPs/s", "cores": cores, "kind": "port",
+                         "sample": "one 1000-SNP block (N=100k) per step, numpy/OpenBLAS port of the reference's "
+                                   "Eigen level-0 path (reference binary not buildable: needs Boost/BGEN lib)"},
+        "e2e": {"value": val, "unit": "SNPs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config():
+    c = CFG
+    return {"workload": "BASELINE.json configs[1]: synthetic PLINK .bed N=100k x M=50k, 10 QT, --step 1 --bsize 1000 "
+                        "(level-0 ridge, 5 folds x 5 ridge values, 3 covariates, 1% missing calls)",
+            "n_samples": c["N"], "n_snps": c["M"], "n_pheno": c["P"], "bsize": c["bsize"], "cv_folds": c["K"],
+            "n_ridge_l0": c["R"], "l2_policy": "inputs larger than L2 (1.25 GB packed .bed per step, streamed once)",
+            "parallelism": "snp-block sharding, no data-path collective"}
+
+
+def run_gpu(args):
+    import torch
+    from regenie_b200 import capi, hostprep
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available() or capi.lib().rg_device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    c = CFG
+    N, M, bs, P, C, K, R = c["N"], c["M"], c["bsize"], c["P"], c["C"], c["K"], c["R"]
+    if args.small:
+        N, M = 20_000, 4_000
+    blocks = blocks_of(M, bs)
+    Yr, cov, na = gen_pheno(N, P, C, SEED)
+    X, Y, mask, in_an, neff = hostprep.prepare_qt(Yr, cov, na)
+    fsz = hostprep.fold_sizes(N, K)
+    h = hostprep.ridge_grid(R)
+    lam = M * (1 - h) / h
+    panel = gen_panel_gpu(torch, N, M, bs, SEED + 1000 * rank, dev, c["miss"])
+    stride = panel.shape[1]
+    torch.cuda.synchronize()
+    host_panel = torch.empty(panel.shape, dtype=torch.uint8, pin_memory=True)
+    host_panel.copy_(panel)
+    torch.cuda.synchronize()
+
+    st = capi.Step1(X, Y, mask, in_an, fsz, lam, neff, N, bs, len(blocks), device=local)
+    ext = torch.cuda.ExternalStream(st.stream(), device=dev)
+
+    def one_pass(base_ptr):
+        for b, (s, n) in enumerate(blocks):
+            st.l0_block_bed(base_ptr + s * stride, n, b, row_stride=stride)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(base_ptr, steps, read_status):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        l0 = st.launch_count()
+        e0.record(ext)
+        for _ in range(steps):
+            one_pass(base_ptr)
+            if read_status:
+                if st.status() != 0:
+                    raise SystemExit("level-0 reported an error: " + capi.lib().rg_last_error().decode())
+        e1.record(ext)
+        e1.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, st.launch_count() - l0
+
+    dev_ptr, host_ptr = panel.data_ptr(), host_panel.data_ptr()
+    for _ in range(max(args.warmup, 3)):
+        one_pass(dev_ptr)
+    if st.status() != 0:
+        raise SystemExit("level-0 reported an error: " + capi.lib().rg_last_error().decode())
+
+    # ---- device-resident throughput (timed region; per-kernel CUDA events on the same stream)
+    st.set_timing(True)
+    clocks = ClockSampler(local); clocks.start()
+    ms, launches = timed(dev_ptr, args.steps, read_status=False)
+    clk = clocks.stop()
+    st.sync()
+    kern = {}
+    for k in ["bed_relayout", "bed_expand", "l0_stats", "gram_tcgen05", "l0_assemble", "chol_factor",
+              "chol_backsolve", "l0_predict"]:
+        t, n = st.timing(k)
+        kern[k] = {"ms_total": round(t, 3), "launches": n}
+    st.set_timing(False)
+    total_snps = M * args.steps * world
+    value = total_snps / (ms / 1e3)
+
+    # ---- end to end: pinned host rows -> H2D -> same pass -> status word D2H, every step
+    for _ in range(1):
+        one_pass(host_ptr)
+    ms_e2e, _ = timed(host_ptr, args.steps, read_status=True)
+    e2e_val = total_snps / (ms_e2e / 1e3)
+
+    if rank != 0:
+        return
+    peaks, peak_src = load_peaks()
+    gram_ms, gram_n = kern["gram_tcgen05"]["ms_total"], max(1, kern["gram_tcgen05"]["launches"])
+    flops_per_launch = 2.0 * bs * bs * N          # 2*N*bs per SNP x bs SNPs (reference src/Data.cpp:748)
+    ach = flops_per_launch / (gram_ms / gram_n * 1e-3) / 1e12
+    # the Gram runs in e4m3 (exact for hard calls); FP8 dense peak = 2 x the measured BF16 cuBLAS rate
+    peak_bf16 = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
+    peak = 2.0 * peak_bf16
+    ktot = sum(v["ms_total"] for v in kern.values()) or 1.0
+    for v in kern.values():
+        v["share"] = round(v["ms_total"] / ktot, 4)
+    # FP64 solver: K*R Cholesky factorisations of bs x bs per block
+    chol_ms = kern["chol_factor"]["ms_total"] / max(1, kern["chol_factor"]["launches"])
+    chol_tf = (K * R * bs ** 3 / 3.0) / (chol_ms * 1e-3) / 1e12 if chol_ms > 0 else None
+
+    cpu = None
+    if not args.no_cpu:
+        rows = [host_panel[s:s + n].numpy() for (s, n) in blocks[: args.cpu_blocks]]
+        nsnp, dt = cpu_level0_blocks(rows, N, X, Y, mask, in_an, fsz, lam, neff)
+        cpu = {"value": nsnp / dt, "unit": "SNPs/s", "cores": host_threads(), "kind": "port",
+               "sample": "%d block(s) of %d SNPs at N=%d from the same panel (numpy/OpenBLAS port of the Eigen "
+                         "level-0 path; %.1f s)" % (len(rows), bs, N, dt)}
+
+    line = {
+        "metric": "step1_level0_snps_per_sec", "value": value, "unit": "SNPs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "e4m3 Gram (exact) + f64",
+        "data": "synthetic", "config": workload_config() if not args.small else {"workload": "SMALL smoke config", "n_samples": N, "n_snps": M},
+        "clocks": clk,
+        "e2e": {"value": e2e_val, "unit": "SNPs/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(M) * int(stride), "d2h_bytes_per_step": 8},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "gram_fp8_tcgen05_kernel", "bound": "tensor", "achieved": ach, "peak": peak,
+                     "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                     "peak_basis": "2 x %s bf16 cuBLAS rate (%s TF/s) = dense FP8" % (peak_src, peak_bf16),
+                     "algorithmic_flops_per_launch": flops_per_launch,
+                     "note": "kernel executes 2x this (lower triangle of the [G0;Miss] Gram) to handle missing calls exactly"},
+        "solver": {"kernel": "chol_update/chol_panel (fp64)", "achieved_tflops": chol_tf, "fp64_peak_nominal": 40.0},
+        "kernels": kern,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--small", action="store_true", help="tiny config for smoke runs (not a bench value)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-blocks", type=int, default=1)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()
