@@ -206,6 +206,9 @@ def run_gpu(args):
     if args.small:
         N, M = 20_000, 4_000
     blocks = blocks_of(M, bs)
+    if args.blocks:
+        blocks = blocks[: args.blocks]
+        M = sum(n for _, n in blocks)
     Yr, cov, na = gen_pheno(N, P, C, SEED)
     X, Y, mask, in_an, neff = hostprep.prepare_qt(Yr, cov, na)
     fsz = hostprep.fold_sizes(N, K)
@@ -332,6 +335,7 @@ def main():
     ap.add_argument("--small", action="store_true", help="tiny config for smoke runs (not a bench value)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-blocks", type=int, default=1)
+    ap.add_argument("--blocks", type=int, default=0, help="profiling only: restrict the pass to the first n blocks")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

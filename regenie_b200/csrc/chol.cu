@@ -101,13 +101,16 @@ chol_panel_kernel(double* __restrict__ cm, int64_t stride, int ld, int k, int ti
       T[threadIdx.x - TB][c] *= inv;
     }
     __syncthreads();
-    // rank-1 update of the remaining columns
-    const int rem = TB - 1 - c;
-    for (int e = threadIdx.x; e < TB * rem; e += 256) {
-      const int r = e / rem, cc = c + 1 + e % rem;
-      const double l = D[cc][c];
-      if (r >= cc) D[r][cc] -= D[r][c] * l;
-      if (!is_diag) T[r][cc] -= T[r][c] * l;
+    // rank-1 update of the remaining columns: thread = (row, column phase), no divisions
+    {
+      const int r = threadIdx.x & (TB - 1);
+      const double dr = D[r][c];
+      const double tr = is_diag ? 0.0 : T[r][c];
+      for (int cc = c + 1 + (threadIdx.x >> 6); cc < TB; cc += 4) {
+        const double l = D[cc][c];
+        if (r >= cc) D[r][cc] -= dr * l;
+        if (!is_diag) T[r][cc] -= tr * l;
+      }
     }
     // (the next iteration's first __syncthreads orders these writes before the column scale)
     __syncthreads();
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(256)
 chol_backsolve_kernel(double* __restrict__ cm, int64_t stride, int ld, int nC, int P) {
   extern __shared__ double back_sm[];
   double (*Lkk)[TB + 1] = reinterpret_cast<double (*)[TB + 1]>(back_sm);
-  double* bsm = back_sm + TB * (TB + 1);   // beta of the current block: [TB][P]
+  double* bsm = back_sm + TB * (TB + 1);   // y / beta of the current block: [TB][P]
   double* A = cm + (int64_t)blockIdx.x * stride;
   for (int kb = nC / TB - 1; kb >= 0; --kb) {
     const int k = kb * TB;
@@ -142,13 +145,14 @@ chol_backsolve_kernel(double* __restrict__ cm, int64_t stride, int ld, int nC, i
       const int r = e % TB, p = e / TB;
       bsm[r * P + p] = A[(int64_t)(nC + p) * ld + k + r];
     }
-    __syncthreads();
-    // solve L_kk^T x = y_k : thread p handles one right-hand side sequentially (64 steps)
-    for (int p = threadIdx.x; p < P; p += 256) {
-      for (int r = TB - 1; r >= 0; --r) {
-        double v = bsm[r * P + p];
-        for (int q = r + 1; q < TB; ++q) v -= Lkk[q][r] * bsm[q * P + p];
-        bsm[r * P + p] = v / Lkk[r][r];
+    // column-oriented solve of L_kk^T x = y_k: one row per step, the rest updated in parallel
+    for (int r = TB - 1; r >= 0; --r) {
+      __syncthreads();
+      if (threadIdx.x < P) bsm[r * P + threadIdx.x] /= Lkk[r][r];
+      __syncthreads();
+      for (int e = threadIdx.x; e < r * P; e += 256) {
+        const int rr = e / P, p = e - rr * P;
+        bsm[rr * P + p] -= Lkk[r][rr] * bsm[r * P + p];
       }
     }
     __syncthreads();
@@ -156,19 +160,25 @@ chol_backsolve_kernel(double* __restrict__ cm, int64_t stride, int ld, int nC, i
       const int r = e % TB, p = e / TB;
       A[(int64_t)(nC + p) * ld + k + r] = bsm[r * P + p];
     }
-    // y[p][j] -= sum_r L[k+r][j] * beta[r][p]   for all j < k
+    // y[p][j] -= sum_r L[k+r][j] * beta[r][p]   for all j < k   (coalesced over j)
     for (int j = threadIdx.x; j < k; j += 256) {
-      for (int p0 = 0; p0 < P; p0 += 8) {
-        double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int p0 = 0; p0 < P; p0 += 10) {
+        double acc[10];
+#pragma unroll
+        for (int q = 0; q < 10; ++q) acc[q] = 0.0;
+        const int np = min(10, P - p0);
+#pragma unroll 8
         for (int r = 0; r < TB; ++r) {
           const double l = A[(int64_t)(k + r) * ld + j];
+          const double* bb = bsm + r * P + p0;
+          if (np == 10) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            if (p0 + q < P) acc[q] = fma(l, bsm[r * P + p0 + q], acc[q]);
+            for (int q = 0; q < 10; ++q) acc[q] = fma(l, bb[q], acc[q]);
+          } else {
+            for (int q = 0; q < np; ++q) acc[q] = fma(l, bb[q], acc[q]);
+          }
         }
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          if (p0 + q < P) A[(int64_t)(nC + p0 + q) * ld + j] -= acc[q];
+        for (int q = 0; q < np; ++q) A[(int64_t)(nC + p0 + q) * ld + j] -= acc[q];
       }
     }
   }

@@ -58,6 +58,16 @@ struct rg_ctx {
   rg::DevBuf<double> W;             // [P][Npad x B] column-major
   int last_bs = 0, last_rows_p = 0, last_nC = 0, last_n_aug = 0, last_nmat = 0;
 
+  // ---- level 1
+  rg::DevBuf<int4> l1_chunks;
+  rg::DevBuf<int2> l1_fold_chunks;
+  int l1_nchunks = 0;
+  rg::DevBuf<double> l1_part, l1_part_y, l1_cm, l1_beta, l1_sums, l1_part_out, l1_tau, l1_pred;
+  rg::DevBuf<int32_t> l1_chr_cols;
+  std::vector<int32_t> best_idx;
+  int l1_nC = 0;
+  bool l1_done = false;
+
   // ---- timing
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

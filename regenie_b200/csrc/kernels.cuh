@@ -6,6 +6,7 @@ namespace rg {
 
 constexpr int kMaxFolds = 16;
 constexpr int kMaxCov = 64;
+constexpr int kMaxRidge = 8;
 
 // ---- bed_kernels.cu
 void launch_bed_relayout(const uint8_t* packed, int64_t row_stride, int bs, int rows_p,
@@ -85,5 +86,20 @@ void launch_l0_standardize(const double* part, int ntiles, int Qp, int Q, int P,
                            double* mean_invsd, double* W, int64_t w_stride, int64_t npad, int col0,
                            const uint8_t* is_real, cudaStream_t s);
 int predict_qt();
+
+// ---- l1_kernels.cu
+void launch_l1_gram(const double* W, int64_t ldw, int B, const int4* chunks, int nchunks, double* part,
+                    int64_t part_stride, int ldp, cudaStream_t s);
+void launch_l1_xty(const double* W, int64_t ldw, const double* xy, int cpp, int ycol, const int4* chunks,
+                   int nchunks, double* part_y, int B, cudaStream_t s);
+void launch_l1_assemble(const double* part, int64_t part_stride, int ldp, const double* part_y,
+                        const int2* fold_chunks, int K, int R1, const double* tau, int B, int nC, double* cm,
+                        int64_t cm_stride, cudaStream_t s);
+void launch_l1_pred_sums(const double* W, int64_t ldw, int B, int R1, const double* beta, int ldb,
+                         const int32_t* tile_fold, const double* xy, int cpp, int ycol, double* part_out,
+                         int ntiles, double* out, cudaStream_t s);
+void launch_l1_chr_pred(const double* W, int64_t ldw, int nchr, const int32_t* chr_col_start, const double* beta,
+                        int ldb, int R1, int best, const int32_t* tile_fold, double* pred, int64_t npad,
+                        cudaStream_t s);
 
 }  // namespace rg

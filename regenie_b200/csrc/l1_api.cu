@@ -1,4 +1,6 @@
 // Level-1 ridge, LOCO assembly and Step-2 entry points of the C ABI (include/rg_b200.h).
+#include <algorithm>
+
 #include "context.cuh"
 
 using namespace rg;
@@ -16,17 +18,154 @@ using namespace rg;
   }                                        \
   return 0;
 
+
+
+static void l1_fit(rg_ctx* h, const double* tau_host, double* cumsum, int32_t* best_idx) {
+  RG_CHECK(h->kind == 1, "handle is not a Step-1 handle");
+  RG_CHECK(!h->loocv, "LOOCV level 1 is not implemented yet");
+  RG_CHECK(h->R1 >= 1 && h->R1 <= kMaxRidge, "n_ridge_l1 out of range");
+  RG_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const int K = h->K, R1 = h->R1, P = h->P;
+  const int B = (int)h->B;
+  const int nC = (int)round_up(B, 64), n_aug = nC + 64, nmat = K * R1;
+  const int ldp = nC;
+  const int64_t Npad = h->Npad;
+  h->l1_nC = nC;
+  // chunk table for the sample-axis reductions: bounded partial storage (<= ~1 GiB)
+  {
+    const int64_t per = (int64_t)nC * ldp * 8;
+    const int64_t max_chunks = std::max<int64_t>(K, (1ll << 30) / per);
+    int64_t len = round_up(std::max<int64_t>(kStatChunk, ceil_div(Npad, max_chunks - K + 1)), 128);
+    std::vector<int4> chunks;
+    std::vector<int2> fold_chunks(K);
+    for (int f = 0; f < K; ++f) {
+      fold_chunks[f].x = (int)chunks.size();
+      for (int64_t o = 0; o < h->fold_pad_len[f]; o += len)
+        chunks.push_back(make_int4((int)(h->fold_pad_start[f] + o),
+                                   (int)std::min<int64_t>(len, h->fold_pad_len[f] - o), f, 0));
+      fold_chunks[f].y = (int)chunks.size();
+    }
+    h->l1_nchunks = (int)chunks.size();
+    h->l1_chunks.alloc(chunks.size());
+    h->l1_fold_chunks.alloc(K);
+    RG_CUDA(cudaMemcpyAsync(h->l1_chunks.p, chunks.data(), chunks.size() * sizeof(int4), cudaMemcpyHostToDevice, s));
+    RG_CUDA(cudaMemcpyAsync(h->l1_fold_chunks.p, fold_chunks.data(), K * sizeof(int2), cudaMemcpyHostToDevice, s));
+    RG_CUDA(cudaStreamSynchronize(s));
+  }
+  const int nch = h->l1_nchunks;
+  const int64_t part_stride = (int64_t)nC * ldp;
+  const int64_t cm_stride = (int64_t)n_aug * nC;
+  const int ntiles = (int)(Npad / 128);
+  const int NV = kMaxRidge * 3 + 2;
+  h->l1_part.alloc((size_t)nch * part_stride);
+  h->l1_part_y.alloc((size_t)nch * B);
+  h->l1_cm.alloc((size_t)nmat * cm_stride);
+  h->l1_beta.alloc((size_t)P * nmat * nC);
+  h->l1_sums.alloc((size_t)P * NV);
+  h->l1_part_out.alloc((size_t)ntiles * NV);
+  h->l1_tau.alloc((size_t)P * R1);
+  RG_CUDA(cudaMemcpyAsync(h->l1_tau.p, tau_host, (size_t)P * R1 * 8, cudaMemcpyHostToDevice, s));
+  RG_CUDA(cudaMemsetAsync(h->l1_cm.p, 0, (size_t)nmat * cm_stride * 8, s));
+  for (int p = 0; p < P; ++p) {
+    const double* Wp = h->W.p + (size_t)p * Npad * h->B;
+    const int ycol = h->C + p;
+    launch_l1_gram(Wp, Npad, B, h->l1_chunks.p, nch, h->l1_part.p, part_stride, ldp, s);
+    launch_l1_xty(Wp, Npad, h->xy.p, h->cpp, ycol, h->l1_chunks.p, nch, h->l1_part_y.p, B, s);
+    launch_l1_assemble(h->l1_part.p, part_stride, ldp, h->l1_part_y.p, h->l1_fold_chunks.p, K, R1,
+                       h->l1_tau.p + (size_t)p * R1, B, nC, h->l1_cm.p, cm_stride, s);
+    launch_chol_factor(h->l1_cm.p, cm_stride, nC, n_aug, nmat, h->err_slot.p, (long long)(1ll << 41) + p * 1024, s);
+    launch_chol_backsolve(h->l1_cm.p, cm_stride, nC, 1, nmat, s);
+    // keep beta[f][r][0:nC] (RHS row nC of every system)
+    RG_CUDA(cudaMemcpy2DAsync(h->l1_beta.p + (size_t)p * nmat * nC, (size_t)nC * 8,
+                              h->l1_cm.p + (size_t)nC * nC, (size_t)cm_stride * 8, (size_t)nC * 8, nmat,
+                              cudaMemcpyDeviceToDevice, s));
+    launch_l1_pred_sums(Wp, Npad, B, R1, h->l1_beta.p + (size_t)p * nmat * nC, nC, h->tile_fold.p, h->xy.p, h->cpp,
+                        ycol, h->l1_part_out.p, ntiles, h->l1_sums.p + (size_t)p * NV, s);
+    h->launches += 5 + chol_num_launches(nC) + 1 + 2;
+  }
+  std::vector<double> sums((size_t)P * NV), neff(P);
+  RG_CUDA(cudaMemcpyAsync(sums.data(), h->l1_sums.p, sums.size() * 8, cudaMemcpyDeviceToHost, s));
+  RG_CUDA(cudaMemcpyAsync(neff.data(), h->neff.p, P * 8, cudaMemcpyDeviceToHost, s));
+  RG_CUDA(cudaStreamSynchronize(s));
+  h->best_idx.assign(P, 0);
+  for (int p = 0; p < P; ++p) {
+    const double* v = &sums[(size_t)p * NV];
+    double best = 1e10;                                   // src/Data.cpp:1021-1037
+    for (int j = 0; j < R1; ++j) {
+      const double sx = v[3 * j], sx2 = v[3 * j + 1], sxy = v[3 * j + 2], sy = v[3 * kMaxRidge], sy2 = v[3 * kMaxRidge + 1];
+      if (cumsum) {
+        cumsum[((size_t)0 * P + p) * R1 + j] = sx;
+        cumsum[((size_t)1 * P + p) * R1 + j] = sy;
+        cumsum[((size_t)2 * P + p) * R1 + j] = sx2;
+        cumsum[((size_t)3 * P + p) * R1 + j] = sy2;
+        cumsum[((size_t)4 * P + p) * R1 + j] = sxy;
+      }
+      const double perf = (sx2 + sy2 - 2 * sxy) / neff[p];
+      if (perf < best) { best = perf; h->best_idx[p] = j; }
+    }
+    if (best_idx) best_idx[p] = h->best_idx[p];
+  }
+  h->l1_done = true;
+}
+
+static void loco(rg_ctx* h, const int32_t* chr_of_block, double* pred_out) {
+  RG_CHECK(h->kind == 1 && h->l1_done, "rg_l1_fit must run before rg_loco");
+  RG_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const int K = h->K, R1 = h->R1, P = h->P, R = h->R;
+  const int nC = h->l1_nC, nmat = K * R1;
+  const int64_t Npad = h->Npad, N = h->N;
+  // chromosomes in block order (blocks never straddle chromosomes, src/Data.cpp:311-334)
+  std::vector<int32_t> chrs, col_start;
+  for (int b = 0; b < h->total_blocks; ++b) {
+    const int c = chr_of_block[b];
+    RG_CHECK(c >= 1 && c <= 23, "chromosome out of range");
+    if (chrs.empty() || chrs.back() != c) {
+      RG_CHECK(chrs.empty() || c > chrs.back(), "blocks must be ordered by chromosome");
+      chrs.push_back(c);
+      col_start.push_back(b * R);
+    }
+  }
+  col_start.push_back(h->total_blocks * R);
+  const int nchr = (int)chrs.size();
+  h->l1_chr_cols.alloc(col_start.size());
+  RG_CUDA(cudaMemcpyAsync(h->l1_chr_cols.p, col_start.data(), col_start.size() * 4, cudaMemcpyHostToDevice, s));
+  h->l1_pred.alloc((size_t)nchr * Npad);
+  std::vector<double> pred((size_t)nchr * Npad);
+  for (int p = 0; p < P; ++p) {
+    launch_l1_chr_pred(h->W.p + (size_t)p * Npad * h->B, Npad, nchr, h->l1_chr_cols.p,
+                       h->l1_beta.p + (size_t)p * nmat * nC, nC, R1, h->best_idx[p], h->tile_fold.p, h->l1_pred.p, Npad, s);
+    h->launches += 1;
+    RG_CUDA(cudaMemcpyAsync(pred.data(), h->l1_pred.p, pred.size() * 8, cudaMemcpyDeviceToHost, s));
+    RG_CUDA(cudaStreamSynchronize(s));
+    // LOCO assembly (src/Data.cpp:1846-1858): all-chromosome sum minus the chromosome's own part
+    double* out = pred_out + (size_t)p * 23 * N;
+    for (int64_t i = 0; i < N; ++i) {
+      const int64_t t = h->pad_of[i];
+      double tot = 0.0;
+      for (int ci = 0; ci < nchr; ++ci) tot += pred[(size_t)ci * Npad + t];
+      for (int c = 0; c < 23; ++c) out[(size_t)c * N + i] = tot;
+      for (int ci = 0; ci < nchr; ++ci) out[(size_t)(chrs[ci] - 1) * N + i] = tot - pred[(size_t)ci * Npad + t];
+    }
+  }
+}
+
 extern "C" {
 
 int rg_l1_fit(rg_handle h, const double* tau, double* cumsum, int32_t* best_idx) {
   RG_API_BEGIN
-  RG_CHECK(false, "rg_l1_fit: not implemented yet");
+  RG_CHECK(h && tau, "null argument");
+  l1_fit(h, tau, cumsum, best_idx);
+  RG_CUDA(cudaGetLastError());
   RG_API_END
 }
 
 int rg_loco(rg_handle h, const int32_t* chr_of_block, double* pred_out) {
   RG_API_BEGIN
-  RG_CHECK(false, "rg_loco: not implemented yet");
+  RG_CHECK(h && chr_of_block && pred_out, "null argument");
+  loco(h, chr_of_block, pred_out);
+  RG_CUDA(cudaGetLastError());
   RG_API_END
 }
 
