@@ -125,44 +125,51 @@ int rg_loco(rg_handle h, const int32_t* chr_of_block, double* pred_out);
 typedef struct rg_step2_config {
   int32_t device;
   int64_t n_samples;       /* N                                                          */
-  int32_t n_cov;           /* C                                                          */
+  int32_t n_cov;           /* C  = params.ncov (orthonormal basis columns)               */
   int32_t n_pheno;         /* P                                                          */
-  int32_t max_block_size;
-  int64_t n_analyzed;
+  int32_t max_block_size;  /* params.block_size                                          */
+  int64_t n_analyzed;      /* params.n_analyzed                                          */
+  int32_t strict_mode;     /* params.strict_mode (forced when P == 1, src/Pheno.cpp:198) */
 } rg_step2_config;
 
 /*
- * rg_step2_create / rg_s2_set_chr -- upload what Data::compute_res (src/Data.cpp:2386-2404)
- * produces for one chromosome: res = (Y - blup) o mask scaled by p_sd_yres, and YtX.
+ * rg_step2_create -- state shared by every variant of a Step-2 run:
+ *   X [N x C] pheno_data.new_cov, mask [N x P] pheno_data.masked_indivs (after blup_read),
+ *   in_analysis [N] filters.ind_in_analysis.
+ * rg_s2_set_chr -- per chromosome, what Data::compute_res (src/Data.cpp:2386-2404) produces:
+ *   res [N x P] = (Y - blup) o mask / p_sd_yres,  scf_sv [P] = scale_Y * p_sd_yres.
+ *   (YtX = res^T X is formed on the device.)
  */
 int rg_step2_create(const rg_step2_config* cfg, const double* X, const uint8_t* mask,
                     const uint8_t* in_analysis, rg_handle* out);
-int rg_s2_set_chr(rg_handle h, const double* res /*[N x P]*/);
+int rg_s2_set_chr(rg_handle h, const double* res, const double* scf_sv);
 
-/* per-variant outputs of one Step-2 block (struct-of-arrays, bs entries each) */
+/* per-variant outputs of one Step-2 block; host arrays, variant-major ([i*P + p]) */
 typedef struct rg_s2_out {
-  double* sum_g;      /* [bs]      total dosage over analysed non-missing samples          */
-  int32_t* n_nonmiss; /* [bs]      ns1: analysed & non-missing                             */
-  int32_t* ns_ph;     /* [bs x P]  per-trait non-missing counts (update_trait_counts)      */
-  double* sum_g_ph;   /* [bs x P]  per-trait dosage sums                                   */
-  int32_t* n_nonzero; /* [bs]      analysed samples with g != 0 after imputation           */
-  double* scale_fac;  /* [bs]      residualize_geno scale (dense path), src/Geno.cpp:3242  */
-  double* num;        /* [bs x P]  res^T g~        (compute_score_qt numerator, :415)      */
-  double* denum;      /* [bs x P]  mask_ph^T (g~ o g~)               (:416)                */
-  double* gtx;        /* [bs x C]  X^T g (imputed, un-residualised)                        */
-  double* sumsq_ph;   /* [bs x P]  mask_ph^T (g o g), imputed un-residualised (sparse :410)*/
-  double* gx_ph;      /* [bs x P x C] (X o mask_ph)^T g  (sparse path :410)                */
-  double* num_raw;    /* [bs x P]  res^T g (imputed, un-residualised; sparse path :404)    */
+  double* af;        /* [bs x P] block_info->af   (A1FREQ per trait)                      */
+  int32_t* ns;       /* [bs x P] block_info->ns   (N per trait)                           */
+  double* mac;       /* [bs x P] block_info->mac                                          */
+  double* af_all;    /* [bs]     af1                                                      */
+  int32_t* ns_all;   /* [bs]     ns1                                                      */
+  double* mac_all;   /* [bs]     mac1                                                     */
+  int32_t* flags;    /* [bs]     bit0 ignored (MAC < minMAC), bit1 ignored (scale_fac <
+                                 numtol), bit2 sparse-genotype formulas were used         */
+  double* scale_fac; /* [bs]     residualize_geno scale (1 on the sparse path)            */
+  double* stat;      /* [bs x P] dt_thr->stats = num / sqrt(denum)                        */
+  double* beta;      /* [bs x P] dt_thr->bhat                                             */
+  double* se;        /* [bs x P] dt_thr->se_b                                             */
+  double* chisq;     /* [bs x P] dt_thr->chisq_val                                        */
 } rg_s2_out;
 
 /*
- * rg_s2_block_bed -- Step-2 sufficient statistics for bs variants from 2-bit PLINK rows.
- * Replaces parseSnpfromBed + compute_mac/compute_aaf_info + residualize_geno +
- * the N-length reductions of compute_score_qt (src/Geno.cpp:2414-2536,3077-3163,3242;
- * src/Step2_Models.cpp:343-467).  The host finishes beta/SE/chisq/log10P per variant.
+ * rg_s2_block_bed -- Step-2 score test for bs variants from 2-bit PLINK rows.  Replaces, per
+ * variant: parseSnpfromBed + compute_mac + compute_aaf_info (src/Geno.cpp:2414-2536,
+ * 3077-3148), check_sparse_G (:3165), residualize_geno (:3242) and compute_score_qt
+ * (src/Step2_Models.cpp:343-467) up to chisq; LOG10P (get_logp) and text are host work.
  */
 int rg_s2_block_bed(rg_handle h, const uint8_t* packed, int64_t row_stride, int32_t bs,
-                    const int32_t* sample_idx, int32_t ref_first, const rg_s2_out* out);
+                    const int32_t* sample_idx, int32_t ref_first, double min_mac,
+                    const rg_s2_out* out);
 
 /* ------------------------------------------------------------------ multi-GPU */
 /* Number of level-0 predictor columns held locally; W of other ranks is attached with

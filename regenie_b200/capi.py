@@ -28,16 +28,13 @@ class Step1Config(C.Structure):
 class Step2Config(C.Structure):
     _fields_ = [
         ("device", C.c_int32), ("n_samples", C.c_int64), ("n_cov", C.c_int32), ("n_pheno", C.c_int32),
-        ("max_block_size", C.c_int32), ("n_analyzed", C.c_int64),
+        ("max_block_size", C.c_int32), ("n_analyzed", C.c_int64), ("strict_mode", C.c_int32),
     ]
 
 
 class S2Out(C.Structure):
-    _fields_ = [
-        ("sum_g", C.c_void_p), ("n_nonmiss", C.c_void_p), ("ns_ph", C.c_void_p), ("sum_g_ph", C.c_void_p),
-        ("n_nonzero", C.c_void_p), ("scale_fac", C.c_void_p), ("num", C.c_void_p), ("denum", C.c_void_p),
-        ("gtx", C.c_void_p), ("sumsq_ph", C.c_void_p), ("gx_ph", C.c_void_p), ("num_raw", C.c_void_p),
-    ]
+    _fields_ = [(k, C.c_void_p) for k in ("af", "ns", "mac", "af_all", "ns_all", "mac_all", "flags", "scale_fac",
+                                           "stat", "beta", "se", "chisq")]
 
 
 # every symbol include/rg_b200.h declares (checked by tests/test_abi.py)
@@ -74,8 +71,6 @@ def lib():
         L.rg_get_timing.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p]
         L.rg_l1_fit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.rg_loco.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-        L.rg_s2_set_chr.argtypes = [C.c_void_p, C.c_void_p]
-        L.rg_s2_block_bed.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
         L.rg_W_info.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
@@ -185,3 +180,49 @@ class Step1:
         ms = C.c_double(); n = C.c_int64()
         check(lib().rg_get_timing(self.h, name.encode(), C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+
+class Step2:
+    """Host-side mirror of the Step-2 QT call sequence of Data::test_snps_fast (src/Data.cpp:2230-2383)."""
+
+    def __init__(self, X, mask, in_analysis, n_analyzed, max_block_size, strict=False, device=0):
+        L = lib()
+        L.rg_s2_set_chr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rg_s2_block_bed.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,
+                                      C.c_double, C.c_void_p]
+        X = _f64(X)
+        mask = np.require(np.asarray(mask, dtype=np.uint8), requirements=["F", "A"])
+        ia = np.ascontiguousarray(in_analysis, dtype=np.uint8)
+        self.N, self.C = X.shape
+        self.P = mask.shape[1]
+        cfg = Step2Config(device, self.N, self.C, self.P, max_block_size, int(n_analyzed), int(strict))
+        h = C.c_void_p()
+        check(L.rg_step2_create(C.byref(cfg), _ptr(X), _ptr(mask), _ptr(ia), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().rg_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def set_chr(self, res, scf_sv):
+        res = _f64(res)
+        scf = np.ascontiguousarray(scf_sv, dtype=np.float64)
+        check(lib().rg_s2_set_chr(self.h, _ptr(res), _ptr(scf)))
+
+    def block_bed(self, packed, sample_idx=None, ref_first=False, min_mac=5.0):
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        bs, P = packed.shape[0], self.P
+        o = dict(af=np.empty((bs, P)), ns=np.empty((bs, P), dtype=np.int32), mac=np.empty((bs, P)),
+                 af_all=np.empty(bs), ns_all=np.empty(bs, dtype=np.int32), mac_all=np.empty(bs),
+                 flags=np.empty(bs, dtype=np.int32), scale_fac=np.empty(bs), stat=np.empty((bs, P)),
+                 beta=np.empty((bs, P)), se=np.empty((bs, P)), chisq=np.empty((bs, P)))
+        so = S2Out(*[o[k].ctypes.data for k in ("af", "ns", "mac", "af_all", "ns_all", "mac_all", "flags",
+                                                "scale_fac", "stat", "beta", "se", "chisq")])
+        if sample_idx is not None:
+            sample_idx = np.ascontiguousarray(sample_idx, dtype=np.int32)
+        check(lib().rg_s2_block_bed(self.h, _ptr(packed), packed.shape[1], bs, _ptr(sample_idx), int(ref_first),
+                                    float(min_mac), C.byref(so)))
+        return o

@@ -68,6 +68,14 @@ struct rg_ctx {
   int l1_nC = 0;
   bool l1_done = false;
 
+  // ---- step 2
+  int strict = 0, dp = 0;
+  std::vector<double> Xh;            // [N x C] host copy
+  std::vector<uint8_t> maskh;        // [N x P]
+  rg::DevBuf<double> F, s2_part, s2_sums, s2_maskcount, s2_YtX, s2_XmX, s2_scf;
+  rg::DevBuf<double> s2_out_d;       // packed f64 outputs
+  rg::DevBuf<int32_t> s2_out_i;      // packed i32 outputs
+
   // ---- timing
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -102,4 +102,21 @@ void launch_l1_chr_pred(const double* W, int64_t ldw, int nchr, const int32_t* c
                         int ldb, int R1, int best, const int32_t* tile_fold, double* pred, int64_t npad,
                         cudaStream_t s);
 
+// ---- s2_kernels.cu
+struct S2FinalizeArgs {
+  int bs, C, P, dp, strict;
+  long long n_analyzed, n_samples;
+  double min_mac, numtol;
+  const double* sums;        // [rows_p][3][dp]
+  const double* mask_count;  // [P]
+  const double* YtX;         // [P][C]
+  const double* XmX;         // [P][C][C]
+  const double* scf_sv;      // [P]
+  double *af, *mac, *af_all, *mac_all, *scale_fac, *stat, *beta, *se, *chisq;
+  int32_t *ns, *ns_all, *flags;
+};
+void launch_s2_stats(const uint32_t* gp, int64_t npad, const double* F, int dp, const int4* chunks, int nchunks,
+                     int rows_p, double* part, double* sums, cudaStream_t s);
+void launch_s2_finalize(const S2FinalizeArgs& a, cudaStream_t s);
+
 }  // namespace rg

@@ -169,26 +169,6 @@ int rg_loco(rg_handle h, const int32_t* chr_of_block, double* pred_out) {
   RG_API_END
 }
 
-int rg_step2_create(const rg_step2_config* cfg, const double* X, const uint8_t* mask,
-                    const uint8_t* in_analysis, rg_handle* out) {
-  RG_API_BEGIN
-  RG_CHECK(false, "rg_step2_create: not implemented yet");
-  RG_API_END
-}
-
-int rg_s2_set_chr(rg_handle h, const double* res) {
-  RG_API_BEGIN
-  RG_CHECK(false, "rg_s2_set_chr: not implemented yet");
-  RG_API_END
-}
-
-int rg_s2_block_bed(rg_handle h, const uint8_t* packed, int64_t row_stride, int32_t bs,
-                    const int32_t* sample_idx, int32_t ref_first, const rg_s2_out* out) {
-  RG_API_BEGIN
-  RG_CHECK(false, "rg_s2_block_bed: not implemented yet");
-  RG_API_END
-}
-
 int rg_W_info(rg_handle h, int32_t ph, void** dev_ptr, int64_t* ld, int64_t* ncols) {
   RG_API_BEGIN
   RG_CHECK(h && h->kind == 1 && ph >= 0 && ph < h->P, "bad argument");

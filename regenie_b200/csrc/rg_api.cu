@@ -359,6 +359,9 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
   }
 }
 
+void require_gpu_public(int device) { require_gpu(device); }
+void build_file_idx_public(rg_ctx* h, const int32_t* sample_idx_host) { build_file_idx(h, sample_idx_host); }
+
 }  // namespace rg
 
 using namespace rg;

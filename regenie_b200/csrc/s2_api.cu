@@ -1,0 +1,195 @@
+// Step-2 entry points of the C ABI (include/rg_b200.h).
+#include <algorithm>
+
+#include "context.cuh"
+
+using namespace rg;
+
+#define RG_API_BEGIN try {
+#define RG_API_END                         \
+  }                                        \
+  catch (const rg::Error& e) {             \
+    rg::set_last_error(e.msg);             \
+    return 1;                              \
+  }                                        \
+  catch (const std::exception& e) {        \
+    rg::set_last_error(e.what());          \
+    return 1;                              \
+  }                                        \
+  return 0;
+
+namespace rg {
+void require_gpu_public(int device);
+}
+
+static void s2_create(rg_ctx* h, const rg_step2_config* cfg, const double* X, const uint8_t* mask,
+                      const uint8_t* in_analysis) {
+  h->kind = 2;
+  h->device = cfg->device;
+  RG_CUDA(cudaSetDevice(h->device));
+  RG_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->N = cfg->n_samples; h->C = cfg->n_cov; h->P = cfg->n_pheno; h->K = 1;
+  h->bs_max = cfg->max_block_size;
+  h->rows_p_max = (int)round_up(h->bs_max, kRowPad);
+  h->n_analyzed = cfg->n_analyzed;
+  h->strict = (cfg->strict_mode || h->P == 1) ? 1 : 0;
+  const int64_t N = h->N;
+  const int C = h->C, P = h->P;
+  h->Npad = round_up(N, kSamplePad);
+  h->pad_of.resize(N);
+  h->src_of.assign(h->Npad, -1);
+  for (int64_t s = 0; s < N; ++s) { h->pad_of[s] = (int32_t)s; h->src_of[s] = (int32_t)s; }
+  h->in_analysis.assign(in_analysis, in_analysis + N);
+  h->Xh.assign(X, X + (size_t)N * C);
+  h->maskh.assign(mask, mask + (size_t)N * P);
+  h->dp = (int)round_up(1 + C + 2 * P + P * C, 16);
+  std::vector<int4> chunks;
+  for (int64_t o = 0; o < h->Npad; o += kStatChunk)
+    chunks.push_back(make_int4((int)o, (int)std::min<int64_t>(kStatChunk, h->Npad - o), 0, 0));
+  h->nchunks = (int)chunks.size();
+  h->chunks.alloc(chunks.size());
+  RG_CUDA(cudaMemcpy(h->chunks.p, chunks.data(), chunks.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  // per-trait constants: mask counts and X_p^T X_p = sum_i m_ip x_i x_i^T
+  std::vector<double> mc(P, 0.0), XmX((size_t)P * C * C, 0.0);
+  for (int p = 0; p < P; ++p)
+    for (int64_t s = 0; s < N; ++s) {
+      if (!mask[(size_t)p * N + s]) continue;
+      mc[p] += 1.0;
+      for (int c = 0; c < C; ++c) {
+        const double xc = X[(size_t)c * N + s];
+        if (xc == 0.0) continue;
+        for (int c2 = 0; c2 < C; ++c2) XmX[((size_t)p * C + c) * C + c2] += xc * X[(size_t)c2 * N + s];
+      }
+    }
+  h->s2_maskcount.alloc(P); h->s2_XmX.alloc(XmX.size()); h->s2_YtX.alloc((size_t)P * C); h->s2_scf.alloc(P);
+  RG_CUDA(cudaMemcpy(h->s2_maskcount.p, mc.data(), P * 8, cudaMemcpyHostToDevice));
+  RG_CUDA(cudaMemcpy(h->s2_XmX.p, XmX.data(), XmX.size() * 8, cudaMemcpyHostToDevice));
+  h->F.alloc((size_t)h->Npad * h->dp);
+  h->err_slot.alloc(1);
+  RG_CUDA(cudaMemset(h->err_slot.p, 0xFF, 8));
+}
+
+static void s2_set_chr(rg_ctx* h, const double* res, const double* scf_sv) {
+  RG_CHECK(h->kind == 2, "handle is not a Step-2 handle");
+  RG_CUDA(cudaSetDevice(h->device));
+  const int64_t N = h->N;
+  const int C = h->C, P = h->P, dp = h->dp;
+  std::vector<double> F((size_t)h->Npad * dp, 0.0), YtX((size_t)P * C, 0.0);
+  for (int64_t s = 0; s < N; ++s) {
+    double* r = &F[(size_t)s * dp];
+    r[0] = h->in_analysis[s] ? 1.0 : 0.0;
+    for (int c = 0; c < C; ++c) r[1 + c] = h->Xh[(size_t)c * N + s];
+    for (int p = 0; p < P; ++p) {
+      const double m = h->maskh[(size_t)p * N + s] ? 1.0 : 0.0;
+      const double rv = res[(size_t)p * N + s];
+      r[1 + C + p] = rv;
+      r[1 + C + P + p] = m;
+      for (int c = 0; c < C; ++c) {
+        r[1 + C + 2 * P + p * C + c] = m * r[1 + c];
+        YtX[(size_t)p * C + c] += rv * r[1 + c];
+      }
+    }
+  }
+  RG_CUDA(cudaMemcpyAsync(h->F.p, F.data(), F.size() * 8, cudaMemcpyHostToDevice, h->stream));
+  RG_CUDA(cudaMemcpyAsync(h->s2_YtX.p, YtX.data(), YtX.size() * 8, cudaMemcpyHostToDevice, h->stream));
+  RG_CUDA(cudaMemcpyAsync(h->s2_scf.p, scf_sv, P * 8, cudaMemcpyHostToDevice, h->stream));
+  RG_CUDA(cudaStreamSynchronize(h->stream));
+}
+
+namespace rg {
+void build_file_idx_public(rg_ctx* h, const int32_t* sample_idx_host);
+}
+
+static void s2_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, int bs, const int32_t* sample_idx,
+                         int ref_first, double min_mac, const rg_s2_out* out) {
+  RG_CHECK(h->kind == 2, "handle is not a Step-2 handle");
+  RG_CHECK(bs > 0 && bs <= h->bs_max, "block size out of range");
+  RG_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const int P = h->P, C = h->C;
+  const int rows_p = (int)round_up(bs, kRowPad);
+  const int64_t Npad = h->Npad;
+  {
+    std::vector<int32_t> host_idx;
+    if (sample_idx) {
+      host_idx.resize(h->N);
+      RG_CUDA(cudaMemcpy(host_idx.data(), sample_idx, h->N * 4, cudaMemcpyDefault));
+      if (!h->file_idx_valid || h->cached_sample_idx != host_idx) {
+        build_file_idx_public(h, host_idx.data());
+        h->cached_sample_idx = host_idx;
+      }
+    } else if (!h->file_idx_valid || !h->cached_sample_idx.empty()) {
+      build_file_idx_public(h, nullptr);
+      h->cached_sample_idx.clear();
+    }
+  }
+  const uint8_t* packed_d = packed;
+  if (!is_device_pointer(packed)) {
+    h->packed_dev.alloc((size_t)h->bs_max * row_stride);
+    copy_to_device(h->packed_dev.p, packed, (size_t)bs * row_stride, s);
+    packed_d = h->packed_dev.p;
+  }
+  h->gp.alloc((size_t)h->rows_p_max * (Npad / 16));
+  h->s2_part.alloc((size_t)h->nchunks * h->rows_p_max * 3 * h->dp);
+  h->s2_sums.alloc((size_t)h->rows_p_max * 3 * h->dp);
+  const size_t nd = (size_t)h->bs_max * (7 * (size_t)P + 3), ni = (size_t)h->bs_max * ((size_t)P + 2);
+  h->s2_out_d.alloc(nd);
+  h->s2_out_i.alloc(ni);
+  launch_bed_relayout(packed_d, row_stride, bs, rows_p, h->file_idx_pad.p, ref_first, h->gp.p, Npad, s);
+  launch_s2_stats(h->gp.p, Npad, h->F.p, h->dp, h->chunks.p, h->nchunks, rows_p, h->s2_part.p, h->s2_sums.p, s);
+  S2FinalizeArgs a;
+  a.bs = bs; a.C = C; a.P = P; a.dp = h->dp; a.strict = h->strict;
+  a.n_analyzed = h->n_analyzed; a.n_samples = h->N; a.min_mac = min_mac; a.numtol = 1e-6;
+  a.sums = h->s2_sums.p; a.mask_count = h->s2_maskcount.p; a.YtX = h->s2_YtX.p; a.XmX = h->s2_XmX.p;
+  a.scf_sv = h->s2_scf.p;
+  double* d = h->s2_out_d.p;
+  const size_t bp = (size_t)h->bs_max * P, b1 = h->bs_max;
+  a.af = d; a.mac = d + bp; a.stat = d + 2 * bp; a.beta = d + 3 * bp; a.se = d + 4 * bp; a.chisq = d + 5 * bp;
+  a.af_all = d + 6 * bp; a.mac_all = d + 6 * bp + b1; a.scale_fac = d + 6 * bp + 2 * b1;
+  int32_t* ii = h->s2_out_i.p;
+  a.ns = ii; a.ns_all = ii + bp; a.flags = ii + bp + b1;
+  launch_s2_finalize(a, s);
+  h->launches += 4;
+  const size_t vp = (size_t)bs * P * 8, v1 = (size_t)bs * 8;
+  auto cp = [&](void* dst, const void* src, size_t bytes) {
+    if (dst) RG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+  };
+  cp(out->af, a.af, vp); cp(out->mac, a.mac, vp); cp(out->stat, a.stat, vp); cp(out->beta, a.beta, vp);
+  cp(out->se, a.se, vp); cp(out->chisq, a.chisq, vp); cp(out->af_all, a.af_all, v1); cp(out->mac_all, a.mac_all, v1);
+  cp(out->scale_fac, a.scale_fac, v1); cp(out->ns, a.ns, (size_t)bs * P * 4); cp(out->ns_all, a.ns_all, (size_t)bs * 4);
+  cp(out->flags, a.flags, (size_t)bs * 4);
+  RG_CUDA(cudaStreamSynchronize(s));
+}
+
+extern "C" {
+
+int rg_step2_create(const rg_step2_config* cfg, const double* X, const uint8_t* mask,
+                    const uint8_t* in_analysis, rg_handle* out) {
+  RG_API_BEGIN
+  RG_CHECK(cfg && X && mask && in_analysis && out, "null argument");
+  require_gpu_public(cfg->device);
+  RG_CHECK(cfg->n_samples > 0 && cfg->n_cov > 0 && cfg->n_pheno > 0 && cfg->max_block_size > 0, "bad sizes");
+  RG_CHECK(cfg->n_cov <= kMaxCov, "too many covariates for this build");
+  std::unique_ptr<rg_ctx> h(new rg_ctx());
+  s2_create(h.get(), cfg, X, mask, in_analysis);
+  *out = h.release();
+  RG_API_END
+}
+
+int rg_s2_set_chr(rg_handle h, const double* res, const double* scf_sv) {
+  RG_API_BEGIN
+  RG_CHECK(h && res && scf_sv, "null argument");
+  s2_set_chr(h, res, scf_sv);
+  RG_API_END
+}
+
+int rg_s2_block_bed(rg_handle h, const uint8_t* packed, int64_t row_stride, int32_t bs,
+                    const int32_t* sample_idx, int32_t ref_first, double min_mac, const rg_s2_out* out) {
+  RG_API_BEGIN
+  RG_CHECK(h && packed && out, "null argument");
+  s2_block_bed(h, packed, row_stride, bs, sample_idx, ref_first, min_mac, out);
+  RG_CUDA(cudaGetLastError());
+  RG_API_END
+}
+
+}  // extern "C"
