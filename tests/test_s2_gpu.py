@@ -53,8 +53,8 @@ def run_case(tmp_path, N, M, P, miss, strict=False, maf_hi=0.5):
                 b = step2.sumstats_row(1, 1, "x", "A", "G", vs["af"][ph], vs["ns"][ph], sc["beta"][ph], sc["se"][ph],
                                        sc["chisq"][ph], sc["logp"][ph])
                 ta, tb = a.split(), b.split()
-                assert ta[:7] == tb[:7]
-                for x, y in zip(ta[7:11], tb[7:11]):
+                assert ta[:8] == tb[:8]          # CHROM..A1FREQ N TEST: exact
+                for x, y in zip(ta[8:12], tb[8:12]):
                     assert abs(float(x) - float(y)) <= 1e-5 * abs(float(y))
             n_checked += 1
     return n_checked, n_sparse
