@@ -1,0 +1,355 @@
+#include "data.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+namespace rgh {
+
+std::set<std::string> read_id_list(const std::string& path, int ncols) {
+  std::set<std::string> out;
+  if (path.empty()) return out;
+  std::ifstream fh(path);
+  if (!fh) throw Fail("cannot open file : " + path);
+  std::string line;
+  while (std::getline(fh, line)) {
+    auto t = split_ws(line);
+    if ((int)t.size() < ncols) continue;
+    out.insert(ncols == 2 ? t[0] + "_" + t[1] : t[0]);
+  }
+  return out;
+}
+
+void BedFile::open(const std::string& pfx, bool ref_first, const std::set<std::string>& exclude,
+                   const std::set<std::string>& extract, const std::set<std::string>& remove,
+                   const std::set<std::string>& keep) {
+  prefix = pfx;
+  // ---- .bim
+  {
+    std::ifstream fh(prefix + ".bim");
+    if (!fh) throw Fail("cannot open file : " + prefix + ".bim");
+    std::string line;
+    uint64_t lineno = 0;
+    int last_chr = 0;
+    std::vector<int> chr_seen;
+    while (std::getline(fh, line)) {
+      auto t = split_ws(line);
+      if (t.size() < 6) throw Fail("incorrectly formatted bim file at line " + std::to_string(lineno + 1));
+      Snp s;
+      s.chrom = chr_str_to_int(t[0]);
+      if (s.chrom == -1) throw Fail("unknown chromosome code in bim file at line " + std::to_string(lineno + 1));
+      if (chr_seen.empty() || chr_seen.back() != s.chrom) {
+        if (s.chrom <= last_chr) throw Fail("chromosomes in bim file are not in ascending order.");
+        chr_seen.push_back(s.chrom);
+        last_chr = s.chrom;
+      }
+      s.id = t[1];
+      s.pos = std::stoull(t[3], nullptr, 0);
+      if (ref_first) { s.allele0 = t[4]; s.allele1 = t[5]; }
+      else           { s.allele0 = t[5]; s.allele1 = t[4]; }
+      s.offset = lineno++;
+      if (exclude.count(s.id)) continue;
+      if (!extract.empty() && !extract.count(s.id)) continue;
+      snps.push_back(s);
+    }
+  }
+  // ---- .fam
+  {
+    std::ifstream fh(prefix + ".fam");
+    if (!fh) throw Fail("cannot open file : " + prefix + ".fam");
+    std::string line;
+    std::set<std::string> seen;
+    while (std::getline(fh, line)) {
+      auto t = split_ws(line);
+      if (t.empty()) continue;
+      if (t.size() < 6) throw Fail("incorrectly formatted fam file.");
+      const std::string k = t[0] + "_" + t[1];
+      if (!seen.insert(k).second) throw Fail("duplicate individual in fam file : FID_IID=" + k);
+      keys_file.push_back(k);
+      sex_file.push_back((t[4] == "1") ? 1 : (t[4] == "2" ? 2 : 0));
+    }
+  }
+  for (size_t i = 0; i < keys_file.size(); ++i) {
+    const std::string& k = keys_file[i];
+    if (remove.count(k)) continue;
+    if (!keep.empty() && !keep.count(k)) continue;
+    key_to_ind[k] = (uint32_t)keys.size();
+    keys.push_back(k);
+    sample_idx.push_back((int32_t)i);
+  }
+  if (keys.empty()) throw Fail("no samples left after --keep/--remove.");
+  row_stride = (keys_file.size() + 3) / 4;
+  // ---- .bed
+  bed.open(prefix + ".bed", std::ios::binary);
+  if (!bed) throw Fail("cannot open file : " + prefix + ".bed");
+  unsigned char magic[3];
+  bed.read(reinterpret_cast<char*>(magic), 3);
+  if (!(magic[0] == 0x6c && magic[1] == 0x1b && magic[2] == 0x01))
+    throw Fail("invalid bed file (expected SNP-major mode, magic 6c 1b 01).");
+}
+
+void BedFile::read_rows(size_t first, size_t n, uint8_t* out) {
+  for (size_t j = 0; j < n; ++j) {
+    bed.seekg(3 + snps[first + j].offset * row_stride, std::ios::beg);
+    bed.read(reinterpret_cast<char*>(out + j * row_stride), row_stride);
+    if (!bed) throw Fail("cannot read from bed file.");
+  }
+}
+
+// [n x k] table keyed by FID_IID; samples absent from the genotype file are ignored
+static void read_table(const std::string& path, const BedFile& g, const std::set<std::string>* skip_cols,
+                       std::vector<std::string>& names, std::vector<double>& vals, std::vector<uint8_t>& present) {
+  std::ifstream fh(path);
+  if (!fh) throw Fail("cannot open file : " + path);
+  std::string line;
+  std::getline(fh, line);
+  auto hdr = split_ws(line);
+  if (hdr.size() < 2 || hdr[0] != "FID" || hdr[1] != "IID") throw Fail("header of file must start with: FID IID.");
+  std::vector<int> keep;
+  for (size_t i = 2; i < hdr.size(); ++i)
+    if (!skip_cols || !skip_cols->count(hdr[i])) { keep.push_back((int)i); names.push_back(hdr[i]); }
+  const size_t n = g.keys.size(), k = keep.size();
+  vals.assign(n * k, 0.0);
+  present.assign(n, 0);
+  while (std::getline(fh, line)) {
+    auto t = split_ws(line);
+    if (t.empty()) continue;
+    if (t.size() != hdr.size()) throw Fail("incorrectly formatted file : " + path);
+    auto it = g.key_to_ind.find(t[0] + "_" + t[1]);
+    if (it == g.key_to_ind.end()) continue;
+    const size_t s = it->second;
+    if (present[s]) throw Fail("individual appears more than once in file: FID=" + t[0] + " IID=" + t[1]);
+    present[s] = 1;
+    for (size_t c = 0; c < k; ++c) vals[c * n + s] = convert_double(t[keep[c]]);
+  }
+}
+
+void read_pheno_and_cov(const BedFile& g, const std::string& pheno_file, const std::string& covar_file,
+                        bool step2, bool strict, Pheno& ph, Log& log) {
+  const int64_t N = (int64_t)g.keys.size();
+  ph.N = N;
+  std::vector<uint8_t> in_ph;
+  read_table(pheno_file, g, nullptr, ph.names, ph.Y, in_ph);
+  ph.P = (int)ph.names.size();
+  if (ph.P < 1) throw Fail("need at least one phenotype.");
+  log << " * phenotypes          : [" << pheno_file << "] n_pheno = " << ph.P << "\n";
+  ph.strict = strict || ph.P == 1;                          // src/Pheno.cpp:198
+  ph.mask.assign((size_t)N * ph.P, 1);
+  for (int64_t s = 0; s < N; ++s) {
+    bool all_miss = true, any_miss = false;
+    for (int p = 0; p < ph.P; ++p) {
+      const bool miss = ph.Y[(size_t)p * N + s] == kMissing;
+      if (!miss) all_miss = false; else any_miss = true;
+      if (miss && step2) ph.mask[(size_t)p * N + s] = 0;    // rm_missing_qt (src/Pheno.cpp:331)
+    }
+    if (ph.strict && any_miss) {
+      for (int p = 0; p < ph.P; ++p) ph.mask[(size_t)p * N + s] = 0;
+      all_miss = true;
+    }
+    if (all_miss) in_ph[s] = 0;
+    if (!in_ph[s]) for (int p = 0; p < ph.P; ++p) ph.mask[(size_t)p * N + s] = 0;
+  }
+  // covariates: intercept first (src/Pheno.cpp:79)
+  std::vector<uint8_t> in_cov(N, 1);
+  std::vector<double> cov;
+  std::vector<std::string> cnames;
+  if (!covar_file.empty()) {
+    std::set<std::string> skip(ph.names.begin(), ph.names.end());
+    read_table(covar_file, g, &skip, cnames, cov, in_cov);
+    log << " * covariates          : [" << covar_file << "] n_cov = " << cnames.size() << "\n";
+    for (int64_t s = 0; s < N; ++s)
+      for (size_t c = 0; c < cnames.size(); ++c)
+        if (cov[c * N + s] == kMissing) in_cov[s] = 0;
+  }
+  ph.C = 1 + (int)cnames.size();
+  ph.X.assign((size_t)N * ph.C, 0.0);
+  for (int64_t s = 0; s < N; ++s) {
+    ph.X[s] = 1.0;
+    for (size_t c = 0; c < cnames.size(); ++c) ph.X[(c + 1) * N + s] = cov[c * N + s];
+  }
+  ph.in_analysis.assign(N, 0);
+  for (int64_t s = 0; s < N; ++s) ph.in_analysis[s] = in_ph[s] && in_cov[s];
+}
+
+// cyclic Jacobi eigen-decomposition of a small symmetric matrix (a: n x n row-major, destroyed);
+// eigenvalues ascending in d, eigenvectors in the columns of v.
+static void jacobi_eig(std::vector<double>& a, int n, std::vector<double>& d, std::vector<double>& v) {
+  v.assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) v[(size_t)i * n + i] = 1.0;
+  for (int sweep = 0; sweep < 100; ++sweep) {
+    double off = 0.0;
+    for (int i = 0; i < n; ++i) for (int j = i + 1; j < n; ++j) off += a[(size_t)i * n + j] * a[(size_t)i * n + j];
+    if (off < 1e-300) break;
+    for (int p = 0; p < n; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const double apq = a[(size_t)p * n + q];
+        if (std::fabs(apq) < 1e-300) continue;
+        const double theta = (a[(size_t)q * n + q] - a[(size_t)p * n + p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < n; ++k) {
+          const double akp = a[(size_t)k * n + p], akq = a[(size_t)k * n + q];
+          a[(size_t)k * n + p] = c * akp - s * akq;
+          a[(size_t)k * n + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double apk = a[(size_t)p * n + k], aqk = a[(size_t)q * n + k];
+          a[(size_t)p * n + k] = c * apk - s * aqk;
+          a[(size_t)q * n + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double vkp = v[(size_t)k * n + p], vkq = v[(size_t)k * n + q];
+          v[(size_t)k * n + p] = c * vkp - s * vkq;
+          v[(size_t)k * n + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  d.resize(n);
+  std::vector<int> ord(n);
+  for (int i = 0; i < n; ++i) { d[i] = a[(size_t)i * n + i]; ord[i] = i; }
+  std::sort(ord.begin(), ord.end(), [&](int x, int y) { return d[x] < d[y]; });
+  std::vector<double> d2(n), v2((size_t)n * n);
+  for (int j = 0; j < n; ++j) {
+    d2[j] = d[ord[j]];
+    for (int k = 0; k < n; ++k) v2[(size_t)k * n + j] = v[(size_t)k * n + ord[j]];
+  }
+  d = d2; v = v2;
+}
+
+// setMasks (src/Pheno.cpp:810-841)
+static void set_masks(Pheno& ph) {
+  const int64_t N = ph.N;
+  const int P = ph.P;
+  for (int64_t s = 0; s < N; ++s) {
+    bool any = false, all = true;
+    for (int p = 0; p < P; ++p) { const bool m = ph.mask[(size_t)p * N + s]; any |= m; all &= m; }
+    ph.in_analysis[s] = ph.in_analysis[s] && (ph.strict ? all : any);
+    for (int p = 0; p < P; ++p) {
+      ph.mask[(size_t)p * N + s] = ph.mask[(size_t)p * N + s] && ph.in_analysis[s];
+      if (!ph.in_analysis[s]) ph.Y[(size_t)p * N + s] *= 0.0;
+    }
+    if (!ph.in_analysis[s]) for (int c = 0; c < ph.C; ++c) ph.X[(size_t)c * N + s] = 0.0;
+  }
+  ph.n_analyzed = 0;
+  for (int64_t s = 0; s < N; ++s) ph.n_analyzed += ph.in_analysis[s];
+  if (ph.n_analyzed < 1) throw Fail("sample size cannot be < 1.");
+  ph.neff.assign(P, 0.0);
+  for (int p = 0; p < P; ++p) for (int64_t s = 0; s < N; ++s) ph.neff[p] += ph.mask[(size_t)p * N + s];
+}
+
+void prep_run(Pheno& ph, const std::vector<uint8_t>* extra_mask, Log& log) {
+  const int64_t N = ph.N;
+  const int P = ph.P;
+  set_masks(ph);                                             // read_pheno_and_cov, src/Pheno.cpp:102
+  // pheno_impute_miss, QT (src/Pheno.cpp:1916-1931)
+  for (int p = 0; p < P; ++p) {
+    double tot = 0.0; int64_t ns = 0;
+    for (int64_t s = 0; s < N; ++s) {
+      const double y = ph.Y[(size_t)p * N + s];
+      if (y != kMissing) { tot += y; if (ph.in_analysis[s]) ++ns; }
+    }
+    for (int64_t s = 0; s < N; ++s) {
+      double& y = ph.Y[(size_t)p * N + s];
+      if (y == kMissing) y = tot / (double)ns;
+      y *= ph.mask[(size_t)p * N + s];
+    }
+  }
+  if (extra_mask) {                                          // blup_read, src/Pheno.cpp:1306
+    for (size_t e = 0; e < ph.mask.size(); ++e) ph.mask[e] = ph.mask[e] && (*extra_mask)[e];
+    set_masks(ph);                                           // prep_run, src/Pheno.cpp:1070
+  }
+  log << " * number of individuals used in analysis = " << ph.n_analyzed << "\n";
+  // getBasis (src/Pheno.cpp:1660-1681)
+  const int C0 = ph.C;
+  std::vector<double> xtx((size_t)C0 * C0, 0.0), d, v;
+  for (int a = 0; a < C0; ++a)
+    for (int b = a; b < C0; ++b) {
+      double s = 0.0;
+      for (int64_t i = 0; i < N; ++i) s += ph.X[(size_t)a * N + i] * ph.X[(size_t)b * N + i];
+      xtx[(size_t)a * C0 + b] = xtx[(size_t)b * C0 + a] = s;
+    }
+  jacobi_eig(xtx, C0, d, v);
+  int nz = 0;
+  for (int j = 0; j < C0; ++j) if (d[j] > d[C0 - 1] * 1e-15) ++nz;
+  std::vector<double> Xb((size_t)N * nz, 0.0);
+  for (int j = 0; j < nz; ++j) {
+    const int col = C0 - nz + j;
+    const double inv = 1.0 / std::sqrt(d[col]);
+    for (int a = 0; a < C0; ++a) {
+      const double w = v[(size_t)a * C0 + col] * inv;
+      if (w == 0.0) continue;
+      for (int64_t i = 0; i < N; ++i) Xb[(size_t)j * N + i] += ph.X[(size_t)a * N + i] * w;
+    }
+  }
+  ph.X = Xb;
+  ph.C = nz;
+  // residualize_phenotypes (src/Pheno.cpp:1813-1829)
+  ph.scale_Y.assign(P, 1.0);
+  for (int p = 0; p < P; ++p) {
+    std::vector<double> beta(nz, 0.0);
+    for (int c = 0; c < nz; ++c)
+      for (int64_t i = 0; i < N; ++i) beta[c] += ph.Y[(size_t)p * N + i] * ph.X[(size_t)c * N + i];
+    double ss = 0.0;
+    for (int64_t i = 0; i < N; ++i) {
+      double f = 0.0;
+      for (int c = 0; c < nz; ++c) f += ph.X[(size_t)c * N + i] * beta[c];
+      double& y = ph.Y[(size_t)p * N + i];
+      y -= f * ph.mask[(size_t)p * N + i];
+      ss += y * y;
+    }
+    ph.scale_Y[p] = std::sqrt(ss) / std::sqrt(ph.neff[p] - nz);
+    if (ph.scale_Y[p] < 1e-6) throw Fail("phenotype '" + ph.names[p] + "' has sd=0.");
+    for (int64_t i = 0; i < N; ++i) ph.Y[(size_t)p * N + i] /= ph.scale_Y[p];
+  }
+}
+
+std::vector<Block> set_blocks(const std::vector<Snp>& snps, int bsize) {
+  std::vector<Block> out;
+  size_t i = 0;
+  while (i < snps.size()) {
+    size_t j = i;
+    while (j < snps.size() && snps[j].chrom == snps[i].chrom) ++j;
+    const size_t n = j - i;
+    const size_t nb = (n + bsize - 1) / bsize;
+    for (size_t b = 0; b < nb; ++b) {
+      const size_t sz = ((b + 1) * bsize > n) ? n - b * bsize : (size_t)bsize;   // get_block_size :579-586
+      out.push_back({snps[i].chrom, i + b * bsize, (int)sz});
+    }
+    i = j;
+  }
+  return out;
+}
+
+std::vector<int64_t> set_folds(const std::vector<uint8_t>& in_analysis, int k) {
+  const int64_t n = (int64_t)in_analysis.size();
+  int64_t na = 0;
+  for (auto a : in_analysis) na += a;
+  const int64_t target = na / k;
+  if (target < 1) throw Fail("not enough samples are present for " + std::to_string(k) + "-fold CV.");
+  std::vector<int64_t> sizes(k, 1);
+  int64_t non_miss = 0, cum = 0;
+  int cur = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    if (in_analysis[i]) ++non_miss;
+    if (non_miss == target) {
+      sizes[cur] = i - cum + 1;
+      cum += sizes[cur];
+      non_miss = 0;
+      ++cur;
+    } else if (cur == k - 1) {
+      sizes[cur] = n - i;
+      break;
+    }
+  }
+  return sizes;
+}
+
+std::vector<double> ridge_grid(int n) {
+  if (n < 2) throw Fail("number of ridge parameters must be at least 2");
+  std::vector<double> v(n);
+  for (int i = 0; i < n; ++i) v[i] = (double)i / (n - 1);
+  v[0] = 0.01;
+  v[n - 1] = 0.99;
+  return v;
+}
+
+}  // namespace rgh

@@ -1,0 +1,69 @@
+// Readers and phenotype/covariate preparation of the rgb200 host driver.
+// Mirrors (restated, not copied) the reference's Geno/Pheno host logic:
+//   read_bim src/Geno.cpp:518-611, read_fam :643-691, prep_bed :735-752,
+//   pheno_read src/Pheno.cpp:148-364, covariate_read :573-700, setMasks :810-841,
+//   pheno_impute_miss :1903-1935, getBasis :1660-1681, residualize_phenotypes :1799-1834,
+//   set_blocks src/Data.cpp:311-334, set_folds :401-431.
+#pragma once
+#include <set>
+
+#include "util.hpp"
+
+namespace rgh {
+
+struct Snp {
+  int chrom;
+  std::string id;
+  uint64_t pos;
+  std::string allele0, allele1;   // ALLELE0 (reference), ALLELE1 (effect)
+  uint64_t offset;                // row in the .bed
+};
+
+struct BedFile {
+  std::string prefix;
+  std::vector<Snp> snps;                      // after --extract/--exclude
+  std::vector<std::string> keys_file;         // FID_IID in .fam order
+  std::vector<int> sex_file;
+  std::vector<std::string> keys;              // after --keep/--remove
+  std::vector<int32_t> sample_idx;            // index in the .bed row of each kept sample
+  std::map<std::string, uint32_t> key_to_ind; // FID_IID_to_ind
+  uint64_t row_stride = 0;
+  std::ifstream bed;
+  void open(const std::string& prefix, bool ref_first, const std::set<std::string>& exclude,
+            const std::set<std::string>& extract, const std::set<std::string>& remove,
+            const std::set<std::string>& keep);
+  // read the rows of snps[first .. first+n) into out (n * row_stride bytes)
+  void read_rows(size_t first, size_t n, uint8_t* out);
+};
+
+std::set<std::string> read_id_list(const std::string& path, int ncols);
+
+struct Pheno {
+  std::vector<std::string> names;
+  int64_t N = 0;
+  int P = 0, C = 0;
+  std::vector<double> Y;          // N x P column-major (residualised + scaled for QT)
+  std::vector<uint8_t> mask;      // N x P column-major
+  std::vector<double> X;          // N x C column-major, orthonormal basis
+  std::vector<uint8_t> in_analysis;
+  std::vector<double> neff, scale_Y;
+  int64_t n_analyzed = 0;
+  bool strict = false;
+};
+
+// read_pheno_and_cov: raw values + masks, before prep_run
+void read_pheno_and_cov(const BedFile& g, const std::string& pheno_file, const std::string& covar_file,
+                        bool step2, bool strict, Pheno& ph, Log& log);
+// setMasks + orthonormal basis + residualise/scale (prep_run); `extra_mask` = LOCO availability (step 2)
+void prep_run(Pheno& ph, const std::vector<uint8_t>* extra_mask, Log& log);
+
+struct Block {
+  int chrom;
+  size_t first;
+  int size;
+};
+std::vector<Block> set_blocks(const std::vector<Snp>& snps, int bsize);
+std::vector<int64_t> set_folds(const std::vector<uint8_t>& in_analysis, int k);
+std::vector<double> ridge_grid(int n);
+
+}  // namespace rgh

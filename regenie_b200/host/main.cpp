@@ -1,0 +1,407 @@
+// rgb200 -- host driver keeping regenie's CLI surface for the Step-1 / Step-2 hot path and calling
+// the sm_100a kernels through the C ABI (include/rg_b200.h).
+// Mirrors the control flow of the reference driver (restated, not copied):
+//   main / read_params_and_check   src/Regenie.cpp:60-142
+//   Data::run_step1                src/Data.cpp:95-133   (level_0_calculations :594, output :956,
+//                                                         write_predictions :1795)
+//   Data::test_snps_fast           src/Data.cpp:2230-2383 (compute_res :2386, printing
+//                                                         src/Step2_Models.cpp:2386-2540)
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <climits>
+#include <cstdlib>
+#include <iomanip>
+
+#include "../../include/rg_b200.h"
+#include "data.hpp"
+
+using namespace rgh;
+
+namespace {
+
+struct Params {
+  int step = 0;
+  std::string bed, bgen, pgen, pheno, covar, out, pred, lowmem_prefix;
+  std::string remove, keep, exclude, extract;
+  int bsize = 0, cv = 5, l0 = 5, l1 = 5, gpu = 0;
+  bool loocv = false, lowmem = false, ref_first = false, strict = false, bt = false, force_step1 = false;
+  bool rel_path = false;
+  double min_mac = 5.0;
+};
+
+void rg_check(int rc) {
+  if (rc != 0) throw Fail(std::string(rg_last_error()));
+}
+
+Params parse_cli(int argc, char** argv) {
+  Params p;
+  auto need = [&](int& i) -> std::string {
+    if (i + 1 >= argc) throw Fail(std::string("option ") + argv[i] + " needs a value");
+    return argv[++i];
+  };
+  for (int i = 1; i < argc; ++i) {
+    const std::string a = argv[i];
+    if (a == "--step") p.step = atoi(need(i).c_str());
+    else if (a == "--bed") p.bed = need(i);
+    else if (a == "--bgen") p.bgen = need(i);
+    else if (a == "--pgen") p.pgen = need(i);
+    else if (a == "--phenoFile") p.pheno = need(i);
+    else if (a == "--covarFile") p.covar = need(i);
+    else if (a == "--bsize") p.bsize = atoi(need(i).c_str());
+    else if (a == "--out") p.out = need(i);
+    else if (a == "--pred") p.pred = need(i);
+    else if (a == "--cv") p.cv = atoi(need(i).c_str());
+    else if (a == "--l0") p.l0 = atoi(need(i).c_str());
+    else if (a == "--l1") p.l1 = atoi(need(i).c_str());
+    else if (a == "--remove") p.remove = need(i);
+    else if (a == "--keep") p.keep = need(i);
+    else if (a == "--exclude") p.exclude = need(i);
+    else if (a == "--extract") p.extract = need(i);
+    else if (a == "--minMAC") p.min_mac = atof(need(i).c_str());
+    else if (a == "--lowmem-prefix") p.lowmem_prefix = need(i);
+    else if (a == "--gpu") p.gpu = atoi(need(i).c_str());
+    else if (a == "--threads") need(i);            // host threads are irrelevant to the GPU path
+    else if (a == "--loocv") p.loocv = true;
+    else if (a == "--lowmem") p.lowmem = true;     // W stays resident in HBM; accepted for CLI parity
+    else if (a == "--ref-first") p.ref_first = true;
+    else if (a == "--strict") p.strict = true;
+    else if (a == "--qt") {}
+    else if (a == "--bt") p.bt = true;
+    else if (a == "--force-step1") p.force_step1 = true;
+    else if (a == "--use-relative-path") p.rel_path = true;
+    else if (a == "--help" || a == "-h") {
+      std::cout << "rgb200: B200-native regenie Step 1 / Step 2 hot path\n"
+                   "  --step 1|2 --bed PREFIX --phenoFile F [--covarFile F] --bsize N --out PREFIX\n"
+                   "  [--pred LIST] [--loocv] [--lowmem] [--cv K] [--l0 R] [--l1 R] [--remove F] [--keep F]\n"
+                   "  [--exclude F] [--extract F] [--ref-first] [--minMAC x] [--strict] [--gpu ordinal]\n";
+      exit(0);
+    } else {
+      throw Fail("option '" + a + "' is outside the hot path covered by rgb200 (see DESIGN.md, out of scope)");
+    }
+  }
+  if (p.step != 1 && p.step != 2) throw Fail("specify which mode regenie should be running using option '--step'.");
+  if (!p.bgen.empty()) throw Fail("--bgen input is not implemented yet in rgb200 (SURVEY 8 row a2, next).");
+  if (!p.pgen.empty()) throw Fail("--pgen input is not implemented yet in rgb200 (SURVEY 8 row a3, next).");
+  if (p.bt) throw Fail("--bt is not implemented yet in rgb200 (SURVEY 8(f)1, next).");
+  if (p.bed.empty()) throw Fail("must specify the genotype file with --bed.");
+  if (p.pheno.empty()) throw Fail("must provide the phenotype file with --phenoFile.");
+  if (p.out.empty()) throw Fail("must specify an output file prefix with --out.");
+  if (p.bsize < 1) throw Fail("must specify the block size using '--bsize'.");
+  if (p.step == 2 && p.pred.empty()) throw Fail("must specify --pred if using --step 2.");
+  return p;
+}
+
+std::string full_path(const std::string& f, bool rel) {
+  if (rel) return f;
+  char buf[PATH_MAX];
+  if (realpath(f.c_str(), buf)) return std::string(buf);
+  // file may not exist yet: resolve the directory part
+  const size_t k = f.find_last_of('/');
+  const std::string dir = (k == std::string::npos) ? "." : f.substr(0, k);
+  const std::string base = (k == std::string::npos) ? f : f.substr(k + 1);
+  if (realpath(dir.c_str(), buf)) return std::string(buf) + "/" + base;
+  return f;
+}
+
+double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+// ------------------------------------------------------------------------------------ step 1
+void run_step1(const Params& p, Log& log) {
+  BedFile g;
+  g.open(p.bed, p.ref_first, read_id_list(p.exclude, 1), read_id_list(p.extract, 1), read_id_list(p.remove, 2),
+         read_id_list(p.keep, 2));
+  log << " * bim                 : [" << p.bed << ".bim] n_snps = " << g.snps.size() << "\n";
+  log << " * fam                 : [" << p.bed << ".fam] n_samples = " << g.keys.size() << "\n";
+  if (g.snps.size() > 1000000 && !p.force_step1)
+    throw Fail("it is not recommened to use more than 1000000 variants in step 1 (otherwise use '--force-step1').");
+  Pheno ph;
+  read_pheno_and_cov(g, p.pheno, p.covar, false, p.strict, ph, log);
+  prep_run(ph, nullptr, log);
+  const auto blocks = set_blocks(g.snps, p.bsize);
+  const int nb = (int)blocks.size();
+  const int64_t N = ph.N;
+  const int P = ph.P;
+  std::vector<int64_t> folds;
+  if (!p.loocv) folds = set_folds(ph.in_analysis, p.cv);
+  const auto h0 = ridge_grid(p.l0), h1 = ridge_grid(p.l1);
+  std::vector<double> lambda(p.l0);
+  const double M = (double)g.snps.size();
+  for (int j = 0; j < p.l0; ++j) lambda[j] = M * (1 - h0[j]) / h0[j];           // src/Data.cpp:607
+  log << " * # blocks            : [" << nb << "] for " << g.snps.size() << " variants\n";
+  log << " * # CV folds          : [" << (p.loocv ? ph.n_analyzed : p.cv) << "]\n";
+
+  rg_step1_config cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.device = p.gpu; cfg.n_samples = N; cfg.n_cov = ph.C; cfg.n_pheno = P; cfg.n_folds = p.cv;
+  cfg.n_ridge_l0 = p.l0; cfg.n_ridge_l1 = p.l1; cfg.loocv = p.loocv; cfg.max_block_size = p.bsize;
+  cfg.total_blocks = nb; cfg.n_analyzed = ph.n_analyzed;
+  rg_handle h = nullptr;
+  rg_check(rg_step1_create(&cfg, ph.X.data(), ph.Y.data(), ph.mask.data(), ph.in_analysis.data(),
+                           p.loocv ? nullptr : folds.data(), lambda.data(), ph.neff.data(), &h));
+
+  // ---- level 0
+  std::vector<uint8_t> rows((size_t)p.bsize * g.row_stride);
+  const bool subset = g.keys.size() != g.keys_file.size();
+  int last_chr = -1;
+  const double t0 = now_ms();
+  for (int b = 0; b < nb; ++b) {
+    if (blocks[b].chrom != last_chr) { log << "Chromosome " << blocks[b].chrom << "\n"; last_chr = blocks[b].chrom; }
+    g.read_rows(blocks[b].first, blocks[b].size, rows.data());
+    rg_check(rg_l0_block_bed(h, rows.data(), (int64_t)g.row_stride, blocks[b].size,
+                             subset ? g.sample_idx.data() : nullptr, p.ref_first, b));
+    rg_check(rg_sync(h));    // `rows` is reused by the next block
+    log << " block [" << b + 1 << "] : " << blocks[b].size << " snps\n";
+  }
+  const int64_t st = rg_l0_status(h);
+  if (st != 0) {
+    if (st > 0 && st < (1ll << 40))
+      throw Fail("!! Uh-oh, SNP " + g.snps[blocks[(st - 1) / p.bsize].first + (st - 1) % p.bsize].id + " has low variance.");
+    throw Fail(std::string(rg_last_error()));
+  }
+  log << " Level 0 done (" << (long)(now_ms() - t0) << "ms)\n\n Level 1 ridge...\n";
+
+  // ---- level 1 (tau = B(1-h)/h, src/Step1_Models.cpp:2115)
+  const double B = (double)nb * p.l0;
+  std::vector<double> tau((size_t)P * p.l1), cs((size_t)5 * P * p.l1);
+  for (int ph_i = 0; ph_i < P; ++ph_i)
+    for (int j = 0; j < p.l1; ++j) tau[(size_t)ph_i * p.l1 + j] = B * (1 - h1[j]) / h1[j];
+  std::vector<int32_t> best(P);
+  rg_check(rg_l1_fit(h, tau.data(), cs.data(), best.data()));
+  std::vector<int32_t> chr_of_block(nb);
+  for (int b = 0; b < nb; ++b) chr_of_block[b] = blocks[b].chrom;
+  std::vector<double> loco((size_t)P * 23 * N);
+  rg_check(rg_loco(h, chr_of_block.data(), loco.data()));
+
+  // ---- output (Data::output src/Data.cpp:956-1120, write_predictions :1795-1982)
+  log << "Output\n------\n";
+  std::ofstream plist(p.out + "_pred.list");
+  std::vector<uint32_t> order;             // std::map key order of FID_IID, analysed samples only
+  for (auto& kv : g.key_to_ind) if (ph.in_analysis[kv.second]) order.push_back(kv.second);
+  for (int ph_i = 0; ph_i < P; ++ph_i) {
+    log << "phenotype " << ph_i + 1 << " (" << ph.names[ph_i] << ") : \n";
+    auto CS = [&](int k, int j) { return cs[((size_t)k * P + ph_i) * p.l1 + j]; };
+    const double ne = ph.neff[ph_i];
+    for (int j = 0; j < p.l1; ++j) {
+      double num = CS(4, j) - CS(0, j) * CS(1, j) / ne;
+      const double rsq = num * num / ((CS(2, j) - CS(0, j) * CS(0, j) / ne) * (CS(3, j) - CS(1, j) * CS(1, j) / ne));
+      const double sse = CS(2, j) + CS(3, j) - 2 * CS(4, j);
+      std::ostringstream l;
+      l << "  " << std::setw(5) << B / (B + tau[(size_t)ph_i * p.l1 + j]) << " : Rsq = " << rsq << ", MSE = " << sse / ne
+        << (j == best[ph_i] ? "<- min value" : "");
+      log << l.str() << "\n";
+    }
+    const std::string loco_file = p.out + "_" + std::to_string(ph_i + 1) + ".loco";
+    std::ofstream of(loco_file);
+    if (!of) throw Fail("cannot write to file : " + loco_file);
+    std::ostringstream buf;
+    buf << "FID_IID ";
+    for (uint32_t i : order) buf << g.keys[i] << " ";
+    buf << "\n";
+    const double* L = loco.data() + (size_t)ph_i * 23 * N;
+    for (int c = 0; c < 23; ++c) {
+      buf << c + 1 << " ";
+      for (uint32_t i : order) {
+        if (ph.mask[(size_t)ph_i * N + i]) buf << L[(size_t)c * N + i] << " ";
+        else buf << "NA ";
+      }
+      buf << "\n";
+    }
+    of << buf.str();
+    of.close();
+    plist << ph.names[ph_i] << " " << full_path(loco_file, p.rel_path) << "\n";
+    log << "  * making predictions...writing LOCO predictions...done\n\n";
+  }
+  plist.close();
+  log << "List of blup files written to: [" << p.out << "_pred.list]\n";
+  rg_destroy(h);
+}
+
+// ------------------------------------------------------------------------------------ step 2
+struct Loco {
+  std::vector<std::string> ids;
+  std::vector<std::vector<std::string>> rows;   // [23]
+};
+
+Loco read_loco(const std::string& path) {
+  std::ifstream fh(path);
+  if (!fh) throw Fail("cannot open file : " + path);
+  Loco l;
+  std::string line;
+  std::getline(fh, line);
+  l.ids = split_ws(line);
+  if (l.ids.empty() || l.ids[0] != "FID_IID") throw Fail("header of blup file must start with FID_IID.");
+  l.ids.erase(l.ids.begin());
+  l.rows.resize(23);
+  while (std::getline(fh, line)) {
+    auto t = split_ws(line);
+    if (t.empty()) continue;
+    const int c = chr_str_to_int(t[0]);
+    if (c < 1) throw Fail("blup file has an invalid chromosome row: " + t[0]);
+    if (t.size() != l.ids.size() + 1) throw Fail("blup file has different number of entries compared to the header");
+    t.erase(t.begin());
+    l.rows[c - 1] = t;
+  }
+  return l;
+}
+
+double get_logp(double t) {   // src/Regenie.cpp:1843-1857; chi2_1 sf = erfc(sqrt(T/2))
+  if (t < 0 && std::fabs(t) < 1e-6) return 0.0;
+  if (t < 0) return -1.0;
+  const double pv = std::erfc(std::sqrt(t / 2.0));
+  double lp;
+  if (pv == 0) lp = std::log10(2.0) - 0.5 * std::log10(2 * M_PI * t) - 0.5 * t * M_LOG10E;
+  else lp = std::log10(pv);
+  return -lp;
+}
+
+void run_step2(const Params& p, Log& log) {
+  BedFile g;
+  g.open(p.bed, p.ref_first, read_id_list(p.exclude, 1), read_id_list(p.extract, 1), read_id_list(p.remove, 2),
+         read_id_list(p.keep, 2));
+  log << " * bim                 : [" << p.bed << ".bim] n_snps = " << g.snps.size() << "\n";
+  log << " * fam                 : [" << p.bed << ".fam] n_samples = " << g.keys.size() << "\n";
+  // pred.list (check_blup src/Pheno.cpp:1204-1229)
+  std::map<std::string, std::string> blup_files;
+  {
+    std::ifstream fh(p.pred);
+    if (!fh) throw Fail("cannot open file : " + p.pred);
+    std::string line;
+    while (std::getline(fh, line)) {
+      auto t = split_ws(line);
+      if (t.empty()) continue;
+      if (t.size() != 2) throw Fail("step 1 list file is not in the right format : " + p.pred);
+      if (blup_files.count(t[0])) throw Fail("phenotype '" + t[0] + "' appears more than once in step 1 list file.");
+      blup_files[t[0]] = t[1];
+    }
+  }
+  Pheno ph;
+  read_pheno_and_cov(g, p.pheno, p.covar, true, p.strict, ph, log);
+  const int64_t N = ph.N;
+  const int P = ph.P;
+  std::vector<Loco> locos(P);
+  std::vector<uint8_t> extra((size_t)N * P, 0);
+  for (int i = 0; i < P; ++i) {
+    auto it = blup_files.find(ph.names[i]);
+    if (it == blup_files.end()) throw Fail("No step 1 file provided for phenotype '" + ph.names[i] + "'.");
+    locos[i] = read_loco(it->second);
+    log << "   -file [" << it->second << "] for phenotype '" << ph.names[i] << "'\n";
+    const auto& first = locos[i].rows[0];                    // blup_read checks the first data row
+    for (size_t c = 0; c < locos[i].ids.size(); ++c) {
+      auto k = g.key_to_ind.find(locos[i].ids[c]);
+      if (k == g.key_to_ind.end() || first.empty()) continue;
+      extra[(size_t)i * N + k->second] = first[c] != "NA";
+    }
+  }
+  prep_run(ph, &extra, log);
+  const auto blocks = set_blocks(g.snps, p.bsize);
+  log << " * # blocks            : [" << blocks.size() << "]\n";
+
+  rg_step2_config cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.device = p.gpu; cfg.n_samples = N; cfg.n_cov = ph.C; cfg.n_pheno = P; cfg.max_block_size = p.bsize;
+  cfg.n_analyzed = ph.n_analyzed; cfg.strict_mode = ph.strict;
+  rg_handle h = nullptr;
+  rg_check(rg_step2_create(&cfg, ph.X.data(), ph.mask.data(), ph.in_analysis.data(), &h));
+
+  std::vector<std::ofstream> outs(P);
+  for (int i = 0; i < P; ++i) {
+    outs[i].open(p.out + "_" + ph.names[i] + ".regenie");
+    if (!outs[i]) throw Fail("cannot write to file : " + p.out + "_" + ph.names[i] + ".regenie");
+    outs[i] << "CHROM GENPOS ID ALLELE0 ALLELE1 A1FREQ N TEST BETA SE CHISQ LOG10P EXTRA\n";
+  }
+  const int bsz = p.bsize;
+  std::vector<uint8_t> rows((size_t)bsz * g.row_stride);
+  std::vector<double> af((size_t)bsz * P), mac((size_t)bsz * P), stat((size_t)bsz * P), beta((size_t)bsz * P),
+      se((size_t)bsz * P), chisq((size_t)bsz * P), af_all(bsz), mac_all(bsz), scale_fac(bsz);
+  std::vector<int32_t> ns((size_t)bsz * P), ns_all(bsz), flags(bsz);
+  rg_s2_out out{af.data(), ns.data(), mac.data(), af_all.data(), ns_all.data(), mac_all.data(), flags.data(),
+                scale_fac.data(), stat.data(), beta.data(), se.data(), chisq.data()};
+  const bool subset = g.keys.size() != g.keys_file.size();
+  std::vector<double> res((size_t)N * P), scf(P);
+  int cur_chr = -1;
+  size_t n_ignored = 0;
+  for (size_t b = 0; b < blocks.size(); ++b) {
+    const int chrom = blocks[b].chrom;
+    if (chrom != cur_chr) {
+      cur_chr = chrom;
+      log << "Chromosome " << chrom << "\n";
+      // blup_read_chr + compute_res (src/Step2_Models.cpp:96-124, src/Data.cpp:2386-2404)
+      for (int i = 0; i < P; ++i) {
+        std::vector<double> blup(N, 0.0);
+        const auto& row = locos[i].rows[chrom - 1];
+        if (row.empty()) throw Fail("blup file for phenotype '" + ph.names[i] + "' has no row for chromosome " + std::to_string(chrom));
+        for (size_t c = 0; c < locos[i].ids.size(); ++c) {
+          auto k = g.key_to_ind.find(locos[i].ids[c]);
+          if (k == g.key_to_ind.end()) continue;
+          const uint32_t s = k->second;
+          if (!ph.in_analysis[s] || !ph.mask[(size_t)i * N + s]) continue;
+          if (row[c] == "NA") throw Fail("individual has missing predictions (FID_IID=" + locos[i].ids[c] + ")");
+          blup[s] = convert_double(row[c]);
+        }
+        double ss = 0.0;
+        for (int64_t s = 0; s < N; ++s) {
+          const double r = (ph.Y[(size_t)i * N + s] - blup[s]) * ph.mask[(size_t)i * N + s];
+          res[(size_t)i * N + s] = r;
+          ss += r * r;
+        }
+        const double psd = std::sqrt(ss) / std::sqrt(ph.neff[i] - ph.C);
+        for (int64_t s = 0; s < N; ++s) res[(size_t)i * N + s] /= psd;
+        scf[i] = ph.scale_Y[i] * psd;
+      }
+      rg_check(rg_s2_set_chr(h, res.data(), scf.data()));
+    }
+    g.read_rows(blocks[b].first, blocks[b].size, rows.data());
+    rg_check(rg_s2_block_bed(h, rows.data(), (int64_t)g.row_stride, blocks[b].size,
+                             subset ? g.sample_idx.data() : nullptr, p.ref_first, p.min_mac, &out));
+    for (int v = 0; v < blocks[b].size; ++v) {
+      if (flags[v] & 3) { ++n_ignored; continue; }            // no row for ignored variants (split mode)
+      const Snp& s = g.snps[blocks[b].first + v];
+      std::ostringstream head;
+      head << s.chrom << " " << s.pos << " " << s.id << " " << s.allele0 << " " << s.allele1 << " ";
+      for (int i = 0; i < P; ++i) {
+        const size_t e = (size_t)v * P + i;
+        if (mac[e] < p.min_mac) continue;                      // ignored_trait (src/Geno.cpp:3102)
+        std::ostringstream buf;                                // print_sum_stats_single :2502-2540
+        buf << head.str() << af[e] << " " << ns[e] << " ADD ";
+        if (se[e] >= 0 && !std::isnan(se[e])) buf << beta[e] << ' ' << se[e];
+        else buf << "NA NA";
+        const double lp = get_logp(chisq[e]);
+        if (chisq[e] >= 0 && !std::isnan(lp)) buf << ' ' << chisq[e] << ' ' << lp;
+        else buf << " NA NA";
+        buf << " NA\n";
+        outs[i] << buf.str();
+      }
+    }
+    log << " block [" << b + 1 << "/" << blocks.size() << "] : done\n";
+  }
+  log << "\nNumber of ignored tests due to low MAC or low variance : " << n_ignored << "\n";
+  rg_destroy(h);
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  Log log;
+  try {
+    const Params p = parse_cli(argc, argv);
+    log.open(p.out + ".log");
+    log << "rgb200 (" << rg_version() << ")\nOptions in effect:\n";
+    for (int i = 1; i < argc; ++i) {
+      const bool next_is_value = (i + 1 < argc) && !(argv[i + 1][0] == '-' && argv[i + 1][1] == '-');
+      log << (argv[i][0] == '-' && argv[i][1] == '-' ? "  " : "") << argv[i] << (next_is_value ? " " : " \\\n");
+    }
+    log << "\n";
+    if (rg_device_count() < 1) throw Fail("no CUDA device available: rgb200 has no CPU fallback");
+    const double t0 = now_ms();
+    if (p.step == 1) run_step1(p, log); else run_step2(p, log);
+    log << "\nElapsed time : " << (now_ms() - t0) / 1e3 << "s\nEnd of rgb200\n";
+  } catch (const std::exception& e) {
+    log << "ERROR: " << e.what() << "\n";          // same shape as the reference (src/Regenie.cpp:67-92)
+    return EXIT_FAILURE;
+  }
+  return 0;
+}

@@ -96,3 +96,94 @@ def synthetic_problem(tmp, N=1000, M=300, P=3, C=3, bsize=128, K=5, miss=0.02, s
     drop_c = {11, 500 % N} if drop else ()
     prefix = write_fileset(str(tmp), g, Y, cov, na, drop_pheno=drop_p, drop_cov=drop_c)
     return Problem(prefix, str(tmp) + "/pheno.txt", str(tmp) + "/covar.txt", bsize, K=K, loocv=loocv)
+
+
+def oracle_step2_rows(prefix, pheno, covar, pred_list, bsize, remove=None):
+    """Full QT Step 2 on the CPU oracle, reading the .loco files like the reference does.
+
+    Returns {phenotype name: [row strings]} in the native split-by-phenotype format.
+    """
+    from oracle import step2
+    bim = plink.read_bim(prefix + ".bim")
+    keys_file, _ = plink.read_fam(prefix + ".fam")
+    remove = set(remove or ())
+    keep = np.array([k not in remove for k in keys_file])
+    keys = [k for k in keys_file if k not in remove]
+    sidx = {k: i for i, k in enumerate(keys)}
+    n = len(keys)
+    pr = prep.prepare(keys, pheno, covar, step=2)
+    files = dict(l.split() for l in open(pred_list) if l.strip())
+    locos = [step2.read_loco(files[nm]) for nm in pr.pheno_names]
+    extra = np.stack([step2.blup_mask(ids, rows[1], sidx, n) for ids, rows in locos], axis=1)
+    # blup_read masks, then prep_run's second setMasks + basis + residualise (src/Pheno.cpp:1060-1175)
+    names, Yraw, in_ph = prep.read_table(pheno, sidx, n)
+    pr = prepare_step2_with_mask(keys, pheno, covar, extra)
+    strict = len(pr.pheno_names) == 1
+    packed = plink.read_bed_rows(prefix + ".bed", len(keys_file), bim.offset)
+    out = {nm: [] for nm in pr.pheno_names}
+    cur = None
+    for i in range(len(bim.ids)):
+        c = int(bim.chrom[i])
+        if c != cur:
+            cur = c
+            blups = np.stack([step2.blup_chr(ids, rows[c], sidx, n, pr.in_analysis, pr.mask[:, ph])
+                              for ph, (ids, rows) in enumerate(locos)], axis=1)
+            res, p_sd, scf = step2.compute_res(pr.Y, blups, pr.mask, pr.neff, pr.ncov, pr.scale_Y)
+            YtX = res.T @ pr.X
+        graw = plink.decode_bed(packed[i:i + 1], len(keys_file), keep=keep)[0]
+        vs = step2.variant_stats(graw, pr.in_analysis, pr.mask)
+        if vs["ignored"]:
+            continue
+        sc = step2.score_qt(vs["g"], pr.X, res, pr.mask, pr.in_analysis, pr.n_analyzed, pr.ncov, scf, YtX, strict)
+        if sc is None:
+            continue
+        for ph, nm in enumerate(pr.pheno_names):
+            if vs["ignored_trait"][ph]:
+                continue
+            out[nm].append(step2.sumstats_row(c, int(bim.pos[i]), bim.ids[i], bim.allele0[i], bim.allele1[i],
+                                              vs["af"][ph], vs["ns"][ph], sc["beta"][ph], sc["se"][ph],
+                                              sc["chisq"][ph], sc["logp"][ph]))
+    return out
+
+
+def prepare_step2_with_mask(keys, pheno, covar, extra_mask):
+    """prep.prepare(step=2) with the LOCO-availability mask applied where blup_read applies it."""
+    n = len(keys)
+    sidx = {k: i for i, k in enumerate(keys)}
+    names, Y, in_ph = prep.read_table(pheno, sidx, n)
+    P = len(names)
+    strict = P == 1
+    miss = Y == prep.MISSING
+    mask = np.ones((n, P), dtype=bool) & ~miss
+    if strict:
+        anym = miss.any(axis=1); mask[anym] = False; all_miss = anym
+    else:
+        all_miss = miss.all(axis=1)
+    in_ph = in_ph & ~all_miss
+    mask &= in_ph[:, None]
+    X = np.ones((n, 1)); in_cov = np.ones(n, dtype=bool)
+    if covar:
+        cn, Cv, in_cov = prep.read_table(covar, sidx, n, lambda nm: nm not in names)
+        in_cov = in_cov & ~(Cv == prep.MISSING).any(axis=1)
+        X = np.hstack([X, Cv])
+    in_an = in_ph & in_cov
+    # first setMasks + impute (read_pheno_and_cov)
+    in_an = in_an & (mask.all(axis=1) if strict else mask.any(axis=1))
+    mask = mask & in_an[:, None]
+    Y = Y * in_an[:, None]; X = X * in_an[:, None]
+    for j in range(P):
+        y = Y[:, j]; ok = y != prep.MISSING
+        y[~ok] = y[ok].sum() / (in_an & ok).sum()
+    Y = Y * mask
+    # blup_read + second setMasks (prep_run)
+    mask = mask & extra_mask
+    in_an = in_an & (mask.all(axis=1) if strict else mask.any(axis=1))
+    mask = mask & in_an[:, None]
+    Y = Y * in_an[:, None]; X = X * in_an[:, None]
+    neff = mask.sum(axis=0).astype(float)
+    Xb, ncov = prep.get_basis(X)
+    beta = Y.T @ Xb
+    Y = Y - (Xb @ beta.T) * mask
+    scale_Y = np.linalg.norm(Y, axis=0) / np.sqrt(neff - ncov)
+    Y = Y / scale_Y[None, :]
+    return prep.Prepared(list(keys), names, Y, None, mask, Xb, in_an, neff, scale_Y, ncov, int(in_an.sum()))

@@ -1,0 +1,96 @@
+"""End to end through the C++ host driver `rgb200` (regenie's CLI surface) vs the oracle:
+.loco / _pred.list / .regenie files produced from the reference's own example filesets."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers
+from oracle import step1
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RGB = os.path.join(ROOT, "regenie_b200", "rgb200")
+
+
+def run(args):
+    r = subprocess.run([RGB] + args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout
+
+
+def close(a, b, rtol=1.5e-5):
+    """Printed 6-significant-digit values: equal up to the reference's own rounding noise."""
+    if a == b:
+        return True
+    if "NA" in (a, b):
+        return False
+    x, y = float(a), float(b)
+    return abs(x - y) <= rtol * max(abs(x), abs(y)) + 1e-12
+
+
+def compare_token_files(fa, fb, exact_cols=0):
+    la, lb = open(fa).read().splitlines(), open(fb).read().splitlines()
+    assert len(la) == len(lb)
+    assert la[0] == lb[0]                      # header: byte-identical
+    for x, y in zip(la[1:], lb[1:]):
+        tx, ty = x.split(), y.split()
+        assert len(tx) == len(ty)
+        assert tx[:exact_cols] == ty[:exact_cols]
+        for a, b in zip(tx[exact_cols:], ty[exact_cols:]):
+            assert close(a, b), (a, b, x[:80])
+
+
+@pytest.mark.parametrize("fileset,bsize,remove", [("example_3chr", 100, False), ("example", 100, True)])
+def test_step1_then_step2_files(tmp_path, golden_dir, fileset, bsize, remove):
+    prefix = os.path.join(golden_dir, fileset)
+    pheno, covar = golden_dir + "/phenotype.txt", golden_dir + "/covariates.txt"
+    out1 = str(tmp_path / "fit")
+    args = ["--step", "1", "--bed", prefix, "--phenoFile", pheno, "--covarFile", covar, "--bsize", str(bsize),
+            "--lowmem", "--out", out1]
+    rm = None
+    if remove:
+        args += ["--remove", golden_dir + "/fid_iid_to_remove.txt"]
+        rm = {"_".join(l.split()[:2]) for l in open(golden_dir + "/fid_iid_to_remove.txt")}
+    log = run(args)
+    assert "<- min value" in log
+    # oracle Step 1
+    pb = helpers.Problem(prefix, pheno, covar, bsize, remove=rm)
+
+    def gen():
+        for b in range(len(pb.blocks)):
+            yield pb.oracle_block(b)[0]
+    o = step1.run_step1_qt(gen(), pb.blocks, pb.prep, pb.fold_sizes, pb.M)
+    for ph in range(2):
+        ref = str(tmp_path / ("oracle_%d.loco" % (ph + 1)))
+        step1.write_loco(ref, pb.keys, pb.prep.in_analysis, pb.prep.mask[:, ph], o["loco"][ph])
+        compare_token_files(out1 + "_%d.loco" % (ph + 1), ref, exact_cols=1)
+    pl = [l.split() for l in open(out1 + "_pred.list")]
+    assert [p[0] for p in pl] == ["Y1", "Y2"] and all(os.path.isabs(p[1]) for p in pl)
+
+    # Step 2 on the same fileset, reading the driver's own .loco files
+    out2 = str(tmp_path / "test")
+    args2 = ["--step", "2", "--bed", prefix, "--phenoFile", pheno, "--covarFile", covar, "--bsize", "200",
+             "--pred", out1 + "_pred.list", "--out", out2]
+    if remove:
+        args2 += ["--remove", golden_dir + "/fid_iid_to_remove.txt"]
+    run(args2)
+    rows = helpers.oracle_step2_rows(prefix, pheno, covar, out1 + "_pred.list", 200, remove=rm)
+    for nm in ("Y1", "Y2"):
+        got = open(out2 + "_%s.regenie" % nm).read().splitlines()
+        exp = ["CHROM GENPOS ID ALLELE0 ALLELE1 A1FREQ N TEST BETA SE CHISQ LOG10P EXTRA"] + [r.rstrip("\n") for r in rows[nm]]
+        assert len(got) == len(exp)
+        assert got[0] == exp[0]
+        for x, y in zip(got[1:], exp[1:]):
+            tx, ty = x.split(), y.split()
+            assert tx[:8] == ty[:8], (x, y)          # CHROM GENPOS ID ALLELE0 ALLELE1 A1FREQ N TEST: byte-identical
+            for a, b in zip(tx[8:12], ty[8:12]):
+                assert close(a, b), (x, y)
+            assert tx[12] == ty[12]
+
+
+def test_driver_rejects_out_of_scope_options(tmp_path):
+    r = subprocess.run([RGB, "--step", "2", "--bed", "x", "--phenoFile", "y", "--bsize", "10", "--out",
+                        str(tmp_path / "o"), "--pred", "z", "--spa"], capture_output=True, text=True)
+    assert r.returncode != 0 and "ERROR" in r.stdout
