@@ -244,6 +244,7 @@ def run_gpu(args):
             if read_status:
                 if st.status() != 0:
                     raise SystemExit("level-0 reported an error: " + capi.lib().rg_last_error().decode())
+        st.fence()
         e1.record(ext)
         e1.synchronize()
         barrier()

@@ -70,7 +70,12 @@ int rg_step1_create(const rg_step1_config* cfg, const double* X, const double* Y
                     const int64_t* fold_sizes, const double* lambda, const double* neff,
                     rg_handle* out);
 void rg_destroy(rg_handle h);
+/* Block the host until every call issued on the handle has finished. */
 int rg_sync(rg_handle h);
+/* Device-side join: consecutive level-0 blocks run on several internal streams ("lanes"); rg_fence
+ * makes the handle's stream (rg_stream) wait for all of them without blocking the host, so an event
+ * recorded on rg_stream afterwards covers all outstanding work. */
+int rg_fence(rg_handle h);
 
 /*
  * rg_l0_block_bed -- one level-0 block from 2-bit PLINK rows.  Replaces, for one block,

@@ -42,7 +42,7 @@ EXPORTS = [
     "rg_last_error", "rg_version", "rg_device_count", "rg_step1_create", "rg_destroy", "rg_sync",
     "rg_l0_block_bed", "rg_l0_status", "rg_l0_fetch_W", "rg_l1_fit", "rg_loco", "rg_step2_create",
     "rg_s2_set_chr", "rg_s2_block_bed", "rg_W_info", "rg_debug_fetch", "rg_launch_count", "rg_stream",
-    "rg_set_timing", "rg_get_timing",
+    "rg_set_timing", "rg_get_timing", "rg_fence",
 ]
 
 _lib = None
@@ -62,7 +62,7 @@ def lib():
         L.rg_launch_count.restype = C.c_int64
         L.rg_stream.restype = C.c_void_p
         L.rg_destroy.restype = None
-        for name in ("rg_destroy", "rg_sync", "rg_l0_status", "rg_launch_count", "rg_stream"):
+        for name in ("rg_destroy", "rg_sync", "rg_l0_status", "rg_launch_count", "rg_stream", "rg_fence"):
             getattr(L, name).argtypes = [C.c_void_p]
         L.rg_l0_block_bed.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]
         L.rg_l0_fetch_W.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
@@ -141,6 +141,9 @@ class Step1:
 
     def sync(self):
         check(lib().rg_sync(self.h))
+
+    def fence(self):
+        check(lib().rg_fence(self.h))
 
     def fetch_W(self, block_id, ph):
         out = np.empty((self.N, self.R), dtype=np.float64, order="F")

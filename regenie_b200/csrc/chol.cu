@@ -53,7 +53,7 @@ chol_update_kernel(double* __restrict__ cm, int64_t stride, int ld, int k, int t
 #pragma unroll
       for (int a = 0; a < 4; ++a) av[a] = As[p][ty * 4 + a];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) bv[b] = Bs[p][tx * 4 + b];
+      for (int b = 0; b < 4; ++b) bv[b] = Bs[p][tx + 16 * b];   // lane-consecutive columns: conflict-free
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -62,9 +62,9 @@ chol_update_kernel(double* __restrict__ cm, int64_t stride, int ld, int k, int t
   }
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
-    double* o = A + (int64_t)(r0 + ty * 4 + a) * ld + k + tx * 4;
+    double* o = A + (int64_t)(r0 + ty * 4 + a) * ld + k + tx;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) o[b] -= acc[a][b];
+    for (int b = 0; b < 4; ++b) o[16 * b] -= acc[a][b];
   }
 }
 

@@ -39,18 +39,26 @@ struct rg_ctx {
   rg::DevBuf<int32_t> file_idx_pad; // [Npad]
   rg::DevBuf<unsigned long long> err_slot;
 
-  // ---- per-block scratch
-  rg::DevBuf<uint8_t> packed_dev;
-  rg::DevBuf<int32_t> sample_idx_dev;
-  rg::DevBuf<uint32_t> gp;          // [rows_p][Npad/16]
-  rg::DevBuf<uint8_t> z;            // [2 rows_p][Npad] e4m3
-  rg::DevBuf<float> zz;             // [K][2 rows_p][2 rows_p]
-  rg::DevBuf<int32_t> cnt_part, cnt_fold;
-  rg::DevBuf<double> sum_part, sum_fold;
-  rg::DevBuf<double> mu, inv_sd, Bv, Af, Qf, gty_f, rhs;
-  rg::DevBuf<double> cm;            // [nmat][n_aug][nC]
-  rg::DevBuf<double> gam, gmu, cvec, part, mean_invsd;
-  std::map<int, CUtensorMap> tmaps;                       // keyed by rows_p
+  // ---- per-lane scratch: consecutive blocks go to different lanes (own stream + buffers) so the
+  //      latency-bound solver phases of one block overlap the tensor/HBM phases of the next
+  struct Lane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    rg::DevBuf<uint8_t> packed_dev;
+    rg::DevBuf<uint32_t> gp;          // [rows_p][Npad/16]
+    rg::DevBuf<uint8_t> z;            // [2 rows_p][Npad] e4m3
+    rg::DevBuf<float> zz;             // [K][2 rows_p][2 rows_p]
+    rg::DevBuf<int32_t> cnt_part, cnt_fold;
+    rg::DevBuf<double> sum_part, sum_fold;
+    rg::DevBuf<double> mu, inv_sd, Bv, Af, Qf, gty_f, rhs;
+    rg::DevBuf<double> cm;            // [nmat][n_aug][nC]
+    rg::DevBuf<double> gam, gmu, cvec, part, mean_invsd;
+    std::map<int, CUtensorMap> tmaps; // keyed by rows_p (z base differs per lane)
+  };
+  std::vector<std::unique_ptr<Lane>> lanes;
+  int next_lane = 0, last_lane = 0;
+  rg::DevBuf<uint8_t> packed_dev;    // step 2 (single lane)
+  rg::DevBuf<uint32_t> gp;           // step 2
   std::map<int, std::unique_ptr<rg::DevBuf<int2>>> tile_lists;
   std::map<int, int> tile_counts;
 

@@ -26,6 +26,7 @@ static void l1_fit(rg_ctx* h, const double* tau_host, double* cumsum, int32_t* b
   RG_CHECK(h->R1 >= 1 && h->R1 <= kMaxRidge, "n_ridge_l1 out of range");
   RG_CUDA(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
+  for (auto& l : h->lanes) RG_CUDA(cudaStreamSynchronize(l->stream));   // all level-0 blocks are in W
   const int K = h->K, R1 = h->R1, P = h->P;
   const int B = (int)h->B;
   const int nC = (int)round_up(B, 64), n_aug = nC + 64, nmat = K * R1;

@@ -50,7 +50,7 @@ l1_gram_kernel(const double* __restrict__ W, int64_t ldw, int B, const int4* __r
 #pragma unroll
       for (int a = 0; a < 4; ++a) av[a] = As[p][ty * 4 + a];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) bv[b] = Bs[p][tx * 4 + b];
+      for (int b = 0; b < 4; ++b) bv[b] = Bs[p][tx + 16 * b];   // lane-consecutive columns: conflict-free
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -63,7 +63,7 @@ l1_gram_kernel(const double* __restrict__ W, int64_t ldw, int B, const int4* __r
     const int i = ti * LT + ty * 4 + a;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      const int j = tj * LT + tx * 4 + b;
+      const int j = tj * LT + tx + 16 * b;
       if (i < B && j < B) o[(int64_t)i * ldp + j] = acc[a][b];
     }
   }

@@ -30,15 +30,16 @@ struct ScopedTimer {
   rg_ctx* h;
   std::string name;
   cudaEvent_t a = nullptr, b = nullptr;
-  ScopedTimer(rg_ctx* h_, const char* n) : h(h_), name(n) {
+  cudaStream_t st;
+  ScopedTimer(rg_ctx* h_, const char* n, cudaStream_t s_) : h(h_), name(n), st(s_) {
     if (!h->timing) return;
     cudaEventCreate(&a);
     cudaEventCreate(&b);
-    cudaEventRecord(a, h->stream);
+    cudaEventRecord(a, st);
   }
   ~ScopedTimer() {
     if (!h->timing) return;
-    cudaEventRecord(b, h->stream);
+    cudaEventRecord(b, st);
     h->pending.emplace_back(name, a, b);
   }
 };
@@ -227,70 +228,76 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
     }
   }
 
-  // --- input rows to the device
+  // --- lane: own stream + scratch
+  rg_ctx::Lane& L = *h->lanes[h->next_lane];
+  h->last_lane = h->next_lane;
+  h->next_lane = (h->next_lane + 1) % (int)h->lanes.size();
+  s = L.stream;
+
+  // --- input rows to the device (pinned host memory is copied asynchronously on the lane's stream)
   const uint8_t* packed_d = packed;
   if (!is_device_pointer(packed)) {
-    h->packed_dev.alloc((size_t)h->bs_max * row_stride);
-    ScopedTimer t(h, "h2d");
-    copy_to_device(h->packed_dev.p, packed, (size_t)bs * row_stride, s);
-    packed_d = h->packed_dev.p;
+    L.packed_dev.alloc((size_t)h->bs_max * row_stride);
+    ScopedTimer t(h, "h2d", s);
+    copy_to_device(L.packed_dev.p, packed, (size_t)bs * row_stride, s);
+    packed_d = L.packed_dev.p;
   }
 
   // --- scratch
-  h->gp.alloc((size_t)h->rows_p_max * (Npad / 16));
-  h->z.alloc((size_t)2 * h->rows_p_max * Npad);
-  h->zz.alloc((size_t)K * 4 * h->rows_p_max * h->rows_p_max);
-  h->cnt_part.alloc((size_t)h->nchunks * h->rows_p_max * 4);
-  h->sum_part.alloc((size_t)h->nchunks * h->rows_p_max * 2 * h->cpp);
-  h->cnt_fold.alloc((size_t)K * h->rows_p_max * 4);
-  h->sum_fold.alloc((size_t)K * h->rows_p_max * 2 * h->cpp);
-  h->mu.alloc(h->rows_p_max);
-  h->inv_sd.alloc(h->rows_p_max);
-  h->Bv.alloc((size_t)h->rows_p_max * C);
-  h->Af.alloc((size_t)K * h->rows_p_max * C);
-  h->Qf.alloc((size_t)K * h->rows_p_max * C);
-  h->gty_f.alloc((size_t)K * h->rows_p_max * P);
-  h->rhs.alloc((size_t)K * h->rows_p_max * P);
+  L.gp.alloc((size_t)h->rows_p_max * (Npad / 16));
+  L.z.alloc((size_t)2 * h->rows_p_max * Npad);
+  L.zz.alloc((size_t)K * 4 * h->rows_p_max * h->rows_p_max);
+  L.cnt_part.alloc((size_t)h->nchunks * h->rows_p_max * 4);
+  L.sum_part.alloc((size_t)h->nchunks * h->rows_p_max * 2 * h->cpp);
+  L.cnt_fold.alloc((size_t)K * h->rows_p_max * 4);
+  L.sum_fold.alloc((size_t)K * h->rows_p_max * 2 * h->cpp);
+  L.mu.alloc(h->rows_p_max);
+  L.inv_sd.alloc(h->rows_p_max);
+  L.Bv.alloc((size_t)h->rows_p_max * C);
+  L.Af.alloc((size_t)K * h->rows_p_max * C);
+  L.Qf.alloc((size_t)K * h->rows_p_max * C);
+  L.gty_f.alloc((size_t)K * h->rows_p_max * P);
+  L.rhs.alloc((size_t)K * h->rows_p_max * P);
   {
     const int nC_max = (int)round_up(h->bs_max, 64);
     const size_t need = (size_t)nmat * (nC_max + Ppad) * nC_max;
-    if (h->cm.n < need) {
-      h->cm.alloc(need);
-      RG_CUDA(cudaMemsetAsync(h->cm.p, 0, need * 8, s));
+    if (L.cm.n < need) {
+      L.cm.alloc(need);
+      RG_CUDA(cudaMemsetAsync(L.cm.p, 0, need * 8, s));
     }
   }
   const int Kg = h->loocv ? 1 : K;
-  h->gam.alloc((size_t)Kg * h->rows_p_max * Qp);
-  h->gmu.alloc((size_t)Kg * h->rows_p_max * Qp);
-  h->cvec.alloc((size_t)Kg * Qp * C);
+  L.gam.alloc((size_t)Kg * h->rows_p_max * Qp);
+  L.gmu.alloc((size_t)Kg * h->rows_p_max * Qp);
+  L.cvec.alloc((size_t)Kg * Qp * C);
   const int ntiles_s = (int)(Npad / 128);
-  h->part.alloc((size_t)ntiles_s * Qp * 2);
-  h->mean_invsd.alloc((size_t)2 * Qp);
+  L.part.alloc((size_t)ntiles_s * Qp * 2);
+  L.mean_invsd.alloc((size_t)2 * Qp);
 
   // --- 1. decode: PLINK rows -> padded 2-bit rows -> e4m3 planes
   {
-    ScopedTimer t(h, "bed_relayout");
-    launch_bed_relayout(packed_d, row_stride, bs, rows_p, h->file_idx_pad.p, ref_first, h->gp.p, Npad, s);
+    ScopedTimer t(h, "bed_relayout", s);
+    launch_bed_relayout(packed_d, row_stride, bs, rows_p, h->file_idx_pad.p, ref_first, L.gp.p, Npad, s);
   }
   {
-    ScopedTimer t(h, "bed_expand");
-    launch_bed_expand_fp8(h->gp.p, rows_p, h->z.p, Npad, s);
+    ScopedTimer t(h, "bed_expand", s);
+    launch_bed_expand_fp8(L.gp.p, rows_p, L.z.p, Npad, s);
   }
   h->launches += 2;
 
   // --- 2. f64 sufficient statistics
   {
-    ScopedTimer t(h, "l0_stats");
-    launch_l0_stats(h->gp.p, Npad, h->xy.p, h->cpp, h->chunks.p, h->nchunks, rows_p, h->cnt_part.p,
-                    h->sum_part.p, s);
-    launch_l0_fold_reduce(h->cnt_part.p, h->sum_part.p, rows_p, h->cpp, h->fold_chunks.p, K,
-                          h->cnt_fold.p, h->sum_fold.p, s);
+    ScopedTimer t(h, "l0_stats", s);
+    launch_l0_stats(L.gp.p, Npad, h->xy.p, h->cpp, h->chunks.p, h->nchunks, rows_p, L.cnt_part.p,
+                    L.sum_part.p, s);
+    launch_l0_fold_reduce(L.cnt_part.p, L.sum_part.p, rows_p, h->cpp, h->fold_chunks.p, K,
+                          L.cnt_fold.p, L.sum_fold.p, s);
     SnpFinalizeArgs a;
     a.bs = bs; a.rows_p = rows_p; a.C = C; a.P = P; a.K = K; a.cpp = h->cpp; a.loocv = h->loocv;
     a.n_analyzed = h->n_analyzed; a.numtol = 1e-6;
-    a.cnt_fold = h->cnt_fold.p; a.sum_fold = h->sum_fold.p; a.XtX_f = h->XtX_f.p; a.XtY_f = h->XtY_f.p;
-    a.mu = h->mu.p; a.inv_sd = h->inv_sd.p; a.Bv = h->Bv.p; a.Af = h->Af.p; a.Qf = h->Qf.p;
-    a.gty_f = h->gty_f.p; a.rhs = h->rhs.p; a.err_slot = h->err_slot.p;
+    a.cnt_fold = L.cnt_fold.p; a.sum_fold = L.sum_fold.p; a.XtX_f = h->XtX_f.p; a.XtY_f = h->XtY_f.p;
+    a.mu = L.mu.p; a.inv_sd = L.inv_sd.p; a.Bv = L.Bv.p; a.Af = L.Af.p; a.Qf = L.Qf.p;
+    a.gty_f = L.gty_f.p; a.rhs = L.rhs.p; a.err_slot = h->err_slot.p;
     a.err_base = (long long)block_id * h->bs_max;
     launch_l0_snp_finalize(a, s);
     h->launches += 3;
@@ -298,10 +305,12 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
 
   // --- 3. exact integer Grams on the tensor cores
   {
-    if (!h->tmaps.count(rows_p)) {
+    if (!L.tmaps.count(rows_p)) {
       CUtensorMap tm;
-      make_gram_tensor_map(&tm, h->z.p, Npad, 2 * rows_p);
-      h->tmaps[rows_p] = tm;
+      make_gram_tensor_map(&tm, L.z.p, Npad, 2 * rows_p);
+      L.tmaps[rows_p] = tm;
+    }
+    if (!h->tile_lists.count(rows_p)) {
       std::vector<int2> tiles;
       gram_tile_list(2 * rows_p, tiles);
       auto buf = std::make_unique<DevBuf<int2>>();
@@ -310,32 +319,32 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
       h->tile_counts[rows_p] = (int)tiles.size();
       h->tile_lists[rows_p] = std::move(buf);
     }
-    ScopedTimer t(h, "gram_tcgen05");
-    launch_gram_tcgen05(h->tmaps[rows_p], h->tile_lists[rows_p]->p, h->tile_counts[rows_p], h->fold_k.p, K,
-                        h->zz.p, 2 * rows_p, (int64_t)4 * rows_p * rows_p, s);
+    ScopedTimer t(h, "gram_tcgen05", s);
+    launch_gram_tcgen05(L.tmaps[rows_p], h->tile_lists[rows_p]->p, h->tile_counts[rows_p], h->fold_k.p, K,
+                        L.zz.p, 2 * rows_p, (int64_t)4 * rows_p * rows_p, s);
     h->launches += 1;
   }
 
   // --- 4. ridge systems
   AssembleArgs aa;
   aa.bs = bs; aa.rows_p = rows_p; aa.nC = nC; aa.C = C; aa.K = K; aa.R = R; aa.loocv = h->loocv;
-  aa.zz = h->zz.p; aa.ldz = 2 * rows_p; aa.zz_fold_stride = (int64_t)4 * rows_p * rows_p;
-  aa.mu = h->mu.p; aa.inv_sd = h->inv_sd.p; aa.Bv = h->Bv.p; aa.Af = h->Af.p; aa.Qf = h->Qf.p;
-  aa.lambda = h->lambda.p; aa.cm = h->cm.p; aa.cm_stride = (int64_t)n_aug * nC; aa.ldc = nC;
+  aa.zz = L.zz.p; aa.ldz = 2 * rows_p; aa.zz_fold_stride = (int64_t)4 * rows_p * rows_p;
+  aa.mu = L.mu.p; aa.inv_sd = L.inv_sd.p; aa.Bv = L.Bv.p; aa.Af = L.Af.p; aa.Qf = L.Qf.p;
+  aa.lambda = h->lambda.p; aa.cm = L.cm.p; aa.cm_stride = (int64_t)n_aug * nC; aa.ldc = nC;
   {
-    ScopedTimer t(h, "l0_assemble");
-    launch_l0_assemble(aa, h->rhs.p, P, Ppad, nmat, s);
+    ScopedTimer t(h, "l0_assemble", s);
+    launch_l0_assemble(aa, L.rhs.p, P, Ppad, nmat, s);
     h->launches += 2;
   }
   {
-    ScopedTimer t(h, "chol_factor");
-    launch_chol_factor(h->cm.p, aa.cm_stride, nC, n_aug, nmat, h->err_slot.p,
+    ScopedTimer t(h, "chol_factor", s);
+    launch_chol_factor(L.cm.p, aa.cm_stride, nC, n_aug, nmat, h->err_slot.p,
                        (long long)(1ll << 40) + (long long)block_id * 1024, s);
     h->launches += chol_num_launches(nC);
   }
   {
-    ScopedTimer t(h, "chol_backsolve");
-    launch_chol_backsolve(h->cm.p, aa.cm_stride, nC, P, nmat, s);
+    ScopedTimer t(h, "chol_backsolve", s);
+    launch_chol_backsolve(L.cm.p, aa.cm_stride, nC, P, nmat, s);
     h->launches += 1;
   }
   h->last_bs = bs; h->last_rows_p = rows_p; h->last_nC = nC; h->last_n_aug = n_aug; h->last_nmat = nmat;
@@ -344,16 +353,16 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
 
   // --- 5. out-of-fold predictions, standardised into W
   {
-    ScopedTimer t(h, "l0_predict");
-    launch_l0_gamma(h->cm.p, aa.cm_stride, nC, nC, R, P, Qp, bs, rows_p, K, h->mu.p, h->inv_sd.p, h->Bv.p, C,
-                    h->gam.p, h->gmu.p, h->cvec.p, s);
+    ScopedTimer t(h, "l0_predict", s);
+    launch_l0_gamma(L.cm.p, aa.cm_stride, nC, nC, R, P, Qp, bs, rows_p, K, L.mu.p, L.inv_sd.p, L.Bv.p, C,
+                    L.gam.p, L.gmu.p, L.cvec.p, s);
     PredictArgs pa;
     pa.bs = bs; pa.rows_p = rows_p; pa.C = C; pa.P = P; pa.R = R; pa.Qp = Qp; pa.cpp = h->cpp;
     pa.col0 = block_id * R; pa.npad = Npad; pa.words_per_row = Npad / 16; pa.w_stride = Npad * h->B;
-    pa.gp = h->gp.p; pa.tile_fold = h->tile_fold.p; pa.gam = h->gam.p; pa.gmu = h->gmu.p;
-    pa.cvec = h->cvec.p; pa.xy = h->xy.p; pa.mask = h->mask.p; pa.W = h->W.p; pa.part = h->part.p;
+    pa.gp = L.gp.p; pa.tile_fold = h->tile_fold.p; pa.gam = L.gam.p; pa.gmu = L.gmu.p;
+    pa.cvec = L.cvec.p; pa.xy = h->xy.p; pa.mask = h->mask.p; pa.W = h->W.p; pa.part = L.part.p;
     launch_l0_predict(pa, ntiles_s, s);
-    launch_l0_standardize(h->part.p, ntiles_s, Qp, Q, P, h->neff.p, h->mean_invsd.p, h->W.p, pa.w_stride, Npad,
+    launch_l0_standardize(L.part.p, ntiles_s, Qp, Q, P, h->neff.p, L.mean_invsd.p, h->W.p, pa.w_stride, Npad,
                           pa.col0, h->is_real.p, s);
     h->launches += 5;
   }
@@ -408,6 +417,16 @@ int rg_step1_create(const rg_step1_config* cfg, const double* X, const double* Y
   h->kind = 1;
   h->device = cfg->device;
   RG_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  {
+    int nl = 4;
+    if (const char* e = getenv("RG_B200_LANES")) nl = std::max(1, std::min(8, atoi(e)));
+    for (int i = 0; i < nl; ++i) {
+      auto l = std::make_unique<rg_ctx::Lane>();
+      RG_CUDA(cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking));
+      RG_CUDA(cudaEventCreateWithFlags(&l->done, cudaEventDisableTiming));
+      h->lanes.push_back(std::move(l));
+    }
+  }
   h->N = cfg->n_samples; h->C = cfg->n_cov; h->P = cfg->n_pheno;
   h->loocv = cfg->loocv ? 1 : 0;
   h->K = h->loocv ? 1 : cfg->n_folds;
@@ -433,8 +452,10 @@ int rg_step1_create(const rg_step1_config* cfg, const double* X, const double* Y
 void rg_destroy(rg_handle h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  for (auto& l : h->lanes) cudaStreamSynchronize(l->stream);
   cudaStreamSynchronize(h->stream);
   rg::flush_timers(h);
+  for (auto& l : h->lanes) { cudaEventDestroy(l->done); cudaStreamDestroy(l->stream); }
   cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -443,8 +464,20 @@ int rg_sync(rg_handle h) {
   RG_API_BEGIN
   RG_CHECK(h, "null handle");
   RG_CUDA(cudaSetDevice(h->device));
+  for (auto& l : h->lanes) RG_CUDA(cudaStreamSynchronize(l->stream));
   RG_CUDA(cudaStreamSynchronize(h->stream));
   rg::flush_timers(h);
+  RG_API_END
+}
+
+int rg_fence(rg_handle h) {
+  RG_API_BEGIN
+  RG_CHECK(h, "null handle");
+  RG_CUDA(cudaSetDevice(h->device));
+  for (auto& l : h->lanes) {
+    RG_CUDA(cudaEventRecord(l->done, l->stream));
+    RG_CUDA(cudaStreamWaitEvent(h->stream, l->done, 0));
+  }
   RG_API_END
 }
 
@@ -460,6 +493,7 @@ int rg_l0_block_bed(rg_handle h, const uint8_t* packed, int64_t row_stride, int3
 int64_t rg_l0_status(rg_handle h) {
   if (!h) return -1;
   cudaSetDevice(h->device);
+  for (auto& l : h->lanes) cudaStreamSynchronize(l->stream);
   if (cudaStreamSynchronize(h->stream) != cudaSuccess) {
     rg::set_last_error(std::string("CUDA error: ") + cudaGetErrorString(cudaGetLastError()));
     return -1;
@@ -481,6 +515,7 @@ int rg_l0_fetch_W(rg_handle h, int32_t block_id, int32_t ph, double* out) {
   RG_CHECK(h && out, "null argument");
   RG_CHECK(h->kind == 1 && block_id >= 0 && block_id < h->total_blocks && ph >= 0 && ph < h->P, "bad index");
   RG_CUDA(cudaSetDevice(h->device));
+  for (auto& l : h->lanes) RG_CUDA(cudaStreamSynchronize(l->stream));
   std::vector<double> tmp((size_t)h->Npad * h->R);
   const double* src = h->W.p + (size_t)ph * h->Npad * h->B + (size_t)block_id * h->R * h->Npad;
   RG_CUDA(cudaMemcpyAsync(tmp.data(), src, tmp.size() * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -493,21 +528,24 @@ int rg_l0_fetch_W(rg_handle h, int32_t block_id, int32_t ph, double* out) {
 int64_t rg_debug_fetch(rg_handle h, const char* name, void* out, int64_t max_bytes) {
   if (!h || !name || !out) return -1;
   cudaSetDevice(h->device);
+  for (auto& l : h->lanes) cudaStreamSynchronize(l->stream);
   cudaStreamSynchronize(h->stream);
+  if (h->lanes.empty()) { rg::set_last_error("no level-0 lane"); return -1; }
+  rg_ctx::Lane& L = *h->lanes[h->last_lane];
   const std::string n(name);
   const void* p = nullptr;
   size_t bytes = 0;
   const int rp = h->last_rows_p;
-  if (n == "gp") { p = h->gp.p; bytes = (size_t)rp * (h->Npad / 16) * 4; }
-  else if (n == "z") { p = h->z.p; bytes = (size_t)2 * rp * h->Npad; }
-  else if (n == "zz") { p = h->zz.p; bytes = (size_t)h->K * 4 * rp * rp * 4; }
-  else if (n == "mu") { p = h->mu.p; bytes = (size_t)rp * 8; }
-  else if (n == "inv_sd") { p = h->inv_sd.p; bytes = (size_t)rp * 8; }
-  else if (n == "Bv") { p = h->Bv.p; bytes = (size_t)rp * h->C * 8; }
-  else if (n == "gty_f") { p = h->gty_f.p; bytes = (size_t)h->K * rp * h->P * 8; }
-  else if (n == "rhs") { p = h->rhs.p; bytes = (size_t)h->K * rp * h->P * 8; }
-  else if (n == "cm") { p = h->cm.p; bytes = (size_t)h->last_nmat * h->last_n_aug * h->last_nC * 8; }
-  else if (n == "mean_invsd") { p = h->mean_invsd.p; bytes = (size_t)2 * h->R * h->P * 8; }
+  if (n == "gp") { p = L.gp.p; bytes = (size_t)rp * (h->Npad / 16) * 4; }
+  else if (n == "z") { p = L.z.p; bytes = (size_t)2 * rp * h->Npad; }
+  else if (n == "zz") { p = L.zz.p; bytes = (size_t)h->K * 4 * rp * rp * 4; }
+  else if (n == "mu") { p = L.mu.p; bytes = (size_t)rp * 8; }
+  else if (n == "inv_sd") { p = L.inv_sd.p; bytes = (size_t)rp * 8; }
+  else if (n == "Bv") { p = L.Bv.p; bytes = (size_t)rp * h->C * 8; }
+  else if (n == "gty_f") { p = L.gty_f.p; bytes = (size_t)h->K * rp * h->P * 8; }
+  else if (n == "rhs") { p = L.rhs.p; bytes = (size_t)h->K * rp * h->P * 8; }
+  else if (n == "cm") { p = L.cm.p; bytes = (size_t)h->last_nmat * h->last_n_aug * h->last_nC * 8; }
+  else if (n == "mean_invsd") { p = L.mean_invsd.p; bytes = (size_t)2 * h->R * h->P * 8; }
   else if (n == "dims") {
     int64_t d[8] = {h->Npad, rp, h->last_nC, h->last_n_aug, h->last_nmat, h->K, h->cpp, h->nchunks};
     if (max_bytes < (int64_t)sizeof(d)) return -1;
@@ -524,7 +562,7 @@ int64_t rg_debug_fetch(rg_handle h, const char* name, void* out, int64_t max_byt
     ref.alloc(per * h->K);
     cudaMemsetAsync(ref.p, 0, per * h->K * 4, h->stream);
     for (int f = 0; f < h->K; ++f)
-      rg::launch_gram_reference(h->z.p, h->Npad, 2 * rp, (int)h->fold_pad_start[f],
+      rg::launch_gram_reference(L.z.p, h->Npad, 2 * rp, (int)h->fold_pad_start[f],
                                 (int)(h->fold_pad_start[f] + h->fold_pad_len[f]), ref.p + per * f, 2 * rp,
                                 h->stream);
     bytes = per * h->K * 4;
@@ -554,6 +592,7 @@ int rg_set_timing(rg_handle h, int32_t enable) {
 int rg_get_timing(rg_handle h, const char* kernel, double* total_ms, int64_t* launches) {
   RG_API_BEGIN
   RG_CHECK(h && kernel, "null argument");
+  for (auto& l : h->lanes) RG_CUDA(cudaStreamSynchronize(l->stream));
   RG_CUDA(cudaStreamSynchronize(h->stream));
   rg::flush_timers(h);
   auto it = h->timers.find(kernel);

@@ -153,7 +153,7 @@ void run_step1(const Params& p, Log& log) {
     g.read_rows(blocks[b].first, blocks[b].size, rows.data());
     rg_check(rg_l0_block_bed(h, rows.data(), (int64_t)g.row_stride, blocks[b].size,
                              subset ? g.sample_idx.data() : nullptr, p.ref_first, b));
-    rg_check(rg_sync(h));    // `rows` is reused by the next block
+    // `rows` is pageable memory: the copy is staged before rg_l0_block_bed returns, so it can be reused
     log << " block [" << b + 1 << "] : " << blocks[b].size << " snps\n";
   }
   const int64_t st = rg_l0_status(h);
