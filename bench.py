@@ -243,7 +243,7 @@ def run_gpu(args):
             one_pass(base_ptr)
             if read_status:
                 if st.status() != 0:
-                    raise SystemExit("level-0 reported an error: " + capi.lib().rg_last_error().decode())
+                    raise SystemExit("level-0 reported an error (timed/e2e pass): " + capi.lib().rg_last_error().decode())
         st.fence()
         e1.record(ext)
         e1.synchronize()
@@ -259,7 +259,7 @@ def run_gpu(args):
     for _ in range(max(args.warmup, 3)):
         one_pass(dev_ptr)
     if st.status() != 0:
-        raise SystemExit("level-0 reported an error: " + capi.lib().rg_last_error().decode())
+        raise SystemExit("level-0 reported an error (warm-up): " + capi.lib().rg_last_error().decode())
 
     # ---- device-resident throughput (timed region; per-kernel CUDA events on the same stream)
     st.set_timing(True)

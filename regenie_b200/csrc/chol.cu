@@ -8,32 +8,34 @@
 // Storage: row-major lower triangle, ld = nC (multiple of 64); matrix m occupies
 // cm + m*stride; rows nC .. nC+Ppad-1 hold the right-hand sides as extra rows, so the
 // factorisation sweep leaves  y^T = (L^-1 b)^T  there (fused forward substitution).
-// Left-looking by 64-column panels: trailing data is read, never rewritten -> n^3/6 * 8 / 64
-// bytes of traffic per matrix instead of n^3/3 * 8 / 64 * 2 for right-looking.
+//
+// Left-looking by 64-column panels, three launches per panel:
+//   chol_update : every row tile at/after the panel subtracts L[rows,0:k] L[k:k+64,0:k]^T
+//                 (FP64 GEMM, the n^3/3 flops)
+//   chol_diag   : one CTA per system factors the diagonal tile in registers and also produces
+//                 M = L_kk^-T (the same column sweep applied to I)
+//   chol_trsm   : row tiles below the panel:  L[rows, k:k+64] = P[rows, k:k+64] * M
+// No CTA ever reads a tile that another CTA of the same launch overwrites: kernels of several
+// "lanes" run concurrently, so launch-wide lockstep cannot be assumed.
+// The stored inverses M also turn the backward substitution's triangular solves into GEMVs.
 #include "kernels.cuh"
 
 namespace rg {
 
 constexpr int TB = 64;  // tile / panel width
 
-// P[r0:r0+64, k:k+64] -= L[r0:r0+64, 0:k] * L[k:k+64, 0:k]^T      (k > 0)
-// grid: (row tiles at/after the panel, 1, batch); 256 threads, 4x4 register tile each.
-__global__ void __launch_bounds__(256)
-chol_update_kernel(double* __restrict__ cm, int64_t stride, int ld, int k, int tile0) {
-  __shared__ double As[16][TB + 2];
-  __shared__ double Bs[16][TB + 2];
-  double* A = cm + (int64_t)blockIdx.z * stride;
-  const int r0 = (tile0 + blockIdx.x) * TB;
+// acc[a][b] = sum_{p<k} A[r0 + ty*4+a][p] * A[rB + tx+16b][p]
+__device__ __forceinline__ void gemm_tile_nt(const double* __restrict__ A, int ld, int r0, int rB, int k,
+                                             double (&acc)[4][4], double (*As)[TB + 2], double (*Bs)[TB + 2]) {
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   const int lrow = threadIdx.x / 4, lp = (threadIdx.x % 4) * 4;   // loader mapping: 64 rows x 16 p
-  double acc[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-
+  if (k == 0) return;
   const double* arow = A + (int64_t)(r0 + lrow) * ld + lp;
-  const double* brow = A + (int64_t)(k + lrow) * ld + lp;
+  const double* brow = A + (int64_t)(rB + lrow) * ld + lp;
   double2 a0 = *reinterpret_cast<const double2*>(arow), a1 = *reinterpret_cast<const double2*>(arow + 2);
   double2 b0 = *reinterpret_cast<const double2*>(brow), b1 = *reinterpret_cast<const double2*>(brow + 2);
   for (int p0 = 0; p0 < k; p0 += 16) {
@@ -60,6 +62,19 @@ chol_update_kernel(double* __restrict__ cm, int64_t stride, int ld, int k, int t
         for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
     }
   }
+}
+
+// P[r0:r0+64, k:k+64] -= L[r0:r0+64, 0:k] * L[k:k+64, 0:k]^T   (k > 0)
+// grid: (row tiles at/after the panel, 1, batch); 256 threads, 4x4 register tile each.
+__global__ void __launch_bounds__(256)
+chol_update_kernel(double* __restrict__ cm, int64_t stride, int ld, int k, int tile0) {
+  __shared__ double As[16][TB + 2];
+  __shared__ double Bs[16][TB + 2];
+  double* A = cm + (int64_t)blockIdx.z * stride;
+  const int r0 = (tile0 + blockIdx.x) * TB;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  double acc[4][4];
+  gemm_tile_nt(A, ld, r0, k, k, acc, As, Bs);
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     double* o = A + (int64_t)(r0 + ty * 4 + a) * ld + k + tx;
@@ -68,145 +83,198 @@ chol_update_kernel(double* __restrict__ cm, int64_t stride, int ld, int k, int t
   }
 }
 
-// Panel step: every CTA factors the (already updated) 64x64 diagonal block redundantly in
-// shared memory and applies the same column sweep to its own 64-row tile:
-//   L_kk = chol(P_kk);   L[r0:r0+64, k:k+64] = P[r0.., k..] * L_kk^-T.
-// grid: (row tiles at/after the panel, 1, batch); tile 0 is the diagonal block itself.
+// Diagonal tile: L_kk = chol(P_kk) and M = L_kk^-T, both in registers (thread (r, q) holds the
+// columns q+4j of row r); one barrier per column, pivots broadcast through a double buffer.
+// grid: (batch); 256 threads.
 __global__ void __launch_bounds__(256)
-chol_panel_kernel(double* __restrict__ cm, int64_t stride, int ld, int k, int tile0,
-                  unsigned long long* __restrict__ err_slot, long long err_base) {
-  extern __shared__ double panel_sm[];
-  double (*D)[TB + 1] = reinterpret_cast<double (*)[TB + 1]>(panel_sm);
-  double (*T)[TB + 1] = reinterpret_cast<double (*)[TB + 1]>(panel_sm + TB * (TB + 1));
-  double* A = cm + (int64_t)blockIdx.z * stride;
-  const bool is_diag = (blockIdx.x == 0);
-  const int r0 = (tile0 + blockIdx.x) * TB;
-  for (int e = threadIdx.x; e < TB * TB; e += 256) {
-    const int r = e / TB, c = e % TB;
-    D[r][c] = (c <= r) ? A[(int64_t)(k + r) * ld + k + c] : 0.0;
-    if (!is_diag) T[r][c] = A[(int64_t)(r0 + r) * ld + k + c];
+chol_diag_kernel(double* __restrict__ cm, int64_t stride, int ld, int k,
+                 double* __restrict__ inv, int64_t inv_stride,
+                 unsigned long long* __restrict__ err_slot, long long err_base) {
+  __shared__ double cb[2][TB], xb[2][TB];
+  double* A = cm + (int64_t)blockIdx.x * stride;
+  const int r = threadIdx.x & (TB - 1), q = threadIdx.x >> 6;
+  double D[16], T[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int cc = q + 4 * j;
+    D[j] = (cc <= r) ? A[(int64_t)(k + r) * ld + k + cc] : 0.0;
+    T[j] = (cc == r) ? 1.0 : 0.0;
   }
-  __syncthreads();
-  for (int c = 0; c < TB; ++c) {
-    const double piv = D[c][c];
-    if (!(piv > 0.0) && threadIdx.x == 0 && is_diag)
-      atomicMin(err_slot, (unsigned long long)(err_base + blockIdx.z + 1));
-    const double inv = 1.0 / sqrt(piv);
-    __syncthreads();
-    // scale column c
-    if (threadIdx.x < TB) {
-      const int r = threadIdx.x;
-      if (r >= c) D[r][c] *= inv;           // r == c: piv/sqrt(piv) = sqrt(piv)
-    } else if (threadIdx.x < 2 * TB && !is_diag) {
-      T[threadIdx.x - TB][c] *= inv;
-    }
-    __syncthreads();
-    // rank-1 update of the remaining columns: thread = (row, column phase), no divisions
-    {
-      const int r = threadIdx.x & (TB - 1);
-      const double dr = D[r][c];
-      const double tr = is_diag ? 0.0 : T[r][c];
-      for (int cc = c + 1 + (threadIdx.x >> 6); cc < TB; cc += 4) {
-        const double l = D[cc][c];
-        if (r >= cc) D[r][cc] -= dr * l;
-        if (!is_diag) T[r][cc] -= tr * l;
+  bool bad = false;
+#pragma unroll
+  for (int jc = 0; jc < 16; ++jc) {
+#pragma unroll
+    for (int qc = 0; qc < 4; ++qc) {
+      const int c = 4 * jc + qc;
+      const int buf = c & 1;
+      if (q == qc) { cb[buf][r] = D[jc]; xb[buf][r] = T[jc]; }
+      __syncthreads();      // one barrier per column: the other buffer is only rewritten after the next barrier
+      const double piv = cb[buf][c];
+      if (!(piv > 0.0)) bad = true;
+      const double inv_p = 1.0 / sqrt(piv);
+      const double lr = cb[buf][r] * inv_p;      // L[r][c]  (meaningful for r >= c)
+      const double xr = xb[buf][r] * inv_p;      // X[r][c] = (L^-T)[r][c]
+      if (q == qc) { D[jc] = (r >= c) ? lr : 0.0; T[jc] = xr; }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (j > jc || (j == jc && q > qc)) {      // columns cc > c
+          const int cc = q + 4 * j;
+          const double lcc = cb[buf][cc] * inv_p;
+          if (r >= cc) D[j] = fma(-lr, lcc, D[j]);
+          T[j] = fma(-xr, lcc, T[j]);
+        }
       }
     }
-    // (the next iteration's first __syncthreads orders these writes before the column scale)
-    __syncthreads();
   }
-  for (int e = threadIdx.x; e < TB * TB; e += 256) {
-    const int r = e / TB, c = e % TB;
-    if (is_diag) {
-      if (c <= r) A[(int64_t)(k + r) * ld + k + c] = D[r][c];
-    } else {
-      A[(int64_t)(r0 + r) * ld + k + c] = T[r][c];
-    }
+  if (bad && threadIdx.x == 0) atomicMin(err_slot, (unsigned long long)(err_base + blockIdx.x + 1));
+  double* Mo = inv + (int64_t)blockIdx.x * inv_stride + (int64_t)(k / TB) * TB * TB;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int cc = q + 4 * j;
+    if (cc <= r) A[(int64_t)(k + r) * ld + k + cc] = D[j];
+    Mo[r * TB + cc] = (cc >= r) ? T[j] : 0.0;
   }
 }
 
-// Backward substitution  L^T beta = y  for all right-hand sides, one CTA per matrix,
-// sweeping 64-column blocks from the last to the first ("right-looking" on y).
-// y lives in the RHS rows (row nC+p, contiguous over columns); beta overwrites it.
+// L[rows, k:k+64] = P[rows, k:k+64] * M,  M = L_kk^-T (upper triangular).
+// grid: (row tiles strictly below the panel, 1, batch); 256 threads, 4x4 outputs each.
 __global__ void __launch_bounds__(256)
-chol_backsolve_kernel(double* __restrict__ cm, int64_t stride, int ld, int nC, int P) {
+chol_trsm_kernel(double* __restrict__ cm, int64_t stride, int ld, int k, int tile0,
+                 const double* __restrict__ inv, int64_t inv_stride) {
+  extern __shared__ double trsm_sm[];
+  double (*Ts)[TB + 1] = reinterpret_cast<double (*)[TB + 1]>(trsm_sm);
+  double (*Ms)[TB + 2] = reinterpret_cast<double (*)[TB + 2]>(trsm_sm + TB * (TB + 1));
+  double* A = cm + (int64_t)blockIdx.z * stride;
+  const double* M = inv + (int64_t)blockIdx.z * inv_stride + (int64_t)(k / TB) * TB * TB;
+  const int r0 = (tile0 + 1 + blockIdx.x) * TB;
+  for (int e = threadIdx.x; e < TB * TB; e += 256) {
+    const int rr = e / TB, cc = e % TB;
+    Ts[rr][cc] = A[(int64_t)(r0 + rr) * ld + k + cc];
+    Ms[rr][cc] = M[e];
+  }
+  __syncthreads();
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+#pragma unroll 8
+  for (int p = 0; p < TB; ++p) {
+    double av[4], bv[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) av[a] = Ts[ty * 4 + a][p];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) bv[b] = Ms[p][tx + 16 * b];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    double* o = A + (int64_t)(r0 + ty * 4 + a) * ld + k + tx;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) o[16 * b] = acc[a][b];
+  }
+}
+
+// Backward substitution  L^T beta = y  for all right-hand sides, one 1024-thread CTA per matrix,
+// sweeping 64-column blocks from the last to the first.  y lives in the RHS rows (row nC+p,
+// contiguous over columns); beta overwrites it.  The diagonal solves are GEMVs with the stored
+// M = L_kk^-T; the sweep  y[:, j] -= L[k+r][j] beta[r]  streams the 64 panel rows once.
+constexpr int BS_THREADS = 1024;
+constexpr int BS_PC = 10;   // right-hand sides per register pass
+
+__global__ void __launch_bounds__(BS_THREADS)
+chol_backsolve_kernel(double* __restrict__ cm, int64_t stride, int ld, int nC, int P,
+                      const double* __restrict__ inv, int64_t inv_stride) {
   extern __shared__ double back_sm[];
-  double (*Lkk)[TB + 1] = reinterpret_cast<double (*)[TB + 1]>(back_sm);
-  double* bsm = back_sm + TB * (TB + 1);   // y / beta of the current block: [TB][P]
+  double* Ms = back_sm;                    // [TB][TB+1]
+  double* ys = Ms + TB * (TB + 1);         // [TB][P]  y block
+  double* bs = ys + TB * P;                // [TB][P]  beta block
   double* A = cm + (int64_t)blockIdx.x * stride;
+  const double* Minv = inv + (int64_t)blockIdx.x * inv_stride;
   for (int kb = nC / TB - 1; kb >= 0; --kb) {
     const int k = kb * TB;
     __syncthreads();
-    for (int e = threadIdx.x; e < TB * TB; e += 256) {
-      const int r = e / TB, c = e % TB;
-      Lkk[r][c] = (c <= r) ? A[(int64_t)(k + r) * ld + k + c] : 0.0;
-    }
-    for (int e = threadIdx.x; e < TB * P; e += 256) {
+    for (int e = threadIdx.x; e < TB * TB; e += BS_THREADS)
+      Ms[(e / TB) * (TB + 1) + (e % TB)] = Minv[(int64_t)kb * TB * TB + e];
+    for (int e = threadIdx.x; e < TB * P; e += BS_THREADS) {
       const int r = e % TB, p = e / TB;
-      bsm[r * P + p] = A[(int64_t)(nC + p) * ld + k + r];
-    }
-    // column-oriented solve of L_kk^T x = y_k: one row per step, the rest updated in parallel
-    for (int r = TB - 1; r >= 0; --r) {
-      __syncthreads();
-      if (threadIdx.x < P) bsm[r * P + threadIdx.x] /= Lkk[r][r];
-      __syncthreads();
-      for (int e = threadIdx.x; e < r * P; e += 256) {
-        const int rr = e / P, p = e - rr * P;
-        bsm[rr * P + p] -= Lkk[r][rr] * bsm[r * P + p];
-      }
+      ys[r * P + p] = A[(int64_t)(nC + p) * ld + k + r];
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < TB * P; e += 256) {
+    // beta = L_kk^-T y = M y   (M upper triangular: M[r][c], c >= r)
+    for (int e = threadIdx.x; e < TB * P; e += BS_THREADS) {
       const int r = e % TB, p = e / TB;
-      A[(int64_t)(nC + p) * ld + k + r] = bsm[r * P + p];
+      double s = 0.0;
+      for (int c = r; c < TB; ++c) s = fma(Ms[r * (TB + 1) + c], ys[c * P + p], s);
+      bs[r * P + p] = s;
+      A[(int64_t)(nC + p) * ld + k + r] = s;
     }
-    // y[p][j] -= sum_r L[k+r][j] * beta[r][p]   for all j < k   (coalesced over j)
-    for (int j = threadIdx.x; j < k; j += 256) {
-      for (int p0 = 0; p0 < P; p0 += 10) {
-        double acc[10];
+    __syncthreads();
+    // y[p][j] -= sum_r L[k+r][j] * beta[r][p]   for all j < k   (coalesced over j, 16 loads in flight)
+    for (int j = threadIdx.x; j < k; j += BS_THREADS) {
+      for (int p0 = 0; p0 < P; p0 += BS_PC) {
+        const int np = min(BS_PC, P - p0);
+        double acc[BS_PC];
 #pragma unroll
-        for (int q = 0; q < 10; ++q) acc[q] = 0.0;
-        const int np = min(10, P - p0);
-#pragma unroll 8
-        for (int r = 0; r < TB; ++r) {
-          const double l = A[(int64_t)(k + r) * ld + j];
-          const double* bb = bsm + r * P + p0;
-          if (np == 10) {
+        for (int qq = 0; qq < BS_PC; ++qq) acc[qq] = 0.0;
+#pragma unroll 1
+        for (int rb = 0; rb < TB; rb += 16) {
+          double l[16];
 #pragma unroll
-            for (int q = 0; q < 10; ++q) acc[q] = fma(l, bb[q], acc[q]);
-          } else {
-            for (int q = 0; q < np; ++q) acc[q] = fma(l, bb[q], acc[q]);
+          for (int u = 0; u < 16; ++u) l[u] = A[(int64_t)(k + rb + u) * ld + j];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const double* bb = bs + (rb + u) * P + p0;
+#pragma unroll
+            for (int qq = 0; qq < BS_PC; ++qq)
+              if (qq < np) acc[qq] = fma(l[u], bb[qq], acc[qq]);
           }
         }
-        for (int q = 0; q < np; ++q) A[(int64_t)(nC + p0 + q) * ld + j] -= acc[q];
+#pragma unroll
+        for (int qq = 0; qq < BS_PC; ++qq)
+          if (qq < np) A[(int64_t)(nC + p0 + qq) * ld + j] -= acc[qq];
       }
     }
   }
 }
 
-void launch_chol_factor(double* cm, int64_t stride, int nC, int n_aug, int batch,
+void launch_chol_factor(double* cm, int64_t stride, int nC, int n_aug, int batch, double* inv,
                         unsigned long long* err_slot, long long err_base, cudaStream_t s) {
   const int ntiles = n_aug / TB;
-  const size_t panel_smem = (size_t)2 * TB * (TB + 1) * sizeof(double);
+  const int64_t inv_stride = (int64_t)(nC / TB) * TB * TB;
+  const size_t trsm_smem = ((size_t)TB * (TB + 1) + (size_t)TB * (TB + 2)) * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
-    RG_CUDA(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem));
+    RG_CUDA(cudaFuncSetAttribute(chol_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem));
     attr_set = true;
   }
   for (int kb = 0; kb < nC / TB; ++kb) {
     const int k = kb * TB;
-    dim3 grid(ntiles - kb, 1, batch);
-    if (k > 0) chol_update_kernel<<<grid, 256, 0, s>>>(cm, stride, nC, k, kb);
-    chol_panel_kernel<<<grid, 256, panel_smem, s>>>(cm, stride, nC, k, kb, err_slot, err_base);
+    dim3 g1(ntiles - kb, 1, batch);
+    if (k > 0) chol_update_kernel<<<g1, 256, 0, s>>>(cm, stride, nC, k, kb);
+    chol_diag_kernel<<<batch, 256, 0, s>>>(cm, stride, nC, k, inv, inv_stride, err_slot, err_base);
+    dim3 g2(ntiles - kb - 1, 1, batch);
+    if (ntiles - kb - 1 > 0) chol_trsm_kernel<<<g2, 256, trsm_smem, s>>>(cm, stride, nC, k, kb, inv, inv_stride);
   }
 }
 
-void launch_chol_backsolve(double* cm, int64_t stride, int nC, int P, int batch, cudaStream_t s) {
-  const size_t smem = ((size_t)TB * (TB + 1) + (size_t)TB * P) * sizeof(double);
-  RG_CUDA(cudaFuncSetAttribute(chol_backsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  chol_backsolve_kernel<<<batch, 256, smem, s>>>(cm, stride, nC, nC, P);
+void launch_chol_backsolve(double* cm, int64_t stride, int nC, int P, int batch, const double* inv,
+                           cudaStream_t s) {
+  const size_t smem = ((size_t)TB * (TB + 1) + (size_t)2 * TB * P) * sizeof(double);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    RG_CUDA(cudaFuncSetAttribute(chol_backsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  const int64_t inv_stride = (int64_t)(nC / TB) * TB * TB;
+  chol_backsolve_kernel<<<batch, BS_THREADS, smem, s>>>(cm, stride, nC, nC, P, inv, inv_stride);
 }
 
-int chol_num_launches(int nC) { return 2 * (nC / TB) - 1 + 1; }
+int chol_num_launches(int nC) { return 3 * (nC / TB) - 1; }
+size_t chol_inv_elems(int nC, int batch) { return (size_t)batch * (nC / TB) * TB * TB; }
 
 }  // namespace rg

@@ -38,6 +38,7 @@ struct rg_ctx {
   rg::DevBuf<double> XtX_f, XtY_f, lambda, neff;
   rg::DevBuf<int32_t> file_idx_pad; // [Npad]
   rg::DevBuf<unsigned long long> err_slot;
+  rg::DevBuf<unsigned long long> dbg_counter;
 
   // ---- per-lane scratch: consecutive blocks go to different lanes (own stream + buffers) so the
   //      latency-bound solver phases of one block overlap the tensor/HBM phases of the next
@@ -52,6 +53,7 @@ struct rg_ctx {
     rg::DevBuf<double> sum_part, sum_fold;
     rg::DevBuf<double> mu, inv_sd, Bv, Af, Qf, gty_f, rhs;
     rg::DevBuf<double> cm;            // [nmat][n_aug][nC]
+    rg::DevBuf<double> inv;           // [nmat][nC/64][64x64]  L_kk^-T blocks
     rg::DevBuf<double> gam, gmu, cvec, part, mean_invsd;
     std::map<int, CUtensorMap> tmaps; // keyed by rows_p (z base differs per lane)
   };
@@ -70,7 +72,7 @@ struct rg_ctx {
   rg::DevBuf<int4> l1_chunks;
   rg::DevBuf<int2> l1_fold_chunks;
   int l1_nchunks = 0;
-  rg::DevBuf<double> l1_part, l1_part_y, l1_cm, l1_beta, l1_sums, l1_part_out, l1_tau, l1_pred;
+  rg::DevBuf<double> l1_part, l1_part_y, l1_cm, l1_inv, l1_beta, l1_sums, l1_part_out, l1_tau, l1_pred;
   rg::DevBuf<int32_t> l1_chr_cols;
   std::vector<int32_t> best_idx;
   int l1_nC = 0;

@@ -13,6 +13,8 @@
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (kind::f8f6f4, M128 N256 K32)
 //   warps 2..5  : epilogue, tcgen05.ld 32x32b -> registers -> coalesced 128-bit global stores
 // K loop = the fold's samples in 128-byte (= 128-sample) swizzle atoms, 4 MMAs per atom.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace rg {
@@ -254,7 +256,10 @@ void make_gram_tensor_map(CUtensorMap* tm, const uint8_t* z, int64_t npad, int r
   RG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
 }
 
-size_t gram_smem_bytes() { return (size_t)STAGES * STAGE_BYTES + 1024 + 128; }
+size_t gram_smem_bytes() {
+  static const bool exclusive = getenv("RG_DBG_GRAM_EXCLUSIVE") != nullptr;
+  return exclusive ? (size_t)232448 : (size_t)STAGES * STAGE_BYTES + 1024 + 128;
+}
 
 void gram_tile_list(int rows2, std::vector<int2>& tiles) {
   tiles.clear();

@@ -12,6 +12,7 @@ constexpr int kMaxRidge = 8;
 void launch_bed_relayout(const uint8_t* packed, int64_t row_stride, int bs, int rows_p,
                          const int32_t* file_idx_pad, int ref_first, uint32_t* gp, int64_t npad,
                          cudaStream_t s);
+void launch_debug_sleep(unsigned ns, cudaStream_t s);
 void launch_bed_expand_fp8(const uint32_t* gp, int rows_p, uint8_t* z, int64_t npad, cudaStream_t s);
 
 // ---- l0_stats.cu
@@ -42,6 +43,8 @@ struct AssembleArgs {
   int ldc;
 };
 
+void launch_dbg_check_diag(const float* zz, int64_t ldz, int64_t fold_stride, const int32_t* cnt_fold, int rows_p,
+                           int bs, int K, unsigned long long* counter, cudaStream_t s);
 void launch_l0_stats(const uint32_t* gp, int64_t npad, const double* xy, int cpp, const int4* chunks,
                      int nchunks, int rows_p, int32_t* cnt_part, double* sum_part, cudaStream_t s);
 void launch_l0_fold_reduce(const int32_t* cnt_part, const double* sum_part, int rows_p, int cpp,
@@ -60,10 +63,12 @@ void launch_gram_reference(const uint8_t* z, int64_t npad, int rows2, int k0, in
                            cudaStream_t s);
 
 // ---- chol.cu
-void launch_chol_factor(double* cm, int64_t stride, int nC, int n_aug, int batch,
+void launch_chol_factor(double* cm, int64_t stride, int nC, int n_aug, int batch, double* inv,
                         unsigned long long* err_slot, long long err_base, cudaStream_t s);
-void launch_chol_backsolve(double* cm, int64_t stride, int nC, int P, int batch, cudaStream_t s);
+void launch_chol_backsolve(double* cm, int64_t stride, int nC, int P, int batch, const double* inv,
+                           cudaStream_t s);
 int chol_num_launches(int nC);
+size_t chol_inv_elems(int nC, int batch);
 
 // ---- l0_predict.cu
 struct PredictArgs {

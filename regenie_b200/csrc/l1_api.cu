@@ -62,6 +62,7 @@ static void l1_fit(rg_ctx* h, const double* tau_host, double* cumsum, int32_t* b
   h->l1_part.alloc((size_t)nch * part_stride);
   h->l1_part_y.alloc((size_t)nch * B);
   h->l1_cm.alloc((size_t)nmat * cm_stride);
+  h->l1_inv.alloc(chol_inv_elems(nC, nmat));
   h->l1_beta.alloc((size_t)P * nmat * nC);
   h->l1_sums.alloc((size_t)P * NV);
   h->l1_part_out.alloc((size_t)ntiles * NV);
@@ -75,8 +76,8 @@ static void l1_fit(rg_ctx* h, const double* tau_host, double* cumsum, int32_t* b
     launch_l1_xty(Wp, Npad, h->xy.p, h->cpp, ycol, h->l1_chunks.p, nch, h->l1_part_y.p, B, s);
     launch_l1_assemble(h->l1_part.p, part_stride, ldp, h->l1_part_y.p, h->l1_fold_chunks.p, K, R1,
                        h->l1_tau.p + (size_t)p * R1, B, nC, h->l1_cm.p, cm_stride, s);
-    launch_chol_factor(h->l1_cm.p, cm_stride, nC, n_aug, nmat, h->err_slot.p, (long long)(1ll << 41) + p * 1024, s);
-    launch_chol_backsolve(h->l1_cm.p, cm_stride, nC, 1, nmat, s);
+    launch_chol_factor(h->l1_cm.p, cm_stride, nC, n_aug, nmat, h->l1_inv.p, h->err_slot.p, (long long)(1ll << 41) + p * 1024, s);
+    launch_chol_backsolve(h->l1_cm.p, cm_stride, nC, 1, nmat, h->l1_inv.p, s);
     // keep beta[f][r][0:nC] (RHS row nC of every system)
     RG_CUDA(cudaMemcpy2DAsync(h->l1_beta.p + (size_t)p * nmat * nC, (size_t)nC * 8,
                               h->l1_cm.p + (size_t)nC * nC, (size_t)cm_stride * 8, (size_t)nC * 8, nmat,

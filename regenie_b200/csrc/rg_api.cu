@@ -240,6 +240,7 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
     L.packed_dev.alloc((size_t)h->bs_max * row_stride);
     ScopedTimer t(h, "h2d", s);
     copy_to_device(L.packed_dev.p, packed, (size_t)bs * row_stride, s);
+    if (getenv("RG_DBG_SYNC_AFTER_H2D")) RG_CUDA(cudaStreamSynchronize(s));
     packed_d = L.packed_dev.p;
   }
 
@@ -266,6 +267,7 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
       RG_CUDA(cudaMemsetAsync(L.cm.p, 0, need * 8, s));
     }
   }
+  L.inv.alloc(chol_inv_elems((int)round_up(h->bs_max, 64), nmat));
   const int Kg = h->loocv ? 1 : K;
   L.gam.alloc((size_t)Kg * h->rows_p_max * Qp);
   L.gmu.alloc((size_t)Kg * h->rows_p_max * Qp);
@@ -273,6 +275,8 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
   const int ntiles_s = (int)(Npad / 128);
   L.part.alloc((size_t)ntiles_s * Qp * 2);
   L.mean_invsd.alloc((size_t)2 * Qp);
+
+  if (const char* e = getenv("RG_DBG_STAGGER_US")) launch_debug_sleep((unsigned)atoi(e) * 1000u, s);
 
   // --- 1. decode: PLINK rows -> padded 2-bit rows -> e4m3 planes
   {
@@ -325,6 +329,12 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
     h->launches += 1;
   }
 
+  if (getenv("RG_DBG_CHECK_DIAG")) {
+    if (!h->dbg_counter.p) { h->dbg_counter.alloc(1); RG_CUDA(cudaMemset(h->dbg_counter.p, 0, 8)); }
+    launch_dbg_check_diag(L.zz.p, 2 * rows_p, (int64_t)4 * rows_p * rows_p, L.cnt_fold.p, rows_p, bs, K,
+                          h->dbg_counter.p, s);
+  }
+
   // --- 4. ridge systems
   AssembleArgs aa;
   aa.bs = bs; aa.rows_p = rows_p; aa.nC = nC; aa.C = C; aa.K = K; aa.R = R; aa.loocv = h->loocv;
@@ -338,13 +348,13 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
   }
   {
     ScopedTimer t(h, "chol_factor", s);
-    launch_chol_factor(L.cm.p, aa.cm_stride, nC, n_aug, nmat, h->err_slot.p,
+    launch_chol_factor(L.cm.p, aa.cm_stride, nC, n_aug, nmat, L.inv.p, h->err_slot.p,
                        (long long)(1ll << 40) + (long long)block_id * 1024, s);
     h->launches += chol_num_launches(nC);
   }
   {
     ScopedTimer t(h, "chol_backsolve", s);
-    launch_chol_backsolve(L.cm.p, aa.cm_stride, nC, P, nmat, s);
+    launch_chol_backsolve(L.cm.p, aa.cm_stride, nC, P, nmat, L.inv.p, s);
     h->launches += 1;
   }
   h->last_bs = bs; h->last_rows_p = rows_p; h->last_nC = nC; h->last_n_aug = n_aug; h->last_nmat = nmat;
@@ -546,7 +556,11 @@ int64_t rg_debug_fetch(rg_handle h, const char* name, void* out, int64_t max_byt
   else if (n == "rhs") { p = L.rhs.p; bytes = (size_t)h->K * rp * h->P * 8; }
   else if (n == "cm") { p = L.cm.p; bytes = (size_t)h->last_nmat * h->last_n_aug * h->last_nC * 8; }
   else if (n == "mean_invsd") { p = L.mean_invsd.p; bytes = (size_t)2 * h->R * h->P * 8; }
-  else if (n == "dims") {
+  else if (n == "dbg_counter") {
+    if (!h->dbg_counter.p || max_bytes < 8) return -1;
+    cudaMemcpy(out, h->dbg_counter.p, 8, cudaMemcpyDeviceToHost);
+    return 8;
+  } else if (n == "dims") {
     int64_t d[8] = {h->Npad, rp, h->last_nC, h->last_n_aug, h->last_nmat, h->K, h->cpp, h->nchunks};
     if (max_bytes < (int64_t)sizeof(d)) return -1;
     memcpy(out, d, sizeof(d));
