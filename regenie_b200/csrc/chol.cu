@@ -278,3 +278,102 @@ int chol_num_launches(int nC) { return 3 * (nC / TB) - 1; }
 size_t chol_inv_elems(int nC, int batch) { return (size_t)batch * (nC / TB) * TB * TB; }
 
 }  // namespace rg
+
+namespace rg {
+
+// Row-wise backward substitution for MANY right-hand sides stored as rows (LOOCV):
+//   rows hold t_i^T = (L^-1 w_i)^T;  on exit they hold z_i^T = t_i^T L^-1 = (L^-T t_i)^T = (H w_i)^T.
+// grid: (row tiles, 1, batch); one CTA owns 64 rows and sweeps the column blocks from last to first:
+//   z_kb = t_kb * L_kk^-1 (= t_kb * M^T),   t[:, 0:k] -= z_kb * L[k:k+64, 0:k].
+__global__ void __launch_bounds__(256)
+chol_rows_backsolve_kernel(double* __restrict__ cm, int64_t stride, int ld, int nC, int row0,
+                           const double* __restrict__ inv, int64_t inv_stride) {
+  extern __shared__ double rb_sm[];
+  double (*Zs)[TB + 1] = reinterpret_cast<double (*)[TB + 1]>(rb_sm);                     // z_kb / t_kb tile
+  double (*Ls)[TB + 2] = reinterpret_cast<double (*)[TB + 2]>(rb_sm + TB * (TB + 1));     // M or an L tile
+  double* A = cm + (int64_t)blockIdx.z * stride;
+  const double* Minv = inv + (int64_t)blockIdx.z * inv_stride;
+  const int r0 = row0 + blockIdx.x * TB;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  for (int kb = nC / TB - 1; kb >= 0; --kb) {
+    const int k = kb * TB;
+    __syncthreads();
+    for (int e = threadIdx.x; e < TB * TB; e += 256) {
+      const int rr = e / TB, cc = e % TB;
+      Zs[rr][cc] = A[(int64_t)(r0 + rr) * ld + k + cc];
+      Ls[rr][cc] = Minv[(int64_t)kb * TB * TB + e];          // M[c][p] at Ls[c][p]
+    }
+    __syncthreads();
+    // z[row][c] = sum_p t[row][p] * M[c][p]
+    double z[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) z[a][b] = 0.0;
+#pragma unroll 8
+    for (int p = 0; p < TB; ++p) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) av[a] = Zs[ty * 4 + a][p];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bv[b] = Ls[tx + 16 * b][p];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) z[a][b] = fma(av[a], bv[b], z[a][b]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        Zs[ty * 4 + a][tx + 16 * b] = z[a][b];
+        A[(int64_t)(r0 + ty * 4 + a) * ld + k + tx + 16 * b] = z[a][b];
+      }
+    // t[:, j0:j0+64] -= z_kb * L[k:k+64, j0:j0+64]
+    for (int j0 = 0; j0 < k; j0 += TB) {
+      __syncthreads();
+      for (int e = threadIdx.x; e < TB * TB; e += 256) {
+        const int rr = e / TB, cc = e % TB;
+        Ls[rr][cc] = A[(int64_t)(k + rr) * ld + j0 + cc];    // L[k+p][j0+c] at Ls[p][c]
+      }
+      __syncthreads();
+      double u[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) u[a][b] = 0.0;
+#pragma unroll 8
+      for (int p = 0; p < TB; ++p) {
+        double av[4], bv[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) av[a] = Zs[ty * 4 + a][p];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bv[b] = Ls[p][tx + 16 * b];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) u[a][b] = fma(av[a], bv[b], u[a][b]);
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) A[(int64_t)(r0 + ty * 4 + a) * ld + j0 + tx + 16 * b] -= u[a][b];
+    }
+  }
+}
+
+void launch_chol_rows_backsolve(double* cm, int64_t stride, int nC, int row0, int nrows, int batch,
+                                const double* inv, cudaStream_t s) {
+  const size_t smem = ((size_t)TB * (TB + 1) + (size_t)TB * (TB + 2)) * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    RG_CUDA(cudaFuncSetAttribute(chol_rows_backsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int64_t inv_stride = (int64_t)(nC / TB) * TB * TB;
+  dim3 grid(nrows / TB, 1, batch);
+  chol_rows_backsolve_kernel<<<grid, 256, smem, s>>>(cm, stride, nC, nC, row0, inv, inv_stride);
+}
+
+}  // namespace rg

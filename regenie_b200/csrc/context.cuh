@@ -74,6 +74,7 @@ struct rg_ctx {
   int l1_nchunks = 0;
   rg::DevBuf<double> l1_part, l1_part_y, l1_cm, l1_inv, l1_beta, l1_sums, l1_part_out, l1_tau, l1_pred;
   rg::DevBuf<int32_t> l1_chr_cols;
+  rg::DevBuf<double> l1_zrows, l1_hvec, l1_bvec;   // LOOCV: H w_i rows, leverages, coefficients per phenotype
   std::vector<int32_t> best_idx;
   int l1_nC = 0;
   bool l1_done = false;

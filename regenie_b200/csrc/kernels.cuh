@@ -7,6 +7,7 @@ namespace rg {
 constexpr int kMaxFolds = 16;
 constexpr int kMaxCov = 64;
 constexpr int kMaxRidge = 8;
+constexpr int kMaxPhenoTile = 8;   // phenotypes per register pass of the LOOCV prediction kernel
 
 // ---- bed_kernels.cu
 void launch_bed_relayout(const uint8_t* packed, int64_t row_stride, int bs, int rows_p,
@@ -69,6 +70,8 @@ void launch_chol_backsolve(double* cm, int64_t stride, int nC, int P, int batch,
                            cudaStream_t s);
 int chol_num_launches(int nC);
 size_t chol_inv_elems(int nC, int batch);
+void launch_chol_rows_backsolve(double* cm, int64_t stride, int nC, int row0, int nrows, int batch,
+                                const double* inv, cudaStream_t s);
 
 // ---- l0_predict.cu
 struct PredictArgs {
@@ -99,13 +102,33 @@ void launch_l1_xty(const double* W, int64_t ldw, const double* xy, int cpp, int 
                    int nchunks, double* part_y, int B, cudaStream_t s);
 void launch_l1_assemble(const double* part, int64_t part_stride, int ldp, const double* part_y,
                         const int2* fold_chunks, int K, int R1, const double* tau, int B, int nC, double* cm,
-                        int64_t cm_stride, cudaStream_t s);
+                        int64_t cm_stride, int loocv, cudaStream_t s);
 void launch_l1_pred_sums(const double* W, int64_t ldw, int B, int R1, const double* beta, int ldb,
                          const int32_t* tile_fold, const double* xy, int cpp, int ycol, double* part_out,
                          int ntiles, double* out, cudaStream_t s);
 void launch_l1_chr_pred(const double* W, int64_t ldw, int nchr, const int32_t* chr_col_start, const double* beta,
                         int ldb, int R1, int best, const int32_t* tile_fold, double* pred, int64_t npad,
                         cudaStream_t s);
+
+// ---- loocv_kernels.cu
+void launch_l0_loocv_fill(const uint32_t* gp, int64_t npad, int bs, int nC, const double* mu, const double* inv_sd,
+                          const double* Bv, int C, const double* xy, int cpp, double* cm, int64_t cm_stride,
+                          int nrow0, int R, cudaStream_t s);
+void launch_l0_loocv_pred(const double* cm, int64_t cm_stride, int nC, int bs, int Ppad, int P, int R,
+                          const double* xy, int cpp, int C, const uint8_t* mask, int64_t npad, double* W,
+                          int64_t w_stride, int col0, double* part, int Qp, cudaStream_t s);
+void launch_l0_loocv_std_apply(double* W, int64_t w_stride, int64_t npad, int col0, int P, int Q, const uint8_t* mask,
+                               const double* mean_invsd, cudaStream_t s);
+void launch_l1_loocv_fill(const double* W, int64_t ldw, int B, int nC, double* cm, int64_t cm_stride, int nrow0,
+                          int R1, int64_t npad, cudaStream_t s);
+void launch_l1_loocv_sums(const double* cm, int64_t cm_stride, int nC, int B, int nrow0, const double* xy, int cpp,
+                          int ycol, double* part, int R1, int ntiles, double* out, cudaStream_t s);
+void launch_rows_sqnorm(const double* rows, int nC, int B, double* out, int ntiles, cudaStream_t s);
+void launch_l1_loocv_chr_pred(const double* W, int64_t ldw, int B, int nC, const double* zrows, const double* hvec,
+                              const double* bvec, const double* xy, int cpp, int ycol, int nchr,
+                              const int32_t* chr_col_start, double* pred, int64_t npad, cudaStream_t s);
+void launch_l0_std_reduce_only(const double* part, int ntiles, int Qp, int Q, int P, const double* neff,
+                               double* mean_invsd, cudaStream_t s);
 
 // ---- s2_kernels.cu
 struct S2FinalizeArgs {

@@ -196,6 +196,11 @@ void launch_l0_standardize(const double* part, int ntiles, int Qp, int Q, int P,
   l0_std_apply_kernel<<<grid, 256, 0, s>>>(W, w_stride, npad, col0, P, is_real, mean_invsd);
 }
 
+void launch_l0_std_reduce_only(const double* part, int ntiles, int Qp, int Q, int P, const double* neff,
+                               double* mean_invsd, cudaStream_t s) {
+  l0_std_reduce_kernel<<<Q, 256, 0, s>>>(part, ntiles, Qp, P, neff, mean_invsd);
+}
+
 int predict_qt() { return QT; }
 
 }  // namespace rg

@@ -1,4 +1,6 @@
 // Level-1 ridge, LOCO assembly and Step-2 entry points of the C ABI (include/rg_b200.h).
+#include <string.h>
+
 #include <algorithm>
 
 #include "context.cuh"
@@ -22,14 +24,14 @@ using namespace rg;
 
 static void l1_fit(rg_ctx* h, const double* tau_host, double* cumsum, int32_t* best_idx) {
   RG_CHECK(h->kind == 1, "handle is not a Step-1 handle");
-  RG_CHECK(!h->loocv, "LOOCV level 1 is not implemented yet");
   RG_CHECK(h->R1 >= 1 && h->R1 <= kMaxRidge, "n_ridge_l1 out of range");
   RG_CUDA(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
   for (auto& l : h->lanes) RG_CUDA(cudaStreamSynchronize(l->stream));   // all level-0 blocks are in W
   const int K = h->K, R1 = h->R1, P = h->P;
   const int B = (int)h->B;
-  const int nC = (int)round_up(B, 64), n_aug = nC + 64, nmat = K * R1;
+  const int loocv = h->loocv;
+  const int nC = (int)round_up(B, 64), n_aug = nC + 64 + (loocv ? (int)h->Npad : 0), nmat = (loocv ? 1 : K) * R1;
   const int ldp = nC;
   const int64_t Npad = h->Npad;
   h->l1_nC = nC;
@@ -69,14 +71,58 @@ static void l1_fit(rg_ctx* h, const double* tau_host, double* cumsum, int32_t* b
   h->l1_tau.alloc((size_t)P * R1);
   RG_CUDA(cudaMemcpyAsync(h->l1_tau.p, tau_host, (size_t)P * R1 * 8, cudaMemcpyHostToDevice, s));
   RG_CUDA(cudaMemsetAsync(h->l1_cm.p, 0, (size_t)nmat * cm_stride * 8, s));
+  std::vector<int> loocv_best(P, 0);
+  std::vector<double> loocv_cs((size_t)5 * P * R1, 0.0);
+  if (loocv) {
+    h->l1_zrows.alloc((size_t)P * Npad * nC);
+    h->l1_hvec.alloc((size_t)P * Npad);
+    h->l1_bvec.alloc((size_t)P * nC);
+  }
   for (int p = 0; p < P; ++p) {
     const double* Wp = h->W.p + (size_t)p * Npad * h->B;
     const int ycol = h->C + p;
     launch_l1_gram(Wp, Npad, B, h->l1_chunks.p, nch, h->l1_part.p, part_stride, ldp, s);
     launch_l1_xty(Wp, Npad, h->xy.p, h->cpp, ycol, h->l1_chunks.p, nch, h->l1_part_y.p, B, s);
     launch_l1_assemble(h->l1_part.p, part_stride, ldp, h->l1_part_y.p, h->l1_fold_chunks.p, K, R1,
-                       h->l1_tau.p + (size_t)p * R1, B, nC, h->l1_cm.p, cm_stride, s);
+                       h->l1_tau.p + (size_t)p * R1, B, nC, h->l1_cm.p, cm_stride, loocv, s);
+    if (loocv) launch_l1_loocv_fill(Wp, Npad, B, nC, h->l1_cm.p, cm_stride, nC + 64, R1, Npad, s);
     launch_chol_factor(h->l1_cm.p, cm_stride, nC, n_aug, nmat, h->l1_inv.p, h->err_slot.p, (long long)(1ll << 41) + p * 1024, s);
+    if (loocv) {
+      // CV sums of the closed-form LOO predictions for every tau, then the state rg_loco needs at tau*
+      const int64_t inv_stride = (int64_t)(nC / 64) * 64 * 64;
+      launch_l1_loocv_sums(h->l1_cm.p, cm_stride, nC, B, nC + 64, h->xy.p, h->cpp, ycol, h->l1_part_out.p, R1, ntiles,
+                           h->l1_sums.p + (size_t)p * NV, s);
+      std::vector<double> sv((size_t)R1 * 3);
+      RG_CUDA(cudaMemcpyAsync(sv.data(), h->l1_sums.p + (size_t)p * NV, sv.size() * 8, cudaMemcpyDeviceToHost, s));
+      double ne = 0.0;
+      RG_CUDA(cudaMemcpyAsync(&ne, h->neff.p + p, 8, cudaMemcpyDeviceToHost, s));
+      RG_CUDA(cudaStreamSynchronize(s));
+      const double sy2 = ne - (double)h->C;                              // src/Step1_Models.cpp:891
+      int bj = 0; double bv = 1e10;
+      for (int j = 0; j < R1; ++j) {
+        const double perf = (sv[3 * j + 1] + sy2 - 2 * sv[3 * j + 2]) / ne;
+        if (perf < bv) { bv = perf; bj = j; }
+      }
+      loocv_best[p] = bj;
+      for (int j = 0; j < R1; ++j) {
+        loocv_cs[((size_t)0 * P + p) * R1 + j] = sv[3 * j];
+        loocv_cs[((size_t)1 * P + p) * R1 + j] = 0.0;
+        loocv_cs[((size_t)2 * P + p) * R1 + j] = sv[3 * j + 1];
+        loocv_cs[((size_t)3 * P + p) * R1 + j] = sy2;
+        loocv_cs[((size_t)4 * P + p) * R1 + j] = sv[3 * j + 2];
+      }
+      double* sys = h->l1_cm.p + (size_t)bj * cm_stride;
+      double* rows = sys + (size_t)(nC + 64) * nC;
+      launch_rows_sqnorm(rows, nC, B, h->l1_hvec.p + (size_t)p * Npad, ntiles, s);
+      launch_chol_backsolve(sys, cm_stride, nC, 1, 1, h->l1_inv.p + (size_t)bj * inv_stride, s);   // b = H W^T y
+      RG_CUDA(cudaMemcpyAsync(h->l1_bvec.p + (size_t)p * nC, sys + (size_t)nC * nC, (size_t)nC * 8,
+                              cudaMemcpyDeviceToDevice, s));
+      launch_chol_rows_backsolve(sys, cm_stride, nC, nC + 64, (int)Npad, 1, h->l1_inv.p + (size_t)bj * inv_stride, s);
+      RG_CUDA(cudaMemcpyAsync(h->l1_zrows.p + (size_t)p * Npad * nC, rows, (size_t)Npad * nC * 8,
+                              cudaMemcpyDeviceToDevice, s));
+      h->launches += 6;
+      continue;
+    }
     launch_chol_backsolve(h->l1_cm.p, cm_stride, nC, 1, nmat, h->l1_inv.p, s);
     // keep beta[f][r][0:nC] (RHS row nC of every system)
     RG_CUDA(cudaMemcpy2DAsync(h->l1_beta.p + (size_t)p * nmat * nC, (size_t)nC * 8,
@@ -85,6 +131,13 @@ static void l1_fit(rg_ctx* h, const double* tau_host, double* cumsum, int32_t* b
     launch_l1_pred_sums(Wp, Npad, B, R1, h->l1_beta.p + (size_t)p * nmat * nC, nC, h->tile_fold.p, h->xy.p, h->cpp,
                         ycol, h->l1_part_out.p, ntiles, h->l1_sums.p + (size_t)p * NV, s);
     h->launches += 5 + chol_num_launches(nC) + 1 + 2;
+  }
+  if (loocv) {
+    h->best_idx.assign(loocv_best.begin(), loocv_best.end());
+    if (cumsum) memcpy(cumsum, loocv_cs.data(), loocv_cs.size() * 8);
+    if (best_idx) for (int p = 0; p < P; ++p) best_idx[p] = loocv_best[p];
+    h->l1_done = true;
+    return;
   }
   std::vector<double> sums((size_t)P * NV), neff(P);
   RG_CUDA(cudaMemcpyAsync(sums.data(), h->l1_sums.p, sums.size() * 8, cudaMemcpyDeviceToHost, s));
@@ -136,8 +189,13 @@ static void loco(rg_ctx* h, const int32_t* chr_of_block, double* pred_out) {
   h->l1_pred.alloc((size_t)nchr * Npad);
   std::vector<double> pred((size_t)nchr * Npad);
   for (int p = 0; p < P; ++p) {
-    launch_l1_chr_pred(h->W.p + (size_t)p * Npad * h->B, Npad, nchr, h->l1_chr_cols.p,
-                       h->l1_beta.p + (size_t)p * nmat * nC, nC, R1, h->best_idx[p], h->tile_fold.p, h->l1_pred.p, Npad, s);
+    if (h->loocv)
+      launch_l1_loocv_chr_pred(h->W.p + (size_t)p * Npad * h->B, Npad, (int)h->B, nC, h->l1_zrows.p + (size_t)p * Npad * nC,
+                               h->l1_hvec.p + (size_t)p * Npad, h->l1_bvec.p + (size_t)p * nC, h->xy.p, h->cpp,
+                               h->C + p, nchr, h->l1_chr_cols.p, h->l1_pred.p, Npad, s);
+    else
+      launch_l1_chr_pred(h->W.p + (size_t)p * Npad * h->B, Npad, nchr, h->l1_chr_cols.p,
+                         h->l1_beta.p + (size_t)p * nmat * nC, nC, R1, h->best_idx[p], h->tile_fold.p, h->l1_pred.p, Npad, s);
     h->launches += 1;
     RG_CUDA(cudaMemcpyAsync(pred.data(), h->l1_pred.p, pred.size() * 8, cudaMemcpyDeviceToHost, s));
     RG_CUDA(cudaStreamSynchronize(s));

@@ -94,7 +94,7 @@ l1_xty_kernel(const double* __restrict__ W, int64_t ldw, const double* __restric
 __global__ void l1_assemble_kernel(const double* __restrict__ part, int64_t part_stride, int ldp,
                                    const double* __restrict__ part_y, const int2* __restrict__ fold_chunks,
                                    int K, int R1, const double* __restrict__ tau, int B, int nC,
-                                   double* __restrict__ cm, int64_t cm_stride) {
+                                   double* __restrict__ cm, int64_t cm_stride, int loocv) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = blockIdx.y;                 // 0..nC-1 matrix rows, nC = RHS row
   if (j >= nC) return;
@@ -117,7 +117,7 @@ __global__ void l1_assemble_kernel(const double* __restrict__ part, int64_t part
     for (int r = 0; r < R1; ++r) {
       double v;
       if (real) {
-        v = tot - fold_v[f];
+        v = loocv ? tot : tot - fold_v[f];          // LOOCV: nothing is held out of X^T X
         if (!is_rhs && i == j) v += tau[r];
       } else {
         v = (!is_rhs && i == j) ? 1.0 : 0.0;
@@ -218,9 +218,10 @@ void launch_l1_xty(const double* W, int64_t ldw, const double* xy, int cpp, int 
 
 void launch_l1_assemble(const double* part, int64_t part_stride, int ldp, const double* part_y,
                         const int2* fold_chunks, int K, int R1, const double* tau, int B, int nC, double* cm,
-                        int64_t cm_stride, cudaStream_t s) {
+                        int64_t cm_stride, int loocv, cudaStream_t s) {
   dim3 grid((unsigned)ceil_div(nC, 128), nC + 1);
-  l1_assemble_kernel<<<grid, 128, 0, s>>>(part, part_stride, ldp, part_y, fold_chunks, K, R1, tau, B, nC, cm, cm_stride);
+  l1_assemble_kernel<<<grid, 128, 0, s>>>(part, part_stride, ldp, part_y, fold_chunks, K, R1, tau, B, nC, cm, cm_stride,
+                                          loocv);
 }
 
 void launch_l1_pred_sums(const double* W, int64_t ldw, int B, int R1, const double* beta, int ldb,

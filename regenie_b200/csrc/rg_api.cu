@@ -204,7 +204,7 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
   const int rows_p = (int)round_up(bs, kRowPad);
   const int nC = (int)round_up(bs, 64);
   const int Ppad = (int)round_up(P, 64);
-  const int n_aug = nC + Ppad;
+  const int n_aug = nC + Ppad + (h->loocv ? (int)h->Npad : 0);   // LOOCV: sample vectors ride along as RHS rows
   const int nmat = (h->loocv ? 1 : K) * R;
   const int QT = predict_qt();
   const int Q = R * P, Qp = (int)round_up(Q, QT);
@@ -261,7 +261,7 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
   L.rhs.alloc((size_t)K * h->rows_p_max * P);
   {
     const int nC_max = (int)round_up(h->bs_max, 64);
-    const size_t need = (size_t)nmat * (nC_max + Ppad) * nC_max;
+    const size_t need = (size_t)nmat * (nC_max + Ppad + (h->loocv ? Npad : 0)) * nC_max;
     if (L.cm.n < need) {
       L.cm.alloc(need);
       RG_CUDA(cudaMemsetAsync(L.cm.p, 0, need * 8, s));
@@ -346,20 +346,36 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
     launch_l0_assemble(aa, L.rhs.p, P, Ppad, nmat, s);
     h->launches += 2;
   }
+  if (h->loocv) {
+    ScopedTimer t(h, "loocv_fill", s);
+    launch_l0_loocv_fill(L.gp.p, Npad, bs, nC, L.mu.p, L.inv_sd.p, L.Bv.p, C, h->xy.p, h->cpp, L.cm.p, aa.cm_stride,
+                         nC + Ppad, R, s);
+    h->launches += 1;
+  }
   {
     ScopedTimer t(h, "chol_factor", s);
     launch_chol_factor(L.cm.p, aa.cm_stride, nC, n_aug, nmat, L.inv.p, h->err_slot.p,
                        (long long)(1ll << 40) + (long long)block_id * 1024, s);
     h->launches += chol_num_launches(nC);
   }
+  h->last_bs = bs; h->last_rows_p = rows_p; h->last_nC = nC; h->last_n_aug = n_aug; h->last_nmat = nmat;
+  const int64_t w_stride = Npad * h->B;
+  const int col0 = block_id * R;
+  if (h->loocv) {
+    // closed-form leave-one-out predictions (src/Step1_Models.cpp:654-663) + LOOCV standardisation (:694-706)
+    ScopedTimer t(h, "l0_predict", s);
+    launch_l0_loocv_pred(L.cm.p, aa.cm_stride, nC, bs, Ppad, P, R, h->xy.p, h->cpp, C, h->mask.p, Npad, h->W.p,
+                         w_stride, col0, L.part.p, Qp, s);
+    launch_l0_std_reduce_only(L.part.p, ntiles_s, Qp, Q, P, h->neff.p, L.mean_invsd.p, s);
+    launch_l0_loocv_std_apply(h->W.p, w_stride, Npad, col0, P, Q, h->mask.p, L.mean_invsd.p, s);
+    h->launches += 3;
+    return;
+  }
   {
     ScopedTimer t(h, "chol_backsolve", s);
     launch_chol_backsolve(L.cm.p, aa.cm_stride, nC, P, nmat, L.inv.p, s);
     h->launches += 1;
   }
-  h->last_bs = bs; h->last_rows_p = rows_p; h->last_nC = nC; h->last_n_aug = n_aug; h->last_nmat = nmat;
-
-  RG_CHECK(!h->loocv, "LOOCV level 0 is not implemented yet");
 
   // --- 5. out-of-fold predictions, standardised into W
   {
@@ -368,7 +384,7 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
                     L.gam.p, L.gmu.p, L.cvec.p, s);
     PredictArgs pa;
     pa.bs = bs; pa.rows_p = rows_p; pa.C = C; pa.P = P; pa.R = R; pa.Qp = Qp; pa.cpp = h->cpp;
-    pa.col0 = block_id * R; pa.npad = Npad; pa.words_per_row = Npad / 16; pa.w_stride = Npad * h->B;
+    pa.col0 = col0; pa.npad = Npad; pa.words_per_row = Npad / 16; pa.w_stride = w_stride;
     pa.gp = L.gp.p; pa.tile_fold = h->tile_fold.p; pa.gam = L.gam.p; pa.gmu = L.gmu.p;
     pa.cvec = L.cvec.p; pa.xy = h->xy.p; pa.mask = h->mask.p; pa.W = h->W.p; pa.part = L.part.p;
     launch_l0_predict(pa, ntiles_s, s);
