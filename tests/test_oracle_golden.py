@@ -1,0 +1,51 @@
+"""Pin the oracle against the reference's OWN known answers (no GPU).
+
+(1) test/test_bash.sh:58-89 runs `--step 1 --bed example/example --exclude snplist_rm.txt --covarFile
+    covariates.txt --phenoFile phenotype_bin.txt --remove fid_iid_to_remove.txt --bsize 100 --bt --lowmem`
+    and requires a log line containing both `0.4504` and `min value`.  N_analyzed = 494 < 5000, so the
+    reference silently runs LOOCV (src/Data.cpp:353-356).  Reproducing that line exercises, end to end,
+    the .bed decode + --exclude/--remove handling, phenotype/covariate prep, the level-0 LOOCV ridge
+    shared with the QT path, the logistic level-1 LOOCV and the selection/printing rules.
+"""
+import numpy as np
+
+from oracle import plink, prep, step1, step1_bt
+
+
+def bt_step1_tables(d):
+    excl = {l.split()[0] for l in open(d + "/snplist_rm.txt") if l.strip()}
+    rm = {"_".join(l.split()[:2]) for l in open(d + "/fid_iid_to_remove.txt") if l.strip()}
+    bim = plink.read_bim(d + "/example.bim", exclude=excl)
+    keys_file, _ = plink.read_fam(d + "/example.fam")
+    keep = np.array([k not in rm for k in keys_file])
+    keys = [k for k in keys_file if k not in rm]
+    pr = prep.prepare(keys, d + "/phenotype_bin.txt", d + "/covariates.txt", bt=True, step=1)
+    assert pr.n_analyzed == 494 and len(bim.ids) == 994
+    blocks = prep.set_blocks(bim.chrom, 100)
+    packed = plink.read_bed_rows(d + "/example.bed", len(keys_file), bim.offset)
+    h = prep.set_ridge_params(5)
+    lam = len(bim.ids) * (1 - h) / h
+    cols = [[] for _ in range(2)]
+    for c, s, bs in blocks:
+        g = plink.decode_bed(packed[s:s + bs], len(keys_file), keep=keep)
+        gi, _ = plink.mean_impute_block(g, pr.in_analysis)
+        Gt, _ = step1.residualize_genotypes(gi, pr.X, pr.in_analysis, pr.n_analyzed, pr.ncov)
+        W = step1.level0_loocv(Gt, pr.Y, pr.mask, lam, pr.neff)
+        for ph in range(2):
+            cols[ph].append(W[ph])
+    out = []
+    for ph in range(2):
+        W = np.hstack(cols[ph])
+        B = W.shape[1]
+        tau = B * (1 - h) / h * 3 / np.pi ** 2                      # src/Step1_Models.cpp:2115-2117
+        off = step1_bt.null_offset(pr.Y_raw[:, ph], pr.X, pr.mask[:, ph])
+        cs = step1_bt.level1_logistic_loocv(W, pr.Y_raw[:, ph], off, pr.mask[:, ph], tau)
+        out.append(step1_bt.output_table(cs, pr.neff[ph], B, tau))
+    return out
+
+
+def test_reference_known_answer_0_4504(golden_dir):
+    tables = bt_step1_tables(golden_dir)
+    lines = [r for _, rows in tables for r in rows if "min value" in r]
+    assert len(lines) == 2
+    assert any("0.4504" in l for l in lines), lines          # test/test_bash.sh:87
