@@ -56,6 +56,9 @@ struct rg_ctx {
     rg::DevBuf<double> inv;           // [nmat][nC/64][64x64]  L_kk^-T blocks
     rg::DevBuf<double> gam, gmu, cvec, part, mean_invsd;
     std::map<int, CUtensorMap> tmaps; // keyed by rows_p (z base differs per lane)
+    rg::DevBuf<uint8_t> dig;          // radix-30 digit rows of gamma for the tensor-core prediction
+    rg::DevBuf<double> dscale;        // [K][Qp] column scales
+    std::map<int, CUtensorMap> dmaps; // digit-matrix tensor maps keyed by rows_p
   };
   std::vector<std::unique_ptr<Lane>> lanes;
   int next_lane = 0, last_lane = 0;

@@ -7,7 +7,9 @@ namespace rg {
 constexpr int kMaxFolds = 16;
 constexpr int kMaxCov = 64;
 constexpr int kMaxRidge = 8;
-constexpr int kMaxPhenoTile = 8;   // phenotypes per register pass of the LOOCV prediction kernel
+constexpr int kMaxPhenoTile = 8;
+constexpr int kLimbs = 9;          // radix-30 digits per coefficient (44 bits)
+constexpr int kLimbQ = 56;         // outputs per tensor-core prediction pass (9 x 56 = 504 <= 512 TMEM columns)   // phenotypes per register pass of the LOOCV prediction kernel
 
 // ---- bed_kernels.cu
 void launch_bed_relayout(const uint8_t* packed, int64_t row_stride, int bs, int rows_p,
@@ -94,6 +96,25 @@ void launch_l0_standardize(const double* part, int ntiles, int Qp, int Q, int P,
                            double* mean_invsd, double* W, int64_t w_stride, int64_t npad, int col0,
                            const uint8_t* is_real, cudaStream_t s);
 int predict_qt();
+
+// ---- predict_tcgen05.cu
+struct PredictTcArgs {
+  int rows_p, C, P, Q, Qp, cpp, col0, ngroups;
+  int64_t npad, w_stride;
+  const int32_t* tile_fold;
+  const double* scale;       // [K][Qp]
+  const double* cvec;        // [K][Qp][C]
+  const double* xy;
+  const uint8_t* mask;
+  double* W;
+  double* part;
+};
+void make_byte_tensor_map(CUtensorMap* tm, const uint8_t* basep, int64_t inner, int64_t rows);
+size_t predict_tc_dig_bytes(int K, int ngroups, int rows_p);
+void launch_l0_gamma_limbs(const double* gam, const double* gmu, int Qp, int Q, int bs, int rows_p, int K,
+                           double* scale, uint8_t* dig, int ngroups, cudaStream_t s);
+void launch_l0_predict_tcgen05(const CUtensorMap& tmZ, const CUtensorMap& tmD, const PredictTcArgs& a, int ntiles,
+                               cudaStream_t s);
 
 // ---- l1_kernels.cu
 void launch_l1_gram(const double* W, int64_t ldw, int B, const int4* chunks, int nchunks, double* part,

@@ -387,9 +387,32 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
     pa.col0 = col0; pa.npad = Npad; pa.words_per_row = Npad / 16; pa.w_stride = w_stride;
     pa.gp = L.gp.p; pa.tile_fold = h->tile_fold.p; pa.gam = L.gam.p; pa.gmu = L.gmu.p;
     pa.cvec = L.cvec.p; pa.xy = h->xy.p; pa.mask = h->mask.p; pa.W = h->W.p; pa.part = L.part.p;
-    launch_l0_predict(pa, ntiles_s, s);
-    launch_l0_standardize(L.part.p, ntiles_s, Qp, Q, P, h->neff.p, L.mean_invsd.p, h->W.p, pa.w_stride, Npad,
-                          pa.col0, h->is_real.p, s);
+    static const bool use_f64_predict = [] { const char* e = getenv("RG_B200_PREDICT"); return e && std::string(e) == "f64"; }();
+    if (use_f64_predict) {
+      launch_l0_predict(pa, ntiles_s, s);
+    } else {
+      // exact tensor-core path: radix-30 digit rows of gamma against the e4m3 genotype planes
+      const int ngroups = (int)ceil_div(Q, kLimbQ);
+      const size_t need = predict_tc_dig_bytes(K, ngroups, h->rows_p_max);
+      if (L.dig.n < need) {
+        L.dig.alloc(need);
+        RG_CUDA(cudaMemsetAsync(L.dig.p, 0, need, s));
+        L.dmaps.clear();
+      }
+      L.dscale.alloc((size_t)K * Qp);
+      if (!L.dmaps.count(rows_p)) {
+        CUtensorMap tm;
+        make_byte_tensor_map(&tm, L.dig.p, 2 * rows_p, (int64_t)K * ngroups * 512);
+        L.dmaps[rows_p] = tm;
+      }
+      launch_l0_gamma_limbs(L.gam.p, L.gmu.p, Qp, Q, bs, rows_p, K, L.dscale.p, L.dig.p, ngroups, s);
+      PredictTcArgs ta;
+      ta.rows_p = rows_p; ta.C = C; ta.P = P; ta.Q = Q; ta.Qp = Qp; ta.cpp = h->cpp; ta.col0 = col0; ta.ngroups = ngroups;
+      ta.npad = Npad; ta.w_stride = w_stride; ta.tile_fold = h->tile_fold.p; ta.scale = L.dscale.p; ta.cvec = L.cvec.p;
+      ta.xy = h->xy.p; ta.mask = h->mask.p; ta.W = h->W.p; ta.part = L.part.p;
+      launch_l0_predict_tcgen05(L.tmaps[rows_p], L.dmaps[rows_p], ta, ntiles_s, s);
+      h->launches += 1;
+    }
     h->launches += 5;
   }
 }
