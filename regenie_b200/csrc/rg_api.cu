@@ -413,6 +413,8 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
       launch_l0_predict_tcgen05(L.tmaps[rows_p], L.dmaps[rows_p], ta, ntiles_s, s);
       h->launches += 1;
     }
+    launch_l0_standardize(L.part.p, ntiles_s, Qp, Q, P, h->neff.p, L.mean_invsd.p, h->W.p, w_stride, Npad, col0,
+                          h->is_real.p, s);
     h->launches += 5;
   }
 }
