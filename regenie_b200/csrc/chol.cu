@@ -18,6 +18,7 @@
 // No CTA ever reads a tile that another CTA of the same launch overwrites: kernels of several
 // "lanes" run concurrently, so launch-wide lockstep cannot be assumed.
 // The stored inverses M also turn the backward substitution's triangular solves into GEMVs.
+#include "gemm_dmma.cuh"
 #include "kernels.cuh"
 
 namespace rg {
@@ -64,23 +65,26 @@ __device__ __forceinline__ void gemm_tile_nt(const double* __restrict__ A, int l
   }
 }
 
-// P[r0:r0+64, k:k+64] -= L[r0:r0+64, 0:k] * L[k:k+64, 0:k]^T   (k > 0)
-// grid: (row tiles at/after the panel, 1, batch); 256 threads, 4x4 register tile each.
+// P[r0:r0+64, k:k+64] -= L[r0:r0+64, 0:k] * L[k:k+64, 0:k]^T   (k > 0), FP64 tensor pipe (DMMA)
+// grid: (row tiles at/after the panel, 1, batch); 256 threads.
 __global__ void __launch_bounds__(256)
 chol_update_kernel(double* __restrict__ cm, int64_t stride, int ld, int k, int tile0) {
-  __shared__ double As[16][TB + 2];
-  __shared__ double Bs[16][TB + 2];
+  __shared__ double As[TB * DM_LD];
+  __shared__ double Bs[TB * DM_LD];
   double* A = cm + (int64_t)blockIdx.z * stride;
   const int r0 = (tile0 + blockIdx.x) * TB;
-  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
-  double acc[4][4];
-  gemm_tile_nt(A, ld, r0, k, k, acc, As, Bs);
+  DmmaAcc acc;
+  gemm_tile_nt_dmma(A + (int64_t)r0 * ld, ld, true, A + (int64_t)k * ld, ld, true, k, acc, As, Bs);
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    double* o = A + (int64_t)(r0 + ty * 4 + a) * ld + k + tx;
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) o[16 * b] -= acc[a][b];
-  }
+    for (int j = 0; j < 4; ++j) {
+      double2* o = reinterpret_cast<double2*>(A + (int64_t)(r0 + dm_row(i)) * ld + k + dm_col(j));
+      double2 v = *o;
+      v.x -= acc.c[i][j][0];
+      v.y -= acc.c[i][j][1];
+      *o = v;
+    }
 }
 
 // Diagonal tile: L_kk = chol(P_kk) and M = L_kk^-T, both in registers (thread (r, q) holds the

@@ -3,6 +3,7 @@
 // Data::make_predictions (src/Data.cpp:1238-1254).  W is real valued, so this stage is FP64
 // throughout: X_folds[f] = W_f^T W_f is an FP64 GEMM over the sample axis (K = fold samples),
 // the K*R1 shifted systems go through the same batched Cholesky as level 0.
+#include "gemm_dmma.cuh"
 #include "kernels.cuh"
 
 namespace rg {
@@ -10,63 +11,33 @@ namespace rg {
 constexpr int LT = 64;   // output tile
 
 // Partial Gram of one sample chunk: part[chunk][i][j] = sum_{t in chunk} W[t,i] W[t,j], i >= j tiles.
-// grid: (B tiles j, B tiles i, nchunks); 256 threads, 4x4 register tile, K chunk = 16 samples.
+// grid: (B tiles j, B tiles i, nchunks); 256 threads, FP64 tensor pipe (DMMA) over the sample axis.
 __global__ void __launch_bounds__(256)
 l1_gram_kernel(const double* __restrict__ W, int64_t ldw, int B, const int4* __restrict__ chunks,
                double* __restrict__ part, int64_t part_stride, int ldp) {
   const int tj = blockIdx.x, ti = blockIdx.y;
   if (tj > ti) return;
-  __shared__ double As[16][LT + 2];
-  __shared__ double Bs[16][LT + 2];
+  __shared__ double As[LT * DM_LD];
+  __shared__ double Bs[LT * DM_LD];
   const int4 ch = chunks[blockIdx.z];
-  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
-  const int lrow = threadIdx.x / 4, lp = (threadIdx.x % 4) * 4;
+  const int lrow = threadIdx.x >> 2;
   const int ia = ti * LT + lrow, ib = tj * LT + lrow;
   const bool va = ia < B, vb = ib < B;
-  const double* arow = W + (int64_t)(va ? ia : 0) * ldw + ch.x + lp;
-  const double* brow = W + (int64_t)(vb ? ib : 0) * ldw + ch.x + lp;
-  double acc[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-  const double2 z2 = make_double2(0.0, 0.0);
-  double2 a0 = va ? *reinterpret_cast<const double2*>(arow) : z2;
-  double2 a1 = va ? *reinterpret_cast<const double2*>(arow + 2) : z2;
-  double2 b0 = vb ? *reinterpret_cast<const double2*>(brow) : z2;
-  double2 b1 = vb ? *reinterpret_cast<const double2*>(brow + 2) : z2;
-  for (int p0 = 0; p0 < ch.y; p0 += 16) {
-    __syncthreads();
-    As[lp + 0][lrow] = a0.x; As[lp + 1][lrow] = a0.y; As[lp + 2][lrow] = a1.x; As[lp + 3][lrow] = a1.y;
-    Bs[lp + 0][lrow] = b0.x; Bs[lp + 1][lrow] = b0.y; Bs[lp + 2][lrow] = b1.x; Bs[lp + 3][lrow] = b1.y;
-    __syncthreads();
-    if (p0 + 16 < ch.y) {
-      if (va) { a0 = *reinterpret_cast<const double2*>(arow + p0 + 16); a1 = *reinterpret_cast<const double2*>(arow + p0 + 18); }
-      if (vb) { b0 = *reinterpret_cast<const double2*>(brow + p0 + 16); b1 = *reinterpret_cast<const double2*>(brow + p0 + 18); }
-    }
-#pragma unroll
-    for (int p = 0; p < 16; ++p) {
-      double av[4], bv[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) av[a] = As[p][ty * 4 + a];
-#pragma unroll
-      for (int b = 0; b < 4; ++b) bv[b] = Bs[p][tx + 16 * b];   // lane-consecutive columns: conflict-free
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
-    }
-  }
+  // rows of the "NT" product are the COLUMNS of W (contiguous over samples)
+  const double* abase = W + (int64_t)(ti * LT) * ldw + ch.x;
+  const double* bbase = W + (int64_t)(tj * LT) * ldw + ch.x;
+  DmmaAcc acc;
+  gemm_tile_nt_dmma(abase, ldw, va, bbase, ldw, vb, ch.y, acc, As, Bs);
   double* o = part + (int64_t)blockIdx.z * part_stride;
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int i = ti * LT + ty * 4 + a;
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int j = tj * LT + tx + 16 * b;
-      if (i < B && j < B) o[(int64_t)i * ldp + j] = acc[a][b];
-    }
-  }
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int ii = ti * LT + dm_row(i), jj = tj * LT + dm_col(j) + e;
+        if (ii < B && jj < B) o[(int64_t)ii * ldp + jj] = acc.c[i][j][e];
+      }
 }
 
 // W_chunk^T y partials: part_y[chunk][i].  grid: (B, nchunks), block 128, fixed-order reduction.
