@@ -105,28 +105,33 @@ chol_diag_kernel(double* __restrict__ cm, int64_t stride, int ld, int k,
     T[j] = (cc == r) ? 1.0 : 0.0;
   }
   bool bad = false;
+#pragma unroll 1
+  for (int c = 0; c < TB; ++c) {
+    const int jc = c >> 2, qc = c & 3, buf = c & 1;
+    if (q == qc) {
+      double dsel = D[0], tsel = T[0];
 #pragma unroll
-  for (int jc = 0; jc < 16; ++jc) {
+      for (int j = 1; j < 16; ++j)
+        if (j == jc) { dsel = D[j]; tsel = T[j]; }
+      cb[buf][r] = dsel;
+      xb[buf][r] = tsel;
+    }
+    __syncthreads();      // one barrier per column: the other buffer is only rewritten after the next barrier
+    const double piv = cb[buf][c];
+    if (!(piv > 0.0)) bad = true;
+    const double inv_p = 1.0 / sqrt(piv);
+    const double lr = cb[buf][r] * inv_p;      // L[r][c]  (meaningful for r >= c)
+    const double xr = xb[buf][r] * inv_p;      // X[r][c] = (L^-T)[r][c]
 #pragma unroll
-    for (int qc = 0; qc < 4; ++qc) {
-      const int c = 4 * jc + qc;
-      const int buf = c & 1;
-      if (q == qc) { cb[buf][r] = D[jc]; xb[buf][r] = T[jc]; }
-      __syncthreads();      // one barrier per column: the other buffer is only rewritten after the next barrier
-      const double piv = cb[buf][c];
-      if (!(piv > 0.0)) bad = true;
-      const double inv_p = 1.0 / sqrt(piv);
-      const double lr = cb[buf][r] * inv_p;      // L[r][c]  (meaningful for r >= c)
-      const double xr = xb[buf][r] * inv_p;      // X[r][c] = (L^-T)[r][c]
-      if (q == qc) { D[jc] = (r >= c) ? lr : 0.0; T[jc] = xr; }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (j > jc || (j == jc && q > qc)) {      // columns cc > c
-          const int cc = q + 4 * j;
-          const double lcc = cb[buf][cc] * inv_p;
-          if (r >= cc) D[j] = fma(-lr, lcc, D[j]);
-          T[j] = fma(-xr, lcc, T[j]);
-        }
+    for (int j = 0; j < 16; ++j) {
+      const int cc = q + 4 * j;
+      if (cc > c) {
+        const double lcc = cb[buf][cc] * inv_p;
+        if (r >= cc) D[j] = fma(-lr, lcc, D[j]);
+        T[j] = fma(-xr, lcc, T[j]);
+      } else if (cc == c) {
+        D[j] = (r >= c) ? lr : 0.0;
+        T[j] = xr;
       }
     }
   }
@@ -187,7 +192,8 @@ chol_trsm_kernel(double* __restrict__ cm, int64_t stride, int ld, int k, int til
 // sweeping 64-column blocks from the last to the first.  y lives in the RHS rows (row nC+p,
 // contiguous over columns); beta overwrites it.  The diagonal solves are GEMVs with the stored
 // M = L_kk^-T; the sweep  y[:, j] -= L[k+r][j] beta[r]  streams the 64 panel rows once.
-constexpr int BS_THREADS = 1024;
+constexpr int BS_THREADS = 256;
+constexpr int BS_JT = 4;        // columns per thread in the sweep (amortises the broadcast beta loads)
 constexpr int BS_PC = 10;   // right-hand sides per register pass
 
 __global__ void __launch_bounds__(BS_THREADS)
@@ -218,29 +224,43 @@ chol_backsolve_kernel(double* __restrict__ cm, int64_t stride, int ld, int nC, i
       A[(int64_t)(nC + p) * ld + k + r] = s;
     }
     __syncthreads();
-    // y[p][j] -= sum_r L[k+r][j] * beta[r][p]   for all j < k   (coalesced over j, 16 loads in flight)
-    for (int j = threadIdx.x; j < k; j += BS_THREADS) {
+    // y[p][j] -= sum_r L[k+r][j] * beta[r][p]   for all j < k   (coalesced over j; each thread owns BS_JT columns)
+    for (int j0 = threadIdx.x; j0 < k; j0 += BS_THREADS * BS_JT) {
       for (int p0 = 0; p0 < P; p0 += BS_PC) {
         const int np = min(BS_PC, P - p0);
-        double acc[BS_PC];
+        double acc[BS_JT][BS_PC];
 #pragma unroll
-        for (int qq = 0; qq < BS_PC; ++qq) acc[qq] = 0.0;
+        for (int m = 0; m < BS_JT; ++m)
+#pragma unroll
+          for (int qq = 0; qq < BS_PC; ++qq) acc[m][qq] = 0.0;
 #pragma unroll 1
-        for (int rb = 0; rb < TB; rb += 16) {
-          double l[16];
+        for (int rb = 0; rb < TB; rb += 8) {
+          double l[BS_JT][8];
 #pragma unroll
-          for (int u = 0; u < 16; ++u) l[u] = A[(int64_t)(k + rb + u) * ld + j];
+          for (int m = 0; m < BS_JT; ++m) {
+            const int j = j0 + m * BS_THREADS;
 #pragma unroll
-          for (int u = 0; u < 16; ++u) {
+            for (int u = 0; u < 8; ++u) l[m][u] = (j < k) ? A[(int64_t)(k + rb + u) * ld + j] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
             const double* bb = bs + (rb + u) * P + p0;
 #pragma unroll
-            for (int qq = 0; qq < BS_PC; ++qq)
-              if (qq < np) acc[qq] = fma(l[u], bb[qq], acc[qq]);
+            for (int qq = 0; qq < BS_PC; ++qq) {
+              const double bv = (qq < np) ? bb[qq] : 0.0;
+#pragma unroll
+              for (int m = 0; m < BS_JT; ++m) acc[m][qq] = fma(l[m][u], bv, acc[m][qq]);
+            }
           }
         }
 #pragma unroll
-        for (int qq = 0; qq < BS_PC; ++qq)
-          if (qq < np) A[(int64_t)(nC + p0 + qq) * ld + j] -= acc[qq];
+        for (int m = 0; m < BS_JT; ++m) {
+          const int j = j0 + m * BS_THREADS;
+          if (j < k)
+#pragma unroll
+            for (int qq = 0; qq < BS_PC; ++qq)
+              if (qq < np) A[(int64_t)(nC + p0 + qq) * ld + j] -= acc[m][qq];
+        }
       }
     }
   }
