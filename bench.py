@@ -348,7 +348,7 @@ def run_gpu(args):
         "solver": {"kernel": "chol_update/chol_panel (fp64)", "achieved_tflops": chol_tf, "fp64_peak_nominal": 40.0},
         "kernels": kern,
         "kernels_concurrent": kern_conc,
-        "lanes": int(os.environ.get("RG_B200_LANES", "4")),
+        "lanes": int(os.environ.get("RG_B200_LANES", "8")),
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)

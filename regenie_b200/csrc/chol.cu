@@ -105,33 +105,28 @@ chol_diag_kernel(double* __restrict__ cm, int64_t stride, int ld, int k,
     T[j] = (cc == r) ? 1.0 : 0.0;
   }
   bool bad = false;
-#pragma unroll 1
-  for (int c = 0; c < TB; ++c) {
-    const int jc = c >> 2, qc = c & 3, buf = c & 1;
-    if (q == qc) {
-      double dsel = D[0], tsel = T[0];
 #pragma unroll
-      for (int j = 1; j < 16; ++j)
-        if (j == jc) { dsel = D[j]; tsel = T[j]; }
-      cb[buf][r] = dsel;
-      xb[buf][r] = tsel;
-    }
-    __syncthreads();      // one barrier per column: the other buffer is only rewritten after the next barrier
-    const double piv = cb[buf][c];
-    if (!(piv > 0.0)) bad = true;
-    const double inv_p = 1.0 / sqrt(piv);
-    const double lr = cb[buf][r] * inv_p;      // L[r][c]  (meaningful for r >= c)
-    const double xr = xb[buf][r] * inv_p;      // X[r][c] = (L^-T)[r][c]
+  for (int jc = 0; jc < 16; ++jc) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int cc = q + 4 * j;
-      if (cc > c) {
-        const double lcc = cb[buf][cc] * inv_p;
-        if (r >= cc) D[j] = fma(-lr, lcc, D[j]);
-        T[j] = fma(-xr, lcc, T[j]);
-      } else if (cc == c) {
-        D[j] = (r >= c) ? lr : 0.0;
-        T[j] = xr;
+    for (int qc = 0; qc < 4; ++qc) {
+      const int c = 4 * jc + qc;
+      const int buf = c & 1;
+      if (q == qc) { cb[buf][r] = D[jc]; xb[buf][r] = T[jc]; }
+      __syncthreads();      // one barrier per column: the other buffer is only rewritten after the next barrier
+      const double piv = cb[buf][c];
+      if (!(piv > 0.0)) bad = true;
+      const double inv_p = rsqrt(piv);
+      const double lr = cb[buf][r] * inv_p;      // L[r][c]  (meaningful for r >= c)
+      const double xr = xb[buf][r] * inv_p;      // X[r][c] = (L^-T)[r][c]
+      if (q == qc) { D[jc] = (r >= c) ? lr : 0.0; T[jc] = xr; }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (j > jc || (j == jc && q > qc)) {      // columns cc > c
+          const int cc = q + 4 * j;
+          const double lcc = cb[buf][cc] * inv_p;
+          if (r >= cc) D[j] = fma(-lr, lcc, D[j]);
+          T[j] = fma(-xr, lcc, T[j]);
+        }
       }
     }
   }
