@@ -39,6 +39,7 @@ struct rg_ctx {
   rg::DevBuf<int32_t> file_idx_pad; // [Npad]
   rg::DevBuf<unsigned long long> err_slot;
   rg::DevBuf<unsigned long long> dbg_counter;
+  rg::DevBuf<long long> dbg_clk;
 
   // ---- per-lane scratch: consecutive blocks go to different lanes (own stream + buffers) so the
   //      latency-bound solver phases of one block overlap the tensor/HBM phases of the next

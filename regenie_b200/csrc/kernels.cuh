@@ -108,11 +108,14 @@ struct PredictTcArgs {
   const uint8_t* mask;
   double* W;
   double* part;
+  long long* dbg;            // optional per-CTA clock64 stamps (profiling aid)
 };
 void make_byte_tensor_map(CUtensorMap* tm, const uint8_t* basep, int64_t inner, int64_t rows);
 size_t predict_tc_dig_bytes(int K, int ngroups, int rows_p);
 void launch_l0_gamma_limbs(const double* gam, const double* gmu, int Qp, int Q, int bs, int rows_p, int K,
                            double* scale, uint8_t* dig, int ngroups, cudaStream_t s);
+int launch_l0_colsum(const double* W, int64_t w_stride, int64_t npad, int col0, int P, int Q, int Qp, double* part,
+                     cudaStream_t s);
 void launch_l0_predict_tcgen05(const CUtensorMap& tmZ, const CUtensorMap& tmD, const PredictTcArgs& a, int ntiles,
                                cudaStream_t s);
 

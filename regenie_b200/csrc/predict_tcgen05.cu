@@ -30,7 +30,8 @@ constexpr int PT_STAGES = 2;
 constexpr int PT_A_BYTES = PT_BK * PT_BM;     // 16 KiB: 128 k-rows x 128 samples
 constexpr int PT_B_BYTES = PT_BN * PT_BK;     // 64 KiB: 512 digit rows x 128 k bytes
 constexpr int PT_STAGE_BYTES = PT_A_BYTES + PT_B_BYTES;
-constexpr int PT_THREADS = 192;
+constexpr int PT_THREADS = 320;          // TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quarter)
+constexpr int PT_QH = kLimbQ / 2;        // outputs per epilogue thread
 constexpr uint32_t PT_SPIN_LIMIT = 1u << 28;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -162,7 +163,6 @@ l0_predict_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * PT_STAGES + 1);
   double* s_scale = reinterpret_cast<double*>(bars + 2 * PT_STAGES + 2);   // [kLimbQ]
   double* s_cvec = s_scale + kLimbQ;                                        // [kLimbQ][C]
-  double* s_red = s_cvec + kLimbQ * a.C;                                    // [2][4][kLimbQ]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x, g = blockIdx.y;
@@ -193,6 +193,7 @@ l0_predict_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_
   __syncthreads();
   fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const long long t_start = clock64();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -233,69 +234,90 @@ l0_predict_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_
       tcgen05_commit(tmem_full_bar);
     }
   } else {
-    // ===== epilogue: thread = sample; fold the 9 limbs of each output in FP64 =====
-    const int qw = warp & 3;
+    // ===== epilogue: thread = (sample, half of the outputs).  The limb sums are exact integers < 2^22:
+    // convert with the 1.5*2^23 magic add, fold limbs 0-3 / 4-7 / 8 in int32 Horner form, then 3 FP64 FMAs.
+    const int qw = warp & 3;                      // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;             // which 28 of the 56 outputs
     const int t = tile * PT_BM + qw * 32 + lane;
     mbar_wait(tmem_full_bar, 0);
     fence_after();
-    double acc[kLimbQ];
+    const long long t_mma = clock64();
+    int ihi[PT_QH], imid[PT_QH], ilo[PT_QH];
 #pragma unroll
-    for (int qq = 0; qq < kLimbQ; ++qq) acc[qq] = 0.0;
+    for (int j = 0; j < PT_QH; ++j) ihi[j] = imid[j] = ilo[j] = 0;
 #pragma unroll
-    for (int c = 0; c < PT_BN / 32; ++c) {
+    for (int l = 0; l < kLimbs; ++l) {
       uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)(c * 32), v);
+      tmem_ld_32x32(tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)(l * kLimbQ + half * PT_QH), v);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int n = c * 32 + j;
-        if (n < kLimbs * kLimbQ) {
-          const int l = n / kLimbQ, qq = n % kLimbQ;     // static after unrolling
-          double w = 1.0;
-#pragma unroll
-          for (int u = 0; u < l; ++u) w *= (1.0 / 30.0);
-          acc[qq] = fma((double)__uint_as_float(v[j]), w, acc[qq]);
-        }
+      for (int j = 0; j < PT_QH; ++j) {
+        const int iv = __float_as_int(__uint_as_float(v[j]) + 12582912.0f) - 0x4B400000;   // exact float -> int
+        if (l < 4) ihi[j] = ihi[j] * 30 + iv;
+        else if (l < 8) imid[j] = imid[j] * 30 + iv;
+        else ilo[j] = iv;
       }
     }
     double xr[kMaxCov];
     for (int c = 0; c < a.C; ++c) xr[c] = a.xy[(int64_t)t * a.cpp + c];
-    const int ew = warp - 2;    // 0..3 slot for the CTA reduction
+    const double w3 = 1.0 / 27000.0, w7 = 1.0 / 21870000000.0, w8 = 1.0 / 656100000000.0;   // 30^-3, 30^-7, 30^-8
 #pragma unroll
-    for (int qq = 0; qq < kLimbQ; ++qq) {
-      double val = 0.0;
+    for (int j = 0; j < PT_QH; ++j) {
+      const int qq = half * PT_QH + j;
       if (qq < nq) {
         const int q = q0 + qq;
         const int r = q / a.P, p = q % a.P;
-        val = acc[qq] * s_scale[qq];
+        double val = fma((double)ihi[j], w3, fma((double)imid[j], w7, (double)ilo[j] * w8)) * s_scale[qq];
         for (int c = 0; c < a.C; ++c) val -= xr[c] * s_cvec[qq * a.C + c];
         val *= (double)a.mask[(int64_t)p * a.npad + t];
         a.W[(int64_t)p * a.w_stride + (int64_t)(a.col0 + r) * a.npad + t] = val;
       }
-      double s1 = val, s2 = val * val;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-      }
-      if (lane == 0) { s_red[(0 * 4 + ew) * kLimbQ + qq] = s1; s_red[(1 * 4 + ew) * kLimbQ + qq] = s2; }
+    }
+    if (a.dbg && threadIdx.x == 64) {
+      long long* d = a.dbg + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 4;
+      d[0] = t_start; d[1] = t_mma; d[2] = clock64(); d[3] = 0;
     }
   }
   fence_before();
   __syncthreads();
-  if (threadIdx.x < nq) {
-    const int qq = threadIdx.x;
-    // fixed-order sum of the 4 epilogue warps (warps 2,3,4,5 -> slots 0..3)
-    const double s1 = ((s_red[(0 * 4 + 0) * kLimbQ + qq] + s_red[(0 * 4 + 1) * kLimbQ + qq]) +
-                       s_red[(0 * 4 + 2) * kLimbQ + qq]) + s_red[(0 * 4 + 3) * kLimbQ + qq];
-    const double s2 = ((s_red[(1 * 4 + 0) * kLimbQ + qq] + s_red[(1 * 4 + 1) * kLimbQ + qq]) +
-                       s_red[(1 * 4 + 2) * kLimbQ + qq]) + s_red[(1 * 4 + 3) * kLimbQ + qq];
-    a.part[((int64_t)tile * a.Qp + q0 + qq) * 2 + 0] = s1;
-    a.part[((int64_t)tile * a.Qp + q0 + qq) * 2 + 1] = s2;
-  }
   if (warp == 1) {
     fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
+}
+
+// Column sums of the raw predictions for the standardisation: part[chunk][q] = (sum, sum of squares) over
+// a chunk of 8192 samples, fixed-order tree reduction.  grid: (Q, nchunks), block 256.
+__global__ void __launch_bounds__(256)
+l0_colsum_kernel(const double* __restrict__ W, int64_t w_stride, int64_t npad, int col0, int P, int Qp,
+                 double* __restrict__ part) {
+  __shared__ double r1[256], r2[256];
+  const int q = blockIdx.x, r = q / P, p = q % P;
+  const int64_t t0 = (int64_t)blockIdx.y * 8192;
+  const double* w = W + (int64_t)p * w_stride + (int64_t)(col0 + r) * npad;
+  double s1 = 0.0, s2 = 0.0;
+  for (int64_t t = t0 + threadIdx.x; t < min(t0 + 8192, npad); t += 256) {
+    const double v = w[t];
+    s1 += v;
+    s2 = fma(v, v, s2);
+  }
+  r1[threadIdx.x] = s1; r2[threadIdx.x] = s2;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { r1[threadIdx.x] += r1[threadIdx.x + o]; r2[threadIdx.x] += r2[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    part[((int64_t)blockIdx.y * Qp + q) * 2 + 0] = r1[0];
+    part[((int64_t)blockIdx.y * Qp + q) * 2 + 1] = r2[0];
+  }
+}
+
+int launch_l0_colsum(const double* W, int64_t w_stride, int64_t npad, int col0, int P, int Q, int Qp, double* part,
+                     cudaStream_t s) {
+  const int nchunks = (int)ceil_div(npad, 8192);
+  dim3 grid(Q, nchunks);
+  l0_colsum_kernel<<<grid, 256, 0, s>>>(W, w_stride, npad, col0, P, Qp, part);
+  return nchunks;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -338,7 +360,7 @@ void launch_l0_gamma_limbs(const double* gam, const double* gmu, int Qp, int Q, 
 void launch_l0_predict_tcgen05(const CUtensorMap& tmZ, const CUtensorMap& tmD, const PredictTcArgs& a, int ntiles,
                                cudaStream_t s) {
   const size_t smem = (size_t)PT_STAGES * PT_STAGE_BYTES + 1024 + 128 +
-                      ((size_t)kLimbQ * (1 + a.C) + 8 * kLimbQ) * sizeof(double);
+                      ((size_t)kLimbQ * (1 + a.C)) * sizeof(double);
   static size_t smem_set = 0;
   if (smem > smem_set) {
     RG_CUDA(cudaFuncSetAttribute(l0_predict_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

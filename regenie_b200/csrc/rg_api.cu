@@ -387,6 +387,7 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
     pa.col0 = col0; pa.npad = Npad; pa.words_per_row = Npad / 16; pa.w_stride = w_stride;
     pa.gp = L.gp.p; pa.tile_fold = h->tile_fold.p; pa.gam = L.gam.p; pa.gmu = L.gmu.p;
     pa.cvec = L.cvec.p; pa.xy = h->xy.p; pa.mask = h->mask.p; pa.W = h->W.p; pa.part = L.part.p;
+    int nparts = ntiles_s;
     static const bool use_f64_predict = [] { const char* e = getenv("RG_B200_PREDICT"); return e && std::string(e) == "f64"; }();
     if (use_f64_predict) {
       launch_l0_predict(pa, ntiles_s, s);
@@ -410,10 +411,13 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
       ta.rows_p = rows_p; ta.C = C; ta.P = P; ta.Q = Q; ta.Qp = Qp; ta.cpp = h->cpp; ta.col0 = col0; ta.ngroups = ngroups;
       ta.npad = Npad; ta.w_stride = w_stride; ta.tile_fold = h->tile_fold.p; ta.scale = L.dscale.p; ta.cvec = L.cvec.p;
       ta.xy = h->xy.p; ta.mask = h->mask.p; ta.W = h->W.p; ta.part = L.part.p;
+      ta.dbg = nullptr;
+      if (getenv("RG_DBG_CLK")) { h->dbg_clk.alloc((size_t)ntiles_s * ngroups * 4); ta.dbg = h->dbg_clk.p; }
       launch_l0_predict_tcgen05(L.tmaps[rows_p], L.dmaps[rows_p], ta, ntiles_s, s);
-      h->launches += 1;
+      nparts = launch_l0_colsum(h->W.p, w_stride, Npad, col0, P, Q, Qp, L.part.p, s);
+      h->launches += 2;
     }
-    launch_l0_standardize(L.part.p, ntiles_s, Qp, Q, P, h->neff.p, L.mean_invsd.p, h->W.p, w_stride, Npad, col0,
+    launch_l0_standardize(L.part.p, nparts, Qp, Q, P, h->neff.p, L.mean_invsd.p, h->W.p, w_stride, Npad, col0,
                           h->is_real.p, s);
     h->launches += 5;
   }
@@ -597,7 +601,12 @@ int64_t rg_debug_fetch(rg_handle h, const char* name, void* out, int64_t max_byt
   else if (n == "rhs") { p = L.rhs.p; bytes = (size_t)h->K * rp * h->P * 8; }
   else if (n == "cm") { p = L.cm.p; bytes = (size_t)h->last_nmat * h->last_n_aug * h->last_nC * 8; }
   else if (n == "mean_invsd") { p = L.mean_invsd.p; bytes = (size_t)2 * h->R * h->P * 8; }
-  else if (n == "dbg_counter") {
+  else if (n == "dbg_clk") {
+    if (!h->dbg_clk.p) return -1;
+    bytes = std::min<size_t>(h->dbg_clk.n * 8, (size_t)max_bytes);
+    cudaMemcpy(out, h->dbg_clk.p, bytes, cudaMemcpyDeviceToHost);
+    return (int64_t)bytes;
+  } else if (n == "dbg_counter") {
     if (!h->dbg_counter.p || max_bytes < 8) return -1;
     cudaMemcpy(out, h->dbg_counter.p, 8, cudaMemcpyDeviceToHost);
     return 8;
