@@ -307,6 +307,8 @@ def run_gpu(args):
     e2e_val = total_snps / (ms_e2e / 1e3)
 
     if rank != 0:
+        if dist is not None:
+            dist.barrier(); dist.destroy_process_group()
         return
     peaks, peak_src = load_peaks()
     gram_ms, gram_n = kern["gram_tcgen05"]["ms_total"], max(1, kern["gram_tcgen05"]["launches"])
@@ -352,6 +354,8 @@ def run_gpu(args):
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
 
 
 def main():
