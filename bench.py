@@ -306,6 +306,32 @@ def run_gpu(args):
     ms_e2e, _ = timed(host_ptr, args.steps, read_status=True)
     e2e_val = total_snps / (ms_e2e / 1e3)
 
+    # ---- secondary metric: Step-2 QT score-test variants/s on the same panel (bed input, P traits)
+    s2 = None
+    if not args.no_step2:
+        try:
+            rng = np.random.default_rng(SEED + 7)
+            res = np.asfortranarray(rng.normal(size=(N, P)))
+            res /= np.linalg.norm(res, axis=0) / np.sqrt(N - C)
+            st2 = capi.Step2(X, mask, in_an, N, bs)
+            st2.set_chr(res, np.ones(P))
+            nb2 = min(len(blocks), 10)
+            hp = host_panel.numpy()
+            for b in range(2):
+                st2.block_bed(hp[blocks[b][0]:blocks[b][0] + blocks[b][1]])
+            t0 = time.perf_counter()
+            nv = 0
+            for b in range(nb2):
+                st2.block_bed(hp[blocks[b][0]:blocks[b][0] + blocks[b][1]])
+                nv += blocks[b][1]
+            dt = time.perf_counter() - t0
+            s2 = {"metric": "step2_qt_variants_per_sec", "value": nv / dt, "unit": "variants/s",
+                  "sample": "%d blocks of %d variants, N=%d, %d traits, host .bed rows in, per-variant stats out "
+                            "(host wall clock incl. H2D/D2H)" % (nb2, bs, N, P)}
+            st2.close()
+        except Exception as e:          # never let the secondary metric break the headline line
+            s2 = {"error": str(e)[:200]}
+
     if rank != 0:
         if dist is not None:
             dist.barrier(); dist.destroy_process_group()
@@ -352,6 +378,7 @@ def run_gpu(args):
         "kernels_concurrent": kern_conc,
         "lanes": int(os.environ.get("RG_B200_LANES", "8")),
         "cpu_baseline": cpu,
+        "step2": s2,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -366,6 +393,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--small", action="store_true", help="tiny config for smoke runs (not a bench value)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-step2", action="store_true")
     ap.add_argument("--cpu-blocks", type=int, default=1)
     ap.add_argument("--blocks", type=int, default=0, help="profiling only: restrict the pass to the first n blocks")
     args = ap.parse_args()
