@@ -7,11 +7,15 @@ follows.  Only `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` /
 `--impl reference` legs of `bench.py` may import it; the product path
 (`regenie_b200`) never does and fails loudly without its CUDA library.
 
-Parity status: the QT Step-1/Step-2 functions have no golden vectors in the
-reference's own tests -> "parity unpinned" for QT-only
-functions; the functions shared with the binary-trait golden run
-(bed/bgen decode, level-0 LOOCV ridge, LOCO assembly, BT score test,
-approximate Firth, summary-statistics printing) are pinned against
-`tests/golden/example/test_bin_out_firth_Y1.regenie` (see
-tests/test_oracle_golden.py).
+Parity status (tests/test_oracle_golden.py):
+  * PINNED on the reference's own known answers:
+      - `0.4504 ... <- min value` in the BT Step-1 log (test/test_bash.sh:58-89): .bed decode,
+        --exclude/--remove, phenotype/covariate prep, level-0 LOOCV ridge, logistic level-1
+        LOOCV, tau selection and table printing;
+      - all 1000 rows of example/test_bin_out_firth_Y1.regenie (docs/docs/options.md:20-51):
+        BGEN v1.2 decode, A1FREQ / INFO / N, allele flip, sparse/dense switch, BT score test,
+        approximate Firth (20 rows), LOG10P, native row format.
+  * "parity unpinned": the QT-only arithmetic (k-fold level 0/1 for QT, compute_score_qt) has
+    no golden vector in the reference's tests; it shares its readers,
+    prep, level-0 algebra, LOCO assembly and printing with the pinned paths.
 """
