@@ -176,6 +176,43 @@ int rg_s2_block_bed(rg_handle h, const uint8_t* packed, int64_t row_stride, int3
                     const int32_t* sample_idx, int32_t ref_first, double min_mac,
                     const rg_s2_out* out);
 
+/* ------------------------------------------------------------------ Step 2 (BT, BGEN dosages) */
+/*
+ * Per-chromosome null-model state of the binary traits, as left by fit_null_logistic in test mode
+ * (src/Step1_Models.cpp:54-140), Data::compute_res_bin (src/Data.cpp:2439-2455) and, for --firth --approx,
+ * fit_null_firth (src/Step2_Models.cpp:985-1060).  All arrays are trait-major [P][N] host arrays.
+ */
+typedef struct rg_s2_bt_chr {
+  const double* gamma_sqrt_mask; /* [P][N]     m_est.Gamma_sqrt_mask                          */
+  const double* gamma_sqrt;      /* [P][N]     m_est.Gamma_sqrt                               */
+  const double* yres;            /* [P][N]     res = (Y - p) / Gamma_sqrt o mask              */
+  const double* x_gamma;         /* [P][C][N]  m_est.X_Gamma (orthonormal basis of Gamma^1/2 X) */
+  const double* y_raw;           /* [P][N]     phenotypes_raw (0/1)                           */
+  const double* firth_offset;    /* [P][N]     firth_est.cov_blup_offset (NULL without --firth) */
+} rg_s2_bt_chr;
+int rg_s2_set_chr_bt(rg_handle h, const rg_s2_bt_chr* st);
+
+/*
+ * rg_s2_block_bgen8_bt -- binary-trait score test for bs variants given as BGEN v1.2 layout-2 8-bit
+ * probability rows (the inflated payload the reference parses in parseSnpfromBGEN, src/Geno.cpp:2186-2345):
+ *   probs          [bs][n_file][2]  P(AA), P(AB) bytes per sample, in file order
+ *   ploidy_missing [bs][n_file]     the ploidy/missingness bytes (bit 7 = missing), or NULL
+ * Computes dosage, A1FREQ / INFO / N / MAC, flip_geno, mean imputation, check_sparse_G and compute_score_bt
+ * (src/Step2_Models.cpp:470-556).  flags bit3 = allele flipped (beta already sign-corrected), bit4 = ignored
+ * (sqrt(denum) < numtol).  info_out [bs x P].  The block stays resident for rg_s2_firth.
+ */
+int rg_s2_block_bgen8_bt(rg_handle h, const uint8_t* probs, const uint8_t* ploidy_missing, int64_t n_file,
+                         int32_t bs, const int32_t* sample_idx, int32_t ref_first, double min_mac,
+                         const rg_s2_out* out, double* info_out);
+
+/*
+ * rg_s2_firth -- approximate Firth test for selected (variant, trait) pairs of the resident block; replaces
+ * fit_firth_logistic_snp_fast + fit_firth_pseudo / fit_firth (src/Step2_Models.cpp:1158-1252, 1527-1737).
+ * beta is reported on the original allele coding; status != 0 in the low 4 bits = did not converge.
+ */
+int rg_s2_firth(rg_handle h, int32_t n_sel, const int32_t* variant_idx, const int32_t* trait_idx, double* beta,
+                double* se, double* lrt, int32_t* status);
+
 /* ------------------------------------------------------------------ multi-GPU */
 /* Number of level-0 predictor columns held locally; W of other ranks is attached with
  * rg_l1_attach_W before rg_l1_fit (the exchange itself is done by the caller with NCCL). */

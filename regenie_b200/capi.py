@@ -32,6 +32,10 @@ class Step2Config(C.Structure):
     ]
 
 
+class S2BtChr(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("gamma_sqrt_mask", "gamma_sqrt", "yres", "x_gamma", "y_raw", "firth_offset")]
+
+
 class S2Out(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("af", "ns", "mac", "af_all", "ns_all", "mac_all", "flags", "scale_fac",
                                            "stat", "beta", "se", "chisq")]
@@ -42,7 +46,7 @@ EXPORTS = [
     "rg_last_error", "rg_version", "rg_device_count", "rg_step1_create", "rg_destroy", "rg_sync",
     "rg_l0_block_bed", "rg_l0_status", "rg_l0_fetch_W", "rg_l1_fit", "rg_loco", "rg_step2_create",
     "rg_s2_set_chr", "rg_s2_block_bed", "rg_W_info", "rg_debug_fetch", "rg_launch_count", "rg_stream",
-    "rg_set_timing", "rg_get_timing", "rg_fence",
+    "rg_set_timing", "rg_get_timing", "rg_fence", "rg_s2_set_chr_bt", "rg_s2_block_bgen8_bt", "rg_s2_firth",
 ]
 
 _lib = None
@@ -229,3 +233,45 @@ class Step2:
         check(lib().rg_s2_block_bed(self.h, _ptr(packed), packed.shape[1], bs, _ptr(sample_idx), int(ref_first),
                                     float(min_mac), C.byref(so)))
         return o
+
+    # ---- binary traits on BGEN 8-bit dosages
+    def set_chr_bt(self, gamma_sqrt_mask, gamma_sqrt, yres, x_gamma, y_raw, firth_offset=None):
+        """Arrays are [N x P] (x_gamma: list of P arrays [N x C]); see rg_s2_bt_chr."""
+        L = lib()
+        L.rg_s2_set_chr_bt.argtypes = [C.c_void_p, C.c_void_p]
+        keep = [_f64(gamma_sqrt_mask), _f64(gamma_sqrt), _f64(yres),
+                np.ascontiguousarray(np.stack([_f64(x) for x in x_gamma]).transpose(0, 2, 1), dtype=np.float64),
+                _f64(y_raw), None if firth_offset is None else _f64(firth_offset)]
+        st = S2BtChr(*[None if a is None else a.ctypes.data for a in keep])
+        check(L.rg_s2_set_chr_bt(self.h, C.byref(st)))
+
+    def block_bgen8_bt(self, probs, missing=None, sample_idx=None, ref_first=False, min_mac=5.0):
+        """probs u8 [bs][n_file][2]; missing u8 [bs][n_file] (bit 7 = missing) or None."""
+        L = lib()
+        L.rg_s2_block_bgen8_bt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                           C.c_int32, C.c_double, C.c_void_p, C.c_void_p]
+        probs = np.ascontiguousarray(probs, dtype=np.uint8)
+        bs, n_file, P = probs.shape[0], probs.shape[1], self.P
+        if missing is not None:
+            missing = np.ascontiguousarray(missing, dtype=np.uint8)
+        o = dict(af=np.empty((bs, P)), ns=np.empty((bs, P), dtype=np.int32), mac=np.empty((bs, P)),
+                 af_all=np.empty(bs), ns_all=np.empty(bs, dtype=np.int32), mac_all=np.empty(bs),
+                 flags=np.empty(bs, dtype=np.int32), scale_fac=np.empty(bs), stat=np.empty((bs, P)),
+                 beta=np.empty((bs, P)), se=np.empty((bs, P)), chisq=np.empty((bs, P)), info=np.empty((bs, P)))
+        so = S2Out(*[o[k].ctypes.data for k in ("af", "ns", "mac", "af_all", "ns_all", "mac_all", "flags",
+                                                "scale_fac", "stat", "beta", "se", "chisq")])
+        if sample_idx is not None:
+            sample_idx = np.ascontiguousarray(sample_idx, dtype=np.int32)
+        check(L.rg_s2_block_bgen8_bt(self.h, _ptr(probs), _ptr(missing), n_file, bs, _ptr(sample_idx),
+                                     int(ref_first), float(min_mac), C.byref(so), _ptr(o["info"])))
+        return o
+
+    def firth(self, variant_idx, trait_idx):
+        L = lib()
+        L.rg_s2_firth.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 6
+        vi = np.ascontiguousarray(variant_idx, dtype=np.int32)
+        ti = np.ascontiguousarray(trait_idx, dtype=np.int32)
+        n = len(vi)
+        beta, se, lrt, status = np.empty(n), np.empty(n), np.empty(n), np.empty(n, dtype=np.int32)
+        check(L.rg_s2_firth(self.h, n, _ptr(vi), _ptr(ti), _ptr(beta), _ptr(se), _ptr(lrt), _ptr(status)))
+        return beta, se, lrt, status

@@ -90,6 +90,16 @@ struct rg_ctx {
   rg::DevBuf<double> F, s2_part, s2_sums, s2_maskcount, s2_YtX, s2_XmX, s2_scf;
   rg::DevBuf<double> s2_out_d;       // packed f64 outputs
   rg::DevBuf<int32_t> s2_out_i;      // packed i32 outputs
+  // binary traits / dosages
+  int bt_mode = 0, bt_dp = 0;
+  bool bt_chr_set = false;
+  int s2_last_bs = 0;                // variants resident in dz (for rg_s2_firth)
+  rg::DevBuf<uint8_t> probs_dev, miss_dev;
+  rg::DevBuf<uint32_t> dz;           // [rows_p][Npad] d | e << 10 | missing << 31
+  rg::DevBuf<double> bt_F, bt_w, bt_gs, bt_xw, bt_off, bt_coltot, bt_xwy, bt_part, bt_sums, bt_nnz, bt_n510;
+  rg::DevBuf<double> bt_xtwg, bt_mu, bt_info, firth_gvec, firth_out;
+  rg::DevBuf<int8_t> bt_ym, firth_cflag;
+  rg::DevBuf<int32_t> firth_sel, firth_status;
 
   // ---- timing
   bool timing = false;

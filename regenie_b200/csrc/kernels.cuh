@@ -171,4 +171,44 @@ void launch_s2_stats(const uint32_t* gp, int64_t npad, const double* F, int dp, 
                      int rows_p, double* part, double* sums, cudaStream_t s);
 void launch_s2_finalize(const S2FinalizeArgs& a, cudaStream_t s);
 
+// ---- s2_dosage_kernels.cu
+struct S2BtFinalizeArgs {
+  int bs, C, P, dp, with_flip;
+  long long n_analyzed, n_samples;
+  double min_mac, numtol;
+  const double* sums;        // [rows_p][4][dp]  S1, S2, Sm, Se in integer dosage units
+  const double* col_tot;     // [dp] sum of every feature column over all samples
+  const double* xwy;         // [P][C]  XW^T yres
+  const double* nz_count;    // [rows_p] analysed samples with non-zero dosage
+  const double* n510;        // [rows_p] analysed samples with dosage exactly 2
+  double *af, *mac, *info, *af_all, *mac_all, *scale_fac, *stat, *beta, *se, *chisq, *xtwg, *mu;
+  int32_t *ns, *ns_all, *flags;
+};
+void launch_dosage_relayout(const uint8_t* probs, const uint8_t* miss, int64_t n_file, int bs, int rows_p,
+                            const int32_t* file_idx_pad, int ref_first, uint32_t* dz, int64_t npad, cudaStream_t s);
+void launch_dosage_stats(const uint32_t* dz, int64_t npad, const double* F, int dp, const int4* chunks, int nchunks,
+                         int rows_p, double* part, double* sums, double* nnz, double* n510, cudaStream_t s);
+void launch_s2_bt_finalize(const S2BtFinalizeArgs& a, cudaStream_t s);
+
+// ---- s2_firth.cu
+struct FirthArgs {
+  int n_sel, C, P, dp, niter;
+  double tol, maxstep;
+  int64_t npad;
+  const int32_t *sel_var, *sel_trait;
+  const uint32_t* dz;
+  const double* F;
+  const double *w, *gs, *xw, *off;   // [P][Npad], xw [P][C][Npad]
+  const int8_t* ym;                  // [P][Npad] 0 masked, 1 control, 2 case
+  const double* xtwg;                // [bs][P][C]
+  const double* mu;                  // [bs] imputed mean (after flip)
+  const double* mac;                 // [bs][P]
+  const int32_t* flags;              // [bs]
+  double* gvec;                      // [n_sel][Npad] scratch
+  int8_t* cflag;                     // [n_sel][Npad] scratch
+  double *beta, *se, *lrt;
+  int32_t* status;
+};
+void launch_s2_firth(const FirthArgs& a, cudaStream_t s);
+
 }  // namespace rg

@@ -161,7 +161,185 @@ static void s2_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
   RG_CUDA(cudaStreamSynchronize(s));
 }
 
+// ---------------------------------------------------------------- binary traits + 8-bit dosages
+static void s2_set_chr_bt(rg_ctx* h, const rg_s2_bt_chr* st) {
+  RG_CHECK(h->kind == 2, "handle is not a Step-2 handle");
+  RG_CUDA(cudaSetDevice(h->device));
+  const int64_t N = h->N, Npad = h->Npad;
+  const int C = h->C, P = h->P;
+  const int dp = (int)round_up(1 + (int64_t)P * (3 + C), 16);
+  h->bt_dp = dp;
+  std::vector<double> F((size_t)Npad * dp, 0.0), coltot(dp, 0.0), xwy((size_t)P * C, 0.0);
+  std::vector<double> w((size_t)P * Npad, 0.0), gs((size_t)P * Npad, 0.0), off((size_t)P * Npad, 0.0),
+      xw((size_t)P * C * Npad, 0.0);
+  std::vector<int8_t> ym((size_t)P * Npad, 0);
+  for (int64_t s = 0; s < N; ++s) {
+    double* r = &F[(size_t)s * dp];
+    const bool ina = h->in_analysis[s] != 0;
+    r[0] = ina ? 1.0 : 0.0;
+    for (int p = 0; p < P; ++p) {
+      const size_t ps = (size_t)p * N + s, pp = (size_t)p * Npad + s;
+      const bool m = h->maskh[ps] != 0;
+      const double wv = ina ? st->gamma_sqrt_mask[ps] : 0.0;
+      const double yr = st->yres[ps];
+      w[pp] = wv; gs[pp] = st->gamma_sqrt[ps]; off[pp] = st->firth_offset ? st->firth_offset[ps] : 0.0;
+      ym[pp] = m ? (st->y_raw[ps] != 0.0 ? 2 : 1) : 0;
+      double* f = r + 1 + p * (3 + C);
+      f[0] = (m && ina) ? 1.0 : 0.0;
+      f[1] = wv * wv;
+      f[2] = wv * yr;
+      for (int c = 0; c < C; ++c) {
+        const double x = st->x_gamma[((size_t)p * C + c) * N + s];
+        xw[((size_t)p * C + c) * Npad + s] = x;
+        f[3 + c] = wv * x;
+        xwy[(size_t)p * C + c] += x * yr;
+      }
+    }
+    if (ina) for (int k = 0; k < dp; ++k) coltot[k] += r[k];
+  }
+  auto up = [&](auto& buf, const auto& v) {
+    buf.alloc(v.size());
+    RG_CUDA(cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice, h->stream));
+  };
+  up(h->bt_F, F); up(h->bt_coltot, coltot); up(h->bt_xwy, xwy); up(h->bt_w, w); up(h->bt_gs, gs);
+  up(h->bt_off, off); up(h->bt_xw, xw); up(h->bt_ym, ym);
+  RG_CUDA(cudaStreamSynchronize(h->stream));
+  h->bt_chr_set = true;
+}
+
+static void s2_block_bgen8_bt(rg_ctx* h, const uint8_t* probs, const uint8_t* miss, int64_t n_file, int bs,
+                              const int32_t* sample_idx, int ref_first, double min_mac, const rg_s2_out* out,
+                              double* info_out) {
+  RG_CHECK(h->kind == 2, "handle is not a Step-2 handle");
+  RG_CHECK(h->bt_chr_set, "rg_s2_set_chr_bt has not been called");
+  RG_CHECK(bs > 0 && bs <= h->bs_max, "block size out of range");
+  RG_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const int P = h->P, C = h->C, dp = h->bt_dp;
+  const int rows_p = (int)round_up(bs, kRowPad);
+  const int64_t Npad = h->Npad;
+  {
+    std::vector<int32_t> host_idx;
+    if (sample_idx) {
+      host_idx.assign(sample_idx, sample_idx + h->N);
+      if (!h->file_idx_valid || h->cached_sample_idx != host_idx) {
+        build_file_idx_public(h, host_idx.data());
+        h->cached_sample_idx = host_idx;
+      }
+    } else if (!h->file_idx_valid || !h->cached_sample_idx.empty()) {
+      build_file_idx_public(h, nullptr);
+      h->cached_sample_idx.clear();
+    }
+  }
+  const uint8_t *probs_d = probs, *miss_d = miss;
+  if (!is_device_pointer(probs)) {
+    h->probs_dev.alloc((size_t)h->bs_max * n_file * 2);
+    copy_to_device(h->probs_dev.p, probs, (size_t)bs * n_file * 2, s);
+    probs_d = h->probs_dev.p;
+    if (miss) {
+      h->miss_dev.alloc((size_t)h->bs_max * n_file);
+      copy_to_device(h->miss_dev.p, miss, (size_t)bs * n_file, s);
+      miss_d = h->miss_dev.p;
+    }
+  }
+  h->dz.alloc((size_t)h->rows_p_max * Npad);
+  h->bt_part.alloc((size_t)h->nchunks * h->rows_p_max * 4 * dp);
+  h->bt_sums.alloc((size_t)h->rows_p_max * 4 * dp);
+  h->bt_nnz.alloc(h->rows_p_max); h->bt_n510.alloc(h->rows_p_max);
+  h->bt_xtwg.alloc((size_t)h->bs_max * P * C); h->bt_mu.alloc(h->bs_max); h->bt_info.alloc((size_t)h->bs_max * P);
+  const size_t nd = (size_t)h->bs_max * (7 * (size_t)P + 3), ni = (size_t)h->bs_max * ((size_t)P + 2);
+  h->s2_out_d.alloc(nd);
+  h->s2_out_i.alloc(ni);
+  launch_dosage_relayout(probs_d, miss_d, n_file, bs, rows_p, h->file_idx_pad.p, ref_first, h->dz.p, Npad, s);
+  launch_dosage_stats(h->dz.p, Npad, h->bt_F.p, dp, h->chunks.p, h->nchunks, rows_p, h->bt_part.p, h->bt_sums.p,
+                      h->bt_nnz.p, h->bt_n510.p, s);
+  S2BtFinalizeArgs a;
+  a.bs = bs; a.C = C; a.P = P; a.dp = dp; a.with_flip = 1;
+  a.n_analyzed = h->n_analyzed; a.n_samples = h->N; a.min_mac = min_mac; a.numtol = 1e-6;
+  a.sums = h->bt_sums.p; a.col_tot = h->bt_coltot.p; a.xwy = h->bt_xwy.p; a.nz_count = h->bt_nnz.p; a.n510 = h->bt_n510.p;
+  double* d = h->s2_out_d.p;
+  const size_t bp = (size_t)h->bs_max * P, b1 = h->bs_max;
+  a.af = d; a.mac = d + bp; a.stat = d + 2 * bp; a.beta = d + 3 * bp; a.se = d + 4 * bp; a.chisq = d + 5 * bp;
+  a.af_all = d + 6 * bp; a.mac_all = d + 6 * bp + b1; a.scale_fac = d + 6 * bp + 2 * b1;
+  a.info = h->bt_info.p; a.xtwg = h->bt_xtwg.p; a.mu = h->bt_mu.p;
+  int32_t* ii = h->s2_out_i.p;
+  a.ns = ii; a.ns_all = ii + bp; a.flags = ii + bp + b1;
+  launch_s2_bt_finalize(a, s);
+  h->launches += 5;
+  h->s2_last_bs = bs;
+  const size_t vp = (size_t)bs * P * 8, v1 = (size_t)bs * 8;
+  auto cp = [&](void* dst, const void* src, size_t bytes) {
+    if (dst) RG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+  };
+  cp(out->af, a.af, vp); cp(out->mac, a.mac, vp); cp(out->stat, a.stat, vp); cp(out->beta, a.beta, vp);
+  cp(out->se, a.se, vp); cp(out->chisq, a.chisq, vp); cp(out->af_all, a.af_all, v1); cp(out->mac_all, a.mac_all, v1);
+  cp(out->scale_fac, a.scale_fac, v1); cp(out->ns, a.ns, (size_t)bs * P * 4); cp(out->ns_all, a.ns_all, (size_t)bs * 4);
+  cp(out->flags, a.flags, (size_t)bs * 4); cp(info_out, a.info, vp);
+  RG_CUDA(cudaStreamSynchronize(s));
+}
+
+static void s2_firth(rg_ctx* h, int n_sel, const int32_t* var_idx, const int32_t* trait_idx, double* beta, double* se,
+                     double* lrt, int32_t* status) {
+  RG_CHECK(h->kind == 2 && h->bt_chr_set && h->s2_last_bs > 0, "rg_s2_firth needs a resident dosage block");
+  RG_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const int P = h->P, C = h->C;
+  for (int k = 0; k < n_sel; ++k)
+    RG_CHECK(var_idx[k] >= 0 && var_idx[k] < h->s2_last_bs && trait_idx[k] >= 0 && trait_idx[k] < P, "selection out of range");
+  const int kBatch = 256;
+  h->firth_gvec.alloc((size_t)kBatch * h->Npad); h->firth_cflag.alloc((size_t)kBatch * h->Npad);
+  h->firth_sel.alloc(2 * kBatch); h->firth_status.alloc(kBatch); h->firth_out.alloc(3 * kBatch);
+  const size_t bp = (size_t)h->bs_max * P, b1 = h->bs_max;
+  for (int o = 0; o < n_sel; o += kBatch) {
+    const int nb = std::min(kBatch, n_sel - o);
+    RG_CUDA(cudaMemcpyAsync(h->firth_sel.p, var_idx + o, nb * 4, cudaMemcpyHostToDevice, s));
+    RG_CUDA(cudaMemcpyAsync(h->firth_sel.p + kBatch, trait_idx + o, nb * 4, cudaMemcpyHostToDevice, s));
+    FirthArgs a;
+    a.n_sel = nb; a.C = C; a.P = P; a.dp = h->bt_dp; a.niter = 250; a.tol = 2.5e-4; a.maxstep = 5.0;
+    a.npad = h->Npad; a.sel_var = h->firth_sel.p; a.sel_trait = h->firth_sel.p + kBatch;
+    a.dz = h->dz.p; a.F = h->bt_F.p; a.w = h->bt_w.p; a.gs = h->bt_gs.p; a.xw = h->bt_xw.p; a.off = h->bt_off.p;
+    a.ym = h->bt_ym.p; a.xtwg = h->bt_xtwg.p; a.mu = h->bt_mu.p; a.mac = h->s2_out_d.p + bp;
+    a.flags = h->s2_out_i.p + bp + b1;
+    a.gvec = h->firth_gvec.p; a.cflag = h->firth_cflag.p;
+    a.beta = h->firth_out.p; a.se = h->firth_out.p + kBatch; a.lrt = h->firth_out.p + 2 * kBatch;
+    a.status = h->firth_status.p;
+    launch_s2_firth(a, s);
+    h->launches += 1;
+    RG_CUDA(cudaMemcpyAsync(beta + o, a.beta, nb * 8, cudaMemcpyDeviceToHost, s));
+    RG_CUDA(cudaMemcpyAsync(se + o, a.se, nb * 8, cudaMemcpyDeviceToHost, s));
+    RG_CUDA(cudaMemcpyAsync(lrt + o, a.lrt, nb * 8, cudaMemcpyDeviceToHost, s));
+    RG_CUDA(cudaMemcpyAsync(status + o, a.status, nb * 4, cudaMemcpyDeviceToHost, s));
+    RG_CUDA(cudaStreamSynchronize(s));
+  }
+}
+
 extern "C" {
+
+int rg_s2_set_chr_bt(rg_handle h, const rg_s2_bt_chr* st) {
+  RG_API_BEGIN
+  RG_CHECK(h && st && st->gamma_sqrt_mask && st->gamma_sqrt && st->yres && st->x_gamma && st->y_raw, "null argument");
+  s2_set_chr_bt(h, st);
+  RG_API_END
+}
+
+int rg_s2_block_bgen8_bt(rg_handle h, const uint8_t* probs, const uint8_t* ploidy_missing, int64_t n_file, int32_t bs,
+                         const int32_t* sample_idx, int32_t ref_first, double min_mac, const rg_s2_out* out,
+                         double* info_out) {
+  RG_API_BEGIN
+  RG_CHECK(h && probs && out, "null argument");
+  s2_block_bgen8_bt(h, probs, ploidy_missing, n_file, bs, sample_idx, ref_first, min_mac, out, info_out);
+  RG_CUDA(cudaGetLastError());
+  RG_API_END
+}
+
+int rg_s2_firth(rg_handle h, int32_t n_sel, const int32_t* variant_idx, const int32_t* trait_idx, double* beta,
+                double* se, double* lrt, int32_t* status) {
+  RG_API_BEGIN
+  RG_CHECK(h && (n_sel == 0 || (variant_idx && trait_idx && beta && se && lrt && status)), "null argument");
+  if (n_sel > 0) s2_firth(h, n_sel, variant_idx, trait_idx, beta, se, lrt, status);
+  RG_CUDA(cudaGetLastError());
+  RG_API_END
+}
 
 int rg_step2_create(const rg_step2_config* cfg, const double* X, const uint8_t* mask,
                     const uint8_t* in_analysis, rg_handle* out) {
