@@ -1,0 +1,162 @@
+#include "bgen.hpp"
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <atomic>
+#include <cstring>
+#include <thread>
+
+namespace rgh {
+
+namespace {
+inline uint16_t rd16(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); return v; }
+inline uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+}  // namespace
+
+BgenFile::~BgenFile() {
+  if (data) munmap(const_cast<uint8_t*>(data), size);
+  if (fd >= 0) close(fd);
+}
+
+void BgenFile::open(const std::string& p, const std::string& sample_file, bool ref_first,
+                    const std::set<std::string>& exclude, const std::set<std::string>& extract,
+                    const std::set<std::string>& remove, const std::set<std::string>& keep) {
+  path = p;
+  fd = ::open(path.c_str(), O_RDONLY);
+  if (fd < 0) throw Fail("cannot open file : " + path);
+  struct stat st;
+  fstat(fd, &st);
+  size = (size_t)st.st_size;
+  if (size < 24) throw Fail("bgen file is too short : " + path);
+  void* m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+  if (m == MAP_FAILED) throw Fail("cannot map file : " + path);
+  data = static_cast<const uint8_t*>(m);
+  const uint32_t offset = rd32(data), lh = rd32(data + 4);
+  n_variants_file = rd32(data + 8);
+  n_file = rd32(data + 12);
+  if (memcmp(data + 16, "bgen", 4) != 0 && memcmp(data + 16, "\0\0\0\0", 4) != 0) throw Fail("not a bgen file : " + path);
+  const uint32_t flags = rd32(data + 4 + lh - 4);
+  compression = flags & 3;
+  const int layout = (flags >> 2) & 0xF;
+  const bool has_ids = (flags >> 31) != 0;
+  if (layout != 2) throw Fail("only BGEN v1.2 (layout 2) files are supported.");
+  if (compression > 1) throw Fail("zstd-compressed bgen files are not supported by rgb200 (zlib or uncompressed only).");
+  // ---- sample identifiers: embedded block, or --sample (read_bgen_sample, src/Geno.cpp:391-440)
+  if (!sample_file.empty()) {
+    std::ifstream fh(sample_file);
+    if (!fh) throw Fail("cannot open file : " + sample_file);
+    std::string line;
+    int lineno = 0;
+    while (std::getline(fh, line)) {
+      auto t = split_ws(line);
+      if (t.empty()) continue;
+      if (lineno++ < 2) {
+        if (lineno == 1 && (t.size() < 2 || t[0] != "ID_1" || t[1] != "ID_2")) throw Fail("header of the sample file must start with: ID_1 ID_2");
+        continue;
+      }
+      if (t.size() < 2) throw Fail("incorrectly formatted sample file.");
+      keys_file.push_back(t[0] + "_" + t[1]);
+    }
+    if (keys_file.size() != n_file) throw Fail("number of samples in BGEN file does not match that in the sample file.");
+  } else {
+    if (!has_ids) throw Fail("the bgen file has no sample identifiers: provide them with --sample.");
+    const uint8_t* q = data + 4 + lh;
+    const uint32_t ns = rd32(q + 4);
+    if (ns != n_file) throw Fail("inconsistent sample identifier block in bgen file.");
+    q += 8;
+    for (uint32_t i = 0; i < ns; ++i) {
+      const uint16_t l = rd16(q);
+      keys_file.emplace_back(reinterpret_cast<const char*>(q + 2), l);
+      q += 2 + l;
+    }
+  }
+  {
+    std::set<std::string> seen;
+    for (const auto& k : keys_file)
+      if (!seen.insert(k).second) throw Fail("duplicate individual in bgen file : FID_IID =" + k);
+  }
+  for (size_t i = 0; i < keys_file.size(); ++i) {
+    const std::string& k = keys_file[i];
+    if (remove.count(k)) continue;
+    if (!keep.empty() && !keep.count(k)) continue;
+    key_to_ind[k] = (uint32_t)keys.size();
+    keys.push_back(k);
+    sample_idx.push_back((int32_t)i);
+  }
+  if (keys.empty()) throw Fail("no samples left after --keep/--remove.");
+  // ---- variant index
+  size_t pos = (size_t)offset + 4;
+  auto need = [&](size_t n) { if (pos + n > size) throw Fail("unexpected end of bgen file."); };
+  for (uint32_t v = 0; v < n_variants_file; ++v) {
+    Snp s;
+    need(2); uint16_t l = rd16(data + pos); pos += 2 + l;                                 // SNPID
+    need(2); l = rd16(data + pos); need(2 + l); s.id.assign(reinterpret_cast<const char*>(data + pos + 2), l); pos += 2 + l;
+    need(2); l = rd16(data + pos); need(2 + l);
+    const std::string chrom(reinterpret_cast<const char*>(data + pos + 2), l); pos += 2 + l;
+    need(6); s.pos = rd32(data + pos); pos += 4;
+    const uint16_t k = rd16(data + pos); pos += 2;
+    if (k != 2) throw Fail("only bi-allelic variants are supported in bgen files (variant " + s.id + ").");
+    std::string al[2];
+    for (int a = 0; a < 2; ++a) {
+      need(4); const uint32_t la = rd32(data + pos); need(4 + la);
+      al[a].assign(reinterpret_cast<const char*>(data + pos + 4), la); pos += 4 + la;
+    }
+    s.chrom = chr_str_to_int(chrom);
+    if (s.chrom == -1) throw Fail("unknown chromosome code in bgen file.");
+    if (ref_first) { s.allele0 = al[0]; s.allele1 = al[1]; }
+    else           { s.allele0 = al[1]; s.allele1 = al[0]; }    // allele0 of the file is ALT
+    s.offset = pos;
+    need(4); const uint32_t c = rd32(data + pos);
+    need(4 + (size_t)c);
+    pos += 4 + (size_t)c;
+    if (exclude.count(s.id)) continue;
+    if (!extract.empty() && !extract.count(s.id)) continue;
+    snps.push_back(s);
+  }
+}
+
+void BgenFile::read_block(size_t first, size_t n, uint8_t* probs, uint8_t* pm, int threads) const {
+  std::atomic<size_t> next{0};
+  std::string err;
+  std::atomic<bool> failed{false};
+  auto work = [&]() {
+    std::vector<uint8_t> buf;
+    for (;;) {
+      const size_t j = next.fetch_add(1);
+      if (j >= n || failed.load()) return;
+      const uint8_t* q = data + snps[first + j].offset;
+      const uint32_t c = rd32(q);
+      const uint8_t* raw;
+      uLongf dl;
+      if (compression == 1) {
+        dl = rd32(q + 4);
+        buf.resize(dl);
+        if (uncompress(buf.data(), &dl, q + 8, c - 4) != Z_OK) { failed = true; return; }
+        raw = buf.data();
+      } else {
+        dl = c;
+        raw = q + 4;
+      }
+      const uint32_t ns = rd32(raw);
+      const uint16_t ka = rd16(raw + 4);
+      const uint8_t pmin = raw[6], pmax = raw[7];
+      if (ns != n_file || ka != 2 || pmin != 2 || pmax != 2 || dl < 10 + 3 * (size_t)ns) { failed = true; return; }
+      const uint8_t phased = raw[8 + ns], bits = raw[9 + ns];
+      if (phased != 0 || bits != 8) { failed = true; return; }
+      memcpy(pm + j * (size_t)n_file, raw + 8, ns);
+      memcpy(probs + j * (size_t)n_file * 2, raw + 10 + ns, 2 * (size_t)ns);
+    }
+  };
+  const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, n));
+  std::vector<std::thread> pool;
+  for (int t = 1; t < T; ++t) pool.emplace_back(work);
+  work();
+  for (auto& t : pool) t.join();
+  if (failed) throw Fail("unsupported or corrupt bgen genotype block (rgb200 reads 8-bit unphased diploid biallelic layout 2 only).");
+}
+
+}  // namespace rgh

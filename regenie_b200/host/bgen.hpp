@@ -1,0 +1,28 @@
+// BGEN v1.2 reader of the rgb200 host driver (layout 2, zlib or uncompressed, 8-bit, unphased, biallelic,
+// diploid - the subset the reference's hand parser handles, src/Geno.cpp:2122-2345).  The file header and the
+// variant identifying blocks (which the reference reads through the BGEN library, src/Geno.cpp:38-178) follow
+// the public BGEN v1.2 specification.  The inflated probability bytes go to the GPU unchanged.
+#pragma once
+#include "data.hpp"
+
+namespace rgh {
+
+struct BgenFile {
+  std::string path;
+  std::vector<Snp> snps;                       // after --extract/--exclude; offset = file offset of the genotype block
+  std::vector<std::string> keys_file, keys;
+  std::vector<int32_t> sample_idx;
+  std::map<std::string, uint32_t> key_to_ind;
+  uint32_t n_file = 0, n_variants_file = 0;
+  int compression = 0;
+  const uint8_t* data = nullptr;               // mmap of the whole file
+  size_t size = 0;
+  int fd = -1;
+  ~BgenFile();
+  void open(const std::string& path, const std::string& sample_file, bool ref_first, const std::set<std::string>& exclude,
+            const std::set<std::string>& extract, const std::set<std::string>& remove, const std::set<std::string>& keep);
+  // inflate variants snps[first .. first+n): probs [n][n_file][2], ploidy_missing [n][n_file]
+  void read_block(size_t first, size_t n, uint8_t* probs, uint8_t* ploidy_missing, int threads) const;
+};
+
+}  // namespace rgh

@@ -1,0 +1,22 @@
+// Per-chromosome null models of the binary-trait Step 2 (host side, O(N C^2) per trait and chromosome):
+//   fit_null_logistic in test mode      reference src/Step1_Models.cpp:54-140, 156-222
+//   Data::compute_res_bin               src/Data.cpp:2439-2455
+//   fit_null_firth / fit_firth_nr       src/Step2_Models.cpp:985-1060, 1267-1383 (approximate Firth null)
+// The per-variant work (score test, Firth fallback) runs on the GPU behind rg_s2_block_bgen8_bt / rg_s2_firth.
+#pragma once
+#include "data.hpp"
+
+namespace rgh {
+
+struct BtNull {
+  std::vector<double> gamma_sqrt, gamma_sqrt_mask, yres, x_gamma, firth_offset;   // [N], [N], [N], [C][N], [N]
+};
+
+// y (0/1), X [C][N] column-major orthonormal basis, blup (LOCO prediction), mask; throws Fail on non-convergence
+BtNull fit_bt_null(const std::string& name, const double* y, const double* X, int64_t N, int C, const double* blup,
+                   const uint8_t* mask, bool firth);
+
+// z threshold of --pThresh: sqrt of the chi2_1 upper quantile (src/Data.cpp:2116-2120)
+double z_threshold(double p_thresh);
+
+}  // namespace rgh

@@ -96,7 +96,7 @@ void BedFile::read_rows(size_t first, size_t n, uint8_t* out) {
 }
 
 // [n x k] table keyed by FID_IID; samples absent from the genotype file are ignored
-static void read_table(const std::string& path, const BedFile& g, const std::set<std::string>* skip_cols,
+static void read_table(const std::string& path, const SampleSet& g, const std::set<std::string>* skip_cols,
                        std::vector<std::string>& names, std::vector<double>& vals, std::vector<uint8_t>& present) {
   std::ifstream fh(path);
   if (!fh) throw Fail("cannot open file : " + path);
@@ -123,10 +123,11 @@ static void read_table(const std::string& path, const BedFile& g, const std::set
   }
 }
 
-void read_pheno_and_cov(const BedFile& g, const std::string& pheno_file, const std::string& covar_file,
-                        bool step2, bool strict, Pheno& ph, Log& log) {
+void read_pheno_and_cov(const SampleSet& g, const std::string& pheno_file, const std::string& covar_file,
+                        bool step2, bool strict, bool bt, Pheno& ph, Log& log) {
   const int64_t N = (int64_t)g.keys.size();
   ph.N = N;
+  ph.bt = bt;
   std::vector<uint8_t> in_ph;
   read_table(pheno_file, g, nullptr, ph.names, ph.Y, in_ph);
   ph.P = (int)ph.names.size();
@@ -134,12 +135,21 @@ void read_pheno_and_cov(const BedFile& g, const std::string& pheno_file, const s
   log << " * phenotypes          : [" << pheno_file << "] n_pheno = " << ph.P << "\n";
   ph.strict = strict || ph.P == 1;                          // src/Pheno.cpp:198
   ph.mask.assign((size_t)N * ph.P, 1);
+  if (bt) {                                                 // src/Pheno.cpp:296-315: controls 0, cases 1, else NA
+    ph.Y_raw = ph.Y;
+    for (size_t e = 0; e < ph.Y_raw.size(); ++e) {
+      const double y = ph.Y_raw[e];
+      if (y == 0.0 || y == 1.0) continue;
+      if (y != kMissing) throw Fail("a phenotype value is not 0/1/NA for a binary trait.");
+      ph.mask[e] = 0;
+    }
+  }
   for (int64_t s = 0; s < N; ++s) {
     bool all_miss = true, any_miss = false;
     for (int p = 0; p < ph.P; ++p) {
       const bool miss = ph.Y[(size_t)p * N + s] == kMissing;
       if (!miss) all_miss = false; else any_miss = true;
-      if (miss && step2) ph.mask[(size_t)p * N + s] = 0;    // rm_missing_qt (src/Pheno.cpp:331)
+      if (miss && step2 && !bt) ph.mask[(size_t)p * N + s] = 0;   // rm_missing_qt (src/Pheno.cpp:331)
     }
     if (ph.strict && any_miss) {
       for (int p = 0; p < ph.P; ++p) ph.mask[(size_t)p * N + s] = 0;
@@ -215,6 +225,29 @@ static void jacobi_eig(std::vector<double>& a, int n, std::vector<double>& d, st
   d = d2; v = v2;
 }
 
+void get_basis(const std::vector<double>& X, int64_t N, int C0, std::vector<double>& Xb, int& nz) {
+  std::vector<double> xtx((size_t)C0 * C0, 0.0), d, v;
+  for (int a = 0; a < C0; ++a)
+    for (int b = a; b < C0; ++b) {
+      double s = 0.0;
+      for (int64_t i = 0; i < N; ++i) s += X[(size_t)a * N + i] * X[(size_t)b * N + i];
+      xtx[(size_t)a * C0 + b] = xtx[(size_t)b * C0 + a] = s;
+    }
+  jacobi_eig(xtx, C0, d, v);
+  nz = 0;
+  for (int j = 0; j < C0; ++j) if (d[j] > d[C0 - 1] * 1e-15) ++nz;
+  Xb.assign((size_t)N * nz, 0.0);
+  for (int j = 0; j < nz; ++j) {
+    const int col = C0 - nz + j;
+    const double inv = 1.0 / std::sqrt(d[col]);
+    for (int a = 0; a < C0; ++a) {
+      const double w = v[(size_t)a * C0 + col] * inv;
+      if (w == 0.0) continue;
+      for (int64_t i = 0; i < N; ++i) Xb[(size_t)j * N + i] += X[(size_t)a * N + i] * w;
+    }
+  }
+}
+
 // setMasks (src/Pheno.cpp:810-841)
 static void set_masks(Pheno& ph) {
   const int64_t N = ph.N;
@@ -225,7 +258,10 @@ static void set_masks(Pheno& ph) {
     ph.in_analysis[s] = ph.in_analysis[s] && (ph.strict ? all : any);
     for (int p = 0; p < P; ++p) {
       ph.mask[(size_t)p * N + s] = ph.mask[(size_t)p * N + s] && ph.in_analysis[s];
-      if (!ph.in_analysis[s]) ph.Y[(size_t)p * N + s] *= 0.0;
+      if (!ph.in_analysis[s]) {
+        ph.Y[(size_t)p * N + s] *= 0.0;
+        if (ph.bt) ph.Y_raw[(size_t)p * N + s] *= 0.0;
+      }
     }
     if (!ph.in_analysis[s]) for (int c = 0; c < ph.C; ++c) ph.X[(size_t)c * N + s] = 0.0;
   }
@@ -240,8 +276,8 @@ void prep_run(Pheno& ph, const std::vector<uint8_t>* extra_mask, Log& log) {
   const int64_t N = ph.N;
   const int P = ph.P;
   set_masks(ph);                                             // read_pheno_and_cov, src/Pheno.cpp:102
-  // pheno_impute_miss, QT (src/Pheno.cpp:1916-1931)
-  for (int p = 0; p < P; ++p) {
+  // pheno_impute_miss, QT (src/Pheno.cpp:1916-1931); binary traits keep the raw 0/1 values in Step 2
+  for (int p = 0; p < P && !ph.bt; ++p) {
     double tot = 0.0; int64_t ns = 0;
     for (int64_t s = 0; s < N; ++s) {
       const double y = ph.Y[(size_t)p * N + s];
@@ -258,33 +294,14 @@ void prep_run(Pheno& ph, const std::vector<uint8_t>* extra_mask, Log& log) {
     set_masks(ph);                                           // prep_run, src/Pheno.cpp:1070
   }
   log << " * number of individuals used in analysis = " << ph.n_analyzed << "\n";
-  // getBasis (src/Pheno.cpp:1660-1681)
-  const int C0 = ph.C;
-  std::vector<double> xtx((size_t)C0 * C0, 0.0), d, v;
-  for (int a = 0; a < C0; ++a)
-    for (int b = a; b < C0; ++b) {
-      double s = 0.0;
-      for (int64_t i = 0; i < N; ++i) s += ph.X[(size_t)a * N + i] * ph.X[(size_t)b * N + i];
-      xtx[(size_t)a * C0 + b] = xtx[(size_t)b * C0 + a] = s;
-    }
-  jacobi_eig(xtx, C0, d, v);
+  std::vector<double> Xb;
   int nz = 0;
-  for (int j = 0; j < C0; ++j) if (d[j] > d[C0 - 1] * 1e-15) ++nz;
-  std::vector<double> Xb((size_t)N * nz, 0.0);
-  for (int j = 0; j < nz; ++j) {
-    const int col = C0 - nz + j;
-    const double inv = 1.0 / std::sqrt(d[col]);
-    for (int a = 0; a < C0; ++a) {
-      const double w = v[(size_t)a * C0 + col] * inv;
-      if (w == 0.0) continue;
-      for (int64_t i = 0; i < N; ++i) Xb[(size_t)j * N + i] += ph.X[(size_t)a * N + i] * w;
-    }
-  }
+  get_basis(ph.X, N, ph.C, Xb, nz);                           // getBasis (src/Pheno.cpp:1660-1681)
   ph.X = Xb;
   ph.C = nz;
   // residualize_phenotypes (src/Pheno.cpp:1813-1829)
   ph.scale_Y.assign(P, 1.0);
-  for (int p = 0; p < P; ++p) {
+  for (int p = 0; p < P && !ph.bt; ++p) {
     std::vector<double> beta(nz, 0.0);
     for (int c = 0; c < nz; ++c)
       for (int64_t i = 0; i < N; ++i) beta[c] += ph.Y[(size_t)p * N + i] * ph.X[(size_t)c * N + i];

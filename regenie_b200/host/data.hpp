@@ -16,7 +16,13 @@ struct Snp {
   std::string id;
   uint64_t pos;
   std::string allele0, allele1;   // ALLELE0 (reference), ALLELE1 (effect)
-  uint64_t offset;                // row in the .bed
+  uint64_t offset;                // row in the .bed / file offset of the genotype block in the .bgen
+};
+
+// the samples of the genotype file after --keep/--remove (params.FID_IID_to_ind)
+struct SampleSet {
+  const std::vector<std::string>& keys;
+  const std::map<std::string, uint32_t>& key_to_ind;
 };
 
 struct BedFile {
@@ -49,11 +55,15 @@ struct Pheno {
   std::vector<double> neff, scale_Y;
   int64_t n_analyzed = 0;
   bool strict = false;
+  bool bt = false;
+  std::vector<double> Y_raw;      // N x P raw 0/1 values (binary traits)
 };
 
 // read_pheno_and_cov: raw values + masks, before prep_run
-void read_pheno_and_cov(const BedFile& g, const std::string& pheno_file, const std::string& covar_file,
-                        bool step2, bool strict, Pheno& ph, Log& log);
+void read_pheno_and_cov(const SampleSet& g, const std::string& pheno_file, const std::string& covar_file,
+                        bool step2, bool strict, bool bt, Pheno& ph, Log& log);
+// orthonormal basis of the columns of X [C0][N] (getBasis, src/Pheno.cpp:1660-1681)
+void get_basis(const std::vector<double>& X, int64_t N, int C0, std::vector<double>& Xb, int& nz);
 // setMasks + orthonormal basis + residualise/scale (prep_run); `extra_mask` = LOCO availability (step 2)
 void prep_run(Pheno& ph, const std::vector<uint8_t>* extra_mask, Log& log);
 

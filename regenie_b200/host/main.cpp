@@ -14,6 +14,10 @@
 #include <iomanip>
 
 #include "../../include/rg_b200.h"
+#include <thread>
+
+#include "bgen.hpp"
+#include "bt_null.hpp"
 #include "data.hpp"
 
 using namespace rgh;
@@ -22,12 +26,13 @@ namespace {
 
 struct Params {
   int step = 0;
-  std::string bed, bgen, pgen, pheno, covar, out, pred, lowmem_prefix;
+  std::string bed, bgen, pgen, sample, pheno, covar, out, pred, lowmem_prefix;
   std::string remove, keep, exclude, extract;
   int bsize = 0, cv = 5, l0 = 5, l1 = 5, gpu = 0;
   bool loocv = false, lowmem = false, ref_first = false, strict = false, bt = false, force_step1 = false;
-  bool rel_path = false;
-  double min_mac = 5.0;
+  bool rel_path = false, firth = false, approx = false;
+  double min_mac = 5.0, p_thresh = 0.05;
+  int threads = 0;
 };
 
 void rg_check(int rc) {
@@ -61,7 +66,11 @@ Params parse_cli(int argc, char** argv) {
     else if (a == "--minMAC") p.min_mac = atof(need(i).c_str());
     else if (a == "--lowmem-prefix") p.lowmem_prefix = need(i);
     else if (a == "--gpu") p.gpu = atoi(need(i).c_str());
-    else if (a == "--threads") need(i);            // host threads are irrelevant to the GPU path
+    else if (a == "--threads") p.threads = atoi(need(i).c_str());   // host threads: BGEN inflate only
+    else if (a == "--sample") p.sample = need(i);
+    else if (a == "--pThresh") p.p_thresh = atof(need(i).c_str());
+    else if (a == "--firth") p.firth = true;
+    else if (a == "--approx") p.approx = true;
     else if (a == "--loocv") p.loocv = true;
     else if (a == "--lowmem") p.lowmem = true;     // W stays resident in HBM; accepted for CLI parity
     else if (a == "--ref-first") p.ref_first = true;
@@ -74,17 +83,21 @@ Params parse_cli(int argc, char** argv) {
       std::cout << "rgb200: B200-native regenie Step 1 / Step 2 hot path\n"
                    "  --step 1|2 --bed PREFIX --phenoFile F [--covarFile F] --bsize N --out PREFIX\n"
                    "  [--pred LIST] [--loocv] [--lowmem] [--cv K] [--l0 R] [--l1 R] [--remove F] [--keep F]\n"
-                   "  [--exclude F] [--extract F] [--ref-first] [--minMAC x] [--strict] [--gpu ordinal]\n";
+                   "  [--exclude F] [--extract F] [--ref-first] [--minMAC x] [--strict] [--gpu ordinal]\n"
+                   "  step 2 binary traits: --bt [--firth --approx] [--pThresh p] with --bed or --bgen F [--sample F]\n";
       exit(0);
     } else {
       throw Fail("option '" + a + "' is outside the hot path covered by rgb200 (see DESIGN.md, out of scope)");
     }
   }
   if (p.step != 1 && p.step != 2) throw Fail("specify which mode regenie should be running using option '--step'.");
-  if (!p.bgen.empty()) throw Fail("--bgen input is not implemented yet in rgb200 (SURVEY 8 row a2, next).");
   if (!p.pgen.empty()) throw Fail("--pgen input is not implemented yet in rgb200 (SURVEY 8 row a3, next).");
-  if (p.bt) throw Fail("--bt is not implemented yet in rgb200 (SURVEY 8(f)1, next).");
-  if (p.bed.empty()) throw Fail("must specify the genotype file with --bed.");
+  if (p.bt && p.step == 1) throw Fail("--bt --step 1 (logistic level 1) is not implemented yet in rgb200 (SURVEY 8(f)1, next).");
+  if (!p.bgen.empty() && p.step == 1) throw Fail("--bgen input in --step 1 is not implemented yet in rgb200 (hard-call .bed only).");
+  if (!p.bgen.empty() && !p.bed.empty()) throw Fail("specify only one genotype input (--bed or --bgen).");
+  if (!p.bgen.empty() && !p.bt) throw Fail("--bgen --step 2 currently needs --bt in rgb200 (quantitative traits on dosages: next).");
+  if (p.firth && !p.approx) throw Fail("exact Firth (--firth without --approx) is outside the hot path covered by rgb200; use --firth --approx.");
+  if (p.bed.empty() && p.bgen.empty()) throw Fail("must specify the genotype file with --bed or --bgen.");
   if (p.pheno.empty()) throw Fail("must provide the phenotype file with --phenoFile.");
   if (p.out.empty()) throw Fail("must specify an output file prefix with --out.");
   if (p.bsize < 1) throw Fail("must specify the block size using '--bsize'.");
@@ -119,7 +132,7 @@ void run_step1(const Params& p, Log& log) {
   if (g.snps.size() > 1000000 && !p.force_step1)
     throw Fail("it is not recommened to use more than 1000000 variants in step 1 (otherwise use '--force-step1').");
   Pheno ph;
-  read_pheno_and_cov(g, p.pheno, p.covar, false, p.strict, ph, log);
+  read_pheno_and_cov(SampleSet{g.keys, g.key_to_ind}, p.pheno, p.covar, false, p.strict, false, ph, log);
   prep_run(ph, nullptr, log);
   const auto blocks = set_blocks(g.snps, p.bsize);
   const int nb = (int)blocks.size();
@@ -258,31 +271,29 @@ double get_logp(double t) {   // src/Regenie.cpp:1843-1857; chi2_1 sf = erfc(sqr
   return -lp;
 }
 
-void run_step2(const Params& p, Log& log) {
-  BedFile g;
-  g.open(p.bed, p.ref_first, read_id_list(p.exclude, 1), read_id_list(p.extract, 1), read_id_list(p.remove, 2),
-         read_id_list(p.keep, 2));
-  log << " * bim                 : [" << p.bed << ".bim] n_snps = " << g.snps.size() << "\n";
-  log << " * fam                 : [" << p.bed << ".fam] n_samples = " << g.keys.size() << "\n";
-  // pred.list (check_blup src/Pheno.cpp:1204-1229)
+// pred.list (check_blup src/Pheno.cpp:1204-1229)
+std::map<std::string, std::string> read_pred_list(const std::string& path) {
   std::map<std::string, std::string> blup_files;
-  {
-    std::ifstream fh(p.pred);
-    if (!fh) throw Fail("cannot open file : " + p.pred);
-    std::string line;
-    while (std::getline(fh, line)) {
-      auto t = split_ws(line);
-      if (t.empty()) continue;
-      if (t.size() != 2) throw Fail("step 1 list file is not in the right format : " + p.pred);
-      if (blup_files.count(t[0])) throw Fail("phenotype '" + t[0] + "' appears more than once in step 1 list file.");
-      blup_files[t[0]] = t[1];
-    }
+  std::ifstream fh(path);
+  if (!fh) throw Fail("cannot open file : " + path);
+  std::string line;
+  while (std::getline(fh, line)) {
+    auto t = split_ws(line);
+    if (t.empty()) continue;
+    if (t.size() != 2) throw Fail("step 1 list file is not in the right format : " + path);
+    if (blup_files.count(t[0])) throw Fail("phenotype '" + t[0] + "' appears more than once in step 1 list file.");
+    blup_files[t[0]] = t[1];
   }
-  Pheno ph;
-  read_pheno_and_cov(g, p.pheno, p.covar, true, p.strict, ph, log);
+  return blup_files;
+}
+
+// phenotypes + covariates + LOCO files for Step 2 (read_pheno_and_cov, blup_read, prep_run)
+void load_step2_inputs(const Params& p, const SampleSet& g, Pheno& ph, std::vector<Loco>& locos, Log& log) {
+  const auto blup_files = read_pred_list(p.pred);
+  read_pheno_and_cov(g, p.pheno, p.covar, true, p.strict, p.bt, ph, log);
   const int64_t N = ph.N;
   const int P = ph.P;
-  std::vector<Loco> locos(P);
+  locos.resize(P);
   std::vector<uint8_t> extra((size_t)N * P, 0);
   for (int i = 0; i < P; ++i) {
     auto it = blup_files.find(ph.names[i]);
@@ -297,6 +308,37 @@ void run_step2(const Params& p, Log& log) {
     }
   }
   prep_run(ph, &extra, log);
+}
+
+// blup_read_chr (src/Step2_Models.cpp:96-124): LOCO prediction of trait i for one chromosome
+std::vector<double> blup_for_chr(const Loco& loco, const SampleSet& g, const Pheno& ph, int i, int chrom) {
+  const int64_t N = ph.N;
+  std::vector<double> blup(N, 0.0);
+  const auto& row = loco.rows[chrom - 1];
+  if (row.empty()) throw Fail("blup file for phenotype '" + ph.names[i] + "' has no row for chromosome " + std::to_string(chrom));
+  for (size_t c = 0; c < loco.ids.size(); ++c) {
+    auto k = g.key_to_ind.find(loco.ids[c]);
+    if (k == g.key_to_ind.end()) continue;
+    const uint32_t s = k->second;
+    if (!ph.in_analysis[s] || !ph.mask[(size_t)i * N + s]) continue;
+    if (row[c] == "NA") throw Fail("individual has missing predictions (FID_IID=" + loco.ids[c] + ")");
+    blup[s] = convert_double(row[c]);
+  }
+  return blup;
+}
+
+void run_step2_qt(const Params& p, Log& log) {
+  BedFile g;
+  g.open(p.bed, p.ref_first, read_id_list(p.exclude, 1), read_id_list(p.extract, 1), read_id_list(p.remove, 2),
+         read_id_list(p.keep, 2));
+  log << " * bim                 : [" << p.bed << ".bim] n_snps = " << g.snps.size() << "\n";
+  log << " * fam                 : [" << p.bed << ".fam] n_samples = " << g.keys.size() << "\n";
+  const SampleSet ss{g.keys, g.key_to_ind};
+  Pheno ph;
+  std::vector<Loco> locos;
+  load_step2_inputs(p, ss, ph, locos, log);
+  const int64_t N = ph.N;
+  const int P = ph.P;
   const auto blocks = set_blocks(g.snps, p.bsize);
   log << " * # blocks            : [" << blocks.size() << "]\n";
 
@@ -331,24 +373,14 @@ void run_step2(const Params& p, Log& log) {
       log << "Chromosome " << chrom << "\n";
       // blup_read_chr + compute_res (src/Step2_Models.cpp:96-124, src/Data.cpp:2386-2404)
       for (int i = 0; i < P; ++i) {
-        std::vector<double> blup(N, 0.0);
-        const auto& row = locos[i].rows[chrom - 1];
-        if (row.empty()) throw Fail("blup file for phenotype '" + ph.names[i] + "' has no row for chromosome " + std::to_string(chrom));
-        for (size_t c = 0; c < locos[i].ids.size(); ++c) {
-          auto k = g.key_to_ind.find(locos[i].ids[c]);
-          if (k == g.key_to_ind.end()) continue;
-          const uint32_t s = k->second;
-          if (!ph.in_analysis[s] || !ph.mask[(size_t)i * N + s]) continue;
-          if (row[c] == "NA") throw Fail("individual has missing predictions (FID_IID=" + locos[i].ids[c] + ")");
-          blup[s] = convert_double(row[c]);
-        }
-        double ss = 0.0;
+        const std::vector<double> blup = blup_for_chr(locos[i], ss, ph, i, chrom);
+        double ssq = 0.0;
         for (int64_t s = 0; s < N; ++s) {
           const double r = (ph.Y[(size_t)i * N + s] - blup[s]) * ph.mask[(size_t)i * N + s];
           res[(size_t)i * N + s] = r;
-          ss += r * r;
+          ssq += r * r;
         }
-        const double psd = std::sqrt(ss) / std::sqrt(ph.neff[i] - ph.C);
+        const double psd = std::sqrt(ssq) / std::sqrt(ph.neff[i] - ph.C);
         for (int64_t s = 0; s < N; ++s) res[(size_t)i * N + s] /= psd;
         scf[i] = ph.scale_Y[i] * psd;
       }
@@ -380,6 +412,157 @@ void run_step2(const Params& p, Log& log) {
   }
   log << "\nNumber of ignored tests due to low MAC or low variance : " << n_ignored << "\n";
   rg_destroy(h);
+}
+
+// Step 2 for binary traits (--bt [--firth --approx]) on BGEN dosages or .bed hard calls.
+// Control flow of Data::test_snps_fast for trait_mode 1 (src/Data.cpp:2230-2383): per chromosome the null
+// logistic / null Firth fits (host, O(N C^2)), per block the score test and the Firth fallback (GPU).
+void run_step2_bt(const Params& p, Log& log) {
+  const bool use_bgen = !p.bgen.empty();
+  BedFile gb;
+  BgenFile gg;
+  const auto excl = read_id_list(p.exclude, 1), extr = read_id_list(p.extract, 1), rem = read_id_list(p.remove, 2),
+             keep = read_id_list(p.keep, 2);
+  if (use_bgen) {
+    gg.open(p.bgen, p.sample, p.ref_first, excl, extr, rem, keep);
+    log << " * bgen                : [" << p.bgen << "] n_snps = " << gg.snps.size() << ", n_samples = " << gg.keys.size() << "\n";
+  } else {
+    gb.open(p.bed, p.ref_first, excl, extr, rem, keep);
+    log << " * bim                 : [" << p.bed << ".bim] n_snps = " << gb.snps.size() << "\n";
+    log << " * fam                 : [" << p.bed << ".fam] n_samples = " << gb.keys.size() << "\n";
+  }
+  const std::vector<Snp>& snps = use_bgen ? gg.snps : gb.snps;
+  const std::vector<std::string>& keys = use_bgen ? gg.keys : gb.keys;
+  const std::vector<int32_t>& sample_idx = use_bgen ? gg.sample_idx : gb.sample_idx;
+  const size_t n_file = use_bgen ? gg.n_file : gb.keys_file.size();
+  const SampleSet ss{keys, use_bgen ? gg.key_to_ind : gb.key_to_ind};
+  Pheno ph;
+  std::vector<Loco> locos;
+  load_step2_inputs(p, ss, ph, locos, log);
+  const int64_t N = ph.N;
+  const int P = ph.P, C = ph.C;
+  const auto blocks = set_blocks(snps, p.bsize);
+  log << " * # blocks            : [" << blocks.size() << "]\n";
+  const double z_thr = z_threshold(p.p_thresh);
+  if (p.firth) log << " * using approximate Firth correction for logistic regression p-values less than " << p.p_thresh << "\n";
+
+  rg_step2_config cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.device = p.gpu; cfg.n_samples = N; cfg.n_cov = C; cfg.n_pheno = P; cfg.max_block_size = p.bsize;
+  cfg.n_analyzed = ph.n_analyzed; cfg.strict_mode = ph.strict;
+  rg_handle h = nullptr;
+  rg_check(rg_step2_create(&cfg, ph.X.data(), ph.mask.data(), ph.in_analysis.data(), &h));
+
+  std::vector<std::ofstream> outs(P);
+  for (int i = 0; i < P; ++i) {
+    outs[i].open(p.out + "_" + ph.names[i] + ".regenie");
+    if (!outs[i]) throw Fail("cannot write to file : " + p.out + "_" + ph.names[i] + ".regenie");
+    outs[i] << "CHROM GENPOS ID ALLELE0 ALLELE1 A1FREQ " << (use_bgen ? "INFO " : "") << "N TEST BETA SE CHISQ LOG10P EXTRA\n";
+  }
+  const int bsz = p.bsize;
+  const int threads = p.threads > 0 ? p.threads : (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  std::vector<uint8_t> probs((size_t)bsz * n_file * 2), pmiss((size_t)bsz * n_file), rows;
+  if (!use_bgen) rows.resize((size_t)bsz * gb.row_stride);
+  std::vector<double> af((size_t)bsz * P), mac((size_t)bsz * P), stat((size_t)bsz * P), beta((size_t)bsz * P),
+      se((size_t)bsz * P), chisq((size_t)bsz * P), info((size_t)bsz * P), af_all(bsz), mac_all(bsz), scale_fac(bsz);
+  std::vector<int32_t> ns((size_t)bsz * P), ns_all(bsz), flags(bsz);
+  rg_s2_out out{af.data(), ns.data(), mac.data(), af_all.data(), ns_all.data(), mac_all.data(), flags.data(),
+                scale_fac.data(), stat.data(), beta.data(), se.data(), chisq.data()};
+  const bool subset = keys.size() != n_file;
+  int cur_chr = -1;
+  size_t n_ignored = 0, n_firth = 0, n_fail = 0;
+  for (size_t b = 0; b < blocks.size(); ++b) {
+    const int chrom = blocks[b].chrom, bs = blocks[b].size;
+    if (chrom != cur_chr) {
+      cur_chr = chrom;
+      log << "Chromosome " << chrom << "\n";
+      std::vector<double> gsm((size_t)P * N), gs((size_t)P * N), yres((size_t)P * N), xg((size_t)P * C * N), off;
+      if (p.firth) off.resize((size_t)P * N);
+      for (int i = 0; i < P; ++i) {
+        const std::vector<double> blup = blup_for_chr(locos[i], ss, ph, i, chrom);
+        const BtNull nm = fit_bt_null(ph.names[i], &ph.Y_raw[(size_t)i * N], ph.X.data(), N, C, blup.data(),
+                                      &ph.mask[(size_t)i * N], p.firth);
+        std::copy(nm.gamma_sqrt_mask.begin(), nm.gamma_sqrt_mask.end(), gsm.begin() + (size_t)i * N);
+        std::copy(nm.gamma_sqrt.begin(), nm.gamma_sqrt.end(), gs.begin() + (size_t)i * N);
+        std::copy(nm.yres.begin(), nm.yres.end(), yres.begin() + (size_t)i * N);
+        std::copy(nm.x_gamma.begin(), nm.x_gamma.end(), xg.begin() + (size_t)i * C * N);
+        if (p.firth) std::copy(nm.firth_offset.begin(), nm.firth_offset.end(), off.begin() + (size_t)i * N);
+      }
+      rg_s2_bt_chr st{gsm.data(), gs.data(), yres.data(), xg.data(), ph.Y_raw.data(), p.firth ? off.data() : nullptr};
+      rg_check(rg_s2_set_chr_bt(h, &st));
+    }
+    if (use_bgen) {
+      gg.read_block(blocks[b].first, bs, probs.data(), pmiss.data(), threads);
+    } else {
+      // hard calls as 8-bit probabilities: 00 hom A1 -> P(AA) = 1, 10 het -> P(AB) = 1, 11 -> 0, 01 missing
+      gb.read_rows(blocks[b].first, bs, rows.data());
+      for (int v = 0; v < bs; ++v)
+        for (size_t s = 0; s < n_file; ++s) {
+          const int code = (rows[(size_t)v * gb.row_stride + (s >> 2)] >> (2 * (s & 3))) & 3;
+          uint8_t* q = &probs[((size_t)v * n_file + s) * 2];
+          q[0] = code == 0 ? 255 : 0;
+          q[1] = code == 2 ? 255 : 0;
+          pmiss[(size_t)v * n_file + s] = code == 1 ? 0x82 : 0x02;
+        }
+    }
+    rg_check(rg_s2_block_bgen8_bt(h, probs.data(), pmiss.data(), (int64_t)n_file, bs, subset ? sample_idx.data() : nullptr,
+                                  p.ref_first, p.min_mac, &out, info.data()));
+    // Firth fallback for |z| above the --pThresh threshold (check_pval_snp, src/Step2_Models.cpp:1988-2041)
+    std::vector<int32_t> sel_v, sel_t, fstatus;
+    std::vector<double> fbeta, fse, flrt;
+    std::map<std::pair<int, int>, int> fidx;
+    if (p.firth) {
+      for (int v = 0; v < bs; ++v) {
+        if (flags[v] & (1 | 16)) continue;
+        for (int i = 0; i < P; ++i) {
+          const size_t e = (size_t)v * P + i;
+          if (mac[e] < p.min_mac || !(std::fabs(stat[e]) > z_thr)) continue;
+          fidx[{v, i}] = (int)sel_v.size();
+          sel_v.push_back(v); sel_t.push_back(i);
+        }
+      }
+      const size_t nsel = sel_v.size();
+      fbeta.resize(nsel); fse.resize(nsel); flrt.resize(nsel); fstatus.resize(nsel);
+      rg_check(rg_s2_firth(h, (int32_t)nsel, sel_v.data(), sel_t.data(), fbeta.data(), fse.data(), flrt.data(), fstatus.data()));
+      n_firth += nsel;
+    }
+    for (int v = 0; v < bs; ++v) {
+      if (flags[v] & (1 | 16)) { ++n_ignored; continue; }
+      const Snp& s = snps[blocks[b].first + v];
+      std::ostringstream head;
+      head << s.chrom << " " << s.pos << " " << s.id << " " << s.allele0 << " " << s.allele1 << " ";
+      for (int i = 0; i < P; ++i) {
+        const size_t e = (size_t)v * P + i;
+        if (mac[e] < p.min_mac) continue;
+        double bo = beta[e], so = se[e], co = chisq[e];
+        bool pass = true;
+        auto f = fidx.find({v, i});
+        if (f != fidx.end()) {
+          if ((fstatus[f->second] & 15) == 0) { bo = fbeta[f->second]; so = fse[f->second]; co = flrt[f->second]; }
+          else { pass = false; ++n_fail; }
+        }
+        std::ostringstream buf;
+        buf << head.str() << af[e] << " ";
+        if (use_bgen) buf << info[e] << " ";
+        buf << ns[e] << " ADD ";
+        if (so >= 0 && !std::isnan(so)) buf << bo << ' ' << so;
+        else buf << "NA NA";
+        const double lp = get_logp(co);
+        if (pass && co >= 0 && !std::isnan(lp)) buf << ' ' << co << ' ' << lp;
+        else buf << " NA NA";
+        buf << (pass ? " NA\n" : " TEST_FAIL\n");
+        outs[i] << buf.str();
+      }
+    }
+    log << " block [" << b + 1 << "/" << blocks.size() << "] : done\n";
+  }
+  log << "\nNumber of ignored tests due to low MAC or low variance : " << n_ignored << "\n";
+  if (p.firth) log << "Number of tests with Firth correction : " << n_firth << " (" << n_fail << " failed)\n";
+  rg_destroy(h);
+}
+
+void run_step2(const Params& p, Log& log) {
+  if (p.bt) run_step2_bt(p, log); else run_step2_qt(p, log);
 }
 
 }  // namespace

@@ -94,3 +94,83 @@ def test_driver_rejects_out_of_scope_options(tmp_path):
     r = subprocess.run([RGB, "--step", "2", "--bed", "x", "--phenoFile", "y", "--bsize", "10", "--out",
                         str(tmp_path / "o"), "--pred", "z", "--spa"], capture_output=True, text=True)
     assert r.returncode != 0 and "ERROR" in r.stdout
+
+
+def _write_zero_loco(tmp_path, golden_dir, traits):
+    """LOCO files as the reference's BT Step 1 writes them for example/ (one chromosome): the row of chr 1
+    is identically 0 (src/Data.cpp:1847-1858); the other rows are never read for this fileset."""
+    from oracle import bgen
+    b = bgen.Bgen(golden_dir + "/example.bgen")
+    lst = tmp_path / "fit_bin_out_pred.list"
+    with open(lst, "w") as fl:
+        for j, t in enumerate(traits):
+            f = tmp_path / ("fit_bin_out_%d.loco" % (j + 1))
+            with open(f, "w") as fh:
+                fh.write("FID_IID " + " ".join(b.sample_ids) + "\n")
+                for c in range(1, 24):
+                    fh.write(str(c) + " " + " ".join(["0"] * len(b.sample_ids)) + "\n")
+            fl.write("%s %s\n" % (t, f))
+    return str(lst)
+
+
+def test_step2_bt_firth_bgen_reproduces_reference_golden_file(tmp_path, golden_dir):
+    """The reference's documented Step-2 command (docs/docs/options.md:20-51, test/test_bash.sh) through rgb200:
+    --step 2 --bgen example.bgen --bt --firth --approx --pThresh 0.01 --remove ... ; its output for Y1 must
+    reproduce the golden file example/test_bin_out_firth_Y1.regenie that the reference ships: text columns
+    (CHROM GENPOS ID ALLELE0 ALLELE1 A1FREQ INFO N TEST ... EXTRA) exactly, BETA/SE/CHISQ/LOG10P to the
+    printed 6 significant digits (1e-4: the golden file was produced by an -ffast-math build)."""
+    d = golden_dir
+    pred = _write_zero_loco(tmp_path, d, ["Y1", "Y2"])
+    out = str(tmp_path / "test_bin_out_firth")
+    run(["--step", "2", "--bgen", d + "/example.bgen", "--covarFile", d + "/covariates.txt", "--phenoFile",
+         d + "/phenotype_bin.txt", "--remove", d + "/fid_iid_to_remove.txt", "--bsize", "200", "--bt", "--firth",
+         "--approx", "--pThresh", "0.01", "--pred", pred, "--out", out])
+    got = open(out + "_Y1.regenie").read().splitlines()
+    ref = open(d + "/test_bin_out_firth_Y1.regenie").read().splitlines()
+    assert got[0] == ref[0]
+    assert len(got) == len(ref) == 1001
+    for x, y in zip(got[1:], ref[1:]):
+        tx, ty = x.split(), y.split()
+        assert tx[:9] == ty[:9], (x, y)
+        assert tx[13] == ty[13]
+        for a, c in zip(tx[9:13], ty[9:13]):
+            assert close(a, c, rtol=1e-4), (x, y)
+    assert os.path.getsize(out + "_Y2.regenie") > 0
+
+
+def test_step2_bt_on_bed_hard_calls(tmp_path, golden_dir):
+    """--bt --firth --approx on a .bed fileset (hard calls go through the same dosage kernels) vs the oracle."""
+    import math
+
+    from oracle import plink, prep, step2, step2_bt
+    d = golden_dir
+    pred = _write_zero_loco(tmp_path, d, ["Y1", "Y2"])
+    out = str(tmp_path / "bt_bed")
+    run(["--step", "2", "--bed", d + "/example", "--covarFile", d + "/covariates.txt", "--phenoFile",
+         d + "/phenotype_bin.txt", "--bsize", "300", "--bt", "--firth", "--approx", "--pThresh", "0.05",
+         "--pred", pred, "--out", out])
+    bim = plink.read_bim(d + "/example.bim")
+    keys, _ = plink.read_fam(d + "/example.fam")
+    G = plink.decode_bed(plink.read_bed_rows(d + "/example.bed", len(keys), bim.offset), len(keys))
+    pr = prep.prepare(keys, d + "/phenotype_bin.txt", d + "/covariates.txt", bt=True, step=2)
+    z_thr = math.sqrt(3.841458820694124)
+    for j, name in enumerate(["Y1", "Y2"]):
+        y, mask = pr.Y_raw[:, j], pr.mask[:, j]
+        st = step2_bt.BtChrom(y, pr.X, np.zeros(len(keys)), mask)
+        got = open(out + "_%s.regenie" % name).read().splitlines()
+        assert got[0] == step2.HEADER.strip()
+        k = 1
+        for v in range(len(bim.ids)):
+            g = G[v]                                        # counts of ALLELE1, -3 = missing
+            r = step2_bt.score_bt(g, np.zeros(len(g)), pr.in_analysis, mask, y, st, z_thr, len(keys))
+            if r is None:
+                continue
+            row = step2.sumstats_row(int(bim.chrom[v]), int(bim.pos[v]), bim.ids[v], bim.allele0[v], bim.allele1[v], r["af"], r["n"],
+                                     r["beta"], r["se"], r["chisq"], r["logp"], test_pass=not r["test_fail"]).split()
+            tx = got[k].split()
+            k += 1
+            assert tx[:8] == row[:8], (tx, row)
+            for a, c in zip(tx[8:12], row[8:12]):
+                assert close(a, c), (tx, row)
+            assert tx[12] == row[12]
+        assert k == len(got)
