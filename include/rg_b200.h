@@ -206,6 +206,16 @@ int rg_s2_block_bgen8_bt(rg_handle h, const uint8_t* probs, const uint8_t* ploid
                          const rg_s2_out* out, double* info_out);
 
 /*
+ * rg_s2_block_bgen8 -- the quantitative-trait score test of rg_s2_block_bed (after rg_s2_set_chr) on BGEN
+ * 8-bit probability rows: parseSnpfromBGEN dosages + INFO (src/Geno.cpp:2186-2345) then check_sparse_G,
+ * residualize_geno and compute_score_qt (src/Step2_Models.cpp:343-467).  No allele flip for QTs (with_flip is
+ * false for trait_mode 0, src/Data.cpp:2108).
+ */
+int rg_s2_block_bgen8(rg_handle h, const uint8_t* probs, const uint8_t* ploidy_missing, int64_t n_file,
+                      int32_t bs, const int32_t* sample_idx, int32_t ref_first, double min_mac,
+                      const rg_s2_out* out, double* info_out);
+
+/*
  * rg_s2_firth -- approximate Firth test for selected (variant, trait) pairs of the resident block; replaces
  * fit_firth_logistic_snp_fast + fit_firth_pseudo / fit_firth (src/Step2_Models.cpp:1158-1252, 1527-1737).
  * beta is reported on the original allele coding; status != 0 in the low 4 bits = did not converge.

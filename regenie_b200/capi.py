@@ -46,7 +46,7 @@ EXPORTS = [
     "rg_last_error", "rg_version", "rg_device_count", "rg_step1_create", "rg_destroy", "rg_sync",
     "rg_l0_block_bed", "rg_l0_status", "rg_l0_fetch_W", "rg_l1_fit", "rg_loco", "rg_step2_create",
     "rg_s2_set_chr", "rg_s2_block_bed", "rg_W_info", "rg_debug_fetch", "rg_launch_count", "rg_stream",
-    "rg_set_timing", "rg_get_timing", "rg_fence", "rg_s2_set_chr_bt", "rg_s2_block_bgen8_bt", "rg_s2_firth",
+    "rg_set_timing", "rg_get_timing", "rg_fence", "rg_s2_set_chr_bt", "rg_s2_block_bgen8_bt", "rg_s2_block_bgen8", "rg_s2_firth",
 ]
 
 _lib = None
@@ -245,10 +245,15 @@ class Step2:
         st = S2BtChr(*[None if a is None else a.ctypes.data for a in keep])
         check(L.rg_s2_set_chr_bt(self.h, C.byref(st)))
 
-    def block_bgen8_bt(self, probs, missing=None, sample_idx=None, ref_first=False, min_mac=5.0):
+    def block_bgen8(self, probs, missing=None, sample_idx=None, ref_first=False, min_mac=5.0):
+        """Quantitative traits on dosages (after set_chr)."""
+        return self.block_bgen8_bt(probs, missing, sample_idx, ref_first, min_mac, _fn="rg_s2_block_bgen8")
+
+    def block_bgen8_bt(self, probs, missing=None, sample_idx=None, ref_first=False, min_mac=5.0,
+                       _fn="rg_s2_block_bgen8_bt"):
         """probs u8 [bs][n_file][2]; missing u8 [bs][n_file] (bit 7 = missing) or None."""
         L = lib()
-        L.rg_s2_block_bgen8_bt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+        getattr(L, _fn).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                            C.c_int32, C.c_double, C.c_void_p, C.c_void_p]
         probs = np.ascontiguousarray(probs, dtype=np.uint8)
         bs, n_file, P = probs.shape[0], probs.shape[1], self.P
@@ -262,7 +267,7 @@ class Step2:
                                                 "scale_fac", "stat", "beta", "se", "chisq")])
         if sample_idx is not None:
             sample_idx = np.ascontiguousarray(sample_idx, dtype=np.int32)
-        check(L.rg_s2_block_bgen8_bt(self.h, _ptr(probs), _ptr(missing), n_file, bs, _ptr(sample_idx),
+        check(getattr(L, _fn)(self.h, _ptr(probs), _ptr(missing), n_file, bs, _ptr(sample_idx),
                                      int(ref_first), float(min_mac), C.byref(so), _ptr(o["info"])))
         return o
 

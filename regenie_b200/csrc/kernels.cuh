@@ -164,6 +164,9 @@ struct S2FinalizeArgs {
   const double* YtX;         // [P][C]
   const double* XmX;         // [P][C][C]
   const double* scf_sv;      // [P]
+  const double* nz_count = nullptr;   // [rows_p] non-zero dosages among analysed samples (dosage input only)
+  const double* info_sums = nullptr;  // [rows_p][dp] sum (4 p0 + p1) F (dosage input only)
+  double* info = nullptr;             // [bs x P] INFO (dosage input only)
   double *af, *mac, *af_all, *mac_all, *scale_fac, *stat, *beta, *se, *chisq;
   int32_t *ns, *ns_all, *flags;
 };
@@ -189,6 +192,8 @@ void launch_dosage_relayout(const uint8_t* probs, const uint8_t* miss, int64_t n
 void launch_dosage_stats(const uint32_t* dz, int64_t npad, const double* F, int dp, const int4* chunks, int nchunks,
                          int rows_p, double* part, double* sums, double* nnz, double* n510, cudaStream_t s);
 void launch_s2_bt_finalize(const S2BtFinalizeArgs& a, cudaStream_t s);
+// integer-unit sums [rows][4][dp] -> dosage-unit [rows][3][dp] (S1, S2, Sm) + [rows][dp] (Se)
+void launch_dosage_scale(const double* sums4, int rows_p, int dp, double* sums3, double* se, cudaStream_t s);
 
 // ---- s2_firth.cu
 struct FirthArgs {

@@ -278,6 +278,79 @@ static void s2_block_bgen8_bt(rg_ctx* h, const uint8_t* probs, const uint8_t* mi
   RG_CUDA(cudaStreamSynchronize(s));
 }
 
+// quantitative traits on 8-bit dosages: same statistics kernel, closed-form finish of s2_kernels.cu
+static void s2_block_bgen8_qt(rg_ctx* h, const uint8_t* probs, const uint8_t* miss, int64_t n_file, int bs,
+                              const int32_t* sample_idx, int ref_first, double min_mac, const rg_s2_out* out,
+                              double* info_out) {
+  RG_CHECK(h->kind == 2, "handle is not a Step-2 handle");
+  RG_CHECK(bs > 0 && bs <= h->bs_max, "block size out of range");
+  RG_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const int P = h->P, C = h->C, dp = h->dp;
+  const int rows_p = (int)round_up(bs, kRowPad);
+  const int64_t Npad = h->Npad;
+  {
+    std::vector<int32_t> host_idx;
+    if (sample_idx) {
+      host_idx.assign(sample_idx, sample_idx + h->N);
+      if (!h->file_idx_valid || h->cached_sample_idx != host_idx) {
+        build_file_idx_public(h, host_idx.data());
+        h->cached_sample_idx = host_idx;
+      }
+    } else if (!h->file_idx_valid || !h->cached_sample_idx.empty()) {
+      build_file_idx_public(h, nullptr);
+      h->cached_sample_idx.clear();
+    }
+  }
+  const uint8_t *probs_d = probs, *miss_d = miss;
+  if (!is_device_pointer(probs)) {
+    h->probs_dev.alloc((size_t)h->bs_max * n_file * 2);
+    copy_to_device(h->probs_dev.p, probs, (size_t)bs * n_file * 2, s);
+    probs_d = h->probs_dev.p;
+    if (miss) {
+      h->miss_dev.alloc((size_t)h->bs_max * n_file);
+      copy_to_device(h->miss_dev.p, miss, (size_t)bs * n_file, s);
+      miss_d = h->miss_dev.p;
+    }
+  }
+  h->dz.alloc((size_t)h->rows_p_max * Npad);
+  h->bt_part.alloc((size_t)h->nchunks * h->rows_p_max * 4 * dp);
+  h->bt_sums.alloc((size_t)h->rows_p_max * 4 * dp);
+  h->bt_nnz.alloc(h->rows_p_max); h->bt_n510.alloc(h->rows_p_max);
+  h->s2_sums.alloc((size_t)h->rows_p_max * 3 * dp);
+  h->bt_xtwg.alloc((size_t)h->rows_p_max * dp);            // Se in dosage units
+  h->bt_info.alloc((size_t)h->bs_max * P);
+  const size_t nd = (size_t)h->bs_max * (7 * (size_t)P + 3), ni = (size_t)h->bs_max * ((size_t)P + 2);
+  h->s2_out_d.alloc(nd);
+  h->s2_out_i.alloc(ni);
+  launch_dosage_relayout(probs_d, miss_d, n_file, bs, rows_p, h->file_idx_pad.p, ref_first, h->dz.p, Npad, s);
+  launch_dosage_stats(h->dz.p, Npad, h->F.p, dp, h->chunks.p, h->nchunks, rows_p, h->bt_part.p, h->bt_sums.p,
+                      h->bt_nnz.p, h->bt_n510.p, s);
+  launch_dosage_scale(h->bt_sums.p, rows_p, dp, h->s2_sums.p, h->bt_xtwg.p, s);
+  S2FinalizeArgs a;
+  a.bs = bs; a.C = C; a.P = P; a.dp = dp; a.strict = h->strict;
+  a.n_analyzed = h->n_analyzed; a.n_samples = h->N; a.min_mac = min_mac; a.numtol = 1e-6;
+  a.sums = h->s2_sums.p; a.mask_count = h->s2_maskcount.p; a.YtX = h->s2_YtX.p; a.XmX = h->s2_XmX.p;
+  a.scf_sv = h->s2_scf.p; a.nz_count = h->bt_nnz.p; a.info_sums = h->bt_xtwg.p; a.info = h->bt_info.p;
+  double* d = h->s2_out_d.p;
+  const size_t bp = (size_t)h->bs_max * P, b1 = h->bs_max;
+  a.af = d; a.mac = d + bp; a.stat = d + 2 * bp; a.beta = d + 3 * bp; a.se = d + 4 * bp; a.chisq = d + 5 * bp;
+  a.af_all = d + 6 * bp; a.mac_all = d + 6 * bp + b1; a.scale_fac = d + 6 * bp + 2 * b1;
+  int32_t* ii = h->s2_out_i.p;
+  a.ns = ii; a.ns_all = ii + bp; a.flags = ii + bp + b1;
+  launch_s2_finalize(a, s);
+  h->launches += 6;
+  const size_t vp = (size_t)bs * P * 8, v1 = (size_t)bs * 8;
+  auto cp = [&](void* dst, const void* src, size_t bytes) {
+    if (dst) RG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+  };
+  cp(out->af, a.af, vp); cp(out->mac, a.mac, vp); cp(out->stat, a.stat, vp); cp(out->beta, a.beta, vp);
+  cp(out->se, a.se, vp); cp(out->chisq, a.chisq, vp); cp(out->af_all, a.af_all, v1); cp(out->mac_all, a.mac_all, v1);
+  cp(out->scale_fac, a.scale_fac, v1); cp(out->ns, a.ns, (size_t)bs * P * 4); cp(out->ns_all, a.ns_all, (size_t)bs * 4);
+  cp(out->flags, a.flags, (size_t)bs * 4); cp(info_out, a.info, vp);
+  RG_CUDA(cudaStreamSynchronize(s));
+}
+
 static void s2_firth(rg_ctx* h, int n_sel, const int32_t* var_idx, const int32_t* trait_idx, double* beta, double* se,
                      double* lrt, int32_t* status) {
   RG_CHECK(h->kind == 2 && h->bt_chr_set && h->s2_last_bs > 0, "rg_s2_firth needs a resident dosage block");
@@ -328,6 +401,16 @@ int rg_s2_block_bgen8_bt(rg_handle h, const uint8_t* probs, const uint8_t* ploid
   RG_API_BEGIN
   RG_CHECK(h && probs && out, "null argument");
   s2_block_bgen8_bt(h, probs, ploidy_missing, n_file, bs, sample_idx, ref_first, min_mac, out, info_out);
+  RG_CUDA(cudaGetLastError());
+  RG_API_END
+}
+
+int rg_s2_block_bgen8(rg_handle h, const uint8_t* probs, const uint8_t* ploidy_missing, int64_t n_file, int32_t bs,
+                      const int32_t* sample_idx, int32_t ref_first, double min_mac, const rg_s2_out* out,
+                      double* info_out) {
+  RG_API_BEGIN
+  RG_CHECK(h && probs && out, "null argument");
+  s2_block_bgen8_qt(h, probs, ploidy_missing, n_file, bs, sample_idx, ref_first, min_mac, out, info_out);
   RG_CUDA(cudaGetLastError());
   RG_API_END
 }

@@ -197,6 +197,24 @@ __global__ void dosage_reduce_kernel(const double* __restrict__ part, int nchunk
   sums[e] = s;
 }
 
+__global__ void dosage_scale_kernel(const double* __restrict__ s4, int rows_p, int dp, double* __restrict__ s3,
+                                    double* __restrict__ se) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= (int64_t)rows_p * dp) return;
+  const int64_t r = e / dp, c = e % dp;
+  const double k = 1.0 / 255.0;
+  const double* in = s4 + (r * 4) * dp + c;
+  double* o = s3 + (r * 3) * dp + c;
+  o[0] = in[0] * k;
+  o[dp] = in[dp] * k * k;
+  o[2 * dp] = in[2 * dp];
+  se[r * dp + c] = in[3 * dp] * k;
+}
+
+void launch_dosage_scale(const double* sums4, int rows_p, int dp, double* sums3, double* se, cudaStream_t s) {
+  dosage_scale_kernel<<<(unsigned)ceil_div((int64_t)rows_p * dp, 256), 256, 0, s>>>(sums4, rows_p, dp, sums3, se);
+}
+
 void launch_dosage_relayout(const uint8_t* probs, const uint8_t* miss, int64_t n_file, int bs, int rows_p,
                             const int32_t* file_idx_pad, int ref_first, uint32_t* dz, int64_t npad, cudaStream_t s) {
   dim3 grid((unsigned)ceil_div(npad, 256), rows_p);

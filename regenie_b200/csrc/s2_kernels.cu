@@ -103,12 +103,17 @@ __global__ void s2_finalize_kernel(S2FinalizeArgs a) {
     const double tp = S1[cm + p];
     a.ns[(int64_t)i * P + p] = (int)ns;
     a.mac[(int64_t)i * P + p] = fmin(tp, 2.0 * ns - tp);
-    a.af[(int64_t)i * P + p] = tp / (2.0 * ns);
+    const double af = tp / (2.0 * ns);
+    a.af[(int64_t)i * P + p] = af;
+    if (a.info) {                                                    // compute_aaf_info, src/Geno.cpp:3140
+      const double num = a.info_sums[(int64_t)i * dp + cm + p] - S2[cm + p];
+      a.info[(int64_t)i * P + p] = (af == 0.0 || af == 1.0) ? 1.0 : 1.0 - num / (2.0 * ns * af * (1.0 - af));
+    }
   }
   if (mac1 < a.min_mac) flags |= 1;                                  // src/Geno.cpp:3104-3105
   // non-zero entries among analysed samples after mean imputation (check_sparse_G)
   const double n2 = (S2[0] - S1[0]) * 0.5, n1 = S1[0] - 2.0 * n2;
-  const double nnz = n1 + n2 + ((mu != 0.0) ? nm : 0.0);
+  const double nnz = (a.nz_count ? a.nz_count[i] : n1 + n2) + ((mu != 0.0) ? nm : 0.0);
   const bool sparse = nnz <= (double)a.n_samples * 0.5;
   if (sparse) flags |= 4;
   double xtg2 = 0.0;

@@ -95,7 +95,6 @@ Params parse_cli(int argc, char** argv) {
   if (p.bt && p.step == 1) throw Fail("--bt --step 1 (logistic level 1) is not implemented yet in rgb200 (SURVEY 8(f)1, next).");
   if (!p.bgen.empty() && p.step == 1) throw Fail("--bgen input in --step 1 is not implemented yet in rgb200 (hard-call .bed only).");
   if (!p.bgen.empty() && !p.bed.empty()) throw Fail("specify only one genotype input (--bed or --bgen).");
-  if (!p.bgen.empty() && !p.bt) throw Fail("--bgen --step 2 currently needs --bt in rgb200 (quantitative traits on dosages: next).");
   if (p.firth && !p.approx) throw Fail("exact Firth (--firth without --approx) is outside the hot path covered by rgb200; use --firth --approx.");
   if (p.bed.empty() && p.bgen.empty()) throw Fail("must specify the genotype file with --bed or --bgen.");
   if (p.pheno.empty()) throw Fail("must provide the phenotype file with --phenoFile.");
@@ -328,18 +327,30 @@ std::vector<double> blup_for_chr(const Loco& loco, const SampleSet& g, const Phe
 }
 
 void run_step2_qt(const Params& p, Log& log) {
+  const bool use_bgen = !p.bgen.empty();
   BedFile g;
-  g.open(p.bed, p.ref_first, read_id_list(p.exclude, 1), read_id_list(p.extract, 1), read_id_list(p.remove, 2),
-         read_id_list(p.keep, 2));
-  log << " * bim                 : [" << p.bed << ".bim] n_snps = " << g.snps.size() << "\n";
-  log << " * fam                 : [" << p.bed << ".fam] n_samples = " << g.keys.size() << "\n";
-  const SampleSet ss{g.keys, g.key_to_ind};
+  BgenFile gg;
+  const auto excl = read_id_list(p.exclude, 1), extr = read_id_list(p.extract, 1), rem = read_id_list(p.remove, 2),
+             keepl = read_id_list(p.keep, 2);
+  if (use_bgen) {
+    gg.open(p.bgen, p.sample, p.ref_first, excl, extr, rem, keepl);
+    log << " * bgen                : [" << p.bgen << "] n_snps = " << gg.snps.size() << ", n_samples = " << gg.keys.size() << "\n";
+  } else {
+    g.open(p.bed, p.ref_first, excl, extr, rem, keepl);
+    log << " * bim                 : [" << p.bed << ".bim] n_snps = " << g.snps.size() << "\n";
+    log << " * fam                 : [" << p.bed << ".fam] n_samples = " << g.keys.size() << "\n";
+  }
+  const std::vector<Snp>& snps = use_bgen ? gg.snps : g.snps;
+  const std::vector<std::string>& keys = use_bgen ? gg.keys : g.keys;
+  const std::vector<int32_t>& sample_idx = use_bgen ? gg.sample_idx : g.sample_idx;
+  const size_t n_file = use_bgen ? gg.n_file : g.keys_file.size();
+  const SampleSet ss{keys, use_bgen ? gg.key_to_ind : g.key_to_ind};
   Pheno ph;
   std::vector<Loco> locos;
   load_step2_inputs(p, ss, ph, locos, log);
   const int64_t N = ph.N;
   const int P = ph.P;
-  const auto blocks = set_blocks(g.snps, p.bsize);
+  const auto blocks = set_blocks(snps, p.bsize);
   log << " * # blocks            : [" << blocks.size() << "]\n";
 
   rg_step2_config cfg;
@@ -353,16 +364,20 @@ void run_step2_qt(const Params& p, Log& log) {
   for (int i = 0; i < P; ++i) {
     outs[i].open(p.out + "_" + ph.names[i] + ".regenie");
     if (!outs[i]) throw Fail("cannot write to file : " + p.out + "_" + ph.names[i] + ".regenie");
-    outs[i] << "CHROM GENPOS ID ALLELE0 ALLELE1 A1FREQ N TEST BETA SE CHISQ LOG10P EXTRA\n";
+    outs[i] << "CHROM GENPOS ID ALLELE0 ALLELE1 A1FREQ " << (use_bgen ? "INFO " : "") << "N TEST BETA SE CHISQ LOG10P EXTRA\n";
   }
   const int bsz = p.bsize;
-  std::vector<uint8_t> rows((size_t)bsz * g.row_stride);
+  std::vector<uint8_t> rows, probs, pmiss;
+  if (use_bgen) { probs.resize((size_t)bsz * n_file * 2); pmiss.resize((size_t)bsz * n_file); }
+  else rows.resize((size_t)bsz * g.row_stride);
+  const int threads = p.threads > 0 ? p.threads : (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  std::vector<double> info((size_t)bsz * P);
   std::vector<double> af((size_t)bsz * P), mac((size_t)bsz * P), stat((size_t)bsz * P), beta((size_t)bsz * P),
       se((size_t)bsz * P), chisq((size_t)bsz * P), af_all(bsz), mac_all(bsz), scale_fac(bsz);
   std::vector<int32_t> ns((size_t)bsz * P), ns_all(bsz), flags(bsz);
   rg_s2_out out{af.data(), ns.data(), mac.data(), af_all.data(), ns_all.data(), mac_all.data(), flags.data(),
                 scale_fac.data(), stat.data(), beta.data(), se.data(), chisq.data()};
-  const bool subset = g.keys.size() != g.keys_file.size();
+  const bool subset = keys.size() != n_file;
   std::vector<double> res((size_t)N * P), scf(P);
   int cur_chr = -1;
   size_t n_ignored = 0;
@@ -386,19 +401,27 @@ void run_step2_qt(const Params& p, Log& log) {
       }
       rg_check(rg_s2_set_chr(h, res.data(), scf.data()));
     }
-    g.read_rows(blocks[b].first, blocks[b].size, rows.data());
-    rg_check(rg_s2_block_bed(h, rows.data(), (int64_t)g.row_stride, blocks[b].size,
-                             subset ? g.sample_idx.data() : nullptr, p.ref_first, p.min_mac, &out));
+    if (use_bgen) {
+      gg.read_block(blocks[b].first, blocks[b].size, probs.data(), pmiss.data(), threads);
+      rg_check(rg_s2_block_bgen8(h, probs.data(), pmiss.data(), (int64_t)n_file, blocks[b].size,
+                                 subset ? sample_idx.data() : nullptr, p.ref_first, p.min_mac, &out, info.data()));
+    } else {
+      g.read_rows(blocks[b].first, blocks[b].size, rows.data());
+      rg_check(rg_s2_block_bed(h, rows.data(), (int64_t)g.row_stride, blocks[b].size,
+                               subset ? sample_idx.data() : nullptr, p.ref_first, p.min_mac, &out));
+    }
     for (int v = 0; v < blocks[b].size; ++v) {
       if (flags[v] & 3) { ++n_ignored; continue; }            // no row for ignored variants (split mode)
-      const Snp& s = g.snps[blocks[b].first + v];
+      const Snp& s = snps[blocks[b].first + v];
       std::ostringstream head;
       head << s.chrom << " " << s.pos << " " << s.id << " " << s.allele0 << " " << s.allele1 << " ";
       for (int i = 0; i < P; ++i) {
         const size_t e = (size_t)v * P + i;
         if (mac[e] < p.min_mac) continue;                      // ignored_trait (src/Geno.cpp:3102)
         std::ostringstream buf;                                // print_sum_stats_single :2502-2540
-        buf << head.str() << af[e] << " " << ns[e] << " ADD ";
+        buf << head.str() << af[e] << " ";
+        if (use_bgen) buf << info[e] << " ";
+        buf << ns[e] << " ADD ";
         if (se[e] >= 0 && !std::isnan(se[e])) buf << beta[e] << ' ' << se[e];
         else buf << "NA NA";
         const double lp = get_logp(chisq[e]);

@@ -174,3 +174,49 @@ def test_step2_bt_on_bed_hard_calls(tmp_path, golden_dir):
                 assert close(a, c), (tx, row)
             assert tx[12] == row[12]
         assert k == len(got)
+
+
+def test_step2_qt_on_bgen_dosages(tmp_path, golden_dir):
+    """Quantitative traits on BGEN dosages (BASELINE configs[2] shape): rgb200 --step 2 --bgen vs the oracle
+    (compute_score_qt on the parseSnpfromBGEN dosages, INFO column included)."""
+    from oracle import bgen, prep, step2
+    d = golden_dir
+    pred = _write_zero_loco(tmp_path, d, ["Y1", "Y2"])
+    out = str(tmp_path / "qt_bgen")
+    run(["--step", "2", "--bgen", d + "/example.bgen", "--covarFile", d + "/covariates.txt", "--phenoFile",
+         d + "/phenotype.txt", "--remove", d + "/fid_iid_to_remove.txt", "--bsize", "400", "--pred", pred, "--out", out])
+    rm = {"_".join(l.split()[:2]) for l in open(d + "/fid_iid_to_remove.txt") if l.strip()}
+    b = bgen.Bgen(d + "/example.bgen")
+    keep = np.array([k not in rm for k in b.sample_ids])
+    keys = [k for k in b.sample_ids if k not in rm]
+    pr = helpers.prepare_step2_with_mask(keys, d + "/phenotype.txt", d + "/covariates.txt",
+                                         np.ones((len(keys), 2), dtype=bool))
+    res, p_sd, scf = step2.compute_res(pr.Y, np.zeros_like(pr.Y), pr.mask, pr.neff, pr.ncov, pr.scale_Y)
+    YtX = res.T @ pr.X
+    rows = {nm: [] for nm in pr.pheno_names}
+    for chrom, pos, rsid, alleles, p0, p1, miss in b.variants():
+        g, iv = bgen.dosage(p0[keep], p1[keep], miss[keep])
+        vs = step2.variant_stats(g, pr.in_analysis, pr.mask)
+        if vs["ignored"]:
+            continue
+        sc = step2.score_qt(vs["g"], pr.X, res, pr.mask, pr.in_analysis, pr.n_analyzed, pr.ncov, scf, YtX, False)
+        if sc is None:
+            continue
+        for ph, nm in enumerate(pr.pheno_names):
+            if vs["ignored_trait"][ph]:
+                continue
+            okp = pr.in_analysis & (g != -3.0) & pr.mask[:, ph]
+            af = vs["af"][ph]
+            info = 1.0 if af in (0.0, 1.0) else 1 - iv[okp].sum() / (2 * vs["ns"][ph] * af * (1 - af))
+            rows[nm].append(step2.sumstats_row(int(chrom), pos, rsid, alleles[1], alleles[0], af, vs["ns"][ph],
+                                               sc["beta"][ph], sc["se"][ph], sc["chisq"][ph], sc["logp"][ph], info=info))
+    for nm in pr.pheno_names:
+        got = open(out + "_%s.regenie" % nm).read().splitlines()
+        assert got[0] == step2.HEADER_INFO.strip()
+        assert len(got) - 1 == len(rows[nm]) > 900
+        for x, y in zip(got[1:], rows[nm]):
+            tx, ty = x.split(), y.split()
+            assert tx[:6] == ty[:6] and tx[7:9] == ty[7:9], (x, y)
+            assert close(tx[6], ty[6]), (x, y)             # INFO: formed from sums in a different order
+            for a, c in zip(tx[9:13], ty[9:13]):
+                assert close(a, c), (x, y)
