@@ -30,7 +30,7 @@ struct Params {
   std::string remove, keep, exclude, extract;
   int bsize = 0, cv = 5, l0 = 5, l1 = 5, gpu = 0;
   bool loocv = false, lowmem = false, ref_first = false, strict = false, bt = false, force_step1 = false;
-  bool rel_path = false, firth = false, approx = false;
+  bool rel_path = false, firth = false, approx = false, keep_l0 = false;
   double min_mac = 5.0, p_thresh = 0.05;
   int threads = 0;
 };
@@ -72,7 +72,8 @@ Params parse_cli(int argc, char** argv) {
     else if (a == "--firth") p.firth = true;
     else if (a == "--approx") p.approx = true;
     else if (a == "--loocv") p.loocv = true;
-    else if (a == "--lowmem") p.lowmem = true;     // W stays resident in HBM; accepted for CLI parity
+    else if (a == "--lowmem") p.lowmem = true;     // W stays resident in HBM; files only with --keep-l0
+    else if (a == "--keep-l0") p.keep_l0 = true;
     else if (a == "--ref-first") p.ref_first = true;
     else if (a == "--strict") p.strict = true;
     else if (a == "--qt") {}
@@ -174,7 +175,24 @@ void run_step1(const Params& p, Log& log) {
       throw Fail("!! Uh-oh, SNP " + g.snps[blocks[(st - 1) / p.bsize].first + (st - 1) % p.bsize].id + " has low variance.");
     throw Fail(std::string(rg_last_error()));
   }
-  log << " Level 0 done (" << (long)(now_ms() - t0) << "ms)\n\n Level 1 ridge...\n";
+  log << " Level 0 done (" << (long)(now_ms() - t0) << "ms)\n";
+  if (p.lowmem && p.keep_l0) {
+    // write_l0_file (src/Step1_Models.cpp:728-733): per phenotype, per block an N x R column-major f64 slab.
+    // The reference deletes these after level 1 unless --keep-l0 (src/Data.cpp:1011,1108,1131-1137); here W
+    // never leaves HBM for level 1, so the files are only materialised when they are kept.
+    const std::string pfx = p.lowmem_prefix.empty() ? p.out : p.lowmem_prefix;
+    log << "   -files will have prefix [" << pfx << "_l0_Y]\n";
+    std::vector<double> slab((size_t)N * p.l0);
+    for (int ph_i = 0; ph_i < P; ++ph_i) {
+      std::ofstream f(pfx + "_l0_Y" + std::to_string(ph_i + 1), std::ios::binary);
+      if (!f) throw Fail("cannot write temporary file " + pfx + "_l0_Y" + std::to_string(ph_i + 1));
+      for (int b = 0; b < nb; ++b) {
+        rg_check(rg_l0_fetch_W(h, b, ph_i, slab.data()));
+        f.write(reinterpret_cast<const char*>(slab.data()), (std::streamsize)(slab.size() * sizeof(double)));
+      }
+    }
+  }
+  log << "\n Level 1 ridge...\n";
 
   // ---- level 1 (tau = B(1-h)/h, src/Step1_Models.cpp:2115)
   const double B = (double)nb * p.l0;

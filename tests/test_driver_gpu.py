@@ -220,3 +220,22 @@ def test_step2_qt_on_bgen_dosages(tmp_path, golden_dir):
             assert close(tx[6], ty[6]), (x, y)             # INFO: formed from sums in a different order
             for a, c in zip(tx[9:13], ty[9:13]):
                 assert close(a, c), (x, y)
+
+
+def test_step1_lowmem_keep_l0_files(tmp_path, golden_dir):
+    """--lowmem --keep-l0: <prefix>_l0_Y<k> holds, per block, the N x R column-major f64 slab the reference's
+    write_l0_file appends (src/Step1_Models.cpp:728-733; size check of read_l0_chunk :1962)."""
+    prefix = os.path.join(golden_dir, "example_3chr")
+    pheno, covar = golden_dir + "/phenotype.txt", golden_dir + "/covariates.txt"
+    out = str(tmp_path / "fit")
+    run(["--step", "1", "--bed", prefix, "--phenoFile", pheno, "--covarFile", covar, "--bsize", "100", "--lowmem",
+         "--lowmem-prefix", str(tmp_path / "tmp_rg"), "--keep-l0", "--out", out])
+    pb = helpers.Problem(prefix, pheno, covar, 100)
+    n, R, nb = len(pb.keys), 5, len(pb.blocks)
+    for ph in range(pb.prep.Y.shape[1]):
+        f = str(tmp_path / ("tmp_rg_l0_Y%d" % (ph + 1)))
+        assert os.path.getsize(f) == 8 * n * R * nb
+        data = np.fromfile(f, dtype=np.float64).reshape(nb, R, n)
+        for b in (0, nb - 1):
+            W = pb.oracle_l0(b)[0]                      # [P][N x R]
+            np.testing.assert_allclose(data[b].T, W[ph], rtol=1e-7, atol=1e-9)
