@@ -126,6 +126,18 @@ int rg_l1_fit(rg_handle h, const double* tau, double* cumsum, int32_t* best_idx)
  */
 int rg_loco(rg_handle h, const int32_t* chr_of_block, double* pred_out);
 
+/*
+ * rg_l1_fit_bt -- binary traits: penalised logistic level 1 with closed-form leave-one-out predictions.
+ * Replaces ridge_logistic_level_1_loocv + run_log_ridge_loocv (src/Step1_Models.cpp:1159-1375); rg_loco then
+ * performs make_predictions_binary_loocv (src/Data.cpp:1484-1573) + the LOCO assembly.  Level 0 is the QT path
+ * (rg_l0_block_bed with the residualised 0/1 phenotypes as Y).  LOOCV handles only (cfg.loocv = 1).
+ *   y_raw  [N x P] phenotypes_raw (0/1), offset [N x P] m_ests.offset_nullreg (covariate-only logistic fit)
+ *   tau    [P x R1] ridge values (B (1-h)/h * 3/pi^2, src/Step1_Models.cpp:2115-2117)
+ *   cumsum [6][P][R1]  Sx, Sy, Sx2, Sy2, Sxy, -logLik (cumsum_values[0..5]);  best_idx = argmin -logLik/Neff
+ */
+int rg_l1_fit_bt(rg_handle h, const double* y_raw, const double* offset, const double* tau, double* cumsum,
+                 int32_t* best_idx);
+
 /* ------------------------------------------------------------------ Step 2 (QT) */
 typedef struct rg_step2_config {
   int32_t device;

@@ -46,7 +46,7 @@ EXPORTS = [
     "rg_last_error", "rg_version", "rg_device_count", "rg_step1_create", "rg_destroy", "rg_sync",
     "rg_l0_block_bed", "rg_l0_status", "rg_l0_fetch_W", "rg_l1_fit", "rg_loco", "rg_step2_create",
     "rg_s2_set_chr", "rg_s2_block_bed", "rg_W_info", "rg_debug_fetch", "rg_launch_count", "rg_stream",
-    "rg_set_timing", "rg_get_timing", "rg_fence", "rg_s2_set_chr_bt", "rg_s2_block_bgen8_bt", "rg_s2_block_bgen8", "rg_s2_firth",
+    "rg_set_timing", "rg_get_timing", "rg_fence", "rg_s2_set_chr_bt", "rg_s2_block_bgen8_bt", "rg_s2_block_bgen8", "rg_s2_firth", "rg_l1_fit_bt",
 ]
 
 _lib = None
@@ -159,6 +159,17 @@ class Step1:
         cs = np.zeros((5, self.P, self.R1))
         best = np.zeros(self.P, dtype=np.int32)
         check(lib().rg_l1_fit(self.h, _ptr(tau), _ptr(cs), _ptr(best)))
+        return cs, best
+
+    def l1_fit_bt(self, y_raw, offset, tau):
+        """Binary traits: logistic level 1 (LOOCV).  Returns cumsums [6, P, R1] and argmin -logLik/N."""
+        L = lib()
+        L.rg_l1_fit_bt.argtypes = [C.c_void_p] * 6
+        tau = np.ascontiguousarray(tau, dtype=np.float64).reshape(self.P, self.R1)
+        y_raw = _f64(y_raw); offset = _f64(offset)
+        cs = np.zeros((6, self.P, self.R1))
+        best = np.zeros(self.P, dtype=np.int32)
+        check(L.rg_l1_fit_bt(self.h, _ptr(y_raw), _ptr(offset), _ptr(tau), _ptr(cs), _ptr(best)))
         return cs, best
 
     def loco(self, chr_of_block):

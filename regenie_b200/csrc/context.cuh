@@ -82,6 +82,9 @@ struct rg_ctx {
   std::vector<int32_t> best_idx;
   int l1_nC = 0;
   bool l1_done = false;
+  bool l1_bt = false;                                // logistic level 1: l1_hvec holds f_i = (y - p) / (1 - q w)
+  rg::DevBuf<double> lg_Ws, lg_eta, lg_p, lg_wm, lg_res, lg_off, lg_beta, lg_score, lg_q, lg_devp, lg_scal;
+  rg::DevBuf<int8_t> lg_ym;
 
   // ---- step 2
   int strict = 0, dp = 0;

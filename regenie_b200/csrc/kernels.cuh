@@ -148,6 +148,19 @@ void launch_l1_loocv_fill(const double* W, int64_t ldw, int B, int nC, double* c
 void launch_l1_loocv_sums(const double* cm, int64_t cm_stride, int nC, int B, int nrow0, const double* xy, int cpp,
                           int ycol, double* part, int R1, int ntiles, double* out, cudaStream_t s);
 void launch_rows_sqnorm(const double* rows, int nC, int B, double* out, int ntiles, cudaStream_t s);
+
+// ---- l1_logistic.cu
+void launch_l1_scale_rows(const double* W, int64_t ldw, int B, const double* wm, double* Ws, cudaStream_t s);
+void launch_l1_bt_eta(const double* W, int64_t ldw, int B, const double* beta, const double* offset, const int8_t* ym,
+                      double* eta, double* pv, double* wm, double* resid, double* dev_part, double* dev_out,
+                      cudaStream_t s);
+void launch_l1_bt_score(const double* part_y, int nchunks, int B, int nC, double tau, const double* beta, double* score,
+                        double* rhs_row, cudaStream_t s);
+void launch_l1_bt_loo_sums(const double* eta, const double* q, const double* wm, const double* resid, const int8_t* ym,
+                           double eps, double* fvec, double* part, double* out6, int64_t npad, cudaStream_t s);
+void launch_l1_bt_chr_pred(const double* W, int64_t ldw, int nC, const double* zrows, const double* fvec,
+                           const double* bvec, int nchr, const int32_t* chr_col_start, double* pred, int64_t npad,
+                           cudaStream_t s);
 void launch_l1_loocv_chr_pred(const double* W, int64_t ldw, int B, int nC, const double* zrows, const double* hvec,
                               const double* bvec, const double* xy, int cpp, int ycol, int nchr,
                               const int32_t* chr_col_start, double* pred, int64_t npad, cudaStream_t s);

@@ -2,6 +2,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
+#include <string>
 
 #include "context.cuh"
 
@@ -22,19 +24,10 @@ using namespace rg;
 
 
 
-static void l1_fit(rg_ctx* h, const double* tau_host, double* cumsum, int32_t* best_idx) {
-  RG_CHECK(h->kind == 1, "handle is not a Step-1 handle");
-  RG_CHECK(h->R1 >= 1 && h->R1 <= kMaxRidge, "n_ridge_l1 out of range");
-  RG_CUDA(cudaSetDevice(h->device));
+static void l1_setup_chunks(rg_ctx* h, int nC, int ldp) {
   cudaStream_t s = h->stream;
-  for (auto& l : h->lanes) RG_CUDA(cudaStreamSynchronize(l->stream));   // all level-0 blocks are in W
-  const int K = h->K, R1 = h->R1, P = h->P;
-  const int B = (int)h->B;
-  const int loocv = h->loocv;
-  const int nC = (int)round_up(B, 64), n_aug = nC + 64 + (loocv ? (int)h->Npad : 0), nmat = (loocv ? 1 : K) * R1;
-  const int ldp = nC;
+  const int K = h->K;
   const int64_t Npad = h->Npad;
-  h->l1_nC = nC;
   // chunk table for the sample-axis reductions: bounded partial storage (<= ~1 GiB)
   {
     const int64_t per = (int64_t)nC * ldp * 8;
@@ -56,6 +49,22 @@ static void l1_fit(rg_ctx* h, const double* tau_host, double* cumsum, int32_t* b
     RG_CUDA(cudaMemcpyAsync(h->l1_fold_chunks.p, fold_chunks.data(), K * sizeof(int2), cudaMemcpyHostToDevice, s));
     RG_CUDA(cudaStreamSynchronize(s));
   }
+}
+
+static void l1_fit(rg_ctx* h, const double* tau_host, double* cumsum, int32_t* best_idx) {
+  RG_CHECK(h->kind == 1, "handle is not a Step-1 handle");
+  RG_CHECK(h->R1 >= 1 && h->R1 <= kMaxRidge, "n_ridge_l1 out of range");
+  RG_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  for (auto& l : h->lanes) RG_CUDA(cudaStreamSynchronize(l->stream));   // all level-0 blocks are in W
+  const int K = h->K, R1 = h->R1, P = h->P;
+  const int B = (int)h->B;
+  const int loocv = h->loocv;
+  const int nC = (int)round_up(B, 64), n_aug = nC + 64 + (loocv ? (int)h->Npad : 0), nmat = (loocv ? 1 : K) * R1;
+  const int ldp = nC;
+  const int64_t Npad = h->Npad;
+  h->l1_nC = nC;
+  l1_setup_chunks(h, nC, ldp);
   const int nch = h->l1_nchunks;
   const int64_t part_stride = (int64_t)nC * ldp;
   const int64_t cm_stride = (int64_t)n_aug * nC;
@@ -164,6 +173,205 @@ static void l1_fit(rg_ctx* h, const double* tau_host, double* cumsum, int32_t* b
   h->l1_done = true;
 }
 
+
+// ------------------------------------------------------------------ binary traits: logistic level 1 (LOOCV)
+namespace {
+constexpr int kNiterRidge = 100, kNiterLsL1 = 25;            // src/Regenie.hpp:287, :338
+constexpr double kL1RidgeTol = 1e-4, kL1RidgeEps = 1e-5, kTolL1 = 1e-8, kNumtolL1 = 1e-6;   // :289, :290, :226
+
+struct LgState {
+  rg_ctx* h;
+  const double* Wp;
+  int B, nC, nch;
+  int64_t Npad, cm_stride, part_stride;
+  const double* off;
+  const int8_t* ym;
+  std::vector<double> beta;     // host copy of the coefficients
+  double dev = 0.0;             // deviance at the last evaluated beta
+};
+
+// eta, p, w, residual and deviance at `b` (device vectors are overwritten)
+double lg_eval(LgState& st, const std::vector<double>& b) {
+  rg_ctx* h = st.h;
+  cudaStream_t s = h->stream;
+  RG_CUDA(cudaMemcpyAsync(h->lg_beta.p, b.data(), (size_t)st.B * 8, cudaMemcpyHostToDevice, s));
+  launch_l1_bt_eta(st.Wp, st.Npad, st.B, h->lg_beta.p, st.off, st.ym, h->lg_eta.p, h->lg_p.p, h->lg_wm.p, h->lg_res.p,
+                   h->lg_devp.p, h->lg_scal.p, s);
+  double d = 0.0;
+  RG_CUDA(cudaMemcpyAsync(&d, h->lg_scal.p, 8, cudaMemcpyDeviceToHost, s));
+  RG_CUDA(cudaStreamSynchronize(s));
+  h->launches += 2;
+  return d;
+}
+
+// score = W^T (y - p) m - tau b at the state of the last lg_eval; optionally also into the RHS row of system 0
+std::vector<double> lg_score(LgState& st, double tau, const std::vector<double>& b, bool to_rhs) {
+  rg_ctx* h = st.h;
+  cudaStream_t s = h->stream;
+  RG_CUDA(cudaMemcpyAsync(h->lg_beta.p, b.data(), (size_t)st.B * 8, cudaMemcpyHostToDevice, s));
+  launch_l1_xty(st.Wp, st.Npad, h->lg_res.p, 1, 0, h->l1_chunks.p, st.nch, h->l1_part_y.p, st.B, s);
+  launch_l1_bt_score(h->l1_part_y.p, st.nch, st.B, st.nC, tau, h->lg_beta.p, h->lg_score.p,
+                     to_rhs ? h->l1_cm.p + (size_t)st.nC * st.nC : nullptr, s);
+  std::vector<double> sc(st.B);
+  RG_CUDA(cudaMemcpyAsync(sc.data(), h->lg_score.p, (size_t)st.B * 8, cudaMemcpyDeviceToHost, s));
+  RG_CUDA(cudaStreamSynchronize(s));
+  h->launches += 2;
+  return sc;
+}
+
+// H = tau I + W^T diag(w m) W at the current weights, factored; n_rows extra RHS rows (sample rows) ride along
+void lg_factor(LgState& st, double tau, bool with_rows) {
+  rg_ctx* h = st.h;
+  cudaStream_t s = h->stream;
+  const int nC = st.nC;
+  launch_l1_scale_rows(st.Wp, st.Npad, st.B, h->lg_wm.p, h->lg_Ws.p, s);
+  launch_l1_gram(h->lg_Ws.p, st.Npad, st.B, h->l1_chunks.p, st.nch, h->l1_part.p, st.part_stride, nC, s);
+  RG_CUDA(cudaMemcpyAsync(h->l1_tau.p, &tau, 8, cudaMemcpyHostToDevice, s));
+  // the RHS row is (re)written by the caller after this; part_y content is irrelevant here
+  launch_l1_assemble(h->l1_part.p, st.part_stride, nC, h->l1_part_y.p, h->l1_fold_chunks.p, h->K, 1, h->l1_tau.p, st.B, nC,
+                     h->l1_cm.p, st.cm_stride, 1, s);
+  h->launches += 3;
+  (void)with_rows;
+}
+
+// run_log_ridge_loocv (src/Step1_Models.cpp:1288-1375); beta in/out (warm start)
+bool lg_newton(LgState& st, double tau) {
+  rg_ctx* h = st.h;
+  cudaStream_t s = h->stream;
+  const int B = st.B, nC = st.nC;
+  std::vector<double>& beta = st.beta;
+  auto pen = [&](const std::vector<double>& b) { double q = 0.0; for (double v : b) q += v * v; return tau * q; };
+  double fn_start = lg_eval(st, beta) + pen(beta), fn_end = fn_start;
+  std::vector<double> score = lg_score(st, tau, beta, false), betanew = beta, step(B);
+  bool dev_conv = false, by_score = false;
+  int it = 0;
+  while (it < kNiterRidge) {
+    ++it;
+    lg_factor(st, tau, false);
+    // RHS row = score
+    std::vector<double> rhs(nC, 0.0);
+    std::copy(score.begin(), score.end(), rhs.begin());
+    RG_CUDA(cudaMemcpyAsync(h->l1_cm.p + (size_t)nC * nC, rhs.data(), (size_t)nC * 8, cudaMemcpyHostToDevice, s));
+    launch_chol_factor(h->l1_cm.p, st.cm_stride, nC, nC + 64, 1, h->l1_inv.p, h->err_slot.p, (long long)(1ll << 42), s);
+    launch_chol_backsolve(h->l1_cm.p, st.cm_stride, nC, 1, 1, h->l1_inv.p, s);
+    RG_CUDA(cudaMemcpyAsync(step.data(), h->l1_cm.p + (size_t)nC * nC, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+    RG_CUDA(cudaStreamSynchronize(s));
+    h->launches += chol_num_launches(nC) + 1;
+    for (int ls = 0; ls < kNiterLsL1; ++ls) {
+      for (int c = 0; c < B; ++c) betanew[c] = beta[c] + step[c];
+      fn_end = lg_eval(st, betanew) + pen(betanew);
+      if (fn_end < fn_start + kNumtolL1) break;
+      for (auto& v : step) v /= 2.0;
+    }
+    score = lg_score(st, tau, betanew, false);
+    dev_conv = std::fabs(fn_end - fn_start) / (0.01 + std::fabs(fn_end)) < kTolL1;
+    double smax = 0.0;
+    for (double v : score) smax = std::max(smax, std::fabs(v));
+    if (smax < kL1RidgeTol) { by_score = true; break; }
+    beta = betanew;
+    fn_start = fn_end;
+  }
+  beta = betanew;
+  return by_score || dev_conv;
+}
+
+// leverages q_i = w_i^T H^-1 w_i at the converged state (sample rows as RHS rows of the factorisation)
+void lg_leverages(LgState& st, double tau, int ntiles) {
+  rg_ctx* h = st.h;
+  cudaStream_t s = h->stream;
+  const int nC = st.nC;
+  lg_factor(st, tau, true);
+  RG_CUDA(cudaMemsetAsync(h->l1_cm.p + (size_t)nC * nC, 0, (size_t)64 * nC * 8, s));
+  launch_l1_loocv_fill(st.Wp, st.Npad, st.B, nC, h->l1_cm.p, st.cm_stride, nC + 64, 1, st.Npad, s);
+  launch_chol_factor(h->l1_cm.p, st.cm_stride, nC, nC + 64 + (int)st.Npad, 1, h->l1_inv.p, h->err_slot.p, (long long)(1ll << 42) + 1, s);
+  launch_rows_sqnorm(h->l1_cm.p + (size_t)(nC + 64) * nC, nC, st.B, h->lg_q.p, ntiles, s);
+  h->launches += chol_num_launches(nC) + 2;
+}
+}  // namespace
+
+static void l1_fit_bt(rg_ctx* h, const double* y_raw, const double* offset, const double* tau_host, double* cumsum,
+                      int32_t* best_idx) {
+  RG_CHECK(h->kind == 1, "handle is not a Step-1 handle");
+  RG_CHECK(h->loocv, "logistic level 1 is implemented for LOOCV only (use --loocv)");
+  RG_CHECK(h->R1 >= 1 && h->R1 <= kMaxRidge, "n_ridge_l1 out of range");
+  RG_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  for (auto& l : h->lanes) RG_CUDA(cudaStreamSynchronize(l->stream));
+  const int R1 = h->R1, P = h->P, B = (int)h->B;
+  const int nC = (int)round_up(B, 64);
+  const int64_t Npad = h->Npad, N = h->N;
+  const int ntiles = (int)(Npad / 128);
+  h->l1_nC = nC;
+  l1_setup_chunks(h, nC, nC);
+  const int nch = h->l1_nchunks;
+  const int64_t cm_stride = (int64_t)(nC + 64 + Npad) * nC;
+  h->l1_part.alloc((size_t)nch * nC * nC);
+  h->l1_part_y.alloc((size_t)nch * B);
+  h->l1_cm.alloc((size_t)cm_stride);
+  h->l1_inv.alloc(chol_inv_elems(nC, 1));
+  h->l1_tau.alloc(1);
+  h->l1_zrows.alloc((size_t)P * Npad * nC);
+  h->l1_hvec.alloc((size_t)P * Npad);
+  h->l1_bvec.alloc((size_t)P * nC);
+  h->lg_Ws.alloc((size_t)Npad * B); h->lg_eta.alloc(Npad); h->lg_p.alloc(Npad); h->lg_wm.alloc(Npad);
+  h->lg_res.alloc(Npad); h->lg_off.alloc(Npad); h->lg_beta.alloc(nC); h->lg_score.alloc(nC); h->lg_q.alloc(Npad);
+  h->lg_devp.alloc((size_t)ntiles * 6); h->lg_scal.alloc(8); h->lg_ym.alloc(Npad);
+  RG_CUDA(cudaMemsetAsync(h->l1_cm.p, 0, (size_t)cm_stride * 8, s));
+  h->best_idx.assign(P, 0);
+  for (int p = 0; p < P; ++p) {
+    // pad-order copies of the trait's 0/1 values, mask and null-model offset
+    std::vector<double> off(Npad, 0.0);
+    std::vector<int8_t> ym(Npad, 0);
+    for (int64_t i = 0; i < N; ++i) {
+      const int64_t t = h->pad_of[i];
+      off[t] = offset[(size_t)p * N + i];
+      ym[t] = h->maskh[(size_t)p * N + i] ? (y_raw[(size_t)p * N + i] != 0.0 ? 2 : 1) : 0;
+    }
+    RG_CUDA(cudaMemcpyAsync(h->lg_off.p, off.data(), Npad * 8, cudaMemcpyHostToDevice, s));
+    RG_CUDA(cudaMemcpyAsync(h->lg_ym.p, ym.data(), Npad, cudaMemcpyHostToDevice, s));
+    RG_CUDA(cudaStreamSynchronize(s));
+    LgState st{h, h->W.p + (size_t)p * Npad * h->B, B, nC, nch, Npad, cm_stride, (int64_t)nC * nC, h->lg_off.p, h->lg_ym.p,
+               std::vector<double>(B, 0.0)};
+    double best = 1e10;
+    double ne = 0.0;
+    for (int64_t i = 0; i < N; ++i) ne += h->maskh[(size_t)p * N + i] ? 1.0 : 0.0;
+    for (int j = 0; j < R1; ++j) {
+      const double tau = tau_host[(size_t)p * R1 + j];
+      if (!lg_newton(st, tau)) throw Error{"ridge logistic regression did not converge (level 1, phenotype " + std::to_string(p + 1) + ")"};
+      lg_eval(st, st.beta);                       // weights / residuals at the converged coefficients
+      lg_leverages(st, tau, ntiles);
+      double cs[6];
+      launch_l1_bt_loo_sums(h->lg_eta.p, h->lg_q.p, h->lg_wm.p, h->lg_res.p, h->lg_ym.p, kL1RidgeEps, nullptr,
+                            h->lg_devp.p, h->lg_scal.p, Npad, s);
+      RG_CUDA(cudaMemcpyAsync(cs, h->lg_scal.p, 48, cudaMemcpyDeviceToHost, s));
+      RG_CUDA(cudaStreamSynchronize(s));
+      h->launches += 2;
+      if (cumsum) for (int k = 0; k < 6; ++k) cumsum[((size_t)k * P + p) * R1 + j] = cs[k];
+      const double perf = cs[5] / ne;             // -logLik / N, src/Data.cpp:1025-1037
+      if (perf < best) { best = perf; h->best_idx[p] = j; }
+    }
+    if (best_idx) best_idx[p] = h->best_idx[p];
+    // state for rg_loco at tau*: refit from zero like make_predictions_binary_loocv (src/Data.cpp:1505-1520)
+    const double tau = tau_host[(size_t)p * R1 + h->best_idx[p]];
+    std::fill(st.beta.begin(), st.beta.end(), 0.0);
+    if (!lg_newton(st, tau)) throw Error{"ridge logistic regression did not converge (predictions, phenotype " + std::to_string(p + 1) + ")"};
+    lg_eval(st, st.beta);
+    lg_leverages(st, tau, ntiles);
+    launch_l1_bt_loo_sums(h->lg_eta.p, h->lg_q.p, h->lg_wm.p, h->lg_res.p, h->lg_ym.p, kL1RidgeEps,
+                          h->l1_hvec.p + (size_t)p * Npad, h->lg_devp.p, h->lg_scal.p, Npad, s);
+    std::vector<double> bpad(nC, 0.0);
+    std::copy(st.beta.begin(), st.beta.end(), bpad.begin());
+    RG_CUDA(cudaMemcpyAsync(h->l1_bvec.p + (size_t)p * nC, bpad.data(), (size_t)nC * 8, cudaMemcpyHostToDevice, s));
+    launch_chol_rows_backsolve(h->l1_cm.p, cm_stride, nC, nC + 64, (int)Npad, 1, h->l1_inv.p, s);
+    RG_CUDA(cudaMemcpyAsync(h->l1_zrows.p + (size_t)p * Npad * nC, h->l1_cm.p + (size_t)(nC + 64) * nC,
+                            (size_t)Npad * nC * 8, cudaMemcpyDeviceToDevice, s));
+    RG_CUDA(cudaStreamSynchronize(s));
+    h->launches += 3;
+  }
+  h->l1_bt = true;
+  h->l1_done = true;
+}
+
 static void loco(rg_ctx* h, const int32_t* chr_of_block, double* pred_out) {
   RG_CHECK(h->kind == 1 && h->l1_done, "rg_l1_fit must run before rg_loco");
   RG_CUDA(cudaSetDevice(h->device));
@@ -189,7 +397,11 @@ static void loco(rg_ctx* h, const int32_t* chr_of_block, double* pred_out) {
   h->l1_pred.alloc((size_t)nchr * Npad);
   std::vector<double> pred((size_t)nchr * Npad);
   for (int p = 0; p < P; ++p) {
-    if (h->loocv)
+    if (h->l1_bt)
+      launch_l1_bt_chr_pred(h->W.p + (size_t)p * Npad * h->B, Npad, nC, h->l1_zrows.p + (size_t)p * Npad * nC,
+                            h->l1_hvec.p + (size_t)p * Npad, h->l1_bvec.p + (size_t)p * nC, nchr, h->l1_chr_cols.p,
+                            h->l1_pred.p, Npad, s);
+    else if (h->loocv)
       launch_l1_loocv_chr_pred(h->W.p + (size_t)p * Npad * h->B, Npad, (int)h->B, nC, h->l1_zrows.p + (size_t)p * Npad * nC,
                                h->l1_hvec.p + (size_t)p * Npad, h->l1_bvec.p + (size_t)p * nC, h->xy.p, h->cpp,
                                h->C + p, nchr, h->l1_chr_cols.p, h->l1_pred.p, Npad, s);
@@ -217,6 +429,15 @@ int rg_l1_fit(rg_handle h, const double* tau, double* cumsum, int32_t* best_idx)
   RG_API_BEGIN
   RG_CHECK(h && tau, "null argument");
   l1_fit(h, tau, cumsum, best_idx);
+  RG_CUDA(cudaGetLastError());
+  RG_API_END
+}
+
+int rg_l1_fit_bt(rg_handle h, const double* y_raw, const double* offset, const double* tau, double* cumsum,
+                 int32_t* best_idx) {
+  RG_API_BEGIN
+  RG_CHECK(h && y_raw && offset && tau, "null argument");
+  l1_fit_bt(h, y_raw, offset, tau, cumsum, best_idx);
   RG_CUDA(cudaGetLastError());
   RG_API_END
 }

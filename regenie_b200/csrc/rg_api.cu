@@ -119,6 +119,7 @@ static void build_layout(rg_ctx* h, const double* X, const double* Y, const uint
   h->cpp = (int)round_up(C + P, 16);
   std::vector<double> xy((size_t)h->Npad * h->cpp, 0.0);
   std::vector<uint8_t> maskp((size_t)P * h->Npad, 0), is_real(h->Npad, 0);
+  h->maskh.assign(mask, mask + (size_t)N * P);
   for (int64_t s = 0; s < N; ++s) {
     const int64_t t = h->pad_of[s];
     is_real[t] = 1;

@@ -243,6 +243,20 @@ BtNull fit_bt_null(const std::string& name, const double* y, const double* X, in
   return out;
 }
 
+std::vector<double> null_logistic_eta(const std::string& name, const double* y, const double* X, int64_t N, int C,
+                                      const uint8_t* mask) {
+  Work w{N, C, y, X, mask, std::vector<double>(N), std::vector<double>(N)};
+  const std::vector<double> zero(N, 0.0);
+  std::vector<double> beta(C, 0.0);
+  bool ok = false;
+  for (int chk = 1; chk >= 0 && !ok; --chk) {
+    std::fill(beta.begin(), beta.end(), 0.0);
+    ok = fit_logistic(w, zero.data(), beta, chk == 1);
+  }
+  if (!ok) throw Fail("logistic regression did not converge for phenotype '" + name + "'.");
+  return w.eta;
+}
+
 // inverse of the standard normal upper tail by bisection-safe Newton on erfc; chi2_1 quantile = z^2
 double z_threshold(double p) {
   if (!(p > 0.0 && p < 1.0)) throw Fail("--pThresh must be in (0,1).");

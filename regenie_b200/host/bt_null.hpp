@@ -16,6 +16,11 @@ struct BtNull {
 BtNull fit_bt_null(const std::string& name, const double* y, const double* X, int64_t N, int C, const double* blup,
                    const uint8_t* mask, bool firth);
 
+// Step 1: linear predictor of the covariate-only logistic fit (offset_nullreg, fit_null_logistic called from
+// src/Pheno.cpp:1608)
+std::vector<double> null_logistic_eta(const std::string& name, const double* y, const double* X, int64_t N, int C,
+                                      const uint8_t* mask);
+
 // z threshold of --pThresh: sqrt of the chi2_1 upper quantile (src/Data.cpp:2116-2120)
 double z_threshold(double p_thresh);
 

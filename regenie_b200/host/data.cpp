@@ -128,6 +128,7 @@ void read_pheno_and_cov(const SampleSet& g, const std::string& pheno_file, const
   const int64_t N = (int64_t)g.keys.size();
   ph.N = N;
   ph.bt = bt;
+  ph.step1 = !step2;
   std::vector<uint8_t> in_ph;
   read_table(pheno_file, g, nullptr, ph.names, ph.Y, in_ph);
   ph.P = (int)ph.names.size();
@@ -277,6 +278,15 @@ void prep_run(Pheno& ph, const std::vector<uint8_t>* extra_mask, Log& log) {
   const int P = ph.P;
   set_masks(ph);                                             // read_pheno_and_cov, src/Pheno.cpp:102
   // pheno_impute_miss, QT (src/Pheno.cpp:1916-1931); binary traits keep the raw 0/1 values in Step 2
+  for (int p = 0; p < P && ph.bt && ph.step1; ++p) {         // binary traits in Step 1: mean over the masked-in samples
+    double tot = 0.0, ns = 0.0;
+    for (int64_t s = 0; s < N; ++s)
+      if (ph.mask[(size_t)p * N + s]) { tot += ph.Y[(size_t)p * N + s]; ns += 1.0; }
+    for (int64_t s = 0; s < N; ++s) {
+      double& y = ph.Y[(size_t)p * N + s];
+      y = ph.mask[(size_t)p * N + s] ? y : 0.0 * (tot / ns);
+    }
+  }
   for (int p = 0; p < P && !ph.bt; ++p) {
     double tot = 0.0; int64_t ns = 0;
     for (int64_t s = 0; s < N; ++s) {
@@ -301,7 +311,7 @@ void prep_run(Pheno& ph, const std::vector<uint8_t>* extra_mask, Log& log) {
   ph.C = nz;
   // residualize_phenotypes (src/Pheno.cpp:1813-1829)
   ph.scale_Y.assign(P, 1.0);
-  for (int p = 0; p < P && !ph.bt; ++p) {
+  for (int p = 0; p < P && (!ph.bt || ph.step1); ++p) {
     std::vector<double> beta(nz, 0.0);
     for (int c = 0; c < nz; ++c)
       for (int64_t i = 0; i < N; ++i) beta[c] += ph.Y[(size_t)p * N + i] * ph.X[(size_t)c * N + i];

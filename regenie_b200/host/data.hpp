@@ -55,7 +55,7 @@ struct Pheno {
   std::vector<double> neff, scale_Y;
   int64_t n_analyzed = 0;
   bool strict = false;
-  bool bt = false;
+  bool bt = false, step1 = false;
   std::vector<double> Y_raw;      // N x P raw 0/1 values (binary traits)
 };
 

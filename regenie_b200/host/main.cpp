@@ -93,7 +93,6 @@ Params parse_cli(int argc, char** argv) {
   }
   if (p.step != 1 && p.step != 2) throw Fail("specify which mode regenie should be running using option '--step'.");
   if (!p.pgen.empty()) throw Fail("--pgen input is not implemented yet in rgb200 (SURVEY 8 row a3, next).");
-  if (p.bt && p.step == 1) throw Fail("--bt --step 1 (logistic level 1) is not implemented yet in rgb200 (SURVEY 8(f)1, next).");
   if (!p.bgen.empty() && p.step == 1) throw Fail("--bgen input in --step 1 is not implemented yet in rgb200 (hard-call .bed only).");
   if (!p.bgen.empty() && !p.bed.empty()) throw Fail("specify only one genotype input (--bed or --bgen).");
   if (p.firth && !p.approx) throw Fail("exact Firth (--firth without --approx) is outside the hot path covered by rgb200; use --firth --approx.");
@@ -123,7 +122,8 @@ double now_ms() {
 }
 
 // ------------------------------------------------------------------------------------ step 1
-void run_step1(const Params& p, Log& log) {
+void run_step1(const Params& p_in, Log& log) {
+  Params p = p_in;
   BedFile g;
   g.open(p.bed, p.ref_first, read_id_list(p.exclude, 1), read_id_list(p.extract, 1), read_id_list(p.remove, 2),
          read_id_list(p.keep, 2));
@@ -132,8 +132,16 @@ void run_step1(const Params& p, Log& log) {
   if (g.snps.size() > 1000000 && !p.force_step1)
     throw Fail("it is not recommened to use more than 1000000 variants in step 1 (otherwise use '--force-step1').");
   Pheno ph;
-  read_pheno_and_cov(SampleSet{g.keys, g.key_to_ind}, p.pheno, p.covar, false, p.strict, false, ph, log);
+  read_pheno_and_cov(SampleSet{g.keys, g.key_to_ind}, p.pheno, p.covar, false, p.strict, p.bt, ph, log);
   prep_run(ph, nullptr, log);
+  if (p.bt && !p.loocv) {
+    if (ph.n_analyzed < 5000) {                       // src/Data.cpp:353-356
+      log << "   -WARNING: Sample size is less than 5,000 so using LOOCV instead of " << p.cv << "-fold CV.\n";
+      p.loocv = true;
+    } else {
+      throw Fail("k-fold logistic level 1 is not implemented yet in rgb200: use --loocv with --bt --step 1.");
+    }
+  }
   const auto blocks = set_blocks(g.snps, p.bsize);
   const int nb = (int)blocks.size();
   const int64_t N = ph.N;
@@ -197,10 +205,23 @@ void run_step1(const Params& p, Log& log) {
   // ---- level 1 (tau = B(1-h)/h, src/Step1_Models.cpp:2115)
   const double B = (double)nb * p.l0;
   std::vector<double> tau((size_t)P * p.l1), cs((size_t)5 * P * p.l1);
+  const double tau_mult = p.bt ? 3.0 / (M_PI * M_PI) : 1.0;                     // src/Step1_Models.cpp:2115-2117
   for (int ph_i = 0; ph_i < P; ++ph_i)
-    for (int j = 0; j < p.l1; ++j) tau[(size_t)ph_i * p.l1 + j] = B * (1 - h1[j]) / h1[j];
+    for (int j = 0; j < p.l1; ++j) tau[(size_t)ph_i * p.l1 + j] = B * (1 - h1[j]) / h1[j] * tau_mult;
   std::vector<int32_t> best(P);
-  rg_check(rg_l1_fit(h, tau.data(), cs.data(), best.data()));
+  if (p.bt) {
+    // offset_nullreg: covariate-only logistic fit per trait (fit_null_logistic, src/Step1_Models.cpp:54-140)
+    std::vector<double> offs((size_t)N * P);
+    for (int ph_i = 0; ph_i < P; ++ph_i) {
+      const std::vector<double> eta = null_logistic_eta(ph.names[ph_i], &ph.Y_raw[(size_t)ph_i * N], ph.X.data(), N, ph.C,
+                                                        &ph.mask[(size_t)ph_i * N]);
+      std::copy(eta.begin(), eta.end(), offs.begin() + (size_t)ph_i * N);
+    }
+    cs.assign((size_t)6 * P * p.l1, 0.0);
+    rg_check(rg_l1_fit_bt(h, ph.Y_raw.data(), offs.data(), tau.data(), cs.data(), best.data()));
+  } else {
+    rg_check(rg_l1_fit(h, tau.data(), cs.data(), best.data()));
+  }
   std::vector<int32_t> chr_of_block(nb);
   for (int b = 0; b < nb; ++b) chr_of_block[b] = blocks[b].chrom;
   std::vector<double> loco((size_t)P * 23 * N);
@@ -220,8 +241,11 @@ void run_step1(const Params& p, Log& log) {
       const double rsq = num * num / ((CS(2, j) - CS(0, j) * CS(0, j) / ne) * (CS(3, j) - CS(1, j) * CS(1, j) / ne));
       const double sse = CS(2, j) + CS(3, j) - 2 * CS(4, j);
       std::ostringstream l;
-      l << "  " << std::setw(5) << B / (B + tau[(size_t)ph_i * p.l1 + j]) << " : Rsq = " << rsq << ", MSE = " << sse / ne
-        << (j == best[ph_i] ? "<- min value" : "");
+      const double tj = tau[(size_t)ph_i * p.l1 + j];
+      l << "  " << std::setw(5) << (p.bt ? B / (B + (M_PI * M_PI / 3.0) * tj) : B / (B + tj)) << " : Rsq = " << rsq
+        << ", MSE = " << sse / ne;
+      if (p.bt) l << ", -logLik/N = " << CS(5, j) / ne;
+      l << (j == best[ph_i] ? "<- min value" : "");
       log << l.str() << "\n";
     }
     const std::string loco_file = p.out + "_" + std::to_string(ph_i + 1) + ".loco";

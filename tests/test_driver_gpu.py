@@ -239,3 +239,50 @@ def test_step1_lowmem_keep_l0_files(tmp_path, golden_dir):
         for b in (0, nb - 1):
             W = pb.oracle_l0(b)[0]                      # [P][N x R]
             np.testing.assert_allclose(data[b].T, W[ph], rtol=1e-7, atol=1e-9)
+
+
+def test_bt_step1_known_answer_then_step2_golden_file_end_to_end(tmp_path, golden_dir):
+    """The reference's two documented commands (docs/docs/options.md:20-51, test/test_bash.sh:58-89) end to end
+    through rgb200:  Step 1 `--bt --lowmem` (LOOCV is forced, N_analyzed = 494) must print the known answer
+    `0.4504 ... <- min value`, its table / .loco files must match the oracle, and Step 2 on its _pred.list must
+    reproduce the golden file the reference ships."""
+    import test_oracle_golden as tog
+    d = golden_dir
+    out1 = str(tmp_path / "fit_bin_out")
+    log = run(["--step", "1", "--bed", d + "/example", "--exclude", d + "/snplist_rm.txt", "--covarFile",
+               d + "/covariates.txt", "--phenoFile", d + "/phenotype_bin.txt", "--remove", d + "/fid_iid_to_remove.txt",
+               "--bsize", "100", "--bt", "--lowmem", "--lowmem-prefix", str(tmp_path / "tmp_rg"), "--out", out1])
+    mins = [l for l in log.splitlines() if "min value" in l]
+    assert len(mins) == 2 and any("0.4504" in l for l in mins), mins           # test/test_bash.sh:87
+    tabs = tog.bt_step1_tables(d, with_loco=True)
+    rows_got = [l for l in log.splitlines() if "Rsq =" in l]
+    rows_ref = [r for t in tabs for r in t[1]]
+    assert len(rows_got) == len(rows_ref) == 10
+    for a, b in zip(rows_got, rows_ref):
+        ta, tb = a.replace("<-", " <-").split(), b.replace("<-", " <-").split()
+        assert len(ta) == len(tb), (a, b)
+        for x, y in zip(ta, tb):
+            x, y = x.rstrip(","), y.rstrip(",")
+            try:
+                float(y)
+            except ValueError:
+                assert x == y, (a, b)
+                continue
+            assert close(x, y), (a, b)
+    for ph, (best, rows, loco, keys, pr) in enumerate(tabs):
+        ref_file = str(tmp_path / ("ref_%d.loco" % (ph + 1)))
+        step1.write_loco(ref_file, keys, pr.in_analysis, pr.mask[:, ph], loco)
+        compare_token_files(out1 + "_%d.loco" % (ph + 1), ref_file, exact_cols=1)
+    # Step 2 with the LOCO predictions rgb200 just wrote
+    out2 = str(tmp_path / "test_bin_out_firth")
+    run(["--step", "2", "--bgen", d + "/example.bgen", "--covarFile", d + "/covariates.txt", "--phenoFile",
+         d + "/phenotype_bin.txt", "--remove", d + "/fid_iid_to_remove.txt", "--bsize", "200", "--bt", "--firth",
+         "--approx", "--pThresh", "0.01", "--pred", out1 + "_pred.list", "--out", out2])
+    got = open(out2 + "_Y1.regenie").read().splitlines()
+    ref = open(d + "/test_bin_out_firth_Y1.regenie").read().splitlines()
+    assert got[0] == ref[0] and len(got) == len(ref) == 1001
+    for x, y in zip(got[1:], ref[1:]):
+        tx, ty = x.split(), y.split()
+        assert tx[:9] == ty[:9] and tx[13] == ty[13], (x, y)
+        for a, c in zip(tx[9:13], ty[9:13]):
+            assert close(a, c, rtol=1e-4), (x, y)

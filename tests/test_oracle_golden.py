@@ -12,7 +12,7 @@ import numpy as np
 from oracle import plink, prep, step1, step1_bt
 
 
-def bt_step1_tables(d):
+def bt_step1_tables(d, with_loco=False):
     excl = {l.split()[0] for l in open(d + "/snplist_rm.txt") if l.strip()}
     rm = {"_".join(l.split()[:2]) for l in open(d + "/fid_iid_to_remove.txt") if l.strip()}
     bim = plink.read_bim(d + "/example.bim", exclude=excl)
@@ -40,7 +40,13 @@ def bt_step1_tables(d):
         tau = B * (1 - h) / h * 3 / np.pi ** 2                      # src/Step1_Models.cpp:2115-2117
         off = step1_bt.null_offset(pr.Y_raw[:, ph], pr.X, pr.mask[:, ph])
         cs = step1_bt.level1_logistic_loocv(W, pr.Y_raw[:, ph], off, pr.mask[:, ph], tau)
-        out.append(step1_bt.output_table(cs, pr.neff[ph], B, tau))
+        best, rows = step1_bt.output_table(cs, pr.neff[ph], B, tau)
+        if with_loco:
+            chr_cols = [(1, 0, B)]                                   # example/ holds chromosome 1 only
+            pred = step1_bt.predictions_binary_loocv(W, pr.Y_raw[:, ph], off, pr.mask[:, ph], tau[best], chr_cols)
+            out.append((best, rows, step1.loco_matrix(pred, chr_cols), keys, pr))
+        else:
+            out.append((best, rows))
     return out
 
 
