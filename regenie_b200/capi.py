@@ -46,7 +46,7 @@ EXPORTS = [
     "rg_last_error", "rg_version", "rg_device_count", "rg_step1_create", "rg_destroy", "rg_sync",
     "rg_l0_block_bed", "rg_l0_status", "rg_l0_fetch_W", "rg_l1_fit", "rg_loco", "rg_step2_create",
     "rg_s2_set_chr", "rg_s2_block_bed", "rg_W_info", "rg_debug_fetch", "rg_launch_count", "rg_stream",
-    "rg_set_timing", "rg_get_timing", "rg_fence", "rg_s2_set_chr_bt", "rg_s2_block_bgen8_bt", "rg_s2_block_bgen8", "rg_s2_firth", "rg_l1_fit_bt",
+    "rg_set_timing", "rg_get_timing", "rg_fence", "rg_s2_set_chr_bt", "rg_s2_block_bgen8_bt", "rg_s2_block_bgen8", "rg_s2_firth", "rg_l1_fit_bt", "rg_W_export", "rg_W_attach_peer", "rg_l1_select",
 ]
 
 _lib = None
@@ -160,6 +160,23 @@ class Step1:
         best = np.zeros(self.P, dtype=np.int32)
         check(lib().rg_l1_fit(self.h, _ptr(tau), _ptr(cs), _ptr(best)))
         return cs, best
+
+    def W_export(self):
+        """64-byte CUDA IPC handle of this rank's W allocation."""
+        buf = (C.c_ubyte * 64)()
+        L = lib(); L.rg_W_export.argtypes = [C.c_void_p, C.c_void_p]
+        check(L.rg_W_export(self.h, buf))
+        return bytes(buf)
+
+    def W_attach_peer(self, handle, owned_by_peer):
+        L = lib(); L.rg_W_attach_peer.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+        ob = np.ascontiguousarray(owned_by_peer, dtype=np.uint8)
+        check(L.rg_W_attach_peer(self.h, handle, _ptr(ob)))
+
+    def l1_select(self, sel):
+        L = lib(); L.rg_l1_select.argtypes = [C.c_void_p, C.c_void_p]
+        sb = np.ascontiguousarray(sel, dtype=np.uint8)
+        check(L.rg_l1_select(self.h, _ptr(sb)))
 
     def l1_fit_bt(self, y_raw, offset, tau):
         """Binary traits: logistic level 1 (LOOCV).  Returns cumsums [6, P, R1] and argmin -logLik/N."""

@@ -78,14 +78,14 @@ void launch_chol_rows_backsolve(double* cm, int64_t stride, int nC, int row0, in
 // ---- l0_predict.cu
 struct PredictArgs {
   int bs, rows_p, C, P, R, Qp, cpp, col0;
-  int64_t npad, words_per_row, w_stride;
+  int64_t npad, words_per_row;
   const uint32_t* gp;
   const int32_t* tile_fold;  // [npad/128]
   const double *gam, *gmu;   // [K][rows_p][Qp]
   const double* cvec;        // [K][Qp][C]
   const double* xy;          // [npad][cpp]
   const uint8_t* mask;       // [P][npad]
-  double* W;                 // [P][w_stride], column-major npad x B per phenotype
+  double* const* W;          // [P] base of each phenotype's npad x B column-major predictor matrix (may be peer memory)
   double* part;              // [ntiles][Qp][2]
 };
 void launch_l0_gamma(const double* cm, int64_t cm_stride, int ldc, int nC, int R, int P, int Qp,
@@ -93,20 +93,20 @@ void launch_l0_gamma(const double* cm, int64_t cm_stride, int ldc, int nC, int R
                      const double* Bv, int C, double* gam, double* gmu, double* cvec, cudaStream_t s);
 void launch_l0_predict(const PredictArgs& a, int ntiles, cudaStream_t s);
 void launch_l0_standardize(const double* part, int ntiles, int Qp, int Q, int P, const double* neff,
-                           double* mean_invsd, double* W, int64_t w_stride, int64_t npad, int col0,
+                           double* mean_invsd, double* const* W, int64_t npad, int col0,
                            const uint8_t* is_real, cudaStream_t s);
 int predict_qt();
 
 // ---- predict_tcgen05.cu
 struct PredictTcArgs {
   int rows_p, C, P, Q, Qp, cpp, col0, ngroups;
-  int64_t npad, w_stride;
+  int64_t npad;
   const int32_t* tile_fold;
   const double* scale;       // [K][Qp]
   const double* cvec;        // [K][Qp][C]
   const double* xy;
   const uint8_t* mask;
-  double* W;
+  double* const* W;
   double* part;
   long long* dbg;            // optional per-CTA clock64 stamps (profiling aid)
 };
@@ -114,7 +114,7 @@ void make_byte_tensor_map(CUtensorMap* tm, const uint8_t* basep, int64_t inner, 
 size_t predict_tc_dig_bytes(int K, int ngroups, int rows_p);
 void launch_l0_gamma_limbs(const double* gam, const double* gmu, int Qp, int Q, int bs, int rows_p, int K,
                            double* scale, uint8_t* dig, int ngroups, cudaStream_t s);
-int launch_l0_colsum(const double* W, int64_t w_stride, int64_t npad, int col0, int P, int Q, int Qp, double* part,
+int launch_l0_colsum(double* const* W, int64_t npad, int col0, int P, int Q, int Qp, double* part,
                      cudaStream_t s);
 void launch_l0_predict_tcgen05(const CUtensorMap& tmZ, const CUtensorMap& tmD, const PredictTcArgs& a, int ntiles,
                                cudaStream_t s);
@@ -139,9 +139,9 @@ void launch_l0_loocv_fill(const uint32_t* gp, int64_t npad, int bs, int nC, cons
                           const double* Bv, int C, const double* xy, int cpp, double* cm, int64_t cm_stride,
                           int nrow0, int R, cudaStream_t s);
 void launch_l0_loocv_pred(const double* cm, int64_t cm_stride, int nC, int bs, int Ppad, int P, int R,
-                          const double* xy, int cpp, int C, const uint8_t* mask, int64_t npad, double* W,
-                          int64_t w_stride, int col0, double* part, int Qp, cudaStream_t s);
-void launch_l0_loocv_std_apply(double* W, int64_t w_stride, int64_t npad, int col0, int P, int Q, const uint8_t* mask,
+                          const double* xy, int cpp, int C, const uint8_t* mask, int64_t npad, double* const* W,
+                          int col0, double* part, int Qp, cudaStream_t s);
+void launch_l0_loocv_std_apply(double* const* W, int64_t npad, int col0, int P, int Q, const uint8_t* mask,
                                const double* mean_invsd, cudaStream_t s);
 void launch_l1_loocv_fill(const double* W, int64_t ldw, int B, int nC, double* cm, int64_t cm_stride, int nrow0,
                           int R1, int64_t npad, cudaStream_t s);

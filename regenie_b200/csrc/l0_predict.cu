@@ -113,7 +113,7 @@ l0_predict_kernel(PredictArgs a) {
       const double* cv = a.cvec + ((int64_t)f * a.Qp + qq) * a.C;
       for (int c = 0; c < a.C; ++c) v -= xr[c] * cv[c];
       v *= (double)a.mask[(int64_t)p * a.npad + t];
-      a.W[(int64_t)p * a.w_stride + (int64_t)(a.col0 + r) * a.npad + t] = v;
+      a.W[p][(int64_t)(a.col0 + r) * a.npad + t] = v;
     }
     // deterministic CTA reduction: warp shuffle tree then fixed-order sum of 4 warps
     double s1 = v, s2 = v * v;
@@ -161,14 +161,14 @@ __global__ void l0_std_reduce_kernel(const double* __restrict__ part, int ntiles
 }
 
 // grid: (Npad/256, Q)
-__global__ void l0_std_apply_kernel(double* __restrict__ W, int64_t w_stride, int64_t npad, int col0,
+__global__ void l0_std_apply_kernel(double* const* __restrict__ W, int64_t npad, int col0,
                                     int P, const uint8_t* __restrict__ is_real,
                                     const double* __restrict__ mean_invsd) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int q = blockIdx.y;
   if (t >= npad) return;
   const int r = q / P, p = q % P;
-  double* w = W + (int64_t)p * w_stride + (int64_t)(col0 + r) * npad + t;
+  double* w = W[p] + (int64_t)(col0 + r) * npad + t;
   // the reference centres every row of the fold (masked samples become -mean*invsd,
   // src/Step1_Models.cpp:556-557); layout padding rows stay exactly zero.
   *w = is_real[t] ? (*w - mean_invsd[2 * q]) * mean_invsd[2 * q + 1] : 0.0;
@@ -189,11 +189,11 @@ void launch_l0_predict(const PredictArgs& a, int ntiles, cudaStream_t s) {
 }
 
 void launch_l0_standardize(const double* part, int ntiles, int Qp, int Q, int P, const double* neff,
-                           double* mean_invsd, double* W, int64_t w_stride, int64_t npad, int col0,
+                           double* mean_invsd, double* const* W, int64_t npad, int col0,
                            const uint8_t* is_real, cudaStream_t s) {
   l0_std_reduce_kernel<<<Q, 256, 0, s>>>(part, ntiles, Qp, P, neff, mean_invsd);
   dim3 grid((unsigned)ceil_div(npad, 256), Q);
-  l0_std_apply_kernel<<<grid, 256, 0, s>>>(W, w_stride, npad, col0, P, is_real, mean_invsd);
+  l0_std_apply_kernel<<<grid, 256, 0, s>>>(W, npad, col0, P, is_real, mean_invsd);
 }
 
 void launch_l0_std_reduce_only(const double* part, int ntiles, int Qp, int Q, int P, const double* neff,

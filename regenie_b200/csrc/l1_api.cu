@@ -88,6 +88,7 @@ static void l1_fit(rg_ctx* h, const double* tau_host, double* cumsum, int32_t* b
     h->l1_bvec.alloc((size_t)P * nC);
   }
   for (int p = 0; p < P; ++p) {
+    if (!h->l1_select[p]) continue;                       // fitted by the rank that owns this phenotype
     const double* Wp = h->W.p + (size_t)p * Npad * h->B;
     const int ycol = h->C + p;
     launch_l1_gram(Wp, Npad, B, h->l1_chunks.p, nch, h->l1_part.p, part_stride, ldp, s);
@@ -154,6 +155,7 @@ static void l1_fit(rg_ctx* h, const double* tau_host, double* cumsum, int32_t* b
   RG_CUDA(cudaStreamSynchronize(s));
   h->best_idx.assign(P, 0);
   for (int p = 0; p < P; ++p) {
+    if (!h->l1_select[p]) continue;
     const double* v = &sums[(size_t)p * NV];
     double best = 1e10;                                   // src/Data.cpp:1021-1037
     for (int j = 0; j < R1; ++j) {
@@ -319,6 +321,7 @@ static void l1_fit_bt(rg_ctx* h, const double* y_raw, const double* offset, cons
   RG_CUDA(cudaMemsetAsync(h->l1_cm.p, 0, (size_t)cm_stride * 8, s));
   h->best_idx.assign(P, 0);
   for (int p = 0; p < P; ++p) {
+    if (!h->l1_select[p]) continue;
     // pad-order copies of the trait's 0/1 values, mask and null-model offset
     std::vector<double> off(Npad, 0.0);
     std::vector<int8_t> ym(Npad, 0);
@@ -397,6 +400,7 @@ static void loco(rg_ctx* h, const int32_t* chr_of_block, double* pred_out) {
   h->l1_pred.alloc((size_t)nchr * Npad);
   std::vector<double> pred((size_t)nchr * Npad);
   for (int p = 0; p < P; ++p) {
+    if (!h->l1_select[p]) continue;
     if (h->l1_bt)
       launch_l1_bt_chr_pred(h->W.p + (size_t)p * Npad * h->B, Npad, nC, h->l1_zrows.p + (size_t)p * Npad * nC,
                             h->l1_hvec.p + (size_t)p * Npad, h->l1_bvec.p + (size_t)p * nC, nchr, h->l1_chr_cols.p,

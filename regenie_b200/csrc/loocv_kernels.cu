@@ -36,7 +36,7 @@ __global__ void l0_loocv_fill_kernel(const uint32_t* __restrict__ gp, int64_t wo
 __global__ void __launch_bounds__(128)
 l0_loocv_pred_kernel(const double* __restrict__ cm, int64_t cm_stride, int nC, int bs, int Ppad, int P, int R,
                      const double* __restrict__ xy, int cpp, int C, const uint8_t* __restrict__ mask, int64_t npad,
-                     double* __restrict__ W, int64_t w_stride, int col0, double* __restrict__ part, int Qp) {
+                     double* const* __restrict__ W, int col0, double* __restrict__ part, int Qp) {
   extern __shared__ double us[];                 // u_p rows [P][nC]
   __shared__ double red[2][4][kMaxPhenoTile];
   const int r = blockIdx.y;
@@ -77,7 +77,7 @@ l0_loocv_pred_kernel(const double* __restrict__ cm, int64_t cm_stride, int nC, i
             const double y = xy[(int64_t)t * cpp + C + pp];
             double v = (yh[p] - h * y) / (1.0 - h);                       // src/Step1_Models.cpp:660-663
             v *= (double)mask[(int64_t)pp * npad + t];                    // :697
-            W[(int64_t)pp * w_stride + (int64_t)(col0 + r) * npad + t] = v;
+            W[pp][(int64_t)(col0 + r) * npad + t] = v;
             s1[p] += v; s2[p] += v * v;
           }
       }
@@ -95,13 +95,13 @@ l0_loocv_pred_kernel(const double* __restrict__ cm, int64_t cm_stride, int nC, i
 
 // LOOCV standardisation: masked entries are re-zeroed (src/Step1_Models.cpp:699-706).
 // grid: (Npad/256, Q)
-__global__ void l0_loocv_std_apply_kernel(double* __restrict__ W, int64_t w_stride, int64_t npad, int col0, int P,
+__global__ void l0_loocv_std_apply_kernel(double* const* __restrict__ W, int64_t npad, int col0, int P,
                                           const uint8_t* __restrict__ mask, const double* __restrict__ mean_invsd) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int q = blockIdx.y;
   if (t >= npad) return;
   const int r = q / P, p = q % P;
-  double* w = W + (int64_t)p * w_stride + (int64_t)(col0 + r) * npad + t;
+  double* w = W[p] + (int64_t)(col0 + r) * npad + t;
   *w = mask[(int64_t)p * npad + t] ? (*w - mean_invsd[2 * q]) * mean_invsd[2 * q + 1] : 0.0;
 }
 
@@ -227,8 +227,8 @@ void launch_l0_loocv_fill(const uint32_t* gp, int64_t npad, int bs, int nC, cons
 }
 
 void launch_l0_loocv_pred(const double* cm, int64_t cm_stride, int nC, int bs, int Ppad, int P, int R,
-                          const double* xy, int cpp, int C, const uint8_t* mask, int64_t npad, double* W,
-                          int64_t w_stride, int col0, double* part, int Qp, cudaStream_t s) {
+                          const double* xy, int cpp, int C, const uint8_t* mask, int64_t npad, double* const* W,
+                          int col0, double* part, int Qp, cudaStream_t s) {
   const size_t smem = (size_t)std::min(P, kMaxPhenoTile) * nC * sizeof(double);
   static size_t smem_set = 0;
   if (smem > smem_set) {
@@ -236,14 +236,14 @@ void launch_l0_loocv_pred(const double* cm, int64_t cm_stride, int nC, int bs, i
     smem_set = smem;
   }
   dim3 grid((unsigned)(npad / 128), R);
-  l0_loocv_pred_kernel<<<grid, 128, smem, s>>>(cm, cm_stride, nC, bs, Ppad, P, R, xy, cpp, C, mask, npad, W, w_stride,
+  l0_loocv_pred_kernel<<<grid, 128, smem, s>>>(cm, cm_stride, nC, bs, Ppad, P, R, xy, cpp, C, mask, npad, W,
                                               col0, part, Qp);
 }
 
-void launch_l0_loocv_std_apply(double* W, int64_t w_stride, int64_t npad, int col0, int P, int Q, const uint8_t* mask,
+void launch_l0_loocv_std_apply(double* const* W, int64_t npad, int col0, int P, int Q, const uint8_t* mask,
                                const double* mean_invsd, cudaStream_t s) {
   dim3 grid((unsigned)ceil_div(npad, 256), Q);
-  l0_loocv_std_apply_kernel<<<grid, 256, 0, s>>>(W, w_stride, npad, col0, P, mask, mean_invsd);
+  l0_loocv_std_apply_kernel<<<grid, 256, 0, s>>>(W, npad, col0, P, mask, mean_invsd);
 }
 
 void launch_l1_loocv_fill(const double* W, int64_t ldw, int B, int nC, double* cm, int64_t cm_stride, int nrow0,

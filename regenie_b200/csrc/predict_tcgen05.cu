@@ -269,7 +269,7 @@ l0_predict_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_
         double val = fma((double)ihi[j], w3, fma((double)imid[j], w7, (double)ilo[j] * w8)) * s_scale[qq];
         for (int c = 0; c < a.C; ++c) val -= xr[c] * s_cvec[qq * a.C + c];
         val *= (double)a.mask[(int64_t)p * a.npad + t];
-        a.W[(int64_t)p * a.w_stride + (int64_t)(a.col0 + r) * a.npad + t] = val;
+        a.W[p][(int64_t)(a.col0 + r) * a.npad + t] = val;
       }
     }
     if (a.dbg && threadIdx.x == 64) {
@@ -288,12 +288,12 @@ l0_predict_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_
 // Column sums of the raw predictions for the standardisation: part[chunk][q] = (sum, sum of squares) over
 // a chunk of 8192 samples, fixed-order tree reduction.  grid: (Q, nchunks), block 256.
 __global__ void __launch_bounds__(256)
-l0_colsum_kernel(const double* __restrict__ W, int64_t w_stride, int64_t npad, int col0, int P, int Qp,
+l0_colsum_kernel(double* const* __restrict__ W, int64_t npad, int col0, int P, int Qp,
                  double* __restrict__ part) {
   __shared__ double r1[256], r2[256];
   const int q = blockIdx.x, r = q / P, p = q % P;
   const int64_t t0 = (int64_t)blockIdx.y * 8192;
-  const double* w = W + (int64_t)p * w_stride + (int64_t)(col0 + r) * npad;
+  const double* w = W[p] + (int64_t)(col0 + r) * npad;
   double s1 = 0.0, s2 = 0.0;
   for (int64_t t = t0 + threadIdx.x; t < min(t0 + 8192, npad); t += 256) {
     const double v = w[t];
@@ -312,11 +312,11 @@ l0_colsum_kernel(const double* __restrict__ W, int64_t w_stride, int64_t npad, i
   }
 }
 
-int launch_l0_colsum(const double* W, int64_t w_stride, int64_t npad, int col0, int P, int Q, int Qp, double* part,
+int launch_l0_colsum(double* const* W, int64_t npad, int col0, int P, int Q, int Qp, double* part,
                      cudaStream_t s) {
   const int nchunks = (int)ceil_div(npad, 8192);
   dim3 grid(Q, nchunks);
-  l0_colsum_kernel<<<grid, 256, 0, s>>>(W, w_stride, npad, col0, P, Qp, part);
+  l0_colsum_kernel<<<grid, 256, 0, s>>>(W, npad, col0, P, Qp, part);
   return nchunks;
 }
 

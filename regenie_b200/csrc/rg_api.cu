@@ -360,15 +360,14 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
     h->launches += chol_num_launches(nC);
   }
   h->last_bs = bs; h->last_rows_p = rows_p; h->last_nC = nC; h->last_n_aug = n_aug; h->last_nmat = nmat;
-  const int64_t w_stride = Npad * h->B;
   const int col0 = block_id * R;
   if (h->loocv) {
     // closed-form leave-one-out predictions (src/Step1_Models.cpp:654-663) + LOOCV standardisation (:694-706)
     ScopedTimer t(h, "l0_predict", s);
-    launch_l0_loocv_pred(L.cm.p, aa.cm_stride, nC, bs, Ppad, P, R, h->xy.p, h->cpp, C, h->mask.p, Npad, h->W.p,
-                         w_stride, col0, L.part.p, Qp, s);
+    launch_l0_loocv_pred(L.cm.p, aa.cm_stride, nC, bs, Ppad, P, R, h->xy.p, h->cpp, C, h->mask.p, Npad, h->W_tab.p,
+                         col0, L.part.p, Qp, s);
     launch_l0_std_reduce_only(L.part.p, ntiles_s, Qp, Q, P, h->neff.p, L.mean_invsd.p, s);
-    launch_l0_loocv_std_apply(h->W.p, w_stride, Npad, col0, P, Q, h->mask.p, L.mean_invsd.p, s);
+    launch_l0_loocv_std_apply(h->W_tab.p, Npad, col0, P, Q, h->mask.p, L.mean_invsd.p, s);
     h->launches += 3;
     return;
   }
@@ -385,9 +384,9 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
                     L.gam.p, L.gmu.p, L.cvec.p, s);
     PredictArgs pa;
     pa.bs = bs; pa.rows_p = rows_p; pa.C = C; pa.P = P; pa.R = R; pa.Qp = Qp; pa.cpp = h->cpp;
-    pa.col0 = col0; pa.npad = Npad; pa.words_per_row = Npad / 16; pa.w_stride = w_stride;
+    pa.col0 = col0; pa.npad = Npad; pa.words_per_row = Npad / 16;
     pa.gp = L.gp.p; pa.tile_fold = h->tile_fold.p; pa.gam = L.gam.p; pa.gmu = L.gmu.p;
-    pa.cvec = L.cvec.p; pa.xy = h->xy.p; pa.mask = h->mask.p; pa.W = h->W.p; pa.part = L.part.p;
+    pa.cvec = L.cvec.p; pa.xy = h->xy.p; pa.mask = h->mask.p; pa.W = h->W_tab.p; pa.part = L.part.p;
     int nparts = ntiles_s;
     static const bool use_f64_predict = [] { const char* e = getenv("RG_B200_PREDICT"); return e && std::string(e) == "f64"; }();
     if (use_f64_predict) {
@@ -410,15 +409,15 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
       launch_l0_gamma_limbs(L.gam.p, L.gmu.p, Qp, Q, bs, rows_p, K, L.dscale.p, L.dig.p, ngroups, s);
       PredictTcArgs ta;
       ta.rows_p = rows_p; ta.C = C; ta.P = P; ta.Q = Q; ta.Qp = Qp; ta.cpp = h->cpp; ta.col0 = col0; ta.ngroups = ngroups;
-      ta.npad = Npad; ta.w_stride = w_stride; ta.tile_fold = h->tile_fold.p; ta.scale = L.dscale.p; ta.cvec = L.cvec.p;
-      ta.xy = h->xy.p; ta.mask = h->mask.p; ta.W = h->W.p; ta.part = L.part.p;
+      ta.npad = Npad; ta.tile_fold = h->tile_fold.p; ta.scale = L.dscale.p; ta.cvec = L.cvec.p;
+      ta.xy = h->xy.p; ta.mask = h->mask.p; ta.W = h->W_tab.p; ta.part = L.part.p;
       ta.dbg = nullptr;
       if (getenv("RG_DBG_CLK")) { h->dbg_clk.alloc((size_t)ntiles_s * ngroups * 4); ta.dbg = h->dbg_clk.p; }
       launch_l0_predict_tcgen05(L.tmaps[rows_p], L.dmaps[rows_p], ta, ntiles_s, s);
-      nparts = launch_l0_colsum(h->W.p, w_stride, Npad, col0, P, Q, Qp, L.part.p, s);
+      nparts = launch_l0_colsum(h->W_tab.p, Npad, col0, P, Q, Qp, L.part.p, s);
       h->launches += 2;
     }
-    launch_l0_standardize(L.part.p, nparts, Qp, Q, P, h->neff.p, L.mean_invsd.p, h->W.p, w_stride, Npad, col0,
+    launch_l0_standardize(L.part.p, nparts, Qp, Q, P, h->neff.p, L.mean_invsd.p, h->W_tab.p, Npad, col0,
                           h->is_real.p, s);
     h->launches += 5;
   }
@@ -501,6 +500,13 @@ int rg_step1_create(const rg_step1_config* cfg, const double* X, const double* Y
   RG_CUDA(cudaMemset(h->err_slot.p, 0xFF, 8));
   h->W.alloc((size_t)h->P * h->Npad * h->B);
   RG_CUDA(cudaMemset(h->W.p, 0, (size_t)h->P * h->Npad * h->B * 8));
+  // every level-0 kernel addresses W through this table; rg_W_attach_peer redirects a phenotype to the HBM of
+  // the GPU that owns its level-1 fit (stores travel over NVLink as the tiles are produced)
+  h->W_host_tab.resize(h->P);
+  for (int p = 0; p < h->P; ++p) h->W_host_tab[p] = h->W.p + (size_t)p * h->Npad * h->B;
+  h->W_tab.alloc(h->P);
+  RG_CUDA(cudaMemcpy(h->W_tab.p, h->W_host_tab.data(), h->P * sizeof(double*), cudaMemcpyHostToDevice));
+  h->l1_select.assign(h->P, 1);
   *out = h.release();
   RG_API_END
 }
@@ -508,12 +514,50 @@ int rg_step1_create(const rg_step1_config* cfg, const double* X, const double* Y
 void rg_destroy(rg_handle h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  for (void* m : h->W_peer_mapped) cudaIpcCloseMemHandle(m);
   for (auto& l : h->lanes) cudaStreamSynchronize(l->stream);
   cudaStreamSynchronize(h->stream);
   rg::flush_timers(h);
   for (auto& l : h->lanes) { cudaEventDestroy(l->done); cudaStreamDestroy(l->stream); }
   cudaStreamDestroy(h->stream);
   delete h;
+}
+
+int rg_W_export(rg_handle h, void* ipc_handle_64) {
+  RG_API_BEGIN
+  RG_CHECK(h && h->kind == 1 && ipc_handle_64, "bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  RG_CUDA(cudaSetDevice(h->device));
+  cudaIpcMemHandle_t mh;
+  RG_CUDA(cudaIpcGetMemHandle(&mh, h->W.p));
+  memcpy(ipc_handle_64, &mh, 64);
+  RG_API_END
+}
+
+int rg_W_attach_peer(rg_handle h, const void* ipc_handle_64, const uint8_t* owned_by_peer) {
+  RG_API_BEGIN
+  RG_CHECK(h && h->kind == 1 && ipc_handle_64 && owned_by_peer, "bad argument");
+  RG_CUDA(cudaSetDevice(h->device));
+  for (auto& l : h->lanes) RG_CUDA(cudaStreamSynchronize(l->stream));
+  cudaIpcMemHandle_t mh;
+  memcpy(&mh, ipc_handle_64, 64);
+  void* base = nullptr;
+  RG_CUDA(cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess));
+  h->W_peer_mapped.push_back(base);
+  for (int p = 0; p < h->P; ++p)
+    if (owned_by_peer[p]) {
+      h->W_host_tab[p] = static_cast<double*>(base) + (size_t)p * h->Npad * h->B;
+      h->l1_select[p] = 0;
+    }
+  RG_CUDA(cudaMemcpy(h->W_tab.p, h->W_host_tab.data(), h->P * sizeof(double*), cudaMemcpyHostToDevice));
+  RG_API_END
+}
+
+int rg_l1_select(rg_handle h, const uint8_t* sel) {
+  RG_API_BEGIN
+  RG_CHECK(h && h->kind == 1 && sel, "bad argument");
+  h->l1_select.assign(sel, sel + h->P);
+  RG_API_END
 }
 
 int rg_sync(rg_handle h) {
@@ -573,7 +617,7 @@ int rg_l0_fetch_W(rg_handle h, int32_t block_id, int32_t ph, double* out) {
   RG_CUDA(cudaSetDevice(h->device));
   for (auto& l : h->lanes) RG_CUDA(cudaStreamSynchronize(l->stream));
   std::vector<double> tmp((size_t)h->Npad * h->R);
-  const double* src = h->W.p + (size_t)ph * h->Npad * h->B + (size_t)block_id * h->R * h->Npad;
+  const double* src = h->W_host_tab[ph] + (size_t)block_id * h->R * h->Npad;   // local or peer-mapped
   RG_CUDA(cudaMemcpyAsync(tmp.data(), src, tmp.size() * 8, cudaMemcpyDeviceToHost, h->stream));
   RG_CUDA(cudaStreamSynchronize(h->stream));
   for (int r = 0; r < h->R; ++r)

@@ -55,3 +55,59 @@ def gather_block_owner(n_blocks: int, device=None):
     if dist.is_initialized():
         dist.all_reduce(owner, op=dist.ReduceOp.MAX)
     return owner.cpu().tolist()
+
+
+# ---------------------------------------------------------------------------------------- Step 1 across GPUs
+def phenotype_owner(n_pheno: int, world: int):
+    """Level 1 is sharded by phenotype: phenotype p is fitted by rank p mod world."""
+    return [p % world for p in range(n_pheno)]
+
+
+def _sum_to_all(arr, device):
+    """Element-wise sum over ranks of a host array (entries not owned by a rank are exactly 0, so this is a
+    gather).  CPU tensors under gloo, CUDA tensors under nccl."""
+    import numpy as np
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    if dist.get_backend() == "nccl":
+        t = t.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy()
+
+
+def step1_distributed(st, n_blocks, feed_block, tau, chr_of_block, device, bt=None):
+    """Step 1 with level-0 blocks sharded across ranks and level 1 sharded by phenotype.
+
+    st          capi.Step1 created identically on every rank (total_blocks = n_blocks)
+    feed_block  callable(block_id) -> None; runs rg_l0_block_bed for that block on this rank
+    bt          None for quantitative traits, or (y_raw, offset) for the logistic level 1
+    There is no data-path collective: each rank's level-0 kernels store the predictor tiles of a phenotype
+    straight into the HBM of the rank that owns it (CUDA IPC mapping over NVLink/NVSwitch,
+    rg_W_export / rg_W_attach_peer); torch.distributed carries the 64-byte handles, the barriers and the
+    final gather of the P x R1 sums and N x 23 LOCO predictions.  Returns (cumsums, best_idx, loco) on every rank.
+    """
+    rank, world = dist.get_rank(), dist.get_world_size()
+    owner = phenotype_owner(st.P, world)
+    handles = [None] * world
+    dist.all_gather_object(handles, st.W_export())
+    for r in range(world):
+        if r != rank:
+            st.W_attach_peer(handles[r], [1 if owner[p] == r else 0 for p in range(st.P)])
+    dist.barrier()
+    first, n = partition_blocks(n_blocks, world)[rank]
+    for b in range(first, first + n):
+        feed_block(b)
+    st.sync()
+    code = first_error(int(st.status()), device if dist.get_backend() == "nccl" else None)
+    if code:
+        raise RuntimeError("level 0 failed on some rank (status %d)" % code)
+    dist.barrier()                      # every rank's tiles have landed in their owners' HBM
+    if bt is None:
+        cs, best = st.l1_fit(tau)
+    else:
+        cs, best = st.l1_fit_bt(bt[0], bt[1], tau)
+    loco = st.loco(chr_of_block)
+    cs = _sum_to_all(cs, device)
+    best = _sum_to_all(best.astype("int64"), device).astype("int32")
+    loco = _sum_to_all(loco, device)
+    dist.barrier()                      # peers may unmap / free W only after every owner is done
+    return cs, best, loco
