@@ -50,6 +50,7 @@ struct rg_ctx {
     rg::DevBuf<uint32_t> gp;          // [rows_p][Npad/16]
     rg::DevBuf<uint8_t> z;            // [2 rows_p][Npad] e4m3
     rg::DevBuf<float> zz;             // [K][2 rows_p][2 rows_p]
+    rg::DevBuf<float> tstat;          // [K][2 rows_p][stat_drows] exact digit sums of the statistics tiles
     rg::DevBuf<int32_t> cnt_part, cnt_fold;
     rg::DevBuf<double> sum_part, sum_fold;
     rg::DevBuf<double> mu, inv_sd, Bv, Af, Qf, gty_f, rhs;
@@ -67,6 +68,14 @@ struct rg_ctx {
   rg::DevBuf<uint32_t> gp;           // step 2
   std::map<int, std::unique_ptr<rg::DevBuf<int2>>> tile_lists;
   std::map<int, int> tile_counts;
+  // statistics on the tensor cores: digit rows of (X | Y), built once
+  bool stats_tc = false;
+  int stat_drows = 0;
+  rg::DevBuf<uint8_t> xyD;
+  rg::DevBuf<double> xy_scale;
+  CUtensorMap tmD;
+  std::map<int, std::unique_ptr<rg::DevBuf<int2>>> stat_tile_lists;
+  std::map<int, int> stat_tile_counts;
 
   // ---- level-0 output
   rg::DevBuf<double> W;             // [P][Npad x B] column-major

@@ -107,7 +107,8 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
 
 // grid: (ntiles, K folds)
 __global__ void __launch_bounds__(NTHREADS, 1)
-gram_fp8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const int2* __restrict__ tiles,
+gram_fp8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmB,
+                        const int2* __restrict__ tiles,
                         const int2* __restrict__ fold_k, float* __restrict__ out, int ldo,
                         int64_t fold_stride) {
   extern __shared__ uint8_t smem_raw[];
@@ -137,6 +138,7 @@ gram_fp8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const int2* __r
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmZ) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -159,8 +161,8 @@ gram_fp8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const int2* __r
         mbar_expect_tx(full_bar + 8 * s, STAGE_BYTES);
         const int kc = (fk.x + kb) * BK;
         tma_load_2d(sA + s * A_BYTES, &tmZ, full_bar + 8 * s, kc, tile.x * BM);
-        tma_load_2d(sB + s * B_BYTES, &tmZ, full_bar + 8 * s, kc, tile.y * BN);
-        tma_load_2d(sB + s * B_BYTES + A_BYTES, &tmZ, full_bar + 8 * s, kc, tile.y * BN + 128);
+        tma_load_2d(sB + s * B_BYTES, &tmB, full_bar + 8 * s, kc, tile.y * BN);
+        tma_load_2d(sB + s * B_BYTES + A_BYTES, &tmB, full_bar + 8 * s, kc, tile.y * BN + 128);
       }
     }
   } else if (warp == 1) {
@@ -267,7 +269,7 @@ void gram_tile_list(int rows2, std::vector<int2>& tiles) {
     for (int mi = 2 * nj; mi < rows2 / BM; ++mi) tiles.push_back(make_int2(mi, nj));
 }
 
-void launch_gram_tcgen05(const CUtensorMap& tm, const int2* tiles, int ntiles, const int2* fold_k, int K,
+void launch_gram_tcgen05(const CUtensorMap& tm, const CUtensorMap& tmB, const int2* tiles, int ntiles, const int2* fold_k, int K,
                          float* out, int ldo, int64_t fold_stride, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -276,7 +278,7 @@ void launch_gram_tcgen05(const CUtensorMap& tm, const int2* tiles, int ntiles, c
     attr_set = true;
   }
   dim3 grid(ntiles, K);
-  gram_fp8_tcgen05_kernel<<<grid, NTHREADS, gram_smem_bytes(), s>>>(tm, tiles, fold_k, out, ldo, fold_stride);
+  gram_fp8_tcgen05_kernel<<<grid, NTHREADS, gram_smem_bytes(), s>>>(tm, tmB, tiles, fold_k, out, ldo, fold_stride);
 }
 
 void launch_gram_reference(const uint8_t* z, int64_t npad, int rows2, int k0, int k1, float* out, int ldo,

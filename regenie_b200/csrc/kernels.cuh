@@ -59,8 +59,16 @@ void launch_l0_assemble(const AssembleArgs& a, const double* rhs, int P, int Ppa
 // ---- gram_tcgen05.cu
 void make_gram_tensor_map(CUtensorMap* tm, const uint8_t* z, int64_t npad, int rows2);
 size_t gram_smem_bytes();
+// ---- l0_stats_tc.cu: the statistics as extra Gram column tiles
+constexpr int kStatQ = 14;          // xy columns per 128-row digit group (14 x 9 limbs = 126 rows)
+constexpr int kStatOnesRow = 126;   // row of the all-ones column (group 0)
+void launch_l0_xy_digits(const double* xy, int cpp, int ncol, int64_t npad, const uint8_t* is_real, double* scale,
+                         uint8_t* D, cudaStream_t s);
+void launch_l0_stats_finish(const float* T, int ldt, int64_t t_fold_stride, const float* zz, int ldz,
+                            int64_t zz_fold_stride, int rows_p, int cpp, int ncol, int K, const double* scale,
+                            int32_t* cnt_fold, double* sum_fold, cudaStream_t s);
 void gram_tile_list(int rows2, std::vector<int2>& tiles);
-void launch_gram_tcgen05(const CUtensorMap& tm, const int2* tiles, int ntiles, const int2* fold_k, int K,
+void launch_gram_tcgen05(const CUtensorMap& tm, const CUtensorMap& tmB, const int2* tiles, int ntiles, const int2* fold_k, int K,
                          float* out, int ldo, int64_t fold_stride, cudaStream_t s);
 void launch_gram_reference(const uint8_t* z, int64_t npad, int rows2, int k0, int k1, float* out, int ldo,
                            cudaStream_t s);

@@ -176,6 +176,22 @@ static void build_layout(rg_ctx* h, const double* X, const double* Y, const uint
   RG_CUDA(cudaMemcpyAsync(h->fold_k.p, fold_k.data(), K * sizeof(int2), cudaMemcpyHostToDevice, s));
   RG_CUDA(cudaMemcpyAsync(h->XtX_f.p, XtX.data(), XtX.size() * 8, cudaMemcpyHostToDevice, s));
   RG_CUDA(cudaMemcpyAsync(h->XtY_f.p, XtY.data(), XtY.size() * 8, cudaMemcpyHostToDevice, s));
+  // statistics as extra Gram tiles: digit rows of (X | Y), once per run.  Exact while 30 * fold length < 2^24.
+  {
+    int64_t max_fold = 0;
+    for (int f = 0; f < K; ++f) max_fold = std::max(max_fold, h->fold_pad_len[f]);
+    const char* e = getenv("RG_B200_STATS");
+    h->stats_tc = !(e && std::string(e) == "f64") && max_fold * 30 < (1ll << 24);
+    if (h->stats_tc) {
+      const int ngroups = (int)ceil_div(C + P, kStatQ);
+      h->stat_drows = (int)round_up((int64_t)ngroups * 128, 256);
+      h->xyD.alloc((size_t)h->stat_drows * h->Npad);
+      h->xy_scale.alloc(h->cpp);
+      RG_CUDA(cudaMemsetAsync(h->xyD.p, 0, (size_t)h->stat_drows * h->Npad, s));
+      launch_l0_xy_digits(h->xy.p, h->cpp, C + P, h->Npad, h->is_real.p, h->xy_scale.p, h->xyD.p, s);
+      make_gram_tensor_map(&h->tmD, h->xyD.p, h->Npad, h->stat_drows);
+    }
+  }
   RG_CUDA(cudaStreamSynchronize(s));   // host vectors go out of scope
 }
 
@@ -290,13 +306,8 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
   }
   h->launches += 2;
 
-  // --- 2. f64 sufficient statistics
-  {
-    ScopedTimer t(h, "l0_stats", s);
-    launch_l0_stats(L.gp.p, Npad, h->xy.p, h->cpp, h->chunks.p, h->nchunks, rows_p, L.cnt_part.p,
-                    L.sum_part.p, s);
-    launch_l0_fold_reduce(L.cnt_part.p, L.sum_part.p, rows_p, h->cpp, h->fold_chunks.p, K,
-                          L.cnt_fold.p, L.sum_fold.p, s);
+  // --- 2. sufficient statistics: FP64 CUDA-core path (fallback) or, after the Gram, as extra tensor-core tiles
+  auto snp_finalize = [&]() {
     SnpFinalizeArgs a;
     a.bs = bs; a.rows_p = rows_p; a.C = C; a.P = P; a.K = K; a.cpp = h->cpp; a.loocv = h->loocv;
     a.n_analyzed = h->n_analyzed; a.numtol = 1e-6;
@@ -305,7 +316,16 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
     a.gty_f = L.gty_f.p; a.rhs = L.rhs.p; a.err_slot = h->err_slot.p;
     a.err_base = (long long)block_id * h->bs_max;
     launch_l0_snp_finalize(a, s);
-    h->launches += 3;
+    h->launches += 1;
+  };
+  if (!h->stats_tc) {
+    ScopedTimer t(h, "l0_stats", s);
+    launch_l0_stats(L.gp.p, Npad, h->xy.p, h->cpp, h->chunks.p, h->nchunks, rows_p, L.cnt_part.p,
+                    L.sum_part.p, s);
+    launch_l0_fold_reduce(L.cnt_part.p, L.sum_part.p, rows_p, h->cpp, h->fold_chunks.p, K,
+                          L.cnt_fold.p, L.sum_fold.p, s);
+    snp_finalize();
+    h->launches += 2;
   }
 
   // --- 3. exact integer Grams on the tensor cores
@@ -325,9 +345,31 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
       h->tile_lists[rows_p] = std::move(buf);
     }
     ScopedTimer t(h, "gram_tcgen05", s);
-    launch_gram_tcgen05(L.tmaps[rows_p], h->tile_lists[rows_p]->p, h->tile_counts[rows_p], h->fold_k.p, K,
+    launch_gram_tcgen05(L.tmaps[rows_p], L.tmaps[rows_p], h->tile_lists[rows_p]->p, h->tile_counts[rows_p], h->fold_k.p, K,
                         L.zz.p, 2 * rows_p, (int64_t)4 * rows_p * rows_p, s);
     h->launches += 1;
+  }
+  if (h->stats_tc) {
+    // Z [X | Y]-digits: one more column tile per row tile of the same kernel, then the FP64 Horner
+    ScopedTimer t(h, "l0_stats", s);
+    if (!h->stat_tile_lists.count(rows_p)) {
+      std::vector<int2> tiles;
+      for (int nj = 0; nj < h->stat_drows / 256; ++nj)
+        for (int mi = 0; mi < 2 * rows_p / 128; ++mi) tiles.push_back(make_int2(mi, nj));
+      auto buf = std::make_unique<DevBuf<int2>>();
+      buf->alloc(tiles.size());
+      RG_CUDA(cudaMemcpy(buf->p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice));
+      h->stat_tile_counts[rows_p] = (int)tiles.size();
+      h->stat_tile_lists[rows_p] = std::move(buf);
+    }
+    L.tstat.alloc((size_t)K * 2 * h->rows_p_max * h->stat_drows);
+    const int64_t tfs = (int64_t)2 * rows_p * h->stat_drows;
+    launch_gram_tcgen05(L.tmaps[rows_p], h->tmD, h->stat_tile_lists[rows_p]->p, h->stat_tile_counts[rows_p], h->fold_k.p,
+                        K, L.tstat.p, h->stat_drows, tfs, s);
+    launch_l0_stats_finish(L.tstat.p, h->stat_drows, tfs, L.zz.p, 2 * rows_p, (int64_t)4 * rows_p * rows_p, rows_p,
+                           h->cpp, C + P, K, h->xy_scale.p, L.cnt_fold.p, L.sum_fold.p, s);
+    snp_finalize();
+    h->launches += 2;
   }
 
   if (getenv("RG_DBG_CHECK_DIAG")) {

@@ -24,7 +24,7 @@ BgenFile::~BgenFile() {
 
 void BgenFile::open(const std::string& p, const std::string& sample_file, bool ref_first,
                     const std::set<std::string>& exclude, const std::set<std::string>& extract,
-                    const std::set<std::string>& remove, const std::set<std::string>& keep) {
+                    const std::set<std::string>& remove, const std::set<std::string>& keep, const std::set<int>& chrs) {
   path = p;
   fd = ::open(path.c_str(), O_RDONLY);
   if (fd < 0) throw Fail("cannot open file : " + path);
@@ -113,6 +113,7 @@ void BgenFile::open(const std::string& p, const std::string& sample_file, bool r
     need(4); const uint32_t c = rd32(data + pos);
     need(4 + (size_t)c);
     pos += 4 + (size_t)c;
+    if (!chrs.empty() && !chrs.count(s.chrom)) continue;
     if (exclude.count(s.id)) continue;
     if (!extract.empty() && !extract.count(s.id)) continue;
     snps.push_back(s);

@@ -20,7 +20,8 @@ struct BgenFile {
   int fd = -1;
   ~BgenFile();
   void open(const std::string& path, const std::string& sample_file, bool ref_first, const std::set<std::string>& exclude,
-            const std::set<std::string>& extract, const std::set<std::string>& remove, const std::set<std::string>& keep);
+            const std::set<std::string>& extract, const std::set<std::string>& remove, const std::set<std::string>& keep,
+            const std::set<int>& chrs = {});
   // inflate variants snps[first .. first+n): probs [n][n_file][2], ploidy_missing [n][n_file]
   void read_block(size_t first, size_t n, uint8_t* probs, uint8_t* ploidy_missing, int threads) const;
 };

@@ -21,7 +21,7 @@ std::set<std::string> read_id_list(const std::string& path, int ncols) {
 
 void BedFile::open(const std::string& pfx, bool ref_first, const std::set<std::string>& exclude,
                    const std::set<std::string>& extract, const std::set<std::string>& remove,
-                   const std::set<std::string>& keep) {
+                   const std::set<std::string>& keep, const std::set<int>& chrs) {
   prefix = pfx;
   // ---- .bim
   {
@@ -47,6 +47,7 @@ void BedFile::open(const std::string& pfx, bool ref_first, const std::set<std::s
       if (ref_first) { s.allele0 = t[4]; s.allele1 = t[5]; }
       else           { s.allele0 = t[5]; s.allele1 = t[4]; }
       s.offset = lineno++;
+      if (!chrs.empty() && !chrs.count(s.chrom)) continue;          // --chr / --chrList (in_chrList, src/Geno.cpp)
       if (exclude.count(s.id)) continue;
       if (!extract.empty() && !extract.count(s.id)) continue;
       snps.push_back(s);

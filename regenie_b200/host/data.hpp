@@ -37,7 +37,7 @@ struct BedFile {
   std::ifstream bed;
   void open(const std::string& prefix, bool ref_first, const std::set<std::string>& exclude,
             const std::set<std::string>& extract, const std::set<std::string>& remove,
-            const std::set<std::string>& keep);
+            const std::set<std::string>& keep, const std::set<int>& chrs = {});
   // read the rows of snps[first .. first+n) into out (n * row_stride bytes)
   void read_rows(size_t first, size_t n, uint8_t* out);
 };

@@ -33,6 +33,7 @@ struct Params {
   bool rel_path = false, firth = false, approx = false, keep_l0 = false;
   double min_mac = 5.0, p_thresh = 0.05;
   int threads = 0;
+  std::set<int> chrs;                 // --chr / --chrList
 };
 
 void rg_check(int rc) {
@@ -68,6 +69,12 @@ Params parse_cli(int argc, char** argv) {
     else if (a == "--gpu") p.gpu = atoi(need(i).c_str());
     else if (a == "--threads") p.threads = atoi(need(i).c_str());   // host threads: BGEN inflate only
     else if (a == "--sample") p.sample = need(i);
+    else if (a == "--chr") { const int c = chr_str_to_int(need(i)); if (c < 1) throw Fail("invalid chromosome for --chr."); p.chrs.insert(c); }
+    else if (a == "--chrList") {
+      std::string v = need(i), tok;
+      std::istringstream ss(v);
+      while (std::getline(ss, tok, ',')) { const int c = chr_str_to_int(tok); if (c < 1) throw Fail("invalid chromosome in --chrList."); p.chrs.insert(c); }
+    }
     else if (a == "--pThresh") p.p_thresh = atof(need(i).c_str());
     else if (a == "--firth") p.firth = true;
     else if (a == "--approx") p.approx = true;
@@ -85,6 +92,7 @@ Params parse_cli(int argc, char** argv) {
                    "  --step 1|2 --bed PREFIX --phenoFile F [--covarFile F] --bsize N --out PREFIX\n"
                    "  [--pred LIST] [--loocv] [--lowmem] [--cv K] [--l0 R] [--l1 R] [--remove F] [--keep F]\n"
                    "  [--exclude F] [--extract F] [--ref-first] [--minMAC x] [--strict] [--gpu ordinal]\n"
+                   "  [--chr c]... [--chrList c1,c2,...]  (Step-2 jobs are split by chromosome like the reference)\n"
                    "  step 2 binary traits: --bt [--firth --approx] [--pThresh p] with --bed or --bgen F [--sample F]\n";
       exit(0);
     } else {
@@ -126,9 +134,10 @@ void run_step1(const Params& p_in, Log& log) {
   Params p = p_in;
   BedFile g;
   g.open(p.bed, p.ref_first, read_id_list(p.exclude, 1), read_id_list(p.extract, 1), read_id_list(p.remove, 2),
-         read_id_list(p.keep, 2));
+         read_id_list(p.keep, 2), p.chrs);
   log << " * bim                 : [" << p.bed << ".bim] n_snps = " << g.snps.size() << "\n";
   log << " * fam                 : [" << p.bed << ".fam] n_samples = " << g.keys.size() << "\n";
+  if (g.snps.empty()) throw Fail("no variant left to include in analysis.");
   if (g.snps.size() > 1000000 && !p.force_step1)
     throw Fail("it is not recommened to use more than 1000000 variants in step 1 (otherwise use '--force-step1').");
   Pheno ph;
@@ -375,10 +384,10 @@ void run_step2_qt(const Params& p, Log& log) {
   const auto excl = read_id_list(p.exclude, 1), extr = read_id_list(p.extract, 1), rem = read_id_list(p.remove, 2),
              keepl = read_id_list(p.keep, 2);
   if (use_bgen) {
-    gg.open(p.bgen, p.sample, p.ref_first, excl, extr, rem, keepl);
+    gg.open(p.bgen, p.sample, p.ref_first, excl, extr, rem, keepl, p.chrs);
     log << " * bgen                : [" << p.bgen << "] n_snps = " << gg.snps.size() << ", n_samples = " << gg.keys.size() << "\n";
   } else {
-    g.open(p.bed, p.ref_first, excl, extr, rem, keepl);
+    g.open(p.bed, p.ref_first, excl, extr, rem, keepl, p.chrs);
     log << " * bim                 : [" << p.bed << ".bim] n_snps = " << g.snps.size() << "\n";
     log << " * fam                 : [" << p.bed << ".fam] n_samples = " << g.keys.size() << "\n";
   }
@@ -489,10 +498,10 @@ void run_step2_bt(const Params& p, Log& log) {
   const auto excl = read_id_list(p.exclude, 1), extr = read_id_list(p.extract, 1), rem = read_id_list(p.remove, 2),
              keep = read_id_list(p.keep, 2);
   if (use_bgen) {
-    gg.open(p.bgen, p.sample, p.ref_first, excl, extr, rem, keep);
+    gg.open(p.bgen, p.sample, p.ref_first, excl, extr, rem, keep, p.chrs);
     log << " * bgen                : [" << p.bgen << "] n_snps = " << gg.snps.size() << ", n_samples = " << gg.keys.size() << "\n";
   } else {
-    gb.open(p.bed, p.ref_first, excl, extr, rem, keep);
+    gb.open(p.bed, p.ref_first, excl, extr, rem, keep, p.chrs);
     log << " * bim                 : [" << p.bed << ".bim] n_snps = " << gb.snps.size() << "\n";
     log << " * fam                 : [" << p.bed << ".fam] n_samples = " << gb.keys.size() << "\n";
   }

@@ -286,3 +286,24 @@ def test_bt_step1_known_answer_then_step2_golden_file_end_to_end(tmp_path, golde
         assert tx[:9] == ty[:9] and tx[13] == ty[13], (x, y)
         for a, c in zip(tx[9:13], ty[9:13]):
             assert close(a, c, rtol=1e-4), (x, y)
+
+
+def test_step2_chr_jobs_concatenate_to_the_full_run(tmp_path, golden_dir):
+    """Step-2 jobs split by chromosome (--chr / --chrList, one process per GPU) give, concatenated, exactly the
+    rows of the single run - the way regenie users shard Step 2."""
+    prefix = os.path.join(golden_dir, "example_3chr")
+    pheno, covar = golden_dir + "/phenotype.txt", golden_dir + "/covariates.txt"
+    out1 = str(tmp_path / "fit")
+    run(["--step", "1", "--bed", prefix, "--phenoFile", pheno, "--covarFile", covar, "--bsize", "100", "--out", out1])
+    base = ["--step", "2", "--bed", prefix, "--phenoFile", pheno, "--covarFile", covar, "--bsize", "200",
+            "--pred", out1 + "_pred.list"]
+    run(base + ["--out", str(tmp_path / "all")])
+    run(base + ["--chr", "1", "--out", str(tmp_path / "c1")])
+    run(base + ["--chrList", "2,3", "--out", str(tmp_path / "c23")])
+    for nm in ("Y1", "Y2"):
+        full = open(str(tmp_path / ("all_%s.regenie" % nm))).read().splitlines()
+        a = open(str(tmp_path / ("c1_%s.regenie" % nm))).read().splitlines()
+        b = open(str(tmp_path / ("c23_%s.regenie" % nm))).read().splitlines()
+        assert a[0] == b[0] == full[0]
+        assert a[1:] + b[1:] == full[1:]
+        assert len(a) > 1 and len(b) > 1
