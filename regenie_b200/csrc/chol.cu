@@ -19,6 +19,9 @@
 // "lanes" run concurrently, so launch-wide lockstep cannot be assumed.
 // The stored inverses M also turn the backward substitution's triangular solves into GEMVs.
 #include "gemm_dmma.cuh"
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace rg {
@@ -271,13 +274,36 @@ void launch_chol_factor(double* cm, int64_t stride, int nC, int n_aug, int batch
     RG_CUDA(cudaFuncSetAttribute(chol_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem));
     attr_set = true;
   }
+  // profiling aid (RG_B200_CHOL_TIMING=1): CUDA-event time of the three kernels of every panel step
+  static const bool timing = getenv("RG_B200_CHOL_TIMING") != nullptr;
+  static double t_acc[3] = {0, 0, 0};
+  static long t_calls = 0;
+  cudaEvent_t ev[4];
+  if (timing) for (auto& e : ev) cudaEventCreate(&e);
+  auto tick = [&](int i) { if (timing) cudaEventRecord(ev[i], s); };
+  auto tock = [&]() {
+    if (!timing) return;
+    cudaEventSynchronize(ev[3]);
+    for (int i = 0; i < 3; ++i) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); t_acc[i] += ms; }
+  };
   for (int kb = 0; kb < nC / TB; ++kb) {
     const int k = kb * TB;
     dim3 g1(ntiles - kb, 1, batch);
+    tick(0);
     if (k > 0) chol_update_kernel<<<g1, 256, 0, s>>>(cm, stride, nC, k, kb);
+    tick(1);
     chol_diag_kernel<<<batch, 256, 0, s>>>(cm, stride, nC, k, inv, inv_stride, err_slot, err_base);
+    tick(2);
     dim3 g2(ntiles - kb - 1, 1, batch);
     if (ntiles - kb - 1 > 0) chol_trsm_kernel<<<g2, 256, trsm_smem, s>>>(cm, stride, nC, k, kb, inv, inv_stride);
+    tick(3);
+    tock();
+  }
+  if (timing) {
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (++t_calls % 50 == 0)
+      fprintf(stderr, "[chol timing] per factorisation (ms): update %.3f diag %.3f trsm %.3f\n", t_acc[0] / t_calls,
+              t_acc[1] / t_calls, t_acc[2] / t_calls);
   }
 }
 
