@@ -350,6 +350,7 @@ def run_gpu(args):
     chol_ms = kern["chol_factor"]["ms_total"] / max(1, kern["chol_factor"]["launches"])
     chol_tf = (K * R * bs ** 3 / 3.0) / (chol_ms * 1e-3) / 1e12 if chol_ms > 0 else None
 
+    traffic, pipe_active = gram_traffic_from_profile()
     cpu = None
     if not args.no_cpu:
         rows = [host_panel[s:s + n].numpy() for (s, n) in blocks[: args.cpu_blocks]]
@@ -368,7 +369,11 @@ def run_gpu(args):
                 "h2d_bytes_per_step": int(M) * int(stride), "d2h_bytes_per_step": 8},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "gram_fp8_tcgen05_kernel", "bound": "tensor", "achieved": ach, "peak": peak,
-                     "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                     "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
+                                     "(profiles/ncu_r1g_key_kernels.txt); algorithmic bytes = 205 MB of Z planes + "
+                                     "47 MB of Gram tiles",
+                     "executed_frac": 2.0 * ach / peak, "tensor_pipe_active_ncu": pipe_active,
                      "peak_basis": "2 x %s bf16 cuBLAS rate (%s TF/s) = dense FP8" % (peak_src, peak_bf16),
                      "algorithmic_flops_per_launch": flops_per_launch,
                      "timed": "alone (single lane), CUDA events on the launching stream",
@@ -383,6 +388,29 @@ def run_gpu(args):
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
+
+
+def gram_traffic_from_profile():
+    """DRAM bytes per launch and tensor-pipe activity of the Gram kernel from the committed ncu --set full summary
+    (bench.py cannot run under a profiler; the capture command is tools/ncu_capture.sh)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_r1g_key_kernels.txt")
+    try:
+        blocks = open(path).read().split("---\n")
+    except OSError:
+        return None, None
+    for b in blocks:
+        if "gram_fp8_tcgen05_kernel" not in b or "launch__grid_size" not in b:
+            continue
+        d = {}
+        for line in b.splitlines():
+            t = line.split()
+            if len(t) >= 2:
+                d[t[0]] = t[1]
+        if d.get("launch__grid_size") != "360":            # the bs x bs Gram launch (72 tiles x 5 folds), not the statistics tiles
+            continue
+        mb = float(d["dram__bytes_read.sum"]) + float(d["dram__bytes_write.sum"])
+        return mb * 1e6, float(d["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]) / 100.0
+    return None, None
 
 
 def main():

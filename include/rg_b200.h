@@ -128,9 +128,11 @@ int rg_loco(rg_handle h, const int32_t* chr_of_block, double* pred_out);
 
 /*
  * rg_l1_fit_bt -- binary traits: penalised logistic level 1 with closed-form leave-one-out predictions.
- * Replaces ridge_logistic_level_1_loocv + run_log_ridge_loocv (src/Step1_Models.cpp:1159-1375); rg_loco then
- * performs make_predictions_binary_loocv (src/Data.cpp:1484-1573) + the LOCO assembly.  Level 0 is the QT path
- * (rg_l0_block_bed with the residualised 0/1 phenotypes as Y).  LOOCV handles only (cfg.loocv = 1).
+ * LOOCV handles (cfg.loocv = 1): replaces ridge_logistic_level_1_loocv + run_log_ridge_loocv
+ * (src/Step1_Models.cpp:1159-1375); rg_loco then performs make_predictions_binary_loocv (src/Data.cpp:1484-1573).
+ * k-fold handles: replaces ridge_logistic_level_1 (src/Step1_Models.cpp:966-1157, IRLS per fold and tau with warm
+ * starts); rg_loco then performs make_predictions_binary (src/Data.cpp:1346-1428).  Level 0 is the QT path
+ * (rg_l0_block_bed with the residualised 0/1 phenotypes as Y).
  *   y_raw  [N x P] phenotypes_raw (0/1), offset [N x P] m_ests.offset_nullreg (covariate-only logistic fit)
  *   tau    [P x R1] ridge values (B (1-h)/h * 3/pi^2, src/Step1_Models.cpp:2115-2117)
  *   cumsum [6][P][R1]  Sx, Sy, Sx2, Sy2, Sxy, -logLik (cumsum_values[0..5]);  best_idx = argmin -logLik/Neff

@@ -12,6 +12,7 @@ Restates rgcgithub/regenie v4.1.2:
   fit_null_logistic (step-1 use)         src/Step1_Models.cpp:54-140  (called from src/Pheno.cpp:1608)
   run_log_ridge_loocv                    src/Step1_Models.cpp:1288-1375
   ridge_logistic_level_1_loocv           src/Step1_Models.cpp:1159-1286
+  ridge_logistic_level_1 (k-fold)        src/Step1_Models.cpp:966-1157  (make_predictions_binary src/Data.cpp:1346-1428)
   make_predictions_binary_loocv          src/Data.cpp:1484-1573
   Data::output (non-QT criterion)        src/Data.cpp:1025-1077
 """
@@ -194,3 +195,72 @@ def output_table(cs, neff, B, tau):
         rows.append("  %5s : Rsq = %g, MSE = %g, -logLik/N = %g%s" % ("%g" % h, rsq, sse / neff, cs[5, j] / neff,
                                                                    "<- min value" if j == best else ""))
     return best, rows
+
+
+def level1_logistic_kfold(W, y_raw, offset, mask, tau, fold_sizes):
+    """ridge_logistic_level_1, k-fold branch (src/Step1_Models.cpp:966-1157, !within_sample_l0).
+
+    Per fold i and ridge value j (warm starts over j): IRLS on the samples outside fold i until
+    max|score| < l1_ridge_tol, then the CV sums over the masked samples of fold i.
+    Returns (cumsum [6 x R1], beta [K][B x R1])."""
+    N, B = W.shape
+    starts = np.concatenate([[0], np.cumsum(fold_sizes)])
+    K = len(fold_sizes)
+    cs = np.zeros((6, len(tau)))
+    betas = []
+    for i in range(K):
+        test = np.zeros(N, dtype=bool)
+        test[starts[i]:starts[i + 1]] = True
+        train = mask & ~test
+        m = train.astype(float)
+        bnew = np.zeros(B)
+        bi = np.zeros((B, len(tau)))
+        for j, t in enumerate(tau):
+            bold = bnew
+            it = 0
+            converged = False
+            while it < NITER_RIDGE:
+                it += 1
+                eta = offset + W @ bold
+                p = get_pvec(eta)
+                w = np.where(train, p * (1 - p), 1.0)
+                if (w == 0).any():
+                    raise ValueError("Zeros occurred in Var(Y) during ridge logistic regression")
+                z = np.where(train, (eta - offset) + (y_raw - p) / w, 0.0)
+                XtW = W.T * (w * m)
+                bnew = np.linalg.solve(t * np.eye(B) + XtW @ W, XtW @ z)
+                for _ in range(NITER_LS):                         # halve only while some weight is exactly 0
+                    p = get_pvec(offset + W @ bnew)
+                    if not (np.where(train, p * (1 - p), 1.0) == 0).any():
+                        break
+                    bnew = (bold + bnew) / 2
+                p = get_pvec(offset + W @ bnew)
+                score = W.T @ np.where(train, y_raw - p, 0.0) - t * bnew
+                if np.abs(score).max() < L1_RIDGE_TOL:
+                    converged = True
+                    break
+                bold = bnew
+            if not converged:
+                raise ValueError("Penalized logistic regression did not converge")
+            bi[:, j] = bnew
+            sel = mask & test
+            etat = offset[sel] + W[sel] @ bnew
+            p1 = np.clip(1 - 1 / (np.exp(etat) + 1), L1_RIDGE_EPS, 1 - L1_RIDGE_EPS)
+            yy = y_raw[sel]
+            cs[0, j] += p1.sum(); cs[1, j] += yy.sum(); cs[2, j] += (p1 ** 2).sum(); cs[3, j] += (yy ** 2).sum()
+            cs[4, j] += (p1 * yy).sum()
+            cs[5, j] += -np.where(yy == 0, np.log(1 - p1), np.log(p1)).sum()
+        betas.append(bi)
+    return cs, betas
+
+
+def predictions_binary_kfold(W, betas, best, fold_sizes, chr_cols):
+    """make_predictions_binary, !within_sample_l0 (src/Data.cpp:1400-1416): out-of-fold per-chromosome dot products."""
+    N = W.shape[0]
+    starts = np.concatenate([[0], np.cumsum(fold_sizes)])
+    pred = np.zeros((N, len(chr_cols)))
+    for i in range(len(fold_sizes)):
+        rows = slice(starts[i], starts[i + 1])
+        for ci, (_, ctr, nn) in enumerate(chr_cols):
+            pred[rows, ci] = W[rows, ctr:ctr + nn] @ betas[i][ctr:ctr + nn, best]
+    return pred

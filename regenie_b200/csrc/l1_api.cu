@@ -230,7 +230,7 @@ void lg_factor(LgState& st, double tau, bool with_rows) {
   launch_l1_gram(h->lg_Ws.p, st.Npad, st.B, h->l1_chunks.p, st.nch, h->l1_part.p, st.part_stride, nC, s);
   RG_CUDA(cudaMemcpyAsync(h->l1_tau.p, &tau, 8, cudaMemcpyHostToDevice, s));
   // the RHS row is (re)written by the caller after this; part_y content is irrelevant here
-  launch_l1_assemble(h->l1_part.p, st.part_stride, nC, h->l1_part_y.p, h->l1_fold_chunks.p, h->K, 1, h->l1_tau.p, st.B, nC,
+  launch_l1_assemble(h->l1_part.p, st.part_stride, nC, h->l1_part_y.p, h->lg_all_chunks.p, 1, 1, h->l1_tau.p, st.B, nC,
                      h->l1_cm.p, st.cm_stride, 1, s);
   h->launches += 3;
   (void)with_rows;
@@ -291,10 +291,70 @@ void lg_leverages(LgState& st, double tau, int ntiles) {
 }
 }  // namespace
 
+// ridge_logistic_level_1, k-fold branch (src/Step1_Models.cpp:966-1157): IRLS on the samples outside fold i
+// (the Newton step beta + H^-1 score is the IRLS solve), warm starts over tau, CV sums over fold i.
+static void l1_fit_bt_kfold_pheno(rg_ctx* h, LgState& st, int p, const std::vector<int8_t>& ym, const double* tau_p,
+                                  double* cs_out /* [6][R1] */) {
+  cudaStream_t s = h->stream;
+  const int K = h->K, R1 = h->R1, B = st.B, nC = st.nC;
+  const int64_t Npad = h->Npad;
+  std::vector<int8_t> ymv(Npad);
+  std::vector<double> bpad(nC, 0.0);
+  for (int j = 0; j < 6 * R1; ++j) cs_out[j] = 0.0;
+  RG_CUDA(cudaMemsetAsync(h->lg_q.p, 0, Npad * 8, s));
+  for (int f = 0; f < K; ++f) {
+    const int64_t f0 = h->fold_pad_start[f], f1 = f0 + h->fold_pad_len[f];
+    auto upload = [&](bool train) {
+      for (int64_t t = 0; t < Npad; ++t) {
+        const bool in_fold = t >= f0 && t < f1;
+        ymv[t] = (in_fold != train) ? ym[t] : 0;
+      }
+      RG_CUDA(cudaMemcpyAsync(h->lg_ym.p, ymv.data(), Npad, cudaMemcpyHostToDevice, s));
+      RG_CUDA(cudaStreamSynchronize(s));
+    };
+    std::fill(st.beta.begin(), st.beta.end(), 0.0);
+    for (int j = 0; j < R1; ++j) {
+      const double tau = tau_p[j];
+      upload(true);
+      lg_eval(st, st.beta);
+      bool converged = false;
+      std::vector<double> score = lg_score(st, tau, st.beta, false), step(B), rhs(nC, 0.0);
+      for (int it = 0; it < kNiterRidge && !converged; ++it) {
+        lg_factor(st, tau, false);
+        std::copy(score.begin(), score.end(), rhs.begin());
+        RG_CUDA(cudaMemcpyAsync(h->l1_cm.p + (size_t)nC * nC, rhs.data(), (size_t)nC * 8, cudaMemcpyHostToDevice, s));
+        launch_chol_factor(h->l1_cm.p, st.cm_stride, nC, nC + 64, 1, h->l1_inv.p, h->err_slot.p, (long long)(1ll << 42) + 2, s);
+        launch_chol_backsolve(h->l1_cm.p, st.cm_stride, nC, 1, 1, h->l1_inv.p, s);
+        RG_CUDA(cudaMemcpyAsync(step.data(), h->l1_cm.p + (size_t)nC * nC, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+        RG_CUDA(cudaStreamSynchronize(s));
+        h->launches += chol_num_launches(nC) + 1;
+        for (int c = 0; c < B; ++c) st.beta[c] += step[c];
+        lg_eval(st, st.beta);
+        score = lg_score(st, tau, st.beta, false);
+        double smax = 0.0;
+        for (double v : score) smax = std::max(smax, std::fabs(v));
+        converged = smax < kL1RidgeTol;
+      }
+      if (!converged) throw Error{"Penalized logistic regression did not converge (level 1, phenotype " + std::to_string(p + 1) + ")"};
+      std::copy(st.beta.begin(), st.beta.end(), bpad.begin());
+      RG_CUDA(cudaMemcpyAsync(h->l1_beta.p + ((size_t)p * K * R1 + (size_t)f * R1 + j) * nC, bpad.data(), (size_t)nC * 8,
+                              cudaMemcpyHostToDevice, s));
+      // CV sums over the held-out fold: eta is already at the converged coefficients for every sample
+      upload(false);
+      double cs[6];
+      launch_l1_bt_loo_sums(h->lg_eta.p, h->lg_q.p, h->lg_wm.p, h->lg_res.p, h->lg_ym.p, kL1RidgeEps, nullptr,
+                            h->lg_devp.p, h->lg_scal.p, Npad, s);
+      RG_CUDA(cudaMemcpyAsync(cs, h->lg_scal.p, 48, cudaMemcpyDeviceToHost, s));
+      RG_CUDA(cudaStreamSynchronize(s));
+      h->launches += 2;
+      for (int k = 0; k < 6; ++k) cs_out[k * R1 + j] += cs[k];
+    }
+  }
+}
+
 static void l1_fit_bt(rg_ctx* h, const double* y_raw, const double* offset, const double* tau_host, double* cumsum,
                       int32_t* best_idx) {
   RG_CHECK(h->kind == 1, "handle is not a Step-1 handle");
-  RG_CHECK(h->loocv, "logistic level 1 is implemented for LOOCV only (use --loocv)");
   RG_CHECK(h->R1 >= 1 && h->R1 <= kMaxRidge, "n_ridge_l1 out of range");
   RG_CUDA(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
@@ -306,15 +366,24 @@ static void l1_fit_bt(rg_ctx* h, const double* y_raw, const double* offset, cons
   h->l1_nC = nC;
   l1_setup_chunks(h, nC, nC);
   const int nch = h->l1_nchunks;
-  const int64_t cm_stride = (int64_t)(nC + 64 + Npad) * nC;
+  const int loocv = h->loocv;
+  const int64_t cm_stride = (int64_t)(nC + 64 + (loocv ? Npad : 0)) * nC;
+  {
+    const int2 all = make_int2(0, nch);
+    h->lg_all_chunks.alloc(1);
+    RG_CUDA(cudaMemcpyAsync(h->lg_all_chunks.p, &all, sizeof(int2), cudaMemcpyHostToDevice, s));
+  }
+  if (!loocv) h->l1_beta.alloc((size_t)P * h->K * R1 * nC);
   h->l1_part.alloc((size_t)nch * nC * nC);
   h->l1_part_y.alloc((size_t)nch * B);
   h->l1_cm.alloc((size_t)cm_stride);
   h->l1_inv.alloc(chol_inv_elems(nC, 1));
   h->l1_tau.alloc(1);
-  h->l1_zrows.alloc((size_t)P * Npad * nC);
-  h->l1_hvec.alloc((size_t)P * Npad);
-  h->l1_bvec.alloc((size_t)P * nC);
+  if (loocv) {
+    h->l1_zrows.alloc((size_t)P * Npad * nC);
+    h->l1_hvec.alloc((size_t)P * Npad);
+    h->l1_bvec.alloc((size_t)P * nC);
+  }
   h->lg_Ws.alloc((size_t)Npad * B); h->lg_eta.alloc(Npad); h->lg_p.alloc(Npad); h->lg_wm.alloc(Npad);
   h->lg_res.alloc(Npad); h->lg_off.alloc(Npad); h->lg_beta.alloc(nC); h->lg_score.alloc(nC); h->lg_q.alloc(Npad);
   h->lg_devp.alloc((size_t)ntiles * 6); h->lg_scal.alloc(8); h->lg_ym.alloc(Npad);
@@ -338,6 +407,17 @@ static void l1_fit_bt(rg_ctx* h, const double* y_raw, const double* offset, cons
     double best = 1e10;
     double ne = 0.0;
     for (int64_t i = 0; i < N; ++i) ne += h->maskh[(size_t)p * N + i] ? 1.0 : 0.0;
+    if (!loocv) {
+      std::vector<double> cs((size_t)6 * R1);
+      l1_fit_bt_kfold_pheno(h, st, p, ym, tau_host + (size_t)p * R1, cs.data());
+      for (int j = 0; j < R1; ++j) {
+        if (cumsum) for (int k = 0; k < 6; ++k) cumsum[((size_t)k * P + p) * R1 + j] = cs[(size_t)k * R1 + j];
+        const double perf = cs[(size_t)5 * R1 + j] / ne;
+        if (perf < best) { best = perf; h->best_idx[p] = j; }
+      }
+      if (best_idx) best_idx[p] = h->best_idx[p];
+      continue;
+    }
     for (int j = 0; j < R1; ++j) {
       const double tau = tau_host[(size_t)p * R1 + j];
       if (!lg_newton(st, tau)) throw Error{"ridge logistic regression did not converge (level 1, phenotype " + std::to_string(p + 1) + ")"};
@@ -401,7 +481,7 @@ static void loco(rg_ctx* h, const int32_t* chr_of_block, double* pred_out) {
   std::vector<double> pred((size_t)nchr * Npad);
   for (int p = 0; p < P; ++p) {
     if (!h->l1_select[p]) continue;
-    if (h->l1_bt)
+    if (h->l1_bt && h->loocv)
       launch_l1_bt_chr_pred(h->W.p + (size_t)p * Npad * h->B, Npad, nC, h->l1_zrows.p + (size_t)p * Npad * nC,
                             h->l1_hvec.p + (size_t)p * Npad, h->l1_bvec.p + (size_t)p * nC, nchr, h->l1_chr_cols.p,
                             h->l1_pred.p, Npad, s);

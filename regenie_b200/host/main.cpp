@@ -147,8 +147,6 @@ void run_step1(const Params& p_in, Log& log) {
     if (ph.n_analyzed < 5000) {                       // src/Data.cpp:353-356
       log << "   -WARNING: Sample size is less than 5,000 so using LOOCV instead of " << p.cv << "-fold CV.\n";
       p.loocv = true;
-    } else {
-      throw Fail("k-fold logistic level 1 is not implemented yet in rgb200: use --loocv with --bt --step 1.");
     }
   }
   const auto blocks = set_blocks(g.snps, p.bsize);
