@@ -14,6 +14,7 @@ With --gpus N (torchrun) every rank runs the same-size workload on its own SNP p
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -331,6 +332,10 @@ def run_gpu(args):
             st2.close()
         except Exception as e:          # never let the secondary metric break the headline line
             s2 = {"error": str(e)[:200]}
+        try:
+            s2["bt_bgen"] = step2_bt_leg(capi, X, in_an, N, C)
+        except Exception as e:
+            s2["bt_bgen"] = {"error": str(e)[:200]}
 
     if rank != 0:
         if dist is not None:
@@ -388,6 +393,45 @@ def run_gpu(args):
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
+
+
+def step2_bt_leg(capi, X, in_an, N, C, nvar=400, nblocks=4):
+    """Secondary: Step-2 binary-trait score test on 8-bit BGEN dosages (BASELINE configs[3] shape at this N):
+    variants/s through rg_s2_block_bgen8_bt with HOST probability bytes (2 N bytes per variant), plus the
+    approximate-Firth kernel on the variants with |z| above the --pThresh 0.05 quantile."""
+    import torch
+    rng = np.random.default_rng(SEED + 11)
+    y = (rng.random(N) < 0.1).astype(np.float64)                       # prevalence 10 %
+    mask = np.ones((N, 1), dtype=np.uint8)
+    p0 = float(y.mean())
+    eta = math.log(p0 / (1 - p0))
+    w = math.sqrt(p0 * (1 - p0))
+    gsm = np.full((N, 1), w); yres = ((y - p0) / w)[:, None]
+    # X is orthonormal with the intercept in its span: X_Gamma = X for a constant weight
+    st = capi.Step2(X, mask, in_an, N, nvar)
+    st.set_chr_bt(gsm, gsm, yres, [X], y[:, None], np.full((N, 1), eta))
+    g = torch.Generator(device="cpu").manual_seed(SEED + 13)
+    maf = 0.01 + 0.49 * torch.rand((nvar, 1), generator=g)
+    u = torch.rand((nvar, N), generator=g)
+    hom = (u < maf * maf)
+    het = (u < 2 * maf - maf * maf) & ~hom
+    probs_t = torch.stack([hom.to(torch.uint8) * 255, het.to(torch.uint8) * 255], dim=2).contiguous().pin_memory()
+    miss_t = torch.full((nvar, N), 0x02, dtype=torch.uint8).pin_memory()
+    probs, miss = probs_t.numpy(), miss_t.numpy()                       # pinned host buffers, like the e2e leg
+    st.block_bgen8_bt(probs, miss)
+    t0 = time.perf_counter()
+    nfirth = 0
+    for _ in range(nblocks):
+        o = st.block_bgen8_bt(probs, miss)
+        sel = np.nonzero((np.abs(o["stat"][:, 0]) > 1.959964) & ((o["flags"] & 17) == 0))[0]
+        st.firth(sel, np.zeros(len(sel), dtype=np.int32))
+        nfirth += len(sel)
+    dt = time.perf_counter() - t0
+    st.close()
+    return {"metric": "step2_bt_bgen_variants_per_sec", "value": nblocks * nvar / dt, "unit": "variants/s",
+            "firth_fraction": nfirth / (nblocks * nvar),
+            "sample": "%d blocks of %d variants, N=%d, 1 binary trait, pinned host probability + ploidy bytes in (3N B/variant), "
+                      "score test + approximate Firth for |z| > 1.96 (host wall clock incl. H2D/D2H)" % (nblocks, nvar, N)}
 
 
 def gram_traffic_from_profile():
