@@ -1,0 +1,79 @@
+"""Parity at BASELINE.json's full block size (configs[1]: N = 100 000, bsize = 1000, P = 10) through size-independent
+properties - the oracle would take minutes per block here, so the checks are identities the reference's algorithm
+guarantees at any size:
+
+  * level-0 predictors are centred and scaled per phenotype exactly as ridge_level_0 leaves them
+    (src/Step1_Models.cpp:539-557):  sum_masked W = 0,  sum_masked W^2 = Neff - 1;
+  * they are invariant to the scale and equivariant to the sign of the phenotype (the ridge solve is linear in Y,
+    the standardisation removes the scale);
+  * the same block under a different block id / stream lane gives bit-identical columns (fixed-order reductions);
+  * Step-2 A1FREQ and N are exact functions of integer counts: compared bit for bit with a numpy popcount.
+"""
+import numpy as np
+import pytest
+
+from regenie_b200 import hostprep, synth
+
+pytestmark = pytest.mark.gpu
+
+N, BS, P, C, K = 100_000, 1000, 10, 3, 5
+
+
+@pytest.fixture(scope="module")
+def panel():
+    g = synth.genotypes(N, BS, seed=77, miss=0.01)
+    Y, cov, na = synth.phenotypes(g, P, C, seed=78, n_causal=50, na_frac=0.02)
+    X, Yr, mask, in_an, neff = hostprep.prepare_qt(Y, cov, na)
+    return g, synth.pack_bed(g), X, Yr, mask, in_an, neff
+
+
+def _step1(X, Y, mask, in_an, neff, total_blocks=3):
+    from regenie_b200 import capi
+    h0 = hostprep.ridge_grid(5)
+    lam = 50_000 * (1 - h0) / h0
+    return capi.Step1(X, Y, mask, in_an, hostprep.fold_sizes(N, K), lam, neff, N, BS, total_blocks)
+
+
+def test_level0_full_block_properties(panel):
+    g, packed, X, Y, mask, in_an, neff = panel
+    st = _step1(X, Y, mask, in_an, neff)
+    st.l0_block_bed(packed, BS, 0)
+    st.l0_block_bed(packed, BS, 2)            # same rows again on another lane / block id
+    assert st.status() == 0
+    W0 = [st.fetch_W(0, p) for p in range(P)]
+    for p in range(P):
+        w = W0[p]
+        assert np.isfinite(w).all()
+        np.testing.assert_allclose(w.sum(axis=0), 0.0, atol=1e-6)                       # centred
+        np.testing.assert_allclose((w * w).sum(axis=0), neff[p] - 1.0, rtol=1e-10)      # unit sd with the Neff - 1 divisor
+        assert np.array_equal(w, st.fetch_W(2, p))                                      # bit-identical across lanes
+    st.close()
+    # scale invariance / sign equivariance in Y
+    Y2 = np.asfortranarray(Y * np.array([3.0, -1.0, 0.25, -7.0, 1.0, 2.0, -2.0, 10.0, 0.5, -0.5])[None, :])
+    st = _step1(X, Y2, mask, in_an, neff)
+    st.l0_block_bed(packed, BS, 0)
+    assert st.status() == 0
+    sgn = np.sign([3.0, -1.0, 0.25, -7.0, 1.0, 2.0, -2.0, 10.0, 0.5, -0.5])
+    for p in range(P):
+        np.testing.assert_allclose(st.fetch_W(0, p), sgn[p] * W0[p], rtol=0, atol=2e-8)
+    st.close()
+
+
+def test_step2_counts_bit_exact_at_full_size(panel):
+    from regenie_b200 import capi
+    g, packed, X, Y, mask, in_an, neff = panel
+    rng = np.random.default_rng(3)
+    m2 = np.asfortranarray((rng.random((N, P)) > 0.03).astype(np.uint8))
+    st = capi.Step2(X, m2, in_an, N, BS)
+    st.set_chr(np.asfortranarray(Y * m2), np.ones(P))
+    o = st.block_bed(packed)
+    st.close()
+    obs = g != 3
+    gz = np.where(obs, g, 0).astype(np.int64)
+    for p in range(P):
+        mp = m2[:, p].astype(np.int64)
+        ns = obs.astype(np.int64) @ mp
+        tot = gz @ mp
+        assert np.array_equal(o["ns"][:, p], ns)
+        assert np.array_equal(o["af"][:, p], tot / (2.0 * ns))                           # bit for bit
+    assert np.array_equal(o["ns_all"], obs.sum(axis=1))
