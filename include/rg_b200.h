@@ -163,6 +163,16 @@ int rg_step2_create(const rg_step2_config* cfg, const double* X, const uint8_t* 
                     const uint8_t* in_analysis, rg_handle* out);
 int rg_s2_set_chr(rg_handle h, const double* res, const double* scf_sv);
 
+/*
+ * chrX: rg_s2_set_sex gives the male indicator of every sample (params.sex == 1; NULL = forget it) and takes
+ * effect at the next rg_s2_set_chr / rg_s2_set_chr_bt; rg_s2_set_non_par flags the variants of the NEXT block
+ * call that lie in the non-PAR part of chrX (in_non_par, src/Geno.cpp:2802-2814).  For those variants males
+ * count half towards the allele count and MAC = min(mac, 2 N - N_males - mac) (src/Geno.cpp:2447-2462,
+ * compute_mac :3077-3108), which decides the --minMAC filter; A1FREQ, N and the test itself are unchanged.
+ */
+int rg_s2_set_sex(rg_handle h, const uint8_t* male);
+int rg_s2_set_non_par(rg_handle h, const uint8_t* flags, int32_t n);
+
 /* per-variant outputs of one Step-2 block; host arrays, variant-major ([i*P + p]) */
 typedef struct rg_s2_out {
   double* af;        /* [bs x P] block_info->af   (A1FREQ per trait)                      */

@@ -85,7 +85,7 @@ def get_logp(t):
     return -lp
 
 
-def variant_stats(g_raw, in_analysis, mask):
+def variant_stats(g_raw, in_analysis, mask, male=None, non_par=False):
     """parseSnpfromBed + compute_mac + compute_aaf_info for one variant (autosomal).
 
     g_raw: N hard calls with -3 = missing.  Returns dict with per-trait af, ns, mac, the
@@ -96,8 +96,18 @@ def variant_stats(g_raw, in_analysis, mask):
     total = float(g_raw[ok].sum())
     ns = (ok[:, None] & mask).sum(axis=0).astype(float)
     tot_p = (np.where(ok, g_raw, 0.0)[:, None] * mask).sum(axis=0)
-    mac1 = min(total, 2 * ns1 - total)
-    mac = np.minimum(tot_p, 2 * ns - tot_p)
+    if non_par and male is not None:
+        # non-PAR chrX: males (coded 0/2) count half; MAC = min(mac, 2N - N_males - mac)  (src/Geno.cpp:2447-2462, :3092-3097)
+        mval = np.where(ok, g_raw, 0.0) * 0.5 * (2 - male.astype(float))
+        macr1 = float(mval.sum())
+        nmales1 = int((ok & male).sum())
+        mac1 = min(macr1, 2 * ns1 - nmales1 - macr1)
+        macr = (mval[:, None] * mask).sum(axis=0)
+        nmales = ((ok & male)[:, None] & mask).sum(axis=0)
+        mac = np.minimum(macr, 2 * ns - nmales - macr)
+    else:
+        mac1 = min(total, 2 * ns1 - total)
+        mac = np.minimum(tot_p, 2 * ns - tot_p)
     out = dict(ns1=ns1, ns=ns.astype(int), mac1=mac1, mac=mac, ignored=mac1 < MIN_MAC,
                ignored_trait=mac < MIN_MAC)
     if out["ignored"]:

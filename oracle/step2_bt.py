@@ -232,7 +232,7 @@ class BtChrom:
         self.cov_blup_offset = X @ bf + blup
 
 
-def score_bt(g_raw, info_term, in_analysis, mask, y_raw, st: BtChrom, z_thr, n_samples):
+def score_bt(g_raw, info_term, in_analysis, mask, y_raw, st: BtChrom, z_thr, n_samples, male=None, non_par=False):
     """One variant, one trait.  g_raw: dosages with -3 = missing.  Returns dict or None if ignored."""
     ok = in_analysis & (g_raw != -3.0)
     ns1 = int(ok.sum())
@@ -241,8 +241,14 @@ def score_bt(g_raw, info_term, in_analysis, mask, y_raw, st: BtChrom, z_thr, n_s
     ns = int(okp.sum())
     tot_p = float(g_raw[okp].sum())
     info_p = float(info_term[okp].sum())
-    mac1 = min(total, 2 * ns1 - total)
-    mac = min(tot_p, 2 * ns - tot_p)
+    if non_par and male is not None:                          # see step2.variant_stats
+        mval = np.where(ok, g_raw, 0.0) * 0.5 * (2 - male.astype(float))
+        m1, mp = float(mval.sum()), float(mval[mask].sum())
+        mac1 = min(m1, 2 * ns1 - int((ok & male).sum()) - m1)
+        mac = min(mp, 2 * ns - int((okp & male).sum()) - mp)
+    else:
+        mac1 = min(total, 2 * ns1 - total)
+        mac = min(tot_p, 2 * ns - tot_p)
     if mac1 < MIN_MAC or mac < MIN_MAC:
         return None
     af = tot_p / (2.0 * ns)

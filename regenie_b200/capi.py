@@ -46,7 +46,7 @@ EXPORTS = [
     "rg_last_error", "rg_version", "rg_device_count", "rg_step1_create", "rg_destroy", "rg_sync",
     "rg_l0_block_bed", "rg_l0_status", "rg_l0_fetch_W", "rg_l1_fit", "rg_loco", "rg_step2_create",
     "rg_s2_set_chr", "rg_s2_block_bed", "rg_W_info", "rg_debug_fetch", "rg_launch_count", "rg_stream",
-    "rg_set_timing", "rg_get_timing", "rg_fence", "rg_s2_set_chr_bt", "rg_s2_block_bgen8_bt", "rg_s2_block_bgen8", "rg_s2_firth", "rg_l1_fit_bt", "rg_W_export", "rg_W_attach_peer", "rg_l1_select",
+    "rg_set_timing", "rg_get_timing", "rg_fence", "rg_s2_set_chr_bt", "rg_s2_block_bgen8_bt", "rg_s2_block_bgen8", "rg_s2_firth", "rg_l1_fit_bt", "rg_W_export", "rg_W_attach_peer", "rg_l1_select", "rg_s2_set_sex", "rg_s2_set_non_par",
 ]
 
 _lib = None
@@ -241,6 +241,16 @@ class Step2:
             self.h = None
 
     __del__ = close
+
+    def set_sex(self, male):
+        L = lib(); L.rg_s2_set_sex.argtypes = [C.c_void_p, C.c_void_p]
+        m = None if male is None else np.ascontiguousarray(male, dtype=np.uint8)
+        check(L.rg_s2_set_sex(self.h, _ptr(m)))
+
+    def set_non_par(self, flags):
+        L = lib(); L.rg_s2_set_non_par.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        f = np.ascontiguousarray(flags, dtype=np.uint8)
+        check(L.rg_s2_set_non_par(self.h, _ptr(f), len(f)))
 
     def set_chr(self, res, scf_sv):
         res = _f64(res)

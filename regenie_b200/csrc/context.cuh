@@ -107,6 +107,12 @@ struct rg_ctx {
   rg::DevBuf<double> F, s2_part, s2_sums, s2_maskcount, s2_YtX, s2_XmX, s2_scf;
   rg::DevBuf<double> s2_out_d;       // packed f64 outputs
   rg::DevBuf<int32_t> s2_out_i;      // packed i32 outputs
+  // chrX: male indicator of every sample (empty = none), F column of it, per-block non-PAR flags
+  std::vector<uint8_t> s2_male;
+  int s2_col_male = -1, bt_col_male = -1;
+  rg::DevBuf<uint8_t> s2_nonpar;
+  bool s2_nonpar_set = false;
+  rg::DevBuf<double> s2_male_tot;
   // binary traits / dosages
   int bt_mode = 0, bt_dp = 0;
   bool bt_chr_set = false;

@@ -185,6 +185,9 @@ struct S2FinalizeArgs {
   const double* YtX;         // [P][C]
   const double* XmX;         // [P][C][C]
   const double* scf_sv;      // [P]
+  const uint8_t* non_par = nullptr;   // [bs] variant lies in the non-PAR part of chrX (males count half towards MAC)
+  int col_male = -1;                  // F column of the male indicator (followed by male x mask_p), -1 = no sex information
+  const double* male_tot = nullptr;   // [1 + P] analysed males, masked-in males per trait
   const double* nz_count = nullptr;   // [rows_p] non-zero dosages among analysed samples (dosage input only)
   const double* info_sums = nullptr;  // [rows_p][dp] sum (4 p0 + p1) F (dosage input only)
   double* info = nullptr;             // [bs x P] INFO (dosage input only)
@@ -203,6 +206,8 @@ struct S2BtFinalizeArgs {
   const double* sums;        // [rows_p][4][dp]  S1, S2, Sm, Se in integer dosage units
   const double* col_tot;     // [dp] sum of every feature column over all samples
   const double* xwy;         // [P][C]  XW^T yres
+  const uint8_t* non_par = nullptr;   // see S2FinalizeArgs
+  int col_male = -1;
   const double* nz_count;    // [rows_p] analysed samples with non-zero dosage
   const double* n510;        // [rows_p] analysed samples with dosage exactly 2
   double *af, *mac, *info, *af_all, *mac_all, *scale_fac, *stat, *beta, *se, *chisq, *xtwg, *mu;

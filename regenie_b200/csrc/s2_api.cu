@@ -73,11 +73,22 @@ static void s2_set_chr(rg_ctx* h, const double* res, const double* scf_sv) {
   RG_CHECK(h->kind == 2, "handle is not a Step-2 handle");
   RG_CUDA(cudaSetDevice(h->device));
   const int64_t N = h->N;
-  const int C = h->C, P = h->P, dp = h->dp;
-  std::vector<double> F((size_t)h->Npad * dp, 0.0), YtX((size_t)P * C, 0.0);
+  const int C = h->C, P = h->P;
+  const bool with_sex = !h->s2_male.empty();
+  const int base = 1 + C + 2 * P + P * C;
+  h->s2_col_male = with_sex ? base : -1;
+  h->dp = (int)round_up(base + (with_sex ? 1 + P : 0), 16);
+  const int dp = h->dp;
+  h->F.alloc((size_t)h->Npad * dp);
+  std::vector<double> F((size_t)h->Npad * dp, 0.0), YtX((size_t)P * C, 0.0), male_tot(1 + P, 0.0);
   for (int64_t s = 0; s < N; ++s) {
     double* r = &F[(size_t)s * dp];
     r[0] = h->in_analysis[s] ? 1.0 : 0.0;
+    if (with_sex && h->s2_male[s] && h->in_analysis[s]) {
+      r[base] = 1.0; male_tot[0] += 1.0;
+      for (int p = 0; p < P; ++p)
+        if (h->maskh[(size_t)p * N + s]) { r[base + 1 + p] = 1.0; male_tot[1 + p] += 1.0; }
+    }
     for (int c = 0; c < C; ++c) r[1 + c] = h->Xh[(size_t)c * N + s];
     for (int p = 0; p < P; ++p) {
       const double m = h->maskh[(size_t)p * N + s] ? 1.0 : 0.0;
@@ -93,7 +104,17 @@ static void s2_set_chr(rg_ctx* h, const double* res, const double* scf_sv) {
   RG_CUDA(cudaMemcpyAsync(h->F.p, F.data(), F.size() * 8, cudaMemcpyHostToDevice, h->stream));
   RG_CUDA(cudaMemcpyAsync(h->s2_YtX.p, YtX.data(), YtX.size() * 8, cudaMemcpyHostToDevice, h->stream));
   RG_CUDA(cudaMemcpyAsync(h->s2_scf.p, scf_sv, P * 8, cudaMemcpyHostToDevice, h->stream));
+  h->s2_male_tot.alloc(1 + P);
+  RG_CUDA(cudaMemcpyAsync(h->s2_male_tot.p, male_tot.data(), (1 + P) * 8, cudaMemcpyHostToDevice, h->stream));
   RG_CUDA(cudaStreamSynchronize(h->stream));
+}
+
+// per-variant non-PAR flags set by rg_s2_set_non_par apply to exactly one block call
+static const uint8_t* take_non_par(rg_ctx* h, int bs) {
+  if (!h->s2_nonpar_set) return nullptr;
+  h->s2_nonpar_set = false;
+  RG_CHECK((int)h->s2_nonpar.n >= bs, "rg_s2_set_non_par was given fewer flags than the block has variants");
+  return h->s2_nonpar.p;
 }
 
 namespace rg {
@@ -142,6 +163,7 @@ static void s2_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
   a.n_analyzed = h->n_analyzed; a.n_samples = h->N; a.min_mac = min_mac; a.numtol = 1e-6;
   a.sums = h->s2_sums.p; a.mask_count = h->s2_maskcount.p; a.YtX = h->s2_YtX.p; a.XmX = h->s2_XmX.p;
   a.scf_sv = h->s2_scf.p;
+  a.non_par = take_non_par(h, bs); a.col_male = h->s2_col_male; a.male_tot = h->s2_male_tot.p;
   double* d = h->s2_out_d.p;
   const size_t bp = (size_t)h->bs_max * P, b1 = h->bs_max;
   a.af = d; a.mac = d + bp; a.stat = d + 2 * bp; a.beta = d + 3 * bp; a.se = d + 4 * bp; a.chisq = d + 5 * bp;
@@ -167,7 +189,10 @@ static void s2_set_chr_bt(rg_ctx* h, const rg_s2_bt_chr* st) {
   RG_CUDA(cudaSetDevice(h->device));
   const int64_t N = h->N, Npad = h->Npad;
   const int C = h->C, P = h->P;
-  const int dp = (int)round_up(1 + (int64_t)P * (3 + C), 16);
+  const bool with_sex = !h->s2_male.empty();
+  const int base = 1 + P * (3 + C);
+  h->bt_col_male = with_sex ? base : -1;
+  const int dp = (int)round_up((int64_t)base + (with_sex ? 1 + P : 0), 16);
   h->bt_dp = dp;
   std::vector<double> F((size_t)Npad * dp, 0.0), coltot(dp, 0.0), xwy((size_t)P * C, 0.0);
   std::vector<double> w((size_t)P * Npad, 0.0), gs((size_t)P * Npad, 0.0), off((size_t)P * Npad, 0.0),
@@ -177,6 +202,10 @@ static void s2_set_chr_bt(rg_ctx* h, const rg_s2_bt_chr* st) {
     double* r = &F[(size_t)s * dp];
     const bool ina = h->in_analysis[s] != 0;
     r[0] = ina ? 1.0 : 0.0;
+    if (with_sex && h->s2_male[s] && ina) {
+      r[base] = 1.0;
+      for (int p = 0; p < P; ++p) if (h->maskh[(size_t)p * N + s]) r[base + 1 + p] = 1.0;
+    }
     for (int p = 0; p < P; ++p) {
       const size_t ps = (size_t)p * N + s, pp = (size_t)p * Npad + s;
       const bool m = h->maskh[ps] != 0;
@@ -257,6 +286,7 @@ static void s2_block_bgen8_bt(rg_ctx* h, const uint8_t* probs, const uint8_t* mi
   a.bs = bs; a.C = C; a.P = P; a.dp = dp; a.with_flip = 1;
   a.n_analyzed = h->n_analyzed; a.n_samples = h->N; a.min_mac = min_mac; a.numtol = 1e-6;
   a.sums = h->bt_sums.p; a.col_tot = h->bt_coltot.p; a.xwy = h->bt_xwy.p; a.nz_count = h->bt_nnz.p; a.n510 = h->bt_n510.p;
+  a.non_par = take_non_par(h, bs); a.col_male = h->bt_col_male;
   double* d = h->s2_out_d.p;
   const size_t bp = (size_t)h->bs_max * P, b1 = h->bs_max;
   a.af = d; a.mac = d + bp; a.stat = d + 2 * bp; a.beta = d + 3 * bp; a.se = d + 4 * bp; a.chisq = d + 5 * bp;
@@ -332,6 +362,7 @@ static void s2_block_bgen8_qt(rg_ctx* h, const uint8_t* probs, const uint8_t* mi
   a.n_analyzed = h->n_analyzed; a.n_samples = h->N; a.min_mac = min_mac; a.numtol = 1e-6;
   a.sums = h->s2_sums.p; a.mask_count = h->s2_maskcount.p; a.YtX = h->s2_YtX.p; a.XmX = h->s2_XmX.p;
   a.scf_sv = h->s2_scf.p; a.nz_count = h->bt_nnz.p; a.info_sums = h->bt_xtwg.p; a.info = h->bt_info.p;
+  a.non_par = take_non_par(h, bs); a.col_male = h->s2_col_male; a.male_tot = h->s2_male_tot.p;
   double* d = h->s2_out_d.p;
   const size_t bp = (size_t)h->bs_max * P, b1 = h->bs_max;
   a.af = d; a.mac = d + bp; a.stat = d + 2 * bp; a.beta = d + 3 * bp; a.se = d + 4 * bp; a.chisq = d + 5 * bp;
@@ -387,6 +418,24 @@ static void s2_firth(rg_ctx* h, int n_sel, const int32_t* var_idx, const int32_t
 }
 
 extern "C" {
+
+int rg_s2_set_sex(rg_handle h, const uint8_t* male) {
+  RG_API_BEGIN
+  RG_CHECK(h && h->kind == 2, "bad argument");
+  if (male) h->s2_male.assign(male, male + h->N); else h->s2_male.clear();
+  RG_API_END
+}
+
+int rg_s2_set_non_par(rg_handle h, const uint8_t* flags, int32_t n) {
+  RG_API_BEGIN
+  RG_CHECK(h && h->kind == 2 && flags && n > 0, "bad argument");
+  RG_CUDA(cudaSetDevice(h->device));
+  h->s2_nonpar.alloc(std::max<size_t>((size_t)n, (size_t)h->bs_max));
+  RG_CUDA(cudaMemcpyAsync(h->s2_nonpar.p, flags, n, cudaMemcpyHostToDevice, h->stream));
+  RG_CUDA(cudaStreamSynchronize(h->stream));
+  h->s2_nonpar_set = true;
+  RG_API_END
+}
 
 int rg_s2_set_chr_bt(rg_handle h, const rg_s2_bt_chr* st) {
   RG_API_BEGIN

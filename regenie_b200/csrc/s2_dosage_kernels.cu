@@ -105,7 +105,14 @@ __global__ void s2_bt_finalize_kernel(S2BtFinalizeArgs a) {
   const double nm = Sm[0];
   const double ns1 = (double)a.n_analyzed - nm;
   const double total = S1[0] * k;                     // dosage sum over analysed, non-missing samples
-  const double mac1 = fmin(total, 2.0 * ns1 - total);
+  const bool xmale = a.non_par && a.non_par[i] && a.col_male >= 0;       // see s2_finalize_kernel
+  double mac1;
+  if (xmale) {
+    const double macr = total - 0.5 * S1[a.col_male] * k;
+    mac1 = fmin(macr, 2.0 * ns1 - (a.col_tot[a.col_male] - Sm[a.col_male]) - macr);
+  } else {
+    mac1 = fmin(total, 2.0 * ns1 - total);
+  }
   int flags = 0;
   a.ns_all[i] = (int)ns1;
   a.mac_all[i] = mac1;
@@ -128,7 +135,13 @@ __global__ void s2_bt_finalize_kernel(S2BtFinalizeArgs a) {
     const double ns = a.col_tot[base] - nmiss_p;      // analysed & masked & non-missing
     const double tp = S1[base] * k;
     a.ns[(int64_t)i * P + p] = (int)ns;
-    a.mac[(int64_t)i * P + p] = fmin(tp, 2.0 * ns - tp);
+    if (xmale) {
+      const int cmale = a.col_male + 1 + p;
+      const double macr = tp - 0.5 * S1[cmale] * k;
+      a.mac[(int64_t)i * P + p] = fmin(macr, 2.0 * ns - (a.col_tot[cmale] - Sm[cmale]) - macr);
+    } else {
+      a.mac[(int64_t)i * P + p] = fmin(tp, 2.0 * ns - tp);
+    }
     const double af = tp / (2.0 * ns);
     a.af[(int64_t)i * P + p] = af;
     // INFO (bgen), src/Geno.cpp:3140:  1 - sum(4 p0 + p1 - g^2) / (2 n af (1 - af))

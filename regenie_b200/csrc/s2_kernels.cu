@@ -92,7 +92,15 @@ __global__ void s2_finalize_kernel(S2FinalizeArgs a) {
   const double nm = Sm[0];
   const double ns1 = (double)a.n_analyzed - nm;
   const double total = S1[0];
-  const double mac1 = fmin(total, 2.0 * ns1 - total);
+  // non-PAR chrX: males are coded 0/2 but count half towards the allele count (src/Geno.cpp:2447-2462, compute_mac :3077)
+  const bool xmale = a.non_par && a.non_par[i] && a.col_male >= 0;
+  double mac1;
+  if (xmale) {
+    const double macr = total - 0.5 * S1[a.col_male];
+    mac1 = fmin(macr, 2.0 * ns1 - (a.male_tot[0] - Sm[a.col_male]) - macr);
+  } else {
+    mac1 = fmin(total, 2.0 * ns1 - total);
+  }
   int flags = 0;
   a.ns_all[i] = (int)ns1;
   a.mac_all[i] = mac1;
@@ -102,7 +110,12 @@ __global__ void s2_finalize_kernel(S2FinalizeArgs a) {
     const double ns = a.mask_count[p] - Sm[cm + p];
     const double tp = S1[cm + p];
     a.ns[(int64_t)i * P + p] = (int)ns;
-    a.mac[(int64_t)i * P + p] = fmin(tp, 2.0 * ns - tp);
+    if (xmale) {
+      const double macr = tp - 0.5 * S1[a.col_male + 1 + p];
+      a.mac[(int64_t)i * P + p] = fmin(macr, 2.0 * ns - (a.male_tot[1 + p] - Sm[a.col_male + 1 + p]) - macr);
+    } else {
+      a.mac[(int64_t)i * P + p] = fmin(tp, 2.0 * ns - tp);
+    }
     const double af = tp / (2.0 * ns);
     a.af[(int64_t)i * P + p] = af;
     if (a.info) {                                                    // compute_aaf_info, src/Geno.cpp:3140

@@ -60,6 +60,7 @@ void BgenFile::open(const std::string& p, const std::string& sample_file, bool r
       }
       if (t.size() < 2) throw Fail("incorrectly formatted sample file.");
       keys_file.push_back(t[0] + "_" + t[1]);
+      sex_file.push_back(t.size() >= 4 ? (t[3] == "1" ? 1 : (t[3] == "2" ? 2 : 0)) : 0);   // src/Geno.cpp:395-456
     }
     if (keys_file.size() != n_file) throw Fail("number of samples in BGEN file does not match that in the sample file.");
   } else {
@@ -71,6 +72,7 @@ void BgenFile::open(const std::string& p, const std::string& sample_file, bool r
     for (uint32_t i = 0; i < ns; ++i) {
       const uint16_t l = rd16(q);
       keys_file.emplace_back(reinterpret_cast<const char*>(q + 2), l);
+      sex_file.push_back(0);
       q += 2 + l;
     }
   }

@@ -11,6 +11,7 @@ struct BgenFile {
   std::string path;
   std::vector<Snp> snps;                       // after --extract/--exclude; offset = file offset of the genotype block
   std::vector<std::string> keys_file, keys;
+  std::vector<int> sex_file;                   // 1 = male, 2 = female, 0 = unknown (from --sample, else all 0)
   std::vector<int32_t> sample_idx;
   std::map<std::string, uint32_t> key_to_ind;
   uint32_t n_file = 0, n_variants_file = 0;

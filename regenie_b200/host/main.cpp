@@ -34,6 +34,7 @@ struct Params {
   double min_mac = 5.0, p_thresh = 0.05;
   int threads = 0;
   std::set<int> chrs;                 // --chr / --chrList
+  uint32_t par1_max = 2781479, par2_min = 155701383;   // hg38 (check_build_code, src/Regenie.cpp:1643-1660)
 };
 
 void rg_check(int rc) {
@@ -69,6 +70,15 @@ Params parse_cli(int argc, char** argv) {
     else if (a == "--gpu") p.gpu = atoi(need(i).c_str());
     else if (a == "--threads") p.threads = atoi(need(i).c_str());   // host threads: BGEN inflate only
     else if (a == "--sample") p.sample = need(i);
+    else if (a == "--par-region") {
+      const std::string v = need(i);
+      int lo = 0, hi = 0;
+      if (v == "b36" || v == "hg18") { p.par1_max = 2709520; p.par2_min = 154584238; }
+      else if (v == "b37" || v == "hg19") { p.par1_max = 2699520; p.par2_min = 154931044; }
+      else if (v == "b38" || v == "hg38") { p.par1_max = 2781479; p.par2_min = 155701383; }
+      else if (sscanf(v.c_str(), "%d,%d", &lo, &hi) == 2 && lo >= 1 && hi >= lo) { p.par1_max = lo - 1; p.par2_min = hi + 1; }
+      else throw Fail("invalid build code given (valid ones are 'b36|b37|b38|hg18|hg19|hg38' or [start,end] position of the non-par region)");
+    }
     else if (a == "--chr") { const int c = chr_str_to_int(need(i)); if (c < 1) throw Fail("invalid chromosome for --chr."); p.chrs.insert(c); }
     else if (a == "--chrList") {
       std::string v = need(i), tok;
@@ -375,6 +385,26 @@ std::vector<double> blup_for_chr(const Loco& loco, const SampleSet& g, const Phe
   return blup;
 }
 
+// in_non_par (src/Geno.cpp:2802-2814) for the variants of one block; returns false when none is flagged
+bool non_par_flags(const Params& p, const std::vector<Snp>& snps, const Block& b, std::vector<uint8_t>& flags) {
+  flags.assign(b.size, 0);
+  if (b.chrom != 23) return false;
+  bool any = false;
+  for (int v = 0; v < b.size; ++v) {
+    const uint64_t pos = snps[b.first + v].pos;
+    flags[v] = !(pos <= p.par1_max || pos >= p.par2_min);
+    any |= flags[v] != 0;
+  }
+  return any;
+}
+
+// params.sex == 1 for the kept samples (read_fam / read_bgen_sample)
+std::vector<uint8_t> male_vector(const std::vector<int>& sex_file, const std::vector<int32_t>& sample_idx) {
+  std::vector<uint8_t> m(sample_idx.size(), 0);
+  for (size_t i = 0; i < sample_idx.size(); ++i) m[i] = sex_file[sample_idx[i]] == 1;
+  return m;
+}
+
 void run_step2_qt(const Params& p, Log& log) {
   const bool use_bgen = !p.bgen.empty();
   BedFile g;
@@ -428,6 +458,7 @@ void run_step2_qt(const Params& p, Log& log) {
                 scale_fac.data(), stat.data(), beta.data(), se.data(), chisq.data()};
   const bool subset = keys.size() != n_file;
   std::vector<double> res((size_t)N * P), scf(P);
+  std::vector<uint8_t> npf;
   int cur_chr = -1;
   size_t n_ignored = 0;
   for (size_t b = 0; b < blocks.size(); ++b) {
@@ -448,8 +479,11 @@ void run_step2_qt(const Params& p, Log& log) {
         for (int64_t s = 0; s < N; ++s) res[(size_t)i * N + s] /= psd;
         scf[i] = ph.scale_Y[i] * psd;
       }
+      const std::vector<uint8_t> male = male_vector(use_bgen ? gg.sex_file : g.sex_file, sample_idx);
+      rg_check(rg_s2_set_sex(h, chrom == 23 ? male.data() : nullptr));
       rg_check(rg_s2_set_chr(h, res.data(), scf.data()));
     }
+    if (non_par_flags(p, snps, blocks[b], npf)) rg_check(rg_s2_set_non_par(h, npf.data(), blocks[b].size));
     if (use_bgen) {
       gg.read_block(blocks[b].first, blocks[b].size, probs.data(), pmiss.data(), threads);
       rg_check(rg_s2_block_bgen8(h, probs.data(), pmiss.data(), (int64_t)n_file, blocks[b].size,
@@ -541,6 +575,7 @@ void run_step2_bt(const Params& p, Log& log) {
   rg_s2_out out{af.data(), ns.data(), mac.data(), af_all.data(), ns_all.data(), mac_all.data(), flags.data(),
                 scale_fac.data(), stat.data(), beta.data(), se.data(), chisq.data()};
   const bool subset = keys.size() != n_file;
+  std::vector<uint8_t> npf;
   int cur_chr = -1;
   size_t n_ignored = 0, n_firth = 0, n_fail = 0;
   for (size_t b = 0; b < blocks.size(); ++b) {
@@ -560,9 +595,12 @@ void run_step2_bt(const Params& p, Log& log) {
         std::copy(nm.x_gamma.begin(), nm.x_gamma.end(), xg.begin() + (size_t)i * C * N);
         if (p.firth) std::copy(nm.firth_offset.begin(), nm.firth_offset.end(), off.begin() + (size_t)i * N);
       }
+      const std::vector<uint8_t> male = male_vector(use_bgen ? gg.sex_file : gb.sex_file, sample_idx);
+      rg_check(rg_s2_set_sex(h, chrom == 23 ? male.data() : nullptr));
       rg_s2_bt_chr st{gsm.data(), gs.data(), yres.data(), xg.data(), ph.Y_raw.data(), p.firth ? off.data() : nullptr};
       rg_check(rg_s2_set_chr_bt(h, &st));
     }
+    if (non_par_flags(p, snps, blocks[b], npf)) rg_check(rg_s2_set_non_par(h, npf.data(), bs));
     if (use_bgen) {
       gg.read_block(blocks[b].first, bs, probs.data(), pmiss.data(), threads);
     } else {
