@@ -88,7 +88,10 @@ void BedFile::open(const std::string& pfx, bool ref_first, const std::set<std::s
     throw Fail("invalid bed file (expected SNP-major mode, magic 6c 1b 01).");
 }
 
+void pgen_read_rows(PgenFile& pg, size_t first, size_t n, uint8_t* out);
+
 void BedFile::read_rows(size_t first, size_t n, uint8_t* out) {
+  if (pg) { pgen_read_rows(*pg, first, n, out); return; }
   for (size_t j = 0; j < n; ++j) {
     bed.seekg(3 + snps[first + j].offset * row_stride, std::ios::beg);
     bed.read(reinterpret_cast<char*>(out + j * row_stride), row_stride);

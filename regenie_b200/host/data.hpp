@@ -5,6 +5,7 @@
 //   pheno_impute_miss :1903-1935, getBasis :1660-1681, residualize_phenotypes :1799-1834,
 //   set_blocks src/Data.cpp:311-334, set_folds :401-431.
 #pragma once
+#include <memory>
 #include <set>
 
 #include "util.hpp"
@@ -25,8 +26,11 @@ struct SampleSet {
   const std::map<std::string, uint32_t>& key_to_ind;
 };
 
+struct PgenFile;
+
 struct BedFile {
   std::string prefix;
+  std::shared_ptr<PgenFile> pg;               // set by open_pgen: rows are decoded from a .pgen into the same 2-bit layout
   std::vector<Snp> snps;                      // after --extract/--exclude
   std::vector<std::string> keys_file;         // FID_IID in .fam order
   std::vector<int> sex_file;
@@ -38,6 +42,9 @@ struct BedFile {
   void open(const std::string& prefix, bool ref_first, const std::set<std::string>& exclude,
             const std::set<std::string>& extract, const std::set<std::string>& remove,
             const std::set<std::string>& keep, const std::set<int>& chrs = {});
+  // .pgen/.pvar/.psam behind the same interface (host/pgen.cpp); kernels then see ref-last PLINK 1 rows
+  void open_pgen(const std::string& prefix, const std::set<std::string>& exclude, const std::set<std::string>& extract,
+                 const std::set<std::string>& remove, const std::set<std::string>& keep, const std::set<int>& chrs = {});
   // read the rows of snps[first .. first+n) into out (n * row_stride bytes)
   void read_rows(size_t first, size_t n, uint8_t* out);
 };

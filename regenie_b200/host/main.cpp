@@ -19,6 +19,7 @@
 #include "bgen.hpp"
 #include "bt_null.hpp"
 #include "data.hpp"
+#include "pgen.hpp"
 
 using namespace rgh;
 
@@ -99,7 +100,7 @@ Params parse_cli(int argc, char** argv) {
     else if (a == "--use-relative-path") p.rel_path = true;
     else if (a == "--help" || a == "-h") {
       std::cout << "rgb200: B200-native regenie Step 1 / Step 2 hot path\n"
-                   "  --step 1|2 --bed PREFIX --phenoFile F [--covarFile F] --bsize N --out PREFIX\n"
+                   "  --step 1|2 --bed PREFIX | --pgen PREFIX | --bgen FILE --phenoFile F [--covarFile F] --bsize N --out PREFIX\n"
                    "  [--pred LIST] [--loocv] [--lowmem] [--cv K] [--l0 R] [--l1 R] [--remove F] [--keep F]\n"
                    "  [--exclude F] [--extract F] [--ref-first] [--minMAC x] [--strict] [--gpu ordinal]\n"
                    "  [--chr c]... [--chrList c1,c2,...]  (Step-2 jobs are split by chromosome like the reference)\n"
@@ -110,11 +111,11 @@ Params parse_cli(int argc, char** argv) {
     }
   }
   if (p.step != 1 && p.step != 2) throw Fail("specify which mode regenie should be running using option '--step'.");
-  if (!p.pgen.empty()) throw Fail("--pgen input is not implemented yet in rgb200 (SURVEY 8 row a3, next).");
   if (!p.bgen.empty() && p.step == 1) throw Fail("--bgen input in --step 1 is not implemented yet in rgb200 (hard-call .bed only).");
-  if (!p.bgen.empty() && !p.bed.empty()) throw Fail("specify only one genotype input (--bed or --bgen).");
+  if ((!p.bgen.empty()) + (!p.bed.empty()) + (!p.pgen.empty()) > 1) throw Fail("specify only one genotype input (--bed, --pgen or --bgen).");
+  if (!p.pgen.empty()) p.ref_first = false;          // .pgen rows are emitted as ref-last PLINK 1 rows counting ALT
   if (p.firth && !p.approx) throw Fail("exact Firth (--firth without --approx) is outside the hot path covered by rgb200; use --firth --approx.");
-  if (p.bed.empty() && p.bgen.empty()) throw Fail("must specify the genotype file with --bed or --bgen.");
+  if (p.bed.empty() && p.bgen.empty() && p.pgen.empty()) throw Fail("must specify the genotype file with --bed, --pgen or --bgen.");
   if (p.pheno.empty()) throw Fail("must provide the phenotype file with --phenoFile.");
   if (p.out.empty()) throw Fail("must specify an output file prefix with --out.");
   if (p.bsize < 1) throw Fail("must specify the block size using '--bsize'.");
@@ -140,13 +141,24 @@ double now_ms() {
 }
 
 // ------------------------------------------------------------------------------------ step 1
+// .bed/.bim/.fam or .pgen/.pvar/.psam behind the same row interface
+void open_rows(const Params& p, BedFile& g, const std::set<std::string>& excl, const std::set<std::string>& extr,
+               const std::set<std::string>& rem, const std::set<std::string>& keep, Log& log) {
+  if (!p.pgen.empty()) {
+    g.open_pgen(p.pgen, excl, extr, rem, keep, p.chrs);
+    log << " * pvar                : [" << p.pgen << ".pvar] n_snps = " << g.snps.size() << "\n";
+    log << " * psam                : [" << p.pgen << ".psam] n_samples = " << g.keys.size() << "\n";
+  } else {
+    g.open(p.bed, p.ref_first, excl, extr, rem, keep, p.chrs);
+    log << " * bim                 : [" << p.bed << ".bim] n_snps = " << g.snps.size() << "\n";
+    log << " * fam                 : [" << p.bed << ".fam] n_samples = " << g.keys.size() << "\n";
+  }
+}
+
 void run_step1(const Params& p_in, Log& log) {
   Params p = p_in;
   BedFile g;
-  g.open(p.bed, p.ref_first, read_id_list(p.exclude, 1), read_id_list(p.extract, 1), read_id_list(p.remove, 2),
-         read_id_list(p.keep, 2), p.chrs);
-  log << " * bim                 : [" << p.bed << ".bim] n_snps = " << g.snps.size() << "\n";
-  log << " * fam                 : [" << p.bed << ".fam] n_samples = " << g.keys.size() << "\n";
+  open_rows(p, g, read_id_list(p.exclude, 1), read_id_list(p.extract, 1), read_id_list(p.remove, 2), read_id_list(p.keep, 2), log);
   if (g.snps.empty()) throw Fail("no variant left to include in analysis.");
   if (g.snps.size() > 1000000 && !p.force_step1)
     throw Fail("it is not recommened to use more than 1000000 variants in step 1 (otherwise use '--force-step1').");
@@ -415,9 +427,7 @@ void run_step2_qt(const Params& p, Log& log) {
     gg.open(p.bgen, p.sample, p.ref_first, excl, extr, rem, keepl, p.chrs);
     log << " * bgen                : [" << p.bgen << "] n_snps = " << gg.snps.size() << ", n_samples = " << gg.keys.size() << "\n";
   } else {
-    g.open(p.bed, p.ref_first, excl, extr, rem, keepl, p.chrs);
-    log << " * bim                 : [" << p.bed << ".bim] n_snps = " << g.snps.size() << "\n";
-    log << " * fam                 : [" << p.bed << ".fam] n_samples = " << g.keys.size() << "\n";
+    open_rows(p, g, excl, extr, rem, keepl, log);
   }
   const std::vector<Snp>& snps = use_bgen ? gg.snps : g.snps;
   const std::vector<std::string>& keys = use_bgen ? gg.keys : g.keys;
@@ -533,9 +543,7 @@ void run_step2_bt(const Params& p, Log& log) {
     gg.open(p.bgen, p.sample, p.ref_first, excl, extr, rem, keep, p.chrs);
     log << " * bgen                : [" << p.bgen << "] n_snps = " << gg.snps.size() << ", n_samples = " << gg.keys.size() << "\n";
   } else {
-    gb.open(p.bed, p.ref_first, excl, extr, rem, keep, p.chrs);
-    log << " * bim                 : [" << p.bed << ".bim] n_snps = " << gb.snps.size() << "\n";
-    log << " * fam                 : [" << p.bed << ".fam] n_samples = " << gb.keys.size() << "\n";
+    open_rows(p, gb, excl, extr, rem, keep, log);
   }
   const std::vector<Snp>& snps = use_bgen ? gg.snps : gb.snps;
   const std::vector<std::string>& keys = use_bgen ? gg.keys : gb.keys;

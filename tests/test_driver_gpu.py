@@ -307,3 +307,59 @@ def test_step2_chr_jobs_concatenate_to_the_full_run(tmp_path, golden_dir):
         assert a[0] == b[0] == full[0]
         assert a[1:] + b[1:] == full[1:]
         assert len(a) > 1 and len(b) > 1
+
+
+def test_pgen_input_equals_bed_input(tmp_path, golden_dir):
+    """--pgen vs --bed on the reference's own fixture pair (example.pgen / example.bed hold the same calls): Step 1 and
+    Step 2 outputs must be byte-identical; then a synthetic .pgen that uses every hard-call record type (plain, 1-bit,
+    difflists over 0 / 2 / missing, all-zero, LD and inverted LD) against the .bed written from the same calls."""
+    import test_pgen_cpu as tp
+    from regenie_b200 import synth
+    d = golden_dir
+    pheno, covar = d + "/phenotype.txt", d + "/covariates.txt"
+    outs = {}
+    for kind, arg in (("bed", ["--bed", d + "/example"]), ("pgen", ["--pgen", d + "/example"])):
+        o1 = str(tmp_path / ("fit_" + kind))
+        run(["--step", "1"] + arg + ["--phenoFile", pheno, "--covarFile", covar, "--bsize", "100", "--out", o1])
+        o2 = str(tmp_path / ("s2_" + kind))
+        run(["--step", "2"] + arg + ["--phenoFile", pheno, "--covarFile", covar, "--bsize", "300", "--pred",
+                                     o1 + "_pred.list", "--out", o2])
+        outs[kind] = (o1, o2)
+    for k in (1, 2):
+        assert open(outs["bed"][0] + "_%d.loco" % k).read() == open(outs["pgen"][0] + "_%d.loco" % k).read()
+    for nm in ("Y1", "Y2"):
+        assert open(outs["bed"][1] + "_%s.regenie" % nm).read() == open(outs["pgen"][1] + "_%s.regenie" % nm).read()
+    # synthetic: all record types
+    g = tp.synthetic_calls(N=700, M=160, seed=3)
+    Y, cov, na = synth.phenotypes(np.where(g == 3, 0, g).astype(np.uint8), 2, 3, seed=2)
+    prefix = helpers.write_fileset(str(tmp_path / "syn"), g, Y, cov, na)          # .bed/.bim/.fam + pheno/covar
+    bim = [l.split() for l in open(prefix + ".bim")]
+    keys = ["_".join(l.split()[:2]) for l in open(prefix + ".fam")]
+    types = helpers.write_pgen(prefix, g, storage=5)
+    assert set(types) == set(range(8))
+    helpers.write_pvar_psam(prefix, [b[0] for b in bim], [b[1] for b in bim], [int(b[3]) for b in bim],
+                            [b[5] for b in bim], [b[4] for b in bim], keys)           # REF = .bim col 6, ALT = col 5
+    sd = str(tmp_path / "syn")
+    res = {}
+    for kind, arg in (("bed", ["--bed", prefix]), ("pgen", ["--pgen", prefix])):
+        o2 = str(tmp_path / ("syn_s2_" + kind))
+        lst = _write_zero_loco_keys(tmp_path, keys, ["Y1", "Y2"], kind)
+        run(["--step", "2"] + arg + ["--phenoFile", sd + "/pheno.txt", "--covarFile", sd + "/covar.txt", "--bsize", "64",
+                                     "--pred", lst, "--out", o2])
+        res[kind] = o2
+    for nm in ("Y1", "Y2"):
+        a, b = open(res["bed"] + "_%s.regenie" % nm).read(), open(res["pgen"] + "_%s.regenie" % nm).read()
+        assert a == b and a.count("\n") > 60
+
+
+def _write_zero_loco_keys(tmp_path, keys, traits, tag):
+    lst = tmp_path / ("zero_%s_pred.list" % tag)
+    with open(lst, "w") as fl:
+        for j, t in enumerate(traits):
+            f = tmp_path / ("zero_%s_%d.loco" % (tag, j + 1))
+            with open(f, "w") as fh:
+                fh.write("FID_IID " + " ".join(keys) + "\n")
+                for c in range(1, 24):
+                    fh.write(str(c) + " " + " ".join(["0"] * len(keys)) + "\n")
+            fl.write("%s %s\n" % (t, f))
+    return str(lst)
