@@ -11,6 +11,17 @@ import zlib
 import numpy as np
 
 
+def _zstd_decompress(buf, dl):
+    import ctypes
+    lib = ctypes.CDLL("libzstd.so.1")
+    lib.ZSTD_decompress.restype = ctypes.c_size_t
+    lib.ZSTD_decompress.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
+    out = ctypes.create_string_buffer(dl)
+    got = lib.ZSTD_decompress(out, dl, bytes(buf), len(buf))
+    assert got == dl
+    return out.raw
+
+
 class Bgen:
     def __init__(self, path):
         self.data = open(path, "rb").read()
@@ -24,8 +35,8 @@ class Bgen:
         self.layout = (flags >> 2) & 0xF
         self.has_ids = bool(flags >> 31)
         self.n_samples, self.n_variants = n, m
-        if self.layout != 2 or self.compression != 1:
-            raise ValueError("oracle reader supports layout 2 + zlib only")
+        if self.layout != 2 or self.compression not in (0, 1, 2):
+            raise ValueError("oracle reader supports layout 2 only")
         self.sample_ids = []
         pos = 4 + lh
         if self.has_ids:
@@ -49,9 +60,14 @@ class Bgen:
             alleles = []
             for _a in range(k):
                 (l,) = struct.unpack_from("<I", d, p); alleles.append(d[p + 4:p + 4 + l].decode()); p += 4 + l
-            c, dl = struct.unpack_from("<II", d, p); p += 8
-            raw = zlib.decompress(d[p:p + c - 4]); p += c - 4
-            assert len(raw) == dl
+            if self.compression == 0:
+                (c,) = struct.unpack_from("<I", d, p); p += 4
+                raw = d[p:p + c]; p += c
+            else:
+                c, dl = struct.unpack_from("<II", d, p); p += 8
+                raw = zlib.decompress(d[p:p + c - 4]) if self.compression == 1 else _zstd_decompress(d[p:p + c - 4], dl)
+                p += c - 4
+                assert len(raw) == dl
             n, ka, pmin, pmax = struct.unpack_from("<IHBB", raw, 0)
             assert ka == 2 and pmin == 2 and pmax == 2
             ploidy = np.frombuffer(raw, dtype=np.uint8, count=n, offset=8)

@@ -89,7 +89,7 @@ def build_driver(verbose=False, force=False):
     hdrs = [os.path.join(HERE, "host", f) for f in os.listdir(os.path.join(HERE, "host")) if f.endswith(".hpp")]
     if force or _newer(srcs + hdrs + [LIB], DRIVER):
         _run([gxx, "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", DRIVER] + srcs +
-             ["-L", HERE, "-lrg_b200", "-Wl,-rpath,$ORIGIN", "-lz", "-lpthread"], verbose)
+             ["-L", HERE, "-lrg_b200", "-Wl,-rpath,$ORIGIN", "-lz", "-lpthread", "-ldl"], verbose)
     return DRIVER
 
 

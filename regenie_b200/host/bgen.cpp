@@ -6,6 +6,8 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <dlfcn.h>
+
 #include <atomic>
 #include <cstring>
 #include <thread>
@@ -13,6 +15,21 @@
 namespace rgh {
 
 namespace {
+// zstd payloads (BGEN compression flag 2; the reference links BGEN's bundled zstd, src/Geno.cpp:1610, :2209).  Only the
+// runtime library ships in this image, so the one entry point needed is bound with dlopen; lossless, no parity risk.
+typedef size_t (*ZstdDecompressFn)(void*, size_t, const void*, size_t);
+typedef unsigned (*ZstdIsErrorFn)(size_t);
+ZstdDecompressFn g_zstd_decompress = nullptr;
+ZstdIsErrorFn g_zstd_is_error = nullptr;
+void load_zstd() {
+  if (g_zstd_decompress) return;
+  void* lib = dlopen("libzstd.so.1", RTLD_NOW);
+  if (!lib) lib = dlopen("libzstd.so", RTLD_NOW);
+  if (!lib) throw Fail("the bgen file is zstd-compressed but libzstd could not be loaded on this host.");
+  g_zstd_decompress = reinterpret_cast<ZstdDecompressFn>(dlsym(lib, "ZSTD_decompress"));
+  g_zstd_is_error = reinterpret_cast<ZstdIsErrorFn>(dlsym(lib, "ZSTD_isError"));
+  if (!g_zstd_decompress || !g_zstd_is_error) throw Fail("libzstd does not export ZSTD_decompress.");
+}
 inline uint16_t rd16(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); return v; }
 inline uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 }  // namespace
@@ -44,7 +61,8 @@ void BgenFile::open(const std::string& p, const std::string& sample_file, bool r
   const int layout = (flags >> 2) & 0xF;
   const bool has_ids = (flags >> 31) != 0;
   if (layout != 2) throw Fail("only BGEN v1.2 (layout 2) files are supported.");
-  if (compression > 1) throw Fail("zstd-compressed bgen files are not supported by rgb200 (zlib or uncompressed only).");
+  if (compression > 2) throw Fail("unknown bgen compression flag.");
+  if (compression == 2) load_zstd();
   // ---- sample identifiers: embedded block, or --sample (read_bgen_sample, src/Geno.cpp:391-440)
   if (!sample_file.empty()) {
     std::ifstream fh(sample_file);
@@ -139,6 +157,12 @@ void BgenFile::read_block(size_t first, size_t n, uint8_t* probs, uint8_t* pm, i
         dl = rd32(q + 4);
         buf.resize(dl);
         if (uncompress(buf.data(), &dl, q + 8, c - 4) != Z_OK) { failed = true; return; }
+        raw = buf.data();
+      } else if (compression == 2) {
+        dl = rd32(q + 4);
+        buf.resize(dl);
+        const size_t got = g_zstd_decompress(buf.data(), dl, q + 8, c - 4);
+        if (g_zstd_is_error(got) || got != dl) { failed = true; return; }
         raw = buf.data();
       } else {
         dl = c;

@@ -1,4 +1,4 @@
-// BGEN v1.2 reader of the rgb200 host driver (layout 2, zlib or uncompressed, 8-bit, unphased, biallelic,
+// BGEN v1.2 reader of the rgb200 host driver (layout 2, zlib / zstd / uncompressed, 8-bit, unphased, biallelic,
 // diploid - the subset the reference's hand parser handles, src/Geno.cpp:2122-2345).  The file header and the
 // variant identifying blocks (which the reference reads through the BGEN library, src/Geno.cpp:38-178) follow
 // the public BGEN v1.2 specification.  The inflated probability bytes go to the GPU unchanged.

@@ -290,3 +290,45 @@ def write_pvar_psam(prefix, chroms, ids, pos, ref, alt, keys, sex=None):
         for j, k in enumerate(keys):
             f, i = k.split("_", 1)
             fh.write("%s\t%s\t%s\n" % (f, i, "NA" if sex is None else sex[j]))
+
+
+# ---------------------------------------------------------------------------------------- BGEN re-compression (tests only)
+def recompress_bgen(src, dst, mode):
+    """Rewrite a zlib-compressed BGEN v1.2 file with compression flag `mode` (0 = none, 2 = zstd via libzstd)."""
+    import ctypes
+    import struct
+    import zlib
+    d = open(src, "rb").read()
+    (offset,) = struct.unpack_from("<I", d, 0)
+    lh, m, n = struct.unpack_from("<III", d, 4)
+    (flags,) = struct.unpack_from("<I", d, 4 + lh - 4)
+    assert flags & 3 == 1
+    out = bytearray(d[:offset + 4])
+    struct.pack_into("<I", out, 4 + lh - 4, (flags & ~3) | mode)
+    zs = None
+    if mode == 2:
+        zs = ctypes.CDLL("libzstd.so.1")
+        zs.ZSTD_compress.restype = ctypes.c_size_t
+        zs.ZSTD_compress.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int]
+        zs.ZSTD_compressBound.restype = ctypes.c_size_t
+        zs.ZSTD_compressBound.argtypes = [ctypes.c_size_t]
+    p = offset + 4
+    for _ in range(m):
+        p0 = p
+        for _k in range(3):
+            (l,) = struct.unpack_from("<H", d, p); p += 2 + l
+        p += 4
+        (k,) = struct.unpack_from("<H", d, p); p += 2
+        for _a in range(k):
+            (l,) = struct.unpack_from("<I", d, p); p += 4 + l
+        out += d[p0:p]
+        c, dl = struct.unpack_from("<II", d, p); p += 8
+        raw = zlib.decompress(d[p:p + c - 4]); p += c - 4
+        if mode == 0:
+            out += struct.pack("<I", len(raw)) + raw
+        else:
+            cap = zs.ZSTD_compressBound(len(raw))
+            buf = ctypes.create_string_buffer(cap)
+            got = zs.ZSTD_compress(buf, cap, raw, len(raw), 3)
+            out += struct.pack("<II", got + 4, len(raw)) + buf.raw[:got]
+    open(dst, "wb").write(bytes(out))

@@ -363,3 +363,22 @@ def _write_zero_loco_keys(tmp_path, keys, traits, tag):
                     fh.write(str(c) + " " + " ".join(["0"] * len(keys)) + "\n")
             fl.write("%s %s\n" % (t, f))
     return str(lst)
+
+
+def test_bgen_zstd_and_uncompressed_payloads(tmp_path, golden_dir):
+    """BGEN compression flags 0 (none) and 2 (zstd) decode to the same probabilities as the zlib file the reference
+    ships: identical Step-2 output (the reference reads both, src/Geno.cpp:1608-1610, :2207-2209)."""
+    d = golden_dir
+    pred = _write_zero_loco(tmp_path, d, ["Y1", "Y2"])
+    outs = []
+    for tag, mode in (("zlib", None), ("none", 0), ("zstd", 2)):
+        f = d + "/example.bgen"
+        if mode is not None:
+            f = str(tmp_path / ("example_%s.bgen" % tag))
+            helpers.recompress_bgen(d + "/example.bgen", f, mode)
+        out = str(tmp_path / ("o_" + tag))
+        run(["--step", "2", "--bgen", f, "--covarFile", d + "/covariates.txt", "--phenoFile", d + "/phenotype_bin.txt",
+             "--remove", d + "/fid_iid_to_remove.txt", "--bsize", "200", "--bt", "--firth", "--approx", "--pThresh", "0.01",
+             "--pred", pred, "--out", out])
+        outs.append(open(out + "_Y1.regenie").read())
+    assert outs[0] == outs[1] == outs[2] and outs[0].count("\n") == 1001
