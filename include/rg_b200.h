@@ -105,6 +105,9 @@ int64_t rg_l0_status(rg_handle h);
  * (write_l0_file, src/Step1_Models.cpp:728-733).
  */
 int rg_l0_fetch_W(rg_handle h, int32_t block_id, int32_t ph, double* out_NxR);
+/* inverse of rg_l0_fetch_W: place a block's N x R slab read from a level-0 file (read_l0_chunk,
+ * src/Step1_Models.cpp:1956-1987; --run-l1 after --run-l0 jobs, possibly produced by the reference itself) */
+int rg_l0_load_W(rg_handle h, int32_t block_id, int32_t ph, const double* in_NxR);
 
 /*
  * rg_l1_fit -- level-1 ridge for all phenotypes.  Replaces ridge_level_1 /

@@ -46,7 +46,7 @@ EXPORTS = [
     "rg_last_error", "rg_version", "rg_device_count", "rg_step1_create", "rg_destroy", "rg_sync",
     "rg_l0_block_bed", "rg_l0_status", "rg_l0_fetch_W", "rg_l1_fit", "rg_loco", "rg_step2_create",
     "rg_s2_set_chr", "rg_s2_block_bed", "rg_W_info", "rg_debug_fetch", "rg_launch_count", "rg_stream",
-    "rg_set_timing", "rg_get_timing", "rg_fence", "rg_s2_set_chr_bt", "rg_s2_block_bgen8_bt", "rg_s2_block_bgen8", "rg_s2_firth", "rg_l1_fit_bt", "rg_W_export", "rg_W_attach_peer", "rg_l1_select", "rg_s2_set_sex", "rg_s2_set_non_par",
+    "rg_set_timing", "rg_get_timing", "rg_fence", "rg_s2_set_chr_bt", "rg_s2_block_bgen8_bt", "rg_s2_block_bgen8", "rg_s2_firth", "rg_l1_fit_bt", "rg_W_export", "rg_W_attach_peer", "rg_l1_select", "rg_s2_set_sex", "rg_s2_set_non_par", "rg_l0_load_W",
 ]
 
 _lib = None
@@ -153,6 +153,11 @@ class Step1:
         out = np.empty((self.N, self.R), dtype=np.float64, order="F")
         check(lib().rg_l0_fetch_W(self.h, block_id, ph, _ptr(out)))
         return out
+
+    def load_W(self, block_id, ph, slab):
+        L = lib(); L.rg_l0_load_W.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        a = _f64(slab)
+        check(L.rg_l0_load_W(self.h, block_id, ph, _ptr(a)))
 
     def l1_fit(self, tau):
         tau = np.ascontiguousarray(tau, dtype=np.float64).reshape(self.P, self.R1)

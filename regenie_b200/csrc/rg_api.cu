@@ -632,6 +632,20 @@ int rg_l0_block_bed(rg_handle h, const uint8_t* packed, int64_t row_stride, int3
   RG_API_END
 }
 
+int rg_l0_load_W(rg_handle h, int32_t block_id, int32_t ph, const double* in) {
+  RG_API_BEGIN
+  RG_CHECK(h && in, "null argument");
+  RG_CHECK(h->kind == 1 && block_id >= 0 && block_id < h->total_blocks && ph >= 0 && ph < h->P, "bad index");
+  RG_CUDA(cudaSetDevice(h->device));
+  std::vector<double> tmp((size_t)h->Npad * h->R, 0.0);
+  for (int r = 0; r < h->R; ++r)
+    for (int64_t s = 0; s < h->N; ++s) tmp[(size_t)r * h->Npad + h->pad_of[s]] = in[(size_t)r * h->N + s];
+  double* dst = h->W_host_tab[ph] + (size_t)block_id * h->R * h->Npad;
+  RG_CUDA(cudaMemcpyAsync(dst, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice, h->stream));
+  RG_CUDA(cudaStreamSynchronize(h->stream));
+  RG_API_END
+}
+
 int64_t rg_l0_status(rg_handle h) {
   if (!h) return -1;
   cudaSetDevice(h->device);

@@ -35,6 +35,9 @@ struct Params {
   double min_mac = 5.0, p_thresh = 0.05;
   int threads = 0;
   std::set<int> chrs;                 // --chr / --chrList
+  std::string split_prefix, master;   // --split-l0 PREFIX,N / --run-l0 FILE,K / --run-l1 FILE
+  int split_jobs = 0, run_l0_job = 0;
+  bool run_l1 = false;
   uint32_t par1_max = 2781479, par2_min = 155701383;   // hg38 (check_build_code, src/Regenie.cpp:1643-1660)
 };
 
@@ -71,6 +74,15 @@ Params parse_cli(int argc, char** argv) {
     else if (a == "--gpu") p.gpu = atoi(need(i).c_str());
     else if (a == "--threads") p.threads = atoi(need(i).c_str());   // host threads: BGEN inflate only
     else if (a == "--sample") p.sample = need(i);
+    else if (a == "--split-l0" || a == "--run-l0") {
+      const std::string v = need(i);
+      const size_t k = v.find_last_of(',');
+      if (k == std::string::npos || atoi(v.c_str() + k + 1) < 1)
+        throw Fail("wrong format for " + a + " (must be FILE,INT).");
+      if (a == "--split-l0") { p.split_prefix = v.substr(0, k); p.split_jobs = atoi(v.c_str() + k + 1); }
+      else { p.master = v.substr(0, k); p.run_l0_job = atoi(v.c_str() + k + 1); }
+    }
+    else if (a == "--run-l1") { p.master = need(i); p.run_l1 = true; }
     else if (a == "--par-region") {
       const std::string v = need(i);
       int lo = 0, hi = 0;
@@ -117,6 +129,7 @@ Params parse_cli(int argc, char** argv) {
   if (p.firth && !p.approx) throw Fail("exact Firth (--firth without --approx) is outside the hot path covered by rgb200; use --firth --approx.");
   if (p.bed.empty() && p.bgen.empty() && p.pgen.empty()) throw Fail("must specify the genotype file with --bed, --pgen or --bgen.");
   if (p.pheno.empty()) throw Fail("must provide the phenotype file with --phenoFile.");
+  if ((p.split_jobs || p.run_l0_job || p.run_l1) && p.step != 1) throw Fail("options --split-l0/--run-l0/--run-l1 only work in step 1.");
   if (p.out.empty()) throw Fail("must specify an output file prefix with --out.");
   if (p.bsize < 1) throw Fail("must specify the block size using '--bsize'.");
   if (p.step == 2 && p.pred.empty()) throw Fail("must specify --pred if using --step 2.");
@@ -155,8 +168,66 @@ void open_rows(const Params& p, BedFile& g, const std::set<std::string>& excl, c
   }
 }
 
+// ---- --split-l0 / --run-l0 / --run-l1 (src/Data.cpp:232-309, 818-908): level 0 as independent jobs that exchange
+// the N x R slabs of write_l0_file through <prefix>_job<j>_l0_Y<k>; files are interchangeable with the reference's.
+struct MasterJob { std::string prefix; int nblocks; long nsnps; };
+struct Master { long n_geno = 0; int bsize = 0; std::vector<MasterJob> jobs; };
+
+Master read_master(const std::string& path, int bsize) {
+  std::ifstream fh(path);
+  if (!fh) throw Fail("cannot open file : " + path);
+  Master m;
+  std::string line;
+  if (!std::getline(fh, line)) throw Fail("cannot read header line in master file.");
+  if (sscanf(line.c_str(), "%ld %d", &m.n_geno, &m.bsize) != 2 || m.bsize != bsize) throw Fail("invalid header line in master file.");
+  while (std::getline(fh, line)) {
+    auto t = split_ws(line);
+    if (t.empty()) continue;
+    if (t.size() != 3) throw Fail("could not read line " + std::to_string(m.jobs.size() + 2) + " (check number of lines and format in file).");
+    m.jobs.push_back({t[0], atoi(t[1].c_str()), atol(t[2].c_str())});
+  }
+  return m;
+}
+
+void write_master(const Params& p, const std::vector<Snp>& snps, const std::vector<Block>& blocks, Log& log) {
+  int njobs = p.split_jobs;
+  const int nb_tot = (int)blocks.size();
+  log << " * running level 0 in parallel across " << nb_tot << " genotype blocks\n";
+  if (njobs <= 1) throw Fail("number of jobs must be >1.");
+  if (njobs > nb_tot) { log << "   -WARNING: Number of jobs cannot be greater than number of blocks.\n"; njobs = nb_tot; }
+  const std::string fout = p.split_prefix + ".master";
+  log << "   -using " << njobs << " jobs\n   -master file written to [" << fout << "]\n"
+      << "   -variant list files written to [" << p.split_prefix << "_job*.snplist]\n";
+  std::ofstream of(fout);
+  if (!of) throw Fail("cannot write to file : " + fout);
+  of << snps.size() << " " << p.bsize << "\n";
+  const int nall = nb_tot / njobs, rem = nb_tot - nall * njobs;
+  int b = 0;
+  for (int j = 0; j < njobs; ++j) {
+    const int target = nall + (j < rem ? 1 : 0);
+    const std::string fname = p.split_prefix + "_job" + std::to_string(j + 1);
+    long ns = 0;
+    std::ofstream sl(fname + ".snplist");
+    if (!sl) throw Fail("cannot write to file : " + fname + ".snplist");
+    for (int k = 0; k < target; ++k, ++b) {
+      for (int v = 0; v < blocks[b].size; ++v) sl << snps[blocks[b].first + v].id << "\n";
+      ns += blocks[b].size;
+    }
+    of << fname << " " << target << " " << ns << "\n";
+  }
+}
+
 void run_step1(const Params& p_in, Log& log) {
   Params p = p_in;
+  Master master;
+  if (p.run_l0_job || p.run_l1) master = read_master(p.master, p.bsize);
+  if (p.run_l0_job) {
+    if (p.run_l0_job > (int)master.jobs.size()) throw Fail("could not read line " + std::to_string(p.run_l0_job + 1) + " (check number of lines in file).");
+    log << " * running jobs in parallel (job #" << p.run_l0_job << ")\n";
+    p.extract = master.jobs[p.run_l0_job - 1].prefix + ".snplist";       // file_snps_include (src/Data.cpp:852-854)
+    p.exclude.clear();
+    p.lowmem_prefix = master.jobs[p.run_l0_job - 1].prefix;
+  }
   BedFile g;
   open_rows(p, g, read_id_list(p.exclude, 1), read_id_list(p.extract, 1), read_id_list(p.remove, 2), read_id_list(p.keep, 2), log);
   if (g.snps.empty()) throw Fail("no variant left to include in analysis.");
@@ -173,13 +244,27 @@ void run_step1(const Params& p_in, Log& log) {
   }
   const auto blocks = set_blocks(g.snps, p.bsize);
   const int nb = (int)blocks.size();
+  if (p.split_jobs) { write_master(p, g.snps, blocks, log); return; }
+  if (p.run_l0_job) {
+    const MasterJob& mj = master.jobs[p.run_l0_job - 1];
+    if (mj.nblocks != nb || mj.nsnps != (long)g.snps.size())
+      throw Fail("number of variants/blocks in file (=" + std::to_string(g.snps.size()) + "/" + std::to_string(nb) +
+                 ") don't match with that in master file (=" + std::to_string(mj.nsnps) + "/" + std::to_string(mj.nblocks) + ").");
+  }
+  if (p.run_l1) {
+    long tb = 0, ts = 0;
+    for (auto& j : master.jobs) { tb += j.nblocks; ts += j.nsnps; }
+    if (tb != nb || ts != (long)g.snps.size())
+      throw Fail("number of blocks/variants in master file '" + p.master + "' doesn't match that in the analysis.");
+    log << " * using results from running " << master.jobs.size() << " parallel jobs at level 0\n";
+  }
   const int64_t N = ph.N;
   const int P = ph.P;
   std::vector<int64_t> folds;
   if (!p.loocv) folds = set_folds(ph.in_analysis, p.cv);
   const auto h0 = ridge_grid(p.l0), h1 = ridge_grid(p.l1);
   std::vector<double> lambda(p.l0);
-  const double M = (double)g.snps.size();
+  const double M = p.run_l0_job ? (double)master.n_geno : (double)g.snps.size();     // src/Data.cpp:607
   for (int j = 0; j < p.l0; ++j) lambda[j] = M * (1 - h0[j]) / h0[j];           // src/Data.cpp:607
   log << " * # blocks            : [" << nb << "] for " << g.snps.size() << " variants\n";
   log << " * # CV folds          : [" << (p.loocv ? ph.n_analyzed : p.cv) << "]\n";
@@ -198,7 +283,27 @@ void run_step1(const Params& p_in, Log& log) {
   const bool subset = g.keys.size() != g.keys_file.size();
   int last_chr = -1;
   const double t0 = now_ms();
-  for (int b = 0; b < nb; ++b) {
+  if (p.run_l1) {
+    // read_l0 / read_l0_chunk (src/Step1_Models.cpp:1921-1987): columns [bstart*R, (bstart+btot)*R) from every job file
+    log << " (skipping to level 1 models)\n";
+    std::vector<double> slab((size_t)N * p.l0);
+    for (int ph_i = 0; ph_i < P; ++ph_i) {
+      int b0 = 0;
+      for (const auto& mj : master.jobs) {
+        const std::string fin = mj.prefix + "_l0_Y" + std::to_string(ph_i + 1);
+        std::ifstream f(fin, std::ios::binary | std::ios::ate);
+        if (!f) throw Fail("cannot open file : " + fin);
+        if ((uint64_t)f.tellg() != (uint64_t)sizeof(double) * N * p.l0 * mj.nblocks) throw Fail("file " + fin + " is not the right size.");
+        f.seekg(0);
+        for (int b = 0; b < mj.nblocks; ++b) {
+          f.read(reinterpret_cast<char*>(slab.data()), (std::streamsize)(slab.size() * sizeof(double)));
+          rg_check(rg_l0_load_W(h, b0 + b, ph_i, slab.data()));
+        }
+        b0 += mj.nblocks;
+      }
+    }
+  }
+  for (int b = 0; b < nb && !p.run_l1; ++b) {
     if (blocks[b].chrom != last_chr) { log << "Chromosome " << blocks[b].chrom << "\n"; last_chr = blocks[b].chrom; }
     g.read_rows(blocks[b].first, blocks[b].size, rows.data());
     rg_check(rg_l0_block_bed(h, rows.data(), (int64_t)g.row_stride, blocks[b].size,
@@ -213,7 +318,7 @@ void run_step1(const Params& p_in, Log& log) {
     throw Fail(std::string(rg_last_error()));
   }
   log << " Level 0 done (" << (long)(now_ms() - t0) << "ms)\n";
-  if (p.lowmem && p.keep_l0) {
+  if ((p.lowmem && p.keep_l0) || p.run_l0_job) {
     // write_l0_file (src/Step1_Models.cpp:728-733): per phenotype, per block an N x R column-major f64 slab.
     // The reference deletes these after level 1 unless --keep-l0 (src/Data.cpp:1011,1108,1131-1137); here W
     // never leaves HBM for level 1, so the files are only materialised when they are kept.
@@ -228,6 +333,11 @@ void run_step1(const Params& p_in, Log& log) {
         f.write(reinterpret_cast<const char*>(slab.data()), (std::streamsize)(slab.size() * sizeof(double)));
       }
     }
+  }
+  if (p.run_l0_job) {
+    log << "\nDone writing level 0 predictions to file.\n";
+    rg_destroy(h);
+    return;
   }
   log << "\n Level 1 ridge...\n";
 
@@ -299,6 +409,11 @@ void run_step1(const Params& p_in, Log& log) {
     log << "  * making predictions...writing LOCO predictions...done\n\n";
   }
   plist.close();
+  if (p.run_l1 && !p.keep_l0)                        // rm_l0_files (src/Data.cpp:1131-1147)
+    for (const auto& mj : master.jobs) {
+      for (int ph_i = 0; ph_i < P; ++ph_i) remove((mj.prefix + "_l0_Y" + std::to_string(ph_i + 1)).c_str());
+      remove((mj.prefix + ".snplist").c_str());
+    }
   log << "List of blup files written to: [" << p.out << "_pred.list]\n";
   rg_destroy(h);
 }

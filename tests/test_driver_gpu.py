@@ -382,3 +382,25 @@ def test_bgen_zstd_and_uncompressed_payloads(tmp_path, golden_dir):
              "--pred", pred, "--out", out])
         outs.append(open(out + "_Y1.regenie").read())
     assert outs[0] == outs[1] == outs[2] and outs[0].count("\n") == 1001
+
+
+def test_split_l0_run_l0_run_l1_equals_single_run(tmp_path, golden_dir):
+    """The reference's multi-job protocol (test/test_bash.sh:127-137): --split-l0 into 3 jobs, --run-l0 per job
+    (one rgb200 process per job / GPU), --run-l1 -> .loco files byte-identical to the single run.  The job files have the
+    layout of write_l0_file, so the jobs could equally be reference CPU jobs."""
+    prefix = os.path.join(golden_dir, "example_3chr")
+    pheno, covar = golden_dir + "/phenotype.txt", golden_dir + "/covariates.txt"
+    base = ["--step", "1", "--bed", prefix, "--phenoFile", pheno, "--covarFile", covar, "--bsize", "100"]
+    run(base + ["--out", str(tmp_path / "single")])
+    mp = str(tmp_path / "par")
+    run(base + ["--split-l0", mp + ",3", "--out", str(tmp_path / "split")])
+    master = open(mp + ".master").read().split("\n")
+    assert master[0].split()[1] == "100" and len([l for l in master[1:] if l.strip()]) == 3
+    for j in (1, 2, 3):
+        log = run(base + ["--run-l0", mp + ".master,%d" % j, "--out", str(tmp_path / ("job%d" % j))])
+        assert "Done writing level 0 predictions to file." in log
+        assert os.path.exists(mp + "_job%d_l0_Y1" % j)
+    run(base + ["--run-l1", mp + ".master", "--out", str(tmp_path / "par_l1")])
+    for k in (1, 2):
+        assert open(str(tmp_path / ("single_%d.loco" % k))).read() == open(str(tmp_path / ("par_l1_%d.loco" % k))).read()
+    assert not os.path.exists(mp + "_job1_l0_Y1")            # removed after level 1 like the reference (no --keep-l0)
