@@ -9,12 +9,13 @@
 // cm + m*stride; rows nC .. nC+Ppad-1 hold the right-hand sides as extra rows, so the
 // factorisation sweep leaves  y^T = (L^-1 b)^T  there (fused forward substitution).
 //
-// Left-looking by 64-column panels, three launches per panel:
-//   chol_update : every row tile at/after the panel subtracts L[rows,0:k] L[k:k+64,0:k]^T
-//                 (FP64 GEMM, the n^3/3 flops)
-//   chol_diag   : one CTA per system factors the diagonal tile in registers and also produces
-//                 M = L_kk^-T (the same column sweep applied to I)
-//   chol_trsm   : row tiles below the panel:  L[rows, k:k+64] = P[rows, k:k+64] * M
+// 64-column panels, two launches per panel step:
+//   chol_diag        : one CTA per system factors the (already updated) diagonal tile in registers and also produces
+//                      M = L_kk^-T and M^T (the same column sweep applied to I)
+//   chol_update_trsm : every row tile below the panel does, on the FP64 tensor pipe (DMMA), the left-looking update
+//                      P = A[rows, k:k+64] - L[rows,0:k] L[k:k+64,0:k]^T  (the n^3/3 flops), the triangular solve as a
+//                      GEMM  L[rows, k:k+64] = P M,  and the rank-64 update of its OWN diagonal tile with the block it
+//                      just produced - so no serial "update the diagonal tile" launch precedes a factorisation.
 // No CTA ever reads a tile that another CTA of the same launch overwrites: kernels of several
 // "lanes" run concurrently, so launch-wide lockstep cannot be assumed.
 // The stored inverses M also turn the backward substitution's triangular solves into GEMVs.
@@ -28,66 +29,57 @@ namespace rg {
 
 constexpr int TB = 64;  // tile / panel width
 
-// acc[a][b] = sum_{p<k} A[r0 + ty*4+a][p] * A[rB + tx+16b][p]
-__device__ __forceinline__ void gemm_tile_nt(const double* __restrict__ A, int ld, int r0, int rB, int k,
-                                             double (&acc)[4][4], double (*As)[TB + 2], double (*Bs)[TB + 2]) {
-  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
-  const int lrow = threadIdx.x / 4, lp = (threadIdx.x % 4) * 4;   // loader mapping: 64 rows x 16 p
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-  if (k == 0) return;
-  const double* arow = A + (int64_t)(r0 + lrow) * ld + lp;
-  const double* brow = A + (int64_t)(rB + lrow) * ld + lp;
-  double2 a0 = *reinterpret_cast<const double2*>(arow), a1 = *reinterpret_cast<const double2*>(arow + 2);
-  double2 b0 = *reinterpret_cast<const double2*>(brow), b1 = *reinterpret_cast<const double2*>(brow + 2);
-  for (int p0 = 0; p0 < k; p0 += 16) {
-    __syncthreads();
-    As[lp + 0][lrow] = a0.x; As[lp + 1][lrow] = a0.y; As[lp + 2][lrow] = a1.x; As[lp + 3][lrow] = a1.y;
-    Bs[lp + 0][lrow] = b0.x; Bs[lp + 1][lrow] = b0.y; Bs[lp + 2][lrow] = b1.x; Bs[lp + 3][lrow] = b1.y;
-    __syncthreads();
-    if (p0 + 16 < k) {   // register prefetch of the next K-chunk
-      a0 = *reinterpret_cast<const double2*>(arow + p0 + 16);
-      a1 = *reinterpret_cast<const double2*>(arow + p0 + 18);
-      b0 = *reinterpret_cast<const double2*>(brow + p0 + 16);
-      b1 = *reinterpret_cast<const double2*>(brow + p0 + 18);
-    }
-#pragma unroll
-    for (int p = 0; p < 16; ++p) {
-      double av[4], bv[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) av[a] = As[p][ty * 4 + a];
-#pragma unroll
-      for (int b = 0; b < 4; ++b) bv[b] = Bs[p][tx + 16 * b];   // lane-consecutive columns: conflict-free
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
-    }
-  }
-}
-
-// P[r0:r0+64, k:k+64] -= L[r0:r0+64, 0:k] * L[k:k+64, 0:k]^T   (k > 0), FP64 tensor pipe (DMMA)
-// grid: (row tiles at/after the panel, 1, batch); 256 threads.
+// Row tiles strictly below the panel: update AND triangular solve in one pass,
+//   P = A[r0:r0+64, k:k+64] - L[r0:, 0:k] L[k:, 0:k]^T,   L[r0:, k:k+64] = P M,   M = L_kk^-T  (both products on the DMMA pipe).
+// The updated tile makes one trip through the CTA's own global tile (L1/L2 resident) instead of a separate kernel.
+// grid: (row tiles below the panel, 1, batch); 256 threads.
 __global__ void __launch_bounds__(256)
-chol_update_kernel(double* __restrict__ cm, int64_t stride, int ld, int k, int tile0) {
+chol_update_trsm_kernel(double* __restrict__ cm, int64_t stride, int ld, int k, int tile0,
+                        const double* __restrict__ inv_t, int64_t inv_stride) {
   __shared__ double As[TB * DM_LD];
   __shared__ double Bs[TB * DM_LD];
   double* A = cm + (int64_t)blockIdx.z * stride;
-  const int r0 = (tile0 + blockIdx.x) * TB;
+  const double* MT = inv_t + (int64_t)blockIdx.z * inv_stride + (int64_t)(k / TB) * TB * TB;
+  const int r0 = (tile0 + 1 + blockIdx.x) * TB;
   DmmaAcc acc;
-  gemm_tile_nt_dmma(A + (int64_t)r0 * ld, ld, true, A + (int64_t)k * ld, ld, true, k, acc, As, Bs);
+  if (k > 0) {
+    gemm_tile_nt_dmma(A + (int64_t)r0 * ld, ld, true, A + (int64_t)k * ld, ld, true, k, acc, As, Bs);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double2* o = reinterpret_cast<double2*>(A + (int64_t)(r0 + dm_row(i)) * ld + k + dm_col(j));
+        double2 v = *o;
+        v.x -= acc.c[i][j][0];
+        v.y -= acc.c[i][j][1];
+        *o = v;
+      }
+  }
+  __syncthreads();             // the updated tile is visible to every thread of this CTA
+  gemm_tile_nt_dmma(A + (int64_t)r0 * ld + k, ld, true, MT, TB, true, TB, acc, As, Bs);
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      double2* o = reinterpret_cast<double2*>(A + (int64_t)(r0 + dm_row(i)) * ld + k + dm_col(j));
-      double2 v = *o;
-      v.x -= acc.c[i][j][0];
-      v.y -= acc.c[i][j][1];
-      *o = v;
-    }
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<double2*>(A + (int64_t)(r0 + dm_row(i)) * ld + k + dm_col(j)) =
+          make_double2(acc.c[i][j][0], acc.c[i][j][1]);
+  // keep this row tile's own diagonal block up to date (right-looking for the diagonal blocks only):
+  //   A[r0:, r0:] -= L[r0:, k:k+64] L[r0:, k:k+64]^T
+  // so a panel step starts with the factorisation of an already updated diagonal tile - no serial update launch.
+  if (r0 < ld) {
+    __syncthreads();
+    gemm_tile_nt_dmma(A + (int64_t)r0 * ld + k, ld, true, A + (int64_t)r0 * ld + k, ld, true, TB, acc, As, Bs);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double2* o = reinterpret_cast<double2*>(A + (int64_t)(r0 + dm_row(i)) * ld + r0 + dm_col(j));
+        double2 v = *o;
+        v.x -= acc.c[i][j][0];
+        v.y -= acc.c[i][j][1];
+        *o = v;
+      }
+  }
 }
 
 // Diagonal tile: L_kk = chol(P_kk) and M = L_kk^-T, both in registers (thread (r, q) holds the
@@ -95,7 +87,7 @@ chol_update_kernel(double* __restrict__ cm, int64_t stride, int ld, int k, int t
 // grid: (batch); 256 threads.
 __global__ void __launch_bounds__(256)
 chol_diag_kernel(double* __restrict__ cm, int64_t stride, int ld, int k,
-                 double* __restrict__ inv, int64_t inv_stride,
+                 double* __restrict__ inv, double* __restrict__ inv_t, int64_t inv_stride,
                  unsigned long long* __restrict__ err_slot, long long err_base) {
   __shared__ double cb[2][TB], xb[2][TB];
   double* A = cm + (int64_t)blockIdx.x * stride;
@@ -135,54 +127,13 @@ chol_diag_kernel(double* __restrict__ cm, int64_t stride, int ld, int k,
   }
   if (bad && threadIdx.x == 0) atomicMin(err_slot, (unsigned long long)(err_base + blockIdx.x + 1));
   double* Mo = inv + (int64_t)blockIdx.x * inv_stride + (int64_t)(k / TB) * TB * TB;
+  double* MTo = inv_t + (int64_t)blockIdx.x * inv_stride + (int64_t)(k / TB) * TB * TB;
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const int cc = q + 4 * j;
     if (cc <= r) A[(int64_t)(k + r) * ld + k + cc] = D[j];
     Mo[r * TB + cc] = (cc >= r) ? T[j] : 0.0;
-  }
-}
-
-// L[rows, k:k+64] = P[rows, k:k+64] * M,  M = L_kk^-T (upper triangular).
-// grid: (row tiles strictly below the panel, 1, batch); 256 threads, 4x4 outputs each.
-__global__ void __launch_bounds__(256)
-chol_trsm_kernel(double* __restrict__ cm, int64_t stride, int ld, int k, int tile0,
-                 const double* __restrict__ inv, int64_t inv_stride) {
-  extern __shared__ double trsm_sm[];
-  double (*Ts)[TB + 1] = reinterpret_cast<double (*)[TB + 1]>(trsm_sm);
-  double (*Ms)[TB + 2] = reinterpret_cast<double (*)[TB + 2]>(trsm_sm + TB * (TB + 1));
-  double* A = cm + (int64_t)blockIdx.z * stride;
-  const double* M = inv + (int64_t)blockIdx.z * inv_stride + (int64_t)(k / TB) * TB * TB;
-  const int r0 = (tile0 + 1 + blockIdx.x) * TB;
-  for (int e = threadIdx.x; e < TB * TB; e += 256) {
-    const int rr = e / TB, cc = e % TB;
-    Ts[rr][cc] = A[(int64_t)(r0 + rr) * ld + k + cc];
-    Ms[rr][cc] = M[e];
-  }
-  __syncthreads();
-  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
-  double acc[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-#pragma unroll 8
-  for (int p = 0; p < TB; ++p) {
-    double av[4], bv[4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a) av[a] = Ts[ty * 4 + a][p];
-#pragma unroll
-    for (int b = 0; b < 4; ++b) bv[b] = Ms[p][tx + 16 * b];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
-  }
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    double* o = A + (int64_t)(r0 + ty * 4 + a) * ld + k + tx;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) o[16 * b] = acc[a][b];
+    MTo[cc * TB + r] = (cc >= r) ? T[j] : 0.0;        // M^T, the "NT" operand of the fused update + solve
   }
 }
 
@@ -268,12 +219,7 @@ void launch_chol_factor(double* cm, int64_t stride, int nC, int n_aug, int batch
                         unsigned long long* err_slot, long long err_base, cudaStream_t s) {
   const int ntiles = n_aug / TB;
   const int64_t inv_stride = (int64_t)(nC / TB) * TB * TB;
-  const size_t trsm_smem = ((size_t)TB * (TB + 1) + (size_t)TB * (TB + 2)) * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    RG_CUDA(cudaFuncSetAttribute(chol_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem));
-    attr_set = true;
-  }
+  double* inv_t = inv + (int64_t)batch * inv_stride;      // M^T blocks live behind the M blocks (chol_inv_elems)
   // profiling aid (RG_B200_CHOL_TIMING=1): CUDA-event time of the three kernels of every panel step
   static const bool timing = getenv("RG_B200_CHOL_TIMING") != nullptr;
   static double t_acc[3] = {0, 0, 0};
@@ -288,21 +234,19 @@ void launch_chol_factor(double* cm, int64_t stride, int nC, int n_aug, int batch
   };
   for (int kb = 0; kb < nC / TB; ++kb) {
     const int k = kb * TB;
-    dim3 g1(ntiles - kb, 1, batch);
     tick(0);
-    if (k > 0) chol_update_kernel<<<g1, 256, 0, s>>>(cm, stride, nC, k, kb);
     tick(1);
-    chol_diag_kernel<<<batch, 256, 0, s>>>(cm, stride, nC, k, inv, inv_stride, err_slot, err_base);
+    chol_diag_kernel<<<batch, 256, 0, s>>>(cm, stride, nC, k, inv, inv_t, inv_stride, err_slot, err_base);
     tick(2);
     dim3 g2(ntiles - kb - 1, 1, batch);
-    if (ntiles - kb - 1 > 0) chol_trsm_kernel<<<g2, 256, trsm_smem, s>>>(cm, stride, nC, k, kb, inv, inv_stride);
+    if (ntiles - kb - 1 > 0) chol_update_trsm_kernel<<<g2, 256, 0, s>>>(cm, stride, nC, k, kb, inv_t, inv_stride);
     tick(3);
     tock();
   }
   if (timing) {
     for (auto& e : ev) cudaEventDestroy(e);
     if (++t_calls % 50 == 0)
-      fprintf(stderr, "[chol timing] per factorisation (ms): update %.3f diag %.3f trsm %.3f\n", t_acc[0] / t_calls,
+      fprintf(stderr, "[chol timing] per factorisation (ms): (unused) %.3f diag %.3f update+solve %.3f\n", t_acc[0] / t_calls,
               t_acc[1] / t_calls, t_acc[2] / t_calls);
   }
 }
@@ -319,8 +263,8 @@ void launch_chol_backsolve(double* cm, int64_t stride, int nC, int P, int batch,
   chol_backsolve_kernel<<<batch, BS_THREADS, smem, s>>>(cm, stride, nC, nC, P, inv, inv_stride);
 }
 
-int chol_num_launches(int nC) { return 3 * (nC / TB) - 1; }
-size_t chol_inv_elems(int nC, int batch) { return (size_t)batch * (nC / TB) * TB * TB; }
+int chol_num_launches(int nC) { return 2 * (nC / TB); }
+size_t chol_inv_elems(int nC, int batch) { return (size_t)2 * batch * (nC / TB) * TB * TB; }   // M and M^T
 
 }  // namespace rg
 
