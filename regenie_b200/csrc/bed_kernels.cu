@@ -16,15 +16,31 @@ __device__ __forceinline__ uint32_t plink_to_code(uint32_t v, int ref_first) {
   return (lut >> (2 * v)) & 3u;
 }
 
-// One thread per output 32-bit word (16 samples) of one row.
+// One thread per output 32-bit word (16 samples) of one row.  Almost every word maps to 16 CONSECUTIVE samples of the
+// file row (folds only shift whole ranges; --remove breaks a word here and there): those take the fast path - five
+// source bytes, one funnel shift, the code translation as bit logic on all 16 lanes, a keep mask for samples outside
+// the analysis.  word_base[w] = file index of the word's first sample, -1 = nothing to read, -2 = not contiguous.
 __global__ void bed_relayout_kernel(const uint8_t* __restrict__ packed, int64_t row_stride, int bs,
-                                    const int32_t* __restrict__ file_idx_pad, int ref_first,
+                                    const int32_t* __restrict__ file_idx_pad, const int32_t* __restrict__ word_base,
+                                    const uint32_t* __restrict__ word_keep, int ref_first,
                                     uint32_t* __restrict__ gp, int64_t words_per_row) {
   const int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int row = blockIdx.y;
   if (w >= words_per_row) return;
   uint32_t out = 0;
-  if (row < bs) {
+  const int base = (row < bs) ? __ldg(word_base + w) : -1;
+  if (base >= 0) {
+    const uint8_t* p = packed + (int64_t)row * row_stride + (base >> 2);
+    const int64_t left = row_stride - (base >> 2);            // bytes available in this row
+    uint64_t x = 0;
+#pragma unroll
+    for (int b = 0; b < 5; ++b)
+      if (b < left) x |= (uint64_t)__ldg(p + b) << (8 * b);
+    const uint32_t v = (uint32_t)(x >> (2 * (base & 3)));
+    const uint32_t H = (v >> 1) & 0x55555555u, Lo = v & 0x55555555u;
+    const uint32_t oh = ref_first ? Lo : (~H & 0x55555555u);  // see plink_to_code
+    out = ((oh << 1) | (H ^ Lo)) & __ldg(word_keep + w);
+  } else if (base == -2) {
     const uint8_t* prow = packed + (int64_t)row * row_stride;
     const int4* fi4 = reinterpret_cast<const int4*>(file_idx_pad + w * 16);
 #pragma unroll
@@ -78,11 +94,12 @@ __global__ void debug_sleep_kernel(unsigned ns) {
 void launch_debug_sleep(unsigned ns, cudaStream_t s) { debug_sleep_kernel<<<1, 1, 0, s>>>(ns); }
 
 void launch_bed_relayout(const uint8_t* packed, int64_t row_stride, int bs, int rows_p,
-                         const int32_t* file_idx_pad, int ref_first, uint32_t* gp, int64_t npad,
+                         const int32_t* file_idx_pad, const int32_t* word_base, const uint32_t* word_keep, int ref_first,
+                         uint32_t* gp, int64_t npad,
                          cudaStream_t s) {
   const int64_t wpr = npad / 16;
   dim3 grid((unsigned)ceil_div(wpr, 256), rows_p);
-  bed_relayout_kernel<<<grid, 256, 0, s>>>(packed, row_stride, bs, file_idx_pad, ref_first, gp, wpr);
+  bed_relayout_kernel<<<grid, 256, 0, s>>>(packed, row_stride, bs, file_idx_pad, word_base, word_keep, ref_first, gp, wpr);
 }
 
 void launch_bed_expand_fp8(const uint32_t* gp, int rows_p, uint8_t* z, int64_t npad, cudaStream_t s) {

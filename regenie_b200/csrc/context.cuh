@@ -37,6 +37,8 @@ struct rg_ctx {
   rg::DevBuf<int2> fold_k;          // [K] (first 128-sample K block, #blocks)
   rg::DevBuf<double> XtX_f, XtY_f, lambda, neff;
   rg::DevBuf<int32_t> file_idx_pad; // [Npad]
+  rg::DevBuf<int32_t> word_base;    // [Npad/16] first file index of a 16-sample word (-1 empty, -2 not contiguous)
+  rg::DevBuf<uint32_t> word_keep;   // [Npad/16] 2-bit lane mask of the samples that are read
   rg::DevBuf<unsigned long long> err_slot;
   rg::DevBuf<unsigned long long> dbg_counter;
   rg::DevBuf<long long> dbg_clk;

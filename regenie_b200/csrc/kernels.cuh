@@ -13,7 +13,8 @@ constexpr int kLimbQ = 56;         // outputs per tensor-core prediction pass (9
 
 // ---- bed_kernels.cu
 void launch_bed_relayout(const uint8_t* packed, int64_t row_stride, int bs, int rows_p,
-                         const int32_t* file_idx_pad, int ref_first, uint32_t* gp, int64_t npad,
+                         const int32_t* file_idx_pad, const int32_t* word_base, const uint32_t* word_keep, int ref_first,
+                         uint32_t* gp, int64_t npad,
                          cudaStream_t s);
 void launch_debug_sleep(unsigned ns, cudaStream_t s);
 void launch_bed_expand_fp8(const uint32_t* gp, int rows_p, uint8_t* z, int64_t npad, cudaStream_t s);

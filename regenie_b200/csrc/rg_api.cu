@@ -204,7 +204,26 @@ static void build_file_idx(rg_ctx* h, const int32_t* sample_idx_host) {
     if (s < 0 || !h->in_analysis[s]) continue;
     fi[t] = sample_idx_host ? sample_idx_host[s] : s;
   }
+  const int64_t nw = h->Npad / 16;
+  std::vector<int32_t> wb(nw, -1);
+  std::vector<uint32_t> wk(nw, 0);
+  for (int64_t w = 0; w < nw; ++w) {
+    int32_t base = -1;
+    bool contiguous = true;
+    for (int j = 0; j < 16; ++j) {
+      const int32_t f = fi[w * 16 + j];
+      if (f < 0) continue;
+      wk[w] |= 3u << (2 * j);
+      if (base == -1) base = f - j;
+      else if (f - j != base) contiguous = false;
+    }
+    wb[w] = (wk[w] == 0) ? -1 : ((contiguous && base >= 0) ? base : -2);
+  }
   h->file_idx_pad.alloc(h->Npad);
+  h->word_base.alloc(nw);
+  h->word_keep.alloc(nw);
+  RG_CUDA(cudaMemcpyAsync(h->word_base.p, wb.data(), nw * 4, cudaMemcpyHostToDevice, h->stream));
+  RG_CUDA(cudaMemcpyAsync(h->word_keep.p, wk.data(), nw * 4, cudaMemcpyHostToDevice, h->stream));
   RG_CUDA(cudaMemcpyAsync(h->file_idx_pad.p, fi.data(), fi.size() * 4, cudaMemcpyHostToDevice, h->stream));
   RG_CUDA(cudaStreamSynchronize(h->stream));
   h->file_idx_valid = true;
@@ -298,7 +317,7 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
   // --- 1. decode: PLINK rows -> padded 2-bit rows -> e4m3 planes
   {
     ScopedTimer t(h, "bed_relayout", s);
-    launch_bed_relayout(packed_d, row_stride, bs, rows_p, h->file_idx_pad.p, ref_first, L.gp.p, Npad, s);
+    launch_bed_relayout(packed_d, row_stride, bs, rows_p, h->file_idx_pad.p, h->word_base.p, h->word_keep.p, ref_first, L.gp.p, Npad, s);
   }
   {
     ScopedTimer t(h, "bed_expand", s);

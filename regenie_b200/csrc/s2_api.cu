@@ -156,7 +156,7 @@ static void s2_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
   const size_t nd = (size_t)h->bs_max * (7 * (size_t)P + 3), ni = (size_t)h->bs_max * ((size_t)P + 2);
   h->s2_out_d.alloc(nd);
   h->s2_out_i.alloc(ni);
-  launch_bed_relayout(packed_d, row_stride, bs, rows_p, h->file_idx_pad.p, ref_first, h->gp.p, Npad, s);
+  launch_bed_relayout(packed_d, row_stride, bs, rows_p, h->file_idx_pad.p, h->word_base.p, h->word_keep.p, ref_first, h->gp.p, Npad, s);
   launch_s2_stats(h->gp.p, Npad, h->F.p, h->dp, h->chunks.p, h->nchunks, rows_p, h->s2_part.p, h->s2_sums.p, s);
   S2FinalizeArgs a;
   a.bs = bs; a.C = C; a.P = P; a.dp = h->dp; a.strict = h->strict;

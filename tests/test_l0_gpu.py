@@ -26,9 +26,13 @@ def run_blocks(pb):
     return st, out
 
 
-@pytest.mark.parametrize("N,M,bs,miss", [(1000, 300, 128, 0.02), (777, 150, 100, 0.0), (2051, 130, 130, 0.05)])
-def test_l0_kfold_matches_oracle(tmp_path, N, M, bs, miss):
-    pb = helpers.synthetic_problem(tmp_path, N=N, M=M, bsize=bs, miss=miss)
+@pytest.mark.parametrize("N,M,bs,miss,P,K", [(1000, 300, 128, 0.02, 3, 5), (777, 150, 100, 0.0, 3, 5), (2051, 130, 130, 0.05, 3, 5),
+                                            # ragged edges: N not a multiple of 4, one phenotype (strict mode), 3 uneven folds,
+                                            # chromosomes whose last block holds a single SNP (M = 3 * 43, bsize 42)
+                                            (203, 129, 42, 0.03, 1, 3)])
+def test_l0_kfold_matches_oracle(tmp_path, N, M, bs, miss, P, K):
+    pb = helpers.synthetic_problem(tmp_path, N=N, M=M, bsize=bs, miss=miss, P=P, K=K)
+    assert N != 203 or min(b[2] for b in pb.blocks) == 1
     st, out = run_blocks(pb)
     for b in range(len(pb.blocks)):
         W_o, mu_o, sd_o, _ = pb.oracle_l0(b)
