@@ -255,13 +255,16 @@ int rg_s2_firth(rg_handle h, int32_t n_sel, const int32_t* variant_idx, const in
  * One process per GPU.  Level-0 blocks are sharded across ranks (the reference's --split-l0 partition,
  * src/Data.cpp:268-301); level 1 is sharded by phenotype.  Instead of a separate exchange step, every rank
  * maps the predictor matrix W of the phenotype owners into its address space (CUDA IPC over NVLink/NVSwitch):
+ *   all:    rg_W_set_owned(h, owned)           -> local W storage only for the phenotypes this rank fits (N x B x P/nranks)
  *   owner:  rg_W_export(h, handle)             -> 64-byte cudaIpcMemHandle_t of its W allocation
  *   peers:  rg_W_attach_peer(h, handle, owned) -> level-0 kernels of this rank store the W tiles of every
- *                                                 phenotype with owned[p] != 0 directly into the owner's HBM
+ *                                                 phenotype with owned[p] != 0 (the mask the peer passed to
+ *                                                 rg_W_set_owned) directly into the owner's HBM
  * After all ranks have finished level 0 (rg_sync + a barrier in the caller), each owner holds the complete
  * N x B matrix of its phenotypes and runs rg_l1_fit / rg_l1_fit_bt / rg_loco, which skip phenotypes that
  * were handed to a peer (rg_l1_select overrides the selection).  No collective is on the data path.
  */
+int rg_W_set_owned(rg_handle h, const uint8_t* owned);
 int rg_W_export(rg_handle h, void* ipc_handle_64);
 int rg_W_attach_peer(rg_handle h, const void* ipc_handle_64, const uint8_t* owned_by_peer);
 int rg_l1_select(rg_handle h, const uint8_t* selected);

@@ -46,7 +46,7 @@ EXPORTS = [
     "rg_last_error", "rg_version", "rg_device_count", "rg_step1_create", "rg_destroy", "rg_sync",
     "rg_l0_block_bed", "rg_l0_status", "rg_l0_fetch_W", "rg_l1_fit", "rg_loco", "rg_step2_create",
     "rg_s2_set_chr", "rg_s2_block_bed", "rg_W_info", "rg_debug_fetch", "rg_launch_count", "rg_stream",
-    "rg_set_timing", "rg_get_timing", "rg_fence", "rg_s2_set_chr_bt", "rg_s2_block_bgen8_bt", "rg_s2_block_bgen8", "rg_s2_firth", "rg_l1_fit_bt", "rg_W_export", "rg_W_attach_peer", "rg_l1_select", "rg_s2_set_sex", "rg_s2_set_non_par", "rg_l0_load_W",
+    "rg_set_timing", "rg_get_timing", "rg_fence", "rg_s2_set_chr_bt", "rg_s2_block_bgen8_bt", "rg_s2_block_bgen8", "rg_s2_firth", "rg_l1_fit_bt", "rg_W_set_owned", "rg_W_export", "rg_W_attach_peer", "rg_l1_select", "rg_s2_set_sex", "rg_s2_set_non_par", "rg_l0_load_W",
 ]
 
 _lib = None
@@ -165,6 +165,11 @@ class Step1:
         best = np.zeros(self.P, dtype=np.int32)
         check(lib().rg_l1_fit(self.h, _ptr(tau), _ptr(cs), _ptr(best)))
         return cs, best
+
+    def W_set_owned(self, owned):
+        L = lib(); L.rg_W_set_owned.argtypes = [C.c_void_p, C.c_void_p]
+        ob = np.ascontiguousarray(owned, dtype=np.uint8)
+        check(L.rg_W_set_owned(self.h, _ptr(ob)))
 
     def W_export(self):
         """64-byte CUDA IPC handle of this rank's W allocation."""

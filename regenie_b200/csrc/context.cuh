@@ -6,6 +6,9 @@
 #include "../../include/rg_b200.h"
 #include "kernels.cuh"
 
+struct rg_ctx;
+namespace rg { void ensure_W(::rg_ctx* h); }
+
 struct rg_ctx {
   int kind = 0;  // 1 = step 1, 2 = step 2
   int device = 0;
@@ -95,6 +98,7 @@ struct rg_ctx {
   bool l1_done = false;
   rg::DevBuf<double*> W_tab;                         // [P] where each phenotype's W lives (local or peer HBM)
   std::vector<double*> W_host_tab;
+  std::vector<uint8_t> W_owned;                      // phenotypes with local storage (rg_W_set_owned)
   std::vector<void*> W_peer_mapped;                  // cudaIpcOpenMemHandle results to close
   std::vector<uint8_t> l1_select;                    // phenotypes this handle fits at level 1
   bool l1_bt = false;                                // logistic level 1: l1_hvec holds f_i = (y - p) / (1 - q w)

@@ -57,6 +57,7 @@ static void l1_fit(rg_ctx* h, const double* tau_host, double* cumsum, int32_t* b
   RG_CUDA(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
   for (auto& l : h->lanes) RG_CUDA(cudaStreamSynchronize(l->stream));   // all level-0 blocks are in W
+  ensure_W(h);
   const int K = h->K, R1 = h->R1, P = h->P;
   const int B = (int)h->B;
   const int loocv = h->loocv;
@@ -89,7 +90,7 @@ static void l1_fit(rg_ctx* h, const double* tau_host, double* cumsum, int32_t* b
   }
   for (int p = 0; p < P; ++p) {
     if (!h->l1_select[p]) continue;                       // fitted by the rank that owns this phenotype
-    const double* Wp = h->W.p + (size_t)p * Npad * h->B;
+    const double* Wp = h->W_host_tab[p];
     const int ycol = h->C + p;
     launch_l1_gram(Wp, Npad, B, h->l1_chunks.p, nch, h->l1_part.p, part_stride, ldp, s);
     launch_l1_xty(Wp, Npad, h->xy.p, h->cpp, ycol, h->l1_chunks.p, nch, h->l1_part_y.p, B, s);
@@ -402,7 +403,7 @@ static void l1_fit_bt(rg_ctx* h, const double* y_raw, const double* offset, cons
     RG_CUDA(cudaMemcpyAsync(h->lg_off.p, off.data(), Npad * 8, cudaMemcpyHostToDevice, s));
     RG_CUDA(cudaMemcpyAsync(h->lg_ym.p, ym.data(), Npad, cudaMemcpyHostToDevice, s));
     RG_CUDA(cudaStreamSynchronize(s));
-    LgState st{h, h->W.p + (size_t)p * Npad * h->B, B, nC, nch, Npad, cm_stride, (int64_t)nC * nC, h->lg_off.p, h->lg_ym.p,
+    LgState st{h, h->W_host_tab[p], B, nC, nch, Npad, cm_stride, (int64_t)nC * nC, h->lg_off.p, h->lg_ym.p,
                std::vector<double>(B, 0.0)};
     double best = 1e10;
     double ne = 0.0;
@@ -482,15 +483,15 @@ static void loco(rg_ctx* h, const int32_t* chr_of_block, double* pred_out) {
   for (int p = 0; p < P; ++p) {
     if (!h->l1_select[p]) continue;
     if (h->l1_bt && h->loocv)
-      launch_l1_bt_chr_pred(h->W.p + (size_t)p * Npad * h->B, Npad, nC, h->l1_zrows.p + (size_t)p * Npad * nC,
+      launch_l1_bt_chr_pred(h->W_host_tab[p], Npad, nC, h->l1_zrows.p + (size_t)p * Npad * nC,
                             h->l1_hvec.p + (size_t)p * Npad, h->l1_bvec.p + (size_t)p * nC, nchr, h->l1_chr_cols.p,
                             h->l1_pred.p, Npad, s);
     else if (h->loocv)
-      launch_l1_loocv_chr_pred(h->W.p + (size_t)p * Npad * h->B, Npad, (int)h->B, nC, h->l1_zrows.p + (size_t)p * Npad * nC,
+      launch_l1_loocv_chr_pred(h->W_host_tab[p], Npad, (int)h->B, nC, h->l1_zrows.p + (size_t)p * Npad * nC,
                                h->l1_hvec.p + (size_t)p * Npad, h->l1_bvec.p + (size_t)p * nC, h->xy.p, h->cpp,
                                h->C + p, nchr, h->l1_chr_cols.p, h->l1_pred.p, Npad, s);
     else
-      launch_l1_chr_pred(h->W.p + (size_t)p * Npad * h->B, Npad, nchr, h->l1_chr_cols.p,
+      launch_l1_chr_pred(h->W_host_tab[p], Npad, nchr, h->l1_chr_cols.p,
                          h->l1_beta.p + (size_t)p * nmat * nC, nC, R1, h->best_idx[p], h->tile_fold.p, h->l1_pred.p, Npad, s);
     h->launches += 1;
     RG_CUDA(cudaMemcpyAsync(pred.data(), h->l1_pred.p, pred.size() * 8, cudaMemcpyDeviceToHost, s));
@@ -537,7 +538,7 @@ int rg_loco(rg_handle h, const int32_t* chr_of_block, double* pred_out) {
 int rg_W_info(rg_handle h, int32_t ph, void** dev_ptr, int64_t* ld, int64_t* ncols) {
   RG_API_BEGIN
   RG_CHECK(h && h->kind == 1 && ph >= 0 && ph < h->P, "bad argument");
-  if (dev_ptr) *dev_ptr = h->W.p + (size_t)ph * h->Npad * h->B;
+  if (dev_ptr) *dev_ptr = h->W_host_tab[ph];
   if (ld) *ld = h->Npad;
   if (ncols) *ncols = h->B;
   RG_API_END

@@ -229,8 +229,27 @@ static void build_file_idx(rg_ctx* h, const int32_t* sample_idx_host) {
   h->file_idx_valid = true;
 }
 
+// Storage of the level-0 predictors, allocated on first use: one compact slab per phenotype this rank owns
+// (all of them unless rg_W_set_owned said otherwise); entries of phenotypes owned elsewhere stay null until
+// rg_W_attach_peer maps the owner's memory.
+void ensure_W(::rg_ctx* h) {
+  if (h->W.p) return;
+  size_t n_owned = 0;
+  for (int p = 0; p < h->P; ++p) n_owned += h->W_owned[p] ? 1 : 0;
+  const size_t per = (size_t)h->Npad * h->B;
+  h->W.alloc(std::max<size_t>(1, n_owned) * per);
+  RG_CUDA(cudaMemset(h->W.p, 0, std::max<size_t>(1, n_owned) * per * 8));
+  size_t slot = 0;
+  for (int p = 0; p < h->P; ++p)
+    if (h->W_owned[p]) h->W_host_tab[p] = h->W.p + (slot++) * per;
+  RG_CUDA(cudaMemcpy(h->W_tab.p, h->W_host_tab.data(), h->P * sizeof(double*), cudaMemcpyHostToDevice));
+}
+
 static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, int bs,
                          const int32_t* sample_idx, int ref_first, int block_id) {
+  ensure_W(h);
+  for (int p = 0; p < h->P; ++p)
+    RG_CHECK(h->W_host_tab[p] != nullptr, "a phenotype has neither local storage nor an attached owner (rg_W_set_owned / rg_W_attach_peer)");
   RG_CHECK(h->kind == 1, "handle is not a Step-1 handle");
   RG_CHECK(bs > 0 && bs <= h->bs_max, "block size out of range");
   RG_CHECK(block_id >= 0 && block_id < h->total_blocks, "block_id out of range");
@@ -559,14 +578,12 @@ int rg_step1_create(const rg_step1_config* cfg, const double* X, const double* Y
   RG_CUDA(cudaMemcpy(h->neff.p, neff, h->P * 8, cudaMemcpyHostToDevice));
   h->err_slot.alloc(1);
   RG_CUDA(cudaMemset(h->err_slot.p, 0xFF, 8));
-  h->W.alloc((size_t)h->P * h->Npad * h->B);
-  RG_CUDA(cudaMemset(h->W.p, 0, (size_t)h->P * h->Npad * h->B * 8));
+  h->W_owned.assign(h->P, 1);                 // storage itself is allocated on first use (rg::ensure_W)
   // every level-0 kernel addresses W through this table; rg_W_attach_peer redirects a phenotype to the HBM of
   // the GPU that owns its level-1 fit (stores travel over NVLink as the tiles are produced)
   h->W_host_tab.resize(h->P);
-  for (int p = 0; p < h->P; ++p) h->W_host_tab[p] = h->W.p + (size_t)p * h->Npad * h->B;
+  h->W_host_tab.assign(h->P, nullptr);
   h->W_tab.alloc(h->P);
-  RG_CUDA(cudaMemcpy(h->W_tab.p, h->W_host_tab.data(), h->P * sizeof(double*), cudaMemcpyHostToDevice));
   h->l1_select.assign(h->P, 1);
   *out = h.release();
   RG_API_END
@@ -589,9 +606,22 @@ int rg_W_export(rg_handle h, void* ipc_handle_64) {
   RG_CHECK(h && h->kind == 1 && ipc_handle_64, "bad argument");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
   RG_CUDA(cudaSetDevice(h->device));
+  ensure_W(h);
   cudaIpcMemHandle_t mh;
   RG_CUDA(cudaIpcGetMemHandle(&mh, h->W.p));
   memcpy(ipc_handle_64, &mh, 64);
+  RG_API_END
+}
+
+int rg_W_set_owned(rg_handle h, const uint8_t* owned) {
+  RG_API_BEGIN
+  RG_CHECK(h && h->kind == 1 && owned, "bad argument");
+  RG_CUDA(cudaSetDevice(h->device));
+  for (auto& l : h->lanes) RG_CUDA(cudaStreamSynchronize(l->stream));
+  RG_CHECK(!h->W.p, "rg_W_set_owned must be called before the first block / export");
+  h->W_owned.assign(owned, owned + h->P);
+  for (int p = 0; p < h->P; ++p) h->l1_select[p] = owned[p] ? 1 : 0;
+  ensure_W(h);
   RG_API_END
 }
 
@@ -600,14 +630,17 @@ int rg_W_attach_peer(rg_handle h, const void* ipc_handle_64, const uint8_t* owne
   RG_CHECK(h && h->kind == 1 && ipc_handle_64 && owned_by_peer, "bad argument");
   RG_CUDA(cudaSetDevice(h->device));
   for (auto& l : h->lanes) RG_CUDA(cudaStreamSynchronize(l->stream));
+  ensure_W(h);
   cudaIpcMemHandle_t mh;
   memcpy(&mh, ipc_handle_64, 64);
   void* base = nullptr;
   RG_CUDA(cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess));
   h->W_peer_mapped.push_back(base);
+  // the peer's allocation is compact over ITS owned phenotypes (rg_W_set_owned with the same mask on that rank)
+  size_t slot = 0;
   for (int p = 0; p < h->P; ++p)
     if (owned_by_peer[p]) {
-      h->W_host_tab[p] = static_cast<double*>(base) + (size_t)p * h->Npad * h->B;
+      h->W_host_tab[p] = static_cast<double*>(base) + (slot++) * (size_t)h->Npad * h->B;
       h->l1_select[p] = 0;
     }
   RG_CUDA(cudaMemcpy(h->W_tab.p, h->W_host_tab.data(), h->P * sizeof(double*), cudaMemcpyHostToDevice));
@@ -659,6 +692,8 @@ int rg_l0_load_W(rg_handle h, int32_t block_id, int32_t ph, const double* in) {
   std::vector<double> tmp((size_t)h->Npad * h->R, 0.0);
   for (int r = 0; r < h->R; ++r)
     for (int64_t s = 0; s < h->N; ++s) tmp[(size_t)r * h->Npad + h->pad_of[s]] = in[(size_t)r * h->N + s];
+  ensure_W(h);
+  RG_CHECK(h->W_host_tab[ph] != nullptr, "this rank holds no storage for that phenotype (rg_W_set_owned)");
   double* dst = h->W_host_tab[ph] + (size_t)block_id * h->R * h->Npad;
   RG_CUDA(cudaMemcpyAsync(dst, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice, h->stream));
   RG_CUDA(cudaStreamSynchronize(h->stream));
@@ -692,6 +727,8 @@ int rg_l0_fetch_W(rg_handle h, int32_t block_id, int32_t ph, double* out) {
   RG_CUDA(cudaSetDevice(h->device));
   for (auto& l : h->lanes) RG_CUDA(cudaStreamSynchronize(l->stream));
   std::vector<double> tmp((size_t)h->Npad * h->R);
+  ensure_W(h);
+  RG_CHECK(h->W_host_tab[ph] != nullptr, "this rank holds no storage for that phenotype (rg_W_set_owned)");
   const double* src = h->W_host_tab[ph] + (size_t)block_id * h->R * h->Npad;   // local or peer-mapped
   RG_CUDA(cudaMemcpyAsync(tmp.data(), src, tmp.size() * 8, cudaMemcpyDeviceToHost, h->stream));
   RG_CUDA(cudaStreamSynchronize(h->stream));

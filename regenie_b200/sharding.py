@@ -87,6 +87,7 @@ def step1_distributed(st, n_blocks, feed_block, tau, chr_of_block, device, bt=No
     """
     rank, world = dist.get_rank(), dist.get_world_size()
     owner = phenotype_owner(st.P, world)
+    st.W_set_owned([1 if owner[p] == rank else 0 for p in range(st.P)])      # N x B x P/world of HBM per rank
     handles = [None] * world
     dist.all_gather_object(handles, st.W_export())
     for r in range(world):

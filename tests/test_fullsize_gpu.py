@@ -77,3 +77,30 @@ def test_step2_counts_bit_exact_at_full_size(panel):
         assert np.array_equal(o["ns"][:, p], ns)
         assert np.array_equal(o["af"][:, p], tot / (2.0 * ns))                           # bit for bit
     assert np.array_equal(o["ns_all"], obs.sum(axis=1))
+
+
+def test_level0_block_at_n_500k():
+    """BASELINE configs[2] sample count (N = 500 000, bsize = 1000, 10 traits): one block, same size-independent
+    identities - standardisation sums, finite values, bit-identical columns when the block is replayed on another lane."""
+    from regenie_b200 import capi
+    n = 500_000
+    rng = np.random.default_rng(123)
+    maf = rng.uniform(0.01, 0.5, size=BS)
+    g = rng.binomial(2, maf[:, None], size=(BS, n)).astype(np.uint8)
+    g[rng.random(size=g.shape) < 0.01] = 3
+    Y = rng.standard_normal((n, P))
+    cov = rng.standard_normal((n, C - 1))
+    X, Yr, mask, in_an, neff = hostprep.prepare_qt(Y, cov, None)
+    h0 = hostprep.ridge_grid(5)
+    st = capi.Step1(X, Yr, mask, in_an, hostprep.fold_sizes(n, K), 500_000 * (1 - h0) / h0, neff, n, BS, 2)
+    packed = synth.pack_bed(g)
+    st.l0_block_bed(packed, BS, 0)
+    st.l0_block_bed(packed, BS, 1)
+    assert st.status() == 0
+    for p in (0, P - 1):
+        w = st.fetch_W(0, p)
+        assert np.isfinite(w).all()
+        np.testing.assert_allclose(w.sum(axis=0), 0.0, atol=1e-5)
+        np.testing.assert_allclose((w * w).sum(axis=0), neff[p] - 1.0, rtol=1e-10)
+        assert np.array_equal(w, st.fetch_W(1, p))
+    st.close()
