@@ -206,6 +206,9 @@ def run_gpu(args):
     N, M, bs, P, C, K, R = c["N"], c["M"], c["bsize"], c["P"], c["C"], c["K"], c["R"]
     if args.small:
         N, M = 20_000, 4_000
+    if args.n_samples:                      # exploration only (e.g. the N = 500k shape of configs[2] on a slice of blocks)
+        N = args.n_samples
+        M = (args.blocks or 20) * bs
     blocks = blocks_of(M, bs)
     if args.blocks:
         blocks = blocks[: args.blocks]
@@ -368,7 +371,7 @@ def run_gpu(args):
         "metric": "step1_level0_snps_per_sec", "value": value, "unit": "SNPs/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "e4m3 Gram (exact) + f64",
-        "data": "synthetic", "config": workload_config() if not args.small else {"workload": "SMALL smoke config", "n_samples": N, "n_snps": M},
+        "data": "synthetic", "config": workload_config() if not (args.small or args.n_samples) else {"workload": "NOT the benchmark configuration (smoke / exploration run)", "n_samples": N, "n_snps": M},
         "clocks": clk,
         "e2e": {"value": e2e_val, "unit": "SNPs/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(M) * int(stride), "d2h_bytes_per_step": 8},
@@ -468,6 +471,7 @@ def main():
     ap.add_argument("--no-step2", action="store_true")
     ap.add_argument("--cpu-blocks", type=int, default=1)
     ap.add_argument("--blocks", type=int, default=0, help="profiling only: restrict the pass to the first n blocks")
+    ap.add_argument("--n-samples", type=int, default=0, help="exploration only: other sample count, --blocks blocks (default 20)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

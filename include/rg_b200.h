@@ -216,6 +216,7 @@ typedef struct rg_s2_bt_chr {
   const double* x_gamma;         /* [P][C][N]  m_est.X_Gamma (orthonormal basis of Gamma^1/2 X) */
   const double* y_raw;           /* [P][N]     phenotypes_raw (0/1)                           */
   const double* firth_offset;    /* [P][N]     firth_est.cov_blup_offset (NULL without --firth) */
+  const double* y_hat_p;         /* [P][N]     m_ests.Y_hat_p, fitted null probabilities (NULL without --spa) */
 } rg_s2_bt_chr;
 int rg_s2_set_chr_bt(rg_handle h, const rg_s2_bt_chr* st);
 
@@ -231,6 +232,16 @@ int rg_s2_set_chr_bt(rg_handle h, const rg_s2_bt_chr* st);
 int rg_s2_block_bgen8_bt(rg_handle h, const uint8_t* probs, const uint8_t* ploidy_missing, int64_t n_file,
                          int32_t bs, const int32_t* sample_idx, int32_t ref_first, double min_mac,
                          const rg_s2_out* out, double* info_out);
+
+/*
+ * rg_s2_spa -- saddlepoint approximation for selected (variant, trait) pairs of the resident block; replaces
+ * run_SPA_test_snp / solve_K1_snp / get_SPA_pvalue_snp (src/Step2_Models.cpp:2072-2294, fast variant for sparse
+ * genotypes included).  pval = sum of the two tail probabilities; the caller finishes like check_pval_snp
+ * (:2021-2029): chisq = chi2_1 quantile of max(pval, 10 DBL_MIN), SE = 1/sqrt(G'WG), beta = sign(z) sqrt(chisq) SE.
+ * status & 15 != 0: the test failed (TEST_FAIL).
+ */
+int rg_s2_spa(rg_handle h, int32_t n_sel, const int32_t* variant_idx, const int32_t* trait_idx, double* pval,
+              int32_t* status);
 
 /*
  * rg_s2_block_bgen8 -- the quantitative-trait score test of rg_s2_block_bed (after rg_s2_set_chr) on BGEN

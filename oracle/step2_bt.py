@@ -225,6 +225,7 @@ class BtChrom:
         self.gamma_sqrt_mask = self.gamma_sqrt * mask
         self.Xg, _ = get_basis(self.gamma_sqrt_mask[:, None] * X)  # X_Gamma, :130-131
         self.yres = (y_raw - p) / self.gamma_sqrt * mask           # src/Data.cpp:2443-2445
+        self.phat = p                                              # m_ests.Y_hat_p, src/Step1_Models.cpp:128
         # null approximate Firth: covariate effects become an offset (src/Step2_Models.cpp:899-983, 1014-1017)
         ok, bf = firth_nr(y_raw, X, blup, mask, self.beta0.copy(), MAXSTEP_NULL, NITER_FIRTH_NULL, 50 * NUMTOL)
         if not ok:
@@ -232,7 +233,125 @@ class BtChrom:
         self.cov_blup_offset = X @ bf + blup
 
 
-def score_bt(g_raw, info_term, in_analysis, mask, y_raw, st: BtChrom, z_thr, n_samples, male=None, non_par=False):
+# ------------------------------------------------------------------------------------------------ saddlepoint (SPA)
+TOL_SPA = float(np.finfo(float).eps) ** 0.25        # src/Regenie.hpp:330
+NITER_SPA = 1000                                    # :329
+MAX_EXP_LIM = 708                                   # src/Step2_Models.hpp:30
+NL_DBL_DMIN = 10.0 * np.finfo(float).tiny           # src/Regenie.hpp:229
+
+
+def _norm_cdf(x):
+    return 0.5 * math.erfc(-x / math.sqrt(2.0))
+
+
+def chisq1_from_pvalue(pv):
+    """quantile(complement(chi2_1, p)) = (Phi^-1(1 - p/2))^2, by Newton on the erfc tail (src/Regenie.cpp:1859-1873)."""
+    target = math.log(pv)
+    z = math.sqrt(max(-2.0 * math.log(pv) - math.log(max(-2.0 * math.log(pv), 1.0)), 0.0)) if pv < 0.5 else 0.5
+    for _ in range(200):
+        f = math.erfc(z / math.sqrt(2.0))
+        if f <= 0.0:
+            z *= 0.5
+            continue
+        d = math.log(f) - target
+        dz = d / (-math.sqrt(2.0 / math.pi) * math.exp(-0.5 * z * z) / f)
+        z -= dz
+        if abs(dz) < 1e-14 * max(1.0, abs(z)):
+            break
+    return z * z
+
+
+def spa_test(stat, denum, gres, st, mask, nz, fast):
+    """run_SPA_test_snp + solve_K1_snp + get_SPA_pvalue_snp (src/Step2_Models.cpp:2072-2294).
+    gres: residualised genotype (length N); nz: g != 0 (the entries of Gsparse); fast = is_sparse.
+    Returns (ok, chisq, logp)."""
+    c = math.sqrt(denum)
+    gmod = np.where(mask, gres / st.gamma_sqrt, 0.0)
+    phat = st.phat
+    gmu = gmod * phat
+    a = gmu.sum()
+    sel = (mask & nz) if fast else mask
+    gm, ph, gs = gmod[sel], phat[sel], st.gamma_sqrt[sel]
+    if fast:
+        b = denum - float((gres[sel] ** 2).sum())
+        d = float(gmu[sel].sum())
+    lim_lo = gmod[gmod < 0].sum() - a
+    lim_hi = gmod[gmod > 0].sum() - a
+    score_num = stat * c
+    if score_num < lim_lo or score_num > lim_hi:
+        return False, 0.0, 0.0
+
+    def K(t):
+        v = np.log(1 - ph + ph * np.exp(t / c * gm)).sum()
+        return v - t * d / c + t * t / 2 / denum * b if fast else v - t * a / c
+
+    def K1(t):
+        v = ((gm * ph / c) / (ph + (1 - ph) * np.exp(-t / c * gm))).sum()
+        return v - d / c + t / denum * b if fast else v - a / c
+
+    def K2(t):
+        vexp = -t / c * gm
+        if (vexp > MAX_EXP_LIM).any():
+            return 0.0
+        e = np.exp(vexp)
+        v = ((gm * gm * gs * gs / (c * c) * e) / (ph + (1 - ph) * e) ** 2).sum()
+        return v + b / denum if fast else v
+
+    tval = -stat if stat >= 0 else stat
+    ptot = 0.0
+    for lam in (1, -1):
+        if tval >= 0:
+            min_x, max_x = 0.0, float(np.finfo(float).max)
+        else:
+            min_x, max_x = -float(np.finfo(float).max), 0.0
+        t_old = 0.0
+        f_old = lam * K1(lam * t_old) - tval
+        t_new = -1.0
+        it = 0
+        while True:
+            it += 1
+            if it > NITER_SPA:
+                return False, 0.0, 0.0
+            hess = K2(lam * t_old)
+            if hess == 0:
+                return False, 0.0, 0.0
+            t_new = t_old - f_old / hess
+            f_new = lam * K1(lam * t_new) - tval
+            if abs(f_new) < TOL_SPA:
+                break
+            if t_new and min_x < t_new < max_x:
+                if f_new > 0:
+                    max_x = t_new
+                else:
+                    min_x = t_new
+            else:
+                t_new = (min_x + max_x) / 2
+                f_new = lam * K1(lam * t_new) - tval
+                if f_new <= 0:
+                    min_x = t_new
+                else:
+                    max_x = t_new
+            t_old, f_old = t_new, f_new
+        root = t_new
+        kval = K(lam * root)
+        k2 = K2(lam * root)
+        if k2 == 0:
+            return False, 0.0, 0.0
+        wval = math.copysign(1.0, root) * math.sqrt(2 * (root * tval - kval)) if root != 0 else 0.0
+        vval = root * math.sqrt(k2)
+        if vval == 0:
+            pv = 0.5
+        else:
+            pv = _norm_cdf(wval + math.log(vval / wval) / wval)
+        ptot += pv
+    if ptot > 1:
+        return False, 0.0, 0.0
+    pval = max(NL_DBL_DMIN, ptot)
+    return True, chisq1_from_pvalue(pval), -math.log10(pval)
+
+
+def score_bt(g_raw, info_term, in_analysis, mask, y_raw, st: BtChrom, z_thr, n_samples, male=None, non_par=False,
+             correction="firth"):
     """One variant, one trait.  g_raw: dosages with -3 = missing.  Returns dict or None if ignored."""
     ok = in_analysis & (g_raw != -3.0)
     ns1 = int(ok.sum())
@@ -277,6 +396,15 @@ def score_bt(g_raw, info_term, in_analysis, mask, y_raw, st: BtChrom, z_thr, n_s
     if abs(stat) <= z_thr:
         se = 1 / sq
         out.update(beta=stat * se, se=se, chisq=stat * stat, logp=get_logp(stat * stat))
+    elif correction == "spa":
+        if is_sparse:
+            gres = gw - st.Xg @ xtwg
+        ok_spa, chisq, logp = spa_test(stat, den, gres, st, mask, (g != 0), is_sparse)
+        se0 = 1 / sq
+        if not ok_spa:
+            out.update(beta=stat * se0, se=se0, chisq=float("nan"), logp=float("nan"), test_fail=True)
+        else:                                                                      # check_pval_snp :2021-2029
+            out.update(beta=math.copysign(1.0, stat) * math.sqrt(chisq) * se0, se=se0, chisq=chisq, logp=logp)
     else:
         if is_sparse:
             gres = gw - st.Xg @ xtwg

@@ -33,7 +33,8 @@ class Step2Config(C.Structure):
 
 
 class S2BtChr(C.Structure):
-    _fields_ = [(k, C.c_void_p) for k in ("gamma_sqrt_mask", "gamma_sqrt", "yres", "x_gamma", "y_raw", "firth_offset")]
+    _fields_ = [(k, C.c_void_p) for k in ("gamma_sqrt_mask", "gamma_sqrt", "yres", "x_gamma", "y_raw", "firth_offset",
+                                           "y_hat_p")]
 
 
 class S2Out(C.Structure):
@@ -46,7 +47,7 @@ EXPORTS = [
     "rg_last_error", "rg_version", "rg_device_count", "rg_step1_create", "rg_destroy", "rg_sync",
     "rg_l0_block_bed", "rg_l0_status", "rg_l0_fetch_W", "rg_l1_fit", "rg_loco", "rg_step2_create",
     "rg_s2_set_chr", "rg_s2_block_bed", "rg_W_info", "rg_debug_fetch", "rg_launch_count", "rg_stream",
-    "rg_set_timing", "rg_get_timing", "rg_fence", "rg_s2_set_chr_bt", "rg_s2_block_bgen8_bt", "rg_s2_block_bgen8", "rg_s2_firth", "rg_l1_fit_bt", "rg_W_set_owned", "rg_W_export", "rg_W_attach_peer", "rg_l1_select", "rg_s2_set_sex", "rg_s2_set_non_par", "rg_l0_load_W",
+    "rg_set_timing", "rg_get_timing", "rg_fence", "rg_s2_set_chr_bt", "rg_s2_block_bgen8_bt", "rg_s2_block_bgen8", "rg_s2_firth", "rg_l1_fit_bt", "rg_W_set_owned", "rg_W_export", "rg_W_attach_peer", "rg_l1_select", "rg_s2_set_sex", "rg_s2_set_non_par", "rg_l0_load_W", "rg_s2_spa",
 ]
 
 _lib = None
@@ -283,13 +284,14 @@ class Step2:
         return o
 
     # ---- binary traits on BGEN 8-bit dosages
-    def set_chr_bt(self, gamma_sqrt_mask, gamma_sqrt, yres, x_gamma, y_raw, firth_offset=None):
+    def set_chr_bt(self, gamma_sqrt_mask, gamma_sqrt, yres, x_gamma, y_raw, firth_offset=None, y_hat_p=None):
         """Arrays are [N x P] (x_gamma: list of P arrays [N x C]); see rg_s2_bt_chr."""
         L = lib()
         L.rg_s2_set_chr_bt.argtypes = [C.c_void_p, C.c_void_p]
         keep = [_f64(gamma_sqrt_mask), _f64(gamma_sqrt), _f64(yres),
                 np.ascontiguousarray(np.stack([_f64(x) for x in x_gamma]).transpose(0, 2, 1), dtype=np.float64),
-                _f64(y_raw), None if firth_offset is None else _f64(firth_offset)]
+                _f64(y_raw), None if firth_offset is None else _f64(firth_offset),
+                None if y_hat_p is None else _f64(y_hat_p)]
         st = S2BtChr(*[None if a is None else a.ctypes.data for a in keep])
         check(L.rg_s2_set_chr_bt(self.h, C.byref(st)))
 
@@ -318,6 +320,15 @@ class Step2:
         check(getattr(L, _fn)(self.h, _ptr(probs), _ptr(missing), n_file, bs, _ptr(sample_idx),
                                      int(ref_first), float(min_mac), C.byref(so), _ptr(o["info"])))
         return o
+
+    def spa(self, variant_idx, trait_idx):
+        L = lib()
+        L.rg_s2_spa.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 4
+        vi = np.ascontiguousarray(variant_idx, dtype=np.int32)
+        ti = np.ascontiguousarray(trait_idx, dtype=np.int32)
+        pv, status = np.empty(len(vi)), np.empty(len(vi), dtype=np.int32)
+        check(L.rg_s2_spa(self.h, len(vi), _ptr(vi), _ptr(ti), _ptr(pv), _ptr(status)))
+        return pv, status
 
     def firth(self, variant_idx, trait_idx):
         L = lib()

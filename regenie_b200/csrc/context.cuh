@@ -126,7 +126,7 @@ struct rg_ctx {
   rg::DevBuf<uint8_t> probs_dev, miss_dev;
   rg::DevBuf<uint32_t> dz;           // [rows_p][Npad] d | e << 10 | missing << 31
   rg::DevBuf<double> bt_F, bt_w, bt_gs, bt_xw, bt_off, bt_coltot, bt_xwy, bt_part, bt_sums, bt_nnz, bt_n510;
-  rg::DevBuf<double> bt_xtwg, bt_mu, bt_info, firth_gvec, firth_out;
+  rg::DevBuf<double> bt_xtwg, bt_mu, bt_info, firth_gvec, firth_out, bt_den, bt_phat;
   rg::DevBuf<int8_t> bt_ym, firth_cflag;
   rg::DevBuf<int32_t> firth_sel, firth_status;
 

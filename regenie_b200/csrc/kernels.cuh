@@ -211,7 +211,7 @@ struct S2BtFinalizeArgs {
   int col_male = -1;
   const double* nz_count;    // [rows_p] analysed samples with non-zero dosage
   const double* n510;        // [rows_p] analysed samples with dosage exactly 2
-  double *af, *mac, *info, *af_all, *mac_all, *scale_fac, *stat, *beta, *se, *chisq, *xtwg, *mu;
+  double *af, *mac, *info, *af_all, *mac_all, *scale_fac, *stat, *beta, *se, *chisq, *xtwg, *mu, *den;
   int32_t *ns, *ns_all, *flags;
 };
 void launch_dosage_relayout(const uint8_t* probs, const uint8_t* miss, int64_t n_file, int bs, int rows_p,
@@ -242,5 +242,26 @@ struct FirthArgs {
   int32_t* status;
 };
 void launch_s2_firth(const FirthArgs& a, cudaStream_t s);
+
+// ---- s2_spa.cu
+struct SpaArgs {
+  int n_sel, C, P, dp, niter;
+  double tol;
+  int64_t npad;
+  const int32_t *sel_var, *sel_trait;
+  const uint32_t* dz;
+  const double* F;
+  const double *w, *gs, *xw, *phat;  // [P][Npad], xw [P][C][Npad]
+  const int8_t* ym;
+  const double* xtwg;                // [bs][P][C]
+  const double* mu;                  // [bs]
+  const double *stat, *den;          // [bs][P] score statistic and its denominator G'WG
+  const int32_t* flags;
+  double* gvec;                      // [n_sel][Npad] scratch
+  int8_t* cflag;                     // [n_sel][Npad] scratch (active-set flags)
+  double* pval;                      // [n_sel] sum of the two tail probabilities
+  int32_t* status;
+};
+void launch_s2_spa(const SpaArgs& a, cudaStream_t s);
 
 }  // namespace rg

@@ -196,7 +196,7 @@ static void s2_set_chr_bt(rg_ctx* h, const rg_s2_bt_chr* st) {
   h->bt_dp = dp;
   std::vector<double> F((size_t)Npad * dp, 0.0), coltot(dp, 0.0), xwy((size_t)P * C, 0.0);
   std::vector<double> w((size_t)P * Npad, 0.0), gs((size_t)P * Npad, 0.0), off((size_t)P * Npad, 0.0),
-      xw((size_t)P * C * Npad, 0.0);
+      xw((size_t)P * C * Npad, 0.0), phat((size_t)P * Npad, 0.0);
   std::vector<int8_t> ym((size_t)P * Npad, 0);
   for (int64_t s = 0; s < N; ++s) {
     double* r = &F[(size_t)s * dp];
@@ -212,6 +212,7 @@ static void s2_set_chr_bt(rg_ctx* h, const rg_s2_bt_chr* st) {
       const double wv = ina ? st->gamma_sqrt_mask[ps] : 0.0;
       const double yr = st->yres[ps];
       w[pp] = wv; gs[pp] = st->gamma_sqrt[ps]; off[pp] = st->firth_offset ? st->firth_offset[ps] : 0.0;
+      phat[pp] = st->y_hat_p ? st->y_hat_p[ps] : 0.0;
       ym[pp] = m ? (st->y_raw[ps] != 0.0 ? 2 : 1) : 0;
       double* f = r + 1 + p * (3 + C);
       f[0] = (m && ina) ? 1.0 : 0.0;
@@ -231,7 +232,7 @@ static void s2_set_chr_bt(rg_ctx* h, const rg_s2_bt_chr* st) {
     RG_CUDA(cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice, h->stream));
   };
   up(h->bt_F, F); up(h->bt_coltot, coltot); up(h->bt_xwy, xwy); up(h->bt_w, w); up(h->bt_gs, gs);
-  up(h->bt_off, off); up(h->bt_xw, xw); up(h->bt_ym, ym);
+  up(h->bt_off, off); up(h->bt_xw, xw); up(h->bt_ym, ym); up(h->bt_phat, phat);
   RG_CUDA(cudaStreamSynchronize(h->stream));
   h->bt_chr_set = true;
 }
@@ -276,6 +277,7 @@ static void s2_block_bgen8_bt(rg_ctx* h, const uint8_t* probs, const uint8_t* mi
   h->bt_sums.alloc((size_t)h->rows_p_max * 4 * dp);
   h->bt_nnz.alloc(h->rows_p_max); h->bt_n510.alloc(h->rows_p_max);
   h->bt_xtwg.alloc((size_t)h->bs_max * P * C); h->bt_mu.alloc(h->bs_max); h->bt_info.alloc((size_t)h->bs_max * P);
+  h->bt_den.alloc((size_t)h->bs_max * P);
   const size_t nd = (size_t)h->bs_max * (7 * (size_t)P + 3), ni = (size_t)h->bs_max * ((size_t)P + 2);
   h->s2_out_d.alloc(nd);
   h->s2_out_i.alloc(ni);
@@ -291,7 +293,7 @@ static void s2_block_bgen8_bt(rg_ctx* h, const uint8_t* probs, const uint8_t* mi
   const size_t bp = (size_t)h->bs_max * P, b1 = h->bs_max;
   a.af = d; a.mac = d + bp; a.stat = d + 2 * bp; a.beta = d + 3 * bp; a.se = d + 4 * bp; a.chisq = d + 5 * bp;
   a.af_all = d + 6 * bp; a.mac_all = d + 6 * bp + b1; a.scale_fac = d + 6 * bp + 2 * b1;
-  a.info = h->bt_info.p; a.xtwg = h->bt_xtwg.p; a.mu = h->bt_mu.p;
+  a.info = h->bt_info.p; a.xtwg = h->bt_xtwg.p; a.mu = h->bt_mu.p; a.den = h->bt_den.p;
   int32_t* ii = h->s2_out_i.p;
   a.ns = ii; a.ns_all = ii + bp; a.flags = ii + bp + b1;
   launch_s2_bt_finalize(a, s);
@@ -417,7 +419,46 @@ static void s2_firth(rg_ctx* h, int n_sel, const int32_t* var_idx, const int32_t
   }
 }
 
+static void s2_spa(rg_ctx* h, int n_sel, const int32_t* var_idx, const int32_t* trait_idx, double* pval, int32_t* status) {
+  RG_CHECK(h->kind == 2 && h->bt_chr_set && h->s2_last_bs > 0, "rg_s2_spa needs a resident dosage block");
+  RG_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const int P = h->P, C = h->C;
+  for (int k = 0; k < n_sel; ++k)
+    RG_CHECK(var_idx[k] >= 0 && var_idx[k] < h->s2_last_bs && trait_idx[k] >= 0 && trait_idx[k] < P, "selection out of range");
+  const int kBatch = 256;
+  h->firth_gvec.alloc((size_t)kBatch * h->Npad); h->firth_cflag.alloc((size_t)kBatch * h->Npad);
+  h->firth_sel.alloc(2 * kBatch); h->firth_status.alloc(kBatch); h->firth_out.alloc(3 * kBatch);
+  const size_t bp = (size_t)h->bs_max * P, b1 = h->bs_max;
+  for (int o = 0; o < n_sel; o += kBatch) {
+    const int nb = std::min(kBatch, n_sel - o);
+    RG_CUDA(cudaMemcpyAsync(h->firth_sel.p, var_idx + o, nb * 4, cudaMemcpyHostToDevice, s));
+    RG_CUDA(cudaMemcpyAsync(h->firth_sel.p + kBatch, trait_idx + o, nb * 4, cudaMemcpyHostToDevice, s));
+    SpaArgs a;
+    a.n_sel = nb; a.C = C; a.P = P; a.dp = h->bt_dp; a.niter = 1000; a.tol = 1.220703125e-4;   // eps^(1/4), src/Regenie.hpp:330
+    a.npad = h->Npad; a.sel_var = h->firth_sel.p; a.sel_trait = h->firth_sel.p + kBatch;
+    a.dz = h->dz.p; a.F = h->bt_F.p; a.w = h->bt_w.p; a.gs = h->bt_gs.p; a.xw = h->bt_xw.p; a.phat = h->bt_phat.p;
+    a.ym = h->bt_ym.p; a.xtwg = h->bt_xtwg.p; a.mu = h->bt_mu.p; a.stat = h->s2_out_d.p + 2 * bp; a.den = h->bt_den.p;
+    a.flags = h->s2_out_i.p + bp + b1;
+    a.gvec = h->firth_gvec.p; a.cflag = h->firth_cflag.p; a.pval = h->firth_out.p; a.status = h->firth_status.p;
+    launch_s2_spa(a, s);
+    h->launches += 1;
+    RG_CUDA(cudaMemcpyAsync(pval + o, a.pval, nb * 8, cudaMemcpyDeviceToHost, s));
+    RG_CUDA(cudaMemcpyAsync(status + o, a.status, nb * 4, cudaMemcpyDeviceToHost, s));
+    RG_CUDA(cudaStreamSynchronize(s));
+  }
+}
+
 extern "C" {
+
+int rg_s2_spa(rg_handle h, int32_t n_sel, const int32_t* variant_idx, const int32_t* trait_idx, double* pval,
+              int32_t* status) {
+  RG_API_BEGIN
+  RG_CHECK(h && (n_sel == 0 || (variant_idx && trait_idx && pval && status)), "null argument");
+  if (n_sel > 0) s2_spa(h, n_sel, variant_idx, trait_idx, pval, status);
+  RG_CUDA(cudaGetLastError());
+  RG_API_END
+}
 
 int rg_s2_set_sex(rg_handle h, const uint8_t* male) {
   RG_API_BEGIN

@@ -165,6 +165,7 @@ __global__ void s2_bt_finalize_kernel(S2BtFinalizeArgs a) {
       xty += v * a.xwy[(int64_t)p * C + c];           // (XW^T yres)_c
     }
     const double den = gw2 - xt2;                     // = |GW - XW XW^T GW|^2  (XW orthonormal)
+    a.den[(int64_t)i * P + p] = den;
     double num = lin(cwy);                            // GW . yres
     if (!sparse) num -= xty;                          // dense path projects the covariates out of G first (:500,:521)
     const double sq = sqrt(den);

@@ -217,6 +217,7 @@ BtNull fit_bt_null(const std::string& name, const double* y, const double* X, in
   if (!ok) throw Fail("logistic regression did not converge for phenotype '" + name + "'.");
   BtNull out;
   out.gamma_sqrt.resize(N); out.gamma_sqrt_mask.resize(N); out.yres.resize(N);
+  out.y_hat_p = w.p;                                               // m_ests.Y_hat_p (src/Step1_Models.cpp:128)
   std::vector<double> XG((size_t)N * C);
   for (int64_t i = 0; i < N; ++i) {
     const double wi = mask[i] ? w.p[i] * (1.0 - w.p[i]) : 1.0;     // get_wvec, src/Step1_Models.cpp:1760
@@ -255,6 +256,19 @@ std::vector<double> null_logistic_eta(const std::string& name, const double* y, 
   }
   if (!ok) throw Fail("logistic regression did not converge for phenotype '" + name + "'.");
   return w.eta;
+}
+
+double chisq1_from_pvalue(double p) {
+  if (!(p > 0.0)) return 0.0;
+  if (p >= 1.0) return 0.0;
+  // erfc(z / sqrt 2) = p, bisection on the (monotone) tail; 40 sigma covers 10 * DBL_MIN
+  double lo = 0.0, hi = 40.0;
+  for (int i = 0; i < 200; ++i) {
+    const double mid = 0.5 * (lo + hi);
+    if (std::erfc(mid / std::sqrt(2.0)) > p) lo = mid; else hi = mid;
+  }
+  const double z = 0.5 * (lo + hi);
+  return z * z;
 }
 
 // inverse of the standard normal upper tail by bisection-safe Newton on erfc; chi2_1 quantile = z^2

@@ -9,7 +9,7 @@
 namespace rgh {
 
 struct BtNull {
-  std::vector<double> gamma_sqrt, gamma_sqrt_mask, yres, x_gamma, firth_offset;   // [N], [N], [N], [C][N], [N]
+  std::vector<double> gamma_sqrt, gamma_sqrt_mask, yres, x_gamma, firth_offset, y_hat_p;   // [N] each, x_gamma [C][N]
 };
 
 // y (0/1), X [C][N] column-major orthonormal basis, blup (LOCO prediction), mask; throws Fail on non-convergence
@@ -20,6 +20,9 @@ BtNull fit_bt_null(const std::string& name, const double* y, const double* X, in
 // src/Pheno.cpp:1608)
 std::vector<double> null_logistic_eta(const std::string& name, const double* y, const double* X, int64_t N, int C,
                                       const uint8_t* mask);
+
+// chi2_1 upper quantile of a p-value: quantile(complement(chisq1, p)) of get_logp (src/Regenie.cpp:1859-1873)
+double chisq1_from_pvalue(double p);
 
 // z threshold of --pThresh: sqrt of the chi2_1 upper quantile (src/Data.cpp:2116-2120)
 double z_threshold(double p_thresh);

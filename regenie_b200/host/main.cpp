@@ -12,6 +12,7 @@
 #include <climits>
 #include <cstdlib>
 #include <iomanip>
+#include <limits>
 
 #include "../../include/rg_b200.h"
 #include <thread>
@@ -31,7 +32,7 @@ struct Params {
   std::string remove, keep, exclude, extract;
   int bsize = 0, cv = 5, l0 = 5, l1 = 5, gpu = 0;
   bool loocv = false, lowmem = false, ref_first = false, strict = false, bt = false, force_step1 = false;
-  bool rel_path = false, firth = false, approx = false, keep_l0 = false;
+  bool rel_path = false, firth = false, approx = false, keep_l0 = false, spa = false;
   double min_mac = 5.0, p_thresh = 0.05;
   int threads = 0;
   std::set<int> chrs;                 // --chr / --chrList
@@ -101,6 +102,7 @@ Params parse_cli(int argc, char** argv) {
     else if (a == "--pThresh") p.p_thresh = atof(need(i).c_str());
     else if (a == "--firth") p.firth = true;
     else if (a == "--approx") p.approx = true;
+    else if (a == "--spa") p.spa = true;
     else if (a == "--loocv") p.loocv = true;
     else if (a == "--lowmem") p.lowmem = true;     // W stays resident in HBM; files only with --keep-l0
     else if (a == "--keep-l0") p.keep_l0 = true;
@@ -116,7 +118,7 @@ Params parse_cli(int argc, char** argv) {
                    "  [--pred LIST] [--loocv] [--lowmem] [--cv K] [--l0 R] [--l1 R] [--remove F] [--keep F]\n"
                    "  [--exclude F] [--extract F] [--ref-first] [--minMAC x] [--strict] [--gpu ordinal]\n"
                    "  [--chr c]... [--chrList c1,c2,...]  (Step-2 jobs are split by chromosome like the reference)\n"
-                   "  step 2 binary traits: --bt [--firth --approx] [--pThresh p] with --bed or --bgen F [--sample F]\n";
+                   "  step 2 binary traits: --bt [--firth --approx | --spa] [--pThresh p] with --bed or --bgen F [--sample F]\n";
       exit(0);
     } else {
       throw Fail("option '" + a + "' is outside the hot path covered by rgb200 (see DESIGN.md, out of scope)");
@@ -126,6 +128,7 @@ Params parse_cli(int argc, char** argv) {
   if (!p.bgen.empty() && p.step == 1) throw Fail("--bgen input in --step 1 is not implemented yet in rgb200 (hard-call .bed only).");
   if ((!p.bgen.empty()) + (!p.bed.empty()) + (!p.pgen.empty()) > 1) throw Fail("specify only one genotype input (--bed, --pgen or --bgen).");
   if (!p.pgen.empty()) p.ref_first = false;          // .pgen rows are emitted as ref-last PLINK 1 rows counting ALT
+  if (p.firth && p.spa) throw Fail("cannot use both --firth and --spa.");
   if (p.firth && !p.approx) throw Fail("exact Firth (--firth without --approx) is outside the hot path covered by rgb200; use --firth --approx.");
   if (p.bed.empty() && p.bgen.empty() && p.pgen.empty()) throw Fail("must specify the genotype file with --bed, --pgen or --bgen.");
   if (p.pheno.empty()) throw Fail("must provide the phenotype file with --phenoFile.");
@@ -674,6 +677,7 @@ void run_step2_bt(const Params& p, Log& log) {
   log << " * # blocks            : [" << blocks.size() << "]\n";
   const double z_thr = z_threshold(p.p_thresh);
   if (p.firth) log << " * using approximate Firth correction for logistic regression p-values less than " << p.p_thresh << "\n";
+  if (p.spa) log << " * using SPA correction for logistic regression p-values less than " << p.p_thresh << "\n";
 
   rg_step2_config cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -706,8 +710,9 @@ void run_step2_bt(const Params& p, Log& log) {
     if (chrom != cur_chr) {
       cur_chr = chrom;
       log << "Chromosome " << chrom << "\n";
-      std::vector<double> gsm((size_t)P * N), gs((size_t)P * N), yres((size_t)P * N), xg((size_t)P * C * N), off;
+      std::vector<double> gsm((size_t)P * N), gs((size_t)P * N), yres((size_t)P * N), xg((size_t)P * C * N), off, yhat;
       if (p.firth) off.resize((size_t)P * N);
+      if (p.spa) yhat.resize((size_t)P * N);
       for (int i = 0; i < P; ++i) {
         const std::vector<double> blup = blup_for_chr(locos[i], ss, ph, i, chrom);
         const BtNull nm = fit_bt_null(ph.names[i], &ph.Y_raw[(size_t)i * N], ph.X.data(), N, C, blup.data(),
@@ -717,10 +722,12 @@ void run_step2_bt(const Params& p, Log& log) {
         std::copy(nm.yres.begin(), nm.yres.end(), yres.begin() + (size_t)i * N);
         std::copy(nm.x_gamma.begin(), nm.x_gamma.end(), xg.begin() + (size_t)i * C * N);
         if (p.firth) std::copy(nm.firth_offset.begin(), nm.firth_offset.end(), off.begin() + (size_t)i * N);
+        if (p.spa) std::copy(nm.y_hat_p.begin(), nm.y_hat_p.end(), yhat.begin() + (size_t)i * N);
       }
       const std::vector<uint8_t> male = male_vector(use_bgen ? gg.sex_file : gb.sex_file, sample_idx);
       rg_check(rg_s2_set_sex(h, chrom == 23 ? male.data() : nullptr));
-      rg_s2_bt_chr st{gsm.data(), gs.data(), yres.data(), xg.data(), ph.Y_raw.data(), p.firth ? off.data() : nullptr};
+      rg_s2_bt_chr st{gsm.data(), gs.data(), yres.data(), xg.data(), ph.Y_raw.data(), p.firth ? off.data() : nullptr,
+                      p.spa ? yhat.data() : nullptr};
       rg_check(rg_s2_set_chr_bt(h, &st));
     }
     if (non_par_flags(p, snps, blocks[b], npf)) rg_check(rg_s2_set_non_par(h, npf.data(), bs));
@@ -744,7 +751,8 @@ void run_step2_bt(const Params& p, Log& log) {
     std::vector<int32_t> sel_v, sel_t, fstatus;
     std::vector<double> fbeta, fse, flrt;
     std::map<std::pair<int, int>, int> fidx;
-    if (p.firth) {
+    std::map<std::pair<int, int>, double> spa_logp;
+    if (p.firth || p.spa) {
       for (int v = 0; v < bs; ++v) {
         if (flags[v] & (1 | 16)) continue;
         for (int i = 0; i < P; ++i) {
@@ -756,7 +764,21 @@ void run_step2_bt(const Params& p, Log& log) {
       }
       const size_t nsel = sel_v.size();
       fbeta.resize(nsel); fse.resize(nsel); flrt.resize(nsel); fstatus.resize(nsel);
-      rg_check(rg_s2_firth(h, (int32_t)nsel, sel_v.data(), sel_t.data(), fbeta.data(), fse.data(), flrt.data(), fstatus.data()));
+      if (p.firth) {
+        rg_check(rg_s2_firth(h, (int32_t)nsel, sel_v.data(), sel_t.data(), fbeta.data(), fse.data(), flrt.data(), fstatus.data()));
+      } else {
+        // check_pval_snp, SPA branch (src/Step2_Models.cpp:2021-2029): SE from the score test, beta from the SPA chi-square
+        std::vector<double> pv(nsel);
+        rg_check(rg_s2_spa(h, (int32_t)nsel, sel_v.data(), sel_t.data(), pv.data(), fstatus.data()));
+        for (size_t k = 0; k < nsel; ++k) {
+          const size_t e = (size_t)sel_v[k] * P + sel_t[k];
+          const double pval = std::max(10.0 * std::numeric_limits<double>::min(), pv[k]);
+          flrt[k] = chisq1_from_pvalue(pval);
+          fse[k] = se[e];
+          fbeta[k] = (beta[e] < 0 ? -1.0 : 1.0) * std::sqrt(flrt[k]) * se[e];
+          spa_logp[{sel_v[k], sel_t[k]}] = -std::log10(pval);
+        }
+      }
       n_firth += nsel;
     }
     for (int v = 0; v < bs; ++v) {
@@ -780,7 +802,8 @@ void run_step2_bt(const Params& p, Log& log) {
         buf << ns[e] << " ADD ";
         if (so >= 0 && !std::isnan(so)) buf << bo << ' ' << so;
         else buf << "NA NA";
-        const double lp = get_logp(co);
+        double lp = get_logp(co);
+        if (p.spa && pass && f != fidx.end()) lp = spa_logp[{v, i}];   // SPA reports -log10 of its own p-value
         if (pass && co >= 0 && !std::isnan(lp)) buf << ' ' << co << ' ' << lp;
         else buf << " NA NA";
         buf << (pass ? " NA\n" : " TEST_FAIL\n");
@@ -791,6 +814,7 @@ void run_step2_bt(const Params& p, Log& log) {
   }
   log << "\nNumber of ignored tests due to low MAC or low variance : " << n_ignored << "\n";
   if (p.firth) log << "Number of tests with Firth correction : " << n_firth << " (" << n_fail << " failed)\n";
+  if (p.spa) log << "Number of tests with SPA correction : " << n_firth << " (" << n_fail << " failed)\n";
   rg_destroy(h);
 }
 

@@ -404,3 +404,42 @@ def test_split_l0_run_l0_run_l1_equals_single_run(tmp_path, golden_dir):
     for k in (1, 2):
         assert open(str(tmp_path / ("single_%d.loco" % k))).read() == open(str(tmp_path / ("par_l1_%d.loco" % k))).read()
     assert not os.path.exists(mp + "_job1_l0_Y1")            # removed after level 1 like the reference (no --keep-l0)
+
+
+def test_step2_bt_spa_driver_vs_oracle(tmp_path, golden_dir):
+    """rgb200 --step 2 --bgen --bt --spa --pThresh 0.05 vs the oracle rows (saddlepoint correction)."""
+    import math
+
+    from oracle import bgen, prep, step2, step2_bt
+    d = golden_dir
+    pred = _write_zero_loco(tmp_path, d, ["Y1", "Y2"])
+    out = str(tmp_path / "spa")
+    run(["--step", "2", "--bgen", d + "/example.bgen", "--covarFile", d + "/covariates.txt", "--phenoFile",
+         d + "/phenotype_bin.txt", "--remove", d + "/fid_iid_to_remove.txt", "--bsize", "400", "--bt", "--spa",
+         "--pThresh", "0.05", "--pred", pred, "--out", out])
+    rm = {"_".join(l.split()[:2]) for l in open(d + "/fid_iid_to_remove.txt") if l.strip()}
+    b = bgen.Bgen(d + "/example.bgen")
+    keep = np.array([k not in rm for k in b.sample_ids])
+    keys = [k for k in b.sample_ids if k not in rm]
+    pr = prep.prepare(keys, d + "/phenotype_bin.txt", d + "/covariates.txt", bt=True, step=2)
+    y, mask = pr.Y_raw[:, 0], pr.mask[:, 0]
+    st = step2_bt.BtChrom(y, pr.X, np.zeros(len(keys)), mask)
+    z_thr = math.sqrt(3.841458820694124)
+    got = open(out + "_Y1.regenie").read().splitlines()
+    k = 1
+    n_spa = 0
+    for chrom, pos, rsid, alleles, p0, p1, miss in b.variants():
+        g, iv = bgen.dosage(p0[keep], p1[keep], miss[keep])
+        r = step2_bt.score_bt(g, iv, pr.in_analysis, mask, y, st, z_thr, len(keys), correction="spa")
+        if r is None:
+            continue
+        n_spa += abs(r["stat"]) > z_thr
+        row = step2.sumstats_row(int(chrom), pos, rsid, alleles[1], alleles[0], r["af"], r["n"], r["beta"], r["se"],
+                                 r["chisq"], r["logp"], info=r["info"], test_pass=not r["test_fail"]).split()
+        tx = got[k].split()
+        k += 1
+        assert tx[:6] == row[:6] and tx[7:9] == row[7:9] and tx[13] == row[13], (tx, row)
+        assert close(tx[6], row[6])
+        for a, c in zip(tx[9:13], row[9:13]):
+            assert close(a, c), (tx, row)
+    assert k == len(got) and n_spa > 20

@@ -104,3 +104,50 @@ def test_bt_firth_many_variants_two_traits_missing_dosages(golden_dir):
     blup = 0.3 * rng.standard_normal((len(keys), 2))
     n_rows, n_firth, n_fast, worst = _run(pr, keep, probs, miss, [0, 1], blup, 0.5, 600, block=256)
     assert n_firth > 200 and n_fast > 5
+
+
+def test_bt_spa_matches_oracle(golden_dir):
+    """Saddlepoint approximation (rg_s2_spa) on every variant with |z| > 0.5: dense and sparse ("fast") variants, two
+    traits, missing dosages, flipped alleles; chisq / LOG10P / BETA vs the oracle restatement of run_SPA_test_snp."""
+    from regenie_b200 import capi
+    b, keep, keys, pr, probs, miss = _load(golden_dir)
+    rng = np.random.default_rng(12)
+    probs = probs[:500].copy(); miss = miss[:500].copy()
+    miss[rng.random(miss.shape) < 0.01] |= 0x80
+    probs[::7, :, 0] = np.where(probs[::7, :, 0] + probs[::7, :, 1] <= 255, 255 - probs[::7, :, 0] - probs[::7, :, 1], 0)
+    rare = rng.random(probs[1::3, :, 0].shape) < 0.8
+    probs[1::3][rare] = 0                                              # sparse genotypes -> fast SPA
+    blup = 0.3 * rng.standard_normal((len(keys), 2))
+    N, P = len(keys), 2
+    mask, Y = pr.mask[:, :2], pr.Y_raw[:, :2]
+    sts = [step2_bt.BtChrom(Y[:, j], pr.X, blup[:, j], mask[:, j]) for j in range(P)]
+    s2 = capi.Step2(pr.X, mask, pr.in_analysis, pr.n_analyzed, 250)
+    s2.set_chr_bt(np.stack([s.gamma_sqrt_mask for s in sts], 1), np.stack([s.gamma_sqrt for s in sts], 1),
+                  np.stack([s.yres for s in sts], 1), [s.Xg for s in sts], Y, None,
+                  np.stack([s.phat for s in sts], 1))
+    sample_idx = np.nonzero(keep)[0].astype(np.int32)
+    z_thr = 0.5
+    n_spa = n_fast = n_fail = 0
+    for v0 in range(0, 500, 250):
+        o = s2.block_bgen8_bt(probs[v0:v0 + 250], miss[v0:v0 + 250], sample_idx=sample_idx, min_mac=5.0)
+        sel = [(i, j) for i in range(250) for j in range(P)
+               if not (o["flags"][i] & 17) and o["mac"][i, j] >= 5.0 and abs(o["stat"][i, j]) > z_thr]
+        pv, status = s2.spa([a for a, _ in sel], [c for _, c in sel])
+        for n, (i, j) in enumerate(sel):
+            g, iv = bgen.dosage(probs[v0 + i][keep, 0], probs[v0 + i][keep, 1], (miss[v0 + i][keep] & 0x80) != 0)
+            r = step2_bt.score_bt(g, iv, pr.in_analysis, mask[:, j], Y[:, j], sts[j], z_thr, N, correction="spa")
+            assert r is not None and abs(r["stat"]) > z_thr
+            n_spa += 1
+            n_fast += bool(status[n] & 256)
+            assert bool(status[n] & 15) == r["test_fail"], (v0 + i, j, status[n])
+            if r["test_fail"]:
+                n_fail += 1
+                continue
+            pval = max(step2_bt.NL_DBL_DMIN, pv[n])
+            chisq = step2_bt.chisq1_from_pvalue(pval)
+            assert abs(chisq - r["chisq"]) <= TOL * r["chisq"], (v0 + i, j, chisq, r["chisq"])
+            assert abs(-math.log10(pval) - r["logp"]) <= TOL * max(r["logp"], 1e-3)
+            beta = math.copysign(1.0, o["beta"][i, j]) * math.sqrt(chisq) * o["se"][i, j]
+            assert abs(beta - r["beta"]) <= TOL * abs(r["beta"])
+    s2.close()
+    assert n_spa > 300 and n_fast > 30
