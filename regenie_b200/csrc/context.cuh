@@ -113,6 +113,18 @@ struct rg_ctx {
   rg::DevBuf<double> F, s2_part, s2_sums, s2_maskcount, s2_YtX, s2_XmX, s2_scf;
   rg::DevBuf<double> s2_out_d;       // packed f64 outputs
   rg::DevBuf<int32_t> s2_out_i;      // packed i32 outputs
+  // quantitative-trait statistics on the tensor cores (bed / pgen input)
+  bool s2_tc = false;
+  int s2_drows = 0, s2_nchunk = 0, s2_ncol = 0;
+  rg::DevBuf<uint8_t> s2_z3, s2_FD;           // [3 rows_p][Npad] planes; digit rows of F
+  rg::DevBuf<double> s2_Fscale;
+  rg::DevBuf<float> s2_T;                     // [chunk][3 rows_p][drows]
+  rg::DevBuf<int2> s2_fold_k;
+  std::map<int, std::unique_ptr<rg::DevBuf<int2>>> s2_tile_lists;
+  rg::DevBuf<uint8_t> s2_ones;
+  CUtensorMap s2_tmD;
+  std::map<int, CUtensorMap> s2_tmZ;          // keyed by rows_p
+  std::map<int, int> s2_ntiles;
   // chrX: male indicator of every sample (empty = none), F column of it, per-block non-PAR flags
   std::vector<uint8_t> s2_male;
   int s2_col_male = -1, bt_col_male = -1;

@@ -198,6 +198,9 @@ struct S2FinalizeArgs {
 void launch_s2_stats(const uint32_t* gp, int64_t npad, const double* F, int dp, const int4* chunks, int nchunks,
                      int rows_p, double* part, double* sums, cudaStream_t s);
 void launch_s2_finalize(const S2FinalizeArgs& a, cudaStream_t s);
+void launch_bed_expand3_fp8(const uint32_t* gp, int rows_p, uint8_t* z, int64_t npad, cudaStream_t s);
+void launch_s2_stats_finish(const float* T, int ldt, int64_t chunk_stride, int nchunk, int rows_p, int dp, int D,
+                            const double* scale, double* sums, cudaStream_t s);
 
 // ---- s2_dosage_kernels.cu
 struct S2BtFinalizeArgs {

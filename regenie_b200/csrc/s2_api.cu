@@ -1,5 +1,8 @@
 // Step-2 entry points of the C ABI (include/rg_b200.h).
+#include <stdlib.h>
+
 #include <algorithm>
+#include <string>
 
 #include "context.cuh"
 
@@ -106,6 +109,37 @@ static void s2_set_chr(rg_ctx* h, const double* res, const double* scf_sv) {
   RG_CUDA(cudaMemcpyAsync(h->s2_scf.p, scf_sv, P * 8, cudaMemcpyHostToDevice, h->stream));
   h->s2_male_tot.alloc(1 + P);
   RG_CUDA(cudaMemcpyAsync(h->s2_male_tot.p, male_tot.data(), (1 + P) * 8, cudaMemcpyHostToDevice, h->stream));
+  // tensor-core statistics for 2-bit input: digit rows of F for this chromosome (exact, see s2_kernels.cu)
+  {
+    static const bool f64_only = [] { const char* e = getenv("RG_B200_S2_STATS"); return e && std::string(e) == "f64"; }();
+    h->s2_tc = !f64_only;
+    if (h->s2_tc) {
+      cudaStream_t s = h->stream;
+      const int D = base + (with_sex ? 1 + P : 0);
+      h->s2_ncol = D;
+      h->s2_drows = (int)round_up((int64_t)ceil_div(D, kStatQ) * 128, 256);
+      h->s2_FD.alloc((size_t)h->s2_drows * h->Npad);
+      h->s2_Fscale.alloc(dp);
+      if (!h->s2_ones.p) {
+        h->s2_ones.alloc(h->Npad);
+        RG_CUDA(cudaMemsetAsync(h->s2_ones.p, 1, h->Npad, s));
+      }
+      RG_CUDA(cudaMemsetAsync(h->s2_FD.p, 0, (size_t)h->s2_drows * h->Npad, s));
+      launch_l0_xy_digits(h->F.p, dp, D, h->Npad, h->s2_ones.p, h->s2_Fscale.p, h->s2_FD.p, s);
+      make_gram_tensor_map(&h->s2_tmD, h->s2_FD.p, h->Npad, h->s2_drows);
+      // sample chunks: exact integer sums need 60 * chunk < 2^24; more chunks also fill the SMs
+      const int ntile = (3 * h->rows_p_max / 128) * (h->s2_drows / 256);
+      int64_t nchunk = std::max<int64_t>(ceil_div(h->Npad, (int64_t)262144), ceil_div((int64_t)296, (int64_t)ntile));
+      nchunk = std::max<int64_t>(1, std::min<int64_t>(nchunk, h->Npad / 1024));
+      const int64_t len = round_up(ceil_div(h->Npad, nchunk), 128);
+      std::vector<int2> fk;
+      for (int64_t o = 0; o < h->Npad; o += len)
+        fk.push_back(make_int2((int)(o / 128), (int)(std::min<int64_t>(len, h->Npad - o) / 128)));
+      h->s2_nchunk = (int)fk.size();
+      h->s2_fold_k.alloc(fk.size());
+      RG_CUDA(cudaMemcpyAsync(h->s2_fold_k.p, fk.data(), fk.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+    }
+  }
   RG_CUDA(cudaStreamSynchronize(h->stream));
 }
 
@@ -151,13 +185,40 @@ static void s2_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
     packed_d = h->packed_dev.p;
   }
   h->gp.alloc((size_t)h->rows_p_max * (Npad / 16));
-  h->s2_part.alloc((size_t)h->nchunks * h->rows_p_max * 3 * h->dp);
+  if (!h->s2_tc) h->s2_part.alloc((size_t)h->nchunks * h->rows_p_max * 3 * h->dp);
   h->s2_sums.alloc((size_t)h->rows_p_max * 3 * h->dp);
   const size_t nd = (size_t)h->bs_max * (7 * (size_t)P + 3), ni = (size_t)h->bs_max * ((size_t)P + 2);
   h->s2_out_d.alloc(nd);
   h->s2_out_i.alloc(ni);
   launch_bed_relayout(packed_d, row_stride, bs, rows_p, h->file_idx_pad.p, h->word_base.p, h->word_keep.p, ref_first, h->gp.p, Npad, s);
-  launch_s2_stats(h->gp.p, Npad, h->F.p, h->dp, h->chunks.p, h->nchunks, rows_p, h->s2_part.p, h->s2_sums.p, s);
+  if (h->s2_tc) {
+    const int drows = h->s2_drows;
+    h->s2_z3.alloc((size_t)3 * h->rows_p_max * Npad);
+    h->s2_T.alloc((size_t)h->s2_nchunk * 3 * h->rows_p_max * drows);
+    launch_bed_expand3_fp8(h->gp.p, rows_p, h->s2_z3.p, Npad, s);
+    if (!h->s2_tmZ.count(rows_p)) {
+      CUtensorMap tm;
+      make_gram_tensor_map(&tm, h->s2_z3.p, Npad, 3 * rows_p);
+      h->s2_tmZ[rows_p] = tm;
+    }
+    if (!h->s2_tile_lists.count(rows_p * 4096 + drows / 256)) {
+      std::vector<int2> tiles;
+      for (int nj = 0; nj < drows / 256; ++nj)
+        for (int mi = 0; mi < 3 * rows_p / 128; ++mi) tiles.push_back(make_int2(mi, nj));
+      auto buf = std::make_unique<DevBuf<int2>>();
+      buf->alloc(tiles.size());
+      RG_CUDA(cudaMemcpy(buf->p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice));
+      h->s2_ntiles[rows_p * 4096 + drows / 256] = (int)tiles.size();
+      h->s2_tile_lists[rows_p * 4096 + drows / 256] = std::move(buf);
+    }
+    const int key = rows_p * 4096 + drows / 256;
+    const int64_t cs = (int64_t)3 * rows_p * drows;
+    launch_gram_tcgen05(h->s2_tmZ[rows_p], h->s2_tmD, h->s2_tile_lists[key]->p, h->s2_ntiles[key], h->s2_fold_k.p,
+                        h->s2_nchunk, h->s2_T.p, drows, cs, s);
+    launch_s2_stats_finish(h->s2_T.p, drows, cs, h->s2_nchunk, rows_p, h->dp, h->s2_ncol, h->s2_Fscale.p, h->s2_sums.p, s);
+  } else {
+    launch_s2_stats(h->gp.p, Npad, h->F.p, h->dp, h->chunks.p, h->nchunks, rows_p, h->s2_part.p, h->s2_sums.p, s);
+  }
   S2FinalizeArgs a;
   a.bs = bs; a.C = C; a.P = P; a.dp = h->dp; a.strict = h->strict;
   a.n_analyzed = h->n_analyzed; a.n_samples = h->N; a.min_mac = min_mac; a.numtol = 1e-6;
