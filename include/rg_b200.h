@@ -254,6 +254,13 @@ int rg_s2_block_bgen8(rg_handle h, const uint8_t* probs, const uint8_t* ploidy_m
                       const rg_s2_out* out, double* info_out);
 
 /*
+ * rg_s2_block_bed_bt -- the same binary-trait score test on 2-bit PLINK rows (.bed / decoded .pgen hard calls):
+ * parseSnpfromBed (src/Geno.cpp:2414-2536) + compute_score_bt.  The block stays resident for rg_s2_firth / rg_s2_spa.
+ */
+int rg_s2_block_bed_bt(rg_handle h, const uint8_t* packed, int64_t row_stride, int32_t bs, const int32_t* sample_idx,
+                       int32_t ref_first, double min_mac, const rg_s2_out* out);
+
+/*
  * rg_s2_firth -- approximate Firth test for selected (variant, trait) pairs of the resident block; replaces
  * fit_firth_logistic_snp_fast + fit_firth_pseudo / fit_firth (src/Step2_Models.cpp:1158-1252, 1527-1737).
  * beta is reported on the original allele coding; status != 0 in the low 4 bits = did not converge.

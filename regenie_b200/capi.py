@@ -47,7 +47,7 @@ EXPORTS = [
     "rg_last_error", "rg_version", "rg_device_count", "rg_step1_create", "rg_destroy", "rg_sync",
     "rg_l0_block_bed", "rg_l0_status", "rg_l0_fetch_W", "rg_l1_fit", "rg_loco", "rg_step2_create",
     "rg_s2_set_chr", "rg_s2_block_bed", "rg_W_info", "rg_debug_fetch", "rg_launch_count", "rg_stream",
-    "rg_set_timing", "rg_get_timing", "rg_fence", "rg_s2_set_chr_bt", "rg_s2_block_bgen8_bt", "rg_s2_block_bgen8", "rg_s2_firth", "rg_l1_fit_bt", "rg_W_set_owned", "rg_W_export", "rg_W_attach_peer", "rg_l1_select", "rg_s2_set_sex", "rg_s2_set_non_par", "rg_l0_load_W", "rg_s2_spa",
+    "rg_set_timing", "rg_get_timing", "rg_fence", "rg_s2_set_chr_bt", "rg_s2_block_bgen8_bt", "rg_s2_block_bgen8", "rg_s2_firth", "rg_l1_fit_bt", "rg_W_set_owned", "rg_W_export", "rg_W_attach_peer", "rg_l1_select", "rg_s2_set_sex", "rg_s2_set_non_par", "rg_l0_load_W", "rg_s2_spa", "rg_s2_block_bed_bt",
 ]
 
 _lib = None
@@ -294,6 +294,25 @@ class Step2:
                 None if y_hat_p is None else _f64(y_hat_p)]
         st = S2BtChr(*[None if a is None else a.ctypes.data for a in keep])
         check(L.rg_s2_set_chr_bt(self.h, C.byref(st)))
+
+    def block_bed_bt(self, packed, sample_idx=None, ref_first=False, min_mac=5.0):
+        """Binary traits on 2-bit rows (after set_chr_bt)."""
+        L = lib()
+        L.rg_s2_block_bed_bt.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,
+                                         C.c_double, C.c_void_p]
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        bs, P = packed.shape[0], self.P
+        o = dict(af=np.empty((bs, P)), ns=np.empty((bs, P), dtype=np.int32), mac=np.empty((bs, P)),
+                 af_all=np.empty(bs), ns_all=np.empty(bs, dtype=np.int32), mac_all=np.empty(bs),
+                 flags=np.empty(bs, dtype=np.int32), scale_fac=np.empty(bs), stat=np.empty((bs, P)),
+                 beta=np.empty((bs, P)), se=np.empty((bs, P)), chisq=np.empty((bs, P)))
+        so = S2Out(*[o[k].ctypes.data for k in ("af", "ns", "mac", "af_all", "ns_all", "mac_all", "flags",
+                                                "scale_fac", "stat", "beta", "se", "chisq")])
+        if sample_idx is not None:
+            sample_idx = np.ascontiguousarray(sample_idx, dtype=np.int32)
+        check(L.rg_s2_block_bed_bt(self.h, _ptr(packed), packed.shape[1], bs, _ptr(sample_idx), int(ref_first),
+                                   float(min_mac), C.byref(so)))
+        return o
 
     def block_bgen8(self, probs, missing=None, sample_idx=None, ref_first=False, min_mac=5.0):
         """Quantitative traits on dosages (after set_chr)."""

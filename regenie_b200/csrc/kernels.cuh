@@ -199,6 +199,10 @@ void launch_s2_stats(const uint32_t* gp, int64_t npad, const double* F, int dp, 
                      int rows_p, double* part, double* sums, cudaStream_t s);
 void launch_s2_finalize(const S2FinalizeArgs& a, cudaStream_t s);
 void launch_bed_expand3_fp8(const uint32_t* gp, int rows_p, uint8_t* z, int64_t npad, cudaStream_t s);
+// hard calls for the binary-trait path: tensor sums -> [rows][4][dp] (S1, S2, Sm, 0) + non-zero / hom-alt counts + dz words
+void launch_s2_bt_bed_finish(const float* T, int ldt, int64_t chunk_stride, int nchunk, int rows_p, int dp, int D,
+                             const double* scale, double* sums4, double* nnz, double* n2, cudaStream_t s);
+void launch_gp_to_dz(const uint32_t* gp, int rows_p, uint32_t* dz, int64_t npad, cudaStream_t s);
 void launch_s2_stats_finish(const float* T, int ldt, int64_t chunk_stride, int nchunk, int rows_p, int dp, int D,
                             const double* scale, double* sums, cudaStream_t s);
 
@@ -212,6 +216,7 @@ struct S2BtFinalizeArgs {
   const double* xwy;         // [P][C]  XW^T yres
   const uint8_t* non_par = nullptr;   // see S2FinalizeArgs
   int col_male = -1;
+  double unit = 255.0;                // S1 / S2 / Se are in units of 1/unit (255 for 8-bit dosages, 1 for hard calls)
   const double* nz_count;    // [rows_p] analysed samples with non-zero dosage
   const double* n510;        // [rows_p] analysed samples with dosage exactly 2
   double *af, *mac, *info, *af_all, *mac_all, *scale_fac, *stat, *beta, *se, *chisq, *xtwg, *mu, *den;

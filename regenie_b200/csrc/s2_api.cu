@@ -72,6 +72,63 @@ static void s2_create(rg_ctx* h, const rg_step2_config* cfg, const double* X, co
   RG_CUDA(cudaMemset(h->err_slot.p, 0xFF, 8));
 }
 
+// tensor-core statistics for 2-bit input: digit rows of the chromosome's feature matrix (exact, see s2_kernels.cu)
+static void s2_build_digits(rg_ctx* h, const double* Fdev, int dp, int D) {
+  static const bool f64_only = [] { const char* e = getenv("RG_B200_S2_STATS"); return e && std::string(e) == "f64"; }();
+  h->s2_tc = !f64_only;
+  if (!h->s2_tc) return;
+  cudaStream_t s = h->stream;
+  h->s2_ncol = D;
+  h->s2_drows = (int)round_up((int64_t)ceil_div(D, kStatQ) * 128, 256);
+  h->s2_FD.alloc((size_t)h->s2_drows * h->Npad);
+  h->s2_Fscale.alloc(dp);
+  if (!h->s2_ones.p) {
+    h->s2_ones.alloc(h->Npad);
+    RG_CUDA(cudaMemsetAsync(h->s2_ones.p, 1, h->Npad, s));
+  }
+  RG_CUDA(cudaMemsetAsync(h->s2_FD.p, 0, (size_t)h->s2_drows * h->Npad, s));
+  launch_l0_xy_digits(Fdev, dp, D, h->Npad, h->s2_ones.p, h->s2_Fscale.p, h->s2_FD.p, s);
+  make_gram_tensor_map(&h->s2_tmD, h->s2_FD.p, h->Npad, h->s2_drows);
+  // sample chunks: exact integer sums need 60 * chunk < 2^24; more chunks also fill the SMs
+  const int ntile = (3 * h->rows_p_max / 128) * (h->s2_drows / 256);
+  int64_t nchunk = std::max<int64_t>(ceil_div(h->Npad, (int64_t)262144), ceil_div((int64_t)296, (int64_t)ntile));
+  nchunk = std::max<int64_t>(1, std::min<int64_t>(nchunk, h->Npad / 1024));
+  const int64_t len = round_up(ceil_div(h->Npad, nchunk), 128);
+  std::vector<int2> fk;
+  for (int64_t o = 0; o < h->Npad; o += len)
+    fk.push_back(make_int2((int)(o / 128), (int)(std::min<int64_t>(len, h->Npad - o) / 128)));
+  h->s2_nchunk = (int)fk.size();
+  h->s2_fold_k.alloc(fk.size());
+  RG_CUDA(cudaMemcpyAsync(h->s2_fold_k.p, fk.data(), fk.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+}
+
+// 2-bit rows in h->gp -> S1 / S2 / Sm digit sums in h->s2_T (three e4m3 planes x digit rows, FP8 Gram kernel)
+static void s2_tensor_sums(rg_ctx* h, int rows_p, cudaStream_t s) {
+  const int drows = h->s2_drows;
+  const int64_t Npad = h->Npad;
+  h->s2_z3.alloc((size_t)3 * h->rows_p_max * Npad);
+  h->s2_T.alloc((size_t)h->s2_nchunk * 3 * h->rows_p_max * drows);
+  launch_bed_expand3_fp8(h->gp.p, rows_p, h->s2_z3.p, Npad, s);
+  if (!h->s2_tmZ.count(rows_p)) {
+    CUtensorMap tm;
+    make_gram_tensor_map(&tm, h->s2_z3.p, Npad, 3 * rows_p);
+    h->s2_tmZ[rows_p] = tm;
+  }
+  const int key = rows_p * 4096 + drows / 256;
+  if (!h->s2_tile_lists.count(key)) {
+    std::vector<int2> tiles;
+    for (int nj = 0; nj < drows / 256; ++nj)
+      for (int mi = 0; mi < 3 * rows_p / 128; ++mi) tiles.push_back(make_int2(mi, nj));
+    auto buf = std::make_unique<DevBuf<int2>>();
+    buf->alloc(tiles.size());
+    RG_CUDA(cudaMemcpy(buf->p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    h->s2_ntiles[key] = (int)tiles.size();
+    h->s2_tile_lists[key] = std::move(buf);
+  }
+  launch_gram_tcgen05(h->s2_tmZ[rows_p], h->s2_tmD, h->s2_tile_lists[key]->p, h->s2_ntiles[key], h->s2_fold_k.p,
+                      h->s2_nchunk, h->s2_T.p, drows, (int64_t)3 * rows_p * drows, s);
+}
+
 static void s2_set_chr(rg_ctx* h, const double* res, const double* scf_sv) {
   RG_CHECK(h->kind == 2, "handle is not a Step-2 handle");
   RG_CUDA(cudaSetDevice(h->device));
@@ -109,37 +166,7 @@ static void s2_set_chr(rg_ctx* h, const double* res, const double* scf_sv) {
   RG_CUDA(cudaMemcpyAsync(h->s2_scf.p, scf_sv, P * 8, cudaMemcpyHostToDevice, h->stream));
   h->s2_male_tot.alloc(1 + P);
   RG_CUDA(cudaMemcpyAsync(h->s2_male_tot.p, male_tot.data(), (1 + P) * 8, cudaMemcpyHostToDevice, h->stream));
-  // tensor-core statistics for 2-bit input: digit rows of F for this chromosome (exact, see s2_kernels.cu)
-  {
-    static const bool f64_only = [] { const char* e = getenv("RG_B200_S2_STATS"); return e && std::string(e) == "f64"; }();
-    h->s2_tc = !f64_only;
-    if (h->s2_tc) {
-      cudaStream_t s = h->stream;
-      const int D = base + (with_sex ? 1 + P : 0);
-      h->s2_ncol = D;
-      h->s2_drows = (int)round_up((int64_t)ceil_div(D, kStatQ) * 128, 256);
-      h->s2_FD.alloc((size_t)h->s2_drows * h->Npad);
-      h->s2_Fscale.alloc(dp);
-      if (!h->s2_ones.p) {
-        h->s2_ones.alloc(h->Npad);
-        RG_CUDA(cudaMemsetAsync(h->s2_ones.p, 1, h->Npad, s));
-      }
-      RG_CUDA(cudaMemsetAsync(h->s2_FD.p, 0, (size_t)h->s2_drows * h->Npad, s));
-      launch_l0_xy_digits(h->F.p, dp, D, h->Npad, h->s2_ones.p, h->s2_Fscale.p, h->s2_FD.p, s);
-      make_gram_tensor_map(&h->s2_tmD, h->s2_FD.p, h->Npad, h->s2_drows);
-      // sample chunks: exact integer sums need 60 * chunk < 2^24; more chunks also fill the SMs
-      const int ntile = (3 * h->rows_p_max / 128) * (h->s2_drows / 256);
-      int64_t nchunk = std::max<int64_t>(ceil_div(h->Npad, (int64_t)262144), ceil_div((int64_t)296, (int64_t)ntile));
-      nchunk = std::max<int64_t>(1, std::min<int64_t>(nchunk, h->Npad / 1024));
-      const int64_t len = round_up(ceil_div(h->Npad, nchunk), 128);
-      std::vector<int2> fk;
-      for (int64_t o = 0; o < h->Npad; o += len)
-        fk.push_back(make_int2((int)(o / 128), (int)(std::min<int64_t>(len, h->Npad - o) / 128)));
-      h->s2_nchunk = (int)fk.size();
-      h->s2_fold_k.alloc(fk.size());
-      RG_CUDA(cudaMemcpyAsync(h->s2_fold_k.p, fk.data(), fk.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
-    }
-  }
+  s2_build_digits(h, h->F.p, dp, base + (with_sex ? 1 + P : 0));
   RG_CUDA(cudaStreamSynchronize(h->stream));
 }
 
@@ -192,30 +219,9 @@ static void s2_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
   h->s2_out_i.alloc(ni);
   launch_bed_relayout(packed_d, row_stride, bs, rows_p, h->file_idx_pad.p, h->word_base.p, h->word_keep.p, ref_first, h->gp.p, Npad, s);
   if (h->s2_tc) {
-    const int drows = h->s2_drows;
-    h->s2_z3.alloc((size_t)3 * h->rows_p_max * Npad);
-    h->s2_T.alloc((size_t)h->s2_nchunk * 3 * h->rows_p_max * drows);
-    launch_bed_expand3_fp8(h->gp.p, rows_p, h->s2_z3.p, Npad, s);
-    if (!h->s2_tmZ.count(rows_p)) {
-      CUtensorMap tm;
-      make_gram_tensor_map(&tm, h->s2_z3.p, Npad, 3 * rows_p);
-      h->s2_tmZ[rows_p] = tm;
-    }
-    if (!h->s2_tile_lists.count(rows_p * 4096 + drows / 256)) {
-      std::vector<int2> tiles;
-      for (int nj = 0; nj < drows / 256; ++nj)
-        for (int mi = 0; mi < 3 * rows_p / 128; ++mi) tiles.push_back(make_int2(mi, nj));
-      auto buf = std::make_unique<DevBuf<int2>>();
-      buf->alloc(tiles.size());
-      RG_CUDA(cudaMemcpy(buf->p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice));
-      h->s2_ntiles[rows_p * 4096 + drows / 256] = (int)tiles.size();
-      h->s2_tile_lists[rows_p * 4096 + drows / 256] = std::move(buf);
-    }
-    const int key = rows_p * 4096 + drows / 256;
-    const int64_t cs = (int64_t)3 * rows_p * drows;
-    launch_gram_tcgen05(h->s2_tmZ[rows_p], h->s2_tmD, h->s2_tile_lists[key]->p, h->s2_ntiles[key], h->s2_fold_k.p,
-                        h->s2_nchunk, h->s2_T.p, drows, cs, s);
-    launch_s2_stats_finish(h->s2_T.p, drows, cs, h->s2_nchunk, rows_p, h->dp, h->s2_ncol, h->s2_Fscale.p, h->s2_sums.p, s);
+    s2_tensor_sums(h, rows_p, s);
+    launch_s2_stats_finish(h->s2_T.p, h->s2_drows, (int64_t)3 * rows_p * h->s2_drows, h->s2_nchunk, rows_p, h->dp, h->s2_ncol,
+                           h->s2_Fscale.p, h->s2_sums.p, s);
   } else {
     launch_s2_stats(h->gp.p, Npad, h->F.p, h->dp, h->chunks.p, h->nchunks, rows_p, h->s2_part.p, h->s2_sums.p, s);
   }
@@ -294,6 +300,7 @@ static void s2_set_chr_bt(rg_ctx* h, const rg_s2_bt_chr* st) {
   };
   up(h->bt_F, F); up(h->bt_coltot, coltot); up(h->bt_xwy, xwy); up(h->bt_w, w); up(h->bt_gs, gs);
   up(h->bt_off, off); up(h->bt_xw, xw); up(h->bt_ym, ym); up(h->bt_phat, phat);
+  s2_build_digits(h, h->bt_F.p, dp, base + (with_sex ? 1 + P : 0));        // for rg_s2_block_bed_bt
   RG_CUDA(cudaStreamSynchronize(h->stream));
   h->bt_chr_set = true;
 }
@@ -445,6 +452,77 @@ static void s2_block_bgen8_qt(rg_ctx* h, const uint8_t* probs, const uint8_t* mi
   RG_CUDA(cudaStreamSynchronize(s));
 }
 
+// binary traits on 2-bit hard calls (.bed / .pgen): tensor-core sums, then the same finish as the dosage path
+static void s2_block_bed_bt(rg_ctx* h, const uint8_t* packed, int64_t row_stride, int bs, const int32_t* sample_idx,
+                            int ref_first, double min_mac, const rg_s2_out* out) {
+  RG_CHECK(h->kind == 2, "handle is not a Step-2 handle");
+  RG_CHECK(h->bt_chr_set, "rg_s2_set_chr_bt has not been called");
+  RG_CHECK(h->s2_tc, "rg_s2_block_bed_bt needs the tensor-core statistics (RG_B200_S2_STATS=f64 disables them)");
+  RG_CHECK(bs > 0 && bs <= h->bs_max, "block size out of range");
+  RG_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const int P = h->P, C = h->C, dp = h->bt_dp;
+  const int rows_p = (int)round_up(bs, kRowPad);
+  const int64_t Npad = h->Npad;
+  {
+    std::vector<int32_t> host_idx;
+    if (sample_idx) {
+      host_idx.assign(sample_idx, sample_idx + h->N);
+      if (!h->file_idx_valid || h->cached_sample_idx != host_idx) {
+        build_file_idx_public(h, host_idx.data());
+        h->cached_sample_idx = host_idx;
+      }
+    } else if (!h->file_idx_valid || !h->cached_sample_idx.empty()) {
+      build_file_idx_public(h, nullptr);
+      h->cached_sample_idx.clear();
+    }
+  }
+  const uint8_t* packed_d = packed;
+  if (!is_device_pointer(packed)) {
+    h->packed_dev.alloc((size_t)h->bs_max * row_stride);
+    copy_to_device(h->packed_dev.p, packed, (size_t)bs * row_stride, s);
+    packed_d = h->packed_dev.p;
+  }
+  h->gp.alloc((size_t)h->rows_p_max * (Npad / 16));
+  h->dz.alloc((size_t)h->rows_p_max * Npad);
+  h->bt_sums.alloc((size_t)h->rows_p_max * 4 * dp);
+  h->bt_nnz.alloc(h->rows_p_max); h->bt_n510.alloc(h->rows_p_max);
+  h->bt_xtwg.alloc((size_t)h->bs_max * P * C); h->bt_mu.alloc(h->bs_max); h->bt_info.alloc((size_t)h->bs_max * P);
+  h->bt_den.alloc((size_t)h->bs_max * P);
+  const size_t nd = (size_t)h->bs_max * (7 * (size_t)P + 3), ni = (size_t)h->bs_max * ((size_t)P + 2);
+  h->s2_out_d.alloc(nd);
+  h->s2_out_i.alloc(ni);
+  launch_bed_relayout(packed_d, row_stride, bs, rows_p, h->file_idx_pad.p, h->word_base.p, h->word_keep.p, ref_first, h->gp.p, Npad, s);
+  s2_tensor_sums(h, rows_p, s);
+  launch_s2_bt_bed_finish(h->s2_T.p, h->s2_drows, (int64_t)3 * rows_p * h->s2_drows, h->s2_nchunk, rows_p, dp, h->s2_ncol,
+                          h->s2_Fscale.p, h->bt_sums.p, h->bt_nnz.p, h->bt_n510.p, s);
+  launch_gp_to_dz(h->gp.p, rows_p, h->dz.p, Npad, s);               // what rg_s2_firth / rg_s2_spa read
+  S2BtFinalizeArgs a;
+  a.bs = bs; a.C = C; a.P = P; a.dp = dp; a.with_flip = 1; a.unit = 1.0;
+  a.n_analyzed = h->n_analyzed; a.n_samples = h->N; a.min_mac = min_mac; a.numtol = 1e-6;
+  a.sums = h->bt_sums.p; a.col_tot = h->bt_coltot.p; a.xwy = h->bt_xwy.p; a.nz_count = h->bt_nnz.p; a.n510 = h->bt_n510.p;
+  a.non_par = take_non_par(h, bs); a.col_male = h->bt_col_male;
+  double* d = h->s2_out_d.p;
+  const size_t bp = (size_t)h->bs_max * P, b1 = h->bs_max;
+  a.af = d; a.mac = d + bp; a.stat = d + 2 * bp; a.beta = d + 3 * bp; a.se = d + 4 * bp; a.chisq = d + 5 * bp;
+  a.af_all = d + 6 * bp; a.mac_all = d + 6 * bp + b1; a.scale_fac = d + 6 * bp + 2 * b1;
+  a.info = h->bt_info.p; a.xtwg = h->bt_xtwg.p; a.mu = h->bt_mu.p; a.den = h->bt_den.p;
+  int32_t* ii = h->s2_out_i.p;
+  a.ns = ii; a.ns_all = ii + bp; a.flags = ii + bp + b1;
+  launch_s2_bt_finalize(a, s);
+  h->launches += 7;
+  h->s2_last_bs = bs;
+  const size_t vp = (size_t)bs * P * 8, v1 = (size_t)bs * 8;
+  auto cp = [&](void* dst, const void* src, size_t bytes) {
+    if (dst) RG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+  };
+  cp(out->af, a.af, vp); cp(out->mac, a.mac, vp); cp(out->stat, a.stat, vp); cp(out->beta, a.beta, vp);
+  cp(out->se, a.se, vp); cp(out->chisq, a.chisq, vp); cp(out->af_all, a.af_all, v1); cp(out->mac_all, a.mac_all, v1);
+  cp(out->scale_fac, a.scale_fac, v1); cp(out->ns, a.ns, (size_t)bs * P * 4); cp(out->ns_all, a.ns_all, (size_t)bs * 4);
+  cp(out->flags, a.flags, (size_t)bs * 4);
+  RG_CUDA(cudaStreamSynchronize(s));
+}
+
 static void s2_firth(rg_ctx* h, int n_sel, const int32_t* var_idx, const int32_t* trait_idx, double* beta, double* se,
                      double* lrt, int32_t* status) {
   RG_CHECK(h->kind == 2 && h->bt_chr_set && h->s2_last_bs > 0, "rg_s2_firth needs a resident dosage block");
@@ -562,6 +640,15 @@ int rg_s2_block_bgen8(rg_handle h, const uint8_t* probs, const uint8_t* ploidy_m
   RG_API_BEGIN
   RG_CHECK(h && probs && out, "null argument");
   s2_block_bgen8_qt(h, probs, ploidy_missing, n_file, bs, sample_idx, ref_first, min_mac, out, info_out);
+  RG_CUDA(cudaGetLastError());
+  RG_API_END
+}
+
+int rg_s2_block_bed_bt(rg_handle h, const uint8_t* packed, int64_t row_stride, int32_t bs, const int32_t* sample_idx,
+                       int32_t ref_first, double min_mac, const rg_s2_out* out) {
+  RG_API_BEGIN
+  RG_CHECK(h && packed && out, "null argument");
+  s2_block_bed_bt(h, packed, row_stride, bs, sample_idx, ref_first, min_mac, out);
   RG_CUDA(cudaGetLastError());
   RG_API_END
 }

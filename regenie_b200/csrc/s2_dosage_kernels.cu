@@ -101,7 +101,7 @@ __global__ void s2_bt_finalize_kernel(S2BtFinalizeArgs a) {
   const double* S2 = S1 + dp;
   const double* Sm = S1 + 2 * dp;
   const double* Se = S1 + 3 * dp;
-  const double k = 1.0 / 255.0, k2 = k * k;
+  const double k = 1.0 / a.unit, k2 = k * k;
   const double nm = Sm[0];
   const double ns1 = (double)a.n_analyzed - nm;
   const double total = S1[0] * k;                     // dosage sum over analysed, non-missing samples

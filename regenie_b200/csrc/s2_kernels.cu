@@ -237,6 +237,71 @@ s2_stats_finish_kernel(const float* __restrict__ T, int ldt, int64_t chunk_strid
   o[2 * dp] = out[2];
 }
 
+// binary traits on hard calls: same tensor sums, laid out for s2_bt_finalize_kernel ([row][4][dp]: S1, S2, Sm, Se = 0,
+// unit = 1), plus the counts check_sparse_G needs: non-zero calls n1 + n2 and hom-alt calls n2 from the column of F
+// that flags the analysed samples (n1 = 2 S1 - S2, n2 = (S2 - S1) / 2).  grid: (ceil(dp/128), rows_p), block 128.
+__global__ void __launch_bounds__(128)
+s2_bt_bed_finish_kernel(const float* __restrict__ T, int ldt, int64_t chunk_stride, int nchunk, int rows_p, int dp, int D,
+                        const double* __restrict__ scale, double* __restrict__ sums4, double* __restrict__ nnz,
+                        double* __restrict__ n2o) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  const int i = blockIdx.y;
+  if (c >= dp) return;
+  double out[3] = {0.0, 0.0, 0.0};
+  if (c < D) {
+    const int r0 = (c / kStatQ) * 128 + (c % kStatQ) * kLimbs;
+    const double s = scale[c];
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+      double acc = 0.0;
+#pragma unroll
+      for (int l = kLimbs - 1; l >= 0; --l) {
+        double d = 0.0;
+        for (int ch = 0; ch < nchunk; ++ch) d += (double)T[(int64_t)ch * chunk_stride + (int64_t)(pl * rows_p + i) * ldt + r0 + l];
+        acc = acc * (1.0 / 30.0) + d;
+      }
+      out[pl] = acc * s / 15.0;
+    }
+  }
+  double* o = sums4 + ((int64_t)i * 4) * dp + c;
+  o[0] = out[0];
+  o[dp] = out[1];
+  o[2 * dp] = out[2];
+  o[3 * dp] = 0.0;
+  if (c == 0) {
+    const double hom = (out[1] - out[0]) * 0.5;
+    nnz[i] = (2.0 * out[0] - out[1]) + hom;
+    n2o[i] = hom;
+  }
+}
+
+// 2-bit rows -> the per-sample words the Firth / SPA kernels read (dosage x 255 in bits 0-9, missing in bit 31)
+__global__ void gp_to_dz_kernel(const uint32_t* __restrict__ gp, int64_t words_per_row, uint32_t* __restrict__ dz,
+                                int64_t npad) {
+  const int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int row = blockIdx.y;
+  if (w >= words_per_row) return;
+  const uint32_t word = __ldg(gp + (int64_t)row * words_per_row + w);
+  uint32_t* o = dz + (int64_t)row * npad + w * 16;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const uint32_t code = (word >> (2 * k)) & 3u;
+    o[k] = (code == 3u) ? 0x80000000u : code * 255u;
+  }
+}
+
+void launch_s2_bt_bed_finish(const float* T, int ldt, int64_t chunk_stride, int nchunk, int rows_p, int dp, int D,
+                             const double* scale, double* sums4, double* nnz, double* n2, cudaStream_t s) {
+  dim3 grid((unsigned)ceil_div(dp, 128), rows_p);
+  s2_bt_bed_finish_kernel<<<grid, 128, 0, s>>>(T, ldt, chunk_stride, nchunk, rows_p, dp, D, scale, sums4, nnz, n2);
+}
+
+void launch_gp_to_dz(const uint32_t* gp, int rows_p, uint32_t* dz, int64_t npad, cudaStream_t s) {
+  const int64_t wpr = npad / 16;
+  dim3 grid((unsigned)ceil_div(wpr, 256), rows_p);
+  gp_to_dz_kernel<<<grid, 256, 0, s>>>(gp, wpr, dz, npad);
+}
+
 void launch_bed_expand3_fp8(const uint32_t* gp, int rows_p, uint8_t* z, int64_t npad, cudaStream_t s) {
   const int64_t wpr = npad / 16;
   dim3 grid((unsigned)ceil_div(wpr, 256), rows_p);

@@ -694,8 +694,9 @@ void run_step2_bt(const Params& p, Log& log) {
   }
   const int bsz = p.bsize;
   const int threads = p.threads > 0 ? p.threads : (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
-  std::vector<uint8_t> probs((size_t)bsz * n_file * 2), pmiss((size_t)bsz * n_file), rows;
-  if (!use_bgen) rows.resize((size_t)bsz * gb.row_stride);
+  std::vector<uint8_t> probs, pmiss, rows;
+  if (use_bgen) { probs.resize((size_t)bsz * n_file * 2); pmiss.resize((size_t)bsz * n_file); }
+  else rows.resize((size_t)bsz * gb.row_stride);
   std::vector<double> af((size_t)bsz * P), mac((size_t)bsz * P), stat((size_t)bsz * P), beta((size_t)bsz * P),
       se((size_t)bsz * P), chisq((size_t)bsz * P), info((size_t)bsz * P), af_all(bsz), mac_all(bsz), scale_fac(bsz);
   std::vector<int32_t> ns((size_t)bsz * P), ns_all(bsz), flags(bsz);
@@ -733,20 +734,14 @@ void run_step2_bt(const Params& p, Log& log) {
     if (non_par_flags(p, snps, blocks[b], npf)) rg_check(rg_s2_set_non_par(h, npf.data(), bs));
     if (use_bgen) {
       gg.read_block(blocks[b].first, bs, probs.data(), pmiss.data(), threads);
+      rg_check(rg_s2_block_bgen8_bt(h, probs.data(), pmiss.data(), (int64_t)n_file, bs, subset ? sample_idx.data() : nullptr,
+                                    p.ref_first, p.min_mac, &out, info.data()));
     } else {
-      // hard calls as 8-bit probabilities: 00 hom A1 -> P(AA) = 1, 10 het -> P(AB) = 1, 11 -> 0, 01 missing
+      // hard calls go to the GPU as they are (2 bits per sample)
       gb.read_rows(blocks[b].first, bs, rows.data());
-      for (int v = 0; v < bs; ++v)
-        for (size_t s = 0; s < n_file; ++s) {
-          const int code = (rows[(size_t)v * gb.row_stride + (s >> 2)] >> (2 * (s & 3))) & 3;
-          uint8_t* q = &probs[((size_t)v * n_file + s) * 2];
-          q[0] = code == 0 ? 255 : 0;
-          q[1] = code == 2 ? 255 : 0;
-          pmiss[(size_t)v * n_file + s] = code == 1 ? 0x82 : 0x02;
-        }
+      rg_check(rg_s2_block_bed_bt(h, rows.data(), (int64_t)gb.row_stride, bs, subset ? sample_idx.data() : nullptr,
+                                  p.ref_first, p.min_mac, &out));
     }
-    rg_check(rg_s2_block_bgen8_bt(h, probs.data(), pmiss.data(), (int64_t)n_file, bs, subset ? sample_idx.data() : nullptr,
-                                  p.ref_first, p.min_mac, &out, info.data()));
     // Firth fallback for |z| above the --pThresh threshold (check_pval_snp, src/Step2_Models.cpp:1988-2041)
     std::vector<int32_t> sel_v, sel_t, fstatus;
     std::vector<double> fbeta, fse, flrt;

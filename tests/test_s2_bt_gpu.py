@@ -151,3 +151,66 @@ def test_bt_spa_matches_oracle(golden_dir):
             assert abs(beta - r["beta"]) <= TOL * abs(r["beta"])
     s2.close()
     assert n_spa > 300 and n_fast > 30
+
+
+def test_bt_on_2bit_rows_matches_oracle_and_dosage_path(tmp_path):
+    """rg_s2_block_bed_bt (tensor-core sums on 2-bit rows) vs the oracle and vs the 8-bit dosage path fed the same hard
+    calls: statistics, flip / sparse flags, Firth and SPA on the resident block; N and A1FREQ bit for bit."""
+    from regenie_b200 import capi, synth
+    import helpers
+    from oracle import plink
+    N, M, P = 900, 256, 2
+    g = synth.genotypes(N, M, seed=31, miss=0.02, maf_hi=0.5)
+    g[::5] = np.where(g[::5] == 3, 3, 2 - np.minimum(g[::5], 2))           # some variants coded on the major allele (flip)
+    g[1::4][(np.random.default_rng(1).random(g[1::4].shape) < 0.9) & (g[1::4] != 3)] = 0   # rare / sparse
+    Yq, cov, na = synth.phenotypes(np.where(g == 3, 0, g).astype(np.uint8), P, 3, seed=31, na_frac=0.03)
+    prefix = helpers.write_fileset(str(tmp_path), g, (Yq > 0.3).astype(float), cov, na)
+    keys, _ = plink.read_fam(prefix + ".fam")
+    bim = plink.read_bim(prefix + ".bim")
+    pr = prep.prepare(keys, str(tmp_path) + "/pheno.txt", str(tmp_path) + "/covar.txt", bt=True, step=2)
+    mask, Y = pr.mask, pr.Y_raw
+    rng = np.random.default_rng(3)
+    blup = 0.2 * rng.standard_normal((N, P))
+    sts = [step2_bt.BtChrom(Y[:, j], pr.X, blup[:, j], mask[:, j]) for j in range(P)]
+    s2 = capi.Step2(pr.X, mask, pr.in_analysis, pr.n_analyzed, 256)
+    s2.set_chr_bt(np.stack([s.gamma_sqrt_mask for s in sts], 1), np.stack([s.gamma_sqrt for s in sts], 1),
+                  np.stack([s.yres for s in sts], 1), [s.Xg for s in sts], Y,
+                  np.stack([s.cov_blup_offset for s in sts], 1), np.stack([s.phat for s in sts], 1))
+    packed = plink.read_bed_rows(prefix + ".bed", N, bim.offset)
+    o = s2.block_bed_bt(packed)
+    z_thr = 1.0
+    sel = [(i, j) for i in range(M) for j in range(P)
+           if not (o["flags"][i] & 17) and o["mac"][i, j] >= 5.0 and abs(o["stat"][i, j]) > z_thr]
+    fb, fse, flrt, fst = s2.firth([a for a, _ in sel], [c for _, c in sel])
+    pv, sst = s2.spa([a for a, _ in sel], [c for _, c in sel])
+    # the dosage path on the same calls
+    graw = plink.decode_bed(packed, N)
+    probs = np.zeros((M, N, 2), dtype=np.uint8)
+    probs[:, :, 0] = (graw == 2) * 255
+    probs[:, :, 1] = (graw == 1) * 255
+    miss = np.where(graw == -3, 0x82, 0x02).astype(np.uint8)
+    od = s2.block_bgen8_bt(probs, miss)
+    for k in ("ns", "flags"):
+        assert np.array_equal(o[k], od[k]), k
+    assert np.array_equal(o["af"], od["af"])                                   # bit for bit
+    for k in ("stat", "beta", "se", "mac"):
+        np.testing.assert_allclose(o[k], od[k], rtol=1e-9, atol=1e-12)
+    fmap = {k: n for n, k in enumerate(sel)}
+    n_chk = 0
+    for i in range(M):
+        for j in range(P):
+            r = step2_bt.score_bt(graw[i], np.zeros(N), pr.in_analysis, mask[:, j], Y[:, j], sts[j], z_thr, N)
+            ignored = bool(o["flags"][i] & 17) or o["mac"][i, j] < 5.0
+            assert (r is None) == ignored, (i, j)
+            if r is None:
+                continue
+            assert o["ns"][i, j] == r["n"] and o["af"][i, j] == r["af"]
+            assert abs(o["stat"][i, j] - r["stat"]) <= TOL * max(1.0, abs(r["stat"]))
+            if abs(r["stat"]) > z_thr and not r["test_fail"]:
+                n = fmap[(i, j)]
+                assert (fst[n] & 15) == 0
+                for a, c in zip((fb[n], fse[n], flrt[n]), (r["beta"], r["se"], r["chisq"])):
+                    assert abs(a - c) <= TOL * max(abs(c), 1e-8), (i, j, a, c)
+                n_chk += 1
+    assert n_chk > 50 and (sst & 15).max() == 0 and np.isfinite(pv).all()
+    s2.close()
