@@ -56,3 +56,28 @@ def test_example_3chr_loco(golden_dir):
         assert rel(loco[ph], o["loco"][ph]) < 1e-7
     # chromosomes 4..23 are absent: their rows carry the full prediction
     assert np.allclose(loco[0][:, 3], loco[0][:, 22])
+
+
+def test_fifty_phenotypes_level0_level1(tmp_path):
+    """BASELINE configs[4] trait count (50 quantitative traits): level 0 (5 prediction groups, 4 statistics digit
+    groups), level 1 and LOCO vs the oracle at a size the oracle finishes quickly."""
+    import helpers
+    pb = helpers.synthetic_problem(tmp_path, N=600, M=160, P=50, C=3, bsize=80, K=4, seed=9)
+    st = pb.gpu_step1()
+    nb = len(pb.blocks)
+    for b in range(nb):
+        pb.gpu_l0_block(st, b)
+    assert st.status() == 0
+    for b in (0, nb - 1):
+        W_o = pb.oracle_l0(b)[0]
+        for ph in (0, 17, 49):
+            W = st.fetch_W(b, ph)
+            assert np.abs(W - W_o[ph]).max() / np.abs(W_o[ph]).max() < 1e-9
+    st.close()
+    st, cs, best, loco = full_run(pb)
+    ref = oracle_run(pb)
+    for ph in (0, 23, 49):
+        assert best[ph] == ref["best"][ph]
+        assert rel(cs[:, ph, :], ref["cs"][ph]) < 1e-8
+        assert rel(loco[ph], ref["loco"][ph]) < 1e-7
+    st.close()
