@@ -379,7 +379,7 @@ def run_gpu(args):
         "roofline": {"kernel": "gram_fp8_tcgen05_kernel", "bound": "tensor", "achieved": ach, "peak": peak,
                      "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                      "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-                                     "(profiles/ncu_r1g_key_kernels.txt); algorithmic bytes = 205 MB of Z planes + "
+                                     "(profiles/ncu_r1n_key_kernels.txt); algorithmic bytes = 205 MB of Z planes + "
                                      "47 MB of Gram tiles",
                      "executed_frac": 2.0 * ach / peak, "tensor_pipe_active_ncu": pipe_active,
                      "peak_basis": "2 x %s bf16 cuBLAS rate (%s TF/s) = dense FP8" % (peak_src, peak_bf16),
@@ -440,7 +440,7 @@ def step2_bt_leg(capi, X, in_an, N, C, nvar=400, nblocks=4):
 def gram_traffic_from_profile():
     """DRAM bytes per launch and tensor-pipe activity of the Gram kernel from the committed ncu --set full summary
     (bench.py cannot run under a profiler; the capture command is tools/ncu_capture.sh)."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_r1g_key_kernels.txt")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_r1n_key_kernels.txt")
     try:
         blocks = open(path).read().split("---\n")
     except OSError:
