@@ -15,7 +15,10 @@ Parity status (tests/test_oracle_golden.py):
       - all 1000 rows of example/test_bin_out_firth_Y1.regenie (docs/docs/options.md:20-51):
         BGEN v1.2 decode, A1FREQ / INFO / N, allele flip, sparse/dense switch, BT score test,
         approximate Firth (20 rows), LOG10P, native row format.
-  * "parity unpinned": the QT-only arithmetic (k-fold level 0/1 for QT, compute_score_qt) has
-    no golden vector in the reference's tests; it shares its readers,
-    prep, level-0 algebra, LOCO assembly and printing with the pinned paths.
+      - example/example.pgen decodes to exactly the calls of example/example.bed (the reference ships both
+        for the same 1000 x 500 genotypes): .pgen record decoding, .pvar / .psam parsing.
+  * "parity unpinned": the QT-only arithmetic (k-fold level 0/1 for QT, compute_score_qt), the k-fold
+    logistic level 1 and the saddlepoint approximation (SPA) have no golden vector in the reference's tests
+    (SURVEY.md section 8c); they share their readers, prep, level-0 algebra, null models, LOCO assembly and
+    printing with the pinned paths.
 """
