@@ -22,6 +22,7 @@
 #include "gemm_dmma.cuh"
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "kernels.cuh"
 
@@ -222,6 +223,8 @@ void launch_chol_factor(double* cm, int64_t stride, int nC, int n_aug, int batch
   double* inv_t = inv + (int64_t)batch * inv_stride;      // M^T blocks live behind the M blocks (chol_inv_elems)
   // profiling aid (RG_B200_CHOL_TIMING=1): CUDA-event time of the three kernels of every panel step
   static const bool timing = getenv("RG_B200_CHOL_TIMING") != nullptr;
+  static const char* skip = getenv("RG_DBG_SKIP");                       // profiling aid, see rg_api.cu
+  const bool skip_diag = skip && strstr(skip, "diag"), skip_fused = skip && strstr(skip, "fused");
   static double t_acc[3] = {0, 0, 0};
   static long t_calls = 0;
   cudaEvent_t ev[4];
@@ -236,10 +239,10 @@ void launch_chol_factor(double* cm, int64_t stride, int nC, int n_aug, int batch
     const int k = kb * TB;
     tick(0);
     tick(1);
-    chol_diag_kernel<<<batch, 256, 0, s>>>(cm, stride, nC, k, inv, inv_t, inv_stride, err_slot, err_base);
+    if (!skip_diag) chol_diag_kernel<<<batch, 256, 0, s>>>(cm, stride, nC, k, inv, inv_t, inv_stride, err_slot, err_base);
     tick(2);
     dim3 g2(ntiles - kb - 1, 1, batch);
-    if (ntiles - kb - 1 > 0) chol_update_trsm_kernel<<<g2, 256, 0, s>>>(cm, stride, nC, k, kb, inv_t, inv_stride);
+    if (ntiles - kb - 1 > 0 && !skip_fused) chol_update_trsm_kernel<<<g2, 256, 0, s>>>(cm, stride, nC, k, kb, inv_t, inv_stride);
     tick(3);
     tock();
   }

@@ -245,6 +245,13 @@ void ensure_W(::rg_ctx* h) {
   RG_CUDA(cudaMemcpy(h->W_tab.p, h->W_host_tab.data(), h->P * sizeof(double*), cudaMemcpyHostToDevice));
 }
 
+// profiling aid: RG_DBG_SKIP=<names> drops kernel groups from the pipeline (results are garbage) so the marginal
+// cost of each group under multi-lane overlap can be measured (profiles/ablation_r1.txt)
+static bool dbg_skip(const char* name) {
+  static const char* e = getenv("RG_DBG_SKIP");
+  return e && strstr(e, name) != nullptr;
+}
+
 static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, int bs,
                          const int32_t* sample_idx, int ref_first, int block_id) {
   ensure_W(h);
@@ -340,7 +347,7 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
   }
   {
     ScopedTimer t(h, "bed_expand", s);
-    launch_bed_expand_fp8(L.gp.p, rows_p, L.z.p, Npad, s);
+    if (!dbg_skip("expand")) launch_bed_expand_fp8(L.gp.p, rows_p, L.z.p, Npad, s);
   }
   h->launches += 2;
 
@@ -383,7 +390,7 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
       h->tile_lists[rows_p] = std::move(buf);
     }
     ScopedTimer t(h, "gram_tcgen05", s);
-    launch_gram_tcgen05(L.tmaps[rows_p], L.tmaps[rows_p], h->tile_lists[rows_p]->p, h->tile_counts[rows_p], h->fold_k.p, K,
+    if (!dbg_skip("gram")) launch_gram_tcgen05(L.tmaps[rows_p], L.tmaps[rows_p], h->tile_lists[rows_p]->p, h->tile_counts[rows_p], h->fold_k.p, K,
                         L.zz.p, 2 * rows_p, (int64_t)4 * rows_p * rows_p, s);
     h->launches += 1;
   }
@@ -402,7 +409,7 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
     }
     L.tstat.alloc((size_t)K * 2 * h->rows_p_max * h->stat_drows);
     const int64_t tfs = (int64_t)2 * rows_p * h->stat_drows;
-    launch_gram_tcgen05(L.tmaps[rows_p], h->tmD, h->stat_tile_lists[rows_p]->p, h->stat_tile_counts[rows_p], h->fold_k.p,
+    if (!dbg_skip("stats")) launch_gram_tcgen05(L.tmaps[rows_p], h->tmD, h->stat_tile_lists[rows_p]->p, h->stat_tile_counts[rows_p], h->fold_k.p,
                         K, L.tstat.p, h->stat_drows, tfs, s);
     launch_l0_stats_finish(L.tstat.p, h->stat_drows, tfs, L.zz.p, 2 * rows_p, (int64_t)4 * rows_p * rows_p, rows_p,
                            h->cpp, C + P, K, h->xy_scale.p, L.cnt_fold.p, L.sum_fold.p, s);
@@ -424,7 +431,7 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
   aa.lambda = h->lambda.p; aa.cm = L.cm.p; aa.cm_stride = (int64_t)n_aug * nC; aa.ldc = nC;
   {
     ScopedTimer t(h, "l0_assemble", s);
-    launch_l0_assemble(aa, L.rhs.p, P, Ppad, nmat, s);
+    if (!dbg_skip("assemble")) launch_l0_assemble(aa, L.rhs.p, P, Ppad, nmat, s);
     h->launches += 2;
   }
   if (h->loocv) {
@@ -435,7 +442,7 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
   }
   {
     ScopedTimer t(h, "chol_factor", s);
-    launch_chol_factor(L.cm.p, aa.cm_stride, nC, n_aug, nmat, L.inv.p, h->err_slot.p,
+    if (!dbg_skip("chol")) launch_chol_factor(L.cm.p, aa.cm_stride, nC, n_aug, nmat, L.inv.p, h->err_slot.p,
                        (long long)(1ll << 40) + (long long)block_id * 1024, s);
     h->launches += chol_num_launches(nC);
   }
@@ -453,7 +460,7 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
   }
   {
     ScopedTimer t(h, "chol_backsolve", s);
-    launch_chol_backsolve(L.cm.p, aa.cm_stride, nC, P, nmat, L.inv.p, s);
+    if (!dbg_skip("backsolve")) launch_chol_backsolve(L.cm.p, aa.cm_stride, nC, P, nmat, L.inv.p, s);
     h->launches += 1;
   }
 
@@ -493,7 +500,7 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
       ta.xy = h->xy.p; ta.mask = h->mask.p; ta.W = h->W_tab.p; ta.part = L.part.p;
       ta.dbg = nullptr;
       if (getenv("RG_DBG_CLK")) { h->dbg_clk.alloc((size_t)ntiles_s * ngroups * 4); ta.dbg = h->dbg_clk.p; }
-      launch_l0_predict_tcgen05(L.tmaps[rows_p], L.dmaps[rows_p], ta, ntiles_s, s);
+      if (!dbg_skip("predict")) launch_l0_predict_tcgen05(L.tmaps[rows_p], L.dmaps[rows_p], ta, ntiles_s, s);
       nparts = launch_l0_colsum(h->W_tab.p, Npad, col0, P, Q, Qp, L.part.p, s);
       h->launches += 2;
     }
