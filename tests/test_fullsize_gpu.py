@@ -104,3 +104,46 @@ def test_level0_block_at_n_500k():
         np.testing.assert_allclose((w * w).sum(axis=0), neff[p] - 1.0, rtol=1e-10)
         assert np.array_equal(w, st.fetch_W(1, p))
     st.close()
+
+
+def test_step2_counts_bit_exact_at_n_500k():
+    """Step 2 at N = 500 000 (two sample chunks on the tensor-core path): N and A1FREQ bit for bit vs numpy counts, the
+    test statistic against a direct float64 evaluation of compute_score_qt's dense formula for a few variants."""
+    from regenie_b200 import capi
+    n, m, p = 500_000, 256, 3
+    rng = np.random.default_rng(77)
+    maf = rng.uniform(0.02, 0.5, size=m)
+    g = rng.binomial(2, maf[:, None], size=(m, n)).astype(np.uint8)
+    g[rng.random(size=g.shape) < 0.01] = 3
+    Y = rng.standard_normal((n, p))
+    cov = rng.standard_normal((n, 2))
+    X, Yr, mask, in_an, neff = hostprep.prepare_qt(Y, cov, None)
+    m2 = np.asfortranarray((rng.random((n, p)) > 0.02).astype(np.uint8))
+    res = np.asfortranarray(Yr * m2)
+    st = capi.Step2(X, m2, in_an, n, m)
+    st.set_chr(res, np.ones(p))
+    o = st.block_bed(synth.pack_bed(g))
+    st.close()
+    obs = g != 3
+    gz = np.where(obs, g, 0).astype(np.int64)
+    for j in range(p):
+        mp = m2[:, j].astype(np.int64)
+        ns = obs.astype(np.int64) @ mp
+        assert np.array_equal(o["ns"][:, j], ns)
+        assert np.array_equal(o["af"][:, j], (gz @ mp) / (2.0 * ns))
+    YtX = res.T @ X
+    for i in (0, 100, 255):
+        gi = np.where(obs[i], g[i], gz[i].sum() / obs[i].sum()).astype(np.float64)
+        sparse = (gi != 0).sum() <= n * 0.5                        # check_sparse_G, src/Geno.cpp:3165
+        assert bool(o["flags"][i] & 4) == sparse
+        xtg = X.T @ gi
+        gr = gi - X @ xtg
+        for j in range(p):
+            if sparse:                                             # src/Step2_Models.cpp:404, :410
+                gm = gi * m2[:, j]
+                num = res[:, j] @ gi - YtX[j] @ xtg
+                den = gm @ gm - 2 * (X.T @ gm) @ xtg + xtg @ xtg
+            else:                                                  # :415-416
+                num = res[:, j] @ gr
+                den = (m2[:, j] * gr * gr).sum()
+            assert abs(o["stat"][i, j] - num / np.sqrt(den)) <= 1e-8 * max(1.0, abs(num / np.sqrt(den)))
