@@ -34,42 +34,44 @@ constexpr int TB = 64;  // tile / panel width
 //   P = A[r0:r0+64, k:k+64] - L[r0:, 0:k] L[k:, 0:k]^T,   L[r0:, k:k+64] = P M,   M = L_kk^-T  (both products on the DMMA pipe).
 // The updated tile makes one trip through the CTA's own global tile (L1/L2 resident) instead of a separate kernel.
 // grid: (row tiles below the panel, 1, batch); 256 threads.
+constexpr int PS_LD = TB + 4;                                   // row stride of the staged tile (16-byte aligned rows)
+constexpr size_t kFusedSmem = ((size_t)2 * TB * DM_LD + (size_t)TB * PS_LD) * sizeof(double);
+
 __global__ void __launch_bounds__(256)
 chol_update_trsm_kernel(double* __restrict__ cm, int64_t stride, int ld, int k, int tile0,
                         const double* __restrict__ inv_t, int64_t inv_stride) {
-  __shared__ double As[TB * DM_LD];
-  __shared__ double Bs[TB * DM_LD];
+  extern __shared__ double fused_sm[];
+  double* As = fused_sm;
+  double* Bs = fused_sm + TB * DM_LD;
+  double* Ps = fused_sm + 2 * TB * DM_LD;                       // the updated tile, then the solved tile: no global round trip
   double* A = cm + (int64_t)blockIdx.z * stride;
   const double* MT = inv_t + (int64_t)blockIdx.z * inv_stride + (int64_t)(k / TB) * TB * TB;
   const int r0 = (tile0 + 1 + blockIdx.x) * TB;
   DmmaAcc acc;
-  if (k > 0) {
-    gemm_tile_nt_dmma(A + (int64_t)r0 * ld, ld, true, A + (int64_t)k * ld, ld, true, k, acc, As, Bs);
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        double2* o = reinterpret_cast<double2*>(A + (int64_t)(r0 + dm_row(i)) * ld + k + dm_col(j));
-        double2 v = *o;
-        v.x -= acc.c[i][j][0];
-        v.y -= acc.c[i][j][1];
-        *o = v;
-      }
-  }
-  __syncthreads();             // the updated tile is visible to every thread of this CTA
-  gemm_tile_nt_dmma(A + (int64_t)r0 * ld + k, ld, true, MT, TB, true, TB, acc, As, Bs);
+  gemm_tile_nt_dmma(A + (int64_t)r0 * ld, ld, true, A + (int64_t)k * ld, ld, true, k, acc, As, Bs);   // zero when k == 0
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      *reinterpret_cast<double2*>(A + (int64_t)(r0 + dm_row(i)) * ld + k + dm_col(j)) =
-          make_double2(acc.c[i][j][0], acc.c[i][j][1]);
+    for (int j = 0; j < 4; ++j) {
+      const double2 v = *reinterpret_cast<const double2*>(A + (int64_t)(r0 + dm_row(i)) * ld + k + dm_col(j));
+      *reinterpret_cast<double2*>(Ps + dm_row(i) * PS_LD + dm_col(j)) = make_double2(v.x - acc.c[i][j][0], v.y - acc.c[i][j][1]);
+    }
+  __syncthreads();
+  gemm_tile_nt_dmma(Ps, PS_LD, true, MT, TB, true, TB, acc, As, Bs);                                  // L = P M
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double2 v = make_double2(acc.c[i][j][0], acc.c[i][j][1]);
+      *reinterpret_cast<double2*>(A + (int64_t)(r0 + dm_row(i)) * ld + k + dm_col(j)) = v;
+      *reinterpret_cast<double2*>(Ps + dm_row(i) * PS_LD + dm_col(j)) = v;
+    }
   // keep this row tile's own diagonal block up to date (right-looking for the diagonal blocks only):
   //   A[r0:, r0:] -= L[r0:, k:k+64] L[r0:, k:k+64]^T
   // so a panel step starts with the factorisation of an already updated diagonal tile - no serial update launch.
   if (r0 < ld) {
     __syncthreads();
-    gemm_tile_nt_dmma(A + (int64_t)r0 * ld + k, ld, true, A + (int64_t)r0 * ld + k, ld, true, TB, acc, As, Bs);
+    gemm_tile_nt_dmma(Ps, PS_LD, true, Ps, PS_LD, true, TB, acc, As, Bs);
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -220,6 +222,11 @@ void launch_chol_factor(double* cm, int64_t stride, int nC, int n_aug, int batch
                         unsigned long long* err_slot, long long err_base, cudaStream_t s) {
   const int ntiles = n_aug / TB;
   const int64_t inv_stride = (int64_t)(nC / TB) * TB * TB;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RG_CUDA(cudaFuncSetAttribute(chol_update_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem));
+    attr_set = true;
+  }
   double* inv_t = inv + (int64_t)batch * inv_stride;      // M^T blocks live behind the M blocks (chol_inv_elems)
   // profiling aid (RG_B200_CHOL_TIMING=1): CUDA-event time of the three kernels of every panel step
   static const bool timing = getenv("RG_B200_CHOL_TIMING") != nullptr;
@@ -242,7 +249,7 @@ void launch_chol_factor(double* cm, int64_t stride, int nC, int n_aug, int batch
     if (!skip_diag) chol_diag_kernel<<<batch, 256, 0, s>>>(cm, stride, nC, k, inv, inv_t, inv_stride, err_slot, err_base);
     tick(2);
     dim3 g2(ntiles - kb - 1, 1, batch);
-    if (ntiles - kb - 1 > 0 && !skip_fused) chol_update_trsm_kernel<<<g2, 256, 0, s>>>(cm, stride, nC, k, kb, inv_t, inv_stride);
+    if (ntiles - kb - 1 > 0 && !skip_fused) chol_update_trsm_kernel<<<g2, 256, kFusedSmem, s>>>(cm, stride, nC, k, kb, inv_t, inv_stride);
     tick(3);
     tock();
   }
