@@ -357,6 +357,7 @@ static void l1_fit_bt(rg_ctx* h, const double* y_raw, const double* offset, cons
                       int32_t* best_idx) {
   RG_CHECK(h->kind == 1, "handle is not a Step-1 handle");
   RG_CHECK(h->R1 >= 1 && h->R1 <= kMaxRidge, "n_ridge_l1 out of range");
+  RG_CHECK(h->B <= 6000, "logistic level 1 supports up to 6000 level-0 predictors (blocks x ridge values) in this build");
   RG_CUDA(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
   for (auto& l : h->lanes) RG_CUDA(cudaStreamSynchronize(l->stream));
