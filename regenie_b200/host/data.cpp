@@ -92,10 +92,15 @@ void pgen_read_rows(PgenFile& pg, size_t first, size_t n, uint8_t* out);
 
 void BedFile::read_rows(size_t first, size_t n, uint8_t* out) {
   if (pg) { pgen_read_rows(*pg, first, n, out); return; }
-  for (size_t j = 0; j < n; ++j) {
+  // runs of consecutive file rows (the common case: no --extract holes) are read with one call
+  size_t j = 0;
+  while (j < n) {
+    size_t e = j + 1;
+    while (e < n && snps[first + e].offset == snps[first + e - 1].offset + 1) ++e;
     bed.seekg(3 + snps[first + j].offset * row_stride, std::ios::beg);
-    bed.read(reinterpret_cast<char*>(out + j * row_stride), row_stride);
+    bed.read(reinterpret_cast<char*>(out + j * row_stride), (std::streamsize)((e - j) * row_stride));
     if (!bed) throw Fail("cannot read from bed file.");
+    j = e;
   }
 }
 

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <climits>
 #include <cstdlib>
+#include <future>
 #include <iomanip>
 #include <limits>
 
@@ -306,12 +307,19 @@ void run_step1(const Params& p_in, Log& log) {
       }
     }
   }
+  // a reader thread fetches block b+1 from the file while block b is handed to the GPU (two pageable buffers: the copy
+  // out of a buffer is staged before rg_l0_block_bed returns, so it can be refilled two blocks later)
+  std::vector<uint8_t> rows2(rows.size());
+  uint8_t* bufs[2] = {rows.data(), rows2.data()};
+  std::future<void> pending;
+  auto fetch = [&](int b) { return std::async(std::launch::async, [&, b] { g.read_rows(blocks[b].first, blocks[b].size, bufs[b & 1]); }); };
+  if (nb > 0 && !p.run_l1) pending = fetch(0);
   for (int b = 0; b < nb && !p.run_l1; ++b) {
     if (blocks[b].chrom != last_chr) { log << "Chromosome " << blocks[b].chrom << "\n"; last_chr = blocks[b].chrom; }
-    g.read_rows(blocks[b].first, blocks[b].size, rows.data());
-    rg_check(rg_l0_block_bed(h, rows.data(), (int64_t)g.row_stride, blocks[b].size,
+    pending.get();
+    if (b + 1 < nb) pending = fetch(b + 1);
+    rg_check(rg_l0_block_bed(h, bufs[b & 1], (int64_t)g.row_stride, blocks[b].size,
                              subset ? g.sample_idx.data() : nullptr, p.ref_first, b));
-    // `rows` is pageable memory: the copy is staged before rg_l0_block_bed returns, so it can be reused
     log << " block [" << b + 1 << "] : " << blocks[b].size << " snps\n";
   }
   const int64_t st = rg_l0_status(h);
@@ -393,20 +401,23 @@ void run_step1(const Params& p_in, Log& log) {
     const std::string loco_file = p.out + "_" + std::to_string(ph_i + 1) + ".loco";
     std::ofstream of(loco_file);
     if (!of) throw Fail("cannot write to file : " + loco_file);
-    std::ostringstream buf;
-    buf << "FID_IID ";
-    for (uint32_t i : order) buf << g.keys[i] << " ";
-    buf << "\n";
+    std::string buf;                                         // `ostream << double` == printf("%g") (6 significant digits)
+    buf.reserve((size_t)order.size() * 24 * 12);
+    buf += "FID_IID ";
+    for (uint32_t i : order) { buf += g.keys[i]; buf += ' '; }
+    buf += '\n';
     const double* L = loco.data() + (size_t)ph_i * 23 * N;
+    char num[40];
     for (int c = 0; c < 23; ++c) {
-      buf << c + 1 << " ";
+      buf += std::to_string(c + 1);
+      buf += ' ';
       for (uint32_t i : order) {
-        if (ph.mask[(size_t)ph_i * N + i]) buf << L[(size_t)c * N + i] << " ";
-        else buf << "NA ";
+        if (ph.mask[(size_t)ph_i * N + i]) { buf.append(num, (size_t)snprintf(num, sizeof(num), "%g ", L[(size_t)c * N + i])); }
+        else buf += "NA ";
       }
-      buf << "\n";
+      buf += '\n';
     }
-    of << buf.str();
+    of << buf;
     of.close();
     plist << ph.names[ph_i] << " " << full_path(loco_file, p.rel_path) << "\n";
     log << "  * making predictions...writing LOCO predictions...done\n\n";
