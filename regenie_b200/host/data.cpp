@@ -106,7 +106,7 @@ void BedFile::read_rows(size_t first, size_t n, uint8_t* out) {
 
 // [n x k] table keyed by FID_IID; samples absent from the genotype file are ignored
 static void read_table(const std::string& path, const SampleSet& g, const std::set<std::string>* skip_cols,
-                       std::vector<std::string>& names, std::vector<double>& vals, std::vector<uint8_t>& present) {
+                       const std::set<std::string>* only_cols, std::vector<std::string>& names, std::vector<double>& vals, std::vector<uint8_t>& present) {
   std::ifstream fh(path);
   if (!fh) throw Fail("cannot open file : " + path);
   std::string line;
@@ -115,7 +115,13 @@ static void read_table(const std::string& path, const SampleSet& g, const std::s
   if (hdr.size() < 2 || hdr[0] != "FID" || hdr[1] != "IID") throw Fail("header of file must start with: FID IID.");
   std::vector<int> keep;
   for (size_t i = 2; i < hdr.size(); ++i)
-    if (!skip_cols || !skip_cols->count(hdr[i])) { keep.push_back((int)i); names.push_back(hdr[i]); }
+    if ((!skip_cols || !skip_cols->count(hdr[i])) && (!only_cols || only_cols->empty() || only_cols->count(hdr[i]))) {
+      keep.push_back((int)i);
+      names.push_back(hdr[i]);
+    }
+  if (only_cols)                                           // --phenoCol / --covarCol name a column that must exist
+    for (const auto& c : *only_cols)
+      if (std::find(hdr.begin() + 2, hdr.end(), c) == hdr.end()) throw Fail("column '" + c + "' was not found in file : " + path);
   const size_t n = g.keys.size(), k = keep.size();
   vals.assign(n * k, 0.0);
   present.assign(n, 0);
@@ -139,7 +145,7 @@ void read_pheno_and_cov(const SampleSet& g, const std::string& pheno_file, const
   ph.bt = bt;
   ph.step1 = !step2;
   std::vector<uint8_t> in_ph;
-  read_table(pheno_file, g, nullptr, ph.names, ph.Y, in_ph);
+  read_table(pheno_file, g, nullptr, &ph.pheno_cols, ph.names, ph.Y, in_ph);
   ph.P = (int)ph.names.size();
   if (ph.P < 1) throw Fail("need at least one phenotype.");
   log << " * phenotypes          : [" << pheno_file << "] n_pheno = " << ph.P << "\n";
@@ -174,7 +180,7 @@ void read_pheno_and_cov(const SampleSet& g, const std::string& pheno_file, const
   std::vector<std::string> cnames;
   if (!covar_file.empty()) {
     std::set<std::string> skip(ph.names.begin(), ph.names.end());
-    read_table(covar_file, g, &skip, cnames, cov, in_cov);
+    read_table(covar_file, g, &skip, &ph.covar_cols, cnames, cov, in_cov);
     log << " * covariates          : [" << covar_file << "] n_cov = " << cnames.size() << "\n";
     for (int64_t s = 0; s < N; ++s)
       for (size_t c = 0; c < cnames.size(); ++c)

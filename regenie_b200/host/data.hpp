@@ -64,6 +64,7 @@ struct Pheno {
   bool strict = false;
   bool bt = false, step1 = false;
   std::vector<double> Y_raw;      // N x P raw 0/1 values (binary traits)
+  std::set<std::string> pheno_cols, covar_cols;   // --phenoCol[List] / --covarCol[List] (empty = every column)
 };
 
 // read_pheno_and_cov: raw values + masks, before prep_run

@@ -37,6 +37,9 @@ struct Params {
   double min_mac = 5.0, p_thresh = 0.05;
   int threads = 0;
   std::set<int> chrs;                 // --chr / --chrList
+  std::set<std::string> pheno_cols, covar_cols;   // --phenoCol / --phenoColList / --covarCol / --covarColList
+  double min_info = 0.0;                       // --minINFO (dosage input)
+  bool ignore_pred = false;                    // --ignore-pred: Step 2 without the LOCO offsets
   std::string split_prefix, master;   // --split-l0 PREFIX,N / --run-l0 FILE,K / --run-l1 FILE
   int split_jobs = 0, run_l0_job = 0;
   bool run_l1 = false;
@@ -76,6 +79,15 @@ Params parse_cli(int argc, char** argv) {
     else if (a == "--gpu") p.gpu = atoi(need(i).c_str());
     else if (a == "--threads") p.threads = atoi(need(i).c_str());   // host threads: BGEN inflate only
     else if (a == "--sample") p.sample = need(i);
+    else if (a == "--phenoCol") p.pheno_cols.insert(need(i));
+    else if (a == "--covarCol") p.covar_cols.insert(need(i));
+    else if (a == "--phenoColList" || a == "--covarColList") {
+      std::string v = need(i), tok;
+      std::istringstream ss(v);
+      while (std::getline(ss, tok, ',')) if (!tok.empty()) (a == "--phenoColList" ? p.pheno_cols : p.covar_cols).insert(tok);
+    }
+    else if (a == "--minINFO") p.min_info = atof(need(i).c_str());
+    else if (a == "--ignore-pred") p.ignore_pred = true;
     else if (a == "--split-l0" || a == "--run-l0") {
       const std::string v = need(i);
       const size_t k = v.find_last_of(',');
@@ -118,6 +130,7 @@ Params parse_cli(int argc, char** argv) {
                    "  --step 1|2 --bed PREFIX | --pgen PREFIX | --bgen FILE --phenoFile F [--covarFile F] --bsize N --out PREFIX\n"
                    "  [--pred LIST] [--loocv] [--lowmem] [--cv K] [--l0 R] [--l1 R] [--remove F] [--keep F]\n"
                    "  [--exclude F] [--extract F] [--ref-first] [--minMAC x] [--strict] [--gpu ordinal]\n"
+                   "  [--phenoCol c]... [--phenoColList a,b] [--covarCol c]... [--covarColList a,b] [--minINFO x] [--ignore-pred]\n"
                    "  [--chr c]... [--chrList c1,c2,...]  (Step-2 jobs are split by chromosome like the reference)\n"
                    "  step 2 binary traits: --bt [--firth --approx | --spa] [--pThresh p] with --bed or --bgen F [--sample F]\n";
       exit(0);
@@ -136,7 +149,7 @@ Params parse_cli(int argc, char** argv) {
   if ((p.split_jobs || p.run_l0_job || p.run_l1) && p.step != 1) throw Fail("options --split-l0/--run-l0/--run-l1 only work in step 1.");
   if (p.out.empty()) throw Fail("must specify an output file prefix with --out.");
   if (p.bsize < 1) throw Fail("must specify the block size using '--bsize'.");
-  if (p.step == 2 && p.pred.empty()) throw Fail("must specify --pred if using --step 2.");
+  if (p.step == 2 && p.pred.empty() && !p.ignore_pred) throw Fail("must specify --pred if using --step 2 (otherwise use --ignore-pred).");
   return p;
 }
 
@@ -238,6 +251,7 @@ void run_step1(const Params& p_in, Log& log) {
   if (g.snps.size() > 1000000 && !p.force_step1)
     throw Fail("it is not recommened to use more than 1000000 variants in step 1 (otherwise use '--force-step1').");
   Pheno ph;
+  ph.pheno_cols = p.pheno_cols; ph.covar_cols = p.covar_cols;
   read_pheno_and_cov(SampleSet{g.keys, g.key_to_ind}, p.pheno, p.covar, false, p.strict, p.bt, ph, log);
   prep_run(ph, nullptr, log);
   if (p.bt && !p.loocv) {
@@ -488,8 +502,14 @@ std::map<std::string, std::string> read_pred_list(const std::string& path) {
 
 // phenotypes + covariates + LOCO files for Step 2 (read_pheno_and_cov, blup_read, prep_run)
 void load_step2_inputs(const Params& p, const SampleSet& g, Pheno& ph, std::vector<Loco>& locos, Log& log) {
-  const auto blup_files = read_pred_list(p.pred);
+  ph.pheno_cols = p.pheno_cols; ph.covar_cols = p.covar_cols;
   read_pheno_and_cov(g, p.pheno, p.covar, true, p.strict, p.bt, ph, log);
+  if (p.ignore_pred) {                                      // --ignore-pred: no LOCO files, blup = 0 (src/Pheno.cpp:1060-1068)
+    locos.assign(ph.P, Loco());
+    prep_run(ph, nullptr, log);
+    return;
+  }
+  const auto blup_files = read_pred_list(p.pred);
   const int64_t N = ph.N;
   const int P = ph.P;
   locos.resize(P);
@@ -513,6 +533,7 @@ void load_step2_inputs(const Params& p, const SampleSet& g, Pheno& ph, std::vect
 std::vector<double> blup_for_chr(const Loco& loco, const SampleSet& g, const Pheno& ph, int i, int chrom) {
   const int64_t N = ph.N;
   std::vector<double> blup(N, 0.0);
+  if (loco.rows.empty()) return blup;                       // --ignore-pred
   const auto& row = loco.rows[chrom - 1];
   if (row.empty()) throw Fail("blup file for phenotype '" + ph.names[i] + "' has no row for chromosome " + std::to_string(chrom));
   for (size_t c = 0; c < loco.ids.size(); ++c) {
@@ -640,6 +661,7 @@ void run_step2_qt(const Params& p, Log& log) {
       for (int i = 0; i < P; ++i) {
         const size_t e = (size_t)v * P + i;
         if (mac[e] < p.min_mac) continue;                      // ignored_trait (src/Geno.cpp:3102)
+        if (use_bgen && info[e] < p.min_info) continue;        // --minINFO (src/Geno.cpp:3142-3146)
         std::ostringstream buf;                                // print_sum_stats_single :2502-2540
         buf << head.str() << af[e] << " ";
         if (use_bgen) buf << info[e] << " ";
@@ -795,6 +817,7 @@ void run_step2_bt(const Params& p, Log& log) {
       for (int i = 0; i < P; ++i) {
         const size_t e = (size_t)v * P + i;
         if (mac[e] < p.min_mac) continue;
+        if (use_bgen && info[e] < p.min_info) continue;        // --minINFO
         double bo = beta[e], so = se[e], co = chisq[e];
         bool pass = true;
         auto f = fidx.find({v, i});

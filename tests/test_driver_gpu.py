@@ -443,3 +443,45 @@ def test_step2_bt_spa_driver_vs_oracle(tmp_path, golden_dir):
         for a, c in zip(tx[9:13], row[9:13]):
             assert close(a, c), (tx, row)
     assert k == len(got) and n_spa > 20
+
+
+def test_column_selection_ignore_pred_and_min_info(tmp_path, golden_dir):
+    """--phenoColList / --covarColList pick columns like the reference (a run restricted to Y2 / V1 equals the Y2 file of a
+    run on tables holding only those columns); --ignore-pred runs Step 2 with zero LOCO offsets (== the all-zero .loco
+    files); --minINFO drops rows below the threshold."""
+    d = golden_dir
+    # tables with only Y2 and V1
+    def cut(src, dst, cols):
+        rows = [l.split() for l in open(src)]
+        idx = [0, 1] + [rows[0].index(c) for c in cols]
+        with open(dst, "w") as fh:
+            for r in rows:
+                fh.write(" ".join(r[i] for i in idx) + "\n")
+    cut(d + "/phenotype.txt", str(tmp_path / "ph_y2.txt"), ["Y2"])
+    cut(d + "/covariates.txt", str(tmp_path / "cv_v1.txt"), ["V1"])
+    base = ["--step", "2", "--bgen", d + "/example.bgen", "--bsize", "500", "--ignore-pred"]
+    run(base + ["--phenoFile", d + "/phenotype.txt", "--covarFile", d + "/covariates.txt", "--phenoColList", "Y2",
+                "--covarColList", "V1", "--out", str(tmp_path / "sel")])
+    run(base + ["--phenoFile", str(tmp_path / "ph_y2.txt"), "--covarFile", str(tmp_path / "cv_v1.txt"), "--out",
+                str(tmp_path / "cutf")])
+    a = open(str(tmp_path / "sel_Y2.regenie")).read()
+    assert a == open(str(tmp_path / "cutf_Y2.regenie")).read() and a.count("\n") > 900
+    assert not os.path.exists(str(tmp_path / "sel_Y1.regenie"))
+    # --ignore-pred == zero LOCO predictions
+    pred = _write_zero_loco(tmp_path, d, ["Y1", "Y2"])
+    run(["--step", "2", "--bgen", d + "/example.bgen", "--bsize", "500", "--phenoFile", d + "/phenotype.txt", "--covarFile",
+         d + "/covariates.txt", "--pred", pred, "--out", str(tmp_path / "zero")])
+    run(base + ["--phenoFile", d + "/phenotype.txt", "--covarFile", d + "/covariates.txt", "--out", str(tmp_path / "ign")])
+    for nm in ("Y1", "Y2"):
+        assert open(str(tmp_path / ("zero_%s.regenie" % nm))).read() == open(str(tmp_path / ("ign_%s.regenie" % nm))).read()
+    # --minINFO
+    full = open(str(tmp_path / "ign_Y1.regenie")).read().splitlines()[1:]
+    for thr, tag in (("0.99", "mi_lo"), ("1.01", "mi_hi")):          # example.bgen was made from hard calls: INFO == 1
+        run(base + ["--phenoFile", d + "/phenotype.txt", "--covarFile", d + "/covariates.txt", "--minINFO", thr, "--out",
+                    str(tmp_path / tag)])
+        kept = open(str(tmp_path / (tag + "_Y1.regenie"))).read().splitlines()[1:]
+        assert kept == [l for l in full if float(l.split()[6]) >= float(thr)]
+    assert len(kept) == 0
+    r = subprocess.run([RGB] + base + ["--phenoFile", d + "/phenotype.txt", "--phenoCol", "nope", "--out", str(tmp_path / "x")],
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "column 'nope' was not found" in r.stdout
