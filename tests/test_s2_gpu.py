@@ -73,3 +73,9 @@ def test_s2_qt_strict_single_trait(tmp_path):
 def test_s2_qt_rare_variants_and_mac_filter(tmp_path):
     n, ns = run_case(tmp_path, N=1200, M=300, P=2, miss=0.0, maf_hi=0.02)
     assert ns > 0
+
+
+def test_s2_qt_fifty_traits(tmp_path):
+    """BASELINE configs[4] trait count: 254 feature columns = 19 digit groups = 10 column tiles on the tensor-core path."""
+    n, ns = run_case(tmp_path, N=700, M=256, P=50, miss=0.02)
+    assert n > 200
