@@ -91,7 +91,7 @@ class Prepared:
 
 
 def prepare(keys, pheno_file, covar_file=None, bt=False, step=1, strict=False,
-            pheno_filter=None) -> Prepared:
+            pheno_filter=None, rint=False) -> Prepared:
     """read_pheno_and_cov + prep_run for Step 1 (QT or BT) and Step 2 QT.
 
     For Step 2 the caller applies the LOCO-availability mask and re-runs `finish_prep`.
@@ -128,10 +128,10 @@ def prepare(keys, pheno_file, covar_file=None, bt=False, step=1, strict=False,
         in_cov = in_cov & ~(Cv == MISSING).any(axis=1)           # src/Pheno.cpp:695-698
         X = np.hstack([X, Cv])
     in_an = in_ph & in_cov                                       # src/Pheno.cpp:101
-    return _finish(keys, names, Y, Y_raw, mask, X, in_an, bt, step, strict)
+    return _finish(keys, names, Y, Y_raw, mask, X, in_an, bt, step, strict, rint)
 
 
-def _finish(keys, names, Y, Y_raw, mask, X, in_an, bt, step, strict):
+def _finish(keys, names, Y, Y_raw, mask, X, in_an, bt, step, strict, rint=False):
     # setMasks, src/Pheno.cpp:810-841
     in_an = in_an & (mask.all(axis=1) if strict else mask.any(axis=1))
     mask = mask & in_an[:, None]
@@ -141,6 +141,12 @@ def _finish(keys, names, Y, Y_raw, mask, X, in_an, bt, step, strict):
     X = X * in_an[:, None]
     n_analyzed = int(in_an.sum())
     neff = mask.sum(axis=0).astype(float)
+    if rint and not bt:                                          # apply_rint / rint_pheno, src/Pheno.cpp:1937-2010
+        from scipy.stats import norm, rankdata
+        for j in range(Y.shape[1]):
+            sel = (Y[:, j] != MISSING) & mask[:, j]
+            r = rankdata(Y[sel, j], method="average")
+            Y[sel, j] = norm.ppf((r - 3 / 8.0) / (sel.sum() - 2 * 3 / 8.0 + 1))
 
     # pheno_impute_miss, src/Pheno.cpp:1903-1935
     if (not bt) or step == 1:

@@ -264,6 +264,59 @@ void get_basis(const std::vector<double>& X, int64_t N, int C0, std::vector<doub
   }
 }
 
+// standard normal quantile: Acklam's rational approximation refined by one Halley step on erfc (~1e-16)
+static double qnorm(double p) {
+  static const double a[] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02, 1.383577518672690e+02,
+                             -3.066479806614716e+01, 2.506628277459239e+00};
+  static const double b[] = {-5.447609879822406e+01, 1.615858368580409e+02, -1.556989798598866e+02, 6.680131188771972e+01,
+                             -1.328068155288572e+01};
+  static const double c[] = {-7.784894002430293e-03, -3.223964580411365e-01, -2.400758277161838e+00, -2.549732539343734e+00,
+                             4.374664141464968e+00, 2.938163982698783e+00};
+  static const double d[] = {7.784695709041462e-03, 3.224671290700398e-01, 2.445134137142996e+00, 3.754408661907416e+00};
+  double x;
+  if (p < 0.02425) {
+    const double q = std::sqrt(-2 * std::log(p));
+    x = (((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) / ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1);
+  } else if (p > 1 - 0.02425) {
+    const double q = std::sqrt(-2 * std::log(1 - p));
+    x = -(((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) / ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1);
+  } else {
+    const double q = p - 0.5, r = q * q;
+    x = (((((a[0] * r + a[1]) * r + a[2]) * r + a[3]) * r + a[4]) * r + a[5]) * q /
+        (((((b[0] * r + b[1]) * r + b[2]) * r + b[3]) * r + b[4]) * r + 1);
+  }
+  for (int it = 0; it < 2; ++it) {
+    const double e = 0.5 * std::erfc(-x / std::sqrt(2.0)) - p;
+    const double u = e * std::sqrt(2 * M_PI) * std::exp(x * x / 2);
+    x = x - u / (1 + x * u / 2);
+  }
+  return x;
+}
+
+// rank-based inverse normal transform per phenotype (apply_rint / rint_pheno, src/Pheno.cpp:1937-2010):
+// average ranks for ties, quantile((rank - 3/8) / (n - 2 * 3/8 + 1))
+static void apply_rint(Pheno& ph) {
+  const int64_t N = ph.N;
+  for (int p = 0; p < ph.P; ++p) {
+    std::vector<std::pair<double, int64_t>> v;
+    for (int64_t s = 0; s < N; ++s) {
+      const double y = ph.Y[(size_t)p * N + s];
+      if (y != kMissing && ph.mask[(size_t)p * N + s]) v.emplace_back(y, s);
+    }
+    std::sort(v.begin(), v.end(), [](const std::pair<double, int64_t>& x, const std::pair<double, int64_t>& z) { return x.first < z.first; });
+    const size_t n = v.size();
+    const double kc = 3.0 / 8.0;
+    for (size_t i = 0; i < n;) {
+      size_t e = i + 1;
+      while (e < n && v[e].first == v[i].first) ++e;
+      const double rank = (double)(i + 1) + (double)(e - i - 1) / 2.0;
+      const double q = qnorm((rank - kc) / ((double)n - 2 * kc + 1));
+      for (size_t j = i; j < e; ++j) ph.Y[(size_t)p * N + v[j].second] = q;
+      i = e;
+    }
+  }
+}
+
 // setMasks (src/Pheno.cpp:810-841)
 static void set_masks(Pheno& ph) {
   const int64_t N = ph.N;
@@ -292,6 +345,10 @@ void prep_run(Pheno& ph, const std::vector<uint8_t>* extra_mask, Log& log) {
   const int64_t N = ph.N;
   const int P = ph.P;
   set_masks(ph);                                             // read_pheno_and_cov, src/Pheno.cpp:102
+  if (ph.rint) {                                             // src/Pheno.cpp:111-115
+    log << "   -applying RINT to all phenotypes\n";
+    apply_rint(ph);
+  }
   // pheno_impute_miss, QT (src/Pheno.cpp:1916-1931); binary traits keep the raw 0/1 values in Step 2
   for (int p = 0; p < P && ph.bt && ph.step1; ++p) {         // binary traits in Step 1: mean over the masked-in samples
     double tot = 0.0, ns = 0.0;

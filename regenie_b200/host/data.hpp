@@ -63,6 +63,7 @@ struct Pheno {
   int64_t n_analyzed = 0;
   bool strict = false;
   bool bt = false, step1 = false;
+  bool rint = false;              // --apply-rint
   std::vector<double> Y_raw;      // N x P raw 0/1 values (binary traits)
   std::set<std::string> pheno_cols, covar_cols;   // --phenoCol[List] / --covarCol[List] (empty = every column)
 };

@@ -40,7 +40,7 @@ def write_fileset(d, g, Y, cov, na, n_chr=3, drop_pheno=(), drop_cov=()):
 class Problem:
     """Everything both sides need for a QT Step-1 run on a PLINK fileset."""
 
-    def __init__(self, prefix, pheno, covar, bsize, K=5, loocv=False, remove=None):
+    def __init__(self, prefix, pheno, covar, bsize, K=5, loocv=False, remove=None, rint=False):
         self.bim = plink.read_bim(prefix + ".bim")
         keys_file, _ = plink.read_fam(prefix + ".fam")
         self.n_file = len(keys_file)
@@ -48,7 +48,7 @@ class Problem:
         self.keep = np.array([k not in remove for k in keys_file])
         self.sample_idx = np.nonzero(self.keep)[0].astype(np.int32)
         self.keys = [k for k in keys_file if k not in remove]
-        self.prep = prep.prepare(self.keys, pheno, covar)
+        self.prep = prep.prepare(self.keys, pheno, covar, rint=rint)
         self.blocks = prep.set_blocks(self.bim.chrom, bsize)
         self.bsize = bsize
         self.loocv = loocv

@@ -485,3 +485,26 @@ def test_column_selection_ignore_pred_and_min_info(tmp_path, golden_dir):
     r = subprocess.run([RGB] + base + ["--phenoFile", d + "/phenotype.txt", "--phenoCol", "nope", "--out", str(tmp_path / "x")],
                        capture_output=True, text=True)
     assert r.returncode != 0 and "column 'nope' was not found" in r.stdout
+
+
+def test_apply_rint(tmp_path, golden_dir):
+    """--apply-rint (rank-based inverse normal transform with average ranks for ties, src/Pheno.cpp:1937-2010): the Step-1
+    .loco files vs the oracle run on transformed phenotypes."""
+    prefix = os.path.join(golden_dir, "example_3chr")
+    pheno, covar = golden_dir + "/phenotype.txt", golden_dir + "/covariates.txt"
+    out1 = str(tmp_path / "fit")
+    run(["--step", "1", "--bed", prefix, "--phenoFile", pheno, "--covarFile", covar, "--bsize", "100", "--apply-rint",
+         "--out", out1])
+    pb = helpers.Problem(prefix, pheno, covar, 100, rint=True)
+    def gen():
+        for b in range(len(pb.blocks)):
+            yield pb.oracle_block(b)[0]
+    ref = step1.run_step1_qt(gen(), pb.blocks, pb.prep, pb.fold_sizes, pb.M)
+    for ph in range(pb.prep.Y.shape[1]):
+        rf = str(tmp_path / ("ref_%d.loco" % (ph + 1)))
+        step1.write_loco(rf, pb.keys, pb.prep.in_analysis, pb.prep.mask[:, ph], ref["loco"][ph])
+        compare_token_files(out1 + "_%d.loco" % (ph + 1), rf, exact_cols=1)
+    # and it changes the result
+    run(["--step", "1", "--bed", prefix, "--phenoFile", pheno, "--covarFile", covar, "--bsize", "100", "--out",
+         str(tmp_path / "plain")])
+    assert open(out1 + "_1.loco").read() != open(str(tmp_path / "plain_1.loco")).read()
