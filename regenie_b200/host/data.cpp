@@ -106,7 +106,8 @@ void BedFile::read_rows(size_t first, size_t n, uint8_t* out) {
 
 // [n x k] table keyed by FID_IID; samples absent from the genotype file are ignored
 static void read_table(const std::string& path, const SampleSet& g, const std::set<std::string>* skip_cols,
-                       const std::set<std::string>* only_cols, std::vector<std::string>& names, std::vector<double>& vals, std::vector<uint8_t>& present) {
+                       const std::set<std::string>* only_cols, std::vector<std::string>& names,
+                       const std::set<std::string>* cat_cols, std::vector<std::map<std::string, int>>* cat_levels, std::vector<double>& vals, std::vector<uint8_t>& present) {
   std::ifstream fh(path);
   if (!fh) throw Fail("cannot open file : " + path);
   std::string line;
@@ -123,6 +124,7 @@ static void read_table(const std::string& path, const SampleSet& g, const std::s
     for (const auto& c : *only_cols)
       if (std::find(hdr.begin() + 2, hdr.end(), c) == hdr.end()) throw Fail("column '" + c + "' was not found in file : " + path);
   const size_t n = g.keys.size(), k = keep.size();
+  if (cat_levels) cat_levels->assign(k, {});
   vals.assign(n * k, 0.0);
   present.assign(n, 0);
   while (std::getline(fh, line)) {
@@ -134,7 +136,18 @@ static void read_table(const std::string& path, const SampleSet& g, const std::s
     const size_t s = it->second;
     if (present[s]) throw Fail("individual appears more than once in file: FID=" + t[0] + " IID=" + t[1]);
     present[s] = 1;
-    for (size_t c = 0; c < k; ++c) vals[c * n + s] = convert_double(t[keep[c]]);
+    for (size_t c = 0; c < k; ++c) {
+      const std::string& tok = t[keep[c]];
+      if (cat_cols && cat_cols->count(names[names.size() - k + c])) {        // categorical: level index, NA stays missing
+        if (tok == "NA") { vals[c * n + s] = kMissing; continue; }
+        auto& lv = (*cat_levels)[c];
+        auto it = lv.find(tok);
+        if (it == lv.end()) it = lv.emplace(tok, (int)lv.size()).first;
+        vals[c * n + s] = (double)it->second;
+      } else {
+        vals[c * n + s] = convert_double(tok);
+      }
+    }
   }
 }
 
@@ -145,7 +158,7 @@ void read_pheno_and_cov(const SampleSet& g, const std::string& pheno_file, const
   ph.bt = bt;
   ph.step1 = !step2;
   std::vector<uint8_t> in_ph;
-  read_table(pheno_file, g, nullptr, &ph.pheno_cols, ph.names, ph.Y, in_ph);
+  read_table(pheno_file, g, nullptr, &ph.pheno_cols, ph.names, nullptr, nullptr, ph.Y, in_ph);
   ph.P = (int)ph.names.size();
   if (ph.P < 1) throw Fail("need at least one phenotype.");
   log << " * phenotypes          : [" << pheno_file << "] n_pheno = " << ph.P << "\n";
@@ -180,7 +193,40 @@ void read_pheno_and_cov(const SampleSet& g, const std::string& pheno_file, const
   std::vector<std::string> cnames;
   if (!covar_file.empty()) {
     std::set<std::string> skip(ph.names.begin(), ph.names.end());
-    read_table(covar_file, g, &skip, &ph.covar_cols, cnames, cov, in_cov);
+    std::set<std::string> only = ph.covar_cols;
+    if (!only.empty()) only.insert(ph.cat_cols.begin(), ph.cat_cols.end());   // --catCovarList columns are covariates too
+    std::vector<std::map<std::string, int>> levels;
+    read_table(covar_file, g, &skip, &only, cnames, &ph.cat_cols, &levels, cov, in_cov);
+    for (const auto& c : ph.cat_cols)
+      if (std::find(cnames.begin(), cnames.end(), c) == cnames.end()) throw Fail("column '" + c + "' was not found in file : " + covar_file);
+    // categorical covariates -> K-1 indicator columns (check_categories + get_dummies, src/Pheno.cpp:985-1010, :720-790);
+    // any full-rank coding spans the same space, and only the column space of the covariates enters the analysis
+    if (!ph.cat_cols.empty()) {
+      std::vector<std::string> nn;
+      std::vector<double> ee;
+      for (size_t c = 0; c < cnames.size(); ++c) {
+        if (!ph.cat_cols.count(cnames[c])) {
+          nn.push_back(cnames[c]);
+          ee.insert(ee.end(), cov.begin() + c * N, cov.begin() + (c + 1) * N);
+          continue;
+        }
+        const int L = (int)levels[c].size();
+        if (L > ph.max_cat_levels)
+          throw Fail("too many categories for covariate: " + cnames[c] + " (=" + std::to_string(L) + "). Either use '--maxCatLevels' or combine categories.");
+        if (L == 1) log << "WARNING: covariate ' " << cnames[c] << "' only has a single category so it will be ignored\n";
+        for (int l = 1; l < L; ++l) {
+          nn.push_back(cnames[c] + "_" + std::to_string(l));
+          for (int64_t s = 0; s < N; ++s) {
+            const double v = cov[c * N + s];
+            ee.push_back(v == kMissing ? kMissing : (v == (double)l ? 1.0 : 0.0));
+          }
+        }
+        if (L <= 1)                                            // keep missingness: a sample with NA here is still dropped
+          for (int64_t s = 0; s < N; ++s) if (cov[c * N + s] == kMissing) in_cov[s] = 0;
+      }
+      cnames = nn;
+      cov = ee;
+    }
     log << " * covariates          : [" << covar_file << "] n_cov = " << cnames.size() << "\n";
     for (int64_t s = 0; s < N; ++s)
       for (size_t c = 0; c < cnames.size(); ++c)

@@ -41,6 +41,8 @@ struct Params {
   double min_info = 0.0;                       // --minINFO (dosage input)
   bool ignore_pred = false;                    // --ignore-pred: Step 2 without the LOCO offsets
   bool rint = false;                           // --apply-rint
+  std::set<std::string> cat_cols;              // --catCovarList
+  int max_cat_levels = 10;                     // --maxCatLevels
   std::string split_prefix, master;   // --split-l0 PREFIX,N / --run-l0 FILE,K / --run-l1 FILE
   int split_jobs = 0, run_l0_job = 0;
   bool run_l1 = false;
@@ -90,6 +92,12 @@ Params parse_cli(int argc, char** argv) {
     else if (a == "--minINFO") p.min_info = atof(need(i).c_str());
     else if (a == "--ignore-pred") p.ignore_pred = true;
     else if (a == "--apply-rint") p.rint = true;
+    else if (a == "--catCovarList") {
+      std::string v = need(i), tok;
+      std::istringstream ss(v);
+      while (std::getline(ss, tok, ',')) if (!tok.empty()) p.cat_cols.insert(tok);
+    }
+    else if (a == "--maxCatLevels") p.max_cat_levels = atoi(need(i).c_str());
     else if (a == "--split-l0" || a == "--run-l0") {
       const std::string v = need(i);
       const size_t k = v.find_last_of(',');
@@ -253,7 +261,7 @@ void run_step1(const Params& p_in, Log& log) {
   if (g.snps.size() > 1000000 && !p.force_step1)
     throw Fail("it is not recommened to use more than 1000000 variants in step 1 (otherwise use '--force-step1').");
   Pheno ph;
-  ph.pheno_cols = p.pheno_cols; ph.covar_cols = p.covar_cols; ph.rint = p.rint && !p.bt;
+  ph.pheno_cols = p.pheno_cols; ph.covar_cols = p.covar_cols; ph.rint = p.rint && !p.bt; ph.cat_cols = p.cat_cols; ph.max_cat_levels = p.max_cat_levels;
   read_pheno_and_cov(SampleSet{g.keys, g.key_to_ind}, p.pheno, p.covar, false, p.strict, p.bt, ph, log);
   prep_run(ph, nullptr, log);
   if (p.bt && !p.loocv) {
@@ -504,7 +512,7 @@ std::map<std::string, std::string> read_pred_list(const std::string& path) {
 
 // phenotypes + covariates + LOCO files for Step 2 (read_pheno_and_cov, blup_read, prep_run)
 void load_step2_inputs(const Params& p, const SampleSet& g, Pheno& ph, std::vector<Loco>& locos, Log& log) {
-  ph.pheno_cols = p.pheno_cols; ph.covar_cols = p.covar_cols; ph.rint = p.rint && !p.bt;
+  ph.pheno_cols = p.pheno_cols; ph.covar_cols = p.covar_cols; ph.rint = p.rint && !p.bt; ph.cat_cols = p.cat_cols; ph.max_cat_levels = p.max_cat_levels;
   read_pheno_and_cov(g, p.pheno, p.covar, true, p.strict, p.bt, ph, log);
   if (p.ignore_pred) {                                      // --ignore-pred: no LOCO files, blup = 0 (src/Pheno.cpp:1060-1068)
     locos.assign(ph.P, Loco());

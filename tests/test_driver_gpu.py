@@ -508,3 +508,31 @@ def test_apply_rint(tmp_path, golden_dir):
     run(["--step", "1", "--bed", prefix, "--phenoFile", pheno, "--covarFile", covar, "--bsize", "100", "--out",
          str(tmp_path / "plain")])
     assert open(out1 + "_1.loco").read() != open(str(tmp_path / "plain_1.loco")).read()
+
+
+def test_categorical_covariates(tmp_path, golden_dir):
+    """--catCovarList: a 3-level string covariate gives exactly the run with its K-1 indicator columns written by hand;
+    too many levels are refused like the reference (check_categories, src/Pheno.cpp:985-1010)."""
+    d = golden_dir
+    rows = [l.split() for l in open(d + "/covariates.txt")]
+    rng = np.random.default_rng(2)
+    lv = ["siteA", "siteB", "siteC"]
+    cat = [lv[k] for k in rng.integers(0, 3, len(rows) - 1)]
+    cat[0], cat[1], cat[2] = "siteA", "siteB", "siteC"                 # order of first appearance = A, B, C
+    with open(tmp_path / "cov_cat.txt", "w") as fh:
+        fh.write(" ".join(rows[0] + ["SITE"]) + "\n")
+        for r, c in zip(rows[1:], cat):
+            fh.write(" ".join(r + [c]) + "\n")
+    with open(tmp_path / "cov_dummy.txt", "w") as fh:
+        fh.write(" ".join(rows[0] + ["SITE_1", "SITE_2"]) + "\n")
+        for r, c in zip(rows[1:], cat):
+            fh.write(" ".join(r + [str(int(c == "siteB")), str(int(c == "siteC"))]) + "\n")
+    base = ["--step", "2", "--bed", d + "/example", "--phenoFile", d + "/phenotype.txt", "--bsize", "500", "--ignore-pred"]
+    run(base + ["--covarFile", str(tmp_path / "cov_cat.txt"), "--catCovarList", "SITE", "--out", str(tmp_path / "cat")])
+    run(base + ["--covarFile", str(tmp_path / "cov_dummy.txt"), "--out", str(tmp_path / "dum")])
+    for nm in ("Y1", "Y2"):
+        a = open(str(tmp_path / ("cat_%s.regenie" % nm))).read()
+        assert a == open(str(tmp_path / ("dum_%s.regenie" % nm))).read() and a.count("\n") > 900
+    r = subprocess.run([RGB] + base + ["--covarFile", str(tmp_path / "cov_cat.txt"), "--catCovarList", "SITE", "--maxCatLevels", "2",
+                                       "--out", str(tmp_path / "x")], capture_output=True, text=True)
+    assert r.returncode != 0 and "too many categories for covariate: SITE (=3)" in r.stdout
