@@ -539,6 +539,8 @@ int rg_loco(rg_handle h, const int32_t* chr_of_block, double* pred_out) {
 int rg_W_info(rg_handle h, int32_t ph, void** dev_ptr, int64_t* ld, int64_t* ncols) {
   RG_API_BEGIN
   RG_CHECK(h && h->kind == 1 && ph >= 0 && ph < h->P, "bad argument");
+  RG_CUDA(cudaSetDevice(h->device));
+  ensure_W(h);
   if (dev_ptr) *dev_ptr = h->W_host_tab[ph];
   if (ld) *ld = h->Npad;
   if (ncols) *ncols = h->B;
