@@ -145,7 +145,7 @@ chol_diag_kernel(double* __restrict__ cm, int64_t stride, int ld, int k,
 // contiguous over columns); beta overwrites it.  The diagonal solves are GEMVs with the stored
 // M = L_kk^-T; the sweep  y[:, j] -= L[k+r][j] beta[r]  streams the 64 panel rows once.
 constexpr int BS_THREADS = 256;
-constexpr int BS_JT = 4;        // columns per thread in the sweep (amortises the broadcast beta loads)
+constexpr int BS_JT = 2;        // columns per thread in the sweep (two batches of rows are held in registers)
 constexpr int BS_PC = 10;   // right-hand sides per register pass
 
 __global__ void __launch_bounds__(BS_THREADS)
@@ -176,7 +176,9 @@ chol_backsolve_kernel(double* __restrict__ cm, int64_t stride, int ld, int nC, i
       A[(int64_t)(nC + p) * ld + k + r] = s;
     }
     __syncthreads();
-    // y[p][j] -= sum_r L[k+r][j] * beta[r][p]   for all j < k   (coalesced over j; each thread owns BS_JT columns)
+    // y[p][j] -= sum_r L[k+r][j] * beta[r][p]   for all j < k   (coalesced over j; each thread owns BS_JT columns).
+    // The 64 panel rows are streamed in batches of 8 with the next batch already in flight (software pipelining):
+    // one CTA per system has little else to hide the HBM latency with.
     for (int j0 = threadIdx.x; j0 < k; j0 += BS_THREADS * BS_JT) {
       for (int p0 = 0; p0 < P; p0 += BS_PC) {
         const int np = min(BS_PC, P - p0);
@@ -185,14 +187,22 @@ chol_backsolve_kernel(double* __restrict__ cm, int64_t stride, int ld, int nC, i
         for (int m = 0; m < BS_JT; ++m)
 #pragma unroll
           for (int qq = 0; qq < BS_PC; ++qq) acc[m][qq] = 0.0;
+        double l[BS_JT][8], ln[BS_JT][8];
+#pragma unroll
+        for (int m = 0; m < BS_JT; ++m) {
+          const int j = j0 + m * BS_THREADS;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) l[m][u] = (j < k) ? A[(int64_t)(k + u) * ld + j] : 0.0;
+        }
 #pragma unroll 1
         for (int rb = 0; rb < TB; rb += 8) {
-          double l[BS_JT][8];
+          if (rb + 8 < TB) {
 #pragma unroll
-          for (int m = 0; m < BS_JT; ++m) {
-            const int j = j0 + m * BS_THREADS;
+            for (int m = 0; m < BS_JT; ++m) {
+              const int j = j0 + m * BS_THREADS;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) l[m][u] = (j < k) ? A[(int64_t)(k + rb + u) * ld + j] : 0.0;
+              for (int u = 0; u < 8; ++u) ln[m][u] = (j < k) ? A[(int64_t)(k + rb + 8 + u) * ld + j] : 0.0;
+            }
           }
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
@@ -204,6 +214,10 @@ chol_backsolve_kernel(double* __restrict__ cm, int64_t stride, int ld, int nC, i
               for (int m = 0; m < BS_JT; ++m) acc[m][qq] = fma(l[m][u], bv, acc[m][qq]);
             }
           }
+#pragma unroll
+          for (int m = 0; m < BS_JT; ++m)
+#pragma unroll
+            for (int u = 0; u < 8; ++u) l[m][u] = ln[m][u];
         }
 #pragma unroll
         for (int m = 0; m < BS_JT; ++m) {
