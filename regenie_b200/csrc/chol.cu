@@ -113,7 +113,10 @@ chol_diag_kernel(double* __restrict__ cm, int64_t stride, int ld, int k,
       __syncthreads();      // one barrier per column: the other buffer is only rewritten after the next barrier
       const double piv = cb[buf][c];
       if (!(piv > 0.0)) bad = true;
-      const double inv_p = rsqrt(piv);
+      // 1/sqrt from the FP32 unit + two Newton steps in FP64 (full double accuracy, shorter dependent chain than rsqrt())
+      double inv_p = (double)rsqrtf((float)piv);
+      inv_p = inv_p * (1.5 - 0.5 * piv * inv_p * inv_p);
+      inv_p = inv_p * (1.5 - 0.5 * piv * inv_p * inv_p);
       const double lr = cb[buf][r] * inv_p;      // L[r][c]  (meaningful for r >= c)
       const double xr = xb[buf][r] * inv_p;      // X[r][c] = (L^-T)[r][c]
       if (q == qc) { D[jc] = (r >= c) ? lr : 0.0; T[jc] = xr; }
