@@ -130,6 +130,13 @@ int rg_l1_fit(rg_handle h, const double* tau, double* cumsum, int32_t* best_idx)
 int rg_loco(rg_handle h, const int32_t* chr_of_block, double* pred_out);
 
 /*
+ * rg_prs -- whole-genome predictions of the last rg_loco call: the row sums `predictions[0].rowwise().sum()` that
+ * write_predictions prints with --print-prs (src/Data.cpp:1906-1922).  Host-side copy, no kernel.
+ *   prs_out [P][N]; phenotypes this handle does not fit (rg_l1_select) are zero
+ */
+int rg_prs(rg_handle h, double* prs_out);
+
+/*
  * rg_l1_fit_bt -- binary traits: penalised logistic level 1 with closed-form leave-one-out predictions.
  * LOOCV handles (cfg.loocv = 1): replaces ridge_logistic_level_1_loocv + run_log_ridge_loocv
  * (src/Step1_Models.cpp:1159-1375); rg_loco then performs make_predictions_binary_loocv (src/Data.cpp:1484-1573).

@@ -14,6 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "librg_b200.so")
 DRIVER = os.path.join(HERE, "rgb200")
+PROBE = os.path.join(HERE, "rgb200_hostprobe")     # CPU-only test hook for the host logic (host/probe/)
 
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 NVCC_FLAGS = [
@@ -93,9 +94,23 @@ def build_driver(verbose=False, force=False):
     return DRIVER
 
 
+def build_probe(verbose=False, force=False):
+    """Host sources minus main.cpp plus host/probe/probe_main.cpp; no CUDA library on the link line."""
+    srcs = [s for s in host_sources() if os.path.basename(s) != "main.cpp"]
+    probe_src = os.path.join(HERE, "host", "probe", "probe_main.cpp")
+    gxx = shutil.which("g++")
+    if gxx is None or not os.path.exists(probe_src):
+        return PROBE if os.path.exists(PROBE) else None
+    hdrs = [os.path.join(HERE, "host", f) for f in os.listdir(os.path.join(HERE, "host")) if f.endswith(".hpp")]
+    if force or _newer(srcs + hdrs + [probe_src], PROBE):
+        _run([gxx, "-O2", "-std=c++17", "-Wall", "-o", PROBE, probe_src] + srcs + ["-lz", "-lpthread", "-ldl"], verbose)
+    return PROBE
+
+
 def build_all(verbose=False, force=False):
     build_lib(verbose, force)
     build_driver(verbose, force)
+    build_probe(verbose, force)
 
 
 if __name__ == "__main__":

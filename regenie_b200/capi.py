@@ -47,7 +47,7 @@ EXPORTS = [
     "rg_last_error", "rg_version", "rg_device_count", "rg_step1_create", "rg_destroy", "rg_sync",
     "rg_l0_block_bed", "rg_l0_status", "rg_l0_fetch_W", "rg_l1_fit", "rg_loco", "rg_step2_create",
     "rg_s2_set_chr", "rg_s2_block_bed", "rg_W_info", "rg_debug_fetch", "rg_launch_count", "rg_stream",
-    "rg_set_timing", "rg_get_timing", "rg_fence", "rg_s2_set_chr_bt", "rg_s2_block_bgen8_bt", "rg_s2_block_bgen8", "rg_s2_firth", "rg_l1_fit_bt", "rg_W_set_owned", "rg_W_export", "rg_W_attach_peer", "rg_l1_select", "rg_s2_set_sex", "rg_s2_set_non_par", "rg_l0_load_W", "rg_s2_spa", "rg_s2_block_bed_bt",
+    "rg_set_timing", "rg_get_timing", "rg_fence", "rg_s2_set_chr_bt", "rg_s2_block_bgen8_bt", "rg_s2_block_bgen8", "rg_s2_firth", "rg_l1_fit_bt", "rg_W_set_owned", "rg_W_export", "rg_W_attach_peer", "rg_l1_select", "rg_s2_set_sex", "rg_s2_set_non_par", "rg_l0_load_W", "rg_s2_spa", "rg_s2_block_bed_bt", "rg_prs",
 ]
 
 _lib = None
@@ -76,6 +76,7 @@ def lib():
         L.rg_get_timing.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p]
         L.rg_l1_fit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.rg_loco.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rg_prs.argtypes = [C.c_void_p, C.c_void_p]
         L.rg_W_info.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
@@ -205,6 +206,12 @@ class Step1:
         out = np.zeros((self.P, 23, self.N))          # [P][N x 23] column-major
         check(lib().rg_loco(self.h, _ptr(cb), _ptr(out)))
         return out.transpose(0, 2, 1)                 # -> [P, N, 23]
+
+    def prs(self):
+        """Whole-genome predictions [P, N] of the last loco() call (--print-prs)."""
+        out = np.zeros((self.P, self.N))
+        check(lib().rg_prs(self.h, _ptr(out)))
+        return out
 
     def debug(self, name, dtype, count):
         out = np.empty(count, dtype=dtype)

@@ -94,6 +94,7 @@ struct rg_ctx {
   rg::DevBuf<int32_t> l1_chr_cols;
   rg::DevBuf<double> l1_zrows, l1_hvec, l1_bvec;   // LOOCV: H w_i rows, leverages, coefficients per phenotype
   std::vector<int32_t> best_idx;
+  std::vector<double> prs_host;                      // [P][N] whole-genome predictions kept by rg_loco for rg_prs
   int l1_nC = 0;
   bool l1_done = false;
   rg::DevBuf<double*> W_tab;                         // [P] where each phenotype's W lives (local or peer HBM)

@@ -481,6 +481,7 @@ static void loco(rg_ctx* h, const int32_t* chr_of_block, double* pred_out) {
   RG_CUDA(cudaMemcpyAsync(h->l1_chr_cols.p, col_start.data(), col_start.size() * 4, cudaMemcpyHostToDevice, s));
   h->l1_pred.alloc((size_t)nchr * Npad);
   std::vector<double> pred((size_t)nchr * Npad);
+  h->prs_host.assign((size_t)P * N, 0.0);
   for (int p = 0; p < P; ++p) {
     if (!h->l1_select[p]) continue;
     if (h->l1_bt && h->loocv)
@@ -503,6 +504,7 @@ static void loco(rg_ctx* h, const int32_t* chr_of_block, double* pred_out) {
       const int64_t t = h->pad_of[i];
       double tot = 0.0;
       for (int ci = 0; ci < nchr; ++ci) tot += pred[(size_t)ci * Npad + t];
+      h->prs_host[(size_t)p * N + i] = tot;
       for (int c = 0; c < 23; ++c) out[(size_t)c * N + i] = tot;
       for (int ci = 0; ci < nchr; ++ci) out[(size_t)(chrs[ci] - 1) * N + i] = tot - pred[(size_t)ci * Npad + t];
     }
@@ -533,6 +535,14 @@ int rg_loco(rg_handle h, const int32_t* chr_of_block, double* pred_out) {
   RG_CHECK(h && chr_of_block && pred_out, "null argument");
   loco(h, chr_of_block, pred_out);
   RG_CUDA(cudaGetLastError());
+  RG_API_END
+}
+
+int rg_prs(rg_handle h, double* prs_out) {
+  RG_API_BEGIN
+  RG_CHECK(h && prs_out, "null argument");
+  RG_CHECK(h->kind == 1 && h->prs_host.size() == (size_t)h->P * h->N, "rg_loco must run before rg_prs");
+  memcpy(prs_out, h->prs_host.data(), h->prs_host.size() * sizeof(double));
   RG_API_END
 }
 

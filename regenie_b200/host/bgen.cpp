@@ -1,4 +1,5 @@
 #include "bgen.hpp"
+#include "textio.hpp"
 
 #include <fcntl.h>
 #include <sys/mman.h>
@@ -8,6 +9,7 @@
 
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstring>
 #include <thread>
@@ -30,6 +32,48 @@ void load_zstd() {
   g_zstd_is_error = reinterpret_cast<ZstdIsErrorFn>(dlsym(lib, "ZSTD_isError"));
   if (!g_zstd_decompress || !g_zstd_is_error) throw Fail("libzstd does not export ZSTD_decompress.");
 }
+
+// .bgi index files are SQLite databases (bgenix); the reference reads them through its bundled sqlite3
+// (read_bgi_file, src/Geno.cpp:180-309).  Only the runtime library ships in this image, so the handful of entry points
+// is bound with dlopen, like zstd above.
+struct Sqlite {
+  typedef int (*OpenFn)(const char*, void**, int, const char*);
+  typedef int (*PrepareFn)(void*, const char*, int, void**, const char**);
+  typedef int (*StepFn)(void*);
+  typedef const unsigned char* (*TextFn)(void*, int);
+  typedef long long (*Int64Fn)(void*, int);
+  typedef int (*FinalizeFn)(void*);
+  typedef int (*CloseFn)(void*);
+  typedef const char* (*ErrFn)(void*);
+  OpenFn open = nullptr;
+  PrepareFn prepare = nullptr;
+  StepFn step = nullptr;
+  TextFn text = nullptr;
+  Int64Fn int64 = nullptr;
+  FinalizeFn finalize = nullptr;
+  CloseFn close = nullptr;
+  ErrFn errmsg = nullptr;
+  bool load() {
+    if (open) return true;
+    void* lib = dlopen("libsqlite3.so.0", RTLD_NOW);
+    if (!lib) lib = dlopen("libsqlite3.so", RTLD_NOW);
+    if (!lib) return false;
+    open = reinterpret_cast<OpenFn>(dlsym(lib, "sqlite3_open_v2"));
+    prepare = reinterpret_cast<PrepareFn>(dlsym(lib, "sqlite3_prepare_v2"));
+    step = reinterpret_cast<StepFn>(dlsym(lib, "sqlite3_step"));
+    text = reinterpret_cast<TextFn>(dlsym(lib, "sqlite3_column_text"));
+    int64 = reinterpret_cast<Int64Fn>(dlsym(lib, "sqlite3_column_int64"));
+    finalize = reinterpret_cast<FinalizeFn>(dlsym(lib, "sqlite3_finalize"));
+    close = reinterpret_cast<CloseFn>(dlsym(lib, "sqlite3_close"));
+    errmsg = reinterpret_cast<ErrFn>(dlsym(lib, "sqlite3_errmsg"));
+    if (open && prepare && step && text && int64 && finalize && close && errmsg) return true;
+    open = nullptr;
+    return false;
+  }
+};
+Sqlite g_sqlite;
+constexpr int kSqliteOk = 0, kSqliteRow = 100, kSqliteDone = 101, kSqliteOpenReadonly = 1;
+
 inline uint16_t rd16(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); return v; }
 inline uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 }  // namespace
@@ -41,7 +85,8 @@ BgenFile::~BgenFile() {
 
 void BgenFile::open(const std::string& p, const std::string& sample_file, bool ref_first,
                     const std::set<std::string>& exclude, const std::set<std::string>& extract,
-                    const std::set<std::string>& remove, const std::set<std::string>& keep, const std::set<int>& chrs) {
+                    const std::set<std::string>& remove, const std::set<std::string>& keep, const std::set<int>& chrs,
+                    const std::string& bgi_file, bool no_bgi) {
   path = p;
   fd = ::open(path.c_str(), O_RDONLY);
   if (fd < 0) throw Fail("cannot open file : " + path);
@@ -65,11 +110,10 @@ void BgenFile::open(const std::string& p, const std::string& sample_file, bool r
   if (compression == 2) load_zstd();
   // ---- sample identifiers: embedded block, or --sample (read_bgen_sample, src/Geno.cpp:391-440)
   if (!sample_file.empty()) {
-    std::ifstream fh(sample_file);
-    if (!fh) throw Fail("cannot open file : " + sample_file);
+    LineReader fh(sample_file);
     std::string line;
     int lineno = 0;
-    while (std::getline(fh, line)) {
+    while (fh.getline(line)) {
       auto t = split_ws(line);
       if (t.empty()) continue;
       if (lineno++ < 2) {
@@ -78,6 +122,7 @@ void BgenFile::open(const std::string& p, const std::string& sample_file, bool r
       }
       if (t.size() < 2) throw Fail("incorrectly formatted sample file.");
       keys_file.push_back(t[0] + "_" + t[1]);
+      ids_file.emplace_back(t[0], t[1]);
       sex_file.push_back(t.size() >= 4 ? (t[3] == "1" ? 1 : (t[3] == "2" ? 2 : 0)) : 0);   // src/Geno.cpp:395-456
     }
     if (keys_file.size() != n_file) throw Fail("number of samples in BGEN file does not match that in the sample file.");
@@ -108,11 +153,11 @@ void BgenFile::open(const std::string& p, const std::string& sample_file, bool r
     sample_idx.push_back((int32_t)i);
   }
   if (keys.empty()) throw Fail("no samples left after --keep/--remove.");
-  // ---- variant index
-  size_t pos = (size_t)offset + 4;
+  // ---- variant index: one variant identifying block at file position `pos` (BGEN v1.2 spec); leaves `pos` at the
+  // genotype block and returns false when the variant is filtered out
+  size_t pos = 0;
   auto need = [&](size_t n) { if (pos + n > size) throw Fail("unexpected end of bgen file."); };
-  for (uint32_t v = 0; v < n_variants_file; ++v) {
-    Snp s;
+  auto parse_variant = [&](Snp& s) {
     need(2); uint16_t l = rd16(data + pos); pos += 2 + l;                                 // SNPID
     need(2); l = rd16(data + pos); need(2 + l); s.id.assign(reinterpret_cast<const char*>(data + pos + 2), l); pos += 2 + l;
     need(2); l = rd16(data + pos); need(2 + l);
@@ -133,10 +178,64 @@ void BgenFile::open(const std::string& p, const std::string& sample_file, bool r
     need(4); const uint32_t c = rd32(data + pos);
     need(4 + (size_t)c);
     pos += 4 + (size_t)c;
-    if (!chrs.empty() && !chrs.count(s.chrom)) continue;
-    if (exclude.count(s.id)) continue;
-    if (!extract.empty() && !extract.count(s.id)) continue;
-    snps.push_back(s);
+    if (!chrs.empty() && !chrs.count(s.chrom)) return false;
+    if (exclude.count(s.id)) return false;
+    if (!extract.empty() && !extract.count(s.id)) return false;
+    return true;
+  };
+  // with an index file the variant start positions come from its Variant table (read_bgi_file, src/Geno.cpp:180-309);
+  // the identifying block at each position is still parsed (an O(1) hop in the mapping) because the genotype block
+  // offset is what read_block needs, and it doubles as the reference's consistency check of index against file
+  std::string bgi = bgi_file.empty() ? path + ".bgi" : bgi_file;
+  struct stat bst;
+  const bool have_bgi = !no_bgi && stat(bgi.c_str(), &bst) == 0;
+  if (!bgi_file.empty() && !have_bgi) throw Fail("cannot open file : " + bgi_file);
+  if (have_bgi && g_sqlite.load()) {
+    void *db = nullptr, *stmt = nullptr;
+    if (g_sqlite.open(bgi.c_str(), &db, kSqliteOpenReadonly, nullptr) != kSqliteOk) {
+      const std::string msg = db ? g_sqlite.errmsg(db) : "out of memory";
+      if (db) g_sqlite.close(db);
+      throw Fail("cannot open index file " + bgi + " (" + msg + ")");
+    }
+    if (g_sqlite.prepare(db, "SELECT rsid, file_start_position, size_in_bytes FROM Variant", -1, &stmt, nullptr) != kSqliteOk) {
+      const std::string msg = g_sqlite.errmsg(db);
+      g_sqlite.close(db);
+      throw Fail("failed reading file (" + msg + ").");
+    }
+    std::vector<std::pair<uint64_t, uint64_t>> starts;                                   // (file position, size)
+    std::vector<std::string> ids;
+    int rc;
+    while ((rc = g_sqlite.step(stmt)) == kSqliteRow) {
+      const unsigned char* t = g_sqlite.text(stmt, 0);
+      ids.emplace_back(t ? reinterpret_cast<const char*>(t) : "");
+      starts.emplace_back((uint64_t)g_sqlite.int64(stmt, 1), (uint64_t)g_sqlite.int64(stmt, 2));
+    }
+    const std::string msg = rc == kSqliteDone ? "" : g_sqlite.errmsg(db);
+    g_sqlite.finalize(stmt);
+    g_sqlite.close(db);
+    if (rc != kSqliteDone) throw Fail("failed reading file (" + msg + ").");
+    if (starts.size() != n_variants_file) throw Fail("the bgi index does not match the bgen file (number of variants).");
+    // the Variant table is keyed by (chromosome TEXT, position, ...): rows come back in that order, which is the file
+    // order whenever chromosome names sort like their numbers; blocks need file order, so restore it in any case
+    std::vector<size_t> order(starts.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return starts[a].first < starts[b].first; });
+    for (size_t i : order) {
+      Snp s;
+      pos = (size_t)starts[i].first;
+      if (pos < (size_t)offset + 4) throw Fail("the bgi index does not match the bgen file (variant position).");
+      const bool keep_it = parse_variant(s);
+      if (s.id != ids[i] || pos - (size_t)starts[i].first != (size_t)starts[i].second)
+        throw Fail("the bgi index does not match the bgen file (variant " + ids[i] + ").");
+      if (keep_it) snps.push_back(s);
+    }
+    used_bgi = true;
+    return;
+  }
+  pos = (size_t)offset + 4;
+  for (uint32_t v = 0; v < n_variants_file; ++v) {
+    Snp s;
+    if (parse_variant(s)) snps.push_back(s);
   }
 }
 

@@ -1,7 +1,8 @@
 // BGEN v1.2 reader of the rgb200 host driver (layout 2, zlib / zstd / uncompressed, 8-bit, unphased, biallelic,
 // diploid - the subset the reference's hand parser handles, src/Geno.cpp:2122-2345).  The file header and the
 // variant identifying blocks (which the reference reads through the BGEN library, src/Geno.cpp:38-178) follow
-// the public BGEN v1.2 specification.  The inflated probability bytes go to the GPU unchanged.
+// the public BGEN v1.2 specification; a bgenix index (<file>.bgi, SQLite) supplies the variant positions when present
+// (read_bgi_file, src/Geno.cpp:180-309).  The inflated probability bytes go to the GPU unchanged.
 #pragma once
 #include "data.hpp"
 
@@ -11,6 +12,7 @@ struct BgenFile {
   std::string path;
   std::vector<Snp> snps;                       // after --extract/--exclude; offset = file offset of the genotype block
   std::vector<std::string> keys_file, keys;
+  std::vector<std::pair<std::string, std::string>> ids_file;   // (FID, IID) from --sample; empty for embedded ids
   std::vector<int> sex_file;                   // 1 = male, 2 = female, 0 = unknown (from --sample, else all 0)
   std::vector<int32_t> sample_idx;
   std::map<std::string, uint32_t> key_to_ind;
@@ -22,7 +24,8 @@ struct BgenFile {
   ~BgenFile();
   void open(const std::string& path, const std::string& sample_file, bool ref_first, const std::set<std::string>& exclude,
             const std::set<std::string>& extract, const std::set<std::string>& remove, const std::set<std::string>& keep,
-            const std::set<int>& chrs = {});
+            const std::set<int>& chrs = {}, const std::string& bgi_file = "", bool no_bgi = false);
+  bool used_bgi = false;                       // the variant positions came from <file>.bgi (or --bgi)
   // inflate variants snps[first .. first+n): probs [n][n_file][2], ploidy_missing [n][n_file]
   void read_block(size_t first, size_t n, uint8_t* probs, uint8_t* ploidy_missing, int threads) const;
 };

@@ -1,4 +1,5 @@
 #include "data.hpp"
+#include "textio.hpp"
 
 #include <algorithm>
 #include <cstring>
@@ -8,10 +9,9 @@ namespace rgh {
 std::set<std::string> read_id_list(const std::string& path, int ncols) {
   std::set<std::string> out;
   if (path.empty()) return out;
-  std::ifstream fh(path);
-  if (!fh) throw Fail("cannot open file : " + path);
+  LineReader fh(path);
   std::string line;
-  while (std::getline(fh, line)) {
+  while (fh.getline(line)) {
     auto t = split_ws(line);
     if ((int)t.size() < ncols) continue;
     out.insert(ncols == 2 ? t[0] + "_" + t[1] : t[0]);
@@ -25,13 +25,12 @@ void BedFile::open(const std::string& pfx, bool ref_first, const std::set<std::s
   prefix = pfx;
   // ---- .bim
   {
-    std::ifstream fh(prefix + ".bim");
-    if (!fh) throw Fail("cannot open file : " + prefix + ".bim");
+    LineReader fh(prefix + ".bim");
     std::string line;
     uint64_t lineno = 0;
     int last_chr = 0;
     std::vector<int> chr_seen;
-    while (std::getline(fh, line)) {
+    while (fh.getline(line)) {
       auto t = split_ws(line);
       if (t.size() < 6) throw Fail("incorrectly formatted bim file at line " + std::to_string(lineno + 1));
       Snp s;
@@ -55,17 +54,17 @@ void BedFile::open(const std::string& pfx, bool ref_first, const std::set<std::s
   }
   // ---- .fam
   {
-    std::ifstream fh(prefix + ".fam");
-    if (!fh) throw Fail("cannot open file : " + prefix + ".fam");
+    LineReader fh(prefix + ".fam");
     std::string line;
     std::set<std::string> seen;
-    while (std::getline(fh, line)) {
+    while (fh.getline(line)) {
       auto t = split_ws(line);
       if (t.empty()) continue;
       if (t.size() < 6) throw Fail("incorrectly formatted fam file.");
       const std::string k = t[0] + "_" + t[1];
       if (!seen.insert(k).second) throw Fail("duplicate individual in fam file : FID_IID=" + k);
       keys_file.push_back(k);
+      ids_file.emplace_back(t[0], t[1]);
       sex_file.push_back((t[4] == "1") ? 1 : (t[4] == "2" ? 2 : 0));
     }
   }
@@ -108,10 +107,9 @@ void BedFile::read_rows(size_t first, size_t n, uint8_t* out) {
 static void read_table(const std::string& path, const SampleSet& g, const std::set<std::string>* skip_cols,
                        const std::set<std::string>* only_cols, std::vector<std::string>& names,
                        const std::set<std::string>* cat_cols, std::vector<std::map<std::string, int>>* cat_levels, std::vector<double>& vals, std::vector<uint8_t>& present) {
-  std::ifstream fh(path);
-  if (!fh) throw Fail("cannot open file : " + path);
+  LineReader fh(path);
   std::string line;
-  std::getline(fh, line);
+  fh.getline(line);
   auto hdr = split_ws(line);
   if (hdr.size() < 2 || hdr[0] != "FID" || hdr[1] != "IID") throw Fail("header of file must start with: FID IID.");
   std::vector<int> keep;
@@ -127,7 +125,7 @@ static void read_table(const std::string& path, const SampleSet& g, const std::s
   if (cat_levels) cat_levels->assign(k, {});
   vals.assign(n * k, 0.0);
   present.assign(n, 0);
-  while (std::getline(fh, line)) {
+  while (fh.getline(line)) {
     auto t = split_ws(line);
     if (t.empty()) continue;
     if (t.size() != hdr.size()) throw Fail("incorrectly formatted file : " + path);

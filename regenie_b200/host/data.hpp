@@ -33,6 +33,7 @@ struct BedFile {
   std::shared_ptr<PgenFile> pg;               // set by open_pgen: rows are decoded from a .pgen into the same 2-bit layout
   std::vector<Snp> snps;                      // after --extract/--exclude
   std::vector<std::string> keys_file;         // FID_IID in .fam order
+  std::vector<std::pair<std::string, std::string>> ids_file;   // (FID, IID) in .fam order (--write-samples)
   std::vector<int> sex_file;
   std::vector<std::string> keys;              // after --keep/--remove
   std::vector<int32_t> sample_idx;            // index in the .bed row of each kept sample

@@ -21,6 +21,7 @@
 #include "bgen.hpp"
 #include "bt_null.hpp"
 #include "data.hpp"
+#include "output.hpp"
 #include "pgen.hpp"
 
 using namespace rgh;
@@ -46,6 +47,10 @@ struct Params {
   std::string split_prefix, master;   // --split-l0 PREFIX,N / --run-l0 FILE,K / --run-l1 FILE
   int split_jobs = 0, run_l0_job = 0;
   bool run_l1 = false;
+  bool gz = false;                             // --gz: .loco / .prs / .regenie outputs through zlib (file names gain ".gz")
+  bool write_samples = false, print_pheno = false;   // --write-samples [--print-pheno]: <out>_<pheno>.regenie.ids
+  bool print_prs = false, use_prs = false;     // --print-prs (step 1) / --use-prs (step 2)
+  std::string bgi;                             // --bgi FILE (default: <bgen>.bgi when it exists)
   uint32_t par1_max = 2781479, par2_min = 155701383;   // hg38 (check_build_code, src/Regenie.cpp:1643-1660)
 };
 
@@ -131,7 +136,13 @@ Params parse_cli(int argc, char** argv) {
     else if (a == "--keep-l0") p.keep_l0 = true;
     else if (a == "--ref-first") p.ref_first = true;
     else if (a == "--strict") p.strict = true;
-    else if (a == "--qt") {}
+    else if (a == "--qt" || a == "--force-qt") {}   // QT is the default; 0/1 phenotypes are taken as they are
+    else if (a == "--gz") p.gz = true;
+    else if (a == "--write-samples") p.write_samples = true;
+    else if (a == "--print-pheno") p.print_pheno = true;
+    else if (a == "--print-prs") p.print_prs = true;
+    else if (a == "--use-prs") p.use_prs = true;
+    else if (a == "--bgi") p.bgi = need(i);
     else if (a == "--bt") p.bt = true;
     else if (a == "--force-step1") p.force_step1 = true;
     else if (a == "--use-relative-path") p.rel_path = true;
@@ -142,7 +153,8 @@ Params parse_cli(int argc, char** argv) {
                    "  [--exclude F] [--extract F] [--ref-first] [--minMAC x] [--strict] [--gpu ordinal]\n"
                    "  [--phenoCol c]... [--phenoColList a,b] [--covarCol c]... [--covarColList a,b] [--minINFO x] [--ignore-pred]\n"
                    "  [--chr c]... [--chrList c1,c2,...]  (Step-2 jobs are split by chromosome like the reference)\n"
-                   "  step 2 binary traits: --bt [--firth --approx | --spa] [--pThresh p] with --bed or --bgen F [--sample F]\n";
+                   "  step 2 binary traits: --bt [--firth --approx | --spa] [--pThresh p] with --bed or --bgen F [--sample F] [--bgi F]\n"
+                   "  [--gz] [--print-prs | --use-prs] [--write-samples [--print-pheno]]  (.gz inputs are read by file name)\n";
       exit(0);
     } else {
       throw Fail("option '" + a + "' is outside the hot path covered by rgb200 (see DESIGN.md, out of scope)");
@@ -159,6 +171,8 @@ Params parse_cli(int argc, char** argv) {
   if ((p.split_jobs || p.run_l0_job || p.run_l1) && p.step != 1) throw Fail("options --split-l0/--run-l0/--run-l1 only work in step 1.");
   if (p.out.empty()) throw Fail("must specify an output file prefix with --out.");
   if (p.bsize < 1) throw Fail("must specify the block size using '--bsize'.");
+  if (p.write_samples && !p.bgen.empty() && p.sample.empty())                     // src/Regenie.cpp:903-904
+    throw Fail("must specify sample file (using --sample) if writing sample IDs to file.");
   if (p.step == 2 && p.pred.empty() && !p.ignore_pred) throw Fail("must specify --pred if using --step 2 (otherwise use --ignore-pred).");
   return p;
 }
@@ -403,9 +417,20 @@ void run_step1(const Params& p_in, Log& log) {
 
   // ---- output (Data::output src/Data.cpp:956-1120, write_predictions :1795-1982)
   log << "Output\n------\n";
-  std::ofstream plist(p.out + "_pred.list");
+  std::ofstream plist(p.out + "_pred.list"), prs_list;
+  if (!plist) throw Fail("cannot write to file : " + p.out + "_pred.list");
+  std::vector<double> prs;
+  if (p.print_prs) {                                         // whole-genome PRS next to the LOCO files (src/Data.cpp:1906-1922)
+    prs_list.open(p.out + "_prs.list");
+    if (!prs_list) throw Fail("cannot write to file : " + p.out + "_prs.list");
+    prs.resize((size_t)P * N);
+    rg_check(rg_prs(h, prs.data()));
+  }
+  const std::string gz_ext = p.gz ? ".gz" : "";
   std::vector<uint32_t> order;             // std::map key order of FID_IID, analysed samples only
   for (auto& kv : g.key_to_ind) if (ph.in_analysis[kv.second]) order.push_back(kv.second);
+  std::vector<int> chr_labels(23);
+  for (int c = 0; c < 23; ++c) chr_labels[c] = c + 1;
   for (int ph_i = 0; ph_i < P; ++ph_i) {
     log << "phenotype " << ph_i + 1 << " (" << ph.names[ph_i] << ") : \n";
     auto CS = [&](int k, int j) { return cs[((size_t)k * P + ph_i) * p.l1 + j]; };
@@ -422,29 +447,29 @@ void run_step1(const Params& p_in, Log& log) {
       l << (j == best[ph_i] ? "<- min value" : "");
       log << l.str() << "\n";
     }
-    const std::string loco_file = p.out + "_" + std::to_string(ph_i + 1) + ".loco";
-    std::ofstream of(loco_file);
-    if (!of) throw Fail("cannot write to file : " + loco_file);
-    std::string buf;                                         // `ostream << double` == printf("%g") (6 significant digits)
-    buf.reserve((size_t)order.size() * 24 * 12);
-    buf += "FID_IID ";
-    for (uint32_t i : order) { buf += g.keys[i]; buf += ' '; }
-    buf += '\n';
-    const double* L = loco.data() + (size_t)ph_i * 23 * N;
-    char num[40];
-    for (int c = 0; c < 23; ++c) {
-      buf += std::to_string(c + 1);
-      buf += ' ';
-      for (uint32_t i : order) {
-        if (ph.mask[(size_t)ph_i * N + i]) { buf.append(num, (size_t)snprintf(num, sizeof(num), "%g ", L[(size_t)c * N + i])); }
-        else buf += "NA ";
-      }
-      buf += '\n';
+    const uint8_t* mask_p = &ph.mask[(size_t)ph_i * N];
+    const std::string loco_file = p.out + "_" + std::to_string(ph_i + 1) + ".loco" + gz_ext;
+    {
+      TextWriter of;
+      of.open(loco_file);
+      const double* L = loco.data() + (size_t)ph_i * 23 * N;
+      std::vector<const double*> rows(23);
+      for (int c = 0; c < 23; ++c) rows[c] = L + (size_t)c * N;
+      write_pred_file(of, g.keys, order, mask_p, chr_labels, rows);
+      of.close();
     }
-    of << buf;
-    of.close();
     plist << ph.names[ph_i] << " " << full_path(loco_file, p.rel_path) << "\n";
-    log << "  * making predictions...writing LOCO predictions...done\n\n";
+    log << "  * making predictions...writing LOCO predictions...";
+    if (p.print_prs) {
+      const std::string prs_file = p.out + "_" + std::to_string(ph_i + 1) + ".prs" + gz_ext;
+      TextWriter of;
+      of.open(prs_file);
+      write_pred_file(of, g.keys, order, mask_p, {0}, {prs.data() + (size_t)ph_i * N});
+      of.close();
+      prs_list << ph.names[ph_i] << " " << full_path(prs_file, p.rel_path) << "\n";
+      log << "writing whole genome PRS...";
+    }
+    log << "done\n\n";
   }
   plist.close();
   if (p.run_l1 && !p.keep_l0)                        // rm_l0_files (src/Data.cpp:1131-1147)
@@ -453,81 +478,49 @@ void run_step1(const Params& p_in, Log& log) {
       remove((mj.prefix + ".snplist").c_str());
     }
   log << "List of blup files written to: [" << p.out << "_pred.list]\n";
+  if (p.print_prs) {
+    prs_list.close();
+    log << "List of files with whole genome PRS written to: [" << p.out << "_prs.list]\n";
+  }
   rg_destroy(h);
 }
 
 // ------------------------------------------------------------------------------------ step 2
-struct Loco {
-  std::vector<std::string> ids;
-  std::vector<std::vector<std::string>> rows;   // [23]
-};
-
-Loco read_loco(const std::string& path) {
-  std::ifstream fh(path);
-  if (!fh) throw Fail("cannot open file : " + path);
-  Loco l;
-  std::string line;
-  std::getline(fh, line);
-  l.ids = split_ws(line);
-  if (l.ids.empty() || l.ids[0] != "FID_IID") throw Fail("header of blup file must start with FID_IID.");
-  l.ids.erase(l.ids.begin());
-  l.rows.resize(23);
-  while (std::getline(fh, line)) {
-    auto t = split_ws(line);
-    if (t.empty()) continue;
-    const int c = chr_str_to_int(t[0]);
-    if (c < 1) throw Fail("blup file has an invalid chromosome row: " + t[0]);
-    if (t.size() != l.ids.size() + 1) throw Fail("blup file has different number of entries compared to the header");
-    t.erase(t.begin());
-    l.rows[c - 1] = t;
-  }
-  return l;
-}
-
-double get_logp(double t) {   // src/Regenie.cpp:1843-1857; chi2_1 sf = erfc(sqrt(T/2))
-  if (t < 0 && std::fabs(t) < 1e-6) return 0.0;
-  if (t < 0) return -1.0;
-  const double pv = std::erfc(std::sqrt(t / 2.0));
-  double lp;
-  if (pv == 0) lp = std::log10(2.0) - 0.5 * std::log10(2 * M_PI * t) - 0.5 * t * M_LOG10E;
-  else lp = std::log10(pv);
-  return -lp;
-}
-
-// pred.list (check_blup src/Pheno.cpp:1204-1229)
-std::map<std::string, std::string> read_pred_list(const std::string& path) {
-  std::map<std::string, std::string> blup_files;
-  std::ifstream fh(path);
-  if (!fh) throw Fail("cannot open file : " + path);
-  std::string line;
-  while (std::getline(fh, line)) {
-    auto t = split_ws(line);
-    if (t.empty()) continue;
-    if (t.size() != 2) throw Fail("step 1 list file is not in the right format : " + path);
-    if (blup_files.count(t[0])) throw Fail("phenotype '" + t[0] + "' appears more than once in step 1 list file.");
-    blup_files[t[0]] = t[1];
-  }
-  return blup_files;
-}
-
 // phenotypes + covariates + LOCO files for Step 2 (read_pheno_and_cov, blup_read, prep_run)
-void load_step2_inputs(const Params& p, const SampleSet& g, Pheno& ph, std::vector<Loco>& locos, Log& log) {
+void load_step2_inputs(const Params& p, const SampleSet& g, const std::vector<std::pair<std::string, std::string>>& ids_file,
+                       const std::vector<int32_t>& sample_idx, Pheno& ph, std::vector<Loco>& locos, Log& log) {
   ph.pheno_cols = p.pheno_cols; ph.covar_cols = p.covar_cols; ph.rint = p.rint && !p.bt; ph.cat_cols = p.cat_cols; ph.max_cat_levels = p.max_cat_levels;
   read_pheno_and_cov(g, p.pheno, p.covar, true, p.strict, p.bt, ph, log);
+  const int64_t N = ph.N;
+  const int P = ph.P;
+  // write_ids (src/Pheno.cpp:1538-1576) runs right after blup_read, before setMasks: the samples with a phenotype
+  // value and a prediction
+  auto write_ids = [&](const std::vector<uint8_t>* extra) {
+    if (!p.write_samples) return;
+    log << " * user specified to write sample IDs for each trait\n";
+    std::vector<std::pair<std::string, std::string>> kept(N);
+    for (int64_t s = 0; s < N; ++s) kept[s] = ids_file.at((size_t)sample_idx[s]);
+    std::vector<uint8_t> m(N);
+    for (int i = 0; i < P; ++i) {
+      for (int64_t s = 0; s < N; ++s) m[s] = ph.mask[(size_t)i * N + s] && (!extra || (*extra)[(size_t)i * N + s]);
+      write_ids_file(p.out + "_" + ph.names[i] + ".regenie.ids", ph.names[i], p.print_pheno, kept, m.data());
+    }
+  };
   if (p.ignore_pred) {                                      // --ignore-pred: no LOCO files, blup = 0 (src/Pheno.cpp:1060-1068)
-    locos.assign(ph.P, Loco());
+    log << " * no step 1 predictions given. Simple " << (p.bt ? "logistic" : "linear") << " regression will be performed\n";
+    locos.assign(P, Loco());
+    write_ids(nullptr);
     prep_run(ph, nullptr, log);
     return;
   }
+  log << " * " << (p.use_prs ? "PRS" : "LOCO") << " predictions : [" << p.pred << "]\n";
   const auto blup_files = read_pred_list(p.pred);
-  const int64_t N = ph.N;
-  const int P = ph.P;
   locos.resize(P);
   std::vector<uint8_t> extra((size_t)N * P, 0);
   for (int i = 0; i < P; ++i) {
     auto it = blup_files.find(ph.names[i]);
     if (it == blup_files.end()) throw Fail("No step 1 file provided for phenotype '" + ph.names[i] + "'.");
-    locos[i] = read_loco(it->second);
+    locos[i] = read_loco(it->second, p.use_prs);
     log << "   -file [" << it->second << "] for phenotype '" << ph.names[i] << "'\n";
     const auto& first = locos[i].rows[0];                    // blup_read checks the first data row
     for (size_t c = 0; c < locos[i].ids.size(); ++c) {
@@ -536,6 +529,7 @@ void load_step2_inputs(const Params& p, const SampleSet& g, Pheno& ph, std::vect
       extra[(size_t)i * N + k->second] = first[c] != "NA";
     }
   }
+  write_ids(&extra);
   prep_run(ph, &extra, log);
 }
 
@@ -544,7 +538,7 @@ std::vector<double> blup_for_chr(const Loco& loco, const SampleSet& g, const Phe
   const int64_t N = ph.N;
   std::vector<double> blup(N, 0.0);
   if (loco.rows.empty()) return blup;                       // --ignore-pred
-  const auto& row = loco.rows[chrom - 1];
+  const auto& row = loco.rows[loco.prs ? 0 : chrom - 1];     // --use-prs: the same whole-genome row for every chromosome
   if (row.empty()) throw Fail("blup file for phenotype '" + ph.names[i] + "' has no row for chromosome " + std::to_string(chrom));
   for (size_t c = 0; c < loco.ids.size(); ++c) {
     auto k = g.key_to_ind.find(loco.ids[c]);
@@ -584,7 +578,8 @@ void run_step2_qt(const Params& p, Log& log) {
   const auto excl = read_id_list(p.exclude, 1), extr = read_id_list(p.extract, 1), rem = read_id_list(p.remove, 2),
              keepl = read_id_list(p.keep, 2);
   if (use_bgen) {
-    gg.open(p.bgen, p.sample, p.ref_first, excl, extr, rem, keepl, p.chrs);
+    gg.open(p.bgen, p.sample, p.ref_first, excl, extr, rem, keepl, p.chrs, p.bgi);
+    if (gg.used_bgi) log << "   -index bgi file [" << (p.bgi.empty() ? p.bgen + ".bgi" : p.bgi) << "]\n";
     log << " * bgen                : [" << p.bgen << "] n_snps = " << gg.snps.size() << ", n_samples = " << gg.keys.size() << "\n";
   } else {
     open_rows(p, g, excl, extr, rem, keepl, log);
@@ -596,7 +591,7 @@ void run_step2_qt(const Params& p, Log& log) {
   const SampleSet ss{keys, use_bgen ? gg.key_to_ind : g.key_to_ind};
   Pheno ph;
   std::vector<Loco> locos;
-  load_step2_inputs(p, ss, ph, locos, log);
+  load_step2_inputs(p, ss, use_bgen ? gg.ids_file : g.ids_file, sample_idx, ph, locos, log);
   const int64_t N = ph.N;
   const int P = ph.P;
   const auto blocks = set_blocks(snps, p.bsize);
@@ -609,11 +604,10 @@ void run_step2_qt(const Params& p, Log& log) {
   rg_handle h = nullptr;
   rg_check(rg_step2_create(&cfg, ph.X.data(), ph.mask.data(), ph.in_analysis.data(), &h));
 
-  std::vector<std::ofstream> outs(P);
+  std::vector<TextWriter> outs(P);                          // setup_output, split mode (src/Data.cpp:2026-2035)
   for (int i = 0; i < P; ++i) {
-    outs[i].open(p.out + "_" + ph.names[i] + ".regenie");
-    if (!outs[i]) throw Fail("cannot write to file : " + p.out + "_" + ph.names[i] + ".regenie");
-    outs[i] << "CHROM GENPOS ID ALLELE0 ALLELE1 A1FREQ " << (use_bgen ? "INFO " : "") << "N TEST BETA SE CHISQ LOG10P EXTRA\n";
+    outs[i].open(p.out + "_" + ph.names[i] + ".regenie" + (p.gz ? ".gz" : ""));
+    outs[i] << sumstats_header(use_bgen);
   }
   const int bsz = p.bsize;
   std::vector<uint8_t> rows, probs, pmiss;
@@ -672,21 +666,13 @@ void run_step2_qt(const Params& p, Log& log) {
         const size_t e = (size_t)v * P + i;
         if (mac[e] < p.min_mac) continue;                      // ignored_trait (src/Geno.cpp:3102)
         if (use_bgen && info[e] < p.min_info) continue;        // --minINFO (src/Geno.cpp:3142-3146)
-        std::ostringstream buf;                                // print_sum_stats_single :2502-2540
-        buf << head.str() << af[e] << " ";
-        if (use_bgen) buf << info[e] << " ";
-        buf << ns[e] << " ADD ";
-        if (se[e] >= 0 && !std::isnan(se[e])) buf << beta[e] << ' ' << se[e];
-        else buf << "NA NA";
-        const double lp = get_logp(chisq[e]);
-        if (chisq[e] >= 0 && !std::isnan(lp)) buf << ' ' << chisq[e] << ' ' << lp;
-        else buf << " NA NA";
-        buf << " NA\n";
-        outs[i] << buf.str();
+        outs[i] << sumstats_row(head.str(), af[e], use_bgen, use_bgen ? info[e] : -1.0, ns[e], "ADD", beta[e], se[e], chisq[e],
+                                get_logp(chisq[e]), true);   // print_sum_stats_single :2502-2540
       }
     }
     log << " block [" << b + 1 << "/" << blocks.size() << "] : done\n";
   }
+  for (auto& o : outs) o.close();
   log << "\nNumber of ignored tests due to low MAC or low variance : " << n_ignored << "\n";
   rg_destroy(h);
 }
@@ -701,7 +687,8 @@ void run_step2_bt(const Params& p, Log& log) {
   const auto excl = read_id_list(p.exclude, 1), extr = read_id_list(p.extract, 1), rem = read_id_list(p.remove, 2),
              keep = read_id_list(p.keep, 2);
   if (use_bgen) {
-    gg.open(p.bgen, p.sample, p.ref_first, excl, extr, rem, keep, p.chrs);
+    gg.open(p.bgen, p.sample, p.ref_first, excl, extr, rem, keep, p.chrs, p.bgi);
+    if (gg.used_bgi) log << "   -index bgi file [" << (p.bgi.empty() ? p.bgen + ".bgi" : p.bgi) << "]\n";
     log << " * bgen                : [" << p.bgen << "] n_snps = " << gg.snps.size() << ", n_samples = " << gg.keys.size() << "\n";
   } else {
     open_rows(p, gb, excl, extr, rem, keep, log);
@@ -713,7 +700,7 @@ void run_step2_bt(const Params& p, Log& log) {
   const SampleSet ss{keys, use_bgen ? gg.key_to_ind : gb.key_to_ind};
   Pheno ph;
   std::vector<Loco> locos;
-  load_step2_inputs(p, ss, ph, locos, log);
+  load_step2_inputs(p, ss, use_bgen ? gg.ids_file : gb.ids_file, sample_idx, ph, locos, log);
   const int64_t N = ph.N;
   const int P = ph.P, C = ph.C;
   const auto blocks = set_blocks(snps, p.bsize);
@@ -729,11 +716,10 @@ void run_step2_bt(const Params& p, Log& log) {
   rg_handle h = nullptr;
   rg_check(rg_step2_create(&cfg, ph.X.data(), ph.mask.data(), ph.in_analysis.data(), &h));
 
-  std::vector<std::ofstream> outs(P);
+  std::vector<TextWriter> outs(P);                          // setup_output, split mode (src/Data.cpp:2026-2035)
   for (int i = 0; i < P; ++i) {
-    outs[i].open(p.out + "_" + ph.names[i] + ".regenie");
-    if (!outs[i]) throw Fail("cannot write to file : " + p.out + "_" + ph.names[i] + ".regenie");
-    outs[i] << "CHROM GENPOS ID ALLELE0 ALLELE1 A1FREQ " << (use_bgen ? "INFO " : "") << "N TEST BETA SE CHISQ LOG10P EXTRA\n";
+    outs[i].open(p.out + "_" + ph.names[i] + ".regenie" + (p.gz ? ".gz" : ""));
+    outs[i] << sumstats_header(use_bgen);
   }
   const int bsz = p.bsize;
   const int threads = p.threads > 0 ? p.threads : (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
@@ -835,22 +821,14 @@ void run_step2_bt(const Params& p, Log& log) {
           if ((fstatus[f->second] & 15) == 0) { bo = fbeta[f->second]; so = fse[f->second]; co = flrt[f->second]; }
           else { pass = false; ++n_fail; }
         }
-        std::ostringstream buf;
-        buf << head.str() << af[e] << " ";
-        if (use_bgen) buf << info[e] << " ";
-        buf << ns[e] << " ADD ";
-        if (so >= 0 && !std::isnan(so)) buf << bo << ' ' << so;
-        else buf << "NA NA";
         double lp = get_logp(co);
         if (p.spa && pass && f != fidx.end()) lp = spa_logp[{v, i}];   // SPA reports -log10 of its own p-value
-        if (pass && co >= 0 && !std::isnan(lp)) buf << ' ' << co << ' ' << lp;
-        else buf << " NA NA";
-        buf << (pass ? " NA\n" : " TEST_FAIL\n");
-        outs[i] << buf.str();
+        outs[i] << sumstats_row(head.str(), af[e], use_bgen, use_bgen ? info[e] : -1.0, ns[e], "ADD", bo, so, co, lp, pass);
       }
     }
     log << " block [" << b + 1 << "/" << blocks.size() << "] : done\n";
   }
+  for (auto& o : outs) o.close();
   log << "\nNumber of ignored tests due to low MAC or low variance : " << n_ignored << "\n";
   if (p.firth) log << "Number of tests with Firth correction : " << n_firth << " (" << n_fail << " failed)\n";
   if (p.spa) log << "Number of tests with SPA correction : " << n_firth << " (" << n_fail << " failed)\n";

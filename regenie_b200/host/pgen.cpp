@@ -1,4 +1,5 @@
 #include "pgen.hpp"
+#include "textio.hpp"
 
 #include <cstring>
 
@@ -24,13 +25,12 @@ void PgenFile::open(const std::string& pfx, const std::set<std::string>& exclude
   prefix = pfx;
   // ---- .psam (src/Geno.cpp:941-1011)
   {
-    std::ifstream fh(prefix + ".psam");
-    if (!fh) throw Fail("cannot open file : " + prefix + ".psam");
+    LineReader fh(prefix + ".psam");
     std::string line;
     int sex_col = -1;
     bool header = true;
     std::set<std::string> seen;
-    while (std::getline(fh, line)) {
+    while (fh.getline(line)) {
       auto t = split_ws(line);
       if (t.empty()) continue;
       if (header) {
@@ -43,6 +43,7 @@ void PgenFile::open(const std::string& pfx, const std::set<std::string>& exclude
       const std::string k = t[0] + "_" + t[1];
       if (!seen.insert(k).second) throw Fail("duplicate individual in psam file : FID_IID=" + k);
       keys_file.push_back(k);
+      ids_file.emplace_back(t[0], t[1]);
       int sx = 0;
       if (sex_col >= 0 && (size_t)sex_col < t.size()) sx = t[sex_col] == "1" ? 1 : (t[sex_col] == "2" ? 2 : 0);
       sex_file.push_back(sx);
@@ -59,14 +60,13 @@ void PgenFile::open(const std::string& pfx, const std::set<std::string>& exclude
   if (keys.empty()) throw Fail("no samples left after --keep/--remove.");
   // ---- .pvar (src/Geno.cpp:771-870): ALLELE0 = REF, ALLELE1 = ALT
   {
-    std::ifstream fh(prefix + ".pvar");
-    if (!fh) throw Fail("cannot open file : " + prefix + ".pvar");
+    LineReader fh(prefix + ".pvar");
     std::string line;
     int ipos = -1, iid = -1, iref = -1, ialt = -1;
     uint64_t idx = 0;
     int last_chr = 0;
     std::vector<int> chr_seen;
-    while (std::getline(fh, line)) {
+    while (fh.getline(line)) {
       if (line.rfind("##", 0) == 0) continue;
       auto t = split_ws(line);
       if (t.empty()) continue;
@@ -267,7 +267,7 @@ void BedFile::open_pgen(const std::string& pfx, const std::set<std::string>& exc
   pg = std::make_shared<PgenFile>();
   pg->open(pfx, exclude, extract, remove, keep, chrs);
   prefix = pfx;
-  snps = pg->snps; keys_file = pg->keys_file; sex_file = pg->sex_file; keys = pg->keys;
+  snps = pg->snps; keys_file = pg->keys_file; ids_file = pg->ids_file; sex_file = pg->sex_file; keys = pg->keys;
   sample_idx = pg->sample_idx; key_to_ind = pg->key_to_ind; row_stride = pg->row_stride;
 }
 

@@ -14,6 +14,7 @@ struct PgenFile {
   std::string prefix;
   std::vector<Snp> snps;                        // after filters; offset = variant index in the .pgen
   std::vector<std::string> keys_file, keys;
+  std::vector<std::pair<std::string, std::string>> ids_file;   // (FID, IID) in .psam order
   std::vector<int> sex_file;
   std::vector<int32_t> sample_idx;
   std::map<std::string, uint32_t> key_to_ind;

@@ -536,3 +536,82 @@ def test_categorical_covariates(tmp_path, golden_dir):
     r = subprocess.run([RGB] + base + ["--covarFile", str(tmp_path / "cov_cat.txt"), "--catCovarList", "SITE", "--maxCatLevels", "2",
                                        "--out", str(tmp_path / "x")], capture_output=True, text=True)
     assert r.returncode != 0 and "too many categories for covariate: SITE (=3)" in r.stdout
+
+
+def test_gz_prs_write_samples_and_gz_inputs(tmp_path, golden_dir):
+    """--gz / --print-prs / --use-prs / --write-samples and .gz inputs (src/Files.cpp:39-150, src/Data.cpp:1795-1922,
+    src/Pheno.cpp:1238-1345, :1538-1576): compressed outputs hold exactly the text of the plain run, the .prs row is the
+    all-chromosome sum (= the LOCO row of a chromosome that is absent from the data), Step 2 reads .gz prediction and
+    phenotype files, and --use-prs equals a run on .loco files whose rows all hold the PRS."""
+    import gzip
+    import shutil
+    d = golden_dir
+    pheno, covar = d + "/phenotype.txt", d + "/covariates.txt"
+    base = ["--step", "1", "--bed", d + "/example_3chr", "--phenoFile", pheno, "--covarFile", covar, "--bsize", "100"]
+    o_plain, o_gz = str(tmp_path / "plain"), str(tmp_path / "gz")
+    run(base + ["--out", o_plain])
+    log = run(base + ["--out", o_gz, "--gz", "--print-prs"])
+    assert "List of files with whole genome PRS written to" in log
+    for k in (1, 2):
+        plain = open(o_plain + "_%d.loco" % k).read()
+        assert gzip.open(o_gz + "_%d.loco.gz" % k, "rt").read() == plain
+        rows = {l.split()[0]: l.split()[1:] for l in plain.splitlines()}
+        prs = gzip.open(o_gz + "_%d.prs.gz" % k, "rt").read().splitlines()
+        assert prs[0] == plain.splitlines()[0] and len(prs) == 2
+        t = prs[1].split()
+        assert t[0] == "0" and t[1:] == rows["7"]               # chromosome 7 is not in example_3chr: its LOCO row is the full sum
+        assert t[1:] != rows["2"]
+    pl = [l.split() for l in open(o_gz + "_pred.list")]
+    assert [os.path.basename(p[1]) for p in pl] == ["gz_1.loco.gz", "gz_2.loco.gz"]
+    pr = [l.split() for l in open(o_gz + "_prs.list")]
+    assert [p[0] for p in pr] == ["Y1", "Y2"] and [os.path.basename(p[1]) for p in pr] == ["gz_1.prs.gz", "gz_2.prs.gz"]
+
+    # Step 2: plain inputs vs .gz inputs + --gz output + --write-samples
+    for f in ("phenotype.txt", "covariates.txt"):
+        with open(d + "/" + f, "rb") as src, gzip.open(tmp_path / (f + ".gz"), "wb") as dst:
+            shutil.copyfileobj(src, dst)
+    s2 = ["--step", "2", "--bed", d + "/example_3chr", "--bsize", "200"]
+    run(s2 + ["--phenoFile", pheno, "--covarFile", covar, "--pred", o_plain + "_pred.list", "--out", str(tmp_path / "s2a")])
+    run(s2 + ["--phenoFile", str(tmp_path / "phenotype.txt.gz"), "--covarFile", str(tmp_path / "covariates.txt.gz"), "--pred",
+              o_gz + "_pred.list", "--out", str(tmp_path / "s2b"), "--gz", "--write-samples", "--print-pheno"])
+    for nm in ("Y1", "Y2"):
+        assert gzip.open(str(tmp_path / "s2b") + "_%s.regenie.gz" % nm, "rt").read() == open(str(tmp_path / "s2a") + "_%s.regenie" % nm).read()
+        ids = open(str(tmp_path / "s2b") + "_%s.regenie.ids" % nm).read().split("\n")
+        assert ids[0] == nm + "\tNA" and len(ids) == 501 and ids[1] == "1\t1" and not ids[-1].endswith("\n")
+
+    # --use-prs == LOCO files whose every row is the PRS row
+    lst = tmp_path / "fake_pred.list"
+    with open(lst, "w") as fl:
+        for k, nm in ((1, "Y1"), (2, "Y2")):
+            prs = gzip.open(o_gz + "_%d.prs.gz" % k, "rt").read().splitlines()
+            f = tmp_path / ("fake_%d.loco" % k)
+            with open(f, "w") as fh:
+                fh.write(prs[0] + "\n")
+                for c in range(1, 24):
+                    fh.write(str(c) + " " + prs[1].split(" ", 1)[1] + "\n")
+            fl.write("%s %s\n" % (nm, f))
+    run(s2 + ["--phenoFile", pheno, "--covarFile", covar, "--pred", str(lst), "--out", str(tmp_path / "s2c")])
+    log = run(s2 + ["--phenoFile", pheno, "--covarFile", covar, "--pred", o_gz + "_prs.list", "--use-prs", "--out", str(tmp_path / "s2d")])
+    assert " * PRS predictions : [" in log
+    for nm in ("Y1", "Y2"):
+        a = open(str(tmp_path / "s2c") + "_%s.regenie" % nm).read()
+        assert a == open(str(tmp_path / "s2d") + "_%s.regenie" % nm).read()
+        assert a != open(str(tmp_path / "s2a") + "_%s.regenie" % nm).read()
+
+
+def test_bgen_index_file_is_used_and_gives_the_scan_result(tmp_path, golden_dir):
+    """example_3chr.bgen with its bgenix index (example_3chr.bgen.bgi, next to it) vs a copy of the file without one."""
+    import shutil
+    d = golden_dir
+    shutil.copy(d + "/example_3chr.bgen", tmp_path / "noidx.bgen")
+    common = ["--step", "2", "--phenoFile", d + "/phenotype.txt", "--covarFile", d + "/covariates.txt", "--bsize", "200",
+              "--ignore-pred", "--sample", d + "/example_3chr.sample"]
+    la = run(common + ["--bgen", d + "/example_3chr.bgen", "--out", str(tmp_path / "a")])
+    lb = run(common + ["--bgen", str(tmp_path / "noidx.bgen"), "--out", str(tmp_path / "b")])
+    lc = run(common + ["--bgen", str(tmp_path / "noidx.bgen"), "--bgi", d + "/example_3chr.bgen.bgi", "--chr", "2", "--out", str(tmp_path / "c")])
+    assert "-index bgi file [" in la and "-index bgi file [" not in lb and "-index bgi file [" in lc
+    for nm in ("Y1", "Y2"):
+        a = open(str(tmp_path / "a") + "_%s.regenie" % nm).read()
+        assert a == open(str(tmp_path / "b") + "_%s.regenie" % nm).read() and len(a.splitlines()) > 400
+        c = open(str(tmp_path / "c") + "_%s.regenie" % nm).read().splitlines()
+        assert c[1:] == [l for l in a.splitlines()[1:] if l.startswith("2 ")]
