@@ -610,10 +610,22 @@ void run_step2_qt(const Params& p, Log& log) {
     outs[i] << sumstats_header(use_bgen);
   }
   const int bsz = p.bsize;
-  std::vector<uint8_t> rows, probs, pmiss;
-  if (use_bgen) { probs.resize((size_t)bsz * n_file * 2); pmiss.resize((size_t)bsz * n_file); }
-  else rows.resize((size_t)bsz * g.row_stride);
+  // input blocks are fetched (file read / threaded BGEN inflate) one block ahead of the GPU call: the rg_s2_block_*
+  // calls return with the results on the host, so the buffer of block b is free again when block b+2 is fetched
+  std::vector<uint8_t> rows[2], probs[2], pmiss[2];
+  for (int k = 0; k < 2; ++k) {
+    if (use_bgen) { probs[k].resize((size_t)bsz * n_file * 2); pmiss[k].resize((size_t)bsz * n_file); }
+    else rows[k].resize((size_t)bsz * g.row_stride);
+  }
   const int threads = p.threads > 0 ? p.threads : (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  std::future<void> pending;
+  auto fetch = [&](size_t b) {
+    return std::async(std::launch::async, [&, b] {
+      if (use_bgen) gg.read_block(blocks[b].first, blocks[b].size, probs[b & 1].data(), pmiss[b & 1].data(), threads);
+      else g.read_rows(blocks[b].first, blocks[b].size, rows[b & 1].data());
+    });
+  };
+  if (!blocks.empty()) pending = fetch(0);
   std::vector<double> info((size_t)bsz * P);
   std::vector<double> af((size_t)bsz * P), mac((size_t)bsz * P), stat((size_t)bsz * P), beta((size_t)bsz * P),
       se((size_t)bsz * P), chisq((size_t)bsz * P), af_all(bsz), mac_all(bsz), scale_fac(bsz);
@@ -648,13 +660,13 @@ void run_step2_qt(const Params& p, Log& log) {
       rg_check(rg_s2_set_chr(h, res.data(), scf.data()));
     }
     if (non_par_flags(p, snps, blocks[b], npf)) rg_check(rg_s2_set_non_par(h, npf.data(), blocks[b].size));
+    pending.get();
+    if (b + 1 < blocks.size()) pending = fetch(b + 1);
     if (use_bgen) {
-      gg.read_block(blocks[b].first, blocks[b].size, probs.data(), pmiss.data(), threads);
-      rg_check(rg_s2_block_bgen8(h, probs.data(), pmiss.data(), (int64_t)n_file, blocks[b].size,
+      rg_check(rg_s2_block_bgen8(h, probs[b & 1].data(), pmiss[b & 1].data(), (int64_t)n_file, blocks[b].size,
                                  subset ? sample_idx.data() : nullptr, p.ref_first, p.min_mac, &out, info.data()));
     } else {
-      g.read_rows(blocks[b].first, blocks[b].size, rows.data());
-      rg_check(rg_s2_block_bed(h, rows.data(), (int64_t)g.row_stride, blocks[b].size,
+      rg_check(rg_s2_block_bed(h, rows[b & 1].data(), (int64_t)g.row_stride, blocks[b].size,
                                subset ? sample_idx.data() : nullptr, p.ref_first, p.min_mac, &out));
     }
     for (int v = 0; v < blocks[b].size; ++v) {
@@ -723,9 +735,19 @@ void run_step2_bt(const Params& p, Log& log) {
   }
   const int bsz = p.bsize;
   const int threads = p.threads > 0 ? p.threads : (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
-  std::vector<uint8_t> probs, pmiss, rows;
-  if (use_bgen) { probs.resize((size_t)bsz * n_file * 2); pmiss.resize((size_t)bsz * n_file); }
-  else rows.resize((size_t)bsz * gb.row_stride);
+  std::vector<uint8_t> probs[2], pmiss[2], rows[2];          // fetched one block ahead of the GPU call, like the QT path
+  for (int k = 0; k < 2; ++k) {
+    if (use_bgen) { probs[k].resize((size_t)bsz * n_file * 2); pmiss[k].resize((size_t)bsz * n_file); }
+    else rows[k].resize((size_t)bsz * gb.row_stride);
+  }
+  std::future<void> pending;
+  auto fetch = [&](size_t b) {
+    return std::async(std::launch::async, [&, b] {
+      if (use_bgen) gg.read_block(blocks[b].first, blocks[b].size, probs[b & 1].data(), pmiss[b & 1].data(), threads);
+      else gb.read_rows(blocks[b].first, blocks[b].size, rows[b & 1].data());
+    });
+  };
+  if (!blocks.empty()) pending = fetch(0);
   std::vector<double> af((size_t)bsz * P), mac((size_t)bsz * P), stat((size_t)bsz * P), beta((size_t)bsz * P),
       se((size_t)bsz * P), chisq((size_t)bsz * P), info((size_t)bsz * P), af_all(bsz), mac_all(bsz), scale_fac(bsz);
   std::vector<int32_t> ns((size_t)bsz * P), ns_all(bsz), flags(bsz);
@@ -761,14 +783,14 @@ void run_step2_bt(const Params& p, Log& log) {
       rg_check(rg_s2_set_chr_bt(h, &st));
     }
     if (non_par_flags(p, snps, blocks[b], npf)) rg_check(rg_s2_set_non_par(h, npf.data(), bs));
+    pending.get();
+    if (b + 1 < blocks.size()) pending = fetch(b + 1);
     if (use_bgen) {
-      gg.read_block(blocks[b].first, bs, probs.data(), pmiss.data(), threads);
-      rg_check(rg_s2_block_bgen8_bt(h, probs.data(), pmiss.data(), (int64_t)n_file, bs, subset ? sample_idx.data() : nullptr,
-                                    p.ref_first, p.min_mac, &out, info.data()));
+      rg_check(rg_s2_block_bgen8_bt(h, probs[b & 1].data(), pmiss[b & 1].data(), (int64_t)n_file, bs,
+                                    subset ? sample_idx.data() : nullptr, p.ref_first, p.min_mac, &out, info.data()));
     } else {
       // hard calls go to the GPU as they are (2 bits per sample)
-      gb.read_rows(blocks[b].first, bs, rows.data());
-      rg_check(rg_s2_block_bed_bt(h, rows.data(), (int64_t)gb.row_stride, bs, subset ? sample_idx.data() : nullptr,
+      rg_check(rg_s2_block_bed_bt(h, rows[b & 1].data(), (int64_t)gb.row_stride, bs, subset ? sample_idx.data() : nullptr,
                                   p.ref_first, p.min_mac, &out));
     }
     // Firth fallback for |z| above the --pThresh threshold (check_pval_snp, src/Step2_Models.cpp:1988-2041)
