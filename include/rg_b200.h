@@ -261,6 +261,22 @@ int rg_s2_block_bgen8(rg_handle h, const uint8_t* probs, const uint8_t* ploidy_m
                       const rg_s2_out* out, double* info_out);
 
 /*
+ * rg_bgen_inflate -- inflate the zlib payloads of `bs` BGEN v1.2 variants on the device.  Replaces the host-side
+ * `uncompress` of the reference's BGEN parsers (src/Geno.cpp:1608, :2207): one warp per variant stream, then the payload
+ * header check (N, K = 2, ploidy 2..2, unphased, 8 bits - the subset src/Geno.cpp:2122-2170 handles) and the split into the
+ * two arrays the dosage entry points take.
+ *   comp       the compressed bytes (host or device); stream v is comp[comp_offs[v] .. comp_offs[v+1]): the C-4 bytes
+ *              that follow the 4-byte uncompressed-length field D of the variant's genotype block, D == 10 + 3 n_file
+ *   comp_offs  [bs + 1] byte offsets into comp (host)
+ *   probs_dev / miss_dev   out: DEVICE pointers owned by the handle, valid until the next rg_bgen_inflate /
+ *              rg_s2_block_bgen8[_bt] call with host buffers: [bs][n_file][2] probability bytes and [bs][n_file] ploidy
+ *              bytes (bit 7 = missing); pass them to rg_s2_block_bgen8 / rg_s2_block_bgen8_bt as they are
+ * Fails (with the variant's index in rg_last_error) on a corrupt stream, an Adler-32 mismatch or an unsupported layout.
+ */
+int rg_bgen_inflate(rg_handle h, const uint8_t* comp, const uint64_t* comp_offs, int64_t n_file, int32_t bs,
+                    const uint8_t** probs_dev, const uint8_t** miss_dev);
+
+/*
  * rg_s2_block_bed_bt -- the same binary-trait score test on 2-bit PLINK rows (.bed / decoded .pgen hard calls):
  * parseSnpfromBed (src/Geno.cpp:2414-2536) + compute_score_bt.  The block stays resident for rg_s2_firth / rg_s2_spa.
  */

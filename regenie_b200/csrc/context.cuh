@@ -137,6 +137,9 @@ struct rg_ctx {
   bool bt_chr_set = false;
   int s2_last_bs = 0;                // variants resident in dz (for rg_s2_firth)
   rg::DevBuf<uint8_t> probs_dev, miss_dev;
+  rg::DevBuf<uint8_t> inflate_comp, inflate_raw;      // rg_bgen_inflate: compressed streams, inflated payloads
+  rg::DevBuf<uint64_t> inflate_offs;
+  rg::DevBuf<int32_t> inflate_status;
   rg::DevBuf<uint32_t> dz;           // [rows_p][Npad] d | e << 10 | missing << 31
   rg::DevBuf<double> bt_F, bt_w, bt_gs, bt_xw, bt_off, bt_coltot, bt_xwy, bt_part, bt_sums, bt_nnz, bt_n510;
   rg::DevBuf<double> bt_xtwg, bt_mu, bt_info, firth_gvec, firth_out, bt_den, bt_phat;

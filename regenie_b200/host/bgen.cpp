@@ -285,4 +285,23 @@ void BgenFile::read_block(size_t first, size_t n, uint8_t* probs, uint8_t* pm, i
   if (failed) throw Fail("unsupported or corrupt bgen genotype block (rgb200 reads 8-bit unphased diploid biallelic layout 2 only).");
 }
 
+void BgenFile::read_block_compressed(size_t first, size_t n, std::vector<uint8_t>& comp, std::vector<uint64_t>& offs) const {
+  if (compression != 1) throw Fail("on-device inflate needs zlib-compressed bgen payloads (compression flag 1).");
+  offs.assign(n + 1, 0);
+  size_t total = 0;
+  for (size_t j = 0; j < n; ++j) {
+    const uint8_t* q = data + snps[first + j].offset;
+    const uint32_t c = rd32(q), d = rd32(q + 4);
+    if (c < 4 || (uint64_t)d != 10 + 3 * (uint64_t)n_file)
+      throw Fail("unsupported or corrupt bgen genotype block (rgb200 reads 8-bit unphased diploid biallelic layout 2 only).");
+    total += c - 4;
+    offs[j + 1] = total;
+  }
+  comp.resize(total);
+  for (size_t j = 0; j < n; ++j) {
+    const uint8_t* q = data + snps[first + j].offset;
+    memcpy(comp.data() + offs[j], q + 8, (size_t)(offs[j + 1] - offs[j]));
+  }
+}
+
 }  // namespace rgh

@@ -28,6 +28,9 @@ struct BgenFile {
   bool used_bgi = false;                       // the variant positions came from <file>.bgi (or --bgi)
   // inflate variants snps[first .. first+n): probs [n][n_file][2], ploidy_missing [n][n_file]
   void read_block(size_t first, size_t n, uint8_t* probs, uint8_t* ploidy_missing, int threads) const;
+  // the zlib streams of variants snps[first .. first+n) back to back, for rg_bgen_inflate (compression flag 1 only):
+  // comp = concatenated streams, offs [n + 1]; throws when a variant's declared length is not 10 + 3 n_file
+  void read_block_compressed(size_t first, size_t n, std::vector<uint8_t>& comp, std::vector<uint64_t>& offs) const;
 };
 
 }  // namespace rgh

@@ -51,6 +51,7 @@ struct Params {
   bool write_samples = false, print_pheno = false;   // --write-samples [--print-pheno]: <out>_<pheno>.regenie.ids
   bool print_prs = false, use_prs = false;     // --print-prs (step 1) / --use-prs (step 2)
   std::string bgi;                             // --bgi FILE (default: <bgen>.bgi when it exists)
+  bool gpu_inflate = false;                    // --gpu-inflate: zlib payloads of the .bgen are inflated on the device (rg_bgen_inflate)
   uint32_t par1_max = 2781479, par2_min = 155701383;   // hg38 (check_build_code, src/Regenie.cpp:1643-1660)
 };
 
@@ -143,6 +144,7 @@ Params parse_cli(int argc, char** argv) {
     else if (a == "--print-prs") p.print_prs = true;
     else if (a == "--use-prs") p.use_prs = true;
     else if (a == "--bgi") p.bgi = need(i);
+    else if (a == "--gpu-inflate") p.gpu_inflate = true;
     else if (a == "--bt") p.bt = true;
     else if (a == "--force-step1") p.force_step1 = true;
     else if (a == "--use-relative-path") p.rel_path = true;
@@ -154,7 +156,8 @@ Params parse_cli(int argc, char** argv) {
                    "  [--phenoCol c]... [--phenoColList a,b] [--covarCol c]... [--covarColList a,b] [--minINFO x] [--ignore-pred]\n"
                    "  [--chr c]... [--chrList c1,c2,...]  (Step-2 jobs are split by chromosome like the reference)\n"
                    "  step 2 binary traits: --bt [--firth --approx | --spa] [--pThresh p] with --bed or --bgen F [--sample F] [--bgi F]\n"
-                   "  [--gz] [--print-prs | --use-prs] [--write-samples [--print-pheno]]  (.gz inputs are read by file name)\n";
+                   "  [--gz] [--print-prs | --use-prs] [--write-samples [--print-pheno]]  (.gz inputs are read by file name)\n"
+                   "  [--gpu-inflate]  step 2 on zlib-compressed .bgen: inflate the genotype blocks on the GPU instead of the host\n";
       exit(0);
     } else {
       throw Fail("option '" + a + "' is outside the hot path covered by rgb200 (see DESIGN.md, out of scope)");
@@ -618,10 +621,17 @@ void run_step2_qt(const Params& p, Log& log) {
     else rows[k].resize((size_t)bsz * g.row_stride);
   }
   const int threads = p.threads > 0 ? p.threads : (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  const bool dev_inflate = use_bgen && p.gpu_inflate && gg.compression == 1;
+  if (use_bgen && p.gpu_inflate)
+    log << (dev_inflate ? " * bgen genotype blocks are inflated on the GPU\n"
+                        : "   -WARNING: --gpu-inflate needs zlib-compressed payloads; inflating on the host.\n");
+  std::vector<uint8_t> comp[2];
+  std::vector<uint64_t> comp_offs[2];
   std::future<void> pending;
   auto fetch = [&](size_t b) {
     return std::async(std::launch::async, [&, b] {
-      if (use_bgen) gg.read_block(blocks[b].first, blocks[b].size, probs[b & 1].data(), pmiss[b & 1].data(), threads);
+      if (dev_inflate) gg.read_block_compressed(blocks[b].first, blocks[b].size, comp[b & 1], comp_offs[b & 1]);
+      else if (use_bgen) gg.read_block(blocks[b].first, blocks[b].size, probs[b & 1].data(), pmiss[b & 1].data(), threads);
       else g.read_rows(blocks[b].first, blocks[b].size, rows[b & 1].data());
     });
   };
@@ -663,7 +673,9 @@ void run_step2_qt(const Params& p, Log& log) {
     pending.get();
     if (b + 1 < blocks.size()) pending = fetch(b + 1);
     if (use_bgen) {
-      rg_check(rg_s2_block_bgen8(h, probs[b & 1].data(), pmiss[b & 1].data(), (int64_t)n_file, blocks[b].size,
+      const uint8_t *pd = probs[b & 1].data(), *md = pmiss[b & 1].data();
+      if (dev_inflate) rg_check(rg_bgen_inflate(h, comp[b & 1].data(), comp_offs[b & 1].data(), (int64_t)n_file, blocks[b].size, &pd, &md));
+      rg_check(rg_s2_block_bgen8(h, pd, md, (int64_t)n_file, blocks[b].size,
                                  subset ? sample_idx.data() : nullptr, p.ref_first, p.min_mac, &out, info.data()));
     } else {
       rg_check(rg_s2_block_bed(h, rows[b & 1].data(), (int64_t)g.row_stride, blocks[b].size,
@@ -740,10 +752,17 @@ void run_step2_bt(const Params& p, Log& log) {
     if (use_bgen) { probs[k].resize((size_t)bsz * n_file * 2); pmiss[k].resize((size_t)bsz * n_file); }
     else rows[k].resize((size_t)bsz * gb.row_stride);
   }
+  const bool dev_inflate = use_bgen && p.gpu_inflate && gg.compression == 1;
+  if (use_bgen && p.gpu_inflate)
+    log << (dev_inflate ? " * bgen genotype blocks are inflated on the GPU\n"
+                        : "   -WARNING: --gpu-inflate needs zlib-compressed payloads; inflating on the host.\n");
+  std::vector<uint8_t> comp[2];
+  std::vector<uint64_t> comp_offs[2];
   std::future<void> pending;
   auto fetch = [&](size_t b) {
     return std::async(std::launch::async, [&, b] {
-      if (use_bgen) gg.read_block(blocks[b].first, blocks[b].size, probs[b & 1].data(), pmiss[b & 1].data(), threads);
+      if (dev_inflate) gg.read_block_compressed(blocks[b].first, blocks[b].size, comp[b & 1], comp_offs[b & 1]);
+      else if (use_bgen) gg.read_block(blocks[b].first, blocks[b].size, probs[b & 1].data(), pmiss[b & 1].data(), threads);
       else gb.read_rows(blocks[b].first, blocks[b].size, rows[b & 1].data());
     });
   };
@@ -786,7 +805,9 @@ void run_step2_bt(const Params& p, Log& log) {
     pending.get();
     if (b + 1 < blocks.size()) pending = fetch(b + 1);
     if (use_bgen) {
-      rg_check(rg_s2_block_bgen8_bt(h, probs[b & 1].data(), pmiss[b & 1].data(), (int64_t)n_file, bs,
+      const uint8_t *pd = probs[b & 1].data(), *md = pmiss[b & 1].data();
+      if (dev_inflate) rg_check(rg_bgen_inflate(h, comp[b & 1].data(), comp_offs[b & 1].data(), (int64_t)n_file, bs, &pd, &md));
+      rg_check(rg_s2_block_bgen8_bt(h, pd, md, (int64_t)n_file, bs,
                                     subset ? sample_idx.data() : nullptr, p.ref_first, p.min_mac, &out, info.data()));
     } else {
       // hard calls go to the GPU as they are (2 bits per sample)

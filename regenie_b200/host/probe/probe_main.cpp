@@ -14,9 +14,14 @@
 //   rgb200_hostprobe read-pred FILE [--prs]                 ids + rows back out, one token per line
 //   rgb200_hostprobe sumstats                               stdin: "af info n beta se chisq pass" per line -> rows
 //   rgb200_hostprobe ids OUT NAME PRINTNAME                 stdin: "FID IID keep" per line
+//   rgb200_hostprobe inflate-bgen FILE                      every zlib payload through csrc/inflate_core.h vs zlib
+//   rgb200_hostprobe inflate IN OUTLEN OUT                  one zlib stream through csrc/inflate_core.h (status on stdout)
 #include <cstring>
 #include <iomanip>
 
+#include <zlib.h>
+
+#include "../../csrc/inflate_core.h"
 #include "../bgen.hpp"
 #include "../bt_null.hpp"
 #include "../data.hpp"
@@ -225,6 +230,57 @@ int cmd_ids(char** argv) {
   return 0;
 }
 
+// the decoder the GPU runs (csrc/inflate_core.h, compiled here with a one-lane "warp") against zlib on every variant
+int cmd_inflate_bgen(char** argv) {
+  BgenFile g;
+  g.open(argv[2], "", false, {}, {}, {}, {}, {}, "", true);
+  std::vector<uint8_t> comp;
+  std::vector<uint64_t> offs;
+  g.read_block_compressed(0, g.snps.size(), comp, offs);
+  const uint32_t raw_len = 10 + 3 * g.n_file;
+  std::vector<uint8_t> a(raw_len), b(raw_len);
+  static rgi::Tables t;
+  size_t bad = 0, in_bytes = 0;
+  for (size_t v = 0; v < g.snps.size(); ++v) {
+    const uint32_t n = (uint32_t)(offs[v + 1] - offs[v]);
+    in_bytes += n;
+    std::fill(a.begin(), a.end(), 0xAA);
+    const int st = rgi::inflate_zlib(comp.data() + offs[v], n, a.data(), raw_len, t, true);
+    uLongf dl = raw_len;
+    const int zr = uncompress(b.data(), &dl, comp.data() + offs[v], n);
+    if (st != 0 || zr != Z_OK || dl != raw_len || a != b) {
+      ++bad;
+      std::cout << "variant " << v << " status " << st << " zlib " << zr << "\n";
+    }
+    // a truncated and a corrupted copy must be rejected, never crash
+    if (v % 97 == 0 && n > 16) {
+      std::vector<uint8_t> c(comp.begin() + (long)offs[v], comp.begin() + (long)offs[v + 1]);
+      const int st_trunc = rgi::inflate_zlib(c.data(), n / 2, a.data(), raw_len, t, true);
+      c[n / 2] ^= 0x5a;
+      const int st_flip = rgi::inflate_zlib(c.data(), n, a.data(), raw_len, t, true);
+      if (st_trunc == 0 || st_flip == 0) { ++bad; std::cout << "variant " << v << " damaged stream accepted\n"; }
+    }
+  }
+  std::cout << "variants " << g.snps.size() << " bad " << bad << " compressed " << in_bytes << " raw " << (size_t)raw_len * g.snps.size() << "\n";
+  return bad ? 1 : 0;
+}
+
+int cmd_inflate(char** argv) {
+  std::ifstream f(argv[2], std::ios::binary | std::ios::ate);
+  if (!f) throw Fail(std::string("cannot open file : ") + argv[2]);
+  std::vector<uint8_t> in((size_t)f.tellg());
+  f.seekg(0);
+  f.read(reinterpret_cast<char*>(in.data()), (std::streamsize)in.size());
+  const uint32_t out_len = (uint32_t)atol(argv[3]);
+  std::vector<uint8_t> out(out_len);
+  static rgi::Tables t;
+  const int st = rgi::inflate_zlib(in.data(), (uint32_t)in.size(), out.data(), out_len, t, true);
+  std::ofstream o(argv[4], std::ios::binary);
+  o.write(reinterpret_cast<const char*>(out.data()), (std::streamsize)out.size());
+  std::cout << "status " << st << "\n";
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -240,6 +296,8 @@ int main(int argc, char** argv) {
     if (c == "read-pred" && argc >= 3) return cmd_read_pred(argc, argv);
     if (c == "sumstats") return cmd_sumstats();
     if (c == "ids" && argc == 5) return cmd_ids(argv);
+    if (c == "inflate-bgen" && argc == 3) return cmd_inflate_bgen(argv);
+    if (c == "inflate" && argc == 5) return cmd_inflate(argv);
     throw Fail("unknown probe command or wrong number of arguments: " + c);
   } catch (const std::exception& e) {
     std::cout << "ERROR: " << e.what() << "\n";

@@ -615,3 +615,28 @@ def test_bgen_index_file_is_used_and_gives_the_scan_result(tmp_path, golden_dir)
         assert a == open(str(tmp_path / "b") + "_%s.regenie" % nm).read() and len(a.splitlines()) > 400
         c = open(str(tmp_path / "c") + "_%s.regenie" % nm).read().splitlines()
         assert c[1:] == [l for l in a.splitlines()[1:] if l.startswith("2 ")]
+
+
+def test_gpu_inflate_equals_host_inflate(tmp_path, golden_dir):
+    """--gpu-inflate (rg_bgen_inflate: one warp per zlib stream, csrc/inflate_core.h) must give byte-identical results
+    to the default host-zlib path: the reference's documented BT / Firth command on example.bgen and a QT run on the
+    three-chromosome fileset with a sample subset."""
+    d = golden_dir
+    pred = _write_zero_loco(tmp_path, d, ["Y1", "Y2"])
+    bt = ["--step", "2", "--bgen", d + "/example.bgen", "--covarFile", d + "/covariates.txt", "--phenoFile",
+          d + "/phenotype_bin.txt", "--remove", d + "/fid_iid_to_remove.txt", "--bsize", "200", "--bt", "--firth",
+          "--approx", "--pThresh", "0.01", "--pred", pred]
+    run(bt + ["--out", str(tmp_path / "host")])
+    log = run(bt + ["--out", str(tmp_path / "dev"), "--gpu-inflate"])
+    assert "inflated on the GPU" in log
+    for nm in ("Y1", "Y2"):
+        a = open(str(tmp_path / "host") + "_%s.regenie" % nm).read()
+        assert a == open(str(tmp_path / "dev") + "_%s.regenie" % nm).read() and len(a.splitlines()) == 1001
+    qt = ["--step", "2", "--bgen", d + "/example_3chr.bgen", "--sample", d + "/example_3chr.sample", "--phenoFile",
+          d + "/phenotype.txt", "--covarFile", d + "/covariates.txt", "--bsize", "77", "--ignore-pred", "--remove",
+          d + "/fid_iid_to_remove.txt"]
+    run(qt + ["--out", str(tmp_path / "qh")])
+    run(qt + ["--out", str(tmp_path / "qd"), "--gpu-inflate"])
+    for nm in ("Y1", "Y2"):
+        a = open(str(tmp_path / "qh") + "_%s.regenie" % nm).read()
+        assert a == open(str(tmp_path / "qd") + "_%s.regenie" % nm).read() and len(a.splitlines()) > 400

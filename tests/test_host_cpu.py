@@ -334,3 +334,54 @@ def test_ids_file(tmp_path):
     assert open(tmp_path / "a.ids").read() == "f1\ti1\nf3\ti3\nf4\ti4"
     probe("ids", tmp_path / "b.ids", "Y1", 1, stdin=stdin)
     assert open(tmp_path / "b.ids").read() == "Y1\tNA\nf1\ti1\nf3\ti3\nf4\ti4"
+
+
+# ------------------------------------------------------------------------------------------- device inflate core on the host
+def test_inflate_core_reproduces_zlib_on_every_bgen_payload(golden_dir):
+    """csrc/inflate_core.h is the decoder the GPU runs (one warp per variant stream); compiled for the host with a
+    one-lane warp it must reproduce zlib byte for byte on every variant of the reference's fixtures, and reject
+    truncated / corrupted streams."""
+    for name, m in (("example", 1000), ("example_3chr", 500)):
+        out = probe("inflate-bgen", "%s/%s.bgen" % (golden_dir, name)).stdout.splitlines()[-1].split()
+        assert out[:4] == ["variants", str(m), "bad", "0"], out
+
+
+def test_inflate_core_block_types_and_error_paths(tmp_path):
+    import zlib
+    rng = np.random.default_rng(5)
+    payloads = {
+        "empty": b"",
+        "one": b"x",
+        "run": b"\x00" * 70000,                                                  # distance-1 matches longer than the distance
+        "pairs": bytes([255, 0]) * 40000 + bytes([0, 0]) * 3000,                 # what hard-call-like probabilities look like
+        "random": rng.integers(0, 256, 100000, dtype=np.uint8).tobytes(),        # incompressible: stored blocks at level 0/1
+        "text": (b"the quick brown fox jumps over the lazy dog " * 3000)[:120001],
+        "probs": np.clip(rng.normal(128, 60, 200000), 0, 255).astype(np.uint8).tobytes(),   # long Huffman codes
+        "far": rng.integers(0, 4, 40000, dtype=np.uint8).tobytes() * 3,          # matches at distances up to 32K
+    }
+    strategies = [(zlib.Z_DEFAULT_STRATEGY, "default"), (zlib.Z_FIXED, "fixed"), (zlib.Z_HUFFMAN_ONLY, "huff"), (zlib.Z_RLE, "rle")]
+    n = 0
+    for name, data in payloads.items():
+        for level in (0, 1, 6, 9):
+            for strat, sname in strategies:
+                c = zlib.compressobj(level, zlib.DEFLATED, 15, 9, strat)
+                z = c.compress(data) + c.flush()
+                (tmp_path / "in.z").write_bytes(z)
+                r = probe("inflate", tmp_path / "in.z", len(data), tmp_path / "out.bin").stdout.split()
+                assert r == ["status", "0"], (name, level, sname, r)
+                assert (tmp_path / "out.bin").read_bytes() == data, (name, level, sname)
+                n += 1
+    assert n == 8 * 4 * 4
+    z = zlib.compress(payloads["text"], 6)
+    cases = {
+        "short output": (z, len(payloads["text"]) - 1, 7),          # kErrOutput
+        "long output": (z, len(payloads["text"]) + 1, 9),           # kErrLength
+        "bad header": (b"\x79" + z[1:], len(payloads["text"]), 1),
+        "bad adler": (z[:-1] + bytes([z[-1] ^ 1]), len(payloads["text"]), 10),
+        "truncated": (z[: len(z) // 2], len(payloads["text"]), None),
+        "raw deflate": (z[2:], len(payloads["text"]), None),
+    }
+    for name, (blob, out_len, want) in cases.items():
+        (tmp_path / "in.z").write_bytes(blob)
+        st = int(probe("inflate", tmp_path / "in.z", out_len, tmp_path / "out.bin").stdout.split()[1])
+        assert st != 0 and (want is None or st == want), (name, st)
