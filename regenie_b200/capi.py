@@ -347,6 +347,17 @@ class Step2:
                                      int(ref_first), float(min_mac), C.byref(so), _ptr(o["info"])))
         return o
 
+    def bgen_inflate(self, comp, comp_offs, n_file):
+        """Inflate the zlib payloads of a block on the device (rg_bgen_inflate).  comp: u8 bytes, comp_offs: [bs+1].
+        Returns the two DEVICE addresses (probs, ploidy_missing) to hand to block_bgen8*_dev."""
+        L = lib()
+        L.rg_bgen_inflate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
+        comp = np.ascontiguousarray(comp, dtype=np.uint8)
+        offs = np.ascontiguousarray(comp_offs, dtype=np.uint64)
+        pd, md = C.c_void_p(), C.c_void_p()
+        check(L.rg_bgen_inflate(self.h, _ptr(comp), _ptr(offs), int(n_file), len(offs) - 1, C.byref(pd), C.byref(md)))
+        return pd.value, md.value
+
     def spa(self, variant_idx, trait_idx):
         L = lib()
         L.rg_s2_spa.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 4

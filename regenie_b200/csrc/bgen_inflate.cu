@@ -7,9 +7,12 @@
 // then a second kernel checks the payload header and splits it into the two arrays the dosage kernels take
 // (`probs` [bs][n_file][2], `ploidy_missing` [bs][n_file]), i.e. exactly what host/bgen.cpp produces on the host.
 //
-// STATUS: the decoder core is verified against zlib on the CPU (tests/test_host_cpu.py, every variant of the reference's
-// BGEN fixtures plus synthetic streams of every block type); the kernels below have not run on a B200 yet (written after
-// the round-1 GPU budget was spent) - the driver only takes this path with --gpu-inflate, the default stays host zlib.
+// The decoder core is verified against zlib on the CPU (tests/test_host_cpu.py: every variant of the reference's BGEN
+// fixtures plus 128 synthetic streams covering stored / fixed / dynamic blocks and the error paths) and on a B200 through
+// the driver (`--gpu-inflate` output is byte-identical to the host-zlib path, tests/test_driver_gpu.py).  Measured
+// (profiles/inflate_bench_r1.txt, N = 100k, 1000 variants per block, H2D of the compressed bytes included): 30 ms per
+// block = 9.9 GB/s of inflated bytes, against 1.9 GB/s for zlib on 32 host threads.  The default stays host zlib until the
+// Step-2 bench leg is switched over.
 #include "context.cuh"
 #include "inflate_core.h"
 
