@@ -112,3 +112,21 @@ def step1_distributed(st, n_blocks, feed_block, tau, chr_of_block, device, bt=No
     loco = _sum_to_all(loco, device)
     dist.barrier()                      # peers may unmap / free W only after every owner is done
     return cs, best, loco
+
+
+def step2_distributed(n_blocks, run_block):
+    """Step 2 over more than one GPU: variants are independent (the reference splits Step-2 jobs by chromosome / variant
+    range for the same reason), so the blocks are partitioned contiguously like level 0 and there is no data-path
+    collective at all.  `run_block(b)` returns the finished result of block b (e.g. its `.regenie` rows); rank 0 gets the
+    results of every block in file order, the other ranks get None.  Each rank keeps its own Step-2 handle / GPU."""
+    mine = my_blocks(n_blocks)
+    local = [(b, run_block(b)) for b in mine]
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return [r for _, r in local]
+    gathered = [None] * dist.get_world_size() if dist.get_rank() == 0 else None
+    dist.gather_object(local, gathered, dst=0)
+    if dist.get_rank() != 0:
+        return None
+    flat = sorted((b, r) for part in gathered for b, r in part)
+    assert [b for b, _ in flat] == list(range(n_blocks))
+    return [r for _, r in flat]

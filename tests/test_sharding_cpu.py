@@ -24,7 +24,8 @@ def _worker(rank, world, port, q):
     owner = sharding.gather_block_owner(11)
     tmax = sharding.max_over_ranks(10.0 + rank)
     err = sharding.first_error(0 if rank == 0 else 4242)
-    q.put((rank, mine, owner, tmax, err))
+    rows = sharding.step2_distributed(11, lambda b: ["block %d row %d (rank %d)" % (b, k, rank) for k in range(b % 3 + 1)])
+    q.put((rank, mine, owner, tmax, err, rows))
     dist.destroy_process_group()
 
 
@@ -40,3 +41,7 @@ def test_two_rank_gloo():
     assert res[0][2] == res[1][2] == [0] * 6 + [1] * 5
     assert res[0][3] == res[1][3] == 11.0
     assert res[0][4] == res[1][4] == 4242
+    # Step 2: rank 0 holds the rows of every block in file order, produced by the rank that owns the block
+    assert res[1][5] is None
+    want = [["block %d row %d (rank %d)" % (b, k, 0 if b < 6 else 1) for k in range(b % 3 + 1)] for b in range(11)]
+    assert res[0][5] == want
