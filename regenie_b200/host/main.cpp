@@ -51,6 +51,9 @@ struct Params {
   bool write_samples = false, print_pheno = false;   // --write-samples [--print-pheno]: <out>_<pheno>.regenie.ids
   bool print_prs = false, use_prs = false;     // --print-prs (step 1) / --use-prs (step 2)
   std::string bgi;                             // --bgi FILE (default: <bgen>.bgi when it exists)
+  bool set_range = false;                      // --range CHR:MINPOS-MAXPOS (step 2)
+  int range_chr = 0;
+  double range_min = 0, range_max = 0;
   bool gpu_inflate = false;                    // --gpu-inflate: zlib payloads of the .bgen are inflated on the device (rg_bgen_inflate)
   uint32_t par1_max = 2781479, par2_min = 155701383;   // hg38 (check_build_code, src/Regenie.cpp:1643-1660)
 };
@@ -145,6 +148,17 @@ Params parse_cli(int argc, char** argv) {
     else if (a == "--use-prs") p.use_prs = true;
     else if (a == "--bgi") p.bgi = need(i);
     else if (a == "--gpu-inflate") p.gpu_inflate = true;
+    else if (a == "--range") {                                  // src/Regenie.cpp:741-755
+      char chr[20];
+      double p0 = -1, p1 = -1;
+      const std::string v = need(i);
+      if (sscanf(v.c_str(), "%19[^:]:%lf-%lf", chr, &p0, &p1) != 3 || p0 < 0 || p1 < 0)
+        throw Fail("wrong format for --range (must be CHR:MINPOS-MAXPOS).");
+      p.range_chr = chr_str_to_int(chr);
+      p.range_min = std::min(p0, p1);
+      p.range_max = std::max(p0, p1);
+      p.set_range = true;
+    }
     else if (a == "--bt") p.bt = true;
     else if (a == "--force-step1") p.force_step1 = true;
     else if (a == "--use-relative-path") p.rel_path = true;
@@ -154,7 +168,7 @@ Params parse_cli(int argc, char** argv) {
                    "  [--pred LIST] [--loocv] [--lowmem] [--cv K] [--l0 R] [--l1 R] [--remove F] [--keep F]\n"
                    "  [--exclude F] [--extract F] [--ref-first] [--minMAC x] [--strict] [--gpu ordinal]\n"
                    "  [--phenoCol c]... [--phenoColList a,b] [--covarCol c]... [--covarColList a,b] [--minINFO x] [--ignore-pred]\n"
-                   "  [--chr c]... [--chrList c1,c2,...]  (Step-2 jobs are split by chromosome like the reference)\n"
+                   "  [--chr c]... [--chrList c1,c2,...] [--range CHR:MIN-MAX]  (Step-2 jobs are split by chromosome / window like the reference)\n"
                    "  step 2 binary traits: --bt [--firth --approx | --spa] [--pThresh p] with --bed or --bgen F [--sample F] [--bgi F]\n"
                    "  [--gz] [--print-prs | --use-prs] [--write-samples [--print-pheno]]  (.gz inputs are read by file name)\n"
                    "  [--gpu-inflate]  step 2 on zlib-compressed .bgen: inflate the genotype blocks on the GPU instead of the host\n";
@@ -174,6 +188,7 @@ Params parse_cli(int argc, char** argv) {
   if ((p.split_jobs || p.run_l0_job || p.run_l1) && p.step != 1) throw Fail("options --split-l0/--run-l0/--run-l1 only work in step 1.");
   if (p.out.empty()) throw Fail("must specify an output file prefix with --out.");
   if (p.bsize < 1) throw Fail("must specify the block size using '--bsize'.");
+  if (p.set_range && p.range_chr == -1) throw Fail("unrecognized chromosome in --range.");   // src/Regenie.cpp:1153-1154
   if (p.write_samples && !p.bgen.empty() && p.sample.empty())                     // src/Regenie.cpp:903-904
     throw Fail("must specify sample file (using --sample) if writing sample IDs to file.");
   if (p.step == 2 && p.pred.empty() && !p.ignore_pred) throw Fail("must specify --pred if using --step 2 (otherwise use --ignore-pred).");
@@ -263,6 +278,7 @@ void write_master(const Params& p, const std::vector<Snp>& snps, const std::vect
 
 void run_step1(const Params& p_in, Log& log) {
   Params p = p_in;
+  if (p.set_range) { log << "WARNING: option --range only works for step 2.\n"; p.set_range = false; }
   Master master;
   if (p.run_l0_job || p.run_l1) master = read_master(p.master, p.bsize);
   if (p.run_l0_job) {
@@ -489,6 +505,14 @@ void run_step1(const Params& p_in, Log& log) {
 }
 
 // ------------------------------------------------------------------------------------ step 2
+// --range (in_range, src/Geno.cpp:2790-2800): keep the variants of one chromosome window
+void apply_range(const Params& p, std::vector<Snp>& snps) {
+  if (!p.set_range) return;
+  snps.erase(std::remove_if(snps.begin(), snps.end(), [&](const Snp& s) {
+               return s.chrom != p.range_chr || (double)s.pos < p.range_min || (double)s.pos > p.range_max;
+             }), snps.end());
+}
+
 // phenotypes + covariates + LOCO files for Step 2 (read_pheno_and_cov, blup_read, prep_run)
 void load_step2_inputs(const Params& p, const SampleSet& g, const std::vector<std::pair<std::string, std::string>>& ids_file,
                        const std::vector<int32_t>& sample_idx, Pheno& ph, std::vector<Loco>& locos, Log& log) {
@@ -587,6 +611,10 @@ void run_step2_qt(const Params& p, Log& log) {
   } else {
     open_rows(p, g, excl, extr, rem, keepl, log);
   }
+  apply_range(p, gg.snps);
+  apply_range(p, g.snps);
+  if (g.pg) apply_range(p, g.pg->snps);
+  if (p.set_range && (use_bgen ? gg.snps : g.snps).empty()) throw Fail("no variant left to include in analysis.");
   const std::vector<Snp>& snps = use_bgen ? gg.snps : g.snps;
   const std::vector<std::string>& keys = use_bgen ? gg.keys : g.keys;
   const std::vector<int32_t>& sample_idx = use_bgen ? gg.sample_idx : g.sample_idx;
@@ -717,6 +745,10 @@ void run_step2_bt(const Params& p, Log& log) {
   } else {
     open_rows(p, gb, excl, extr, rem, keep, log);
   }
+  apply_range(p, gg.snps);
+  apply_range(p, gb.snps);
+  if (gb.pg) apply_range(p, gb.pg->snps);
+  if (p.set_range && (use_bgen ? gg.snps : gb.snps).empty()) throw Fail("no variant left to include in analysis.");
   const std::vector<Snp>& snps = use_bgen ? gg.snps : gb.snps;
   const std::vector<std::string>& keys = use_bgen ? gg.keys : gb.keys;
   const std::vector<int32_t>& sample_idx = use_bgen ? gg.sample_idx : gb.sample_idx;

@@ -23,6 +23,10 @@ def test_cli_errors_have_the_reference_shape(tmp_path, golden_dir):
         (["--step", "1", "--bgen", d + "/example.bgen"] + base[2:], "--bgen input in --step 1 is not implemented"),
         (["--step", "2", "--firth", "--bt", "--pred", "x"] + base, "exact Firth"),
         (["--step", "2", "--split-l0", "p,2", "--pred", "x"] + base, "only work in step 1"),
+        (["--step", "2", "--pred", "x", "--range", "1:100"] + base, "wrong format for --range (must be CHR:MINPOS-MAXPOS)."),
+        (["--step", "2", "--pred", "x", "--range", "Z:1-100"] + base, "unrecognized chromosome in --range."),
+        (["--step", "2", "--pred", "x", "--write-samples", "--bgen", d + "/example.bgen"] + base[2:],
+         "must specify sample file (using --sample) if writing sample IDs to file."),
     ]
     for args, msg in cases:
         r = run(args, str(tmp_path))

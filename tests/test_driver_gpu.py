@@ -640,3 +640,20 @@ def test_gpu_inflate_equals_host_inflate(tmp_path, golden_dir):
     for nm in ("Y1", "Y2"):
         a = open(str(tmp_path / "qh") + "_%s.regenie" % nm).read()
         assert a == open(str(tmp_path / "qd") + "_%s.regenie" % nm).read() and len(a.splitlines()) > 400
+
+
+def test_step2_range_is_a_window_of_the_full_run(tmp_path, golden_dir):
+    """--range CHR:MIN-MAX (src/Regenie.cpp:741-755, in_range src/Geno.cpp:2790-2800) on .bed and .bgen input."""
+    d = golden_dir
+    for kind, geno in (("bed", ["--bed", d + "/example_3chr"]),
+                       ("bgen", ["--bgen", d + "/example_3chr.bgen", "--sample", d + "/example_3chr.sample"])):
+        common = ["--step", "2"] + geno + ["--phenoFile", d + "/phenotype.txt", "--covarFile", d + "/covariates.txt",
+                                           "--bsize", "100", "--ignore-pred"]
+        run(common + ["--out", str(tmp_path / (kind + "_all"))])
+        full = open(str(tmp_path / (kind + "_all")) + "_Y1.regenie").read().splitlines()
+        pos = sorted(int(l.split()[1]) for l in full[1:] if l.startswith("2 "))
+        lo, hi = pos[len(pos) // 4], pos[3 * len(pos) // 4]
+        run(common + ["--range", "2:%d-%d" % (hi, lo), "--out", str(tmp_path / (kind + "_win"))])      # min / max in any order
+        win = open(str(tmp_path / (kind + "_win")) + "_Y1.regenie").read().splitlines()
+        want = [l for l in full[1:] if l.startswith("2 ") and lo <= int(l.split()[1]) <= hi]
+        assert win[0] == full[0] and win[1:] == want and len(want) > 50
