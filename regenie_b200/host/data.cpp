@@ -156,7 +156,7 @@ void read_pheno_and_cov(const SampleSet& g, const std::string& pheno_file, const
   ph.bt = bt;
   ph.step1 = !step2;
   std::vector<uint8_t> in_ph;
-  read_table(pheno_file, g, nullptr, &ph.pheno_cols, ph.names, nullptr, nullptr, ph.Y, in_ph);
+  read_table(pheno_file, g, ph.pheno_excl.empty() ? nullptr : &ph.pheno_excl, &ph.pheno_cols, ph.names, nullptr, nullptr, ph.Y, in_ph);
   ph.P = (int)ph.names.size();
   if (ph.P < 1) throw Fail("need at least one phenotype.");
   log << " * phenotypes          : [" << pheno_file << "] n_pheno = " << ph.P << "\n";
@@ -191,6 +191,7 @@ void read_pheno_and_cov(const SampleSet& g, const std::string& pheno_file, const
   std::vector<std::string> cnames;
   if (!covar_file.empty()) {
     std::set<std::string> skip(ph.names.begin(), ph.names.end());
+    skip.insert(ph.covar_excl.begin(), ph.covar_excl.end());
     std::set<std::string> only = ph.covar_cols;
     if (!only.empty()) only.insert(ph.cat_cols.begin(), ph.cat_cols.end());   // --catCovarList columns are covariates too
     std::vector<std::map<std::string, int>> levels;

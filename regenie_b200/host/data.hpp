@@ -67,6 +67,7 @@ struct Pheno {
   bool rint = false;              // --apply-rint
   std::vector<double> Y_raw;      // N x P raw 0/1 values (binary traits)
   std::set<std::string> pheno_cols, covar_cols;   // --phenoCol[List] / --covarCol[List] (empty = every column)
+  std::set<std::string> pheno_excl, covar_excl;   // --phenoExcludeList / --covarExcludeList
   std::set<std::string> cat_cols;                 // --catCovarList: expanded to K-1 indicator columns
   int max_cat_levels = 10;                        // --maxCatLevels
 };

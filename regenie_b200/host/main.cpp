@@ -51,6 +51,8 @@ struct Params {
   bool write_samples = false, print_pheno = false;   // --write-samples [--print-pheno]: <out>_<pheno>.regenie.ids
   bool print_prs = false, use_prs = false;     // --print-prs (step 1) / --use-prs (step 2)
   std::string bgi;                             // --bgi FILE (default: <bgen>.bgi when it exists)
+  std::vector<double> setl0, setl1;            // --setl0 / --setl1: user ridge grids in (0,1)
+  std::set<std::string> pheno_excl, covar_excl, l1_phenos;   // --phenoExcludeList / --covarExcludeList / --l1-phenoList
   bool set_range = false;                      // --range CHR:MINPOS-MAXPOS (step 2)
   int range_chr = 0;
   double range_min = 0, range_max = 0;
@@ -62,8 +64,26 @@ void rg_check(int rc) {
   if (rc != 0) throw Fail(std::string(rg_last_error()));
 }
 
+// get_unit_params (src/Regenie.cpp:1477-1495): sorted unique values strictly inside (0, 1)
+std::vector<double> unit_params(const std::string& opt, const std::string& csv) {
+  std::vector<double> v;
+  std::string tok;
+  std::istringstream ss(csv);
+  while (std::getline(ss, tok, ',')) if (!tok.empty()) v.push_back(convert_double(tok));
+  std::sort(v.begin(), v.end());
+  v.erase(std::unique(v.begin(), v.end()), v.end());
+  for (double x : v) if (x <= 0 || x >= 1) throw Fail("must specify values for " + opt + " in (0,1).");
+  if (v.empty()) throw Fail("must specify values for " + opt + " in (0,1).");
+  return v;
+}
+
 Params parse_cli(int argc, char** argv) {
   Params p;
+  auto csv_into = [](const std::string& v, std::set<std::string>& dst) {
+    std::string tok;
+    std::istringstream ss(v);
+    while (std::getline(ss, tok, ',')) if (!tok.empty()) dst.insert(tok);
+  };
   auto need = [&](int& i) -> std::string {
     if (i + 1 >= argc) throw Fail(std::string("option ") + argv[i] + " needs a value");
     return argv[++i];
@@ -71,13 +91,19 @@ Params parse_cli(int argc, char** argv) {
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     if (a == "--step") p.step = atoi(need(i).c_str());
+    else if (a == "--version" || a == "-v") { std::cout << "rgb200 (" << rg_version() << ")\n"; exit(0); }
+    else if (a == "--setl0") { p.setl0 = unit_params("--l0", need(i)); p.l0 = (int)p.setl0.size(); }
+    else if (a == "--setl1") { p.setl1 = unit_params("--l1", need(i)); p.l1 = (int)p.setl1.size(); }
+    else if (a == "--phenoExcludeList") csv_into(need(i), p.pheno_excl);
+    else if (a == "--covarExcludeList") csv_into(need(i), p.covar_excl);
+    else if (a == "--l1-phenoList") csv_into(need(i), p.l1_phenos);
     else if (a == "--bed") p.bed = need(i);
     else if (a == "--bgen") p.bgen = need(i);
     else if (a == "--pgen") p.pgen = need(i);
-    else if (a == "--phenoFile") p.pheno = need(i);
-    else if (a == "--covarFile") p.covar = need(i);
-    else if (a == "--bsize") p.bsize = atoi(need(i).c_str());
-    else if (a == "--out") p.out = need(i);
+    else if (a == "--phenoFile" || a == "-p") p.pheno = need(i);
+    else if (a == "--covarFile" || a == "-c") p.covar = need(i);
+    else if (a == "--bsize" || a == "-b") p.bsize = atoi(need(i).c_str());
+    else if (a == "--out" || a == "-o") p.out = need(i);
     else if (a == "--pred") p.pred = need(i);
     else if (a == "--cv") p.cv = atoi(need(i).c_str());
     else if (a == "--l0") p.l0 = atoi(need(i).c_str());
@@ -177,6 +203,8 @@ Params parse_cli(int argc, char** argv) {
       throw Fail("option '" + a + "' is outside the hot path covered by rgb200 (see DESIGN.md, out of scope)");
     }
   }
+  if (!p.setl0.empty()) p.l0 = (int)p.setl0.size();
+  if (!p.setl1.empty()) p.l1 = (int)p.setl1.size();
   if (p.step != 1 && p.step != 2) throw Fail("specify which mode regenie should be running using option '--step'.");
   if (!p.bgen.empty() && p.step == 1) throw Fail("--bgen input in --step 1 is not implemented yet in rgb200 (hard-call .bed only).");
   if ((!p.bgen.empty()) + (!p.bed.empty()) + (!p.pgen.empty()) > 1) throw Fail("specify only one genotype input (--bed, --pgen or --bgen).");
@@ -295,6 +323,7 @@ void run_step1(const Params& p_in, Log& log) {
     throw Fail("it is not recommened to use more than 1000000 variants in step 1 (otherwise use '--force-step1').");
   Pheno ph;
   ph.pheno_cols = p.pheno_cols; ph.covar_cols = p.covar_cols; ph.rint = p.rint && !p.bt; ph.cat_cols = p.cat_cols; ph.max_cat_levels = p.max_cat_levels;
+  ph.pheno_excl = p.pheno_excl; ph.covar_excl = p.covar_excl;
   read_pheno_and_cov(SampleSet{g.keys, g.key_to_ind}, p.pheno, p.covar, false, p.strict, p.bt, ph, log);
   prep_run(ph, nullptr, log);
   if (p.bt && !p.loocv) {
@@ -323,7 +352,9 @@ void run_step1(const Params& p_in, Log& log) {
   const int P = ph.P;
   std::vector<int64_t> folds;
   if (!p.loocv) folds = set_folds(ph.in_analysis, p.cv);
-  const auto h0 = ridge_grid(p.l0), h1 = ridge_grid(p.l1);
+  if ((p.setl0.empty() && p.l0 < 2) || (p.setl1.empty() && p.l1 < 2))                 // set_ridge_params, src/Regenie.cpp:1499-1500
+    throw Fail("number of ridge parameters must be at least 2 (=" + std::to_string(p.setl0.empty() && p.l0 < 2 ? p.l0 : p.l1) + ")");
+  const auto h0 = p.setl0.empty() ? ridge_grid(p.l0) : p.setl0, h1 = p.setl1.empty() ? ridge_grid(p.l1) : p.setl1;
   std::vector<double> lambda(p.l0);
   const double M = p.run_l0_job ? (double)master.n_geno : (double)g.snps.size();     // src/Data.cpp:607
   for (int j = 0; j < p.l0; ++j) lambda[j] = M * (1 - h0[j]) / h0[j];           // src/Data.cpp:607
@@ -339,6 +370,15 @@ void run_step1(const Params& p_in, Log& log) {
   rg_check(rg_step1_create(&cfg, ph.X.data(), ph.Y.data(), ph.mask.data(), ph.in_analysis.data(),
                            p.loocv ? nullptr : folds.data(), lambda.data(), ph.neff.data(), &h));
 
+  // --l1-phenoList (with --run-l1): level 1 only for the named phenotypes (select_pheno_l1, src/Regenie.cpp:862-868)
+  std::vector<uint8_t> l1_sel(P, 1);
+  if (p.run_l1 && !p.l1_phenos.empty()) {
+    bool any = false;
+    for (int i = 0; i < P; ++i) { l1_sel[i] = p.l1_phenos.count(ph.names[i]) ? 1 : 0; any |= l1_sel[i] != 0; }
+    if (!any) throw Fail("none of the phenotypes in --l1-phenoList is in the phenotype file.");
+    rg_check(rg_l1_select(h, l1_sel.data()));
+  }
+
   // ---- level 0
   std::vector<uint8_t> rows((size_t)p.bsize * g.row_stride);
   const bool subset = g.keys.size() != g.keys_file.size();
@@ -349,6 +389,7 @@ void run_step1(const Params& p_in, Log& log) {
     log << " (skipping to level 1 models)\n";
     std::vector<double> slab((size_t)N * p.l0);
     for (int ph_i = 0; ph_i < P; ++ph_i) {
+      if (!l1_sel[ph_i]) continue;
       int b0 = 0;
       for (const auto& mj : master.jobs) {
         const std::string fin = mj.prefix + "_l0_Y" + std::to_string(ph_i + 1);
@@ -451,6 +492,7 @@ void run_step1(const Params& p_in, Log& log) {
   std::vector<int> chr_labels(23);
   for (int c = 0; c < 23; ++c) chr_labels[c] = c + 1;
   for (int ph_i = 0; ph_i < P; ++ph_i) {
+    if (!l1_sel[ph_i]) continue;
     log << "phenotype " << ph_i + 1 << " (" << ph.names[ph_i] << ") : \n";
     auto CS = [&](int k, int j) { return cs[((size_t)k * P + ph_i) * p.l1 + j]; };
     const double ne = ph.neff[ph_i];
@@ -517,6 +559,7 @@ void apply_range(const Params& p, std::vector<Snp>& snps) {
 void load_step2_inputs(const Params& p, const SampleSet& g, const std::vector<std::pair<std::string, std::string>>& ids_file,
                        const std::vector<int32_t>& sample_idx, Pheno& ph, std::vector<Loco>& locos, Log& log) {
   ph.pheno_cols = p.pheno_cols; ph.covar_cols = p.covar_cols; ph.rint = p.rint && !p.bt; ph.cat_cols = p.cat_cols; ph.max_cat_levels = p.max_cat_levels;
+  ph.pheno_excl = p.pheno_excl; ph.covar_excl = p.covar_excl;
   read_pheno_and_cov(g, p.pheno, p.covar, true, p.strict, p.bt, ph, log);
   const int64_t N = ph.N;
   const int P = ph.P;

@@ -25,6 +25,8 @@ def test_cli_errors_have_the_reference_shape(tmp_path, golden_dir):
         (["--step", "2", "--split-l0", "p,2", "--pred", "x"] + base, "only work in step 1"),
         (["--step", "2", "--pred", "x", "--range", "1:100"] + base, "wrong format for --range (must be CHR:MINPOS-MAXPOS)."),
         (["--step", "2", "--pred", "x", "--range", "Z:1-100"] + base, "unrecognized chromosome in --range."),
+        (["--step", "1", "--setl0", "0,0.5"] + base, "must specify values for --l0 in (0,1)."),
+        (["--step", "1", "--setl1", "0.5,1"] + base, "must specify values for --l1 in (0,1)."),
         (["--step", "2", "--pred", "x", "--write-samples", "--bgen", d + "/example.bgen"] + base[2:],
          "must specify sample file (using --sample) if writing sample IDs to file."),
     ]
@@ -32,6 +34,13 @@ def test_cli_errors_have_the_reference_shape(tmp_path, golden_dir):
         r = run(args, str(tmp_path))
         assert r.returncode != 0, args
         assert ("ERROR: " in r.stdout) and (msg in r.stdout), (args, r.stdout[-400:])
+
+
+def test_version_and_help(tmp_path):
+    r = run(["--version"], str(tmp_path))
+    assert r.returncode == 0 and r.stdout.startswith("rgb200 (")
+    r = run(["--help"], str(tmp_path))
+    assert r.returncode == 0 and "--gpu-inflate" in r.stdout and "--range" in r.stdout
 
 
 def test_no_cpu_fallback(tmp_path, golden_dir):

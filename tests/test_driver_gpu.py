@@ -657,3 +657,34 @@ def test_step2_range_is_a_window_of_the_full_run(tmp_path, golden_dir):
         win = open(str(tmp_path / (kind + "_win")) + "_Y1.regenie").read().splitlines()
         want = [l for l in full[1:] if l.startswith("2 ") and lo <= int(l.split()[1]) <= hi]
         assert win[0] == full[0] and win[1:] == want and len(want) > 50
+
+
+def test_user_ridge_grids_exclude_lists_aliases_and_l1_subset(tmp_path, golden_dir):
+    """--setl0/--setl1 with the default grid values, --phenoExcludeList/--covarExcludeList against the positive
+    column lists, the short option names, and --l1-phenoList after --split-l0/--run-l0 (src/Regenie.cpp:845-868)."""
+    d = golden_dir
+    pheno, covar = d + "/phenotype.txt", d + "/covariates.txt"
+    base = ["--step", "1", "--bed", d + "/example_3chr", "--phenoFile", pheno, "--covarFile", covar, "--bsize", "100"]
+    run(base + ["--out", str(tmp_path / "a")])
+    run(["--step", "1", "--bed", d + "/example_3chr", "-p", pheno, "-c", covar, "-b", "100", "--setl0", "0.99,0.01,0.25,0.5,0.75",
+         "--setl1", "0.01,0.25,0.5,0.75,0.99,0.5", "-o", str(tmp_path / "b")])
+    for k in (1, 2):
+        assert open(str(tmp_path / "a") + "_%d.loco" % k).read() == open(str(tmp_path / "b") + "_%d.loco" % k).read()
+    # a different grid changes the fit
+    log = run(base + ["--setl1", "0.1,0.9", "--out", str(tmp_path / "c")])
+    assert log.count("Rsq = ") == 4
+    # exclusion lists == positive lists
+    hdr = open(covar).readline().split()[2:]
+    run(base + ["--phenoCol", "Y2", "--covarColList", ",".join(hdr[:2]), "--out", str(tmp_path / "d")])
+    run(base + ["--phenoExcludeList", "Y1", "--covarExcludeList", ",".join(hdr[2:]), "--out", str(tmp_path / "e")])
+    assert open(str(tmp_path / "d") + "_1.loco").read() == open(str(tmp_path / "e") + "_1.loco").read()
+    assert [l.split()[0] for l in open(str(tmp_path / "e") + "_pred.list")] == ["Y2"]
+    # level 1 for a subset of the phenotypes
+    par = str(tmp_path / "par")
+    run(base + ["--split-l0", par + ",2", "--out", str(tmp_path / "l0")])
+    for job in (1, 2):
+        run(base + ["--run-l0", par + ".master,%d" % job, "--out", str(tmp_path / "l0")])
+    run(base + ["--run-l1", par + ".master", "--l1-phenoList", "Y2", "--keep-l0", "--out", str(tmp_path / "l1")])
+    assert open(str(tmp_path / "l1") + "_2.loco").read() == open(str(tmp_path / "a") + "_2.loco").read()
+    assert not os.path.exists(str(tmp_path / "l1") + "_1.loco")
+    assert [l.split()[0] for l in open(str(tmp_path / "l1") + "_pred.list")] == ["Y2"]
