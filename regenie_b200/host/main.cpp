@@ -592,11 +592,11 @@ void load_step2_inputs(const Params& p, const SampleSet& g, const std::vector<st
     if (it == blup_files.end()) throw Fail("No step 1 file provided for phenotype '" + ph.names[i] + "'.");
     locos[i] = read_loco(it->second, p.use_prs);
     log << "   -file [" << it->second << "] for phenotype '" << ph.names[i] << "'\n";
-    const auto& first = locos[i].rows[0];                    // blup_read checks the first data row
+    const auto& first = locos[i].first;                      // blup_read checks the first data row
     for (size_t c = 0; c < locos[i].ids.size(); ++c) {
       auto k = g.key_to_ind.find(locos[i].ids[c]);
       if (k == g.key_to_ind.end() || first.empty()) continue;
-      extra[(size_t)i * N + k->second] = first[c] != "NA";
+      extra[(size_t)i * N + k->second] = !std::isnan(first[c]);
     }
   }
   write_ids(&extra);
@@ -604,19 +604,19 @@ void load_step2_inputs(const Params& p, const SampleSet& g, const std::vector<st
 }
 
 // blup_read_chr (src/Step2_Models.cpp:96-124): LOCO prediction of trait i for one chromosome
-std::vector<double> blup_for_chr(const Loco& loco, const SampleSet& g, const Pheno& ph, int i, int chrom) {
+std::vector<double> blup_for_chr(Loco& loco, const SampleSet& g, const Pheno& ph, int i, int chrom) {
   const int64_t N = ph.N;
   std::vector<double> blup(N, 0.0);
-  if (loco.rows.empty()) return blup;                       // --ignore-pred
-  const auto& row = loco.rows[loco.prs ? 0 : chrom - 1];     // --use-prs: the same whole-genome row for every chromosome
-  if (row.empty()) throw Fail("blup file for phenotype '" + ph.names[i] + "' has no row for chromosome " + std::to_string(chrom));
+  if (loco.empty()) return blup;                            // --ignore-pred
+  if (!loco.has_row(chrom)) throw Fail("blup file for phenotype '" + ph.names[i] + "' has no row for chromosome " + std::to_string(chrom));
+  const std::vector<double>& row = loco.row(chrom);          // --use-prs: the same whole-genome row for every chromosome
   for (size_t c = 0; c < loco.ids.size(); ++c) {
     auto k = g.key_to_ind.find(loco.ids[c]);
     if (k == g.key_to_ind.end()) continue;
     const uint32_t s = k->second;
     if (!ph.in_analysis[s] || !ph.mask[(size_t)i * N + s]) continue;
-    if (row[c] == "NA") throw Fail("individual has missing predictions (FID_IID=" + loco.ids[c] + ")");
-    blup[s] = convert_double(row[c]);
+    if (std::isnan(row[c])) throw Fail("individual has missing predictions (FID_IID=" + loco.ids[c] + ")");
+    blup[s] = row[c];
   }
   return blup;
 }

@@ -1,36 +1,109 @@
 #include "output.hpp"
 
+#include <atomic>
 #include <cmath>
+#include <limits>
+#include <thread>
 
 namespace rgh {
+
+namespace {
+
+// "<label> v1 v2 ... " -> the label and the values (NA / nan / inf -> NaN, like convertDouble's missing code)
+void parse_pred_row(const std::string& line, std::string& label, std::vector<double>& vals, size_t expect) {
+  vals.clear();
+  vals.reserve(expect);
+  const char* p = line.c_str();
+  const char* const end = p + line.size();
+  auto skip = [&] { while (p < end && (*p == ' ' || *p == '\t')) ++p; };
+  skip();
+  const char* t0 = p;
+  while (p < end && *p != ' ' && *p != '\t') ++p;
+  label.assign(t0, (size_t)(p - t0));
+  const double nan = std::numeric_limits<double>::quiet_NaN();
+  for (;;) {
+    skip();
+    if (p >= end) break;
+    if (p[0] == 'N' && p + 1 < end && p[1] == 'A' && (p + 2 == end || p[2] == ' ' || p[2] == '\t')) {
+      vals.push_back(nan);
+      p += 2;
+      continue;
+    }
+    char* q = nullptr;
+    const double v = std::strtod(p, &q);
+    if (q == p) {
+      const char* e = p;
+      while (e < end && *e != ' ' && *e != '\t') ++e;
+      throw Fail("could not convert value to double: '" + std::string(p, (size_t)(e - p)) + "'");
+    }
+    vals.push_back(std::isfinite(v) ? v : nan);
+    p = q;
+  }
+}
+
+}  // namespace
 
 Loco read_loco(const std::string& path, bool prs) {
   LineReader fh(path);
   Loco l;
   l.prs = prs;
-  std::string line;
+  l.path_ = path;
+  l.eager_ = fh.is_gz();
+  l.offs_.assign(23, -1);
+  l.rows_.assign(23, {});
+  std::string line, label;
   fh.getline(line);
   l.ids = split_ws(line);
   if (l.ids.empty() || l.ids[0] != "FID_IID")
     throw Fail("header of blup file must start with FID_IID" + (l.ids.empty() ? std::string(".") : " (=" + l.ids[0] + ")"));
   l.ids.erase(l.ids.begin());
-  l.rows.resize(23);
   bool first = true;
-  while (fh.getline(line)) {
-    auto t = split_ws(line);
-    if (t.empty()) continue;
+  std::vector<double> vals;
+  for (;;) {
+    const int64_t off = fh.tell();
+    if (!fh.getline(line)) break;
+    size_t k = 0;
+    while (k < line.size() && (line[k] == ' ' || line[k] == '\t')) ++k;
+    if (k == line.size()) continue;
+    size_t e = k;
+    while (e < line.size() && line[e] != ' ' && line[e] != '\t') ++e;
+    label.assign(line, k, e - k);
     if (prs) {                                               // src/Pheno.cpp:1297-1298
       if (!first) break;
-      if (t[0] != "0") throw Fail("second line must start with 0 (=" + t[0] + ").");
+      if (label != "0") throw Fail("second line must start with 0 (=" + label + ").");
     }
+    const int c = prs ? 1 : chr_str_to_int(label);
+    if (c < 1) throw Fail("blup file has an invalid chromosome row: " + label);
+    if (first || l.eager_) {
+      parse_pred_row(line, label, vals, l.ids.size());
+      if (vals.size() != l.ids.size()) throw Fail("blup file has different number of entries compared to the header");
+      if (first) l.first = vals;
+      if (l.eager_) l.rows_[c - 1] = vals;
+    }
+    l.offs_[c - 1] = off;
     first = false;
-    const int c = prs ? 1 : chr_str_to_int(t[0]);
-    if (c < 1) throw Fail("blup file has an invalid chromosome row: " + t[0]);
-    if (t.size() != l.ids.size() + 1) throw Fail("blup file has different number of entries compared to the header");
-    t.erase(t.begin());
-    l.rows[c - 1] = std::move(t);
   }
   return l;
+}
+
+bool Loco::has_row(int chrom) const {
+  const int r = prs ? 0 : chrom - 1;
+  return !empty() && r >= 0 && r < 23 && offs_[r] >= 0;
+}
+
+const std::vector<double>& Loco::row(int chrom) {
+  const int r = prs ? 0 : chrom - 1;
+  if (!has_row(chrom)) throw Fail("blup file " + path_ + " has no row for chromosome " + std::to_string(chrom));
+  if (eager_ || cached_ == r) return rows_[r];
+  if (cached_ >= 0) std::vector<double>().swap(rows_[cached_]);
+  LineReader fh(path_);
+  fh.seek(offs_[r]);
+  std::string line, label;
+  if (!fh.getline(line)) throw Fail("cannot read from file : " + path_);
+  parse_pred_row(line, label, rows_[r], ids.size());
+  if (rows_[r].size() != ids.size()) throw Fail("blup file has different number of entries compared to the header");
+  cached_ = r;
+  return rows_[r];
 }
 
 std::map<std::string, std::string> read_pred_list(const std::string& path) {
@@ -55,19 +128,38 @@ void write_pred_file(TextWriter& out, const std::vector<std::string>& keys, cons
   for (uint32_t i : order) { buf += keys[i]; buf += ' '; }
   buf += '\n';
   out << buf;
-  char num[40];
-  for (size_t r = 0; r < row_labels.size(); ++r) {
-    buf.clear();
-    buf += std::to_string(row_labels[r]);
-    buf += ' ';
+  // the rows are independent: format them on a few threads (23 x N numbers; at N = 500k this is the longest host-side
+  // step of Step 1 when done serially), write them in order
+  const size_t R = row_labels.size();
+  std::vector<std::string> bufs(R);
+  auto format_row = [&](size_t r) {
+    std::string& b = bufs[r];
+    b.reserve(order.size() * 10 + 16);
+    b += std::to_string(row_labels[r]);
+    b += ' ';
     const double* v = values[r];
+    char num[40];
     for (uint32_t i : order) {
-      if (mask[i]) buf.append(num, (size_t)snprintf(num, sizeof(num), "%g ", v[i]));
-      else buf += "NA ";
+      if (mask[i]) b.append(num, (size_t)snprintf(num, sizeof(num), "%g ", v[i]));
+      else b += "NA ";
     }
-    buf += '\n';
-    out << buf;
-  }
+    b += '\n';
+  };
+  const size_t work_items = R * order.size();
+  size_t T = work_items > (1u << 20) ? std::min<size_t>({R, 8, std::max(1u, std::thread::hardware_concurrency())}) : 1;
+  std::atomic<size_t> next{0};
+  auto worker = [&] {
+    for (;;) {
+      const size_t r = next.fetch_add(1);
+      if (r >= R) return;
+      format_row(r);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (size_t t = 1; t < T; ++t) pool.emplace_back(worker);
+  worker();
+  for (auto& t : pool) t.join();
+  for (size_t r = 0; r < R; ++r) out << bufs[r];
 }
 
 double get_logp(double t) {   // chi2_1 sf = erfc(sqrt(T/2))

@@ -12,11 +12,28 @@
 
 namespace rgh {
 
-// one prediction file: sample ids of the header line and the token rows by chromosome
-struct Loco {
-  std::vector<std::string> ids;
-  std::vector<std::vector<std::string>> rows;   // [23] for .loco; rows[0] = the single "0" row for .prs
-  bool prs = false;
+// One prediction file (.loco / .prs, plain or .gz).  The header ids and the first data row are parsed when the file is
+// opened (blup_read looks at exactly those, src/Pheno.cpp:1290-1316); the other rows are parsed when a chromosome asks
+// for them (blup_read_chr re-reads the file per chromosome, src/Step2_Models.cpp:51-143): a plain file keeps the byte
+// offset of every row and holds one parsed row at a time - at N = 500k a .loco file is 120 MB of text, 23 x N tokens -
+// a gzip file cannot seek and is parsed once into doubles.
+class Loco {
+ public:
+  std::vector<std::string> ids;                 // sample ids of the header line
+  std::vector<double> first;                    // first data row by header position, NaN = NA
+  bool prs = false;                             // --use-prs: one row labelled "0", valid for every chromosome
+  bool empty() const { return path_.empty(); }  // --ignore-pred
+  bool has_row(int chrom) const;
+  // values of the row of `chrom` (1..23) by header position, NaN = NA; throws when the file has no such row
+  const std::vector<double>& row(int chrom);
+
+ private:
+  friend Loco read_loco(const std::string& path, bool prs);
+  std::string path_;
+  std::vector<int64_t> offs_;                   // [23] byte offset of the row in a plain file, -1 = absent
+  std::vector<std::vector<double>> rows_;       // [23] parsed rows (all of them for .gz, the cached one otherwise)
+  int cached_ = -1;
+  bool eager_ = false;
 };
 
 // `prs`: the file is a whole-genome PRS (--use-prs): one row whose first token must be "0"

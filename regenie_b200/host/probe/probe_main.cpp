@@ -188,13 +188,19 @@ int cmd_pred_file(int argc, char** argv) {
 
 int cmd_read_pred(int argc, char** argv) {
   const bool prs = argc > 3 && std::string(argv[3]) == "--prs";
-  const Loco l = read_loco(argv[2], prs);
+  Loco l = read_loco(argv[2], prs);
   std::cout << "ids " << l.ids.size() << "\n";
   for (auto& s : l.ids) std::cout << s << "\n";
-  for (size_t r = 0; r < l.rows.size(); ++r) {
-    if (l.rows[r].empty()) continue;
-    std::cout << "row " << r << " " << l.rows[r].size() << "\n";
-    for (auto& s : l.rows[r]) std::cout << s << "\n";
+  auto show = [](double v) { if (std::isnan(v)) std::cout << "NA\n"; else std::cout << v << "\n"; };
+  std::cout << "first " << l.first.size() << "\n";
+  for (double v : l.first) show(v);
+  // rows on demand, out of file order on purpose (a plain file seeks, a .gz file was parsed when it was opened)
+  for (int c = 23; c >= 1; --c) {
+    if (!l.has_row(c)) continue;
+    const std::vector<double>& r = l.row(c);
+    std::cout << "row " << c << " " << r.size() << "\n";
+    for (double v : r) show(v);
+    if (prs) break;
   }
   return 0;
 }

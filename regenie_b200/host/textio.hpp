@@ -33,6 +33,16 @@ class LineReader {
     if (gz_) gzclose(gz_);
     if (fp_) fclose(fp_);
   }
+  bool is_gz() const { return gz_ != nullptr; }
+  // byte offset (in the uncompressed text) of the next line getline() will return
+  int64_t tell() const { return consumed_; }
+  // plain files only: continue reading at byte offset `off`
+  void seek(int64_t off) {
+    if (!fp_ || fseeko(fp_, (off_t)off, SEEK_SET) != 0) throw Fail("cannot seek in file : " + path_);
+    pos_ = len_ = 0;
+    eof_ = false;
+    consumed_ = off;
+  }
   // false at end of file; the trailing "\n" / "\r\n" is removed
   bool getline(std::string& line) {
     line.clear();
@@ -48,11 +58,13 @@ class LineReader {
       any = true;
       if (nl) {
         line.append(b, (size_t)(nl - b));
+        consumed_ += (int64_t)(nl - b) + 1;
         pos_ += (size_t)(nl - b) + 1;
         if (!line.empty() && line.back() == '\r') line.pop_back();
         return true;
       }
       line.append(b, len_ - pos_);
+      consumed_ += (int64_t)(len_ - pos_);
       pos_ = len_;
     }
     if (any && !line.empty() && line.back() == '\r') line.pop_back();
@@ -75,6 +87,7 @@ class LineReader {
   std::string path_;
   std::vector<char> buf_;
   size_t pos_ = 0, len_ = 0;
+  int64_t consumed_ = 0;
   bool eof_ = false;
   gzFile gz_ = nullptr;
   FILE* fp_ = nullptr;

@@ -270,10 +270,33 @@ def test_loco_and_prs_files_plain_and_gz(tmp_path, prs, gz):
     assert text == want
     out = probe("read-pred", path, *(["--prs"] if prs else [])).stdout.splitlines()
     assert out[0] == "ids %d" % len(ids) and out[1:1 + len(ids)] == ids
-    nrows = sum(1 for l in out if l.startswith("row "))
-    assert nrows == (1 if prs else 23)
-    first = out[2 + len(ids):2 + 2 * len(ids)]
-    assert first == want.splitlines()[1].split()[1:]
+    k = 1 + len(ids)
+    assert out[k] == "first %d" % len(ids)
+    assert out[k + 1:k + 1 + len(ids)] == want.splitlines()[1].split()[1:]
+    k += 1 + len(ids)
+    want_rows = {l.split()[0]: l.split()[1:] for l in want.splitlines()[1:]}
+    seen = []
+    while k < len(out):
+        tag, c, n = out[k].split()
+        assert tag == "row" and int(n) == len(ids)
+        label = "0" if prs else c
+        assert out[k + 1:k + 1 + len(ids)] == want_rows[label], (c, prs, gz)
+        seen.append(int(c))
+        k += 1 + len(ids)
+    assert seen == ([23] if prs else list(range(23, 0, -1)))
+
+
+def test_loco_writer_threaded_path_and_lazy_rows_at_scale(tmp_path):
+    """Above 2^20 values the rows are formatted on several threads; the file must not depend on that, and the reader
+    must serve any row on demand (seek in the plain file)."""
+    n = 60000
+    path = str(tmp_path / "big.loco")
+    probe("pred-file", path, n)
+    want, ids = _pred_reference(n, False)
+    assert open(path).read() == want
+    out = probe("read-pred", path).stdout.splitlines()
+    k = out.index("row 7 %d" % len(ids))
+    assert out[k + 1:k + 1 + len(ids)] == want.splitlines()[7].split()[1:]
 
 
 def test_prs_reader_rejects_a_loco_file(tmp_path):
