@@ -683,6 +683,8 @@ void run_step2_qt(const Params& p, Log& log) {
     outs[i].open(p.out + "_" + ph.names[i] + ".regenie" + (p.gz ? ".gz" : ""));
     outs[i] << sumstats_header(use_bgen);
   }
+  std::vector<std::string> obuf(P);                          // rows of the current block, one buffer per trait
+  std::string head_s;
   const int bsz = p.bsize;
   // input blocks are fetched (file read / threaded BGEN inflate) one block ahead of the GPU call: the rg_s2_block_*
   // calls return with the results on the host, so the buffer of block b is free again when block b+2 is fetched
@@ -755,16 +757,21 @@ void run_step2_qt(const Params& p, Log& log) {
     for (int v = 0; v < blocks[b].size; ++v) {
       if (flags[v] & 3) { ++n_ignored; continue; }            // no row for ignored variants (split mode)
       const Snp& s = snps[blocks[b].first + v];
-      std::ostringstream head;
-      head << s.chrom << " " << s.pos << " " << s.id << " " << s.allele0 << " " << s.allele1 << " ";
+      head_s.clear();                                        // print_sum_stats_head, src/Step2_Models.cpp:2410-2418
+      head_s += std::to_string(s.chrom); head_s += ' ';
+      head_s += std::to_string(s.pos); head_s += ' ';
+      head_s += s.id; head_s += ' ';
+      head_s += s.allele0; head_s += ' ';
+      head_s += s.allele1; head_s += ' ';
       for (int i = 0; i < P; ++i) {
         const size_t e = (size_t)v * P + i;
         if (mac[e] < p.min_mac) continue;                      // ignored_trait (src/Geno.cpp:3102)
         if (use_bgen && info[e] < p.min_info) continue;        // --minINFO (src/Geno.cpp:3142-3146)
-        outs[i] << sumstats_row(head.str(), af[e], use_bgen, use_bgen ? info[e] : -1.0, ns[e], "ADD", beta[e], se[e], chisq[e],
-                                get_logp(chisq[e]), true);   // print_sum_stats_single :2502-2540
+        append_sumstats_row(obuf[i], head_s, af[e], use_bgen, use_bgen ? info[e] : -1.0, ns[e], "ADD", beta[e], se[e], chisq[e],
+                            get_logp(chisq[e]), true);   // print_sum_stats_single :2502-2540
       }
     }
+    for (int i = 0; i < P; ++i) { outs[i] << obuf[i]; obuf[i].clear(); }
     log << " block [" << b + 1 << "/" << blocks.size() << "] : done\n";
   }
   for (auto& o : outs) o.close();
@@ -820,6 +827,8 @@ void run_step2_bt(const Params& p, Log& log) {
     outs[i].open(p.out + "_" + ph.names[i] + ".regenie" + (p.gz ? ".gz" : ""));
     outs[i] << sumstats_header(use_bgen);
   }
+  std::vector<std::string> obuf(P);                          // rows of the current block, one buffer per trait
+  std::string head_s;
   const int bsz = p.bsize;
   const int threads = p.threads > 0 ? p.threads : (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
   std::vector<uint8_t> probs[2], pmiss[2], rows[2];          // fetched one block ahead of the GPU call, like the QT path
@@ -926,8 +935,12 @@ void run_step2_bt(const Params& p, Log& log) {
     for (int v = 0; v < bs; ++v) {
       if (flags[v] & (1 | 16)) { ++n_ignored; continue; }
       const Snp& s = snps[blocks[b].first + v];
-      std::ostringstream head;
-      head << s.chrom << " " << s.pos << " " << s.id << " " << s.allele0 << " " << s.allele1 << " ";
+      head_s.clear();                                        // print_sum_stats_head, src/Step2_Models.cpp:2410-2418
+      head_s += std::to_string(s.chrom); head_s += ' ';
+      head_s += std::to_string(s.pos); head_s += ' ';
+      head_s += s.id; head_s += ' ';
+      head_s += s.allele0; head_s += ' ';
+      head_s += s.allele1; head_s += ' ';
       for (int i = 0; i < P; ++i) {
         const size_t e = (size_t)v * P + i;
         if (mac[e] < p.min_mac) continue;
@@ -941,9 +954,10 @@ void run_step2_bt(const Params& p, Log& log) {
         }
         double lp = get_logp(co);
         if (p.spa && pass && f != fidx.end()) lp = spa_logp[{v, i}];   // SPA reports -log10 of its own p-value
-        outs[i] << sumstats_row(head.str(), af[e], use_bgen, use_bgen ? info[e] : -1.0, ns[e], "ADD", bo, so, co, lp, pass);
+        append_sumstats_row(obuf[i], head_s, af[e], use_bgen, use_bgen ? info[e] : -1.0, ns[e], "ADD", bo, so, co, lp, pass);
       }
     }
+    for (int i = 0; i < P; ++i) { outs[i] << obuf[i]; obuf[i].clear(); }
     log << " block [" << b + 1 << "/" << blocks.size() << "] : done\n";
   }
   for (auto& o : outs) o.close();

@@ -57,6 +57,10 @@ std::string sumstats_header(bool with_info);
 std::string sumstats_row(const std::string& head, double af, bool with_info, double info, int n, const char* test,
                          double beta, double se, double chisq, double logp, bool test_pass);
 
+// the same row appended to a caller-owned buffer (one buffer per trait, flushed once per block)
+void append_sumstats_row(std::string& out, const std::string& head, double af, bool with_info, double info, int n,
+                         const char* test, double beta, double se, double chisq, double logp, bool test_pass);
+
 // <out>_<pheno>.regenie.ids: "FID\tIID" of the samples of one trait, no newline after the last one
 void write_ids_file(const std::string& path, const std::string& pheno_name, bool print_pheno_name,
                     const std::vector<std::pair<std::string, std::string>>& fid_iid, const uint8_t* mask);
