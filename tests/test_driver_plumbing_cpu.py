@@ -1,0 +1,178 @@
+"""The rgb200 driver end to end WITHOUT a GPU: its own sources linked against tests/mock/mock_abi.cpp, a CPU stand-in
+for the C ABI whose outputs are simple deterministic functions of what the driver hands over (not regenie's
+statistics).  What is checked here is the host control flow around the hot path - the equivalences the reference's own
+test script checks (test/test_bash.sh: sharded == unsharded, job outputs concatenate, compressed == plain) and the
+file formats - so that a change to the driver is caught where no GPU exists.  Numbers are never compared with the
+oracle here; that is what tests/test_driver_gpu.py does on the real library.
+"""
+import glob
+import gzip
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MOCK = os.path.join(ROOT, "tests", "mock", "rgb200_mock")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    srcs = sorted(glob.glob(os.path.join(ROOT, "regenie_b200", "host", "*.cpp"))) + [os.path.join(ROOT, "tests", "mock", "mock_abi.cpp")]
+    deps = srcs + glob.glob(os.path.join(ROOT, "regenie_b200", "host", "*.hpp")) + [os.path.join(ROOT, "include", "rg_b200.h")]
+    if not os.path.exists(MOCK) or any(os.path.getmtime(s) > os.path.getmtime(MOCK) for s in deps):
+        r = subprocess.run(["g++", "-O1", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", MOCK] + srcs +
+                           ["-lz", "-lpthread", "-ldl"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+
+
+def run(args, ok=True):
+    r = subprocess.run([MOCK] + [str(a) for a in args], capture_output=True, text=True, timeout=300)
+    if ok:
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return r.stdout
+
+
+def read(path):
+    return gzip.open(path, "rt").read() if str(path).endswith(".gz") else open(path).read()
+
+
+def step1(d, fileset="example_3chr", extra=(), pheno="/phenotype.txt"):
+    return ["--step", "1", "--bed", d + "/" + fileset, "--phenoFile", d + pheno, "--covarFile", d + "/covariates.txt",
+            "--bsize", "100"] + list(extra)
+
+
+def test_step1_outputs_gz_prs_and_sharded_equals_unsharded(tmp_path, golden_dir):
+    d = golden_dir
+    a, b = str(tmp_path / "a"), str(tmp_path / "b")
+    log = run(step1(d) + ["--out", a])
+    assert "<- min value" in log and "List of blup files written to" in log
+    run(step1(d, extra=["--gz", "--print-prs", "--lowmem", "--keep-l0", "--lowmem-prefix", str(tmp_path / "tmp_rg")]) + ["--out", b])
+    for k in (1, 2):
+        plain = read(a + "_%d.loco" % k)
+        assert read(b + "_%d.loco.gz" % k) == plain
+        rows = {l.split()[0]: l.split()[1:] for l in plain.splitlines()}
+        assert len(rows) == 24 and len(rows["FID_IID"]) == 500
+        prs = read(b + "_%d.prs.gz" % k).splitlines()
+        assert prs[0] == plain.splitlines()[0] and prs[1].split()[0] == "0" and prs[1].split()[1:] == rows["7"]
+        assert os.path.getsize(str(tmp_path / "tmp_rg") + "_l0_Y%d" % k) == 8 * 500 * 5 * 6       # N x R x blocks doubles
+    assert [l.split()[0] for l in open(a + "_pred.list")] == ["Y1", "Y2"]
+    # --split-l0 / --run-l0 / --run-l1 (test/test_bash.sh:91-137), then level 1 for one phenotype only
+    par = str(tmp_path / "par")
+    run(step1(d) + ["--split-l0", par + ",3", "--out", str(tmp_path / "l0")])
+    master = open(par + ".master").read().splitlines()
+    assert master[0] == "500 100" and len(master) == 4
+    for job in (1, 2, 3):
+        run(step1(d) + ["--run-l0", par + ".master,%d" % job, "--out", str(tmp_path / "l0")])
+        assert os.path.exists(par + "_job%d_l0_Y1" % job)
+    run(step1(d) + ["--run-l1", par + ".master", "--keep-l0", "--out", str(tmp_path / "l1")])
+    run(step1(d) + ["--run-l1", par + ".master", "--l1-phenoList", "Y2", "--out", str(tmp_path / "l1b")])
+    for k in (1, 2):
+        assert read(str(tmp_path / "l1") + "_%d.loco" % k) == read(a + "_%d.loco" % k)
+    assert read(str(tmp_path / "l1b") + "_2.loco") == read(a + "_2.loco") and not os.path.exists(str(tmp_path / "l1b") + "_1.loco")
+    assert not os.path.exists(par + "_job1_l0_Y1")                      # removed after level 1 unless --keep-l0
+    # user grids equal to the default ones, short option names, exclusion lists
+    run(["--step", "1", "--bed", d + "/example_3chr", "-p", d + "/phenotype.txt", "-c", d + "/covariates.txt", "-b", "100",
+         "--setl0", "0.99,0.01,0.25,0.5,0.75", "--setl1", "0.01,0.25,0.5,0.75,0.99", "-o", str(tmp_path / "g")])
+    assert read(str(tmp_path / "g") + "_1.loco") == read(a + "_1.loco")
+    run(step1(d, extra=["--phenoCol", "Y2", "--covarColList", "V1,V2"]) + ["--out", str(tmp_path / "h1")])
+    run(step1(d, extra=["--phenoExcludeList", "Y1", "--covarExcludeList", "V3"]) + ["--out", str(tmp_path / "h2")])
+    assert read(str(tmp_path / "h1") + "_1.loco") == read(str(tmp_path / "h2") + "_1.loco")
+
+
+def test_step2_qt_jobs_windows_compressed_io_and_prs(tmp_path, golden_dir):
+    d = golden_dir
+    pheno, covar = d + "/phenotype.txt", d + "/covariates.txt"
+    fit = str(tmp_path / "fit")
+    run(step1(d, extra=["--print-prs"]) + ["--out", fit])
+    s2 = ["--step", "2", "--bed", d + "/example_3chr", "--phenoFile", pheno, "--covarFile", covar, "--bsize", "77", "--pred",
+          fit + "_pred.list"]
+    full = str(tmp_path / "full")
+    run(s2 + ["--out", full])
+    rows = read(full + "_Y1.regenie").splitlines()
+    assert rows[0] == "CHROM GENPOS ID ALLELE0 ALLELE1 A1FREQ N TEST BETA SE CHISQ LOG10P EXTRA" and len(rows) > 400
+    # chromosome jobs concatenate to the full run; a window is the matching slice
+    cat = rows[:1]
+    for c in (1, 2, 3):
+        run(s2 + ["--chr", c, "--out", str(tmp_path / ("chr%d" % c))])
+        cat += read(str(tmp_path / ("chr%d" % c)) + "_Y1.regenie").splitlines()[1:]
+    assert cat == rows
+    pos = sorted(int(l.split()[1]) for l in rows[1:] if l.startswith("2 "))
+    lo, hi = pos[len(pos) // 3], pos[2 * len(pos) // 3]
+    run(s2 + ["--range", "2:%d-%d" % (lo, hi), "--out", str(tmp_path / "win")])
+    assert read(str(tmp_path / "win") + "_Y1.regenie").splitlines()[1:] == \
+        [l for l in rows[1:] if l.startswith("2 ") and lo <= int(l.split()[1]) <= hi]
+    # .gz everywhere: phenotypes, covariates, prediction files, outputs; sample lists
+    for f in ("phenotype.txt", "covariates.txt"):
+        with open(d + "/" + f, "rb") as src, gzip.open(tmp_path / (f + ".gz"), "wb") as dst:
+            shutil.copyfileobj(src, dst)
+    fitz = str(tmp_path / "fitz")
+    run(step1(d, extra=["--gz"]) + ["--out", fitz])
+    gz = str(tmp_path / "gz")
+    run(["--step", "2", "--bed", d + "/example_3chr", "--phenoFile", tmp_path / "phenotype.txt.gz", "--covarFile",
+         tmp_path / "covariates.txt.gz", "--bsize", "77", "--pred", fitz + "_pred.list", "--gz", "--write-samples", "--print-pheno",
+         "--out", gz])
+    for nm in ("Y1", "Y2"):
+        assert read(gz + "_%s.regenie.gz" % nm) == read(full + "_%s.regenie" % nm)
+        ids = open(gz + "_%s.regenie.ids" % nm).read().split("\n")
+        assert ids[0] == nm + "\tNA" and len(ids) == 501 and ids[1] == "1\t1"
+    # --use-prs == LOCO files whose rows all hold the PRS; --ignore-pred differs from both
+    lst = tmp_path / "fake_pred.list"
+    with open(lst, "w") as fl:
+        for k, nm in ((1, "Y1"), (2, "Y2")):
+            prs = read(fit + "_%d.prs" % k).splitlines()
+            with open(tmp_path / ("fake_%d.loco" % k), "w") as fh:
+                fh.write(prs[0] + "\n")
+                for c in range(1, 24):
+                    fh.write(str(c) + " " + prs[1].split(" ", 1)[1] + "\n")
+            fl.write("%s %s\n" % (nm, tmp_path / ("fake_%d.loco" % k)))
+    base = ["--step", "2", "--bed", d + "/example_3chr", "--phenoFile", pheno, "--covarFile", covar, "--bsize", "77"]
+    run(base + ["--pred", lst, "--out", str(tmp_path / "u1")])
+    log = run(base + ["--pred", fit + "_prs.list", "--use-prs", "--out", str(tmp_path / "u2")])
+    run(base + ["--ignore-pred", "--out", str(tmp_path / "u3")])
+    assert " * PRS predictions : [" in log
+    u1, u2, u3 = (read(str(tmp_path / u) + "_Y1.regenie") for u in ("u1", "u2", "u3"))
+    assert u1 == u2 and u1 != read(full + "_Y1.regenie") and u3 != u1 and u3 != read(full + "_Y1.regenie")
+    # .pgen input == .bed input (the reference's fixture pair holds the same calls)
+    one = ["--step", "2", "--phenoFile", pheno, "--covarFile", covar, "--bsize", "200", "--ignore-pred"]
+    run(one + ["--bed", d + "/example", "--out", str(tmp_path / "pb")])
+    run(one + ["--pgen", d + "/example", "--out", str(tmp_path / "pp")])
+    assert read(str(tmp_path / "pb") + "_Y2.regenie") == read(str(tmp_path / "pp") + "_Y2.regenie")
+    # a sample subset changes N, missing step-1 files are reported like the reference
+    run(one + ["--bed", d + "/example", "--remove", d + "/fid_iid_to_remove.txt", "--out", str(tmp_path / "rm")])
+    assert {l.split()[6] for l in read(str(tmp_path / "rm") + "_Y1.regenie").splitlines()[1:]} == {"494"}
+    out = run(base + ["--pred", d + "/nope_pred.list", "--out", str(tmp_path / "x")], ok=False)
+    assert "ERROR: cannot open file : " in out
+
+
+def test_step2_bgen_index_inflate_paths_and_bt_corrections(tmp_path, golden_dir):
+    d = golden_dir
+    shutil.copy(d + "/example_3chr.bgen", tmp_path / "noidx.bgen")
+    qt = ["--step", "2", "--phenoFile", d + "/phenotype.txt", "--covarFile", d + "/covariates.txt", "--bsize", "64", "--ignore-pred",
+          "--sample", d + "/example_3chr.sample"]
+    la = run(qt + ["--bgen", d + "/example_3chr.bgen", "--out", str(tmp_path / "a")])
+    lb = run(qt + ["--bgen", tmp_path / "noidx.bgen", "--out", str(tmp_path / "b")])
+    lc = run(qt + ["--bgen", d + "/example_3chr.bgen", "--gpu-inflate", "--remove", d + "/fid_iid_to_remove.txt", "--out", str(tmp_path / "c")])
+    run(qt + ["--bgen", d + "/example_3chr.bgen", "--remove", d + "/fid_iid_to_remove.txt", "--out", str(tmp_path / "c0")])
+    assert "-index bgi file [" in la and "-index bgi file [" not in lb and "inflated on the GPU" in lc
+    a = read(str(tmp_path / "a") + "_Y1.regenie")
+    assert a.splitlines()[0].split()[6] == "INFO" and a == read(str(tmp_path / "b") + "_Y1.regenie")
+    assert read(str(tmp_path / "c") + "_Y2.regenie") == read(str(tmp_path / "c0") + "_Y2.regenie")
+    # binary traits: Step 1 --bt, then Step 2 with the Firth and the SPA fallbacks on .bgen and .bed
+    fit = str(tmp_path / "fitb")
+    log = run(["--step", "1", "--bed", d + "/example", "--phenoFile", d + "/phenotype_bin.txt", "--covarFile", d + "/covariates.txt",
+               "--remove", d + "/fid_iid_to_remove.txt", "--bsize", "100", "--bt", "--lowmem", "--out", fit])
+    assert "-logLik/N = " in log and "using LOOCV" in log
+    bt = ["--step", "2", "--covarFile", d + "/covariates.txt", "--phenoFile", d + "/phenotype_bin.txt", "--remove",
+          d + "/fid_iid_to_remove.txt", "--bsize", "200", "--bt", "--pThresh", "0.2", "--pred", fit + "_pred.list"]
+    lf = run(bt + ["--bgen", d + "/example.bgen", "--firth", "--approx", "--out", str(tmp_path / "f")])
+    ls = run(bt + ["--bed", d + "/example", "--spa", "--out", str(tmp_path / "s")])
+    lg = run(bt + ["--bgen", d + "/example.bgen", "--firth", "--approx", "--gpu-inflate", "--out", str(tmp_path / "fg")])
+    assert "Number of tests with Firth correction : " in lf and "Number of tests with SPA correction : " in ls
+    f = read(str(tmp_path / "f") + "_Y1.regenie").splitlines()
+    assert read(str(tmp_path / "fg") + "_Y1.regenie").splitlines() == f and "inflated on the GPU" in lg
+    n_fail = sum(l.endswith(" TEST_FAIL") for l in f)
+    assert 0 < n_fail < len(f) and all(l.split()[11:13] == ["NA", "NA"] for l in f if l.endswith(" TEST_FAIL"))
+    assert int(lf.split("Number of tests with Firth correction : ")[1].split("(")[1].split()[0]) >= n_fail
+    assert len(read(str(tmp_path / "s") + "_Y2.regenie").splitlines()) > 900
