@@ -56,6 +56,7 @@ struct Params {
   bool set_range = false;                      // --range CHR:MINPOS-MAXPOS (step 2)
   int range_chr = 0;
   double range_min = 0, range_max = 0;
+  int test_type = 0;                           // --test additive | dominant | recessive (step 2)
   bool gpu_inflate = false;                    // --gpu-inflate: zlib payloads of the .bgen are inflated on the device (rg_bgen_inflate)
   uint32_t par1_max = 2781479, par2_min = 155701383;   // hg38 (check_build_code, src/Regenie.cpp:1643-1660)
 };
@@ -77,12 +78,31 @@ std::vector<double> unit_params(const std::string& opt, const std::string& csv) 
   return v;
 }
 
+// check_name (src/Regenie.cpp:1596-1645): "V{1:3}x" -> V1x, V2x, V3x
+std::vector<std::string> expand_name(const std::string& str) {
+  std::vector<std::string> out;
+  if (str.empty()) return out;
+  const size_t lb = str.find('{');
+  if (lb == std::string::npos) { out.push_back(str); return out; }
+  const std::string err = "invalid string expansion (=" + str + ").";
+  const size_t colon = str.find(':'), rb = str.find('}');
+  if (colon == std::string::npos || rb == std::string::npos || colon < lb || rb < colon) throw Fail(err);
+  char* e1 = nullptr;
+  char* e2 = nullptr;
+  const std::string a = str.substr(lb + 1, colon - lb - 1), b = str.substr(colon + 1, rb - colon - 1);
+  const long imin = strtol(a.c_str(), &e1, 10), imax = strtol(b.c_str(), &e2, 10);
+  if (a.empty() || b.empty() || *e1 || *e2) throw Fail(err);
+  for (long j = imin; j <= imax; ++j) out.push_back(str.substr(0, lb) + std::to_string(j) + str.substr(rb + 1));
+  return out;
+}
+
 Params parse_cli(int argc, char** argv) {
   Params p;
   auto csv_into = [](const std::string& v, std::set<std::string>& dst) {
     std::string tok;
     std::istringstream ss(v);
-    while (std::getline(ss, tok, ',')) if (!tok.empty()) dst.insert(tok);
+    while (std::getline(ss, tok, ','))
+      for (const auto& n : expand_name(tok)) dst.insert(n);
   };
   auto need = [&](int& i) -> std::string {
     if (i + 1 >= argc) throw Fail(std::string("option ") + argv[i] + " needs a value");
@@ -117,21 +137,14 @@ Params parse_cli(int argc, char** argv) {
     else if (a == "--gpu") p.gpu = atoi(need(i).c_str());
     else if (a == "--threads") p.threads = atoi(need(i).c_str());   // host threads: BGEN inflate only
     else if (a == "--sample") p.sample = need(i);
-    else if (a == "--phenoCol") p.pheno_cols.insert(need(i));
-    else if (a == "--covarCol") p.covar_cols.insert(need(i));
-    else if (a == "--phenoColList" || a == "--covarColList") {
-      std::string v = need(i), tok;
-      std::istringstream ss(v);
-      while (std::getline(ss, tok, ',')) if (!tok.empty()) (a == "--phenoColList" ? p.pheno_cols : p.covar_cols).insert(tok);
-    }
+    else if (a == "--phenoCol") csv_into(need(i), p.pheno_cols);
+    else if (a == "--covarCol") csv_into(need(i), p.covar_cols);
+    else if (a == "--phenoColList") csv_into(need(i), p.pheno_cols);
+    else if (a == "--covarColList") csv_into(need(i), p.covar_cols);
     else if (a == "--minINFO") p.min_info = atof(need(i).c_str());
     else if (a == "--ignore-pred") p.ignore_pred = true;
     else if (a == "--apply-rint") p.rint = true;
-    else if (a == "--catCovarList") {
-      std::string v = need(i), tok;
-      std::istringstream ss(v);
-      while (std::getline(ss, tok, ',')) if (!tok.empty()) p.cat_cols.insert(tok);
-    }
+    else if (a == "--catCovarList") csv_into(need(i), p.cat_cols);
     else if (a == "--maxCatLevels") p.max_cat_levels = atoi(need(i).c_str());
     else if (a == "--split-l0" || a == "--run-l0") {
       const std::string v = need(i);
@@ -174,6 +187,13 @@ Params parse_cli(int argc, char** argv) {
     else if (a == "--use-prs") p.use_prs = true;
     else if (a == "--bgi") p.bgi = need(i);
     else if (a == "--gpu-inflate") p.gpu_inflate = true;
+    else if (a == "--test") {                                   // src/Regenie.cpp:735-740
+      const std::string v = need(i);
+      if (v == "additive") p.test_type = 0;
+      else if (v == "dominant") p.test_type = 1;
+      else if (v == "recessive") p.test_type = 2;
+      else throw Fail("unrecognized argument for option --test, must be either 'additive', 'dominant' or 'recessive'.");
+    }
     else if (a == "--range") {                                  // src/Regenie.cpp:741-755
       char chr[20];
       double p0 = -1, p1 = -1;
@@ -197,6 +217,7 @@ Params parse_cli(int argc, char** argv) {
                    "  [--chr c]... [--chrList c1,c2,...] [--range CHR:MIN-MAX]  (Step-2 jobs are split by chromosome / window like the reference)\n"
                    "  step 2 binary traits: --bt [--firth --approx | --spa] [--pThresh p] with --bed or --bgen F [--sample F] [--bgi F]\n"
                    "  [--gz] [--print-prs | --use-prs] [--write-samples [--print-pheno]]  (.gz inputs are read by file name)\n"
+                   "  [--test additive|dominant|recessive]\n"
                    "  [--gpu-inflate]  step 2 on zlib-compressed .bgen: inflate the genotype blocks on the GPU instead of the host\n";
       exit(0);
     } else {
@@ -216,6 +237,7 @@ Params parse_cli(int argc, char** argv) {
   if ((p.split_jobs || p.run_l0_job || p.run_l1) && p.step != 1) throw Fail("options --split-l0/--run-l0/--run-l1 only work in step 1.");
   if (p.out.empty()) throw Fail("must specify an output file prefix with --out.");
   if (p.bsize < 1) throw Fail("must specify the block size using '--bsize'.");
+  if (p.test_type > 0 && p.step != 2) throw Fail("can only use --test in step 2 (association testing).");   // src/Regenie.cpp:905-906
   if (p.set_range && p.range_chr == -1) throw Fail("unrecognized chromosome in --range.");   // src/Regenie.cpp:1153-1154
   if (p.write_samples && !p.bgen.empty() && p.sample.empty())                     // src/Regenie.cpp:903-904
     throw Fail("must specify sample file (using --sample) if writing sample IDs to file.");
@@ -547,6 +569,56 @@ void run_step1(const Params& p_in, Log& log) {
 }
 
 // ------------------------------------------------------------------------------------ step 2
+// --test dominant | recessive (parseSnpfromBed src/Geno.cpp:2509-2530, BGEN :2084-2125): allele frequency, INFO, N and the
+// MAC filters come from the additive coding; the genotypes are then recoded (dominant: 2 -> 1, recessive: 1 -> 0 and
+// 2 -> 1; on dosages P(het) + P(hom) and P(hom)) and the test runs on the recoded values, with no minor-allele flip
+// (src/Data.cpp:2108).  Here: a first pass over the block yields the additive counts, the input bytes are recoded on the
+// host so that the unchanged kernels see the recoded genotype, and a second pass (no MAC filter) yields the test.
+struct Recode {
+  uint8_t lut[256];
+  int type = 0;
+  bool ref_first = false;
+  Recode(int type_, bool ref_first_) : type(type_), ref_first(ref_first_) {
+    // PLINK 1 codes: 00 = two copies of the first .bim allele, 10 = one, 11 = none, 01 = missing.  The kernels count
+    // the first allele (ref-last) or 2 minus that (--ref-first), so "two copies of the effect allele" is 00 or 11.
+    int map[4] = {0, 1, 2, 3};
+    const int two = ref_first ? 3 : 0, none = ref_first ? 0 : 3;
+    if (type == 1) map[two] = 2;                       // dominant: 2 -> 1
+    if (type == 2) { map[two] = 2; map[2] = none; }    // recessive: 2 -> 1, 1 -> 0
+    for (int b = 0; b < 256; ++b) {
+      int o = 0;
+      for (int k = 0; k < 4; ++k) o |= map[(b >> (2 * k)) & 3] << (2 * k);
+      lut[b] = (uint8_t)o;
+    }
+  }
+  void bed(uint8_t* rows, size_t nbytes) const {
+    for (size_t i = 0; i < nbytes; ++i) rows[i] = lut[rows[i]];
+  }
+  // 8-bit probability pairs (p0, p1) of the first-allele homozygote and the heterozygote; the kernels form
+  // p1 + 2 p0 (ref-last) or p1 + 2 (255 - p0 - p1) (--ref-first).  The recoded value t goes into p1, with p0 chosen so
+  // that the homozygote term vanishes.
+  void probs(uint8_t* pr, size_t n_pairs) const {
+    for (size_t i = 0; i < n_pairs; ++i) {
+      const int p0 = pr[2 * i], p1 = pr[2 * i + 1], p2 = std::max(0, 255 - p0 - p1);
+      const int hom = ref_first ? p2 : p0;
+      const int t = type == 1 ? std::min(255, hom + p1) : hom;
+      pr[2 * i + 1] = (uint8_t)t;
+      pr[2 * i] = ref_first ? (uint8_t)(255 - t) : 0;
+    }
+  }
+};
+
+const char* test_name(int test_type) { return test_type == 1 ? "DOM" : test_type == 2 ? "REC" : "ADD"; }
+
+// flags of the two passes: bit 0 (MAC) from the additive pass, everything else from the pass on the recoded genotypes,
+// plus `total < numtol` on the recoded mean (src/Geno.cpp:2523-2527)
+void merge_recode_flags(int bs, int32_t* flags, const int32_t* flags2, const double* af_all2) {
+  for (int v = 0; v < bs; ++v) {
+    flags[v] = (flags[v] & 1) | (flags2[v] & ~1);
+    if (2.0 * af_all2[v] < 1e-6) flags[v] |= 1;
+  }
+}
+
 // --range (in_range, src/Geno.cpp:2790-2800): keep the variants of one chromosome window
 void apply_range(const Params& p, std::vector<Snp>& snps) {
   if (!p.set_range) return;
@@ -694,10 +766,10 @@ void run_step2_qt(const Params& p, Log& log) {
     else rows[k].resize((size_t)bsz * g.row_stride);
   }
   const int threads = p.threads > 0 ? p.threads : (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
-  const bool dev_inflate = use_bgen && p.gpu_inflate && gg.compression == 1;
+  const bool dev_inflate = use_bgen && p.gpu_inflate && gg.compression == 1 && p.test_type == 0;
   if (use_bgen && p.gpu_inflate)
     log << (dev_inflate ? " * bgen genotype blocks are inflated on the GPU\n"
-                        : "   -WARNING: --gpu-inflate needs zlib-compressed payloads; inflating on the host.\n");
+                        : "   -WARNING: --gpu-inflate needs zlib-compressed payloads and the additive test; inflating on the host.\n");
   std::vector<uint8_t> comp[2];
   std::vector<uint64_t> comp_offs[2];
   std::future<void> pending;
@@ -716,6 +788,16 @@ void run_step2_qt(const Params& p, Log& log) {
   rg_s2_out out{af.data(), ns.data(), mac.data(), af_all.data(), ns_all.data(), mac_all.data(), flags.data(),
                 scale_fac.data(), stat.data(), beta.data(), se.data(), chisq.data()};
   const bool subset = keys.size() != n_file;
+  // second pass of --test dominant / recessive: counts go to scratch, the test columns to the arrays that are printed
+  const Recode recode(p.test_type, p.ref_first);
+  std::vector<double> af2, mac2, af_all2, mac_all2, info2;
+  std::vector<int32_t> ns2, ns_all2, flags2;
+  if (p.test_type) {
+    af2.resize((size_t)bsz * P); mac2.resize((size_t)bsz * P); info2.resize((size_t)bsz * P); ns2.resize((size_t)bsz * P);
+    af_all2.resize(bsz); mac_all2.resize(bsz); ns_all2.resize(bsz); flags2.resize(bsz);
+  }
+  rg_s2_out out2{af2.data(), ns2.data(), mac2.data(), af_all2.data(), ns_all2.data(), mac_all2.data(), flags2.data(),
+                 scale_fac.data(), stat.data(), beta.data(), se.data(), chisq.data()};
   std::vector<double> res((size_t)N * P), scf(P);
   std::vector<uint8_t> npf;
   int cur_chr = -1;
@@ -750,10 +832,21 @@ void run_step2_qt(const Params& p, Log& log) {
       if (dev_inflate) rg_check(rg_bgen_inflate(h, comp[b & 1].data(), comp_offs[b & 1].data(), (int64_t)n_file, blocks[b].size, &pd, &md));
       rg_check(rg_s2_block_bgen8(h, pd, md, (int64_t)n_file, blocks[b].size,
                                  subset ? sample_idx.data() : nullptr, p.ref_first, p.min_mac, &out, info.data()));
+      if (p.test_type) {
+        recode.probs(probs[b & 1].data(), (size_t)blocks[b].size * n_file);
+        rg_check(rg_s2_block_bgen8(h, pd, md, (int64_t)n_file, blocks[b].size, subset ? sample_idx.data() : nullptr, p.ref_first,
+                                   0.0, &out2, info2.data()));
+      }
     } else {
       rg_check(rg_s2_block_bed(h, rows[b & 1].data(), (int64_t)g.row_stride, blocks[b].size,
                                subset ? sample_idx.data() : nullptr, p.ref_first, p.min_mac, &out));
+      if (p.test_type) {
+        recode.bed(rows[b & 1].data(), (size_t)blocks[b].size * g.row_stride);
+        rg_check(rg_s2_block_bed(h, rows[b & 1].data(), (int64_t)g.row_stride, blocks[b].size,
+                                 subset ? sample_idx.data() : nullptr, p.ref_first, 0.0, &out2));
+      }
     }
+    if (p.test_type) merge_recode_flags(blocks[b].size, flags.data(), flags2.data(), af_all2.data());
     for (int v = 0; v < blocks[b].size; ++v) {
       if (flags[v] & 3) { ++n_ignored; continue; }            // no row for ignored variants (split mode)
       const Snp& s = snps[blocks[b].first + v];
@@ -767,7 +860,7 @@ void run_step2_qt(const Params& p, Log& log) {
         const size_t e = (size_t)v * P + i;
         if (mac[e] < p.min_mac) continue;                      // ignored_trait (src/Geno.cpp:3102)
         if (use_bgen && info[e] < p.min_info) continue;        // --minINFO (src/Geno.cpp:3142-3146)
-        append_sumstats_row(obuf[i], head_s, af[e], use_bgen, use_bgen ? info[e] : -1.0, ns[e], "ADD", beta[e], se[e], chisq[e],
+        append_sumstats_row(obuf[i], head_s, af[e], use_bgen, use_bgen ? info[e] : -1.0, ns[e], test_name(p.test_type), beta[e], se[e], chisq[e],
                             get_logp(chisq[e]), true);   // print_sum_stats_single :2502-2540
       }
     }
@@ -836,10 +929,10 @@ void run_step2_bt(const Params& p, Log& log) {
     if (use_bgen) { probs[k].resize((size_t)bsz * n_file * 2); pmiss[k].resize((size_t)bsz * n_file); }
     else rows[k].resize((size_t)bsz * gb.row_stride);
   }
-  const bool dev_inflate = use_bgen && p.gpu_inflate && gg.compression == 1;
+  const bool dev_inflate = use_bgen && p.gpu_inflate && gg.compression == 1 && p.test_type == 0;
   if (use_bgen && p.gpu_inflate)
     log << (dev_inflate ? " * bgen genotype blocks are inflated on the GPU\n"
-                        : "   -WARNING: --gpu-inflate needs zlib-compressed payloads; inflating on the host.\n");
+                        : "   -WARNING: --gpu-inflate needs zlib-compressed payloads and the additive test; inflating on the host.\n");
   std::vector<uint8_t> comp[2];
   std::vector<uint64_t> comp_offs[2];
   std::future<void> pending;
@@ -857,6 +950,15 @@ void run_step2_bt(const Params& p, Log& log) {
   rg_s2_out out{af.data(), ns.data(), mac.data(), af_all.data(), ns_all.data(), mac_all.data(), flags.data(),
                 scale_fac.data(), stat.data(), beta.data(), se.data(), chisq.data()};
   const bool subset = keys.size() != n_file;
+  const Recode recode(p.test_type, p.ref_first);             // --test dominant / recessive: see run_step2_qt
+  std::vector<double> af2, mac2, af_all2, mac_all2, info2;
+  std::vector<int32_t> ns2, ns_all2, flags2;
+  if (p.test_type) {
+    af2.resize((size_t)bsz * P); mac2.resize((size_t)bsz * P); info2.resize((size_t)bsz * P); ns2.resize((size_t)bsz * P);
+    af_all2.resize(bsz); mac_all2.resize(bsz); ns_all2.resize(bsz); flags2.resize(bsz);
+  }
+  rg_s2_out out2{af2.data(), ns2.data(), mac2.data(), af_all2.data(), ns_all2.data(), mac_all2.data(), flags2.data(),
+                 scale_fac.data(), stat.data(), beta.data(), se.data(), chisq.data()};
   std::vector<uint8_t> npf;
   int cur_chr = -1;
   size_t n_ignored = 0, n_firth = 0, n_fail = 0;
@@ -893,11 +995,22 @@ void run_step2_bt(const Params& p, Log& log) {
       if (dev_inflate) rg_check(rg_bgen_inflate(h, comp[b & 1].data(), comp_offs[b & 1].data(), (int64_t)n_file, bs, &pd, &md));
       rg_check(rg_s2_block_bgen8_bt(h, pd, md, (int64_t)n_file, bs,
                                     subset ? sample_idx.data() : nullptr, p.ref_first, p.min_mac, &out, info.data()));
+      if (p.test_type) {
+        recode.probs(probs[b & 1].data(), (size_t)bs * n_file);
+        rg_check(rg_s2_block_bgen8_bt(h, pd, md, (int64_t)n_file, bs, subset ? sample_idx.data() : nullptr, p.ref_first, 0.0,
+                                      &out2, info2.data()));
+      }
     } else {
       // hard calls go to the GPU as they are (2 bits per sample)
       rg_check(rg_s2_block_bed_bt(h, rows[b & 1].data(), (int64_t)gb.row_stride, bs, subset ? sample_idx.data() : nullptr,
                                   p.ref_first, p.min_mac, &out));
+      if (p.test_type) {
+        recode.bed(rows[b & 1].data(), (size_t)bs * gb.row_stride);
+        rg_check(rg_s2_block_bed_bt(h, rows[b & 1].data(), (int64_t)gb.row_stride, bs, subset ? sample_idx.data() : nullptr,
+                                    p.ref_first, 0.0, &out2));
+      }
     }
+    if (p.test_type) merge_recode_flags(bs, flags.data(), flags2.data(), af_all2.data());
     // Firth fallback for |z| above the --pThresh threshold (check_pval_snp, src/Step2_Models.cpp:1988-2041)
     std::vector<int32_t> sel_v, sel_t, fstatus;
     std::vector<double> fbeta, fse, flrt;
@@ -954,7 +1067,7 @@ void run_step2_bt(const Params& p, Log& log) {
         }
         double lp = get_logp(co);
         if (p.spa && pass && f != fidx.end()) lp = spa_logp[{v, i}];   // SPA reports -log10 of its own p-value
-        append_sumstats_row(obuf[i], head_s, af[e], use_bgen, use_bgen ? info[e] : -1.0, ns[e], "ADD", bo, so, co, lp, pass);
+        append_sumstats_row(obuf[i], head_s, af[e], use_bgen, use_bgen ? info[e] : -1.0, ns[e], test_name(p.test_type), bo, so, co, lp, pass);
       }
     }
     for (int i = 0; i < P; ++i) { outs[i] << obuf[i]; obuf[i].clear(); }

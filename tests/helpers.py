@@ -332,3 +332,55 @@ def recompress_bgen(src, dst, mode):
             got = zs.ZSTD_compress(buf, cap, raw, len(raw), 3)
             out += struct.pack("<II", got + 4, len(raw)) + buf.raw[:got]
     open(dst, "wb").write(bytes(out))
+
+
+# ---------------------------------------------------------------------------------------- --test dominant / recessive (tests only)
+def recode_bed(src_prefix, dst_prefix, test, ref_first=False):
+    """Copy a PLINK 1 fileset with every genotype recoded the way the reference recodes it before a dominant
+    (2 -> 1) or recessive (1 -> 0, 2 -> 1) test (src/Geno.cpp:2509-2516), counting the effect allele (.bim column 5, or
+    column 6 with --ref-first).  An additive run on the copy must give the test columns of `--test <test>` on the
+    original."""
+    import shutil
+    import numpy as np
+    raw = np.fromfile(src_prefix + ".bed", dtype=np.uint8)
+    two, none = (3, 0) if ref_first else (0, 3)                  # PLINK codes of 2 / 0 copies of the effect allele
+    m = [0, 1, 2, 3]
+    if test == "dominant":
+        m[two] = 2
+    else:
+        m[two] = 2
+        m[2] = none
+    lut = np.zeros(256, dtype=np.uint8)
+    for b in range(256):
+        o = 0
+        for k in range(4):
+            o |= m[(b >> (2 * k)) & 3] << (2 * k)
+        lut[b] = o
+    out = raw.copy()
+    out[3:] = lut[raw[3:]]
+    out.tofile(dst_prefix + ".bed")
+    shutil.copy(src_prefix + ".bim", dst_prefix + ".bim")
+    shutil.copy(src_prefix + ".fam", dst_prefix + ".fam")
+
+
+def check_recoded_test(run, read, tmp_path, golden_dir, extra=()):
+    """`--test dominant|recessive` == additive test on the recoded fileset for BETA/SE/CHISQ/LOG10P, with A1FREQ and N of
+    the additive coding of the original; shared by the CPU (mock ABI) and the GPU driver tests."""
+    d = golden_dir
+    base = ["--step", "2", "--phenoFile", d + "/phenotype.txt", "--covarFile", d + "/covariates.txt", "--bsize", "100",
+            "--ignore-pred", "--minMAC", "1"] + list(extra)
+    ref_first = "--ref-first" in extra
+    orig = d + "/example_3chr"
+    run(base + ["--bed", orig, "--out", str(tmp_path / "add")])
+    add = {l.split()[2]: l.split() for l in read(str(tmp_path / "add") + "_Y1.regenie").splitlines()[1:]}
+    for test, name in (("dominant", "DOM"), ("recessive", "REC")):
+        rec = str(tmp_path / ("rec_" + test))
+        recode_bed(orig, rec, test, ref_first)
+        run(base + ["--bed", orig, "--test", test, "--out", str(tmp_path / test)])
+        run(base + ["--bed", rec, "--out", str(tmp_path / (test + "_ref"))])
+        got = [l.split() for l in read(str(tmp_path / test) + "_Y1.regenie").splitlines()[1:]]
+        want = {l.split()[2]: l.split() for l in read(str(tmp_path / (test + "_ref")) + "_Y1.regenie").splitlines()[1:]}
+        assert len(got) > 300 and [t[2] for t in got] == [k for k in add if k in want]
+        for t in got:
+            assert t[7] == name and t[:7] == add[t[2]][:7], t             # CHROM..ALLELE1, A1FREQ, N of the additive coding
+            assert t[8:] == want[t[2]][8:], (t, want[t[2]])               # BETA SE CHISQ LOG10P EXTRA of the recoded genotypes

@@ -26,6 +26,9 @@ def test_cli_errors_have_the_reference_shape(tmp_path, golden_dir):
         (["--step", "2", "--pred", "x", "--range", "1:100"] + base, "wrong format for --range (must be CHR:MINPOS-MAXPOS)."),
         (["--step", "2", "--pred", "x", "--range", "Z:1-100"] + base, "unrecognized chromosome in --range."),
         (["--step", "1", "--setl0", "0,0.5"] + base, "must specify values for --l0 in (0,1)."),
+        (["--step", "2", "--pred", "x", "--test", "overdominant"] + base, "unrecognized argument for option --test"),
+        (["--step", "1", "--test", "dominant"] + base, "can only use --test in step 2"),
+        (["--step", "1", "--covarColList", "V{1:x}"] + base, "invalid string expansion (=V{1:x})."),
         (["--step", "1", "--setl1", "0.5,1"] + base, "must specify values for --l1 in (0,1)."),
         (["--step", "2", "--pred", "x", "--write-samples", "--bgen", d + "/example.bgen"] + base[2:],
          "must specify sample file (using --sample) if writing sample IDs to file."),

@@ -688,3 +688,12 @@ def test_user_ridge_grids_exclude_lists_aliases_and_l1_subset(tmp_path, golden_d
     assert open(str(tmp_path / "l1") + "_2.loco").read() == open(str(tmp_path / "a") + "_2.loco").read()
     assert not os.path.exists(str(tmp_path / "l1") + "_1.loco")
     assert [l.split()[0] for l in open(str(tmp_path / "l1") + "_pred.list")] == ["Y2"]
+
+
+@pytest.mark.parametrize("extra", [(), ("--ref-first",)])
+def test_dominant_recessive_equal_additive_on_recoded_genotypes(tmp_path, golden_dir, extra):
+    """--test dominant / recessive (src/Geno.cpp:2509-2530): A1FREQ / N / MAC filter from the additive coding, the test on
+    the recoded genotypes == an additive run on a fileset recoded the same way."""
+    def read(path):
+        return open(path).read()
+    helpers.check_recoded_test(run, read, tmp_path, golden_dir, extra)

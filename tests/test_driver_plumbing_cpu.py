@@ -176,3 +176,19 @@ def test_step2_bgen_index_inflate_paths_and_bt_corrections(tmp_path, golden_dir)
     assert 0 < n_fail < len(f) and all(l.split()[11:13] == ["NA", "NA"] for l in f if l.endswith(" TEST_FAIL"))
     assert int(lf.split("Number of tests with Firth correction : ")[1].split("(")[1].split()[0]) >= n_fail
     assert len(read(str(tmp_path / "s") + "_Y2.regenie").splitlines()) > 900
+
+
+@pytest.mark.parametrize("extra", [(), ("--ref-first",)])
+def test_dominant_and_recessive_tests_are_two_passes_over_recoded_genotypes(tmp_path, golden_dir, extra):
+    import helpers
+    helpers.check_recoded_test(run, read, tmp_path, golden_dir, extra)
+    # dosages: the option is accepted, the TEST column changes, counts stay those of the additive coding
+    d = golden_dir
+    b = ["--step", "2", "--bgen", d + "/example.bgen", "--phenoFile", d + "/phenotype_bin.txt", "--covarFile", d + "/covariates.txt",
+         "--bsize", "200", "--ignore-pred", "--bt", "--spa"] + list(extra)
+    run(b + ["--out", str(tmp_path / "ba")])
+    run(b + ["--test", "recessive", "--gpu-inflate", "--out", str(tmp_path / "br")])
+    a = {l.split()[2]: l.split() for l in read(str(tmp_path / "ba") + "_Y1.regenie").splitlines()[1:]}
+    r = [l.split() for l in read(str(tmp_path / "br") + "_Y1.regenie").splitlines()[1:]]
+    assert len(r) > 500 and all(t[8] == "REC" and t[:8] == a[t[2]][:8] for t in r)
+    assert any(t[9:] != a[t[2]][9:] for t in r)
