@@ -384,3 +384,27 @@ def check_recoded_test(run, read, tmp_path, golden_dir, extra=()):
         for t in got:
             assert t[7] == name and t[:7] == add[t[2]][:7], t             # CHROM..ALLELE1, A1FREQ, N of the additive coding
             assert t[8:] == want[t[2]][8:], (t, want[t[2]])               # BETA SE CHISQ LOG10P EXTRA of the recoded genotypes
+
+
+def check_na_invariance(run, read, tmp_path, golden_dir, bt):
+    """The reference's test/check_na.sh: a single-trait run must not change when the samples whose phenotype is NA are
+    deleted from the phenotype and covariate files instead (Step 1 on example.bed, Step 2 on example_3chr.bed)."""
+    d = golden_dir
+    rows = open(d + "/phenotype_bin_wNA.txt").read().splitlines()
+    kept = [l for l in rows if "NA" not in l.split()]
+    assert len(kept) < len(rows)
+    (tmp_path / "noNA.txt").write_text("\n".join(kept) + "\n")
+    ids = {tuple(l.split()[:2]) for l in kept[1:]}
+    cov = open(d + "/covariates.txt").read().splitlines()
+    (tmp_path / "noNA_covs.txt").write_text("\n".join([cov[0]] + [l for l in cov[1:] if tuple(l.split()[:2]) in ids]) + "\n")
+    mode = ["--bt"] if bt else []
+    outs = []
+    for tag, ph, cv in (("wna", d + "/phenotype_bin_wNA.txt", d + "/covariates.txt"), ("nona", tmp_path / "noNA.txt", tmp_path / "noNA_covs.txt")):
+        fit, res = str(tmp_path / ("fit_" + tag)), str(tmp_path / ("test_" + tag))
+        run(["--step", "1", "--bed", d + "/example", "--covarFile", cv, "--phenoFile", ph, "--phenoCol", "Y1", "--bsize", "100",
+             "--lowmem", "--lowmem-prefix", str(tmp_path / "tmp_rg"), "--out", fit] + mode)
+        run(["--step", "2", "--bed", d + "/example_3chr", "--covarFile", cv, "--phenoFile", ph, "--phenoCol", "Y1", "--bsize", "200",
+             "--pThresh", "0.01", "--pred", fit + "_pred.list", "--out", res] + mode + (["--firth", "--approx"] if bt else []))
+        outs.append((read(fit + "_1.loco"), read(res + "_Y1.regenie")))
+    assert len(outs[0][1].splitlines()) > 10
+    assert outs[0] == outs[1]

@@ -697,3 +697,11 @@ def test_dominant_recessive_equal_additive_on_recoded_genotypes(tmp_path, golden
     def read(path):
         return open(path).read()
     helpers.check_recoded_test(run, read, tmp_path, golden_dir, extra)
+
+
+@pytest.mark.parametrize("bt", [False, True])
+def test_na_rows_are_equivalent_to_absent_rows(tmp_path, golden_dir, bt):
+    """test/check_na.sh of the reference, for quantitative and binary (Firth) runs, on the real library."""
+    def read(path):
+        return open(path).read()
+    helpers.check_na_invariance(run, read, tmp_path, golden_dir, bt)

@@ -192,3 +192,28 @@ def test_dominant_and_recessive_tests_are_two_passes_over_recoded_genotypes(tmp_
     r = [l.split() for l in read(str(tmp_path / "br") + "_Y1.regenie").splitlines()[1:]]
     assert len(r) > 500 and all(t[8] == "REC" and t[:8] == a[t[2]][:8] for t in r)
     assert any(t[9:] != a[t[2]][9:] for t in r)
+
+
+def test_reference_script_case_column_mapping_from_bim(tmp_path, golden_dir):
+    """The checks of the reference's test/test_bash.sh:225-259 (its covariate file with a binary column is not among the
+    fixtures; V{1:2},V3 of covariates.txt stand in): sample lists only for the selected trait, first line `Y2<TAB>NA`,
+    no chromosome-1 variants with --chrList 2,3, no ADD rows with --test dominant, and CHROM GENPOS ID ALLELE0 ALLELE1 =
+    .bim columns 1,4,2,5,6 under --ref-first."""
+    d = golden_dir
+    out = str(tmp_path / "test_out")
+    run(["--step", "2", "--bed", d + "/example_3chr", "--ref-first", "--covarFile", d + "/covariates.txt", "--covarColList",
+         "V{1:2},V3", "--phenoFile", d + "/phenotype_bin.txt", "--phenoColList", "Y2", "--bsize", "100", "--test", "dominant",
+         "--force-qt", "--ignore-pred", "--chrList", "2,3", "--write-samples", "--print-pheno", "--out", out])
+    assert os.path.exists(out + "_Y2.regenie.ids") and not os.path.exists(out + "_Y1.regenie.ids")
+    first = open(out + "_Y2.regenie.ids").readline().rstrip("\n").split("\t")
+    assert first == ["Y2", "NA"]
+    rows = read(out + "_Y2.regenie").splitlines()
+    assert not any("mog_" in l for l in rows) and not any(" ADD " in l for l in rows) and all(" DOM " in l for l in rows[1:])
+    bim2 = next(l.split() for l in open(d + "/example_3chr.bim") if l.startswith("2"))
+    assert rows[1].split()[:5] == [bim2[0], bim2[3], bim2[1], bim2[4], bim2[5]]
+
+
+@pytest.mark.parametrize("bt", [False, True])
+def test_na_rows_are_equivalent_to_absent_rows(tmp_path, golden_dir, bt):
+    import helpers
+    helpers.check_na_invariance(run, read, tmp_path, golden_dir, bt)
