@@ -56,6 +56,7 @@ struct Params {
   bool set_range = false;                      // --range CHR:MINPOS-MAXPOS (step 2)
   int range_chr = 0;
   double range_min = 0, range_max = 0;
+  bool no_split = false;                       // --no-split: one <out>.regenie for all traits (hard-call input)
   int test_type = 0;                           // --test additive | dominant | recessive (step 2)
   bool gpu_inflate = false;                    // --gpu-inflate: zlib payloads of the .bgen are inflated on the device (rg_bgen_inflate)
   uint32_t par1_max = 2781479, par2_min = 155701383;   // hg38 (check_build_code, src/Regenie.cpp:1643-1660)
@@ -187,6 +188,7 @@ Params parse_cli(int argc, char** argv) {
     else if (a == "--use-prs") p.use_prs = true;
     else if (a == "--bgi") p.bgi = need(i);
     else if (a == "--gpu-inflate") p.gpu_inflate = true;
+    else if (a == "--no-split") p.no_split = true;
     else if (a == "--test") {                                   // src/Regenie.cpp:735-740
       const std::string v = need(i);
       if (v == "additive") p.test_type = 0;
@@ -217,7 +219,7 @@ Params parse_cli(int argc, char** argv) {
                    "  [--chr c]... [--chrList c1,c2,...] [--range CHR:MIN-MAX]  (Step-2 jobs are split by chromosome / window like the reference)\n"
                    "  step 2 binary traits: --bt [--firth --approx | --spa] [--pThresh p] with --bed or --bgen F [--sample F] [--bgi F]\n"
                    "  [--gz] [--print-prs | --use-prs] [--write-samples [--print-pheno]]  (.gz inputs are read by file name)\n"
-                   "  [--test additive|dominant|recessive]\n"
+                   "  [--test additive|dominant|recessive] [--no-split]\n"
                    "  [--gpu-inflate]  step 2 on zlib-compressed .bgen: inflate the genotype blocks on the GPU instead of the host\n";
       exit(0);
     } else {
@@ -237,6 +239,8 @@ Params parse_cli(int argc, char** argv) {
   if ((p.split_jobs || p.run_l0_job || p.run_l1) && p.step != 1) throw Fail("options --split-l0/--run-l0/--run-l1 only work in step 1.");
   if (p.out.empty()) throw Fail("must specify an output file prefix with --out.");
   if (p.bsize < 1) throw Fail("must specify the block size using '--bsize'.");
+  if (p.no_split && !p.bgen.empty())
+    throw Fail("--no-split with --bgen is not available in rgb200 yet (the variant-level INFO and the dosage genotype counts need a kernel output); use the split output.");
   if (p.test_type > 0 && p.step != 2) throw Fail("can only use --test in step 2 (association testing).");   // src/Regenie.cpp:905-906
   if (p.set_range && p.range_chr == -1) throw Fail("unrecognized chromosome in --range.");   // src/Regenie.cpp:1153-1154
   if (p.write_samples && !p.bgen.empty() && p.sample.empty())                     // src/Regenie.cpp:903-904
@@ -619,6 +623,84 @@ void merge_recode_flags(int bs, int32_t* flags, const int32_t* flags2, const dou
   }
 }
 
+// Step-2 output files: one per trait (setup_output, split mode, src/Data.cpp:2026-2035) or, with --no-split, one file
+// for all traits plus the <out>.regenie.Ydict dictionary (src/Data.cpp:2011-2022).  Rows are collected per block.
+struct S2Writers {
+  bool no_split = false;
+  std::vector<TextWriter> outs;
+  TextWriter all;
+  std::vector<std::string> obuf;
+  std::string obuf_all;
+  void open(const Params& p, const Pheno& ph, bool with_info) {
+    no_split = p.no_split;
+    const std::string gz_ext = p.gz ? ".gz" : "";
+    obuf.resize(ph.P);
+    if (no_split) {
+      all.open(p.out + ".regenie" + gz_ext);
+      all << sumstats_header_all(ph.P);
+      TextWriter dict;
+      dict.open(p.out + ".regenie.Ydict");
+      for (int i = 0; i < ph.P; ++i) dict << ("Y" + std::to_string(i + 1) + " " + ph.names[i] + "\n");
+      dict.close();
+      return;
+    }
+    outs = std::vector<TextWriter>(ph.P);
+    for (int i = 0; i < ph.P; ++i) {
+      outs[i].open(p.out + "_" + ph.names[i] + ".regenie" + gz_ext);
+      outs[i] << sumstats_header(with_info);
+    }
+  }
+  void flush() {
+    if (no_split) { all << obuf_all; obuf_all.clear(); return; }
+    for (size_t i = 0; i < outs.size(); ++i) { outs[i] << obuf[i]; obuf[i].clear(); }
+  }
+  void close() {
+    flush();
+    if (no_split) all.close();
+    for (auto& o : outs) o.close();
+  }
+};
+
+// --no-split prints N_RR N_RA N_AA of all analysed samples (src/Geno.cpp:2480-2486).  For hard calls they follow from two
+// allele sums the kernels already return: a pass over the block recoded as "recessive" (1 -> 0, 2 -> 1) counts the
+// homozygotes, N_AA = sum of the recoded genotypes; with S = 2 N A1FREQ the additive sum, N_RA = S - 2 N_AA and
+// N_RR = N - N_RA - N_AA.  The pass runs before the test passes so that the block left on the device is the tested one.
+struct GenoCounts {
+  bool on = false;
+  Recode rec;
+  std::vector<uint8_t> rows;
+  std::vector<double> af, mac, af_all, mac_all, stat, beta, se, chisq, scale;
+  std::vector<int32_t> ns, ns_all, flags;
+  std::vector<long> n_aa;
+  rg_s2_out out;
+  GenoCounts(bool on_, int bsz, int P, size_t row_bytes, bool ref_first) : on(on_), rec(2, ref_first) {
+    if (on) {
+      rows.resize((size_t)bsz * row_bytes);
+      const size_t bp = (size_t)bsz * P;
+      af.resize(bp); mac.resize(bp); stat.resize(bp); beta.resize(bp); se.resize(bp); chisq.resize(bp); ns.resize(bp);
+      af_all.resize(bsz); mac_all.resize(bsz); scale.resize(bsz); ns_all.resize(bsz); flags.resize(bsz); n_aa.resize(bsz);
+    }
+    out = rg_s2_out{af.data(), ns.data(), mac.data(), af_all.data(), ns_all.data(), mac_all.data(), flags.data(),
+                    scale.data(), stat.data(), beta.data(), se.data(), chisq.data()};
+  }
+  // `call(rows, &out)` runs the block entry point on the recoded copy with the MAC filter off
+  template <typename Call>
+  void run(const uint8_t* src, size_t nbytes, int bs, Call&& call) {
+    if (!on) return;
+    memcpy(rows.data(), src, nbytes);
+    rec.bed(rows.data(), nbytes);
+    call(rows.data(), &out);
+    for (int v = 0; v < bs; ++v) n_aa[v] = std::lround(2.0 * af_all[v] * ns_all[v]);
+  }
+  // N_RR, N_RA, N_AA of variant v given the additive pass
+  void counts(int v, double af_add, int n, long& n_rr, long& n_ra, long& n_aa_out) const {
+    const long s = std::lround(2.0 * af_add * n);
+    n_aa_out = n_aa[v];
+    n_ra = s - 2 * n_aa_out;
+    n_rr = n - n_ra - n_aa_out;
+  }
+};
+
 // --range (in_range, src/Geno.cpp:2790-2800): keep the variants of one chromosome window
 void apply_range(const Params& p, std::vector<Snp>& snps) {
   if (!p.set_range) return;
@@ -750,14 +832,12 @@ void run_step2_qt(const Params& p, Log& log) {
   rg_handle h = nullptr;
   rg_check(rg_step2_create(&cfg, ph.X.data(), ph.mask.data(), ph.in_analysis.data(), &h));
 
-  std::vector<TextWriter> outs(P);                          // setup_output, split mode (src/Data.cpp:2026-2035)
-  for (int i = 0; i < P; ++i) {
-    outs[i].open(p.out + "_" + ph.names[i] + ".regenie" + (p.gz ? ".gz" : ""));
-    outs[i] << sumstats_header(use_bgen);
-  }
-  std::vector<std::string> obuf(P);                          // rows of the current block, one buffer per trait
+  S2Writers w;
+  w.open(p, ph, use_bgen);
+  std::vector<std::string>& obuf = w.obuf;                   // rows of the current block, one buffer per trait
   std::string head_s;
   const int bsz = p.bsize;
+  GenoCounts gc(p.no_split, bsz, P, use_bgen ? 0 : g.row_stride, p.ref_first);
   // input blocks are fetched (file read / threaded BGEN inflate) one block ahead of the GPU call: the rg_s2_block_*
   // calls return with the results on the host, so the buffer of block b is free again when block b+2 is fetched
   std::vector<uint8_t> rows[2], probs[2], pmiss[2];
@@ -824,9 +904,13 @@ void run_step2_qt(const Params& p, Log& log) {
       rg_check(rg_s2_set_sex(h, chrom == 23 ? male.data() : nullptr));
       rg_check(rg_s2_set_chr(h, res.data(), scf.data()));
     }
-    if (non_par_flags(p, snps, blocks[b], npf)) rg_check(rg_s2_set_non_par(h, npf.data(), blocks[b].size));
     pending.get();
     if (b + 1 < blocks.size()) pending = fetch(b + 1);
+    if (!use_bgen)
+      gc.run(rows[b & 1].data(), (size_t)blocks[b].size * g.row_stride, blocks[b].size, [&](const uint8_t* r, const rg_s2_out* o) {
+        rg_check(rg_s2_block_bed(h, r, (int64_t)g.row_stride, blocks[b].size, subset ? sample_idx.data() : nullptr, p.ref_first, 0.0, o));
+      });
+    if (non_par_flags(p, snps, blocks[b], npf)) rg_check(rg_s2_set_non_par(h, npf.data(), blocks[b].size));
     if (use_bgen) {
       const uint8_t *pd = probs[b & 1].data(), *md = pmiss[b & 1].data();
       if (dev_inflate) rg_check(rg_bgen_inflate(h, comp[b & 1].data(), comp_offs[b & 1].data(), (int64_t)n_file, blocks[b].size, &pd, &md));
@@ -856,18 +940,26 @@ void run_step2_qt(const Params& p, Log& log) {
       head_s += s.id; head_s += ' ';
       head_s += s.allele0; head_s += ' ';
       head_s += s.allele1; head_s += ' ';
+      if (p.no_split) {                                        // print_sum_stats_all :2441-2493
+        long n_rr, n_ra, n_aa;
+        gc.counts(v, af_all[v], ns_all[v], n_rr, n_ra, n_aa);
+        append_sumstats_all_start(w.obuf_all, head_s, af_all[v], ns_all[v], n_rr, n_ra, n_aa, test_name(p.test_type));
+      }
       for (int i = 0; i < P; ++i) {
         const size_t e = (size_t)v * P + i;
-        if (mac[e] < p.min_mac) continue;                      // ignored_trait (src/Geno.cpp:3102)
-        if (use_bgen && info[e] < p.min_info) continue;        // --minINFO (src/Geno.cpp:3142-3146)
+        const bool have = !(mac[e] < p.min_mac) &&             // ignored_trait (src/Geno.cpp:3102)
+                          !(use_bgen && info[e] < p.min_info);  // --minINFO (src/Geno.cpp:3142-3146)
+        if (p.no_split) { append_sumstats_all_trait(w.obuf_all, have, beta[e], se[e], chisq[e], get_logp(chisq[e]), true); continue; }
+        if (!have) continue;
         append_sumstats_row(obuf[i], head_s, af[e], use_bgen, use_bgen ? info[e] : -1.0, ns[e], test_name(p.test_type), beta[e], se[e], chisq[e],
                             get_logp(chisq[e]), true);   // print_sum_stats_single :2502-2540
       }
+      if (p.no_split) w.obuf_all += " NA\n";
     }
-    for (int i = 0; i < P; ++i) { outs[i] << obuf[i]; obuf[i].clear(); }
+    w.flush();
     log << " block [" << b + 1 << "/" << blocks.size() << "] : done\n";
   }
-  for (auto& o : outs) o.close();
+  w.close();
   log << "\nNumber of ignored tests due to low MAC or low variance : " << n_ignored << "\n";
   rg_destroy(h);
 }
@@ -915,14 +1007,12 @@ void run_step2_bt(const Params& p, Log& log) {
   rg_handle h = nullptr;
   rg_check(rg_step2_create(&cfg, ph.X.data(), ph.mask.data(), ph.in_analysis.data(), &h));
 
-  std::vector<TextWriter> outs(P);                          // setup_output, split mode (src/Data.cpp:2026-2035)
-  for (int i = 0; i < P; ++i) {
-    outs[i].open(p.out + "_" + ph.names[i] + ".regenie" + (p.gz ? ".gz" : ""));
-    outs[i] << sumstats_header(use_bgen);
-  }
-  std::vector<std::string> obuf(P);                          // rows of the current block, one buffer per trait
+  S2Writers w;
+  w.open(p, ph, use_bgen);
+  std::vector<std::string>& obuf = w.obuf;                   // rows of the current block, one buffer per trait
   std::string head_s;
   const int bsz = p.bsize;
+  GenoCounts gc(p.no_split, bsz, P, use_bgen ? 0 : gb.row_stride, p.ref_first);
   const int threads = p.threads > 0 ? p.threads : (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
   std::vector<uint8_t> probs[2], pmiss[2], rows[2];          // fetched one block ahead of the GPU call, like the QT path
   for (int k = 0; k < 2; ++k) {
@@ -987,9 +1077,13 @@ void run_step2_bt(const Params& p, Log& log) {
                       p.spa ? yhat.data() : nullptr};
       rg_check(rg_s2_set_chr_bt(h, &st));
     }
-    if (non_par_flags(p, snps, blocks[b], npf)) rg_check(rg_s2_set_non_par(h, npf.data(), bs));
     pending.get();
     if (b + 1 < blocks.size()) pending = fetch(b + 1);
+    if (!use_bgen)
+      gc.run(rows[b & 1].data(), (size_t)bs * gb.row_stride, bs, [&](const uint8_t* r, const rg_s2_out* o) {
+        rg_check(rg_s2_block_bed_bt(h, r, (int64_t)gb.row_stride, bs, subset ? sample_idx.data() : nullptr, p.ref_first, 0.0, o));
+      });
+    if (non_par_flags(p, snps, blocks[b], npf)) rg_check(rg_s2_set_non_par(h, npf.data(), bs));
     if (use_bgen) {
       const uint8_t *pd = probs[b & 1].data(), *md = pmiss[b & 1].data();
       if (dev_inflate) rg_check(rg_bgen_inflate(h, comp[b & 1].data(), comp_offs[b & 1].data(), (int64_t)n_file, bs, &pd, &md));
@@ -1054,10 +1148,18 @@ void run_step2_bt(const Params& p, Log& log) {
       head_s += s.id; head_s += ' ';
       head_s += s.allele0; head_s += ' ';
       head_s += s.allele1; head_s += ' ';
+      if (p.no_split) {                                        // print_sum_stats_all :2441-2493
+        long n_rr, n_ra, n_aa;
+        gc.counts(v, af_all[v], ns_all[v], n_rr, n_ra, n_aa);
+        append_sumstats_all_start(w.obuf_all, head_s, af_all[v], ns_all[v], n_rr, n_ra, n_aa, test_name(p.test_type));
+      }
       for (int i = 0; i < P; ++i) {
         const size_t e = (size_t)v * P + i;
-        if (mac[e] < p.min_mac) continue;
-        if (use_bgen && info[e] < p.min_info) continue;        // --minINFO
+        const bool have = !(mac[e] < p.min_mac) && !(use_bgen && info[e] < p.min_info);   // ignored_trait, --minINFO
+        if (!have) {
+          if (p.no_split) append_sumstats_all_trait(w.obuf_all, false, 0, 0, 0, 0, false);
+          continue;
+        }
         double bo = beta[e], so = se[e], co = chisq[e];
         bool pass = true;
         auto f = fidx.find({v, i});
@@ -1067,13 +1169,15 @@ void run_step2_bt(const Params& p, Log& log) {
         }
         double lp = get_logp(co);
         if (p.spa && pass && f != fidx.end()) lp = spa_logp[{v, i}];   // SPA reports -log10 of its own p-value
-        append_sumstats_row(obuf[i], head_s, af[e], use_bgen, use_bgen ? info[e] : -1.0, ns[e], test_name(p.test_type), bo, so, co, lp, pass);
+        if (p.no_split) append_sumstats_all_trait(w.obuf_all, true, bo, so, co, lp, pass);
+        else append_sumstats_row(obuf[i], head_s, af[e], use_bgen, use_bgen ? info[e] : -1.0, ns[e], test_name(p.test_type), bo, so, co, lp, pass);
       }
+      if (p.no_split) w.obuf_all += " NA\n";
     }
-    for (int i = 0; i < P; ++i) { outs[i] << obuf[i]; obuf[i].clear(); }
+    w.flush();
     log << " block [" << b + 1 << "/" << blocks.size() << "] : done\n";
   }
-  for (auto& o : outs) o.close();
+  w.close();
   log << "\nNumber of ignored tests due to low MAC or low variance : " << n_ignored << "\n";
   if (p.firth) log << "Number of tests with Firth correction : " << n_firth << " (" << n_fail << " failed)\n";
   if (p.spa) log << "Number of tests with SPA correction : " << n_firth << " (" << n_fail << " failed)\n";

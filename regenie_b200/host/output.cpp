@@ -206,6 +206,36 @@ std::string sumstats_row(const std::string& head, double af, bool with_info, dou
   return out;
 }
 
+std::string sumstats_header_all(int n_pheno) {
+  std::string h = "CHROM GENPOS ID ALLELE0 ALLELE1 A1FREQ N N_RR N_RA N_AA TEST";
+  for (int i = 1; i <= n_pheno; ++i) {
+    const std::string k = std::to_string(i);
+    h += " BETA.Y" + k + " SE.Y" + k + " CHISQ.Y" + k + " LOG10P.Y" + k;
+  }
+  return h + " EXTRA\n";
+}
+
+void append_sumstats_all_start(std::string& out, const std::string& head, double af, int n, long n_rr, long n_ra, long n_aa,
+                               const char* test) {
+  char num[128];
+  out += head;
+  if (af >= 0) out.append(num, (size_t)snprintf(num, sizeof(num), "%g", af));
+  else out += "NA";
+  out.append(num, (size_t)snprintf(num, sizeof(num), " %d", n));
+  if (n_rr >= 0) out.append(num, (size_t)snprintf(num, sizeof(num), " %ld %ld %ld", n_rr, n_ra, n_aa));
+  else out += " NA NA NA";
+  out += ' ';
+  out += test;
+}
+
+void append_sumstats_all_trait(std::string& out, bool have, double beta, double se, double chisq, double logp, bool test_pass) {
+  char num[96];
+  if (have && se >= 0 && !std::isnan(se)) out.append(num, (size_t)snprintf(num, sizeof(num), " %g %g", beta, se));
+  else out += " NA NA";
+  if (have && chisq >= 0 && test_pass && !std::isnan(logp)) out.append(num, (size_t)snprintf(num, sizeof(num), " %g %g", chisq, logp));
+  else out += " NA NA";
+}
+
 void write_ids_file(const std::string& path, const std::string& pheno_name, bool print_pheno_name,
                     const std::vector<std::pair<std::string, std::string>>& fid_iid, const uint8_t* mask) {
   TextWriter out;

@@ -61,6 +61,15 @@ std::string sumstats_row(const std::string& head, double af, bool with_info, dou
 void append_sumstats_row(std::string& out, const std::string& head, double af, bool with_info, double info, int n,
                          const char* test, double beta, double se, double chisq, double logp, bool test_pass);
 
+// --no-split (print_header_output_all / print_sum_stats_all, src/Step2_Models.cpp:2364-2383, 2441-2493): one file for all
+// traits; the variant columns are those of all analysed samples, followed by BETA/SE/CHISQ/LOG10P per trait
+std::string sumstats_header_all(int n_pheno);
+// start of a row: "<head>A1FREQ N N_RR N_RA N_AA TEST"
+void append_sumstats_all_start(std::string& out, const std::string& head, double af, int n, long n_rr, long n_ra, long n_aa,
+                               const char* test);
+// one trait: " BETA SE CHISQ LOG10P"; `have` false = the trait was ignored for this variant (all NA)
+void append_sumstats_all_trait(std::string& out, bool have, double beta, double se, double chisq, double logp, bool test_pass);
+
 // <out>_<pheno>.regenie.ids: "FID\tIID" of the samples of one trait, no newline after the last one
 void write_ids_file(const std::string& path, const std::string& pheno_name, bool print_pheno_name,
                     const std::vector<std::pair<std::string, std::string>>& fid_iid, const uint8_t* mask);

@@ -408,3 +408,40 @@ def check_na_invariance(run, read, tmp_path, golden_dir, bt):
         outs.append((read(fit + "_1.loco"), read(res + "_Y1.regenie")))
     assert len(outs[0][1].splitlines()) > 10
     assert outs[0] == outs[1]
+
+
+def check_no_split(run, read, tmp_path, golden_dir, extra=(), bt=False):
+    """--no-split (src/Step2_Models.cpp:2364-2383, 2441-2493): one file for all traits whose per-trait columns are those of
+    the split files, with N_RR / N_RA / N_AA of all analysed samples (src/Geno.cpp:2480-2486) checked against the .bed."""
+    import numpy as np
+    from oracle import plink
+    d = golden_dir
+    pheno = d + ("/phenotype_bin.txt" if bt else "/phenotype.txt")
+    base = ["--step", "2", "--bed", d + "/example_3chr", "--phenoFile", pheno, "--covarFile", d + "/covariates.txt", "--bsize", "100",
+            "--ignore-pred"] + (["--bt", "--firth", "--approx", "--pThresh", "0.1"] if bt else []) + list(extra)
+    run(base + ["--out", str(tmp_path / "split")])
+    run(base + ["--no-split", "--out", str(tmp_path / "all")])
+    assert read(str(tmp_path / "all") + ".regenie.Ydict").splitlines() == ["Y1 Y1", "Y2 Y2"]
+    rows = read(str(tmp_path / "all") + ".regenie").splitlines()
+    assert rows[0] == ("CHROM GENPOS ID ALLELE0 ALLELE1 A1FREQ N N_RR N_RA N_AA TEST BETA.Y1 SE.Y1 CHISQ.Y1 LOG10P.Y1 "
+                       "BETA.Y2 SE.Y2 CHISQ.Y2 LOG10P.Y2 EXTRA")
+    split = [{l.split()[2]: l.split() for l in read(str(tmp_path / "split") + "_%s.regenie" % nm).splitlines()[1:]} for nm in ("Y1", "Y2")]
+    bim = plink.read_bim(d + "/example_3chr.bim")
+    keys, _ = plink.read_fam(d + "/example_3chr.fam")
+    G = plink.decode_bed(plink.read_bed_rows(d + "/example_3chr.bed", len(keys), bim.offset), len(keys), ref_first="--ref-first" in extra)
+    idx = {v: k for k, v in enumerate(bim.ids)}
+    assert len(rows) > 400
+    for l in rows[1:]:
+        t = l.split()
+        assert len(t) == 20 and t[19] == "NA"
+        g = G[idx[t[2]]]
+        ok = g != -3
+        assert [int(x) for x in t[6:10]] == [int(ok.sum()), int((g[ok] == 0).sum()), int((g[ok] == 1).sum()), int((g[ok] == 2).sum())], t
+        for k in range(2):
+            s = split[k].get(t[2])
+            cols = t[11 + 4 * k: 15 + 4 * k]
+            if s is None:
+                assert cols == ["NA"] * 4
+            else:
+                assert t[:6] == s[:6] and t[10] == s[7] and cols == s[8:12], (t, s)
+    assert {t.split()[2] for t in rows[1:]} == set(split[0]) | set(split[1])

@@ -705,3 +705,11 @@ def test_na_rows_are_equivalent_to_absent_rows(tmp_path, golden_dir, bt):
     def read(path):
         return open(path).read()
     helpers.check_na_invariance(run, read, tmp_path, golden_dir, bt)
+
+
+@pytest.mark.parametrize("extra,bt", [((), False), (("--ref-first",), True)])
+def test_no_split_output(tmp_path, golden_dir, extra, bt):
+    """--no-split on the real library: per-trait columns == the split files, N_RR / N_RA / N_AA == the .bed counts."""
+    def read(path):
+        return open(path).read()
+    helpers.check_no_split(run, read, tmp_path, golden_dir, extra, bt)

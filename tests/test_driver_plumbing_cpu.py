@@ -217,3 +217,9 @@ def test_reference_script_case_column_mapping_from_bim(tmp_path, golden_dir):
 def test_na_rows_are_equivalent_to_absent_rows(tmp_path, golden_dir, bt):
     import helpers
     helpers.check_na_invariance(run, read, tmp_path, golden_dir, bt)
+
+
+@pytest.mark.parametrize("extra,bt", [((), False), (("--ref-first",), False), ((), True), (("--test", "dominant"), False)])
+def test_no_split_output(tmp_path, golden_dir, extra, bt):
+    import helpers
+    helpers.check_no_split(run, read, tmp_path, golden_dir, extra, bt)
