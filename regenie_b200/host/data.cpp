@@ -185,6 +185,50 @@ void read_pheno_and_cov(const SampleSet& g, const std::string& pheno_file, const
     if (all_miss) in_ph[s] = 0;
     if (!in_ph[s]) for (int p = 0; p < ph.P; ++p) ph.mask[(size_t)p * N + s] = 0;
   }
+  // every trait needs at least one observation (src/Pheno.cpp:343-351)
+  {
+    std::vector<int64_t> nobs(ph.P, 0);
+    for (int p = 0; p < ph.P; ++p)
+      for (int64_t s = 0; s < N; ++s) nobs[p] += ph.mask[(size_t)p * N + s];
+    if (std::all_of(nobs.begin(), nobs.end(), [](int64_t n) { return n == 0; }))
+      throw Fail("all individuals have missing/invalid values for all traits.");
+    for (int p = 0; p < ph.P; ++p)
+      if (nobs[p] == 0) throw Fail("all individuals have missing/invalid values for phenotype '" + ph.names[p] + "'.");
+  }
+  // binary traits with fewer than --minCaseCount cases are dropped (rm_phenoCols, src/Pheno.cpp:527-570)
+  if (bt) {
+    std::vector<int> keep;
+    for (int p = 0; p < ph.P; ++p) {
+      int64_t cases = 0;
+      for (int64_t s = 0; s < N; ++s) cases += ph.Y_raw[(size_t)p * N + s] == 1.0;
+      if (cases >= ph.min_case_count) keep.push_back(p);
+    }
+    if (keep.empty()) throw Fail("all phenotypes have less than " + std::to_string(ph.min_case_count) + " cases.");
+    if ((int)keep.size() < ph.P) {
+      log << "   -removing phenotypes with fewer than " << ph.min_case_count << " cases\n";
+      for (int p = 0, k = 0; p < ph.P; ++p) {
+        if (k < (int)keep.size() && keep[k] == p) { ++k; continue; }
+        log << "    +WARNING: Phenotype '" << ph.names[p] << "' has too few cases so it will be ignored.\n";
+      }
+      std::vector<std::string> names;
+      std::vector<double> Y, Yr;
+      std::vector<uint8_t> mask;
+      for (int p : keep) {
+        names.push_back(ph.names[p]);
+        Y.insert(Y.end(), ph.Y.begin() + (size_t)p * N, ph.Y.begin() + (size_t)(p + 1) * N);
+        Yr.insert(Yr.end(), ph.Y_raw.begin() + (size_t)p * N, ph.Y_raw.begin() + (size_t)(p + 1) * N);
+        mask.insert(mask.end(), ph.mask.begin() + (size_t)p * N, ph.mask.begin() + (size_t)(p + 1) * N);
+      }
+      ph.names.swap(names); ph.Y.swap(Y); ph.Y_raw.swap(Yr); ph.mask.swap(mask);
+      ph.P = (int)keep.size();
+      for (int64_t s = 0; s < N; ++s) {                      // samples left without any phenotype value
+        bool any = false;
+        for (int p = 0; p < ph.P; ++p) any |= ph.mask[(size_t)p * N + s] != 0;
+        if (!any) in_ph[s] = 0;
+      }
+      log << "    + n_pheno = " << ph.P << "\n";
+    }
+  }
   // covariates: intercept first (src/Pheno.cpp:79)
   std::vector<uint8_t> in_cov(N, 1);
   std::vector<double> cov;

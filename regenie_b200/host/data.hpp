@@ -70,6 +70,7 @@ struct Pheno {
   std::set<std::string> pheno_excl, covar_excl;   // --phenoExcludeList / --covarExcludeList
   std::set<std::string> cat_cols;                 // --catCovarList: expanded to K-1 indicator columns
   int max_cat_levels = 10;                        // --maxCatLevels
+  int min_case_count = 10;                        // --minCaseCount (binary traits)
 };
 
 // read_pheno_and_cov: raw values + masks, before prep_run

@@ -56,6 +56,7 @@ struct Params {
   bool set_range = false;                      // --range CHR:MINPOS-MAXPOS (step 2)
   int range_chr = 0;
   double range_min = 0, range_max = 0;
+  int min_case_count = 10;                     // --minCaseCount
   bool no_split = false;                       // --no-split: one <out>.regenie for all traits (hard-call input)
   int test_type = 0;                           // --test additive | dominant | recessive (step 2)
   bool gpu_inflate = false;                    // --gpu-inflate: zlib payloads of the .bgen are inflated on the device (rg_bgen_inflate)
@@ -189,6 +190,7 @@ Params parse_cli(int argc, char** argv) {
     else if (a == "--bgi") p.bgi = need(i);
     else if (a == "--gpu-inflate") p.gpu_inflate = true;
     else if (a == "--no-split") p.no_split = true;
+    else if (a == "--minCaseCount") p.min_case_count = atoi(need(i).c_str());
     else if (a == "--test") {                                   // src/Regenie.cpp:735-740
       const std::string v = need(i);
       if (v == "additive") p.test_type = 0;
@@ -349,7 +351,7 @@ void run_step1(const Params& p_in, Log& log) {
     throw Fail("it is not recommened to use more than 1000000 variants in step 1 (otherwise use '--force-step1').");
   Pheno ph;
   ph.pheno_cols = p.pheno_cols; ph.covar_cols = p.covar_cols; ph.rint = p.rint && !p.bt; ph.cat_cols = p.cat_cols; ph.max_cat_levels = p.max_cat_levels;
-  ph.pheno_excl = p.pheno_excl; ph.covar_excl = p.covar_excl;
+  ph.pheno_excl = p.pheno_excl; ph.covar_excl = p.covar_excl; ph.min_case_count = p.min_case_count;
   read_pheno_and_cov(SampleSet{g.keys, g.key_to_ind}, p.pheno, p.covar, false, p.strict, p.bt, ph, log);
   prep_run(ph, nullptr, log);
   if (p.bt && !p.loocv) {
@@ -713,7 +715,7 @@ void apply_range(const Params& p, std::vector<Snp>& snps) {
 void load_step2_inputs(const Params& p, const SampleSet& g, const std::vector<std::pair<std::string, std::string>>& ids_file,
                        const std::vector<int32_t>& sample_idx, Pheno& ph, std::vector<Loco>& locos, Log& log) {
   ph.pheno_cols = p.pheno_cols; ph.covar_cols = p.covar_cols; ph.rint = p.rint && !p.bt; ph.cat_cols = p.cat_cols; ph.max_cat_levels = p.max_cat_levels;
-  ph.pheno_excl = p.pheno_excl; ph.covar_excl = p.covar_excl;
+  ph.pheno_excl = p.pheno_excl; ph.covar_excl = p.covar_excl; ph.min_case_count = p.min_case_count;
   read_pheno_and_cov(g, p.pheno, p.covar, true, p.strict, p.bt, ph, log);
   const int64_t N = ph.N;
   const int P = ph.P;

@@ -223,3 +223,22 @@ def test_na_rows_are_equivalent_to_absent_rows(tmp_path, golden_dir, bt):
 def test_no_split_output(tmp_path, golden_dir, extra, bt):
     import helpers
     helpers.check_no_split(run, read, tmp_path, golden_dir, extra, bt)
+
+
+def test_min_case_count_drops_rare_binary_traits(tmp_path, golden_dir):
+    """rm_phenoCols (src/Pheno.cpp:527-570): binary traits with fewer than --minCaseCount (10) cases are ignored."""
+    d = golden_dir
+    rows = open(d + "/phenotype_bin.txt").read().splitlines()
+    out = [rows[0] + " Y3"]
+    for k, l in enumerate(rows[1:]):
+        out.append(l + (" 1" if k < 5 else " 0"))
+    (tmp_path / "ph.txt").write_text("\n".join(out) + "\n")
+    base = ["--step", "2", "--bed", d + "/example_3chr", "--phenoFile", tmp_path / "ph.txt", "--covarFile", d + "/covariates.txt",
+            "--bsize", "200", "--bt", "--ignore-pred"]
+    log = run(base + ["--out", str(tmp_path / "a")])
+    assert "Phenotype 'Y3' has too few cases so it will be ignored." in log and "+ n_pheno = 2" in log
+    assert os.path.exists(str(tmp_path / "a") + "_Y2.regenie") and not os.path.exists(str(tmp_path / "a") + "_Y3.regenie")
+    run(base + ["--minCaseCount", "3", "--out", str(tmp_path / "b")])
+    assert os.path.exists(str(tmp_path / "b") + "_Y3.regenie")
+    r = run(base + ["--phenoCol", "Y3", "--out", str(tmp_path / "c")], ok=False)
+    assert "ERROR: all phenotypes have less than 10 cases." in r
