@@ -542,9 +542,9 @@ void run_step1(const Params& p_in, Log& log) {
       TextWriter of;
       of.open(loco_file);
       const double* L = loco.data() + (size_t)ph_i * 23 * N;
-      std::vector<const double*> rows(23);
-      for (int c = 0; c < 23; ++c) rows[c] = L + (size_t)c * N;
-      write_pred_file(of, g.keys, order, mask_p, chr_labels, rows);
+      std::vector<const double*> chr_rows(23);
+      for (int c = 0; c < 23; ++c) chr_rows[c] = L + (size_t)c * N;
+      write_pred_file(of, g.keys, order, mask_p, chr_labels, chr_rows);
       of.close();
     }
     plist << ph.names[ph_i] << " " << full_path(loco_file, p.rel_path) << "\n";
