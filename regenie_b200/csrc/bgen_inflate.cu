@@ -13,6 +13,8 @@
 // (profiles/inflate_bench_r1.txt, N = 100k, 1000 variants per block, H2D of the compressed bytes included): 30 ms per
 // block = 9.9 GB/s of inflated bytes, against 1.9 GB/s for zlib on 32 host threads.  The default stays host zlib until the
 // Step-2 bench leg is switched over.
+#include <stdlib.h>
+
 #include "context.cuh"
 #include "inflate_core.h"
 
@@ -44,6 +46,28 @@ bgen_inflate_kernel(const uint8_t* __restrict__ comp, const uint64_t* __restrict
   const uint64_t o = offs[v];
   const int st = rgi::inflate_zlib(comp + o, (uint32_t)(offs[v + 1] - o), raw + (uint64_t)v * raw_stride, raw_len,
                                    tabs[warp], true);
+  if ((threadIdx.x & 31) == 0) status[v] = st;
+}
+
+// Variant with the last 16 KB of every stream's output in shared memory (inflate_zlib_window): matches are ring-to-ring
+// copies and global memory is written in coalesced runs.  Selected with RG_B200_INFLATE=window; verified against zlib on
+// the CPU like the direct variant (tests/test_host_cpu.py, tools/inflate_fuzz.cpp, both lane orders), NOT yet run or timed
+// on a B200 - the direct kernel above stays the default until it has been.
+constexpr int kWindowWarps = 4;
+constexpr size_t kWindowWarpBytes = rgi::kWinBytes + ((sizeof(rgi::Tables) + 15) / 16) * 16;
+constexpr size_t kWindowSmem = kWindowWarps * kWindowWarpBytes;
+
+__global__ void __launch_bounds__(kWindowWarps * 32)
+bgen_inflate_window_kernel(const uint8_t* __restrict__ comp, const uint64_t* __restrict__ offs, uint8_t* __restrict__ raw,
+                           uint64_t raw_stride, uint32_t raw_len, int bs, int32_t* __restrict__ status) {
+  extern __shared__ __align__(16) uint8_t inflate_smem[];
+  const int warp = threadIdx.x >> 5;
+  const int v = blockIdx.x * kWindowWarps + warp;
+  if (v >= bs) return;
+  uint8_t* win = inflate_smem + (size_t)warp * kWindowWarpBytes;
+  rgi::Tables& tab = *reinterpret_cast<rgi::Tables*>(win + rgi::kWinBytes);
+  const uint64_t o = offs[v];
+  const int st = rgi::inflate_zlib_window(comp + o, (uint32_t)(offs[v + 1] - o), raw + (uint64_t)v * raw_stride, raw_len, tab, win, true);
   if ((threadIdx.x & 31) == 0) status[v] = st;
 }
 
@@ -92,8 +116,20 @@ static void bgen_inflate(rg_ctx* h, const uint8_t* comp, const uint64_t* comp_of
   h->miss_dev.alloc((size_t)h->bs_max * n_file);
   copy_to_device(h->inflate_comp.p, comp + base, (size_t)total, s);
   RG_CUDA(cudaMemcpyAsync(h->inflate_offs.p, rel.data(), rel.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-  bgen_inflate_kernel<<<(unsigned)ceil_div(bs, kInflateWarps), kInflateWarps * 32, 0, s>>>(
-      h->inflate_comp.p, h->inflate_offs.p, h->inflate_raw.p, raw_stride, raw_len, bs, h->inflate_status.p);
+  static const bool use_window = [] {
+    const char* e = getenv("RG_B200_INFLATE");
+    return e && std::string(e) == "window";
+  }();
+  if (use_window) {
+    static const cudaError_t attr = cudaFuncSetAttribute(bgen_inflate_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         (int)kWindowSmem);
+    RG_CUDA(attr);
+    bgen_inflate_window_kernel<<<(unsigned)ceil_div(bs, kWindowWarps), kWindowWarps * 32, kWindowSmem, s>>>(
+        h->inflate_comp.p, h->inflate_offs.p, h->inflate_raw.p, raw_stride, raw_len, bs, h->inflate_status.p);
+  } else {
+    bgen_inflate_kernel<<<(unsigned)ceil_div(bs, kInflateWarps), kInflateWarps * 32, 0, s>>>(
+        h->inflate_comp.p, h->inflate_offs.p, h->inflate_raw.p, raw_stride, raw_len, bs, h->inflate_status.p);
+  }
   RG_CUDA(cudaGetLastError());
   const unsigned chunks = (unsigned)std::min<int64_t>(64, ceil_div(n_file, 1024));
   bgen_unpack_kernel<<<dim3(chunks, (unsigned)bs), 256, 0, s>>>(h->inflate_raw.p, raw_stride, (uint32_t)n_file, bs,

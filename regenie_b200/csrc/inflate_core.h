@@ -27,6 +27,17 @@
 #define RGI_SYNC() ((void)0)
 #endif
 
+// copy loops of the ring variant: lane l takes elements first + l, first + l + LANES, ...  On the host the elements of a
+// 32-wide batch can be visited in descending order instead (RGI_HOST_REVERSED_BATCHES, used by tools/inflate_fuzz.cpp) to
+// show that the result does not depend on the order in which the lanes of a warp get to their loads and stores.
+#if defined(__CUDA_ARCH__) || !defined(RGI_HOST_REVERSED_BATCHES)
+#define RGI_FOR_LANES(i, first, n) for (uint32_t i = (first) + (uint32_t)RGI_LANE; i < (n); i += RGI_LANES)
+#else
+#define RGI_FOR_LANES(i, first, n)                                                               \
+  for (uint32_t i##_b = (first); i##_b < (n); i##_b += 32)                                       \
+    for (uint32_t i##_k = ((n) - i##_b < 32 ? (n) - i##_b : 32), i = i##_b + i##_k - 1; i##_k > 0; --i##_k, --i)
+#endif
+
 namespace rgi {
 
 constexpr int kLitBits = 10, kDistBits = 8;
@@ -339,6 +350,197 @@ RGI_HD int inflate_zlib(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32
     int st = kOk;
     if (lane == 0) {
       // the trailer follows the last block at the next byte boundary; whole bytes still in the bit buffer are given back
+      const uint32_t tp = b.pos - (uint32_t)(b.cnt >> 3);
+      if (tp + 4 > in_len) st = kErrInput;
+      else want = ((uint32_t)in[tp] << 24) | ((uint32_t)in[tp + 1] << 16) | ((uint32_t)in[tp + 2] << 8) | in[tp + 3];
+    }
+    st = RGI_BCAST(st);
+    if (st != kOk) return st;
+    want = RGI_BCAST(want);
+    RGI_SYNC();
+    if (adler32_warp(out, out_len) != want) return kErrAdler;
+  }
+  return kOk;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Variant with a per-stream output window in shared memory.  inflate_zlib above writes every byte straight to global
+// memory and reads match sources back from it, so each match costs round trips to L2 and literals are single-byte
+// global stores.  Here the last kWinBytes of output live in a ring the caller provides (shared memory on the device):
+// lane 0 stores literals into the ring, matches up to kWinMaxDist back are copied ring -> ring by the warp, and the ring
+// is written out to global memory in coalesced runs (`flush`).  Matches that reach further back (about 8 % of them at a
+// 16 KB ring on BGEN payloads) flush first and read their source from global memory.  Same contract and status codes as
+// inflate_zlib; the host build (one lane, `win` on the heap) goes through exactly the same ring arithmetic.
+constexpr uint32_t kWinBytes = 16384;                  // power of two
+constexpr uint32_t kWinMask = kWinBytes - 1;
+constexpr uint32_t kWinMaxDist = kWinBytes - 258;      // a match of up to 258 bytes never overwrites its own source slots
+constexpr uint32_t kWinPending = kWinBytes / 2;        // lane 0 asks for a flush once this many bytes are unwritten
+constexpr uint32_t kWinChunk = 4096;                   // stored blocks are moved in chunks of this size
+
+RGI_HD int inflate_zlib_window(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len, Tables& t, uint8_t* win,
+                               bool check_adler) {
+  const int lane = RGI_LANE;
+  Bits b;
+  bits_init(b, in, in_len);
+  uint32_t pos = 0, flushed = 0;                  // bytes produced / bytes already in global memory (lane 0's copy is the truth)
+  int status = kOk;
+  if (lane == 0) {
+    if (in_len < 6) status = kErrHeader;
+    else {
+      const uint32_t cmf = in[0], flg = in[1];
+      if ((cmf & 15) != 8 || (cmf >> 4) > 7 || (flg & 32) || ((cmf << 8) | flg) % 31 != 0) status = kErrHeader;
+      b.pos = 2;
+    }
+  }
+  status = RGI_BCAST(status);
+  if (status != kOk) return status;
+
+  const uint16_t len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+  const uint8_t len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+  const uint16_t dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+  const uint8_t dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+
+  // events lane 0 hands to the warp: 1 = match inside the ring, 2 = stored bytes, 3 = end, 4 = flush, 5 = match whose
+  // source is read from global memory.  Events 2 and 5 are preceded by a flush (lane 0 emits event 4 first).
+  int mode = 0, last = 0;
+  uint32_t stored_left = 0;                       // bytes of the current stored block not yet handed over
+  bool want_flush = false;                        // the next event must be a flush, then the held event is replayed
+  int held_kind = 0;
+  uint32_t held_a0 = 0, held_a1 = 0;
+  for (;;) {
+    int kind = 0;
+    uint32_t a0 = 0, a1 = 0;
+    if (lane == 0) {
+      while (kind == 0 && status == kOk) {
+        if (want_flush || pos - flushed > kWinPending) {
+          want_flush = false;
+          if (pos > flushed) { kind = 4; break; }
+        }
+        if (held_kind != 0) {                     // the event that had to wait for its flush
+          kind = held_kind; a0 = held_a0; a1 = held_a1; held_kind = 0;
+          break;
+        }
+        if (stored_left > 0) {                    // rest of a stored block, chunk by chunk
+          const uint32_t n = stored_left < kWinChunk ? stored_left : kWinChunk;
+          held_kind = 2; held_a0 = n; held_a1 = b.pos;
+          b.pos += n; stored_left -= n;
+          if (pos > flushed) { want_flush = true; continue; }
+          kind = held_kind; a0 = held_a0; a1 = held_a1; held_kind = 0;
+          break;
+        }
+        if (mode == 0) {
+          if (last) { mode = 2; kind = 3; break; }
+          last = (int)bits_get(b, 1);
+          const int type = (int)bits_get(b, 2);
+          if (type == 0) {
+            bits_drop(b, b.cnt & 7);
+            b.pos -= (uint32_t)(b.cnt >> 3);
+            b.buf = 0; b.cnt = 0;
+            if (b.pos + 4 > in_len) { status = kErrInput; break; }
+            const uint32_t len = in[b.pos] | ((uint32_t)in[b.pos + 1] << 8);
+            const uint32_t nlen = in[b.pos + 2] | ((uint32_t)in[b.pos + 3] << 8);
+            b.pos += 4;
+            if ((len ^ 0xffffu) != nlen) { status = kErrStored; break; }
+            if (b.pos + len > in_len) { status = kErrInput; break; }
+            if (pos + len > out_len) { status = kErrOutput; break; }
+            stored_left = len;
+          } else if (type == 1) {
+            build_fixed(t);
+            mode = 1;
+          } else if (type == 2) {
+            status = build_dynamic(b, t);
+            mode = 1;
+          } else {
+            status = kErrBlockType;
+          }
+        } else {
+          const int sym = decode_symbol(b, t.lit_count, t.lit_sym, t.lit_fast, kLitBits);
+          if (sym < 0) { status = kErrSymbol; break; }
+          if (sym < 256) {
+            if (pos >= out_len) { status = kErrOutput; break; }
+            win[pos & kWinMask] = (uint8_t)sym;
+            ++pos;
+          } else if (sym == 256) {
+            mode = 0;
+          } else {
+            const int li = sym - 257;
+            if (li >= 29) { status = kErrSymbol; break; }
+            const uint32_t len = len_base[li] + bits_get(b, len_extra[li]);
+            const int ds = decode_symbol(b, t.dist_count, t.dist_sym, t.dist_fast, kDistBits);
+            if (ds < 0 || ds >= 30) { status = kErrSymbol; break; }
+            uint32_t dist = dist_base[ds];
+            const int de = dist_extra[ds];
+            if (de > 0) {
+              if (b.cnt < de) bits_fill(b);
+              dist += bits_peek(b, de);
+              bits_drop(b, de);
+            }
+            if (dist > pos) { status = kErrDistance; break; }
+            if (pos + len > out_len) { status = kErrOutput; break; }
+            if (dist <= kWinMaxDist) { kind = 1; a0 = len; a1 = dist; }
+            else {                                // source in global memory: everything produced so far must be there
+              held_kind = 5; held_a0 = len; held_a1 = dist;
+              if (pos > flushed) { want_flush = true; }
+              else { kind = 5; a0 = len; a1 = dist; held_kind = 0; }
+            }
+          }
+        }
+        if (b.over) status = kErrInput;
+      }
+      if (status != kOk) kind = 3;
+    }
+    kind = RGI_BCAST(kind);
+    if (kind == 3) break;
+    a0 = RGI_BCAST(a0);
+    a1 = RGI_BCAST(a1);
+    const uint32_t p0 = RGI_BCAST(pos);
+    const uint32_t f0 = RGI_BCAST(flushed);
+    RGI_SYNC();                                    // lane 0's ring stores are visible to the warp
+    if (kind == 1) {                               // ring -> ring; sources lie before p0 (index modulo the distance when
+      const uint32_t s0 = p0 - a1;                 // the match overlaps its own output)
+      if (a1 >= a0) {
+        RGI_FOR_LANES(i, 0u, a0) win[(p0 + i) & kWinMask] = win[(s0 + i) & kWinMask];
+      } else {
+        RGI_FOR_LANES(i, 0u, a0) win[(p0 + i) & kWinMask] = win[(s0 + i % a1) & kWinMask];
+      }
+    } else if (kind == 4) {                        // ring -> global, [f0, p0)
+      RGI_FOR_LANES(i, f0, p0) out[i] = win[i & kWinMask];
+    } else if (kind == 2) {                        // stored bytes: input -> global and ring (f0 == p0 here)
+      const uint8_t* src = in + a1;
+      RGI_FOR_LANES(i, 0u, a0) {
+        const uint8_t v = src[i];
+        out[p0 + i] = v;
+        win[(p0 + i) & kWinMask] = v;
+      }
+    } else {                                       // kind 5: far match, source already in global memory (f0 == p0, a1 > a0)
+      const uint8_t* src = out + (p0 - a1);
+      RGI_FOR_LANES(i, 0u, a0) {
+        const uint8_t v = src[i];
+        out[p0 + i] = v;
+        win[(p0 + i) & kWinMask] = v;
+      }
+    }
+    RGI_SYNC();
+    if (lane == 0) {
+      if (kind == 4) flushed = p0;
+      else {
+        pos = p0 + a0;
+        if (kind != 1) flushed = pos;
+      }
+    }
+  }
+  status = RGI_BCAST(status);
+  pos = RGI_BCAST(pos);
+  flushed = RGI_BCAST(flushed);
+  if (status != kOk) return status;
+  RGI_SYNC();
+  RGI_FOR_LANES(i, flushed, pos) out[i] = win[i & kWinMask];   // the tail of the ring
+  RGI_SYNC();
+  if (pos != out_len) return kErrLength;
+  if (check_adler) {
+    uint32_t want = 0;
+    int st = kOk;
+    if (lane == 0) {
       const uint32_t tp = b.pos - (uint32_t)(b.cnt >> 3);
       if (tp + 4 > in_len) st = kErrInput;
       else want = ((uint32_t)in[tp] << 24) | ((uint32_t)in[tp + 1] << 16) | ((uint32_t)in[tp + 2] << 8) | in[tp + 3];

@@ -14,8 +14,9 @@
 //   rgb200_hostprobe read-pred FILE [--prs]                 ids + rows back out, one token per line
 //   rgb200_hostprobe sumstats                               stdin: "af info n beta se chisq pass" per line -> rows
 //   rgb200_hostprobe ids OUT NAME PRINTNAME                 stdin: "FID IID keep" per line
-//   rgb200_hostprobe inflate-bgen FILE                      every zlib payload through csrc/inflate_core.h vs zlib
-//   rgb200_hostprobe inflate IN OUTLEN OUT                  one zlib stream through csrc/inflate_core.h (status on stdout)
+//   rgb200_hostprobe inflate-bgen FILE [window]             every zlib payload through csrc/inflate_core.h vs zlib
+//   rgb200_hostprobe inflate IN OUTLEN OUT [window]         one zlib stream through csrc/inflate_core.h (status on stdout)
+//                                                           `window` selects inflate_zlib_window (ring in shared memory)
 #include <cstring>
 #include <iomanip>
 
@@ -237,7 +238,15 @@ int cmd_ids(char** argv) {
 }
 
 // the decoder the GPU runs (csrc/inflate_core.h, compiled here with a one-lane "warp") against zlib on every variant
-int cmd_inflate_bgen(char** argv) {
+// one stream through the selected variant of the decoder
+int run_inflate(bool window, const uint8_t* in, uint32_t n, uint8_t* out, uint32_t out_len) {
+  static rgi::Tables t;
+  static std::vector<uint8_t> win(rgi::kWinBytes);
+  return window ? rgi::inflate_zlib_window(in, n, out, out_len, t, win.data(), true) : rgi::inflate_zlib(in, n, out, out_len, t, true);
+}
+
+int cmd_inflate_bgen(int argc, char** argv) {
+  const bool window = argc > 3 && std::string(argv[3]) == "window";
   BgenFile g;
   g.open(argv[2], "", false, {}, {}, {}, {}, {}, "", true);
   std::vector<uint8_t> comp;
@@ -245,13 +254,12 @@ int cmd_inflate_bgen(char** argv) {
   g.read_block_compressed(0, g.snps.size(), comp, offs);
   const uint32_t raw_len = 10 + 3 * g.n_file;
   std::vector<uint8_t> a(raw_len), b(raw_len);
-  static rgi::Tables t;
   size_t bad = 0, in_bytes = 0;
   for (size_t v = 0; v < g.snps.size(); ++v) {
     const uint32_t n = (uint32_t)(offs[v + 1] - offs[v]);
     in_bytes += n;
     std::fill(a.begin(), a.end(), 0xAA);
-    const int st = rgi::inflate_zlib(comp.data() + offs[v], n, a.data(), raw_len, t, true);
+    const int st = run_inflate(window, comp.data() + offs[v], n, a.data(), raw_len);
     uLongf dl = raw_len;
     const int zr = uncompress(b.data(), &dl, comp.data() + offs[v], n);
     if (st != 0 || zr != Z_OK || dl != raw_len || a != b) {
@@ -261,9 +269,9 @@ int cmd_inflate_bgen(char** argv) {
     // a truncated and a corrupted copy must be rejected, never crash
     if (v % 97 == 0 && n > 16) {
       std::vector<uint8_t> c(comp.begin() + (long)offs[v], comp.begin() + (long)offs[v + 1]);
-      const int st_trunc = rgi::inflate_zlib(c.data(), n / 2, a.data(), raw_len, t, true);
+      const int st_trunc = run_inflate(window, c.data(), n / 2, a.data(), raw_len);
       c[n / 2] ^= 0x5a;
-      const int st_flip = rgi::inflate_zlib(c.data(), n, a.data(), raw_len, t, true);
+      const int st_flip = run_inflate(window, c.data(), n, a.data(), raw_len);
       if (st_trunc == 0 || st_flip == 0) { ++bad; std::cout << "variant " << v << " damaged stream accepted\n"; }
     }
   }
@@ -271,7 +279,8 @@ int cmd_inflate_bgen(char** argv) {
   return bad ? 1 : 0;
 }
 
-int cmd_inflate(char** argv) {
+int cmd_inflate(int argc, char** argv) {
+  const bool window = argc > 5 && std::string(argv[5]) == "window";
   std::ifstream f(argv[2], std::ios::binary | std::ios::ate);
   if (!f) throw Fail(std::string("cannot open file : ") + argv[2]);
   std::vector<uint8_t> in((size_t)f.tellg());
@@ -279,8 +288,7 @@ int cmd_inflate(char** argv) {
   f.read(reinterpret_cast<char*>(in.data()), (std::streamsize)in.size());
   const uint32_t out_len = (uint32_t)atol(argv[3]);
   std::vector<uint8_t> out(out_len);
-  static rgi::Tables t;
-  const int st = rgi::inflate_zlib(in.data(), (uint32_t)in.size(), out.data(), out_len, t, true);
+  const int st = run_inflate(window, in.data(), (uint32_t)in.size(), out.data(), out_len);
   std::ofstream o(argv[4], std::ios::binary);
   o.write(reinterpret_cast<const char*>(out.data()), (std::streamsize)out.size());
   std::cout << "status " << st << "\n";
@@ -302,8 +310,8 @@ int main(int argc, char** argv) {
     if (c == "read-pred" && argc >= 3) return cmd_read_pred(argc, argv);
     if (c == "sumstats") return cmd_sumstats();
     if (c == "ids" && argc == 5) return cmd_ids(argv);
-    if (c == "inflate-bgen" && argc == 3) return cmd_inflate_bgen(argv);
-    if (c == "inflate" && argc == 5) return cmd_inflate(argv);
+    if (c == "inflate-bgen" && argc >= 3) return cmd_inflate_bgen(argc, argv);
+    if (c == "inflate" && argc >= 5) return cmd_inflate(argc, argv);
     throw Fail("unknown probe command or wrong number of arguments: " + c);
   } catch (const std::exception& e) {
     std::cout << "ERROR: " << e.what() << "\n";

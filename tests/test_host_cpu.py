@@ -360,16 +360,18 @@ def test_ids_file(tmp_path):
 
 
 # ------------------------------------------------------------------------------------------- device inflate core on the host
-def test_inflate_core_reproduces_zlib_on_every_bgen_payload(golden_dir):
+@pytest.mark.parametrize("variant", [(), ("window",)])
+def test_inflate_core_reproduces_zlib_on_every_bgen_payload(golden_dir, variant):
     """csrc/inflate_core.h is the decoder the GPU runs (one warp per variant stream); compiled for the host with a
     one-lane warp it must reproduce zlib byte for byte on every variant of the reference's fixtures, and reject
     truncated / corrupted streams."""
     for name, m in (("example", 1000), ("example_3chr", 500)):
-        out = probe("inflate-bgen", "%s/%s.bgen" % (golden_dir, name)).stdout.splitlines()[-1].split()
+        out = probe("inflate-bgen", "%s/%s.bgen" % (golden_dir, name), *variant).stdout.splitlines()[-1].split()
         assert out[:4] == ["variants", str(m), "bad", "0"], out
 
 
-def test_inflate_core_block_types_and_error_paths(tmp_path):
+@pytest.mark.parametrize("variant", [(), ("window",)])
+def test_inflate_core_block_types_and_error_paths(tmp_path, variant):
     import zlib
     rng = np.random.default_rng(5)
     payloads = {
@@ -390,7 +392,7 @@ def test_inflate_core_block_types_and_error_paths(tmp_path):
                 c = zlib.compressobj(level, zlib.DEFLATED, 15, 9, strat)
                 z = c.compress(data) + c.flush()
                 (tmp_path / "in.z").write_bytes(z)
-                r = probe("inflate", tmp_path / "in.z", len(data), tmp_path / "out.bin").stdout.split()
+                r = probe("inflate", tmp_path / "in.z", len(data), tmp_path / "out.bin", *variant).stdout.split()
                 assert r == ["status", "0"], (name, level, sname, r)
                 assert (tmp_path / "out.bin").read_bytes() == data, (name, level, sname)
                 n += 1
@@ -406,5 +408,5 @@ def test_inflate_core_block_types_and_error_paths(tmp_path):
     }
     for name, (blob, out_len, want) in cases.items():
         (tmp_path / "in.z").write_bytes(blob)
-        st = int(probe("inflate", tmp_path / "in.z", out_len, tmp_path / "out.bin").stdout.split()[1])
+        st = int(probe("inflate", tmp_path / "in.z", out_len, tmp_path / "out.bin", *variant).stdout.split()[1])
         assert st != 0 and (want is None or st == want), (name, st)

@@ -1,9 +1,10 @@
 // Differential fuzz of csrc/inflate_core.h (the decoder the GPU runs) against zlib, host build:
 //   g++ -O1 -g -fsanitize=address,undefined -std=c++17 tools/inflate_fuzz.cpp -o /tmp/inflate_fuzz -lz && /tmp/inflate_fuzz
-// 20000 streams (random / low-entropy / periodic / probability-like payloads, zlib levels 0-9), each damaged by 0-3 bit
-// flips, a random truncation and a random declared output length, inputs and outputs in exact-size heap blocks so that
-// the sanitizers see any out-of-bounds access (an overrun on the device would be a fault).  The decoder must accept
-// exactly the streams zlib accepts at that output length, with identical bytes.
+// 20000 streams (random / low-entropy / periodic / probability-like payloads of up to 120 KB, zlib levels 0-9), each
+// damaged by 0-3 bit flips, a random truncation and a random declared output length, inputs and outputs in exact-size
+// heap blocks so that the sanitizers see any out-of-bounds access (an overrun on the device would be a fault).  Both
+// variants of the decoder (direct, and with the 16 KB output ring) must accept exactly the streams zlib accepts at that
+// output length, with identical bytes.
 #include <zlib.h>
 
 #include <cstdio>
@@ -19,7 +20,7 @@ int main() {
   static rgi::Tables t;
   size_t accepted = 0, rejected = 0, disagree = 0;
   for (int iter = 0; iter < 20000; ++iter) {
-    const size_t n = 1 + rng() % 5000;
+    const size_t n = 1 + rng() % (iter % 8 == 0 ? 120000 : 5000);
     std::vector<uint8_t> raw(n);
     const int kind = rng() % 4;
     for (size_t i = 0; i < n; ++i)
@@ -37,7 +38,10 @@ int main() {
     size_t out_len = n;
     if (rng() % 7 == 0) out_len = rng() % (2 * n + 1);
     uint8_t* out = (uint8_t*)malloc(out_len ? out_len : 1);
-    const int st = rgi::inflate_zlib(in, (uint32_t)len, out, (uint32_t)out_len, t, true);
+    static std::vector<uint8_t> win(rgi::kWinBytes);
+    const bool window = iter & 1;
+    const int st = window ? rgi::inflate_zlib_window(in, (uint32_t)len, out, (uint32_t)out_len, t, win.data(), true)
+                          : rgi::inflate_zlib(in, (uint32_t)len, out, (uint32_t)out_len, t, true);
     std::vector<uint8_t> z(out_len ? out_len : 1);
     uLongf dl = out_len;
     const int zr = uncompress(z.data(), &dl, in, len);
