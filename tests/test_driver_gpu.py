@@ -713,3 +713,17 @@ def test_no_split_output(tmp_path, golden_dir, extra, bt):
     def read(path):
         return open(path).read()
     helpers.check_no_split(run, read, tmp_path, golden_dir, extra, bt)
+
+
+@pytest.mark.xfail(strict=False, reason="the ring-buffer inflate kernel (RG_B200_INFLATE=window) is verified against zlib on the CPU "
+                                        "but was written after the round's GPU budget was spent: first run on hardware")
+def test_gpu_inflate_window_variant_equals_host_inflate(tmp_path, golden_dir, monkeypatch):
+    d = golden_dir
+    qt = ["--step", "2", "--bgen", d + "/example_3chr.bgen", "--sample", d + "/example_3chr.sample", "--phenoFile",
+          d + "/phenotype.txt", "--covarFile", d + "/covariates.txt", "--bsize", "77", "--ignore-pred"]
+    run(qt + ["--out", str(tmp_path / "host")])
+    monkeypatch.setenv("RG_B200_INFLATE", "window")
+    log = run(qt + ["--out", str(tmp_path / "dev"), "--gpu-inflate"])
+    assert "inflated on the GPU" in log
+    for nm in ("Y1", "Y2"):
+        assert open(str(tmp_path / "host") + "_%s.regenie" % nm).read() == open(str(tmp_path / "dev") + "_%s.regenie" % nm).read()
