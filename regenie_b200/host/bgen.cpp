@@ -285,6 +285,43 @@ void BgenFile::read_block(size_t first, size_t n, uint8_t* probs, uint8_t* pm, i
   if (failed) throw Fail("unsupported or corrupt bgen genotype block (rgb200 reads 8-bit unphased diploid biallelic layout 2 only).");
 }
 
+void BgenFile::info_all(const uint8_t* probs, const uint8_t* pm, size_t n, const uint8_t* in_analysis, bool ref_first,
+                        double* info_out, int threads) const {
+  std::atomic<size_t> next{0};
+  const size_t nk = sample_idx.size();
+  auto work = [&]() {
+    for (;;) {
+      const size_t j = next.fetch_add(1);
+      if (j >= n) return;
+      const uint8_t* pr = probs + j * (size_t)n_file * 2;
+      const uint8_t* m = pm + j * (size_t)n_file;
+      // integer sums in units of 1/255 (dosage) and 1/255^2 (its square): exact, order-independent
+      uint64_t s_d = 0, s_d2 = 0, s_e = 0, ns = 0;
+      for (size_t k = 0; k < nk; ++k) {
+        if (!in_analysis[k]) continue;
+        const size_t f = (size_t)sample_idx[k];
+        if (m[f] & 0x80) continue;
+        const uint32_t p0 = pr[2 * f], p1 = pr[2 * f + 1];
+        const uint32_t hom = ref_first ? (p0 + p1 > 255 ? 0 : 255 - p0 - p1) : p0;
+        const uint32_t d = p1 + 2 * hom;
+        s_d += d;
+        s_d2 += (uint64_t)d * d;
+        s_e += 4 * hom + p1;
+        ++ns;
+      }
+      if (ns == 0) { info_out[j] = 1.0; continue; }
+      const double total = (double)s_d / 255.0, af = total / (2.0 * (double)ns);
+      const double info_num = (double)s_e / 255.0 - (double)s_d2 / 65025.0;
+      info_out[j] = (af == 0.0 || af == 1.0) ? 1.0 : 1.0 - info_num / (2.0 * (double)ns * af * (1.0 - af));
+    }
+  };
+  const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, n));
+  std::vector<std::thread> pool;
+  for (int t = 1; t < T; ++t) pool.emplace_back(work);
+  work();
+  for (auto& t : pool) t.join();
+}
+
 void BgenFile::read_block_compressed(size_t first, size_t n, std::vector<uint8_t>& comp, std::vector<uint64_t>& offs) const {
   if (compression != 1) throw Fail("on-device inflate needs zlib-compressed bgen payloads (compression flag 1).");
   offs.assign(n + 1, 0);

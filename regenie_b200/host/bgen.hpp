@@ -28,6 +28,11 @@ struct BgenFile {
   bool used_bgi = false;                       // the variant positions came from <file>.bgi (or --bgi)
   // inflate variants snps[first .. first+n): probs [n][n_file][2], ploidy_missing [n][n_file]
   void read_block(size_t first, size_t n, uint8_t* probs, uint8_t* ploidy_missing, int threads) const;
+  // variant-level imputation INFO over the analysed samples (info1 of compute_aaf_info, src/Geno.cpp:3134-3137, which
+  // --minINFO compares against before any trait is looked at, :2074): 1 - sum(4 p_AA + p_het - g^2) / (2 n af (1 - af)),
+  // from the inflated bytes of `n` variants; in_analysis is indexed like sample_idx (kept samples)
+  void info_all(const uint8_t* probs, const uint8_t* ploidy_missing, size_t n, const uint8_t* in_analysis, bool ref_first,
+                double* info_out, int threads) const;
   // the zlib streams of variants snps[first .. first+n) back to back, for rg_bgen_inflate (compression flag 1 only):
   // comp = concatenated streams, offs [n + 1]; throws when a variant's declared length is not 10 + 3 n_file
   void read_block_compressed(size_t first, size_t n, std::vector<uint8_t>& comp, std::vector<uint64_t>& offs) const;

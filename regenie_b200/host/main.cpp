@@ -848,17 +848,26 @@ void run_step2_qt(const Params& p, Log& log) {
     else rows[k].resize((size_t)bsz * g.row_stride);
   }
   const int threads = p.threads > 0 ? p.threads : (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
-  const bool dev_inflate = use_bgen && p.gpu_inflate && gg.compression == 1 && p.test_type == 0;
+  // --minINFO also drops a variant whose INFO over all analysed samples is too low (src/Geno.cpp:2074): computed from the
+  // inflated bytes on the host, in the fetch thread
+  const bool use_info1 = use_bgen && p.min_info > 0;
+  const bool dev_inflate = use_bgen && p.gpu_inflate && gg.compression == 1 && p.test_type == 0 && !use_info1;
   if (use_bgen && p.gpu_inflate)
     log << (dev_inflate ? " * bgen genotype blocks are inflated on the GPU\n"
-                        : "   -WARNING: --gpu-inflate needs zlib-compressed payloads and the additive test; inflating on the host.\n");
+                        : "   -WARNING: --gpu-inflate needs zlib-compressed payloads, the additive test and no --minINFO; inflating on the host.\n");
   std::vector<uint8_t> comp[2];
   std::vector<uint64_t> comp_offs[2];
+  std::vector<double> info1[2];
+  if (use_info1) { info1[0].resize(bsz); info1[1].resize(bsz); }
   std::future<void> pending;
   auto fetch = [&](size_t b) {
     return std::async(std::launch::async, [&, b] {
       if (dev_inflate) gg.read_block_compressed(blocks[b].first, blocks[b].size, comp[b & 1], comp_offs[b & 1]);
-      else if (use_bgen) gg.read_block(blocks[b].first, blocks[b].size, probs[b & 1].data(), pmiss[b & 1].data(), threads);
+      else if (use_bgen) {
+        gg.read_block(blocks[b].first, blocks[b].size, probs[b & 1].data(), pmiss[b & 1].data(), threads);
+        if (use_info1) gg.info_all(probs[b & 1].data(), pmiss[b & 1].data(), blocks[b].size, ph.in_analysis.data(), p.ref_first,
+                                   info1[b & 1].data(), threads);
+      }
       else g.read_rows(blocks[b].first, blocks[b].size, rows[b & 1].data());
     });
   };
@@ -935,6 +944,7 @@ void run_step2_qt(const Params& p, Log& log) {
     if (p.test_type) merge_recode_flags(blocks[b].size, flags.data(), flags2.data(), af_all2.data());
     for (int v = 0; v < blocks[b].size; ++v) {
       if (flags[v] & 3) { ++n_ignored; continue; }            // no row for ignored variants (split mode)
+      if (use_info1 && info1[b & 1][v] < p.min_info) { ++n_ignored; continue; }
       const Snp& s = snps[blocks[b].first + v];
       head_s.clear();                                        // print_sum_stats_head, src/Step2_Models.cpp:2410-2418
       head_s += std::to_string(s.chrom); head_s += ' ';
@@ -1021,17 +1031,24 @@ void run_step2_bt(const Params& p, Log& log) {
     if (use_bgen) { probs[k].resize((size_t)bsz * n_file * 2); pmiss[k].resize((size_t)bsz * n_file); }
     else rows[k].resize((size_t)bsz * gb.row_stride);
   }
-  const bool dev_inflate = use_bgen && p.gpu_inflate && gg.compression == 1 && p.test_type == 0;
+  const bool use_info1 = use_bgen && p.min_info > 0;         // variant-level --minINFO, see run_step2_qt
+  const bool dev_inflate = use_bgen && p.gpu_inflate && gg.compression == 1 && p.test_type == 0 && !use_info1;
   if (use_bgen && p.gpu_inflate)
     log << (dev_inflate ? " * bgen genotype blocks are inflated on the GPU\n"
-                        : "   -WARNING: --gpu-inflate needs zlib-compressed payloads and the additive test; inflating on the host.\n");
+                        : "   -WARNING: --gpu-inflate needs zlib-compressed payloads, the additive test and no --minINFO; inflating on the host.\n");
   std::vector<uint8_t> comp[2];
   std::vector<uint64_t> comp_offs[2];
+  std::vector<double> info1[2];
+  if (use_info1) { info1[0].resize(bsz); info1[1].resize(bsz); }
   std::future<void> pending;
   auto fetch = [&](size_t b) {
     return std::async(std::launch::async, [&, b] {
       if (dev_inflate) gg.read_block_compressed(blocks[b].first, blocks[b].size, comp[b & 1], comp_offs[b & 1]);
-      else if (use_bgen) gg.read_block(blocks[b].first, blocks[b].size, probs[b & 1].data(), pmiss[b & 1].data(), threads);
+      else if (use_bgen) {
+        gg.read_block(blocks[b].first, blocks[b].size, probs[b & 1].data(), pmiss[b & 1].data(), threads);
+        if (use_info1) gg.info_all(probs[b & 1].data(), pmiss[b & 1].data(), blocks[b].size, ph.in_analysis.data(), p.ref_first,
+                                   info1[b & 1].data(), threads);
+      }
       else gb.read_rows(blocks[b].first, blocks[b].size, rows[b & 1].data());
     });
   };
@@ -1107,6 +1124,8 @@ void run_step2_bt(const Params& p, Log& log) {
       }
     }
     if (p.test_type) merge_recode_flags(bs, flags.data(), flags2.data(), af_all2.data());
+    if (use_info1)                                           // ignored_snp: counts as one ignored variant, no Firth / SPA
+      for (int v = 0; v < bs; ++v) if (info1[b & 1][v] < p.min_info) flags[v] |= 1;
     // Firth fallback for |z| above the --pThresh threshold (check_pval_snp, src/Step2_Models.cpp:1988-2041)
     std::vector<int32_t> sel_v, sel_t, fstatus;
     std::vector<double> fbeta, fse, flrt;

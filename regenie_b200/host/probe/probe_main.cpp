@@ -5,6 +5,7 @@
 //
 //   rgb200_hostprobe bgen-variants FILE [--bgi F] [--no-bgi] [--ref-first] [--sample F] [--chr C]...
 //   rgb200_hostprobe bgen-probs FILE FIRST N OUT            raw probability + ploidy bytes of N variants
+//   rgb200_hostprobe bgen-info FILE [--ref-first]           variant-level INFO (info1) of every variant
 //   rgb200_hostprobe rows (--bed|--pgen) PREFIX OUT          every variant as PLINK 1 2-bit rows
 //   rgb200_hostprobe prep OUT (--bed|--pgen|--bgen) X --phenoFile F [--covarFile F] [--bt] [--step2] [--strict]
 //                    [--remove F] [--keep F] [--apply-rint] [--catCovarList a,b] [--phenoColList a,b] [--covarColList a,b]
@@ -77,6 +78,21 @@ int cmd_bgen_probs(char** argv) {
   std::ofstream f(argv[5], std::ios::binary);
   f.write(reinterpret_cast<const char*>(probs.data()), (std::streamsize)probs.size());
   f.write(reinterpret_cast<const char*>(pm.data()), (std::streamsize)pm.size());
+  return 0;
+}
+
+// variant-level INFO of every variant (all samples analysed), one value per line
+int cmd_bgen_info(int argc, char** argv) {
+  const bool ref_first = argc > 3 && std::string(argv[3]) == "--ref-first";
+  BgenFile g;
+  g.open(argv[2], "", ref_first, {}, {}, {}, {}, {}, "", true);
+  const size_t n = g.snps.size();
+  std::vector<uint8_t> probs(n * g.n_file * 2), pm(n * g.n_file), ina(g.keys.size(), 1);
+  g.read_block(0, n, probs.data(), pm.data(), 4);
+  std::vector<double> info(n);
+  g.info_all(probs.data(), pm.data(), n, ina.data(), ref_first, info.data(), 4);
+  std::cout << std::setprecision(17);
+  for (double v : info) std::cout << v << "\n";
   return 0;
 }
 
@@ -303,6 +319,7 @@ int main(int argc, char** argv) {
     const std::string c = argv[1];
     if (c == "bgen-variants" && argc >= 3) return cmd_bgen_variants(argc, argv);
     if (c == "bgen-probs" && argc == 6) return cmd_bgen_probs(argv);
+    if (c == "bgen-info" && argc >= 3) return cmd_bgen_info(argc, argv);
     if (c == "rows" && argc == 5) return cmd_rows(argv);
     if (c == "prep" && argc >= 3) return cmd_prep(argc, argv);
     if (c == "cat" && argc == 3) return cmd_cat(argv);

@@ -445,3 +445,51 @@ def check_no_split(run, read, tmp_path, golden_dir, extra=(), bt=False):
             else:
                 assert t[:6] == s[:6] and t[10] == s[7] and cols == s[8:12], (t, s)
     assert {t.split()[2] for t in rows[1:]} == set(split[0]) | set(split[1])
+
+
+# ---------------------------------------------------------------------------------------- minimal BGEN v1.2 writer (tests only)
+def write_bgen(path, probs, missing, chroms, positions, ids, alleles=("A", "G"), sample_ids=None, level=6):
+    """Layout 2, zlib, 8-bit, unphased, biallelic, diploid - the subset rgb200 and the reference's fast parser read.
+    probs: u8 [M, N, 2] (P(first-allele homozygote), P(het)) with p0 + p1 <= 255; missing: bool [M, N]."""
+    import struct
+    import zlib
+    import numpy as np
+    M, N, _ = probs.shape
+    if sample_ids is None:
+        sample_ids = ["s%d_s%d" % (i, i) for i in range(N)]
+    sblock = b"".join(struct.pack("<H", len(s)) + s.encode() for s in sample_ids)
+    sblock = struct.pack("<II", 8 + len(sblock), N) + sblock
+    header = struct.pack("<I", 20) + struct.pack("<II", M, N) + b"bgen" + struct.pack("<I", 1 | (2 << 2) | (1 << 31))
+    out = [struct.pack("<I", len(header) + len(sblock)), header, sblock]
+    for v in range(M):
+        vid = ids[v].encode()
+        c = str(chroms[v]).encode()
+        rec = struct.pack("<H", len(vid)) + vid + struct.pack("<H", len(vid)) + vid + struct.pack("<H", len(c)) + c
+        rec += struct.pack("<IH", int(positions[v]), 2)
+        for a in alleles:
+            rec += struct.pack("<I", len(a)) + a.encode()
+        ploidy = np.where(missing[v], 0x82, 0x02).astype(np.uint8)
+        pr = np.where(missing[v][:, None], 0, probs[v]).astype(np.uint8)
+        raw = struct.pack("<IHBB", N, 2, 2, 2) + ploidy.tobytes() + bytes([0, 8]) + pr.tobytes()
+        z = zlib.compress(raw, level)
+        rec += struct.pack("<II", len(z) + 4, len(raw)) + z
+        out.append(rec)
+    with open(path, "wb") as fh:
+        fh.write(b"".join(out))
+
+
+def synthetic_dosage_probs(M, N, seed=0, miss_rate=0.01):
+    """Imputed-looking probability pairs: most calls certain, the rest spread, 1 % missing."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    maf = rng.uniform(0.02, 0.5, M)
+    g = rng.binomial(2, maf[:, None], (M, N))
+    p = np.zeros((M, N, 2), dtype=np.uint8)
+    p[..., 0] = np.where(g == 2, 255, 0)
+    p[..., 1] = np.where(g == 1, 255, 0)
+    unsure = rng.random((M, N)) < rng.uniform(0.0, 0.6, M)[:, None]
+    a = rng.integers(0, 256, (M, N))
+    b = (rng.random((M, N)) * (255 - a)).astype(np.int64)
+    p[..., 0] = np.where(unsure, a, p[..., 0])
+    p[..., 1] = np.where(unsure, b, p[..., 1])
+    return p, rng.random((M, N)) < miss_rate

@@ -242,3 +242,32 @@ def test_min_case_count_drops_rare_binary_traits(tmp_path, golden_dir):
     assert os.path.exists(str(tmp_path / "b") + "_Y3.regenie")
     r = run(base + ["--phenoCol", "Y3", "--out", str(tmp_path / "c")], ok=False)
     assert "ERROR: all phenotypes have less than 10 cases." in r
+
+
+def test_min_info_drops_whole_variants_on_the_all_sample_info(tmp_path, golden_dir):
+    """--minINFO: a variant whose INFO over all analysed samples is below the threshold is ignored altogether
+    (src/Geno.cpp:2074), on top of the per-trait rule; the expected set comes from the oracle's formula."""
+    import numpy as np
+    import helpers
+    from oracle import bgen as obgen
+    d = golden_dir
+    keys = ["_".join(l.split()[:2]) for l in open(d + "/example.fam")]
+    M, N = 80, len(keys)
+    probs, miss = helpers.synthetic_dosage_probs(M, N, seed=9)
+    f = str(tmp_path / "syn.bgen")
+    helpers.write_bgen(f, probs, miss, [1] * 40 + [2] * 40, range(1, M + 1), ["v%d" % v for v in range(M)], sample_ids=keys)
+    info1 = []
+    for v in range(M):
+        g, ival = obgen.dosage(probs[v, :, 0], probs[v, :, 1], miss[v])
+        ok = ~miss[v]
+        af = g[ok].sum() / (2 * ok.sum())
+        info1.append(1 - ival[ok].sum() / (2 * ok.sum() * af * (1 - af)))
+    base = ["--step", "2", "--bgen", f, "--phenoFile", d + "/phenotype.txt", "--covarFile", d + "/covariates.txt", "--bsize", "32",
+            "--ignore-pred", "--minMAC", "1"]
+    run(base + ["--out", str(tmp_path / "all")])
+    log = run(base + ["--minINFO", "0.5", "--gpu-inflate", "--out", str(tmp_path / "thr")])
+    assert "inflating on the host" in log
+    ids_all = [l.split()[2] for l in read(str(tmp_path / "all") + "_Y1.regenie").splitlines()[1:]]
+    ids_thr = [l.split()[2] for l in read(str(tmp_path / "thr") + "_Y1.regenie").splitlines()[1:]]
+    want = [i for i in ids_all if info1[int(i[1:])] >= 0.5]
+    assert ids_thr == want and 0 < len(want) < len(ids_all)

@@ -410,3 +410,32 @@ def test_inflate_core_block_types_and_error_paths(tmp_path, variant):
         (tmp_path / "in.z").write_bytes(blob)
         st = int(probe("inflate", tmp_path / "in.z", out_len, tmp_path / "out.bin", *variant).stdout.split()[1])
         assert st != 0 and (want is None or st == want), (name, st)
+
+
+# ------------------------------------------------------------------------------------------- variant-level INFO (--minINFO)
+@pytest.mark.parametrize("ref_first", [False, True])
+def test_variant_level_info_matches_the_oracle_formula(tmp_path, ref_first):
+    """info1 of compute_aaf_info (src/Geno.cpp:3134-3137) from the host's integer sums vs the per-sample floating-point
+    formula of oracle/bgen.py, on a synthetic file with real imputation uncertainty and missing calls; the file also goes
+    through the oracle's own BGEN reader and the device decoder's host build."""
+    import helpers
+    M, N = 60, 700
+    probs, miss = helpers.synthetic_dosage_probs(M, N, seed=4)
+    f = str(tmp_path / "syn.bgen")
+    helpers.write_bgen(f, probs, miss, [1] * M, range(1, M + 1), ["v%d" % v for v in range(M)])
+    got = [float(x) for x in probe("bgen-info", f, *(["--ref-first"] if ref_first else [])).stdout.split()]
+    assert len(got) == M
+    ob = list(obgen.Bgen(f).variants())
+    assert len(ob) == M
+    lo = 2.0
+    for v, (_c, _p, rsid, _a, p0, p1, m) in enumerate(ob):
+        assert rsid == "v%d" % v and np.array_equal(p0[~m], probs[v, ~miss[v], 0]) and np.array_equal(m, miss[v])
+        g, ival = obgen.dosage(p0, p1, m, ref_first)
+        ok = ~m
+        ns, tot = ok.sum(), g[ok].sum()
+        af = tot / (2 * ns)
+        want = 1.0 if af in (0.0, 1.0) else 1 - ival[ok].sum() / (2 * ns * af * (1 - af))
+        assert abs(got[v] - want) < 1e-10, (v, got[v], want)
+        lo = min(lo, want)
+    assert lo < 0.8                                                  # the file really has low-INFO variants
+    assert probe("inflate-bgen", f, "window").stdout.splitlines()[-1].split()[:4] == ["variants", str(M), "bad", "0"]
