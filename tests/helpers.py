@@ -493,3 +493,35 @@ def synthetic_dosage_probs(M, N, seed=0, miss_rate=0.01):
     p[..., 0] = np.where(unsure, a, p[..., 0])
     p[..., 1] = np.where(unsure, b, p[..., 1])
     return p, rng.random((M, N)) < miss_rate
+
+
+def check_recoded_test_bgen(run, read, tmp_path, golden_dir, bt=False):
+    """--test dominant|recessive on dosages (src/Geno.cpp:2084-2100: P(het) + P(hom) / P(hom)): the test columns equal an
+    additive run on a .bgen whose probability pairs were recoded the same way; A1FREQ / INFO / N stay additive."""
+    import numpy as np
+    d = golden_dir
+    keys = ["_".join(l.split()[:2]) for l in open(d + "/example.fam")]
+    M, N = 120, len(keys)
+    probs, miss = synthetic_dosage_probs(M, N, seed=11)
+    chroms, pos, ids = [1] * 60 + [3] * 60, range(1, M + 1), ["v%d" % v for v in range(M)]
+    f = str(tmp_path / "orig.bgen")
+    write_bgen(f, probs, miss, chroms, pos, ids, sample_ids=keys)
+    pheno = d + ("/phenotype_bin.txt" if bt else "/phenotype.txt")
+    base = ["--step", "2", "--phenoFile", pheno, "--covarFile", d + "/covariates.txt", "--bsize", "50", "--ignore-pred", "--minMAC", "0"] + \
+        (["--bt"] if bt else [])
+    run(base + ["--bgen", f, "--out", str(tmp_path / "add")])
+    add = {l.split()[2]: l.split() for l in read(str(tmp_path / "add") + "_Y1.regenie").splitlines()[1:]}
+    for test, name in (("dominant", "DOM"), ("recessive", "REC")):
+        rp = np.zeros_like(probs)
+        hom, het = probs[..., 0].astype(np.int64), probs[..., 1].astype(np.int64)
+        rp[..., 1] = np.minimum(255, hom + het) if test == "dominant" else hom
+        g = str(tmp_path / (test + ".bgen"))
+        write_bgen(g, rp, miss, chroms, pos, ids, sample_ids=keys)
+        run(base + ["--bgen", f, "--test", test, "--out", str(tmp_path / test)])
+        run(base + ["--bgen", g, "--out", str(tmp_path / (test + "_ref"))])
+        got = [l.split() for l in read(str(tmp_path / test) + "_Y1.regenie").splitlines()[1:]]
+        want = {l.split()[2]: l.split() for l in read(str(tmp_path / (test + "_ref")) + "_Y1.regenie").splitlines()[1:]}
+        assert len(got) > 100 and [t[2] for t in got] == [k for k in add if k in want]
+        for t in got:
+            assert t[8] == name and t[:8] == add[t[2]][:8], t             # ..., A1FREQ, INFO, N of the additive coding
+            assert t[9:] == want[t[2]][9:], (t, want[t[2]])

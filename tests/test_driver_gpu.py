@@ -727,3 +727,11 @@ def test_gpu_inflate_window_variant_equals_host_inflate(tmp_path, golden_dir, mo
     assert "inflated on the GPU" in log
     for nm in ("Y1", "Y2"):
         assert open(str(tmp_path / "host") + "_%s.regenie" % nm).read() == open(str(tmp_path / "dev") + "_%s.regenie" % nm).read()
+
+
+@pytest.mark.parametrize("bt", [False, True])
+def test_dominant_recessive_on_dosages(tmp_path, golden_dir, bt):
+    """--test dominant / recessive on a synthetic .bgen with real imputation uncertainty (real library)."""
+    def read(path):
+        return open(path).read()
+    helpers.check_recoded_test_bgen(run, read, tmp_path, golden_dir, bt)

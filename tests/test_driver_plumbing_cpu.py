@@ -271,3 +271,9 @@ def test_min_info_drops_whole_variants_on_the_all_sample_info(tmp_path, golden_d
     ids_thr = [l.split()[2] for l in read(str(tmp_path / "thr") + "_Y1.regenie").splitlines()[1:]]
     want = [i for i in ids_all if info1[int(i[1:])] >= 0.5]
     assert ids_thr == want and 0 < len(want) < len(ids_all)
+
+
+@pytest.mark.parametrize("bt", [False, True])
+def test_dominant_recessive_on_dosages(tmp_path, golden_dir, bt):
+    import helpers
+    helpers.check_recoded_test_bgen(run, read, tmp_path, golden_dir, bt)
