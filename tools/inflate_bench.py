@@ -4,6 +4,7 @@ layout-2 shape (10 + 3N bytes per variant: header, ploidy bytes, 8-bit probabili
     python tools/inflate_bench.py [N] [bs] [reps]
 
 Wall-clock around the C-ABI call (it returns after the device finished): includes the H2D copy of the compressed bytes.
+RG_B200_INFLATE=window in the environment selects the ring-buffer kernel (inflate_zlib_window) instead of the direct one.
 """
 import os
 import sys
