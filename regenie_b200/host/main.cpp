@@ -56,6 +56,7 @@ struct Params {
   bool set_range = false;                      // --range CHR:MINPOS-MAXPOS (step 2)
   int range_chr = 0;
   double range_min = 0, range_max = 0;
+  bool af_cc = false;                          // --af-cc: A1FREQ / N among cases and controls (binary traits, split output)
   int min_case_count = 10;                     // --minCaseCount
   bool no_split = false;                       // --no-split: one <out>.regenie for all traits (hard-call input)
   int test_type = 0;                           // --test additive | dominant | recessive (step 2)
@@ -190,6 +191,7 @@ Params parse_cli(int argc, char** argv) {
     else if (a == "--bgi") p.bgi = need(i);
     else if (a == "--gpu-inflate") p.gpu_inflate = true;
     else if (a == "--no-split") p.no_split = true;
+    else if (a == "--af-cc") p.af_cc = true;
     else if (a == "--minCaseCount") p.min_case_count = atoi(need(i).c_str());
     else if (a == "--test") {                                   // src/Regenie.cpp:735-740
       const std::string v = need(i);
@@ -221,7 +223,7 @@ Params parse_cli(int argc, char** argv) {
                    "  [--chr c]... [--chrList c1,c2,...] [--range CHR:MIN-MAX]  (Step-2 jobs are split by chromosome / window like the reference)\n"
                    "  step 2 binary traits: --bt [--firth --approx | --spa] [--pThresh p] with --bed or --bgen F [--sample F] [--bgi F]\n"
                    "  [--gz] [--print-prs | --use-prs] [--write-samples [--print-pheno]]  (.gz inputs are read by file name)\n"
-                   "  [--test additive|dominant|recessive] [--no-split]\n"
+                   "  [--test additive|dominant|recessive] [--no-split] [--af-cc] [--minCaseCount n]\n"
                    "  [--gpu-inflate]  step 2 on zlib-compressed .bgen: inflate the genotype blocks on the GPU instead of the host\n";
       exit(0);
     } else {
@@ -334,6 +336,7 @@ void write_master(const Params& p, const std::vector<Snp>& snps, const std::vect
 
 void run_step1(const Params& p_in, Log& log) {
   Params p = p_in;
+  if (p.af_cc) log << "WARNING: disabling option --af-cc (only for BTs in step 2 in native output format split by trait).\n";
   if (p.set_range) { log << "WARNING: option --range only works for step 2.\n"; p.set_range = false; }
   Master master;
   if (p.run_l0_job || p.run_l1) master = read_master(p.master, p.bsize);
@@ -649,7 +652,7 @@ struct S2Writers {
     outs = std::vector<TextWriter>(ph.P);
     for (int i = 0; i < ph.P; ++i) {
       outs[i].open(p.out + "_" + ph.names[i] + ".regenie" + gz_ext);
-      outs[i] << sumstats_header(with_info);
+      outs[i] << sumstats_header(with_info, p.af_cc);
     }
   }
   void flush() {
@@ -1025,6 +1028,27 @@ void run_step2_bt(const Params& p, Log& log) {
   std::string head_s;
   const int bsz = p.bsize;
   GenoCounts gc(p.no_split, bsz, P, use_bgen ? 0 : gb.row_stride, p.ref_first);
+  // --af-cc (update_af_cc / compute_aaf_info, src/Geno.cpp:3069-3075, :3120-3127): a second handle whose sample masks are
+  // the cases of each trait returns their allele frequency and count from the same block bytes; controls follow by
+  // difference of the (exactly reconstructed) allele sums.
+  rg_handle hc = nullptr;
+  std::vector<double> afc, macc, afc_all, macc_all, statc, betac, sec, chisqc, scalec, infoc;
+  std::vector<int32_t> nsc, nsc_all, flagsc;
+  if (p.af_cc) {
+    std::vector<uint8_t> mask_case(ph.mask.size());
+    for (size_t e = 0; e < mask_case.size(); ++e) mask_case[e] = ph.mask[e] && ph.Y_raw[e] == 1.0;
+    rg_step2_config cfgc = cfg;
+    cfgc.strict_mode = 0;                                    // per-trait masks differ from the analysis set here
+    rg_check(rg_step2_create(&cfgc, ph.X.data(), mask_case.data(), ph.in_analysis.data(), &hc));
+    const std::vector<double> zero((size_t)N * P, 0.0), one(P, 1.0);
+    rg_check(rg_s2_set_chr(hc, zero.data(), one.data()));
+    const size_t bp = (size_t)bsz * P;
+    afc.resize(bp); macc.resize(bp); statc.resize(bp); betac.resize(bp); sec.resize(bp); chisqc.resize(bp); infoc.resize(bp); nsc.resize(bp);
+    afc_all.resize(bsz); macc_all.resize(bsz); scalec.resize(bsz); nsc_all.resize(bsz); flagsc.resize(bsz);
+  }
+  rg_s2_out outc{afc.data(), nsc.data(), macc.data(), afc_all.data(), nsc_all.data(), macc_all.data(), flagsc.data(),
+                 scalec.data(), statc.data(), betac.data(), sec.data(), chisqc.data()};
+  const double unit = use_bgen ? 255.0 : 1.0;                // allele sums are multiples of 1 / unit
   const int threads = p.threads > 0 ? p.threads : (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
   std::vector<uint8_t> probs[2], pmiss[2], rows[2];          // fetched one block ahead of the GPU call, like the QT path
   for (int k = 0; k < 2; ++k) {
@@ -1108,6 +1132,8 @@ void run_step2_bt(const Params& p, Log& log) {
       if (dev_inflate) rg_check(rg_bgen_inflate(h, comp[b & 1].data(), comp_offs[b & 1].data(), (int64_t)n_file, bs, &pd, &md));
       rg_check(rg_s2_block_bgen8_bt(h, pd, md, (int64_t)n_file, bs,
                                     subset ? sample_idx.data() : nullptr, p.ref_first, p.min_mac, &out, info.data()));
+      if (hc) rg_check(rg_s2_block_bgen8(hc, pd, md, (int64_t)n_file, bs, subset ? sample_idx.data() : nullptr, p.ref_first, 0.0,
+                                         &outc, infoc.data()));
       if (p.test_type) {
         recode.probs(probs[b & 1].data(), (size_t)bs * n_file);
         rg_check(rg_s2_block_bgen8_bt(h, pd, md, (int64_t)n_file, bs, subset ? sample_idx.data() : nullptr, p.ref_first, 0.0,
@@ -1117,6 +1143,8 @@ void run_step2_bt(const Params& p, Log& log) {
       // hard calls go to the GPU as they are (2 bits per sample)
       rg_check(rg_s2_block_bed_bt(h, rows[b & 1].data(), (int64_t)gb.row_stride, bs, subset ? sample_idx.data() : nullptr,
                                   p.ref_first, p.min_mac, &out));
+      if (hc) rg_check(rg_s2_block_bed(hc, rows[b & 1].data(), (int64_t)gb.row_stride, bs, subset ? sample_idx.data() : nullptr,
+                                       p.ref_first, 0.0, &outc));
       if (p.test_type) {
         recode.bed(rows[b & 1].data(), (size_t)bs * gb.row_stride);
         rg_check(rg_s2_block_bed_bt(h, rows[b & 1].data(), (int64_t)gb.row_stride, bs, subset ? sample_idx.data() : nullptr,
@@ -1190,8 +1218,17 @@ void run_step2_bt(const Params& p, Log& log) {
         }
         double lp = get_logp(co);
         if (p.spa && pass && f != fidx.end()) lp = spa_logp[{v, i}];   // SPA reports -log10 of its own p-value
+        AfCc cc;
+        if (hc) {
+          const double s_all = std::round(af[e] * 2.0 * ns[e] * unit), s_case = std::round(afc[e] * 2.0 * nsc[e] * unit);
+          cc.ns_case = nsc[e];
+          cc.ns_control = ns[e] - nsc[e];
+          cc.af_case = afc[e];
+          cc.af_control = (s_all - s_case) / unit / (2.0 * cc.ns_control);
+        }
         if (p.no_split) append_sumstats_all_trait(w.obuf_all, true, bo, so, co, lp, pass);
-        else append_sumstats_row(obuf[i], head_s, af[e], use_bgen, use_bgen ? info[e] : -1.0, ns[e], test_name(p.test_type), bo, so, co, lp, pass);
+        else append_sumstats_row(obuf[i], head_s, af[e], use_bgen, use_bgen ? info[e] : -1.0, ns[e], test_name(p.test_type), bo, so, co, lp, pass,
+                                 hc ? &cc : nullptr);
       }
       if (p.no_split) w.obuf_all += " NA\n";
     }
@@ -1202,10 +1239,16 @@ void run_step2_bt(const Params& p, Log& log) {
   log << "\nNumber of ignored tests due to low MAC or low variance : " << n_ignored << "\n";
   if (p.firth) log << "Number of tests with Firth correction : " << n_firth << " (" << n_fail << " failed)\n";
   if (p.spa) log << "Number of tests with SPA correction : " << n_firth << " (" << n_fail << " failed)\n";
+  if (hc) rg_destroy(hc);
   rg_destroy(h);
 }
 
-void run_step2(const Params& p, Log& log) {
+void run_step2(const Params& p_in, Log& log) {
+  Params p = p_in;
+  if (p.af_cc && (!p.bt || p.no_split)) {                    // src/Regenie.cpp:1076-1079
+    log << "WARNING: disabling option --af-cc (only for BTs in step 2 in native output format split by trait).\n";
+    p.af_cc = false;
+  }
   if (p.bt) run_step2_bt(p, log); else run_step2_qt(p, log);
 }
 

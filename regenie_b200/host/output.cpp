@@ -172,24 +172,30 @@ double get_logp(double t) {   // chi2_1 sf = erfc(sqrt(T/2))
   return -lp;
 }
 
-std::string sumstats_header(bool with_info) {
-  return std::string("CHROM GENPOS ID ALLELE0 ALLELE1 A1FREQ ") + (with_info ? "INFO " : "") +
-         "N TEST BETA SE CHISQ LOG10P EXTRA\n";
+std::string sumstats_header(bool with_info, bool af_cc) {
+  return std::string("CHROM GENPOS ID ALLELE0 ALLELE1 A1FREQ ") + (af_cc ? "A1FREQ_CASES A1FREQ_CONTROLS " : "") +
+         (with_info ? "INFO " : "") + "N " + (af_cc ? "N_CASES N_CONTROLS " : "") + "TEST BETA SE CHISQ LOG10P EXTRA\n";
 }
 
 // `ostream << double` at the default precision prints like printf("%g"); snprintf into the caller's buffer is several
 // times cheaper than a stringstream per row, which matters at 10^7 variants x P traits
 void append_sumstats_row(std::string& out, const std::string& head, double af, bool with_info, double info, int n,
-                         const char* test, double beta, double se, double chisq, double logp, bool test_pass) {
+                         const char* test, double beta, double se, double chisq, double logp, bool test_pass,
+                         const AfCc* cc) {
   char num[96];
   out += head;
   if (af >= 0) out.append(num, (size_t)snprintf(num, sizeof(num), "%g ", af));
   else out += "NA ";
+  if (cc) {
+    if (af >= 0) out.append(num, (size_t)snprintf(num, sizeof(num), "%g %g ", cc->af_case, cc->af_control));
+    else out += "NA NA ";
+  }
   if (with_info) {
     if (info >= 0) out.append(num, (size_t)snprintf(num, sizeof(num), "%g ", info));
     else out += "NA ";
   }
   out.append(num, (size_t)snprintf(num, sizeof(num), "%d ", n));
+  if (cc) out.append(num, (size_t)snprintf(num, sizeof(num), "%d %d ", cc->ns_case, cc->ns_control));
   out += test;
   out += ' ';
   if (se >= 0 && !std::isnan(se)) out.append(num, (size_t)snprintf(num, sizeof(num), "%g %g", beta, se));

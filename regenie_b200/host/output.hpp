@@ -51,7 +51,13 @@ void write_pred_file(TextWriter& out, const std::vector<std::string>& keys, cons
 // -log10 of the chi-square(1) tail probability of `t`, with the reference's underflow fallback
 double get_logp(double t);
 
-std::string sumstats_header(bool with_info);
+std::string sumstats_header(bool with_info, bool af_cc = false);
+
+// --af-cc (binary traits): allele frequency and sample count among cases / controls, printed after A1FREQ and after N
+struct AfCc {
+  double af_case = 0, af_control = 0;
+  int ns_case = 0, ns_control = 0;
+};
 
 // `head` = "CHROM GENPOS ID ALLELE0 ALLELE1 " of the variant; `logp` < 0 or NaN prints NA like a failed test
 std::string sumstats_row(const std::string& head, double af, bool with_info, double info, int n, const char* test,
@@ -59,7 +65,8 @@ std::string sumstats_row(const std::string& head, double af, bool with_info, dou
 
 // the same row appended to a caller-owned buffer (one buffer per trait, flushed once per block)
 void append_sumstats_row(std::string& out, const std::string& head, double af, bool with_info, double info, int n,
-                         const char* test, double beta, double se, double chisq, double logp, bool test_pass);
+                         const char* test, double beta, double se, double chisq, double logp, bool test_pass,
+                         const AfCc* cc = nullptr);
 
 // --no-split (print_header_output_all / print_sum_stats_all, src/Step2_Models.cpp:2364-2383, 2441-2493): one file for all
 // traits; the variant columns are those of all analysed samples, followed by BETA/SE/CHISQ/LOG10P per trait

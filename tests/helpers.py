@@ -525,3 +525,36 @@ def check_recoded_test_bgen(run, read, tmp_path, golden_dir, bt=False):
         for t in got:
             assert t[8] == name and t[:8] == add[t[2]][:8], t             # ..., A1FREQ, INFO, N of the additive coding
             assert t[9:] == want[t[2]][9:], (t, want[t[2]])
+
+
+def check_af_cc(run, read, tmp_path, golden_dir, extra=()):
+    """--af-cc (src/Geno.cpp:3069-3075, :3120-3127; print_sum_stats_single src/Step2_Models.cpp:2509-2521): allele frequency
+    and sample count among cases and controls, checked against the .bed and the phenotype file; all other columns must
+    be those of the run without the option."""
+    import numpy as np
+    from oracle import plink
+    d = golden_dir
+    base = ["--step", "2", "--bed", d + "/example_3chr", "--phenoFile", d + "/phenotype_bin_wNA.txt", "--covarFile", d + "/covariates.txt",
+            "--bsize", "100", "--ignore-pred", "--bt"] + list(extra)
+    run(base + ["--out", str(tmp_path / "plain")])
+    log = run(base + ["--af-cc", "--out", str(tmp_path / "cc")])
+    assert "disabling option --af-cc" not in log
+    bim = plink.read_bim(d + "/example_3chr.bim")
+    keys, _ = plink.read_fam(d + "/example_3chr.fam")
+    G = plink.decode_bed(plink.read_bed_rows(d + "/example_3chr.bed", len(keys), bim.offset), len(keys), ref_first="--ref-first" in extra)
+    idx = {v: k for k, v in enumerate(bim.ids)}
+    ph = {"_".join(l.split()[:2]): l.split()[2:] for l in open(d + "/phenotype_bin_wNA.txt").read().splitlines()[1:]}
+    for j, nm in enumerate(("Y1", "Y2")):
+        y = np.array([np.nan if ph[k][j] == "NA" else float(ph[k][j]) for k in keys])
+        plain = read(str(tmp_path / "plain") + "_%s.regenie" % nm).splitlines()
+        cc = read(str(tmp_path / "cc") + "_%s.regenie" % nm).splitlines()
+        assert cc[0] == "CHROM GENPOS ID ALLELE0 ALLELE1 A1FREQ A1FREQ_CASES A1FREQ_CONTROLS N N_CASES N_CONTROLS TEST BETA SE CHISQ LOG10P EXTRA"
+        assert len(cc) == len(plain) > 300
+        for a, b in zip(plain[1:], cc[1:]):
+            t, u = a.split(), b.split()
+            assert u[:6] == t[:6] and u[8] == t[6] and u[11:] == t[7:], (a, b)
+            g = G[idx[t[2]]]
+            ok = (g != -3) & ~np.isnan(y)
+            ca, co = ok & (y == 1), ok & (y == 0)
+            want = ["%g" % (g[ca].sum() / (2.0 * ca.sum())), "%g" % (g[co].sum() / (2.0 * co.sum())), str(int(ca.sum())), str(int(co.sum()))]
+            assert [u[6], u[7], u[9], u[10]] == want, (b, want)

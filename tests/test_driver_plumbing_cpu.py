@@ -277,3 +277,15 @@ def test_min_info_drops_whole_variants_on_the_all_sample_info(tmp_path, golden_d
 def test_dominant_recessive_on_dosages(tmp_path, golden_dir, bt):
     import helpers
     helpers.check_recoded_test_bgen(run, read, tmp_path, golden_dir, bt)
+
+
+@pytest.mark.parametrize("extra", [(), ("--ref-first", "--firth", "--approx", "--pThresh", "0.2")])
+def test_af_cc_columns(tmp_path, golden_dir, extra):
+    import helpers
+    helpers.check_af_cc(run, read, tmp_path, golden_dir, extra)
+    # the option is switched off, with the reference's warning, where it does not apply
+    d = golden_dir
+    log = run(["--step", "2", "--bed", d + "/example_3chr", "--phenoFile", d + "/phenotype.txt", "--covarFile", d + "/covariates.txt",
+               "--bsize", "100", "--ignore-pred", "--af-cc", "--out", str(tmp_path / "qt")])
+    assert "WARNING: disabling option --af-cc" in log
+    assert read(str(tmp_path / "qt") + "_Y1.regenie").splitlines()[0].split()[6] == "N"

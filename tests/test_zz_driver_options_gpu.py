@@ -113,3 +113,11 @@ def test_dominant_recessive_on_dosages(tmp_path, golden_dir, bt):
     def read(path):
         return open(path).read()
     helpers.check_recoded_test_bgen(run, read, tmp_path, golden_dir, bt)
+
+
+@pytest.mark.parametrize("extra", [(), ("--ref-first", "--firth", "--approx", "--pThresh", "0.2")])
+def test_af_cc_columns(tmp_path, golden_dir, extra):
+    """--af-cc on the real library: a second Step-2 handle masked to the cases of each trait."""
+    def read(path):
+        return open(path).read()
+    helpers.check_af_cc(run, read, tmp_path, golden_dir, extra)
