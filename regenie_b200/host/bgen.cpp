@@ -286,7 +286,7 @@ void BgenFile::read_block(size_t first, size_t n, uint8_t* probs, uint8_t* pm, i
 }
 
 void BgenFile::info_all(const uint8_t* probs, const uint8_t* pm, size_t n, const uint8_t* in_analysis, bool ref_first,
-                        double* info_out, int threads) const {
+                        double* info_out, int threads, long* n_rr, long* n_aa) const {
   std::atomic<size_t> next{0};
   const size_t nk = sample_idx.size();
   auto work = [&]() {
@@ -297,6 +297,7 @@ void BgenFile::info_all(const uint8_t* probs, const uint8_t* pm, size_t n, const
       const uint8_t* m = pm + j * (size_t)n_file;
       // integer sums in units of 1/255 (dosage) and 1/255^2 (its square): exact, order-independent
       uint64_t s_d = 0, s_d2 = 0, s_e = 0, ns = 0;
+      long rr = 0, aa = 0;
       for (size_t k = 0; k < nk; ++k) {
         if (!in_analysis[k]) continue;
         const size_t f = (size_t)sample_idx[k];
@@ -308,7 +309,11 @@ void BgenFile::info_all(const uint8_t* probs, const uint8_t* pm, size_t n, const
         s_d2 += (uint64_t)d * d;
         s_e += 4 * hom + p1;
         ++ns;
+        aa += 2 * d >= 765;                                  // dosage d / 255 >= 1.5
+        rr += 2 * d < 255;                                   // dosage < 0.5
       }
+      if (n_rr) n_rr[j] = rr;
+      if (n_aa) n_aa[j] = aa;
       if (ns == 0) { info_out[j] = 1.0; continue; }
       const double total = (double)s_d / 255.0, af = total / (2.0 * (double)ns);
       const double info_num = (double)s_e / 255.0 - (double)s_d2 / 65025.0;

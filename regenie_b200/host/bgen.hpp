@@ -31,8 +31,9 @@ struct BgenFile {
   // variant-level imputation INFO over the analysed samples (info1 of compute_aaf_info, src/Geno.cpp:3134-3137, which
   // --minINFO compares against before any trait is looked at, :2074): 1 - sum(4 p_AA + p_het - g^2) / (2 n af (1 - af)),
   // from the inflated bytes of `n` variants; in_analysis is indexed like sample_idx (kept samples)
+  // n_rr / n_aa (optional): the --no-split genotype counts of the same samples, dosage < 0.5 / >= 1.5 (src/Geno.cpp:2048-2050)
   void info_all(const uint8_t* probs, const uint8_t* ploidy_missing, size_t n, const uint8_t* in_analysis, bool ref_first,
-                double* info_out, int threads) const;
+                double* info_out, int threads, long* n_rr = nullptr, long* n_aa = nullptr) const;
   // the zlib streams of variants snps[first .. first+n) back to back, for rg_bgen_inflate (compression flag 1 only):
   // comp = concatenated streams, offs [n + 1]; throws when a variant's declared length is not 10 + 3 n_file
   void read_block_compressed(size_t first, size_t n, std::vector<uint8_t>& comp, std::vector<uint64_t>& offs) const;

@@ -243,8 +243,6 @@ Params parse_cli(int argc, char** argv) {
   if ((p.split_jobs || p.run_l0_job || p.run_l1) && p.step != 1) throw Fail("options --split-l0/--run-l0/--run-l1 only work in step 1.");
   if (p.out.empty()) throw Fail("must specify an output file prefix with --out.");
   if (p.bsize < 1) throw Fail("must specify the block size using '--bsize'.");
-  if (p.no_split && !p.bgen.empty())
-    throw Fail("--no-split with --bgen is not available in rgb200 yet (the variant-level INFO and the dosage genotype counts need a kernel output); use the split output.");
   if (p.test_type > 0 && p.step != 2) throw Fail("can only use --test in step 2 (association testing).");   // src/Regenie.cpp:905-906
   if (p.set_range && p.range_chr == -1) throw Fail("unrecognized chromosome in --range.");   // src/Regenie.cpp:1153-1154
   if (p.write_samples && !p.bgen.empty() && p.sample.empty())                     // src/Regenie.cpp:903-904
@@ -642,7 +640,7 @@ struct S2Writers {
     obuf.resize(ph.P);
     if (no_split) {
       all.open(p.out + ".regenie" + gz_ext);
-      all << sumstats_header_all(ph.P);
+      all << sumstats_header_all(ph.P, with_info);
       TextWriter dict;
       dict.open(p.out + ".regenie.Ydict");
       for (int i = 0; i < ph.P; ++i) dict << ("Y" + std::to_string(i + 1) + " " + ph.names[i] + "\n");
@@ -853,15 +851,16 @@ void run_step2_qt(const Params& p, Log& log) {
   const int threads = p.threads > 0 ? p.threads : (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
   // --minINFO also drops a variant whose INFO over all analysed samples is too low (src/Geno.cpp:2074): computed from the
   // inflated bytes on the host, in the fetch thread
-  const bool use_info1 = use_bgen && p.min_info > 0;
+  const bool use_info1 = use_bgen && (p.min_info > 0 || p.no_split);   // --no-split prints it and the dosage genotype counts
   const bool dev_inflate = use_bgen && p.gpu_inflate && gg.compression == 1 && p.test_type == 0 && !use_info1;
   if (use_bgen && p.gpu_inflate)
     log << (dev_inflate ? " * bgen genotype blocks are inflated on the GPU\n"
-                        : "   -WARNING: --gpu-inflate needs zlib-compressed payloads, the additive test and no --minINFO; inflating on the host.\n");
+                        : "   -WARNING: --gpu-inflate needs zlib-compressed payloads, the additive test and no --minINFO / --no-split; inflating on the host.\n");
   std::vector<uint8_t> comp[2];
   std::vector<uint64_t> comp_offs[2];
   std::vector<double> info1[2];
-  if (use_info1) { info1[0].resize(bsz); info1[1].resize(bsz); }
+  std::vector<long> d_rr[2], d_aa[2];
+  if (use_info1) for (int k = 0; k < 2; ++k) { info1[k].resize(bsz); d_rr[k].resize(bsz); d_aa[k].resize(bsz); }
   std::future<void> pending;
   auto fetch = [&](size_t b) {
     return std::async(std::launch::async, [&, b] {
@@ -869,7 +868,7 @@ void run_step2_qt(const Params& p, Log& log) {
       else if (use_bgen) {
         gg.read_block(blocks[b].first, blocks[b].size, probs[b & 1].data(), pmiss[b & 1].data(), threads);
         if (use_info1) gg.info_all(probs[b & 1].data(), pmiss[b & 1].data(), blocks[b].size, ph.in_analysis.data(), p.ref_first,
-                                   info1[b & 1].data(), threads);
+                                   info1[b & 1].data(), threads, d_rr[b & 1].data(), d_aa[b & 1].data());
       }
       else g.read_rows(blocks[b].first, blocks[b].size, rows[b & 1].data());
     });
@@ -947,7 +946,7 @@ void run_step2_qt(const Params& p, Log& log) {
     if (p.test_type) merge_recode_flags(blocks[b].size, flags.data(), flags2.data(), af_all2.data());
     for (int v = 0; v < blocks[b].size; ++v) {
       if (flags[v] & 3) { ++n_ignored; continue; }            // no row for ignored variants (split mode)
-      if (use_info1 && info1[b & 1][v] < p.min_info) { ++n_ignored; continue; }
+      if (use_info1 && p.min_info > 0 && info1[b & 1][v] < p.min_info) { ++n_ignored; continue; }
       const Snp& s = snps[blocks[b].first + v];
       head_s.clear();                                        // print_sum_stats_head, src/Step2_Models.cpp:2410-2418
       head_s += std::to_string(s.chrom); head_s += ' ';
@@ -957,8 +956,10 @@ void run_step2_qt(const Params& p, Log& log) {
       head_s += s.allele1; head_s += ' ';
       if (p.no_split) {                                        // print_sum_stats_all :2441-2493
         long n_rr, n_ra, n_aa;
-        gc.counts(v, af_all[v], ns_all[v], n_rr, n_ra, n_aa);
-        append_sumstats_all_start(w.obuf_all, head_s, af_all[v], ns_all[v], n_rr, n_ra, n_aa, test_name(p.test_type));
+        if (use_bgen) { n_rr = d_rr[b & 1][v]; n_aa = d_aa[b & 1][v]; n_ra = ns_all[v] - n_rr - n_aa; }
+        else gc.counts(v, af_all[v], ns_all[v], n_rr, n_ra, n_aa);
+        append_sumstats_all_start(w.obuf_all, head_s, af_all[v], ns_all[v], n_rr, n_ra, n_aa, test_name(p.test_type), use_bgen,
+                                  use_bgen ? info1[b & 1][v] : -1.0);
       }
       for (int i = 0; i < P; ++i) {
         const size_t e = (size_t)v * P + i;
@@ -1055,15 +1056,16 @@ void run_step2_bt(const Params& p, Log& log) {
     if (use_bgen) { probs[k].resize((size_t)bsz * n_file * 2); pmiss[k].resize((size_t)bsz * n_file); }
     else rows[k].resize((size_t)bsz * gb.row_stride);
   }
-  const bool use_info1 = use_bgen && p.min_info > 0;         // variant-level --minINFO, see run_step2_qt
+  const bool use_info1 = use_bgen && (p.min_info > 0 || p.no_split);   // variant-level --minINFO / --no-split, see run_step2_qt
   const bool dev_inflate = use_bgen && p.gpu_inflate && gg.compression == 1 && p.test_type == 0 && !use_info1;
   if (use_bgen && p.gpu_inflate)
     log << (dev_inflate ? " * bgen genotype blocks are inflated on the GPU\n"
-                        : "   -WARNING: --gpu-inflate needs zlib-compressed payloads, the additive test and no --minINFO; inflating on the host.\n");
+                        : "   -WARNING: --gpu-inflate needs zlib-compressed payloads, the additive test and no --minINFO / --no-split; inflating on the host.\n");
   std::vector<uint8_t> comp[2];
   std::vector<uint64_t> comp_offs[2];
   std::vector<double> info1[2];
-  if (use_info1) { info1[0].resize(bsz); info1[1].resize(bsz); }
+  std::vector<long> d_rr[2], d_aa[2];
+  if (use_info1) for (int k = 0; k < 2; ++k) { info1[k].resize(bsz); d_rr[k].resize(bsz); d_aa[k].resize(bsz); }
   std::future<void> pending;
   auto fetch = [&](size_t b) {
     return std::async(std::launch::async, [&, b] {
@@ -1071,7 +1073,7 @@ void run_step2_bt(const Params& p, Log& log) {
       else if (use_bgen) {
         gg.read_block(blocks[b].first, blocks[b].size, probs[b & 1].data(), pmiss[b & 1].data(), threads);
         if (use_info1) gg.info_all(probs[b & 1].data(), pmiss[b & 1].data(), blocks[b].size, ph.in_analysis.data(), p.ref_first,
-                                   info1[b & 1].data(), threads);
+                                   info1[b & 1].data(), threads, d_rr[b & 1].data(), d_aa[b & 1].data());
       }
       else gb.read_rows(blocks[b].first, blocks[b].size, rows[b & 1].data());
     });
@@ -1153,7 +1155,7 @@ void run_step2_bt(const Params& p, Log& log) {
     }
     if (p.test_type) merge_recode_flags(bs, flags.data(), flags2.data(), af_all2.data());
     if (use_info1)                                           // ignored_snp: counts as one ignored variant, no Firth / SPA
-      for (int v = 0; v < bs; ++v) if (info1[b & 1][v] < p.min_info) flags[v] |= 1;
+      for (int v = 0; v < bs; ++v) if (p.min_info > 0 && info1[b & 1][v] < p.min_info) flags[v] |= 1;
     // Firth fallback for |z| above the --pThresh threshold (check_pval_snp, src/Step2_Models.cpp:1988-2041)
     std::vector<int32_t> sel_v, sel_t, fstatus;
     std::vector<double> fbeta, fse, flrt;
@@ -1199,8 +1201,10 @@ void run_step2_bt(const Params& p, Log& log) {
       head_s += s.allele1; head_s += ' ';
       if (p.no_split) {                                        // print_sum_stats_all :2441-2493
         long n_rr, n_ra, n_aa;
-        gc.counts(v, af_all[v], ns_all[v], n_rr, n_ra, n_aa);
-        append_sumstats_all_start(w.obuf_all, head_s, af_all[v], ns_all[v], n_rr, n_ra, n_aa, test_name(p.test_type));
+        if (use_bgen) { n_rr = d_rr[b & 1][v]; n_aa = d_aa[b & 1][v]; n_ra = ns_all[v] - n_rr - n_aa; }
+        else gc.counts(v, af_all[v], ns_all[v], n_rr, n_ra, n_aa);
+        append_sumstats_all_start(w.obuf_all, head_s, af_all[v], ns_all[v], n_rr, n_ra, n_aa, test_name(p.test_type), use_bgen,
+                                  use_bgen ? info1[b & 1][v] : -1.0);
       }
       for (int i = 0; i < P; ++i) {
         const size_t e = (size_t)v * P + i;

@@ -212,8 +212,8 @@ std::string sumstats_row(const std::string& head, double af, bool with_info, dou
   return out;
 }
 
-std::string sumstats_header_all(int n_pheno) {
-  std::string h = "CHROM GENPOS ID ALLELE0 ALLELE1 A1FREQ N N_RR N_RA N_AA TEST";
+std::string sumstats_header_all(int n_pheno, bool with_info) {
+  std::string h = std::string("CHROM GENPOS ID ALLELE0 ALLELE1 A1FREQ ") + (with_info ? "INFO " : "") + "N N_RR N_RA N_AA TEST";
   for (int i = 1; i <= n_pheno; ++i) {
     const std::string k = std::to_string(i);
     h += " BETA.Y" + k + " SE.Y" + k + " CHISQ.Y" + k + " LOG10P.Y" + k;
@@ -222,11 +222,15 @@ std::string sumstats_header_all(int n_pheno) {
 }
 
 void append_sumstats_all_start(std::string& out, const std::string& head, double af, int n, long n_rr, long n_ra, long n_aa,
-                               const char* test) {
+                               const char* test, bool with_info, double info) {
   char num[128];
   out += head;
   if (af >= 0) out.append(num, (size_t)snprintf(num, sizeof(num), "%g", af));
   else out += "NA";
+  if (with_info) {
+    if (info >= 0) out.append(num, (size_t)snprintf(num, sizeof(num), " %g", info));
+    else out += " NA";
+  }
   out.append(num, (size_t)snprintf(num, sizeof(num), " %d", n));
   if (n_rr >= 0) out.append(num, (size_t)snprintf(num, sizeof(num), " %ld %ld %ld", n_rr, n_ra, n_aa));
   else out += " NA NA NA";

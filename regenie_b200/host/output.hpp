@@ -70,10 +70,10 @@ void append_sumstats_row(std::string& out, const std::string& head, double af, b
 
 // --no-split (print_header_output_all / print_sum_stats_all, src/Step2_Models.cpp:2364-2383, 2441-2493): one file for all
 // traits; the variant columns are those of all analysed samples, followed by BETA/SE/CHISQ/LOG10P per trait
-std::string sumstats_header_all(int n_pheno);
+std::string sumstats_header_all(int n_pheno, bool with_info = false);
 // start of a row: "<head>A1FREQ N N_RR N_RA N_AA TEST"
 void append_sumstats_all_start(std::string& out, const std::string& head, double af, int n, long n_rr, long n_ra, long n_aa,
-                               const char* test);
+                               const char* test, bool with_info = false, double info = -1.0);
 // one trait: " BETA SE CHISQ LOG10P"; `have` false = the trait was ignored for this variant (all NA)
 void append_sumstats_all_trait(std::string& out, bool have, double beta, double se, double chisq, double logp, bool test_pass);
 

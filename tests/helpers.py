@@ -558,3 +558,39 @@ def check_af_cc(run, read, tmp_path, golden_dir, extra=()):
             ca, co = ok & (y == 1), ok & (y == 0)
             want = ["%g" % (g[ca].sum() / (2.0 * ca.sum())), "%g" % (g[co].sum() / (2.0 * co.sum())), str(int(ca.sum())), str(int(co.sum()))]
             assert [u[6], u[7], u[9], u[10]] == want, (b, want)
+
+
+def check_no_split_bgen(run, read, tmp_path, golden_dir):
+    """--no-split on dosages: INFO over all analysed samples and the threshold genotype counts (dosage < 0.5 / >= 1.5,
+    src/Geno.cpp:2048-2050) come from the inflated bytes; per-trait columns are those of the split files."""
+    import numpy as np
+    from oracle import bgen as obgen
+    d = golden_dir
+    keys = ["_".join(l.split()[:2]) for l in open(d + "/example.fam")]
+    M, N = 90, len(keys)
+    probs, miss = synthetic_dosage_probs(M, N, seed=21)
+    f = str(tmp_path / "syn.bgen")
+    write_bgen(f, probs, miss, [1] * 50 + [2] * 40, range(1, M + 1), ["v%d" % v for v in range(M)], sample_ids=keys)
+    base = ["--step", "2", "--bgen", f, "--phenoFile", d + "/phenotype.txt", "--covarFile", d + "/covariates.txt", "--bsize", "40",
+            "--ignore-pred", "--minMAC", "1"]
+    run(base + ["--out", str(tmp_path / "split")])
+    run(base + ["--no-split", "--gpu-inflate", "--out", str(tmp_path / "all")])
+    rows = read(str(tmp_path / "all") + ".regenie").splitlines()
+    assert rows[0].split()[:12] == "CHROM GENPOS ID ALLELE0 ALLELE1 A1FREQ INFO N N_RR N_RA N_AA TEST".split()
+    split = [{l.split()[2]: l.split() for l in read(str(tmp_path / "split") + "_%s.regenie" % nm).splitlines()[1:]} for nm in ("Y1", "Y2")]
+    assert len(rows) > 60
+    for l in rows[1:]:
+        t = l.split()
+        v = int(t[2][1:])
+        g, ival = obgen.dosage(probs[v, :, 0], probs[v, :, 1], miss[v])
+        ok = ~miss[v]
+        af = g[ok].sum() / (2 * ok.sum())
+        info = 1 - ival[ok].sum() / (2 * ok.sum() * af * (1 - af))
+        dd = probs[v, ok, 1].astype(int) + 2 * probs[v, ok, 0].astype(int)
+        n_aa, n_rr = int((2 * dd >= 765).sum()), int((2 * dd < 255).sum())
+        assert [int(x) for x in t[7:11]] == [int(ok.sum()), n_rr, int(ok.sum()) - n_rr - n_aa, n_aa], t
+        assert abs(float(t[6]) - info) <= 2e-6 * max(1.0, abs(info)) and t[11] == "ADD"
+        for k in range(2):
+            s = split[k].get(t[2])
+            cols = t[12 + 4 * k: 16 + 4 * k]
+            assert cols == (["NA"] * 4 if s is None else s[9:13]), (t, s)

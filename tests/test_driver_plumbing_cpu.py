@@ -289,3 +289,8 @@ def test_af_cc_columns(tmp_path, golden_dir, extra):
                "--bsize", "100", "--ignore-pred", "--af-cc", "--out", str(tmp_path / "qt")])
     assert "WARNING: disabling option --af-cc" in log
     assert read(str(tmp_path / "qt") + "_Y1.regenie").splitlines()[0].split()[6] == "N"
+
+
+def test_no_split_output_on_dosages(tmp_path, golden_dir):
+    import helpers
+    helpers.check_no_split_bgen(run, read, tmp_path, golden_dir)

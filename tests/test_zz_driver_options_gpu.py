@@ -121,3 +121,9 @@ def test_af_cc_columns(tmp_path, golden_dir, extra):
     def read(path):
         return open(path).read()
     helpers.check_af_cc(run, read, tmp_path, golden_dir, extra)
+
+
+def test_no_split_output_on_dosages(tmp_path, golden_dir):
+    def read(path):
+        return open(path).read()
+    helpers.check_no_split_bgen(run, read, tmp_path, golden_dir)
