@@ -148,11 +148,12 @@ void BgenFile::open(const std::string& p, const std::string& sample_file, bool r
     const std::string& k = keys_file[i];
     if (remove.count(k)) continue;
     if (!keep.empty() && !keep.count(k)) continue;
+    if (sex_specific && sex_file[i] != sex_specific) continue;   // --sex-specific (src/Geno.cpp:1287-1293)
     key_to_ind[k] = (uint32_t)keys.size();
     keys.push_back(k);
     sample_idx.push_back((int32_t)i);
   }
-  if (keys.empty()) throw Fail("no samples left after --keep/--remove.");
+  if (keys.empty()) throw Fail("no samples left after --keep/--remove/--sex-specific.");
   // ---- variant index: one variant identifying block at file position `pos` (BGEN v1.2 spec); leaves `pos` at the
   // genotype block and returns false when the variant is filtered out
   size_t pos = 0;

@@ -10,6 +10,7 @@ namespace rgh {
 
 struct BgenFile {
   std::string path;
+  int sex_specific = 0;                        // 1 = males only, 2 = females only (set before open)
   std::vector<Snp> snps;                       // after --extract/--exclude; offset = file offset of the genotype block
   std::vector<std::string> keys_file, keys;
   std::vector<std::pair<std::string, std::string>> ids_file;   // (FID, IID) from --sample; empty for embedded ids

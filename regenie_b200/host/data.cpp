@@ -72,11 +72,12 @@ void BedFile::open(const std::string& pfx, bool ref_first, const std::set<std::s
     const std::string& k = keys_file[i];
     if (remove.count(k)) continue;
     if (!keep.empty() && !keep.count(k)) continue;
+    if (sex_specific && sex_file[i] != sex_specific) continue;   // --sex-specific (src/Geno.cpp:1287-1293)
     key_to_ind[k] = (uint32_t)keys.size();
     keys.push_back(k);
     sample_idx.push_back((int32_t)i);
   }
-  if (keys.empty()) throw Fail("no samples left after --keep/--remove.");
+  if (keys.empty()) throw Fail("no samples left after --keep/--remove/--sex-specific.");
   row_stride = (keys_file.size() + 3) / 4;
   // ---- .bed
   bed.open(prefix + ".bed", std::ios::binary);

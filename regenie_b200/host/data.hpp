@@ -30,6 +30,7 @@ struct PgenFile;
 
 struct BedFile {
   std::string prefix;
+  int sex_specific = 0;                       // 1 = males only, 2 = females only (set before open)
   std::shared_ptr<PgenFile> pg;               // set by open_pgen: rows are decoded from a .pgen into the same 2-bit layout
   std::vector<Snp> snps;                      // after --extract/--exclude
   std::vector<std::string> keys_file;         // FID_IID in .fam order

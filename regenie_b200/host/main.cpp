@@ -56,6 +56,8 @@ struct Params {
   bool set_range = false;                      // --range CHR:MINPOS-MAXPOS (step 2)
   int range_chr = 0;
   double range_min = 0, range_max = 0;
+  int sex_specific = 0;                        // --sex-specific male|female
+  int start_block = 1;                         // --starting-block (step 2)
   bool af_cc = false;                          // --af-cc: A1FREQ / N among cases and controls (binary traits, split output)
   int min_case_count = 10;                     // --minCaseCount
   bool no_split = false;                       // --no-split: one <out>.regenie for all traits (hard-call input)
@@ -192,6 +194,13 @@ Params parse_cli(int argc, char** argv) {
     else if (a == "--gpu-inflate") p.gpu_inflate = true;
     else if (a == "--no-split") p.no_split = true;
     else if (a == "--af-cc") p.af_cc = true;
+    else if (a == "--sex-specific") {                          // src/Regenie.cpp:756-762
+      const std::string v = need(i);
+      if (v == "male") p.sex_specific = 1;
+      else if (v == "female") p.sex_specific = 2;
+      else throw Fail("unrecognized argument for option --sex-specific, must be either 'male' or 'female'.");
+    }
+    else if (a == "--starting-block") p.start_block = atoi(need(i).c_str());
     else if (a == "--minCaseCount") p.min_case_count = atoi(need(i).c_str());
     else if (a == "--test") {                                   // src/Regenie.cpp:735-740
       const std::string v = need(i);
@@ -272,6 +281,8 @@ double now_ms() {
 // .bed/.bim/.fam or .pgen/.pvar/.psam behind the same row interface
 void open_rows(const Params& p, BedFile& g, const std::set<std::string>& excl, const std::set<std::string>& extr,
                const std::set<std::string>& rem, const std::set<std::string>& keep, Log& log) {
+  g.sex_specific = p.sex_specific;
+  if (p.sex_specific) log << "   -keeping only " << (p.sex_specific == 1 ? "male" : "female") << " individuals in the analysis\n";
   if (!p.pgen.empty()) {
     g.open_pgen(p.pgen, excl, extr, rem, keep, p.chrs);
     log << " * pvar                : [" << p.pgen << ".pvar] n_snps = " << g.snps.size() << "\n";
@@ -805,6 +816,7 @@ void run_step2_qt(const Params& p, Log& log) {
   const auto excl = read_id_list(p.exclude, 1), extr = read_id_list(p.extract, 1), rem = read_id_list(p.remove, 2),
              keepl = read_id_list(p.keep, 2);
   if (use_bgen) {
+    gg.sex_specific = p.sex_specific;
     gg.open(p.bgen, p.sample, p.ref_first, excl, extr, rem, keepl, p.chrs, p.bgi);
     if (gg.used_bgi) log << "   -index bgi file [" << (p.bgi.empty() ? p.bgen + ".bgi" : p.bgi) << "]\n";
     log << " * bgen                : [" << p.bgen << "] n_snps = " << gg.snps.size() << ", n_samples = " << gg.keys.size() << "\n";
@@ -873,7 +885,10 @@ void run_step2_qt(const Params& p, Log& log) {
       else g.read_rows(blocks[b].first, blocks[b].size, rows[b & 1].data());
     });
   };
-  if (!blocks.empty()) pending = fetch(0);
+  if (p.start_block > (int)blocks.size()) throw Fail("Starting block > number of blocks analyzed");   // src/Data.cpp:2863-2864
+  const size_t b_first = p.start_block > 1 ? (size_t)p.start_block - 1 : 0;
+  if (b_first) log << "    + skipping to block #" << p.start_block << "\n";
+  if (!blocks.empty()) pending = fetch(b_first);
   std::vector<double> info((size_t)bsz * P);
   std::vector<double> af((size_t)bsz * P), mac((size_t)bsz * P), stat((size_t)bsz * P), beta((size_t)bsz * P),
       se((size_t)bsz * P), chisq((size_t)bsz * P), af_all(bsz), mac_all(bsz), scale_fac(bsz);
@@ -895,7 +910,7 @@ void run_step2_qt(const Params& p, Log& log) {
   std::vector<uint8_t> npf;
   int cur_chr = -1;
   size_t n_ignored = 0;
-  for (size_t b = 0; b < blocks.size(); ++b) {
+  for (size_t b = b_first; b < blocks.size(); ++b) {
     const int chrom = blocks[b].chrom;
     if (chrom != cur_chr) {
       cur_chr = chrom;
@@ -990,6 +1005,7 @@ void run_step2_bt(const Params& p, Log& log) {
   const auto excl = read_id_list(p.exclude, 1), extr = read_id_list(p.extract, 1), rem = read_id_list(p.remove, 2),
              keep = read_id_list(p.keep, 2);
   if (use_bgen) {
+    gg.sex_specific = p.sex_specific;
     gg.open(p.bgen, p.sample, p.ref_first, excl, extr, rem, keep, p.chrs, p.bgi);
     if (gg.used_bgi) log << "   -index bgi file [" << (p.bgi.empty() ? p.bgen + ".bgi" : p.bgi) << "]\n";
     log << " * bgen                : [" << p.bgen << "] n_snps = " << gg.snps.size() << ", n_samples = " << gg.keys.size() << "\n";
@@ -1078,7 +1094,10 @@ void run_step2_bt(const Params& p, Log& log) {
       else gb.read_rows(blocks[b].first, blocks[b].size, rows[b & 1].data());
     });
   };
-  if (!blocks.empty()) pending = fetch(0);
+  if (p.start_block > (int)blocks.size()) throw Fail("Starting block > number of blocks analyzed");   // src/Data.cpp:2863-2864
+  const size_t b_first = p.start_block > 1 ? (size_t)p.start_block - 1 : 0;
+  if (b_first) log << "    + skipping to block #" << p.start_block << "\n";
+  if (!blocks.empty()) pending = fetch(b_first);
   std::vector<double> af((size_t)bsz * P), mac((size_t)bsz * P), stat((size_t)bsz * P), beta((size_t)bsz * P),
       se((size_t)bsz * P), chisq((size_t)bsz * P), info((size_t)bsz * P), af_all(bsz), mac_all(bsz), scale_fac(bsz);
   std::vector<int32_t> ns((size_t)bsz * P), ns_all(bsz), flags(bsz);
@@ -1097,7 +1116,7 @@ void run_step2_bt(const Params& p, Log& log) {
   std::vector<uint8_t> npf;
   int cur_chr = -1;
   size_t n_ignored = 0, n_firth = 0, n_fail = 0;
-  for (size_t b = 0; b < blocks.size(); ++b) {
+  for (size_t b = b_first; b < blocks.size(); ++b) {
     const int chrom = blocks[b].chrom, bs = blocks[b].size;
     if (chrom != cur_chr) {
       cur_chr = chrom;

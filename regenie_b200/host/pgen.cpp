@@ -53,11 +53,12 @@ void PgenFile::open(const std::string& pfx, const std::set<std::string>& exclude
     const std::string& k = keys_file[i];
     if (remove.count(k)) continue;
     if (!keep.empty() && !keep.count(k)) continue;
+    if (sex_specific && sex_file[i] != sex_specific) continue;   // --sex-specific (src/Geno.cpp:1287-1293)
     key_to_ind[k] = (uint32_t)keys.size();
     keys.push_back(k);
     sample_idx.push_back((int32_t)i);
   }
-  if (keys.empty()) throw Fail("no samples left after --keep/--remove.");
+  if (keys.empty()) throw Fail("no samples left after --keep/--remove/--sex-specific.");
   // ---- .pvar (src/Geno.cpp:771-870): ALLELE0 = REF, ALLELE1 = ALT
   {
     LineReader fh(prefix + ".pvar");
@@ -265,6 +266,7 @@ void pgen_read_rows(PgenFile& pg, size_t first, size_t n, uint8_t* out) { pg.rea
 void BedFile::open_pgen(const std::string& pfx, const std::set<std::string>& exclude, const std::set<std::string>& extract,
                         const std::set<std::string>& remove, const std::set<std::string>& keep, const std::set<int>& chrs) {
   pg = std::make_shared<PgenFile>();
+  pg->sex_specific = sex_specific;
   pg->open(pfx, exclude, extract, remove, keep, chrs);
   prefix = pfx;
   snps = pg->snps; keys_file = pg->keys_file; ids_file = pg->ids_file; sex_file = pg->sex_file; keys = pg->keys;

@@ -12,6 +12,7 @@ namespace rgh {
 
 struct PgenFile {
   std::string prefix;
+  int sex_specific = 0;                         // 1 = males only, 2 = females only (set before open)
   std::vector<Snp> snps;                        // after filters; offset = variant index in the .pgen
   std::vector<std::string> keys_file, keys;
   std::vector<std::pair<std::string, std::string>> ids_file;   // (FID, IID) in .psam order

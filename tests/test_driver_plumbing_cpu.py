@@ -294,3 +294,34 @@ def test_af_cc_columns(tmp_path, golden_dir, extra):
 def test_no_split_output_on_dosages(tmp_path, golden_dir):
     import helpers
     helpers.check_no_split_bgen(run, read, tmp_path, golden_dir)
+
+
+def test_sex_specific_and_starting_block(tmp_path, golden_dir):
+    """--sex-specific keeps one sex like --keep would (src/Geno.cpp:1287-1293); --starting-block resumes a Step-2 run at a
+    block (src/Data.cpp:2168, :2275): its rows are the tail of the full run."""
+    d = golden_dir
+    # the fixtures carry no sex information: write a .fam with alternating sexes
+    for ext in (".bed", ".bim"):
+        shutil.copy(d + "/example_3chr" + ext, tmp_path / ("sx" + ext))
+    fam = [l.split() for l in open(d + "/example_3chr.fam")]
+    with open(tmp_path / "sx.fam", "w") as fh:
+        for k, t in enumerate(fam):
+            t[4] = "1" if k % 2 == 0 else "2"
+            fh.write(" ".join(t) + "\n")
+    with open(tmp_path / "males.txt", "w") as fh:
+        fh.write("".join("%s %s\n" % (t[0], t[1]) for k, t in enumerate(fam) if k % 2 == 0))
+    base = ["--step", "2", "--bed", tmp_path / "sx", "--phenoFile", d + "/phenotype.txt", "--covarFile", d + "/covariates.txt", "--bsize", "100",
+            "--ignore-pred"]
+    log = run(base + ["--sex-specific", "male", "--out", str(tmp_path / "m1")])
+    run(base + ["--keep", tmp_path / "males.txt", "--out", str(tmp_path / "m2")])
+    assert "-keeping only male individuals in the analysis" in log
+    m1 = read(str(tmp_path / "m1") + "_Y1.regenie")
+    assert m1 == read(str(tmp_path / "m2") + "_Y1.regenie") and {l.split()[6] for l in m1.splitlines()[1:]} == {"250"}
+    run(base + ["--out", str(tmp_path / "full")])
+    log = run(base + ["--starting-block", "4", "--out", str(tmp_path / "tail")])
+    assert "+ skipping to block #4" in log
+    full, tail = read(str(tmp_path / "full") + "_Y2.regenie").splitlines(), read(str(tmp_path / "tail") + "_Y2.regenie").splitlines()
+    assert tail[0] == full[0] and 0 < len(tail) < len(full) and full[-(len(tail) - 1):] == tail[1:]
+    assert tail[1].split()[2] == open(d + "/example_3chr.bim").read().splitlines()[250].split()[1]        # blocks: 50 + 100 + 100 + ...
+    r = run(base + ["--starting-block", "99", "--out", str(tmp_path / "x")], ok=False)
+    assert "ERROR: Starting block > number of blocks analyzed" in r
