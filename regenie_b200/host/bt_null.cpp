@@ -192,9 +192,23 @@ bool firth_nr(Work& w, const double* offset, std::vector<double>& beta, double m
       const FirthEval e2 = firth_eval(w, offset, bn.data(), L2, nullptr);
       if (e2.ok && e2.dev < dev_old) { ok = true; break; }
     }
-    if (!ok) return false;
+    if (!ok) return smax < tol;   // no decrease possible at a stationary point (a warm start that already is the solution)
     for (int c = 0; c < C; ++c) beta[c] += step[c];
     score_old = smax;
+  }
+  return false;
+}
+
+// the retry ladder of fit_approx_firth_null (src/Step2_Models.cpp:899-972) around the Newton solver: the given starting
+// values, then zero, then zero with a fifth of the step and five times the iterations, then the given values again
+bool firth_nr_ladder(Work& w, const double* offset, std::vector<double>& beta) {
+  const std::vector<double> start = beta;
+  double maxstep = kMaxstepNull;
+  int niter = kNiterFirthNull;
+  for (int trial = 0; trial < 4; ++trial) {
+    std::vector<double> b = (trial == 0 || trial == 3) ? start : std::vector<double>(start.size(), 0.0);
+    if (firth_nr(w, offset, b, maxstep, niter, 50 * kNumtol)) { beta = b; return true; }
+    if (trial == 1) { maxstep /= 5; niter *= 5; }
   }
   return false;
 }
@@ -204,7 +218,7 @@ bool firth_nr(Work& w, const double* offset, std::vector<double>& beta, double m
 void get_basis(const std::vector<double>& X, int64_t N, int C0, std::vector<double>& Xb, int& nz);
 
 BtNull fit_bt_null(const std::string& name, const double* y, const double* X, int64_t N, int C, const double* blup,
-                   const uint8_t* mask, bool firth) {
+                   const uint8_t* mask, bool firth, const std::vector<double>* firth_start) {
   Work w{N, C, y, X, mask, std::vector<double>(N), std::vector<double>(N)};
   std::vector<double> loco(N);
   for (int64_t i = 0; i < N; ++i) loco[i] = blup[i] * (mask[i] ? 1.0 : 0.0);
@@ -232,7 +246,8 @@ BtNull fit_bt_null(const std::string& name, const double* y, const double* X, in
   if (nz != C) throw Fail("the weighted covariate matrix is rank deficient for phenotype '" + name + "'.");
   if (firth) {
     std::vector<double> bf = beta;
-    if (!firth_nr(w, blup, bf, kMaxstepNull, kNiterFirthNull, 50 * kNumtol))
+    if (firth_start) for (int c = 0; c < C && c < (int)firth_start->size(); ++c) bf[c] = (*firth_start)[c];   // get_beta_start_firth, :1936-1980
+    if (!firth_nr_ladder(w, blup, bf))
       throw Fail("Firth penalized logistic regression failed to converge for phenotype '" + name + "' (null model).");
     out.firth_offset.resize(N);
     for (int64_t i = 0; i < N; ++i) {
@@ -242,6 +257,30 @@ BtNull fit_bt_null(const std::string& name, const double* y, const double* X, in
     }
   }
   return out;
+}
+
+std::vector<double> null_logistic_beta(const std::string& name, const double* y, const double* X, int64_t N, int C,
+                                       const uint8_t* mask) {
+  Work w{N, C, y, X, mask, std::vector<double>(N), std::vector<double>(N)};
+  const std::vector<double> zero(N, 0.0);
+  std::vector<double> beta(C, 0.0);
+  bool ok = false;
+  for (int chk = 1; chk >= 0 && !ok; --chk) {
+    std::fill(beta.begin(), beta.end(), 0.0);
+    ok = fit_logistic(w, zero.data(), beta, chk == 1);
+  }
+  if (!ok) throw Fail("logistic regression did not converge for phenotype '" + name + "'.");
+  return beta;
+}
+
+bool fit_null_firth(const double* y, const double* X, int64_t N, int C, const double* blup, const uint8_t* mask,
+                    std::vector<double>& beta) {
+  Work w{N, C, y, X, mask, std::vector<double>(N), std::vector<double>(N)};
+  std::vector<double> b = beta;
+  b.resize(C, 0.0);
+  if (!firth_nr_ladder(w, blup, b)) return false;
+  beta = b;
+  return true;
 }
 
 std::vector<double> null_logistic_eta(const std::string& name, const double* y, const double* X, int64_t N, int C,

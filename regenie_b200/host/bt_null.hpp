@@ -13,8 +13,17 @@ struct BtNull {
 };
 
 // y (0/1), X [C][N] column-major orthonormal basis, blup (LOCO prediction), mask; throws Fail on non-convergence
+// firth_start (optional, --use-null-firth): starting values of the null Firth fit instead of the logistic estimates
 BtNull fit_bt_null(const std::string& name, const double* y, const double* X, int64_t N, int C, const double* blup,
-                   const uint8_t* mask, bool firth);
+                   const uint8_t* mask, bool firth, const std::vector<double>* firth_start = nullptr);
+
+// --write-null-firth (Step 1, src/Data.cpp:1873-1903): coefficients of the covariate-only logistic fit (bhat_start) and
+// one null approximate-Firth fit with the LOCO predictions of a chromosome as offset, warm-started from `beta`
+// (in: starting values, out: estimates); false = did not converge
+std::vector<double> null_logistic_beta(const std::string& name, const double* y, const double* X, int64_t N, int C,
+                                       const uint8_t* mask);
+bool fit_null_firth(const double* y, const double* X, int64_t N, int C, const double* blup, const uint8_t* mask,
+                    std::vector<double>& beta);
 
 // Step 1: linear predictor of the covariate-only logistic fit (offset_nullreg, fit_null_logistic called from
 // src/Pheno.cpp:1608)

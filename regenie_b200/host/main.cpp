@@ -56,6 +56,8 @@ struct Params {
   bool set_range = false;                      // --range CHR:MINPOS-MAXPOS (step 2)
   int range_chr = 0;
   double range_min = 0, range_max = 0;
+  bool write_null_firth = false;               // --write-null-firth (step 1, binary traits)
+  std::string null_firth_list;                 // --use-null-firth FILE (step 2)
   int sex_specific = 0;                        // --sex-specific male|female
   int start_block = 1;                         // --starting-block (step 2)
   bool af_cc = false;                          // --af-cc: A1FREQ / N among cases and controls (binary traits, split output)
@@ -201,6 +203,8 @@ Params parse_cli(int argc, char** argv) {
       else throw Fail("unrecognized argument for option --sex-specific, must be either 'male' or 'female'.");
     }
     else if (a == "--starting-block") p.start_block = atoi(need(i).c_str());
+    else if (a == "--write-null-firth") p.write_null_firth = true;
+    else if (a == "--use-null-firth") p.null_firth_list = need(i);
     else if (a == "--minCaseCount") p.min_case_count = atoi(need(i).c_str());
     else if (a == "--test") {                                   // src/Regenie.cpp:735-740
       const std::string v = need(i);
@@ -232,7 +236,7 @@ Params parse_cli(int argc, char** argv) {
                    "  [--chr c]... [--chrList c1,c2,...] [--range CHR:MIN-MAX]  (Step-2 jobs are split by chromosome / window like the reference)\n"
                    "  step 2 binary traits: --bt [--firth --approx | --spa] [--pThresh p] with --bed or --bgen F [--sample F] [--bgi F]\n"
                    "  [--gz] [--print-prs | --use-prs] [--write-samples [--print-pheno]]  (.gz inputs are read by file name)\n"
-                   "  [--test additive|dominant|recessive] [--no-split] [--af-cc] [--minCaseCount n]\n"
+                   "  [--test additive|dominant|recessive] [--no-split] [--af-cc] [--minCaseCount n] [--write-null-firth | --use-null-firth F]\n"
                    "  [--gpu-inflate]  step 2 on zlib-compressed .bgen: inflate the genotype blocks on the GPU instead of the host\n";
       exit(0);
     } else {
@@ -571,6 +575,36 @@ void run_step1(const Params& p_in, Log& log) {
       log << "writing whole genome PRS...";
     }
     log << "done\n\n";
+  }
+  if (p.write_null_firth && p.bt) {
+    // null approximate-Firth estimates per chromosome, warm-started along the chromosomes (src/Data.cpp:1873-1903); they are
+    // starting values for Step 2 (--use-null-firth), not results
+    std::ofstream flist(p.out + "_firth.list");
+    if (!flist) throw Fail("cannot write to file : " + p.out + "_firth.list");
+    for (int ph_i = 0; ph_i < P; ++ph_i) {
+      if (!l1_sel[ph_i]) continue;
+      const std::string ffile = p.out + "_" + std::to_string(ph_i + 1) + ".firth" + gz_ext;
+      std::vector<double> bhat = null_logistic_beta(ph.names[ph_i], &ph.Y_raw[(size_t)ph_i * N], ph.X.data(), N, ph.C,
+                                                    &ph.mask[(size_t)ph_i * N]);
+      std::string text;
+      bool ok = true;
+      char num[40];
+      for (int c = 0; c < 23 && ok; ++c) {
+        ok = fit_null_firth(&ph.Y_raw[(size_t)ph_i * N], ph.X.data(), N, ph.C, loco.data() + ((size_t)ph_i * 23 + c) * N,
+                            &ph.mask[(size_t)ph_i * N], bhat);
+        text += std::to_string(c + 1);
+        for (double v : bhat) text.append(num, (size_t)snprintf(num, sizeof(num), " %g", v));
+        text += '\n';
+      }
+      if (!ok) { log << "WARNING: Firth failed to converge for phenotype '" << ph.names[ph_i] << "'\n"; continue; }
+      TextWriter of;
+      of.open(ffile);
+      of << text;
+      of.close();
+      flist << ph.names[ph_i] << " " << full_path(ffile, p.rel_path) << "\n";
+    }
+    flist.close();
+    log << "List of files with null Firth estimates written to: [" << p.out << "_firth.list]\n";
   }
   plist.close();
   if (p.run_l1 && !p.keep_l0)                        // rm_l0_files (src/Data.cpp:1131-1147)
@@ -1030,6 +1064,24 @@ void run_step2_bt(const Params& p, Log& log) {
   log << " * # blocks            : [" << blocks.size() << "]\n";
   const double z_thr = z_threshold(p.p_thresh);
   if (p.firth) log << " * using approximate Firth correction for logistic regression p-values less than " << p.p_thresh << "\n";
+  std::vector<std::string> null_firth_files;                 // check_blup-like list (src/Step2_Models.cpp:1896-1927)
+  if (p.firth && !p.null_firth_list.empty()) {
+    log << " * reading null Firth estimates using file : [" << p.null_firth_list << "]\n";
+    null_firth_files.assign(P, "");
+    LineReader fr(p.null_firth_list);
+    std::string line;
+    std::set<std::string> seen;
+    while (fr.getline(line)) {
+      const auto t = split_ws(line);
+      if (t.empty()) continue;
+      if (t.size() != 2) throw Fail("incorrectly formatted blup list file : " + p.null_firth_list);
+      const auto it = std::find(ph.names.begin(), ph.names.end(), t[0]);
+      if (it == ph.names.end()) continue;                    // unrecognised phenotypes are ignored
+      if (!seen.insert(t[0]).second) throw Fail("phenotype '" + t[0] + "' appears more than once in file.");
+      { std::ifstream probe_f(t[1]); if (!probe_f) throw Fail("file " + t[1] + " cannot be opened."); }
+      null_firth_files[(size_t)(it - ph.names.begin())] = t[1];
+    }
+  }
   if (p.spa) log << " * using SPA correction for logistic regression p-values less than " << p.p_thresh << "\n";
 
   rg_step2_config cfg;
@@ -1126,8 +1178,26 @@ void run_step2_bt(const Params& p, Log& log) {
       if (p.spa) yhat.resize((size_t)P * N);
       for (int i = 0; i < P; ++i) {
         const std::vector<double> blup = blup_for_chr(locos[i], ss, ph, i, chrom);
+        // --use-null-firth: starting values of this chromosome from the Step-1 file (get_beta_start_firth, :1936-1980)
+        std::vector<double> fstart;
+        if (p.firth && !null_firth_files.empty() && !null_firth_files[i].empty()) {
+          LineReader fr(null_firth_files[i]);
+          std::string line;
+          while (fr.getline(line)) {
+            const auto t = split_ws(line);
+            if (t.empty()) throw Fail("error reading null firth estimates file");
+            if (chr_str_to_int(t[0]) != chrom) continue;
+            if ((int)t.size() - 1 > C) throw Fail("file has more predictors than included in analysis (=" + std::to_string(t.size()) + " vs " + std::to_string(C) + ")");
+            for (size_t j = 1; j < t.size(); ++j) {
+              const double v = convert_double(t[j]);
+              if (v == kMissing) throw Fail("no missing values allowed in file");
+              fstart.push_back(v);
+            }
+            break;
+          }
+        }
         const BtNull nm = fit_bt_null(ph.names[i], &ph.Y_raw[(size_t)i * N], ph.X.data(), N, C, blup.data(),
-                                      &ph.mask[(size_t)i * N], p.firth);
+                                      &ph.mask[(size_t)i * N], p.firth, fstart.empty() ? nullptr : &fstart);
         std::copy(nm.gamma_sqrt_mask.begin(), nm.gamma_sqrt_mask.end(), gsm.begin() + (size_t)i * N);
         std::copy(nm.gamma_sqrt.begin(), nm.gamma_sqrt.end(), gs.begin() + (size_t)i * N);
         std::copy(nm.yres.begin(), nm.yres.end(), yres.begin() + (size_t)i * N);

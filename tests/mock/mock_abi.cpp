@@ -192,7 +192,7 @@ int rg_loco(rg_handle h, const int32_t* chr_of_block, double* out) {
       const std::vector<double>& w = h->W[{b, p}];
       for (int64_t s = 0; s < N; ++s) {
         double v = 0;
-        for (int r = 0; r < h->R; ++r) v += w[(size_t)r * N + s] / (r + 2.0);
+        for (int r = 0; r < h->R; ++r) v += 0.02 * w[(size_t)r * N + s] / (r + 2.0);   // small, like real polygenic predictions
         per_chr[(size_t)(chr_of_block[b] - 1) * N + s] += v;
         tot[s] += v;
       }

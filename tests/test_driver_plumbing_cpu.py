@@ -325,3 +325,49 @@ def test_sex_specific_and_starting_block(tmp_path, golden_dir):
     assert tail[1].split()[2] == open(d + "/example_3chr.bim").read().splitlines()[250].split()[1]        # blocks: 50 + 100 + 100 + ...
     r = run(base + ["--starting-block", "99", "--out", str(tmp_path / "x")], ok=False)
     assert "ERROR: Starting block > number of blocks analyzed" in r
+
+
+def test_write_and_use_null_firth(tmp_path, golden_dir):
+    """--write-null-firth (Step 1, src/Data.cpp:1873-1903) / --use-null-firth (Step 2, src/Step2_Models.cpp:1896-1980): file
+    layout, and the written coefficients are a stationary point of the oracle's null Firth fit with the same LOCO offsets
+    (the covariate basis comes from the driver's own prep through the host probe; the LOCO numbers are the mock's)."""
+    import numpy as np
+    from oracle import step2_bt
+    from test_host_cpu import probe, read_dump
+    d = golden_dir
+    fit = str(tmp_path / "fit")
+    args = ["--bed", d + "/example", "--phenoFile", d + "/phenotype_bin.txt", "--covarFile", d + "/covariates.txt", "--remove",
+            d + "/fid_iid_to_remove.txt"]
+    log = run(["--step", "1"] + args + ["--bsize", "100", "--bt", "--write-null-firth", "--out", fit])
+    assert "List of files with null Firth estimates written to" in log
+    lst = [l.split() for l in open(fit + "_firth.list")]
+    assert [t[0] for t in lst] == ["Y1", "Y2"] and all(os.path.isabs(t[1]) for t in lst)
+    probe("prep", tmp_path / "d.bin", *args, "--bt")
+    dump = read_dump(tmp_path / "d.bin")
+    N, P, C = dump["hdr"]["N"], dump["hdr"]["P"], dump["hdr"]["C"]
+    X = dump["X"].reshape(C, N).T
+    keys = ["_".join(l.split()[:2]) for l in open(d + "/example.fam")]
+    rm = {"_".join(l.split()[:2]) for l in open(d + "/fid_iid_to_remove.txt") if l.strip()}
+    keys = [k for k in keys if k not in rm]
+    pos = {k: i for i, k in enumerate(keys)}
+    for j in range(P):
+        rows = [l.split() for l in open(fit + "_%d.firth" % (j + 1))]
+        assert [t[0] for t in rows] == [str(c) for c in range(1, 24)] and all(len(t) == 1 + C for t in rows)
+        loco = [l.split() for l in open(fit + "_%d.loco" % (j + 1))]
+        mask = dump["mask"].reshape(P, N)[j].astype(bool)
+        y = dump["Y_raw"].reshape(P, N)[j]
+        for c in (0, 1, 22):
+            blup = np.zeros(N)
+            for k, v in zip(loco[0][1:], loco[1 + c][1:]):
+                blup[pos[k]] = 0.0 if v == "NA" else float(v)
+            beta = np.array([float(x) for x in rows[c][1:]])
+            ok, b2 = step2_bt.firth_nr(y, X, blup * mask, mask, beta.copy(), 25, 1000, 5e-5)
+            assert ok and np.abs(b2 - beta).max() < 1e-4 * max(1.0, np.abs(beta).max()), (j, c, beta, b2)
+    # Step 2 reads them as starting values
+    s2 = ["--step", "2"] + args + ["--bsize", "200", "--bt", "--firth", "--approx", "--pred", fit + "_pred.list"]
+    run(s2 + ["--out", str(tmp_path / "a")])
+    log = run(s2 + ["--use-null-firth", fit + "_firth.list", "--out", str(tmp_path / "b")])
+    assert " * reading null Firth estimates using file : [" in log
+    assert read(str(tmp_path / "a") + "_Y1.regenie") == read(str(tmp_path / "b") + "_Y1.regenie")
+    r = run(s2 + ["--use-null-firth", str(tmp_path / "nope.list"), "--out", str(tmp_path / "c")], ok=False)
+    assert "ERROR: cannot open file : " in r
