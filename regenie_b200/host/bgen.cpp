@@ -101,6 +101,8 @@ void BgenFile::open(const std::string& p, const std::string& sample_file, bool r
   n_variants_file = rd32(data + 8);
   n_file = rd32(data + 12);
   if (memcmp(data + 16, "bgen", 4) != 0 && memcmp(data + 16, "\0\0\0\0", 4) != 0) throw Fail("not a bgen file : " + path);
+  if (lh < 20 || (uint64_t)4 + lh > size || (uint64_t)offset + 4 > size || offset < lh)
+    throw Fail("corrupt bgen header (block lengths do not fit the file) : " + path);
   const uint32_t flags = rd32(data + 4 + lh - 4);
   compression = flags & 3;
   const int layout = (flags >> 2) & 0xF;
@@ -129,11 +131,15 @@ void BgenFile::open(const std::string& p, const std::string& sample_file, bool r
   } else {
     if (!has_ids) throw Fail("the bgen file has no sample identifiers: provide them with --sample.");
     const uint8_t* q = data + 4 + lh;
+    if ((uint64_t)4 + lh + 8 > (uint64_t)offset + 4) throw Fail("corrupt sample identifier block in bgen file.");
     const uint32_t ns = rd32(q + 4);
     if (ns != n_file) throw Fail("inconsistent sample identifier block in bgen file.");
     q += 8;
+    const uint8_t* const qend = data + (size_t)offset + 4;   // the sample block ends where the variant blocks start
     for (uint32_t i = 0; i < ns; ++i) {
+      if (q + 2 > qend) throw Fail("corrupt sample identifier block in bgen file.");
       const uint16_t l = rd16(q);
+      if (q + 2 + l > qend) throw Fail("corrupt sample identifier block in bgen file.");
       keys_file.emplace_back(reinterpret_cast<const char*>(q + 2), l);
       sex_file.push_back(0);
       q += 2 + l;

@@ -13,6 +13,7 @@ inline uint32_t vint(const std::vector<uint8_t>& d, size_t& p) {
   for (;;) {
     if (p >= d.size()) throw Fail("malformed .pgen file (variable-length integer runs past the end).");
     const uint8_t b = d[p++];
+    if (shift > 28) throw Fail("malformed .pgen file (variable-length integer is too long).");
     v |= (uint32_t)(b & 0x7F) << shift;
     if (!(b & 0x80)) return v;
     shift += 7;
@@ -257,7 +258,10 @@ void PgenFile::read_rows(size_t first, size_t n, uint8_t* out) {
     decode((uint32_t)snps[first + j].offset);
     uint8_t* row = out + j * row_stride;
     memset(row, 0, row_stride);
-    for (uint32_t i = 0; i < n_file; ++i) row[i >> 2] |= (uint8_t)(kBed[cur_[i]] << (2 * (i & 3)));
+    for (uint32_t i = 0; i < n_file; ++i) {
+      if (cur_[i] > 3) throw Fail("malformed .pgen record (genotype value out of range).");
+      row[i >> 2] |= (uint8_t)(kBed[cur_[i]] << (2 * (i & 3)));
+    }
   }
 }
 
