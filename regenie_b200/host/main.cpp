@@ -72,6 +72,15 @@ void rg_check(int rc) {
   if (rc != 0) throw Fail(std::string(rg_last_error()));
 }
 
+// releases a handle on every way out of a run function (errors unwind through here)
+struct HandleGuard {
+  rg_handle& h;
+  ~HandleGuard() {
+    if (h) rg_destroy(h);
+    h = nullptr;
+  }
+};
+
 // get_unit_params (src/Regenie.cpp:1477-1495): sorted unique values strictly inside (0, 1)
 std::vector<double> unit_params(const std::string& opt, const std::string& csv) {
   std::vector<double> v;
@@ -411,6 +420,7 @@ void run_step1(const Params& p_in, Log& log) {
   cfg.n_ridge_l0 = p.l0; cfg.n_ridge_l1 = p.l1; cfg.loocv = p.loocv; cfg.max_block_size = p.bsize;
   cfg.total_blocks = nb; cfg.n_analyzed = ph.n_analyzed;
   rg_handle h = nullptr;
+  HandleGuard guard{h};
   rg_check(rg_step1_create(&cfg, ph.X.data(), ph.Y.data(), ph.mask.data(), ph.in_analysis.data(),
                            p.loocv ? nullptr : folds.data(), lambda.data(), ph.neff.data(), &h));
 
@@ -489,7 +499,6 @@ void run_step1(const Params& p_in, Log& log) {
   }
   if (p.run_l0_job) {
     log << "\nDone writing level 0 predictions to file.\n";
-    rg_destroy(h);
     return;
   }
   log << "\n Level 1 ridge...\n";
@@ -617,7 +626,6 @@ void run_step1(const Params& p_in, Log& log) {
     prs_list.close();
     log << "List of files with whole genome PRS written to: [" << p.out << "_prs.list]\n";
   }
-  rg_destroy(h);
 }
 
 // ------------------------------------------------------------------------------------ step 2
@@ -879,6 +887,7 @@ void run_step2_qt(const Params& p, Log& log) {
   cfg.device = p.gpu; cfg.n_samples = N; cfg.n_cov = ph.C; cfg.n_pheno = P; cfg.max_block_size = p.bsize;
   cfg.n_analyzed = ph.n_analyzed; cfg.strict_mode = ph.strict;
   rg_handle h = nullptr;
+  HandleGuard guard{h};
   rg_check(rg_step2_create(&cfg, ph.X.data(), ph.mask.data(), ph.in_analysis.data(), &h));
 
   S2Writers w;
@@ -1026,7 +1035,6 @@ void run_step2_qt(const Params& p, Log& log) {
   }
   w.close();
   log << "\nNumber of ignored tests due to low MAC or low variance : " << n_ignored << "\n";
-  rg_destroy(h);
 }
 
 // Step 2 for binary traits (--bt [--firth --approx]) on BGEN dosages or .bed hard calls.
@@ -1089,6 +1097,7 @@ void run_step2_bt(const Params& p, Log& log) {
   cfg.device = p.gpu; cfg.n_samples = N; cfg.n_cov = C; cfg.n_pheno = P; cfg.max_block_size = p.bsize;
   cfg.n_analyzed = ph.n_analyzed; cfg.strict_mode = ph.strict;
   rg_handle h = nullptr;
+  HandleGuard guard{h};
   rg_check(rg_step2_create(&cfg, ph.X.data(), ph.mask.data(), ph.in_analysis.data(), &h));
 
   S2Writers w;
@@ -1101,6 +1110,7 @@ void run_step2_bt(const Params& p, Log& log) {
   // the cases of each trait returns their allele frequency and count from the same block bytes; controls follow by
   // difference of the (exactly reconstructed) allele sums.
   rg_handle hc = nullptr;
+  HandleGuard guard_cases{hc};
   std::vector<double> afc, macc, afc_all, macc_all, statc, betac, sec, chisqc, scalec, infoc;
   std::vector<int32_t> nsc, nsc_all, flagsc;
   if (p.af_cc) {
@@ -1332,8 +1342,6 @@ void run_step2_bt(const Params& p, Log& log) {
   log << "\nNumber of ignored tests due to low MAC or low variance : " << n_ignored << "\n";
   if (p.firth) log << "Number of tests with Firth correction : " << n_firth << " (" << n_fail << " failed)\n";
   if (p.spa) log << "Number of tests with SPA correction : " << n_firth << " (" << n_fail << " failed)\n";
-  if (hc) rg_destroy(hc);
-  rg_destroy(h);
 }
 
 void run_step2(const Params& p_in, Log& log) {
