@@ -121,19 +121,30 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-# ----------------------------------------------------------------------------- CPU port
-def cpu_level0_blocks(packed_rows_list, N, X, Y, mask, in_an, fsz, lam, neff):
-    """Time the oracle's level-0 (decode + impute + residualise + cv matrices + ridge) per block."""
-    from oracle import plink, step1          # the one place bench.py runs the oracle: the CPU baseline
+# ----------------------------------------------------------------------------- CPU baseline (Eigen restatement)
+def cpu_level0_blocks(packed_rows_list, N, X, Y, mask, in_an, fsz, lam, neff, threads=0):
+    """Time the reference's level-0 path on the host cores: oracle/ref_eigen = C++ restatement of
+    readChunkFromBedFileToG + residualize_genotypes + calc_cv_matrices + ridge_level_0 compiled against the
+    reference's vendored Eigen 3.4.0 with -O3 -ffast-math -fopenmp (the reference binary itself cannot be built
+    here: Boost / BGEN library absent).  Returns (SNPs, seconds, W of the first block, per-phase seconds)."""
+    from oracle import ref_eigen             # the one place bench.py runs the oracle: the CPU baseline / parity check
     t0 = time.perf_counter()
-    nsnp = 0
+    nsnp, W0, phases = 0, None, np.zeros(4)
     for rows in packed_rows_list:
-        g = plink.decode_bed(rows, N)
-        gi, _ = plink.mean_impute_block(g, in_an.astype(bool))
-        Gt, _ = step1.residualize_genotypes(gi, X, in_an.astype(bool), int(in_an.sum()), X.shape[1])
-        step1.level0_kfold(Gt, Y, mask.astype(bool), fsz, lam, neff)
+        W, ph = ref_eigen.l0_block_kfold(rows, N, in_an, X, Y, mask, fsz, lam, neff, int(np.asarray(in_an).sum()),
+                                         threads=threads)
+        phases += ph
+        if W0 is None:
+            W0 = W
         nsnp += rows.shape[0]
-    return nsnp, time.perf_counter() - t0
+    return nsnp, time.perf_counter() - t0, W0, phases
+
+
+def cpu_baseline_desc(phases, dt, nblocks, bs, N, threads):
+    from oracle import ref_eigen
+    return ("%d block(s) of %d SNPs at N=%d from the same panel; C++ restatement of the reference's level-0 path on %s, "
+            "%d OpenMP threads; %.1f s = decode+impute %.1f / residualise %.1f / cv matrices %.1f / eigensolver+ridge %.1f"
+            % (nblocks, bs, N, ref_eigen.build_info(), threads, dt, phases[0], phases[1], phases[2], phases[3]))
 
 
 def host_threads():
@@ -145,7 +156,7 @@ def host_threads():
 
 # ----------------------------------------------------------------------------- main arms
 def run_reference(args):
-    """--impl reference: the CPU port (oracle/, numpy+OpenBLAS on all host threads), one block per step."""
+    """--impl reference: the reference's CPU level-0 path (Eigen/OpenMP restatement, all host threads), one block per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -159,21 +170,22 @@ def run_reference(args):
     n_steps = args.steps + args.warmup
     rows = [synth.pack_bed(synth.genotypes(N, bs, seed=SEED + i, miss=c["miss"])) for i in range(min(n_steps, 2))]
     times = []
+    cores = host_threads()
+    phases = np.zeros(4)
     for i in range(n_steps):
-        n, dt = cpu_level0_blocks([rows[i % len(rows)]], N, X, Y, mask, in_an, fsz, lam, neff)
+        n, dt, _, ph = cpu_level0_blocks([rows[i % len(rows)]], N, X, Y, mask, in_an, fsz, lam, neff, threads=cores)
         if i >= args.warmup:
             times.append(dt)
+            phases += ph
     tot = sum(times)
     val = bs * len(times) / tot
-    cores = host_threads()
     line = {
         "impl": "reference", "metric": "step1_level0_snps_per_sec", "value": val, "unit": "SNPs/s",
         "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(),
         "cpu_baseline": {"value": val, "unit": "SNPs/s", "cores": cores, "kind": "port",
-                         "sample": "one 1000-SNP block (N=100k) per step, numpy/OpenBLAS port of the reference's "
-                                   "Eigen level-0 path (reference binary not buildable: needs Boost/BGEN lib)"},
+                         "sample": "one 1000-SNP block per step; " + cpu_baseline_desc(phases, tot, len(times), bs, N, cores)},
         "e2e": {"value": val, "unit": "SNPs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -358,14 +370,27 @@ def run_gpu(args):
     chol_ms = kern["chol_factor"]["ms_total"] / max(1, kern["chol_factor"]["launches"])
     chol_tf = (K * R * bs ** 3 / 3.0) / (chol_ms * 1e-3) / 1e12 if chol_ms > 0 else None
 
+    # step-level roofline: algorithmic flops per SNP F0 = 2 N bs + 2 N P (1 + R) + 4 N C, whole-job rate
+    F0 = 2.0 * N * bs + 2.0 * N * P * (1 + R) + 4.0 * N * C
+    step_tf = value * F0 / 1e12 / world
+    peak_sust = 2.0 * (peaks.get("bf16_tflops_sustained") or peak_bf16)
     traffic, pipe_active = gram_traffic_from_profile()
-    cpu = None
+    cpu, parity = None, None
     if not args.no_cpu:
         rows = [host_panel[s:s + n].numpy() for (s, n) in blocks[: args.cpu_blocks]]
-        nsnp, dt = cpu_level0_blocks(rows, N, X, Y, mask, in_an, fsz, lam, neff)
-        cpu = {"value": nsnp / dt, "unit": "SNPs/s", "cores": host_threads(), "kind": "port",
-               "sample": "%d block(s) of %d SNPs at N=%d from the same panel (numpy/OpenBLAS port of the Eigen "
-                         "level-0 path; %.1f s)" % (len(rows), bs, N, dt)}
+        thr = host_threads()
+        nsnp, dt, W_cpu, phases = cpu_level0_blocks(rows, N, X, Y, mask, in_an, fsz, lam, neff, threads=thr)
+        cpu = {"value": nsnp / dt, "unit": "SNPs/s", "cores": thr, "kind": "port",
+               "sample": cpu_baseline_desc(phases, dt, len(rows), bs, N, thr)}
+        # parity on the benchmarked configuration: block 0 of the timed panel, every predictor column, GPU vs Eigen
+        err = 0.0
+        for p in range(P):
+            Wg = st.fetch_W(0, p)
+            err = max(err, float(np.abs(Wg - W_cpu[p]).max() / np.abs(W_cpu[p]).max()))
+        parity = {"max_rel_err": err, "tol": 1e-9, "what": "level-0 predictors W of block 0 (N x %d columns x %d traits) of the "
+                  "timed panel, B200 path vs the Eigen restatement of ridge_level_0" % (R, P)}
+        if not (err < 1e-9):
+            raise SystemExit("bench.py: parity check failed on the benchmarked configuration: max rel err %g" % err)
 
     line = {
         "metric": "step1_level0_snps_per_sec", "value": value, "unit": "SNPs/s", "n_gpus": world,
@@ -386,11 +411,17 @@ def run_gpu(args):
                      "algorithmic_flops_per_launch": flops_per_launch,
                      "timed": "alone (single lane), CUDA events on the launching stream",
                      "note": "kernel executes 2x this (lower triangle of the [G0;Miss] Gram) to handle missing calls exactly"},
-        "solver": {"kernel": "chol_update/chol_panel (fp64)", "achieved_tflops": chol_tf, "fp64_peak_nominal": 40.0},
+        "step_roofline": {"flops_per_snp": F0, "achieved_tflops_per_gpu": step_tf, "peak": peak_sust, "frac": step_tf / peak_sust,
+                          "peak_basis": "2 x %s SUSTAINED bf16 cuBLAS rate = dense FP8, kernel mix timed inside a long step" % peak_src,
+                          "note": "whole level-0 step (decode, statistics, Gram, solver, predictions) against the tensor "
+                                  "roofline of its algorithmic flops; the solver's share is in `solver`"},
+        "solver": {"kernel": "chol_factor (+ backsolve)", "achieved_tflops": chol_tf, "fp64_peak_nominal": 40.0,
+                   "share_of_single_lane_kernel_time": round((kern["chol_factor"]["ms_total"] + kern["chol_backsolve"]["ms_total"]) / ktot, 4)},
         "kernels": kern,
         "kernels_concurrent": kern_conc,
         "lanes": int(os.environ.get("RG_B200_LANES", "8")),
         "cpu_baseline": cpu,
+        "parity": parity,
         "step2": s2,
     }
     print(json.dumps(line), flush=True)

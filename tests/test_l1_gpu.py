@@ -46,6 +46,19 @@ def test_l1_and_loco_match_oracle(tmp_path, N, M, bs):
         assert rel(loco[ph], o["loco"][ph]) < 1e-7
 
 
+def test_l1_at_250_stacked_predictors(tmp_path):
+    """Level 1 at a stacked width the benchmark shapes reach (B = 50 blocks x 5 ridge values = 250 columns: 4 Cholesky
+    panels per system, multi-tile DMMA Gram) vs ridge_level_1 (src/Step1_Models.cpp:772-872) and the LOCO assembly."""
+    pb = helpers.synthetic_problem(tmp_path, N=3000, M=2000, P=2, bsize=40, miss=0.01)
+    assert len(pb.blocks) * 5 >= 250
+    st, cs, best, loco = full_run(pb)
+    o = oracle_run(pb)
+    for ph in range(2):
+        assert rel(cs[:, ph, :], o["cs"][ph]) < 1e-8
+        assert best[ph] == o["best"][ph]
+        assert rel(loco[ph], o["loco"][ph]) < 1e-7
+
+
 def test_example_3chr_loco(golden_dir):
     """example_3chr (50/400/50 SNPs on chr 1/2/3) exercises the leave-one-chromosome-out rows."""
     pb = helpers.Problem(golden_dir + "/example_3chr", golden_dir + "/phenotype.txt", golden_dir + "/covariates.txt", 100)
