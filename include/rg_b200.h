@@ -318,6 +318,17 @@ int rg_W_info(rg_handle h, int32_t ph, void** dev_ptr, int64_t* ld, int64_t* nco
 /* Copy a named intermediate of the last level-0 block to the host (tests only).
  * Returns the number of bytes written, or <0 on error.  See DESIGN.md for names. */
 int64_t rg_debug_fetch(rg_handle h, const char* name, void* out, int64_t max_bytes);
+/* Level-0 ridge solver bookkeeping: blocks whose K*R systems were solved by the tensor-core factorisation + FP64
+ * iterative refinement (csrc/chol_mixed.cu), and how many of those raised the convergence flag and were re-solved
+ * by the FP64 Cholesky.  RG_B200_SOLVER=f64 selects the FP64 path for every block. */
+int rg_l0_solver_stats(rg_handle h, int64_t* mixed_blocks, int64_t* f64_fallbacks);
+/* Test hook for the mixed-precision solver alone: solves (Af[f] + lambda[r] I) x = b[f] for all K*R pairs
+ * (system index f*R + r) on `device`.  All pointers are host memory: Af [K][n][n] full symmetric FP64, lambda [R],
+ * b [K][P][n]; x_out [K*R][P][n]; X_out (optional) [K*R][n][n] FP32 approximate inverses; fail_out: 0 = every system
+ * met `tol` within `steps` corrections.  n must be 128 * 2^k <= 2048. */
+int rg_dbg_mixed_solve(int32_t device, int32_t n, int32_t K, int32_t R, int32_t P, const double* Af,
+                       const double* lambda, const double* b, int32_t steps, double tol, double* x_out,
+                       float* X_out, uint32_t* fail_out);
 /* Number of kernels launched by this handle since creation (for bench.py gpu_launches). */
 int64_t rg_launch_count(rg_handle h);
 /* CUDA stream of the handle as a void* (cudaStream_t), so callers can record events. */

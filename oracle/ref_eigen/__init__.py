@@ -57,6 +57,17 @@ def max_threads():
     return int(lib().rge_max_threads())
 
 
+def default_threads():
+    """Eigen's OpenMP GEMM stops scaling (and then collapses) well before 128 threads on a bs x bs result: measured on
+    the 128-thread GPU host, one N=100k block takes 94 s with 128 threads against ~7 s with 8.  Callers that do not
+    calibrate (the parity tests) use at most 32."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    return max(1, min(32, n))
+
+
 def _p(a, t):
     return a.ctypes.data_as(t)
 
@@ -77,7 +88,7 @@ def l0_block_kfold(bed_rows, N, in_analysis, X, Y, mask, fold_sizes, lam, neff, 
                                   _p(ia, _u8p), ctypes.c_int32(1 if ref_first else 0), _p(X, _f64p), ctypes.c_int32(C),
                                   _p(Y, _f64p), _p(mask, _u8p), ctypes.c_int32(P), _p(fs, _i64p), ctypes.c_int32(len(fs)),
                                   _p(lam, _f64p), ctypes.c_int32(R), _p(neff, _f64p), ctypes.c_int64(int(n_analyzed)),
-                                  ctypes.c_int32(threads or max_threads()), _p(W, _f64p), _p(ph, _f64p))
+                                  ctypes.c_int32(threads or default_threads()), _p(W, _f64p), _p(ph, _f64p))
     if rc != 0:
         raise ValueError("SNP %d has low variance" % (rc - 1))
     return [W[p].T for p in range(P)], ph
@@ -95,7 +106,7 @@ def s2_block_qt_bed(bed_rows, N, in_analysis, X, res, mask, YtX, scf_sv, n_analy
     lib().rge_s2_block_qt_bed(_p(bed_rows, _u8p), ctypes.c_int64(stride), ctypes.c_int32(bs), ctypes.c_int64(N), _p(ia, _u8p),
                               _p(X, _f64p), ctypes.c_int32(C), _p(res, _f64p), _p(mask, _u8p), ctypes.c_int32(P),
                               _p(YtX, _f64p), _p(scf, _f64p), ctypes.c_int64(int(n_analyzed)), ctypes.c_double(min_mac),
-                              ctypes.c_int32(threads or max_threads()), _p(out, _f64p))
+                              ctypes.c_int32(threads or default_threads()), _p(out, _f64p))
     return out
 
 
@@ -108,5 +119,5 @@ def s2_block_bt_probs(probs, ploidy_missing, N, in_analysis, gsm, XG, yres, min_
     out = np.zeros((bs, 4))
     lib().rge_s2_block_bt_probs(_p(probs, _u8p), _p(pm, _u8p), ctypes.c_int32(bs), ctypes.c_int64(N), _p(ia, _u8p),
                                 _p(gsm, _f64p), _p(XG, _f64p), ctypes.c_int32(XG.shape[1]), _p(yres, _f64p),
-                                ctypes.c_double(min_mac), ctypes.c_int32(threads or max_threads()), _p(out, _f64p))
+                                ctypes.c_double(min_mac), ctypes.c_int32(threads or default_threads()), _p(out, _f64p))
     return out

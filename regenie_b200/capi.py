@@ -48,6 +48,7 @@ EXPORTS = [
     "rg_l0_block_bed", "rg_l0_status", "rg_l0_fetch_W", "rg_l1_fit", "rg_loco", "rg_step2_create",
     "rg_s2_set_chr", "rg_s2_block_bed", "rg_W_info", "rg_debug_fetch", "rg_launch_count", "rg_stream",
     "rg_set_timing", "rg_get_timing", "rg_fence", "rg_s2_set_chr_bt", "rg_s2_block_bgen8_bt", "rg_s2_block_bgen8", "rg_s2_firth", "rg_l1_fit_bt", "rg_W_set_owned", "rg_W_export", "rg_W_attach_peer", "rg_l1_select", "rg_s2_set_sex", "rg_s2_set_non_par", "rg_l0_load_W", "rg_s2_spa", "rg_s2_block_bed_bt", "rg_prs", "rg_bgen_inflate",
+    "rg_l0_solver_stats", "rg_dbg_mixed_solve",
 ]
 
 _lib = None
@@ -223,6 +224,13 @@ class Step1:
     def launch_count(self):
         return lib().rg_launch_count(self.h)
 
+    def solver_stats(self):
+        """(blocks solved by the tensor-core + refinement path, of which re-solved by the FP64 Cholesky)."""
+        L = lib(); L.rg_l0_solver_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        a, b = C.c_int64(0), C.c_int64(0)
+        check(L.rg_l0_solver_stats(self.h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def stream(self):
         return lib().rg_stream(self.h)
 
@@ -376,3 +384,21 @@ class Step2:
         beta, se, lrt, status = np.empty(n), np.empty(n), np.empty(n), np.empty(n, dtype=np.int32)
         check(L.rg_s2_firth(self.h, n, _ptr(vi), _ptr(ti), _ptr(beta), _ptr(se), _ptr(lrt), _ptr(status)))
         return beta, se, lrt, status
+
+
+def mixed_solve(Af, lam, b, steps=3, tol=1e-9, device=0, want_inverse=False):
+    """Test hook (rg_dbg_mixed_solve): solve (Af[f] + lam[r] I) x = b[f] for every (f, r) with the mixed-precision solver.
+    Af [K, n, n] symmetric, lam [R], b [K, P, n].  Returns (x [K*R, P, n], fail flag, X [K*R, n, n] float32 or None)."""
+    Af = np.ascontiguousarray(Af, dtype=np.float64); lam = np.ascontiguousarray(lam, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    K, n, _ = Af.shape
+    R, P = len(lam), b.shape[1]
+    x = np.zeros((K * R, P, n))
+    X = np.zeros((K * R, n, n), dtype=np.float32) if want_inverse else None
+    fail = C.c_uint32(0)
+    L = lib()
+    L.rg_dbg_mixed_solve.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    check(L.rg_dbg_mixed_solve(device, n, K, R, P, _ptr(Af), _ptr(lam), _ptr(b), steps, tol, _ptr(x),
+                               _ptr(X) if X is not None else None, C.byref(fail)))
+    return x, int(fail.value), X

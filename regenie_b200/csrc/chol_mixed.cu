@@ -1,0 +1,521 @@
+// Mixed-precision solve of the K*R level-0 ridge systems  (A_f + lambda_r I) x = b_f :
+//   factorisation, triangular inverse and A^-1 in FP32-accurate 3xTF32 arithmetic on the tcgen05 tensor pipe
+//   (tf32_gemm.cu), then FP64 iterative refinement  x <- x + X (b - A x)  against the FP64 systems.
+//
+// Reference semantics (src/Step1_Models.cpp:484-494): beta = V (D + lambda I)^-1 V^T (GtY - GtY_f) from one
+// eigendecomposition per fold.  Same vectors; the FP64 Cholesky path (chol.cu) stays as the fallback: a system whose
+// refinement has not contracted below `tol` after `max_steps` corrections raises the lane's fallback flag and the
+// host re-solves that block in FP64 (rg_api.cu).
+//
+// Why this shape: a right/left-looking FP64 Cholesky of 25 systems of 1024 unknowns is 16 panel steps of latency-bound
+// 25-CTA grids on the DMMA pipe (profiles/ncu_r1n_key_kernels.txt: 7 TF/s).  Here
+//   * the n^3/3 update flops run as 128x128 tcgen05 tiles (3xTF32, FP32 accumulate in TMEM),
+//   * the only serial piece is the 128x128 diagonal tile (FP32, one CTA per system, warp-register Cholesky),
+//   * the substitutions disappear: W = L^-1 by recursive doubling and X = W^T W are more of the same tiles, and every
+//     refinement step is two fully parallel matrix-vector passes.
+//
+// Storage per lane (n = round_up(bs, 128), nmat = K*R):
+//   Lp, Wp, Wt, Tt : [nmat][2][n][n] FP32 hi/lo planes (L / P in place, W = L^-1, W^T, scratch for T^T)
+//   X              : [nmat][n][n] FP32  ~ (A + lambda I)^-1, full symmetric
+//   Af             : [K][n][n] FP64 full symmetric fold systems WITHOUT the ridge shift (l0_assemble_sym_kernel)
+//   bvec, xvec, rvec : [.][Pp][n] FP64 right-hand sides (per fold), solutions and residuals (per system)
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "kernels.cuh"
+
+namespace rg {
+
+namespace {
+
+constexpr int PT = 128;            // diagonal tile
+constexpr int PLD = 132;           // smem row stride (floats): 16-byte aligned rows, conflict-free 128-bit row reads
+constexpr int PB = 32;             // register block of the warp-level Cholesky
+
+// C[m][n] (+)= sign * sum_{p < plen} A[m][p] * Bt[n][p] for one 32x32 block; lane = row m.  A, Bt: smem, stride PLD.
+// tri = 1: Bt is lower triangular in this block pair (Bt[n][p] = 0 for p > n) - used for the diagonal solves.
+__device__ __forceinline__ void blk_nt(float (&acc)[PB], const float* __restrict__ Arow, const float* __restrict__ Bt, int plen) {
+  for (int p0 = 0; p0 < plen; p0 += 4) {
+    const float4 a = *reinterpret_cast<const float4*>(Arow + p0);
+#pragma unroll
+    for (int n = 0; n < PB; ++n) {
+      const float4 b = *reinterpret_cast<const float4*>(Bt + n * PLD + p0);
+      acc[n] = fmaf(a.x, b.x, acc[n]);
+      acc[n] = fmaf(a.y, b.y, acc[n]);
+      acc[n] = fmaf(a.z, b.z, acc[n]);
+      acc[n] = fmaf(a.w, b.w, acc[n]);
+    }
+  }
+}
+
+}  // namespace
+
+// Diagonal tile of panel step k:  L_kk = chol(P_kk)  and  M = L_kk^-1  (FP32), one CTA per system.
+//   in : Lp tile (k,k) = P_kk (hi + lo), lower part
+//   out: Lp tile (k,k) = L_kk (lower, zeros above);  Wp tile (k,k) = M;  Wt tile (k,k) = M^T   (hi / lo planes)
+// 256 threads = 8 warps; shared: S (P -> L, scratch above the diagonal blocks), Wm (M), Wq (M^T).
+__global__ void __launch_bounds__(256)
+potrf128_kernel(float* __restrict__ Lp, float* __restrict__ Wp, float* __restrict__ Wt, int n, int k,
+                unsigned int* __restrict__ fail_flag) {
+  extern __shared__ float pt_sm[];
+  float* S = pt_sm;
+  float* Wm = pt_sm + PT * PLD;
+  float* Wq = pt_sm + 2 * PT * PLD;
+  float* dinv = pt_sm + 3 * PT * PLD;                    // reciprocal diagonal of L
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t plane = (int64_t)n * n;
+  const int64_t moff = (int64_t)blockIdx.x * 2 * plane + (int64_t)k * PT * n + (int64_t)k * PT;
+  float* Lh = Lp + moff;
+  float* Ll = Lh + plane;
+  for (int e = threadIdx.x; e < PT * PT; e += 256) {
+    const int r = e >> 7, c = e & 127;
+    S[r * PLD + c] = (c <= r) ? Lh[(int64_t)r * n + c] + Ll[(int64_t)r * n + c] : 0.f;
+    Wm[r * PLD + c] = 0.f;
+    Wq[r * PLD + c] = 0.f;
+  }
+  __syncthreads();
+  bool bad = false;
+  for (int jb = 0; jb < PT / PB; ++jb) {
+    const int j0 = jb * PB;
+    if (warp == 0) {
+      // ---- 32x32 Cholesky in registers: lane r holds row r, pivots travel by shuffle (no block barrier)
+      float a[PB];
+#pragma unroll
+      for (int c = 0; c < PB; ++c) a[c] = (c <= lane) ? S[(j0 + lane) * PLD + j0 + c] : 0.f;
+#pragma unroll
+      for (int c = 0; c < PB; ++c) {
+        const float d = __shfl_sync(0xffffffffu, a[c], c);
+        if (!(d > 0.f)) bad = true;
+        float inv = rsqrtf(d);
+        inv = inv * (1.5f - 0.5f * d * inv * inv);
+        const float l = a[c] * inv;
+        a[c] = l;
+        if (lane == c) dinv[j0 + c] = inv;
+#pragma unroll
+        for (int cc = c + 1; cc < PB; ++cc) {
+          const float lcc = __shfl_sync(0xffffffffu, l, cc);
+          a[cc] = fmaf(-l, lcc, a[cc]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < PB; ++c) S[(j0 + lane) * PLD + j0 + c] = a[c];     // zeros above the diagonal
+    }
+    __syncthreads();
+    // ---- blocks below: L_ij = S_ij L_jj^-T by forward substitution along the row (lane = row, all in registers)
+    if (warp >= 1 && warp < PT / PB - jb) {
+      const int i0 = (jb + warp) * PB;
+      float x[PB];
+#pragma unroll
+      for (int c = 0; c < PB; ++c) x[c] = S[(i0 + lane) * PLD + j0 + c];
+#pragma unroll
+      for (int c = 0; c < PB; ++c) {
+        const float* lrow = S + (j0 + c) * PLD + j0;
+        float s = x[c];
+#pragma unroll
+        for (int p = 0; p < c; ++p) s = fmaf(-x[p], lrow[p], s);
+        x[c] = s * dinv[j0 + c];
+      }
+#pragma unroll
+      for (int c = 0; c < PB; ++c) S[(i0 + lane) * PLD + j0 + c] = x[c];
+    }
+    __syncthreads();
+    // ---- trailing update of the lower blocks: S[ib][i2] -= L_ib,j L_i2,j^T,  jb < i2 <= ib
+    {
+      const int nb = PT / PB - jb - 1;                   // blocks per side below the panel
+      int t = 0;
+      for (int a1 = 0; a1 < nb; ++a1)
+        for (int a2 = 0; a2 <= a1; ++a2, ++t) {
+          if ((t & 7) != warp) continue;
+          const int ib = jb + 1 + a1, i2 = jb + 1 + a2;
+          float acc[PB];
+#pragma unroll
+          for (int c = 0; c < PB; ++c) acc[c] = 0.f;
+          blk_nt(acc, S + (ib * PB + lane) * PLD + j0, S + (i2 * PB) * PLD + j0, PB);
+          float* o = S + (ib * PB + lane) * PLD + i2 * PB;
+#pragma unroll
+          for (int c = 0; c < PB; ++c) o[c] -= acc[c];
+        }
+    }
+    __syncthreads();
+  }
+  if (bad && lane == 0) atomicOr(fail_flag, 2u);
+  // ---- M = L^-1: 32x32 diagonal blocks by substitution (lane = column), then recursive doubling 32 -> 64 -> 128
+  if (warp < PT / PB) {
+    const int j0 = warp * PB;
+    float x[PB];                                       // column `lane` of L_jj^-1
+#pragma unroll
+    for (int r = 0; r < PB; ++r) {
+      const float* lrow = S + (j0 + r) * PLD + j0;
+      float s = (r == lane) ? 1.f : 0.f;
+#pragma unroll
+      for (int p = 0; p < r; ++p) s = fmaf(-lrow[p], x[p], s);
+      x[r] = s * dinv[j0 + r];
+    }
+#pragma unroll
+    for (int r = 0; r < PB; ++r) {
+      Wm[(j0 + r) * PLD + j0 + lane] = x[r];
+      Wq[(j0 + lane) * PLD + j0 + r] = x[r];
+    }
+  }
+  __syncthreads();
+  for (int sb = 1; sb < PT / PB; sb *= 2) {             // s-block = sb 32-blocks; pairs (a, b = a + sb)
+    const int npair = PT / PB / (2 * sb);
+    // T = L21 W11, stored transposed above the diagonal of S:  Tt[n][m] at S[a rows][b cols]
+    for (int t = warp; t < npair * sb * sb; t += 8) {
+      const int pr = t / (sb * sb), bi = (t / sb) % sb, aj = t % sb;
+      const int a0 = pr * 2 * sb, b0 = a0 + sb;
+      float acc[PB];
+#pragma unroll
+      for (int c = 0; c < PB; ++c) acc[c] = 0.f;
+      // W11[p][n] != 0 only for p >= n: contraction over 32-blocks aj .. sb-1 of the a range
+      blk_nt(acc, S + ((b0 + bi) * PB + lane) * PLD + (a0 + aj) * PB, Wq + ((a0 + aj) * PB) * PLD + (a0 + aj) * PB, (sb - aj) * PB);
+#pragma unroll
+      for (int c = 0; c < PB; ++c) S[((a0 + aj) * PB + c) * PLD + (b0 + bi) * PB + lane] = acc[c];
+    }
+    __syncthreads();
+    // W21 = - W22 T:  A = Wm[b rows][b cols] (lower: p-blocks 0 .. bi), Bt = Tt = S[a rows][b cols]
+    for (int t = warp; t < npair * sb * sb; t += 8) {
+      const int pr = t / (sb * sb), bi = (t / sb) % sb, aj = t % sb;
+      const int a0 = pr * 2 * sb, b0 = a0 + sb;
+      float acc[PB];
+#pragma unroll
+      for (int c = 0; c < PB; ++c) acc[c] = 0.f;
+      blk_nt(acc, Wm + ((b0 + bi) * PB + lane) * PLD + b0 * PB, S + ((a0 + aj) * PB) * PLD + b0 * PB, (bi + 1) * PB);
+#pragma unroll
+      for (int c = 0; c < PB; ++c) {
+        Wm[((b0 + bi) * PB + lane) * PLD + (a0 + aj) * PB + c] = -acc[c];
+        Wq[((a0 + aj) * PB + c) * PLD + (b0 + bi) * PB + lane] = -acc[c];
+      }
+    }
+    __syncthreads();
+  }
+  // ---- write back as hi / lo planes
+  float* Wh = Wp + moff;
+  float* Wl = Wh + plane;
+  float* Th = Wt + moff;
+  float* Tl = Th + plane;
+  for (int e = threadIdx.x; e < PT * PT; e += 256) {
+    const int r = e >> 7, c = e & 127;
+    const float vl = (c <= r) ? S[r * PLD + c] : 0.f;
+    const float vw = Wm[r * PLD + c], vt = Wq[r * PLD + c];
+    uint32_t t;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(vl));
+    Lh[(int64_t)r * n + c] = __uint_as_float(t);
+    Ll[(int64_t)r * n + c] = vl - __uint_as_float(t);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(vw));
+    Wh[(int64_t)r * n + c] = __uint_as_float(t);
+    Wl[(int64_t)r * n + c] = vw - __uint_as_float(t);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(vt));
+    Th[(int64_t)r * n + c] = __uint_as_float(t);
+    Tl[(int64_t)r * n + c] = vt - __uint_as_float(t);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Refinement.  conv[step][m] = (max |dx|, max |x|) as float bit patterns (non-negative floats order like unsigned
+// integers, so atomicMax is exact and order-independent).  A system is finished as soon as one step's correction
+// satisfied  max|dx| <= tol * max|x|; finished systems are skipped by every later launch.
+__device__ __forceinline__ bool mx_finished(const unsigned int* conv, int nmat, int m, int upto_step, float tol) {
+  for (int s = 1; s <= upto_step; ++s) {
+    const float dx = __uint_as_float(conv[((int64_t)s * nmat + m) * 2]);
+    const float xx = __uint_as_float(conv[((int64_t)s * nmat + m) * 2 + 1]);
+    if (dx <= tol * xx) return true;
+  }
+  return false;
+}
+
+// x[m][p][i] += sum_j X[m][i][j] r[m or f][p][j]   (FP32 products, FP32 accumulation: a correction needs few digits)
+// grid: (n / 32, nmat), block 256: warp w owns rows 4w .. 4w+3 of the CTA's 32.  smem: r as float [P][n].
+template <int PMAX>
+__global__ void __launch_bounds__(256)
+mx_apply_kernel(const float* __restrict__ X, const double* __restrict__ rvec, int64_t r_mat_stride, int r_mat_div,
+                double* __restrict__ xvec, int n, int P, int Pp, int nmat, int step, unsigned int* __restrict__ conv, float tol) {
+  extern __shared__ float ap_sm[];
+  const int m = blockIdx.y;
+  if (step > 1 && mx_finished(conv, nmat, m, step - 1, tol)) return;
+  const double* r = rvec + (int64_t)(r_mat_div > 0 ? m / r_mat_div : m) * r_mat_stride;
+  for (int e = threadIdx.x; e < P * n; e += 256) ap_sm[e] = (float)r[(int64_t)(e / n) * n + (e % n)];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float dmax = 0.f, xmax = 0.f;
+  for (int rr = 0; rr < 4; ++rr) {
+    const int i = blockIdx.x * 32 + warp * 4 + rr;
+    const float* xr = X + ((int64_t)m * n + i) * n;
+    float acc[PMAX];
+#pragma unroll
+    for (int p = 0; p < PMAX; ++p) acc[p] = 0.f;
+    for (int j = lane * 4; j < n; j += 128) {
+      const float4 a = *reinterpret_cast<const float4*>(xr + j);
+#pragma unroll
+      for (int p = 0; p < PMAX; ++p) {
+        if (p < P) {
+          const float4 b = *reinterpret_cast<const float4*>(ap_sm + p * n + j);
+          acc[p] = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc[p]))));
+        }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < PMAX; ++p) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[p] += __shfl_xor_sync(0xffffffffu, acc[p], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int p = 0; p < PMAX; ++p)
+        if (p < P) {
+          double* xp = xvec + ((int64_t)m * Pp + p) * n + i;
+          const double xn = (step == 0 ? 0.0 : *xp) + (double)acc[p];
+          *xp = xn;
+          // fmaxf drops NaNs: map anything non-finite to +inf so the final check sees it
+          dmax = (fabsf(acc[p]) <= 3.0e38f) ? fmaxf(dmax, fabsf(acc[p])) : __int_as_float(0x7f800000);
+          xmax = fmaxf(xmax, fabsf((float)xn));
+        }
+    }
+  }
+  if (lane == 0 && step > 0) {
+    atomicMax(conv + ((int64_t)step * nmat + m) * 2, __float_as_uint(dmax));
+    atomicMax(conv + ((int64_t)step * nmat + m) * 2 + 1, __float_as_uint(xmax));
+  }
+}
+
+// r[m][p][i] = b[f][p][i] - lambda_r x[m][p][i] - sum_j A_f[i][j] x[m][p][j]    (all FP64, fixed summation order)
+// grid: (n / 32, nmat), block 256.  smem: x[m] as double [P][n].
+template <int PMAX>
+__global__ void __launch_bounds__(256)
+mx_residual_kernel(const double* __restrict__ Af, const double* __restrict__ lambda, int R, const double* __restrict__ bvec,
+                   const double* __restrict__ xvec, double* __restrict__ rvec, int n, int P, int Pp, int nmat, int step,
+                   const unsigned int* __restrict__ conv, float tol) {
+  extern __shared__ double rs_sm[];
+  const int m = blockIdx.y;
+  if (step > 1 && mx_finished(conv, nmat, m, step - 1, tol)) return;
+  const int f = m / R;
+  const double lam = lambda[m % R];
+  const double* x = xvec + (int64_t)m * Pp * n;
+  for (int e = threadIdx.x; e < P * n; e += 256) rs_sm[e] = x[(int64_t)(e / n) * n + (e % n)];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int rr = 0; rr < 4; ++rr) {
+    const int i = blockIdx.x * 32 + warp * 4 + rr;
+    const double* ar = Af + ((int64_t)f * n + i) * n;
+    double acc[PMAX];
+#pragma unroll
+    for (int p = 0; p < PMAX; ++p) acc[p] = 0.0;
+    for (int j = lane * 2; j < n; j += 64) {
+      const double2 a = *reinterpret_cast<const double2*>(ar + j);
+#pragma unroll
+      for (int p = 0; p < PMAX; ++p) {
+        if (p < P) {
+          const double2 b = *reinterpret_cast<const double2*>(rs_sm + p * n + j);
+          acc[p] = fma(a.x, b.x, fma(a.y, b.y, acc[p]));
+        }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < PMAX; ++p) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[p] += __shfl_xor_sync(0xffffffffu, acc[p], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int p = 0; p < PMAX; ++p)
+        if (p < P)
+          rvec[((int64_t)m * Pp + p) * n + i] = bvec[((int64_t)f * Pp + p) * n + i] - lam * rs_sm[p * n + i] - acc[p];
+    }
+  }
+}
+
+// after the last correction: every system must have met the tolerance at some step, else the lane's fallback flag is raised
+__global__ void mx_final_check_kernel(const unsigned int* __restrict__ conv, int nmat, int steps, float tol,
+                                      unsigned int* __restrict__ fail_flag) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= nmat) return;
+  bool ok = mx_finished(conv, nmat, m, steps, tol);
+  // NaN / inf anywhere shows up as a non-finite maximum
+  for (int s = 1; s <= steps; ++s) {
+    const float dx = __uint_as_float(conv[((int64_t)s * nmat + m) * 2]);
+    if (!(dx == dx) || !(fabsf(dx) <= 3.0e38f)) ok = false;
+  }
+  if (!ok) atomicOr(fail_flag, 1u);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side: tile lists of every launch of one solve, built once per n.
+struct MxPlan {
+  int n = 0, nt = 0;
+  DevBuf<int4> tiles;                       // all lists back to back
+  std::vector<int2> upd, trsm;              // per panel step: (offset, count)
+  std::vector<int2> tri_t, tri_w;           // per doubling level
+  int2 xx{0, 0};
+};
+
+static void build_plan(MxPlan& pl, int n) {
+  pl.n = n;
+  const int nt = n / PT;
+  pl.nt = nt;
+  std::vector<int4> all;
+  pl.upd.clear(); pl.trsm.clear(); pl.tri_t.clear(); pl.tri_w.clear();
+  for (int k = 0; k < nt; ++k) {
+    int2 u{(int)all.size(), 0};
+    for (int i = k; i < nt; ++i) all.push_back(make_int4(i, k, 0, 4 * k));          // P_ik = A_ik - L_i,0:k L_k,0:k^T
+    u.y = (int)all.size() - u.x;
+    pl.upd.push_back(u);
+    int2 t{(int)all.size(), 0};
+    for (int i = k + 1; i < nt; ++i) all.push_back(make_int4(i, k, 4 * k, 4));      // L_ik = P_ik M_k^T
+    t.y = (int)all.size() - t.x;
+    pl.trsm.push_back(t);
+  }
+  for (int sb = 1; sb < nt; sb *= 2) {
+    int2 a{(int)all.size(), 0};
+    for (int a0 = 0; a0 + 2 * sb <= nt; a0 += 2 * sb)
+      for (int bi = 0; bi < sb; ++bi)
+        for (int aj = 0; aj < sb; ++aj)        // T[m in b][n in a] = sum_{p >= n} L21[m][p] W11[p][n]
+          all.push_back(make_int4(a0 + sb + bi, a0 + aj, 4 * (a0 + aj), 4 * (sb - aj)));
+    a.y = (int)all.size() - a.x;
+    pl.tri_t.push_back(a);
+    int2 w{(int)all.size(), 0};
+    for (int a0 = 0; a0 + 2 * sb <= nt; a0 += 2 * sb)
+      for (int bi = 0; bi < sb; ++bi)
+        for (int aj = 0; aj < sb; ++aj)        // W21[m in b][n in a] = - sum_{p <= m} W22[m][p] T[p][n]
+          all.push_back(make_int4(a0 + sb + bi, a0 + aj, 4 * (a0 + sb), 4 * (bi + 1)));
+    w.y = (int)all.size() - w.x;
+    pl.tri_w.push_back(w);
+  }
+  pl.xx.x = (int)all.size();
+  for (int i = 0; i < nt; ++i)
+    for (int j = 0; j <= i; ++j) all.push_back(make_int4(i, j, 4 * i, 4 * (nt - i)));   // X_ij = sum_{p >= i} W[p][i] W[p][j]
+  pl.xx.y = (int)all.size() - pl.xx.x;
+  pl.tiles.alloc(all.size());
+  RG_CUDA(cudaMemcpy(pl.tiles.p, all.data(), all.size() * sizeof(int4), cudaMemcpyHostToDevice));
+}
+
+struct MixedSolver::Impl {
+  int n = 0, nmat = 0, K = 0, R = 0, Pp = 0;
+  DevBuf<float> Lp, Wp, Wt, Tt, X;
+  DevBuf<unsigned int> conv;
+  CUtensorMap tmL, tmW, tmWt, tmT;
+  MxPlan plan;
+};
+
+MixedSolver::MixedSolver() : impl(new Impl()) {}
+MixedSolver::~MixedSolver() { delete impl; }
+
+int MixedSolver::dim_for(int bs) {
+  int n = PT;
+  while (n < bs) n *= 2;
+  return n <= 2048 ? n : 0;
+}
+
+void MixedSolver::prepare(int n, int K, int R, int Pp) {
+  Impl& d = *impl;
+  const int nmat = K * R;
+  if (d.n == n && d.nmat == nmat && d.Pp == Pp) return;
+  RG_CHECK(n % PT == 0 && n >= PT && ((n / PT) & (n / PT - 1)) == 0 && n <= 2048,
+           "mixed solver: dimension must be 128 * 2^k <= 2048");
+  d.n = n; d.nmat = nmat; d.K = K; d.R = R; d.Pp = Pp;
+  const size_t planes = (size_t)nmat * 2 * n * n;
+  d.Lp.alloc(planes); d.Wp.alloc(planes); d.Wt.alloc(planes); d.Tt.alloc(planes);
+  d.X.alloc((size_t)nmat * n * n);
+  // strictly-upper tiles of W / lower tiles of W^T are read by nothing; zero once so stale data can never matter
+  RG_CUDA(cudaMemset(d.Lp.p, 0, planes * 4));
+  RG_CUDA(cudaMemset(d.Wp.p, 0, planes * 4));
+  RG_CUDA(cudaMemset(d.Wt.p, 0, planes * 4));
+  RG_CUDA(cudaMemset(d.Tt.p, 0, planes * 4));
+  d.conv.alloc((size_t)(kMxMaxSteps + 1) * nmat * 2);
+  make_tf32_planes_tensor_map(&d.tmL, d.Lp.p, n, nmat);
+  make_tf32_planes_tensor_map(&d.tmW, d.Wp.p, n, nmat);
+  make_tf32_planes_tensor_map(&d.tmWt, d.Wt.p, n, nmat);
+  make_tf32_planes_tensor_map(&d.tmT, d.Tt.p, n, nmat);
+  build_plan(d.plan, n);
+}
+
+static int rhs_chunk(int n) { return std::max(1, std::min(12, (int)(98304 / (8 * (size_t)n)))); }
+
+int MixedSolver::launches_per_solve(int n, int steps, int P) {
+  const int nt = n / PT;
+  int lv = 0;
+  for (int sb = 1; sb < nt; sb *= 2) ++lv;
+  const int nch = (P + rhs_chunk(n) - 1) / rhs_chunk(n);
+  return 3 * nt - 1 + 2 * lv + 1 + nch * (1 + 2 * steps) + 1;
+}
+
+// Af: [K][n][n] FP64 full symmetric;  lambda: [R] (device);  bvec: [K][Pp][n];  xvec, rvec: [K*R][Pp][n]
+void MixedSolver::solve(const double* Af, const double* lambda, const double* bvec, double* xvec, double* rvec, int P,
+                        int steps, float tol, unsigned int* fail_flag, cudaStream_t s) {
+  Impl& d = *impl;
+  const int n = d.n, nmat = d.nmat, nt = d.plan.nt;
+  RG_CHECK(n > 0, "mixed solver: prepare() first");
+  RG_CHECK(P <= d.Pp, "mixed solver: more right-hand sides than the row pitch");
+  RG_CHECK(steps >= 1 && steps <= kMxMaxSteps, "mixed solver: bad step count");
+  static bool attr = false;
+  const size_t potrf_smem = ((size_t)3 * PT * PLD + PT) * sizeof(float);
+  if (!attr) {
+    RG_CUDA(cudaFuncSetAttribute(potrf128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_smem));
+    RG_CUDA(cudaFuncSetAttribute(mx_apply_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
+    RG_CUDA(cudaFuncSetAttribute(mx_residual_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
+    attr = true;
+  }
+  RG_CHECK(n <= 2048, "mixed solver: n <= 2048");
+  RG_CUDA(cudaMemsetAsync(d.conv.p, 0, d.conv.n * sizeof(unsigned int), s));
+  const int4* tl = d.plan.tiles.p;
+  Tf32GemmEpilogue e0{};
+  e0.n = n; e0.out_mat_stride = (int64_t)n * n;
+  // ---- factorisation: left-looking, 128-wide panels
+  for (int k = 0; k < nt; ++k) {
+    Tf32GemmEpilogue e = e0;
+    e.out = d.Lp.p;
+    e.cin = Af; e.cin_mat_stride = (int64_t)n * n; e.cin_ld = n; e.cin_mat_div = d.R;
+    e.diag_add = lambda; e.diag_mod = d.R;
+    launch_tf32x3_gemm(d.tmL, d.tmL, tl + d.plan.upd[k].x, d.plan.upd[k].y, nmat, e, s);
+    potrf128_kernel<<<nmat, 256, potrf_smem, s>>>(d.Lp.p, d.Wp.p, d.Wt.p, n, k, fail_flag);
+    if (d.plan.trsm[k].y > 0) {
+      Tf32GemmEpilogue t = e0;
+      t.out = d.Lp.p;
+      launch_tf32x3_gemm(d.tmL, d.tmW, tl + d.plan.trsm[k].x, d.plan.trsm[k].y, nmat, t, s);
+    }
+  }
+  // ---- W = L^-1 by recursive doubling:  W21 = - W22 (L21 W11)
+  for (size_t lv = 0; lv < d.plan.tri_t.size(); ++lv) {
+    Tf32GemmEpilogue t = e0;
+    t.out_t = d.Tt.p;
+    launch_tf32x3_gemm(d.tmL, d.tmWt, tl + d.plan.tri_t[lv].x, d.plan.tri_t[lv].y, nmat, t, s);
+    Tf32GemmEpilogue w = e0;
+    w.out = d.Wp.p; w.out_t = d.Wt.p; w.negate = 1;
+    launch_tf32x3_gemm(d.tmW, d.tmT, tl + d.plan.tri_w[lv].x, d.plan.tri_w[lv].y, nmat, w, s);
+  }
+  // ---- X = W^T W  ~ (A + lambda I)^-1, one FP32 plane, both triangles
+  {
+    Tf32GemmEpilogue x = e0;
+    x.out_plain = d.X.p; x.mirror = 1;
+    launch_tf32x3_gemm(d.tmWt, d.tmWt, tl + d.plan.xx.x, d.plan.xx.y, nmat, x, s);
+  }
+  // ---- x0 = X b, then  x += X (b - A x)
+  dim3 grid(n / 32, nmat);
+  const int pc = rhs_chunk(n);                       // right-hand sides per launch (shared-memory budget of the FP64 pass)
+  for (int st = 0; st <= steps; ++st)
+    for (int p0 = 0; p0 < P; p0 += pc) {
+      const int np = std::min(pc, P - p0);
+      const size_t sm_a = (size_t)np * n * sizeof(float), sm_r = (size_t)np * n * sizeof(double);
+      const int64_t o = (int64_t)p0 * n;
+      if (st == 0) {
+        mx_apply_kernel<12><<<grid, 256, sm_a, s>>>(d.X.p, bvec + o, (int64_t)d.Pp * n, d.R, xvec + o, n, np, d.Pp, nmat, 0, d.conv.p, tol);
+      } else {
+        mx_residual_kernel<12><<<grid, 256, sm_r, s>>>(Af, lambda, d.R, bvec + o, xvec + o, rvec + o, n, np, d.Pp, nmat, st, d.conv.p, tol);
+        mx_apply_kernel<12><<<grid, 256, sm_a, s>>>(d.X.p, rvec + o, (int64_t)d.Pp * n, 0, xvec + o, n, np, d.Pp, nmat, st, d.conv.p, tol);
+      }
+    }
+  mx_final_check_kernel<<<(nmat + 63) / 64, 64, 0, s>>>(d.conv.p, nmat, steps, tol, fail_flag);
+}
+
+const float* MixedSolver::debug_planes(int which) const {
+  switch (which) {
+    case 0: return impl->Lp.p;
+    case 1: return impl->Wp.p;
+    case 2: return impl->Wt.p;
+    case 3: return impl->X.p;
+    default: return nullptr;
+  }
+}
+
+}  // namespace rg

@@ -66,6 +66,14 @@ struct rg_ctx {
     rg::DevBuf<uint8_t> dig;          // radix-30 digit rows of gamma for the tensor-core prediction
     rg::DevBuf<double> dscale;        // [K][Qp] column scales
     std::map<int, CUtensorMap> dmaps; // digit-matrix tensor maps keyed by rows_p
+    // mixed-precision ridge solver (chol_mixed.cu): tensor-core factorisation + FP64 refinement, FP64 Cholesky fallback
+    std::unique_ptr<rg::MixedSolver> mx;
+    rg::DevBuf<double> mx_Af, mx_b, mx_x, mx_r;   // [K][n][n] fold systems; [K][Pp][n] rhs; [K R][Pp][n] solutions / residuals
+    rg::DevBuf<unsigned int> mx_fail;            // device flag: refinement did not converge / pivot not positive
+    unsigned int* mx_fail_host = nullptr;         // pinned copy, valid once mx_ev has fired
+    cudaEvent_t mx_ev = nullptr;
+    bool mx_pending = false;                      // a block went through the mixed path and its flag has not been read yet
+    int mx_bs = 0, mx_block_id = 0;               // the block to re-solve in FP64 if the flag is set
   };
   std::vector<std::unique_ptr<Lane>> lanes;
   int next_lane = 0, last_lane = 0;
@@ -146,6 +154,12 @@ struct rg_ctx {
   rg::DevBuf<int8_t> bt_ym, firth_cflag;
   rg::DevBuf<int32_t> firth_sel, firth_status;
 
+  // ---- level-0 solver selection (RG_B200_SOLVER = mixed | f64) and its counters
+  int solver_mixed = 1;
+  int mx_steps = 3;
+  float mx_tol = 1e-9f;
+  int64_t mx_blocks = 0, mx_fallbacks = 0;
+
   // ---- timing
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -155,4 +169,6 @@ struct rg_ctx {
 
 namespace rg {
 void flush_timers(rg_ctx* h);
+// read the mixed-solver flags of every lane (re-solving flagged blocks in FP64) and wait for all level-0 work
+void sync_lanes(rg_ctx* h);
 }

@@ -84,6 +84,48 @@ size_t chol_inv_elems(int nC, int batch);
 void launch_chol_rows_backsolve(double* cm, int64_t stride, int nC, int row0, int nrows, int batch,
                                 const double* inv, cudaStream_t s);
 
+// ---- tf32_gemm.cu: batched 128x128 "NT" tiles in 3xTF32 on tcgen05 (operands = hi/lo FP32 planes [batch][2][n][n])
+struct Tf32GemmEpilogue {
+  int n;                      // matrix dimension = row stride of every output
+  int64_t out_mat_stride;     // elements per plane per matrix (n * n)
+  float* out;                 // D   as hi / lo planes [batch][2][n][n], or null
+  float* out_t;               // D^T as hi / lo planes, or null
+  float* out_plain;           // D   as one FP32 plane [batch][n][n], or null
+  int mirror;                 // out_plain: also store D^T (symmetric result computed on its lower tiles)
+  int negate;                 // D = -acc
+  int lower_only;             // zero the strict upper part of diagonal tiles
+  const double* cin;          // D = (float)(cin - acc) with FP64 matrices cin[mat / cin_mat_div][row][col], or null
+  int64_t cin_mat_stride;
+  int cin_ld, cin_mat_div;
+  const double* diag_add;     // added to cin's diagonal: diag_add[mat % diag_mod] (the ridge shift), or null
+  int diag_mod;
+};
+void make_tf32_planes_tensor_map(CUtensorMap* tm, const float* planes, int n, int batch);
+void launch_tf32x3_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const int4* tiles, int ntiles, int batch,
+                        const Tf32GemmEpilogue& ep, cudaStream_t s);
+
+// ---- chol_mixed.cu: tensor-core factorisation + FP64 iterative refinement of the level-0 ridge systems
+constexpr int kMxMaxSteps = 6;
+class MixedSolver {
+ public:
+  MixedSolver();
+  ~MixedSolver();
+  MixedSolver(const MixedSolver&) = delete;
+  MixedSolver& operator=(const MixedSolver&) = delete;
+  static int dim_for(int bs);                 // 128 * 2^k >= bs, or 0 when the block is too large for this path
+  void prepare(int n, int K, int R, int Pp);
+  // Af [K][n][n] FP64 full symmetric (no ridge shift), lambda [R], bvec [K][Pp][n]; xvec / rvec [K*R][Pp][n]
+  void solve(const double* Af, const double* lambda, const double* bvec, double* xvec, double* rvec, int P, int steps,
+             float tol, unsigned int* fail_flag, cudaStream_t s);
+  static int launches_per_solve(int n, int steps, int P);
+  const float* debug_planes(int which) const;  // 0 L, 1 W, 2 W^T (hi/lo planes), 3 X
+ private:
+  struct Impl;
+  Impl* impl;
+};
+// K full symmetric fold systems (no ridge shift) + right-hand sides as rows, for the mixed solver
+void launch_l0_assemble_sym(const AssembleArgs& a, const double* rhs, int P, int Pp, double* bvec, cudaStream_t s);
+
 // ---- l0_predict.cu
 struct PredictArgs {
   int bs, rows_p, C, P, R, Qp, cpp, col0;

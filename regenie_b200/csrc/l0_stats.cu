@@ -249,6 +249,90 @@ l0_assemble_kernel(AssembleArgs a) {
   }
 }
 
+
+// Mixed-precision solver input (chol_mixed.cu): the K fold systems  A_f = GGt - G_folds[f]  WITHOUT the ridge shift, as
+// full symmetric FP64 matrices of dimension n = a.nC (128 * 2^k; rows >= bs carry the identity), so that the refinement
+// residual is a plain row-wise matrix-vector pass and the R ridge values of a fold share one matrix.
+// a.cm = base of [K][n][n], a.ldc = n.  grid: (n/32, n/32), block (32, 8); tiles with ti >= tj do the work and also
+// write the mirror image through shared memory (coalesced both ways).
+__global__ void __launch_bounds__(256)
+l0_assemble_sym_kernel(AssembleArgs a) {
+  const int ti = blockIdx.y, tj = blockIdx.x;
+  if (ti < tj) return;
+  __shared__ float mgT[32][33];
+  __shared__ double tl[32][33];
+  const int K = a.K, C = a.C;
+  const int j = tj * 32 + threadIdx.x;
+  const int64_t ldz = a.ldz;
+  double gsum[4] = {0, 0, 0, 0};
+  double gf[4][kMaxFolds];
+  const bool jv = j < a.bs;
+  const double mu_j = jv ? a.mu[j] : 0.0, isd_j = jv ? a.inv_sd[j] : 0.0;
+  for (int f = 0; f < K; ++f) {
+    const float* zz = a.zz + (int64_t)f * a.zz_fold_stride;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int jj = tj * 32 + threadIdx.y * 4 + r, ii = ti * 32 + threadIdx.x;
+      mgT[threadIdx.y * 4 + r][threadIdx.x] = (jj < a.bs && ii < a.bs) ? zz[(int64_t)(a.rows_p + jj) * ldz + ii] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int il = threadIdx.y * 4 + r;
+      const int i = ti * 32 + il;
+      double v = 0.0;
+      if (i >= j && i < a.bs) {
+        const double mu_i = a.mu[i];
+        const double gg = zz[(int64_t)i * ldz + j];
+        const double mg_ij = zz[(int64_t)(a.rows_p + i) * ldz + j];
+        const double mg_ji = mgT[threadIdx.x][il];
+        const double mm = zz[(int64_t)(a.rows_p + i) * ldz + a.rows_p + j];
+        double t = gg + mu_i * mg_ij + mu_j * mg_ji + mu_i * mu_j * mm;
+        const double* Afi = a.Af + ((int64_t)f * a.rows_p + i) * C;
+        const double* Afj = a.Af + ((int64_t)f * a.rows_p + j) * C;
+        const double* Qfj = a.Qf + ((int64_t)f * a.rows_p + j) * C;
+        const double* Bi = a.Bv + (int64_t)i * C;
+        const double* Bj = a.Bv + (int64_t)j * C;
+        for (int c = 0; c < C; ++c) t += -Afi[c] * Bj[c] - Bi[c] * Afj[c] + Bi[c] * Qfj[c];
+        v = t * a.inv_sd[i] * isd_j;
+      }
+      gf[r][f] = v;
+      gsum[r] += v;
+    }
+  }
+  for (int f = 0; f < K; ++f) {
+    double* out = a.cm + (int64_t)f * a.cm_stride;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int il = threadIdx.y * 4 + r;
+      const int i = ti * 32 + il;
+      double v = 0.0;
+      if (i >= j) v = (i < a.bs) ? gsum[r] - gf[r][f] : (i == j ? 1.0 : 0.0);
+      if (i >= j) out[(int64_t)i * a.ldc + j] = v;
+      tl[il][threadIdx.x] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int jl = threadIdx.y * 4 + r;
+      const int i2 = ti * 32 + threadIdx.x, j2 = tj * 32 + jl;
+      if (i2 > j2) out[(int64_t)j2 * a.ldc + i2] = tl[threadIdx.x][jl];
+    }
+    __syncthreads();
+  }
+}
+
+// bvec[f][p][i] = rhs_f[i][p]  (zero beyond bs / P).  grid: (ceil(n/256), Pp, K)
+__global__ void l0_rhs_sym_kernel(const double* __restrict__ rhs, int rows_p, int bs, int P, int n, double* __restrict__ bvec) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.y, f = blockIdx.z;
+  if (i >= n) return;
+  double v = 0.0;
+  if (p < P && i < bs) v = rhs[((int64_t)f * rows_p + i) * P + p];
+  bvec[((int64_t)f * gridDim.y + p) * n + i] = v;
+}
+
 // Right-hand-side rows of the augmented systems: cm[m][nC + p][i] = rhs_f[i][p].
 // grid: (ceil(nC/256), Ppad, nmat)
 __global__ void l0_rhs_rows_kernel(AssembleArgs a, const double* __restrict__ rhs, int P) {
@@ -301,6 +385,13 @@ void launch_l0_assemble(const AssembleArgs& a, const double* rhs, int P, int Ppa
   l0_assemble_kernel<<<grid, dim3(32, 8), 0, s>>>(a);
   dim3 g2((unsigned)ceil_div(a.nC, 256), Ppad, nmat);
   l0_rhs_rows_kernel<<<g2, 256, 0, s>>>(a, rhs, P);
+}
+
+void launch_l0_assemble_sym(const AssembleArgs& a, const double* rhs, int P, int Pp, double* bvec, cudaStream_t s) {
+  dim3 grid(a.nC / 32, a.nC / 32);
+  l0_assemble_sym_kernel<<<grid, dim3(32, 8), 0, s>>>(a);
+  dim3 g2((unsigned)ceil_div(a.nC, 256), Pp, a.K);
+  l0_rhs_sym_kernel<<<g2, 256, 0, s>>>(rhs, a.rows_p, a.bs, P, a.nC, bvec);
 }
 
 }  // namespace rg

@@ -56,7 +56,7 @@ static void l1_fit(rg_ctx* h, const double* tau_host, double* cumsum, int32_t* b
   RG_CHECK(h->R1 >= 1 && h->R1 <= kMaxRidge, "n_ridge_l1 out of range");
   RG_CUDA(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
-  for (auto& l : h->lanes) RG_CUDA(cudaStreamSynchronize(l->stream));   // all level-0 blocks are in W
+  rg::sync_lanes(h);   // all level-0 blocks are in W
   ensure_W(h);
   const int K = h->K, R1 = h->R1, P = h->P;
   const int B = (int)h->B;
@@ -360,7 +360,7 @@ static void l1_fit_bt(rg_ctx* h, const double* y_raw, const double* offset, cons
   RG_CHECK(h->B <= 6000, "logistic level 1 supports up to 6000 level-0 predictors (blocks x ridge values) in this build");
   RG_CUDA(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
-  for (auto& l : h->lanes) RG_CUDA(cudaStreamSynchronize(l->stream));
+  rg::sync_lanes(h);
   const int R1 = h->R1, P = h->P, B = (int)h->B;
   const int nC = (int)round_up(B, 64);
   const int64_t Npad = h->Npad, N = h->N;

@@ -252,6 +252,177 @@ static bool dbg_skip(const char* name) {
   return e && strstr(e, name) != nullptr;
 }
 
+
+struct BlockDims {
+  int bs, rows_p, nC, Ppad, n_aug, nmat, Q, Qp, col0, block_id, ntiles_s;
+};
+
+static int mx_pp(int P) { return (int)round_up(P, 2); }
+
+// FP64 path: assemble the K*R shifted systems, batched Cholesky (DMMA), backward substitution; LOOCV predictions
+// included (they read the factorisation directly).  Solutions end up in the right-hand-side rows of L.cm.
+static void enqueue_solve_f64(rg_ctx* h, rg_ctx::Lane& L, const BlockDims& d, cudaStream_t s) {
+  const int C = h->C, P = h->P, K = h->K, R = h->R;
+  AssembleArgs aa;
+  aa.bs = d.bs; aa.rows_p = d.rows_p; aa.nC = d.nC; aa.C = C; aa.K = K; aa.R = R; aa.loocv = h->loocv;
+  aa.zz = L.zz.p; aa.ldz = 2 * d.rows_p; aa.zz_fold_stride = (int64_t)4 * d.rows_p * d.rows_p;
+  aa.mu = L.mu.p; aa.inv_sd = L.inv_sd.p; aa.Bv = L.Bv.p; aa.Af = L.Af.p; aa.Qf = L.Qf.p;
+  aa.lambda = h->lambda.p; aa.cm = L.cm.p; aa.cm_stride = (int64_t)d.n_aug * d.nC; aa.ldc = d.nC;
+  {
+    const int nC_max = (int)round_up(h->bs_max, 64);
+    const size_t need = (size_t)d.nmat * (nC_max + d.Ppad + (h->loocv ? h->Npad : 0)) * nC_max;
+    if (L.cm.n < need) {
+      L.cm.alloc(need);
+      RG_CUDA(cudaMemsetAsync(L.cm.p, 0, need * 8, s));
+    }
+    L.inv.alloc(chol_inv_elems((int)round_up(h->bs_max, 64), d.nmat));
+  }
+  {
+    ScopedTimer t(h, "l0_assemble", s);
+    if (!dbg_skip("assemble")) launch_l0_assemble(aa, L.rhs.p, P, d.Ppad, d.nmat, s);
+    h->launches += 2;
+  }
+  if (h->loocv) {
+    ScopedTimer t(h, "loocv_fill", s);
+    launch_l0_loocv_fill(L.gp.p, h->Npad, d.bs, d.nC, L.mu.p, L.inv_sd.p, L.Bv.p, C, h->xy.p, h->cpp, L.cm.p, aa.cm_stride,
+                         d.nC + d.Ppad, R, s);
+    h->launches += 1;
+  }
+  {
+    ScopedTimer t(h, "chol_factor", s);
+    if (!dbg_skip("chol")) launch_chol_factor(L.cm.p, aa.cm_stride, d.nC, d.n_aug, d.nmat, L.inv.p, h->err_slot.p,
+                       (long long)(1ll << 40) + (long long)d.block_id * 1024, s);
+    h->launches += chol_num_launches(d.nC);
+  }
+  if (h->loocv) {
+    // closed-form leave-one-out predictions (src/Step1_Models.cpp:654-663) + LOOCV standardisation (:694-706)
+    ScopedTimer t(h, "l0_predict", s);
+    launch_l0_loocv_pred(L.cm.p, aa.cm_stride, d.nC, d.bs, d.Ppad, P, R, h->xy.p, h->cpp, C, h->mask.p, h->Npad, h->W_tab.p,
+                         d.col0, L.part.p, d.Qp, s);
+    launch_l0_std_reduce_only(L.part.p, d.ntiles_s, d.Qp, d.Q, P, h->neff.p, L.mean_invsd.p, s);
+    launch_l0_loocv_std_apply(h->W_tab.p, h->Npad, d.col0, P, d.Q, h->mask.p, L.mean_invsd.p, s);
+    h->launches += 3;
+    return;
+  }
+  {
+    ScopedTimer t(h, "chol_backsolve", s);
+    if (!dbg_skip("backsolve")) launch_chol_backsolve(L.cm.p, aa.cm_stride, d.nC, P, d.nmat, L.inv.p, s);
+    h->launches += 1;
+  }
+}
+
+// Mixed path: K symmetric FP64 fold systems -> tcgen05 factorisation / inverse -> FP64 refinement.  Solutions in L.mx_x.
+static void enqueue_solve_mixed(rg_ctx* h, rg_ctx::Lane& L, const BlockDims& d, int n, cudaStream_t s) {
+  const int C = h->C, P = h->P, K = h->K, R = h->R;
+  const int Pp = mx_pp(P);
+  const int n_max = MixedSolver::dim_for(h->bs_max);
+  if (!L.mx) {
+    L.mx = std::make_unique<MixedSolver>();
+    L.mx_fail.alloc(1);
+    RG_CUDA(cudaMallocHost(&L.mx_fail_host, sizeof(unsigned int)));
+    RG_CUDA(cudaEventCreateWithFlags(&L.mx_ev, cudaEventDisableTiming));
+    L.mx_Af.alloc((size_t)K * n_max * n_max);
+    L.mx_b.alloc((size_t)K * Pp * n_max);
+    L.mx_x.alloc((size_t)K * R * Pp * n_max);
+    L.mx_r.alloc((size_t)K * R * Pp * n_max);
+  }
+  L.mx->prepare(n, K, R, Pp);
+  RG_CUDA(cudaMemsetAsync(L.mx_fail.p, 0, sizeof(unsigned int), s));
+  AssembleArgs aa;
+  aa.bs = d.bs; aa.rows_p = d.rows_p; aa.nC = n; aa.C = C; aa.K = K; aa.R = R; aa.loocv = 0;
+  aa.zz = L.zz.p; aa.ldz = 2 * d.rows_p; aa.zz_fold_stride = (int64_t)4 * d.rows_p * d.rows_p;
+  aa.mu = L.mu.p; aa.inv_sd = L.inv_sd.p; aa.Bv = L.Bv.p; aa.Af = L.Af.p; aa.Qf = L.Qf.p;
+  aa.lambda = h->lambda.p; aa.cm = L.mx_Af.p; aa.cm_stride = (int64_t)n * n; aa.ldc = n;
+  {
+    ScopedTimer t(h, "l0_assemble", s);
+    launch_l0_assemble_sym(aa, L.rhs.p, P, Pp, L.mx_b.p, s);
+    h->launches += 2;
+  }
+  {
+    ScopedTimer t(h, "mx_solve", s);
+    L.mx->solve(L.mx_Af.p, h->lambda.p, L.mx_b.p, L.mx_x.p, L.mx_r.p, P, h->mx_steps, h->mx_tol, L.mx_fail.p, s);
+    h->launches += MixedSolver::launches_per_solve(n, h->mx_steps, P);
+  }
+}
+
+// Out-of-fold predictions from the coefficients x[m][p][i] at xsrc + m * xstride + (xrow0 + p) * xld + i.
+static void enqueue_predict(rg_ctx* h, rg_ctx::Lane& L, const BlockDims& d, const double* xsrc, int64_t xstride, int xld,
+                            int xrow0, cudaStream_t s) {
+  const int C = h->C, P = h->P, K = h->K, R = h->R;
+  const int64_t Npad = h->Npad;
+  ScopedTimer t(h, "l0_predict", s);
+  launch_l0_gamma(xsrc, xstride, xld, xrow0, R, P, d.Qp, d.bs, d.rows_p, K, L.mu.p, L.inv_sd.p, L.Bv.p, C,
+                  L.gam.p, L.gmu.p, L.cvec.p, s);
+  PredictArgs pa;
+  pa.bs = d.bs; pa.rows_p = d.rows_p; pa.C = C; pa.P = P; pa.R = R; pa.Qp = d.Qp; pa.cpp = h->cpp;
+  pa.col0 = d.col0; pa.npad = Npad; pa.words_per_row = Npad / 16;
+  pa.gp = L.gp.p; pa.tile_fold = h->tile_fold.p; pa.gam = L.gam.p; pa.gmu = L.gmu.p;
+  pa.cvec = L.cvec.p; pa.xy = h->xy.p; pa.mask = h->mask.p; pa.W = h->W_tab.p; pa.part = L.part.p;
+  int nparts = d.ntiles_s;
+  static const bool use_f64_predict = [] { const char* e = getenv("RG_B200_PREDICT"); return e && std::string(e) == "f64"; }();
+  if (use_f64_predict) {
+    launch_l0_predict(pa, d.ntiles_s, s);
+  } else {
+    // exact tensor-core path: radix-30 digit rows of gamma against the e4m3 genotype planes
+    const int ngroups = (int)ceil_div(d.Q, kLimbQ);
+    const size_t need = predict_tc_dig_bytes(K, ngroups, h->rows_p_max);
+    if (L.dig.n < need) {
+      L.dig.alloc(need);
+      RG_CUDA(cudaMemsetAsync(L.dig.p, 0, need, s));
+      L.dmaps.clear();
+    }
+    L.dscale.alloc((size_t)K * d.Qp);
+    if (!L.dmaps.count(d.rows_p)) {
+      CUtensorMap tm;
+      make_byte_tensor_map(&tm, L.dig.p, 2 * d.rows_p, (int64_t)K * ngroups * 512);
+      L.dmaps[d.rows_p] = tm;
+    }
+    launch_l0_gamma_limbs(L.gam.p, L.gmu.p, d.Qp, d.Q, d.bs, d.rows_p, K, L.dscale.p, L.dig.p, ngroups, s);
+    PredictTcArgs ta;
+    ta.rows_p = d.rows_p; ta.C = C; ta.P = P; ta.Q = d.Q; ta.Qp = d.Qp; ta.cpp = h->cpp; ta.col0 = d.col0; ta.ngroups = ngroups;
+    ta.npad = Npad; ta.tile_fold = h->tile_fold.p; ta.scale = L.dscale.p; ta.cvec = L.cvec.p;
+    ta.xy = h->xy.p; ta.mask = h->mask.p; ta.W = h->W_tab.p; ta.part = L.part.p;
+    ta.dbg = nullptr;
+    if (getenv("RG_DBG_CLK")) { h->dbg_clk.alloc((size_t)d.ntiles_s * ngroups * 4); ta.dbg = h->dbg_clk.p; }
+    if (!dbg_skip("predict")) launch_l0_predict_tcgen05(L.tmaps[d.rows_p], L.dmaps[d.rows_p], ta, d.ntiles_s, s);
+    nparts = launch_l0_colsum(h->W_tab.p, Npad, d.col0, P, d.Q, d.Qp, L.part.p, s);
+    h->launches += 2;
+  }
+  launch_l0_standardize(L.part.p, nparts, d.Qp, d.Q, P, h->neff.p, L.mean_invsd.p, h->W_tab.p, Npad, d.col0,
+                        h->is_real.p, s);
+  h->launches += 5;
+}
+
+static BlockDims block_dims(const rg_ctx* h, int bs, int block_id) {
+  BlockDims d;
+  d.bs = bs; d.rows_p = (int)round_up(bs, kRowPad); d.nC = (int)round_up(bs, 64); d.Ppad = (int)round_up(h->P, 64);
+  d.n_aug = d.nC + d.Ppad + (h->loocv ? (int)h->Npad : 0);
+  d.nmat = (h->loocv ? 1 : h->K) * h->R;
+  d.Q = h->R * h->P; d.Qp = (int)round_up(d.Q, predict_qt());
+  d.col0 = block_id * h->R; d.block_id = block_id; d.ntiles_s = (int)(h->Npad / 128);
+  return d;
+}
+
+// Read the mixed-solver flag of the block this lane ran last; if the refinement did not converge (ill-conditioned
+// system) or a pivot was not positive, re-solve that block in FP64 from the lane's scratch (statistics, Grams and 2-bit
+// rows of the block are still there) and redo its predictions.
+void resolve_lane(rg_ctx* h, rg_ctx::Lane& L) {
+  if (!L.mx_pending) return;
+  RG_CUDA(cudaEventSynchronize(L.mx_ev));
+  L.mx_pending = false;
+  if (*L.mx_fail_host == 0) return;
+  h->mx_fallbacks += 1;
+  const BlockDims d = block_dims(h, L.mx_bs, L.mx_block_id);
+  enqueue_solve_f64(h, L, d, L.stream);
+  enqueue_predict(h, L, d, L.cm.p, (int64_t)d.n_aug * d.nC, d.nC, d.nC, L.stream);
+}
+
+void sync_lanes(rg_ctx* h) {
+  RG_CUDA(cudaSetDevice(h->device));
+  for (auto& l : h->lanes) resolve_lane(h, *l);
+  for (auto& l : h->lanes) RG_CUDA(cudaStreamSynchronize(l->stream));
+}
+
 static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, int bs,
                          const int32_t* sample_idx, int ref_first, int block_id) {
   ensure_W(h);
@@ -292,6 +463,7 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
 
   // --- lane: own stream + scratch
   rg_ctx::Lane& L = *h->lanes[h->next_lane];
+  resolve_lane(h, L);                      // flag of the block this lane ran before (FP64 re-solve if it was raised)
   h->last_lane = h->next_lane;
   h->next_lane = (h->next_lane + 1) % (int)h->lanes.size();
   s = L.stream;
@@ -321,15 +493,6 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
   L.Qf.alloc((size_t)K * h->rows_p_max * C);
   L.gty_f.alloc((size_t)K * h->rows_p_max * P);
   L.rhs.alloc((size_t)K * h->rows_p_max * P);
-  {
-    const int nC_max = (int)round_up(h->bs_max, 64);
-    const size_t need = (size_t)nmat * (nC_max + Ppad + (h->loocv ? Npad : 0)) * nC_max;
-    if (L.cm.n < need) {
-      L.cm.alloc(need);
-      RG_CUDA(cudaMemsetAsync(L.cm.p, 0, need * 8, s));
-    }
-  }
-  L.inv.alloc(chol_inv_elems((int)round_up(h->bs_max, 64), nmat));
   const int Kg = h->loocv ? 1 : K;
   L.gam.alloc((size_t)Kg * h->rows_p_max * Qp);
   L.gmu.alloc((size_t)Kg * h->rows_p_max * Qp);
@@ -423,91 +586,25 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
                           h->dbg_counter.p, s);
   }
 
-  // --- 4. ridge systems
-  AssembleArgs aa;
-  aa.bs = bs; aa.rows_p = rows_p; aa.nC = nC; aa.C = C; aa.K = K; aa.R = R; aa.loocv = h->loocv;
-  aa.zz = L.zz.p; aa.ldz = 2 * rows_p; aa.zz_fold_stride = (int64_t)4 * rows_p * rows_p;
-  aa.mu = L.mu.p; aa.inv_sd = L.inv_sd.p; aa.Bv = L.Bv.p; aa.Af = L.Af.p; aa.Qf = L.Qf.p;
-  aa.lambda = h->lambda.p; aa.cm = L.cm.p; aa.cm_stride = (int64_t)n_aug * nC; aa.ldc = nC;
-  {
-    ScopedTimer t(h, "l0_assemble", s);
-    if (!dbg_skip("assemble")) launch_l0_assemble(aa, L.rhs.p, P, Ppad, nmat, s);
-    h->launches += 2;
-  }
-  if (h->loocv) {
-    ScopedTimer t(h, "loocv_fill", s);
-    launch_l0_loocv_fill(L.gp.p, Npad, bs, nC, L.mu.p, L.inv_sd.p, L.Bv.p, C, h->xy.p, h->cpp, L.cm.p, aa.cm_stride,
-                         nC + Ppad, R, s);
-    h->launches += 1;
-  }
-  {
-    ScopedTimer t(h, "chol_factor", s);
-    if (!dbg_skip("chol")) launch_chol_factor(L.cm.p, aa.cm_stride, nC, n_aug, nmat, L.inv.p, h->err_slot.p,
-                       (long long)(1ll << 40) + (long long)block_id * 1024, s);
-    h->launches += chol_num_launches(nC);
-  }
+  BlockDims d;
+  d.bs = bs; d.rows_p = rows_p; d.nC = nC; d.Ppad = Ppad; d.n_aug = n_aug; d.nmat = nmat; d.Q = Q; d.Qp = Qp;
+  d.col0 = block_id * R; d.block_id = block_id; d.ntiles_s = (int)(Npad / 128);
   h->last_bs = bs; h->last_rows_p = rows_p; h->last_nC = nC; h->last_n_aug = n_aug; h->last_nmat = nmat;
-  const int col0 = block_id * R;
-  if (h->loocv) {
-    // closed-form leave-one-out predictions (src/Step1_Models.cpp:654-663) + LOOCV standardisation (:694-706)
-    ScopedTimer t(h, "l0_predict", s);
-    launch_l0_loocv_pred(L.cm.p, aa.cm_stride, nC, bs, Ppad, P, R, h->xy.p, h->cpp, C, h->mask.p, Npad, h->W_tab.p,
-                         col0, L.part.p, Qp, s);
-    launch_l0_std_reduce_only(L.part.p, ntiles_s, Qp, Q, P, h->neff.p, L.mean_invsd.p, s);
-    launch_l0_loocv_std_apply(h->W_tab.p, Npad, col0, P, Q, h->mask.p, L.mean_invsd.p, s);
-    h->launches += 3;
+
+  // --- 4./5. ridge systems -> coefficients -> out-of-fold predictions, standardised into W
+  const int mx_n = (!h->loocv && h->solver_mixed) ? MixedSolver::dim_for(bs) : 0;
+  if (mx_n > 0) {
+    enqueue_solve_mixed(h, L, d, mx_n, s);
+    enqueue_predict(h, L, d, L.mx_x.p, (int64_t)mx_pp(P) * mx_n, mx_n, 0, s);
+    // the flag travels to pinned host memory behind the block; it is read when this lane is next used or at a sync
+    RG_CUDA(cudaMemcpyAsync(L.mx_fail_host, L.mx_fail.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+    RG_CUDA(cudaEventRecord(L.mx_ev, s));
+    L.mx_pending = true; L.mx_bs = bs; L.mx_block_id = block_id;
+    h->mx_blocks += 1;
     return;
   }
-  {
-    ScopedTimer t(h, "chol_backsolve", s);
-    if (!dbg_skip("backsolve")) launch_chol_backsolve(L.cm.p, aa.cm_stride, nC, P, nmat, L.inv.p, s);
-    h->launches += 1;
-  }
-
-  // --- 5. out-of-fold predictions, standardised into W
-  {
-    ScopedTimer t(h, "l0_predict", s);
-    launch_l0_gamma(L.cm.p, aa.cm_stride, nC, nC, R, P, Qp, bs, rows_p, K, L.mu.p, L.inv_sd.p, L.Bv.p, C,
-                    L.gam.p, L.gmu.p, L.cvec.p, s);
-    PredictArgs pa;
-    pa.bs = bs; pa.rows_p = rows_p; pa.C = C; pa.P = P; pa.R = R; pa.Qp = Qp; pa.cpp = h->cpp;
-    pa.col0 = col0; pa.npad = Npad; pa.words_per_row = Npad / 16;
-    pa.gp = L.gp.p; pa.tile_fold = h->tile_fold.p; pa.gam = L.gam.p; pa.gmu = L.gmu.p;
-    pa.cvec = L.cvec.p; pa.xy = h->xy.p; pa.mask = h->mask.p; pa.W = h->W_tab.p; pa.part = L.part.p;
-    int nparts = ntiles_s;
-    static const bool use_f64_predict = [] { const char* e = getenv("RG_B200_PREDICT"); return e && std::string(e) == "f64"; }();
-    if (use_f64_predict) {
-      launch_l0_predict(pa, ntiles_s, s);
-    } else {
-      // exact tensor-core path: radix-30 digit rows of gamma against the e4m3 genotype planes
-      const int ngroups = (int)ceil_div(Q, kLimbQ);
-      const size_t need = predict_tc_dig_bytes(K, ngroups, h->rows_p_max);
-      if (L.dig.n < need) {
-        L.dig.alloc(need);
-        RG_CUDA(cudaMemsetAsync(L.dig.p, 0, need, s));
-        L.dmaps.clear();
-      }
-      L.dscale.alloc((size_t)K * Qp);
-      if (!L.dmaps.count(rows_p)) {
-        CUtensorMap tm;
-        make_byte_tensor_map(&tm, L.dig.p, 2 * rows_p, (int64_t)K * ngroups * 512);
-        L.dmaps[rows_p] = tm;
-      }
-      launch_l0_gamma_limbs(L.gam.p, L.gmu.p, Qp, Q, bs, rows_p, K, L.dscale.p, L.dig.p, ngroups, s);
-      PredictTcArgs ta;
-      ta.rows_p = rows_p; ta.C = C; ta.P = P; ta.Q = Q; ta.Qp = Qp; ta.cpp = h->cpp; ta.col0 = col0; ta.ngroups = ngroups;
-      ta.npad = Npad; ta.tile_fold = h->tile_fold.p; ta.scale = L.dscale.p; ta.cvec = L.cvec.p;
-      ta.xy = h->xy.p; ta.mask = h->mask.p; ta.W = h->W_tab.p; ta.part = L.part.p;
-      ta.dbg = nullptr;
-      if (getenv("RG_DBG_CLK")) { h->dbg_clk.alloc((size_t)ntiles_s * ngroups * 4); ta.dbg = h->dbg_clk.p; }
-      if (!dbg_skip("predict")) launch_l0_predict_tcgen05(L.tmaps[rows_p], L.dmaps[rows_p], ta, ntiles_s, s);
-      nparts = launch_l0_colsum(h->W_tab.p, Npad, col0, P, Q, Qp, L.part.p, s);
-      h->launches += 2;
-    }
-    launch_l0_standardize(L.part.p, nparts, Qp, Q, P, h->neff.p, L.mean_invsd.p, h->W_tab.p, Npad, col0,
-                          h->is_real.p, s);
-    h->launches += 5;
-  }
+  enqueue_solve_f64(h, L, d, s);
+  if (!h->loocv) enqueue_predict(h, L, d, L.cm.p, (int64_t)d.n_aug * d.nC, d.nC, d.nC, s);
 }
 
 void require_gpu_public(int device) { require_gpu(device); }
@@ -578,6 +675,9 @@ int rg_step1_create(const rg_step1_config* cfg, const double* X, const double* Y
   h->total_blocks = cfg->total_blocks;
   h->B = (int64_t)h->total_blocks * h->R;
   h->n_analyzed = cfg->n_analyzed;
+  if (const char* e = getenv("RG_B200_SOLVER")) h->solver_mixed = std::string(e) == "f64" ? 0 : 1;
+  if (const char* e = getenv("RG_B200_MX_STEPS")) h->mx_steps = std::max(1, std::min(kMxMaxSteps, atoi(e)));
+  if (const char* e = getenv("RG_B200_MX_TOL")) h->mx_tol = (float)atof(e);
   build_layout(h.get(), X, Y, mask, in_analysis, fold_sizes);
   h->lambda.alloc(h->R);
   h->neff.alloc(h->P);
@@ -603,7 +703,12 @@ void rg_destroy(rg_handle h) {
   for (auto& l : h->lanes) cudaStreamSynchronize(l->stream);
   cudaStreamSynchronize(h->stream);
   rg::flush_timers(h);
-  for (auto& l : h->lanes) { cudaEventDestroy(l->done); cudaStreamDestroy(l->stream); }
+  for (auto& l : h->lanes) {
+    if (l->mx_ev) cudaEventDestroy(l->mx_ev);
+    if (l->mx_fail_host) cudaFreeHost(l->mx_fail_host);
+    cudaEventDestroy(l->done);
+    cudaStreamDestroy(l->stream);
+  }
   cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -623,8 +728,7 @@ int rg_W_export(rg_handle h, void* ipc_handle_64) {
 int rg_W_set_owned(rg_handle h, const uint8_t* owned) {
   RG_API_BEGIN
   RG_CHECK(h && h->kind == 1 && owned, "bad argument");
-  RG_CUDA(cudaSetDevice(h->device));
-  for (auto& l : h->lanes) RG_CUDA(cudaStreamSynchronize(l->stream));
+  rg::sync_lanes(h);
   RG_CHECK(!h->W.p, "rg_W_set_owned must be called before the first block / export");
   h->W_owned.assign(owned, owned + h->P);
   for (int p = 0; p < h->P; ++p) h->l1_select[p] = owned[p] ? 1 : 0;
@@ -635,8 +739,7 @@ int rg_W_set_owned(rg_handle h, const uint8_t* owned) {
 int rg_W_attach_peer(rg_handle h, const void* ipc_handle_64, const uint8_t* owned_by_peer) {
   RG_API_BEGIN
   RG_CHECK(h && h->kind == 1 && ipc_handle_64 && owned_by_peer, "bad argument");
-  RG_CUDA(cudaSetDevice(h->device));
-  for (auto& l : h->lanes) RG_CUDA(cudaStreamSynchronize(l->stream));
+  rg::sync_lanes(h);
   ensure_W(h);
   cudaIpcMemHandle_t mh;
   memcpy(&mh, ipc_handle_64, 64);
@@ -664,8 +767,7 @@ int rg_l1_select(rg_handle h, const uint8_t* sel) {
 int rg_sync(rg_handle h) {
   RG_API_BEGIN
   RG_CHECK(h, "null handle");
-  RG_CUDA(cudaSetDevice(h->device));
-  for (auto& l : h->lanes) RG_CUDA(cudaStreamSynchronize(l->stream));
+  rg::sync_lanes(h);
   RG_CUDA(cudaStreamSynchronize(h->stream));
   rg::flush_timers(h);
   RG_API_END
@@ -675,6 +777,8 @@ int rg_fence(rg_handle h) {
   RG_API_BEGIN
   RG_CHECK(h, "null handle");
   RG_CUDA(cudaSetDevice(h->device));
+  // blocks whose mixed-precision solve raised its flag are re-solved in FP64 first (host waits on those lanes' events)
+  if (h->kind == 1) for (auto& l : h->lanes) rg::resolve_lane(h, *l);
   for (auto& l : h->lanes) {
     RG_CUDA(cudaEventRecord(l->done, l->stream));
     RG_CUDA(cudaStreamWaitEvent(h->stream, l->done, 0));
@@ -710,7 +814,7 @@ int rg_l0_load_W(rg_handle h, int32_t block_id, int32_t ph, const double* in) {
 int64_t rg_l0_status(rg_handle h) {
   if (!h) return -1;
   cudaSetDevice(h->device);
-  for (auto& l : h->lanes) cudaStreamSynchronize(l->stream);
+  try { rg::sync_lanes(h); } catch (const rg::Error& e) { rg::set_last_error(e.msg); return -1; }
   if (cudaStreamSynchronize(h->stream) != cudaSuccess) {
     rg::set_last_error(std::string("CUDA error: ") + cudaGetErrorString(cudaGetLastError()));
     return -1;
@@ -731,8 +835,7 @@ int rg_l0_fetch_W(rg_handle h, int32_t block_id, int32_t ph, double* out) {
   RG_API_BEGIN
   RG_CHECK(h && out, "null argument");
   RG_CHECK(h->kind == 1 && block_id >= 0 && block_id < h->total_blocks && ph >= 0 && ph < h->P, "bad index");
-  RG_CUDA(cudaSetDevice(h->device));
-  for (auto& l : h->lanes) RG_CUDA(cudaStreamSynchronize(l->stream));
+  rg::sync_lanes(h);
   std::vector<double> tmp((size_t)h->Npad * h->R);
   ensure_W(h);
   RG_CHECK(h->W_host_tab[ph] != nullptr, "this rank holds no storage for that phenotype (rg_W_set_owned)");
@@ -747,7 +850,7 @@ int rg_l0_fetch_W(rg_handle h, int32_t block_id, int32_t ph, double* out) {
 int64_t rg_debug_fetch(rg_handle h, const char* name, void* out, int64_t max_bytes) {
   if (!h || !name || !out) return -1;
   cudaSetDevice(h->device);
-  for (auto& l : h->lanes) cudaStreamSynchronize(l->stream);
+  try { rg::sync_lanes(h); } catch (const rg::Error& e) { rg::set_last_error(e.msg); return -1; }
   cudaStreamSynchronize(h->stream);
   if (h->lanes.empty()) { rg::set_last_error("no level-0 lane"); return -1; }
   rg_ctx::Lane& L = *h->lanes[h->last_lane];
@@ -807,6 +910,49 @@ int64_t rg_debug_fetch(rg_handle h, const char* name, void* out, int64_t max_byt
   return (int64_t)bytes;
 }
 
+int rg_l0_solver_stats(rg_handle h, int64_t* mixed_blocks, int64_t* f64_fallbacks) {
+  RG_API_BEGIN
+  RG_CHECK(h && h->kind == 1, "not a Step-1 handle");
+  rg::sync_lanes(h);
+  if (mixed_blocks) *mixed_blocks = h->mx_blocks;
+  if (f64_fallbacks) *f64_fallbacks = h->mx_fallbacks;
+  RG_API_END
+}
+
+int rg_dbg_mixed_solve(int32_t device, int32_t n, int32_t K, int32_t R, int32_t P, const double* Af,
+                       const double* lambda, const double* b, int32_t steps, double tol, double* x_out,
+                       float* X_out, uint32_t* fail_out) {
+  RG_API_BEGIN
+  RG_CHECK(Af && lambda && b && x_out && fail_out, "null argument");
+  rg::require_gpu_public(device);
+  RG_CUDA(cudaSetDevice(device));
+  const int Pp = (int)rg::round_up(P, 2), nmat = K * R;
+  rg::MixedSolver mx;
+  mx.prepare(n, K, R, Pp);
+  rg::DevBuf<double> dA, dl, db, dx, dr;
+  rg::DevBuf<unsigned int> dfail;
+  dA.alloc((size_t)K * n * n); dl.alloc(R); db.alloc((size_t)K * Pp * n); dx.alloc((size_t)nmat * Pp * n); dr.alloc((size_t)nmat * Pp * n);
+  dfail.alloc(1);
+  RG_CUDA(cudaMemset(db.p, 0, db.n * 8));
+  RG_CUDA(cudaMemset(dx.p, 0, dx.n * 8));
+  RG_CUDA(cudaMemset(dfail.p, 0, 4));
+  RG_CUDA(cudaMemcpy(dA.p, Af, dA.n * 8, cudaMemcpyHostToDevice));
+  RG_CUDA(cudaMemcpy(dl.p, lambda, R * 8, cudaMemcpyHostToDevice));
+  for (int f = 0; f < K; ++f)
+    RG_CUDA(cudaMemcpy(db.p + (size_t)f * Pp * n, b + (size_t)f * P * n, (size_t)P * n * 8, cudaMemcpyHostToDevice));
+  cudaStream_t st;
+  RG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  mx.solve(dA.p, dl.p, db.p, dx.p, dr.p, P, steps, (float)tol, dfail.p, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  RG_CHECK(e == cudaSuccess, std::string("mixed solver kernels failed: ") + cudaGetErrorString(e));
+  for (int m = 0; m < nmat; ++m)
+    RG_CUDA(cudaMemcpy(x_out + (size_t)m * P * n, dx.p + (size_t)m * Pp * n, (size_t)P * n * 8, cudaMemcpyDeviceToHost));
+  if (X_out) RG_CUDA(cudaMemcpy(X_out, mx.debug_planes(3), (size_t)nmat * n * n * 4, cudaMemcpyDeviceToHost));
+  RG_CUDA(cudaMemcpy(fail_out, dfail.p, 4, cudaMemcpyDeviceToHost));
+  RG_API_END
+}
+
 int64_t rg_launch_count(rg_handle h) { return h ? h->launches : 0; }
 void* rg_stream(rg_handle h) { return h ? (void*)h->stream : nullptr; }
 
@@ -820,7 +966,7 @@ int rg_set_timing(rg_handle h, int32_t enable) {
 int rg_get_timing(rg_handle h, const char* kernel, double* total_ms, int64_t* launches) {
   RG_API_BEGIN
   RG_CHECK(h && kernel, "null argument");
-  for (auto& l : h->lanes) RG_CUDA(cudaStreamSynchronize(l->stream));
+  rg::sync_lanes(h);
   RG_CUDA(cudaStreamSynchronize(h->stream));
   rg::flush_timers(h);
   auto it = h->timers.find(kernel);

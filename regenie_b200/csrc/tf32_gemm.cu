@@ -1,0 +1,313 @@
+// Batched "NT" GEMM tiles  D = A B^T  in 3xTF32 on the 5th-generation tensor cores (tcgen05 + TMEM + TMA):
+// the arithmetic engine of the mixed-precision ridge solver (chol_mixed.cu).
+//
+// Every FP32 operand lives in global memory as two planes, hi = rn_tf32(x) and lo = x - hi (exact in FP32, itself
+// truncated to TF32 by the tensor core), so that
+//     a b  ~  a_hi b_hi + a_hi b_lo + a_lo b_hi          (relative error ~2^-21, FP32 accumulation in TMEM)
+// which is what an FP32 factorisation needs; the FP64 iterative refinement on top (chol_mixed.cu) removes the rest.
+//
+// Operand buffers are [batch][2 planes][n rows][n cols] FP32, row-major: a tile of A is 128 rows of one matrix, a
+// tile of B 128 rows of another (or the same) matrix, the contraction runs along the contiguous column index
+// ("K-major" on both sides), exactly the shape of a left-looking Cholesky update  L_i,0:k L_k,0:k^T, of a triangular
+// solve against a stored inverse  P_ik M_k^T, and of the triangular-inverse products.
+//
+// One CTA per (tile, matrix of the batch):
+//   warp 0     : TMA producer - 3-D boxes {32 floats, 128 rows, 2 planes} with 128B swizzle, 3-stage mbarrier ring
+//   warp 1     : TMEM allocator + single-thread tcgen05.mma issuer (kind::tf32, M128 N128 K8, 12 MMAs per stage)
+//   warps 2..5 : epilogue: tcgen05.ld -> registers -> optional  C_in - acc  in FP64 -> hi/lo planes (and / or the
+//                transposed tile, and / or a plain FP32 plane) with 128-bit or lane-coalesced stores
+#include <stdlib.h>
+
+#include "kernels.cuh"
+
+namespace rg {
+
+namespace {
+
+constexpr int TG_M = 128, TG_N = 128;
+constexpr int TG_KC = 32;                          // floats per K chunk = one 128-byte swizzle atom
+constexpr int TG_STAGES = 3;
+constexpr int TG_PLANE_BYTES = TG_M * 128;         // 16 KiB
+constexpr int TG_OP_BYTES = 2 * TG_PLANE_BYTES;    // hi + lo
+constexpr int TG_STAGE_BYTES = 2 * TG_OP_BYTES;    // A + B = 64 KiB
+constexpr int TG_TMEM_COLS = 128;
+constexpr int TG_THREADS = 192;
+constexpr uint32_t TG_SPIN_LIMIT = 1u << 28;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    if (++spins > TG_SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128B-swizzled shared-memory matrix descriptor (8-row groups 1024 B apart): same bytes as the e4m3 Gram
+// kernel's - a row is one 128-byte atom = 32 TF32 values.
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// kind::tf32: D = F32 (bits 4-5 = 1), A = B = TF32 (format 2 at bits 7-9 / 10-12), both K-major, N = 128, M = 128
+constexpr uint32_t kTf32Idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TG_N >> 3) << 17) | ((uint32_t)(TG_M >> 4) << 24);
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(kTf32Idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+}  // namespace
+
+// grid: (ntiles, batch); tile entry = (A row tile, B row tile, first K chunk, number of K chunks)
+__global__ void __launch_bounds__(TG_THREADS, 1)
+tf32x3_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const int4* __restrict__ tiles, Tf32GemmEpilogue ep) {
+  extern __shared__ uint8_t tg_smem_raw[];
+  const uint32_t raw = smem_u32(tg_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;            // 128B swizzle needs 1024-byte aligned stage buffers
+  uint8_t* gen_base = tg_smem_raw + (base - raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gen_base + TG_STAGES * TG_STAGE_BYTES);
+  const uint32_t full_bar = smem_u32(bars);
+  const uint32_t empty_bar = smem_u32(bars + TG_STAGES);
+  const uint32_t tmem_full_bar = smem_u32(bars + 2 * TG_STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TG_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int4 tile = tiles[blockIdx.x];
+  const int mat = blockIdx.y;
+  const int nkc = tile.w;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < TG_STAGES; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TG_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kc = 0; kc < nkc; ++kc) {
+        const int s = kc % TG_STAGES;
+        const uint32_t ph = (kc / TG_STAGES) & 1;
+        mbar_wait(empty_bar + 8 * s, ph ^ 1);
+        mbar_expect_tx(full_bar + 8 * s, TG_STAGE_BYTES);
+        const int col = (tile.z + kc) * TG_KC;
+        tma_load_3d(base + s * TG_STAGE_BYTES, &tmA, full_bar + 8 * s, col, tile.x * TG_M, 2 * mat);
+        tma_load_3d(base + s * TG_STAGE_BYTES + TG_OP_BYTES, &tmB, full_bar + 8 * s, col, tile.y * TG_N, 2 * mat);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int kc = 0; kc < nkc; ++kc) {
+        const int s = kc % TG_STAGES;
+        const uint32_t ph = (kc / TG_STAGES) & 1;
+        mbar_wait(full_bar + 8 * s, ph);
+        fence_after();
+        const uint64_t a_hi = make_desc(base + s * TG_STAGE_BYTES);
+        const uint64_t a_lo = make_desc(base + s * TG_STAGE_BYTES + TG_PLANE_BYTES);
+        const uint64_t b_hi = make_desc(base + s * TG_STAGE_BYTES + TG_OP_BYTES);
+        const uint64_t b_lo = make_desc(base + s * TG_STAGE_BYTES + TG_OP_BYTES + TG_PLANE_BYTES);
+#pragma unroll
+        for (int k = 0; k < TG_KC / 8; ++k) {
+          // +32 bytes per K = 8 step inside the swizzle atom: +2 in 16-byte descriptor units; small terms first
+          mma_tf32(tmem_base, a_lo + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), (kc | k) ? 1u : 0u);
+          mma_tf32(tmem_base, a_hi + (uint64_t)(2 * k), b_lo + (uint64_t)(2 * k), 1u);
+          mma_tf32(tmem_base, a_hi + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), 1u);
+        }
+        tcgen05_commit(empty_bar + 8 * s);
+      }
+      tcgen05_commit(tmem_full_bar);
+    }
+  } else {
+    // ===== epilogue: one thread per tile row =====
+    const int q = warp & 3;
+    if (nkc > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      fence_after();
+    }
+    const int r_loc = q * 32 + lane;
+    const int row = tile.x * TG_M + r_loc;               // output row (A row index)
+    const int col0 = tile.y * TG_N;                      // first output column (B row index)
+    const int64_t n = ep.n;
+    const int64_t mat_off = (int64_t)mat * ep.out_mat_stride;
+    const double* cin = ep.cin ? ep.cin + (int64_t)(ep.cin_mat_div > 0 ? mat / ep.cin_mat_div : mat) * ep.cin_mat_stride + (int64_t)row * ep.cin_ld + col0
+                               : nullptr;
+    const double diag_add = (ep.diag_add != nullptr && tile.x == tile.y) ? ep.diag_add[ep.diag_mod > 0 ? mat % ep.diag_mod : mat] : 0.0;
+    const bool diag_tile = tile.x == tile.y;
+#pragma unroll 1
+    for (int c = 0; c < TG_N / 32; ++c) {
+      uint32_t v[32];
+      if (nkc > 0) {
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      float o[32];
+      if (cin) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const double2 cc = *reinterpret_cast<const double2*>(cin + c * 32 + j);
+          double c0 = cc.x, c1 = cc.y;
+          if (diag_tile) {
+            if (c * 32 + j == r_loc) c0 += diag_add;
+            if (c * 32 + j + 1 == r_loc) c1 += diag_add;
+          }
+          o[j] = (float)(c0 - (double)__uint_as_float(v[j]));
+          o[j + 1] = (float)(c1 - (double)__uint_as_float(v[j + 1]));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = ep.negate ? -__uint_as_float(v[j]) : __uint_as_float(v[j]);
+      }
+      if (ep.lower_only && diag_tile) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (c * 32 + j > r_loc) o[j] = 0.f;
+      }
+      float hi[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        uint32_t t;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(o[j]));
+        hi[j] = __uint_as_float(t);
+      }
+      if (ep.out) {                                       // D as hi / lo planes, row-major
+        float* oh = ep.out + 2 * mat_off + (int64_t)row * n + col0 + c * 32;
+        float* ol = oh + n * n;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          *reinterpret_cast<float4*>(oh + j) = make_float4(hi[j], hi[j + 1], hi[j + 2], hi[j + 3]);
+          *reinterpret_cast<float4*>(ol + j) = make_float4(o[j] - hi[j], o[j + 1] - hi[j + 1], o[j + 2] - hi[j + 2], o[j + 3] - hi[j + 3]);
+        }
+      }
+      if (ep.out_t) {                                     // D^T as hi / lo planes: lanes of a warp hold consecutive rows
+        float* th = ep.out_t + 2 * mat_off + (int64_t)(col0 + c * 32) * n + row;
+        float* tl = th + n * n;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          th[(int64_t)j * n] = hi[j];
+          tl[(int64_t)j * n] = o[j] - hi[j];
+        }
+      }
+      if (ep.out_plain) {                                 // D as one FP32 plane (+ its mirror image for symmetric results)
+        float* po = ep.out_plain + mat_off + (int64_t)row * n + col0 + c * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(po + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        if (ep.mirror && !diag_tile) {
+          float* pt = ep.out_plain + mat_off + (int64_t)(col0 + c * 32) * n + row;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) pt[(int64_t)j * n] = o[j];
+        }
+      }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TG_TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn tg_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    RG_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    RG_CHECK(p != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// planes: [batch][2][n][n] FP32 -> 3-D map (col, row, 2*batch + plane), box {32, 128, 2}
+void make_tf32_planes_tensor_map(CUtensorMap* tm, const float* planes, int n, int batch) {
+  const cuuint64_t gdim[3] = {(cuuint64_t)n, (cuuint64_t)n, (cuuint64_t)(2 * batch)};
+  const cuuint64_t gstride[2] = {(cuuint64_t)n * 4, (cuuint64_t)n * n * 4};
+  const cuuint32_t box[3] = {TG_KC, 128, 2};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = tg_encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(planes), gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (tf32 planes) failed (" + std::to_string((int)r) + ")");
+}
+
+void launch_tf32x3_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const int4* tiles, int ntiles, int batch,
+                        const Tf32GemmEpilogue& ep, cudaStream_t s) {
+  if (ntiles <= 0 || batch <= 0) return;
+  constexpr size_t smem = (size_t)TG_STAGES * TG_STAGE_BYTES + 1024 + 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RG_CUDA(cudaFuncSetAttribute(tf32x3_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid(ntiles, batch);
+  tf32x3_gemm_nt_kernel<<<grid, TG_THREADS, smem, s>>>(tmA, tmB, tiles, ep);
+}
+
+}  // namespace rg
