@@ -339,35 +339,18 @@ def run_gpu(args):
     ms_e2e, _ = timed(host_ptr, args.steps, read_status=True)
     e2e_val = total_snps / (ms_e2e / 1e3)
 
-    # ---- secondary metric: Step-2 QT score-test variants/s on the same panel (bed input, P traits)
+    # ---- second half of the metric: Step-2 variants/s (QT on .bed rows, BT on 8-bit BGEN dosages), each with a
+    # host-fed rate, a device-resident rate, an HBM roofline and a CPU baseline (rank 0 only)
     s2 = None
-    if not args.no_step2:
+    if not args.no_step2 and rank == 0:
         try:
-            rng = np.random.default_rng(SEED + 7)
-            res = np.asfortranarray(rng.normal(size=(N, P)))
-            res /= np.linalg.norm(res, axis=0) / np.sqrt(N - C)
-            st2 = capi.Step2(X, mask, in_an, N, bs)
-            st2.set_chr(res, np.ones(P))
-            nb2 = min(len(blocks), 10)
-            hp = host_panel.numpy()
-            for b in range(2):
-                st2.block_bed(hp[blocks[b][0]:blocks[b][0] + blocks[b][1]])
-            t0 = time.perf_counter()
-            nv = 0
-            for b in range(nb2):
-                st2.block_bed(hp[blocks[b][0]:blocks[b][0] + blocks[b][1]])
-                nv += blocks[b][1]
-            dt = time.perf_counter() - t0
-            s2 = {"metric": "step2_qt_variants_per_sec", "value": nv / dt, "unit": "variants/s",
-                  "sample": "%d blocks of %d variants, N=%d, %d traits, host .bed rows in, per-variant stats out "
-                            "(host wall clock incl. H2D/D2H)" % (nb2, bs, N, P)}
-            st2.close()
+            s2 = step2_qt_leg(capi, X, mask, in_an, N, P, C, bs, blocks, host_panel, dev_ptr, stride, args)
         except Exception as e:          # never let the secondary metric break the headline line
-            s2 = {"error": str(e)[:200]}
+            s2 = {"error": str(e)[:300]}
         try:
-            s2["bt_bgen"] = step2_bt_leg(capi, X, in_an, N, C)
+            s2["bt_bgen"] = step2_bt_leg(capi, X, in_an, N, C, args)
         except Exception as e:
-            s2["bt_bgen"] = {"error": str(e)[:200]}
+            s2["bt_bgen"] = {"error": str(e)[:300]}
 
     if rank != 0:
         if dist is not None:
@@ -456,11 +439,94 @@ def run_gpu(args):
         dist.barrier(); dist.destroy_process_group()
 
 
-def step2_bt_leg(capi, X, in_an, N, C, nvar=400, nblocks=4):
-    """Secondary: Step-2 binary-trait score test on 8-bit BGEN dosages (BASELINE configs[3] shape at this N):
-    variants/s through rg_s2_block_bgen8_bt with HOST probability bytes (2 N bytes per variant), plus the
-    approximate-Firth kernel on the variants with |z| above the --pThresh 0.05 quantile."""
+def hbm_roofline(rate, bytes_per_variant, what):
+    peaks, src = load_peaks()
+    gbs = rate * bytes_per_variant / 1e9
+    return {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+            "traffic": None, "algorithmic_bytes_per_variant": bytes_per_variant, "peak_basis": "%s copy bandwidth" % src,
+            "rate_used": "device-resident variants/s x algorithmic bytes per variant (%s)" % what}
+
+
+def step2_qt_leg(capi, X, mask, in_an, N, P, C, bs, blocks, host_panel, dev_ptr, stride, args):
+    """Step-2 QT score test on the benchmark panel's .bed rows (compute_score_qt, src/Step2_Models.cpp:343-467)."""
+    from oracle import ref_eigen
+    rng = np.random.default_rng(SEED + 7)
+    res = np.asfortranarray(rng.normal(size=(N, P)) * mask)
+    res /= np.linalg.norm(res, axis=0) / np.sqrt(mask.sum(axis=0) - C)
+    st2 = capi.Step2(X, mask, in_an, N, bs)
+    st2.set_chr(res, np.ones(P))
+    nb2 = min(len(blocks), 10)
+    out = st2._out(bs)
+    hbase = host_panel.data_ptr()
+    for b in range(2):                                              # warm-up (allocations, tensor maps)
+        st2.block_bed_raw(hbase + blocks[b][0] * stride, blocks[b][1], stride, out)
+        st2.block_bed_raw(dev_ptr + blocks[b][0] * stride, blocks[b][1], stride, out)
+
+    def run(base):
+        t0 = time.perf_counter(); nv = 0
+        for b in range(nb2):
+            st2.block_bed_raw(base + blocks[b][0] * stride, blocks[b][1], stride, out)
+            nv += blocks[b][1]
+        return nv / (time.perf_counter() - t0)
+    host_rate = run(hbase)
+    dev_rate = run(dev_ptr)
+    st2.close()
+    # CPU: the Eigen restatement, one OpenMP task per variant like Data::test_snps_fast
+    cpu = None
+    if not args.no_cpu:
+        nv_cpu = 256
+        rows = host_panel[:nv_cpu].numpy()
+        YtX = res.T @ X
+        thr = host_threads()
+        ref_eigen.s2_block_qt_bed(rows[:32], N, in_an, X, res, mask, YtX, np.ones(P), int(in_an.sum()), threads=thr)
+        t0 = time.perf_counter()
+        ref_eigen.s2_block_qt_bed(rows, N, in_an, X, res, mask, YtX, np.ones(P), int(in_an.sum()), threads=thr)
+        dt = time.perf_counter() - t0
+        cpu = {"value": nv_cpu / dt, "unit": "variants/s", "cores": thr, "kind": "port",
+               "sample": "%d variants at N=%d, %d traits: C++/Eigen restatement of parseSnpfromBed + residualize_geno + "
+                         "compute_score_qt, one OpenMP task per variant (%.2f s)" % (nv_cpu, N, P, dt)}
+    return {"metric": "step2_qt_variants_per_sec", "value": dev_rate, "unit": "variants/s",
+            "e2e": {"value": host_rate, "unit": "variants/s", "h2d_bytes_per_variant": int(stride),
+                    "d2h_bytes_per_variant": 8 * (6 * P + 3) + 4 * (P + 2)},
+            "roofline": hbm_roofline(dev_rate, N / 4.0, "N/4 bytes of 2-bit calls"),
+            "cpu_baseline": cpu,
+            "sample": "%d blocks of %d variants, N=%d, %d traits; value = .bed rows resident in HBM, e2e = pinned host rows; "
+                      "both through rg_s2_block_bed (synchronous call, per-variant statistics copied back every block)" % (nb2, bs, N, P)}
+
+
+def bgen_payloads(N, nvar, seed):
+    """Imputed-looking 8-bit probability pairs + their BGEN v1.2 layout-2 payloads, zlib level 6 like qctool writes."""
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+    rng = np.random.default_rng(seed)
+    probs = np.zeros((nvar, N, 2), dtype=np.uint8)
+    for v, maf in enumerate(rng.uniform(0.01, 0.5, nvar)):
+        g = rng.binomial(2, maf, N)
+        probs[v, g == 2, 0] = 255
+        probs[v, g == 1, 1] = 255
+        u = rng.random(N) < 0.15                                   # 15 % of calls are uncertain
+        a = rng.integers(0, 256, int(u.sum()))
+        probs[v, u, 0] = a
+        probs[v, u, 1] = (rng.random(int(u.sum())) * (255 - a)).astype(np.uint8)
+    hdr = np.zeros(8, dtype=np.uint8)
+    hdr[:4] = np.frombuffer(np.uint32(N).tobytes(), dtype=np.uint8)
+    hdr[4], hdr[6], hdr[7] = 2, 2, 2
+    pl = np.full(N, 2, dtype=np.uint8)
+    tail = np.array([0, 8], dtype=np.uint8)
+    raws = [np.concatenate([hdr, pl, tail, probs[v].reshape(-1)]).tobytes() for v in range(nvar)]
+    with ThreadPoolExecutor(16) as ex:
+        comps = list(ex.map(lambda r: zlib.compress(r, 6), raws))
+    offs = np.zeros(nvar + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(c) for c in comps])
+    return probs, np.frombuffer(b"".join(comps), dtype=np.uint8), offs
+
+
+def step2_bt_leg(capi, X, in_an, N, C, args, nvar=400, nblocks=4):
+    """Step-2 binary-trait score test + approximate Firth on 8-bit BGEN dosages (BASELINE configs[3] shape at this N,
+    compute_score_bt src/Step2_Models.cpp:470-556): pinned host probability bytes, bytes resident in HBM, and
+    compressed payloads inflated on the device (both inflate kernels) in front of the same score test."""
     import torch
+    from oracle import ref_eigen
     rng = np.random.default_rng(SEED + 11)
     y = (rng.random(N) < 0.1).astype(np.float64)                       # prevalence 10 %
     mask = np.ones((N, 1), dtype=np.uint8)
@@ -471,29 +537,68 @@ def step2_bt_leg(capi, X, in_an, N, C, nvar=400, nblocks=4):
     # X is orthonormal with the intercept in its span: X_Gamma = X for a constant weight
     st = capi.Step2(X, mask, in_an, N, nvar)
     st.set_chr_bt(gsm, gsm, yres, [X], y[:, None], np.full((N, 1), eta))
-    g = torch.Generator(device="cpu").manual_seed(SEED + 13)
-    maf = 0.01 + 0.49 * torch.rand((nvar, 1), generator=g)
-    u = torch.rand((nvar, N), generator=g)
-    hom = (u < maf * maf)
-    het = (u < 2 * maf - maf * maf) & ~hom
-    probs_t = torch.stack([hom.to(torch.uint8) * 255, het.to(torch.uint8) * 255], dim=2).contiguous().pin_memory()
+    probs_np, comp, offs = bgen_payloads(N, nvar, SEED + 13)
+    probs_t = torch.from_numpy(probs_np).pin_memory()
     miss_t = torch.full((nvar, N), 0x02, dtype=torch.uint8).pin_memory()
-    probs, miss = probs_t.numpy(), miss_t.numpy()                       # pinned host buffers, like the e2e leg
-    o = st.block_bgen8_bt(probs, miss)
-    st.firth(np.arange(4, dtype=np.int32), np.zeros(4, dtype=np.int32))       # warm-up: scratch allocation
-    t0 = time.perf_counter()
-    nfirth = 0
-    for _ in range(nblocks):
-        o = st.block_bgen8_bt(probs, miss)
+    probs_d, miss_d = probs_t.cuda(), miss_t.cuda()
+    out = st._out(nvar, with_info=True)
+
+    def block(pp, mp):
+        o = st.block_bgen8_bt_raw(pp, mp, N, nvar, out)
         sel = np.nonzero((np.abs(o["stat"][:, 0]) > 1.959964) & ((o["flags"] & 17) == 0))[0]
         st.firth(sel, np.zeros(len(sel), dtype=np.int32))
-        nfirth += len(sel)
-    dt = time.perf_counter() - t0
+        return len(sel)
+
+    block(probs_t.data_ptr(), miss_t.data_ptr())                       # warm-up: scratch allocation
+
+    def run(fn):
+        t0 = time.perf_counter(); nf = 0
+        for _ in range(nblocks):
+            nf += fn()
+        return nblocks * nvar / (time.perf_counter() - t0), nf / (nblocks * nvar)
+    host_rate, ff = run(lambda: block(probs_t.data_ptr(), miss_t.data_ptr()))
+    dev_rate, _ = run(lambda: block(probs_d.data_ptr(), miss_d.data_ptr()))
+    inflate = {}
+    for mode in ("direct", "window"):
+        os.environ["RG_B200_INFLATE"] = mode
+        try:
+            def fn():
+                pd, md = st.bgen_inflate(comp, offs, N)
+                return block(pd, md)
+            fn()
+            r, _ = run(fn)
+            t0 = time.perf_counter()
+            for _ in range(nblocks):
+                st.bgen_inflate(comp, offs, N)
+            ti = (time.perf_counter() - t0) / nblocks
+            inflate[mode] = {"variants_per_sec_with_score_test": r, "inflate_ms_per_block": 1e3 * ti,
+                             "inflated_GBps": nvar * (10 + 3 * N) / ti / 1e9}
+        except Exception as e:
+            inflate[mode] = {"error": str(e)[:200]}
+    os.environ.pop("RG_B200_INFLATE", None)
     st.close()
-    return {"metric": "step2_bt_bgen_variants_per_sec", "value": nblocks * nvar / dt, "unit": "variants/s",
-            "firth_fraction": nfirth / (nblocks * nvar),
-            "sample": "%d blocks of %d variants, N=%d, 1 binary trait, pinned host probability + ploidy bytes in (3N B/variant), "
-                      "score test + approximate Firth for |z| > 1.96 (host wall clock incl. H2D/D2H)" % (nblocks, nvar, N)}
+    cpu = None
+    if not args.no_cpu:
+        thr = host_threads()
+        nv_cpu = 256
+        pm = np.full((nv_cpu, N), 2, dtype=np.uint8)
+        ref_eigen.s2_block_bt_probs(probs_np[:32], pm[:32], N, in_an, gsm, X, yres, threads=thr)
+        t0 = time.perf_counter()
+        ref_eigen.s2_block_bt_probs(probs_np[:nv_cpu], pm, N, in_an, gsm, X, yres, threads=thr)
+        dt = time.perf_counter() - t0
+        cpu = {"value": nv_cpu / dt, "unit": "variants/s", "cores": thr, "kind": "port",
+               "sample": "%d variants at N=%d: C++/Eigen restatement of the BGEN dosage loop + compute_score_bt (score statistic "
+                         "only, no Firth, payloads already inflated), one OpenMP task per variant (%.2f s)" % (nv_cpu, N, dt)}
+    return {"metric": "step2_bt_bgen_variants_per_sec", "value": dev_rate, "unit": "variants/s",
+            "e2e": {"value": host_rate, "unit": "variants/s", "h2d_bytes_per_variant": 3 * N, "d2h_bytes_per_variant": 8 * 10 + 12},
+            "e2e_compressed_input": inflate,
+            "compressed_bytes_per_variant": float(offs[-1]) / nvar,
+            "roofline": hbm_roofline(dev_rate, 3.0 * N, "2N probability bytes + N ploidy bytes"),
+            "cpu_baseline": cpu, "firth_fraction": ff,
+            "sample": "%d blocks of %d variants, N=%d, 1 binary trait (prevalence 10 %%), score test + approximate Firth for |z| > 1.96; "
+                      "value = inflated bytes resident in HBM, e2e = pinned host probability + ploidy bytes (3N B/variant), "
+                      "e2e_compressed_input = zlib payloads from host memory, inflated on the device (direct / shared-memory "
+                      "window kernel) in front of the same calls" % (nblocks, nvar, N)}
 
 
 def gram_traffic_from_profile():

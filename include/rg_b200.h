@@ -85,7 +85,10 @@ int rg_fence(rg_handle h);
  *   ridge_level_0 / ridge_level_0_loocv              src/Step1_Models.cpp:458-613 / 615-726
  * and leaves the block's N x R level-0 predictors of every phenotype in the device
  * resident W (columns block_id*R .. block_id*R+R-1).
- *   packed      [host|device] bs rows of row_stride bytes, the .bed rows of the block
+ *   packed      [host|device] bs rows of row_stride bytes, the .bed rows of the block.
+ *               LIFETIME: the call only enqueues work.  A pageable host buffer is staged before the call returns and
+ *               may be reused at once; a PINNED host buffer is read by DMA later - do not overwrite it before
+ *               rg_l0_wait_input(h) (or rg_sync) returns.  Device buffers: until the block has run (rg_sync / rg_fence).
  *   sample_idx  [host|device] N entries: index in the .bed row of sample i (handles
  *               --keep/--remove, i.e. filters.ind_ignore); NULL = identity
  *   ref_first   params.ref_first
@@ -94,6 +97,9 @@ int rg_fence(rg_handle h);
  */
 int rg_l0_block_bed(rg_handle h, const uint8_t* packed, int64_t row_stride, int32_t bs,
                     const int32_t* sample_idx, int32_t ref_first, int32_t block_id);
+
+/* Wait until the input rows of the most recent rg_l0_block_bed call have been copied to the device (see LIFETIME). */
+int rg_l0_wait_input(rg_handle h);
 
 /* 0 = all blocks so far fine; otherwise 1 + index (block_id * max_block_size + snp) of the
  * first low-variance SNP (src/Data.cpp:205-209).  Synchronises the stream. */

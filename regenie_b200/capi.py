@@ -48,7 +48,7 @@ EXPORTS = [
     "rg_l0_block_bed", "rg_l0_status", "rg_l0_fetch_W", "rg_l1_fit", "rg_loco", "rg_step2_create",
     "rg_s2_set_chr", "rg_s2_block_bed", "rg_W_info", "rg_debug_fetch", "rg_launch_count", "rg_stream",
     "rg_set_timing", "rg_get_timing", "rg_fence", "rg_s2_set_chr_bt", "rg_s2_block_bgen8_bt", "rg_s2_block_bgen8", "rg_s2_firth", "rg_l1_fit_bt", "rg_W_set_owned", "rg_W_export", "rg_W_attach_peer", "rg_l1_select", "rg_s2_set_sex", "rg_s2_set_non_par", "rg_l0_load_W", "rg_s2_spa", "rg_s2_block_bed_bt", "rg_prs", "rg_bgen_inflate",
-    "rg_l0_solver_stats", "rg_dbg_mixed_solve",
+    "rg_l0_solver_stats", "rg_dbg_mixed_solve", "rg_l0_wait_input",
 ]
 
 _lib = None
@@ -296,6 +296,34 @@ class Step2:
             sample_idx = np.ascontiguousarray(sample_idx, dtype=np.int32)
         check(lib().rg_s2_block_bed(self.h, _ptr(packed), packed.shape[1], bs, _ptr(sample_idx), int(ref_first),
                                     float(min_mac), C.byref(so)))
+        return o
+
+    def _out(self, bs, with_info=False):
+        P = self.P
+        o = dict(af=np.empty((bs, P)), ns=np.empty((bs, P), dtype=np.int32), mac=np.empty((bs, P)),
+                 af_all=np.empty(bs), ns_all=np.empty(bs, dtype=np.int32), mac_all=np.empty(bs),
+                 flags=np.empty(bs, dtype=np.int32), scale_fac=np.empty(bs), stat=np.empty((bs, P)),
+                 beta=np.empty((bs, P)), se=np.empty((bs, P)), chisq=np.empty((bs, P)))
+        if with_info:
+            o["info"] = np.empty((bs, P))
+        so = S2Out(*[o[k].ctypes.data for k in ("af", "ns", "mac", "af_all", "ns_all", "mac_all", "flags",
+                                                "scale_fac", "stat", "beta", "se", "chisq")])
+        return o, so
+
+    def block_bed_raw(self, ptr, bs, row_stride, out=None, min_mac=5.0):
+        """rg_s2_block_bed on a raw (host or DEVICE) address; `out` = a (dict, S2Out) pair from _out() to reuse."""
+        o, so = out or self._out(bs)
+        check(lib().rg_s2_block_bed(self.h, C.c_void_p(ptr), int(row_stride), int(bs), None, 0, float(min_mac), C.byref(so)))
+        return o
+
+    def block_bgen8_bt_raw(self, probs_ptr, miss_ptr, n_file, bs, out=None, min_mac=5.0):
+        """rg_s2_block_bgen8_bt on raw (host or DEVICE) addresses, e.g. the pair rg_bgen_inflate returned."""
+        L = lib()
+        L.rg_s2_block_bgen8_bt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                           C.c_int32, C.c_double, C.c_void_p, C.c_void_p]
+        o, so = out or self._out(bs, with_info=True)
+        check(L.rg_s2_block_bgen8_bt(self.h, C.c_void_p(probs_ptr), C.c_void_p(miss_ptr), int(n_file), int(bs), None, 0,
+                                     float(min_mac), C.byref(so), _ptr(o["info"])))
         return o
 
     # ---- binary traits on BGEN 8-bit dosages

@@ -116,10 +116,8 @@ static void bgen_inflate(rg_ctx* h, const uint8_t* comp, const uint64_t* comp_of
   h->miss_dev.alloc((size_t)h->bs_max * n_file);
   copy_to_device(h->inflate_comp.p, comp + base, (size_t)total, s);
   RG_CUDA(cudaMemcpyAsync(h->inflate_offs.p, rel.data(), rel.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-  static const bool use_window = [] {
-    const char* e = getenv("RG_B200_INFLATE");
-    return e && std::string(e) == "window";
-  }();
+  const char* mode_env = getenv("RG_B200_INFLATE");          // read per call: the bench times both kernels in one process
+  const bool use_window = mode_env && std::string(mode_env) == "window";
   if (use_window) {
     static const cudaError_t attr = cudaFuncSetAttribute(bgen_inflate_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                          (int)kWindowSmem);

@@ -50,6 +50,17 @@ __device__ __forceinline__ void blk_nt(float (&acc)[PB], const float* __restrict
   }
 }
 
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t t;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x));
+  return __uint_as_float(t);
+}
+__device__ __forceinline__ void split_store(const float4 v, float* hp, float* lp, float4& hi) {
+  hi = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+  *reinterpret_cast<float4*>(hp) = hi;
+  *reinterpret_cast<float4*>(lp) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+}
+
 }  // namespace
 
 // Diagonal tile of panel step k:  L_kk = chol(P_kk)  and  M = L_kk^-1  (FP32), one CTA per system.
@@ -69,11 +80,20 @@ potrf128_kernel(float* __restrict__ Lp, float* __restrict__ Wp, float* __restric
   const int64_t moff = (int64_t)blockIdx.x * 2 * plane + (int64_t)k * PT * n + (int64_t)k * PT;
   float* Lh = Lp + moff;
   float* Ll = Lh + plane;
-  for (int e = threadIdx.x; e < PT * PT; e += 256) {
-    const int r = e >> 7, c = e & 127;
-    S[r * PLD + c] = (c <= r) ? Lh[(int64_t)r * n + c] + Ll[(int64_t)r * n + c] : 0.f;
-    Wm[r * PLD + c] = 0.f;
-    Wq[r * PLD + c] = 0.f;
+#pragma unroll
+  for (int it = 0; it < PT * PT / 4 / 256; ++it) {          // 128-bit loads, all in flight before the first use
+    const int e = threadIdx.x + 256 * it;
+    const int r = e >> 5, c = (e & 31) * 4;
+    const float4 h4 = *reinterpret_cast<const float4*>(Lh + (int64_t)r * n + c);
+    const float4 l4 = *reinterpret_cast<const float4*>(Ll + (int64_t)r * n + c);
+    float4 v = make_float4(h4.x + l4.x, h4.y + l4.y, h4.z + l4.z, h4.w + l4.w);
+    if (c + 0 > r) v.x = 0.f;
+    if (c + 1 > r) v.y = 0.f;
+    if (c + 2 > r) v.z = 0.f;
+    if (c + 3 > r) v.w = 0.f;
+    *reinterpret_cast<float4*>(S + r * PLD + c) = v;
+    *reinterpret_cast<float4*>(Wm + r * PLD + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(Wq + r * PLD + c) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
   bool bad = false;
@@ -196,20 +216,21 @@ potrf128_kernel(float* __restrict__ Lp, float* __restrict__ Wp, float* __restric
   float* Wl = Wh + plane;
   float* Th = Wt + moff;
   float* Tl = Th + plane;
-  for (int e = threadIdx.x; e < PT * PT; e += 256) {
-    const int r = e >> 7, c = e & 127;
-    const float vl = (c <= r) ? S[r * PLD + c] : 0.f;
-    const float vw = Wm[r * PLD + c], vt = Wq[r * PLD + c];
-    uint32_t t;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(vl));
-    Lh[(int64_t)r * n + c] = __uint_as_float(t);
-    Ll[(int64_t)r * n + c] = vl - __uint_as_float(t);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(vw));
-    Wh[(int64_t)r * n + c] = __uint_as_float(t);
-    Wl[(int64_t)r * n + c] = vw - __uint_as_float(t);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(vt));
-    Th[(int64_t)r * n + c] = __uint_as_float(t);
-    Tl[(int64_t)r * n + c] = vt - __uint_as_float(t);
+#pragma unroll 4
+  for (int it = 0; it < PT * PT / 4 / 256; ++it) {
+    const int e = threadIdx.x + 256 * it;
+    const int r = e >> 5, c = (e & 31) * 4;
+    float4 vl = *reinterpret_cast<const float4*>(S + r * PLD + c);
+    if (c + 0 > r) vl.x = 0.f;
+    if (c + 1 > r) vl.y = 0.f;
+    if (c + 2 > r) vl.z = 0.f;
+    if (c + 3 > r) vl.w = 0.f;
+    const float4 vw = *reinterpret_cast<const float4*>(Wm + r * PLD + c);
+    const float4 vt = *reinterpret_cast<const float4*>(Wq + r * PLD + c);
+    float4 hi;
+    split_store(vl, Lh + (int64_t)r * n + c, Ll + (int64_t)r * n + c, hi);
+    split_store(vw, Wh + (int64_t)r * n + c, Wl + (int64_t)r * n + c, hi);
+    split_store(vt, Th + (int64_t)r * n + c, Tl + (int64_t)r * n + c, hi);
   }
 }
 
@@ -227,7 +248,9 @@ __device__ __forceinline__ bool mx_finished(const unsigned int* conv, int nmat, 
 }
 
 // x[m][p][i] += sum_j X[m][i][j] r[m or f][p][j]   (FP32 products, FP32 accumulation: a correction needs few digits)
-// grid: (n / 32, nmat), block 256: warp w owns rows 4w .. 4w+3 of the CTA's 32.  smem: r as float [P][n].
+// grid: (n / 32, nmat), block 256: warp w owns rows 4w .. 4w+3 of the CTA's 32 and sweeps them TOGETHER, so every
+// right-hand-side value read from shared memory feeds four rows (the shared-memory broadcast of r, not HBM, bounded the
+// one-row-at-a-time version: profiles/launches_r2b_mixed_v1.txt).  smem: r as float [P][n].
 template <int PMAX>
 __global__ void __launch_bounds__(256)
 mx_apply_kernel(const float* __restrict__ X, const double* __restrict__ rvec, int64_t r_mat_stride, int r_mat_div,
@@ -236,52 +259,70 @@ mx_apply_kernel(const float* __restrict__ X, const double* __restrict__ rvec, in
   const int m = blockIdx.y;
   if (step > 1 && mx_finished(conv, nmat, m, step - 1, tol)) return;
   const double* r = rvec + (int64_t)(r_mat_div > 0 ? m / r_mat_div : m) * r_mat_stride;
-  for (int e = threadIdx.x; e < P * n; e += 256) ap_sm[e] = (float)r[(int64_t)(e / n) * n + (e % n)];
+  for (int e = threadIdx.x * 2; e < P * n; e += 512) {
+    const double2 v = *reinterpret_cast<const double2*>(r + e);        // rows of r are contiguous: [p][n]
+    *reinterpret_cast<float2*>(ap_sm + e) = make_float2((float)v.x, (float)v.y);
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float dmax = 0.f, xmax = 0.f;
-  for (int rr = 0; rr < 4; ++rr) {
-    const int i = blockIdx.x * 32 + warp * 4 + rr;
-    const float* xr = X + ((int64_t)m * n + i) * n;
-    float acc[PMAX];
+  const int i0 = blockIdx.x * 32 + warp * 4;
+  const float* x0 = X + ((int64_t)m * n + i0) * n;
+  float acc[4][PMAX];
 #pragma unroll
-    for (int p = 0; p < PMAX; ++p) acc[p] = 0.f;
-    for (int j = lane * 4; j < n; j += 128) {
-      const float4 a = *reinterpret_cast<const float4*>(xr + j);
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int p = 0; p < PMAX; ++p) {
-        if (p < P) {
-          const float4 b = *reinterpret_cast<const float4*>(ap_sm + p * n + j);
-          acc[p] = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc[p]))));
-        }
-      }
+    for (int p = 0; p < PMAX; ++p) acc[a][p] = 0.f;
+  float4 xn4[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) xn4[a] = *reinterpret_cast<const float4*>(x0 + (int64_t)a * n + lane * 4);
+  for (int j = lane * 4; j < n; j += 128) {
+    float4 xa[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) xa[a] = xn4[a];
+    if (j + 128 < n) {                       // next chunk of the four rows is in flight while this one is consumed
+#pragma unroll
+      for (int a = 0; a < 4; ++a) xn4[a] = *reinterpret_cast<const float4*>(x0 + (int64_t)a * n + j + 128);
     }
 #pragma unroll
     for (int p = 0; p < PMAX; ++p) {
+      if (p < P) {
+        const float4 b = *reinterpret_cast<const float4*>(ap_sm + p * n + j);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[p] += __shfl_xor_sync(0xffffffffu, acc[p], o);
+        for (int a = 0; a < 4; ++a)
+          acc[a][p] = fmaf(xa[a].x, b.x, fmaf(xa[a].y, b.y, fmaf(xa[a].z, b.z, fmaf(xa[a].w, b.w, acc[a][p]))));
+      }
     }
-    if (lane == 0) {
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int p = 0; p < PMAX; ++p) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[a][p] += __shfl_xor_sync(0xffffffffu, acc[a][p], o);
+    }
+  float dmax = 0.f, xmax = 0.f;
+  if (lane == 0) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int p = 0; p < PMAX; ++p)
         if (p < P) {
-          double* xp = xvec + ((int64_t)m * Pp + p) * n + i;
-          const double xn = (step == 0 ? 0.0 : *xp) + (double)acc[p];
+          double* xp = xvec + ((int64_t)m * Pp + p) * n + i0 + a;
+          const double xn = (step == 0 ? 0.0 : *xp) + (double)acc[a][p];
           *xp = xn;
           // fmaxf drops NaNs: map anything non-finite to +inf so the final check sees it
-          dmax = (fabsf(acc[p]) <= 3.0e38f) ? fmaxf(dmax, fabsf(acc[p])) : __int_as_float(0x7f800000);
+          dmax = (fabsf(acc[a][p]) <= 3.0e38f) ? fmaxf(dmax, fabsf(acc[a][p])) : __int_as_float(0x7f800000);
           xmax = fmaxf(xmax, fabsf((float)xn));
         }
+    if (step > 0) {
+      atomicMax(conv + ((int64_t)step * nmat + m) * 2, __float_as_uint(dmax));
+      atomicMax(conv + ((int64_t)step * nmat + m) * 2 + 1, __float_as_uint(xmax));
     }
-  }
-  if (lane == 0 && step > 0) {
-    atomicMax(conv + ((int64_t)step * nmat + m) * 2, __float_as_uint(dmax));
-    atomicMax(conv + ((int64_t)step * nmat + m) * 2 + 1, __float_as_uint(xmax));
   }
 }
 
 // r[m][p][i] = b[f][p][i] - lambda_r x[m][p][i] - sum_j A_f[i][j] x[m][p][j]    (all FP64, fixed summation order)
-// grid: (n / 32, nmat), block 256.  smem: x[m] as double [P][n].
+// grid: (n / 32, nmat), block 256, four rows per warp in flight like mx_apply_kernel.  smem: x[m] as double [P][n].
 template <int PMAX>
 __global__ void __launch_bounds__(256)
 mx_residual_kernel(const double* __restrict__ Af, const double* __restrict__ lambda, int R, const double* __restrict__ bvec,
@@ -293,36 +334,50 @@ mx_residual_kernel(const double* __restrict__ Af, const double* __restrict__ lam
   const int f = m / R;
   const double lam = lambda[m % R];
   const double* x = xvec + (int64_t)m * Pp * n;
-  for (int e = threadIdx.x; e < P * n; e += 256) rs_sm[e] = x[(int64_t)(e / n) * n + (e % n)];
+  for (int e = threadIdx.x * 2; e < P * n; e += 512) *reinterpret_cast<double2*>(rs_sm + e) = *reinterpret_cast<const double2*>(x + e);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int rr = 0; rr < 4; ++rr) {
-    const int i = blockIdx.x * 32 + warp * 4 + rr;
-    const double* ar = Af + ((int64_t)f * n + i) * n;
-    double acc[PMAX];
+  const int i0 = blockIdx.x * 32 + warp * 4;
+  const double* a0 = Af + ((int64_t)f * n + i0) * n;
+  double acc[4][PMAX];
 #pragma unroll
-    for (int p = 0; p < PMAX; ++p) acc[p] = 0.0;
-    for (int j = lane * 2; j < n; j += 64) {
-      const double2 a = *reinterpret_cast<const double2*>(ar + j);
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int p = 0; p < PMAX; ++p) {
-        if (p < P) {
-          const double2 b = *reinterpret_cast<const double2*>(rs_sm + p * n + j);
-          acc[p] = fma(a.x, b.x, fma(a.y, b.y, acc[p]));
-        }
-      }
+    for (int p = 0; p < PMAX; ++p) acc[a][p] = 0.0;
+  double2 an2[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) an2[a] = *reinterpret_cast<const double2*>(a0 + (int64_t)a * n + lane * 2);
+  for (int j = lane * 2; j < n; j += 64) {
+    double2 av[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) av[a] = an2[a];
+    if (j + 64 < n) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) an2[a] = *reinterpret_cast<const double2*>(a0 + (int64_t)a * n + j + 64);
     }
 #pragma unroll
     for (int p = 0; p < PMAX; ++p) {
+      if (p < P) {
+        const double2 b = *reinterpret_cast<const double2*>(rs_sm + p * n + j);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[p] += __shfl_xor_sync(0xffffffffu, acc[p], o);
+        for (int a = 0; a < 4; ++a) acc[a][p] = fma(av[a].x, b.x, fma(av[a].y, b.y, acc[a][p]));
+      }
     }
-    if (lane == 0) {
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int p = 0; p < PMAX; ++p) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[a][p] += __shfl_xor_sync(0xffffffffu, acc[a][p], o);
+    }
+  if (lane == 0) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int p = 0; p < PMAX; ++p)
         if (p < P)
-          rvec[((int64_t)m * Pp + p) * n + i] = bvec[((int64_t)f * Pp + p) * n + i] - lam * rs_sm[p * n + i] - acc[p];
-    }
+          rvec[((int64_t)m * Pp + p) * n + i0 + a] = bvec[((int64_t)f * Pp + p) * n + i0 + a] - lam * rs_sm[p * n + i0 + a] - acc[a][p];
   }
 }
 
@@ -392,9 +447,9 @@ static void build_plan(MxPlan& pl, int n) {
 
 struct MixedSolver::Impl {
   int n = 0, nmat = 0, K = 0, R = 0, Pp = 0;
-  DevBuf<float> Lp, Wp, Wt, Tt, X;
+  DevBuf<float> Lp, Wp, Wt, Tt, X, Ap, Ident;
   DevBuf<unsigned int> conv;
-  CUtensorMap tmL, tmW, tmWt, tmT;
+  CUtensorMap tmL, tmW, tmWt, tmT, tmAp, tmI;
   MxPlan plan;
 };
 
@@ -417,6 +472,10 @@ void MixedSolver::prepare(int n, int K, int R, int Pp) {
   const size_t planes = (size_t)nmat * 2 * n * n;
   d.Lp.alloc(planes); d.Wp.alloc(planes); d.Wt.alloc(planes); d.Tt.alloc(planes);
   d.X.alloc((size_t)nmat * n * n);
+  d.Ap.alloc((size_t)K * 2 * n * n);
+  RG_CUDA(cudaMemset(d.Ap.p, 0, (size_t)K * 2 * n * n * 4));
+  make_tf32_planes_tensor_map(&d.tmAp, d.Ap.p, n, K);
+  make_tf32_identity_planes(d.Ident, &d.tmI);
   // strictly-upper tiles of W / lower tiles of W^T are read by nothing; zero once so stale data can never matter
   RG_CUDA(cudaMemset(d.Lp.p, 0, planes * 4));
   RG_CUDA(cudaMemset(d.Wp.p, 0, planes * 4));
@@ -465,9 +524,11 @@ void MixedSolver::solve(const double* Af, const double* lambda, const double* bv
   for (int k = 0; k < nt; ++k) {
     Tf32GemmEpilogue e = e0;
     e.out = d.Lp.p;
-    e.cin = Af; e.cin_mat_stride = (int64_t)n * n; e.cin_ld = n; e.cin_mat_div = d.R;
+    // P_ik = (A_f + lambda_r I)_ik - L_i,0:k L_k,0:k^T: the A tile enters through the tensor pipe (A_planes x identity),
+    // the product with A negated, the ridge shift on the diagonal in the epilogue - no epilogue loads at all
+    e.c_chunks = 4; e.c_mat_div = d.R;
     e.diag_add = lambda; e.diag_mod = d.R;
-    launch_tf32x3_gemm(d.tmL, d.tmL, tl + d.plan.upd[k].x, d.plan.upd[k].y, nmat, e, s);
+    launch_tf32x3_gemm(d.tmL, d.tmL, tl + d.plan.upd[k].x, d.plan.upd[k].y, nmat, e, s, &d.tmAp, &d.tmI);
     potrf128_kernel<<<nmat, 256, potrf_smem, s>>>(d.Lp.p, d.Wp.p, d.Wt.p, n, k, fail_flag);
     if (d.plan.trsm[k].y > 0) {
       Tf32GemmEpilogue t = e0;
@@ -507,6 +568,8 @@ void MixedSolver::solve(const double* Af, const double* lambda, const double* bv
     }
   mx_final_check_kernel<<<(nmat + 63) / 64, 64, 0, s>>>(d.conv.p, nmat, steps, tol, fail_flag);
 }
+
+float* MixedSolver::a_planes() { return impl->Ap.p; }
 
 const float* MixedSolver::debug_planes(int which) const {
   switch (which) {

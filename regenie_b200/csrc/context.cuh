@@ -51,6 +51,8 @@ struct rg_ctx {
   struct Lane {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
+    cudaEvent_t h2d_done = nullptr;   // recorded behind the host-to-device copy of the block's input rows
+    bool h2d_recorded = false;
     rg::DevBuf<uint8_t> packed_dev;
     rg::DevBuf<uint32_t> gp;          // [rows_p][Npad/16]
     rg::DevBuf<uint8_t> z;            // [2 rows_p][Npad] e4m3

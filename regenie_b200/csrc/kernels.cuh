@@ -45,6 +45,7 @@ struct AssembleArgs {
   double* cm;                // batched row-major lower systems
   int64_t cm_stride;
   int ldc;
+  float* planes = nullptr;   // l0_assemble_sym only: FP32 hi / lo planes [K][2][n][n] of the same matrices (tensor-core operand)
 };
 
 void launch_dbg_check_diag(const float* zz, int64_t ldz, int64_t fold_stride, const int32_t* cnt_fold, int rows_p,
@@ -97,12 +98,16 @@ struct Tf32GemmEpilogue {
   const double* cin;          // D = (float)(cin - acc) with FP64 matrices cin[mat / cin_mat_div][row][col], or null
   int64_t cin_mat_stride;
   int cin_ld, cin_mat_div;
-  const double* diag_add;     // added to cin's diagonal: diag_add[mat % diag_mod] (the ridge shift), or null
+  const double* diag_add;     // added to the diagonal of diagonal tiles: diag_add[mat % diag_mod] (the ridge shift), or null
   int diag_mod;
+  int c_chunks;               // 0, or 4: leading K chunks  acc = C_tile * I  followed by the main chunks with A negated
+  int c_mat_div;              // C matrix index = mat / c_mat_div
 };
 void make_tf32_planes_tensor_map(CUtensorMap* tm, const float* planes, int n, int batch);
+void make_tf32_identity_planes(DevBuf<float>& buf, CUtensorMap* tm);
 void launch_tf32x3_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const int4* tiles, int ntiles, int batch,
-                        const Tf32GemmEpilogue& ep, cudaStream_t s);
+                        const Tf32GemmEpilogue& ep, cudaStream_t s, const CUtensorMap* tmC = nullptr,
+                        const CUtensorMap* tmI = nullptr);
 
 // ---- chol_mixed.cu: tensor-core factorisation + FP64 iterative refinement of the level-0 ridge systems
 constexpr int kMxMaxSteps = 6;
@@ -114,7 +119,9 @@ class MixedSolver {
   MixedSolver& operator=(const MixedSolver&) = delete;
   static int dim_for(int bs);                 // 128 * 2^k >= bs, or 0 when the block is too large for this path
   void prepare(int n, int K, int R, int Pp);
-  // Af [K][n][n] FP64 full symmetric (no ridge shift), lambda [R], bvec [K][Pp][n]; xvec / rvec [K*R][Pp][n]
+  // Af [K][n][n] FP64 full symmetric (no ridge shift) and its FP32 hi / lo planes Ap [K][2][n][n], lambda [R],
+  // bvec [K][Pp][n]; xvec / rvec [K*R][Pp][n]
+  float* a_planes();                          // where the assembler writes Ap (owned by the solver, valid after prepare)
   void solve(const double* Af, const double* lambda, const double* bvec, double* xvec, double* rvec, int P, int steps,
              float tol, unsigned int* fail_flag, cudaStream_t s);
   static int launches_per_solve(int n, int steps, int P);

@@ -267,7 +267,6 @@ static void enqueue_solve_f64(rg_ctx* h, rg_ctx::Lane& L, const BlockDims& d, cu
   aa.bs = d.bs; aa.rows_p = d.rows_p; aa.nC = d.nC; aa.C = C; aa.K = K; aa.R = R; aa.loocv = h->loocv;
   aa.zz = L.zz.p; aa.ldz = 2 * d.rows_p; aa.zz_fold_stride = (int64_t)4 * d.rows_p * d.rows_p;
   aa.mu = L.mu.p; aa.inv_sd = L.inv_sd.p; aa.Bv = L.Bv.p; aa.Af = L.Af.p; aa.Qf = L.Qf.p;
-  aa.lambda = h->lambda.p; aa.cm = L.cm.p; aa.cm_stride = (int64_t)d.n_aug * d.nC; aa.ldc = d.nC;
   {
     const int nC_max = (int)round_up(h->bs_max, 64);
     const size_t need = (size_t)d.nmat * (nC_max + d.Ppad + (h->loocv ? h->Npad : 0)) * nC_max;
@@ -277,6 +276,7 @@ static void enqueue_solve_f64(rg_ctx* h, rg_ctx::Lane& L, const BlockDims& d, cu
     }
     L.inv.alloc(chol_inv_elems((int)round_up(h->bs_max, 64), d.nmat));
   }
+  aa.lambda = h->lambda.p; aa.cm = L.cm.p; aa.cm_stride = (int64_t)d.n_aug * d.nC; aa.ldc = d.nC;
   {
     ScopedTimer t(h, "l0_assemble", s);
     if (!dbg_skip("assemble")) launch_l0_assemble(aa, L.rhs.p, P, d.Ppad, d.nmat, s);
@@ -333,6 +333,7 @@ static void enqueue_solve_mixed(rg_ctx* h, rg_ctx::Lane& L, const BlockDims& d, 
   aa.zz = L.zz.p; aa.ldz = 2 * d.rows_p; aa.zz_fold_stride = (int64_t)4 * d.rows_p * d.rows_p;
   aa.mu = L.mu.p; aa.inv_sd = L.inv_sd.p; aa.Bv = L.Bv.p; aa.Af = L.Af.p; aa.Qf = L.Qf.p;
   aa.lambda = h->lambda.p; aa.cm = L.mx_Af.p; aa.cm_stride = (int64_t)n * n; aa.ldc = n;
+  aa.planes = L.mx->a_planes();
   {
     ScopedTimer t(h, "l0_assemble", s);
     launch_l0_assemble_sym(aa, L.rhs.p, P, Pp, L.mx_b.p, s);
@@ -474,6 +475,9 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
     L.packed_dev.alloc((size_t)h->bs_max * row_stride);
     ScopedTimer t(h, "h2d", s);
     copy_to_device(L.packed_dev.p, packed, (size_t)bs * row_stride, s);
+    if (!L.h2d_done) RG_CUDA(cudaEventCreateWithFlags(&L.h2d_done, cudaEventDisableTiming));
+    RG_CUDA(cudaEventRecord(L.h2d_done, s));
+    L.h2d_recorded = true;
     if (getenv("RG_DBG_SYNC_AFTER_H2D")) RG_CUDA(cudaStreamSynchronize(s));
     packed_d = L.packed_dev.p;
   }
@@ -705,6 +709,7 @@ void rg_destroy(rg_handle h) {
   rg::flush_timers(h);
   for (auto& l : h->lanes) {
     if (l->mx_ev) cudaEventDestroy(l->mx_ev);
+    if (l->h2d_done) cudaEventDestroy(l->h2d_done);
     if (l->mx_fail_host) cudaFreeHost(l->mx_fail_host);
     cudaEventDestroy(l->done);
     cudaStreamDestroy(l->stream);
@@ -792,6 +797,15 @@ int rg_l0_block_bed(rg_handle h, const uint8_t* packed, int64_t row_stride, int3
   RG_CHECK(h && packed, "null argument");
   l0_block_bed(h, packed, row_stride, bs, sample_idx, ref_first, block_id);
   RG_CUDA(cudaGetLastError());
+  RG_API_END
+}
+
+int rg_l0_wait_input(rg_handle h) {
+  RG_API_BEGIN
+  RG_CHECK(h && h->kind == 1, "not a Step-1 handle");
+  RG_CUDA(cudaSetDevice(h->device));
+  rg_ctx::Lane& L = *h->lanes[h->last_lane];
+  if (L.h2d_recorded) RG_CUDA(cudaEventSynchronize(L.h2d_done));
   RG_API_END
 }
 
@@ -937,6 +951,22 @@ int rg_dbg_mixed_solve(int32_t device, int32_t n, int32_t K, int32_t R, int32_t 
   RG_CUDA(cudaMemset(dx.p, 0, dx.n * 8));
   RG_CUDA(cudaMemset(dfail.p, 0, 4));
   RG_CUDA(cudaMemcpy(dA.p, Af, dA.n * 8, cudaMemcpyHostToDevice));
+  {
+    // FP32 hi / lo planes of the systems (the product path gets them from l0_assemble_sym_kernel)
+    std::vector<float> pl((size_t)K * 2 * n * n);
+    for (int f = 0; f < K; ++f)
+      for (size_t e = 0; e < (size_t)n * n; ++e) {
+        const float v = (float)Af[(size_t)f * n * n + e];
+        uint32_t u;
+        memcpy(&u, &v, 4);
+        u = (u + 0x1000u) & 0xFFFFE000u;                      // round to nearest TF32 (ties away), like cvt.rna.tf32.f32
+        float hi;
+        memcpy(&hi, &u, 4);
+        pl[((size_t)f * 2) * n * n + e] = hi;
+        pl[((size_t)f * 2 + 1) * n * n + e] = v - hi;
+      }
+    RG_CUDA(cudaMemcpy(mx.a_planes(), pl.data(), pl.size() * 4, cudaMemcpyHostToDevice));
+  }
   RG_CUDA(cudaMemcpy(dl.p, lambda, R * 8, cudaMemcpyHostToDevice));
   for (int f = 0; f < K; ++f)
     RG_CUDA(cudaMemcpy(db.p + (size_t)f * Pp * n, b + (size_t)f * P * n, (size_t)P * n * 8, cudaMemcpyHostToDevice));

@@ -79,12 +79,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
 // kind::tf32: D = F32 (bits 4-5 = 1), A = B = TF32 (format 2 at bits 7-9 / 10-12), both K-major, N = 128, M = 128
 constexpr uint32_t kTf32Idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TG_N >> 3) << 17) | ((uint32_t)(TG_M >> 4) << 24);
 
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+constexpr uint32_t kTf32IdescNegA = kTf32Idesc | (1u << 13);      // D (+)= (-A) B^T
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate, uint32_t idesc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(kTf32Idesc), "r"(accumulate) : "memory");
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -105,6 +107,7 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
 // grid: (ntiles, batch); tile entry = (A row tile, B row tile, first K chunk, number of K chunks)
 __global__ void __launch_bounds__(TG_THREADS, 1)
 tf32x3_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmI,
                       const int4* __restrict__ tiles, Tf32GemmEpilogue ep) {
   extern __shared__ uint8_t tg_smem_raw[];
   const uint32_t raw = smem_u32(tg_smem_raw);
@@ -119,7 +122,10 @@ tf32x3_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int4 tile = tiles[blockIdx.x];
   const int mat = blockIdx.y;
-  const int nkc = tile.w;
+  // optional leading chunks:  acc = C_tile * I  (C = FP32 hi/lo planes of the matrix the product is subtracted from,
+  // I = identity planes), then the main chunks with A negated:  acc = C - A B^T  without a single epilogue load
+  const int ncc = ep.c_chunks;
+  const int nkc = tile.w + ncc;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < TG_STAGES; ++s) {
@@ -131,6 +137,10 @@ tf32x3_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (ncc > 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmI) : "memory");
+    }
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -149,9 +159,15 @@ tf32x3_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const uint32_t ph = (kc / TG_STAGES) & 1;
         mbar_wait(empty_bar + 8 * s, ph ^ 1);
         mbar_expect_tx(full_bar + 8 * s, TG_STAGE_BYTES);
-        const int col = (tile.z + kc) * TG_KC;
-        tma_load_3d(base + s * TG_STAGE_BYTES, &tmA, full_bar + 8 * s, col, tile.x * TG_M, 2 * mat);
-        tma_load_3d(base + s * TG_STAGE_BYTES + TG_OP_BYTES, &tmB, full_bar + 8 * s, col, tile.y * TG_N, 2 * mat);
+        if (kc < ncc) {
+          tma_load_3d(base + s * TG_STAGE_BYTES, &tmC, full_bar + 8 * s, tile.y * TG_N + kc * TG_KC, tile.x * TG_M,
+                      2 * (ep.c_mat_div > 0 ? mat / ep.c_mat_div : mat));
+          tma_load_3d(base + s * TG_STAGE_BYTES + TG_OP_BYTES, &tmI, full_bar + 8 * s, kc * TG_KC, 0, 0);
+        } else {
+          const int col = (tile.z + kc - ncc) * TG_KC;
+          tma_load_3d(base + s * TG_STAGE_BYTES, &tmA, full_bar + 8 * s, col, tile.x * TG_M, 2 * mat);
+          tma_load_3d(base + s * TG_STAGE_BYTES + TG_OP_BYTES, &tmB, full_bar + 8 * s, col, tile.y * TG_N, 2 * mat);
+        }
       }
     }
   } else if (warp == 1) {
@@ -165,12 +181,21 @@ tf32x3_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const uint64_t a_lo = make_desc(base + s * TG_STAGE_BYTES + TG_PLANE_BYTES);
         const uint64_t b_hi = make_desc(base + s * TG_STAGE_BYTES + TG_OP_BYTES);
         const uint64_t b_lo = make_desc(base + s * TG_STAGE_BYTES + TG_OP_BYTES + TG_PLANE_BYTES);
+        if (kc < ncc) {
 #pragma unroll
-        for (int k = 0; k < TG_KC / 8; ++k) {
-          // +32 bytes per K = 8 step inside the swizzle atom: +2 in 16-byte descriptor units; small terms first
-          mma_tf32(tmem_base, a_lo + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), (kc | k) ? 1u : 0u);
-          mma_tf32(tmem_base, a_hi + (uint64_t)(2 * k), b_lo + (uint64_t)(2 * k), 1u);
-          mma_tf32(tmem_base, a_hi + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), 1u);
+          for (int k = 0; k < TG_KC / 8; ++k) {           // (C_lo + C_hi) * 1: the lo plane of the identity is zero
+            mma_tf32(tmem_base, a_lo + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), (kc | k) ? 1u : 0u, kTf32Idesc);
+            mma_tf32(tmem_base, a_hi + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), 1u, kTf32Idesc);
+          }
+        } else {
+          const uint32_t idesc = ncc > 0 ? kTf32IdescNegA : kTf32Idesc;
+#pragma unroll
+          for (int k = 0; k < TG_KC / 8; ++k) {
+            // +32 bytes per K = 8 step inside the swizzle atom: +2 in 16-byte descriptor units; small terms first
+            mma_tf32(tmem_base, a_lo + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), (kc | k) ? 1u : 0u, idesc);
+            mma_tf32(tmem_base, a_hi + (uint64_t)(2 * k), b_lo + (uint64_t)(2 * k), 1u, idesc);
+            mma_tf32(tmem_base, a_hi + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), 1u, idesc);
+          }
         }
         tcgen05_commit(empty_bar + 8 * s);
       }
@@ -206,17 +231,16 @@ tf32x3_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           const double2 cc = *reinterpret_cast<const double2*>(cin + c * 32 + j);
-          double c0 = cc.x, c1 = cc.y;
-          if (diag_tile) {
-            if (c * 32 + j == r_loc) c0 += diag_add;
-            if (c * 32 + j + 1 == r_loc) c1 += diag_add;
-          }
-          o[j] = (float)(c0 - (double)__uint_as_float(v[j]));
-          o[j + 1] = (float)(c1 - (double)__uint_as_float(v[j + 1]));
+          o[j] = (float)(cc.x - (double)__uint_as_float(v[j]));
+          o[j + 1] = (float)(cc.y - (double)__uint_as_float(v[j + 1]));
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) o[j] = ep.negate ? -__uint_as_float(v[j]) : __uint_as_float(v[j]);
+      }
+      if (diag_tile && diag_add != 0.0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (c * 32 + j == r_loc) o[j] = (float)((double)o[j] + diag_add);
       }
       if (ep.lower_only && diag_tile) {
 #pragma unroll
@@ -297,8 +321,18 @@ void make_tf32_planes_tensor_map(CUtensorMap* tm, const float* planes, int n, in
   RG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (tf32 planes) failed (" + std::to_string((int)r) + ")");
 }
 
+// identity planes [1][2][128][128] (hi = I, lo = 0) for the C phase
+void make_tf32_identity_planes(DevBuf<float>& buf, CUtensorMap* tm) {
+  std::vector<float> h((size_t)2 * 128 * 128, 0.f);
+  for (int i = 0; i < 128; ++i) h[(size_t)i * 128 + i] = 1.f;
+  buf.alloc(h.size());
+  RG_CUDA(cudaMemcpy(buf.p, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+  make_tf32_planes_tensor_map(tm, buf.p, 128, 1);
+}
+
 void launch_tf32x3_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const int4* tiles, int ntiles, int batch,
-                        const Tf32GemmEpilogue& ep, cudaStream_t s) {
+                        const Tf32GemmEpilogue& ep, cudaStream_t s, const CUtensorMap* tmC, const CUtensorMap* tmI) {
+  RG_CHECK(ep.c_chunks == 0 || (tmC && tmI), "tf32 gemm: the C phase needs its tensor maps");
   if (ntiles <= 0 || batch <= 0) return;
   constexpr size_t smem = (size_t)TG_STAGES * TG_STAGE_BYTES + 1024 + 128;
   static bool attr_set = false;
@@ -307,7 +341,7 @@ void launch_tf32x3_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const in
     attr_set = true;
   }
   dim3 grid(ntiles, batch);
-  tf32x3_gemm_nt_kernel<<<grid, TG_THREADS, smem, s>>>(tmA, tmB, tiles, ep);
+  tf32x3_gemm_nt_kernel<<<grid, TG_THREADS, smem, s>>>(tmA, tmB, tmC ? *tmC : tmA, tmI ? *tmI : tmB, tiles, ep);
 }
 
 }  // namespace rg

@@ -259,25 +259,31 @@ void BgenFile::read_block(size_t first, size_t n, uint8_t* probs, uint8_t* pm, i
       const uint32_t c = rd32(q);
       const uint8_t* raw;
       uLongf dl;
-      if (compression == 1) {
+      const size_t want = 10 + 3 * (size_t)n_file;          // the only payload this reader accepts (8-bit, ploidy 2, biallelic)
+      // lengths come from the file: validate them BEFORE they size a buffer or a source span (same rules as
+      // read_block_compressed); parse_variant already checked that the c bytes lie inside the mapping
+      if (compression != 0) {
+        if (c < 8) { failed = true; return; }
         dl = rd32(q + 4);
+        if ((size_t)dl != want) { failed = true; return; }
         buf.resize(dl);
-        if (uncompress(buf.data(), &dl, q + 8, c - 4) != Z_OK) { failed = true; return; }
+      }
+      if (compression == 1) {
+        if (uncompress(buf.data(), &dl, q + 8, c - 4) != Z_OK || (size_t)dl != want) { failed = true; return; }
         raw = buf.data();
       } else if (compression == 2) {
-        dl = rd32(q + 4);
-        buf.resize(dl);
         const size_t got = g_zstd_decompress(buf.data(), dl, q + 8, c - 4);
-        if (g_zstd_is_error(got) || got != dl) { failed = true; return; }
+        if (g_zstd_is_error(got) || got != want) { failed = true; return; }
         raw = buf.data();
       } else {
         dl = c;
+        if ((size_t)dl != want) { failed = true; return; }
         raw = q + 4;
       }
       const uint32_t ns = rd32(raw);
       const uint16_t ka = rd16(raw + 4);
       const uint8_t pmin = raw[6], pmax = raw[7];
-      if (ns != n_file || ka != 2 || pmin != 2 || pmax != 2 || dl < 10 + 3 * (size_t)ns) { failed = true; return; }
+      if (ns != n_file || ka != 2 || pmin != 2 || pmax != 2) { failed = true; return; }
       const uint8_t phased = raw[8 + ns], bits = raw[9 + ns];
       if (phased != 0 || bits != 8) { failed = true; return; }
       memcpy(pm + j * (size_t)n_file, raw + 8, ns);

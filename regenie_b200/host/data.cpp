@@ -519,7 +519,7 @@ std::vector<int64_t> set_folds(const std::vector<uint8_t>& in_analysis, int k) {
   int cur = 0;
   for (int64_t i = 0; i < n; ++i) {
     if (in_analysis[i]) ++non_miss;
-    if (non_miss == target) {
+    if (non_miss == target && cur < k - 1) {      // the last fold always takes the remainder (k < n_analyzed < 2k would overrun)
       sizes[cur] = i - cum + 1;
       cum += sizes[cur];
       non_miss = 0;

@@ -928,6 +928,7 @@ void run_step2_qt(const Params& p, Log& log) {
       else g.read_rows(blocks[b].first, blocks[b].size, rows[b & 1].data());
     });
   };
+  if (blocks.empty()) throw Fail("no variant left to include in analysis.");
   if (p.start_block > (int)blocks.size()) throw Fail("Starting block > number of blocks analyzed");   // src/Data.cpp:2863-2864
   const size_t b_first = p.start_block > 1 ? (size_t)p.start_block - 1 : 0;
   if (b_first) log << "    + skipping to block #" << p.start_block << "\n";
@@ -1156,6 +1157,7 @@ void run_step2_bt(const Params& p, Log& log) {
       else gb.read_rows(blocks[b].first, blocks[b].size, rows[b & 1].data());
     });
   };
+  if (blocks.empty()) throw Fail("no variant left to include in analysis.");
   if (p.start_block > (int)blocks.size()) throw Fail("Starting block > number of blocks analyzed");   // src/Data.cpp:2863-2864
   const size_t b_first = p.start_block > 1 ? (size_t)p.start_block - 1 : 0;
   if (b_first) log << "    + skipping to block #" << p.start_block << "\n";
