@@ -98,6 +98,24 @@ int rg_fence(rg_handle h);
 int rg_l0_block_bed(rg_handle h, const uint8_t* packed, int64_t row_stride, int32_t bs,
                     const int32_t* sample_idx, int32_t ref_first, int32_t block_id);
 
+/*
+ * rg_l0_block_dosage_u8 -- the same level-0 block from 8-bit BGEN probability pairs (after inflate).  Replaces
+ *   readChunkFromBGENFileToG_fast   src/Geno.cpp:1574-1699  (dosage = p1/255 + 2 p0/255, or p1/255 + 2 p2/255 with
+ *                                   --ref-first; missing = bit 7 of the ploidy byte; mean imputation)
+ * followed by the functions rg_l0_block_bed lists.  Real-valued genotypes take the dense FP64 route (csrc/l0_dense.cu:
+ * per-fold Gram on the FP64 tensor pipe, batched Cholesky) instead of the exact-integer tensor-core route of hard calls.
+ *   probs           [host|device] [bs][n_file][2] bytes (P(hom first allele), P(het)) - the layout rg_bgen_inflate and
+ *                   the host BGEN reader produce
+ *   ploidy_missing  [host|device] [bs][n_file] bytes, bit 7 = missing; NULL = nothing missing
+ *   n_file          samples per variant in the file; sample_idx as in rg_l0_block_bed
+ */
+int rg_l0_block_dosage_u8(rg_handle h, const uint8_t* probs, const uint8_t* ploidy_missing, int64_t n_file, int32_t bs,
+                          const int32_t* sample_idx, int32_t ref_first, int32_t block_id);
+
+/* rg_l0_block_f64 -- the same from an FP64 genotype matrix G [bs][n_file] (row-major, -3 = missing): the shape the
+ * reference's PGEN dosage reader fills (readChunkFromPGENFileToG, src/Geno.cpp:1773-1821). */
+int rg_l0_block_f64(rg_handle h, const double* G, int64_t n_file, int32_t bs, const int32_t* sample_idx, int32_t block_id);
+
 /* Wait until the input rows of the most recent rg_l0_block_bed call have been copied to the device (see LIFETIME). */
 int rg_l0_wait_input(rg_handle h);
 

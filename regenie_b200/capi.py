@@ -48,7 +48,7 @@ EXPORTS = [
     "rg_l0_block_bed", "rg_l0_status", "rg_l0_fetch_W", "rg_l1_fit", "rg_loco", "rg_step2_create",
     "rg_s2_set_chr", "rg_s2_block_bed", "rg_W_info", "rg_debug_fetch", "rg_launch_count", "rg_stream",
     "rg_set_timing", "rg_get_timing", "rg_fence", "rg_s2_set_chr_bt", "rg_s2_block_bgen8_bt", "rg_s2_block_bgen8", "rg_s2_firth", "rg_l1_fit_bt", "rg_W_set_owned", "rg_W_export", "rg_W_attach_peer", "rg_l1_select", "rg_s2_set_sex", "rg_s2_set_non_par", "rg_l0_load_W", "rg_s2_spa", "rg_s2_block_bed_bt", "rg_prs", "rg_bgen_inflate",
-    "rg_l0_solver_stats", "rg_dbg_mixed_solve", "rg_l0_wait_input",
+    "rg_l0_solver_stats", "rg_dbg_mixed_solve", "rg_l0_wait_input", "rg_l0_block_dosage_u8", "rg_l0_block_f64",
 ]
 
 _lib = None
@@ -223,6 +223,26 @@ class Step1:
 
     def launch_count(self):
         return lib().rg_launch_count(self.h)
+
+    def l0_block_dosage_u8(self, probs, missing, block_id, sample_idx=None, ref_first=False):
+        """probs u8 [bs][n_file][2], missing u8 [bs][n_file] (bit 7) or None."""
+        L = lib()
+        L.rg_l0_block_dosage_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]
+        probs = np.ascontiguousarray(probs, dtype=np.uint8)
+        if missing is not None:
+            missing = np.ascontiguousarray(missing, dtype=np.uint8)
+        if sample_idx is not None:
+            sample_idx = np.ascontiguousarray(sample_idx, dtype=np.int32)
+        check(L.rg_l0_block_dosage_u8(self.h, _ptr(probs), _ptr(missing), probs.shape[1], probs.shape[0], _ptr(sample_idx),
+                                      int(ref_first), int(block_id)))
+
+    def l0_block_f64(self, G, block_id, sample_idx=None):
+        L = lib()
+        L.rg_l0_block_f64.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32]
+        G = np.ascontiguousarray(G, dtype=np.float64)
+        if sample_idx is not None:
+            sample_idx = np.ascontiguousarray(sample_idx, dtype=np.int32)
+        check(L.rg_l0_block_f64(self.h, _ptr(G), G.shape[1], G.shape[0], _ptr(sample_idx), int(block_id)))
 
     def solver_stats(self):
         """(blocks solved by the tensor-core + refinement path, of which re-solved by the FP64 Cholesky)."""

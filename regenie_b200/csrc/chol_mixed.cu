@@ -33,6 +33,7 @@ namespace {
 constexpr int PT = 128;            // diagonal tile
 constexpr int PLD = 132;           // smem row stride (floats): 16-byte aligned rows, conflict-free 128-bit row reads
 constexpr int PB = 32;             // register block of the warp-level Cholesky
+constexpr int kMxRowsPerCta = 64;  // rows of a refinement pass per CTA (the right-hand sides are staged once per CTA)
 
 // C[m][n] (+)= sign * sum_{p < plen} A[m][p] * Bt[n][p] for one 32x32 block; lane = row m.  A, Bt: smem, stride PLD.
 // tri = 1: Bt is lower triangular in this block pair (Bt[n][p] = 0 for p > n) - used for the diagonal solves.
@@ -265,7 +266,9 @@ mx_apply_kernel(const float* __restrict__ X, const double* __restrict__ rvec, in
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i0 = blockIdx.x * 32 + warp * 4;
+  float dmax = 0.f, xmax = 0.f;
+  for (int rg = 0; rg < kMxRowsPerCta / 32; ++rg) {
+  const int i0 = blockIdx.x * kMxRowsPerCta + rg * 32 + warp * 4;
   const float* x0 = X + ((int64_t)m * n + i0) * n;
   float acc[4][PMAX];
 #pragma unroll
@@ -300,7 +303,6 @@ mx_apply_kernel(const float* __restrict__ X, const double* __restrict__ rvec, in
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc[a][p] += __shfl_xor_sync(0xffffffffu, acc[a][p], o);
     }
-  float dmax = 0.f, xmax = 0.f;
   if (lane == 0) {
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -314,17 +316,18 @@ mx_apply_kernel(const float* __restrict__ X, const double* __restrict__ rvec, in
           dmax = (fabsf(acc[a][p]) <= 3.0e38f) ? fmaxf(dmax, fabsf(acc[a][p])) : __int_as_float(0x7f800000);
           xmax = fmaxf(xmax, fabsf((float)xn));
         }
-    if (step > 0) {
-      atomicMax(conv + ((int64_t)step * nmat + m) * 2, __float_as_uint(dmax));
-      atomicMax(conv + ((int64_t)step * nmat + m) * 2 + 1, __float_as_uint(xmax));
-    }
+  }
+  }   // row groups
+  if (lane == 0 && step > 0) {
+    atomicMax(conv + ((int64_t)step * nmat + m) * 2, __float_as_uint(dmax));
+    atomicMax(conv + ((int64_t)step * nmat + m) * 2 + 1, __float_as_uint(xmax));
   }
 }
 
 // r[m][p][i] = b[f][p][i] - lambda_r x[m][p][i] - sum_j A_f[i][j] x[m][p][j]    (all FP64, fixed summation order)
 // grid: (n / 32, nmat), block 256, four rows per warp in flight like mx_apply_kernel.  smem: x[m] as double [P][n].
 template <int PMAX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 mx_residual_kernel(const double* __restrict__ Af, const double* __restrict__ lambda, int R, const double* __restrict__ bvec,
                    const double* __restrict__ xvec, double* __restrict__ rvec, int n, int P, int Pp, int nmat, int step,
                    const unsigned int* __restrict__ conv, float tol) {
@@ -337,7 +340,8 @@ mx_residual_kernel(const double* __restrict__ Af, const double* __restrict__ lam
   for (int e = threadIdx.x * 2; e < P * n; e += 512) *reinterpret_cast<double2*>(rs_sm + e) = *reinterpret_cast<const double2*>(x + e);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i0 = blockIdx.x * 32 + warp * 4;
+  for (int rg = 0; rg < kMxRowsPerCta / 32; ++rg) {
+  const int i0 = blockIdx.x * kMxRowsPerCta + rg * 32 + warp * 4;
   const double* a0 = Af + ((int64_t)f * n + i0) * n;
   double acc[4][PMAX];
 #pragma unroll
@@ -379,6 +383,7 @@ mx_residual_kernel(const double* __restrict__ Af, const double* __restrict__ lam
         if (p < P)
           rvec[((int64_t)m * Pp + p) * n + i0 + a] = bvec[((int64_t)f * Pp + p) * n + i0 + a] - lam * rs_sm[p * n + i0 + a] - acc[a][p];
   }
+  }   // row groups
 }
 
 // after the last correction: every system must have met the tolerance at some step, else the lane's fallback flag is raised
@@ -513,6 +518,8 @@ void MixedSolver::solve(const double* Af, const double* lambda, const double* bv
     RG_CUDA(cudaFuncSetAttribute(potrf128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_smem));
     RG_CUDA(cudaFuncSetAttribute(mx_apply_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
     RG_CUDA(cudaFuncSetAttribute(mx_residual_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
+    RG_CUDA(cudaFuncSetAttribute(mx_apply_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
+    RG_CUDA(cudaFuncSetAttribute(mx_residual_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
     attr = true;
   }
   RG_CHECK(n <= 2048, "mixed solver: n <= 2048");
@@ -552,21 +559,43 @@ void MixedSolver::solve(const double* Af, const double* lambda, const double* bv
     launch_tf32x3_gemm(d.tmWt, d.tmWt, tl + d.plan.xx.x, d.plan.xx.y, nmat, x, s);
   }
   // ---- x0 = X b, then  x += X (b - A x)
-  dim3 grid(n / 32, nmat);
+  dim3 grid(n / kMxRowsPerCta, nmat);
   const int pc = rhs_chunk(n);                       // right-hand sides per launch (shared-memory budget of the FP64 pass)
   for (int st = 0; st <= steps; ++st)
     for (int p0 = 0; p0 < P; p0 += pc) {
       const int np = std::min(pc, P - p0);
       const size_t sm_a = (size_t)np * n * sizeof(float), sm_r = (size_t)np * n * sizeof(double);
       const int64_t o = (int64_t)p0 * n;
+      // right-hand-side count is a template parameter (register blocking): 10 is the benchmark's trait count
+      auto apply = [&](const double* rv, int64_t rs, int rdiv, int step) {
+        if (np <= 10) mx_apply_kernel<10><<<grid, 256, sm_a, s>>>(d.X.p, rv, rs, rdiv, xvec + o, n, np, d.Pp, nmat, step, d.conv.p, tol);
+        else mx_apply_kernel<12><<<grid, 256, sm_a, s>>>(d.X.p, rv, rs, rdiv, xvec + o, n, np, d.Pp, nmat, step, d.conv.p, tol);
+      };
       if (st == 0) {
-        mx_apply_kernel<12><<<grid, 256, sm_a, s>>>(d.X.p, bvec + o, (int64_t)d.Pp * n, d.R, xvec + o, n, np, d.Pp, nmat, 0, d.conv.p, tol);
+        apply(bvec + o, (int64_t)d.Pp * n, d.R, 0);
       } else {
-        mx_residual_kernel<12><<<grid, 256, sm_r, s>>>(Af, lambda, d.R, bvec + o, xvec + o, rvec + o, n, np, d.Pp, nmat, st, d.conv.p, tol);
-        mx_apply_kernel<12><<<grid, 256, sm_a, s>>>(d.X.p, rvec + o, (int64_t)d.Pp * n, 0, xvec + o, n, np, d.Pp, nmat, st, d.conv.p, tol);
+        if (np <= 10) mx_residual_kernel<10><<<grid, 256, sm_r, s>>>(Af, lambda, d.R, bvec + o, xvec + o, rvec + o, n, np, d.Pp, nmat, st, d.conv.p, tol);
+        else mx_residual_kernel<12><<<grid, 256, sm_r, s>>>(Af, lambda, d.R, bvec + o, xvec + o, rvec + o, n, np, d.Pp, nmat, st, d.conv.p, tol);
+        apply(rvec + o, (int64_t)d.Pp * n, 0, st);
       }
     }
   mx_final_check_kernel<<<(nmat + 63) / 64, 64, 0, s>>>(d.conv.p, nmat, steps, tol, fail_flag);
+  static const bool dbg_conv = getenv("RG_DBG_MX_CONV") != nullptr;      // diagnostic: correction sizes per step
+  if (dbg_conv) {
+    std::vector<unsigned int> hc(d.conv.n);
+    RG_CUDA(cudaStreamSynchronize(s));
+    RG_CUDA(cudaMemcpy(hc.data(), d.conv.p, hc.size() * 4, cudaMemcpyDeviceToHost));
+    for (int m = 0; m < nmat; m += std::max(1, nmat / 5)) {
+      fprintf(stderr, "[mx conv] system %d:", m);
+      for (int st = 1; st <= steps; ++st) {
+        float dx, xx;
+        memcpy(&dx, &hc[((size_t)st * nmat + m) * 2], 4);
+        memcpy(&xx, &hc[((size_t)st * nmat + m) * 2 + 1], 4);
+        fprintf(stderr, "  step %d dx/x = %.3g", st, xx > 0 ? dx / xx : 0.0);
+      }
+      fprintf(stderr, "\n");
+    }
+  }
 }
 
 float* MixedSolver::a_planes() { return impl->Ap.p; }

@@ -68,6 +68,9 @@ struct rg_ctx {
     rg::DevBuf<uint8_t> dig;          // radix-30 digit rows of gamma for the tensor-core prediction
     rg::DevBuf<double> dscale;        // [K][Qp] column scales
     std::map<int, CUtensorMap> dmaps; // digit-matrix tensor maps keyed by rows_p
+    // dense FP64 route for real-valued genotypes (l0_dense.cu)
+    rg::DevBuf<uint8_t> dense_in;                 // staged host input (probability / ploidy bytes or FP64 rows)
+    rg::DevBuf<double> gd, dpart, dpart_y;        // [bs][Npad] G~; chunk partials of G G^T and G Y
     // mixed-precision ridge solver (chol_mixed.cu): tensor-core factorisation + FP64 refinement, FP64 Cholesky fallback
     std::unique_ptr<rg::MixedSolver> mx;
     rg::DevBuf<double> mx_Af, mx_b, mx_x, mx_r;   // [K][n][n] fold systems; [K][Pp][n] rhs; [K R][Pp][n] solutions / residuals

@@ -133,6 +133,22 @@ class MixedSolver {
 // K full symmetric fold systems (no ridge shift) + right-hand sides as rows, for the mixed solver
 void launch_l0_assemble_sym(const AssembleArgs& a, const double* rhs, int P, int Pp, double* bvec, cudaStream_t s);
 
+// ---- l0_dense.cu: level-0 block on real-valued genotypes (8-bit dosages / FP64), dense FP64 like the reference
+void launch_dense_from_dosage(const uint8_t* probs, const uint8_t* miss, int64_t n_file, int bs, const int32_t* file_idx_pad,
+                              int ref_first, double* gd, int64_t npad, cudaStream_t s);
+void launch_dense_from_f64(const double* G, int64_t n_file, int bs, const int32_t* file_idx_pad, double* gd, int64_t npad,
+                           cudaStream_t s);
+void launch_dense_prepare(double* gd, int64_t npad, int bs, const int32_t* file_idx_pad, const double* xy, int cpp, int C,
+                          long long n_analyzed, double numtol, double* mu, double* sd, unsigned long long* err_slot,
+                          long long err_base, cudaStream_t s);
+void launch_dense_assemble(const double* part, int64_t part_stride, int ldp, const double* part_y, int64_t part_y_stride,
+                           const int2* fold_chunks, int K, int R, const double* lambda, int bs, int nC, int P, double* cm,
+                           int64_t cm_stride, int loocv, cudaStream_t s);
+void launch_dense_loocv_fill(const double* gd, int64_t npad, int bs, int nC, double* cm, int64_t cm_stride, int row0, int R,
+                             cudaStream_t s);
+void launch_dense_predict(const double* gd, int64_t npad, int bs, const double* cm, int64_t cm_stride, int ldc, int nC, int R,
+                          int P, const int32_t* tile_fold, const uint8_t* mask, double* const* W, int col0, cudaStream_t s);
+
 // ---- l0_predict.cu
 struct PredictArgs {
   int bs, rows_p, C, P, R, Qp, cpp, col0;

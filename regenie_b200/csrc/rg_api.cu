@@ -424,6 +424,22 @@ void sync_lanes(rg_ctx* h) {
   for (auto& l : h->lanes) RG_CUDA(cudaStreamSynchronize(l->stream));
 }
 
+// sample index map of the genotype file (cached): rebuilt only when the caller's sample_idx changes
+static void ensure_file_idx(rg_ctx* h, const int32_t* sample_idx) {
+  std::vector<int32_t> host_idx;
+  if (sample_idx) {
+    host_idx.resize(h->N);
+    RG_CUDA(cudaMemcpy(host_idx.data(), sample_idx, h->N * 4, cudaMemcpyDefault));
+    if (!h->file_idx_valid || h->cached_sample_idx != host_idx) {
+      build_file_idx(h, host_idx.data());
+      h->cached_sample_idx = host_idx;
+    }
+  } else if (!h->file_idx_valid || !h->cached_sample_idx.empty()) {
+    build_file_idx(h, nullptr);
+    h->cached_sample_idx.clear();
+  }
+}
+
 static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, int bs,
                          const int32_t* sample_idx, int ref_first, int block_id) {
   ensure_W(h);
@@ -444,23 +460,7 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
   const int Q = R * P, Qp = (int)round_up(Q, QT);
   const int64_t Npad = h->Npad;
 
-  // --- sample index map (cached)
-  {
-    std::vector<int32_t> host_idx;
-    const int32_t* hidx = nullptr;
-    if (sample_idx) {
-      host_idx.resize(h->N);
-      RG_CUDA(cudaMemcpy(host_idx.data(), sample_idx, h->N * 4, cudaMemcpyDefault));
-      hidx = host_idx.data();
-      if (!h->file_idx_valid || h->cached_sample_idx != host_idx) {
-        build_file_idx(h, hidx);
-        h->cached_sample_idx = host_idx;
-      }
-    } else if (!h->file_idx_valid || !h->cached_sample_idx.empty()) {
-      build_file_idx(h, nullptr);
-      h->cached_sample_idx.clear();
-    }
-  }
+  ensure_file_idx(h, sample_idx);
 
   // --- lane: own stream + scratch
   rg_ctx::Lane& L = *h->lanes[h->next_lane];
@@ -609,6 +609,99 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
   }
   enqueue_solve_f64(h, L, d, s);
   if (!h->loocv) enqueue_predict(h, L, d, L.cm.p, (int64_t)d.n_aug * d.nC, d.nC, d.nC, s);
+}
+
+
+// One level-0 block from real-valued genotypes: 8-bit BGEN probability pairs (probs / miss) or an FP64 matrix (G64).
+// Dense FP64 throughout, like the reference: decode + impute + residualise + scale, per-fold Gram / G Y on the FP64
+// tensor pipe, batched Cholesky, out-of-fold (or closed-form leave-one-out) predictions, standardisation into W.
+static void l0_block_dense(rg_ctx* h, const uint8_t* probs, const uint8_t* miss, const double* G64, int64_t n_file, int bs,
+                           const int32_t* sample_idx, int ref_first, int block_id) {
+  ensure_W(h);
+  for (int p = 0; p < h->P; ++p)
+    RG_CHECK(h->W_host_tab[p] != nullptr, "a phenotype has neither local storage nor an attached owner (rg_W_set_owned / rg_W_attach_peer)");
+  RG_CHECK(h->kind == 1, "handle is not a Step-1 handle");
+  RG_CHECK(bs > 0 && bs <= h->bs_max, "block size out of range");
+  RG_CHECK(block_id >= 0 && block_id < h->total_blocks, "block_id out of range");
+  RG_CHECK(n_file > 0, "bad sample count of the genotype file");
+  RG_CUDA(cudaSetDevice(h->device));
+  const int C = h->C, P = h->P, K = h->K, R = h->R;
+  const int64_t Npad = h->Npad;
+  ensure_file_idx(h, sample_idx);
+  rg_ctx::Lane& L = *h->lanes[h->next_lane];
+  resolve_lane(h, L);
+  h->last_lane = h->next_lane;
+  h->next_lane = (h->next_lane + 1) % (int)h->lanes.size();
+  cudaStream_t s = L.stream;
+  const BlockDims d = block_dims(h, bs, block_id);
+  h->last_bs = bs; h->last_rows_p = d.rows_p; h->last_nC = d.nC; h->last_n_aug = d.n_aug; h->last_nmat = d.nmat;
+
+  L.gd.alloc((size_t)h->bs_max * Npad);
+  L.mu.alloc(h->rows_p_max);
+  L.inv_sd.alloc(h->rows_p_max);
+  // --- input to the device, then G (FP64, padded fold layout)
+  if (G64) {
+    const double* src = G64;
+    if (!is_device_pointer(G64)) {
+      L.dense_in.alloc((size_t)h->bs_max * n_file * 8);
+      copy_to_device(L.dense_in.p, G64, (size_t)bs * n_file * 8, s);
+      src = reinterpret_cast<const double*>(L.dense_in.p);
+    }
+    launch_dense_from_f64(src, n_file, bs, h->file_idx_pad.p, L.gd.p, Npad, s);
+  } else {
+    const uint8_t *pd = probs, *md = miss;
+    if (!is_device_pointer(probs)) {
+      L.dense_in.alloc((size_t)h->bs_max * n_file * 3);
+      copy_to_device(L.dense_in.p, probs, (size_t)bs * n_file * 2, s);
+      pd = L.dense_in.p;
+      if (miss) {
+        copy_to_device(L.dense_in.p + (size_t)h->bs_max * n_file * 2, miss, (size_t)bs * n_file, s);
+        md = L.dense_in.p + (size_t)h->bs_max * n_file * 2;
+      }
+    }
+    launch_dense_from_dosage(pd, md, n_file, bs, h->file_idx_pad.p, ref_first, L.gd.p, Npad, s);
+  }
+  launch_dense_prepare(L.gd.p, Npad, bs, h->file_idx_pad.p, h->xy.p, h->cpp, C, h->n_analyzed, 1e-6, L.mu.p, L.inv_sd.p,
+                       h->err_slot.p, (long long)block_id * h->bs_max, s);
+  // --- per-chunk G G^T (DMMA) and G Y, summed per fold in a fixed order by the assembler
+  const int nC = d.nC, nch = h->nchunks;
+  const int64_t part_stride = (int64_t)nC * nC;
+  L.dpart.alloc((size_t)nch * round_up(h->bs_max, 64) * round_up(h->bs_max, 64));
+  L.dpart_y.alloc((size_t)P * nch * h->bs_max);
+  launch_l1_gram(L.gd.p, Npad, bs, h->chunks.p, nch, L.dpart.p, part_stride, nC, s);
+  for (int p = 0; p < P; ++p)
+    launch_l1_xty(L.gd.p, Npad, h->xy.p, h->cpp, C + p, h->chunks.p, nch, L.dpart_y.p + (size_t)p * nch * bs, bs, s);
+  {
+    const int nC_max = (int)round_up(h->bs_max, 64);
+    const size_t need = (size_t)d.nmat * (nC_max + d.Ppad + (h->loocv ? Npad : 0)) * nC_max;
+    if (L.cm.n < need) {
+      L.cm.alloc(need);
+      RG_CUDA(cudaMemsetAsync(L.cm.p, 0, need * 8, s));
+    }
+    L.inv.alloc(chol_inv_elems(nC_max, d.nmat));
+  }
+  const int64_t cm_stride = (int64_t)d.n_aug * nC;
+  launch_dense_assemble(L.dpart.p, part_stride, nC, L.dpart_y.p, (int64_t)nch * bs, h->fold_chunks.p, K, R, h->lambda.p, bs, nC,
+                        P, L.cm.p, cm_stride, h->loocv, s);
+  if (h->loocv) launch_dense_loocv_fill(L.gd.p, Npad, bs, nC, L.cm.p, cm_stride, nC + d.Ppad, R, s);
+  launch_chol_factor(L.cm.p, cm_stride, nC, d.n_aug, d.nmat, L.inv.p, h->err_slot.p,
+                     (long long)(1ll << 40) + (long long)block_id * 1024, s);
+  h->launches += 5 + P + chol_num_launches(nC);
+  L.part.alloc((size_t)d.ntiles_s * d.Qp * 2);
+  L.mean_invsd.alloc((size_t)2 * d.Qp);
+  if (h->loocv) {
+    launch_l0_loocv_pred(L.cm.p, cm_stride, nC, bs, d.Ppad, P, R, h->xy.p, h->cpp, C, h->mask.p, Npad, h->W_tab.p, d.col0,
+                         L.part.p, d.Qp, s);
+    launch_l0_std_reduce_only(L.part.p, d.ntiles_s, d.Qp, d.Q, P, h->neff.p, L.mean_invsd.p, s);
+    launch_l0_loocv_std_apply(h->W_tab.p, Npad, d.col0, P, d.Q, h->mask.p, L.mean_invsd.p, s);
+    h->launches += 3;
+    return;
+  }
+  launch_chol_backsolve(L.cm.p, cm_stride, nC, P, d.nmat, L.inv.p, s);
+  launch_dense_predict(L.gd.p, Npad, bs, L.cm.p, cm_stride, nC, nC, R, P, h->tile_fold.p, h->mask.p, h->W_tab.p, d.col0, s);
+  const int nparts = launch_l0_colsum(h->W_tab.p, Npad, d.col0, P, d.Q, d.Qp, L.part.p, s);
+  launch_l0_standardize(L.part.p, nparts, d.Qp, d.Q, P, h->neff.p, L.mean_invsd.p, h->W_tab.p, Npad, d.col0, h->is_real.p, s);
+  h->launches += 6;
 }
 
 void require_gpu_public(int device) { require_gpu(device); }
@@ -796,6 +889,23 @@ int rg_l0_block_bed(rg_handle h, const uint8_t* packed, int64_t row_stride, int3
   RG_API_BEGIN
   RG_CHECK(h && packed, "null argument");
   l0_block_bed(h, packed, row_stride, bs, sample_idx, ref_first, block_id);
+  RG_CUDA(cudaGetLastError());
+  RG_API_END
+}
+
+int rg_l0_block_dosage_u8(rg_handle h, const uint8_t* probs, const uint8_t* ploidy_missing, int64_t n_file, int32_t bs,
+                          const int32_t* sample_idx, int32_t ref_first, int32_t block_id) {
+  RG_API_BEGIN
+  RG_CHECK(h && probs, "null argument");
+  l0_block_dense(h, probs, ploidy_missing, nullptr, n_file, bs, sample_idx, ref_first, block_id);
+  RG_CUDA(cudaGetLastError());
+  RG_API_END
+}
+
+int rg_l0_block_f64(rg_handle h, const double* G, int64_t n_file, int32_t bs, const int32_t* sample_idx, int32_t block_id) {
+  RG_API_BEGIN
+  RG_CHECK(h && G, "null argument");
+  l0_block_dense(h, nullptr, nullptr, G, n_file, bs, sample_idx, 0, block_id);
   RG_CUDA(cudaGetLastError());
   RG_API_END
 }

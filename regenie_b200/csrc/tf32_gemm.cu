@@ -26,7 +26,9 @@ namespace {
 
 constexpr int TG_M = 128, TG_N = 128;
 constexpr int TG_KC = 32;                          // floats per K chunk = one 128-byte swizzle atom
-constexpr int TG_STAGES = 3;
+constexpr int TG_STAGES = 1;                          // one 64 KiB stage per CTA, THREE CTAs per SM: the tiles of this
+                                                   // solver are short (K <= 1024) and the launches small, so latency is hidden
+                                                   // across co-resident CTAs instead of a deep per-CTA ring (profiles/ncu_r2c_*)
 constexpr int TG_PLANE_BYTES = TG_M * 128;         // 16 KiB
 constexpr int TG_OP_BYTES = 2 * TG_PLANE_BYTES;    // hi + lo
 constexpr int TG_STAGE_BYTES = 2 * TG_OP_BYTES;    // A + B = 64 KiB
@@ -102,10 +104,20 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 }  // namespace
 
 // grid: (ntiles, batch); tile entry = (A row tile, B row tile, first K chunk, number of K chunks)
-__global__ void __launch_bounds__(TG_THREADS, 1)
+__global__ void __launch_bounds__(TG_THREADS, 3)
 tf32x3_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmI,
                       const int4* __restrict__ tiles, Tf32GemmEpilogue ep) {
@@ -217,68 +229,71 @@ tf32x3_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                                : nullptr;
     const double diag_add = (ep.diag_add != nullptr && tile.x == tile.y) ? ep.diag_add[ep.diag_mod > 0 ? mat % ep.diag_mod : mat] : 0.0;
     const bool diag_tile = tile.x == tile.y;
+    constexpr int EC = 16;                               // columns per epilogue pass (register budget of 3 CTAs / SM)
 #pragma unroll 1
-    for (int c = 0; c < TG_N / 32; ++c) {
-      uint32_t v[32];
+    for (int c = 0; c < TG_N / EC; ++c) {
+      uint32_t v[EC];
       if (nkc > 0) {
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+        tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * EC), v);
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0u;
+        for (int j = 0; j < EC; ++j) v[j] = 0u;
       }
-      float o[32];
+      float o[EC];
       if (cin) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const double2 cc = *reinterpret_cast<const double2*>(cin + c * 32 + j);
+        for (int j = 0; j < EC; j += 2) {
+          const double2 cc = *reinterpret_cast<const double2*>(cin + c * EC + j);
           o[j] = (float)(cc.x - (double)__uint_as_float(v[j]));
           o[j + 1] = (float)(cc.y - (double)__uint_as_float(v[j + 1]));
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) o[j] = ep.negate ? -__uint_as_float(v[j]) : __uint_as_float(v[j]);
+        for (int j = 0; j < EC; ++j) o[j] = ep.negate ? -__uint_as_float(v[j]) : __uint_as_float(v[j]);
       }
       if (diag_tile && diag_add != 0.0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) if (c * 32 + j == r_loc) o[j] = (float)((double)o[j] + diag_add);
+        for (int j = 0; j < EC; ++j) if (c * EC + j == r_loc) o[j] = (float)((double)o[j] + diag_add);
       }
       if (ep.lower_only && diag_tile) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) if (c * 32 + j > r_loc) o[j] = 0.f;
+        for (int j = 0; j < EC; ++j) if (c * EC + j > r_loc) o[j] = 0.f;
       }
-      float hi[32];
+      if (ep.out || ep.out_t) {
+        float hi[EC];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        uint32_t t;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(o[j]));
-        hi[j] = __uint_as_float(t);
-      }
-      if (ep.out) {                                       // D as hi / lo planes, row-major
-        float* oh = ep.out + 2 * mat_off + (int64_t)row * n + col0 + c * 32;
-        float* ol = oh + n * n;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          *reinterpret_cast<float4*>(oh + j) = make_float4(hi[j], hi[j + 1], hi[j + 2], hi[j + 3]);
-          *reinterpret_cast<float4*>(ol + j) = make_float4(o[j] - hi[j], o[j + 1] - hi[j + 1], o[j + 2] - hi[j + 2], o[j + 3] - hi[j + 3]);
+        for (int j = 0; j < EC; ++j) {
+          uint32_t t;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(o[j]));
+          hi[j] = __uint_as_float(t);
         }
-      }
-      if (ep.out_t) {                                     // D^T as hi / lo planes: lanes of a warp hold consecutive rows
-        float* th = ep.out_t + 2 * mat_off + (int64_t)(col0 + c * 32) * n + row;
-        float* tl = th + n * n;
+        if (ep.out) {                                       // D as hi / lo planes, row-major
+          float* oh = ep.out + 2 * mat_off + (int64_t)row * n + col0 + c * EC;
+          float* ol = oh + n * n;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          th[(int64_t)j * n] = hi[j];
-          tl[(int64_t)j * n] = o[j] - hi[j];
+          for (int j = 0; j < EC; j += 4) {
+            *reinterpret_cast<float4*>(oh + j) = make_float4(hi[j], hi[j + 1], hi[j + 2], hi[j + 3]);
+            *reinterpret_cast<float4*>(ol + j) = make_float4(o[j] - hi[j], o[j + 1] - hi[j + 1], o[j + 2] - hi[j + 2], o[j + 3] - hi[j + 3]);
+          }
+        }
+        if (ep.out_t) {                                     // D^T as hi / lo planes: lanes of a warp hold consecutive rows
+          float* th = ep.out_t + 2 * mat_off + (int64_t)(col0 + c * EC) * n + row;
+          float* tl = th + n * n;
+#pragma unroll
+          for (int j = 0; j < EC; ++j) {
+            th[(int64_t)j * n] = hi[j];
+            tl[(int64_t)j * n] = o[j] - hi[j];
+          }
         }
       }
       if (ep.out_plain) {                                 // D as one FP32 plane (+ its mirror image for symmetric results)
-        float* po = ep.out_plain + mat_off + (int64_t)row * n + col0 + c * 32;
+        float* po = ep.out_plain + mat_off + (int64_t)row * n + col0 + c * EC;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(po + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        for (int j = 0; j < EC; j += 4) *reinterpret_cast<float4*>(po + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
         if (ep.mirror && !diag_tile) {
-          float* pt = ep.out_plain + mat_off + (int64_t)(col0 + c * 32) * n + row;
+          float* pt = ep.out_plain + mat_off + (int64_t)(col0 + c * EC) * n + row;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) pt[(int64_t)j * n] = o[j];
+          for (int j = 0; j < EC; ++j) pt[(int64_t)j * n] = o[j];
         }
       }
     }

@@ -255,7 +255,6 @@ Params parse_cli(int argc, char** argv) {
   if (!p.setl0.empty()) p.l0 = (int)p.setl0.size();
   if (!p.setl1.empty()) p.l1 = (int)p.setl1.size();
   if (p.step != 1 && p.step != 2) throw Fail("specify which mode regenie should be running using option '--step'.");
-  if (!p.bgen.empty() && p.step == 1) throw Fail("--bgen input in --step 1 is not implemented yet in rgb200 (hard-call .bed only).");
   if ((!p.bgen.empty()) + (!p.bed.empty()) + (!p.pgen.empty()) > 1) throw Fail("specify only one genotype input (--bed, --pgen or --bgen).");
   if (!p.pgen.empty()) p.ref_first = false;          // .pgen rows are emitted as ref-last PLINK 1 rows counting ALT
   if (p.firth && p.spa) throw Fail("cannot use both --firth and --spa.");
@@ -369,8 +368,29 @@ void run_step1(const Params& p_in, Log& log) {
     p.exclude.clear();
     p.lowmem_prefix = master.jobs[p.run_l0_job - 1].prefix;
   }
-  BedFile g;
-  open_rows(p, g, read_id_list(p.exclude, 1), read_id_list(p.extract, 1), read_id_list(p.remove, 2), read_id_list(p.keep, 2), log);
+  // genotype input: 2-bit rows (.bed / decoded .pgen) or 8-bit dosages (.bgen, readChunkFromBGENFileToG_fast src/Geno.cpp:1574)
+  const bool use_bgen = !p.bgen.empty();
+  BedFile gbed;
+  BgenFile gg;
+  if (use_bgen) {
+    gg.open(p.bgen, p.sample, p.ref_first, read_id_list(p.exclude, 1), read_id_list(p.extract, 1), read_id_list(p.remove, 2),
+            read_id_list(p.keep, 2), p.chrs, p.bgi);
+    if (gg.used_bgi) log << "   -index bgi file [" << (p.bgi.empty() ? p.bgen + ".bgi" : p.bgi) << "]\n";
+    log << " * bgen                : [" << p.bgen << "] n_snps = " << gg.snps.size() << ", n_samples = " << gg.keys.size() << "\n";
+  } else {
+    open_rows(p, gbed, read_id_list(p.exclude, 1), read_id_list(p.extract, 1), read_id_list(p.remove, 2), read_id_list(p.keep, 2), log);
+  }
+  // the fields of either reader the rest of Step 1 needs
+  struct GenoView {
+    const std::vector<Snp>& snps;
+    const std::vector<std::string>& keys;
+    const std::map<std::string, uint32_t>& key_to_ind;
+    const std::vector<int32_t>& sample_idx;
+    size_t n_file;
+    size_t row_stride;
+  };
+  const GenoView g = use_bgen ? GenoView{gg.snps, gg.keys, gg.key_to_ind, gg.sample_idx, (size_t)gg.n_file, 0}
+                              : GenoView{gbed.snps, gbed.keys, gbed.key_to_ind, gbed.sample_idx, gbed.keys_file.size(), (size_t)gbed.row_stride};
   if (g.snps.empty()) throw Fail("no variant left to include in analysis.");
   if (g.snps.size() > 1000000 && !p.force_step1)
     throw Fail("it is not recommened to use more than 1000000 variants in step 1 (otherwise use '--force-step1').");
@@ -434,8 +454,8 @@ void run_step1(const Params& p_in, Log& log) {
   }
 
   // ---- level 0
-  std::vector<uint8_t> rows((size_t)p.bsize * g.row_stride);
-  const bool subset = g.keys.size() != g.keys_file.size();
+  std::vector<uint8_t> rows(use_bgen ? 0 : (size_t)p.bsize * g.row_stride);
+  const bool subset = g.keys.size() != g.n_file;
   int last_chr = -1;
   const double t0 = now_ms();
   if (p.run_l1) {
@@ -463,15 +483,28 @@ void run_step1(const Params& p_in, Log& log) {
   // out of a buffer is staged before rg_l0_block_bed returns, so it can be refilled two blocks later)
   std::vector<uint8_t> rows2(rows.size());
   uint8_t* bufs[2] = {rows.data(), rows2.data()};
+  std::vector<uint8_t> probs[2], pmiss[2];                     // .bgen: inflated probability pairs + ploidy bytes of a block
+  if (use_bgen && !p.run_l1)
+    for (int k = 0; k < 2; ++k) { probs[k].resize((size_t)p.bsize * g.n_file * 2); pmiss[k].resize((size_t)p.bsize * g.n_file); }
+  const int io_threads = std::max(1, std::min(32, (int)std::thread::hardware_concurrency()));
   std::future<void> pending;
-  auto fetch = [&](int b) { return std::async(std::launch::async, [&, b] { g.read_rows(blocks[b].first, blocks[b].size, bufs[b & 1]); }); };
+  auto fetch = [&](int b) {
+    return std::async(std::launch::async, [&, b] {
+      if (use_bgen) gg.read_block(blocks[b].first, blocks[b].size, probs[b & 1].data(), pmiss[b & 1].data(), io_threads);
+      else gbed.read_rows(blocks[b].first, blocks[b].size, bufs[b & 1]);
+    });
+  };
   if (nb > 0 && !p.run_l1) pending = fetch(0);
   for (int b = 0; b < nb && !p.run_l1; ++b) {
     if (blocks[b].chrom != last_chr) { log << "Chromosome " << blocks[b].chrom << "\n"; last_chr = blocks[b].chrom; }
     pending.get();
     if (b + 1 < nb) pending = fetch(b + 1);
-    rg_check(rg_l0_block_bed(h, bufs[b & 1], (int64_t)g.row_stride, blocks[b].size,
-                             subset ? g.sample_idx.data() : nullptr, p.ref_first, b));
+    if (use_bgen)
+      rg_check(rg_l0_block_dosage_u8(h, probs[b & 1].data(), pmiss[b & 1].data(), (int64_t)g.n_file, blocks[b].size,
+                                     subset ? g.sample_idx.data() : nullptr, p.ref_first, b));
+    else
+      rg_check(rg_l0_block_bed(h, bufs[b & 1], (int64_t)g.row_stride, blocks[b].size,
+                               subset ? g.sample_idx.data() : nullptr, p.ref_first, b));
     log << " block [" << b + 1 << "] : " << blocks[b].size << " snps\n";
   }
   const int64_t st = rg_l0_status(h);

@@ -74,6 +74,22 @@ def _sum_to_all(arr, device):
     return t.cpu().numpy()
 
 
+def attach_peers(st):
+    """Give every phenotype's level-0 predictors a home: phenotype p lives in the HBM of rank p mod world; this rank
+    maps the other ranks' W allocations (CUDA IPC over NVLink / NVSwitch) so that its level-0 kernels store their tiles
+    straight into the owner's memory.  Returns the owner list.  Collective: every rank must call it."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    owner = phenotype_owner(st.P, world)
+    st.W_set_owned([1 if owner[p] == rank else 0 for p in range(st.P)])      # N x B x P/world of HBM per rank
+    handles = [None] * world
+    dist.all_gather_object(handles, st.W_export())
+    for r in range(world):
+        if r != rank:
+            st.W_attach_peer(handles[r], [1 if owner[p] == r else 0 for p in range(st.P)])
+    dist.barrier()
+    return owner
+
+
 def step1_distributed(st, n_blocks, feed_block, tau, chr_of_block, device, bt=None):
     """Step 1 with level-0 blocks sharded across ranks and level 1 sharded by phenotype.
 
@@ -86,14 +102,7 @@ def step1_distributed(st, n_blocks, feed_block, tau, chr_of_block, device, bt=No
     final gather of the P x R1 sums and N x 23 LOCO predictions.  Returns (cumsums, best_idx, loco) on every rank.
     """
     rank, world = dist.get_rank(), dist.get_world_size()
-    owner = phenotype_owner(st.P, world)
-    st.W_set_owned([1 if owner[p] == rank else 0 for p in range(st.P)])      # N x B x P/world of HBM per rank
-    handles = [None] * world
-    dist.all_gather_object(handles, st.W_export())
-    for r in range(world):
-        if r != rank:
-            st.W_attach_peer(handles[r], [1 if owner[p] == r else 0 for p in range(st.P)])
-    dist.barrier()
+    attach_peers(st)
     first, n = partition_blocks(n_blocks, world)[rank]
     for b in range(first, first + n):
         feed_block(b)

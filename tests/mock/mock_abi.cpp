@@ -143,6 +143,28 @@ int rg_l0_block_bed(rg_handle h, const uint8_t* packed, int64_t row_stride, int3
   }
   return 0;
 }
+int rg_l0_block_dosage_u8(rg_handle h, const uint8_t* probs, const uint8_t* pm, int64_t n_file, int32_t bs, const int32_t* sample_idx,
+                          int32_t ref_first, int32_t block_id) {
+  if (block_id < 0 || block_id >= h->nb || bs > h->bs_max) return fail("mock: bad block");
+  // same deterministic function of the inputs as rg_l0_block_bed, on dosage units of 1/255
+  std::vector<double> colsum(h->N, 0.0);
+  for (int v = 0; v < bs; ++v)
+    for (int64_t s = 0; s < h->N; ++s) {
+      const int64_t f = sample_idx ? sample_idx[s] : s;
+      const uint8_t* pr = probs + ((size_t)v * n_file + f) * 2;
+      const bool miss = pm && (pm[(size_t)v * n_file + f] & 0x80);
+      const double g = miss ? 0.25 : (ref_first ? 2.0 - (2.0 * pr[0] + pr[1]) / 255.0 : (2.0 * pr[0] + pr[1]) / 255.0);
+      colsum[s] += g * (1.0 + 0.001 * (v % 17));
+    }
+  for (int p = 0; p < h->P; ++p) {
+    std::vector<double>& w = h->W[{block_id, p}];
+    w.assign((size_t)h->N * h->R, 0.0);
+    for (int r = 0; r < h->R; ++r)
+      for (int64_t s = 0; s < h->N; ++s)
+        w[(size_t)r * h->N + s] = h->mask[(size_t)p * h->N + s] ? (colsum[s] / bs - 1.0) * (r + 1) * 0.1 + 0.01 * h->Y[(size_t)p * h->N + s] : 0.0;
+  }
+  return 0;
+}
 int64_t rg_l0_status(rg_handle) { return 0; }
 int rg_l0_fetch_W(rg_handle h, int32_t b, int32_t ph, double* out) {
   auto it = h->W.find({b, ph});

@@ -20,7 +20,6 @@ def test_cli_errors_have_the_reference_shape(tmp_path, golden_dir):
         (["--step", "2"] + base, "must specify --pred if using --step 2"),
         (["--step", "1", "--skat"] + base, "outside the hot path covered by rgb200"),
         (["--step", "2", "--pred", "x", "--bed", d + "/example", "--bgen", d + "/example.bgen"] + base[2:], "specify only one genotype input"),
-        (["--step", "1", "--bgen", d + "/example.bgen"] + base[2:], "--bgen input in --step 1 is not implemented"),
         (["--step", "2", "--firth", "--bt", "--pred", "x"] + base, "exact Firth"),
         (["--step", "2", "--split-l0", "p,2", "--pred", "x"] + base, "only work in step 1"),
         (["--step", "2", "--pred", "x", "--range", "1:100"] + base, "wrong format for --range (must be CHR:MINPOS-MAXPOS)."),
