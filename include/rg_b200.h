@@ -338,6 +338,12 @@ int rg_l1_select(rg_handle h, const uint8_t* selected);
  * rg_l1_attach_W before rg_l1_fit (the exchange itself is done by the caller with NCCL). */
 int rg_W_info(rg_handle h, int32_t ph, void** dev_ptr, int64_t* ld, int64_t* ncols);
 
+/* Same redirection as rg_W_attach_peer for a peer handle that lives in THIS process on another GPU (one host thread per
+ * GPU, rgb200 --gpus N): peer access is enabled from h's device to peer's device and the entries of the phenotypes
+ * `owned_by_peer` marks point straight at the peer's W allocation (no CUDA IPC: an IPC handle cannot be opened by the
+ * process that exported it).  Both handles must have had rg_W_set_owned called with their own masks. */
+int rg_W_attach_local(rg_handle h, rg_handle peer, const uint8_t* owned_by_peer);
+
 /* ------------------------------------------------------------------ test / profiling hooks */
 /* Copy a named intermediate of the last level-0 block to the host (tests only).
  * Returns the number of bytes written, or <0 on error.  See DESIGN.md for names. */

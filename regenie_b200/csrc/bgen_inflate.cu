@@ -119,9 +119,7 @@ static void bgen_inflate(rg_ctx* h, const uint8_t* comp, const uint64_t* comp_of
   const char* mode_env = getenv("RG_B200_INFLATE");          // read per call: the bench times both kernels in one process
   const bool use_window = mode_env && std::string(mode_env) == "window";
   if (use_window) {
-    static const cudaError_t attr = cudaFuncSetAttribute(bgen_inflate_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         (int)kWindowSmem);
-    RG_CUDA(attr);
+    ensure_dyn_smem(reinterpret_cast<const void*>(bgen_inflate_window_kernel), kWindowSmem);
     bgen_inflate_window_kernel<<<(unsigned)ceil_div(bs, kWindowWarps), kWindowWarps * 32, kWindowSmem, s>>>(
         h->inflate_comp.p, h->inflate_offs.p, h->inflate_raw.p, raw_stride, raw_len, bs, h->inflate_status.p);
   } else {

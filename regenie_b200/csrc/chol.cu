@@ -239,11 +239,7 @@ void launch_chol_factor(double* cm, int64_t stride, int nC, int n_aug, int batch
                         unsigned long long* err_slot, long long err_base, cudaStream_t s) {
   const int ntiles = n_aug / TB;
   const int64_t inv_stride = (int64_t)(nC / TB) * TB * TB;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RG_CUDA(cudaFuncSetAttribute(chol_update_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem));
-    attr_set = true;
-  }
+  ensure_dyn_smem(reinterpret_cast<const void*>(chol_update_trsm_kernel), kFusedSmem);
   double* inv_t = inv + (int64_t)batch * inv_stride;      // M^T blocks live behind the M blocks (chol_inv_elems)
   // profiling aid (RG_B200_CHOL_TIMING=1): CUDA-event time of the three kernels of every panel step
   static const bool timing = getenv("RG_B200_CHOL_TIMING") != nullptr;
@@ -281,11 +277,7 @@ void launch_chol_factor(double* cm, int64_t stride, int nC, int n_aug, int batch
 void launch_chol_backsolve(double* cm, int64_t stride, int nC, int P, int batch, const double* inv,
                            cudaStream_t s) {
   const size_t smem = ((size_t)TB * (TB + 1) + (size_t)2 * TB * P) * sizeof(double);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    RG_CUDA(cudaFuncSetAttribute(chol_backsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  ensure_dyn_smem(reinterpret_cast<const void*>(chol_backsolve_kernel), smem);
   const int64_t inv_stride = (int64_t)(nC / TB) * TB * TB;
   chol_backsolve_kernel<<<batch, BS_THREADS, smem, s>>>(cm, stride, nC, nC, P, inv, inv_stride);
 }
@@ -382,11 +374,7 @@ chol_rows_backsolve_kernel(double* __restrict__ cm, int64_t stride, int ld, int 
 void launch_chol_rows_backsolve(double* cm, int64_t stride, int nC, int row0, int nrows, int batch,
                                 const double* inv, cudaStream_t s) {
   const size_t smem = ((size_t)TB * (TB + 1) + (size_t)TB * (TB + 2)) * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    RG_CUDA(cudaFuncSetAttribute(chol_rows_backsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  ensure_dyn_smem(reinterpret_cast<const void*>(chol_rows_backsolve_kernel), smem);
   const int64_t inv_stride = (int64_t)(nC / TB) * TB * TB;
   dim3 grid(nrows / TB, 1, batch);
   chol_rows_backsolve_kernel<<<grid, 256, smem, s>>>(cm, stride, nC, nC, row0, inv, inv_stride);

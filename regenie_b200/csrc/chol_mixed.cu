@@ -512,16 +512,12 @@ void MixedSolver::solve(const double* Af, const double* lambda, const double* bv
   RG_CHECK(n > 0, "mixed solver: prepare() first");
   RG_CHECK(P <= d.Pp, "mixed solver: more right-hand sides than the row pitch");
   RG_CHECK(steps >= 1 && steps <= kMxMaxSteps, "mixed solver: bad step count");
-  static bool attr = false;
   const size_t potrf_smem = ((size_t)3 * PT * PLD + PT) * sizeof(float);
-  if (!attr) {
-    RG_CUDA(cudaFuncSetAttribute(potrf128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_smem));
-    RG_CUDA(cudaFuncSetAttribute(mx_apply_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
-    RG_CUDA(cudaFuncSetAttribute(mx_residual_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
-    RG_CUDA(cudaFuncSetAttribute(mx_apply_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
-    RG_CUDA(cudaFuncSetAttribute(mx_residual_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
-    attr = true;
-  }
+  ensure_dyn_smem(reinterpret_cast<const void*>(potrf128_kernel), potrf_smem);
+  ensure_dyn_smem(reinterpret_cast<const void*>(mx_apply_kernel<12>), 98304);
+  ensure_dyn_smem(reinterpret_cast<const void*>(mx_residual_kernel<12>), 98304);
+  ensure_dyn_smem(reinterpret_cast<const void*>(mx_apply_kernel<10>), 98304);
+  ensure_dyn_smem(reinterpret_cast<const void*>(mx_residual_kernel<10>), 98304);
   RG_CHECK(n <= 2048, "mixed solver: n <= 2048");
   RG_CUDA(cudaMemsetAsync(d.conv.p, 0, d.conv.n * sizeof(unsigned int), s));
   const int4* tl = d.plan.tiles.p;

@@ -4,7 +4,10 @@
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace rg {
@@ -67,6 +70,21 @@ struct DevBuf {
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
 };
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of (kernel, DEVICE): several handles on different GPUs may
+// live in one process (rgb200 --gpus N, one host thread per GPU), so the "already set" memo is kept per device.
+inline void ensure_dyn_smem(const void* func, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> done;
+  int dev = 0;
+  RG_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& cur = done[std::make_pair(dev, func)];
+  if (bytes > cur) {
+    RG_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    cur = bytes;
+  }
+}
 
 // Copy `bytes` from a host-or-device pointer to device memory on `stream`.
 void copy_to_device(void* dst, const void* src, size_t bytes, cudaStream_t stream);

@@ -271,12 +271,7 @@ void gram_tile_list(int rows2, std::vector<int2>& tiles) {
 
 void launch_gram_tcgen05(const CUtensorMap& tm, const CUtensorMap& tmB, const int2* tiles, int ntiles, const int2* fold_k, int K,
                          float* out, int ldo, int64_t fold_stride, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    RG_CUDA(cudaFuncSetAttribute(gram_fp8_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)gram_smem_bytes()));
-    attr_set = true;
-  }
+  ensure_dyn_smem(reinterpret_cast<const void*>(gram_fp8_tcgen05_kernel), gram_smem_bytes());
   dim3 grid(ntiles, K);
   gram_fp8_tcgen05_kernel<<<grid, NTHREADS, gram_smem_bytes(), s>>>(tm, tmB, tiles, fold_k, out, ldo, fold_stride);
 }

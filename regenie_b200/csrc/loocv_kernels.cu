@@ -230,11 +230,7 @@ void launch_l0_loocv_pred(const double* cm, int64_t cm_stride, int nC, int bs, i
                           const double* xy, int cpp, int C, const uint8_t* mask, int64_t npad, double* const* W,
                           int col0, double* part, int Qp, cudaStream_t s) {
   const size_t smem = (size_t)std::min(P, kMaxPhenoTile) * nC * sizeof(double);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    RG_CUDA(cudaFuncSetAttribute(l0_loocv_pred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  ensure_dyn_smem(reinterpret_cast<const void*>(l0_loocv_pred_kernel), smem);
   dim3 grid((unsigned)(npad / 128), R);
   l0_loocv_pred_kernel<<<grid, 128, smem, s>>>(cm, cm_stride, nC, bs, Ppad, P, R, xy, cpp, C, mask, npad, W,
                                               col0, part, Qp);

@@ -361,11 +361,7 @@ void launch_l0_predict_tcgen05(const CUtensorMap& tmZ, const CUtensorMap& tmD, c
                                cudaStream_t s) {
   const size_t smem = (size_t)PT_STAGES * PT_STAGE_BYTES + 1024 + 128 +
                       ((size_t)kLimbQ * (1 + a.C)) * sizeof(double);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    RG_CUDA(cudaFuncSetAttribute(l0_predict_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  ensure_dyn_smem(reinterpret_cast<const void*>(l0_predict_tcgen05_kernel), smem);
   dim3 grid(ntiles, a.ngroups);
   l0_predict_tcgen05_kernel<<<grid, PT_THREADS, smem, s>>>(tmZ, tmD, a);
 }

@@ -855,6 +855,33 @@ int rg_W_attach_peer(rg_handle h, const void* ipc_handle_64, const uint8_t* owne
   RG_API_END
 }
 
+int rg_W_attach_local(rg_handle h, rg_handle peer, const uint8_t* owned_by_peer) {
+  RG_API_BEGIN
+  RG_CHECK(h && peer && h != peer && h->kind == 1 && peer->kind == 1 && owned_by_peer, "bad argument");
+  RG_CHECK(h->P == peer->P && h->Npad == peer->Npad && h->B == peer->B, "handles describe different problems");
+  RG_CUDA(cudaSetDevice(peer->device));
+  ensure_W(peer);
+  rg::sync_lanes(h);
+  ensure_W(h);
+  if (h->device != peer->device) {
+    int can = 0;
+    RG_CUDA(cudaDeviceCanAccessPeer(&can, h->device, peer->device));
+    RG_CHECK(can, "no peer access between the two devices");
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+    else RG_CUDA(e);
+  }
+  size_t slot = 0;
+  for (int p = 0; p < h->P; ++p)
+    if (owned_by_peer[p]) {
+      RG_CHECK(peer->W_owned[p], "the peer does not own storage for a phenotype it is said to own");
+      h->W_host_tab[p] = peer->W.p + (slot++) * (size_t)h->Npad * h->B;
+      h->l1_select[p] = 0;
+    }
+  RG_CUDA(cudaMemcpy(h->W_tab.p, h->W_host_tab.data(), h->P * sizeof(double*), cudaMemcpyHostToDevice));
+  RG_API_END
+}
+
 int rg_l1_select(rg_handle h, const uint8_t* sel) {
   RG_API_BEGIN
   RG_CHECK(h && h->kind == 1 && sel, "bad argument");

@@ -350,11 +350,7 @@ void launch_tf32x3_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const in
   RG_CHECK(ep.c_chunks == 0 || (tmC && tmI), "tf32 gemm: the C phase needs its tensor maps");
   if (ntiles <= 0 || batch <= 0) return;
   constexpr size_t smem = (size_t)TG_STAGES * TG_STAGE_BYTES + 1024 + 128;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RG_CUDA(cudaFuncSetAttribute(tf32x3_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  ensure_dyn_smem(reinterpret_cast<const void*>(tf32x3_gemm_nt_kernel), smem);
   dim3 grid(ntiles, batch);
   tf32x3_gemm_nt_kernel<<<grid, TG_THREADS, smem, s>>>(tmA, tmB, tmC ? *tmC : tmA, tmI ? *tmI : tmB, tiles, ep);
 }

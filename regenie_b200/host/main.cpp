@@ -16,6 +16,7 @@
 #include <limits>
 
 #include "../../include/rg_b200.h"
+#include <mutex>
 #include <thread>
 
 #include "bgen.hpp"
@@ -64,6 +65,7 @@ struct Params {
   int min_case_count = 10;                     // --minCaseCount
   bool no_split = false;                       // --no-split: one <out>.regenie for all traits (hard-call input)
   int test_type = 0;                           // --test additive | dominant | recessive (step 2)
+  int gpus = 1;                                // --gpus N (step 1): level-0 blocks sharded over N GPUs of this node, level 1 by phenotype
   bool gpu_inflate = false;                    // --gpu-inflate: zlib payloads of the .bgen are inflated on the device (rg_bgen_inflate)
   uint32_t par1_max = 2781479, par2_min = 155701383;   // hg38 (check_build_code, src/Regenie.cpp:1643-1660)
 };
@@ -151,6 +153,7 @@ Params parse_cli(int argc, char** argv) {
     else if (a == "--minMAC") p.min_mac = atof(need(i).c_str());
     else if (a == "--lowmem-prefix") p.lowmem_prefix = need(i);
     else if (a == "--gpu") p.gpu = atoi(need(i).c_str());
+    else if (a == "--gpus") p.gpus = atoi(need(i).c_str());
     else if (a == "--threads") p.threads = atoi(need(i).c_str());   // host threads: BGEN inflate only
     else if (a == "--sample") p.sample = need(i);
     else if (a == "--phenoCol") csv_into(need(i), p.pheno_cols);
@@ -246,6 +249,7 @@ Params parse_cli(int argc, char** argv) {
                    "  step 2 binary traits: --bt [--firth --approx | --spa] [--pThresh p] with --bed or --bgen F [--sample F] [--bgi F]\n"
                    "  [--gz] [--print-prs | --use-prs] [--write-samples [--print-pheno]]  (.gz inputs are read by file name)\n"
                    "  [--test additive|dominant|recessive] [--no-split] [--af-cc] [--minCaseCount n] [--write-null-firth | --use-null-firth F]\n"
+                   "  [--gpus N]  step 1: shard the level-0 blocks over N GPUs of this node (level 1 by phenotype), same output files\n"
                    "  [--gpu-inflate]  step 2 on zlib-compressed .bgen: inflate the genotype blocks on the GPU instead of the host\n";
       exit(0);
     } else {
@@ -439,10 +443,37 @@ void run_step1(const Params& p_in, Log& log) {
   cfg.device = p.gpu; cfg.n_samples = N; cfg.n_cov = ph.C; cfg.n_pheno = P; cfg.n_folds = p.cv;
   cfg.n_ridge_l0 = p.l0; cfg.n_ridge_l1 = p.l1; cfg.loocv = p.loocv; cfg.max_block_size = p.bsize;
   cfg.total_blocks = nb; cfg.n_analyzed = ph.n_analyzed;
-  rg_handle h = nullptr;
-  HandleGuard guard{h};
-  rg_check(rg_step1_create(&cfg, ph.X.data(), ph.Y.data(), ph.mask.data(), ph.in_analysis.data(),
-                           p.loocv ? nullptr : folds.data(), lambda.data(), ph.neff.data(), &h));
+  // --gpus G: one handle per device, all describing the same problem.  Level-0 blocks are partitioned contiguously by the
+  // reference's --split-l0 rule (write_l0_master, src/Data.cpp:268-301), level 1 by phenotype (p mod G); every GPU stores the
+  // predictor tiles of a phenotype straight into the HBM of the GPU that owns it (peer access over NVLink), so there is no
+  // exchange step and no file protocol.  Results do not depend on G (fixed-order reductions).
+  const int G = std::max(1, p.gpus);
+  if (G > 1) {
+    if (G > rg_device_count()) throw Fail("--gpus " + std::to_string(G) + " but only " + std::to_string(rg_device_count()) + " CUDA device(s) visible.");
+    if (G > nb) throw Fail("number of GPUs cannot be greater than number of blocks.");
+    if (p.run_l0_job || p.run_l1 || p.split_jobs) throw Fail("--gpus N shards one run; it cannot be combined with --split-l0 / --run-l0 / --run-l1.");
+    log << " * sharding level 0 over " << G << " GPUs (blocks), level 1 by phenotype\n";
+  }
+  std::vector<rg_handle> hs(G, nullptr);
+  struct HandlesGuard {
+    std::vector<rg_handle>& v;
+    ~HandlesGuard() { for (auto& x : v) { if (x) rg_destroy(x); x = nullptr; } }
+  } guards{hs};
+  for (int d = 0; d < G; ++d) {
+    cfg.device = (G > 1 ? d : p.gpu);
+    rg_check(rg_step1_create(&cfg, ph.X.data(), ph.Y.data(), ph.mask.data(), ph.in_analysis.data(),
+                             p.loocv ? nullptr : folds.data(), lambda.data(), ph.neff.data(), &hs[d]));
+  }
+  rg_handle h = hs[0];
+  std::vector<std::vector<uint8_t>> owned(G, std::vector<uint8_t>(P, 0));
+  if (G > 1) {
+    for (int i = 0; i < P; ++i) owned[i % G][i] = 1;
+    for (int d = 0; d < G; ++d) rg_check(rg_W_set_owned(hs[d], owned[d].data()));
+    for (int d = 0; d < G; ++d)
+      for (int e = 0; e < G; ++e)
+        if (e != d) rg_check(rg_W_attach_local(hs[d], hs[e], owned[e].data()));
+  }
+  auto owner_of = [&](int ph_i) { return hs[G > 1 ? ph_i % G : 0]; };
 
   // --l1-phenoList (with --run-l1): level 1 only for the named phenotypes (select_pheno_l1, src/Regenie.cpp:862-868)
   std::vector<uint8_t> l1_sel(P, 1);
@@ -473,7 +504,7 @@ void run_step1(const Params& p_in, Log& log) {
         f.seekg(0);
         for (int b = 0; b < mj.nblocks; ++b) {
           f.read(reinterpret_cast<char*>(slab.data()), (std::streamsize)(slab.size() * sizeof(double)));
-          rg_check(rg_l0_load_W(h, b0 + b, ph_i, slab.data()));
+          rg_check(rg_l0_load_W(owner_of(ph_i), b0 + b, ph_i, slab.data()));
         }
         b0 += mj.nblocks;
       }
@@ -494,24 +525,61 @@ void run_step1(const Params& p_in, Log& log) {
       else gbed.read_rows(blocks[b].first, blocks[b].size, bufs[b & 1]);
     });
   };
-  if (nb > 0 && !p.run_l1) pending = fetch(0);
-  for (int b = 0; b < nb && !p.run_l1; ++b) {
-    if (blocks[b].chrom != last_chr) { log << "Chromosome " << blocks[b].chrom << "\n"; last_chr = blocks[b].chrom; }
-    pending.get();
-    if (b + 1 < nb) pending = fetch(b + 1);
-    if (use_bgen)
-      rg_check(rg_l0_block_dosage_u8(h, probs[b & 1].data(), pmiss[b & 1].data(), (int64_t)g.n_file, blocks[b].size,
-                                     subset ? g.sample_idx.data() : nullptr, p.ref_first, b));
-    else
-      rg_check(rg_l0_block_bed(h, bufs[b & 1], (int64_t)g.row_stride, blocks[b].size,
-                               subset ? g.sample_idx.data() : nullptr, p.ref_first, b));
-    log << " block [" << b + 1 << "] : " << blocks[b].size << " snps\n";
+  if (G == 1) {
+    if (nb > 0 && !p.run_l1) pending = fetch(0);
+    for (int b = 0; b < nb && !p.run_l1; ++b) {
+      if (blocks[b].chrom != last_chr) { log << "Chromosome " << blocks[b].chrom << "\n"; last_chr = blocks[b].chrom; }
+      pending.get();
+      if (b + 1 < nb) pending = fetch(b + 1);
+      if (use_bgen)
+        rg_check(rg_l0_block_dosage_u8(h, probs[b & 1].data(), pmiss[b & 1].data(), (int64_t)g.n_file, blocks[b].size,
+                                       subset ? g.sample_idx.data() : nullptr, p.ref_first, b));
+      else
+        rg_check(rg_l0_block_bed(h, bufs[b & 1], (int64_t)g.row_stride, blocks[b].size,
+                                 subset ? g.sample_idx.data() : nullptr, p.ref_first, b));
+      log << " block [" << b + 1 << "] : " << blocks[b].size << " snps\n";
+    }
+  } else {
+    // one host thread per GPU, each feeding its contiguous block range; the .bed stream is shared, so reads take a lock
+    std::mutex io_mu, log_mu;
+    std::vector<std::string> errs(G);
+    std::vector<std::thread> workers;
+    const int nall = nb / G, rem = nb - nall * G;
+    int b0 = 0;
+    for (int d = 0; d < G; ++d) {
+      const int cnt = nall + (d < rem ? 1 : 0), first = b0;
+      b0 += cnt;
+      workers.emplace_back([&, d, first, cnt] {
+        try {
+          std::vector<uint8_t> buf(use_bgen ? 0 : (size_t)p.bsize * g.row_stride), pr, pm;
+          if (use_bgen) { pr.resize((size_t)p.bsize * g.n_file * 2); pm.resize((size_t)p.bsize * g.n_file); }
+          for (int b = first; b < first + cnt; ++b) {
+            if (use_bgen) {
+              gg.read_block(blocks[b].first, blocks[b].size, pr.data(), pm.data(), std::max(1, io_threads / G));
+              rg_check(rg_l0_block_dosage_u8(hs[d], pr.data(), pm.data(), (int64_t)g.n_file, blocks[b].size,
+                                             subset ? g.sample_idx.data() : nullptr, p.ref_first, b));
+            } else {
+              { std::lock_guard<std::mutex> lk(io_mu); gbed.read_rows(blocks[b].first, blocks[b].size, buf.data()); }
+              rg_check(rg_l0_block_bed(hs[d], buf.data(), (int64_t)g.row_stride, blocks[b].size,
+                                       subset ? g.sample_idx.data() : nullptr, p.ref_first, b));
+            }
+            std::lock_guard<std::mutex> lk(log_mu);
+            log << " block [" << b + 1 << "] : " << blocks[b].size << " snps (gpu " << d << ")\n";
+          }
+        } catch (const Fail& f) { errs[d] = f.what(); }
+        catch (const std::exception& e) { errs[d] = e.what(); }
+      });
+    }
+    for (auto& w : workers) w.join();
+    for (int d = 0; d < G; ++d) if (!errs[d].empty()) throw Fail(errs[d]);
   }
-  const int64_t st = rg_l0_status(h);
-  if (st != 0) {
-    if (st > 0 && st < (1ll << 40))
-      throw Fail("!! Uh-oh, SNP " + g.snps[blocks[(st - 1) / p.bsize].first + (st - 1) % p.bsize].id + " has low variance.");
-    throw Fail(std::string(rg_last_error()));
+  for (int d = 0; d < G; ++d) {
+    const int64_t st = rg_l0_status(hs[d]);
+    if (st != 0) {
+      if (st > 0 && st < (1ll << 40))
+        throw Fail("!! Uh-oh, SNP " + g.snps[blocks[(st - 1) / p.bsize].first + (st - 1) % p.bsize].id + " has low variance.");
+      throw Fail(std::string(rg_last_error()));
+    }
   }
   log << " Level 0 done (" << (long)(now_ms() - t0) << "ms)\n";
   if ((p.lowmem && p.keep_l0) || p.run_l0_job) {
@@ -525,7 +593,7 @@ void run_step1(const Params& p_in, Log& log) {
       std::ofstream f(pfx + "_l0_Y" + std::to_string(ph_i + 1), std::ios::binary);
       if (!f) throw Fail("cannot write temporary file " + pfx + "_l0_Y" + std::to_string(ph_i + 1));
       for (int b = 0; b < nb; ++b) {
-        rg_check(rg_l0_fetch_W(h, b, ph_i, slab.data()));
+        rg_check(rg_l0_fetch_W(owner_of(ph_i), b, ph_i, slab.data()));
         f.write(reinterpret_cast<const char*>(slab.data()), (std::streamsize)(slab.size() * sizeof(double)));
       }
     }
@@ -543,6 +611,7 @@ void run_step1(const Params& p_in, Log& log) {
   for (int ph_i = 0; ph_i < P; ++ph_i)
     for (int j = 0; j < p.l1; ++j) tau[(size_t)ph_i * p.l1 + j] = B * (1 - h1[j]) / h1[j] * tau_mult;
   std::vector<int32_t> best(P);
+  std::vector<double> bt_offs;
   if (p.bt) {
     // offset_nullreg: covariate-only logistic fit per trait (fit_null_logistic, src/Step1_Models.cpp:54-140)
     std::vector<double> offs((size_t)N * P);
@@ -552,14 +621,44 @@ void run_step1(const Params& p_in, Log& log) {
       std::copy(eta.begin(), eta.end(), offs.begin() + (size_t)ph_i * N);
     }
     cs.assign((size_t)6 * P * p.l1, 0.0);
-    rg_check(rg_l1_fit_bt(h, ph.Y_raw.data(), offs.data(), tau.data(), cs.data(), best.data()));
-  } else {
+    if (G == 1) rg_check(rg_l1_fit_bt(h, ph.Y_raw.data(), offs.data(), tau.data(), cs.data(), best.data()));
+    else bt_offs = offs;
+  } else if (G == 1) {
     rg_check(rg_l1_fit(h, tau.data(), cs.data(), best.data()));
   }
   std::vector<int32_t> chr_of_block(nb);
   for (int b = 0; b < nb; ++b) chr_of_block[b] = blocks[b].chrom;
   std::vector<double> loco((size_t)P * 23 * N);
-  rg_check(rg_loco(h, chr_of_block.data(), loco.data()));
+  if (G == 1) {
+    rg_check(rg_loco(h, chr_of_block.data(), loco.data()));
+  } else {
+    // every GPU fits and assembles the phenotypes it owns, concurrently; the host merges disjoint supports
+    std::vector<std::string> errs(G);
+    std::vector<std::vector<double>> cs_d(G, std::vector<double>(cs.size(), 0.0)), loco_d(G);
+    std::vector<std::vector<int32_t>> best_d(G, std::vector<int32_t>(P, 0));
+    std::vector<std::thread> workers;
+    for (int d = 0; d < G; ++d)
+      workers.emplace_back([&, d] {
+        try {
+          if (p.bt) rg_check(rg_l1_fit_bt(hs[d], ph.Y_raw.data(), bt_offs.data(), tau.data(), cs_d[d].data(), best_d[d].data()));
+          else rg_check(rg_l1_fit(hs[d], tau.data(), cs_d[d].data(), best_d[d].data()));
+          loco_d[d].assign((size_t)P * 23 * N, 0.0);
+          rg_check(rg_loco(hs[d], chr_of_block.data(), loco_d[d].data()));
+        } catch (const Fail& f) { errs[d] = f.what(); }
+        catch (const std::exception& e) { errs[d] = e.what(); }
+      });
+    for (auto& w : workers) w.join();
+    for (int d = 0; d < G; ++d) if (!errs[d].empty()) throw Fail(errs[d]);
+    const int nsum = (int)(cs.size() / ((size_t)P * p.l1));
+    for (int ph_i = 0; ph_i < P; ++ph_i) {
+      const int d = ph_i % G;
+      best[ph_i] = best_d[d][ph_i];
+      for (int k = 0; k < nsum; ++k)
+        for (int j = 0; j < p.l1; ++j) cs[((size_t)k * P + ph_i) * p.l1 + j] = cs_d[d][((size_t)k * P + ph_i) * p.l1 + j];
+      std::copy(loco_d[d].begin() + (size_t)ph_i * 23 * N, loco_d[d].begin() + (size_t)(ph_i + 1) * 23 * N,
+                loco.begin() + (size_t)ph_i * 23 * N);
+    }
+  }
 
   // ---- output (Data::output src/Data.cpp:956-1120, write_predictions :1795-1982)
   log << "Output\n------\n";
@@ -570,7 +669,15 @@ void run_step1(const Params& p_in, Log& log) {
     prs_list.open(p.out + "_prs.list");
     if (!prs_list) throw Fail("cannot write to file : " + p.out + "_prs.list");
     prs.resize((size_t)P * N);
-    rg_check(rg_prs(h, prs.data()));
+    if (G == 1) {
+      rg_check(rg_prs(h, prs.data()));
+    } else {
+      std::vector<double> tmp((size_t)P * N);
+      for (int d = 0; d < G; ++d) {
+        rg_check(rg_prs(hs[d], tmp.data()));
+        for (int ph_i = d; ph_i < P; ph_i += G) std::copy(tmp.begin() + (size_t)ph_i * N, tmp.begin() + (size_t)(ph_i + 1) * N, prs.begin() + (size_t)ph_i * N);
+      }
+    }
   }
   const std::string gz_ext = p.gz ? ".gz" : "";
   std::vector<uint32_t> order;             // std::map key order of FID_IID, analysed samples only
