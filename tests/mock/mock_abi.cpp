@@ -176,6 +176,10 @@ int rg_l0_load_W(rg_handle h, int32_t b, int32_t ph, const double* in) {
   h->W[{b, ph}].assign(in, in + (size_t)h->N * h->R);
   return 0;
 }
+// multi-GPU plumbing: the mock keeps one W map per handle, so "attaching" a peer shares nothing - the driver's
+// --gpus path is exercised on hardware only (tests/test_multigpu_gpu.py)
+int rg_W_set_owned(rg_handle, const uint8_t*) { return fail("mock: --gpus is not modelled"); }
+int rg_W_attach_local(rg_handle, rg_handle, const uint8_t*) { return fail("mock: --gpus is not modelled"); }
 int rg_l1_select(rg_handle h, const uint8_t* sel) { h->l1_sel.assign(sel, sel + h->P); return 0; }
 
 static int l1_common(rg_handle h, const double* tau, double* cs, int32_t* best, int nsums) {
