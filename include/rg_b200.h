@@ -354,7 +354,8 @@ int64_t rg_debug_fetch(rg_handle h, const char* name, void* out, int64_t max_byt
 int rg_l0_solver_stats(rg_handle h, int64_t* mixed_blocks, int64_t* f64_fallbacks);
 /* Test hook for the mixed-precision solver alone: solves (Af[f] + lambda[r] I) x = b[f] for all K*R pairs
  * (system index f*R + r) on `device`.  All pointers are host memory: Af [K][n][n] full symmetric FP64, lambda [R],
- * b [K][P][n]; x_out [K*R][P][n]; X_out (optional) [K*R][n][n] FP32 approximate inverses; fail_out: 0 = every system
+ * b [K][P][n]; x_out [K*R][P][n]; X_out (optional) [K*R][n][n] FP32: the off-diagonal tiles of the Cholesky factors
+ * (diagnostic only); fail_out: 0 = every system
  * met `tol` within `steps` corrections.  n must be 128 * 2^k <= 2048. */
 int rg_dbg_mixed_solve(int32_t device, int32_t n, int32_t K, int32_t R, int32_t P, const double* Af,
                        const double* lambda, const double* b, int32_t steps, double tol, double* x_out,

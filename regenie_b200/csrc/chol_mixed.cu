@@ -11,12 +11,12 @@
 // 25-CTA grids on the DMMA pipe (profiles/ncu_r1n_key_kernels.txt: 7 TF/s).  Here
 //   * the n^3/3 update flops run as 128x128 tcgen05 tiles (3xTF32, FP32 accumulate in TMEM),
 //   * the only serial piece is the 128x128 diagonal tile (FP32, one CTA per system, warp-register Cholesky),
-//   * the substitutions disappear: W = L^-1 by recursive doubling and X = W^T W are more of the same tiles, and every
-//     refinement step is two fully parallel matrix-vector passes.
+//   * the substitutions run block-wise against the stored inverses M_k = L_kk^-1 of the diagonal tiles, one CTA per
+//     system streaming L once per sweep (mx_trisolve_kernel); a refinement step is one FP64 residual pass + one such solve.
 //
 // Storage per lane (n = round_up(bs, 128), nmat = K*R):
-//   Lp, Wp, Wt, Tt : [nmat][2][n][n] FP32 hi/lo planes (L / P in place, W = L^-1, W^T, scratch for T^T)
-//   X              : [nmat][n][n] FP32  ~ (A + lambda I)^-1, full symmetric
+//   Lp, Wp         : [nmat][2][n][n] FP32 hi/lo planes (L / P in place; diagonal tiles of Wp = M_k for the TRSM tiles)
+//   Lplain, Mplain : [nmat][n][n] L as one FP32 plane (off-diagonal tiles), [nmat][n/128][128][128] the M_k
 //   Af             : [K][n][n] FP64 full symmetric fold systems WITHOUT the ridge shift (l0_assemble_sym_kernel)
 //   bvec, xvec, rvec : [.][Pp][n] FP64 right-hand sides (per fold), solutions and residuals (per system)
 #include <stdlib.h>
@@ -69,7 +69,7 @@ __device__ __forceinline__ void split_store(const float4 v, float* hp, float* lp
 //   out: Lp tile (k,k) = L_kk (lower, zeros above);  Wp tile (k,k) = M;  Wt tile (k,k) = M^T   (hi / lo planes)
 // 256 threads = 8 warps; shared: S (P -> L, scratch above the diagonal blocks), Wm (M), Wq (M^T).
 __global__ void __launch_bounds__(256)
-potrf128_kernel(float* __restrict__ Lp, float* __restrict__ Wp, float* __restrict__ Wt, int n, int k,
+potrf128_kernel(float* __restrict__ Lp, float* __restrict__ Wp, float* __restrict__ Mplain, int n, int k,
                 unsigned int* __restrict__ fail_flag) {
   extern __shared__ float pt_sm[];
   float* S = pt_sm;
@@ -215,8 +215,7 @@ potrf128_kernel(float* __restrict__ Lp, float* __restrict__ Wp, float* __restric
   // ---- write back as hi / lo planes
   float* Wh = Wp + moff;
   float* Wl = Wh + plane;
-  float* Th = Wt + moff;
-  float* Tl = Th + plane;
+  float* Mp = Mplain + ((int64_t)blockIdx.x * (n / PT) + k) * PT * PT;       // M_k as one FP32 tile for the substitutions
 #pragma unroll 4
   for (int it = 0; it < PT * PT / 4 / 256; ++it) {
     const int e = threadIdx.x + 256 * it;
@@ -227,11 +226,10 @@ potrf128_kernel(float* __restrict__ Lp, float* __restrict__ Wp, float* __restric
     if (c + 2 > r) vl.z = 0.f;
     if (c + 3 > r) vl.w = 0.f;
     const float4 vw = *reinterpret_cast<const float4*>(Wm + r * PLD + c);
-    const float4 vt = *reinterpret_cast<const float4*>(Wq + r * PLD + c);
     float4 hi;
     split_store(vl, Lh + (int64_t)r * n + c, Ll + (int64_t)r * n + c, hi);
     split_store(vw, Wh + (int64_t)r * n + c, Wl + (int64_t)r * n + c, hi);
-    split_store(vt, Th + (int64_t)r * n + c, Tl + (int64_t)r * n + c, hi);
+    *reinterpret_cast<float4*>(Mp + r * PT + c) = vw;
   }
 }
 
@@ -248,84 +246,8 @@ __device__ __forceinline__ bool mx_finished(const unsigned int* conv, int nmat, 
   return false;
 }
 
-// x[m][p][i] += sum_j X[m][i][j] r[m or f][p][j]   (FP32 products, FP32 accumulation: a correction needs few digits)
-// grid: (n / 32, nmat), block 256: warp w owns rows 4w .. 4w+3 of the CTA's 32 and sweeps them TOGETHER, so every
-// right-hand-side value read from shared memory feeds four rows (the shared-memory broadcast of r, not HBM, bounded the
-// one-row-at-a-time version: profiles/launches_r2b_mixed_v1.txt).  smem: r as float [P][n].
-template <int PMAX>
-__global__ void __launch_bounds__(256)
-mx_apply_kernel(const float* __restrict__ X, const double* __restrict__ rvec, int64_t r_mat_stride, int r_mat_div,
-                double* __restrict__ xvec, int n, int P, int Pp, int nmat, int step, unsigned int* __restrict__ conv, float tol) {
-  extern __shared__ float ap_sm[];
-  const int m = blockIdx.y;
-  if (step > 1 && mx_finished(conv, nmat, m, step - 1, tol)) return;
-  const double* r = rvec + (int64_t)(r_mat_div > 0 ? m / r_mat_div : m) * r_mat_stride;
-  for (int e = threadIdx.x * 2; e < P * n; e += 512) {
-    const double2 v = *reinterpret_cast<const double2*>(r + e);        // rows of r are contiguous: [p][n]
-    *reinterpret_cast<float2*>(ap_sm + e) = make_float2((float)v.x, (float)v.y);
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float dmax = 0.f, xmax = 0.f;
-  for (int rg = 0; rg < kMxRowsPerCta / 32; ++rg) {
-  const int i0 = blockIdx.x * kMxRowsPerCta + rg * 32 + warp * 4;
-  const float* x0 = X + ((int64_t)m * n + i0) * n;
-  float acc[4][PMAX];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int p = 0; p < PMAX; ++p) acc[a][p] = 0.f;
-  float4 xn4[4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a) xn4[a] = *reinterpret_cast<const float4*>(x0 + (int64_t)a * n + lane * 4);
-  for (int j = lane * 4; j < n; j += 128) {
-    float4 xa[4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a) xa[a] = xn4[a];
-    if (j + 128 < n) {                       // next chunk of the four rows is in flight while this one is consumed
-#pragma unroll
-      for (int a = 0; a < 4; ++a) xn4[a] = *reinterpret_cast<const float4*>(x0 + (int64_t)a * n + j + 128);
-    }
-#pragma unroll
-    for (int p = 0; p < PMAX; ++p) {
-      if (p < P) {
-        const float4 b = *reinterpret_cast<const float4*>(ap_sm + p * n + j);
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-          acc[a][p] = fmaf(xa[a].x, b.x, fmaf(xa[a].y, b.y, fmaf(xa[a].z, b.z, fmaf(xa[a].w, b.w, acc[a][p]))));
-      }
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int p = 0; p < PMAX; ++p) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[a][p] += __shfl_xor_sync(0xffffffffu, acc[a][p], o);
-    }
-  if (lane == 0) {
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int p = 0; p < PMAX; ++p)
-        if (p < P) {
-          double* xp = xvec + ((int64_t)m * Pp + p) * n + i0 + a;
-          const double xn = (step == 0 ? 0.0 : *xp) + (double)acc[a][p];
-          *xp = xn;
-          // fmaxf drops NaNs: map anything non-finite to +inf so the final check sees it
-          dmax = (fabsf(acc[a][p]) <= 3.0e38f) ? fmaxf(dmax, fabsf(acc[a][p])) : __int_as_float(0x7f800000);
-          xmax = fmaxf(xmax, fabsf((float)xn));
-        }
-  }
-  }   // row groups
-  if (lane == 0 && step > 0) {
-    atomicMax(conv + ((int64_t)step * nmat + m) * 2, __float_as_uint(dmax));
-    atomicMax(conv + ((int64_t)step * nmat + m) * 2 + 1, __float_as_uint(xmax));
-  }
-}
-
 // r[m][p][i] = b[f][p][i] - lambda_r x[m][p][i] - sum_j A_f[i][j] x[m][p][j]    (all FP64, fixed summation order)
-// grid: (n / 32, nmat), block 256, four rows per warp in flight like mx_apply_kernel.  smem: x[m] as double [P][n].
+// grid: (n / 32, nmat), block 256, four rows per warp in flight.  smem: x[m] as double [P][n].
 template <int PMAX>
 __global__ void __launch_bounds__(256, 2)
 mx_residual_kernel(const double* __restrict__ Af, const double* __restrict__ lambda, int R, const double* __restrict__ bvec,
@@ -386,6 +308,179 @@ mx_residual_kernel(const double* __restrict__ Af, const double* __restrict__ lam
   }   // row groups
 }
 
+
+// dx = (L L^T)^-1 r by block forward / backward substitution, one CTA per system (no inter-CTA dependency):
+//   forward  k = 0 .. nt-1 :  y_k = M_k (r_k - sum_{j<k} L_kj y_j)          rows of L, lanes along the contraction
+//   backward k = nt-1 .. 0 :  x_k = M_k^T (y_k - sum_{j>k} L_jk^T x_j)      rows of L again, lanes along the OUTPUT columns
+// with M_k = L_kk^-1 from potrf128_kernel, so no triangular solve is ever done element by element.  Every element of L
+// is read once per sweep with 128-bit loads, eight rows per warp in flight; FP32 throughout (a correction needs few
+// digits), the result is added to the FP64 solution.  Replaces W = L^-1, X = W^T W and the X r products of the first
+// version (profiles/launches_r2d_mixed_v3.txt: 285 us of tiles + 3 x 80 us full-GPU passes per block).
+// grid: (nmat), block 512.  smem: rs [P][n] | sbuf [P][128] | part [16][P][128]
+template <int PMAX>
+__global__ void __launch_bounds__(512)
+mx_trisolve_kernel(const float* __restrict__ Lpl, const float* __restrict__ Mpl, const double* __restrict__ rvec,
+                   int64_t r_mat_stride, int r_mat_div, double* __restrict__ xvec, int n, int P, int Pp, int nmat, int step,
+                   unsigned int* __restrict__ conv, float tol) {
+  extern __shared__ float ts_sm[];
+  const int m = blockIdx.x;
+  if (step > 1 && mx_finished(conv, nmat, m, step - 1, tol)) return;
+  float* rs = ts_sm;                       // [P][n]   r -> y -> x, block by block
+  float* sbuf = rs + (size_t)P * n;        // [P][128]
+  float* part = sbuf + (size_t)P * PT;     // [16][P][128]
+  const int nt = n / PT;
+  const double* r = rvec + (int64_t)(r_mat_div > 0 ? m / r_mat_div : m) * r_mat_stride;
+  for (int e = threadIdx.x * 2; e < P * n; e += 1024) {
+    const double2 v = *reinterpret_cast<const double2*>(r + e);
+    *reinterpret_cast<float2*>(rs + e) = make_float2((float)v.x, (float)v.y);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* L = Lpl + (int64_t)m * n * n;
+  const float* M = Mpl + (int64_t)m * nt * PT * PT;
+
+  // rows [row0, row0 + 8) of `mat` (row stride ld) against the vectors vec[p][0 .. 128 * nchunk): returns per-lane partial
+  // sums in acc[a][p]; lanes cover 4 consecutive columns of each 128-column chunk
+  auto row_sweep = [&](const float* mat, int64_t ld, int nchunk, const float* vec, int vec_ld, float (&acc)[4][PMAX]) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int p = 0; p < PMAX; ++p) acc[a][p] = 0.f;
+    for (int q = 0; q < nchunk; ++q) {
+      float4 la[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) la[a] = *reinterpret_cast<const float4*>(mat + (int64_t)a * ld + q * PT + lane * 4);
+#pragma unroll
+      for (int p = 0; p < PMAX; ++p) {
+        if (p < P) {
+          const float4 b = *reinterpret_cast<const float4*>(vec + (size_t)p * vec_ld + q * PT + lane * 4);
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+            acc[a][p] = fmaf(la[a].x, b.x, fmaf(la[a].y, b.y, fmaf(la[a].z, b.z, fmaf(la[a].w, b.w, acc[a][p]))));
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int p = 0; p < PMAX; ++p) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[a][p] += __shfl_xor_sync(0xffffffffu, acc[a][p], o);
+      }
+  };
+
+  // ---- forward: warp w owns rows 8w .. 8w+7 of the block, swept four at a time
+  for (int k = 0; k < nt; ++k) {
+    float acc[4][PMAX];
+#pragma unroll 1
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int r0 = warp * 8 + h2 * 4;
+      row_sweep(L + (int64_t)(k * PT + r0) * n, n, k, rs, n, acc);
+      if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int p = 0; p < PMAX; ++p)
+            if (p < P) sbuf[p * PT + r0 + a] = rs[(size_t)p * n + k * PT + r0 + a] - acc[a][p];
+      }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int r0 = warp * 8 + h2 * 4;
+      row_sweep(M + ((int64_t)k * PT + r0) * PT, PT, 1, sbuf, PT, acc);      // y_k = M_k s
+      if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int p = 0; p < PMAX; ++p)
+            if (p < P) rs[(size_t)p * n + k * PT + r0 + a] = acc[a][p];       // block k of rs is read by nobody in this phase
+      }
+    }
+    __syncthreads();
+  }
+
+  // rows `rfirst + warp + 16 i` (i < nrow16) of `mat`, the 128 columns at col0: out[p][c] partial = sum_r mat[r][c] vec[p][r]
+  auto col_sweep = [&](const float* mat, int64_t ld, int col0, int rfirst, int nrows, const float* vec, int vec_ld, int vec_off) {
+    float4 acc[PMAX];
+#pragma unroll
+    for (int p = 0; p < PMAX; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i0 = warp; i0 < nrows; i0 += 64) {                 // four rows of this warp per trip, loads first
+      float4 l4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + 16 * u;
+        l4[u] = i < nrows ? *reinterpret_cast<const float4*>(mat + (int64_t)(rfirst + i) * ld + col0 + lane * 4)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + 16 * u;
+        if (i < nrows) {
+#pragma unroll
+          for (int p = 0; p < PMAX; ++p)
+            if (p < P) {
+              const float xv = vec[(size_t)p * vec_ld + vec_off + i];
+              acc[p].x = fmaf(l4[u].x, xv, acc[p].x); acc[p].y = fmaf(l4[u].y, xv, acc[p].y);
+              acc[p].z = fmaf(l4[u].z, xv, acc[p].z); acc[p].w = fmaf(l4[u].w, xv, acc[p].w);
+            }
+        }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < PMAX; ++p)
+      if (p < P) *reinterpret_cast<float4*>(part + ((size_t)warp * P + p) * PT + lane * 4) = acc[p];
+  };
+
+  // ---- backward
+  for (int k = nt - 1; k >= 0; --k) {
+    const int nbelow = n - (k + 1) * PT;
+    col_sweep(L, n, k * PT, (k + 1) * PT, nbelow, rs, n, (k + 1) * PT);
+    __syncthreads();
+    for (int e = threadIdx.x; e < P * PT; e += 512) {           // t = y_k - sum of the 16 partials (fixed order)
+      const int p = e / PT, c = e % PT;
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < 16; ++w) sum += part[((size_t)w * P + p) * PT + c];
+      sbuf[p * PT + c] = rs[(size_t)p * n + k * PT + c] - sum;
+    }
+    __syncthreads();
+    col_sweep(M + (int64_t)k * PT * PT, PT, 0, 0, PT, sbuf, PT, 0);          // x_k = M_k^T t
+    __syncthreads();
+    for (int e = threadIdx.x; e < P * PT; e += 512) {
+      const int p = e / PT, c = e % PT;
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < 16; ++w) sum += part[((size_t)w * P + p) * PT + c];
+      rs[(size_t)p * n + k * PT + c] = sum;
+    }
+    __syncthreads();
+  }
+
+  // ---- x += dx, convergence bookkeeping
+  float dmax = 0.f, xmax = 0.f;
+  for (int e = threadIdx.x; e < P * n; e += 512) {
+    const int p = e / n, i = e % n;
+    double* xp = xvec + ((int64_t)m * Pp + p) * n + i;
+    const float dx = rs[e];
+    const double xn = (step == 0 ? 0.0 : *xp) + (double)dx;
+    *xp = xn;
+    dmax = (fabsf(dx) <= 3.0e38f) ? fmaxf(dmax, fabsf(dx)) : __int_as_float(0x7f800000);
+    xmax = fmaxf(xmax, fabsf((float)xn));
+  }
+  if (step > 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+      xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+    }
+    if (lane == 0) {
+      atomicMax(conv + ((int64_t)step * nmat + m) * 2, __float_as_uint(dmax));
+      atomicMax(conv + ((int64_t)step * nmat + m) * 2 + 1, __float_as_uint(xmax));
+    }
+  }
+}
+
 // after the last correction: every system must have met the tolerance at some step, else the lane's fallback flag is raised
 __global__ void mx_final_check_kernel(const unsigned int* __restrict__ conv, int nmat, int steps, float tol,
                                       unsigned int* __restrict__ fail_flag) {
@@ -406,8 +501,6 @@ struct MxPlan {
   int n = 0, nt = 0;
   DevBuf<int4> tiles;                       // all lists back to back
   std::vector<int2> upd, trsm;              // per panel step: (offset, count)
-  std::vector<int2> tri_t, tri_w;           // per doubling level
-  int2 xx{0, 0};
 };
 
 static void build_plan(MxPlan& pl, int n) {
@@ -415,7 +508,7 @@ static void build_plan(MxPlan& pl, int n) {
   const int nt = n / PT;
   pl.nt = nt;
   std::vector<int4> all;
-  pl.upd.clear(); pl.trsm.clear(); pl.tri_t.clear(); pl.tri_w.clear();
+  pl.upd.clear(); pl.trsm.clear();
   for (int k = 0; k < nt; ++k) {
     int2 u{(int)all.size(), 0};
     for (int i = k; i < nt; ++i) all.push_back(make_int4(i, k, 0, 4 * k));          // P_ik = A_ik - L_i,0:k L_k,0:k^T
@@ -426,35 +519,15 @@ static void build_plan(MxPlan& pl, int n) {
     t.y = (int)all.size() - t.x;
     pl.trsm.push_back(t);
   }
-  for (int sb = 1; sb < nt; sb *= 2) {
-    int2 a{(int)all.size(), 0};
-    for (int a0 = 0; a0 + 2 * sb <= nt; a0 += 2 * sb)
-      for (int bi = 0; bi < sb; ++bi)
-        for (int aj = 0; aj < sb; ++aj)        // T[m in b][n in a] = sum_{p >= n} L21[m][p] W11[p][n]
-          all.push_back(make_int4(a0 + sb + bi, a0 + aj, 4 * (a0 + aj), 4 * (sb - aj)));
-    a.y = (int)all.size() - a.x;
-    pl.tri_t.push_back(a);
-    int2 w{(int)all.size(), 0};
-    for (int a0 = 0; a0 + 2 * sb <= nt; a0 += 2 * sb)
-      for (int bi = 0; bi < sb; ++bi)
-        for (int aj = 0; aj < sb; ++aj)        // W21[m in b][n in a] = - sum_{p <= m} W22[m][p] T[p][n]
-          all.push_back(make_int4(a0 + sb + bi, a0 + aj, 4 * (a0 + sb), 4 * (bi + 1)));
-    w.y = (int)all.size() - w.x;
-    pl.tri_w.push_back(w);
-  }
-  pl.xx.x = (int)all.size();
-  for (int i = 0; i < nt; ++i)
-    for (int j = 0; j <= i; ++j) all.push_back(make_int4(i, j, 4 * i, 4 * (nt - i)));   // X_ij = sum_{p >= i} W[p][i] W[p][j]
-  pl.xx.y = (int)all.size() - pl.xx.x;
   pl.tiles.alloc(all.size());
   RG_CUDA(cudaMemcpy(pl.tiles.p, all.data(), all.size() * sizeof(int4), cudaMemcpyHostToDevice));
 }
 
 struct MixedSolver::Impl {
   int n = 0, nmat = 0, K = 0, R = 0, Pp = 0;
-  DevBuf<float> Lp, Wp, Wt, Tt, X, Ap, Ident;
+  DevBuf<float> Lp, Wp, Lplain, Mplain, Ap, Ident;
   DevBuf<unsigned int> conv;
-  CUtensorMap tmL, tmW, tmWt, tmT, tmAp, tmI;
+  CUtensorMap tmL, tmW, tmAp, tmI;
   MxPlan plan;
 };
 
@@ -475,22 +548,20 @@ void MixedSolver::prepare(int n, int K, int R, int Pp) {
            "mixed solver: dimension must be 128 * 2^k <= 2048");
   d.n = n; d.nmat = nmat; d.K = K; d.R = R; d.Pp = Pp;
   const size_t planes = (size_t)nmat * 2 * n * n;
-  d.Lp.alloc(planes); d.Wp.alloc(planes); d.Wt.alloc(planes); d.Tt.alloc(planes);
-  d.X.alloc((size_t)nmat * n * n);
+  d.Lp.alloc(planes); d.Wp.alloc(planes);
+  d.Lplain.alloc((size_t)nmat * n * n);
+  d.Mplain.alloc((size_t)nmat * n * PT);
+  // tiles that nothing writes (upper triangle) are read by nothing either; zero once so stale data can never matter
+  RG_CUDA(cudaMemset(d.Lp.p, 0, planes * 4));
+  RG_CUDA(cudaMemset(d.Wp.p, 0, planes * 4));
+  RG_CUDA(cudaMemset(d.Lplain.p, 0, (size_t)nmat * n * n * 4));
+  d.conv.alloc((size_t)(kMxMaxSteps + 1) * nmat * 2);
+  make_tf32_planes_tensor_map(&d.tmL, d.Lp.p, n, nmat);
+  make_tf32_planes_tensor_map(&d.tmW, d.Wp.p, n, nmat);
   d.Ap.alloc((size_t)K * 2 * n * n);
   RG_CUDA(cudaMemset(d.Ap.p, 0, (size_t)K * 2 * n * n * 4));
   make_tf32_planes_tensor_map(&d.tmAp, d.Ap.p, n, K);
   make_tf32_identity_planes(d.Ident, &d.tmI);
-  // strictly-upper tiles of W / lower tiles of W^T are read by nothing; zero once so stale data can never matter
-  RG_CUDA(cudaMemset(d.Lp.p, 0, planes * 4));
-  RG_CUDA(cudaMemset(d.Wp.p, 0, planes * 4));
-  RG_CUDA(cudaMemset(d.Wt.p, 0, planes * 4));
-  RG_CUDA(cudaMemset(d.Tt.p, 0, planes * 4));
-  d.conv.alloc((size_t)(kMxMaxSteps + 1) * nmat * 2);
-  make_tf32_planes_tensor_map(&d.tmL, d.Lp.p, n, nmat);
-  make_tf32_planes_tensor_map(&d.tmW, d.Wp.p, n, nmat);
-  make_tf32_planes_tensor_map(&d.tmWt, d.Wt.p, n, nmat);
-  make_tf32_planes_tensor_map(&d.tmT, d.Tt.p, n, nmat);
   build_plan(d.plan, n);
 }
 
@@ -498,10 +569,8 @@ static int rhs_chunk(int n) { return std::max(1, std::min(12, (int)(98304 / (8 *
 
 int MixedSolver::launches_per_solve(int n, int steps, int P) {
   const int nt = n / PT;
-  int lv = 0;
-  for (int sb = 1; sb < nt; sb *= 2) ++lv;
   const int nch = (P + rhs_chunk(n) - 1) / rhs_chunk(n);
-  return 3 * nt - 1 + 2 * lv + 1 + nch * (1 + 2 * steps) + 1;
+  return 3 * nt - 1 + nch * (1 + 2 * steps) + 1;
 }
 
 // Af: [K][n][n] FP64 full symmetric;  lambda: [R] (device);  bvec: [K][Pp][n];  xvec, rvec: [K*R][Pp][n]
@@ -514,10 +583,10 @@ void MixedSolver::solve(const double* Af, const double* lambda, const double* bv
   RG_CHECK(steps >= 1 && steps <= kMxMaxSteps, "mixed solver: bad step count");
   const size_t potrf_smem = ((size_t)3 * PT * PLD + PT) * sizeof(float);
   ensure_dyn_smem(reinterpret_cast<const void*>(potrf128_kernel), potrf_smem);
-  ensure_dyn_smem(reinterpret_cast<const void*>(mx_apply_kernel<12>), 98304);
   ensure_dyn_smem(reinterpret_cast<const void*>(mx_residual_kernel<12>), 98304);
-  ensure_dyn_smem(reinterpret_cast<const void*>(mx_apply_kernel<10>), 98304);
   ensure_dyn_smem(reinterpret_cast<const void*>(mx_residual_kernel<10>), 98304);
+  ensure_dyn_smem(reinterpret_cast<const void*>(mx_trisolve_kernel<12>), 200 * 1024);
+  ensure_dyn_smem(reinterpret_cast<const void*>(mx_trisolve_kernel<10>), 200 * 1024);
   RG_CHECK(n <= 2048, "mixed solver: n <= 2048");
   RG_CUDA(cudaMemsetAsync(d.conv.p, 0, d.conv.n * sizeof(unsigned int), s));
   const int4* tl = d.plan.tiles.p;
@@ -532,47 +601,34 @@ void MixedSolver::solve(const double* Af, const double* lambda, const double* bv
     e.c_chunks = 4; e.c_mat_div = d.R;
     e.diag_add = lambda; e.diag_mod = d.R;
     launch_tf32x3_gemm(d.tmL, d.tmL, tl + d.plan.upd[k].x, d.plan.upd[k].y, nmat, e, s, &d.tmAp, &d.tmI);
-    potrf128_kernel<<<nmat, 256, potrf_smem, s>>>(d.Lp.p, d.Wp.p, d.Wt.p, n, k, fail_flag);
+    potrf128_kernel<<<nmat, 256, potrf_smem, s>>>(d.Lp.p, d.Wp.p, d.Mplain.p, n, k, fail_flag);
     if (d.plan.trsm[k].y > 0) {
       Tf32GemmEpilogue t = e0;
       t.out = d.Lp.p;
+      t.out_plain = d.Lplain.p;                      // the same tiles as one FP32 plane: what the substitutions stream
       launch_tf32x3_gemm(d.tmL, d.tmW, tl + d.plan.trsm[k].x, d.plan.trsm[k].y, nmat, t, s);
     }
   }
-  // ---- W = L^-1 by recursive doubling:  W21 = - W22 (L21 W11)
-  for (size_t lv = 0; lv < d.plan.tri_t.size(); ++lv) {
-    Tf32GemmEpilogue t = e0;
-    t.out_t = d.Tt.p;
-    launch_tf32x3_gemm(d.tmL, d.tmWt, tl + d.plan.tri_t[lv].x, d.plan.tri_t[lv].y, nmat, t, s);
-    Tf32GemmEpilogue w = e0;
-    w.out = d.Wp.p; w.out_t = d.Wt.p; w.negate = 1;
-    launch_tf32x3_gemm(d.tmW, d.tmT, tl + d.plan.tri_w[lv].x, d.plan.tri_w[lv].y, nmat, w, s);
-  }
-  // ---- X = W^T W  ~ (A + lambda I)^-1, one FP32 plane, both triangles
-  {
-    Tf32GemmEpilogue x = e0;
-    x.out_plain = d.X.p; x.mirror = 1;
-    launch_tf32x3_gemm(d.tmWt, d.tmWt, tl + d.plan.xx.x, d.plan.xx.y, nmat, x, s);
-  }
-  // ---- x0 = X b, then  x += X (b - A x)
+  // ---- x0 = (L L^T)^-1 b, then  x += (L L^T)^-1 (b - A x)  by block substitution, one CTA per system
   dim3 grid(n / kMxRowsPerCta, nmat);
   const int pc = rhs_chunk(n);                       // right-hand sides per launch (shared-memory budget of the FP64 pass)
   for (int st = 0; st <= steps; ++st)
     for (int p0 = 0; p0 < P; p0 += pc) {
       const int np = std::min(pc, P - p0);
-      const size_t sm_a = (size_t)np * n * sizeof(float), sm_r = (size_t)np * n * sizeof(double);
+      const size_t sm_r = (size_t)np * n * sizeof(double);
+      const size_t sm_t = ((size_t)np * n + (size_t)np * PT * 17) * sizeof(float);
       const int64_t o = (int64_t)p0 * n;
       // right-hand-side count is a template parameter (register blocking): 10 is the benchmark's trait count
-      auto apply = [&](const double* rv, int64_t rs, int rdiv, int step) {
-        if (np <= 10) mx_apply_kernel<10><<<grid, 256, sm_a, s>>>(d.X.p, rv, rs, rdiv, xvec + o, n, np, d.Pp, nmat, step, d.conv.p, tol);
-        else mx_apply_kernel<12><<<grid, 256, sm_a, s>>>(d.X.p, rv, rs, rdiv, xvec + o, n, np, d.Pp, nmat, step, d.conv.p, tol);
+      auto tri = [&](const double* rv, int64_t rs, int rdiv, int step) {
+        if (np <= 10) mx_trisolve_kernel<10><<<nmat, 512, sm_t, s>>>(d.Lplain.p, d.Mplain.p, rv, rs, rdiv, xvec + o, n, np, d.Pp, nmat, step, d.conv.p, tol);
+        else mx_trisolve_kernel<12><<<nmat, 512, sm_t, s>>>(d.Lplain.p, d.Mplain.p, rv, rs, rdiv, xvec + o, n, np, d.Pp, nmat, step, d.conv.p, tol);
       };
       if (st == 0) {
-        apply(bvec + o, (int64_t)d.Pp * n, d.R, 0);
+        tri(bvec + o, (int64_t)d.Pp * n, d.R, 0);
       } else {
         if (np <= 10) mx_residual_kernel<10><<<grid, 256, sm_r, s>>>(Af, lambda, d.R, bvec + o, xvec + o, rvec + o, n, np, d.Pp, nmat, st, d.conv.p, tol);
         else mx_residual_kernel<12><<<grid, 256, sm_r, s>>>(Af, lambda, d.R, bvec + o, xvec + o, rvec + o, n, np, d.Pp, nmat, st, d.conv.p, tol);
-        apply(rvec + o, (int64_t)d.Pp * n, 0, st);
+        tri(rvec + o, (int64_t)d.Pp * n, 0, st);
       }
     }
   mx_final_check_kernel<<<(nmat + 63) / 64, 64, 0, s>>>(d.conv.p, nmat, steps, tol, fail_flag);
@@ -600,8 +656,8 @@ const float* MixedSolver::debug_planes(int which) const {
   switch (which) {
     case 0: return impl->Lp.p;
     case 1: return impl->Wp.p;
-    case 2: return impl->Wt.p;
-    case 3: return impl->X.p;
+    case 2: return impl->Lplain.p;
+    case 3: return impl->Mplain.p;
     default: return nullptr;
   }
 }

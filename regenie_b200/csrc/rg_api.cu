@@ -1115,7 +1115,7 @@ int rg_dbg_mixed_solve(int32_t device, int32_t n, int32_t K, int32_t R, int32_t 
   RG_CHECK(e == cudaSuccess, std::string("mixed solver kernels failed: ") + cudaGetErrorString(e));
   for (int m = 0; m < nmat; ++m)
     RG_CUDA(cudaMemcpy(x_out + (size_t)m * P * n, dx.p + (size_t)m * Pp * n, (size_t)P * n * 8, cudaMemcpyDeviceToHost));
-  if (X_out) RG_CUDA(cudaMemcpy(X_out, mx.debug_planes(3), (size_t)nmat * n * n * 4, cudaMemcpyDeviceToHost));
+  if (X_out) RG_CUDA(cudaMemcpy(X_out, mx.debug_planes(2), (size_t)nmat * n * n * 4, cudaMemcpyDeviceToHost));
   RG_CUDA(cudaMemcpy(fail_out, dfail.p, 4, cudaMemcpyDeviceToHost));
   RG_API_END
 }

@@ -33,7 +33,7 @@ def test_mixed_solve_matches_numpy(n, K, R, P, n_real):
     from regenie_b200 import capi
     Af, b = _systems(n, K, P, seed=n + K, n_real=n_real)
     lam = np.array([5000.0, 50.0, 0.5])[:R]
-    x, fail, X = capi.mixed_solve(Af, lam, b, steps=3, tol=1e-9, want_inverse=True)
+    x, fail, Lt = capi.mixed_solve(Af, lam, b, steps=3, tol=1e-9, want_inverse=True)
     assert fail == 0
     for f in range(K):
         for r in range(R):
@@ -41,9 +41,11 @@ def test_mixed_solve_matches_numpy(n, K, R, P, n_real):
             ref = np.linalg.solve(A, b[f].T).T
             err = np.abs(x[f * R + r] - ref).max() / np.abs(ref).max()
             assert err < 1e-11, (f, r, err)
-            # the FP32-accurate inverse the refinement multiplies with (diagnostic bound, not a parity claim)
-            inv_err = np.abs(X[f * R + r].astype(np.float64) @ A - np.eye(n)).max()
-            assert inv_err < 1e-2, (f, r, inv_err)
+            if n > 128:
+                # the FP32-accurate factor the refinement solves with: tile (1, 0) of L vs numpy's Cholesky (diagnostic)
+                Lref = np.linalg.cholesky(A)
+                t = Lt[f * R + r][128:256, 0:128].astype(np.float64)
+                assert np.abs(t - Lref[128:256, 0:128]).max() / np.abs(Lref[128:256, 0:128]).max() < 1e-4
 
 
 def test_mixed_solve_flags_an_ill_conditioned_system():
