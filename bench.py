@@ -382,6 +382,14 @@ def run_gpu(args):
                            "stores to peers ride inside the prediction / standardisation kernels, overlapped with compute"
                            % (P, world, max(owner.count(r) for r in range(world)))}
 
+    # ---- end to end from files through the C++ driver (rank 0, single GPU run only)
+    file_e2e = None
+    if world == 1 and not args.no_step2 and not (args.small or args.n_samples or args.blocks):
+        try:
+            file_e2e = file_e2e_leg(host_panel, N, M, bs, P, Yr, cov, na)
+        except Exception as e:
+            file_e2e = {"error": str(e)[:300]}
+
     # ---- second half of the metric: Step-2 variants/s (QT on .bed rows, BT on 8-bit BGEN dosages), each with a
     # host-fed rate, a device-resident rate, an HBM roofline and a CPU baseline (rank 0 only)
     s2 = None
@@ -476,12 +484,64 @@ def run_gpu(args):
         "lanes": int(os.environ.get("RG_B200_LANES", "8")),
         "cpu_baseline": cpu,
         "sharded_step1": sharded,
+        "from_files": file_e2e,
         "parity": parity,
         "step2": s2,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
+
+
+def file_e2e_leg(host_panel, N, M, bs, P, Yr, cov, na, gpus=1):
+    """End to end FROM FILES through the C++ driver: write the benchmark panel as a real PLINK fileset + phenotype /
+    covariate text files, run `rgb200 --step 1` (reader thread -> rg_l0_block_bed -> level 1 -> LOCO -> .loco text) and
+    time the whole process.  This is the reference's own user-facing path (regenie --step 1 --bed ... --out ...)."""
+    import tempfile
+    rgb = os.path.join(ROOT, "regenie_b200", "rgb200")
+    d = tempfile.mkdtemp(prefix="rgbench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        t0 = time.perf_counter()
+        with open(os.path.join(d, "p.bed"), "wb") as fh:
+            fh.write(b"\x6c\x1b\x01")
+            fh.write(host_panel.numpy().tobytes())
+        per = (M + 21) // 22
+        with open(os.path.join(d, "p.bim"), "w") as fh:
+            fh.write("".join("%d rs%d 0 %d A G\n" % (i // per + 1, i, 1000 + i) for i in range(M)))
+        with open(os.path.join(d, "p.fam"), "w") as fh:
+            fh.write("".join("F%d I%d 0 0 %d -9\n" % (s, s, 1 + s % 2) for s in range(N)))
+        Yt = np.where(na, np.nan, Yr)
+        with open(os.path.join(d, "pheno.txt"), "w") as fh:
+            fh.write("FID IID " + " ".join("Y%d" % (p + 1) for p in range(P)) + "\n")
+            for s_ in range(N):
+                fh.write("F%d I%d " % (s_, s_) + " ".join("NA" if na[s_, p] else "%.17g" % Yt[s_, p] for p in range(P)) + "\n")
+        with open(os.path.join(d, "covar.txt"), "w") as fh:
+            fh.write("FID IID " + " ".join("V%d" % (c + 1) for c in range(cov.shape[1])) + "\n")
+            for s_ in range(N):
+                fh.write("F%d I%d " % (s_, s_) + " ".join("%.17g" % v for v in cov[s_]) + "\n")
+        t_write = time.perf_counter() - t0
+        cmd = [rgb, "--step", "1", "--bed", os.path.join(d, "p"), "--phenoFile", os.path.join(d, "pheno.txt"), "--covarFile",
+               os.path.join(d, "covar.txt"), "--bsize", str(bs), "--out", os.path.join(d, "fit")]
+        if gpus > 1:
+            cmd += ["--gpus", str(gpus)]
+        t0 = time.perf_counter()
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+        dt = time.perf_counter() - t0
+        if r.returncode != 0:
+            return {"error": (r.stdout + r.stderr)[-300:]}
+        l0 = [l for l in r.stdout.splitlines() if "Level 0 done" in l]
+        l0_ms = float(l0[0].split("(")[1].split("ms")[0]) if l0 else None
+        ok = all(os.path.exists(os.path.join(d, "fit_%d.loco" % (p + 1))) for p in range(P))
+        return {"metric": "step1_from_files_snps_per_sec", "value": M / dt, "unit": "SNPs/s", "seconds": dt,
+                "level0_seconds_driver_log": None if l0_ms is None else l0_ms / 1e3,
+                "level0_snps_per_sec_driver_log": None if not l0_ms else M / (l0_ms / 1e3),
+                "loco_files_written": ok, "fileset_write_seconds": t_write,
+                "what": "rgb200 --step 1 --bed (1.25 GB .bed in /dev/shm) --phenoFile --covarFile --bsize %d --out: process start to exit, "
+                        "i.e. text parsing, phenotype preparation, level 0 from the file, level 1 (B = %d), LOCO and the %d .loco files"
+                        % (bs, (M // bs) * 5, P)}
+    finally:
+        import shutil
+        shutil.rmtree(d, ignore_errors=True)
 
 
 def hbm_roofline(rate, bytes_per_variant, what):

@@ -346,10 +346,19 @@ mx_trisolve_kernel(const float* __restrict__ Lpl, const float* __restrict__ Mpl,
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int p = 0; p < PMAX; ++p) acc[a][p] = 0.f;
+    float4 nx[4];
+    if (nchunk > 0) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) nx[a] = *reinterpret_cast<const float4*>(mat + (int64_t)a * ld + lane * 4);
+    }
     for (int q = 0; q < nchunk; ++q) {
       float4 la[4];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) la[a] = *reinterpret_cast<const float4*>(mat + (int64_t)a * ld + q * PT + lane * 4);
+      for (int a = 0; a < 4; ++a) la[a] = nx[a];
+      if (q + 1 < nchunk) {                            // the next chunk of the four rows is in flight during this one
+#pragma unroll
+        for (int a = 0; a < 4; ++a) nx[a] = *reinterpret_cast<const float4*>(mat + (int64_t)a * ld + (q + 1) * PT + lane * 4);
+      }
 #pragma unroll
       for (int p = 0; p < PMAX; ++p) {
         if (p < P) {
@@ -405,16 +414,16 @@ mx_trisolve_kernel(const float* __restrict__ Lpl, const float* __restrict__ Mpl,
     float4 acc[PMAX];
 #pragma unroll
     for (int p = 0; p < PMAX; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i0 = warp; i0 < nrows; i0 += 64) {                 // four rows of this warp per trip, loads first
-      float4 l4[4];
+    for (int i0 = warp; i0 < nrows; i0 += 128) {                // eight rows of this warp per trip, loads first
+      float4 l4[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const int i = i0 + 16 * u;
         l4[u] = i < nrows ? *reinterpret_cast<const float4*>(mat + (int64_t)(rfirst + i) * ld + col0 + lane * 4)
                           : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const int i = i0 + 16 * u;
         if (i < nrows) {
 #pragma unroll
@@ -588,6 +597,11 @@ void MixedSolver::solve(const double* Af, const double* lambda, const double* bv
   ensure_dyn_smem(reinterpret_cast<const void*>(mx_trisolve_kernel<12>), 200 * 1024);
   ensure_dyn_smem(reinterpret_cast<const void*>(mx_trisolve_kernel<10>), 200 * 1024);
   RG_CHECK(n <= 2048, "mixed solver: n <= 2048");
+  // profiling aid (results are garbage): RG_DBG_SKIP=mxgemm|mxpotrf|mxtri|mxres drops one kernel family of the solver so
+  // its marginal cost under multi-lane overlap can be read off (profiles/ablation_r2_*.txt)
+  static const char* skip_env = getenv("RG_DBG_SKIP");
+  const bool sk_gemm = skip_env && strstr(skip_env, "mxgemm"), sk_potrf = skip_env && strstr(skip_env, "mxpotrf");
+  const bool sk_tri = skip_env && strstr(skip_env, "mxtri"), sk_res = skip_env && strstr(skip_env, "mxres");
   RG_CUDA(cudaMemsetAsync(d.conv.p, 0, d.conv.n * sizeof(unsigned int), s));
   const int4* tl = d.plan.tiles.p;
   Tf32GemmEpilogue e0{};
@@ -600,13 +614,13 @@ void MixedSolver::solve(const double* Af, const double* lambda, const double* bv
     // the product with A negated, the ridge shift on the diagonal in the epilogue - no epilogue loads at all
     e.c_chunks = 4; e.c_mat_div = d.R;
     e.diag_add = lambda; e.diag_mod = d.R;
-    launch_tf32x3_gemm(d.tmL, d.tmL, tl + d.plan.upd[k].x, d.plan.upd[k].y, nmat, e, s, &d.tmAp, &d.tmI);
-    potrf128_kernel<<<nmat, 256, potrf_smem, s>>>(d.Lp.p, d.Wp.p, d.Mplain.p, n, k, fail_flag);
+    if (!sk_gemm) launch_tf32x3_gemm(d.tmL, d.tmL, tl + d.plan.upd[k].x, d.plan.upd[k].y, nmat, e, s, &d.tmAp, &d.tmI);
+    if (!sk_potrf) potrf128_kernel<<<nmat, 256, potrf_smem, s>>>(d.Lp.p, d.Wp.p, d.Mplain.p, n, k, fail_flag);
     if (d.plan.trsm[k].y > 0) {
       Tf32GemmEpilogue t = e0;
       t.out = d.Lp.p;
       t.out_plain = d.Lplain.p;                      // the same tiles as one FP32 plane: what the substitutions stream
-      launch_tf32x3_gemm(d.tmL, d.tmW, tl + d.plan.trsm[k].x, d.plan.trsm[k].y, nmat, t, s);
+      if (!sk_gemm) launch_tf32x3_gemm(d.tmL, d.tmW, tl + d.plan.trsm[k].x, d.plan.trsm[k].y, nmat, t, s);
     }
   }
   // ---- x0 = (L L^T)^-1 b, then  x += (L L^T)^-1 (b - A x)  by block substitution, one CTA per system
@@ -620,13 +634,15 @@ void MixedSolver::solve(const double* Af, const double* lambda, const double* bv
       const int64_t o = (int64_t)p0 * n;
       // right-hand-side count is a template parameter (register blocking): 10 is the benchmark's trait count
       auto tri = [&](const double* rv, int64_t rs, int rdiv, int step) {
+        if (sk_tri) return;
         if (np <= 10) mx_trisolve_kernel<10><<<nmat, 512, sm_t, s>>>(d.Lplain.p, d.Mplain.p, rv, rs, rdiv, xvec + o, n, np, d.Pp, nmat, step, d.conv.p, tol);
         else mx_trisolve_kernel<12><<<nmat, 512, sm_t, s>>>(d.Lplain.p, d.Mplain.p, rv, rs, rdiv, xvec + o, n, np, d.Pp, nmat, step, d.conv.p, tol);
       };
       if (st == 0) {
         tri(bvec + o, (int64_t)d.Pp * n, d.R, 0);
       } else {
-        if (np <= 10) mx_residual_kernel<10><<<grid, 256, sm_r, s>>>(Af, lambda, d.R, bvec + o, xvec + o, rvec + o, n, np, d.Pp, nmat, st, d.conv.p, tol);
+        if (sk_res) {}
+        else if (np <= 10) mx_residual_kernel<10><<<grid, 256, sm_r, s>>>(Af, lambda, d.R, bvec + o, xvec + o, rvec + o, n, np, d.Pp, nmat, st, d.conv.p, tol);
         else mx_residual_kernel<12><<<grid, 256, sm_r, s>>>(Af, lambda, d.R, bvec + o, xvec + o, rvec + o, n, np, d.Pp, nmat, st, d.conv.p, tol);
         tri(rvec + o, (int64_t)d.Pp * n, 0, st);
       }

@@ -341,7 +341,7 @@ static void enqueue_solve_mixed(rg_ctx* h, rg_ctx::Lane& L, const BlockDims& d, 
   }
   {
     ScopedTimer t(h, "mx_solve", s);
-    L.mx->solve(L.mx_Af.p, h->lambda.p, L.mx_b.p, L.mx_x.p, L.mx_r.p, P, h->mx_steps, h->mx_tol, L.mx_fail.p, s);
+    if (!dbg_skip("mx")) L.mx->solve(L.mx_Af.p, h->lambda.p, L.mx_b.p, L.mx_x.p, L.mx_r.p, P, h->mx_steps, h->mx_tol, L.mx_fail.p, s);
     h->launches += MixedSolver::launches_per_solve(n, h->mx_steps, P);
   }
 }
