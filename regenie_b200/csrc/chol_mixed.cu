@@ -69,8 +69,8 @@ __device__ __forceinline__ void split_store(const float4 v, float* hp, float* lp
 //   out: Lp tile (k,k) = L_kk (lower, zeros above);  Wp tile (k,k) = M;  Wt tile (k,k) = M^T   (hi / lo planes)
 // 256 threads = 8 warps; shared: S (P -> L, scratch above the diagonal blocks), Wm (M), Wq (M^T).
 __global__ void __launch_bounds__(256)
-potrf128_kernel(float* __restrict__ Lp, float* __restrict__ Wp, float* __restrict__ Mplain, int n, int k,
-                unsigned int* __restrict__ fail_flag) {
+potrf128_kernel(float* __restrict__ Lp, float* __restrict__ Wp, float* __restrict__ Mplain, float* __restrict__ MTplain,
+                int n, int k, unsigned int* __restrict__ fail_flag) {
   extern __shared__ float pt_sm[];
   float* S = pt_sm;
   float* Wm = pt_sm + PT * PLD;
@@ -215,7 +215,8 @@ potrf128_kernel(float* __restrict__ Lp, float* __restrict__ Wp, float* __restric
   // ---- write back as hi / lo planes
   float* Wh = Wp + moff;
   float* Wl = Wh + plane;
-  float* Mp = Mplain + ((int64_t)blockIdx.x * (n / PT) + k) * PT * PT;       // M_k as one FP32 tile for the substitutions
+  float* Mp = Mplain + ((int64_t)blockIdx.x * (n / PT) + k) * PT * PT;       // M_k / M_k^T as FP32 tiles for the substitutions
+  float* MTp = MTplain + ((int64_t)blockIdx.x * (n / PT) + k) * PT * PT;
 #pragma unroll 4
   for (int it = 0; it < PT * PT / 4 / 256; ++it) {
     const int e = threadIdx.x + 256 * it;
@@ -230,6 +231,7 @@ potrf128_kernel(float* __restrict__ Lp, float* __restrict__ Wp, float* __restric
     split_store(vl, Lh + (int64_t)r * n + c, Ll + (int64_t)r * n + c, hi);
     split_store(vw, Wh + (int64_t)r * n + c, Wl + (int64_t)r * n + c, hi);
     *reinterpret_cast<float4*>(Mp + r * PT + c) = vw;
+    *reinterpret_cast<float4*>(MTp + r * PT + c) = *reinterpret_cast<const float4*>(Wq + r * PLD + c);
   }
 }
 
@@ -310,168 +312,170 @@ mx_residual_kernel(const double* __restrict__ Af, const double* __restrict__ lam
 
 
 // dx = (L L^T)^-1 r by block forward / backward substitution, one CTA per system (no inter-CTA dependency):
-//   forward  k = 0 .. nt-1 :  y_k = M_k (r_k - sum_{j<k} L_kj y_j)          rows of L, lanes along the contraction
-//   backward k = nt-1 .. 0 :  x_k = M_k^T (y_k - sum_{j>k} L_jk^T x_j)      rows of L again, lanes along the OUTPUT columns
-// with M_k = L_kk^-1 from potrf128_kernel, so no triangular solve is ever done element by element.  Every element of L
-// is read once per sweep with 128-bit loads, eight rows per warp in flight; FP32 throughout (a correction needs few
-// digits), the result is added to the FP64 solution.  Replaces W = L^-1, X = W^T W and the X r products of the first
-// version (profiles/launches_r2d_mixed_v3.txt: 285 us of tiles + 3 x 80 us full-GPU passes per block).
-// grid: (nmat), block 512.  smem: rs [P][n] | sbuf [P][128] | part [16][P][128]
+//   forward  k = 0 .. nt-1 :  y_k = M_k   (r_k - sum_{j<k} L_kj   y_j)
+//   backward k = nt-1 .. 0 :  x_k = M_k^T (y_k - sum_{j>k} L_jk^T x_j)
+// with M_k = L_kk^-1 from potrf128_kernel, so no triangular system is ever solved element by element.
+//
+// The loads do not depend on the arithmetic, only their ORDER does: a producer thread streams every tile the sweep needs,
+// in consumption order, through a 6-stage TMA ring (16 KiB sub-tiles of 32 contraction indices x 128 output rows), and
+// runs as far ahead as the ring allows; eight consumer warps own one output row per lane and half of each sub-tile's
+// contraction range, so a sub-tile costs no shuffles and no bank conflicts (the tile is read [c][r], r contiguous).  L is
+// kept as one FP32 plane with BOTH triangles (lower = L, upper = L^T, written by the TRSM tiles' epilogue) and M_k in both
+// orientations, which makes the two sweeps the same code on different triangles.  FP32 throughout - a correction needs
+// few digits - and the result is added to the FP64 solution.  The first version (plain loads, one CTA per system) reached
+// 13 GB/s per SM and 365 us per solve (profiles/launches_r2e_mixed.txt); per-SM TMA streaming is what fixes that.
+// grid: (nmat), block 288 = 8 consumer warps + 1 producer warp.
+constexpr int TS_STAGES = 6;
+constexpr int TS_SUB = 32;                          // contraction indices per sub-tile
+constexpr int TS_STAGE_BYTES = TS_SUB * PT * 4;     // 16 KiB
+constexpr int TS_VP = 12;                           // floats per row of the vector buffers (P <= 12, 16-byte aligned rows)
+
+__device__ __forceinline__ uint32_t ts_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ts_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    if (++spins > (1u << 28)) __trap();
+  }
+}
+
 template <int PMAX>
-__global__ void __launch_bounds__(512)
-mx_trisolve_kernel(const float* __restrict__ Lpl, const float* __restrict__ Mpl, const double* __restrict__ rvec,
-                   int64_t r_mat_stride, int r_mat_div, double* __restrict__ xvec, int n, int P, int Pp, int nmat, int step,
+__global__ void __launch_bounds__(288)
+mx_trisolve_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmM,
+                   const __grid_constant__ CUtensorMap tmMT, const double* __restrict__ rvec, int64_t r_mat_stride,
+                   int r_mat_div, double* __restrict__ xvec, int n, int P, int Pp, int nmat, int step,
                    unsigned int* __restrict__ conv, float tol) {
-  extern __shared__ float ts_sm[];
+  extern __shared__ uint8_t ts_raw[];
   const int m = blockIdx.x;
   if (step > 1 && mx_finished(conv, nmat, m, step - 1, tol)) return;
-  float* rs = ts_sm;                       // [P][n]   r -> y -> x, block by block
-  float* sbuf = rs + (size_t)P * n;        // [P][128]
-  float* part = sbuf + (size_t)P * PT;     // [16][P][128]
+  const uint32_t raw = ts_smem_u32(ts_raw);
+  const uint32_t base = (raw + 127u) & ~127u;
+  uint8_t* gen = ts_raw + (base - raw);
+  float* tiles = reinterpret_cast<float*>(gen);                                        // [TS_STAGES][32][128]
+  float* v = reinterpret_cast<float*>(gen + TS_STAGES * TS_STAGE_BYTES);               // [n][TS_VP]  r -> y -> x
+  float* sbuf = v + (size_t)n * TS_VP;                                                 // [128][TS_VP]
+  float* comb = sbuf + PT * TS_VP;                                                     // [128][TS_VP] upper half's partial sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>(comb + PT * TS_VP);
+  const uint32_t full_bar = ts_smem_u32(bars), empty_bar = ts_smem_u32(bars + TS_STAGES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = n / PT;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TS_STAGES; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_bar + 8 * s), "r"(1) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty_bar + 8 * s), "r"(8) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  // right-hand sides -> v[i][p] (FP32)
   const double* r = rvec + (int64_t)(r_mat_div > 0 ? m / r_mat_div : m) * r_mat_stride;
-  for (int e = threadIdx.x * 2; e < P * n; e += 1024) {
-    const double2 v = *reinterpret_cast<const double2*>(r + e);
-    *reinterpret_cast<float2*>(rs + e) = make_float2((float)v.x, (float)v.y);
+  for (int e = threadIdx.x; e < n * TS_VP; e += 288) {
+    const int i = e / TS_VP, p = e % TS_VP;
+    v[e] = p < P ? (float)r[(int64_t)p * n + i] : 0.f;
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* L = Lpl + (int64_t)m * n * n;
-  const float* M = Mpl + (int64_t)m * nt * PT * PT;
 
-  // rows [row0, row0 + 8) of `mat` (row stride ld) against the vectors vec[p][0 .. 128 * nchunk): returns per-lane partial
-  // sums in acc[a][p]; lanes cover 4 consecutive columns of each 128-column chunk
-  auto row_sweep = [&](const float* mat, int64_t ld, int nchunk, const float* vec, int vec_ld, float (&acc)[4][PMAX]) {
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int p = 0; p < PMAX; ++p) acc[a][p] = 0.f;
-    float4 nx[4];
-    if (nchunk > 0) {
-#pragma unroll
-      for (int a = 0; a < 4; ++a) nx[a] = *reinterpret_cast<const float4*>(mat + (int64_t)a * ld + lane * 4);
-    }
-    for (int q = 0; q < nchunk; ++q) {
-      float4 la[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) la[a] = nx[a];
-      if (q + 1 < nchunk) {                            // the next chunk of the four rows is in flight during this one
-#pragma unroll
-        for (int a = 0; a < 4; ++a) nx[a] = *reinterpret_cast<const float4*>(mat + (int64_t)a * ld + (q + 1) * PT + lane * 4);
-      }
-#pragma unroll
-      for (int p = 0; p < PMAX; ++p) {
-        if (p < P) {
-          const float4 b = *reinterpret_cast<const float4*>(vec + (size_t)p * vec_ld + q * PT + lane * 4);
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-            acc[a][p] = fmaf(la[a].x, b.x, fmaf(la[a].y, b.y, fmaf(la[a].z, b.z, fmaf(la[a].w, b.w, acc[a][p]))));
+  if (warp == 8) {
+    // ===== producer: every sub-tile of both sweeps, in consumption order =====
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmL) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmM) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmMT) : "memory");
+      int it = 0;
+      auto push = [&](const CUtensorMap* tm, int c0, int c1) {
+        const int s = it % TS_STAGES;
+        const uint32_t ph = (it / TS_STAGES) & 1;
+        ts_mbar_wait(empty_bar + 8 * s, ph ^ 1);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_bar + 8 * s), "r"(TS_STAGE_BYTES) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+            ::"r"(base + s * TS_STAGE_BYTES), "l"(tm), "r"(full_bar + 8 * s), "r"(c0), "r"(c1) : "memory");
+        ++it;
+      };
+      for (int sweep = 0; sweep < 2; ++sweep)
+        for (int kk = 0; kk < nt; ++kk) {
+          const int k = sweep == 0 ? kk : nt - 1 - kk;
+          const int j0 = sweep == 0 ? 0 : k + 1, j1 = sweep == 0 ? k : nt;
+          for (int j = j0; j < j1; ++j)
+            for (int sub = 0; sub < PT / TS_SUB; ++sub) push(&tmL, k * PT, m * n + j * PT + sub * TS_SUB);
+          for (int sub = 0; sub < PT / TS_SUB; ++sub)
+            push(sweep == 0 ? &tmMT : &tmM, 0, (m * nt + k) * PT + sub * TS_SUB);
         }
-      }
     }
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int p = 0; p < PMAX; ++p) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[a][p] += __shfl_xor_sync(0xffffffffu, acc[a][p], o);
-      }
-  };
-
-  // ---- forward: warp w owns rows 8w .. 8w+7 of the block, swept four at a time
-  for (int k = 0; k < nt; ++k) {
-    float acc[4][PMAX];
-#pragma unroll 1
-    for (int h2 = 0; h2 < 2; ++h2) {
-      const int r0 = warp * 8 + h2 * 4;
-      row_sweep(L + (int64_t)(k * PT + r0) * n, n, k, rs, n, acc);
-      if (lane == 0) {
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int p = 0; p < PMAX; ++p)
-            if (p < P) sbuf[p * PT + r0 + a] = rs[(size_t)p * n + k * PT + r0 + a] - acc[a][p];
-      }
-    }
-    __syncthreads();
-#pragma unroll 1
-    for (int h2 = 0; h2 < 2; ++h2) {
-      const int r0 = warp * 8 + h2 * 4;
-      row_sweep(M + ((int64_t)k * PT + r0) * PT, PT, 1, sbuf, PT, acc);      // y_k = M_k s
-      if (lane == 0) {
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int p = 0; p < PMAX; ++p)
-            if (p < P) rs[(size_t)p * n + k * PT + r0 + a] = acc[a][p];       // block k of rs is read by nobody in this phase
-      }
-    }
-    __syncthreads();
+    return;
   }
 
-  // rows `rfirst + warp + 16 i` (i < nrow16) of `mat`, the 128 columns at col0: out[p][c] partial = sum_r mat[r][c] vec[p][r]
-  auto col_sweep = [&](const float* mat, int64_t ld, int col0, int rfirst, int nrows, const float* vec, int vec_ld, int vec_off) {
-    float4 acc[PMAX];
+  // ===== consumers: lane <-> output row, warp halves split the contraction range of every sub-tile =====
+  const int half = warp >> 2;                                  // 0: c in [0,16), 1: c in [16,32) of each sub-tile
+  const int row = (warp & 3) * 32 + lane;                      // output row inside the current block
+  int it = 0;
+  float acc[PMAX];
+  auto consume = [&](const float* vec /* [.][TS_VP], row 0 = first contraction index of this sub-tile */) {
+    const int s = it % TS_STAGES;
+    const uint32_t ph = (it / TS_STAGES) & 1;
+    ts_mbar_wait(full_bar + 8 * s, ph);
+    const float* t = tiles + (size_t)s * (TS_STAGE_BYTES / 4) + (size_t)(half * 16) * PT + row;
+    const float* y = vec + (size_t)(half * 16) * TS_VP;
 #pragma unroll
-    for (int p = 0; p < PMAX; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i0 = warp; i0 < nrows; i0 += 128) {                // eight rows of this warp per trip, loads first
-      float4 l4[8];
+    for (int c = 0; c < 16; ++c) {
+      const float tv = t[(size_t)c * PT];
+      const float4 y0 = *reinterpret_cast<const float4*>(y + c * TS_VP);
+      const float4 y1 = *reinterpret_cast<const float4*>(y + c * TS_VP + 4);
+      const float4 y2 = *reinterpret_cast<const float4*>(y + c * TS_VP + 8);
+      const float yy[12] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w, y2.x, y2.y, y2.z, y2.w};
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int i = i0 + 16 * u;
-        l4[u] = i < nrows ? *reinterpret_cast<const float4*>(mat + (int64_t)(rfirst + i) * ld + col0 + lane * 4)
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int i = i0 + 16 * u;
-        if (i < nrows) {
-#pragma unroll
-          for (int p = 0; p < PMAX; ++p)
-            if (p < P) {
-              const float xv = vec[(size_t)p * vec_ld + vec_off + i];
-              acc[p].x = fmaf(l4[u].x, xv, acc[p].x); acc[p].y = fmaf(l4[u].y, xv, acc[p].y);
-              acc[p].z = fmaf(l4[u].z, xv, acc[p].z); acc[p].w = fmaf(l4[u].w, xv, acc[p].w);
-            }
-        }
-      }
+      for (int p = 0; p < PMAX; ++p) acc[p] = fmaf(tv, yy[p], acc[p]);
     }
-#pragma unroll
-    for (int p = 0; p < PMAX; ++p)
-      if (p < P) *reinterpret_cast<float4*>(part + ((size_t)warp * P + p) * PT + lane * 4) = acc[p];
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_bar + 8 * s) : "memory");
+    ++it;
   };
+  auto consumer_sync = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
 
-  // ---- backward
-  for (int k = nt - 1; k >= 0; --k) {
-    const int nbelow = n - (k + 1) * PT;
-    col_sweep(L, n, k * PT, (k + 1) * PT, nbelow, rs, n, (k + 1) * PT);
-    __syncthreads();
-    for (int e = threadIdx.x; e < P * PT; e += 512) {           // t = y_k - sum of the 16 partials (fixed order)
-      const int p = e / PT, c = e % PT;
-      float sum = 0.f;
+  for (int sweep = 0; sweep < 2; ++sweep)
+    for (int kk = 0; kk < nt; ++kk) {
+      const int k = sweep == 0 ? kk : nt - 1 - kk;
+      const int j0 = sweep == 0 ? 0 : k + 1, j1 = sweep == 0 ? k : nt;
 #pragma unroll
-      for (int w = 0; w < 16; ++w) sum += part[((size_t)w * P + p) * PT + c];
-      sbuf[p * PT + c] = rs[(size_t)p * n + k * PT + c] - sum;
-    }
-    __syncthreads();
-    col_sweep(M + (int64_t)k * PT * PT, PT, 0, 0, PT, sbuf, PT, 0);          // x_k = M_k^T t
-    __syncthreads();
-    for (int e = threadIdx.x; e < P * PT; e += 512) {
-      const int p = e / PT, c = e % PT;
-      float sum = 0.f;
+      for (int p = 0; p < PMAX; ++p) acc[p] = 0.f;
+      for (int j = j0; j < j1; ++j)
+        for (int sub = 0; sub < PT / TS_SUB; ++sub) consume(v + (size_t)(j * PT + sub * TS_SUB) * TS_VP);
+      if (half == 1) {
 #pragma unroll
-      for (int w = 0; w < 16; ++w) sum += part[((size_t)w * P + p) * PT + c];
-      rs[(size_t)p * n + k * PT + c] = sum;
+        for (int p = 0; p < PMAX; ++p) comb[row * TS_VP + p] = acc[p];
+      }
+      consumer_sync();
+      if (half == 0) {
+#pragma unroll
+        for (int p = 0; p < PMAX; ++p) sbuf[row * TS_VP + p] = v[(size_t)(k * PT + row) * TS_VP + p] - acc[p] - comb[row * TS_VP + p];
+      }
+      consumer_sync();
+#pragma unroll
+      for (int p = 0; p < PMAX; ++p) acc[p] = 0.f;
+      for (int sub = 0; sub < PT / TS_SUB; ++sub) consume(sbuf + (size_t)(sub * TS_SUB) * TS_VP);      // v_k = D_k s
+      if (half == 1) {
+#pragma unroll
+        for (int p = 0; p < PMAX; ++p) comb[row * TS_VP + p] = acc[p];
+      }
+      consumer_sync();
+      if (half == 0) {
+#pragma unroll
+        for (int p = 0; p < PMAX; ++p) v[(size_t)(k * PT + row) * TS_VP + p] = acc[p] + comb[row * TS_VP + p];
+      }
+      consumer_sync();
     }
-    __syncthreads();
-  }
 
-  // ---- x += dx, convergence bookkeeping
+  // ---- x += dx, convergence bookkeeping (consumer threads only)
   float dmax = 0.f, xmax = 0.f;
-  for (int e = threadIdx.x; e < P * n; e += 512) {
+  for (int e = threadIdx.x; e < P * n; e += 256) {
     const int p = e / n, i = e % n;
     double* xp = xvec + ((int64_t)m * Pp + p) * n + i;
-    const float dx = rs[e];
+    const float dx = v[(size_t)i * TS_VP + p];
     const double xn = (step == 0 ? 0.0 : *xp) + (double)dx;
     *xp = xn;
     dmax = (fabsf(dx) <= 3.0e38f) ? fmaxf(dmax, fabsf(dx)) : __int_as_float(0x7f800000);
@@ -534,9 +538,9 @@ static void build_plan(MxPlan& pl, int n) {
 
 struct MixedSolver::Impl {
   int n = 0, nmat = 0, K = 0, R = 0, Pp = 0;
-  DevBuf<float> Lp, Wp, Lplain, Mplain, Ap, Ident;
+  DevBuf<float> Lp, Wp, Lplain, Mplain, MTplain, Ap, Ident;
   DevBuf<unsigned int> conv;
-  CUtensorMap tmL, tmW, tmAp, tmI;
+  CUtensorMap tmL, tmW, tmAp, tmI, tmLpl, tmMpl, tmMTpl;
   MxPlan plan;
 };
 
@@ -560,6 +564,10 @@ void MixedSolver::prepare(int n, int K, int R, int Pp) {
   d.Lp.alloc(planes); d.Wp.alloc(planes);
   d.Lplain.alloc((size_t)nmat * n * n);
   d.Mplain.alloc((size_t)nmat * n * PT);
+  d.MTplain.alloc((size_t)nmat * n * PT);
+  make_f32_rows_tensor_map(&d.tmLpl, d.Lplain.p, n, (int64_t)nmat * n, PT, TS_SUB);
+  make_f32_rows_tensor_map(&d.tmMpl, d.Mplain.p, PT, (int64_t)nmat * n, PT, TS_SUB);
+  make_f32_rows_tensor_map(&d.tmMTpl, d.MTplain.p, PT, (int64_t)nmat * n, PT, TS_SUB);
   // tiles that nothing writes (upper triangle) are read by nothing either; zero once so stale data can never matter
   RG_CUDA(cudaMemset(d.Lp.p, 0, planes * 4));
   RG_CUDA(cudaMemset(d.Wp.p, 0, planes * 4));
@@ -594,8 +602,8 @@ void MixedSolver::solve(const double* Af, const double* lambda, const double* bv
   ensure_dyn_smem(reinterpret_cast<const void*>(potrf128_kernel), potrf_smem);
   ensure_dyn_smem(reinterpret_cast<const void*>(mx_residual_kernel<12>), 98304);
   ensure_dyn_smem(reinterpret_cast<const void*>(mx_residual_kernel<10>), 98304);
-  ensure_dyn_smem(reinterpret_cast<const void*>(mx_trisolve_kernel<12>), 200 * 1024);
-  ensure_dyn_smem(reinterpret_cast<const void*>(mx_trisolve_kernel<10>), 200 * 1024);
+  ensure_dyn_smem(reinterpret_cast<const void*>(mx_trisolve_kernel<12>), 220 * 1024);
+  ensure_dyn_smem(reinterpret_cast<const void*>(mx_trisolve_kernel<10>), 220 * 1024);
   RG_CHECK(n <= 2048, "mixed solver: n <= 2048");
   // profiling aid (results are garbage): RG_DBG_SKIP=mxgemm|mxpotrf|mxtri|mxres drops one kernel family of the solver so
   // its marginal cost under multi-lane overlap can be read off (profiles/ablation_r2_*.txt)
@@ -615,11 +623,12 @@ void MixedSolver::solve(const double* Af, const double* lambda, const double* bv
     e.c_chunks = 4; e.c_mat_div = d.R;
     e.diag_add = lambda; e.diag_mod = d.R;
     if (!sk_gemm) launch_tf32x3_gemm(d.tmL, d.tmL, tl + d.plan.upd[k].x, d.plan.upd[k].y, nmat, e, s, &d.tmAp, &d.tmI);
-    if (!sk_potrf) potrf128_kernel<<<nmat, 256, potrf_smem, s>>>(d.Lp.p, d.Wp.p, d.Mplain.p, n, k, fail_flag);
+    if (!sk_potrf) potrf128_kernel<<<nmat, 256, potrf_smem, s>>>(d.Lp.p, d.Wp.p, d.Mplain.p, d.MTplain.p, n, k, fail_flag);
     if (d.plan.trsm[k].y > 0) {
       Tf32GemmEpilogue t = e0;
       t.out = d.Lp.p;
-      t.out_plain = d.Lplain.p;                      // the same tiles as one FP32 plane: what the substitutions stream
+      t.out_plain = d.Lplain.p;                      // the same tiles as one FP32 plane, and their transposes in the upper
+      t.mirror = 1;                                  // triangle: what the two substitution sweeps stream
       if (!sk_gemm) launch_tf32x3_gemm(d.tmL, d.tmW, tl + d.plan.trsm[k].x, d.plan.trsm[k].y, nmat, t, s);
     }
   }
@@ -630,13 +639,13 @@ void MixedSolver::solve(const double* Af, const double* lambda, const double* bv
     for (int p0 = 0; p0 < P; p0 += pc) {
       const int np = std::min(pc, P - p0);
       const size_t sm_r = (size_t)np * n * sizeof(double);
-      const size_t sm_t = ((size_t)np * n + (size_t)np * PT * 17) * sizeof(float);
+      const size_t sm_t = (size_t)TS_STAGES * TS_STAGE_BYTES + ((size_t)n + 2 * PT) * TS_VP * sizeof(float) + 2 * TS_STAGES * 8 + 256;
       const int64_t o = (int64_t)p0 * n;
       // right-hand-side count is a template parameter (register blocking): 10 is the benchmark's trait count
       auto tri = [&](const double* rv, int64_t rs, int rdiv, int step) {
         if (sk_tri) return;
-        if (np <= 10) mx_trisolve_kernel<10><<<nmat, 512, sm_t, s>>>(d.Lplain.p, d.Mplain.p, rv, rs, rdiv, xvec + o, n, np, d.Pp, nmat, step, d.conv.p, tol);
-        else mx_trisolve_kernel<12><<<nmat, 512, sm_t, s>>>(d.Lplain.p, d.Mplain.p, rv, rs, rdiv, xvec + o, n, np, d.Pp, nmat, step, d.conv.p, tol);
+        if (np <= 10) mx_trisolve_kernel<10><<<nmat, 288, sm_t, s>>>(d.tmLpl, d.tmMpl, d.tmMTpl, rv, rs, rdiv, xvec + o, n, np, d.Pp, nmat, step, d.conv.p, tol);
+        else mx_trisolve_kernel<12><<<nmat, 288, sm_t, s>>>(d.tmLpl, d.tmMpl, d.tmMTpl, rv, rs, rdiv, xvec + o, n, np, d.Pp, nmat, step, d.conv.p, tol);
       };
       if (st == 0) {
         tri(bvec + o, (int64_t)d.Pp * n, d.R, 0);

@@ -105,6 +105,7 @@ struct Tf32GemmEpilogue {
 };
 void make_tf32_planes_tensor_map(CUtensorMap* tm, const float* planes, int n, int batch);
 void make_tf32_identity_planes(DevBuf<float>& buf, CUtensorMap* tm);
+void make_f32_rows_tensor_map(CUtensorMap* tm, const float* base, int cols, int64_t rows, int box_cols, int box_rows);
 void launch_tf32x3_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const int4* tiles, int ntiles, int batch,
                         const Tf32GemmEpilogue& ep, cudaStream_t s, const CUtensorMap* tmC = nullptr,
                         const CUtensorMap* tmI = nullptr);

@@ -336,6 +336,18 @@ void make_tf32_planes_tensor_map(CUtensorMap* tm, const float* planes, int n, in
   RG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (tf32 planes) failed (" + std::to_string((int)r) + ")");
 }
 
+// plain row-major FP32 matrix [rows][cols] -> 2-D map, box {box_cols, box_rows}, no swizzle (the substitution sweeps)
+void make_f32_rows_tensor_map(CUtensorMap* tm, const float* base, int cols, int64_t rows, int box_cols, int box_rows) {
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)cols * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = tg_encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (f32 rows) failed (" + std::to_string((int)r) + ")");
+}
+
 // identity planes [1][2][128][128] (hi = I, lo = 0) for the C phase
 void make_tf32_identity_planes(DevBuf<float>& buf, CUtensorMap* tm) {
   std::vector<float> h((size_t)2 * 128 * 128, 0.f);
