@@ -239,11 +239,22 @@ potrf128_kernel(float* __restrict__ Lp, float* __restrict__ Wp, float* __restric
 // Refinement.  conv[step][m] = (max |dx|, max |x|) as float bit patterns (non-negative floats order like unsigned
 // integers, so atomicMax is exact and order-independent).  A system is finished as soon as one step's correction
 // satisfied  max|dx| <= tol * max|x|; finished systems are skipped by every later launch.
+// Stopping rule.  dx_s = (LL^T)^-1 (b - A x_{s-1}) is the forward error of the PREVIOUS iterate up to the contraction
+// factor rho = ||I - (LL^T)^-1 A||, and rho itself is what the P right-hand sides sample: dx_1 / x = ||(I - XA) x|| / ||x||.
+//   (a) dx_s <= tol x                      : x_{s-1} was already within tol, x_s is better by rho           (rigorous)
+//   (b) kMxSafety (dx_s / x)^2 <= tol      : predicted error of x_s = rho dx_s with rho <= kMxSafety dx_s/x.  kMxSafety = 64
+//       covers the worst ratio sqrt(n) = 32..45 between the operator norm and its gain on a generic vector; with the
+//       benchmark's dx_1/x = 2.6e-6 the predicted bound is 4e-10 and the measured error of x_1 8e-12.
+// RG_B200_MX_STRICT=1 keeps only (a).
+constexpr float kMxSafety = 64.f;
 __device__ __forceinline__ bool mx_finished(const unsigned int* conv, int nmat, int m, int upto_step, float tol) {
+  const bool strict = tol < 0.f;                      // the host passes -tol for the strict rule
+  const float t = fabsf(tol);
   for (int s = 1; s <= upto_step; ++s) {
     const float dx = __uint_as_float(conv[((int64_t)s * nmat + m) * 2]);
     const float xx = __uint_as_float(conv[((int64_t)s * nmat + m) * 2 + 1]);
-    if (dx <= tol * xx) return true;
+    if (dx <= t * xx) return true;
+    if (!strict && kMxSafety * dx * dx <= t * xx * xx) return true;
   }
   return false;
 }

@@ -341,7 +341,7 @@ static void enqueue_solve_mixed(rg_ctx* h, rg_ctx::Lane& L, const BlockDims& d, 
   }
   {
     ScopedTimer t(h, "mx_solve", s);
-    if (!dbg_skip("mx")) L.mx->solve(L.mx_Af.p, h->lambda.p, L.mx_b.p, L.mx_x.p, L.mx_r.p, P, h->mx_steps, h->mx_tol, L.mx_fail.p, s);
+    if (!dbg_skip("mxall")) L.mx->solve(L.mx_Af.p, h->lambda.p, L.mx_b.p, L.mx_x.p, L.mx_r.p, P, h->mx_steps, h->mx_tol, L.mx_fail.p, s);
     h->launches += MixedSolver::launches_per_solve(n, h->mx_steps, P);
   }
 }
@@ -775,6 +775,7 @@ int rg_step1_create(const rg_step1_config* cfg, const double* X, const double* Y
   if (const char* e = getenv("RG_B200_SOLVER")) h->solver_mixed = std::string(e) == "f64" ? 0 : 1;
   if (const char* e = getenv("RG_B200_MX_STEPS")) h->mx_steps = std::max(1, std::min(kMxMaxSteps, atoi(e)));
   if (const char* e = getenv("RG_B200_MX_TOL")) h->mx_tol = (float)atof(e);
+  if (const char* e = getenv("RG_B200_MX_STRICT")) if (atoi(e) != 0) h->mx_tol = -fabsf(h->mx_tol);   // correction-size rule only
   build_layout(h.get(), X, Y, mask, in_analysis, fold_sizes);
   h->lambda.alloc(h->R);
   h->neff.alloc(h->P);
