@@ -579,7 +579,7 @@ def step2_qt_leg(capi, X, mask, in_an, N, P, C, bs, blocks, host_panel, dev_ptr,
     # CPU: the Eigen restatement, one OpenMP task per variant like Data::test_snps_fast
     cpu = None
     if not args.no_cpu:
-        nv_cpu = 256
+        nv_cpu = 8192                                  # ~ a few seconds of CPU work on the host cores
         rows = host_panel[:nv_cpu].numpy()
         YtX = res.T @ X
         thr = host_threads()
@@ -685,11 +685,13 @@ def step2_bt_leg(capi, X, in_an, N, C, args, nvar=400, nblocks=4):
     cpu = None
     if not args.no_cpu:
         thr = host_threads()
-        nv_cpu = 256
-        pm = np.full((nv_cpu, N), 2, dtype=np.uint8)
+        reps = 16                                      # the 400 synthetic variants, 16 times over: a few seconds of CPU work
+        nv_cpu = reps * nvar
+        pm = np.full((nvar, N), 2, dtype=np.uint8)
         ref_eigen.s2_block_bt_probs(probs_np[:32], pm[:32], N, in_an, gsm, X, yres, threads=thr)
         t0 = time.perf_counter()
-        ref_eigen.s2_block_bt_probs(probs_np[:nv_cpu], pm, N, in_an, gsm, X, yres, threads=thr)
+        for _ in range(reps):
+            ref_eigen.s2_block_bt_probs(probs_np, pm, N, in_an, gsm, X, yres, threads=thr)
         dt = time.perf_counter() - t0
         cpu = {"value": nv_cpu / dt, "unit": "variants/s", "cores": thr, "kind": "port",
                "sample": "%d variants at N=%d: C++/Eigen restatement of the BGEN dosage loop + compute_score_bt (score statistic "
