@@ -105,15 +105,18 @@ potrf128_kernel(float* __restrict__ Lp, float* __restrict__ Wp, float* __restric
       float a[PB];
 #pragma unroll
       for (int c = 0; c < PB; ++c) a[c] = (c <= lane) ? S[(j0 + lane) * PLD + j0 + c] : 0.f;
+      // software-pipelined pivot chain: the NEXT pivot A[c+1][c+1] - L[c+1][c]^2 is formed by its own lane and broadcast
+      // before the bulk of column c's rank-1 update is issued, so rsqrt + broadcast latency hides behind that update
+      float d = __shfl_sync(0xffffffffu, a[0], 0);
 #pragma unroll
       for (int c = 0; c < PB; ++c) {
-        const float d = __shfl_sync(0xffffffffu, a[c], c);
         if (!(d > 0.f)) bad = true;
         float inv = rsqrtf(d);
         inv = inv * (1.5f - 0.5f * d * inv * inv);
         const float l = a[c] * inv;
         a[c] = l;
         if (lane == c) dinv[j0 + c] = inv;
+        if (c + 1 < PB) d = __shfl_sync(0xffffffffu, fmaf(-l, l, a[c + 1]), c + 1);   // lane c+1: l = L[c+1][c]
 #pragma unroll
         for (int cc = c + 1; cc < PB; ++cc) {
           const float lcc = __shfl_sync(0xffffffffu, l, cc);
