@@ -61,7 +61,11 @@ __global__ void bed_relayout_kernel(const uint8_t* __restrict__ packed, int64_t 
   gp[(int64_t)row * words_per_row + w] = out;
 }
 
-// 2-bit codes -> two e4m3 planes.  e4m3: 0 = 0x00, 1.0 = 0x38, 2.0 = 0x40.
+// 2-bit codes -> two operand planes whose bytes are valid in BOTH 8-bit tensor-core formats:
+//   dosage 0 / 1 / 2 -> 0x00 / 0x08 / 0x10  =  2^-6 * (0, 1, 2) as e4m3 (0x08 is the smallest normal)  =  8 * (0, 1, 2) as int8,
+//   missing indicator -> 0x08.
+// The FP8 Gram (kind::f8f6f4) therefore accumulates 2^-12 x the integer Gram - still exact in FP32, a power-of-two scale the
+// epilogue removes (kZScaleGram) - and the INT8 prediction kernel (kind::i8) reads the same bytes as small integers.
 // Byte-permute does the 4-way table lookup: selector nibble k = code of sample k.
 __device__ __forceinline__ uint32_t spread_sel(uint32_t b) {
   return (b & 0x3u) | ((b & 0xCu) << 2) | ((b & 0x30u) << 4) | ((b & 0xC0u) << 6);
@@ -73,8 +77,8 @@ __global__ void bed_expand_fp8_kernel(const uint32_t* __restrict__ gp, int64_t w
   const int row = blockIdx.y;
   if (w >= words_per_row) return;
   const uint32_t word = __ldg(gp + (int64_t)row * words_per_row + w);
-  const uint32_t kLutG = 0x00403800u;  // idx0 -> 0, idx1 -> 1.0, idx2 -> 2.0, idx3(missing) -> 0
-  const uint32_t kLutM = 0x38000000u;  // idx3 -> 1.0
+  const uint32_t kLutG = 0x00100800u;  // idx0 -> 0, idx1 -> 0x08, idx2 -> 0x10, idx3(missing) -> 0
+  const uint32_t kLutM = 0x08000000u;  // idx3 -> 0x08
   uint4 g, m;
   uint32_t* gv = reinterpret_cast<uint32_t*>(&g);
   uint32_t* mv = reinterpret_cast<uint32_t*>(&m);

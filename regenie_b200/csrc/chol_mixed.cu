@@ -325,6 +325,112 @@ mx_residual_kernel(const double* __restrict__ Af, const double* __restrict__ lam
 }
 
 
+// Same residuals, all R systems of a fold in ONE CTA: a register-tiled FP64 GEMM  Y = A_f[rows, :] X_f  with X_f the R * P
+// current solutions of the fold as columns, so the A_f rows are read once instead of once per ridge value (the pass above is
+// bound by those L2 reads: 5 x 42 MB per pass) and nothing is reduced across threads (fixed summation order: k ascending).
+//   CTA = (64 rows, fold), 256 threads = 16 row lanes x 16 vector lanes, thread tile 4 rows x 4 vectors,
+//   A and X staged through shared memory in chunks of 32 contraction indices (k-major, double-buffered, register prefetch).
+// grid: (n / 64, K folds); at most 64 vectors (R * np <= 64), else the per-system kernel above is used.
+constexpr int RF_ROWS = 64;
+constexpr int RF_KC = 32;
+constexpr int RF_NV = 64;
+constexpr int RF_LD = 65;                                   // doubles per k-row of the staged tiles (odd: 2-way store conflicts at most)
+constexpr size_t kResFusedSmem = (size_t)2 * 2 * RF_KC * RF_LD * sizeof(double);
+
+__global__ void __launch_bounds__(256)
+mx_residual_fused_kernel(const double* __restrict__ Af, const double* __restrict__ lambda, int R, const double* __restrict__ bvec,
+                         const double* __restrict__ xvec, double* __restrict__ rvec, int n, int P, int Pp, int nmat, int step,
+                         const unsigned int* __restrict__ conv, float tol) {
+  extern __shared__ double rf_sm[];
+  const int f = blockIdx.y;
+  if (step > 1) {
+    bool all_done = true;
+    for (int r = 0; r < R; ++r) all_done = all_done && mx_finished(conv, nmat, f * R + r, step - 1, tol);
+    if (all_done) return;
+  }
+  const int NV = R * P;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int row0 = blockIdx.x * RF_ROWS;
+  double* As = rf_sm;                                        // [2][RF_KC][RF_LD]
+  double* Xs = rf_sm + 2 * RF_KC * RF_LD;                    // [2][RF_KC][RF_LD]
+  for (int e = threadIdx.x; e < 2 * RF_KC * RF_LD; e += 256) Xs[e] = 0.0;     // vector slots >= NV stay zero
+  __syncthreads();
+  // staging map: element e = threadIdx.x + 256 * q  ->  (row or vector e / 16, k pair e % 16)
+  const double* arow = Af + ((int64_t)f * n + row0) * n;
+  double2 pa[4], px[4];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = threadIdx.x + 256 * q;
+      const int rr = e >> 4, kp = e & 15;
+      pa[q] = *reinterpret_cast<const double2*>(arow + (int64_t)rr * n + k0 + 2 * kp);
+      px[q] = make_double2(0.0, 0.0);
+      if (rr < NV) {
+        const int m = f * R + rr / P, p = rr % P;
+        px[q] = *reinterpret_cast<const double2*>(xvec + ((int64_t)m * Pp + p) * n + k0 + 2 * kp);
+      }
+    }
+  };
+  auto sstore = [&](int buf) {
+    double* a = As + buf * RF_KC * RF_LD;
+    double* x = Xs + buf * RF_KC * RF_LD;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = threadIdx.x + 256 * q;
+      const int rr = e >> 4, kp = e & 15;
+      a[(2 * kp) * RF_LD + rr] = pa[q].x;
+      a[(2 * kp + 1) * RF_LD + rr] = pa[q].y;
+      if (rr < NV) {
+        x[(2 * kp) * RF_LD + rr] = px[q].x;
+        x[(2 * kp + 1) * RF_LD + rr] = px[q].y;
+      }
+    }
+  };
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) acc[i][v] = 0.0;
+  const int nch = n / RF_KC;
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int c = 0; c < nch; ++c) {
+    if (c + 1 < nch) gload((c + 1) * RF_KC);
+    const double* a = As + (c & 1) * RF_KC * RF_LD + tx;
+    const double* x = Xs + (c & 1) * RF_KC * RF_LD + ty;
+#pragma unroll 8
+    for (int k = 0; k < RF_KC; ++k) {
+      double av[4], xv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = a[k * RF_LD + 16 * i];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) xv[v] = x[k * RF_LD + 16 * v];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[i][v] = fma(av[i], xv[v], acc[i][v]);
+    }
+    if (c + 1 < nch) sstore((c + 1) & 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const int vec = ty + 16 * v;
+    if (vec < NV) {
+      const int r = vec / P, p = vec % P, m = f * R + r;
+      const double lam = lambda[r];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = row0 + tx + 16 * i;
+        const int64_t o = ((int64_t)m * Pp + p) * n + row;
+        rvec[o] = bvec[((int64_t)f * Pp + p) * n + row] - lam * xvec[o] - acc[i][v];
+      }
+    }
+  }
+}
+
+
 // dx = (L L^T)^-1 r by block forward / backward substitution, one CTA per system (no inter-CTA dependency):
 //   forward  k = 0 .. nt-1 :  y_k = M_k   (r_k - sum_{j<k} L_kj   y_j)
 //   backward k = nt-1 .. 0 :  x_k = M_k^T (y_k - sum_{j>k} L_jk^T x_j)
@@ -616,6 +722,8 @@ void MixedSolver::solve(const double* Af, const double* lambda, const double* bv
   ensure_dyn_smem(reinterpret_cast<const void*>(potrf128_kernel), potrf_smem);
   ensure_dyn_smem(reinterpret_cast<const void*>(mx_residual_kernel<12>), 98304);
   ensure_dyn_smem(reinterpret_cast<const void*>(mx_residual_kernel<10>), 98304);
+  ensure_dyn_smem(reinterpret_cast<const void*>(mx_residual_fused_kernel), kResFusedSmem);
+  static const bool res_fused = [] { const char* e = getenv("RG_B200_MX_RES"); return !(e && strcmp(e, "plain") == 0); }();
   ensure_dyn_smem(reinterpret_cast<const void*>(mx_trisolve_kernel<12>), 220 * 1024);
   ensure_dyn_smem(reinterpret_cast<const void*>(mx_trisolve_kernel<10>), 220 * 1024);
   RG_CHECK(n <= 2048, "mixed solver: n <= 2048");
@@ -665,6 +773,8 @@ void MixedSolver::solve(const double* Af, const double* lambda, const double* bv
         tri(bvec + o, (int64_t)d.Pp * n, d.R, 0);
       } else {
         if (sk_res) {}
+        else if (res_fused && d.R * np <= RF_NV && n % RF_ROWS == 0)
+          mx_residual_fused_kernel<<<dim3(n / RF_ROWS, d.K), 256, kResFusedSmem, s>>>(Af, lambda, d.R, bvec + o, xvec + o, rvec + o, n, np, d.Pp, nmat, st, d.conv.p, tol);
         else if (np <= 10) mx_residual_kernel<10><<<grid, 256, sm_r, s>>>(Af, lambda, d.R, bvec + o, xvec + o, rvec + o, n, np, d.Pp, nmat, st, d.conv.p, tol);
         else mx_residual_kernel<12><<<grid, 256, sm_r, s>>>(Af, lambda, d.R, bvec + o, xvec + o, rvec + o, n, np, d.Pp, nmat, st, d.conv.p, tol);
         tri(rvec + o, (int64_t)d.Pp * n, 0, st);

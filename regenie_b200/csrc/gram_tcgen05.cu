@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 gram_fp8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmB,
                         const int2* __restrict__ tiles,
                         const int2* __restrict__ fold_k, float* __restrict__ out, int ldo,
-                        int64_t fold_stride) {
+                        int64_t fold_stride, float out_scale) {
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned stage buffers
   const uint32_t raw = smem_u32(smem_raw);
@@ -198,8 +198,8 @@ gram_fp8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_co
       float4* o4 = reinterpret_cast<float4*>(orow + c * 32);
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        o4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                            __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        o4[j] = make_float4(__uint_as_float(v[4 * j]) * out_scale, __uint_as_float(v[4 * j + 1]) * out_scale,
+                            __uint_as_float(v[4 * j + 2]) * out_scale, __uint_as_float(v[4 * j + 3]) * out_scale);
     }
   }
   tcgen05_fence_before();
@@ -223,8 +223,8 @@ __global__ void gram_reference_kernel(const uint8_t* __restrict__ z, int64_t npa
   const uint8_t* zj = z + (int64_t)j * npad;
   int acc = 0;
   for (int t = k0; t < k1; ++t) {
-    const int a = zi[t] == 0x38 ? 1 : (zi[t] == 0x40 ? 2 : 0);
-    const int b = zj[t] == 0x38 ? 1 : (zj[t] == 0x40 ? 2 : 0);
+    const int a = zi[t] >> 3;        // plane bytes 0x00 / 0x08 / 0x10 (bed_expand_fp8_kernel)
+    const int b = zj[t] >> 3;
     acc += a * b;
   }
   out[(int64_t)i * ldo + j] = (float)acc;
@@ -270,10 +270,10 @@ void gram_tile_list(int rows2, std::vector<int2>& tiles) {
 }
 
 void launch_gram_tcgen05(const CUtensorMap& tm, const CUtensorMap& tmB, const int2* tiles, int ntiles, const int2* fold_k, int K,
-                         float* out, int ldo, int64_t fold_stride, cudaStream_t s) {
+                         float* out, int ldo, int64_t fold_stride, float out_scale, cudaStream_t s) {
   ensure_dyn_smem(reinterpret_cast<const void*>(gram_fp8_tcgen05_kernel), gram_smem_bytes());
   dim3 grid(ntiles, K);
-  gram_fp8_tcgen05_kernel<<<grid, NTHREADS, gram_smem_bytes(), s>>>(tm, tmB, tiles, fold_k, out, ldo, fold_stride);
+  gram_fp8_tcgen05_kernel<<<grid, NTHREADS, gram_smem_bytes(), s>>>(tm, tmB, tiles, fold_k, out, ldo, fold_stride, out_scale);
 }
 
 void launch_gram_reference(const uint8_t* z, int64_t npad, int rows2, int k0, int k1, float* out, int ldo,

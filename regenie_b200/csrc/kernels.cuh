@@ -9,6 +9,8 @@ constexpr int kMaxCov = 64;
 constexpr int kMaxRidge = 8;
 constexpr int kMaxPhenoTile = 8;
 constexpr int kLimbs = 9;          // radix-30 digits per coefficient (44 bits)
+constexpr int kLimbsI8 = 5;        // radix-254 int8 digits per coefficient of the INT8 prediction kernel (40 bits)
+constexpr int kLimbQI8 = 50;       // outputs per INT8 prediction pass (5 x 50 = 250 <= 256 TMEM columns)
 constexpr int kLimbQ = 56;         // outputs per tensor-core prediction pass (9 x 56 = 504 <= 512 TMEM columns)   // phenotypes per register pass of the LOOCV prediction kernel
 
 // ---- bed_kernels.cu
@@ -71,7 +73,10 @@ void launch_l0_stats_finish(const float* T, int ldt, int64_t t_fold_stride, cons
                             int32_t* cnt_fold, double* sum_fold, cudaStream_t s);
 void gram_tile_list(int rows2, std::vector<int2>& tiles);
 void launch_gram_tcgen05(const CUtensorMap& tm, const CUtensorMap& tmB, const int2* tiles, int ntiles, const int2* fold_k, int K,
-                         float* out, int ldo, int64_t fold_stride, cudaStream_t s);
+                         float* out, int ldo, int64_t fold_stride, float out_scale, cudaStream_t s);
+// operand-plane bytes of the Step-1 block (bed_expand_fp8_kernel): dosage d -> 8 d as int8 = 2^-6 d as e4m3
+constexpr float kZScaleGram = 4096.f;     // Z Z^T tiles: both operands carry 2^-6
+constexpr float kZScaleStat = 64.f;       // Z [X|Y]-digit tiles: the digit rows are plain e4m3 integers
 void launch_gram_reference(const uint8_t* z, int64_t npad, int rows2, int k0, int k1, float* out, int ldo,
                            cudaStream_t s);
 
@@ -193,6 +198,12 @@ int launch_l0_colsum(double* const* W, int64_t npad, int col0, int P, int Q, int
                      cudaStream_t s);
 void launch_l0_predict_tcgen05(const CUtensorMap& tmZ, const CUtensorMap& tmD, const PredictTcArgs& a, int ntiles,
                                cudaStream_t s);
+// INT8 variant (kind::i8): 5 radix-254 digit rows per output, 256 TMEM columns, two CTAs per SM
+size_t predict_i8_dig_bytes(int K, int ngroups, int rows_p);
+void launch_l0_gamma_limbs_i8(const double* gam, const double* gmu, int Qp, int Q, int bs, int rows_p, int K,
+                              double* scale, uint8_t* dig, int ngroups, cudaStream_t s);
+void launch_l0_predict_i8(const CUtensorMap& tmZ, const CUtensorMap& tmD, const PredictTcArgs& a, int ntiles,
+                          cudaStream_t s);
 
 // ---- l1_kernels.cu
 void launch_l1_gram(const double* W, int64_t ldw, int B, const int4* chunks, int nchunks, double* part,

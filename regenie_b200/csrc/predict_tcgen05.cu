@@ -251,7 +251,7 @@ l0_predict_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_
       tmem_ld_32x32(tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)(l * kLimbQ + half * PT_QH), v);
 #pragma unroll
       for (int j = 0; j < PT_QH; ++j) {
-        const int iv = __float_as_int(__uint_as_float(v[j]) + 12582912.0f) - 0x4B400000;   // exact float -> int
+        const int iv = __float_as_int(fmaf(__uint_as_float(v[j]), 64.0f, 12582912.0f)) - 0x4B400000;   // planes carry 2^-6; exact float -> int
         if (l < 4) ihi[j] = ihi[j] * 30 + iv;
         else if (l < 8) imid[j] = imid[j] * 30 + iv;
         else ilo[j] = iv;
@@ -282,6 +282,205 @@ l0_predict_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_
   if (warp == 1) {
     fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// =============================================================================================
+// INT8 variant (default).  The operand planes' bytes are 8 x dosage as int8 (bed_expand_fp8_kernel), the coefficients are
+// split into FIVE balanced radix-254 digits
+//   gamma[i,q] = (s_q / 127) * sum_l d_l[i,q] 254^-l,   d_l in {-127..127}  (int8),
+// so tcgen05.mma kind::i8 accumulates exact int32 sums (|sum| <= K2 * 16 * 127 < 2^24 for K2 <= 4096) and the FP64 epilogue
+// reassembles the prediction to 254^-5 / 2 = 4.7e-13 s_q per coefficient.  Against the e4m3 version above: 250 instead of 504
+// digit rows per pass (5 limbs x 8 bits instead of 9 x 4.9 bits) - half the B-operand traffic from L2, which bounds this
+// kernel, half the tensor work, 256 TMEM columns and 96 KiB of shared memory, so TWO CTAs share an SM and one's epilogue
+// overlaps the other's main loop.
+namespace {
+constexpr int PI_BN = 256;
+constexpr int PI_STAGES = 2;
+constexpr int PI_A_BYTES = PT_BK * PT_BM;          // 16 KiB
+constexpr int PI_B_BYTES = PI_BN * PT_BK;          // 32 KiB
+constexpr int PI_STAGE_BYTES = PI_A_BYTES + PI_B_BYTES;
+constexpr int PI_QH = kLimbQI8 / 2;                // outputs per epilogue thread (25)
+static_assert(kLimbsI8 * kLimbQI8 <= PI_BN && kLimbQI8 % 2 == 0 && PI_QH <= 32 && kLimbQI8 >= 32, "INT8 prediction layout");
+
+// kind::i8, A = B = signed 8-bit (format 1), D = S32 (2), A MN-major (bit 15), B K-major, M = 128, N = 256
+constexpr uint32_t kPiIdesc = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(PI_BN >> 3) << 17) |
+                              ((uint32_t)(128 >> 4) << 24);
+
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(kPiIdesc), "r"(accumulate) : "memory");
+}
+}  // namespace
+
+// digit rows  dig[f][g][l*50 + qq][k]  (int8), scales s[f][q].  grid: (Qp, K folds), block 256.
+__global__ void __launch_bounds__(256)
+l0_gamma_limbs_i8_kernel(const double* __restrict__ gam, const double* __restrict__ gmu, int Qp, int Q, int bs,
+                         int rows_p, double* __restrict__ scale, uint8_t* __restrict__ dig, int ngroups) {
+  __shared__ double red[256];
+  const int q = blockIdx.x, f = blockIdx.y;
+  if (q >= Q) return;
+  const double* gcol = gam + (int64_t)f * rows_p * Qp + q;
+  const double* mcol = gmu + (int64_t)f * rows_p * Qp + q;
+  double mx = 0.0;
+  for (int i = threadIdx.x; i < bs; i += 256)
+    mx = fmax(mx, fmax(fabs(gcol[(int64_t)i * Qp]), fabs(mcol[(int64_t)i * Qp])));
+  red[threadIdx.x] = mx;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]);
+    __syncthreads();
+  }
+  const double s = red[0] > 0.0 ? red[0] : 1.0;
+  if (threadIdx.x == 0) scale[(int64_t)f * Qp + q] = s;
+  const int g = q / kLimbQI8, qq = q % kLimbQI8;
+  const int K2 = 2 * rows_p;
+  uint8_t* base = dig + ((int64_t)f * ngroups + g) * (int64_t)PI_BN * K2;
+  for (int k = threadIdx.x; k < K2; k += 256) {
+    const int plane = k >= rows_p, i = plane ? k - rows_p : k;
+    double v = 0.0;
+    if (i < bs) v = (plane ? mcol[(int64_t)i * Qp] : gcol[(int64_t)i * Qp]) / s * 127.0;
+#pragma unroll
+    for (int l = 0; l < kLimbsI8; ++l) {
+      const double d = rint(v);                    // |v| <= 127: the remainder (<= 1/2) x 254 stays in range
+      base[(int64_t)(l * kLimbQI8 + qq) * K2 + k] = (uint8_t)(int8_t)(int)d;
+      v = (v - d) * 254.0;
+    }
+  }
+}
+
+// grid: (Npad/128 sample tiles, q groups); 320 threads, two CTAs per SM.
+__global__ void __launch_bounds__(PT_THREADS, 2)
+l0_predict_i8_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmD, PredictTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (base - raw);
+  const uint32_t sA = base;
+  const uint32_t sB = base + PI_STAGES * PI_A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gen_base + PI_STAGES * PI_STAGE_BYTES);
+  const uint32_t full_bar = smem_u32(bars);
+  const uint32_t empty_bar = smem_u32(bars + PI_STAGES);
+  const uint32_t tmem_full_bar = smem_u32(bars + 2 * PI_STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * PI_STAGES + 1);
+  double* s_scale = reinterpret_cast<double*>(bars + 2 * PI_STAGES + 2);   // [kLimbQI8]
+  double* s_cvec = s_scale + kLimbQI8;                                      // [kLimbQI8][C]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, g = blockIdx.y;
+  const int f = a.tile_fold[tile];
+  const int nkb = (2 * a.rows_p) / PT_BK;
+  const int q0 = g * kLimbQI8;
+  const int nq = min(kLimbQI8, a.Q - q0);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < PI_STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmZ) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmD) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)PI_BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int e = threadIdx.x; e < kLimbQI8; e += PT_THREADS)
+    s_scale[e] = (e < nq) ? a.scale[(int64_t)f * a.Qp + q0 + e] / 127.0 : 0.0;
+  for (int e = threadIdx.x; e < kLimbQI8 * a.C; e += PT_THREADS) {
+    const int qq = e / a.C, c = e % a.C;
+    s_cvec[e] = (qq < nq) ? a.cvec[((int64_t)f * a.Qp + q0 + qq) * a.C + c] : 0.0;
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: A = 128 plane rows x 128 samples; B = 256 digit rows x 128 k bytes =====
+      const int drow0 = (f * a.ngroups + g) * PI_BN;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % PI_STAGES;
+        const uint32_t ph = (kb / PI_STAGES) & 1;
+        mbar_wait(empty_bar + 8 * s, ph ^ 1);
+        mbar_expect_tx(full_bar + 8 * s, PI_STAGE_BYTES);
+        tma_load_2d(sA + s * PI_A_BYTES, &tmZ, full_bar + 8 * s, tile * PT_BM, kb * PT_BK);
+        tma_load_2d(sB + s * PI_B_BYTES, &tmD, full_bar + 8 * s, kb * PT_BK, drow0);
+        tma_load_2d(sB + s * PI_B_BYTES + 16384, &tmD, full_bar + 8 * s, kb * PT_BK, drow0 + 128);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % PI_STAGES;
+        const uint32_t ph = (kb / PI_STAGES) & 1;
+        mbar_wait(full_bar + 8 * s, ph);
+        fence_after();
+        const uint64_t da = make_desc(sA + s * PI_A_BYTES);
+        const uint64_t db = make_desc(sB + s * PI_B_BYTES);
+#pragma unroll
+        for (int k = 0; k < PT_BK / 32; ++k)
+          mma_i8(tmem_base, da + (uint64_t)(256 * k), db + (uint64_t)(2 * k), (kb | k) ? 1u : 0u);
+        tcgen05_commit(empty_bar + 8 * s);
+      }
+      tcgen05_commit(tmem_full_bar);
+    }
+  } else {
+    // ===== epilogue: thread = (sample, half of the outputs).  Limb sums are exact int32 multiples of 8; FP64 Horner from the
+    // lowest limb up.  The second half reads the 32 columns that END at its last output, so no load leaves the allocation.
+    const int qw = warp & 3;                      // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;
+    const int t = tile * PT_BM + qw * 32 + lane;
+    double acc[PI_QH];
+#pragma unroll
+    for (int j = 0; j < PI_QH; ++j) acc[j] = 0.0;
+    mbar_wait(tmem_full_bar, 0);
+    fence_after();
+    const uint32_t tbase = tmem_base + ((uint32_t)(qw * 32) << 16);
+    const double inv254 = 1.0 / 254.0;
+    if (half == 0) {
+#pragma unroll
+      for (int l = kLimbsI8 - 1; l >= 0; --l) {
+        uint32_t v[32];
+        tmem_ld_32x32(tbase + (uint32_t)(l * kLimbQI8), v);
+#pragma unroll
+        for (int j = 0; j < PI_QH; ++j) acc[j] = fma(acc[j], inv254, (double)((int)v[j] >> 3));
+      }
+    } else {
+#pragma unroll
+      for (int l = kLimbsI8 - 1; l >= 0; --l) {
+        uint32_t v[32];
+        tmem_ld_32x32(tbase + (uint32_t)(l * kLimbQI8 + kLimbQI8 - 32), v);
+#pragma unroll
+        for (int j = 0; j < PI_QH; ++j) acc[j] = fma(acc[j], inv254, (double)((int)v[32 - PI_QH + j] >> 3));
+      }
+    }
+    double xr[kMaxCov];
+    for (int c = 0; c < a.C; ++c) xr[c] = a.xy[(int64_t)t * a.cpp + c];
+#pragma unroll
+    for (int j = 0; j < PI_QH; ++j) {
+      const int qq = half * PI_QH + j;
+      if (qq < nq) {
+        const int q = q0 + qq;
+        const int r = q / a.P, p = q % a.P;
+        double val = acc[j] * s_scale[qq];
+        for (int c = 0; c < a.C; ++c) val -= xr[c] * s_cvec[qq * a.C + c];
+        val *= (double)a.mask[(int64_t)p * a.npad + t];
+        a.W[p][(int64_t)(a.col0 + r) * a.npad + t] = val;
+      }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)PI_BN) : "memory");
   }
 }
 
@@ -364,6 +563,23 @@ void launch_l0_predict_tcgen05(const CUtensorMap& tmZ, const CUtensorMap& tmD, c
   ensure_dyn_smem(reinterpret_cast<const void*>(l0_predict_tcgen05_kernel), smem);
   dim3 grid(ntiles, a.ngroups);
   l0_predict_tcgen05_kernel<<<grid, PT_THREADS, smem, s>>>(tmZ, tmD, a);
+}
+
+size_t predict_i8_dig_bytes(int K, int ngroups, int rows_p) { return (size_t)K * ngroups * PI_BN * 2 * rows_p; }
+
+void launch_l0_gamma_limbs_i8(const double* gam, const double* gmu, int Qp, int Q, int bs, int rows_p, int K,
+                              double* scale, uint8_t* dig, int ngroups, cudaStream_t s) {
+  dim3 grid(Qp, K);
+  l0_gamma_limbs_i8_kernel<<<grid, 256, 0, s>>>(gam, gmu, Qp, Q, bs, rows_p, scale, dig, ngroups);
+}
+
+void launch_l0_predict_i8(const CUtensorMap& tmZ, const CUtensorMap& tmD, const PredictTcArgs& a, int ntiles,
+                          cudaStream_t s) {
+  RG_CHECK(2 * a.rows_p <= 4096, "INT8 prediction: 2 * rows_p <= 4096 (int32 Horner bound)");
+  const size_t smem = (size_t)PI_STAGES * PI_STAGE_BYTES + 1024 + 128 + ((size_t)kLimbQI8 * (1 + a.C)) * sizeof(double);
+  ensure_dyn_smem(reinterpret_cast<const void*>(l0_predict_i8_kernel), smem);
+  dim3 grid(ntiles, a.ngroups);
+  l0_predict_i8_kernel<<<grid, PT_THREADS, smem, s>>>(tmZ, tmD, a);
 }
 
 }  // namespace rg

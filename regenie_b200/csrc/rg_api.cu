@@ -360,13 +360,17 @@ static void enqueue_predict(rg_ctx* h, rg_ctx::Lane& L, const BlockDims& d, cons
   pa.gp = L.gp.p; pa.tile_fold = h->tile_fold.p; pa.gam = L.gam.p; pa.gmu = L.gmu.p;
   pa.cvec = L.cvec.p; pa.xy = h->xy.p; pa.mask = h->mask.p; pa.W = h->W_tab.p; pa.part = L.part.p;
   int nparts = d.ntiles_s;
-  static const bool use_f64_predict = [] { const char* e = getenv("RG_B200_PREDICT"); return e && std::string(e) == "f64"; }();
-  if (use_f64_predict) {
+  // RG_B200_PREDICT = i8 (default: kind::i8, 5 radix-254 limbs) | f8 (kind::f8f6f4, 9 radix-30 limbs) | f64 (CUDA cores)
+  static const std::string predict_kind = [] { const char* e = getenv("RG_B200_PREDICT"); return std::string(e ? e : "i8"); }();
+  RG_CHECK(predict_kind == "i8" || predict_kind == "f8" || predict_kind == "f64", "RG_B200_PREDICT must be i8, f8 or f64");
+  const bool use_i8 = predict_kind == "i8" && 2 * d.rows_p <= 4096;
+  if (predict_kind == "f64") {
     launch_l0_predict(pa, d.ntiles_s, s);
   } else {
-    // exact tensor-core path: radix-30 digit rows of gamma against the e4m3 genotype planes
-    const int ngroups = (int)ceil_div(d.Q, kLimbQ);
-    const size_t need = predict_tc_dig_bytes(K, ngroups, h->rows_p_max);
+    // exact tensor-core path: digit rows of gamma against the genotype operand planes
+    const int ngroups = (int)ceil_div(d.Q, use_i8 ? kLimbQI8 : kLimbQ);
+    const int drows_per_group = use_i8 ? 256 : 512;
+    const size_t need = use_i8 ? predict_i8_dig_bytes(K, ngroups, h->rows_p_max) : predict_tc_dig_bytes(K, ngroups, h->rows_p_max);
     if (L.dig.n < need) {
       L.dig.alloc(need);
       RG_CUDA(cudaMemsetAsync(L.dig.p, 0, need, s));
@@ -375,17 +379,21 @@ static void enqueue_predict(rg_ctx* h, rg_ctx::Lane& L, const BlockDims& d, cons
     L.dscale.alloc((size_t)K * d.Qp);
     if (!L.dmaps.count(d.rows_p)) {
       CUtensorMap tm;
-      make_byte_tensor_map(&tm, L.dig.p, 2 * d.rows_p, (int64_t)K * ngroups * 512);
+      make_byte_tensor_map(&tm, L.dig.p, 2 * d.rows_p, (int64_t)K * ngroups * drows_per_group);
       L.dmaps[d.rows_p] = tm;
     }
-    launch_l0_gamma_limbs(L.gam.p, L.gmu.p, d.Qp, d.Q, d.bs, d.rows_p, K, L.dscale.p, L.dig.p, ngroups, s);
+    if (use_i8) launch_l0_gamma_limbs_i8(L.gam.p, L.gmu.p, d.Qp, d.Q, d.bs, d.rows_p, K, L.dscale.p, L.dig.p, ngroups, s);
+    else launch_l0_gamma_limbs(L.gam.p, L.gmu.p, d.Qp, d.Q, d.bs, d.rows_p, K, L.dscale.p, L.dig.p, ngroups, s);
     PredictTcArgs ta;
     ta.rows_p = d.rows_p; ta.C = C; ta.P = P; ta.Q = d.Q; ta.Qp = d.Qp; ta.cpp = h->cpp; ta.col0 = d.col0; ta.ngroups = ngroups;
     ta.npad = Npad; ta.tile_fold = h->tile_fold.p; ta.scale = L.dscale.p; ta.cvec = L.cvec.p;
     ta.xy = h->xy.p; ta.mask = h->mask.p; ta.W = h->W_tab.p; ta.part = L.part.p;
     ta.dbg = nullptr;
-    if (getenv("RG_DBG_CLK")) { h->dbg_clk.alloc((size_t)d.ntiles_s * ngroups * 4); ta.dbg = h->dbg_clk.p; }
-    if (!dbg_skip("predict")) launch_l0_predict_tcgen05(L.tmaps[d.rows_p], L.dmaps[d.rows_p], ta, d.ntiles_s, s);
+    if (!use_i8 && getenv("RG_DBG_CLK")) { h->dbg_clk.alloc((size_t)d.ntiles_s * ngroups * 4); ta.dbg = h->dbg_clk.p; }
+    if (!dbg_skip("predict")) {
+      if (use_i8) launch_l0_predict_i8(L.tmaps[d.rows_p], L.dmaps[d.rows_p], ta, d.ntiles_s, s);
+      else launch_l0_predict_tcgen05(L.tmaps[d.rows_p], L.dmaps[d.rows_p], ta, d.ntiles_s, s);
+    }
     nparts = launch_l0_colsum(h->W_tab.p, Npad, d.col0, P, d.Q, d.Qp, L.part.p, s);
     h->launches += 2;
   }
@@ -558,7 +566,7 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
     }
     ScopedTimer t(h, "gram_tcgen05", s);
     if (!dbg_skip("gram")) launch_gram_tcgen05(L.tmaps[rows_p], L.tmaps[rows_p], h->tile_lists[rows_p]->p, h->tile_counts[rows_p], h->fold_k.p, K,
-                        L.zz.p, 2 * rows_p, (int64_t)4 * rows_p * rows_p, s);
+                        L.zz.p, 2 * rows_p, (int64_t)4 * rows_p * rows_p, kZScaleGram, s);
     h->launches += 1;
   }
   if (h->stats_tc) {
@@ -577,7 +585,7 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
     L.tstat.alloc((size_t)K * 2 * h->rows_p_max * h->stat_drows);
     const int64_t tfs = (int64_t)2 * rows_p * h->stat_drows;
     if (!dbg_skip("stats")) launch_gram_tcgen05(L.tmaps[rows_p], h->tmD, h->stat_tile_lists[rows_p]->p, h->stat_tile_counts[rows_p], h->fold_k.p,
-                        K, L.tstat.p, h->stat_drows, tfs, s);
+                        K, L.tstat.p, h->stat_drows, tfs, kZScaleStat, s);
     launch_l0_stats_finish(L.tstat.p, h->stat_drows, tfs, L.zz.p, 2 * rows_p, (int64_t)4 * rows_p * rows_p, rows_p,
                            h->cpp, C + P, K, h->xy_scale.p, L.cnt_fold.p, L.sum_fold.p, s);
     snp_finalize();

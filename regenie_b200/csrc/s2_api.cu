@@ -126,7 +126,7 @@ static void s2_tensor_sums(rg_ctx* h, int rows_p, cudaStream_t s) {
     h->s2_tile_lists[key] = std::move(buf);
   }
   launch_gram_tcgen05(h->s2_tmZ[rows_p], h->s2_tmD, h->s2_tile_lists[key]->p, h->s2_ntiles[key], h->s2_fold_k.p,
-                      h->s2_nchunk, h->s2_T.p, drows, (int64_t)3 * rows_p * drows, s);
+                      h->s2_nchunk, h->s2_T.p, drows, (int64_t)3 * rows_p * drows, 1.f, s);
 }
 
 static void s2_set_chr(rg_ctx* h, const double* res, const double* scf_sv) {
