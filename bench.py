@@ -241,6 +241,8 @@ def run_gpu(args):
     if args.n_samples:                      # exploration only (e.g. the N = 500k shape of configs[2] on a slice of blocks)
         N = args.n_samples
         M = (args.blocks or 20) * bs
+    if args.n_pheno:                        # exploration only (the 50-trait shape of configs[4])
+        P = args.n_pheno
     blocks = blocks_of(M, bs)
     if args.blocks:
         blocks = blocks[: args.blocks]
@@ -384,7 +386,7 @@ def run_gpu(args):
 
     # ---- end to end from files through the C++ driver (rank 0, single GPU run only)
     file_e2e = None
-    if world == 1 and not args.no_step2 and not (args.small or args.n_samples or args.blocks):
+    if world == 1 and not args.no_step2 and not (args.small or args.n_samples or args.blocks or args.n_pheno):
         try:
             file_e2e = file_e2e_leg(host_panel, N, M, bs, P, Yr, cov, na)
         except Exception as e:
@@ -452,7 +454,7 @@ def run_gpu(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "e4m3 Gram (exact) + tf32x3 factorisation + f64 refinement / statistics",
-        "data": "synthetic", "config": workload_config() if not (args.small or args.n_samples) else {"workload": "NOT the benchmark configuration (smoke / exploration run)", "n_samples": N, "n_snps": M},
+        "data": "synthetic", "config": workload_config() if not (args.small or args.n_samples or args.n_pheno) else {"workload": "NOT the benchmark configuration (smoke / exploration run)", "n_samples": N, "n_snps": M, "n_pheno": P},
         "clocks": clk,
         "e2e": {"value": e2e_val, "unit": "SNPs/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(M) * int(stride), "d2h_bytes_per_step": 8},
@@ -743,6 +745,7 @@ def main():
     ap.add_argument("--cpu-blocks", type=int, default=1)
     ap.add_argument("--blocks", type=int, default=0, help="profiling only: restrict the pass to the first n blocks")
     ap.add_argument("--n-samples", type=int, default=0, help="exploration only: other sample count, --blocks blocks (default 20)")
+    ap.add_argument("--n-pheno", type=int, default=0, help="exploration only: other trait count (configs[4] has 50)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -24,6 +24,7 @@
 
 #include <algorithm>
 
+#include "gemm_dmma.cuh"
 #include "kernels.cuh"
 
 namespace rg {
@@ -325,23 +326,19 @@ mx_residual_kernel(const double* __restrict__ Af, const double* __restrict__ lam
 }
 
 
-// Same residuals, all R systems of a fold in ONE CTA: a register-tiled FP64 GEMM  Y = A_f[rows, :] X_f  with X_f the R * P
-// current solutions of the fold as columns, so the A_f rows are read once instead of once per ridge value (the pass above is
-// bound by those L2 reads: 5 x 42 MB per pass) and nothing is reduced across threads (fixed summation order: k ascending).
-//   CTA = (64 rows, fold), 256 threads = 16 row lanes x 16 vector lanes, thread tile 4 rows x 4 vectors,
-//   A and X staged through shared memory in chunks of 32 contraction indices (k-major, double-buffered, register prefetch).
-// grid: (n / 64, K folds); at most 64 vectors (R * np <= 64), else the per-system kernel above is used.
+// Same residuals, all R systems of a fold in ONE CTA: a 64 x 64 FP64 "NT" tile  Y = A_f[rows, :] X_f^T  on the FP64 tensor
+// pipe (DMMA m8n8k4, gemm_dmma.cuh) with X_f the R * P current solutions of the fold as rows, so the A_f rows are read once
+// instead of once per ridge value (the per-system pass above is bound by those L2 reads: 5 x 42 MB per pass), 8x fewer
+// instructions than FMA for the same flops, and a fixed summation order (k ascending inside the tensor op sequence).
+// grid: (n / 64, K folds), block 256; at most 64 vectors (R * np <= 64), else the per-system kernel above is used.
 constexpr int RF_ROWS = 64;
-constexpr int RF_KC = 32;
 constexpr int RF_NV = 64;
-constexpr int RF_LD = 65;                                   // doubles per k-row of the staged tiles (odd: 2-way store conflicts at most)
-constexpr size_t kResFusedSmem = (size_t)2 * 2 * RF_KC * RF_LD * sizeof(double);
 
 __global__ void __launch_bounds__(256)
 mx_residual_fused_kernel(const double* __restrict__ Af, const double* __restrict__ lambda, int R, const double* __restrict__ bvec,
                          const double* __restrict__ xvec, double* __restrict__ rvec, int n, int P, int Pp, int nmat, int step,
                          const unsigned int* __restrict__ conv, float tol) {
-  extern __shared__ double rf_sm[];
+  __shared__ double As[64 * DM_LD], Bs[64 * DM_LD];
   const int f = blockIdx.y;
   if (step > 1) {
     bool all_done = true;
@@ -349,87 +346,30 @@ mx_residual_fused_kernel(const double* __restrict__ Af, const double* __restrict
     if (all_done) return;
   }
   const int NV = R * P;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int row0 = blockIdx.x * RF_ROWS;
-  double* As = rf_sm;                                        // [2][RF_KC][RF_LD]
-  double* Xs = rf_sm + 2 * RF_KC * RF_LD;                    // [2][RF_KC][RF_LD]
-  for (int e = threadIdx.x; e < 2 * RF_KC * RF_LD; e += 256) Xs[e] = 0.0;     // vector slots >= NV stay zero
-  __syncthreads();
-  // staging map: element e = threadIdx.x + 256 * q  ->  (row or vector e / 16, k pair e % 16)
-  const double* arow = Af + ((int64_t)f * n + row0) * n;
-  double2 pa[4], px[4];
-  auto gload = [&](int k0) {
+  const int lrow = threadIdx.x >> 2, lp = (threadIdx.x & 3) * 4;
+  const bool vb = lrow < NV;
+  const double* ap = Af + ((int64_t)f * n + row0 + lrow) * n + lp;
+  const double* bp = xvec + ((int64_t)(f * R + (vb ? lrow / P : 0)) * Pp + (vb ? lrow % P : 0)) * n + lp;
+  DmmaAcc acc;
+  gemm_tile_nt_dmma_ptr(ap, true, bp, vb, n, acc, As, Bs);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int e = threadIdx.x + 256 * q;
-      const int rr = e >> 4, kp = e & 15;
-      pa[q] = *reinterpret_cast<const double2*>(arow + (int64_t)rr * n + k0 + 2 * kp);
-      px[q] = make_double2(0.0, 0.0);
-      if (rr < NV) {
-        const int m = f * R + rr / P, p = rr % P;
-        px[q] = *reinterpret_cast<const double2*>(xvec + ((int64_t)m * Pp + p) * n + k0 + 2 * kp);
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int vec = dm_col(j) + e;
+      if (vec < NV) {
+        const int r = vec / P, p = vec % P, m = f * R + r;
+        const double lam = lambda[r];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int row = row0 + dm_row(i);
+          const int64_t o = ((int64_t)m * Pp + p) * n + row;
+          rvec[o] = bvec[((int64_t)f * Pp + p) * n + row] - lam * xvec[o] - acc.c[i][j][e];
+        }
       }
     }
-  };
-  auto sstore = [&](int buf) {
-    double* a = As + buf * RF_KC * RF_LD;
-    double* x = Xs + buf * RF_KC * RF_LD;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int e = threadIdx.x + 256 * q;
-      const int rr = e >> 4, kp = e & 15;
-      a[(2 * kp) * RF_LD + rr] = pa[q].x;
-      a[(2 * kp + 1) * RF_LD + rr] = pa[q].y;
-      if (rr < NV) {
-        x[(2 * kp) * RF_LD + rr] = px[q].x;
-        x[(2 * kp + 1) * RF_LD + rr] = px[q].y;
-      }
-    }
-  };
-  double acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int v = 0; v < 4; ++v) acc[i][v] = 0.0;
-  const int nch = n / RF_KC;
-  gload(0);
-  sstore(0);
-  __syncthreads();
-  for (int c = 0; c < nch; ++c) {
-    if (c + 1 < nch) gload((c + 1) * RF_KC);
-    const double* a = As + (c & 1) * RF_KC * RF_LD + tx;
-    const double* x = Xs + (c & 1) * RF_KC * RF_LD + ty;
-#pragma unroll 8
-    for (int k = 0; k < RF_KC; ++k) {
-      double av[4], xv[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) av[i] = a[k * RF_LD + 16 * i];
-#pragma unroll
-      for (int v = 0; v < 4; ++v) xv[v] = x[k * RF_LD + 16 * v];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int v = 0; v < 4; ++v) acc[i][v] = fma(av[i], xv[v], acc[i][v]);
-    }
-    if (c + 1 < nch) sstore((c + 1) & 1);
-    __syncthreads();
-  }
-#pragma unroll
-  for (int v = 0; v < 4; ++v) {
-    const int vec = ty + 16 * v;
-    if (vec < NV) {
-      const int r = vec / P, p = vec % P, m = f * R + r;
-      const double lam = lambda[r];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int row = row0 + tx + 16 * i;
-        const int64_t o = ((int64_t)m * Pp + p) * n + row;
-        rvec[o] = bvec[((int64_t)f * Pp + p) * n + row] - lam * xvec[o] - acc[i][v];
-      }
-    }
-  }
 }
-
 
 // dx = (L L^T)^-1 r by block forward / backward substitution, one CTA per system (no inter-CTA dependency):
 //   forward  k = 0 .. nt-1 :  y_k = M_k   (r_k - sum_{j<k} L_kj   y_j)
@@ -444,11 +384,12 @@ mx_residual_fused_kernel(const double* __restrict__ Af, const double* __restrict
 // orientations, which makes the two sweeps the same code on different triangles.  FP32 throughout - a correction needs
 // few digits - and the result is added to the FP64 solution.  The first version (plain loads, one CTA per system) reached
 // 13 GB/s per SM and 365 us per solve (profiles/launches_r2e_mixed.txt); per-SM TMA streaming is what fixes that.
-// grid: (nmat), block 288 = 8 consumer warps + 1 producer warp.
+// grid: (nmat), block TS_THREADS = TS_CW consumer warps + 1 producer warp.
 constexpr int TS_STAGES = 6;
 constexpr int TS_SUB = 32;                          // contraction indices per sub-tile
 constexpr int TS_STAGE_BYTES = TS_SUB * PT * 4;     // 16 KiB
 constexpr int TS_VP = 12;                           // floats per row of the vector buffers (P <= 12, 16-byte aligned rows)
+// consumer warps (template parameter TS_CW, 8 or 16): 4 row groups x TS_CW / 4 slices of each sub-tile's contraction range
 
 __device__ __forceinline__ uint32_t ts_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ts_mbar_wait(uint32_t bar, uint32_t parity) {
@@ -464,12 +405,15 @@ __device__ __forceinline__ void ts_mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
-template <int PMAX>
-__global__ void __launch_bounds__(288)
+template <int PMAX, int TS_CW>
+__global__ void __launch_bounds__(32 * (TS_CW + 1))
 mx_trisolve_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmM,
                    const __grid_constant__ CUtensorMap tmMT, const double* __restrict__ rvec, int64_t r_mat_stride,
                    int r_mat_div, double* __restrict__ xvec, int n, int P, int Pp, int nmat, int step,
                    unsigned int* __restrict__ conv, float tol) {
+  constexpr int TS_PARTS = TS_CW / 4;
+  constexpr int TS_CPP = TS_SUB / TS_PARTS;           // contraction indices per slice
+  constexpr int TS_THREADS = 32 * (TS_CW + 1);        // + the producer warp
   extern __shared__ uint8_t ts_raw[];
   const int m = blockIdx.x;
   if (step > 1 && mx_finished(conv, nmat, m, step - 1, tol)) return;
@@ -479,28 +423,28 @@ mx_trisolve_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
   float* tiles = reinterpret_cast<float*>(gen);                                        // [TS_STAGES][32][128]
   float* v = reinterpret_cast<float*>(gen + TS_STAGES * TS_STAGE_BYTES);               // [n][TS_VP]  r -> y -> x
   float* sbuf = v + (size_t)n * TS_VP;                                                 // [128][TS_VP]
-  float* comb = sbuf + PT * TS_VP;                                                     // [128][TS_VP] upper half's partial sums
-  uint64_t* bars = reinterpret_cast<uint64_t*>(comb + PT * TS_VP);
+  float* comb = sbuf + PT * TS_VP;                                                     // [TS_PARTS - 1][128][TS_VP] partial sums of slices 1..
+  uint64_t* bars = reinterpret_cast<uint64_t*>(comb + (TS_PARTS - 1) * PT * TS_VP);
   const uint32_t full_bar = ts_smem_u32(bars), empty_bar = ts_smem_u32(bars + TS_STAGES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = n / PT;
   if (threadIdx.x == 0) {
     for (int s = 0; s < TS_STAGES; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_bar + 8 * s), "r"(1) : "memory");
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty_bar + 8 * s), "r"(8) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty_bar + 8 * s), "r"(TS_CW) : "memory");
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   // right-hand sides -> v[i][p] (FP32)
   const double* r = rvec + (int64_t)(r_mat_div > 0 ? m / r_mat_div : m) * r_mat_stride;
-  for (int e = threadIdx.x; e < n * TS_VP; e += 288) {
+  for (int e = threadIdx.x; e < n * TS_VP; e += TS_THREADS) {
     const int i = e / TS_VP, p = e % TS_VP;
     v[e] = p < P ? (float)r[(int64_t)p * n + i] : 0.f;
   }
   __syncthreads();
 
-  if (warp == 8) {
+  if (warp == TS_CW) {
     // ===== producer: every sub-tile of both sweeps, in consumption order =====
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmL) : "memory");
@@ -531,7 +475,7 @@ mx_trisolve_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
   }
 
   // ===== consumers: lane <-> output row, warp halves split the contraction range of every sub-tile =====
-  const int half = warp >> 2;                                  // 0: c in [0,16), 1: c in [16,32) of each sub-tile
+  const int half = warp >> 2;                                  // slice of each sub-tile's contraction range: c in [half * TS_CPP, + TS_CPP)
   const int row = (warp & 3) * 32 + lane;                      // output row inside the current block
   int it = 0;
   float acc[PMAX];
@@ -539,10 +483,10 @@ mx_trisolve_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
     const int s = it % TS_STAGES;
     const uint32_t ph = (it / TS_STAGES) & 1;
     ts_mbar_wait(full_bar + 8 * s, ph);
-    const float* t = tiles + (size_t)s * (TS_STAGE_BYTES / 4) + (size_t)(half * 16) * PT + row;
-    const float* y = vec + (size_t)(half * 16) * TS_VP;
+    const float* t = tiles + (size_t)s * (TS_STAGE_BYTES / 4) + (size_t)(half * TS_CPP) * PT + row;
+    const float* y = vec + (size_t)(half * TS_CPP) * TS_VP;
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
+    for (int c = 0; c < TS_CPP; ++c) {
       const float tv = t[(size_t)c * PT];
       const float4 y0 = *reinterpret_cast<const float4*>(y + c * TS_VP);
       const float4 y1 = *reinterpret_cast<const float4*>(y + c * TS_VP + 4);
@@ -555,7 +499,7 @@ mx_trisolve_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_bar + 8 * s) : "memory");
     ++it;
   };
-  auto consumer_sync = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+  auto consumer_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(32 * TS_CW) : "memory"); };
 
   for (int sweep = 0; sweep < 2; ++sweep)
     for (int kk = 0; kk < nt; ++kk) {
@@ -565,34 +509,44 @@ mx_trisolve_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
       for (int p = 0; p < PMAX; ++p) acc[p] = 0.f;
       for (int j = j0; j < j1; ++j)
         for (int sub = 0; sub < PT / TS_SUB; ++sub) consume(v + (size_t)(j * PT + sub * TS_SUB) * TS_VP);
-      if (half == 1) {
+      if (half > 0) {
 #pragma unroll
-        for (int p = 0; p < PMAX; ++p) comb[row * TS_VP + p] = acc[p];
+        for (int p = 0; p < PMAX; ++p) comb[((half - 1) * PT + row) * TS_VP + p] = acc[p];
       }
       consumer_sync();
       if (half == 0) {
 #pragma unroll
-        for (int p = 0; p < PMAX; ++p) sbuf[row * TS_VP + p] = v[(size_t)(k * PT + row) * TS_VP + p] - acc[p] - comb[row * TS_VP + p];
+        for (int p = 0; p < PMAX; ++p) {
+          float sum = acc[p];
+#pragma unroll
+          for (int h = 0; h < TS_PARTS - 1; ++h) sum += comb[(h * PT + row) * TS_VP + p];
+          sbuf[row * TS_VP + p] = v[(size_t)(k * PT + row) * TS_VP + p] - sum;
+        }
       }
       consumer_sync();
 #pragma unroll
       for (int p = 0; p < PMAX; ++p) acc[p] = 0.f;
       for (int sub = 0; sub < PT / TS_SUB; ++sub) consume(sbuf + (size_t)(sub * TS_SUB) * TS_VP);      // v_k = D_k s
-      if (half == 1) {
+      if (half > 0) {
 #pragma unroll
-        for (int p = 0; p < PMAX; ++p) comb[row * TS_VP + p] = acc[p];
+        for (int p = 0; p < PMAX; ++p) comb[((half - 1) * PT + row) * TS_VP + p] = acc[p];
       }
       consumer_sync();
       if (half == 0) {
 #pragma unroll
-        for (int p = 0; p < PMAX; ++p) v[(size_t)(k * PT + row) * TS_VP + p] = acc[p] + comb[row * TS_VP + p];
+        for (int p = 0; p < PMAX; ++p) {
+          float sum = acc[p];
+#pragma unroll
+          for (int h = 0; h < TS_PARTS - 1; ++h) sum += comb[(h * PT + row) * TS_VP + p];
+          v[(size_t)(k * PT + row) * TS_VP + p] = sum;
+        }
       }
       consumer_sync();
     }
 
   // ---- x += dx, convergence bookkeeping (consumer threads only)
   float dmax = 0.f, xmax = 0.f;
-  for (int e = threadIdx.x; e < P * n; e += 256) {
+  for (int e = threadIdx.x; e < P * n; e += 32 * TS_CW) {
     const int p = e / n, i = e % n;
     double* xp = xvec + ((int64_t)m * Pp + p) * n + i;
     const float dx = v[(size_t)i * TS_VP + p];
@@ -722,10 +676,11 @@ void MixedSolver::solve(const double* Af, const double* lambda, const double* bv
   ensure_dyn_smem(reinterpret_cast<const void*>(potrf128_kernel), potrf_smem);
   ensure_dyn_smem(reinterpret_cast<const void*>(mx_residual_kernel<12>), 98304);
   ensure_dyn_smem(reinterpret_cast<const void*>(mx_residual_kernel<10>), 98304);
-  ensure_dyn_smem(reinterpret_cast<const void*>(mx_residual_fused_kernel), kResFusedSmem);
   static const bool res_fused = [] { const char* e = getenv("RG_B200_MX_RES"); return !(e && strcmp(e, "plain") == 0); }();
-  ensure_dyn_smem(reinterpret_cast<const void*>(mx_trisolve_kernel<12>), 220 * 1024);
-  ensure_dyn_smem(reinterpret_cast<const void*>(mx_trisolve_kernel<10>), 220 * 1024);
+  ensure_dyn_smem(reinterpret_cast<const void*>(mx_trisolve_kernel<12, 8>), 220 * 1024);
+  ensure_dyn_smem(reinterpret_cast<const void*>(mx_trisolve_kernel<10, 8>), 220 * 1024);
+  ensure_dyn_smem(reinterpret_cast<const void*>(mx_trisolve_kernel<12, 16>), 220 * 1024);
+  ensure_dyn_smem(reinterpret_cast<const void*>(mx_trisolve_kernel<10, 16>), 220 * 1024);
   RG_CHECK(n <= 2048, "mixed solver: n <= 2048");
   // profiling aid (results are garbage): RG_DBG_SKIP=mxgemm|mxpotrf|mxtri|mxres drops one kernel family of the solver so
   // its marginal cost under multi-lane overlap can be read off (profiles/ablation_r2_*.txt)
@@ -761,20 +716,23 @@ void MixedSolver::solve(const double* Af, const double* lambda, const double* bv
     for (int p0 = 0; p0 < P; p0 += pc) {
       const int np = std::min(pc, P - p0);
       const size_t sm_r = (size_t)np * n * sizeof(double);
-      const size_t sm_t = (size_t)TS_STAGES * TS_STAGE_BYTES + ((size_t)n + 2 * PT) * TS_VP * sizeof(float) + 2 * TS_STAGES * 8 + 256;
+      static const int tri_warps = [] { const char* e = getenv("RG_B200_MX_TRI_WARPS"); return (e && atoi(e) == 8) ? 8 : 16; }();
+      const size_t sm_t = (size_t)TS_STAGES * TS_STAGE_BYTES + ((size_t)n + (1 + tri_warps / 4) * PT) * TS_VP * sizeof(float) + 2 * TS_STAGES * 8 + 256;
       const int64_t o = (int64_t)p0 * n;
       // right-hand-side count is a template parameter (register blocking): 10 is the benchmark's trait count
       auto tri = [&](const double* rv, int64_t rs, int rdiv, int step) {
         if (sk_tri) return;
-        if (np <= 10) mx_trisolve_kernel<10><<<nmat, 288, sm_t, s>>>(d.tmLpl, d.tmMpl, d.tmMTpl, rv, rs, rdiv, xvec + o, n, np, d.Pp, nmat, step, d.conv.p, tol);
-        else mx_trisolve_kernel<12><<<nmat, 288, sm_t, s>>>(d.tmLpl, d.tmMpl, d.tmMTpl, rv, rs, rdiv, xvec + o, n, np, d.Pp, nmat, step, d.conv.p, tol);
+#define RG_TRI(PM, CW) mx_trisolve_kernel<PM, CW><<<nmat, 32 * (CW + 1), sm_t, s>>>(d.tmLpl, d.tmMpl, d.tmMTpl, rv, rs, rdiv, xvec + o, n, np, d.Pp, nmat, step, d.conv.p, tol)
+        if (np <= 10) { if (tri_warps == 8) RG_TRI(10, 8); else RG_TRI(10, 16); }
+        else { if (tri_warps == 8) RG_TRI(12, 8); else RG_TRI(12, 16); }
+#undef RG_TRI
       };
       if (st == 0) {
         tri(bvec + o, (int64_t)d.Pp * n, d.R, 0);
       } else {
         if (sk_res) {}
         else if (res_fused && d.R * np <= RF_NV && n % RF_ROWS == 0)
-          mx_residual_fused_kernel<<<dim3(n / RF_ROWS, d.K), 256, kResFusedSmem, s>>>(Af, lambda, d.R, bvec + o, xvec + o, rvec + o, n, np, d.Pp, nmat, st, d.conv.p, tol);
+          mx_residual_fused_kernel<<<dim3(n / RF_ROWS, d.K), 256, 0, s>>>(Af, lambda, d.R, bvec + o, xvec + o, rvec + o, n, np, d.Pp, nmat, st, d.conv.p, tol);
         else if (np <= 10) mx_residual_kernel<10><<<grid, 256, sm_r, s>>>(Af, lambda, d.R, bvec + o, xvec + o, rvec + o, n, np, d.Pp, nmat, st, d.conv.p, tol);
         else mx_residual_kernel<12><<<grid, 256, sm_r, s>>>(Af, lambda, d.R, bvec + o, xvec + o, rvec + o, n, np, d.Pp, nmat, st, d.conv.p, tol);
         tri(rvec + o, (int64_t)d.Pp * n, 0, st);

@@ -20,11 +20,11 @@ __device__ __forceinline__ void dmma_8x8x4(double (&d)[2], double a, double b) {
                : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
 }
 
-// arow/brow: pointers to element [tile row 0][0]; lda/ldb: row strides (doubles); va/vb: per-loader-row validity
-// (invalid rows are read as zero).  klen must be a multiple of 16.  As/Bs: [64][DM_LD] doubles each.
-__device__ __forceinline__ void gemm_tile_nt_dmma(const double* __restrict__ arow, int64_t lda, bool va,
-                                                  const double* __restrict__ brow, int64_t ldb, bool vb, int klen,
-                                                  DmmaAcc& acc, double* As, double* Bs) {
+// ap/bp: THIS thread's loader pointers (row threadIdx.x >> 2 of the tile, element (threadIdx.x & 3) * 4 of the row), so the
+// rows of an operand need not be equally spaced; va/vb: per-loader-row validity (invalid rows are read as zero).
+// klen must be a multiple of 16.  As/Bs: [64][DM_LD] doubles each.
+__device__ __forceinline__ void gemm_tile_nt_dmma_ptr(const double* __restrict__ ap, bool va, const double* __restrict__ bp,
+                                                      bool vb, int klen, DmmaAcc& acc, double* As, double* Bs) {
   const int lrow = threadIdx.x >> 2, lp = (threadIdx.x & 3) * 4;     // loader: 64 rows x 16 p
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wm = warp >> 1, wn = warp & 1;
@@ -34,8 +34,6 @@ __device__ __forceinline__ void gemm_tile_nt_dmma(const double* __restrict__ aro
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc.c[i][j][0] = acc.c[i][j][1] = 0.0;
   if (klen <= 0) return;
-  const double* ap = arow + (int64_t)lrow * lda + lp;
-  const double* bp = brow + (int64_t)lrow * ldb + lp;
   const double2 z2 = make_double2(0.0, 0.0);
   double2 a0 = va ? *reinterpret_cast<const double2*>(ap) : z2, a1 = va ? *reinterpret_cast<const double2*>(ap + 2) : z2;
   double2 b0 = vb ? *reinterpret_cast<const double2*>(bp) : z2, b1 = vb ? *reinterpret_cast<const double2*>(bp + 2) : z2;
@@ -63,6 +61,14 @@ __device__ __forceinline__ void gemm_tile_nt_dmma(const double* __restrict__ aro
         for (int j = 0; j < 4; ++j) dmma_8x8x4(acc.c[i][j], af[i], bf[j]);
     }
   }
+}
+
+// arow/brow: pointers to element [tile row 0][0]; lda/ldb: row strides (doubles).
+__device__ __forceinline__ void gemm_tile_nt_dmma(const double* __restrict__ arow, int64_t lda, bool va,
+                                                  const double* __restrict__ brow, int64_t ldb, bool vb, int klen,
+                                                  DmmaAcc& acc, double* As, double* Bs) {
+  const int lrow = threadIdx.x >> 2, lp = (threadIdx.x & 3) * 4;
+  gemm_tile_nt_dmma_ptr(arow + (int64_t)lrow * lda + lp, va, brow + (int64_t)lrow * ldb + lp, vb, klen, acc, As, Bs);
 }
 
 // element (i, j, e) of the accumulator sits at tile row dm_row(i), tile column dm_col(j) + e
