@@ -44,6 +44,7 @@ static inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }
 // tensor-core K-range and every 2-bit word is fold-aligned.  Padding samples carry
 // genotype code 0, X = Y = 0 and mask = 0, so they contribute to nothing.
 constexpr int kSamplePad = 128;   // = one 128-byte swizzle atom of fp8 operands
+constexpr int kFoldPad = 256;     // Step-1 fold ranges: two sample tiles, so a 256-sample prediction CTA never straddles folds
 constexpr int kRowPad = 128;      // SNP rows padded to the UMMA M tile
 constexpr int kStatChunk = 2048;  // samples per partial-sum chunk of the f64 reductions
 

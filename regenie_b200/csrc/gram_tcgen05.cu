@@ -22,13 +22,10 @@ namespace rg {
 namespace {
 
 constexpr int BM = 128;
-constexpr int BN = 256;
 constexpr int BK = 128;             // bytes == samples per K step (one 128B swizzle atom)
 constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK;    // 16 KiB
-constexpr int B_BYTES = BN * BK;    // 32 KiB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int TMEM_COLS = 256;
+// BN (template parameter): 256 for the Gram and wide statistics tiles (B stage 32 KiB), 128 for a single 128-row digit group
 constexpr int NTHREADS = 192;
 constexpr uint32_t SPIN_LIMIT = 1u << 28;   // bounded waits: a protocol bug traps instead of hanging
 
@@ -78,15 +75,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
   return d;
 }
 
-// kind::f8f6f4, A = B = E4M3 (format 0), D = F32 (1), both K-major, M = 128, N = 256.
-constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::f8f6f4, A = B = E4M3 (format 0), D = F32 (1), both K-major, M = 128, N = bn.
+__host__ __device__ constexpr uint32_t gram_idesc(int bn) { return (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24); }
 
-__device__ __forceinline__ void mma_f8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void mma_f8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate, uint32_t idesc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate)
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
@@ -106,11 +103,15 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
 }  // namespace
 
 // grid: (ntiles, K folds)
+template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gram_fp8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmB,
                         const int2* __restrict__ tiles,
                         const int2* __restrict__ fold_k, float* __restrict__ out, int ldo,
                         int64_t fold_stride, float out_scale) {
+  constexpr int B_BYTES = BN * BK;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int TMEM_COLS = BN;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned stage buffers
   const uint32_t raw = smem_u32(smem_raw);
@@ -162,7 +163,7 @@ gram_fp8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_co
         const int kc = (fk.x + kb) * BK;
         tma_load_2d(sA + s * A_BYTES, &tmZ, full_bar + 8 * s, kc, tile.x * BM);
         tma_load_2d(sB + s * B_BYTES, &tmB, full_bar + 8 * s, kc, tile.y * BN);
-        tma_load_2d(sB + s * B_BYTES + A_BYTES, &tmB, full_bar + 8 * s, kc, tile.y * BN + 128);
+        if (BN == 256) tma_load_2d(sB + s * B_BYTES + A_BYTES, &tmB, full_bar + 8 * s, kc, tile.y * BN + 128);
       }
     }
   } else if (warp == 1) {
@@ -178,7 +179,7 @@ gram_fp8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_co
 #pragma unroll
         for (int k = 0; k < BK / 32; ++k) {
           // advance 32 bytes (= K of one f8 MMA) inside the swizzle atom: +2 in 16-byte units
-          mma_f8(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), (kb | k) ? 1u : 0u);
+          mma_f8(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), (kb | k) ? 1u : 0u, gram_idesc(BN));
         }
         tcgen05_commit(empty_bar + 8 * s);     // frees the smem stage when these MMAs retire
       }
@@ -258,22 +259,28 @@ void make_gram_tensor_map(CUtensorMap* tm, const uint8_t* z, int64_t npad, int r
   RG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
 }
 
-size_t gram_smem_bytes() {
+size_t gram_smem_bytes(int bn) {
   static const bool exclusive = getenv("RG_DBG_GRAM_EXCLUSIVE") != nullptr;
-  return exclusive ? (size_t)232448 : (size_t)STAGES * STAGE_BYTES + 1024 + 128;
+  return exclusive ? (size_t)232448 : (size_t)STAGES * (A_BYTES + bn * BK) + 1024 + 128;
 }
 
 void gram_tile_list(int rows2, std::vector<int2>& tiles) {
   tiles.clear();
-  for (int nj = 0; nj < rows2 / BN; ++nj)
+  for (int nj = 0; nj < rows2 / 256; ++nj)
     for (int mi = 2 * nj; mi < rows2 / BM; ++mi) tiles.push_back(make_int2(mi, nj));
 }
 
 void launch_gram_tcgen05(const CUtensorMap& tm, const CUtensorMap& tmB, const int2* tiles, int ntiles, const int2* fold_k, int K,
-                         float* out, int ldo, int64_t fold_stride, float out_scale, cudaStream_t s) {
-  ensure_dyn_smem(reinterpret_cast<const void*>(gram_fp8_tcgen05_kernel), gram_smem_bytes());
+                         float* out, int ldo, int64_t fold_stride, float out_scale, cudaStream_t s, int bn) {
+  RG_CHECK(bn == 256 || bn == 128, "gram tiles are 128 x 256 or 128 x 128");
   dim3 grid(ntiles, K);
-  gram_fp8_tcgen05_kernel<<<grid, NTHREADS, gram_smem_bytes(), s>>>(tm, tmB, tiles, fold_k, out, ldo, fold_stride, out_scale);
+  if (bn == 256) {
+    ensure_dyn_smem(reinterpret_cast<const void*>(gram_fp8_tcgen05_kernel<256>), gram_smem_bytes(256));
+    gram_fp8_tcgen05_kernel<256><<<grid, NTHREADS, gram_smem_bytes(256), s>>>(tm, tmB, tiles, fold_k, out, ldo, fold_stride, out_scale);
+  } else {
+    ensure_dyn_smem(reinterpret_cast<const void*>(gram_fp8_tcgen05_kernel<128>), gram_smem_bytes(128));
+    gram_fp8_tcgen05_kernel<128><<<grid, NTHREADS, gram_smem_bytes(128), s>>>(tm, tmB, tiles, fold_k, out, ldo, fold_stride, out_scale);
+  }
 }
 
 void launch_gram_reference(const uint8_t* z, int64_t npad, int rows2, int k0, int k1, float* out, int ldo,

@@ -62,7 +62,7 @@ void launch_l0_assemble(const AssembleArgs& a, const double* rhs, int P, int Ppa
 
 // ---- gram_tcgen05.cu
 void make_gram_tensor_map(CUtensorMap* tm, const uint8_t* z, int64_t npad, int rows2);
-size_t gram_smem_bytes();
+size_t gram_smem_bytes(int bn = 256);
 // ---- l0_stats_tc.cu: the statistics as extra Gram column tiles
 constexpr int kStatQ = 14;          // xy columns per 128-row digit group (14 x 9 limbs = 126 rows)
 constexpr int kStatOnesRow = 126;   // row of the all-ones column (group 0)
@@ -73,7 +73,7 @@ void launch_l0_stats_finish(const float* T, int ldt, int64_t t_fold_stride, cons
                             int32_t* cnt_fold, double* sum_fold, cudaStream_t s);
 void gram_tile_list(int rows2, std::vector<int2>& tiles);
 void launch_gram_tcgen05(const CUtensorMap& tm, const CUtensorMap& tmB, const int2* tiles, int ntiles, const int2* fold_k, int K,
-                         float* out, int ldo, int64_t fold_stride, float out_scale, cudaStream_t s);
+                         float* out, int ldo, int64_t fold_stride, float out_scale, cudaStream_t s, int bn = 256);
 // operand-plane bytes of the Step-1 block (bed_expand_fp8_kernel): dosage d -> 8 d as int8 = 2^-6 d as e4m3
 constexpr float kZScaleGram = 4096.f;     // Z Z^T tiles: both operands carry 2^-6
 constexpr float kZScaleStat = 64.f;       // Z [X|Y]-digit tiles: the digit rows are plain e4m3 integers

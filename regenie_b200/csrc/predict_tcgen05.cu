@@ -296,10 +296,8 @@ l0_predict_tcgen05_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_
 // overlaps the other's main loop.
 namespace {
 constexpr int PI_BN = 256;
-constexpr int PI_STAGES = 2;
 constexpr int PI_A_BYTES = PT_BK * PT_BM;          // 16 KiB
 constexpr int PI_B_BYTES = PI_BN * PT_BK;          // 32 KiB
-constexpr int PI_STAGE_BYTES = PI_A_BYTES + PI_B_BYTES;
 constexpr int PI_QH = kLimbQI8 / 2;                // outputs per epilogue thread (25)
 static_assert(kLimbsI8 * kLimbQI8 <= PI_BN && kLimbQI8 % 2 == 0 && PI_QH <= 32 && kLimbQI8 >= 32, "INT8 prediction layout");
 
@@ -352,32 +350,41 @@ l0_gamma_limbs_i8_kernel(const double* __restrict__ gam, const double* __restric
   }
 }
 
-// grid: (Npad/128 sample tiles, q groups); 320 threads, two CTAs per SM.
-__global__ void __launch_bounds__(PT_THREADS, 2)
+// MT = sample tiles (of 128) per CTA.  MT = 1 (default): 2 stages of 48 KiB, 256 TMEM columns, two CTAs per SM.  MT = 2
+// (RG_B200_PREDICT_MT=2): both tiles share every digit-row stage - the B operand, 2/3 of this kernel's L2 -> shared-memory
+// traffic, is read once per 256 samples - 3 stages of 64 KiB, all 512 TMEM columns, one CTA per SM.  Measured SLOWER
+// (profiles/ab_r2j_ablation.txt: 12.4 vs 10.0 ms per 50 blocks alone, 44.5 vs 42.6 ms overlapped): two co-resident CTAs hide
+// the epilogue and the TMA latency better than the saved traffic pays.  (The fold padding is a multiple of 256 samples, so
+// the two tiles of a CTA always belong to the same fold.)
+// grid: (Npad / (128 MT) sample tiles, q groups); 320 threads.
+template <int MT>
+__global__ void __launch_bounds__(PT_THREADS, MT == 1 ? 2 : 1)
 l0_predict_i8_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmD, PredictTcArgs a) {
+  constexpr int NST = MT == 1 ? 2 : 3;
+  constexpr int STAGE_BYTES = MT * PI_A_BYTES + PI_B_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (base - raw);
-  const uint32_t sA = base;
-  const uint32_t sB = base + PI_STAGES * PI_A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(gen_base + PI_STAGES * PI_STAGE_BYTES);
+  const uint32_t sA = base;                                   // [NST][MT][16 KiB]
+  const uint32_t sB = base + NST * MT * PI_A_BYTES;           // [NST][32 KiB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gen_base + NST * STAGE_BYTES);
   const uint32_t full_bar = smem_u32(bars);
-  const uint32_t empty_bar = smem_u32(bars + PI_STAGES);
-  const uint32_t tmem_full_bar = smem_u32(bars + 2 * PI_STAGES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * PI_STAGES + 1);
-  double* s_scale = reinterpret_cast<double*>(bars + 2 * PI_STAGES + 2);   // [kLimbQI8]
+  const uint32_t empty_bar = smem_u32(bars + NST);
+  const uint32_t tmem_full_bar = smem_u32(bars + 2 * NST);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 1);
+  double* s_scale = reinterpret_cast<double*>(bars + 2 * NST + 2);         // [kLimbQI8]
   double* s_cvec = s_scale + kLimbQI8;                                      // [kLimbQI8][C]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x, g = blockIdx.y;
-  const int f = a.tile_fold[tile];
+  const int f = a.tile_fold[tile * MT];
   const int nkb = (2 * a.rows_p) / PT_BK;
   const int q0 = g * kLimbQI8;
   const int nq = min(kLimbQI8, a.Q - q0);
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < PI_STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    for (int s = 0; s < NST; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -386,7 +393,7 @@ l0_predict_i8_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)PI_BN) : "memory");
+                 "r"((uint32_t)(MT * PI_BN)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int e = threadIdx.x; e < kLimbQI8; e += PT_THREADS)
@@ -402,14 +409,16 @@ l0_predict_i8_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===== TMA producer: A = 128 plane rows x 128 samples; B = 256 digit rows x 128 k bytes =====
+      // ===== TMA producer: A = MT x (128 plane rows x 128 samples); B = 256 digit rows x 128 k bytes =====
       const int drow0 = (f * a.ngroups + g) * PI_BN;
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % PI_STAGES;
-        const uint32_t ph = (kb / PI_STAGES) & 1;
+        const int s = kb % NST;
+        const uint32_t ph = (kb / NST) & 1;
         mbar_wait(empty_bar + 8 * s, ph ^ 1);
-        mbar_expect_tx(full_bar + 8 * s, PI_STAGE_BYTES);
-        tma_load_2d(sA + s * PI_A_BYTES, &tmZ, full_bar + 8 * s, tile * PT_BM, kb * PT_BK);
+        mbar_expect_tx(full_bar + 8 * s, STAGE_BYTES);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+          tma_load_2d(sA + (s * MT + mt) * PI_A_BYTES, &tmZ, full_bar + 8 * s, (tile * MT + mt) * PT_BM, kb * PT_BK);
         tma_load_2d(sB + s * PI_B_BYTES, &tmD, full_bar + 8 * s, kb * PT_BK, drow0);
         tma_load_2d(sB + s * PI_B_BYTES + 16384, &tmD, full_bar + 8 * s, kb * PT_BK, drow0 + 128);
       }
@@ -418,15 +427,19 @@ l0_predict_i8_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
     if (lane == 0) {
       // ===== MMA issuer =====
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % PI_STAGES;
-        const uint32_t ph = (kb / PI_STAGES) & 1;
+        const int s = kb % NST;
+        const uint32_t ph = (kb / NST) & 1;
         mbar_wait(full_bar + 8 * s, ph);
         fence_after();
-        const uint64_t da = make_desc(sA + s * PI_A_BYTES);
         const uint64_t db = make_desc(sB + s * PI_B_BYTES);
 #pragma unroll
-        for (int k = 0; k < PT_BK / 32; ++k)
-          mma_i8(tmem_base, da + (uint64_t)(256 * k), db + (uint64_t)(2 * k), (kb | k) ? 1u : 0u);
+        for (int k = 0; k < PT_BK / 32; ++k) {
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t da = make_desc(sA + (s * MT + mt) * PI_A_BYTES);
+            mma_i8(tmem_base + (uint32_t)(mt * PI_BN), da + (uint64_t)(256 * k), db + (uint64_t)(2 * k), (kb | k) ? 1u : 0u);
+          }
+        }
         tcgen05_commit(empty_bar + 8 * s);
       }
       tcgen05_commit(tmem_full_bar);
@@ -436,43 +449,46 @@ l0_predict_i8_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
     // lowest limb up.  The second half reads the 32 columns that END at its last output, so no load leaves the allocation.
     const int qw = warp & 3;                      // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;
-    const int t = tile * PT_BM + qw * 32 + lane;
-    double acc[PI_QH];
-#pragma unroll
-    for (int j = 0; j < PI_QH; ++j) acc[j] = 0.0;
     mbar_wait(tmem_full_bar, 0);
     fence_after();
-    const uint32_t tbase = tmem_base + ((uint32_t)(qw * 32) << 16);
     const double inv254 = 1.0 / 254.0;
-    if (half == 0) {
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
+      const int t = (tile * MT + mt) * PT_BM + qw * 32 + lane;
+      const uint32_t tbase = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)(mt * PI_BN);
+      double acc[PI_QH];
 #pragma unroll
-      for (int l = kLimbsI8 - 1; l >= 0; --l) {
-        uint32_t v[32];
-        tmem_ld_32x32(tbase + (uint32_t)(l * kLimbQI8), v);
+      for (int j = 0; j < PI_QH; ++j) acc[j] = 0.0;
+      if (half == 0) {
 #pragma unroll
-        for (int j = 0; j < PI_QH; ++j) acc[j] = fma(acc[j], inv254, (double)((int)v[j] >> 3));
+        for (int l = kLimbsI8 - 1; l >= 0; --l) {
+          uint32_t v[32];
+          tmem_ld_32x32(tbase + (uint32_t)(l * kLimbQI8), v);
+#pragma unroll
+          for (int j = 0; j < PI_QH; ++j) acc[j] = fma(acc[j], inv254, (double)((int)v[j] >> 3));
+        }
+      } else {
+#pragma unroll
+        for (int l = kLimbsI8 - 1; l >= 0; --l) {
+          uint32_t v[32];
+          tmem_ld_32x32(tbase + (uint32_t)(l * kLimbQI8 + kLimbQI8 - 32), v);
+#pragma unroll
+          for (int j = 0; j < PI_QH; ++j) acc[j] = fma(acc[j], inv254, (double)((int)v[32 - PI_QH + j] >> 3));
+        }
       }
-    } else {
+      double xr[kMaxCov];
+      for (int c = 0; c < a.C; ++c) xr[c] = a.xy[(int64_t)t * a.cpp + c];
 #pragma unroll
-      for (int l = kLimbsI8 - 1; l >= 0; --l) {
-        uint32_t v[32];
-        tmem_ld_32x32(tbase + (uint32_t)(l * kLimbQI8 + kLimbQI8 - 32), v);
-#pragma unroll
-        for (int j = 0; j < PI_QH; ++j) acc[j] = fma(acc[j], inv254, (double)((int)v[32 - PI_QH + j] >> 3));
-      }
-    }
-    double xr[kMaxCov];
-    for (int c = 0; c < a.C; ++c) xr[c] = a.xy[(int64_t)t * a.cpp + c];
-#pragma unroll
-    for (int j = 0; j < PI_QH; ++j) {
-      const int qq = half * PI_QH + j;
-      if (qq < nq) {
-        const int q = q0 + qq;
-        const int r = q / a.P, p = q % a.P;
-        double val = acc[j] * s_scale[qq];
-        for (int c = 0; c < a.C; ++c) val -= xr[c] * s_cvec[qq * a.C + c];
-        val *= (double)a.mask[(int64_t)p * a.npad + t];
-        a.W[p][(int64_t)(a.col0 + r) * a.npad + t] = val;
+      for (int j = 0; j < PI_QH; ++j) {
+        const int qq = half * PI_QH + j;
+        if (qq < nq) {
+          const int q = q0 + qq;
+          const int r = q / a.P, p = q % a.P;
+          double val = acc[j] * s_scale[qq];
+          for (int c = 0; c < a.C; ++c) val -= xr[c] * s_cvec[qq * a.C + c];
+          val *= (double)a.mask[(int64_t)p * a.npad + t];
+          a.W[p][(int64_t)(a.col0 + r) * a.npad + t] = val;
+        }
       }
     }
   }
@@ -480,7 +496,7 @@ l0_predict_i8_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
   __syncthreads();
   if (warp == 1) {
     fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)PI_BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(MT * PI_BN)) : "memory");
   }
 }
 
@@ -576,10 +592,17 @@ void launch_l0_gamma_limbs_i8(const double* gam, const double* gmu, int Qp, int 
 void launch_l0_predict_i8(const CUtensorMap& tmZ, const CUtensorMap& tmD, const PredictTcArgs& a, int ntiles,
                           cudaStream_t s) {
   RG_CHECK(2 * a.rows_p <= 4096, "INT8 prediction: 2 * rows_p <= 4096 (int32 Horner bound)");
-  const size_t smem = (size_t)PI_STAGES * PI_STAGE_BYTES + 1024 + 128 + ((size_t)kLimbQI8 * (1 + a.C)) * sizeof(double);
-  ensure_dyn_smem(reinterpret_cast<const void*>(l0_predict_i8_kernel), smem);
-  dim3 grid(ntiles, a.ngroups);
-  l0_predict_i8_kernel<<<grid, PT_THREADS, smem, s>>>(tmZ, tmD, a);
+  static const int mt = [] { const char* e = getenv("RG_B200_PREDICT_MT"); return (e && atoi(e) == 2) ? 2 : 1; }();
+  const size_t extra = 1024 + 128 + ((size_t)kLimbQI8 * (1 + a.C)) * sizeof(double);
+  if (mt == 2 && ntiles % 2 == 0) {
+    const size_t smem = (size_t)3 * (2 * PI_A_BYTES + PI_B_BYTES) + extra;
+    ensure_dyn_smem(reinterpret_cast<const void*>(l0_predict_i8_kernel<2>), smem);
+    l0_predict_i8_kernel<2><<<dim3(ntiles / 2, a.ngroups), PT_THREADS, smem, s>>>(tmZ, tmD, a);
+  } else {
+    const size_t smem = (size_t)2 * (PI_A_BYTES + PI_B_BYTES) + extra;
+    ensure_dyn_smem(reinterpret_cast<const void*>(l0_predict_i8_kernel<1>), smem);
+    l0_predict_i8_kernel<1><<<dim3(ntiles, a.ngroups), PT_THREADS, smem, s>>>(tmZ, tmD, a);
+  }
 }
 
 }  // namespace rg

@@ -94,7 +94,7 @@ static void build_layout(rg_ctx* h, const double* X, const double* Y, const uint
   int64_t off = 0;
   for (int f = 0; f < K; ++f) {
     h->fold_pad_start[f] = off;
-    h->fold_pad_len[f] = round_up(h->fold_sizes[f], kSamplePad);
+    h->fold_pad_len[f] = round_up(h->fold_sizes[f], kFoldPad);
     off += h->fold_pad_len[f];
   }
   h->Npad = off;
@@ -184,7 +184,7 @@ static void build_layout(rg_ctx* h, const double* X, const double* Y, const uint
     h->stats_tc = !(e && std::string(e) == "f64") && max_fold * 30 < (1ll << 24);
     if (h->stats_tc) {
       const int ngroups = (int)ceil_div(C + P, kStatQ);
-      h->stat_drows = (int)round_up((int64_t)ngroups * 128, 256);
+      h->stat_drows = ngroups * 128;          // an odd group count runs as 128 x 128 tiles (stat_bn)
       h->xyD.alloc((size_t)h->stat_drows * h->Npad);
       h->xy_scale.alloc(h->cpp);
       RG_CUDA(cudaMemsetAsync(h->xyD.p, 0, (size_t)h->stat_drows * h->Npad, s));
@@ -572,9 +572,10 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
   if (h->stats_tc) {
     // Z [X | Y]-digits: one more column tile per row tile of the same kernel, then the FP64 Horner
     ScopedTimer t(h, "l0_stats", s);
+    const int stat_bn = (h->stat_drows % 256 == 0) ? 256 : 128;
     if (!h->stat_tile_lists.count(rows_p)) {
       std::vector<int2> tiles;
-      for (int nj = 0; nj < h->stat_drows / 256; ++nj)
+      for (int nj = 0; nj < h->stat_drows / stat_bn; ++nj)
         for (int mi = 0; mi < 2 * rows_p / 128; ++mi) tiles.push_back(make_int2(mi, nj));
       auto buf = std::make_unique<DevBuf<int2>>();
       buf->alloc(tiles.size());
@@ -585,7 +586,7 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
     L.tstat.alloc((size_t)K * 2 * h->rows_p_max * h->stat_drows);
     const int64_t tfs = (int64_t)2 * rows_p * h->stat_drows;
     if (!dbg_skip("stats")) launch_gram_tcgen05(L.tmaps[rows_p], h->tmD, h->stat_tile_lists[rows_p]->p, h->stat_tile_counts[rows_p], h->fold_k.p,
-                        K, L.tstat.p, h->stat_drows, tfs, kZScaleStat, s);
+                        K, L.tstat.p, h->stat_drows, tfs, kZScaleStat, s, stat_bn);
     launch_l0_stats_finish(L.tstat.p, h->stat_drows, tfs, L.zz.p, 2 * rows_p, (int64_t)4 * rows_p * rows_p, rows_p,
                            h->cpp, C + P, K, h->xy_scale.p, L.cnt_fold.p, L.sum_fold.p, s);
     snp_finalize();
