@@ -577,6 +577,20 @@ def step2_qt_leg(capi, X, mask, in_an, N, P, C, bs, blocks, host_panel, dev_ptr,
         return nv / (time.perf_counter() - t0)
     host_rate = run(hbase)
     dev_rate = run(dev_ptr)
+
+    def run_staged():
+        # the rows of block b+1 cross PCIe (rg_s2_stage, copy stream) while block b is tested
+        t0 = time.perf_counter(); nv = 0
+        nxt = st2.stage(0, hbase + blocks[0][0] * stride, blocks[0][1] * stride)
+        for b in range(nb2):
+            cur = nxt
+            if b + 1 < nb2:
+                nxt = st2.stage((b + 1) & 1, hbase + blocks[b + 1][0] * stride, blocks[b + 1][1] * stride)
+            st2.block_bed_raw(cur, blocks[b][1], stride, out)
+            nv += blocks[b][1]
+        return nv / (time.perf_counter() - t0)
+    run_staged()
+    staged_rate = run_staged()
     st2.close()
     # CPU: the Eigen restatement, one OpenMP task per variant like Data::test_snps_fast
     cpu = None
@@ -593,8 +607,11 @@ def step2_qt_leg(capi, X, mask, in_an, N, P, C, bs, blocks, host_panel, dev_ptr,
                "sample": "%d variants at N=%d, %d traits: C++/Eigen restatement of parseSnpfromBed + residualize_geno + "
                          "compute_score_qt, one OpenMP task per variant (%.2f s)" % (nv_cpu, N, P, dt)}
     return {"metric": "step2_qt_variants_per_sec", "value": dev_rate, "unit": "variants/s",
-            "e2e": {"value": host_rate, "unit": "variants/s", "h2d_bytes_per_variant": int(stride),
-                    "d2h_bytes_per_variant": 8 * (6 * P + 3) + 4 * (P + 2)},
+            "e2e": {"value": max(host_rate, staged_rate), "unit": "variants/s", "h2d_bytes_per_variant": int(stride),
+                    "d2h_bytes_per_variant": 8 * (6 * P + 3) + 4 * (P + 2),
+                    "staged": staged_rate, "unstaged": host_rate,
+                    "note": "staged = rg_s2_stage copies block b+1 on a copy stream under the kernels of block b; unstaged = "
+                            "the block call copies its own rows first"},
             "roofline": hbm_roofline(dev_rate, N / 4.0, "N/4 bytes of 2-bit calls"),
             "cpu_baseline": cpu,
             "sample": "%d blocks of %d variants, N=%d, %d traits; value = .bed rows resident in HBM, e2e = pinned host rows; "
@@ -665,6 +682,20 @@ def step2_bt_leg(capi, X, in_an, N, C, args, nvar=400, nblocks=4):
         return nblocks * nvar / (time.perf_counter() - t0), nf / (nblocks * nvar)
     host_rate, ff = run(lambda: block(probs_t.data_ptr(), miss_t.data_ptr()))
     dev_rate, _ = run(lambda: block(probs_d.data_ptr(), miss_d.data_ptr()))
+    # staged: the (same) pinned bytes of the NEXT block cross PCIe on the copy stream while this block is tested
+    stage_state = {"n": 0, "next": None}
+
+    def staged_block():
+        k = stage_state["n"]
+        if stage_state["next"] is None:
+            stage_state["next"] = (st.stage(0, probs_t.data_ptr(), probs_t.numel()), st.stage(1, miss_t.data_ptr(), miss_t.numel()))
+        cur = stage_state["next"]
+        sl = 2 * ((k + 1) & 1)
+        stage_state["next"] = (st.stage(sl, probs_t.data_ptr(), probs_t.numel()), st.stage(sl + 1, miss_t.data_ptr(), miss_t.numel()))
+        stage_state["n"] = k + 1
+        return block(cur[0], cur[1])
+    staged_block()
+    staged_rate, _ = run(staged_block)
     inflate = {}
     for mode in ("direct", "window"):
         os.environ["RG_B200_INFLATE"] = mode
@@ -699,7 +730,8 @@ def step2_bt_leg(capi, X, in_an, N, C, args, nvar=400, nblocks=4):
                "sample": "%d variants at N=%d: C++/Eigen restatement of the BGEN dosage loop + compute_score_bt (score statistic "
                          "only, no Firth, payloads already inflated), one OpenMP task per variant (%.2f s)" % (nv_cpu, N, dt)}
     return {"metric": "step2_bt_bgen_variants_per_sec", "value": dev_rate, "unit": "variants/s",
-            "e2e": {"value": host_rate, "unit": "variants/s", "h2d_bytes_per_variant": 3 * N, "d2h_bytes_per_variant": 8 * 10 + 12},
+            "e2e": {"value": max(host_rate, staged_rate), "unit": "variants/s", "h2d_bytes_per_variant": 3 * N, "d2h_bytes_per_variant": 8 * 10 + 12,
+                    "staged": staged_rate, "unstaged": host_rate},
             "e2e_compressed_input": inflate,
             "compressed_bytes_per_variant": float(offs[-1]) / nvar,
             "roofline": hbm_roofline(dev_rate, 3.0 * N, "2N probability bytes + N ploidy bytes"),

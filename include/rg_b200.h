@@ -225,6 +225,22 @@ typedef struct rg_s2_out {
 } rg_s2_out;
 
 /*
+ * rg_s2_stage -- start the host -> device copy of a LATER block's input bytes (PLINK rows, BGEN probability or
+ * ploidy bytes) on the handle's copy stream and return the device address to pass as `packed` / `probs` /
+ * `ploidy_missing` to the rg_s2_block_* call of that block, which waits for exactly this copy.  The reference
+ * overlaps reading block b+1 with testing block b on its OpenMP threads (src/Data.cpp:2284-2312, Gblock read ahead
+ * of compute_tests_mt); here the PCIe transfer of block b+1 rides under the kernels of block b.  slot in 0..3: a slot's
+ * buffer is reused, so stage block b+2 into the slot of block b only after block b's call has returned.  `host` must
+ * stay untouched until the consuming block call returns; the copy is asynchronous only from pinned memory
+ * (rg_host_alloc).
+ */
+int rg_s2_stage(rg_handle h, int32_t slot, const void* host, int64_t bytes, const uint8_t** dev);
+
+/* pinned host memory for staged inputs (cudaMallocHost / cudaFreeHost behind the C ABI) */
+int rg_host_alloc(void** p, int64_t bytes);
+int rg_host_free(void* p);
+
+/*
  * rg_s2_block_bed -- Step-2 score test for bs variants from 2-bit PLINK rows.  Replaces, per
  * variant: parseSnpfromBed + compute_mac + compute_aaf_info (src/Geno.cpp:2414-2536,
  * 3077-3148), check_sparse_G (:3165), residualize_geno (:3242) and compute_score_qt

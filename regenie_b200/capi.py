@@ -49,6 +49,7 @@ EXPORTS = [
     "rg_s2_set_chr", "rg_s2_block_bed", "rg_W_info", "rg_debug_fetch", "rg_launch_count", "rg_stream",
     "rg_set_timing", "rg_get_timing", "rg_fence", "rg_s2_set_chr_bt", "rg_s2_block_bgen8_bt", "rg_s2_block_bgen8", "rg_s2_firth", "rg_l1_fit_bt", "rg_W_set_owned", "rg_W_export", "rg_W_attach_peer", "rg_l1_select", "rg_s2_set_sex", "rg_s2_set_non_par", "rg_l0_load_W", "rg_s2_spa", "rg_s2_block_bed_bt", "rg_prs", "rg_bgen_inflate",
     "rg_l0_solver_stats", "rg_dbg_mixed_solve", "rg_l0_wait_input", "rg_l0_block_dosage_u8", "rg_l0_block_f64", "rg_W_attach_local",
+    "rg_s2_stage", "rg_host_alloc", "rg_host_free",
 ]
 
 _lib = None
@@ -329,6 +330,15 @@ class Step2:
         so = S2Out(*[o[k].ctypes.data for k in ("af", "ns", "mac", "af_all", "ns_all", "mac_all", "flags",
                                                 "scale_fac", "stat", "beta", "se", "chisq")])
         return o, so
+
+    def stage(self, slot, host_ptr, nbytes):
+        """rg_s2_stage: start the H2D copy of a later block's input (raw host address, ideally pinned); returns the device
+        address to hand to the *_raw block call of that block."""
+        L = lib()
+        L.rg_s2_stage.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
+        dev = C.c_void_p()
+        check(L.rg_s2_stage(self.h, int(slot), C.c_void_p(host_ptr), int(nbytes), C.byref(dev)))
+        return dev.value
 
     def block_bed_raw(self, ptr, bs, row_stride, out=None, min_mac=5.0):
         """rg_s2_block_bed on a raw (host or DEVICE) address; `out` = a (dict, S2Out) pair from _out() to reuse."""

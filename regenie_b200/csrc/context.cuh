@@ -149,6 +149,12 @@ struct rg_ctx {
   int bt_mode = 0, bt_dp = 0;
   bool bt_chr_set = false;
   int s2_last_bs = 0;                // variants resident in dz (for rg_s2_firth)
+  // rg_s2_stage: input bytes of the NEXT block travel on a copy stream while the current block computes
+  static constexpr int kStageSlots = 4;
+  rg::DevBuf<uint8_t> s2_stage[kStageSlots];
+  cudaStream_t s2_copy_stream = nullptr;
+  cudaEvent_t s2_stage_ev[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
+  bool s2_stage_pending[kStageSlots] = {false, false, false, false};
   rg::DevBuf<uint8_t> probs_dev, miss_dev;
   rg::DevBuf<uint8_t> inflate_comp, inflate_raw;      // rg_bgen_inflate: compressed streams, inflated payloads
   rg::DevBuf<uint64_t> inflate_offs;

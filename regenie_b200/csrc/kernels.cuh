@@ -107,6 +107,7 @@ struct Tf32GemmEpilogue {
   int diag_mod;
   int c_chunks;               // 0, or 4: leading K chunks  acc = C_tile * I  followed by the main chunks with A negated
   int c_mat_div;              // C matrix index = mat / c_mat_div
+  int l2_prefetch;            // K chunks whose operand boxes are prefetched into L2 ahead of the single shared-memory stage
 };
 void make_tf32_planes_tensor_map(CUtensorMap* tm, const float* planes, int n, int batch);
 void make_tf32_identity_planes(DevBuf<float>& buf, CUtensorMap* tm);
@@ -189,6 +190,7 @@ struct PredictTcArgs {
   double* const* W;
   double* part;
   long long* dbg;            // optional per-CTA clock64 stamps (profiling aid)
+  int l2_prefetch = 0;       // INT8 kernel: k-blocks of the genotype planes prefetched into L2 ahead of the ring
 };
 void make_byte_tensor_map(CUtensorMap* tm, const uint8_t* basep, int64_t inner, int64_t rows);
 size_t predict_tc_dig_bytes(int K, int ngroups, int rows_p);

@@ -58,6 +58,9 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -411,9 +414,18 @@ l0_predict_i8_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
     if (lane == 0) {
       // ===== TMA producer: A = MT x (128 plane rows x 128 samples); B = 256 digit rows x 128 k bytes =====
       const int drow0 = (f * a.ngroups + g) * PI_BN;
+      // the genotype planes stream from DRAM (206 MB per block at N = 100k): their boxes are prefetched into L2 `pf` k-blocks
+      // ahead of the shared-memory ring (the digit rows are L2-resident anyway)
+      const int pf = a.l2_prefetch;
+      auto prefetch = [&](int kb) {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) tma_prefetch_2d(&tmZ, (tile * MT + mt) * PT_BM, kb * PT_BK);
+      };
+      for (int kb = NST; kb < NST + pf && kb < nkb; ++kb) prefetch(kb);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % NST;
         const uint32_t ph = (kb / NST) & 1;
+        if (pf > 0 && kb + NST + pf < nkb) prefetch(kb + NST + pf);
         mbar_wait(empty_bar + 8 * s, ph ^ 1);
         mbar_expect_tx(full_bar + 8 * s, STAGE_BYTES);
 #pragma unroll

@@ -180,6 +180,20 @@ static const uint8_t* take_non_par(rg_ctx* h, int bs) {
 
 namespace rg {
 void build_file_idx_public(rg_ctx* h, const int32_t* sample_idx_host);
+
+// A block whose input pointer lies in a staging buffer (rg_s2_stage) waits for that slot's copy, and only for it: the
+// copy of the block AFTER it may already be in flight on the copy stream.
+static void s2_wait_stage(rg_ctx* h, const void* in, cudaStream_t s) {
+  if (!in) return;
+  for (int k = 0; k < rg_ctx::kStageSlots; ++k) {
+    if (!h->s2_stage_pending[k] || !h->s2_stage[k].p) continue;
+    const uint8_t* b = h->s2_stage[k].p;
+    if ((const uint8_t*)in >= b && (const uint8_t*)in < b + h->s2_stage[k].n) {
+      RG_CUDA(cudaStreamWaitEvent(s, h->s2_stage_ev[k], 0));
+      h->s2_stage_pending[k] = false;
+    }
+  }
+}
 }
 
 static void s2_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, int bs, const int32_t* sample_idx,
@@ -188,6 +202,7 @@ static void s2_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
   RG_CHECK(bs > 0 && bs <= h->bs_max, "block size out of range");
   RG_CUDA(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
+  s2_wait_stage(h, packed, s);
   const int P = h->P, C = h->C;
   const int rows_p = (int)round_up(bs, kRowPad);
   const int64_t Npad = h->Npad;
@@ -313,6 +328,8 @@ static void s2_block_bgen8_bt(rg_ctx* h, const uint8_t* probs, const uint8_t* mi
   RG_CHECK(bs > 0 && bs <= h->bs_max, "block size out of range");
   RG_CUDA(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
+  s2_wait_stage(h, probs, s);
+  s2_wait_stage(h, miss, s);
   const int P = h->P, C = h->C, dp = h->bt_dp;
   const int rows_p = (int)round_up(bs, kRowPad);
   const int64_t Npad = h->Npad;
@@ -386,6 +403,8 @@ static void s2_block_bgen8_qt(rg_ctx* h, const uint8_t* probs, const uint8_t* mi
   RG_CHECK(bs > 0 && bs <= h->bs_max, "block size out of range");
   RG_CUDA(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
+  s2_wait_stage(h, probs, s);
+  s2_wait_stage(h, miss, s);
   const int P = h->P, C = h->C, dp = h->dp;
   const int rows_p = (int)round_up(bs, kRowPad);
   const int64_t Npad = h->Npad;
@@ -461,6 +480,7 @@ static void s2_block_bed_bt(rg_ctx* h, const uint8_t* packed, int64_t row_stride
   RG_CHECK(bs > 0 && bs <= h->bs_max, "block size out of range");
   RG_CUDA(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
+  s2_wait_stage(h, packed, s);
   const int P = h->P, C = h->C, dp = h->bt_dp;
   const int rows_p = (int)round_up(bs, kRowPad);
   const int64_t Npad = h->Npad;
@@ -659,6 +679,39 @@ int rg_s2_firth(rg_handle h, int32_t n_sel, const int32_t* variant_idx, const in
   RG_CHECK(h && (n_sel == 0 || (variant_idx && trait_idx && beta && se && lrt && status)), "null argument");
   if (n_sel > 0) s2_firth(h, n_sel, variant_idx, trait_idx, beta, se, lrt, status);
   RG_CUDA(cudaGetLastError());
+  RG_API_END
+}
+
+int rg_s2_stage(rg_handle h, int32_t slot, const void* host, int64_t bytes, const uint8_t** dev) {
+  RG_API_BEGIN
+  RG_CHECK(h && host && dev && bytes > 0, "null argument");
+  RG_CHECK(h->kind == 2, "handle is not a Step-2 handle");
+  RG_CHECK(slot >= 0 && slot < rg_ctx::kStageSlots, "staging slot out of range");
+  RG_CUDA(cudaSetDevice(h->device));
+  if (!h->s2_copy_stream) RG_CUDA(cudaStreamCreateWithFlags(&h->s2_copy_stream, cudaStreamNonBlocking));
+  if (!h->s2_stage_ev[slot]) RG_CUDA(cudaEventCreateWithFlags(&h->s2_stage_ev[slot], cudaEventDisableTiming));
+  if (h->s2_stage[slot].n < (size_t)bytes) {            // grows only between blocks: nothing reads the old buffer any more
+    RG_CUDA(cudaStreamSynchronize(h->s2_copy_stream));
+    RG_CUDA(cudaStreamSynchronize(h->stream));
+    h->s2_stage[slot].alloc((size_t)bytes);
+  }
+  RG_CUDA(cudaMemcpyAsync(h->s2_stage[slot].p, host, (size_t)bytes, cudaMemcpyHostToDevice, h->s2_copy_stream));
+  RG_CUDA(cudaEventRecord(h->s2_stage_ev[slot], h->s2_copy_stream));
+  h->s2_stage_pending[slot] = true;
+  *dev = h->s2_stage[slot].p;
+  RG_API_END
+}
+
+int rg_host_alloc(void** p, int64_t bytes) {
+  RG_API_BEGIN
+  RG_CHECK(p && bytes > 0, "bad argument");
+  RG_CUDA(cudaMallocHost(p, (size_t)bytes));
+  RG_API_END
+}
+
+int rg_host_free(void* p) {
+  RG_API_BEGIN
+  if (p) RG_CUDA(cudaFreeHost(p));
   RG_API_END
 }
 

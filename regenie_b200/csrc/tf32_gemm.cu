@@ -60,6 +60,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// L2 prefetch of a box (no shared memory, no barrier): the operands of this solver stream from DRAM (8 lanes x 0.5 GB of
+// factor planes do not stay in the 126 MB L2) and a CTA has ONE 64 KiB stage, so the TMA load of chunk k+1 cannot start
+// before the MMAs of chunk k retire - but its bytes can already be on their way into L2.
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -166,14 +172,27 @@ tf32x3_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
+      const int cmat = 2 * (ep.c_mat_div > 0 ? mat / ep.c_mat_div : mat);
+      // chunk kc: (kc < ncc) C tile x identity, else A / B row tiles at column (tile.z + kc - ncc) * TG_KC
+      auto prefetch = [&](int kc) {
+        if (kc < ncc) {
+          tma_prefetch_3d(&tmC, tile.y * TG_N + kc * TG_KC, tile.x * TG_M, cmat);
+        } else {
+          const int col = (tile.z + kc - ncc) * TG_KC;
+          tma_prefetch_3d(&tmA, col, tile.x * TG_M, 2 * mat);
+          tma_prefetch_3d(&tmB, col, tile.y * TG_N, 2 * mat);
+        }
+      };
+      const int pf = ep.l2_prefetch;                        // chunks kept in flight towards L2 ahead of the stage
+      for (int kc = 1; kc <= pf && kc < nkc; ++kc) prefetch(kc);
       for (int kc = 0; kc < nkc; ++kc) {
         const int s = kc % TG_STAGES;
         const uint32_t ph = (kc / TG_STAGES) & 1;
+        if (pf > 0 && kc + pf + 1 <= nkc - 1) prefetch(kc + pf + 1);
         mbar_wait(empty_bar + 8 * s, ph ^ 1);
         mbar_expect_tx(full_bar + 8 * s, TG_STAGE_BYTES);
         if (kc < ncc) {
-          tma_load_3d(base + s * TG_STAGE_BYTES, &tmC, full_bar + 8 * s, tile.y * TG_N + kc * TG_KC, tile.x * TG_M,
-                      2 * (ep.c_mat_div > 0 ? mat / ep.c_mat_div : mat));
+          tma_load_3d(base + s * TG_STAGE_BYTES, &tmC, full_bar + 8 * s, tile.y * TG_N + kc * TG_KC, tile.x * TG_M, cmat);
           tma_load_3d(base + s * TG_STAGE_BYTES + TG_OP_BYTES, &tmI, full_bar + 8 * s, kc * TG_KC, 0, 0);
         } else {
           const int col = (tile.z + kc - ncc) * TG_KC;
@@ -259,42 +278,55 @@ tf32x3_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
         for (int j = 0; j < EC; ++j) if (c * EC + j > r_loc) o[j] = 0.f;
       }
-      if (ep.out || ep.out_t) {
-        float hi[EC];
+      // row-major outputs go through shared memory (below) so that a warp stores whole 512-byte rows; the transposed
+      // copies are already lane-coalesced (lanes hold consecutive rows) and leave from registers
+      {
+        float* st = reinterpret_cast<float*>(gen_base) + (size_t)q * (32 * TG_N) + (size_t)lane * TG_N;
+#pragma unroll
+        for (int j = 0; j < EC; j += 4) {
+          const int chunk = (c * EC + j) >> 2;                              // 16-byte chunk of the row, XOR-swizzled by the row
+          *reinterpret_cast<float4*>(st + 4 * (chunk ^ lane)) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        }
+      }
+      if (ep.out_t) {                                     // D^T as hi / lo planes: lanes of a warp hold consecutive rows
+        float* th = ep.out_t + 2 * mat_off + (int64_t)(col0 + c * EC) * n + row;
+        float* tl = th + n * n;
 #pragma unroll
         for (int j = 0; j < EC; ++j) {
           uint32_t t;
           asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(o[j]));
-          hi[j] = __uint_as_float(t);
-        }
-        if (ep.out) {                                       // D as hi / lo planes, row-major
-          float* oh = ep.out + 2 * mat_off + (int64_t)row * n + col0 + c * EC;
-          float* ol = oh + n * n;
-#pragma unroll
-          for (int j = 0; j < EC; j += 4) {
-            *reinterpret_cast<float4*>(oh + j) = make_float4(hi[j], hi[j + 1], hi[j + 2], hi[j + 3]);
-            *reinterpret_cast<float4*>(ol + j) = make_float4(o[j] - hi[j], o[j + 1] - hi[j + 1], o[j + 2] - hi[j + 2], o[j + 3] - hi[j + 3]);
-          }
-        }
-        if (ep.out_t) {                                     // D^T as hi / lo planes: lanes of a warp hold consecutive rows
-          float* th = ep.out_t + 2 * mat_off + (int64_t)(col0 + c * EC) * n + row;
-          float* tl = th + n * n;
-#pragma unroll
-          for (int j = 0; j < EC; ++j) {
-            th[(int64_t)j * n] = hi[j];
-            tl[(int64_t)j * n] = o[j] - hi[j];
-          }
+          const float hi = __uint_as_float(t);
+          th[(int64_t)j * n] = hi;
+          tl[(int64_t)j * n] = o[j] - hi;
         }
       }
-      if (ep.out_plain) {                                 // D as one FP32 plane (+ its mirror image for symmetric results)
-        float* po = ep.out_plain + mat_off + (int64_t)row * n + col0 + c * EC;
+      if (ep.out_plain && ep.mirror && !diag_tile) {      // mirror image of the plain plane (symmetric results)
+        float* pt = ep.out_plain + mat_off + (int64_t)(col0 + c * EC) * n + row;
 #pragma unroll
-        for (int j = 0; j < EC; j += 4) *reinterpret_cast<float4*>(po + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-        if (ep.mirror && !diag_tile) {
-          float* pt = ep.out_plain + mat_off + (int64_t)(col0 + c * EC) * n + row;
-#pragma unroll
-          for (int j = 0; j < EC; ++j) pt[(int64_t)j * n] = o[j];
+        for (int j = 0; j < EC; ++j) pt[(int64_t)j * n] = o[j];
+      }
+    }
+    // ---- row-major planes: warp q owns tile rows 32 q .. 32 q + 31; one row (128 floats) per store instruction
+    __syncwarp();
+    {
+      const float* stw = reinterpret_cast<const float*>(gen_base) + (size_t)q * (32 * TG_N);
+      float* oh = ep.out ? ep.out + 2 * mat_off + (int64_t)(tile.x * TG_M + q * 32) * n + col0 + lane * 4 : nullptr;
+      float* ol = oh ? oh + n * n : nullptr;
+      float* po = ep.out_plain ? ep.out_plain + mat_off + (int64_t)(tile.x * TG_M + q * 32) * n + col0 + lane * 4 : nullptr;
+#pragma unroll 4
+      for (int rr = 0; rr < 32; ++rr) {
+        const float4 v = *reinterpret_cast<const float4*>(stw + (size_t)rr * TG_N + 4 * (lane ^ rr));
+        if (oh) {
+          float4 h;
+          uint32_t t;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t);
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t);
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t);
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t);
+          *reinterpret_cast<float4*>(oh + (int64_t)rr * n) = h;
+          *reinterpret_cast<float4*>(ol + (int64_t)rr * n) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
         }
+        if (po) *reinterpret_cast<float4*>(po + (int64_t)rr * n) = v;
       }
     }
   }

@@ -28,6 +28,7 @@ struct rg_ctx {
   std::vector<double> prs;
   std::vector<double> last_stat;                               // [bs x P] of the last block (Firth / SPA)
   std::vector<uint8_t> inflate_probs, inflate_miss;
+  std::vector<uint8_t> stage[4];                               // rg_s2_stage slots (host copies)
   int last_bs = 0;
 };
 
@@ -326,5 +327,15 @@ int rg_bgen_inflate(rg_handle h, const uint8_t* comp, const uint64_t* offs, int6
   *miss = h->inflate_miss.data();
   return 0;
 }
+
+// staging: a plain copy into the slot (what the block call later reads is the bytes as they were when staged)
+int rg_s2_stage(rg_handle h, int32_t slot, const void* host, int64_t bytes, const uint8_t** dev) {
+  if (!h || !host || !dev || bytes <= 0 || slot < 0 || slot > 3) return fail("mock: bad staging arguments");
+  h->stage[slot].assign((const uint8_t*)host, (const uint8_t*)host + bytes);
+  *dev = h->stage[slot].data();
+  return 0;
+}
+int rg_host_alloc(void** p, int64_t bytes) { *p = malloc((size_t)bytes); return *p ? 0 : fail("mock: out of memory"); }
+int rg_host_free(void* p) { free(p); return 0; }
 
 }  // extern "C"
