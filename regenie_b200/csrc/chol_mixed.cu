@@ -485,16 +485,29 @@ mx_trisolve_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constan
     ts_mbar_wait(full_bar + 8 * s, ph);
     const float* t = tiles + (size_t)s * (TS_STAGE_BYTES / 4) + (size_t)(half * TS_CPP) * PT + row;
     const float* y = vec + (size_t)(half * TS_CPP) * TS_VP;
+    // packed FP32 FMAs (fma.rn.f32x2, two right-hand sides per instruction: same roundings as scalar fmaf): this sweep
+    // is issue-bound (profiles/ncu_r2k_*: 2.1 warp instructions per cycle and SM), a c step is 1 + 3 loads and PMAX / 2 FMAs
+    unsigned long long a2[PMAX / 2];
+#pragma unroll
+    for (int p = 0; p < PMAX / 2; ++p) asm("mov.b64 %0, {%1, %2};" : "=l"(a2[p]) : "f"(acc[2 * p]), "f"(acc[2 * p + 1]));
 #pragma unroll
     for (int c = 0; c < TS_CPP; ++c) {
       const float tv = t[(size_t)c * PT];
+      unsigned long long tv2;
+      asm("mov.b64 %0, {%1, %1};" : "=l"(tv2) : "f"(tv));
       const float4 y0 = *reinterpret_cast<const float4*>(y + c * TS_VP);
       const float4 y1 = *reinterpret_cast<const float4*>(y + c * TS_VP + 4);
       const float4 y2 = *reinterpret_cast<const float4*>(y + c * TS_VP + 8);
       const float yy[12] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w, y2.x, y2.y, y2.z, y2.w};
 #pragma unroll
-      for (int p = 0; p < PMAX; ++p) acc[p] = fmaf(tv, yy[p], acc[p]);
+      for (int p = 0; p < PMAX / 2; ++p) {
+        unsigned long long yp;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(yp) : "f"(yy[2 * p]), "f"(yy[2 * p + 1]));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a2[p]) : "l"(tv2), "l"(yp));
+      }
     }
+#pragma unroll
+    for (int p = 0; p < PMAX / 2; ++p) asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[2 * p]), "=f"(acc[2 * p + 1]) : "l"(a2[p]));
     __syncwarp();
     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_bar + 8 * s) : "memory");
     ++it;
@@ -666,7 +679,7 @@ int MixedSolver::launches_per_solve(int n, int steps, int P) {
 
 // Af: [K][n][n] FP64 full symmetric;  lambda: [R] (device);  bvec: [K][Pp][n];  xvec, rvec: [K*R][Pp][n]
 void MixedSolver::solve(const double* Af, const double* lambda, const double* bvec, double* xvec, double* rvec, int P,
-                        int steps, float tol, unsigned int* fail_flag, cudaStream_t s) {
+                        int steps, float tol, unsigned int* fail_flag, cudaStream_t s, bool first_col_ready) {
   Impl& d = *impl;
   const int n = d.n, nmat = d.nmat, nt = d.plan.nt;
   RG_CHECK(n > 0, "mixed solver: prepare() first");
@@ -701,7 +714,8 @@ void MixedSolver::solve(const double* Af, const double* lambda, const double* bv
     // the product with A negated, the ridge shift on the diagonal in the epilogue - no epilogue loads at all
     e.c_chunks = 4; e.c_mat_div = d.R;
     e.diag_add = lambda; e.diag_mod = d.R;
-    if (!sk_gemm) launch_tf32x3_gemm(d.tmL, d.tmL, tl + d.plan.upd[k].x, d.plan.upd[k].y, nmat, e, s, &d.tmAp, &d.tmI);
+    // panel step 0 has nothing to subtract: the assembler already wrote block column 0 of every system (first_col_ready)
+    if (!sk_gemm && !(k == 0 && first_col_ready)) launch_tf32x3_gemm(d.tmL, d.tmL, tl + d.plan.upd[k].x, d.plan.upd[k].y, nmat, e, s, &d.tmAp, &d.tmI);
     if (!sk_potrf) potrf128_kernel<<<nmat, 256, potrf_smem, s>>>(d.Lp.p, d.Wp.p, d.Mplain.p, d.MTplain.p, n, k, fail_flag);
     if (d.plan.trsm[k].y > 0) {
       Tf32GemmEpilogue t = e0;
@@ -760,6 +774,7 @@ void MixedSolver::solve(const double* Af, const double* lambda, const double* bv
 }
 
 float* MixedSolver::a_planes() { return impl->Ap.p; }
+float* MixedSolver::l_planes() { return impl->Lp.p; }
 
 const float* MixedSolver::debug_planes(int which) const {
   switch (which) {

@@ -48,6 +48,8 @@ struct AssembleArgs {
   int64_t cm_stride;
   int ldc;
   float* planes = nullptr;   // l0_assemble_sym only: FP32 hi / lo planes [K][2][n][n] of the same matrices (tensor-core operand)
+  float* lplanes = nullptr;  // l0_assemble_sym only: factor planes [K*R][2][n][n] of the mixed solver; their first 128 columns
+                             // receive A_f + lambda_r I (panel step 0 of the left-looking factorisation has nothing to subtract)
 };
 
 void launch_dbg_check_diag(const float* zz, int64_t ldz, int64_t fold_stride, const int32_t* cnt_fold, int rows_p,
@@ -129,8 +131,9 @@ class MixedSolver {
   // Af [K][n][n] FP64 full symmetric (no ridge shift) and its FP32 hi / lo planes Ap [K][2][n][n], lambda [R],
   // bvec [K][Pp][n]; xvec / rvec [K*R][Pp][n]
   float* a_planes();                          // where the assembler writes Ap (owned by the solver, valid after prepare)
+  float* l_planes();                          // factor planes: the assembler may fill block column 0 (first_col_ready)
   void solve(const double* Af, const double* lambda, const double* bvec, double* xvec, double* rvec, int P, int steps,
-             float tol, unsigned int* fail_flag, cudaStream_t s);
+             float tol, unsigned int* fail_flag, cudaStream_t s, bool first_col_ready = false);
   static int launches_per_solve(int n, int steps, int P);
   const float* debug_planes(int which) const;  // 0 L, 1 W, 2 W^T (hi/lo planes), 3 X
  private:

@@ -324,6 +324,15 @@ l0_assemble_sym_kernel(AssembleArgs a) {
           ph[(int64_t)i * a.ldc + j] = hi;
           pl[(int64_t)i * a.ldc + j] = (float)v - hi;
         }
+        if (a.lplanes && j < 128) {          // block column 0 of every ridge system of this fold: P_i0 = (A_f + lambda_r I)_i0
+          for (int r2 = 0; r2 < a.R; ++r2) {
+            const float w = (float)(i == j ? v + a.lambda[r2] : v);
+            const float hi = tf32_round(w);
+            float* lh = a.lplanes + (int64_t)(f * a.R + r2) * 2 * a.cm_stride + (int64_t)i * a.ldc + j;
+            lh[0] = hi;
+            lh[a.cm_stride] = w - hi;
+          }
+        }
       }
       tl[il][threadIdx.x] = v;
     }

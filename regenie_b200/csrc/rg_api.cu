@@ -334,6 +334,8 @@ static void enqueue_solve_mixed(rg_ctx* h, rg_ctx::Lane& L, const BlockDims& d, 
   aa.mu = L.mu.p; aa.inv_sd = L.inv_sd.p; aa.Bv = L.Bv.p; aa.Af = L.Af.p; aa.Qf = L.Qf.p;
   aa.lambda = h->lambda.p; aa.cm = L.mx_Af.p; aa.cm_stride = (int64_t)n * n; aa.ldc = n;
   aa.planes = L.mx->a_planes();
+  static const bool first_col = [] { const char* e = getenv("RG_B200_MX_FIRSTCOL"); return !(e && atoi(e) == 0); }();
+  if (first_col) aa.lplanes = L.mx->l_planes();
   {
     ScopedTimer t(h, "l0_assemble", s);
     launch_l0_assemble_sym(aa, L.rhs.p, P, Pp, L.mx_b.p, s);
@@ -341,8 +343,8 @@ static void enqueue_solve_mixed(rg_ctx* h, rg_ctx::Lane& L, const BlockDims& d, 
   }
   {
     ScopedTimer t(h, "mx_solve", s);
-    if (!dbg_skip("mxall")) L.mx->solve(L.mx_Af.p, h->lambda.p, L.mx_b.p, L.mx_x.p, L.mx_r.p, P, h->mx_steps, h->mx_tol, L.mx_fail.p, s);
-    h->launches += MixedSolver::launches_per_solve(n, h->mx_steps, P);
+    if (!dbg_skip("mxall")) L.mx->solve(L.mx_Af.p, h->lambda.p, L.mx_b.p, L.mx_x.p, L.mx_r.p, P, h->mx_steps, h->mx_tol, L.mx_fail.p, s, first_col);
+    h->launches += MixedSolver::launches_per_solve(n, h->mx_steps, P) - (first_col ? 1 : 0);
   }
 }
 

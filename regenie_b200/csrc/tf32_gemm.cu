@@ -26,7 +26,7 @@ namespace {
 
 constexpr int TG_M = 128, TG_N = 128;
 constexpr int TG_KC = 32;                          // floats per K chunk = one 128-byte swizzle atom
-constexpr int TG_STAGES = 1;                          // one 64 KiB stage per CTA, THREE CTAs per SM: the tiles of this
+// TG_STAGES is a template parameter: 1 (default) = one 64 KiB stage per CTA, THREE CTAs per SM: the tiles of this
                                                    // solver are short (K <= 1024) and the launches small, so latency is hidden
                                                    // across co-resident CTAs instead of a deep per-CTA ring (profiles/ncu_r2c_*)
 constexpr int TG_PLANE_BYTES = TG_M * 128;         // 16 KiB
@@ -123,7 +123,8 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
 }  // namespace
 
 // grid: (ntiles, batch); tile entry = (A row tile, B row tile, first K chunk, number of K chunks)
-__global__ void __launch_bounds__(TG_THREADS, 3)
+template <int TG_STAGES>
+__global__ void __launch_bounds__(TG_THREADS, TG_STAGES == 1 ? 3 : 1)
 tf32x3_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmI,
                       const int4* __restrict__ tiles, Tf32GemmEpilogue ep) {
@@ -393,10 +394,20 @@ void launch_tf32x3_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const in
                         const Tf32GemmEpilogue& ep, cudaStream_t s, const CUtensorMap* tmC, const CUtensorMap* tmI) {
   RG_CHECK(ep.c_chunks == 0 || (tmC && tmI), "tf32 gemm: the C phase needs its tensor maps");
   if (ntiles <= 0 || batch <= 0) return;
-  constexpr size_t smem = (size_t)TG_STAGES * TG_STAGE_BYTES + 1024 + 128;
-  ensure_dyn_smem(reinterpret_cast<const void*>(tf32x3_gemm_nt_kernel), smem);
+  // RG_B200_MX_STAGES = 1 (default: three co-resident CTAs hide the TMA latency) | 2 | 3 (one CTA per SM with a deeper ring)
+  static const int nst = [] { const char* e = getenv("RG_B200_MX_STAGES"); const int v = e ? atoi(e) : 1; return (v == 2 || v == 3) ? v : 1; }();
+  const size_t smem = (size_t)nst * TG_STAGE_BYTES + 1024 + 128;
   dim3 grid(ntiles, batch);
-  tf32x3_gemm_nt_kernel<<<grid, TG_THREADS, smem, s>>>(tmA, tmB, tmC ? *tmC : tmA, tmI ? *tmI : tmB, tiles, ep);
+  if (nst == 1) {
+    ensure_dyn_smem(reinterpret_cast<const void*>(tf32x3_gemm_nt_kernel<1>), smem);
+    tf32x3_gemm_nt_kernel<1><<<grid, TG_THREADS, smem, s>>>(tmA, tmB, tmC ? *tmC : tmA, tmI ? *tmI : tmB, tiles, ep);
+  } else if (nst == 2) {
+    ensure_dyn_smem(reinterpret_cast<const void*>(tf32x3_gemm_nt_kernel<2>), smem);
+    tf32x3_gemm_nt_kernel<2><<<grid, TG_THREADS, smem, s>>>(tmA, tmB, tmC ? *tmC : tmA, tmI ? *tmI : tmB, tiles, ep);
+  } else {
+    ensure_dyn_smem(reinterpret_cast<const void*>(tf32x3_gemm_nt_kernel<3>), smem);
+    tf32x3_gemm_nt_kernel<3><<<grid, TG_THREADS, smem, s>>>(tmA, tmB, tmC ? *tmC : tmA, tmI ? *tmI : tmB, tiles, ep);
+  }
 }
 
 }  // namespace rg
