@@ -77,6 +77,7 @@ potrf128_kernel(float* __restrict__ Lp, float* __restrict__ Wp, float* __restric
   float* Wm = pt_sm + PT * PLD;
   float* Wq = pt_sm + 2 * PT * PLD;
   float* dinv = pt_sm + 3 * PT * PLD;                    // reciprocal diagonal of L
+  float* lcol = dinv + PT;                               // [2][PB] current column of the 32 x 32 register Cholesky
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t plane = (int64_t)n * n;
   const int64_t moff = (int64_t)blockIdx.x * 2 * plane + (int64_t)k * PT * n + (int64_t)k * PT;
@@ -107,7 +108,9 @@ potrf128_kernel(float* __restrict__ Lp, float* __restrict__ Wp, float* __restric
 #pragma unroll
       for (int c = 0; c < PB; ++c) a[c] = (c <= lane) ? S[(j0 + lane) * PLD + j0 + c] : 0.f;
       // software-pipelined pivot chain: the NEXT pivot A[c+1][c+1] - L[c+1][c]^2 is formed by its own lane and broadcast
-      // before the bulk of column c's rank-1 update is issued, so rsqrt + broadcast latency hides behind that update
+      // before the bulk of column c's rank-1 update is issued, so rsqrt + broadcast latency hides behind that update.
+      // The column itself reaches the other lanes through shared memory (one store, eight broadcast 128-bit loads,
+      // double-buffered by column parity) instead of 31 - c shuffles: the chain is bound by the shuffle / LSU pipe.
       float d = __shfl_sync(0xffffffffu, a[0], 0);
 #pragma unroll
       for (int c = 0; c < PB; ++c) {
@@ -117,11 +120,19 @@ potrf128_kernel(float* __restrict__ Lp, float* __restrict__ Wp, float* __restric
         const float l = a[c] * inv;
         a[c] = l;
         if (lane == c) dinv[j0 + c] = inv;
-        if (c + 1 < PB) d = __shfl_sync(0xffffffffu, fmaf(-l, l, a[c + 1]), c + 1);   // lane c+1: l = L[c+1][c]
+        if (c + 1 < PB) {
+          float* lb = lcol + (c & 1) * PB;
+          lb[lane] = l;
+          d = __shfl_sync(0xffffffffu, fmaf(-l, l, a[c + 1]), c + 1);   // lane c+1: l = L[c+1][c]; also orders the store
+          __syncwarp();
+          float lv[PB];
 #pragma unroll
-        for (int cc = c + 1; cc < PB; ++cc) {
-          const float lcc = __shfl_sync(0xffffffffu, l, cc);
-          a[cc] = fmaf(-l, lcc, a[cc]);
+          for (int q = (c + 1) / 4; q < PB / 4; ++q) {
+            const float4 t4 = *reinterpret_cast<const float4*>(lb + 4 * q);
+            lv[4 * q] = t4.x; lv[4 * q + 1] = t4.y; lv[4 * q + 2] = t4.z; lv[4 * q + 3] = t4.w;
+          }
+#pragma unroll
+          for (int cc = c + 1; cc < PB; ++cc) a[cc] = fmaf(-l, lv[cc], a[cc]);
         }
       }
 #pragma unroll
@@ -685,7 +696,7 @@ void MixedSolver::solve(const double* Af, const double* lambda, const double* bv
   RG_CHECK(n > 0, "mixed solver: prepare() first");
   RG_CHECK(P <= d.Pp, "mixed solver: more right-hand sides than the row pitch");
   RG_CHECK(steps >= 1 && steps <= kMxMaxSteps, "mixed solver: bad step count");
-  const size_t potrf_smem = ((size_t)3 * PT * PLD + PT) * sizeof(float);
+  const size_t potrf_smem = ((size_t)3 * PT * PLD + PT + 2 * PB) * sizeof(float);
   ensure_dyn_smem(reinterpret_cast<const void*>(potrf128_kernel), potrf_smem);
   ensure_dyn_smem(reinterpret_cast<const void*>(mx_residual_kernel<12>), 98304);
   ensure_dyn_smem(reinterpret_cast<const void*>(mx_residual_kernel<10>), 98304);
