@@ -715,8 +715,8 @@ void MixedSolver::solve(const double* Af, const double* lambda, const double* bv
   const int4* tl = d.plan.tiles.p;
   Tf32GemmEpilogue e0{};
   e0.n = n; e0.out_mat_stride = (int64_t)n * n;
-  static const int l2pf = [] { const char* e = getenv("RG_B200_MX_L2PF"); return e ? std::max(0, std::min(8, atoi(e))) : 3; }();
-  e0.l2_prefetch = l2pf;
+  static const int l2pf = [] { const char* e = getenv("RG_B200_MX_L2PF"); return e ? std::max(0, std::min(8, atoi(e))) : 0; }();
+  e0.l2_prefetch = l2pf;       // measured: no gain (0 / 3 / 6 chunks ahead: 38.3 / 39.0 / 40.6 ms per step, profiles/ab_r2m_solver_variants.txt)
   // ---- factorisation: left-looking, 128-wide panels
   for (int k = 0; k < nt; ++k) {
     Tf32GemmEpilogue e = e0;

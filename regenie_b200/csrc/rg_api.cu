@@ -391,8 +391,8 @@ static void enqueue_predict(rg_ctx* h, rg_ctx::Lane& L, const BlockDims& d, cons
     ta.npad = Npad; ta.tile_fold = h->tile_fold.p; ta.scale = L.dscale.p; ta.cvec = L.cvec.p;
     ta.xy = h->xy.p; ta.mask = h->mask.p; ta.W = h->W_tab.p; ta.part = L.part.p;
     ta.dbg = nullptr;
-    static const int pred_pf = [] { const char* e = getenv("RG_B200_PREDICT_L2PF"); return e ? std::max(0, std::min(8, atoi(e))) : 4; }();
-    ta.l2_prefetch = pred_pf;
+    static const int pred_pf = [] { const char* e = getenv("RG_B200_PREDICT_L2PF"); return e ? std::max(0, std::min(8, atoi(e))) : 0; }();
+    ta.l2_prefetch = pred_pf;       // measured: no gain (profiles/ab_r2m_solver_variants.txt)
     if (!use_i8 && getenv("RG_DBG_CLK")) { h->dbg_clk.alloc((size_t)d.ntiles_s * ngroups * 4); ta.dbg = h->dbg_clk.p; }
     if (!dbg_skip("predict")) {
       if (use_i8) launch_l0_predict_i8(L.tmaps[d.rows_p], L.dmaps[d.rows_p], ta, d.ntiles_s, s);
