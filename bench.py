@@ -453,7 +453,7 @@ def run_gpu(args):
         "metric": "step1_level0_snps_per_sec", "value": value, "unit": "SNPs/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "e4m3 Gram (exact) + tf32x3 factorisation + f64 refinement / statistics",
+        "dtype": "e4m3 Gram + int8 prediction (both exact integer sums) + tf32x3 factorisation + f64 refinement / statistics",
         "data": "synthetic", "config": workload_config() if not (args.small or args.n_samples or args.n_pheno) else {"workload": "NOT the benchmark configuration (smoke / exploration run)", "n_samples": N, "n_snps": M, "n_pheno": P},
         "clocks": clk,
         "e2e": {"value": e2e_val, "unit": "SNPs/s", "ms_per_step": ms_e2e / args.steps,

@@ -79,3 +79,42 @@ def test_s2_qt_fifty_traits(tmp_path):
     """BASELINE configs[4] trait count: 254 feature columns = 19 digit groups = 10 column tiles on the tensor-core path."""
     n, ns = run_case(tmp_path, N=700, M=256, P=50, miss=0.02)
     assert n > 200
+
+
+def test_staged_input_gives_the_same_rows(tmp_path):
+    """rg_s2_stage: the rows of block b+1 copied on the copy stream while block b is tested (pinned memory from
+    rg_host_alloc) - every output equal, bit for bit, to the call that copies its own rows."""
+    import ctypes as C
+    from regenie_b200 import capi, synth
+    N, M, P, bs = 3000, 768, 3, 256
+    g = synth.genotypes(N, M, seed=3, miss=0.02)
+    Y, cov, na = synth.phenotypes(g, P, 3, seed=3, na_frac=0.03)
+    prefix = helpers.write_fileset(str(tmp_path), g, Y, cov, na)
+    bim = plink.read_bim(prefix + ".bim")
+    keys, _ = plink.read_fam(prefix + ".fam")
+    pr = prep.prepare(keys, str(tmp_path) + "/pheno.txt", str(tmp_path) + "/covar.txt", step=2)
+    res, p_sd, scf = step2.compute_res(pr.Y, np.zeros_like(pr.Y), pr.mask, pr.neff, pr.ncov, pr.scale_Y)
+    st = capi.Step2(pr.X, pr.mask, pr.in_analysis, pr.n_analyzed, bs)
+    st.set_chr(res, scf)
+    packed = np.ascontiguousarray(plink.read_bed_rows(prefix + ".bed", len(keys), bim.offset))
+    stride = packed.shape[1]
+    plain = [st.block_bed(packed[s:s + bs]) for s in range(0, M, bs)]
+    L = capi.lib()
+    L.rg_host_alloc.argtypes = [C.c_void_p, C.c_int64]
+    L.rg_host_free.argtypes = [C.c_void_p]
+    hp = C.c_void_p()
+    capi.check(L.rg_host_alloc(C.byref(hp), packed.nbytes))
+    try:
+        C.memmove(hp, packed.ctypes.data, packed.nbytes)
+        nb = M // bs
+        nxt = st.stage(0, hp.value, bs * stride)
+        for b in range(nb):
+            cur = nxt
+            if b + 1 < nb:
+                nxt = st.stage((b + 1) & 1, hp.value + (b + 1) * bs * stride, bs * stride)
+            o = st.block_bed_raw(cur, bs, stride)
+            for k in ("af", "ns", "mac", "af_all", "ns_all", "flags", "stat", "beta", "se", "chisq"):
+                assert np.array_equal(o[k], plain[b][k]), (k, b)
+    finally:
+        capi.check(L.rg_host_free(hp))
+    st.close()
