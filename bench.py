@@ -146,8 +146,12 @@ def cpu_level0_blocks(packed_rows_list, N, X, Y, mask, in_an, fsz, lam, neff, th
 def calibrate_threads(rows, N, X, Y, mask, in_an, fsz, lam, neff):
     """Eigen's OpenMP GEMM does not scale to every hardware thread of a big host (128 threads: 94 s per block, slower
     than 8).  Time one block at a few thread counts and keep the fastest: the CPU arm gets its best configuration."""
-    nthr = host_threads()
-    cands = sorted({max(1, nthr // 8), max(1, nthr // 4), max(1, nthr // 2)})
+    q = cpu_quota()
+    if q:                                          # around the quota: fewer, exactly, and oversubscribed
+        cands = sorted({max(1, q // 2), q, min(hw_threads(), 2 * q)})
+    else:
+        nthr = hw_threads()
+        cands = sorted({max(1, nthr // 8), max(1, nthr // 4), max(1, nthr // 2)})
     if os.environ.get("OMP_NUM_THREADS"):          # torchrun pins this to 1; the CPU arm is a separate measurement
         os.environ.pop("OMP_NUM_THREADS")
     best, log = None, []
@@ -166,11 +170,41 @@ def cpu_baseline_desc(phases, dt, nblocks, bs, N, threads):
             % (nblocks, bs, N, ref_eigen.build_info(), threads, dt, phases[0], phases[1], phases[2], phases[3]))
 
 
-def host_threads():
+def cpu_quota():
+    """CPUs the container may use at once (cgroup v2 cpu.max / v1 cfs quota), or None when unlimited.  The GPU boxes of this
+    pool show 128 hardware threads but cpu.max = "1600000 100000": 16 CPUs - more threads than that only time-share."""
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            return max(1, int(math.ceil(float(q) / float(per))))
+    except Exception:
+        pass
+    try:
+        q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if q > 0:
+            return max(1, int(math.ceil(q / per)))
+    except Exception:
+        pass
+    return None
+
+
+def hw_threads():
     try:
         return len(os.sched_getaffinity(0))
     except Exception:
         return os.cpu_count() or 1
+
+
+def host_threads():
+    """Threads the CPU arm can really run concurrently: hardware threads in the affinity mask, capped by the cgroup quota."""
+    q = cpu_quota()
+    return min(hw_threads(), q) if q else hw_threads()
+
+
+def host_desc():
+    q = cpu_quota()
+    return "%d hardware threads visible, cgroup CPU quota %s" % (hw_threads(), ("%d CPUs" % q) if q else "none")
 
 
 # ----------------------------------------------------------------------------- main arms
@@ -205,7 +239,7 @@ def run_reference(args):
         "config": workload_config(),
         "cpu_baseline": {"value": val, "unit": "SNPs/s", "cores": cores, "kind": "port",
                          "sample": "one 1000-SNP block per step; " + cpu_baseline_desc(phases, tot, len(times), bs, N, cores)
-                                   + "; thread-count calibration on one block (fastest kept, of %d hardware threads): %s" % (host_threads(), calib)},
+                                   + "; thread-count calibration on one block (fastest kept; %s): %s" % (host_desc(), calib)},
         "e2e": {"value": val, "unit": "SNPs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -438,7 +472,7 @@ def run_gpu(args):
         nsnp, dt, W_cpu, phases = cpu_level0_blocks(rows, N, X, Y, mask, in_an, fsz, lam, neff, threads=thr)
         cpu = {"value": nsnp / dt, "unit": "SNPs/s", "cores": thr, "kind": "port",
                "sample": cpu_baseline_desc(phases, dt, len(rows), bs, N, thr)
-                         + "; thread-count calibration on one block (fastest kept, of %d hardware threads): %s" % (host_threads(), calib)}
+                         + "; thread-count calibration on one block (fastest kept; %s): %s" % (host_desc(), calib)}
         # parity on the benchmarked configuration: block 0 of the timed panel, every predictor column, GPU vs Eigen
         err = 0.0
         for p in range(P):

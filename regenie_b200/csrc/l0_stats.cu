@@ -355,129 +355,6 @@ l0_assemble_sym_kernel(AssembleArgs a) {
   }
 }
 
-// The same matrices for K <= KT folds with everything that indexes a fold unrolled: the per-fold values stay in registers
-// (the generic kernel above keeps gf[4][kMaxFolds] in local memory), the transposed Miss x G0 tiles of ALL folds are staged with
-// one barrier, every load of the first phase is issued before the first use, and the mirror image goes through a double-buffered
-// shared tile (one barrier per fold instead of two).  grid: lower-triangle 32 x 32 tiles only (tile list index = blockIdx.x).
-template <int KT>
-__global__ void __launch_bounds__(256)
-l0_assemble_sym_unrolled_kernel(AssembleArgs a) {
-  // blockIdx.x -> (ti, tj) with ti >= tj: row-major enumeration of the lower triangle
-  int ti = (int)((sqrtf(8.f * (float)blockIdx.x + 1.f) - 1.f) * 0.5f);
-  while ((ti + 1) * (ti + 2) / 2 <= (int)blockIdx.x) ++ti;
-  while (ti * (ti + 1) / 2 > (int)blockIdx.x) --ti;
-  const int tj = (int)blockIdx.x - ti * (ti + 1) / 2;
-  __shared__ float mgT[KT][32][33];
-  __shared__ double tl[2][32][33];
-  const int K = a.K, C = a.C;
-  const int j = tj * 32 + threadIdx.x;
-  const int64_t ldz = a.ldz;
-  const bool jv = j < a.bs;
-  const double mu_j = jv ? a.mu[j] : 0.0, isd_j = jv ? a.inv_sd[j] : 0.0;
-#pragma unroll
-  for (int f = 0; f < KT; ++f) {
-    if (f < K) {
-      const float* zz = a.zz + (int64_t)f * a.zz_fold_stride;
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int jj = tj * 32 + threadIdx.y * 4 + r, ii = ti * 32 + threadIdx.x;
-        mgT[f][threadIdx.y * 4 + r][threadIdx.x] = (jj < a.bs && ii < a.bs) ? zz[(int64_t)(a.rows_p + jj) * ldz + ii] : 0.f;
-      }
-    }
-  }
-  // integer Grams of this thread's four rows, all folds: loads first
-  float gg[4][KT], mg[4][KT], mm[4][KT];
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int i = ti * 32 + threadIdx.y * 4 + r;
-    const bool act = i >= j && i < a.bs;
-#pragma unroll
-    for (int f = 0; f < KT; ++f) {
-      gg[r][f] = mg[r][f] = mm[r][f] = 0.f;
-      if (act && f < K) {
-        const float* zz = a.zz + (int64_t)f * a.zz_fold_stride;
-        gg[r][f] = zz[(int64_t)i * ldz + j];
-        mg[r][f] = zz[(int64_t)(a.rows_p + i) * ldz + j];
-        mm[r][f] = zz[(int64_t)(a.rows_p + i) * ldz + a.rows_p + j];
-      }
-    }
-  }
-  __syncthreads();
-  double gsum[4] = {0, 0, 0, 0};
-  double gf[4][KT];
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int il = threadIdx.y * 4 + r;
-    const int i = ti * 32 + il;
-    const bool act = i >= j && i < a.bs;
-    const double mu_i = act ? a.mu[i] : 0.0, isd_i = act ? a.inv_sd[i] : 0.0;
-#pragma unroll
-    for (int f = 0; f < KT; ++f) {
-      double v = 0.0;
-      if (act && f < K) {
-        double t = (double)gg[r][f] + mu_i * (double)mg[r][f] + mu_j * (double)mgT[f][threadIdx.x][il] + mu_i * mu_j * (double)mm[r][f];
-        const double* Afi = a.Af + ((int64_t)f * a.rows_p + i) * C;
-        const double* Afj = a.Af + ((int64_t)f * a.rows_p + j) * C;
-        const double* Qfj = a.Qf + ((int64_t)f * a.rows_p + j) * C;
-        const double* Bi = a.Bv + (int64_t)i * C;
-        const double* Bj = a.Bv + (int64_t)j * C;
-        for (int c = 0; c < C; ++c) t += -Afi[c] * Bj[c] - Bi[c] * Afj[c] + Bi[c] * Qfj[c];
-        v = t * isd_i * isd_j;
-      }
-      gf[r][f] = v;
-      gsum[r] += v;
-    }
-  }
-#pragma unroll
-  for (int f = 0; f < KT; ++f) {
-    if (f < K) {
-      double* out = a.cm + (int64_t)f * a.cm_stride;
-      float* ph = a.planes ? a.planes + (int64_t)f * 2 * a.cm_stride : nullptr;      // hi plane, lo plane behind it
-      float* pl = ph ? ph + a.cm_stride : nullptr;
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int il = threadIdx.y * 4 + r;
-        const int i = ti * 32 + il;
-        double v = 0.0;
-        if (i >= j) v = (i < a.bs) ? gsum[r] - gf[r][f] : (i == j ? 1.0 : 0.0);
-        if (i >= j) {
-          out[(int64_t)i * a.ldc + j] = v;
-          if (ph) {
-            const float hi = tf32_round((float)v);
-            ph[(int64_t)i * a.ldc + j] = hi;
-            pl[(int64_t)i * a.ldc + j] = (float)v - hi;
-          }
-          if (a.lplanes && j < 128) {          // block column 0 of every ridge system of this fold: P_i0 = (A_f + lambda_r I)_i0
-            for (int r2 = 0; r2 < a.R; ++r2) {
-              const float w = (float)(i == j ? v + a.lambda[r2] : v);
-              const float hi = tf32_round(w);
-              float* lh = a.lplanes + (int64_t)(f * a.R + r2) * 2 * a.cm_stride + (int64_t)i * a.ldc + j;
-              lh[0] = hi;
-              lh[a.cm_stride] = w - hi;
-            }
-          }
-        }
-        tl[f & 1][il][threadIdx.x] = v;
-      }
-      __syncthreads();
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int jl = threadIdx.y * 4 + r;
-        const int i2 = ti * 32 + threadIdx.x, j2 = tj * 32 + jl;
-        if (i2 > j2) {
-          const double v = tl[f & 1][threadIdx.x][jl];
-          out[(int64_t)j2 * a.ldc + i2] = v;
-          if (ph) {
-            const float hi = tf32_round((float)v);
-            ph[(int64_t)j2 * a.ldc + i2] = hi;
-            pl[(int64_t)j2 * a.ldc + i2] = (float)v - hi;
-          }
-        }
-      }
-    }
-  }
-}
-
 // bvec[f][p][i] = rhs_f[i][p]  (zero beyond bs / P).  grid: (ceil(n/256), Pp, K)
 __global__ void l0_rhs_sym_kernel(const double* __restrict__ rhs, int rows_p, int bs, int P, int n, double* __restrict__ bvec) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -543,14 +420,10 @@ void launch_l0_assemble(const AssembleArgs& a, const double* rhs, int P, int Ppa
 }
 
 void launch_l0_assemble_sym(const AssembleArgs& a, const double* rhs, int P, int Pp, double* bvec, cudaStream_t s) {
-  static const bool generic = [] { const char* e = getenv("RG_B200_ASSEMBLE"); return e && std::string(e) == "generic"; }();
-  const int nt = a.nC / 32;
-  if (a.K <= 5 && !generic) {
-    l0_assemble_sym_unrolled_kernel<5><<<nt * (nt + 1) / 2, dim3(32, 8), 0, s>>>(a);
-  } else {
-    dim3 grid(nt, nt);
-    l0_assemble_sym_kernel<<<grid, dim3(32, 8), 0, s>>>(a);
-  }
+  // (a fold-unrolled variant with every per-fold value in registers and one barrier for all transposed tiles measured
+  // SLOWER under lane overlap - 40.8 vs 38.3 ms per step, profiles/ab_r2n_assemble.txt: 128 registers, 2 CTAs per SM)
+  dim3 grid(a.nC / 32, a.nC / 32);
+  l0_assemble_sym_kernel<<<grid, dim3(32, 8), 0, s>>>(a);
   dim3 g2((unsigned)ceil_div(a.nC, 256), Pp, a.K);
   l0_rhs_sym_kernel<<<g2, 256, 0, s>>>(rhs, a.rows_p, a.bs, P, a.nC, bvec);
 }
