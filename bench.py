@@ -496,8 +496,8 @@ def run_gpu(args):
         "roofline": {"kernel": "gram_fp8_tcgen05_kernel", "bound": "tensor", "achieved": ach, "peak": peak,
                      "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                      "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-                                     "(profiles/ncu_r1n_key_kernels.txt); algorithmic bytes = 205 MB of Z planes + "
-                                     "47 MB of Gram tiles",
+                                     "(profiles/ncu_r2o_key_kernels.txt, else ncu_r1n_key_kernels.txt); algorithmic bytes = 205 MB of "
+                                     "Z planes + 47 MB of Gram tiles",
                      "executed_frac": 2.0 * ach / peak, "tensor_pipe_active_ncu": pipe_active,
                      "peak_basis": "2 x %s bf16 cuBLAS rate (%s TF/s) = dense FP8" % (peak_src, peak_bf16),
                      "algorithmic_flops_per_launch": flops_per_launch,
@@ -779,11 +779,13 @@ def step2_bt_leg(capi, X, in_an, N, C, args, nvar=400, nblocks=4):
 def gram_traffic_from_profile():
     """DRAM bytes per launch and tensor-pipe activity of the Gram kernel from the committed ncu --set full summary
     (bench.py cannot run under a profiler; the capture command is tools/ncu_capture.sh)."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_r1n_key_kernels.txt")
-    try:
-        blocks = open(path).read().split("---\n")
-    except OSError:
-        return None, None
+    blocks = []
+    for name in ("ncu_r2o_key_kernels.txt", "ncu_r1n_key_kernels.txt"):      # newest committed capture first
+        try:
+            blocks = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", name)).read().split("---\n")
+            break
+        except OSError:
+            continue
     for b in blocks:
         if "gram_fp8_tcgen05_kernel" not in b or "launch__grid_size" not in b:
             continue
