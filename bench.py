@@ -588,6 +588,24 @@ def hbm_roofline(rate, bytes_per_variant, what):
             "rate_used": "device-resident variants/s x algorithmic bytes per variant (%s)" % what}
 
 
+def s2_tensor_roofline(rate, N, P, C):
+    """What really bounds the hard-call Step-2 path: with per-trait masks a variant needs D = 1 + C + 2P + PC exact sums over
+    its N calls (not one pass over N/4 bytes), done as FP8 tensor tiles against 9 radix-30 digit rows per feature column for the
+    three planes g0, g0^2, missing (csrc/s2_kernels.cu, s2_api.cu: digit rows padded to 14 columns per 128-row group)."""
+    peaks, src = load_peaks()
+    D = 1 + C + 2 * P + P * C
+    drows = int(math.ceil(math.ceil(D / 14.0) * 128 / 256.0) * 256)
+    executed = 2.0 * N * 3 * drows                      # flops per variant on the tensor pipe
+    peak = 2.0 * (peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops"))
+    tf = rate * executed / 1e12
+    return {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+            "executed_flops_per_variant": executed, "feature_columns": D, "digit_rows": drows,
+            "algorithmic_flops_per_variant": 2.0 * N * D,
+            "peak_basis": "2 x %s sustained bf16 cuBLAS rate = dense FP8" % src,
+            "note": "the HBM line above is SURVEY 8(d)'s scan bound (N/4 bytes per variant); at %d traits the exact digit-plane "
+                    "tiles are the binding resource, not the bytes" % P}
+
+
 def step2_qt_leg(capi, X, mask, in_an, N, P, C, bs, blocks, host_panel, dev_ptr, stride, args):
     """Step-2 QT score test on the benchmark panel's .bed rows (compute_score_qt, src/Step2_Models.cpp:343-467)."""
     from oracle import ref_eigen
@@ -647,6 +665,7 @@ def step2_qt_leg(capi, X, mask, in_an, N, P, C, bs, blocks, host_panel, dev_ptr,
                     "note": "staged = rg_s2_stage copies block b+1 on a copy stream under the kernels of block b; unstaged = "
                             "the block call copies its own rows first"},
             "roofline": hbm_roofline(dev_rate, N / 4.0, "N/4 bytes of 2-bit calls"),
+            "tensor_roofline": s2_tensor_roofline(dev_rate, N, P, C),
             "cpu_baseline": cpu,
             "sample": "%d blocks of %d variants, N=%d, %d traits; value = .bed rows resident in HBM, e2e = pinned host rows; "
                       "both through rg_s2_block_bed (synchronous call, per-variant statistics copied back every block)" % (nb2, bs, N, P)}

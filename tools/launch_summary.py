@@ -12,6 +12,8 @@ ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
 data = [(r[ki].split("(")[0], float(r[vi].replace(",", ""))) for r in rows[hi + 1:] if len(r) > vi]
 idx = [i for i, (k, v) in enumerate(data) if "bed_relayout" in k]
 blk = data[idx[-1]:]
+if len(idx) >= 2 and not any('l0_std_apply' in k for k, v in blk):      # capture ended inside the last block: take the one before
+    blk = data[idx[-2]:idx[-1]]
 tot = collections.OrderedDict()
 for k, v in blk:
     tot.setdefault(k, [0.0, 0])
