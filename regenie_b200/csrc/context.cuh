@@ -163,6 +163,7 @@ struct rg_ctx {
   rg::DevBuf<double> bt_F, bt_w, bt_gs, bt_xw, bt_off, bt_coltot, bt_xwy, bt_part, bt_sums, bt_nnz, bt_n510;
   rg::DevBuf<double> bt_xtwg, bt_mu, bt_info, firth_gvec, firth_out, bt_den, bt_phat;
   rg::DevBuf<int8_t> bt_ym, firth_cflag;
+  rg::DevBuf<int2> bt_cnt_part;      // [chunk][rows_p] non-zero / hom-alt counts of the dosage statistics kernel
   rg::DevBuf<int32_t> firth_sel, firth_status;
 
   // ---- level-0 solver selection (RG_B200_SOLVER = mixed | f64) and its counters

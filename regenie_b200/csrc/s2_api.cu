@@ -367,7 +367,8 @@ static void s2_block_bgen8_bt(rg_ctx* h, const uint8_t* probs, const uint8_t* mi
   h->s2_out_d.alloc(nd);
   h->s2_out_i.alloc(ni);
   launch_dosage_relayout(probs_d, miss_d, n_file, bs, rows_p, h->file_idx_pad.p, ref_first, h->dz.p, Npad, s);
-  launch_dosage_stats(h->dz.p, Npad, h->bt_F.p, dp, h->chunks.p, h->nchunks, rows_p, h->bt_part.p, h->bt_sums.p,
+  h->bt_cnt_part.alloc((size_t)h->nchunks * h->rows_p_max);
+  launch_dosage_stats(h->dz.p, Npad, h->bt_F.p, dp, h->chunks.p, h->nchunks, rows_p, h->bt_part.p, h->bt_cnt_part.p, h->bt_sums.p,
                       h->bt_nnz.p, h->bt_n510.p, s);
   S2BtFinalizeArgs a;
   a.bs = bs; a.C = C; a.P = P; a.dp = dp; a.with_flip = 1;
@@ -443,7 +444,8 @@ static void s2_block_bgen8_qt(rg_ctx* h, const uint8_t* probs, const uint8_t* mi
   h->s2_out_d.alloc(nd);
   h->s2_out_i.alloc(ni);
   launch_dosage_relayout(probs_d, miss_d, n_file, bs, rows_p, h->file_idx_pad.p, ref_first, h->dz.p, Npad, s);
-  launch_dosage_stats(h->dz.p, Npad, h->F.p, dp, h->chunks.p, h->nchunks, rows_p, h->bt_part.p, h->bt_sums.p,
+  h->bt_cnt_part.alloc((size_t)h->nchunks * h->rows_p_max);
+  launch_dosage_stats(h->dz.p, Npad, h->F.p, dp, h->chunks.p, h->nchunks, rows_p, h->bt_part.p, h->bt_cnt_part.p, h->bt_sums.p,
                       h->bt_nnz.p, h->bt_n510.p, s);
   launch_dosage_scale(h->bt_sums.p, rows_p, dp, h->s2_sums.p, h->bt_xtwg.p, s);
   S2FinalizeArgs a;

@@ -17,79 +17,132 @@ constexpr int kDzCols = 16;
 constexpr int kDzSub = 128;
 
 // BGEN probability rows [bs][n_file][2] (+ optional ploidy/missing bytes [bs][n_file]) -> padded sample
-// layout, one uint32 per sample: d (bits 0-9) | e (bits 10-20) | missing (bit 31).  grid: (Npad/256, rows_p)
+// layout, one uint32 per sample: d (bits 0-9) | e (bits 10-20) | missing (bit 31).
+__device__ __forceinline__ uint32_t dosage_word(uint32_t p0, uint32_t p1, bool m, int ref_first) {
+  if (m) return 0x80000000u;
+  // ref-last: g = p1 + 2 p0 (allele0 is ALT);  ref-first: g = p1 + 2 p2, p2 = 255 - p0 - p1 (>= 0)
+  const uint32_t p2 = (p0 + p1 <= 255u) ? 255u - p0 - p1 : 0u;
+  const uint32_t hom = ref_first ? p2 : p0;
+  return (p1 + 2u * hom) | ((4u * hom + p1) << 10);
+}
+
+// grid: (Npad/1024, rows_p), block 256: four consecutive padded samples per thread.  Almost every quad maps to four
+// CONSECUTIVE samples of the file row (folds only shift ranges, --remove breaks a quad here and there): those take one
+// 8-byte probability load, one 4-byte ploidy load and one 16-byte store when the addresses are aligned.
 __global__ void dosage_relayout_kernel(const uint8_t* __restrict__ probs, const uint8_t* __restrict__ miss,
                                        int64_t n_file, int bs, const int32_t* __restrict__ file_idx_pad,
                                        int ref_first, uint32_t* __restrict__ dz, int64_t npad) {
-  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
   const int row = blockIdx.y;
   if (t >= npad) return;
-  uint32_t out = 0;
-  const int fi = file_idx_pad[t];
-  if (row < bs && fi >= 0) {
-    const uint8_t* pr = probs + ((int64_t)row * n_file + fi) * 2;
-    const uint32_t p0 = pr[0], p1 = pr[1];
-    const bool m = miss ? (miss[(int64_t)row * n_file + fi] & 0x80) != 0 : false;
-    if (m) {
-      out = 0x80000000u;
+  uint4 out = make_uint4(0u, 0u, 0u, 0u);
+  if (row < bs) {
+    const int4 f = *reinterpret_cast<const int4*>(file_idx_pad + t);
+    const int64_t e0 = (int64_t)row * n_file + f.x;
+    if (f.x >= 0 && f.y == f.x + 1 && f.z == f.x + 2 && f.w == f.x + 3 &&
+        (reinterpret_cast<uintptr_t>(probs + e0 * 2) & 7) == 0 && (!miss || (reinterpret_cast<uintptr_t>(miss + e0) & 3) == 0)) {
+      const uint2 pr = *reinterpret_cast<const uint2*>(probs + e0 * 2);
+      const uint32_t mm = miss ? *reinterpret_cast<const uint32_t*>(miss + e0) : 0u;
+      out.x = dosage_word(pr.x & 0xFFu, (pr.x >> 8) & 0xFFu, (mm & 0x80u) != 0, ref_first);
+      out.y = dosage_word((pr.x >> 16) & 0xFFu, pr.x >> 24, (mm & 0x8000u) != 0, ref_first);
+      out.z = dosage_word(pr.y & 0xFFu, (pr.y >> 8) & 0xFFu, (mm & 0x800000u) != 0, ref_first);
+      out.w = dosage_word((pr.y >> 16) & 0xFFu, pr.y >> 24, (mm & 0x80000000u) != 0, ref_first);
     } else {
-      // ref-last: g = p1 + 2 p0 (allele0 is ALT);  ref-first: g = p1 + 2 p2, p2 = 255 - p0 - p1 (>= 0)
-      const uint32_t p2 = (p0 + p1 <= 255u) ? 255u - p0 - p1 : 0u;
-      const uint32_t hom = ref_first ? p2 : p0;
-      out = (p1 + 2u * hom) | ((4u * hom + p1) << 10);
+      const int fi[4] = {f.x, f.y, f.z, f.w};
+      uint32_t o[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (fi[k] < 0) continue;
+        const uint8_t* pr = probs + ((int64_t)row * n_file + fi[k]) * 2;
+        const bool m = miss ? (miss[(int64_t)row * n_file + fi[k]] & 0x80) != 0 : false;
+        o[k] = dosage_word(pr[0], pr[1], m, ref_first);
+      }
+      out = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
-  dz[(int64_t)row * npad + t] = out;
+  *reinterpret_cast<uint4*>(dz + (int64_t)row * npad + t) = out;
 }
 
-// grid: (rows_p/128, nchunks, Dp/16); block 128: thread = variant row.  part: [chunk][row][4][dp]
-__global__ void __launch_bounds__(128)
+// S1 / S2 / Sm / Se partial sums of one chunk of samples for 64 variant rows x 16 feature columns, plus the non-zero /
+// hom-alt counts check_sparse_G needs (analysed, non-missing samples with d != 0 resp. d == 510).
+//   grid: (rows_p/64, nchunks, Dp/16); block 256: thread = (variant row, 4 of the 16 columns).  part: [chunk][row][4][dp]
+// Both operands of a 64-sample sub-tile go through shared memory: the feature rows (broadcast to every variant row, as before)
+// and the dz words of the 64 rows, loaded with coalesced 256-byte row segments (the first version read them per thread with
+// a stride of one whole row: 592 us per 400 variants at N = 100k, ~10x its FP64 bound; four threads per row also quadruple
+// the warps that feed the FP64 pipe).  Summation order per (row, column): samples ascending inside the chunk; chunks are
+// added in order by dosage_reduce_kernel - fixed, independent of the launch shape.
+constexpr int kDzRows = 64;
+constexpr int kDzSubS = 64;
+
+__global__ void __launch_bounds__(256)
 dosage_stats_kernel(const uint32_t* __restrict__ dz, int64_t npad, const double* __restrict__ F, int dp,
-                    const int4* __restrict__ chunks, int rows_p, double* __restrict__ part) {
-  __shared__ double2 tile[kDzSub][kDzCols / 2];
-  const int row = blockIdx.x * 128 + threadIdx.x;
+                    const int4* __restrict__ chunks, int rows_p, double* __restrict__ part, int2* __restrict__ part_cnt) {
+  __shared__ double2 tile[kDzSubS][kDzCols / 2];          // 8 KiB
+  __shared__ uint32_t dzs[kDzRows][kDzSubS + 1];          // 16.25 KiB
+  const int r = threadIdx.x >> 2, cg = threadIdx.x & 3;   // variant row of the tile, column group (4 columns)
+  const int row0 = blockIdx.x * kDzRows;
   const int4 ch = chunks[blockIdx.y];
   const int col0 = blockIdx.z * kDzCols;
-  const uint32_t* drow = dz + (int64_t)row * npad;
-  double a1[kDzCols], a2[kDzCols], am[kDzCols], ae[kDzCols];
+  const bool counter = blockIdx.z == 0 && cg == 0;        // this thread sees column 0 = the analysed-sample indicator
+  double a1[4], a2[4], am[4], ae[4];
 #pragma unroll
-  for (int c = 0; c < kDzCols; ++c) a1[c] = a2[c] = am[c] = ae[c] = 0.0;
-  for (int sub = 0; sub < ch.y; sub += kDzSub) {
+  for (int c = 0; c < 4; ++c) a1[c] = a2[c] = am[c] = ae[c] = 0.0;
+  int nz = 0, n510 = 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int sub = 0; sub < ch.y; sub += kDzSubS) {
     const int t0 = ch.x + sub;
     __syncthreads();
-    for (int e = threadIdx.x; e < kDzSub * (kDzCols / 2); e += 128) {
+    for (int e = threadIdx.x; e < kDzSubS * (kDzCols / 2); e += 256) {
       const int s = e / (kDzCols / 2), c2 = e % (kDzCols / 2);
       tile[s][c2] = *reinterpret_cast<const double2*>(F + (int64_t)(t0 + s) * dp + col0 + 2 * c2);
     }
+    for (int rr = warp; rr < kDzRows; rr += 8) {           // one row segment (64 words) per warp pass, two words per lane
+      const uint2 v2 = *reinterpret_cast<const uint2*>(dz + (int64_t)(row0 + rr) * npad + t0 + 2 * lane);
+      dzs[rr][2 * lane] = v2.x;
+      dzs[rr][2 * lane + 1] = v2.y;
+    }
     __syncthreads();
-#pragma unroll 2
-    for (int s = 0; s < kDzSub; ++s) {
-      const uint32_t v = __ldg(drow + t0 + s);
+#pragma unroll 4
+    for (int s = 0; s < kDzSubS; ++s) {
+      const uint32_t v = dzs[r][s];
       if (v == 0u) continue;
-      const double2* xr = tile[s];
+      const double2 f0 = tile[s][2 * cg], f1 = tile[s][2 * cg + 1];
       if (v & 0x80000000u) {
-#pragma unroll
-        for (int c2 = 0; c2 < kDzCols / 2; ++c2) { const double2 f = xr[c2]; am[2 * c2] += f.x; am[2 * c2 + 1] += f.y; }
+        am[0] += f0.x; am[1] += f0.y; am[2] += f1.x; am[3] += f1.y;
       } else {
-        const double d = (double)(v & 0x3FFu), e = (double)((v >> 10) & 0x7FFu), d2 = d * d;
-#pragma unroll
-        for (int c2 = 0; c2 < kDzCols / 2; ++c2) {
-          const double2 f = xr[c2];
-          a1[2 * c2] = fma(d, f.x, a1[2 * c2]);   a1[2 * c2 + 1] = fma(d, f.y, a1[2 * c2 + 1]);
-          a2[2 * c2] = fma(d2, f.x, a2[2 * c2]);  a2[2 * c2 + 1] = fma(d2, f.y, a2[2 * c2 + 1]);
-          ae[2 * c2] = fma(e, f.x, ae[2 * c2]);   ae[2 * c2 + 1] = fma(e, f.y, ae[2 * c2 + 1]);
-        }
+        const uint32_t di = v & 0x3FFu;
+        const double d = (double)di, e = (double)((v >> 10) & 0x7FFu), d2 = d * d;
+        a1[0] = fma(d, f0.x, a1[0]);  a1[1] = fma(d, f0.y, a1[1]);  a1[2] = fma(d, f1.x, a1[2]);  a1[3] = fma(d, f1.y, a1[3]);
+        a2[0] = fma(d2, f0.x, a2[0]); a2[1] = fma(d2, f0.y, a2[1]); a2[2] = fma(d2, f1.x, a2[2]); a2[3] = fma(d2, f1.y, a2[3]);
+        ae[0] = fma(e, f0.x, ae[0]);  ae[1] = fma(e, f0.y, ae[1]);  ae[2] = fma(e, f1.x, ae[2]);  ae[3] = fma(e, f1.y, ae[3]);
+        if (counter && f0.x != 0.0) { nz += di != 0u; n510 += di == 510u; }
       }
     }
   }
-  double* o = part + (((int64_t)blockIdx.y * rows_p + row) * 4) * dp + col0;
+  const int row = row0 + r;
+  double* o = part + (((int64_t)blockIdx.y * rows_p + row) * 4) * dp + col0 + 4 * cg;
 #pragma unroll
-  for (int c = 0; c < kDzCols; ++c) {
+  for (int c = 0; c < 4; ++c) {
     o[c] = a1[c];
     o[dp + c] = a2[c];
     o[2 * dp + c] = am[c];
     o[3 * dp + c] = ae[c];
   }
+  if (counter) part_cnt[(int64_t)blockIdx.y * rows_p + row] = make_int2(nz, n510);
+}
+
+// non-zero / hom-alt counts: fixed-order sum of the chunk counts.  grid: ceil(rows_p / 256)
+__global__ void dosage_count_reduce_kernel(const int2* __restrict__ part_cnt, int nchunks, int rows_p, double* __restrict__ out,
+                                           double* __restrict__ out510) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows_p) return;
+  long long a = 0, b = 0;
+  for (int c = 0; c < nchunks; ++c) {
+    const int2 v = part_cnt[(int64_t)c * rows_p + row];
+    a += v.x; b += v.y;
+  }
+  out[row] = (double)a;
+  out510[row] = (double)b;
 }
 
 // one thread per variant: AF / INFO / N / MAC, flip, sparse switch and the BT score test.
@@ -181,27 +234,6 @@ __global__ void s2_bt_finalize_kernel(S2BtFinalizeArgs a) {
   }
 }
 
-// number of analysed samples with a non-zero dosage, per variant (for check_sparse_G). grid: rows_p, block 256
-__global__ void dosage_nnz_kernel(const uint32_t* __restrict__ dz, int64_t npad, const double* __restrict__ F, int dp,
-                                  double* __restrict__ out, double* __restrict__ out510) {
-  __shared__ int red[256], red2[256];
-  const uint32_t* drow = dz + (int64_t)blockIdx.x * npad;
-  int c = 0, c2 = 0;
-  for (int64_t t = threadIdx.x; t < npad; t += 256) {
-    const uint32_t v = drow[t];
-    if ((v & 0x80000000u) || F[t * dp] == 0.0) continue;
-    c += ((v & 0x3FFu) != 0u) ? 1 : 0;
-    c2 += ((v & 0x3FFu) == 510u) ? 1 : 0;
-  }
-  red[threadIdx.x] = c; red2[threadIdx.x] = c2;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) { red[threadIdx.x] += red[threadIdx.x + o]; red2[threadIdx.x] += red2[threadIdx.x + o]; }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) { out[blockIdx.x] = (double)red[0]; out510[blockIdx.x] = (double)red2[0]; }
-}
-
 // fixed-order sum over chunks.
 __global__ void dosage_reduce_kernel(const double* __restrict__ part, int nchunks, int64_t per, double* __restrict__ sums) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -231,17 +263,18 @@ void launch_dosage_scale(const double* sums4, int rows_p, int dp, double* sums3,
 
 void launch_dosage_relayout(const uint8_t* probs, const uint8_t* miss, int64_t n_file, int bs, int rows_p,
                             const int32_t* file_idx_pad, int ref_first, uint32_t* dz, int64_t npad, cudaStream_t s) {
-  dim3 grid((unsigned)ceil_div(npad, 256), rows_p);
+  dim3 grid((unsigned)ceil_div(npad, 1024), rows_p);
   dosage_relayout_kernel<<<grid, 256, 0, s>>>(probs, miss, n_file, bs, file_idx_pad, ref_first, dz, npad);
 }
 
 void launch_dosage_stats(const uint32_t* dz, int64_t npad, const double* F, int dp, const int4* chunks, int nchunks,
-                         int rows_p, double* part, double* sums, double* nnz, double* n510, cudaStream_t s) {
-  dim3 grid(rows_p / 128, nchunks, dp / kDzCols);
-  dosage_stats_kernel<<<grid, 128, 0, s>>>(dz, npad, F, dp, chunks, rows_p, part);
+                         int rows_p, double* part, int2* part_cnt, double* sums, double* nnz, double* n510, cudaStream_t s) {
+  RG_CHECK(rows_p % kDzRows == 0 && dp % kDzCols == 0, "dosage statistics: rows_p % 64 == 0 and dp % 16 == 0");
+  dim3 grid(rows_p / kDzRows, nchunks, dp / kDzCols);
+  dosage_stats_kernel<<<grid, 256, 0, s>>>(dz, npad, F, dp, chunks, rows_p, part, part_cnt);
   const int64_t per = (int64_t)rows_p * 4 * dp;
   dosage_reduce_kernel<<<(unsigned)ceil_div(per, 256), 256, 0, s>>>(part, nchunks, per, sums);
-  dosage_nnz_kernel<<<rows_p, 256, 0, s>>>(dz, npad, F, dp, nnz, n510);
+  dosage_count_reduce_kernel<<<(unsigned)ceil_div(rows_p, 256), 256, 0, s>>>(part_cnt, nchunks, rows_p, nnz, n510);
 }
 
 void launch_s2_bt_finalize(const S2BtFinalizeArgs& a, cudaStream_t s) {
