@@ -127,6 +127,9 @@ struct rg_ctx {
   rg::DevBuf<double> F, s2_part, s2_sums, s2_maskcount, s2_YtX, s2_XmX, s2_scf;
   rg::DevBuf<double> s2_out_d;       // packed f64 outputs
   rg::DevBuf<int32_t> s2_out_i;      // packed i32 outputs
+  double* s2_hd = nullptr;           // pinned mirrors of the two output buffers (+ the INFO block)
+  int32_t* s2_hi = nullptr;
+  size_t s2_host_cap = 0;
   // quantitative-trait statistics on the tensor cores (bed / pgen input)
   bool s2_tc = false;
   int s2_drows = 0, s2_nchunk = 0, s2_ncol = 0;
@@ -146,7 +149,8 @@ struct rg_ctx {
   bool s2_nonpar_set = false;
   rg::DevBuf<double> s2_male_tot;
   // binary traits / dosages
-  int bt_mode = 0, bt_dp = 0;
+  int bt_mode = 0, bt_dp = 0, bt_ncol = 0;   // bt_ncol: used feature columns of the bt_dp padded ones
+  int s2_fcols = 0;                           // the same for the quantitative-trait feature rows (dp)
   bool bt_chr_set = false;
   int s2_last_bs = 0;                // variants resident in dz (for rg_s2_firth)
   // rg_s2_stage: input bytes of the NEXT block travel on a copy stream while the current block computes

@@ -307,7 +307,8 @@ struct S2BtFinalizeArgs {
 void launch_dosage_relayout(const uint8_t* probs, const uint8_t* miss, int64_t n_file, int bs, int rows_p,
                             const int32_t* file_idx_pad, int ref_first, uint32_t* dz, int64_t npad, cudaStream_t s);
 void launch_dosage_stats(const uint32_t* dz, int64_t npad, const double* F, int dp, const int4* chunks, int nchunks,
-                         int rows_p, double* part, int2* part_cnt, double* sums, double* nnz, double* n510, cudaStream_t s);
+                         int rows_p, double* part, int2* part_cnt, double* sums, double* nnz, double* n510, cudaStream_t s,
+                         int ncol = 0 /* used feature columns (<= dp), 0 = all */);
 void launch_s2_bt_finalize(const S2BtFinalizeArgs& a, cudaStream_t s);
 // integer-unit sums [rows][4][dp] -> dosage-unit [rows][3][dp] (S1, S2, Sm) + [rows][dp] (Se)
 void launch_dosage_scale(const double* sums4, int rows_p, int dp, double* sums3, double* se, cudaStream_t s);

@@ -822,6 +822,8 @@ void rg_destroy(rg_handle h) {
     cudaStreamDestroy(l->stream);
   }
   cudaStreamDestroy(h->stream);
+  if (h->s2_hd) cudaFreeHost(h->s2_hd);
+  if (h->s2_hi) cudaFreeHost(h->s2_hi);
   if (h->s2_copy_stream) { cudaStreamSynchronize(h->s2_copy_stream); cudaStreamDestroy(h->s2_copy_stream); }
   for (int k = 0; k < rg_ctx::kStageSlots; ++k) if (h->s2_stage_ev[k]) cudaEventDestroy(h->s2_stage_ev[k]);
   delete h;

@@ -138,6 +138,7 @@ static void s2_set_chr(rg_ctx* h, const double* res, const double* scf_sv) {
   const int base = 1 + C + 2 * P + P * C;
   h->s2_col_male = with_sex ? base : -1;
   h->dp = (int)round_up(base + (with_sex ? 1 + P : 0), 16);
+  h->s2_fcols = base + (with_sex ? 1 + P : 0);
   const int dp = h->dp;
   h->F.alloc((size_t)h->Npad * dp);
   std::vector<double> F((size_t)h->Npad * dp, 0.0), YtX((size_t)P * C, 0.0), male_tot(1 + P, 0.0);
@@ -194,6 +195,35 @@ static void s2_wait_stage(rg_ctx* h, const void* in, cudaStream_t s) {
     }
   }
 }
+}
+
+// Results of a block back to the caller: the packed f64 / i32 output buffers cross PCIe as TWO copies into pinned mirrors
+// (instead of twelve copies into whatever memory the caller's arrays live in) and are handed out with memcpy after the
+// stream has drained - the block calls are synchronous, so every microsecond of this tail is exposed.
+static void s2_copy_out(rg_ctx* h, int bs, const rg_s2_out* out, double* info_out, const double* info_dev, cudaStream_t s) {
+  const int P = h->P;
+  const size_t bp = (size_t)h->bs_max * P, b1 = h->bs_max;
+  const size_t nd = 6 * bp + 3 * b1, ni = bp + 2 * b1;
+  if (h->s2_host_cap < nd + bp) {
+    if (h->s2_hd) RG_CUDA(cudaFreeHost(h->s2_hd));
+    if (h->s2_hi) RG_CUDA(cudaFreeHost(h->s2_hi));
+    RG_CUDA(cudaMallocHost(&h->s2_hd, (nd + bp) * sizeof(double)));
+    RG_CUDA(cudaMallocHost(&h->s2_hi, ni * sizeof(int32_t)));
+    h->s2_host_cap = nd + bp;
+  }
+  RG_CUDA(cudaMemcpyAsync(h->s2_hd, h->s2_out_d.p, nd * sizeof(double), cudaMemcpyDeviceToHost, s));
+  RG_CUDA(cudaMemcpyAsync(h->s2_hi, h->s2_out_i.p, ni * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (info_out) RG_CUDA(cudaMemcpyAsync(h->s2_hd + nd, info_dev, (size_t)bs * P * 8, cudaMemcpyDeviceToHost, s));
+  RG_CUDA(cudaStreamSynchronize(s));
+  const double* d = h->s2_hd;
+  const int32_t* ii = h->s2_hi;
+  const size_t vp = (size_t)bs * P * 8, v1 = (size_t)bs * 8;
+  auto cp = [](void* dst, const void* src, size_t bytes) { if (dst) memcpy(dst, src, bytes); };
+  cp(out->af, d, vp); cp(out->mac, d + bp, vp); cp(out->stat, d + 2 * bp, vp); cp(out->beta, d + 3 * bp, vp);
+  cp(out->se, d + 4 * bp, vp); cp(out->chisq, d + 5 * bp, vp); cp(out->af_all, d + 6 * bp, v1);
+  cp(out->mac_all, d + 6 * bp + b1, v1); cp(out->scale_fac, d + 6 * bp + 2 * b1, v1);
+  cp(out->ns, ii, (size_t)bs * P * 4); cp(out->ns_all, ii + bp, (size_t)bs * 4); cp(out->flags, ii + bp + b1, (size_t)bs * 4);
+  cp(info_out, d + nd, vp);
 }
 
 static void s2_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, int bs, const int32_t* sample_idx,
@@ -254,15 +284,7 @@ static void s2_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
   a.ns = ii; a.ns_all = ii + bp; a.flags = ii + bp + b1;
   launch_s2_finalize(a, s);
   h->launches += 4;
-  const size_t vp = (size_t)bs * P * 8, v1 = (size_t)bs * 8;
-  auto cp = [&](void* dst, const void* src, size_t bytes) {
-    if (dst) RG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
-  };
-  cp(out->af, a.af, vp); cp(out->mac, a.mac, vp); cp(out->stat, a.stat, vp); cp(out->beta, a.beta, vp);
-  cp(out->se, a.se, vp); cp(out->chisq, a.chisq, vp); cp(out->af_all, a.af_all, v1); cp(out->mac_all, a.mac_all, v1);
-  cp(out->scale_fac, a.scale_fac, v1); cp(out->ns, a.ns, (size_t)bs * P * 4); cp(out->ns_all, a.ns_all, (size_t)bs * 4);
-  cp(out->flags, a.flags, (size_t)bs * 4);
-  RG_CUDA(cudaStreamSynchronize(s));
+  s2_copy_out(h, bs, out, nullptr, nullptr, s);
 }
 
 // ---------------------------------------------------------------- binary traits + 8-bit dosages
@@ -276,6 +298,7 @@ static void s2_set_chr_bt(rg_ctx* h, const rg_s2_bt_chr* st) {
   h->bt_col_male = with_sex ? base : -1;
   const int dp = (int)round_up((int64_t)base + (with_sex ? 1 + P : 0), 16);
   h->bt_dp = dp;
+  h->bt_ncol = base + (with_sex ? 1 + P : 0);
   std::vector<double> F((size_t)Npad * dp, 0.0), coltot(dp, 0.0), xwy((size_t)P * C, 0.0);
   std::vector<double> w((size_t)P * Npad, 0.0), gs((size_t)P * Npad, 0.0), off((size_t)P * Npad, 0.0),
       xw((size_t)P * C * Npad, 0.0), phat((size_t)P * Npad, 0.0);
@@ -369,7 +392,7 @@ static void s2_block_bgen8_bt(rg_ctx* h, const uint8_t* probs, const uint8_t* mi
   launch_dosage_relayout(probs_d, miss_d, n_file, bs, rows_p, h->file_idx_pad.p, ref_first, h->dz.p, Npad, s);
   h->bt_cnt_part.alloc((size_t)h->nchunks * h->rows_p_max);
   launch_dosage_stats(h->dz.p, Npad, h->bt_F.p, dp, h->chunks.p, h->nchunks, rows_p, h->bt_part.p, h->bt_cnt_part.p, h->bt_sums.p,
-                      h->bt_nnz.p, h->bt_n510.p, s);
+                      h->bt_nnz.p, h->bt_n510.p, s, h->bt_ncol);
   S2BtFinalizeArgs a;
   a.bs = bs; a.C = C; a.P = P; a.dp = dp; a.with_flip = 1;
   a.n_analyzed = h->n_analyzed; a.n_samples = h->N; a.min_mac = min_mac; a.numtol = 1e-6;
@@ -385,15 +408,7 @@ static void s2_block_bgen8_bt(rg_ctx* h, const uint8_t* probs, const uint8_t* mi
   launch_s2_bt_finalize(a, s);
   h->launches += 5;
   h->s2_last_bs = bs;
-  const size_t vp = (size_t)bs * P * 8, v1 = (size_t)bs * 8;
-  auto cp = [&](void* dst, const void* src, size_t bytes) {
-    if (dst) RG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
-  };
-  cp(out->af, a.af, vp); cp(out->mac, a.mac, vp); cp(out->stat, a.stat, vp); cp(out->beta, a.beta, vp);
-  cp(out->se, a.se, vp); cp(out->chisq, a.chisq, vp); cp(out->af_all, a.af_all, v1); cp(out->mac_all, a.mac_all, v1);
-  cp(out->scale_fac, a.scale_fac, v1); cp(out->ns, a.ns, (size_t)bs * P * 4); cp(out->ns_all, a.ns_all, (size_t)bs * 4);
-  cp(out->flags, a.flags, (size_t)bs * 4); cp(info_out, a.info, vp);
-  RG_CUDA(cudaStreamSynchronize(s));
+  s2_copy_out(h, bs, out, info_out, a.info, s);
 }
 
 // quantitative traits on 8-bit dosages: same statistics kernel, closed-form finish of s2_kernels.cu
@@ -446,7 +461,7 @@ static void s2_block_bgen8_qt(rg_ctx* h, const uint8_t* probs, const uint8_t* mi
   launch_dosage_relayout(probs_d, miss_d, n_file, bs, rows_p, h->file_idx_pad.p, ref_first, h->dz.p, Npad, s);
   h->bt_cnt_part.alloc((size_t)h->nchunks * h->rows_p_max);
   launch_dosage_stats(h->dz.p, Npad, h->F.p, dp, h->chunks.p, h->nchunks, rows_p, h->bt_part.p, h->bt_cnt_part.p, h->bt_sums.p,
-                      h->bt_nnz.p, h->bt_n510.p, s);
+                      h->bt_nnz.p, h->bt_n510.p, s, h->s2_fcols);
   launch_dosage_scale(h->bt_sums.p, rows_p, dp, h->s2_sums.p, h->bt_xtwg.p, s);
   S2FinalizeArgs a;
   a.bs = bs; a.C = C; a.P = P; a.dp = dp; a.strict = h->strict;
@@ -462,15 +477,7 @@ static void s2_block_bgen8_qt(rg_ctx* h, const uint8_t* probs, const uint8_t* mi
   a.ns = ii; a.ns_all = ii + bp; a.flags = ii + bp + b1;
   launch_s2_finalize(a, s);
   h->launches += 6;
-  const size_t vp = (size_t)bs * P * 8, v1 = (size_t)bs * 8;
-  auto cp = [&](void* dst, const void* src, size_t bytes) {
-    if (dst) RG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
-  };
-  cp(out->af, a.af, vp); cp(out->mac, a.mac, vp); cp(out->stat, a.stat, vp); cp(out->beta, a.beta, vp);
-  cp(out->se, a.se, vp); cp(out->chisq, a.chisq, vp); cp(out->af_all, a.af_all, v1); cp(out->mac_all, a.mac_all, v1);
-  cp(out->scale_fac, a.scale_fac, v1); cp(out->ns, a.ns, (size_t)bs * P * 4); cp(out->ns_all, a.ns_all, (size_t)bs * 4);
-  cp(out->flags, a.flags, (size_t)bs * 4); cp(info_out, a.info, vp);
-  RG_CUDA(cudaStreamSynchronize(s));
+  s2_copy_out(h, bs, out, info_out, a.info, s);
 }
 
 // binary traits on 2-bit hard calls (.bed / .pgen): tensor-core sums, then the same finish as the dosage path
@@ -534,15 +541,7 @@ static void s2_block_bed_bt(rg_ctx* h, const uint8_t* packed, int64_t row_stride
   launch_s2_bt_finalize(a, s);
   h->launches += 7;
   h->s2_last_bs = bs;
-  const size_t vp = (size_t)bs * P * 8, v1 = (size_t)bs * 8;
-  auto cp = [&](void* dst, const void* src, size_t bytes) {
-    if (dst) RG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
-  };
-  cp(out->af, a.af, vp); cp(out->mac, a.mac, vp); cp(out->stat, a.stat, vp); cp(out->beta, a.beta, vp);
-  cp(out->se, a.se, vp); cp(out->chisq, a.chisq, vp); cp(out->af_all, a.af_all, v1); cp(out->mac_all, a.mac_all, v1);
-  cp(out->scale_fac, a.scale_fac, v1); cp(out->ns, a.ns, (size_t)bs * P * 4); cp(out->ns_all, a.ns_all, (size_t)bs * 4);
-  cp(out->flags, a.flags, (size_t)bs * 4);
-  RG_CUDA(cudaStreamSynchronize(s));
+  s2_copy_out(h, bs, out, nullptr, nullptr, s);
 }
 
 static void s2_firth(rg_ctx* h, int n_sel, const int32_t* var_idx, const int32_t* trait_idx, double* beta, double* se,

@@ -75,11 +75,13 @@ constexpr int kDzRows = 64;
 constexpr int kDzSubS = 64;
 
 __global__ void __launch_bounds__(256)
-dosage_stats_kernel(const uint32_t* __restrict__ dz, int64_t npad, const double* __restrict__ F, int dp,
+dosage_stats_kernel(const uint32_t* __restrict__ dz, int64_t npad, const double* __restrict__ F, int dp, int ncol,
                     const int4* __restrict__ chunks, int rows_p, double* __restrict__ part, int2* __restrict__ part_cnt) {
   __shared__ double2 tile[kDzSubS][kDzCols / 2];          // 8 KiB
   __shared__ uint32_t dzs[kDzRows][kDzSubS + 1];          // 16.25 KiB
-  const int r = threadIdx.x >> 2, cg = threadIdx.x & 3;   // variant row of the tile, column group (4 columns)
+  // variant row of the tile, column group (4 columns).  The column group is WARP-uniform (two warps per group), so the
+  // groups beyond the last used column (ncol of the dp padded columns: 6 of 16 for one binary trait) cost nothing
+  const int r = threadIdx.x & 63, cg = threadIdx.x >> 6;
   const int row0 = blockIdx.x * kDzRows;
   const int4 ch = chunks[blockIdx.y];
   const int col0 = blockIdx.z * kDzCols;
@@ -89,6 +91,7 @@ dosage_stats_kernel(const uint32_t* __restrict__ dz, int64_t npad, const double*
   for (int c = 0; c < 4; ++c) a1[c] = a2[c] = am[c] = ae[c] = 0.0;
   int nz = 0, n510 = 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool live = col0 + 4 * cg < ncol;
   for (int sub = 0; sub < ch.y; sub += kDzSubS) {
     const int t0 = ch.x + sub;
     __syncthreads();
@@ -102,6 +105,7 @@ dosage_stats_kernel(const uint32_t* __restrict__ dz, int64_t npad, const double*
       dzs[rr][2 * lane + 1] = v2.y;
     }
     __syncthreads();
+    if (!live) continue;
 #pragma unroll 4
     for (int s = 0; s < kDzSubS; ++s) {
       const uint32_t v = dzs[r][s];
@@ -268,10 +272,13 @@ void launch_dosage_relayout(const uint8_t* probs, const uint8_t* miss, int64_t n
 }
 
 void launch_dosage_stats(const uint32_t* dz, int64_t npad, const double* F, int dp, const int4* chunks, int nchunks,
-                         int rows_p, double* part, int2* part_cnt, double* sums, double* nnz, double* n510, cudaStream_t s) {
+                         int rows_p, double* part, int2* part_cnt, double* sums, double* nnz, double* n510, cudaStream_t s,
+                         int ncol) {
   RG_CHECK(rows_p % kDzRows == 0 && dp % kDzCols == 0, "dosage statistics: rows_p % 64 == 0 and dp % 16 == 0");
-  dim3 grid(rows_p / kDzRows, nchunks, dp / kDzCols);
-  dosage_stats_kernel<<<grid, 256, 0, s>>>(dz, npad, F, dp, chunks, rows_p, part, part_cnt);
+  if (ncol <= 0 || ncol > dp) ncol = dp;
+  dim3 grid(rows_p / kDzRows, nchunks, (unsigned)ceil_div(ncol, kDzCols));
+  if ((int)grid.z * kDzCols < dp) RG_CUDA(cudaMemsetAsync(part, 0, (size_t)nchunks * rows_p * 4 * dp * sizeof(double), s));
+  dosage_stats_kernel<<<grid, 256, 0, s>>>(dz, npad, F, dp, ncol, chunks, rows_p, part, part_cnt);
   const int64_t per = (int64_t)rows_p * 4 * dp;
   dosage_reduce_kernel<<<(unsigned)ceil_div(per, 256), 256, 0, s>>>(part, nchunks, per, sums);
   dosage_count_reduce_kernel<<<(unsigned)ceil_div(rows_p, 256), 256, 0, s>>>(part_cnt, nchunks, rows_p, nnz, n510);
