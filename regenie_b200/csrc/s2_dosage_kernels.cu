@@ -65,7 +65,8 @@ __global__ void dosage_relayout_kernel(const uint8_t* __restrict__ probs, const 
 
 // S1 / S2 / Sm / Se partial sums of one chunk of samples for 64 variant rows x 16 feature columns, plus the non-zero /
 // hom-alt counts check_sparse_G needs (analysed, non-missing samples with d != 0 resp. d == 510).
-//   grid: (rows_p/64, nchunks, Dp/16); block 256: thread = (variant row, 4 of the 16 columns).  part: [chunk][row][4][dp]
+//   grid: (rows_p/64, nchunks, ceil(ncol/16)); block 64 x (live column groups, <= 4): thread = (variant row, 4 of the 16
+//   columns).  part: [chunk][row][4][dp]
 // Both operands of a 64-sample sub-tile go through shared memory: the feature rows (broadcast to every variant row, as before)
 // and the dz words of the 64 rows, loaded with coalesced 256-byte row segments (the first version read them per thread with
 // a stride of one whole row: 592 us per 400 variants at N = 100k, ~10x its FP64 bound; four threads per row also quadruple
@@ -95,11 +96,11 @@ dosage_stats_kernel(const uint32_t* __restrict__ dz, int64_t npad, const double*
   for (int sub = 0; sub < ch.y; sub += kDzSubS) {
     const int t0 = ch.x + sub;
     __syncthreads();
-    for (int e = threadIdx.x; e < kDzSubS * (kDzCols / 2); e += 256) {
+    for (int e = threadIdx.x; e < kDzSubS * (kDzCols / 2); e += blockDim.x) {
       const int s = e / (kDzCols / 2), c2 = e % (kDzCols / 2);
       tile[s][c2] = *reinterpret_cast<const double2*>(F + (int64_t)(t0 + s) * dp + col0 + 2 * c2);
     }
-    for (int rr = warp; rr < kDzRows; rr += 8) {           // one row segment (64 words) per warp pass, two words per lane
+    for (int rr = warp; rr < kDzRows; rr += (int)(blockDim.x >> 5)) {   // one row segment (64 words) per warp pass, two words per lane
       const uint2 v2 = *reinterpret_cast<const uint2*>(dz + (int64_t)(row0 + rr) * npad + t0 + 2 * lane);
       dzs[rr][2 * lane] = v2.x;
       dzs[rr][2 * lane + 1] = v2.y;
@@ -277,8 +278,10 @@ void launch_dosage_stats(const uint32_t* dz, int64_t npad, const double* F, int 
   RG_CHECK(rows_p % kDzRows == 0 && dp % kDzCols == 0, "dosage statistics: rows_p % 64 == 0 and dp % 16 == 0");
   if (ncol <= 0 || ncol > dp) ncol = dp;
   dim3 grid(rows_p / kDzRows, nchunks, (unsigned)ceil_div(ncol, kDzCols));
-  if ((int)grid.z * kDzCols < dp) RG_CUDA(cudaMemsetAsync(part, 0, (size_t)nchunks * rows_p * 4 * dp * sizeof(double), s));
-  dosage_stats_kernel<<<grid, 256, 0, s>>>(dz, npad, F, dp, ncol, chunks, rows_p, part, part_cnt);
+  // threads only for the column groups (of 4) that hold used columns: one binary trait with 3 covariates has 7 of 16
+  const int groups = grid.z > 1 ? 4 : (int)ceil_div(ncol, 4);
+  if ((int)grid.z * kDzCols < dp || groups < 4) RG_CUDA(cudaMemsetAsync(part, 0, (size_t)nchunks * rows_p * 4 * dp * sizeof(double), s));
+  dosage_stats_kernel<<<grid, 64 * groups, 0, s>>>(dz, npad, F, dp, ncol, chunks, rows_p, part, part_cnt);
   const int64_t per = (int64_t)rows_p * 4 * dp;
   dosage_reduce_kernel<<<(unsigned)ceil_div(per, 256), 256, 0, s>>>(part, nchunks, per, sums);
   dosage_count_reduce_kernel<<<(unsigned)ceil_div(rows_p, 256), 256, 0, s>>>(part_cnt, nchunks, rows_p, nnz, n510);
