@@ -768,6 +768,28 @@ def step2_bt_leg(capi, X, in_an, N, C, args, nvar=400, nblocks=4):
             inflate[mode] = {"error": str(e)[:200]}
     os.environ.pop("RG_B200_INFLATE", None)
     st.close()
+    # one warp owns one stream and a stream takes ~27 ms whatever else runs: the inflate kernel's throughput is the number
+    # of streams in flight.  Same payloads, one launch over 4096 of them (the 400 streams repeated) through a handle with
+    # that block size - what `rgb200 --gpu-inflate --bsize 4096` does
+    try:
+        big = 4096
+        reps = -(-big // nvar)
+        lens = np.diff(offs.astype(np.int64))
+        offs_big = np.zeros(big + 1, dtype=np.uint64)
+        offs_big[1:] = np.cumsum(np.tile(lens, reps)[:big])
+        comp_big = torch.from_numpy(np.tile(comp, reps)[: int(offs_big[-1])].copy()).pin_memory().numpy()
+        st_big = capi.Step2(X, mask, in_an, N, big)
+        st_big.bgen_inflate(comp_big, offs_big, N)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            st_big.bgen_inflate(comp_big, offs_big, N)
+        ti = (time.perf_counter() - t0) / 2
+        st_big.close()
+        inflate["direct_4096_streams_per_launch"] = {"inflate_ms_per_launch": 1e3 * ti, "inflated_GBps": big * (10 + 3 * N) / ti / 1e9,
+                                                     "variants_per_sec_inflate_only": big / ti,
+                                                     "note": "compressed bytes (pinned host) -> device, inflate kernel, payload split; no score test"}
+    except Exception as e:
+        inflate["direct_4096_streams_per_launch"] = {"error": str(e)[:200]}
     cpu = None
     if not args.no_cpu:
         thr = host_threads()

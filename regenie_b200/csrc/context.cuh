@@ -66,6 +66,8 @@ struct rg_ctx {
     rg::DevBuf<double> gam, gmu, cvec, part, mean_invsd;
     std::map<int, CUtensorMap> tmaps; // keyed by rows_p (z base differs per lane)
     rg::DevBuf<uint8_t> dig;          // radix-30 digit rows of gamma for the tensor-core prediction
+    rg::DevBuf<double> wraw;          // [P][R][Npad] raw (unstandardised) predictions of the block, local to this GPU
+    rg::DevBuf<double*> wraw_tab;     // [P] per-phenotype base pointers into wraw (same addressing as W_tab with col0 = 0)
     rg::DevBuf<double> dscale;        // [K][Qp] column scales
     std::map<int, CUtensorMap> dmaps; // digit-matrix tensor maps keyed by rows_p
     // dense FP64 route for real-valued genotypes (l0_dense.cu)

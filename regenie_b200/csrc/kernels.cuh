@@ -178,7 +178,7 @@ void launch_l0_gamma(const double* cm, int64_t cm_stride, int ldc, int nC, int R
 void launch_l0_predict(const PredictArgs& a, int ntiles, cudaStream_t s);
 void launch_l0_standardize(const double* part, int ntiles, int Qp, int Q, int P, const double* neff,
                            double* mean_invsd, double* const* W, int64_t npad, int col0,
-                           const uint8_t* is_real, cudaStream_t s);
+                           const uint8_t* is_real, cudaStream_t s, const double* const* src = nullptr, int src_col0 = 0);
 int predict_qt();
 
 // ---- predict_tcgen05.cu

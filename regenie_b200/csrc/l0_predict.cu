@@ -160,18 +160,20 @@ __global__ void l0_std_reduce_kernel(const double* __restrict__ part, int ntiles
   }
 }
 
-// grid: (Npad/256, Q)
-__global__ void l0_std_apply_kernel(double* const* __restrict__ W, int64_t npad, int col0,
-                                    int P, const uint8_t* __restrict__ is_real,
+// grid: (Npad/256, Q).  src / dst may be the same table (in place) or the lane's local scratch -> the owners' W: with
+// phenotypes owned by other GPUs the raw predictions are then produced, summed and read LOCALLY and only the finished
+// values cross NVLink, as plain stores (the in-place version read-modify-wrote the peer's HBM: 75 % scaling at N = 500k).
+__global__ void l0_std_apply_kernel(const double* const* __restrict__ src, int src_col0, double* const* __restrict__ W,
+                                    int64_t npad, int col0, int P, const uint8_t* __restrict__ is_real,
                                     const double* __restrict__ mean_invsd) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int q = blockIdx.y;
   if (t >= npad) return;
   const int r = q / P, p = q % P;
-  double* w = W[p] + (int64_t)(col0 + r) * npad + t;
+  const double v = src[p][(int64_t)(src_col0 + r) * npad + t];
   // the reference centres every row of the fold (masked samples become -mean*invsd,
   // src/Step1_Models.cpp:556-557); layout padding rows stay exactly zero.
-  *w = is_real[t] ? (*w - mean_invsd[2 * q]) * mean_invsd[2 * q + 1] : 0.0;
+  W[p][(int64_t)(col0 + r) * npad + t] = is_real[t] ? (v - mean_invsd[2 * q]) * mean_invsd[2 * q + 1] : 0.0;
 }
 
 void launch_l0_gamma(const double* cm, int64_t cm_stride, int ldc, int nC, int R, int P, int Qp,
@@ -190,10 +192,11 @@ void launch_l0_predict(const PredictArgs& a, int ntiles, cudaStream_t s) {
 
 void launch_l0_standardize(const double* part, int ntiles, int Qp, int Q, int P, const double* neff,
                            double* mean_invsd, double* const* W, int64_t npad, int col0,
-                           const uint8_t* is_real, cudaStream_t s) {
+                           const uint8_t* is_real, cudaStream_t s, const double* const* src, int src_col0) {
   l0_std_reduce_kernel<<<Q, 256, 0, s>>>(part, ntiles, Qp, P, neff, mean_invsd);
   dim3 grid((unsigned)ceil_div(npad, 256), Q);
-  l0_std_apply_kernel<<<grid, 256, 0, s>>>(W, npad, col0, P, is_real, mean_invsd);
+  if (src) l0_std_apply_kernel<<<grid, 256, 0, s>>>(src, src_col0, W, npad, col0, P, is_real, mean_invsd);
+  else l0_std_apply_kernel<<<grid, 256, 0, s>>>(W, col0, W, npad, col0, P, is_real, mean_invsd);
 }
 
 void launch_l0_std_reduce_only(const double* part, int ntiles, int Qp, int Q, int P, const double* neff,

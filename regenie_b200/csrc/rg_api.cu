@@ -356,11 +356,21 @@ static void enqueue_predict(rg_ctx* h, rg_ctx::Lane& L, const BlockDims& d, cons
   ScopedTimer t(h, "l0_predict", s);
   launch_l0_gamma(xsrc, xstride, xld, xrow0, R, P, d.Qp, d.bs, d.rows_p, K, L.mu.p, L.inv_sd.p, L.Bv.p, C,
                   L.gam.p, L.gmu.p, L.cvec.p, s);
+  // raw predictions go to the lane's LOCAL scratch; the standardisation pass reads them there and writes the finished
+  // columns into W - the owner's HBM, which may be another GPU's (then only plain stores cross NVLink)
+  if (L.wraw.n < (size_t)P * R * Npad) {
+    L.wraw.alloc((size_t)P * R * Npad);
+    L.wraw_tab.alloc(P);
+    std::vector<double*> tab(P);
+    for (int p = 0; p < P; ++p) tab[p] = L.wraw.p + (size_t)p * R * Npad;
+    RG_CUDA(cudaMemcpyAsync(L.wraw_tab.p, tab.data(), P * sizeof(double*), cudaMemcpyHostToDevice, s));
+    RG_CUDA(cudaStreamSynchronize(s));           // tab goes out of scope (once per lane)
+  }
   PredictArgs pa;
   pa.bs = d.bs; pa.rows_p = d.rows_p; pa.C = C; pa.P = P; pa.R = R; pa.Qp = d.Qp; pa.cpp = h->cpp;
-  pa.col0 = d.col0; pa.npad = Npad; pa.words_per_row = Npad / 16;
+  pa.col0 = 0; pa.npad = Npad; pa.words_per_row = Npad / 16;
   pa.gp = L.gp.p; pa.tile_fold = h->tile_fold.p; pa.gam = L.gam.p; pa.gmu = L.gmu.p;
-  pa.cvec = L.cvec.p; pa.xy = h->xy.p; pa.mask = h->mask.p; pa.W = h->W_tab.p; pa.part = L.part.p;
+  pa.cvec = L.cvec.p; pa.xy = h->xy.p; pa.mask = h->mask.p; pa.W = L.wraw_tab.p; pa.part = L.part.p;
   int nparts = d.ntiles_s;
   // RG_B200_PREDICT = i8 (default: kind::i8, 5 radix-254 limbs) | f8 (kind::f8f6f4, 9 radix-30 limbs) | f64 (CUDA cores)
   static const std::string predict_kind = [] { const char* e = getenv("RG_B200_PREDICT"); return std::string(e ? e : "i8"); }();
@@ -387,9 +397,9 @@ static void enqueue_predict(rg_ctx* h, rg_ctx::Lane& L, const BlockDims& d, cons
     if (use_i8) launch_l0_gamma_limbs_i8(L.gam.p, L.gmu.p, d.Qp, d.Q, d.bs, d.rows_p, K, L.dscale.p, L.dig.p, ngroups, s);
     else launch_l0_gamma_limbs(L.gam.p, L.gmu.p, d.Qp, d.Q, d.bs, d.rows_p, K, L.dscale.p, L.dig.p, ngroups, s);
     PredictTcArgs ta;
-    ta.rows_p = d.rows_p; ta.C = C; ta.P = P; ta.Q = d.Q; ta.Qp = d.Qp; ta.cpp = h->cpp; ta.col0 = d.col0; ta.ngroups = ngroups;
+    ta.rows_p = d.rows_p; ta.C = C; ta.P = P; ta.Q = d.Q; ta.Qp = d.Qp; ta.cpp = h->cpp; ta.col0 = 0; ta.ngroups = ngroups;
     ta.npad = Npad; ta.tile_fold = h->tile_fold.p; ta.scale = L.dscale.p; ta.cvec = L.cvec.p;
-    ta.xy = h->xy.p; ta.mask = h->mask.p; ta.W = h->W_tab.p; ta.part = L.part.p;
+    ta.xy = h->xy.p; ta.mask = h->mask.p; ta.W = L.wraw_tab.p; ta.part = L.part.p;
     ta.dbg = nullptr;
     static const int pred_pf = [] { const char* e = getenv("RG_B200_PREDICT_L2PF"); return e ? std::max(0, std::min(8, atoi(e))) : 0; }();
     ta.l2_prefetch = pred_pf;       // measured: no gain (profiles/ab_r2m_solver_variants.txt)
@@ -398,11 +408,11 @@ static void enqueue_predict(rg_ctx* h, rg_ctx::Lane& L, const BlockDims& d, cons
       if (use_i8) launch_l0_predict_i8(L.tmaps[d.rows_p], L.dmaps[d.rows_p], ta, d.ntiles_s, s);
       else launch_l0_predict_tcgen05(L.tmaps[d.rows_p], L.dmaps[d.rows_p], ta, d.ntiles_s, s);
     }
-    nparts = launch_l0_colsum(h->W_tab.p, Npad, d.col0, P, d.Q, d.Qp, L.part.p, s);
+    nparts = launch_l0_colsum(L.wraw_tab.p, Npad, 0, P, d.Q, d.Qp, L.part.p, s);
     h->launches += 2;
   }
   launch_l0_standardize(L.part.p, nparts, d.Qp, d.Q, P, h->neff.p, L.mean_invsd.p, h->W_tab.p, Npad, d.col0,
-                        h->is_real.p, s);
+                        h->is_real.p, s, L.wraw_tab.p, 0);
   h->launches += 5;
 }
 
