@@ -331,9 +331,45 @@ int rg_s2_block_bed_bt(rg_handle h, const uint8_t* packed, int64_t row_stride, i
 int rg_s2_firth(rg_handle h, int32_t n_sel, const int32_t* variant_idx, const int32_t* trait_idx, double* beta,
                 double* se, double* lrt, int32_t* status);
 
+/* ------------------------------------------------------------------ PGEN records */
+/*
+ * rg_pgen_decode -- the variant records of one block of a PLINK 2 .pgen (hard calls), decoded ON THE DEVICE into
+ * PLINK 1 2-bit rows (ALT count 0 / 1 / 2 / missing -> codes 11 / 10 / 00 / 01, ref-last).  Replaces the per-variant
+ * pgenlib reads of the reference: PgenReader::Read in readChunkFromPGENFileToG (src/Geno.cpp:1773-1821, Step 1) and in
+ * readChunkFromPGENFileToG / parseSnpfromPGEN of Step 2 (src/Geno.cpp:2538-2594, :2596-2712).  The caller only slices
+ * the file: it passes the bytes of the records as they are (record types 0-7: plain 2-bit, 1 bit + difflist, difflist
+ * over a constant, LD-compressed against an earlier record), the device expands them (csrc/pgen_decode.cu).
+ *   bytes      [host] the records the block needs (own records and the bases of LD-compressed ones), each starting at a
+ *              multiple of 4 bytes: record r is bytes[rec_off[r] .. rec_off[r] + rec_len[r])
+ *   rec_type   [n_rec] low 3 bits of the variant record type
+ *   own        [bs] record index of variant j of the block;  base [bs] record index of the most recent record that is
+ *              not LD-compressed when own[j] is of type 2 / 3, -1 otherwise
+ *   n_file     samples in the file (rows are in file order: pass sample_idx to the block call as for a .bed)
+ *   block_id   only used in error messages
+ *   rows_dev / row_stride   out: DEVICE pointer to bs rows and their stride in bytes (>= ceil(n_file / 4)); pass both
+ *              to rg_l0_block_bed / rg_s2_block_bed / rg_s2_block_bed_bt as `packed` / `row_stride`.
+ * Step-1 handle: asynchronous, on the stream of the lane that the NEXT rg_l0_block_bed call uses - that call must be
+ * the consumer; a malformed record is reported by rg_l0_status / rg_sync like a low-variance SNP.  Step-2 handle: returns
+ * after the decode, errors at once; the rows stay valid until the next rg_pgen_decode on the handle.
+ */
+typedef struct rg_pgen_block {
+  const uint8_t* bytes;
+  int64_t n_bytes;
+  const uint64_t* rec_off;
+  const uint32_t* rec_len;
+  const uint8_t* rec_type;
+  int32_t n_rec;
+  const int32_t* own;
+  const int32_t* base;
+  int32_t bs;
+  int64_t n_file;
+  int32_t block_id;
+} rg_pgen_block;
+int rg_pgen_decode(rg_handle h, const rg_pgen_block* blk, const uint8_t** rows_dev, int64_t* row_stride);
+
 /* ------------------------------------------------------------------ multi-GPU */
 /*
- * One process per GPU.  Level-0 blocks are sharded across ranks (the reference's --split-l0 partition,
+ * One process per GPU. Level-0 blocks are sharded across ranks (the reference's --split-l0 partition,
  * src/Data.cpp:268-301); level 1 is sharded by phenotype.  Instead of a separate exchange step, every rank
  * maps the predictor matrix W of the phenotype owners into its address space (CUDA IPC over NVLink/NVSwitch):
  *   all:    rg_W_set_owned(h, owned)           -> local W storage only for the phenotypes this rank fits (N x B x P/nranks)

@@ -102,7 +102,8 @@ def build_probe(verbose=False, force=False):
     if gxx is None or not os.path.exists(probe_src):
         return PROBE if os.path.exists(PROBE) else None
     hdrs = [os.path.join(HERE, "host", f) for f in os.listdir(os.path.join(HERE, "host")) if f.endswith(".hpp")]
-    hdrs.append(os.path.join(CSRC, "inflate_core.h"))          # the device decoder, compiled for the host with one lane
+    hdrs.append(os.path.join(CSRC, "inflate_core.h"))          # the device decoders, compiled for the host with one lane
+    hdrs.append(os.path.join(CSRC, "pgen_core.h"))
     if force or _newer(srcs + hdrs + [probe_src], PROBE):
         _run([gxx, "-O2", "-std=c++17", "-Wall", "-o", PROBE, probe_src] + srcs + ["-lz", "-lpthread", "-ldl"], verbose)
     return PROBE

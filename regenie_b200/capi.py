@@ -42,6 +42,36 @@ class S2Out(C.Structure):
                                            "stat", "beta", "se", "chisq")]
 
 
+class PgenBlock(C.Structure):
+    _fields_ = [("bytes", C.c_void_p), ("n_bytes", C.c_int64), ("rec_off", C.c_void_p), ("rec_len", C.c_void_p),
+                ("rec_type", C.c_void_p), ("n_rec", C.c_int32), ("own", C.c_void_p), ("base", C.c_void_p),
+                ("bs", C.c_int32), ("n_file", C.c_int64), ("block_id", C.c_int32)]
+
+
+def pgen_decode(handle, data, rec_off, rec_len, rec_type, own, base, n_file, block_id=0):
+    """rg_pgen_decode on a Step1 / Step2 object: record bytes + tables (see include/rg_b200.h) -> (device pointer of the
+    PLINK 1 rows, row stride).  Mirrors what host/pgen.cpp PgenFile::gather + the rgb200 driver pass."""
+    L = lib()
+    L.rg_pgen_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    keep = [np.ascontiguousarray(data, dtype=np.uint8), np.ascontiguousarray(rec_off, dtype=np.uint64),
+            np.ascontiguousarray(rec_len, dtype=np.uint32), np.ascontiguousarray(rec_type, dtype=np.uint8),
+            np.ascontiguousarray(own, dtype=np.int32), np.ascontiguousarray(base, dtype=np.int32)]
+    blk = PgenBlock(keep[0].ctypes.data, keep[0].size, keep[1].ctypes.data, keep[2].ctypes.data, keep[3].ctypes.data,
+                    keep[1].size, keep[4].ctypes.data, keep[5].ctypes.data, keep[4].size, int(n_file), int(block_id))
+    rows, stride = C.c_void_p(0), C.c_int64(0)
+    check(L.rg_pgen_decode(handle.h, C.byref(blk), C.byref(rows), C.byref(stride)))
+    return int(rows.value), int(stride.value)
+
+
+def debug_fetch(handle, name, dtype, count):
+    """rg_debug_fetch for either handle kind (test hook)."""
+    out = np.empty(count, dtype=dtype)
+    n = lib().rg_debug_fetch(handle.h, name.encode(), _ptr(out), out.nbytes)
+    if n < 0:
+        raise RgError("debug fetch failed for %s: %s" % (name, lib().rg_last_error().decode()))
+    return out[: n // out.itemsize]
+
+
 # every symbol include/rg_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "rg_last_error", "rg_version", "rg_device_count", "rg_step1_create", "rg_destroy", "rg_sync",
@@ -49,7 +79,7 @@ EXPORTS = [
     "rg_s2_set_chr", "rg_s2_block_bed", "rg_W_info", "rg_debug_fetch", "rg_launch_count", "rg_stream",
     "rg_set_timing", "rg_get_timing", "rg_fence", "rg_s2_set_chr_bt", "rg_s2_block_bgen8_bt", "rg_s2_block_bgen8", "rg_s2_firth", "rg_l1_fit_bt", "rg_W_set_owned", "rg_W_export", "rg_W_attach_peer", "rg_l1_select", "rg_s2_set_sex", "rg_s2_set_non_par", "rg_l0_load_W", "rg_s2_spa", "rg_s2_block_bed_bt", "rg_prs", "rg_bgen_inflate",
     "rg_l0_solver_stats", "rg_dbg_mixed_solve", "rg_l0_wait_input", "rg_l0_block_dosage_u8", "rg_l0_block_f64", "rg_W_attach_local",
-    "rg_s2_stage", "rg_host_alloc", "rg_host_free",
+    "rg_s2_stage", "rg_host_alloc", "rg_host_free", "rg_pgen_decode",
 ]
 
 _lib = None
@@ -304,9 +334,13 @@ class Step2:
         scf = np.ascontiguousarray(scf_sv, dtype=np.float64)
         check(lib().rg_s2_set_chr(self.h, _ptr(res), _ptr(scf)))
 
-    def block_bed(self, packed, sample_idx=None, ref_first=False, min_mac=5.0):
-        packed = np.ascontiguousarray(packed, dtype=np.uint8)
-        bs, P = packed.shape[0], self.P
+    def block_bed(self, packed, sample_idx=None, ref_first=False, min_mac=5.0, row_stride=None, bs=None):
+        """packed: uint8 ndarray [bs, stride] (host), or an int device pointer with row_stride and bs."""
+        if isinstance(packed, int):
+            P = self.P
+        else:
+            packed = np.ascontiguousarray(packed, dtype=np.uint8)
+            bs, P, row_stride = packed.shape[0], self.P, packed.shape[1]
         o = dict(af=np.empty((bs, P)), ns=np.empty((bs, P), dtype=np.int32), mac=np.empty((bs, P)),
                  af_all=np.empty(bs), ns_all=np.empty(bs, dtype=np.int32), mac_all=np.empty(bs),
                  flags=np.empty(bs, dtype=np.int32), scale_fac=np.empty(bs), stat=np.empty((bs, P)),
@@ -315,7 +349,7 @@ class Step2:
                                                 "scale_fac", "stat", "beta", "se", "chisq")])
         if sample_idx is not None:
             sample_idx = np.ascontiguousarray(sample_idx, dtype=np.int32)
-        check(lib().rg_s2_block_bed(self.h, _ptr(packed), packed.shape[1], bs, _ptr(sample_idx), int(ref_first),
+        check(lib().rg_s2_block_bed(self.h, _ptr(packed), row_stride, bs, _ptr(sample_idx), int(ref_first),
                                     float(min_mac), C.byref(so)))
         return o
 

@@ -54,6 +54,7 @@ struct rg_ctx {
     cudaEvent_t h2d_done = nullptr;   // recorded behind the host-to-device copy of the block's input rows
     bool h2d_recorded = false;
     rg::DevBuf<uint8_t> packed_dev;
+    rg::DevBuf<uint8_t> pgen_in;      // rg_pgen_decode: metadata blob + record bytes of the block this lane runs next
     rg::DevBuf<uint32_t> gp;          // [rows_p][Npad/16]
     rg::DevBuf<uint8_t> z;            // [2 rows_p][Npad] e4m3
     rg::DevBuf<float> zz;             // [K][2 rows_p][2 rows_p]
@@ -165,6 +166,8 @@ struct rg_ctx {
   rg::DevBuf<uint8_t> inflate_comp, inflate_raw;      // rg_bgen_inflate: compressed streams, inflated payloads
   rg::DevBuf<uint64_t> inflate_offs;
   rg::DevBuf<int32_t> inflate_status;
+  rg::DevBuf<uint8_t> pgen_in, pgen_rows;             // rg_pgen_decode on a Step-2 handle: records in, 2-bit rows out
+  rg::DevBuf<unsigned long long> pgen_err;            // first malformed record: (block + 1) << 32 | variant << 4 | code
   rg::DevBuf<uint32_t> dz;           // [rows_p][Npad] d | e << 10 | missing << 31
   rg::DevBuf<double> bt_F, bt_w, bt_gs, bt_xw, bt_off, bt_coltot, bt_xwy, bt_part, bt_sums, bt_nnz, bt_n510;
   rg::DevBuf<double> bt_xtwg, bt_mu, bt_info, firth_gvec, firth_out, bt_den, bt_phat;
@@ -189,4 +192,6 @@ namespace rg {
 void flush_timers(rg_ctx* h);
 // read the mixed-solver flags of every lane (re-solving flagged blocks in FP64) and wait for all level-0 work
 void sync_lanes(rg_ctx* h);
+// throws when a kernel of rg_pgen_decode flagged a malformed record (pgen_decode.cu)
+void pgen_check_errors(rg_ctx* h);
 }

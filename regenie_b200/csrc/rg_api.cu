@@ -923,6 +923,7 @@ int rg_sync(rg_handle h) {
   rg::sync_lanes(h);
   RG_CUDA(cudaStreamSynchronize(h->stream));
   rg::flush_timers(h);
+  rg::pgen_check_errors(h);
   RG_API_END
 }
 
@@ -999,6 +1000,7 @@ int64_t rg_l0_status(rg_handle h) {
     return -1;
   }
   rg::flush_timers(h);
+  try { rg::pgen_check_errors(h); } catch (const rg::Error& e) { rg::set_last_error(e.msg); return (int64_t)1 << 41; }
   unsigned long long v = 0;
   cudaMemcpy(&v, h->err_slot.p, 8, cudaMemcpyDeviceToHost);
   if (v == ~0ull) return 0;
@@ -1031,9 +1033,16 @@ int64_t rg_debug_fetch(rg_handle h, const char* name, void* out, int64_t max_byt
   cudaSetDevice(h->device);
   try { rg::sync_lanes(h); } catch (const rg::Error& e) { rg::set_last_error(e.msg); return -1; }
   cudaStreamSynchronize(h->stream);
+  const std::string n(name);
+  if (n == "pgen_rows") {              // test-only: the rows the last rg_pgen_decode produced (Step 1: the next lane's input)
+    const rg::DevBuf<uint8_t>& r = h->kind == 1 && !h->lanes.empty() ? h->lanes[h->next_lane]->packed_dev : h->pgen_rows;
+    if (!r.p) { rg::set_last_error("no decoded .pgen rows"); return -1; }
+    const size_t nb = std::min<size_t>(r.n, (size_t)max_bytes);
+    if (cudaMemcpy(out, r.p, nb, cudaMemcpyDeviceToHost) != cudaSuccess) { rg::set_last_error("copy failed"); return -1; }
+    return (int64_t)nb;
+  }
   if (h->lanes.empty()) { rg::set_last_error("no level-0 lane"); return -1; }
   rg_ctx::Lane& L = *h->lanes[h->last_lane];
-  const std::string n(name);
   const void* p = nullptr;
   size_t bytes = 0;
   const int rp = h->last_rows_p;

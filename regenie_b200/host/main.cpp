@@ -294,6 +294,20 @@ double now_ms() {
 }
 
 // ------------------------------------------------------------------------------------ step 1
+// .pgen input: the records of a block go to the GPU as they are and are expanded there (rg_pgen_decode).
+// RG_B200_PGEN=host selects the host decoder (host/pgen.cpp), which also serves the options that edit rows on the host
+// (--no-split genotype counts, --test dominant / recessive, --af-cc).
+static bool pgen_on_device() {
+  const char* e = getenv("RG_B200_PGEN");
+  return !(e && std::string(e) == "host");
+}
+static void pgen_rows_device(rg_handle h, const PgenBatch& pb, int bs, int64_t n_file, int block_id, const uint8_t** rows,
+                             int64_t* stride) {
+  rg_pgen_block blk{pb.bytes.data(), (int64_t)pb.bytes.size(), pb.rec_off.data(), pb.rec_len.data(), pb.rec_type.data(),
+                    (int32_t)pb.rec_off.size(), pb.own.data(), pb.base.data(), bs, n_file, block_id};
+  rg_check(rg_pgen_decode(h, &blk, rows, stride));
+}
+
 // .bed/.bim/.fam or .pgen/.pvar/.psam behind the same row interface
 void open_rows(const Params& p, BedFile& g, const std::set<std::string>& excl, const std::set<std::string>& extr,
                const std::set<std::string>& rem, const std::set<std::string>& keep, Log& log) {
@@ -518,10 +532,14 @@ void run_step1(const Params& p_in, Log& log) {
   if (use_bgen && !p.run_l1)
     for (int k = 0; k < 2; ++k) { probs[k].resize((size_t)p.bsize * g.n_file * 2); pmiss[k].resize((size_t)p.bsize * g.n_file); }
   const int io_threads = std::max(1, std::min(32, (int)std::thread::hardware_concurrency()));
+  const bool pgen_dev = !use_bgen && gbed.pg && pgen_on_device();
+  if (pgen_dev) log << " * pgen records are decoded on the GPU\n";
+  PgenBatch pbatch[2];
   std::future<void> pending;
   auto fetch = [&](int b) {
     return std::async(std::launch::async, [&, b] {
       if (use_bgen) gg.read_block(blocks[b].first, blocks[b].size, probs[b & 1].data(), pmiss[b & 1].data(), io_threads);
+      else if (pgen_dev) gbed.pg->gather(blocks[b].first, blocks[b].size, pbatch[b & 1]);
       else gbed.read_rows(blocks[b].first, blocks[b].size, bufs[b & 1]);
     });
   };
@@ -534,7 +552,12 @@ void run_step1(const Params& p_in, Log& log) {
       if (use_bgen)
         rg_check(rg_l0_block_dosage_u8(h, probs[b & 1].data(), pmiss[b & 1].data(), (int64_t)g.n_file, blocks[b].size,
                                        subset ? g.sample_idx.data() : nullptr, p.ref_first, b));
-      else
+      else if (pgen_dev) {
+        const uint8_t* drows = nullptr;
+        int64_t dstride = 0;
+        pgen_rows_device(h, pbatch[b & 1], blocks[b].size, (int64_t)gbed.pg->n_file, b, &drows, &dstride);
+        rg_check(rg_l0_block_bed(h, drows, dstride, blocks[b].size, subset ? g.sample_idx.data() : nullptr, p.ref_first, b));
+      } else
         rg_check(rg_l0_block_bed(h, bufs[b & 1], (int64_t)g.row_stride, blocks[b].size,
                                  subset ? g.sample_idx.data() : nullptr, p.ref_first, b));
       log << " block [" << b + 1 << "] : " << blocks[b].size << " snps\n";
@@ -558,6 +581,13 @@ void run_step1(const Params& p_in, Log& log) {
               gg.read_block(blocks[b].first, blocks[b].size, pr.data(), pm.data(), std::max(1, io_threads / G));
               rg_check(rg_l0_block_dosage_u8(hs[d], pr.data(), pm.data(), (int64_t)g.n_file, blocks[b].size,
                                              subset ? g.sample_idx.data() : nullptr, p.ref_first, b));
+            } else if (pgen_dev) {
+              PgenBatch pb;                                  // gather only reads the mapped file: no lock
+              gbed.pg->gather(blocks[b].first, blocks[b].size, pb);
+              const uint8_t* drows = nullptr;
+              int64_t dstride = 0;
+              pgen_rows_device(hs[d], pb, blocks[b].size, (int64_t)gbed.pg->n_file, b, &drows, &dstride);
+              rg_check(rg_l0_block_bed(hs[d], drows, dstride, blocks[b].size, subset ? g.sample_idx.data() : nullptr, p.ref_first, b));
             } else {
               { std::lock_guard<std::mutex> lk(io_mu); gbed.read_rows(blocks[b].first, blocks[b].size, buf.data()); }
               rg_check(rg_l0_block_bed(hs[d], buf.data(), (int64_t)g.row_stride, blocks[b].size,
@@ -1056,6 +1086,10 @@ void run_step2_qt(const Params& p, Log& log) {
   std::vector<double> info1[2];
   std::vector<long> d_rr[2], d_aa[2];
   if (use_info1) for (int k = 0; k < 2; ++k) { info1[k].resize(bsz); d_rr[k].resize(bsz); d_aa[k].resize(bsz); }
+  // .pgen records are expanded on the GPU unless an option edits the rows on the host (see pgen_on_device)
+  const bool pgen_dev = !use_bgen && g.pg && pgen_on_device() && !p.no_split && p.test_type == 0;
+  if (pgen_dev) log << " * pgen records are decoded on the GPU\n";
+  PgenBatch pbatch[2];
   std::future<void> pending;
   auto fetch = [&](size_t b) {
     return std::async(std::launch::async, [&, b] {
@@ -1065,6 +1099,7 @@ void run_step2_qt(const Params& p, Log& log) {
         if (use_info1) gg.info_all(probs[b & 1].data(), pmiss[b & 1].data(), blocks[b].size, ph.in_analysis.data(), p.ref_first,
                                    info1[b & 1].data(), threads, d_rr[b & 1].data(), d_aa[b & 1].data());
       }
+      else if (pgen_dev) g.pg->gather(blocks[b].first, blocks[b].size, pbatch[b & 1]);
       else g.read_rows(blocks[b].first, blocks[b].size, rows[b & 1].data());
     });
   };
@@ -1133,6 +1168,11 @@ void run_step2_qt(const Params& p, Log& log) {
         rg_check(rg_s2_block_bgen8(h, pd, md, (int64_t)n_file, blocks[b].size, subset ? sample_idx.data() : nullptr, p.ref_first,
                                    0.0, &out2, info2.data()));
       }
+    } else if (pgen_dev) {
+      const uint8_t* drows = nullptr;
+      int64_t dstride = 0;
+      pgen_rows_device(h, pbatch[b & 1], blocks[b].size, (int64_t)g.pg->n_file, (int)b, &drows, &dstride);
+      rg_check(rg_s2_block_bed(h, drows, dstride, blocks[b].size, subset ? sample_idx.data() : nullptr, p.ref_first, p.min_mac, &out));
     } else {
       rg_check(rg_s2_block_bed(h, rows[b & 1].data(), (int64_t)g.row_stride, blocks[b].size,
                                subset ? sample_idx.data() : nullptr, p.ref_first, p.min_mac, &out));
@@ -1285,6 +1325,9 @@ void run_step2_bt(const Params& p, Log& log) {
   std::vector<double> info1[2];
   std::vector<long> d_rr[2], d_aa[2];
   if (use_info1) for (int k = 0; k < 2; ++k) { info1[k].resize(bsz); d_rr[k].resize(bsz); d_aa[k].resize(bsz); }
+  const bool pgen_dev = !use_bgen && gb.pg && pgen_on_device() && !p.no_split && p.test_type == 0 && !hc;
+  if (pgen_dev) log << " * pgen records are decoded on the GPU\n";
+  PgenBatch pbatch[2];
   std::future<void> pending;
   auto fetch = [&](size_t b) {
     return std::async(std::launch::async, [&, b] {
@@ -1294,6 +1337,7 @@ void run_step2_bt(const Params& p, Log& log) {
         if (use_info1) gg.info_all(probs[b & 1].data(), pmiss[b & 1].data(), blocks[b].size, ph.in_analysis.data(), p.ref_first,
                                    info1[b & 1].data(), threads, d_rr[b & 1].data(), d_aa[b & 1].data());
       }
+      else if (pgen_dev) gb.pg->gather(blocks[b].first, blocks[b].size, pbatch[b & 1]);
       else gb.read_rows(blocks[b].first, blocks[b].size, rows[b & 1].data());
     });
   };
@@ -1382,6 +1426,11 @@ void run_step2_bt(const Params& p, Log& log) {
         rg_check(rg_s2_block_bgen8_bt(h, pd, md, (int64_t)n_file, bs, subset ? sample_idx.data() : nullptr, p.ref_first, 0.0,
                                       &out2, info2.data()));
       }
+    } else if (pgen_dev) {
+      const uint8_t* drows = nullptr;
+      int64_t dstride = 0;
+      pgen_rows_device(h, pbatch[b & 1], bs, (int64_t)gb.pg->n_file, (int)b, &drows, &dstride);
+      rg_check(rg_s2_block_bed_bt(h, drows, dstride, bs, subset ? sample_idx.data() : nullptr, p.ref_first, p.min_mac, &out));
     } else {
       // hard calls go to the GPU as they are (2 bits per sample)
       rg_check(rg_s2_block_bed_bt(h, rows[b & 1].data(), (int64_t)gb.row_stride, bs, subset ? sample_idx.data() : nullptr,

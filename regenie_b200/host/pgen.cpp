@@ -265,6 +265,40 @@ void PgenFile::read_rows(size_t first, size_t n, uint8_t* out) {
   }
 }
 
+void PgenFile::gather(size_t first, size_t n, PgenBatch& out) const {
+  out.bytes.clear(); out.rec_off.clear(); out.rec_len.clear(); out.rec_type.clear();
+  out.own.assign(n, -1); out.base.assign(n, -1);
+  long last_base_v = -1;
+  int32_t last_base_rec = -1;
+  auto add = [&](uint32_t v) -> int32_t {
+    const uint64_t len = fpos[v + 1] - fpos[v];
+    if (fpos[v + 1] < fpos[v] || fpos[v + 1] > data.size() || len >= (1ull << 32)) throw Fail("malformed .pgen file (record offsets).");
+    const size_t off = (out.bytes.size() + 15) / 16 * 16;
+    out.bytes.resize(off + len, 0);
+    if (len) memcpy(&out.bytes[off], &data[fpos[v]], len);
+    out.rec_off.push_back(off);
+    out.rec_len.push_back((uint32_t)len);
+    out.rec_type.push_back(vrtype[v] & 7);
+    return (int32_t)out.rec_off.size() - 1;
+  };
+  for (size_t j = 0; j < n; ++j) {
+    const uint32_t v = (uint32_t)snps[first + j].offset;
+    const uint32_t t = vrtype[v] & 7;
+    out.own[j] = add(v);
+    if ((t & 6) != 2) {                          // a later LD record of the block may refer to this one
+      last_base_v = v;
+      last_base_rec = out.own[j];
+      continue;
+    }
+    long b = (long)v - 1;
+    while (b >= 0 && (vrtype[b] & 6) == 2) --b;
+    if (b < 0) throw Fail("malformed .pgen file (LD-compressed record without a base).");
+    if (b != last_base_v) { last_base_rec = add((uint32_t)b); last_base_v = b; }
+    out.base[j] = last_base_rec;
+  }
+  if (out.bytes.empty()) out.bytes.resize(16, 0);           // a block of all-reference records has no bytes at all
+}
+
 void pgen_read_rows(PgenFile& pg, size_t first, size_t n, uint8_t* out) { pg.read_rows(first, n, out); }
 
 void BedFile::open_pgen(const std::string& pfx, const std::set<std::string>& exclude, const std::set<std::string>& extract,

@@ -10,6 +10,16 @@
 
 namespace rgh {
 
+// The records a block of variants needs, sliced out of the file for rg_pgen_decode (the device expands them; the
+// reference's counterpart is one PgenReader::Read per variant, src/Geno.cpp:1773-1821 / :2538-2594).
+struct PgenBatch {
+  std::vector<uint8_t> bytes;                   // records, each starting at a multiple of 16 bytes
+  std::vector<uint64_t> rec_off;
+  std::vector<uint32_t> rec_len;
+  std::vector<uint8_t> rec_type;                // low 3 bits of the variant record type
+  std::vector<int32_t> own, base;               // per variant: its record; the non-LD record an LD-compressed one refers to
+};
+
 struct PgenFile {
   std::string prefix;
   int sex_specific = 0;                         // 1 = males only, 2 = females only (set before open)
@@ -28,6 +38,8 @@ struct PgenFile {
             const std::set<std::string>& remove, const std::set<std::string>& keep, const std::set<int>& chrs);
   // rows of snps[first .. first+n) as PLINK 1 2-bit rows (ref-last coding: code 00 = two copies of ALT)
   void read_rows(size_t first, size_t n, uint8_t* out);
+  // the same variants as record bytes + indices (no decode on the host)
+  void gather(size_t first, size_t n, PgenBatch& out) const;
 
  private:
   long base_idx_ = -1;

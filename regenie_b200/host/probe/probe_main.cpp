@@ -24,6 +24,7 @@
 #include <zlib.h>
 
 #include "../../csrc/inflate_core.h"
+#include "../../csrc/pgen_core.h"
 #include "../bgen.hpp"
 #include "../bt_null.hpp"
 #include "../data.hpp"
@@ -105,6 +106,37 @@ int cmd_rows(char** argv) {
   std::ofstream f(argv[4], std::ios::binary);
   f.write(reinterpret_cast<const char*>(rows.data()), (std::streamsize)rows.size());
   std::cout << g.snps.size() << " " << g.row_stride << " " << g.keys.size() << "\n";
+  return 0;
+}
+
+// The device decoder's arithmetic (csrc/pgen_core.h) on the host, lanes of a warp one after the other, fed exactly like
+// rg_pgen_decode: PgenFile::gather per block of `bs` variants, rows written with the .bed stride for comparison with `rows`.
+int cmd_pgen_rows(char** argv) {
+  BedFile g;
+  g.open_pgen(argv[2], {}, {}, {}, {}, {});
+  const size_t bs = (size_t)atoi(argv[4]), m = g.snps.size();
+  const uint32_t n = g.pg->n_file, words = ((n + 15) / 16 + 3) / 4 * 4;
+  std::vector<uint8_t> rows(m * g.row_stride);
+  std::vector<uint32_t> row(words);
+  PgenBatch pb;
+  size_t nrec = 0, nbytes = 0;
+  for (size_t first = 0; first < m; first += bs) {
+    const size_t cnt = std::min(bs, m - first);
+    g.pg->gather(first, cnt, pb);
+    nrec += pb.rec_off.size(); nbytes += pb.bytes.size();
+    for (size_t j = 0; j < cnt; ++j) {
+      auto rec = [&](int32_t r) { return rgp::Rec{pb.bytes.data() + pb.rec_off[r], pb.rec_len[r], pb.rec_type[r]}; };
+      const rgp::Rec own = rec(pb.own[j]);
+      rgp::Rec base{nullptr, 0, 0};
+      if (pb.base[j] >= 0) base = rec(pb.base[j]);
+      const int e = rgp::decode_row_serial(own, pb.base[j] >= 0 ? &base : nullptr, n, row.data(), words, 32);
+      if (e) throw Fail("pgen core: error " + std::to_string(e) + " at variant " + std::to_string(first + j));
+      memcpy(&rows[(first + j) * g.row_stride], row.data(), g.row_stride);
+    }
+  }
+  std::ofstream f(argv[3], std::ios::binary);
+  f.write(reinterpret_cast<const char*>(rows.data()), (std::streamsize)rows.size());
+  std::cout << m << " " << g.row_stride << " " << g.keys.size() << " " << nrec << " " << nbytes << "\n";
   return 0;
 }
 
@@ -321,6 +353,7 @@ int main(int argc, char** argv) {
     if (c == "bgen-probs" && argc == 6) return cmd_bgen_probs(argv);
     if (c == "bgen-info" && argc >= 3) return cmd_bgen_info(argc, argv);
     if (c == "rows" && argc == 5) return cmd_rows(argv);
+    if (c == "pgen-rows" && argc == 5) return cmd_pgen_rows(argv);
     if (c == "prep" && argc >= 3) return cmd_prep(argc, argv);
     if (c == "cat" && argc == 3) return cmd_cat(argv);
     if (c == "pred-file" && argc >= 4) return cmd_pred_file(argc, argv);

@@ -280,6 +280,38 @@ def write_pgen(prefix, g, storage=1):
     return types
 
 
+def gather_pgen(pg, variants):
+    """What host/pgen.cpp PgenFile::gather hands to rg_pgen_decode, from an oracle.pgen.Pgen: the record bytes of the
+    variants (and of the bases of LD-compressed ones) at 16-byte aligned offsets + the index tables."""
+    data = bytearray()
+    rec_off, rec_len, rec_type, own, base = [], [], [], [], []
+    last = (-1, -1)
+
+    def add(v):
+        while len(data) % 16:
+            data.append(0)
+        a, b = int(pg.fpos[v]), int(pg.fpos[v + 1])
+        rec_off.append(len(data)); rec_len.append(b - a); rec_type.append(int(pg.vrtype[v]) & 7)
+        data.extend(pg.d[a:b])
+        return len(rec_off) - 1
+    for v in variants:
+        t = int(pg.vrtype[v]) & 7
+        own.append(add(v))
+        if (t & 6) != 2:
+            last = (v, own[-1]); base.append(-1)
+            continue
+        b = v - 1
+        while (int(pg.vrtype[b]) & 6) == 2:
+            b -= 1
+        if last[0] != b:
+            last = (b, add(b))
+        base.append(last[1])
+    if not data:
+        data.extend(b"\0" * 16)
+    return dict(data=np.frombuffer(bytes(data), dtype=np.uint8), rec_off=rec_off, rec_len=rec_len, rec_type=rec_type,
+                own=own, base=base)
+
+
 def write_pvar_psam(prefix, chroms, ids, pos, ref, alt, keys, sex=None):
     with open(prefix + ".pvar", "w") as fh:
         fh.write("##fileformat=test\n#CHROM\tPOS\tID\tREF\tALT\n")

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/rg_b200.h"
+#include "../../regenie_b200/csrc/pgen_core.h"
 
 struct rg_ctx {
   int kind = 0;
@@ -28,6 +29,7 @@ struct rg_ctx {
   std::vector<double> prs;
   std::vector<double> last_stat;                               // [bs x P] of the last block (Firth / SPA)
   std::vector<uint8_t> inflate_probs, inflate_miss;
+  std::vector<uint32_t> pgen_rows;
   std::vector<uint8_t> stage[4];                               // rg_s2_stage slots (host copies)
   int last_bs = 0;
 };
@@ -325,6 +327,25 @@ int rg_bgen_inflate(rg_handle h, const uint8_t* comp, const uint64_t* offs, int6
   }
   *probs = h->inflate_probs.data();
   *miss = h->inflate_miss.data();
+  return 0;
+}
+
+// the device decoder's arithmetic (csrc/pgen_core.h), lanes run serially; rows live in the handle like the device buffer
+int rg_pgen_decode(rg_handle h, const rg_pgen_block* b, const uint8_t** rows_dev, int64_t* row_stride) {
+  if (!h || !b || !rows_dev || !row_stride || !b->bytes || b->bs <= 0 || b->n_file <= 0) return fail("mock: bad pgen block");
+  const uint32_t n = (uint32_t)b->n_file, words = ((n + 15) / 16 + 3) / 4 * 4;
+  h->pgen_rows.assign((size_t)b->bs * words, 0u);
+  for (int j = 0; j < b->bs; ++j) {
+    auto rec = [&](int32_t r) { return rgp::Rec{b->bytes + b->rec_off[r], b->rec_len[r], b->rec_type[r]}; };
+    if (b->own[j] < 0 || b->own[j] >= b->n_rec || b->base[j] >= b->n_rec) return fail("mock: pgen record index out of range");
+    const rgp::Rec own = rec(b->own[j]);
+    rgp::Rec base{nullptr, 0, 0};
+    if (b->base[j] >= 0) base = rec(b->base[j]);
+    if (rgp::decode_row_serial(own, b->base[j] >= 0 ? &base : nullptr, n, &h->pgen_rows[(size_t)j * words], words, 32))
+      return fail("mock: malformed .pgen record");
+  }
+  *rows_dev = reinterpret_cast<const uint8_t*>(h->pgen_rows.data());
+  *row_stride = (int64_t)words * 4;
   return 0;
 }
 

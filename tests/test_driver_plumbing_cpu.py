@@ -20,7 +20,8 @@ MOCK = os.path.join(ROOT, "tests", "mock", "rgb200_mock")
 @pytest.fixture(scope="module", autouse=True)
 def _built():
     srcs = sorted(glob.glob(os.path.join(ROOT, "regenie_b200", "host", "*.cpp"))) + [os.path.join(ROOT, "tests", "mock", "mock_abi.cpp")]
-    deps = srcs + glob.glob(os.path.join(ROOT, "regenie_b200", "host", "*.hpp")) + [os.path.join(ROOT, "include", "rg_b200.h")]
+    deps = (srcs + glob.glob(os.path.join(ROOT, "regenie_b200", "host", "*.hpp")) + [os.path.join(ROOT, "include", "rg_b200.h"),
+            os.path.join(ROOT, "regenie_b200", "csrc", "pgen_core.h")])
     if not os.path.exists(MOCK) or any(os.path.getmtime(s) > os.path.getmtime(MOCK) for s in deps):
         r = subprocess.run(["g++", "-O1", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", MOCK] + srcs +
                            ["-lz", "-lpthread", "-ldl"], capture_output=True, text=True)

@@ -142,6 +142,77 @@ def test_host_pgen_decoder_all_record_types(tmp_path):
     assert np.array_equal(codes, want)
 
 
+def big_pgen_calls(N, M, seed=5):
+    """Calls whose records need difflists of many groups (> 32 groups = more than one round of a warp), every record type,
+    LD records whose base lies in an earlier block, and a sample count that leaves a partial last word."""
+    rng = np.random.default_rng(seed)
+    g = np.zeros((M, N), dtype=np.uint8)
+    inv = np.array([2, 1, 0, 3], dtype=np.uint8)
+
+    def near(src):                                                                # src with N / 12 calls redrawn
+        t = src.copy()
+        idx = rng.choice(N, size=N // 12, replace=False)
+        t[idx] = rng.integers(0, 4, idx.size)
+        return t
+    for v in range(M):
+        kind = v % 10
+        if kind == 0:
+            g[v] = rng.binomial(2, 0.35, N)                                       # plain 2-bit
+        elif kind == 1:
+            g[v] = near(g[v - 1])                                                 # LD against a plain record
+        elif kind == 2:
+            g[v] = rng.binomial(2, 0.03, N)                                       # difflist over 0, many groups
+        elif kind == 3:
+            g[v] = inv[near(g[v - 1])]                                            # inverted LD against a difflist record
+        elif kind == 4:
+            g[v] = 2 - rng.binomial(2, 0.02, N)                                   # difflist over 2
+        elif kind == 5:
+            g[v] = np.where(rng.random(N) < 0.93, 3, rng.binomial(2, 0.5, N))     # difflist over missing
+        elif kind == 6:
+            g[v] = np.where(rng.random(N) < 0.04, 3, 1 + rng.binomial(1, 0.4, N))  # 1 bit (1 / 2) + exceptions
+        elif kind == 7:
+            g[v] = near(g[v - 1])                                                 # LD against a 1-bit record
+        elif kind == 8:
+            g[v] = inv[near(g[v - 2])]                                            # inverted LD, base two records back
+        # kind 9: all hom-ref
+    return g
+
+
+@pytest.mark.parametrize("N,M,bs,storage", [(700, 160, 7, 5), (33333, 40, 3, 6), (70001, 20, 20, 2)])
+def test_pgen_device_core_on_the_host_equals_the_host_decoder(tmp_path, N, M, bs, storage):
+    """csrc/pgen_core.h (what pgen_fill_kernel / pgen_patch_kernel execute), lanes run serially, fed through
+    PgenFile::gather in blocks of bs variants: byte-identical to host/pgen.cpp and to the calls that were written."""
+    import helpers
+    if N == 700:
+        from test_pgen_cpu import synthetic_calls
+        g = synthetic_calls()
+    else:
+        g = big_pgen_calls(N, M)
+    pfx = str(tmp_path / "syn")
+    types = helpers.write_pgen(pfx, g, storage=storage)
+    assert set(types) >= {0, 1, 2, 3, 4, 5, 6, 7}, sorted(set(types))
+    M, N = g.shape
+    helpers.write_pvar_psam(pfx, [1] * M, ["v%d" % v for v in range(M)], list(range(1, M + 1)), ["A"] * M, ["G"] * M,
+                            ["f%d_i%d" % (i, i) for i in range(N)])
+    probe("rows", "--pgen", pfx, tmp_path / "host.bin")
+    out = probe("pgen-rows", pfx, tmp_path / "core.bin", bs).stdout.split()
+    m, stride, n, nrec = int(out[0]), int(out[1]), int(out[2]), int(out[3])
+    assert (m, n) == g.shape and nrec >= m
+    a = np.fromfile(tmp_path / "host.bin", dtype=np.uint8)
+    b = np.fromfile(tmp_path / "core.bin", dtype=np.uint8)
+    assert np.array_equal(a, b)
+    rows = b.reshape(m, stride)
+    codes = np.stack([(rows >> (2 * k)) & 3 for k in range(4)], axis=-1).reshape(m, -1)
+    assert np.array_equal(codes[:, :n], np.array([3, 2, 0, 1], dtype=np.uint8)[g]) and not codes[:, n:].any()
+
+
+def test_pgen_device_core_on_the_reference_fixture(golden_dir, tmp_path):
+    probe("rows", "--bed", golden_dir + "/example", tmp_path / "bed.bin")
+    for bs in (1, 100):
+        probe("pgen-rows", golden_dir + "/example", tmp_path / "core.bin", bs)
+        assert np.array_equal(np.fromfile(tmp_path / "bed.bin", dtype=np.uint8), np.fromfile(tmp_path / "core.bin", dtype=np.uint8))
+
+
 # ------------------------------------------------------------------------------------------- phenotype preparation
 def _keys(golden_dir, remove=False):
     keys, _ = plink.read_fam(golden_dir + "/example.fam")
