@@ -561,17 +561,21 @@ def file_e2e_leg(host_panel, N, M, bs, P, Yr, cov, na, gpus=1):
         if gpus > 1:
             cmd += ["--gpus", str(gpus)]
         t0 = time.perf_counter()
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, RG_B200_PHASES="1"))
         dt = time.perf_counter() - t0
         if r.returncode != 0:
             return {"error": (r.stdout + r.stderr)[-300:]}
+        phases = {}                                        # the driver's own wall clock per phase (stderr, RG_B200_PHASES)
+        for l in r.stderr.splitlines():
+            if l.startswith("[phase]") and "(+" in l:
+                phases[l[7:].split("  ")[0].strip()] = float(l.split("(+")[1].split(")")[0])
         l0 = [l for l in r.stdout.splitlines() if "Level 0 done" in l]
         l0_ms = float(l0[0].split("(")[1].split("ms")[0]) if l0 else None
         ok = all(os.path.exists(os.path.join(d, "fit_%d.loco" % (p + 1))) for p in range(P))
         return {"metric": "step1_from_files_snps_per_sec", "value": M / dt, "unit": "SNPs/s", "seconds": dt,
                 "level0_seconds_driver_log": None if l0_ms is None else l0_ms / 1e3,
                 "level0_snps_per_sec_driver_log": None if not l0_ms else M / (l0_ms / 1e3),
-                "loco_files_written": ok, "fileset_write_seconds": t_write,
+                "loco_files_written": ok, "fileset_write_seconds": t_write, "phase_ms": phases,
                 "what": "rgb200 --step 1 --bed (1.25 GB .bed in /dev/shm) --phenoFile --covarFile --bsize %d --out: process start to exit, "
                         "i.e. text parsing, phenotype preparation, level 0 from the file, level 1 (B = %d), LOCO and the %d .loco files"
                         % (bs, (M // bs) * 5, P)}

@@ -38,6 +38,10 @@ const char* rg_last_error(void);
 const char* rg_version(void);
 /* number of usable CUDA devices (0 => nothing below can run) */
 int rg_device_count(void);
+/* Optional: create the CUDA context of `device` now (driver initialisation + context creation take of the order of a
+ * second on a multi-GPU node).  A caller may run it on a side thread while it parses its text inputs, as rgb200 does;
+ * the create calls below do the same work when it has not been done. */
+int rg_warmup(int32_t device);
 
 /* ------------------------------------------------------------------ Step 1 */
 typedef struct rg_step1_config {

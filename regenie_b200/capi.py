@@ -79,7 +79,7 @@ EXPORTS = [
     "rg_s2_set_chr", "rg_s2_block_bed", "rg_W_info", "rg_debug_fetch", "rg_launch_count", "rg_stream",
     "rg_set_timing", "rg_get_timing", "rg_fence", "rg_s2_set_chr_bt", "rg_s2_block_bgen8_bt", "rg_s2_block_bgen8", "rg_s2_firth", "rg_l1_fit_bt", "rg_W_set_owned", "rg_W_export", "rg_W_attach_peer", "rg_l1_select", "rg_s2_set_sex", "rg_s2_set_non_par", "rg_l0_load_W", "rg_s2_spa", "rg_s2_block_bed_bt", "rg_prs", "rg_bgen_inflate",
     "rg_l0_solver_stats", "rg_dbg_mixed_solve", "rg_l0_wait_input", "rg_l0_block_dosage_u8", "rg_l0_block_f64", "rg_W_attach_local",
-    "rg_s2_stage", "rg_host_alloc", "rg_host_free", "rg_pgen_decode",
+    "rg_s2_stage", "rg_host_alloc", "rg_host_free", "rg_pgen_decode", "rg_warmup",
 ]
 
 _lib = None

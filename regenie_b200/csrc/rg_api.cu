@@ -761,6 +761,14 @@ int rg_device_count(void) {
   return n;
 }
 
+int rg_warmup(int32_t device) {
+  RG_API_BEGIN
+  require_gpu(device);
+  RG_CUDA(cudaSetDevice(device));
+  RG_CUDA(cudaFree(nullptr));
+  RG_API_END
+}
+
 int rg_step1_create(const rg_step1_config* cfg, const double* X, const double* Y, const uint8_t* mask,
                     const uint8_t* in_analysis, const int64_t* fold_sizes, const double* lambda,
                     const double* neff, rg_handle* out) {

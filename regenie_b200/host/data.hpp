@@ -41,6 +41,11 @@ struct BedFile {
   std::map<std::string, uint32_t> key_to_ind; // FID_IID_to_ind
   uint64_t row_stride = 0;
   std::ifstream bed;
+  int bed_fd = -1;                            // the same file for pread(): positioned reads from several threads, no shared cursor
+  BedFile() = default;
+  BedFile(const BedFile&) = delete;
+  BedFile& operator=(const BedFile&) = delete;
+  ~BedFile();
   void open(const std::string& prefix, bool ref_first, const std::set<std::string>& exclude,
             const std::set<std::string>& extract, const std::set<std::string>& remove,
             const std::set<std::string>& keep, const std::set<int>& chrs = {});

@@ -293,6 +293,22 @@ double now_ms() {
   return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
+// RG_B200_PHASES=1: wall-clock of the driver's phases on stderr (bench.py's from-files leg reads them); no effect on outputs
+static void phase(const char* name) {
+  static const bool on = getenv("RG_B200_PHASES") != nullptr;
+  static const double t_start = now_ms();
+  static double t_last = t_start;
+  if (!on) return;
+  const double t = now_ms();
+  fprintf(stderr, "[phase] %-22s %9.1f ms  (+%.1f)\n", name, t - t_start, t - t_last);
+  t_last = t;
+}
+
+static std::shared_future<int> g_ndev;              // number of CUDA devices, from the warm-up thread started in main()
+static void require_device() {
+  if (g_ndev.valid() && g_ndev.get() < 1) throw Fail("no CUDA device available: rgb200 has no CPU fallback");
+}
+
 // ------------------------------------------------------------------------------------ step 1
 // .pgen input: the records of a block go to the GPU as they are and are expanded there (rg_pgen_decode).
 // RG_B200_PGEN=host selects the host decoder (host/pgen.cpp), which also serves the options that edit rows on the host
@@ -468,6 +484,9 @@ void run_step1(const Params& p_in, Log& log) {
     if (p.run_l0_job || p.run_l1 || p.split_jobs) throw Fail("--gpus N shards one run; it cannot be combined with --split-l0 / --run-l0 / --run-l1.");
     log << " * sharding level 0 over " << G << " GPUs (blocks), level 1 by phenotype\n";
   }
+  phase("inputs parsed");
+  require_device();
+  phase("cuda context");
   std::vector<rg_handle> hs(G, nullptr);
   struct HandlesGuard {
     std::vector<rg_handle>& v;
@@ -479,6 +498,7 @@ void run_step1(const Params& p_in, Log& log) {
                              p.loocv ? nullptr : folds.data(), lambda.data(), ph.neff.data(), &hs[d]));
   }
   rg_handle h = hs[0];
+  phase("rg_step1_create");
   std::vector<std::vector<uint8_t>> owned(G, std::vector<uint8_t>(P, 0));
   if (G > 1) {
     for (int i = 0; i < P; ++i) owned[i % G][i] = 1;
@@ -526,8 +546,19 @@ void run_step1(const Params& p_in, Log& log) {
   }
   // a reader thread fetches block b+1 from the file while block b is handed to the GPU (two pageable buffers: the copy
   // out of a buffer is staged before rg_l0_block_bed returns, so it can be refilled two blocks later)
-  std::vector<uint8_t> rows2(rows.size());
-  uint8_t* bufs[2] = {rows.data(), rows2.data()};
+  // .bed rows: two PINNED buffers (rg_host_alloc), so the block crosses PCIe by DMA straight from the buffer the reader
+  // filled (a pageable buffer is first copied into the driver's staging area, ~5 ms per 25 MB block); rg_l0_wait_input
+  // after each call tells when the buffer may be refilled
+  struct PinnedPair {
+    void* p[2] = {nullptr, nullptr};
+    ~PinnedPair() { for (void* q : p) if (q) rg_host_free(q); }
+  } pinned;
+  std::vector<uint8_t> rows2;
+  uint8_t* bufs[2] = {rows.data(), nullptr};
+  const bool pin_rows = !use_bgen && !p.run_l1 && G == 1 && !rows.empty() && !(gbed.pg && pgen_on_device()) &&
+                        rg_host_alloc(&pinned.p[0], (int64_t)rows.size()) == 0 && rg_host_alloc(&pinned.p[1], (int64_t)rows.size()) == 0;
+  if (pin_rows) { bufs[0] = (uint8_t*)pinned.p[0]; bufs[1] = (uint8_t*)pinned.p[1]; }
+  else { rows2.resize(rows.size()); bufs[1] = rows2.data(); }
   std::vector<uint8_t> probs[2], pmiss[2];                     // .bgen: inflated probability pairs + ploidy bytes of a block
   if (use_bgen && !p.run_l1)
     for (int k = 0; k < 2; ++k) { probs[k].resize((size_t)p.bsize * g.n_file * 2); pmiss[k].resize((size_t)p.bsize * g.n_file); }
@@ -557,9 +588,11 @@ void run_step1(const Params& p_in, Log& log) {
         int64_t dstride = 0;
         pgen_rows_device(h, pbatch[b & 1], blocks[b].size, (int64_t)gbed.pg->n_file, b, &drows, &dstride);
         rg_check(rg_l0_block_bed(h, drows, dstride, blocks[b].size, subset ? g.sample_idx.data() : nullptr, p.ref_first, b));
-      } else
+      } else {
         rg_check(rg_l0_block_bed(h, bufs[b & 1], (int64_t)g.row_stride, blocks[b].size,
                                  subset ? g.sample_idx.data() : nullptr, p.ref_first, b));
+        if (pin_rows) rg_check(rg_l0_wait_input(h));
+      }
       log << " block [" << b + 1 << "] : " << blocks[b].size << " snps\n";
     }
   } else {
@@ -612,6 +645,7 @@ void run_step1(const Params& p_in, Log& log) {
     }
   }
   log << " Level 0 done (" << (long)(now_ms() - t0) << "ms)\n";
+  phase("level 0");
   if ((p.lowmem && p.keep_l0) || p.run_l0_job) {
     // write_l0_file (src/Step1_Models.cpp:728-733): per phenotype, per block an N x R column-major f64 slab.
     // The reference deletes these after level 1 unless --keep-l0 (src/Data.cpp:1011,1108,1131-1137); here W
@@ -656,6 +690,7 @@ void run_step1(const Params& p_in, Log& log) {
   } else if (G == 1) {
     rg_check(rg_l1_fit(h, tau.data(), cs.data(), best.data()));
   }
+  phase("level 1");
   std::vector<int32_t> chr_of_block(nb);
   for (int b = 0; b < nb; ++b) chr_of_block[b] = blocks[b].chrom;
   std::vector<double> loco((size_t)P * 23 * N);
@@ -714,6 +749,7 @@ void run_step1(const Params& p_in, Log& log) {
   for (auto& kv : g.key_to_ind) if (ph.in_analysis[kv.second]) order.push_back(kv.second);
   std::vector<int> chr_labels(23);
   for (int c = 0; c < 23; ++c) chr_labels[c] = c + 1;
+  phase("loco assembled");
   for (int ph_i = 0; ph_i < P; ++ph_i) {
     if (!l1_sel[ph_i]) continue;
     log << "phenotype " << ph_i + 1 << " (" << ph.names[ph_i] << ") : \n";
@@ -786,6 +822,7 @@ void run_step1(const Params& p_in, Log& log) {
     log << "List of files with null Firth estimates written to: [" << p.out << "_firth.list]\n";
   }
   plist.close();
+  phase("prediction files");
   if (p.run_l1 && !p.keep_l0)                        // rm_l0_files (src/Data.cpp:1131-1147)
     for (const auto& mj : master.jobs) {
       for (int ph_i = 0; ph_i < P; ++ph_i) remove((mj.prefix + "_l0_Y" + std::to_string(ph_i + 1)).c_str());
@@ -1058,6 +1095,7 @@ void run_step2_qt(const Params& p, Log& log) {
   cfg.n_analyzed = ph.n_analyzed; cfg.strict_mode = ph.strict;
   rg_handle h = nullptr;
   HandleGuard guard{h};
+  require_device();
   rg_check(rg_step2_create(&cfg, ph.X.data(), ph.mask.data(), ph.in_analysis.data(), &h));
 
   S2Writers w;
@@ -1279,6 +1317,7 @@ void run_step2_bt(const Params& p, Log& log) {
   cfg.n_analyzed = ph.n_analyzed; cfg.strict_mode = ph.strict;
   rg_handle h = nullptr;
   HandleGuard guard{h};
+  require_device();
   rg_check(rg_step2_create(&cfg, ph.X.data(), ph.mask.data(), ph.in_analysis.data(), &h));
 
   S2Writers w;
@@ -1549,6 +1588,7 @@ void run_step2(const Params& p_in, Log& log) {
 int main(int argc, char** argv) {
   Log log;
   try {
+    phase("start");
     const Params p = parse_cli(argc, argv);
     log.open(p.out + ".log");
     log << "rgb200 (" << rg_version() << ")\nOptions in effect:\n";
@@ -1557,7 +1597,15 @@ int main(int argc, char** argv) {
       log << (argv[i][0] == '-' && argv[i][1] == '-' ? "  " : "") << argv[i] << (next_is_value ? " " : " \\\n");
     }
     log << "\n";
-    if (rg_device_count() < 1) throw Fail("no CUDA device available: rgb200 has no CPU fallback");
+    // CUDA driver initialisation and context creation (of the order of a second on a multi-GPU node) run on a side thread
+    // while the text inputs are parsed; a host without any device answers at once and stops here, before touching data
+    g_ndev = std::async(std::launch::async, [gpu = p.gpu, G = std::max(1, p.gpus)] {
+      const int n = rg_device_count();
+      for (int d = 0; d < G && n > 0; ++d) rg_warmup(G > 1 ? d : gpu);
+      return n;
+    }).share();
+    if (g_ndev.wait_for(std::chrono::milliseconds(20)) == std::future_status::ready) require_device();
+    phase("rg_device_count");
     const double t0 = now_ms();
     if (p.step == 1) run_step1(p, log); else run_step2(p, log);
     log << "\nElapsed time : " << (now_ms() - t0) / 1e3 << "s\nEnd of rgb200\n";

@@ -111,6 +111,8 @@ extern "C" {
 const char* rg_last_error(void) { return g_err.c_str(); }
 const char* rg_version(void) { return "mock ABI for host-plumbing tests"; }
 int rg_device_count(void) { return 1; }
+int rg_warmup(int32_t) { return 0; }
+int rg_l0_wait_input(rg_handle) { return 0; }
 void rg_destroy(rg_handle h) { delete h; }
 int rg_sync(rg_handle) { return 0; }
 
