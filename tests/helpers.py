@@ -189,127 +189,20 @@ def prepare_step2_with_mask(keys, pheno, covar, extra_mask):
     return prep.Prepared(list(keys), names, Y, None, mask, Xb, in_an, neff, scale_Y, ncov, int(in_an.sum()))
 
 
-# ---------------------------------------------------------------------------------------- .pgen writer (tests only)
-def _vint_bytes(v):
-    out = bytearray()
-    while True:
-        b = v & 0x7F
-        v >>= 7
-        if v:
-            out.append(b | 0x80)
-        else:
-            out.append(b)
-            return bytes(out)
-
-
-def _pack2(vals):
-    vals = np.asarray(vals, dtype=np.uint8)
-    pad = (-len(vals)) % 4
-    v = np.concatenate([vals, np.zeros(pad, dtype=np.uint8)]).reshape(-1, 4)
-    return (v[:, 0] | (v[:, 1] << 2) | (v[:, 2] << 4) | (v[:, 3] << 6)).astype(np.uint8).tobytes()
-
-
-def _difflist_bytes(ids, vals, n):
-    ids = list(map(int, ids))
-    out = bytearray(_vint_bytes(len(ids)))
-    if not ids:
-        return bytes(out)
-    sb = 1 if n <= 0xFF else 2 if n <= 0xFFFF else 3 if n <= 0xFFFFFF else 4
-    ng = (len(ids) + 63) // 64
-    deltas = []
-    for g in range(ng):
-        grp = ids[g * 64:(g + 1) * 64]
-        out += grp[0].to_bytes(sb, "little")
-        deltas.append(b"".join(_vint_bytes(b - a) for a, b in zip(grp[:-1], grp[1:])))
-    for g in range(ng - 1):
-        out.append((len(deltas[g]) - 63) & 0xFF)          # group byte counts (only used for random access)
-    out += _pack2(vals)
-    for dl in deltas:
-        out += dl
-    return bytes(out)
-
-
-def write_pgen(prefix, g, storage=1):
-    """Write <prefix>.pgen (mode 0x10) for g [M, N] with values 0/1/2 (ALT counts) and 3 (missing), choosing for every
-    variant the most compressed record type that applies, like plink2 does: all-zero (5), difflist over a constant
-    (4/6/7), LD difflist against the previous non-LD record (2) or its inversion (3), 1-bit + difflist (1), plain (0).
-    Returns the list of record types used."""
-    M, N = g.shape
-    recs, types = [], []
-    base = None
-    inv = np.array([2, 1, 0, 3], dtype=np.uint8)
-    for v in range(M):
-        x = g[v].astype(np.uint8)
-        cands = []
-        if not x.any():
-            cands.append((5, b""))
-        for const, t in ((0, 4), (2, 6), (3, 7)):
-            ids = np.nonzero(x != const)[0]
-            if len(ids) <= N // 8:
-                cands.append((t, _difflist_bytes(ids, x[ids], N)))
-        if base is not None:
-            for t, tgt in ((2, x), (3, inv[x])):
-                ids = np.nonzero(tgt != base)[0]
-                if len(ids) <= N // 8:
-                    cands.append((t, _difflist_bytes(ids, tgt[ids], N)))
-        cnt = np.bincount(x, minlength=4)
-        top = sorted(np.argsort(-cnt, kind="stable")[:2])
-        lo, hi = int(top[0]), int(top[1])
-        ids = np.nonzero((x != lo) & (x != hi))[0]
-        if len(ids) <= N // 8:
-            bits = np.packbits((x == hi).astype(np.uint8), bitorder="little").tobytes()
-            cands.append((1, bytes([(lo << 2) | (hi - lo)]) + bits + _difflist_bytes(ids, x[ids], N)))
-        cands.append((0, _pack2(x)))
-        t, rec = min(cands, key=lambda c: (len(c[1]), c[0]))
-        if (t & 6) != 2:
-            base = x.copy()
-        recs.append(rec); types.append(t)
-    lb = 1 + (storage & 3)
-    hdr = bytearray(b"\x6c\x1b\x10") + M.to_bytes(4, "little") + N.to_bytes(4, "little") + bytes([0x80 | storage])
-    body_hdr = bytearray()
-    if storage < 4:
-        tt = types + [0] * (len(types) % 2)
-        body_hdr += bytes(tt[i] | (tt[i + 1] << 4) for i in range(0, len(tt), 2))
-    else:
-        body_hdr += bytes(types)
-    for r in recs:
-        body_hdr += len(r).to_bytes(lb, "little")
-    first = len(hdr) + 8 + len(body_hdr)
-    with open(prefix + ".pgen", "wb") as fh:
-        fh.write(hdr + first.to_bytes(8, "little") + body_hdr + b"".join(recs))
-    return types
+# ---------------------------------------------------------------------------------------- .pgen writer
+from regenie_b200.synth import write_pgen, gather_pgen_records  # noqa: E402,F401  (synthetic-data generator; checked by pgenlib in tests)
 
 
 def gather_pgen(pg, variants):
     """What host/pgen.cpp PgenFile::gather hands to rg_pgen_decode, from an oracle.pgen.Pgen: the record bytes of the
     variants (and of the bases of LD-compressed ones) at 16-byte aligned offsets + the index tables."""
-    data = bytearray()
-    rec_off, rec_len, rec_type, own, base = [], [], [], [], []
-    last = (-1, -1)
+    recs = {}
 
-    def add(v):
-        while len(data) % 16:
-            data.append(0)
-        a, b = int(pg.fpos[v]), int(pg.fpos[v + 1])
-        rec_off.append(len(data)); rec_len.append(b - a); rec_type.append(int(pg.vrtype[v]) & 7)
-        data.extend(pg.d[a:b])
-        return len(rec_off) - 1
-    for v in variants:
-        t = int(pg.vrtype[v]) & 7
-        own.append(add(v))
-        if (t & 6) != 2:
-            last = (v, own[-1]); base.append(-1)
-            continue
-        b = v - 1
-        while (int(pg.vrtype[b]) & 6) == 2:
-            b -= 1
-        if last[0] != b:
-            last = (b, add(b))
-        base.append(last[1])
-    if not data:
-        data.extend(b"\0" * 16)
-    return dict(data=np.frombuffer(bytes(data), dtype=np.uint8), rec_off=rec_off, rec_len=rec_len, rec_type=rec_type,
-                own=own, base=base)
+    def rec(v):
+        if v not in recs:
+            recs[v] = pg.d[int(pg.fpos[v]):int(pg.fpos[v + 1])]
+        return recs[v]
+    return gather_pgen_records(rec, lambda v: int(pg.vrtype[v]) & 7, variants)
 
 
 def write_pvar_psam(prefix, chroms, ids, pos, ref, alt, keys, sex=None):
