@@ -158,7 +158,8 @@ def score_qt(g, X, res, mask, in_analysis, n_analyzed, ncov, scf_sv, YtX, strict
     se = beta / stats
     chisq = stats ** 2
     logp = np.array([get_logp(c) for c in chisq])
-    return dict(beta=beta, se=se, chisq=chisq, logp=logp, stats=stats, is_sparse=is_sparse, scale_fac=sf)
+    return dict(beta=beta, se=se, chisq=chisq, logp=logp, stats=stats, is_sparse=is_sparse, scale_fac=sf,
+                score=num, skat_var=den)               # dt_thr->scores / skat_var with --htp (:372-373, :391-394, :421-424)
 
 
 def fmt(x):
@@ -187,3 +188,112 @@ def sumstats_row(chrom, pos, vid, a0, a1, af, n, beta, se, chisq, logp, test="AD
 
 HEADER = "CHROM GENPOS ID ALLELE0 ALLELE1 A1FREQ N TEST BETA SE CHISQ LOG10P EXTRA\n"
 HEADER_INFO = "CHROM GENPOS ID ALLELE0 ALLELE1 A1FREQ INFO N TEST BETA SE CHISQ LOG10P EXTRA\n"
+
+
+# ------------------------------------------------------------------------------------------ --htp (HTPv4 rows)
+ZCRIT = 1.959963984540054                      # quantile(complement(normal, .025)), src/Data.cpp:2118
+LOG10_NL_DBL_DMIN = -math.log10(10.0 * 2.2250738585072014e-308)     # src/Regenie.hpp:229-230
+
+HTP_HEADER = "\t".join(["Name", "Chr", "Pos", "Ref", "Alt", "Trait", "Cohort", "Model", "Effect", "LCI_Effect", "UCI_Effect",
+                         "Pval", "AAF", "Num_Cases", "Cases_Ref", "Cases_Het", "Cases_Alt", "Num_Controls", "Controls_Ref",
+                         "Controls_Het", "Controls_Alt", "Info"]) + "\n"      # print_header_output_htp, src/Step2_Models.cpp:2400
+
+
+def convert_double_to_str(v):
+    """src/Regenie.cpp:1691-1698."""
+    return ("%.6f" % v) if (v < 5000 and v > 1e-5) else ("%g" % v)
+
+
+def convert_logp_raw(logp, log_dbl_min=-math.log10(2.2250738585072014e-308) - 1):
+    """src/Regenie.cpp:1700-1717 (default argument: src/Regenie.hpp:533)."""
+    if logp <= 3:
+        return "%f" % (10.0 ** -logp)
+    if logp <= log_dbl_min:
+        return "%g" % (10.0 ** -logp)
+    thr = math.log(9.95) / math.log(10)
+    base = math.ceil(logp)
+    res = base - logp
+    if res >= thr:
+        res = 0
+        base += 1
+    return "%.1fe-%d" % (10.0 ** res, base)
+
+
+def htp_model(test="ADD", wgr=True, bt=False, firth=False, spa=False):
+    """test_string + wgr_string + correction_type, src/Data.cpp:2075-2102."""
+    return test + ("-WGR" if wgr else "") + ("-FIRTH" if bt and firth else "-SPA" if bt and spa else "-LOG" if bt else "-LR")
+
+
+def genocounts(g_raw, cases, controls=None):
+    """update_genocounts (src/Geno.cpp:2986-3018) off chrX: thresholded counts (>= 1.5 alt, >= 0.5 het, < 0 missing) in the
+    samples of `cases` (all samples with the trait for a QT) and, for a binary trait, of `controls`. -> 6 ints."""
+    out = [0] * 6
+    for k, idx in enumerate((cases, controls)):
+        if idx is None:
+            continue
+        v = g_raw[idx]
+        miss = int((v < 0).sum())
+        alt = int((v >= 1.5).sum())
+        het = int(((v >= 0.5) & (v < 1.5)).sum())
+        out[3 * k: 3 * k + 3] = [len(idx) - het - alt - miss, het, alt]
+    return out
+
+
+def htp_row(vid, chrom, pos, a0, a1, trait, cohort, model, beta, se, chisq, lpv, af, mac, gc, test_pass=True, bt=False,
+            firth=False, score=None, skat_var=None, cal_factor=-1.0, info=None):
+    """print_sum_stats_head_htp + print_sum_stats_htp (src/Step2_Models.cpp:2419-2426, :2542-2646) for the single-variant
+    tests of this repo (df = 1, no joint / burden columns).  gc = the 6 genotype counts of the trait."""
+    s = "%s\t%d\t%d\t%s\t%s\t%s\t%s\t%s\t" % (vid, chrom, pos, a0, a1, trait, cohort, model)
+    print_beta = test_pass and se >= 0 and not math.isnan(se)
+    print_pv = test_pass and chisq >= 0 and not math.isnan(lpv)
+    outp = "-1"
+    if print_pv:
+        if lpv > LOG10_NL_DBL_DMIN:
+            outp = convert_logp_raw(LOG10_NL_DBL_DMIN)
+        elif lpv > 0:
+            outp = convert_logp_raw(lpv)
+        else:
+            outp = "0.9999999"
+    outse = None
+    if print_pv and not print_beta:
+        s += "NA\tNA\tNA\t" + outp + "\t"
+    elif not print_pv and not print_beta:
+        s += "NA\tNA\tNA\tNA\t"
+    elif (not bt) or (bt and firth and test_pass):
+        if not bt:
+            s += "%s\t%s\t%s\t" % (fmt(beta), fmt(beta - ZCRIT * se), fmt(beta + ZCRIT * se))
+        else:
+            s += "%s\t%s\t%s\t" % (fmt(math.exp(beta)), fmt(math.exp(beta - ZCRIT * se)), fmt(math.exp(beta + ZCRIT * se)))
+        s += (outp if print_pv else "NA") + "\t"
+    else:
+        if print_pv:                                   # SPA / uncorrected logistic score test: allelic odds ratio
+            eff = ((2 * gc[3] + gc[4] + .5) * (2 * gc[2] + gc[1] + .5) / (2 * gc[5] + gc[4] + .5) / (2 * gc[0] + gc[1] + .5))
+            outse = abs(math.log(eff)) / math.sqrt(chisq)
+            s += "%s\t%s\t%s\t%s\t" % (fmt(eff), fmt(eff * math.exp(-ZCRIT * outse)), fmt(eff * math.exp(ZCRIT * outse)), outp)
+        else:
+            s += "%s\t%s\t%s\tNA\t" % (fmt(math.exp(beta)), fmt(math.exp(beta - ZCRIT * se)), fmt(math.exp(beta + ZCRIT * se)))
+    s += (fmt(af) + "\t") if af >= 0 else "NA\t"
+    s += "%d\t%d\t%d\t%d\t" % (gc[0] + gc[1] + gc[2], gc[0], gc[1], gc[2])
+    s += ("%d\t%d\t%d\t%d" % (gc[3] + gc[4] + gc[5], gc[3], gc[4], gc[5])) if bt else "NA\tNA\tNA\tNA"
+    col = []
+    if print_beta:
+        if bt and test_pass:
+            col += ["REGENIE_BETA=" + convert_double_to_str(beta), "REGENIE_SE=" + convert_double_to_str(se)]
+            if print_pv and not firth:
+                col.append("SE=" + convert_double_to_str(outse))
+        elif bt:
+            col += ["REGENIE_BETA=NA", "REGENIE_SE=NA"]
+        else:
+            col.append("REGENIE_SE=%f" % se)
+    if info is not None and info >= 0:
+        col.append("INFO=" + convert_double_to_str(info))
+    if mac >= 0:
+        col.append("MAC=%f" % mac)
+    if score is not None:
+        col.append("SCORE=" + convert_double_to_str(score))
+    if skat_var is not None:
+        col.append("SKATV=" + convert_double_to_str(skat_var * abs(cal_factor)))
+    col.append("LOG10P=" + (convert_double_to_str(lpv) if print_pv else "NA"))
+    if se < 0:
+        col.append("NO_BETA")
+    return s + "\t" + ";".join(col) + "\n"

@@ -64,6 +64,8 @@ struct Params {
   bool af_cc = false;                          // --af-cc: A1FREQ / N among cases and controls (binary traits, split output)
   int min_case_count = 10;                     // --minCaseCount
   bool no_split = false;                       // --no-split: one <out>.regenie for all traits (hard-call input)
+  std::string htp_cohort;                      // --htp COHORT: HTPv4 rows (src/Step2_Models.cpp:2400-2426, :2542-2646); quantitative traits, hard calls
+  bool htp = false;
   int test_type = 0;                           // --test additive | dominant | recessive (step 2)
   int gpus = 1;                                // --gpus N (step 1): level-0 blocks sharded over N GPUs of this node, level 1 by phenotype
   bool gpu_inflate = false;                    // --gpu-inflate: zlib payloads of the .bgen are inflated on the device (rg_bgen_inflate)
@@ -207,6 +209,7 @@ Params parse_cli(int argc, char** argv) {
     else if (a == "--bgi") p.bgi = need(i);
     else if (a == "--gpu-inflate") p.gpu_inflate = true;
     else if (a == "--no-split") p.no_split = true;
+    else if (a == "--htp") { p.htp_cohort = need(i); p.htp = true; }
     else if (a == "--af-cc") p.af_cc = true;
     else if (a == "--sex-specific") {                          // src/Regenie.cpp:756-762
       const std::string v = need(i);
@@ -273,6 +276,14 @@ Params parse_cli(int argc, char** argv) {
   if (p.write_samples && !p.bgen.empty() && p.sample.empty())                     // src/Regenie.cpp:903-904
     throw Fail("must specify sample file (using --sample) if writing sample IDs to file.");
   if (p.step == 2 && p.pred.empty() && !p.ignore_pred) throw Fail("must specify --pred if using --step 2 (otherwise use --ignore-pred).");
+  if (p.htp) {
+    if (p.step != 2) throw Fail("option --htp only works in step 2.");
+    // print_sum_stats_htp also serves binary traits (odds ratios, case / control genotype counts) and dosages (INFO=):
+    // this driver writes HTP rows for quantitative traits on hard calls and says so for the rest
+    if (p.bt) throw Fail("--htp with --bt is outside the hot path covered by rgb200 (HTP rows are written for quantitative traits).");
+    if (!p.bgen.empty()) throw Fail("--htp with --bgen is outside the hot path covered by rgb200 (HTP rows are written for hard-call input).");
+    if (p.no_split) p.no_split = false;                       // src/Regenie.cpp:1068-1071: --no-split is ignored with --htp
+  }
   return p;
 }
 
@@ -910,7 +921,7 @@ struct S2Writers {
     outs = std::vector<TextWriter>(ph.P);
     for (int i = 0; i < ph.P; ++i) {
       outs[i].open(p.out + "_" + ph.names[i] + ".regenie" + gz_ext);
-      outs[i] << sumstats_header(with_info, p.af_cc);
+      outs[i] << (p.htp ? htp_header() : sumstats_header(with_info, p.af_cc));
     }
   }
   void flush() {
@@ -1103,7 +1114,7 @@ void run_step2_qt(const Params& p, Log& log) {
   std::vector<std::string>& obuf = w.obuf;                   // rows of the current block, one buffer per trait
   std::string head_s;
   const int bsz = p.bsize;
-  GenoCounts gc(p.no_split, bsz, P, use_bgen ? 0 : g.row_stride, p.ref_first);
+  GenoCounts gc(p.no_split || p.htp, bsz, P, use_bgen ? 0 : g.row_stride, p.ref_first);
   // input blocks are fetched (file read / threaded BGEN inflate) one block ahead of the GPU call: the rg_s2_block_*
   // calls return with the results on the host, so the buffer of block b is free again when block b+2 is fetched
   std::vector<uint8_t> rows[2], probs[2], pmiss[2];
@@ -1125,7 +1136,7 @@ void run_step2_qt(const Params& p, Log& log) {
   std::vector<long> d_rr[2], d_aa[2];
   if (use_info1) for (int k = 0; k < 2; ++k) { info1[k].resize(bsz); d_rr[k].resize(bsz); d_aa[k].resize(bsz); }
   // .pgen records are expanded on the GPU unless an option edits the rows on the host (see pgen_on_device)
-  const bool pgen_dev = !use_bgen && g.pg && pgen_on_device() && !p.no_split && p.test_type == 0;
+  const bool pgen_dev = !use_bgen && g.pg && pgen_on_device() && !p.no_split && !p.htp && p.test_type == 0;
   if (pgen_dev) log << " * pgen records are decoded on the GPU\n";
   PgenBatch pbatch[2];
   std::future<void> pending;
@@ -1153,6 +1164,8 @@ void run_step2_qt(const Params& p, Log& log) {
   rg_s2_out out{af.data(), ns.data(), mac.data(), af_all.data(), ns_all.data(), mac_all.data(), flags.data(),
                 scale_fac.data(), stat.data(), beta.data(), se.data(), chisq.data()};
   const bool subset = keys.size() != n_file;
+  // --htp: test_string + wgr_string + correction_type (src/Data.cpp:2075-2102)
+  const std::string htp_model = std::string(test_name(p.test_type)) + (p.ignore_pred ? "" : "-WGR") + "-LR";
   // second pass of --test dominant / recessive: counts go to scratch, the test columns to the arrays that are printed
   const Recode recode(p.test_type, p.ref_first);
   std::vector<double> af2, mac2, af_all2, mac_all2, info2;
@@ -1231,6 +1244,10 @@ void run_step2_qt(const Params& p, Log& log) {
       head_s += s.id; head_s += ' ';
       head_s += s.allele0; head_s += ' ';
       head_s += s.allele1; head_s += ' ';
+      if (p.htp) {                                             // print_sum_stats_head_htp :2419-2426
+        if (chrom == 23) throw Fail("--htp on chromosome X is outside the hot path covered by rgb200 (sex-aware genotype counts).");
+        head_s = s.id + "\t" + std::to_string(s.chrom) + "\t" + std::to_string(s.pos) + "\t" + s.allele0 + "\t" + s.allele1 + "\t";
+      }
       if (p.no_split) {                                        // print_sum_stats_all :2441-2493
         long n_rr, n_ra, n_aa;
         if (use_bgen) { n_rr = d_rr[b & 1][v]; n_aa = d_aa[b & 1][v]; n_ra = ns_all[v] - n_rr - n_aa; }
@@ -1244,6 +1261,21 @@ void run_step2_qt(const Params& p, Log& log) {
                           !(use_bgen && info[e] < p.min_info);  // --minINFO (src/Geno.cpp:3142-3146)
         if (p.no_split) { append_sumstats_all_trait(w.obuf_all, have, beta[e], se[e], chisq[e], get_logp(chisq[e]), true); continue; }
         if (!have) continue;
+        if (p.htp) {
+          // print_sum_stats_htp for a quantitative trait.  Genotype counts of the trait's samples (update_genocounts,
+          // src/Geno.cpp:2986-3003) from exact allele sums: hom-alt = allele sum of the recessive recoding, het = additive sum
+          // - 2 hom-alt.  SCORE / SKATV are the numerator and denominator of the statistic (dt_thr->scores / skat_var,
+          // src/Step2_Models.cpp:391-394, :421-424): se = scf / sqrt(denum), stat = num / sqrt(denum).
+          HtpRow r;
+          r.model = htp_model.c_str();
+          r.beta = beta[e]; r.se = se[e]; r.chisq = chisq[e]; r.logp = get_logp(chisq[e]); r.af = af[e]; r.mac = mac[e];
+          const long hom = std::lround(2.0 * gc.af[e] * gc.ns[e]), sum = std::lround(2.0 * af[e] * ns[e]);
+          r.gc[2] = hom; r.gc[1] = sum - 2 * hom; r.gc[0] = ns[e] - r.gc[1] - r.gc[2];
+          const double sqrt_den = scf[i] / se[e];
+          r.score = stat[e] * sqrt_den; r.skat_var = sqrt_den * sqrt_den;
+          append_htp_row(obuf[i], head_s, ph.names[i], p.htp_cohort, r);
+          continue;
+        }
         append_sumstats_row(obuf[i], head_s, af[e], use_bgen, use_bgen ? info[e] : -1.0, ns[e], test_name(p.test_type), beta[e], se[e], chisq[e],
                             get_logp(chisq[e]), true);   // print_sum_stats_single :2502-2540
       }

@@ -257,6 +257,92 @@ void append_sumstats_all_trait(std::string& out, bool have, double beta, double 
   else out += " NA NA";
 }
 
+std::string htp_header() {
+  return "Name\tChr\tPos\tRef\tAlt\tTrait\tCohort\tModel\tEffect\tLCI_Effect\tUCI_Effect\tPval\tAAF\tNum_Cases\tCases_Ref\tCases_Het\t"
+         "Cases_Alt\tNum_Controls\tControls_Ref\tControls_Het\tControls_Alt\tInfo\n";
+}
+
+static std::string dbl_to_str(double v) {                      // convert_double_to_str, src/Regenie.cpp:1691-1698
+  char b[64];
+  if (v < 5000 && v > 1e-5) snprintf(b, sizeof(b), "%.6f", v);
+  else snprintf(b, sizeof(b), "%g", v);
+  return b;
+}
+
+static std::string logp_raw(double logp) {                     // convert_logp_raw, src/Regenie.cpp:1700-1717
+  char b[64];
+  const double log_dbl_min = -std::log10(std::numeric_limits<double>::min()) - 1;
+  if (logp <= 3) snprintf(b, sizeof(b), "%f", std::pow(10, -logp));
+  else if (logp <= log_dbl_min) snprintf(b, sizeof(b), "%g", std::pow(10, -logp));
+  else {
+    const double thr = std::log(9.95) / std::log(10);
+    int base = (int)std::ceil(logp);
+    double res = base - logp;
+    if (res >= thr) { res = 0; base++; }
+    snprintf(b, sizeof(b), "%.1fe-%d", std::pow(10, res), base);
+  }
+  return b;
+}
+
+void append_htp_row(std::string& out, const std::string& head, const std::string& trait, const std::string& cohort, const HtpRow& r) {
+  static const double zcrit = 1.959963984540054;              // quantile(complement(normal, .025)), src/Data.cpp:2118
+  static const double log10_nl_dbl_dmin = -std::log10(10.0 * std::numeric_limits<double>::min());   // src/Regenie.hpp:229-230
+  char num[160];
+  auto g = [&](double v) { out.append(num, (size_t)snprintf(num, sizeof(num), "%g", v)); };
+  out += head; out += trait; out += '\t'; out += cohort; out += '\t'; out += r.model; out += '\t';
+  const bool print_beta = r.test_pass && r.se >= 0 && !std::isnan(r.se);
+  const bool print_pv = r.test_pass && r.chisq >= 0 && !std::isnan(r.logp);
+  std::string outp = "-1";
+  if (print_pv) {
+    if (r.logp > log10_nl_dbl_dmin) outp = logp_raw(log10_nl_dbl_dmin);
+    else if (r.logp > 0) outp = logp_raw(r.logp);
+    else outp = "0.9999999";
+  }
+  double outse = 0;
+  if (print_pv && !print_beta) { out += "NA\tNA\tNA\t"; out += outp; out += '\t'; }
+  else if (!print_pv && !print_beta) out += "NA\tNA\tNA\tNA\t";
+  else if (!r.bt || (r.bt && r.firth && r.test_pass)) {
+    if (!r.bt) { g(r.beta); out += '\t'; g(r.beta - zcrit * r.se); out += '\t'; g(r.beta + zcrit * r.se); out += '\t'; }
+    else { g(std::exp(r.beta)); out += '\t'; g(std::exp(r.beta - zcrit * r.se)); out += '\t'; g(std::exp(r.beta + zcrit * r.se)); out += '\t'; }
+    out += print_pv ? outp : "NA";
+    out += '\t';
+  } else if (print_pv) {                                       // SPA / uncorrected logistic score test: allelic odds ratio
+    const double eff = (2 * r.gc[3] + r.gc[4] + .5) * (2 * r.gc[2] + r.gc[1] + .5) / (2 * r.gc[5] + r.gc[4] + .5) / (2 * r.gc[0] + r.gc[1] + .5);
+    outse = std::fabs(std::log(eff)) / std::sqrt(r.chisq);
+    g(eff); out += '\t'; g(eff * std::exp(-zcrit * outse)); out += '\t'; g(eff * std::exp(zcrit * outse)); out += '\t';
+    out += outp; out += '\t';
+  } else {
+    g(std::exp(r.beta)); out += '\t'; g(std::exp(r.beta - zcrit * r.se)); out += '\t'; g(std::exp(r.beta + zcrit * r.se)); out += "\tNA\t";
+  }
+  if (r.af >= 0) { g(r.af); out += '\t'; } else out += "NA\t";
+  out.append(num, (size_t)snprintf(num, sizeof(num), "%ld\t%ld\t%ld\t%ld\t", r.gc[0] + r.gc[1] + r.gc[2], r.gc[0], r.gc[1], r.gc[2]));
+  if (r.bt) out.append(num, (size_t)snprintf(num, sizeof(num), "%ld\t%ld\t%ld\t%ld", r.gc[3] + r.gc[4] + r.gc[5], r.gc[3], r.gc[4], r.gc[5]));
+  else out += "NA\tNA\tNA\tNA";
+  std::string col;
+  auto add = [&](const std::string& t) { if (!col.empty()) col += ';'; col += t; };
+  if (print_beta) {
+    if (r.bt && r.test_pass) {
+      add("REGENIE_BETA=" + dbl_to_str(r.beta));
+      add("REGENIE_SE=" + dbl_to_str(r.se));
+      if (print_pv && !r.firth) add("SE=" + dbl_to_str(outse));
+    } else if (r.bt) {
+      add("REGENIE_BETA=NA");
+      add("REGENIE_SE=NA");
+    } else add("REGENIE_SE=" + std::to_string(r.se));
+  }
+  if (r.info >= 0) add("INFO=" + dbl_to_str(r.info));
+  if (r.mac >= 0) add("MAC=" + std::to_string(r.mac));
+  if (r.has_score) {
+    add("SCORE=" + dbl_to_str(r.score));
+    add("SKATV=" + dbl_to_str(r.skat_var * std::fabs(r.cal_factor)));
+  }
+  add("LOG10P=" + (print_pv ? dbl_to_str(r.logp) : std::string("NA")));
+  if (r.se < 0) add("NO_BETA");
+  out += '\t';
+  out += col;
+  out += '\n';
+}
+
 void write_ids_file(const std::string& path, const std::string& pheno_name, bool print_pheno_name,
                     const std::vector<std::pair<std::string, std::string>>& fid_iid, const uint8_t* mask) {
   TextWriter out;

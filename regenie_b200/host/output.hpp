@@ -77,6 +77,22 @@ void append_sumstats_all_start(std::string& out, const std::string& head, double
 // one trait: " BETA SE CHISQ LOG10P"; `have` false = the trait was ignored for this variant (all NA)
 void append_sumstats_all_trait(std::string& out, bool have, double beta, double se, double chisq, double logp, bool test_pass);
 
+// --htp COHORT (HTPv4 rows: print_header_output_htp / print_sum_stats_head_htp / print_sum_stats_htp,
+// src/Step2_Models.cpp:2400-2426, :2542-2646) for the single-variant tests of this driver.
+struct HtpRow {
+  const char* model = "ADD-WGR-LR";   // test + "-WGR" + correction (src/Data.cpp:2075-2102)
+  bool bt = false, firth = false;     // trait_mode == 1; --firth
+  double beta = 0, se = 0, chisq = 0, logp = 0, af = 0, mac = 0;
+  bool test_pass = true;
+  long gc[6] = {0, 0, 0, 0, 0, 0};    // cases ref / het / alt, controls ref / het / alt (QT: all samples of the trait in 0-2)
+  bool has_score = true;
+  double score = 0, skat_var = 0, cal_factor = -1.0;
+  double info = -1.0;                 // printed when >= 0 (dosage input)
+};
+std::string htp_header();
+// `head` = "Name\tChr\tPos\tRef\tAlt\t" of the variant
+void append_htp_row(std::string& out, const std::string& head, const std::string& trait, const std::string& cohort, const HtpRow& r);
+
 // <out>_<pheno>.regenie.ids: "FID\tIID" of the samples of one trait, no newline after the last one
 void write_ids_file(const std::string& path, const std::string& pheno_name, bool print_pheno_name,
                     const std::vector<std::pair<std::string, std::string>>& fid_iid, const uint8_t* mask);

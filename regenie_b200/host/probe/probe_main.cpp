@@ -271,6 +271,28 @@ int cmd_sumstats() {
   return 0;
 }
 
+// stdin lines: bt firth pass beta se chisq logp af mac gc0..gc5 score skat_var cal_factor info  (info < 0: none) -> HTP rows
+int cmd_htp() {
+  std::string line;
+  std::cout << htp_header();
+  while (std::getline(std::cin, line)) {
+    auto t = split_ws(line);
+    if (t.size() != 19) continue;
+    HtpRow r;
+    r.bt = t[0] == "1"; r.firth = t[1] == "1"; r.test_pass = t[2] == "1";
+    r.beta = strtod(t[3].c_str(), nullptr); r.se = strtod(t[4].c_str(), nullptr); r.chisq = strtod(t[5].c_str(), nullptr);
+    r.logp = strtod(t[6].c_str(), nullptr); r.af = strtod(t[7].c_str(), nullptr); r.mac = strtod(t[8].c_str(), nullptr);
+    for (int k = 0; k < 6; ++k) r.gc[k] = atol(t[9 + k].c_str());
+    r.score = strtod(t[15].c_str(), nullptr); r.skat_var = strtod(t[16].c_str(), nullptr); r.cal_factor = strtod(t[17].c_str(), nullptr);
+    r.info = strtod(t[18].c_str(), nullptr);
+    r.model = r.bt ? (r.firth ? "ADD-WGR-FIRTH" : "ADD-WGR-LOG") : "ADD-WGR-LR";
+    std::string out;
+    append_htp_row(out, "rs1\t1\t100\tA\tG\t", "Y1", "COHORT", r);
+    std::cout << out;
+  }
+  return 0;
+}
+
 int cmd_ids(char** argv) {
   std::vector<std::pair<std::string, std::string>> ids;
   std::vector<uint8_t> mask;
@@ -359,6 +381,7 @@ int main(int argc, char** argv) {
     if (c == "pred-file" && argc >= 4) return cmd_pred_file(argc, argv);
     if (c == "read-pred" && argc >= 3) return cmd_read_pred(argc, argv);
     if (c == "sumstats") return cmd_sumstats();
+    if (c == "htp") return cmd_htp();
     if (c == "ids" && argc == 5) return cmd_ids(argv);
     if (c == "inflate-bgen" && argc >= 3) return cmd_inflate_bgen(argc, argv);
     if (c == "inflate" && argc >= 5) return cmd_inflate(argc, argv);

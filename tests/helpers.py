@@ -98,10 +98,10 @@ def synthetic_problem(tmp, N=1000, M=300, P=3, C=3, bsize=128, K=5, miss=0.02, s
     return Problem(prefix, str(tmp) + "/pheno.txt", str(tmp) + "/covar.txt", bsize, K=K, loocv=loocv)
 
 
-def oracle_step2_rows(prefix, pheno, covar, pred_list, bsize, remove=None):
+def oracle_step2_rows(prefix, pheno, covar, pred_list, bsize, remove=None, htp=None):
     """Full QT Step 2 on the CPU oracle, reading the .loco files like the reference does.
 
-    Returns {phenotype name: [row strings]} in the native split-by-phenotype format.
+    Returns {phenotype name: [row strings]} in the native split-by-phenotype format, or (htp = cohort name) as HTP rows.
     """
     from oracle import step2
     bim = plink.read_bim(prefix + ".bim")
@@ -139,6 +139,12 @@ def oracle_step2_rows(prefix, pheno, covar, pred_list, bsize, remove=None):
             continue
         for ph, nm in enumerate(pr.pheno_names):
             if vs["ignored_trait"][ph]:
+                continue
+            if htp is not None:
+                gc = step2.genocounts(graw, np.nonzero(pr.mask[:, ph])[0])
+                out[nm].append(step2.htp_row(bim.ids[i], c, int(bim.pos[i]), bim.allele0[i], bim.allele1[i], nm, htp,
+                                             step2.htp_model(), sc["beta"][ph], sc["se"][ph], sc["chisq"][ph], sc["logp"][ph],
+                                             vs["af"][ph], vs["mac"][ph], gc, score=sc["score"][ph], skat_var=sc["skat_var"][ph]))
                 continue
             out[nm].append(step2.sumstats_row(c, int(bim.pos[i]), bim.ids[i], bim.allele0[i], bim.allele1[i],
                                               vs["af"][ph], vs["ns"][ph], sc["beta"][ph], sc["se"][ph],
@@ -333,6 +339,43 @@ def check_na_invariance(run, read, tmp_path, golden_dir, bt):
         outs.append((read(fit + "_1.loco"), read(res + "_Y1.regenie")))
     assert len(outs[0][1].splitlines()) > 10
     assert outs[0] == outs[1]
+
+
+def check_htp(run, read, tmp_path, golden_dir, extra=()):
+    """--htp COHORT for quantitative traits (src/Step2_Models.cpp:2400-2426, :2542-2646): same variants and the same AAF as
+    the native file, per-trait genotype counts checked against the .bed and the phenotype masks, Info column keys, and
+    --no-split is ignored (src/Regenie.cpp:1068-1071).  Shared by the CPU (mock ABI) and GPU driver tests."""
+    import numpy as np
+    from oracle import plink, prep
+    d = golden_dir
+    base = ["--step", "2", "--bed", d + "/example_3chr", "--phenoFile", d + "/phenotype.txt", "--covarFile", d + "/covariates.txt",
+            "--bsize", "100", "--ignore-pred"] + list(extra)
+    run(base + ["--out", str(tmp_path / "native")])
+    run(base + ["--htp", "MYCOHORT", "--no-split", "--out", str(tmp_path / "htp")])
+    bim = plink.read_bim(d + "/example_3chr.bim")
+    keys, _ = plink.read_fam(d + "/example_3chr.fam")
+    rf = "--ref-first" in extra
+    G = plink.decode_bed(plink.read_bed_rows(d + "/example_3chr.bed", len(keys), bim.offset), len(keys), ref_first=rf)
+    pr = prep.prepare(keys, d + "/phenotype.txt", d + "/covariates.txt", step=2)
+    idx = {v: k for k, v in enumerate(bim.ids)}
+    for ph, nm in enumerate(("Y1", "Y2")):
+        nat = [l.split() for l in read(str(tmp_path / "native") + "_%s.regenie" % nm).splitlines()[1:]]
+        rows = read(str(tmp_path / "htp") + "_%s.regenie" % nm).splitlines()
+        assert rows[0].split("\t") == ["Name", "Chr", "Pos", "Ref", "Alt", "Trait", "Cohort", "Model", "Effect", "LCI_Effect",
+                                       "UCI_Effect", "Pval", "AAF", "Num_Cases", "Cases_Ref", "Cases_Het", "Cases_Alt",
+                                       "Num_Controls", "Controls_Ref", "Controls_Het", "Controls_Alt", "Info"]
+        assert len(rows) - 1 == len(nat) > 400
+        m = pr.mask[:, ph].astype(bool)
+        for l, n in zip(rows[1:], nat):
+            t = l.split("\t")
+            assert len(t) == 22
+            assert [t[1], t[2], t[0], t[3], t[4]] == n[:5] and t[5:8] == [nm, "MYCOHORT", "ADD-LR"]
+            assert t[12] == n[5] and t[13] == n[6]                                   # AAF = A1FREQ, Num_Cases = N
+            g = G[idx[t[0]]][m]
+            assert [int(x) for x in t[14:17]] == [int((g == 0).sum()), int((g == 1).sum()), int((g == 2).sum())], l
+            assert t[17:21] == ["NA"] * 4
+            assert [k.split("=")[0] for k in t[21].split(";")] == ["REGENIE_SE", "MAC", "SCORE", "SKATV", "LOG10P"]
+            assert float(t[8]) == float(n[8])                                         # Effect = BETA
 
 
 def check_no_split(run, read, tmp_path, golden_dir, extra=(), bt=False):

@@ -90,6 +90,33 @@ def test_step1_then_step2_files(tmp_path, golden_dir, fileset, bsize, remove):
             assert tx[12] == ty[12]
 
 
+def test_step2_htp_rows_match_the_oracle(tmp_path, golden_dir):
+    """--htp COHORT (print_sum_stats_htp, src/Step2_Models.cpp:2542-2646) for quantitative traits: Name .. Model, AAF and the
+    genotype counts byte-identical to the oracle restatement; Effect / CI / Pval and the numbers of the Info column within
+    1e-5 relative."""
+    prefix = os.path.join(golden_dir, "example")
+    pheno, covar = golden_dir + "/phenotype.txt", golden_dir + "/covariates.txt"
+    out1, out2 = str(tmp_path / "fit"), str(tmp_path / "htp")
+    run(["--step", "1", "--bed", prefix, "--phenoFile", pheno, "--covarFile", covar, "--bsize", "100", "--out", out1])
+    run(["--step", "2", "--bed", prefix, "--phenoFile", pheno, "--covarFile", covar, "--bsize", "200", "--pred",
+         out1 + "_pred.list", "--htp", "TESTCOHORT", "--out", out2])
+    rows = helpers.oracle_step2_rows(prefix, pheno, covar, out1 + "_pred.list", 200, htp="TESTCOHORT")
+    from oracle import step2
+    for nm in ("Y1", "Y2"):
+        got = open(out2 + "_%s.regenie" % nm).read().splitlines()
+        exp = [step2.HTP_HEADER.rstrip("\n")] + [r.rstrip("\n") for r in rows[nm]]
+        assert got[0] == exp[0] and len(got) == len(exp) and len(got) > 900
+        for x, y in zip(got[1:], exp[1:]):
+            tx, ty = x.split("\t"), y.split("\t")
+            assert len(tx) == 22 and tx[:8] == ty[:8] and tx[12:21] == ty[12:21], (x, y)   # ids, model; AAF + counts: identical
+            for a, b in zip(tx[8:12], ty[8:12]):
+                assert close(a, b), (x, y)
+            ia, ib = tx[21].split(";"), ty[21].split(";")
+            assert [t.split("=")[0] for t in ia] == [t.split("=")[0] for t in ib], (x, y)
+            for a, b in zip(ia, ib):
+                assert close(a.split("=")[1], b.split("=")[1]), (x, y)
+
+
 def test_driver_rejects_out_of_scope_options(tmp_path):
     r = subprocess.run([RGB, "--step", "2", "--bed", "x", "--phenoFile", "y", "--bsize", "10", "--out",
                         str(tmp_path / "o"), "--pred", "z", "--spa"], capture_output=True, text=True)

@@ -226,6 +226,15 @@ def test_no_split_output(tmp_path, golden_dir, extra, bt):
     helpers.check_no_split(run, read, tmp_path, golden_dir, extra, bt)
 
 
+@pytest.mark.parametrize("extra", [(), ("--ref-first",)])
+def test_htp_output(tmp_path, golden_dir, extra):
+    import helpers
+    helpers.check_htp(run, read, tmp_path, golden_dir, extra)
+    r = run(["--step", "2", "--bed", golden_dir + "/example", "--phenoFile", golden_dir + "/phenotype_bin.txt", "--bsize", "100",
+             "--ignore-pred", "--bt", "--htp", "X", "--out", str(tmp_path / "no")], ok=False)
+    assert "ERROR" in r and "--htp with --bt" in r
+
+
 def test_min_case_count_drops_rare_binary_traits(tmp_path, golden_dir):
     """rm_phenoCols (src/Pheno.cpp:527-570): binary traits with fewer than --minCaseCount (10) cases are ignored."""
     d = golden_dir

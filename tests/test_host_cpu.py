@@ -403,6 +403,42 @@ def test_sumstats_rows_and_log10p():
         assert r2 == "23 5 rs2 AT G %s %d ADD %s %s %s" % (_g(af), n, bs, cp, extra)
 
 
+def test_htp_rows_match_the_oracle_restatement():
+    """host/output.cpp append_htp_row vs oracle/step2.htp_row (print_sum_stats_htp, src/Step2_Models.cpp:2542-2646) on
+    randomised inputs covering every branch: QT, BT with Firth, BT without (allelic odds ratio + SE=), failed tests, missing
+    SE, capped / tiny / large p-values (the three convert_logp_raw ranges), INFO present or not."""
+    from oracle import step2
+    rng = np.random.default_rng(9)
+    cases = []
+    for k in range(400):
+        bt = int(k % 3 != 0)
+        firth = int(bt and k % 2)
+        ok = int(k % 11 != 5)
+        beta = float(rng.normal() * 10 ** rng.uniform(-4, 1))
+        se = float(abs(rng.normal()) * 10 ** rng.uniform(-4, 0)) if k % 13 != 7 else -1.0
+        chisq = float(rng.chisquare(1) * 10 ** rng.uniform(-1, 2.5)) if k % 17 != 3 else -1.0
+        logp = float(10 ** rng.uniform(-3, 2.6)) if k % 19 != 4 else 400.0
+        if k % 23 == 6:
+            logp = 0.0
+        af = float(rng.uniform(0, 1)) if k % 29 != 8 else -1.0
+        mac = float(rng.uniform(0.5, 5000))
+        gc = [int(x) for x in rng.integers(0, 3000, 6)]
+        score, skat = float(rng.normal() * 100), float(abs(rng.normal()) * 10 ** rng.uniform(-6, 5))
+        cal = -1.0 if not bt else float(rng.uniform(0.1, 2))
+        info = float(rng.uniform(0, 1)) if k % 5 == 0 else -1.0
+        cases.append((bt, firth, ok, beta, se, chisq, logp, af, mac, *gc, score, skat, cal, info))
+    stdin = "".join(" ".join(repr(x) for x in c) + "\n" for c in cases)
+    out = probe("htp", stdin=stdin).stdout.splitlines(keepends=True)
+    assert out[0] == step2.HTP_HEADER
+    assert len(out) == 1 + len(cases)
+    for row, c in zip(out[1:], cases):
+        bt, firth, ok, beta, se, chisq, logp, af, mac = c[:9]
+        want = step2.htp_row("rs1", 1, 100, "A", "G", "Y1", "COHORT", step2.htp_model(bt=bool(bt), firth=bool(firth)), beta, se,
+                             chisq, logp, af, mac, list(c[9:15]), test_pass=bool(ok), bt=bool(bt), firth=bool(firth),
+                             score=c[15], skat_var=c[16], cal_factor=c[17], info=c[18] if c[18] >= 0 else None)
+        assert row == want, (c, row, want)
+
+
 def test_golden_rows_are_reproduced_by_the_row_formatter(golden_dir):
     """Feed the numbers of the reference's golden file back through the formatter: every row must come out identical
     (the LOG10P column is recomputed from CHISQ, so rows whose CHISQ was rounded to 6 digits are compared on the other

@@ -123,6 +123,13 @@ def test_af_cc_columns(tmp_path, golden_dir, extra):
     helpers.check_af_cc(run, read, tmp_path, golden_dir, extra)
 
 
+def test_htp_output(tmp_path, golden_dir):
+    """--htp on the real library: variants, AAF and N of the native file; genotype counts == the .bed counts per trait."""
+    def read(path):
+        return open(path).read()
+    helpers.check_htp(run, read, tmp_path, golden_dir, ())
+
+
 def test_no_split_output_on_dosages(tmp_path, golden_dir):
     def read(path):
         return open(path).read()
