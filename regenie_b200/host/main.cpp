@@ -25,6 +25,8 @@
 #include "output.hpp"
 #include "pgen.hpp"
 
+#include <unistd.h>
+
 using namespace rgh;
 
 namespace {
@@ -76,11 +78,17 @@ void rg_check(int rc) {
   if (rc != 0) throw Fail(std::string(rg_last_error()));
 }
 
+// The driver is one run per process: when it is done, device buffers, pinned memory and the CUDA context go back with
+// the process, so main() leaves through _exit once every output file is closed (freeing ~10 GB of device buffers one
+// cudaFree at a time and tearing the context down costs more than level 0 of the benchmark panel).
+// RG_B200_CLEAN_EXIT=1 runs every destructor instead (leak checkers, compute-sanitizer).
+static const bool g_fast_exit = getenv("RG_B200_CLEAN_EXIT") == nullptr;
+
 // releases a handle on every way out of a run function (errors unwind through here)
 struct HandleGuard {
   rg_handle& h;
   ~HandleGuard() {
-    if (h) rg_destroy(h);
+    if (h && !g_fast_exit) rg_destroy(h);
     h = nullptr;
   }
 };
@@ -501,7 +509,7 @@ void run_step1(const Params& p_in, Log& log) {
   std::vector<rg_handle> hs(G, nullptr);
   struct HandlesGuard {
     std::vector<rg_handle>& v;
-    ~HandlesGuard() { for (auto& x : v) { if (x) rg_destroy(x); x = nullptr; } }
+    ~HandlesGuard() { for (auto& x : v) { if (x && !g_fast_exit) rg_destroy(x); x = nullptr; } }
   } guards{hs};
   for (int d = 0; d < G; ++d) {
     cfg.device = (G > 1 ? d : p.gpu);
@@ -555,52 +563,60 @@ void run_step1(const Params& p_in, Log& log) {
       }
     }
   }
-  // a reader thread fetches block b+1 from the file while block b is handed to the GPU (two pageable buffers: the copy
-  // out of a buffer is staged before rg_l0_block_bed returns, so it can be refilled two blocks later)
-  // .bed rows: two PINNED buffers (rg_host_alloc), so the block crosses PCIe by DMA straight from the buffer the reader
+  // reader threads fetch blocks b+1 and b+2 from the file while block b is handed to the GPU (three buffers in rotation).
+  // .bed rows sit in PINNED buffers (rg_host_alloc), so a block crosses PCIe by DMA straight from the buffer the reader
   // filled (a pageable buffer is first copied into the driver's staging area, ~5 ms per 25 MB block); rg_l0_wait_input
-  // after each call tells when the buffer may be refilled
-  struct PinnedPair {
-    void* p[2] = {nullptr, nullptr};
-    ~PinnedPair() { for (void* q : p) if (q) rg_host_free(q); }
+  // after each call tells when the buffer may be refilled.  Pageable inputs (.bgen bytes, .pgen records) are staged
+  // before their call returns and can be refilled at once.
+  constexpr int kBuf = 3, kAhead = 2;
+  struct PinnedSet {
+    void* p[kBuf] = {nullptr, nullptr, nullptr};
+    ~PinnedSet() { for (void* q : p) if (q && !g_fast_exit) rg_host_free(q); }
   } pinned;
-  std::vector<uint8_t> rows2;
-  uint8_t* bufs[2] = {rows.data(), nullptr};
-  const bool pin_rows = !use_bgen && !p.run_l1 && G == 1 && !rows.empty() && !(gbed.pg && pgen_on_device()) &&
-                        rg_host_alloc(&pinned.p[0], (int64_t)rows.size()) == 0 && rg_host_alloc(&pinned.p[1], (int64_t)rows.size()) == 0;
-  if (pin_rows) { bufs[0] = (uint8_t*)pinned.p[0]; bufs[1] = (uint8_t*)pinned.p[1]; }
-  else { rows2.resize(rows.size()); bufs[1] = rows2.data(); }
-  std::vector<uint8_t> probs[2], pmiss[2];                     // .bgen: inflated probability pairs + ploidy bytes of a block
+  std::vector<uint8_t> rows_extra[kBuf];
+  uint8_t* bufs[kBuf] = {rows.data(), nullptr, nullptr};
+  bool pin_rows = !use_bgen && !p.run_l1 && G == 1 && !rows.empty() && !(gbed.pg && pgen_on_device());
+  for (int k = 0; k < kBuf && pin_rows; ++k) pin_rows = rg_host_alloc(&pinned.p[k], (int64_t)rows.size()) == 0;
+  for (int k = 0; k < kBuf; ++k) {
+    if (pin_rows) bufs[k] = (uint8_t*)pinned.p[k];
+    else if (k > 0) { rows_extra[k].resize(rows.size()); bufs[k] = rows_extra[k].data(); }
+  }
+  std::vector<uint8_t> probs[kBuf], pmiss[kBuf];               // .bgen: inflated probability pairs + ploidy bytes of a block
   if (use_bgen && !p.run_l1)
-    for (int k = 0; k < 2; ++k) { probs[k].resize((size_t)p.bsize * g.n_file * 2); pmiss[k].resize((size_t)p.bsize * g.n_file); }
+    for (int k = 0; k < kBuf; ++k) { probs[k].resize((size_t)p.bsize * g.n_file * 2); pmiss[k].resize((size_t)p.bsize * g.n_file); }
   const int io_threads = std::max(1, std::min(32, (int)std::thread::hardware_concurrency()));
   const bool pgen_dev = !use_bgen && gbed.pg && pgen_on_device();
   if (pgen_dev) log << " * pgen records are decoded on the GPU\n";
-  PgenBatch pbatch[2];
-  std::future<void> pending;
+  PgenBatch pbatch[kBuf];
+  std::future<void> pending[kBuf];
   auto fetch = [&](int b) {
     return std::async(std::launch::async, [&, b] {
-      if (use_bgen) gg.read_block(blocks[b].first, blocks[b].size, probs[b & 1].data(), pmiss[b & 1].data(), io_threads);
-      else if (pgen_dev) gbed.pg->gather(blocks[b].first, blocks[b].size, pbatch[b & 1]);
-      else gbed.read_rows(blocks[b].first, blocks[b].size, bufs[b & 1]);
+      const int k = b % kBuf;
+      if (use_bgen) gg.read_block(blocks[b].first, blocks[b].size, probs[k].data(), pmiss[k].data(), io_threads);
+      else if (pgen_dev) gbed.pg->gather(blocks[b].first, blocks[b].size, pbatch[k]);
+      else gbed.read_rows(blocks[b].first, blocks[b].size, bufs[k]);
     });
   };
   if (G == 1) {
-    if (nb > 0 && !p.run_l1) pending = fetch(0);
+    // two reads in flight only where the reader is re-entrant (pread on the .bed, the in-memory .pgen); the .bgen reader
+    // and the stream fallback of the .bed reader share a file cursor
+    const int ahead = (use_bgen || (!gbed.pg && gbed.bed_fd < 0)) ? 1 : kAhead;
+    for (int b = 0; b < ahead && b < nb && !p.run_l1; ++b) pending[b % kBuf] = fetch(b);
     for (int b = 0; b < nb && !p.run_l1; ++b) {
       if (blocks[b].chrom != last_chr) { log << "Chromosome " << blocks[b].chrom << "\n"; last_chr = blocks[b].chrom; }
-      pending.get();
-      if (b + 1 < nb) pending = fetch(b + 1);
+      const int k = b % kBuf;
+      pending[k].get();
+      if (b + ahead < nb) pending[(b + ahead) % kBuf] = fetch(b + ahead);      // its buffer was block b-1's (or b's own slot + 1): consumed
       if (use_bgen)
-        rg_check(rg_l0_block_dosage_u8(h, probs[b & 1].data(), pmiss[b & 1].data(), (int64_t)g.n_file, blocks[b].size,
+        rg_check(rg_l0_block_dosage_u8(h, probs[k].data(), pmiss[k].data(), (int64_t)g.n_file, blocks[b].size,
                                        subset ? g.sample_idx.data() : nullptr, p.ref_first, b));
       else if (pgen_dev) {
         const uint8_t* drows = nullptr;
         int64_t dstride = 0;
-        pgen_rows_device(h, pbatch[b & 1], blocks[b].size, (int64_t)gbed.pg->n_file, b, &drows, &dstride);
+        pgen_rows_device(h, pbatch[k], blocks[b].size, (int64_t)gbed.pg->n_file, b, &drows, &dstride);
         rg_check(rg_l0_block_bed(h, drows, dstride, blocks[b].size, subset ? g.sample_idx.data() : nullptr, p.ref_first, b));
       } else {
-        rg_check(rg_l0_block_bed(h, bufs[b & 1], (int64_t)g.row_stride, blocks[b].size,
+        rg_check(rg_l0_block_bed(h, bufs[k], (int64_t)g.row_stride, blocks[b].size,
                                  subset ? g.sample_idx.data() : nullptr, p.ref_first, b));
         if (pin_rows) rg_check(rg_l0_wait_input(h));
       }
@@ -1619,6 +1635,11 @@ void run_step2(const Params& p_in, Log& log) {
 
 int main(int argc, char** argv) {
   Log log;
+  // never leave main() while the warm-up thread is still inside the CUDA driver: process exit would tear the runtime
+  // down under it (an early input error otherwise hangs at exit)
+  struct WarmupJoin {
+    ~WarmupJoin() { if (g_ndev.valid()) g_ndev.wait(); }
+  } warmup_join;
   try {
     phase("start");
     const Params p = parse_cli(argc, argv);
@@ -1643,7 +1664,12 @@ int main(int argc, char** argv) {
     log << "\nElapsed time : " << (now_ms() - t0) / 1e3 << "s\nEnd of rgb200\n";
   } catch (const std::exception& e) {
     log << "ERROR: " << e.what() << "\n";          // same shape as the reference (src/Regenie.cpp:67-92)
+    log.close();
+    if (g_fast_exit) { fflush(nullptr); _exit(EXIT_FAILURE); }
     return EXIT_FAILURE;
   }
+  phase("run finished");
+  log.close();
+  if (g_fast_exit) { fflush(nullptr); _exit(0); }
   return 0;
 }

@@ -22,6 +22,10 @@ struct Fail : std::runtime_error {
 class Log {
  public:
   void open(const std::string& path) { file_.open(path); }
+  void close() {
+    std::cout.flush();
+    if (file_.is_open()) file_.close();
+  }
   template <typename T>
   Log& operator<<(const T& v) {
     std::cout << v;
