@@ -319,9 +319,16 @@ def run_gpu(args):
         e0.record(ext)
         for _ in range(steps):
             one_pass(base_ptr)
-            if read_status:
-                if st.status() != 0:
-                    raise SystemExit("level-0 reported an error (timed/e2e pass): " + capi.lib().rg_last_error().decode())
+            if read_status == "drain":
+                bad = st.status() != 0        # waits for every block of the pass before the next pass is enqueued
+            elif read_status:
+                bad = st.poll_status() != 0   # 8-byte D2H read of the sticky error word beside the running lanes
+            else:
+                bad = False
+            if bad:
+                raise SystemExit("level-0 reported an error (timed/e2e pass): " + capi.lib().rg_last_error().decode())
+        if read_status and st.status() != 0:  # the draining read: every block of every pass has reported by now
+            raise SystemExit("level-0 reported an error (timed/e2e pass): " + capi.lib().rg_last_error().decode())
         st.fence()
         e1.record(ext)
         e1.synchronize()
@@ -381,7 +388,7 @@ def run_gpu(args):
     # ---- end to end: pinned host rows -> H2D -> same pass -> status word D2H, every step
     for _ in range(1):
         one_pass(host_ptr)
-    ms_e2e, _ = timed(host_ptr, args.steps, read_status=True)
+    ms_e2e, _ = timed(host_ptr, args.steps, read_status=os.environ.get("RG_BENCH_E2E_STATUS", "poll"))   # env "drain": A/B only
     e2e_val = total_snps / (ms_e2e / 1e3)
 
     # ---- the rest of the sharded Step 1, once: level 1 by phenotype on the owners, LOCO assembly, gather to all ranks
@@ -495,7 +502,9 @@ def run_gpu(args):
         "data": "synthetic", "config": workload_config() if not (args.small or args.n_samples or args.n_pheno) else {"workload": "NOT the benchmark configuration (smoke / exploration run)", "n_samples": N, "n_snps": M, "n_pheno": P},
         "clocks": clk,
         "e2e": {"value": e2e_val, "unit": "SNPs/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(M) * int(stride), "d2h_bytes_per_step": 8},
+                "h2d_bytes_per_step": int(M) * int(stride), "d2h_bytes_per_step": 8,
+                "result_read": "every pass: rg_l0_poll_status (8-byte D2H read of the sticky error word, lanes keep running); "
+                               "after the last pass, inside the timed region: rg_l0_status (waits for every block)"},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "gram_fp8_tcgen05_kernel", "bound": "tensor", "achieved": ach, "peak": peak,
                      "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,

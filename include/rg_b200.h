@@ -127,6 +127,12 @@ int rg_l0_wait_input(rg_handle h);
  * first low-variance SNP (src/Data.cpp:205-209).  Synchronises the stream. */
 int64_t rg_l0_status(rg_handle h);
 
+/* The same word WITHOUT waiting for the blocks in flight: what the blocks that have finished so far reported (the word is
+ * sticky - the first low-variance SNP stays until the handle is destroyed - so a caller that polls once per pass and
+ * calls rg_l0_status / rg_sync at the end misses nothing).  One 8-byte device-to-host read on a stream of its own; the
+ * lanes keep running.  Does not re-solve blocks whose mixed-precision solve was flagged (rg_l0_status / rg_sync do). */
+int64_t rg_l0_poll_status(rg_handle h);
+
 /*
  * rg_l0_fetch_W -- copy a block's level-0 predictors of phenotype ph to the host as the
  * N x R column-major slab the reference appends to <prefix>_l0_Y<ph+1> under --lowmem

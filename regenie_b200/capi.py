@@ -79,7 +79,7 @@ EXPORTS = [
     "rg_s2_set_chr", "rg_s2_block_bed", "rg_W_info", "rg_debug_fetch", "rg_launch_count", "rg_stream",
     "rg_set_timing", "rg_get_timing", "rg_fence", "rg_s2_set_chr_bt", "rg_s2_block_bgen8_bt", "rg_s2_block_bgen8", "rg_s2_firth", "rg_l1_fit_bt", "rg_W_set_owned", "rg_W_export", "rg_W_attach_peer", "rg_l1_select", "rg_s2_set_sex", "rg_s2_set_non_par", "rg_l0_load_W", "rg_s2_spa", "rg_s2_block_bed_bt", "rg_prs", "rg_bgen_inflate",
     "rg_l0_solver_stats", "rg_dbg_mixed_solve", "rg_l0_wait_input", "rg_l0_block_dosage_u8", "rg_l0_block_f64", "rg_W_attach_local",
-    "rg_s2_stage", "rg_host_alloc", "rg_host_free", "rg_pgen_decode", "rg_warmup",
+    "rg_s2_stage", "rg_host_alloc", "rg_host_free", "rg_pgen_decode", "rg_warmup", "rg_l0_poll_status",
 ]
 
 _lib = None
@@ -95,6 +95,8 @@ def lib():
         L.rg_last_error.restype = C.c_char_p
         L.rg_version.restype = C.c_char_p
         L.rg_l0_status.restype = C.c_int64
+        L.rg_l0_poll_status.restype = C.c_int64
+        L.rg_l0_poll_status.argtypes = [C.c_void_p]
         L.rg_debug_fetch.restype = C.c_int64
         L.rg_launch_count.restype = C.c_int64
         L.rg_stream.restype = C.c_void_p
@@ -176,6 +178,10 @@ class Step1:
 
     def status(self):
         return lib().rg_l0_status(self.h)
+
+    def poll_status(self):
+        """The sticky error word as the finished blocks left it; does not wait for the lanes."""
+        return lib().rg_l0_poll_status(self.h)
 
     def sync(self):
         check(lib().rg_sync(self.h))

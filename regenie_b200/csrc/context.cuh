@@ -43,6 +43,8 @@ struct rg_ctx {
   rg::DevBuf<int32_t> word_base;    // [Npad/16] first file index of a 16-sample word (-1 empty, -2 not contiguous)
   rg::DevBuf<uint32_t> word_keep;   // [Npad/16] 2-bit lane mask of the samples that are read
   rg::DevBuf<unsigned long long> err_slot;
+  cudaStream_t poll_stream = nullptr;              // rg_l0_poll_status: the error word is read here, beside the lanes
+  unsigned long long* poll_host = nullptr;         // pinned
   rg::DevBuf<unsigned long long> dbg_counter;
   rg::DevBuf<long long> dbg_clk;
 
@@ -53,7 +55,14 @@ struct rg_ctx {
     cudaEvent_t done = nullptr;
     cudaEvent_t h2d_done = nullptr;   // recorded behind the host-to-device copy of the block's input rows
     bool h2d_recorded = false;
-    rg::DevBuf<uint8_t> packed_dev;
+    rg::DevBuf<uint8_t> packed_dev;   // rows decoded on the device (rg_pgen_decode)
+    // host rows: two staging buffers in rotation, filled on the lane's COPY stream, so the PCIe transfer of this lane's
+    // next block runs under the kernels of its current one (on the lane's own stream the copy waited for them)
+    rg::DevBuf<uint8_t> packed_buf[2];
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t relayout_done[2] = {nullptr, nullptr};   // behind the kernel that last read packed_buf[k]
+    bool relayout_recorded[2] = {false, false};
+    int packed_flip = 0;
     rg::DevBuf<uint8_t> pgen_in;      // rg_pgen_decode: metadata blob + record bytes of the block this lane runs next
     rg::DevBuf<uint32_t> gp;          // [rows_p][Npad/16]
     rg::DevBuf<uint8_t> z;            // [2 rows_p][Npad] e4m3

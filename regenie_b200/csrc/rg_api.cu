@@ -486,23 +486,35 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
 
   // --- lane: own stream + scratch
   rg_ctx::Lane& L = *h->lanes[h->next_lane];
-  resolve_lane(h, L);                      // flag of the block this lane ran before (FP64 re-solve if it was raised)
   h->last_lane = h->next_lane;
   h->next_lane = (h->next_lane + 1) % (int)h->lanes.size();
   s = L.stream;
 
-  // --- input rows to the device (pinned host memory is copied asynchronously on the lane's stream)
+  // --- input rows to the device: enqueued BEFORE the host waits for the solver flag of the lane's previous block
+  // (resolve_lane below), so the PCIe transfer runs while that block is still in its kernels
   const uint8_t* packed_d = packed;
+  int staged = -1;                         // index of the staging buffer the rows went to (host input)
   if (!is_device_pointer(packed)) {
-    L.packed_dev.alloc((size_t)h->bs_max * row_stride);
-    ScopedTimer t(h, "h2d", s);
-    copy_to_device(L.packed_dev.p, packed, (size_t)bs * row_stride, s);
+    static const bool on_lane = getenv("RG_B200_H2D_ON_LANE") != nullptr;   // A/B: the copy on the lane's own stream
+    staged = (L.packed_flip ^= 1);
+    rg::DevBuf<uint8_t>& buf = L.packed_buf[staged];
+    buf.alloc((size_t)h->bs_max * row_stride);
+    if (!L.copy_stream) RG_CUDA(cudaStreamCreateWithFlags(&L.copy_stream, cudaStreamNonBlocking));
     if (!L.h2d_done) RG_CUDA(cudaEventCreateWithFlags(&L.h2d_done, cudaEventDisableTiming));
-    RG_CUDA(cudaEventRecord(L.h2d_done, s));
+    cudaStream_t cs = on_lane ? s : L.copy_stream;
+    // the buffer was last read by the relayout kernel of the block this lane ran two blocks ago
+    if (!on_lane && L.relayout_recorded[staged]) RG_CUDA(cudaStreamWaitEvent(cs, L.relayout_done[staged], 0));
+    {
+      ScopedTimer t(h, "h2d", cs);
+      copy_to_device(buf.p, packed, (size_t)bs * row_stride, cs);
+    }
+    RG_CUDA(cudaEventRecord(L.h2d_done, cs));
     L.h2d_recorded = true;
+    if (!on_lane) RG_CUDA(cudaStreamWaitEvent(s, L.h2d_done, 0));
     if (getenv("RG_DBG_SYNC_AFTER_H2D")) RG_CUDA(cudaStreamSynchronize(s));
-    packed_d = L.packed_dev.p;
+    packed_d = buf.p;
   }
+  resolve_lane(h, L);                      // flag of the block this lane ran before (FP64 re-solve if it was raised)
 
   // --- scratch
   L.gp.alloc((size_t)h->rows_p_max * (Npad / 16));
@@ -533,6 +545,11 @@ static void l0_block_bed(rg_ctx* h, const uint8_t* packed, int64_t row_stride, i
   {
     ScopedTimer t(h, "bed_relayout", s);
     launch_bed_relayout(packed_d, row_stride, bs, rows_p, h->file_idx_pad.p, h->word_base.p, h->word_keep.p, ref_first, L.gp.p, Npad, s);
+    if (staged >= 0) {
+      if (!L.relayout_done[staged]) RG_CUDA(cudaEventCreateWithFlags(&L.relayout_done[staged], cudaEventDisableTiming));
+      RG_CUDA(cudaEventRecord(L.relayout_done[staged], s));
+      L.relayout_recorded[staged] = true;
+    }
   }
   {
     ScopedTimer t(h, "bed_expand", s);
@@ -829,12 +846,16 @@ void rg_destroy(rg_handle h) {
   if (!h) return;
   cudaSetDevice(h->device);
   for (void* m : h->W_peer_mapped) cudaIpcCloseMemHandle(m);
+  if (h->poll_stream) { cudaStreamSynchronize(h->poll_stream); cudaStreamDestroy(h->poll_stream); }
+  if (h->poll_host) cudaFreeHost(h->poll_host);
   for (auto& l : h->lanes) cudaStreamSynchronize(l->stream);
   cudaStreamSynchronize(h->stream);
   rg::flush_timers(h);
   for (auto& l : h->lanes) {
     if (l->mx_ev) cudaEventDestroy(l->mx_ev);
     if (l->h2d_done) cudaEventDestroy(l->h2d_done);
+    for (int k = 0; k < 2; ++k) if (l->relayout_done[k]) cudaEventDestroy(l->relayout_done[k]);
+    if (l->copy_stream) { cudaStreamSynchronize(l->copy_stream); cudaStreamDestroy(l->copy_stream); }
     if (l->mx_fail_host) cudaFreeHost(l->mx_fail_host);
     cudaEventDestroy(l->done);
     cudaStreamDestroy(l->stream);
@@ -1017,6 +1038,23 @@ int64_t rg_l0_status(rg_handle h) {
     return (int64_t)v;
   }
   rg::set_last_error("SNP has low variance (index " + std::to_string(v - 1) + ")");
+  return (int64_t)v;
+}
+
+int64_t rg_l0_poll_status(rg_handle h) {
+  if (!h || h->kind != 1 || !h->err_slot.p) return -1;
+  cudaSetDevice(h->device);
+  if (!h->poll_stream && cudaStreamCreateWithFlags(&h->poll_stream, cudaStreamNonBlocking) != cudaSuccess) return -1;
+  if (!h->poll_host && cudaHostAlloc((void**)&h->poll_host, 8, cudaHostAllocDefault) != cudaSuccess) return -1;
+  if (cudaMemcpyAsync(h->poll_host, h->err_slot.p, 8, cudaMemcpyDeviceToHost, h->poll_stream) != cudaSuccess ||
+      cudaStreamSynchronize(h->poll_stream) != cudaSuccess) {
+    rg::set_last_error(std::string("CUDA error: ") + cudaGetErrorString(cudaGetLastError()));
+    return -1;
+  }
+  const unsigned long long v = *h->poll_host;
+  if (v == ~0ull) return 0;
+  if (v >= (1ull << 40)) rg::set_last_error("Cholesky pivot not positive (system id " + std::to_string(v - (1ull << 40)) + ")");
+  else rg::set_last_error("SNP has low variance (index " + std::to_string(v - 1) + ")");
   return (int64_t)v;
 }
 

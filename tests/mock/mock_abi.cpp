@@ -171,6 +171,7 @@ int rg_l0_block_dosage_u8(rg_handle h, const uint8_t* probs, const uint8_t* pm, 
   return 0;
 }
 int64_t rg_l0_status(rg_handle) { return 0; }
+int64_t rg_l0_poll_status(rg_handle) { return 0; }
 int rg_l0_fetch_W(rg_handle h, int32_t b, int32_t ph, double* out) {
   auto it = h->W.find({b, ph});
   if (it == h->W.end()) return fail("mock: slab not computed");

@@ -87,6 +87,22 @@ def test_l0_sample_subset_and_shard_invariance(tmp_path):
             assert np.array_equal(st2.fetch_W(b, ph), out[b][ph])
 
 
+@pytest.mark.parametrize("lanes", ["2", "8"])
+def test_many_blocks_per_lane_from_host_rows(tmp_path, monkeypatch, lanes):
+    """Host rows go through two staging buffers per lane, filled on the lane's copy stream ahead of the lane's kernels:
+    with 40 blocks on 2 (and 8) lanes every buffer is reused many times while earlier blocks are still in flight; every
+    block must still match the oracle, and a run from one big device-resident... host array must equal a run that hands
+    over the same bytes block by block from a buffer that is overwritten right after rg_l0_wait_input."""
+    monkeypatch.setenv("RG_B200_LANES", lanes)
+    pb = helpers.synthetic_problem(tmp_path, N=700, M=640, P=2, C=3, bsize=16, miss=0.02)
+    st, out = run_blocks(pb)
+    for b in range(len(pb.blocks)):
+        W_o, _, _, _ = pb.oracle_l0(b)
+        for ph in range(len(W_o)):
+            assert rel(out[b][ph], W_o[ph]) < TOL, b
+    st.close()
+
+
 def test_l0_example_fileset(golden_dir):
     """The reference's own example/ fileset (500 x 1000, 2 QTs), --bsize 100."""
     pb = helpers.Problem(golden_dir + "/example", golden_dir + "/phenotype.txt", golden_dir + "/covariates.txt", 100)
@@ -108,3 +124,30 @@ def test_low_variance_snp_is_reported(tmp_path):
     st = pb.gpu_step1()
     pb.gpu_l0_block(st, 0)
     assert st.status() == 11   # 1 + SNP index
+
+
+def test_poll_status_reads_the_sticky_word_without_draining(tmp_path):
+    """rg_l0_poll_status: 0 while nothing was flagged, and - once the block that holds the monomorphic SNP has run - the
+    same word rg_l0_status returns; polling between blocks must not disturb the results."""
+    from regenie_b200 import synth
+    pb = helpers.synthetic_problem(tmp_path, N=900, M=192, P=2, bsize=64, miss=0.01)
+    st = pb.gpu_step1()
+    for b in range(len(pb.blocks)):
+        pb.gpu_l0_block(st, b)
+        assert st.poll_status() == 0
+    assert st.status() == 0 and st.poll_status() == 0
+    W_o, _, _, _ = pb.oracle_l0(1)
+    assert rel(st.fetch_W(1, 0), W_o[0]) < TOL
+    st.close()
+    g = synth.genotypes(600, 64, seed=3, miss=0.0)
+    g[10] = 1
+    Y, cov, na = synth.phenotypes(g, 2, 3, seed=3)
+    d = tmp_path / "mono"; d.mkdir()
+    prefix = helpers.write_fileset(str(d), g, Y, cov, na)
+    pb2 = helpers.Problem(prefix, str(d) + "/pheno.txt", str(d) + "/covar.txt", 64)
+    st2 = pb2.gpu_step1()
+    pb2.gpu_l0_block(st2, 0)
+    st2.fence()
+    import torch
+    torch.cuda.synchronize()
+    assert st2.poll_status() == 11 and st2.status() == 11
