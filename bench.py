@@ -28,6 +28,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# hardware queues for the 12 lane streams of a Step-1 handle (regenie_b200/csrc/rg_api.cu: rg_set_connection_count does the
+# same when the library is loaded; torch creates the CUDA context first in this script, so it is set here too)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 SEED = 20260924
 CFG = dict(N=100_000, M=50_000, P=10, C=3, bsize=1000, K=5, R=5, miss=0.01)
@@ -530,7 +533,8 @@ def run_gpu(args):
                    "share_of_single_lane_kernel_time": round(solver_ms_tot / ktot, 4)},
         "kernels": kern,
         "kernels_concurrent": kern_conc,
-        "lanes": int(os.environ.get("RG_B200_LANES", "8")),
+        "lanes": int(os.environ.get("RG_B200_LANES", "12")),
+        "cuda_device_max_connections": int(os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS", "8")),
         "cpu_baseline": cpu,
         "sharded_step1": sharded,
         "from_files": file_e2e,
@@ -597,12 +601,41 @@ def file_e2e_leg(host_panel, N, M, bs, P, Yr, cov, na, gpus=1):
         shutil.rmtree(d, ignore_errors=True)
 
 
-def hbm_roofline(rate, bytes_per_variant, what):
+def step2_traffic_from_profile(kernels, variants_per_launch):
+    """DRAM bytes per variant (dram__bytes_read.sum + dram__bytes_write.sum of one launch of each named kernel, divided by the
+    variants a launch covers) from the committed ncu --set full summary of the Step-2 kernels (tools/ncu_capture_s2.sh ->
+    profiles/ncu_r2t_step2_kernels.txt; captured at N = 100k: 1000 .bed variants / 400 dosage variants per launch)."""
+    try:
+        blocks = open(os.path.join(ROOT, "profiles", "ncu_r2t_step2_kernels.txt")).read().split("---\n")
+    except OSError:
+        return None, None
+    per = {}
+    for b in blocks:                                   # the LAST captured launch of each kernel (warm handle)
+        name = next((k for k in kernels if k in b), None)
+        if name is None:
+            continue
+        d = {}
+        for line in b.splitlines():
+            t = line.split()
+            if len(t) >= 2:
+                d[t[0]] = t[1]
+        if "dram__bytes_read.sum" in d:
+            per[name] = (float(d["dram__bytes_read.sum"]) + float(d["dram__bytes_write.sum"])) * 1e6 / variants_per_launch
+    if len(per) != len(kernels):
+        return None, None
+    return sum(per.values()), {k: round(v) for k, v in per.items()}
+
+
+def hbm_roofline(rate, bytes_per_variant, what, traffic=(None, None)):
     peaks, src = load_peaks()
     gbs = rate * bytes_per_variant / 1e9
-    return {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-            "traffic": None, "algorithmic_bytes_per_variant": bytes_per_variant, "peak_basis": "%s copy bandwidth" % src,
-            "rate_used": "device-resident variants/s x algorithmic bytes per variant (%s)" % what}
+    out = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+           "traffic": traffic[0], "algorithmic_bytes_per_variant": bytes_per_variant, "peak_basis": "%s copy bandwidth" % src,
+           "rate_used": "device-resident variants/s x algorithmic bytes per variant (%s)" % what}
+    if traffic[0] is not None:
+        out["traffic_unit"] = "DRAM bytes per variant, all kernels of a block (ncu --set full at N = 100k, profiles/ncu_r2t_step2_kernels.txt)"
+        out["traffic_by_kernel"] = traffic[1]
+    return out
 
 
 def s2_tensor_roofline(rate, N, P, C):
@@ -681,7 +714,9 @@ def step2_qt_leg(capi, X, mask, in_an, N, P, C, bs, blocks, host_panel, dev_ptr,
                     "staged": staged_rate, "unstaged": host_rate,
                     "note": "staged = rg_s2_stage copies block b+1 on a copy stream under the kernels of block b; unstaged = "
                             "the block call copies its own rows first"},
-            "roofline": hbm_roofline(dev_rate, N / 4.0, "N/4 bytes of 2-bit calls"),
+            "roofline": hbm_roofline(dev_rate, N / 4.0, "N/4 bytes of 2-bit calls",
+                                     step2_traffic_from_profile(("bed_relayout_kernel", "bed_expand3_fp8_kernel", "gram_fp8_tcgen05_kernel",
+                                                                 "s2_stats_finish_kernel", "s2_finalize_kernel"), 1000) if N == 100_000 else (None, None)),
             "tensor_roofline": s2_tensor_roofline(dev_rate, N, P, C),
             "cpu_baseline": cpu,
             "sample": "%d blocks of %d variants, N=%d, %d traits; value = .bed rows resident in HBM, e2e = pinned host rows; "
@@ -893,7 +928,9 @@ def step2_bt_leg(capi, X, in_an, N, C, args, nvar=400, nblocks=4):
                     "staged": staged_rate, "unstaged": host_rate},
             "e2e_compressed_input": inflate,
             "compressed_bytes_per_variant": float(offs[-1]) / nvar,
-            "roofline": hbm_roofline(dev_rate, 3.0 * N, "2N probability bytes + N ploidy bytes"),
+            "roofline": hbm_roofline(dev_rate, 3.0 * N, "2N probability bytes + N ploidy bytes",
+                                     step2_traffic_from_profile(("dosage_relayout_kernel", "dosage_stats_kernel", "s2_bt_finalize_kernel"), 400)
+                                     if N == 100_000 else (None, None)),
             "cpu_baseline": cpu, "firth_fraction": ff,
             "sample": "%d blocks of %d variants, N=%d, 1 binary trait (prevalence 10 %%), score test + approximate Firth for |z| > 1.96; "
                       "value = inflated bytes resident in HBM, e2e = pinned host probability + ploidy bytes (3N B/variant), "

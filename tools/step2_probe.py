@@ -10,7 +10,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 from regenie_b200 import capi, hostprep  # noqa: E402
 
-N, P, C, bs, nb = 100_000, 10, 3, 1000, 3
+N, P, C, bs, nb = 100_000, 10, 3, 1000, int(os.environ.get("RG_PROBE_BLOCKS", "3"))
+REPS = int(os.environ.get("RG_PROBE_REPS", "2"))
 dev = torch.device("cuda", 0)
 Yr, cov, na = bench.gen_pheno(N, P, C, bench.SEED)
 X, Y, mask, in_an, neff = hostprep.prepare_qt(Yr, cov, na)
@@ -21,7 +22,7 @@ res = np.asfortranarray(rng.normal(size=(N, P)) * mask)
 st = capi.Step2(X, mask, in_an, N, bs)
 st.set_chr(res, np.ones(P))
 out = st._out(bs)
-for rep in range(2):
+for rep in range(REPS):
     for b in range(nb):
         st.block_bed_raw(panel.data_ptr() + b * bs * stride, bs, stride, out)
 st.close()
@@ -36,7 +37,7 @@ st.set_chr_bt(gsm, gsm, yres, [X], y[:, None], np.full((N, 1), np.log(p0 / (1 - 
 probs = torch.randint(0, 120, (nvar, N, 2), dtype=torch.uint8, device=dev)
 miss = torch.full((nvar, N), 2, dtype=torch.uint8, device=dev)
 o = st._out(nvar, with_info=True)
-for rep in range(3):
+for rep in range(REPS + 1):
     st.block_bgen8_bt_raw(probs.data_ptr(), miss.data_ptr(), N, nvar, o)
 st.close()
 print("step2 probe done")
