@@ -28,8 +28,11 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# hardware queues for the 12 lane streams of a Step-1 handle (regenie_b200/csrc/rg_api.cu: rg_set_connection_count does the
-# same when the library is loaded; torch creates the CUDA context first in this script, so it is set here too)
+# Hardware queues for the lane streams of a Step-1 handle: with 32 instead of the driver's default 8 the library runs 12 lanes
+# (csrc/rg_api.cu, rg_step1_create; profiles/ab_r2u_connections_lanes.txt).  The variable is read when the CUDA context is
+# created, i.e. it has to be in the environment before torch touches the device.  A 32-queue context takes ~1 s longer to
+# create, which a long job does not notice and a 1.3 s from-files run does: that leg's child process gets the default back.
+_CONN_WAS_SET = "CUDA_DEVICE_MAX_CONNECTIONS" in os.environ
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 SEED = 20260924
@@ -533,7 +536,7 @@ def run_gpu(args):
                    "share_of_single_lane_kernel_time": round(solver_ms_tot / ktot, 4)},
         "kernels": kern,
         "kernels_concurrent": kern_conc,
-        "lanes": int(os.environ.get("RG_B200_LANES", "12")),
+        "lanes": int(os.environ.get("RG_B200_LANES", "12" if int(os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS", "8")) >= 16 else "8")),
         "cuda_device_max_connections": int(os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS", "8")),
         "cpu_baseline": cpu,
         "sharded_step1": sharded,
@@ -578,7 +581,10 @@ def file_e2e_leg(host_panel, N, M, bs, P, Yr, cov, na, gpus=1):
         if gpus > 1:
             cmd += ["--gpus", str(gpus)]
         t0 = time.perf_counter()
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, RG_B200_PHASES="1"))
+        child_env = dict(os.environ, RG_B200_PHASES="1")
+        if not _CONN_WAS_SET:
+            child_env.pop("CUDA_DEVICE_MAX_CONNECTIONS", None)      # short job: default queue count (fast context creation), 8 lanes
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=child_env)
         dt = time.perf_counter() - t0
         if r.returncode != 0:
             return {"error": (r.stdout + r.stderr)[-300:]}

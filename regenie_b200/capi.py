@@ -72,10 +72,6 @@ def debug_fetch(handle, name, dtype, count):
     return out[: n // out.itemsize]
 
 
-# hardware queues for the lanes' streams (csrc/rg_api.cu: rg_set_connection_count); read at CUDA context creation, so it
-# has to be in the environment before torch (or anything else in the process) initialises CUDA
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-
 # every symbol include/rg_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "rg_last_error", "rg_version", "rg_device_count", "rg_step1_create", "rg_destroy", "rg_sync",

@@ -764,13 +764,6 @@ using namespace rg;
   }                                        \
   return 0;
 
-// A Step-1 handle runs 12 lanes (+ a copy stream each, the main stream, the poll stream).  The driver multiplexes streams
-// onto CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8); streams that share a queue serialise behind each other,
-// which is what kept more than 8 lanes from paying (profiles/ab_r2u_connections_lanes.txt: 8 queues / 8 lanes 1.305 M
-// SNPs/s, 32 queues / 12 lanes 1.343 M; from host rows 1.22 -> 1.31 M).  The variable is read when the CUDA context is
-// created, so it is set when the library is loaded - unless the caller has set it (or created the context) already.
-__attribute__((constructor)) static void rg_set_connection_count() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
-
 extern "C" {
 
 const char* rg_last_error(void) { return rg::g_last_error.c_str(); }
@@ -809,8 +802,14 @@ int rg_step1_create(const rg_step1_config* cfg, const double* X, const double* Y
   h->device = cfg->device;
   RG_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   {
-    int nl = 12;  // measured: 4 -> 8 lanes +7%, 8 -> 12 +3% once the streams have hardware queues of their own (see
-                  // rg_set_connection_count), flat beyond (14, 16, 20)
+    // The CUDA driver multiplexes streams onto CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8, read when the context
+    // is created); streams that share a queue serialise behind each other, which is why more than 8 lanes do not pay at the
+    // default.  With 32 queues 12 lanes do (profiles/ab_r2u_connections_lanes.txt: 8 queues / 8 lanes 1.305 M SNPs/s, 32 / 12
+    // 1.343 M, flat beyond; from host rows 1.22 -> 1.31 M) - but a context with 32 queues takes 1.2 s to create instead of
+    // 0.2 s (RG_B200_PHASES of rgb200), so the library leaves the choice to the process: a long job exports
+    // CUDA_DEVICE_MAX_CONNECTIONS=32 before its first CUDA call (bench.py does), a short one does not.
+    int nl = 8;
+    if (const char* q = getenv("CUDA_DEVICE_MAX_CONNECTIONS")) if (atoi(q) >= 16) nl = 12;
     if (const char* e = getenv("RG_B200_LANES")) nl = std::max(1, std::min(32, atoi(e)));
     for (int i = 0; i < nl; ++i) {
       auto l = std::make_unique<rg_ctx::Lane>();
