@@ -66,7 +66,7 @@ struct Params {
   bool af_cc = false;                          // --af-cc: A1FREQ / N among cases and controls (binary traits, split output)
   int min_case_count = 10;                     // --minCaseCount
   bool no_split = false;                       // --no-split: one <out>.regenie for all traits (hard-call input)
-  std::string htp_cohort;                      // --htp COHORT: HTPv4 rows (src/Step2_Models.cpp:2400-2426, :2542-2646); quantitative traits, hard calls
+  std::string htp_cohort;                      // --htp COHORT: HTPv4 rows (src/Step2_Models.cpp:2400-2426, :2542-2646); hard calls
   bool htp = false;
   int test_type = 0;                           // --test additive | dominant | recessive (step 2)
   int gpus = 1;                                // --gpus N (step 1): level-0 blocks sharded over N GPUs of this node, level 1 by phenotype
@@ -286,9 +286,8 @@ Params parse_cli(int argc, char** argv) {
   if (p.step == 2 && p.pred.empty() && !p.ignore_pred) throw Fail("must specify --pred if using --step 2 (otherwise use --ignore-pred).");
   if (p.htp) {
     if (p.step != 2) throw Fail("option --htp only works in step 2.");
-    // print_sum_stats_htp also serves binary traits (odds ratios, case / control genotype counts) and dosages (INFO=):
-    // this driver writes HTP rows for quantitative traits on hard calls and says so for the rest
-    if (p.bt) throw Fail("--htp with --bt is outside the hot path covered by rgb200 (HTP rows are written for quantitative traits).");
+    // print_sum_stats_htp also serves dosages (INFO=, thresholded genotype counts per trait): this driver writes HTP rows
+    // for hard-call input (quantitative and binary traits) and says so for the rest
     if (!p.bgen.empty()) throw Fail("--htp with --bgen is outside the hot path covered by rgb200 (HTP rows are written for hard-call input).");
     if (p.no_split) p.no_split = false;                       // src/Regenie.cpp:1068-1071: --no-split is ignored with --htp
   }
@@ -1338,6 +1337,8 @@ void run_step2_bt(const Params& p, Log& log) {
   const auto blocks = set_blocks(snps, p.bsize);
   log << " * # blocks            : [" << blocks.size() << "]\n";
   const double z_thr = z_threshold(p.p_thresh);
+  // --htp: test_string + wgr_string + correction_type (src/Data.cpp:2075-2102)
+  const std::string htp_model = std::string(test_name(p.test_type)) + (p.ignore_pred ? "" : "-WGR") + (p.firth ? "-FIRTH" : p.spa ? "-SPA" : "-LOG");
   if (p.firth) log << " * using approximate Firth correction for logistic regression p-values less than " << p.p_thresh << "\n";
   std::vector<std::string> null_firth_files;                 // check_blup-like list (src/Step2_Models.cpp:1896-1927)
   if (p.firth && !p.null_firth_list.empty()) {
@@ -1373,7 +1374,10 @@ void run_step2_bt(const Params& p, Log& log) {
   std::vector<std::string>& obuf = w.obuf;                   // rows of the current block, one buffer per trait
   std::string head_s;
   const int bsz = p.bsize;
-  GenoCounts gc(p.no_split, bsz, P, use_bgen ? 0 : gb.row_stride, p.ref_first);
+  GenoCounts gc(p.no_split || p.htp, bsz, P, use_bgen ? 0 : gb.row_stride, p.ref_first);
+  // --htp: the hom-alt counts of the CASES of each trait, from the same recessive recoding run on the case handle below
+  // (update_genocounts, src/Geno.cpp:2986-3018: rows 0-2 = cases, 3-5 = controls; controls = all - cases here)
+  GenoCounts gcc(p.htp, bsz, P, use_bgen ? 0 : gb.row_stride, p.ref_first);
   // --af-cc (update_af_cc / compute_aaf_info, src/Geno.cpp:3069-3075, :3120-3127): a second handle whose sample masks are
   // the cases of each trait returns their allele frequency and count from the same block bytes; controls follow by
   // difference of the (exactly reconstructed) allele sums.
@@ -1381,7 +1385,7 @@ void run_step2_bt(const Params& p, Log& log) {
   HandleGuard guard_cases{hc};
   std::vector<double> afc, macc, afc_all, macc_all, statc, betac, sec, chisqc, scalec, infoc;
   std::vector<int32_t> nsc, nsc_all, flagsc;
-  if (p.af_cc) {
+  if (p.af_cc || p.htp) {
     std::vector<uint8_t> mask_case(ph.mask.size());
     for (size_t e = 0; e < mask_case.size(); ++e) mask_case[e] = ph.mask[e] && ph.Y_raw[e] == 1.0;
     rg_step2_config cfgc = cfg;
@@ -1496,10 +1500,14 @@ void run_step2_bt(const Params& p, Log& log) {
     }
     pending.get();
     if (b + 1 < blocks.size()) pending = fetch(b + 1);
-    if (!use_bgen)
+    if (!use_bgen) {
       gc.run(rows[b & 1].data(), (size_t)bs * gb.row_stride, bs, [&](const uint8_t* r, const rg_s2_out* o) {
         rg_check(rg_s2_block_bed_bt(h, r, (int64_t)gb.row_stride, bs, subset ? sample_idx.data() : nullptr, p.ref_first, 0.0, o));
       });
+      gcc.run(rows[b & 1].data(), (size_t)bs * gb.row_stride, bs, [&](const uint8_t* r, const rg_s2_out* o) {
+        rg_check(rg_s2_block_bed(hc, r, (int64_t)gb.row_stride, bs, subset ? sample_idx.data() : nullptr, p.ref_first, 0.0, o));
+      });
+    }
     if (non_par_flags(p, snps, blocks[b], npf)) rg_check(rg_s2_set_non_par(h, npf.data(), bs));
     if (use_bgen) {
       const uint8_t *pd = probs[b & 1].data(), *md = pmiss[b & 1].data();
@@ -1576,6 +1584,10 @@ void run_step2_bt(const Params& p, Log& log) {
       head_s += s.id; head_s += ' ';
       head_s += s.allele0; head_s += ' ';
       head_s += s.allele1; head_s += ' ';
+      if (p.htp) {                                             // print_sum_stats_head_htp :2419-2426
+        if (chrom == 23) throw Fail("--htp on chromosome X is outside the hot path covered by rgb200 (sex-aware genotype counts).");
+        head_s = s.id + "\t" + std::to_string(s.chrom) + "\t" + std::to_string(s.pos) + "\t" + s.allele0 + "\t" + s.allele1 + "\t";
+      }
       if (p.no_split) {                                        // print_sum_stats_all :2441-2493
         long n_rr, n_ra, n_aa;
         if (use_bgen) { n_rr = d_rr[b & 1][v]; n_aa = d_aa[b & 1][v]; n_ra = ns_all[v] - n_rr - n_aa; }
@@ -1607,9 +1619,30 @@ void run_step2_bt(const Params& p, Log& log) {
           cc.af_case = afc[e];
           cc.af_control = (s_all - s_case) / unit / (2.0 * cc.ns_control);
         }
+        if (p.htp) {
+          // print_sum_stats_htp for a binary trait (src/Step2_Models.cpp:2542-2646).  Genotype counts (update_genocounts,
+          // src/Geno.cpp:2986-3018) from exact allele sums: hom-alt = allele sum of the recessive recoding, het = additive
+          // sum - 2 hom-alt, once over the trait's samples (handle h) and once over its cases (handle hc); controls by
+          // difference.  SCORE / SKATV (compute_score_bt :523-526, :546): stats * sqrt(denum) with the sign of the minor-allele
+          // flip undone, and denum = 1 / se^2 of the score test; cal_factor (check_pval_snp :1993, :2027) = 1 without a
+          // correction, stats^2 / corrected chi-square with one.  After a FAILED correction the reference prints whatever
+          // cal_factor the thread held before (it returns before the assignment): 1 here.
+          HtpRow r;
+          r.model = htp_model.c_str(); r.bt = true; r.firth = p.firth;
+          r.beta = bo; r.se = so; r.chisq = co; r.logp = lp; r.af = af[e]; r.mac = mac[e]; r.test_pass = pass;
+          const long hom_all = std::lround(2.0 * gc.af[e] * gc.ns[e]), sum_all = std::lround(2.0 * af[e] * ns[e]);
+          const long hom_case = std::lround(2.0 * gcc.af[e] * gcc.ns[e]), sum_case = std::lround(2.0 * afc[e] * nsc[e]);
+          r.gc[2] = hom_case; r.gc[1] = sum_case - 2 * hom_case; r.gc[0] = nsc[e] - r.gc[1] - r.gc[2];
+          r.gc[5] = hom_all - hom_case; r.gc[4] = (sum_all - sum_case) - 2 * r.gc[5]; r.gc[3] = (ns[e] - nsc[e]) - r.gc[4] - r.gc[5];
+          const double sqrt_den = 1.0 / se[e];
+          r.score = stat[e] * sqrt_den * ((flags[v] & 8) ? -1.0 : 1.0); r.skat_var = sqrt_den * sqrt_den;
+          r.cal_factor = (f != fidx.end() && pass) ? (co == 0 ? 0.0 : stat[e] * stat[e] / co) : 1.0;
+          append_htp_row(obuf[i], head_s, ph.names[i], p.htp_cohort, r);
+          continue;
+        }
         if (p.no_split) append_sumstats_all_trait(w.obuf_all, true, bo, so, co, lp, pass);
         else append_sumstats_row(obuf[i], head_s, af[e], use_bgen, use_bgen ? info[e] : -1.0, ns[e], test_name(p.test_type), bo, so, co, lp, pass,
-                                 hc ? &cc : nullptr);
+                                 (hc && p.af_cc) ? &cc : nullptr);
       }
       if (p.no_split) w.obuf_all += " NA\n";
     }
@@ -1628,6 +1661,7 @@ void run_step2(const Params& p_in, Log& log) {
     log << "WARNING: disabling option --af-cc (only for BTs in step 2 in native output format split by trait).\n";
     p.af_cc = false;
   }
+  if (p.htp) p.af_cc = false;                                // HTP rows carry genotype counts, not the --af-cc columns
   if (p.bt) run_step2_bt(p, log); else run_step2_qt(p, log);
 }
 

@@ -378,6 +378,74 @@ def check_htp(run, read, tmp_path, golden_dir, extra=()):
             assert float(t[8]) == float(n[8])                                         # Effect = BETA
 
 
+def check_htp_bt(run, read, tmp_path, golden_dir, extra=(), numbers=True):
+    """--htp COHORT for binary traits on hard calls (print_sum_stats_htp, src/Step2_Models.cpp:2542-2646; update_genocounts,
+    src/Geno.cpp:2986-3018): same variants and AAF as the native file, genotype counts of the cases and of the controls of
+    each trait checked against the .bed and the phenotype file, model string, Info keys; with `numbers` (the real library -
+    the mock's statistics are not regenie's) Effect / CI / Pval / REGENIE_BETA / REGENIE_SE / LOG10P against the native
+    file of the same options and SCORE^2 / SKATV = the score-test chi-square where no correction was applied."""
+    import math
+    import numpy as np
+    from oracle import plink, prep
+    d = golden_dir
+    firth = "--firth" in extra
+    base = ["--step", "2", "--bed", d + "/example_3chr", "--phenoFile", d + "/phenotype_bin.txt", "--covarFile", d + "/covariates.txt",
+            "--bsize", "100", "--ignore-pred", "--bt"] + list(extra)
+    run(base + ["--out", str(tmp_path / "native")])
+    run(base + ["--htp", "MYCOHORT", "--af-cc", "--out", str(tmp_path / "htp")])      # --af-cc has no HTP columns: ignored
+    bim = plink.read_bim(d + "/example_3chr.bim")
+    keys, _ = plink.read_fam(d + "/example_3chr.fam")
+    G = plink.decode_bed(plink.read_bed_rows(d + "/example_3chr.bed", len(keys), bim.offset), len(keys), ref_first="--ref-first" in extra)
+    pr = prep.prepare(keys, d + "/phenotype_bin.txt", d + "/covariates.txt", step=2, bt=True)
+    idx = {v: k for k, v in enumerate(bim.ids)}
+    model = "ADD" + ("-FIRTH" if firth else "-SPA" if "--spa" in extra else "-LOG")
+    zc = 1.959963984540054
+    n_rows = 0
+    for ph, nm in enumerate(("Y1", "Y2")):
+        nat = [l.split() for l in read(str(tmp_path / "native") + "_%s.regenie" % nm).splitlines()[1:]]
+        rows = read(str(tmp_path / "htp") + "_%s.regenie" % nm).splitlines()
+        assert rows[0].split("\t")[13:21] == ["Num_Cases", "Cases_Ref", "Cases_Het", "Cases_Alt", "Num_Controls", "Controls_Ref",
+                                              "Controls_Het", "Controls_Alt"]
+        assert len(rows) - 1 == len(nat) > 300
+        m = pr.mask[:, ph].astype(bool)
+        y = pr.Y_raw[:, ph]
+        for l, n in zip(rows[1:], nat):
+            t = l.split("\t")
+            assert len(t) == 22
+            assert [t[1], t[2], t[0], t[3], t[4]] == n[:5] and t[5:8] == [nm, "MYCOHORT", model], l
+            assert t[12] == n[5]                                                       # AAF = A1FREQ
+            for cols, sel in ((t[13:17], m & (y == 1)), (t[17:21], m & (y == 0))):
+                g = G[idx[t[0]]][sel]
+                want = [int((g == 0).sum()), int((g == 1).sum()), int((g == 2).sum())]
+                assert [int(x) for x in cols] == [sum(want)] + want, l
+            info = dict(kv.split("=") for kv in t[21].split(";"))
+            failed = n[-1] == "TEST_FAIL"
+            keys_want = [] if failed else ["REGENIE_BETA", "REGENIE_SE"] + ([] if firth else ["SE"])
+            assert list(info) == keys_want + ["MAC", "SCORE", "SKATV", "LOG10P"], l
+            n_rows += 1
+            if not numbers or failed:
+                continue
+            beta, se, chisq, lp = (float(x) for x in n[-5:-1])
+            assert abs(float(info["REGENIE_BETA"]) - beta) <= 2e-6 * abs(beta) + 1e-12, l
+            assert abs(float(info["REGENIE_SE"]) - se) <= 2e-6 * se, l
+            assert abs(float(info["LOG10P"]) - lp) <= 2e-6 * lp + 1e-12, l
+            if lp > 0:
+                assert abs(math.log10(float(t[11])) + lp) < 1e-5, l                    # Pval
+            if firth:                                                                  # odds ratio scale
+                assert abs(float(t[8]) - math.exp(beta)) <= 1e-5 * math.exp(beta), l
+                assert abs(float(t[9]) - math.exp(beta - zc * se)) <= 1e-5 * math.exp(beta - zc * se), l
+            else:                                                                      # allelic odds ratio from the counts
+                c = [int(x) for x in t[14:17]] + [int(x) for x in t[18:21]]
+                eff = (2 * c[3] + c[4] + .5) * (2 * c[2] + c[1] + .5) / (2 * c[5] + c[4] + .5) / (2 * c[0] + c[1] + .5)
+                assert abs(float(t[8]) - eff) <= 1e-5 * eff, l
+                assert abs(float(info["SE"]) - abs(math.log(eff)) / math.sqrt(chisq)) <= 2e-6 * abs(float(info["SE"])) + 1e-12, l
+            score, skv = float(info["SCORE"]), float(info["SKATV"])
+            assert skv > 0 and (score > 0) == (beta > 0) or beta == 0, l              # sign: flip undone like BETA
+            if not firth or abs(score) / math.sqrt(skv) <= zc * 0.999:                 # no correction: SKATV = denum, SCORE^2 / SKATV = CHISQ
+                assert abs(score * score / skv - chisq) <= 1e-5 * chisq + 1e-9, l
+    assert n_rows > 600
+
+
 def check_no_split(run, read, tmp_path, golden_dir, extra=(), bt=False):
     """--no-split (src/Step2_Models.cpp:2364-2383, 2441-2493): one file for all traits whose per-trait columns are those of
     the split files, with N_RR / N_RA / N_AA of all analysed samples (src/Geno.cpp:2480-2486) checked against the .bed."""

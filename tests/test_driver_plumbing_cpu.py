@@ -230,9 +230,17 @@ def test_no_split_output(tmp_path, golden_dir, extra, bt):
 def test_htp_output(tmp_path, golden_dir, extra):
     import helpers
     helpers.check_htp(run, read, tmp_path, golden_dir, extra)
-    r = run(["--step", "2", "--bed", golden_dir + "/example", "--phenoFile", golden_dir + "/phenotype_bin.txt", "--bsize", "100",
+    r = run(["--step", "2", "--bgen", golden_dir + "/example.bgen", "--phenoFile", golden_dir + "/phenotype_bin.txt", "--bsize", "100",
              "--ignore-pred", "--bt", "--htp", "X", "--out", str(tmp_path / "no")], ok=False)
-    assert "ERROR" in r and "--htp with --bt" in r
+    assert "ERROR" in r and "--htp with --bgen" in r
+
+
+@pytest.mark.parametrize("extra", [(), ("--firth", "--approx", "--pThresh", "0.1"), ("--ref-first",)])
+def test_htp_output_binary_traits(tmp_path, golden_dir, extra):
+    """Control flow of --htp --bt against the mock ABI (its allele sums are real, its statistics are not regenie's): rows,
+    model string, case / control genotype counts, Info keys."""
+    import helpers
+    helpers.check_htp_bt(run, read, tmp_path, golden_dir, extra, numbers=False)
 
 
 def test_min_case_count_drops_rare_binary_traits(tmp_path, golden_dir):
