@@ -340,6 +340,52 @@ void BgenFile::info_all(const uint8_t* probs, const uint8_t* pm, size_t n, const
   for (auto& t : pool) t.join();
 }
 
+void BgenFile::trait_counts(const uint8_t* probs, const uint8_t* pm, size_t n, const uint8_t* cls, int P, bool binary,
+                            bool ref_first, long* out, int threads) const {
+  std::atomic<size_t> next{0};
+  const size_t nk = sample_idx.size();
+  // samples per (trait, class): the reference class follows by difference, so only het / alt / missing calls touch the traits
+  std::vector<long> size((size_t)P * 3, 0);
+  for (int p = 0; p < P; ++p)
+    for (size_t k = 0; k < nk; ++k) ++size[(size_t)p * 3 + cls[(size_t)p * nk + k]];
+  auto work = [&]() {
+    std::vector<long> c((size_t)P * 3 * 3);                  // [trait][class][het, alt, missing]
+    for (;;) {
+      const size_t j = next.fetch_add(1);
+      if (j >= n) return;
+      const uint8_t* pr = probs + j * (size_t)n_file * 2;
+      const uint8_t* m = pm + j * (size_t)n_file;
+      std::fill(c.begin(), c.end(), 0);
+      for (size_t k = 0; k < nk; ++k) {
+        const size_t f = (size_t)sample_idx[k];
+        int g;
+        if (m[f] & 0x80) g = 2;
+        else {
+          const uint32_t p0 = pr[2 * f], p1 = pr[2 * f + 1];
+          const uint32_t hom = ref_first ? (p0 + p1 > 255 ? 0 : 255 - p0 - p1) : p0;
+          const uint32_t d = p1 + 2 * hom;                   // dosage in units of 1 / 255
+          if (2 * d >= 765) g = 1; else if (2 * d >= 255) g = 0; else continue;
+        }
+        for (int p = 0; p < P; ++p) ++c[((size_t)p * 3 + cls[(size_t)p * nk + k]) * 3 + g];
+      }
+      long* o = out + j * (size_t)P * 6;
+      for (int p = 0; p < P; ++p) {
+        const int first = binary ? 2 : 1;                    // class printed in the "cases" columns
+        const long* a = &c[((size_t)p * 3 + first) * 3];
+        o[p * 6 + 1] = a[0]; o[p * 6 + 2] = a[1]; o[p * 6 + 0] = size[(size_t)p * 3 + first] - a[0] - a[1] - a[2];
+        const long* b = &c[((size_t)p * 3 + 1) * 3];
+        o[p * 6 + 4] = binary ? b[0] : 0; o[p * 6 + 5] = binary ? b[1] : 0;
+        o[p * 6 + 3] = binary ? size[(size_t)p * 3 + 1] - b[0] - b[1] - b[2] : 0;
+      }
+    }
+  };
+  const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, n));
+  std::vector<std::thread> pool;
+  for (int t = 1; t < T; ++t) pool.emplace_back(work);
+  work();
+  for (auto& t : pool) t.join();
+}
+
 void BgenFile::read_block_compressed(size_t first, size_t n, std::vector<uint8_t>& comp, std::vector<uint64_t>& offs) const {
   if (compression != 1) throw Fail("on-device inflate needs zlib-compressed bgen payloads (compression flag 1).");
   offs.assign(n + 1, 0);

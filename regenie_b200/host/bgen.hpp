@@ -35,6 +35,12 @@ struct BgenFile {
   // n_rr / n_aa (optional): the --no-split genotype counts of the same samples, dosage < 0.5 / >= 1.5 (src/Geno.cpp:2048-2050)
   void info_all(const uint8_t* probs, const uint8_t* ploidy_missing, size_t n, const uint8_t* in_analysis, bool ref_first,
                 double* info_out, int threads, long* n_rr = nullptr, long* n_aa = nullptr) const;
+  // --htp genotype counts of dosages per trait (update_genocounts, src/Geno.cpp:2986-3018: dosage >= 1.5 alt, >= 0.5 het,
+  // missing calls skipped).  cls [P][kept samples]: 0 = sample not in the trait, 1 = in the trait (a control of a binary
+  // trait), 2 = case; out [n][P][6] = ref / het / alt of class 2 (class 1 for a quantitative trait: pass no 2s), then of
+  // class 1 (binary traits)
+  void trait_counts(const uint8_t* probs, const uint8_t* ploidy_missing, size_t n, const uint8_t* cls, int P, bool binary,
+                    bool ref_first, long* out, int threads) const;
   // the zlib streams of variants snps[first .. first+n) back to back, for rg_bgen_inflate (compression flag 1 only):
   // comp = concatenated streams, offs [n + 1]; throws when a variant's declared length is not 10 + 3 n_file
   void read_block_compressed(size_t first, size_t n, std::vector<uint8_t>& comp, std::vector<uint64_t>& offs) const;

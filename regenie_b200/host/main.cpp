@@ -66,7 +66,7 @@ struct Params {
   bool af_cc = false;                          // --af-cc: A1FREQ / N among cases and controls (binary traits, split output)
   int min_case_count = 10;                     // --minCaseCount
   bool no_split = false;                       // --no-split: one <out>.regenie for all traits (hard-call input)
-  std::string htp_cohort;                      // --htp COHORT: HTPv4 rows (src/Step2_Models.cpp:2400-2426, :2542-2646); hard calls
+  std::string htp_cohort;                      // --htp COHORT: HTPv4 rows (src/Step2_Models.cpp:2400-2426, :2542-2646); autosomes
   bool htp = false;
   int test_type = 0;                           // --test additive | dominant | recessive (step 2)
   int gpus = 1;                                // --gpus N (step 1): level-0 blocks sharded over N GPUs of this node, level 1 by phenotype
@@ -286,9 +286,6 @@ Params parse_cli(int argc, char** argv) {
   if (p.step == 2 && p.pred.empty() && !p.ignore_pred) throw Fail("must specify --pred if using --step 2 (otherwise use --ignore-pred).");
   if (p.htp) {
     if (p.step != 2) throw Fail("option --htp only works in step 2.");
-    // print_sum_stats_htp also serves dosages (INFO=, thresholded genotype counts per trait): this driver writes HTP rows
-    // for hard-call input (quantitative and binary traits) and says so for the rest
-    if (!p.bgen.empty()) throw Fail("--htp with --bgen is outside the hot path covered by rgb200 (HTP rows are written for hard-call input).");
     if (p.no_split) p.no_split = false;                       // src/Regenie.cpp:1068-1071: --no-split is ignored with --htp
   }
   return p;
@@ -1141,10 +1138,20 @@ void run_step2_qt(const Params& p, Log& log) {
   // --minINFO also drops a variant whose INFO over all analysed samples is too low (src/Geno.cpp:2074): computed from the
   // inflated bytes on the host, in the fetch thread
   const bool use_info1 = use_bgen && (p.min_info > 0 || p.no_split);   // --no-split prints it and the dosage genotype counts
-  const bool dev_inflate = use_bgen && p.gpu_inflate && gg.compression == 1 && p.test_type == 0 && !use_info1;
+  // --htp on dosages: thresholded genotype counts per trait (update_genocounts, src/Geno.cpp:2986-3018) from the inflated
+  // bytes, in the fetch thread (BgenFile::trait_counts)
+  const bool htp_bgen = use_bgen && p.htp;
+  std::vector<uint8_t> htp_cls;
+  std::vector<long> htp_cnt[2];
+  if (htp_bgen) {
+    htp_cls.resize((size_t)P * N);
+    for (size_t e = 0; e < htp_cls.size(); ++e) htp_cls[e] = ph.mask[e] ? 1 : 0;
+    for (int k = 0; k < 2; ++k) htp_cnt[k].resize((size_t)bsz * P * 6);
+  }
+  const bool dev_inflate = use_bgen && p.gpu_inflate && gg.compression == 1 && p.test_type == 0 && !use_info1 && !htp_bgen;
   if (use_bgen && p.gpu_inflate)
     log << (dev_inflate ? " * bgen genotype blocks are inflated on the GPU\n"
-                        : "   -WARNING: --gpu-inflate needs zlib-compressed payloads, the additive test and no --minINFO / --no-split; inflating on the host.\n");
+                        : "   -WARNING: --gpu-inflate needs zlib-compressed payloads, the additive test and no --minINFO / --no-split / --htp; inflating on the host.\n");
   std::vector<uint8_t> comp[2];
   std::vector<uint64_t> comp_offs[2];
   std::vector<double> info1[2];
@@ -1162,6 +1169,8 @@ void run_step2_qt(const Params& p, Log& log) {
         gg.read_block(blocks[b].first, blocks[b].size, probs[b & 1].data(), pmiss[b & 1].data(), threads);
         if (use_info1) gg.info_all(probs[b & 1].data(), pmiss[b & 1].data(), blocks[b].size, ph.in_analysis.data(), p.ref_first,
                                    info1[b & 1].data(), threads, d_rr[b & 1].data(), d_aa[b & 1].data());
+        if (htp_bgen) gg.trait_counts(probs[b & 1].data(), pmiss[b & 1].data(), blocks[b].size, htp_cls.data(), P, false, p.ref_first,
+                                      htp_cnt[b & 1].data(), threads);
       }
       else if (pgen_dev) g.pg->gather(blocks[b].first, blocks[b].size, pbatch[b & 1]);
       else g.read_rows(blocks[b].first, blocks[b].size, rows[b & 1].data());
@@ -1284,8 +1293,13 @@ void run_step2_qt(const Params& p, Log& log) {
           HtpRow r;
           r.model = htp_model.c_str();
           r.beta = beta[e]; r.se = se[e]; r.chisq = chisq[e]; r.logp = get_logp(chisq[e]); r.af = af[e]; r.mac = mac[e];
-          const long hom = std::lround(2.0 * gc.af[e] * gc.ns[e]), sum = std::lround(2.0 * af[e] * ns[e]);
-          r.gc[2] = hom; r.gc[1] = sum - 2 * hom; r.gc[0] = ns[e] - r.gc[1] - r.gc[2];
+          if (use_bgen) {                                      // dosages: thresholded counts + the trait's INFO
+            for (int k = 0; k < 3; ++k) r.gc[k] = htp_cnt[b & 1][e * 6 + k];
+            r.info = info[e];
+          } else {
+            const long hom = std::lround(2.0 * gc.af[e] * gc.ns[e]), sum = std::lround(2.0 * af[e] * ns[e]);
+            r.gc[2] = hom; r.gc[1] = sum - 2 * hom; r.gc[0] = ns[e] - r.gc[1] - r.gc[2];
+          }
           const double sqrt_den = scf[i] / se[e];
           r.score = stat[e] * sqrt_den; r.skat_var = sqrt_den * sqrt_den;
           append_htp_row(obuf[i], head_s, ph.names[i], p.htp_cohort, r);
@@ -1385,7 +1399,7 @@ void run_step2_bt(const Params& p, Log& log) {
   HandleGuard guard_cases{hc};
   std::vector<double> afc, macc, afc_all, macc_all, statc, betac, sec, chisqc, scalec, infoc;
   std::vector<int32_t> nsc, nsc_all, flagsc;
-  if (p.af_cc || p.htp) {
+  if (p.af_cc || (p.htp && !use_bgen)) {
     std::vector<uint8_t> mask_case(ph.mask.size());
     for (size_t e = 0; e < mask_case.size(); ++e) mask_case[e] = ph.mask[e] && ph.Y_raw[e] == 1.0;
     rg_step2_config cfgc = cfg;
@@ -1407,10 +1421,19 @@ void run_step2_bt(const Params& p, Log& log) {
     else rows[k].resize((size_t)bsz * gb.row_stride);
   }
   const bool use_info1 = use_bgen && (p.min_info > 0 || p.no_split);   // variant-level --minINFO / --no-split, see run_step2_qt
-  const bool dev_inflate = use_bgen && p.gpu_inflate && gg.compression == 1 && p.test_type == 0 && !use_info1;
+  // --htp on dosages: thresholded genotype counts of the cases and controls of each trait (BgenFile::trait_counts)
+  const bool htp_bgen = use_bgen && p.htp;
+  std::vector<uint8_t> htp_cls;
+  std::vector<long> htp_cnt[2];
+  if (htp_bgen) {
+    htp_cls.resize((size_t)P * N);
+    for (size_t e = 0; e < htp_cls.size(); ++e) htp_cls[e] = !ph.mask[e] ? 0 : ph.Y_raw[e] == 1.0 ? 2 : 1;
+    for (int k = 0; k < 2; ++k) htp_cnt[k].resize((size_t)bsz * P * 6);
+  }
+  const bool dev_inflate = use_bgen && p.gpu_inflate && gg.compression == 1 && p.test_type == 0 && !use_info1 && !htp_bgen;
   if (use_bgen && p.gpu_inflate)
     log << (dev_inflate ? " * bgen genotype blocks are inflated on the GPU\n"
-                        : "   -WARNING: --gpu-inflate needs zlib-compressed payloads, the additive test and no --minINFO / --no-split; inflating on the host.\n");
+                        : "   -WARNING: --gpu-inflate needs zlib-compressed payloads, the additive test and no --minINFO / --no-split / --htp; inflating on the host.\n");
   std::vector<uint8_t> comp[2];
   std::vector<uint64_t> comp_offs[2];
   std::vector<double> info1[2];
@@ -1427,6 +1450,8 @@ void run_step2_bt(const Params& p, Log& log) {
         gg.read_block(blocks[b].first, blocks[b].size, probs[b & 1].data(), pmiss[b & 1].data(), threads);
         if (use_info1) gg.info_all(probs[b & 1].data(), pmiss[b & 1].data(), blocks[b].size, ph.in_analysis.data(), p.ref_first,
                                    info1[b & 1].data(), threads, d_rr[b & 1].data(), d_aa[b & 1].data());
+        if (htp_bgen) gg.trait_counts(probs[b & 1].data(), pmiss[b & 1].data(), blocks[b].size, htp_cls.data(), P, true, p.ref_first,
+                                      htp_cnt[b & 1].data(), threads);
       }
       else if (pgen_dev) gb.pg->gather(blocks[b].first, blocks[b].size, pbatch[b & 1]);
       else gb.read_rows(blocks[b].first, blocks[b].size, rows[b & 1].data());
@@ -1630,10 +1655,15 @@ void run_step2_bt(const Params& p, Log& log) {
           HtpRow r;
           r.model = htp_model.c_str(); r.bt = true; r.firth = p.firth;
           r.beta = bo; r.se = so; r.chisq = co; r.logp = lp; r.af = af[e]; r.mac = mac[e]; r.test_pass = pass;
-          const long hom_all = std::lround(2.0 * gc.af[e] * gc.ns[e]), sum_all = std::lround(2.0 * af[e] * ns[e]);
-          const long hom_case = std::lround(2.0 * gcc.af[e] * gcc.ns[e]), sum_case = std::lround(2.0 * afc[e] * nsc[e]);
-          r.gc[2] = hom_case; r.gc[1] = sum_case - 2 * hom_case; r.gc[0] = nsc[e] - r.gc[1] - r.gc[2];
-          r.gc[5] = hom_all - hom_case; r.gc[4] = (sum_all - sum_case) - 2 * r.gc[5]; r.gc[3] = (ns[e] - nsc[e]) - r.gc[4] - r.gc[5];
+          if (use_bgen) {                                      // dosages: thresholded counts + the trait's INFO
+            for (int k = 0; k < 6; ++k) r.gc[k] = htp_cnt[b & 1][e * 6 + k];
+            r.info = info[e];
+          } else {
+            const long hom_all = std::lround(2.0 * gc.af[e] * gc.ns[e]), sum_all = std::lround(2.0 * af[e] * ns[e]);
+            const long hom_case = std::lround(2.0 * gcc.af[e] * gcc.ns[e]), sum_case = std::lround(2.0 * afc[e] * nsc[e]);
+            r.gc[2] = hom_case; r.gc[1] = sum_case - 2 * hom_case; r.gc[0] = nsc[e] - r.gc[1] - r.gc[2];
+            r.gc[5] = hom_all - hom_case; r.gc[4] = (sum_all - sum_case) - 2 * r.gc[5]; r.gc[3] = (ns[e] - nsc[e]) - r.gc[4] - r.gc[5];
+          }
           const double sqrt_den = 1.0 / se[e];
           r.score = stat[e] * sqrt_den * ((flags[v] & 8) ? -1.0 : 1.0); r.skat_var = sqrt_den * sqrt_den;
           r.cal_factor = (f != fidx.end() && pass) ? (co == 0 ? 0.0 : stat[e] * stat[e] / co) : 1.0;

@@ -596,6 +596,51 @@ def check_af_cc(run, read, tmp_path, golden_dir, extra=()):
             assert [u[6], u[7], u[9], u[10]] == want, (b, want)
 
 
+def check_htp_bgen(run, read, tmp_path, golden_dir, bt=False):
+    """--htp on dosages: the thresholded genotype counts of each trait's samples (cases / controls for a binary trait) against
+    oracle.step2.genocounts on the float dosages (update_genocounts, src/Geno.cpp:2986-3018), INFO= in the Info column, same
+    variants as the native file.  The driver forms the counts on the host from the inflated bytes (BgenFile::trait_counts)."""
+    from oracle import bgen as obgen, prep, step2
+    d = golden_dir
+    keys = ["_".join(l.split()[:2]) for l in open(d + "/example.fam")]
+    M, N = 90, len(keys)
+    probs, miss = synthetic_dosage_probs(M, N, seed=23)
+    f = str(tmp_path / "syn.bgen")
+    write_bgen(f, probs, miss, [1] * 50 + [2] * 40, range(1, M + 1), ["v%d" % v for v in range(M)], sample_ids=keys)
+    pheno = d + ("/phenotype_bin.txt" if bt else "/phenotype.txt")
+    base = ["--step", "2", "--bgen", f, "--phenoFile", pheno, "--covarFile", d + "/covariates.txt", "--bsize", "40",
+            "--ignore-pred", "--minMAC", "1"] + (["--bt"] if bt else [])
+    run(base + ["--out", str(tmp_path / "native")])
+    run(base + ["--htp", "C1", "--gpu-inflate", "--out", str(tmp_path / "htp")])       # --gpu-inflate falls back to the host here
+    pr = prep.prepare(keys, pheno, d + "/covariates.txt", step=2, bt=bt)
+    n_rows = 0
+    for ph, nm in enumerate(("Y1", "Y2")):
+        nat = [l.split() for l in read(str(tmp_path / "native") + "_%s.regenie" % nm).splitlines()[1:]]
+        rows = read(str(tmp_path / "htp") + "_%s.regenie" % nm).splitlines()[1:]
+        assert len(rows) == len(nat) > 60
+        m = pr.mask[:, ph].astype(bool)
+        if bt:
+            cases, controls = np.nonzero(m & (pr.Y_raw[:, ph] == 1))[0], np.nonzero(m & (pr.Y_raw[:, ph] == 0))[0]
+        else:
+            cases, controls = np.nonzero(m)[0], None
+        for l, n in zip(rows, nat):
+            t = l.split("\t")
+            assert len(t) == 22 and t[0] == n[2] and t[7] == ("ADD-LOG" if bt else "ADD-LR")
+            v = int(t[0][1:])
+            g, _ = obgen.dosage(probs[v, :, 0], probs[v, :, 1], miss[v])
+            want = step2.genocounts(g, cases, controls)
+            assert [int(x) for x in t[14:17]] == want[:3] and int(t[13]) == sum(want[:3]), l
+            if bt:
+                assert [int(x) for x in t[18:21]] == want[3:] and int(t[17]) == sum(want[3:]), l
+            else:
+                assert t[17:21] == ["NA"] * 4
+            info = dict(kv.split("=") for kv in t[21].split(";"))
+            assert list(info) == (["REGENIE_BETA", "REGENIE_SE", "SE"] if bt else ["REGENIE_SE"]) + ["INFO", "MAC", "SCORE", "SKATV", "LOG10P"], l
+            assert abs(float(info["INFO"]) - float(n[6])) <= 2e-6 * max(1.0, abs(float(n[6]))), l     # the trait's INFO column
+            n_rows += 1
+    assert n_rows > 120
+
+
 def check_no_split_bgen(run, read, tmp_path, golden_dir):
     """--no-split on dosages: INFO over all analysed samples and the threshold genotype counts (dosage < 0.5 / >= 1.5,
     src/Geno.cpp:2048-2050) come from the inflated bytes; per-trait columns are those of the split files."""

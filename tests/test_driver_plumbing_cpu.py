@@ -230,9 +230,12 @@ def test_no_split_output(tmp_path, golden_dir, extra, bt):
 def test_htp_output(tmp_path, golden_dir, extra):
     import helpers
     helpers.check_htp(run, read, tmp_path, golden_dir, extra)
-    r = run(["--step", "2", "--bgen", golden_dir + "/example.bgen", "--phenoFile", golden_dir + "/phenotype_bin.txt", "--bsize", "100",
-             "--ignore-pred", "--bt", "--htp", "X", "--out", str(tmp_path / "no")], ok=False)
-    assert "ERROR" in r and "--htp with --bgen" in r
+
+
+@pytest.mark.parametrize("bt", [False, True])
+def test_htp_output_on_dosages(tmp_path, golden_dir, bt):
+    import helpers
+    helpers.check_htp_bgen(run, read, tmp_path, golden_dir, bt)
 
 
 @pytest.mark.parametrize("extra", [(), ("--firth", "--approx", "--pThresh", "0.1"), ("--ref-first",)])
