@@ -341,7 +341,7 @@ void BgenFile::info_all(const uint8_t* probs, const uint8_t* pm, size_t n, const
 }
 
 void BgenFile::trait_counts(const uint8_t* probs, const uint8_t* pm, size_t n, const uint8_t* cls, int P, bool binary,
-                            bool ref_first, long* out, int threads) const {
+                            bool ref_first, long* out, int threads, const uint8_t* male, const uint8_t* non_par) const {
   std::atomic<size_t> next{0};
   const size_t nk = sample_idx.size();
   // samples per (trait, class): the reference class follows by difference, so only het / alt / missing calls touch the traits
@@ -364,7 +364,14 @@ void BgenFile::trait_counts(const uint8_t* probs, const uint8_t* pm, size_t n, c
           const uint32_t p0 = pr[2 * f], p1 = pr[2 * f + 1];
           const uint32_t hom = ref_first ? (p0 + p1 > 255 ? 0 : 255 - p0 - p1) : p0;
           const uint32_t d = p1 + 2 * hom;                   // dosage in units of 1 / 255
-          if (2 * d >= 765) g = 1; else if (2 * d >= 255) g = 0; else continue;
+          if (male && non_par && non_par[j] && male[k]) {
+            // dosage >= 1 is the one threshold an 8-bit pair can hit exactly (p1 + 2 hom = 255): decided in the reference's own
+            // floating-point expression (parseSnpfromBGEN, src/Geno.cpp:2273-2281); the others (0.5, 1.5) cannot be hit
+            const double a = p0 / 255.0, b = p1 / 255.0;
+            const double val = ref_first ? b + 2 * std::max(1 - a - b, 0.0) : b + 2 * a;
+            if (val >= 1) g = 1; else continue;
+          }
+          else if (2 * d >= 765) g = 1; else if (2 * d >= 255) g = 0; else continue;
         }
         for (int p = 0; p < P; ++p) ++c[((size_t)p * 3 + cls[(size_t)p * nk + k]) * 3 + g];
       }

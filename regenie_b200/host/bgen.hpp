@@ -39,8 +39,10 @@ struct BgenFile {
   // missing calls skipped).  cls [P][kept samples]: 0 = sample not in the trait, 1 = in the trait (a control of a binary
   // trait), 2 = case; out [n][P][6] = ref / het / alt of class 2 (class 1 for a quantitative trait: pass no 2s), then of
   // class 1 (binary traits)
+  // male [kept samples] + non_par [n] (optional): on the non-PAR part of chromosome X a male with dosage >= 1 counts as alt,
+  // any other male call as ref
   void trait_counts(const uint8_t* probs, const uint8_t* ploidy_missing, size_t n, const uint8_t* cls, int P, bool binary,
-                    bool ref_first, long* out, int threads) const;
+                    bool ref_first, long* out, int threads, const uint8_t* male = nullptr, const uint8_t* non_par = nullptr) const;
   // the zlib streams of variants snps[first .. first+n) back to back, for rg_bgen_inflate (compression flag 1 only):
   // comp = concatenated streams, offs [n + 1]; throws when a variant's declared length is not 10 + 3 n_file
   void read_block_compressed(size_t first, size_t n, std::vector<uint8_t>& comp, std::vector<uint64_t>& offs) const;

@@ -987,6 +987,84 @@ struct GenoCounts {
   }
 };
 
+// --htp on hard calls: the genotype counts of each trait's samples (update_genocounts, src/Geno.cpp:2986-3018: rows 0-2 =
+// cases - all samples of a quantitative trait -, rows 3-5 = controls) straight from the 2-bit rows on the host: per
+// (trait, class) a sample mask in FILE order with one bit per 2-bit field, three popcounts per 32 samples.  On the
+// non-PAR part of chromosome X the reference counts a male with g >= 1 as alt and any other male call as ref; females and
+// everything else: het / alt as they are, missing calls skipped.
+struct BedTraitCounts {
+  int P = 0;
+  bool binary = false, ref_first = false;
+  size_t words = 0;
+  std::vector<uint64_t> m_all, m_male;                       // [P][2 classes][words]
+  size_t at(int p, int c) const { return ((size_t)p * 2 + c) * words; }
+  // cls [P][N] in kept-sample order: 0 = not in the trait, 1 = in the trait (control of a binary trait), 2 = case
+  void init(int P_, bool binary_, bool ref_first_, size_t n_file, const std::vector<int32_t>& sample_idx, const uint8_t* cls,
+            const uint8_t* male) {
+    P = P_; binary = binary_; ref_first = ref_first_;
+    words = (n_file + 31) / 32;
+    m_all.assign((size_t)P * 2 * words, 0);
+    m_male.assign((size_t)P * 2 * words, 0);
+    const size_t N = sample_idx.size();
+    for (int p = 0; p < P; ++p)
+      for (size_t k = 0; k < N; ++k) {
+        const int c = cls[(size_t)p * N + k];
+        if (!c) continue;
+        const size_t f = (size_t)sample_idx[k];
+        const uint64_t bit = 1ull << (2 * (f % 32));
+        m_all[at(p, c - 1) + f / 32] |= bit;
+        if (male && male[k]) m_male[at(p, c - 1) + f / 32] |= bit;
+      }
+  }
+  // out [bs][P][6]; non_par [bs] or null
+  void count(const uint8_t* rows, size_t row_stride, int bs, const uint8_t* non_par, long* out, int threads) const {
+    std::atomic<int> next{0};
+    auto work = [&]() {
+      std::vector<long> c((size_t)P * 2 * 6);                // [trait][class][all: het, two, none | male: het, two, none]
+      for (;;) {
+        const int v = next.fetch_add(1);
+        if (v >= bs) return;
+        const uint8_t* r = rows + (size_t)v * row_stride;
+        const bool np = non_par && non_par[v];
+        std::fill(c.begin(), c.end(), 0);
+        for (size_t w = 0; w < words; ++w) {
+          uint64_t x = 0;
+          const size_t off = w * 8, nb = off + 8 <= row_stride ? 8 : row_stride - off;
+          memcpy(&x, r + off, nb);                           // little endian: field s of the word = sample 32 w + s
+          const uint64_t lo = x & 0x5555555555555555ull, hi = (x >> 1) & 0x5555555555555555ull;
+          const uint64_t het = hi & ~lo, c11 = hi & lo, c00 = ~hi & ~lo & 0x5555555555555555ull;   // 01 = missing
+          for (int pc = 0; pc < 2 * P; ++pc) {
+            const uint64_t ma = m_all[(size_t)pc * words + w];
+            if (!ma) continue;
+            long* cc = &c[(size_t)pc * 6];
+            cc[0] += __builtin_popcountll(het & ma); cc[1] += __builtin_popcountll(c00 & ma); cc[2] += __builtin_popcountll(c11 & ma);
+            if (np) {
+              const uint64_t mm = m_male[(size_t)pc * words + w];
+              cc[3] += __builtin_popcountll(het & mm); cc[4] += __builtin_popcountll(c00 & mm); cc[5] += __builtin_popcountll(c11 & mm);
+            }
+          }
+        }
+        long* o = out + (size_t)v * P * 6;
+        for (int p = 0; p < P; ++p)
+          for (int k = 0; k < 2; ++k) {                       // k = 0: the "cases" columns, 1: the "controls" columns
+            long* t = o + p * 6 + 3 * k;
+            if (k == 1 && !binary) { t[0] = t[1] = t[2] = 0; continue; }
+            const long* cc = &c[((size_t)p * 2 + (binary ? 1 - k : 0)) * 6];   // class 2 (cases) first for a binary trait
+            // code 00 = two copies of the first .bim allele: the counted allele unless --ref-first (see Recode)
+            const long het = cc[0], alt = ref_first ? cc[2] : cc[1], ref = ref_first ? cc[1] : cc[2];
+            const long het_m = cc[3];
+            t[0] = ref; t[1] = het - het_m; t[2] = alt + het_m;  // non-PAR males: g >= 1 -> alt (het_m = 0 elsewhere)
+          }
+      }
+    };
+    const int T = std::max(1, std::min(threads, bs));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < T; ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+  }
+};
+
 // --range (in_range, src/Geno.cpp:2790-2800): keep the variants of one chromosome window
 void apply_range(const Params& p, std::vector<Snp>& snps) {
   if (!p.set_range) return;
@@ -1126,7 +1204,7 @@ void run_step2_qt(const Params& p, Log& log) {
   std::vector<std::string>& obuf = w.obuf;                   // rows of the current block, one buffer per trait
   std::string head_s;
   const int bsz = p.bsize;
-  GenoCounts gc(p.no_split || p.htp, bsz, P, use_bgen ? 0 : g.row_stride, p.ref_first);
+  GenoCounts gc(p.no_split, bsz, P, use_bgen ? 0 : g.row_stride, p.ref_first);
   // input blocks are fetched (file read / threaded BGEN inflate) one block ahead of the GPU call: the rg_s2_block_*
   // calls return with the results on the host, so the buffer of block b is free again when block b+2 is fetched
   std::vector<uint8_t> rows[2], probs[2], pmiss[2];
@@ -1140,13 +1218,17 @@ void run_step2_qt(const Params& p, Log& log) {
   const bool use_info1 = use_bgen && (p.min_info > 0 || p.no_split);   // --no-split prints it and the dosage genotype counts
   // --htp on dosages: thresholded genotype counts per trait (update_genocounts, src/Geno.cpp:2986-3018) from the inflated
   // bytes, in the fetch thread (BgenFile::trait_counts)
+  // hard calls: the same counts by popcounts over the 2-bit rows (BedTraitCounts).  Both run in the fetch thread.
   const bool htp_bgen = use_bgen && p.htp;
-  std::vector<uint8_t> htp_cls;
+  std::vector<uint8_t> htp_cls, htp_npf[2];
+  const std::vector<uint8_t> htp_male = p.htp ? male_vector(use_bgen ? gg.sex_file : g.sex_file, sample_idx) : std::vector<uint8_t>();
   std::vector<long> htp_cnt[2];
-  if (htp_bgen) {
+  BedTraitCounts btc;
+  if (p.htp) {
     htp_cls.resize((size_t)P * N);
     for (size_t e = 0; e < htp_cls.size(); ++e) htp_cls[e] = ph.mask[e] ? 1 : 0;
     for (int k = 0; k < 2; ++k) htp_cnt[k].resize((size_t)bsz * P * 6);
+    if (!use_bgen) btc.init(P, false, p.ref_first, n_file, sample_idx, htp_cls.data(), htp_male.data());
   }
   const bool dev_inflate = use_bgen && p.gpu_inflate && gg.compression == 1 && p.test_type == 0 && !use_info1 && !htp_bgen;
   if (use_bgen && p.gpu_inflate)
@@ -1169,11 +1251,20 @@ void run_step2_qt(const Params& p, Log& log) {
         gg.read_block(blocks[b].first, blocks[b].size, probs[b & 1].data(), pmiss[b & 1].data(), threads);
         if (use_info1) gg.info_all(probs[b & 1].data(), pmiss[b & 1].data(), blocks[b].size, ph.in_analysis.data(), p.ref_first,
                                    info1[b & 1].data(), threads, d_rr[b & 1].data(), d_aa[b & 1].data());
-        if (htp_bgen) gg.trait_counts(probs[b & 1].data(), pmiss[b & 1].data(), blocks[b].size, htp_cls.data(), P, false, p.ref_first,
-                                      htp_cnt[b & 1].data(), threads);
+        if (htp_bgen) {
+          const bool np = non_par_flags(p, snps, blocks[b], htp_npf[b & 1]);
+          gg.trait_counts(probs[b & 1].data(), pmiss[b & 1].data(), blocks[b].size, htp_cls.data(), P, false, p.ref_first,
+                          htp_cnt[b & 1].data(), threads, htp_male.data(), np ? htp_npf[b & 1].data() : nullptr);
+        }
       }
       else if (pgen_dev) g.pg->gather(blocks[b].first, blocks[b].size, pbatch[b & 1]);
-      else g.read_rows(blocks[b].first, blocks[b].size, rows[b & 1].data());
+      else {
+        g.read_rows(blocks[b].first, blocks[b].size, rows[b & 1].data());
+        if (p.htp) {
+          const bool np = non_par_flags(p, snps, blocks[b], htp_npf[b & 1]);
+          btc.count(rows[b & 1].data(), g.row_stride, blocks[b].size, np ? htp_npf[b & 1].data() : nullptr, htp_cnt[b & 1].data(), threads);
+        }
+      }
     });
   };
   if (blocks.empty()) throw Fail("no variant left to include in analysis.");
@@ -1269,7 +1360,6 @@ void run_step2_qt(const Params& p, Log& log) {
       head_s += s.allele0; head_s += ' ';
       head_s += s.allele1; head_s += ' ';
       if (p.htp) {                                             // print_sum_stats_head_htp :2419-2426
-        if (chrom == 23) throw Fail("--htp on chromosome X is outside the hot path covered by rgb200 (sex-aware genotype counts).");
         head_s = s.id + "\t" + std::to_string(s.chrom) + "\t" + std::to_string(s.pos) + "\t" + s.allele0 + "\t" + s.allele1 + "\t";
       }
       if (p.no_split) {                                        // print_sum_stats_all :2441-2493
@@ -1287,19 +1377,14 @@ void run_step2_qt(const Params& p, Log& log) {
         if (!have) continue;
         if (p.htp) {
           // print_sum_stats_htp for a quantitative trait.  Genotype counts of the trait's samples (update_genocounts,
-          // src/Geno.cpp:2986-3003) from exact allele sums: hom-alt = allele sum of the recessive recoding, het = additive sum
-          // - 2 hom-alt.  SCORE / SKATV are the numerator and denominator of the statistic (dt_thr->scores / skat_var,
+          // src/Geno.cpp:2986-3003) counted on the host in the fetch thread (BedTraitCounts / BgenFile::trait_counts).
+          // SCORE / SKATV are the numerator and denominator of the statistic (dt_thr->scores / skat_var,
           // src/Step2_Models.cpp:391-394, :421-424): se = scf / sqrt(denum), stat = num / sqrt(denum).
           HtpRow r;
           r.model = htp_model.c_str();
           r.beta = beta[e]; r.se = se[e]; r.chisq = chisq[e]; r.logp = get_logp(chisq[e]); r.af = af[e]; r.mac = mac[e];
-          if (use_bgen) {                                      // dosages: thresholded counts + the trait's INFO
-            for (int k = 0; k < 3; ++k) r.gc[k] = htp_cnt[b & 1][e * 6 + k];
-            r.info = info[e];
-          } else {
-            const long hom = std::lround(2.0 * gc.af[e] * gc.ns[e]), sum = std::lround(2.0 * af[e] * ns[e]);
-            r.gc[2] = hom; r.gc[1] = sum - 2 * hom; r.gc[0] = ns[e] - r.gc[1] - r.gc[2];
-          }
+          for (int k = 0; k < 3; ++k) r.gc[k] = htp_cnt[b & 1][e * 6 + k];
+          if (use_bgen) r.info = info[e];                      // dosages: the trait's INFO
           const double sqrt_den = scf[i] / se[e];
           r.score = stat[e] * sqrt_den; r.skat_var = sqrt_den * sqrt_den;
           append_htp_row(obuf[i], head_s, ph.names[i], p.htp_cohort, r);
@@ -1388,10 +1473,7 @@ void run_step2_bt(const Params& p, Log& log) {
   std::vector<std::string>& obuf = w.obuf;                   // rows of the current block, one buffer per trait
   std::string head_s;
   const int bsz = p.bsize;
-  GenoCounts gc(p.no_split || p.htp, bsz, P, use_bgen ? 0 : gb.row_stride, p.ref_first);
-  // --htp: the hom-alt counts of the CASES of each trait, from the same recessive recoding run on the case handle below
-  // (update_genocounts, src/Geno.cpp:2986-3018: rows 0-2 = cases, 3-5 = controls; controls = all - cases here)
-  GenoCounts gcc(p.htp, bsz, P, use_bgen ? 0 : gb.row_stride, p.ref_first);
+  GenoCounts gc(p.no_split, bsz, P, use_bgen ? 0 : gb.row_stride, p.ref_first);
   // --af-cc (update_af_cc / compute_aaf_info, src/Geno.cpp:3069-3075, :3120-3127): a second handle whose sample masks are
   // the cases of each trait returns their allele frequency and count from the same block bytes; controls follow by
   // difference of the (exactly reconstructed) allele sums.
@@ -1399,7 +1481,7 @@ void run_step2_bt(const Params& p, Log& log) {
   HandleGuard guard_cases{hc};
   std::vector<double> afc, macc, afc_all, macc_all, statc, betac, sec, chisqc, scalec, infoc;
   std::vector<int32_t> nsc, nsc_all, flagsc;
-  if (p.af_cc || (p.htp && !use_bgen)) {
+  if (p.af_cc) {
     std::vector<uint8_t> mask_case(ph.mask.size());
     for (size_t e = 0; e < mask_case.size(); ++e) mask_case[e] = ph.mask[e] && ph.Y_raw[e] == 1.0;
     rg_step2_config cfgc = cfg;
@@ -1422,13 +1504,17 @@ void run_step2_bt(const Params& p, Log& log) {
   }
   const bool use_info1 = use_bgen && (p.min_info > 0 || p.no_split);   // variant-level --minINFO / --no-split, see run_step2_qt
   // --htp on dosages: thresholded genotype counts of the cases and controls of each trait (BgenFile::trait_counts)
+  // hard calls: the same by popcounts over the 2-bit rows (BedTraitCounts)
   const bool htp_bgen = use_bgen && p.htp;
-  std::vector<uint8_t> htp_cls;
+  std::vector<uint8_t> htp_cls, htp_npf[2];
+  const std::vector<uint8_t> htp_male = p.htp ? male_vector(use_bgen ? gg.sex_file : gb.sex_file, sample_idx) : std::vector<uint8_t>();
   std::vector<long> htp_cnt[2];
-  if (htp_bgen) {
+  BedTraitCounts btc;
+  if (p.htp) {
     htp_cls.resize((size_t)P * N);
     for (size_t e = 0; e < htp_cls.size(); ++e) htp_cls[e] = !ph.mask[e] ? 0 : ph.Y_raw[e] == 1.0 ? 2 : 1;
     for (int k = 0; k < 2; ++k) htp_cnt[k].resize((size_t)bsz * P * 6);
+    if (!use_bgen) btc.init(P, true, p.ref_first, n_file, sample_idx, htp_cls.data(), htp_male.data());
   }
   const bool dev_inflate = use_bgen && p.gpu_inflate && gg.compression == 1 && p.test_type == 0 && !use_info1 && !htp_bgen;
   if (use_bgen && p.gpu_inflate)
@@ -1450,11 +1536,20 @@ void run_step2_bt(const Params& p, Log& log) {
         gg.read_block(blocks[b].first, blocks[b].size, probs[b & 1].data(), pmiss[b & 1].data(), threads);
         if (use_info1) gg.info_all(probs[b & 1].data(), pmiss[b & 1].data(), blocks[b].size, ph.in_analysis.data(), p.ref_first,
                                    info1[b & 1].data(), threads, d_rr[b & 1].data(), d_aa[b & 1].data());
-        if (htp_bgen) gg.trait_counts(probs[b & 1].data(), pmiss[b & 1].data(), blocks[b].size, htp_cls.data(), P, true, p.ref_first,
-                                      htp_cnt[b & 1].data(), threads);
+        if (htp_bgen) {
+          const bool np = non_par_flags(p, snps, blocks[b], htp_npf[b & 1]);
+          gg.trait_counts(probs[b & 1].data(), pmiss[b & 1].data(), blocks[b].size, htp_cls.data(), P, true, p.ref_first,
+                          htp_cnt[b & 1].data(), threads, htp_male.data(), np ? htp_npf[b & 1].data() : nullptr);
+        }
       }
       else if (pgen_dev) gb.pg->gather(blocks[b].first, blocks[b].size, pbatch[b & 1]);
-      else gb.read_rows(blocks[b].first, blocks[b].size, rows[b & 1].data());
+      else {
+        gb.read_rows(blocks[b].first, blocks[b].size, rows[b & 1].data());
+        if (p.htp) {
+          const bool np = non_par_flags(p, snps, blocks[b], htp_npf[b & 1]);
+          btc.count(rows[b & 1].data(), gb.row_stride, blocks[b].size, np ? htp_npf[b & 1].data() : nullptr, htp_cnt[b & 1].data(), threads);
+        }
+      }
     });
   };
   if (blocks.empty()) throw Fail("no variant left to include in analysis.");
@@ -1525,14 +1620,10 @@ void run_step2_bt(const Params& p, Log& log) {
     }
     pending.get();
     if (b + 1 < blocks.size()) pending = fetch(b + 1);
-    if (!use_bgen) {
+    if (!use_bgen)
       gc.run(rows[b & 1].data(), (size_t)bs * gb.row_stride, bs, [&](const uint8_t* r, const rg_s2_out* o) {
         rg_check(rg_s2_block_bed_bt(h, r, (int64_t)gb.row_stride, bs, subset ? sample_idx.data() : nullptr, p.ref_first, 0.0, o));
       });
-      gcc.run(rows[b & 1].data(), (size_t)bs * gb.row_stride, bs, [&](const uint8_t* r, const rg_s2_out* o) {
-        rg_check(rg_s2_block_bed(hc, r, (int64_t)gb.row_stride, bs, subset ? sample_idx.data() : nullptr, p.ref_first, 0.0, o));
-      });
-    }
     if (non_par_flags(p, snps, blocks[b], npf)) rg_check(rg_s2_set_non_par(h, npf.data(), bs));
     if (use_bgen) {
       const uint8_t *pd = probs[b & 1].data(), *md = pmiss[b & 1].data();
@@ -1610,7 +1701,6 @@ void run_step2_bt(const Params& p, Log& log) {
       head_s += s.allele0; head_s += ' ';
       head_s += s.allele1; head_s += ' ';
       if (p.htp) {                                             // print_sum_stats_head_htp :2419-2426
-        if (chrom == 23) throw Fail("--htp on chromosome X is outside the hot path covered by rgb200 (sex-aware genotype counts).");
         head_s = s.id + "\t" + std::to_string(s.chrom) + "\t" + std::to_string(s.pos) + "\t" + s.allele0 + "\t" + s.allele1 + "\t";
       }
       if (p.no_split) {                                        // print_sum_stats_all :2441-2493
@@ -1645,25 +1735,17 @@ void run_step2_bt(const Params& p, Log& log) {
           cc.af_control = (s_all - s_case) / unit / (2.0 * cc.ns_control);
         }
         if (p.htp) {
-          // print_sum_stats_htp for a binary trait (src/Step2_Models.cpp:2542-2646).  Genotype counts (update_genocounts,
-          // src/Geno.cpp:2986-3018) from exact allele sums: hom-alt = allele sum of the recessive recoding, het = additive
-          // sum - 2 hom-alt, once over the trait's samples (handle h) and once over its cases (handle hc); controls by
-          // difference.  SCORE / SKATV (compute_score_bt :523-526, :546): stats * sqrt(denum) with the sign of the minor-allele
+          // print_sum_stats_htp for a binary trait (src/Step2_Models.cpp:2542-2646).  Genotype counts of the trait's cases
+          // and controls (update_genocounts, src/Geno.cpp:2986-3018) counted on the host in the fetch thread (BedTraitCounts /
+          // BgenFile::trait_counts).  SCORE / SKATV (compute_score_bt :523-526, :546): stats * sqrt(denum) with the sign of the minor-allele
           // flip undone, and denum = 1 / se^2 of the score test; cal_factor (check_pval_snp :1993, :2027) = 1 without a
           // correction, stats^2 / corrected chi-square with one.  After a FAILED correction the reference prints whatever
           // cal_factor the thread held before (it returns before the assignment): 1 here.
           HtpRow r;
           r.model = htp_model.c_str(); r.bt = true; r.firth = p.firth;
           r.beta = bo; r.se = so; r.chisq = co; r.logp = lp; r.af = af[e]; r.mac = mac[e]; r.test_pass = pass;
-          if (use_bgen) {                                      // dosages: thresholded counts + the trait's INFO
-            for (int k = 0; k < 6; ++k) r.gc[k] = htp_cnt[b & 1][e * 6 + k];
-            r.info = info[e];
-          } else {
-            const long hom_all = std::lround(2.0 * gc.af[e] * gc.ns[e]), sum_all = std::lround(2.0 * af[e] * ns[e]);
-            const long hom_case = std::lround(2.0 * gcc.af[e] * gcc.ns[e]), sum_case = std::lround(2.0 * afc[e] * nsc[e]);
-            r.gc[2] = hom_case; r.gc[1] = sum_case - 2 * hom_case; r.gc[0] = nsc[e] - r.gc[1] - r.gc[2];
-            r.gc[5] = hom_all - hom_case; r.gc[4] = (sum_all - sum_case) - 2 * r.gc[5]; r.gc[3] = (ns[e] - nsc[e]) - r.gc[4] - r.gc[5];
-          }
+          for (int k = 0; k < 6; ++k) r.gc[k] = htp_cnt[b & 1][e * 6 + k];
+          if (use_bgen) r.info = info[e];                      // dosages: the trait's INFO
           const double sqrt_den = 1.0 / se[e];
           r.score = stat[e] * sqrt_den * ((flags[v] & 8) ? -1.0 : 1.0); r.skat_var = sqrt_den * sqrt_den;
           r.cal_factor = (f != fidx.end() && pass) ? (co == 0 ? 0.0 : stat[e] * stat[e] / co) : 1.0;

@@ -596,6 +596,81 @@ def check_af_cc(run, read, tmp_path, golden_dir, extra=()):
             assert [u[6], u[7], u[9], u[10]] == want, (b, want)
 
 
+def check_htp_chrx(run, read, tmp_path):
+    """--htp on chromosome X, hard calls: on the non-PAR part a male with g >= 1 counts as alt and any other male call as ref,
+    females and the PAR variants count as on the autosomes (update_genocounts, src/Geno.cpp:2986-3018; in_non_par :2802-2814)."""
+    g = synth.genotypes(240, 120, seed=31, miss=0.03)
+    Y, cov, na = synth.phenotypes(g, 2, 2, seed=31)
+    prefix = write_fileset(str(tmp_path), g, Y, cov, na, n_chr=1)
+    M, N = g.shape
+    pos = [1000 + i if i % 2 == 0 else 5_000_000 + i for i in range(M)]               # even: PAR1, odd: non-PAR (default bounds)
+    with open(prefix + ".bim", "w") as fh:
+        for i in range(M):
+            fh.write("23 rs%d 0 %d A G\n" % (i, pos[i]))
+    run(["--step", "2", "--bed", prefix, "--phenoFile", str(tmp_path) + "/pheno.txt", "--covarFile", str(tmp_path) + "/covar.txt",
+         "--bsize", "50", "--ignore-pred", "--minMAC", "1", "--htp", "CX", "--out", str(tmp_path / "x")])
+    keys, _ = plink.read_fam(prefix + ".fam")
+    pr = prep.prepare(keys, str(tmp_path) + "/pheno.txt", str(tmp_path) + "/covar.txt", step=2)
+    male = np.array([(s % 2) == 0 for s in range(N)])                                  # write_fileset: sex = 1 + s % 2
+    n_np = 0
+    for ph, nm in enumerate(("Y1", "Y2")):
+        rows = read(str(tmp_path / "x") + "_%s.regenie" % nm).splitlines()[1:]
+        assert len(rows) > 80
+        m = pr.mask[:, ph].astype(bool)
+        for l in rows:
+            t = l.split("\t")
+            i = int(t[0][2:])
+            gi = g[i].astype(int)                                                      # codes: 0 / 1 / 2 copies, 3 = missing
+            ok = m & (gi != 3)
+            if i % 2 == 1:
+                alt = int((ok & ~male & (gi == 2)).sum() + (ok & male & (gi >= 1)).sum())
+                het = int((ok & ~male & (gi == 1)).sum())
+                n_np += 1
+            else:
+                alt, het = int((ok & (gi == 2)).sum()), int((ok & (gi == 1)).sum())
+            assert [int(x) for x in t[13:17]] == [int(ok.sum()), int(ok.sum()) - het - alt, het, alt], l
+    assert n_np > 40
+
+
+def check_htp_bgen_chrx(run, read, tmp_path, golden_dir):
+    """--htp on chromosome X dosages: the male rule of update_genocounts on the non-PAR part (dosage >= 1 -> alt, else ref)."""
+    from oracle import bgen as obgen, prep
+    d = golden_dir
+    fam = [l.split() for l in open(d + "/example.fam")]
+    keys = ["_".join(t[:2]) for t in fam]
+    M, N = 60, len(keys)
+    probs, miss = synthetic_dosage_probs(M, N, seed=29)
+    f = str(tmp_path / "x.bgen")
+    pos = [1000 + i if i % 2 == 0 else 5_000_000 + i for i in range(M)]
+    write_bgen(f, probs, miss, [23] * M, pos, ["v%d" % v for v in range(M)], sample_ids=keys)
+    male = np.array([(k % 3) == 0 for k in range(N)])
+    with open(str(tmp_path / "x.sample"), "w") as fh:
+        fh.write("ID_1 ID_2 missing sex\n0 0 0 D\n")
+        for k, t in enumerate(fam):
+            fh.write("%s %s 0 %d\n" % (t[0], t[1], 1 if male[k] else 2))
+    run(["--step", "2", "--bgen", f, "--sample", str(tmp_path / "x.sample"), "--phenoFile", d + "/phenotype.txt", "--covarFile",
+         d + "/covariates.txt", "--bsize", "25", "--ignore-pred", "--minMAC", "1", "--htp", "CX", "--out", str(tmp_path / "x")])
+    pr = prep.prepare(keys, d + "/phenotype.txt", d + "/covariates.txt", step=2)
+    n_np = 0
+    for ph, nm in enumerate(("Y1", "Y2")):
+        rows = read(str(tmp_path / "x") + "_%s.regenie" % nm).splitlines()[1:]
+        assert len(rows) > 40
+        m = pr.mask[:, ph].astype(bool)
+        for l in rows:
+            t = l.split("\t")
+            v = int(t[0][1:])
+            g, _ = obgen.dosage(probs[v, :, 0], probs[v, :, 1], miss[v])
+            ok = m & ~miss[v]
+            if v % 2 == 1:
+                alt = int((ok & ~male & (g >= 1.5)).sum() + (ok & male & (g >= 1)).sum())
+                het = int((ok & ~male & (g >= 0.5) & (g < 1.5)).sum())
+                n_np += 1
+            else:
+                alt, het = int((ok & (g >= 1.5)).sum()), int((ok & (g >= 0.5) & (g < 1.5)).sum())
+            assert [int(x) for x in t[13:17]] == [int(ok.sum()), int(ok.sum()) - het - alt, het, alt], l
+    assert n_np > 20
+
+
 def check_htp_bgen(run, read, tmp_path, golden_dir, bt=False):
     """--htp on dosages: the thresholded genotype counts of each trait's samples (cases / controls for a binary trait) against
     oracle.step2.genocounts on the float dosages (update_genocounts, src/Geno.cpp:2986-3018), INFO= in the Info column, same

@@ -232,6 +232,12 @@ def test_htp_output(tmp_path, golden_dir, extra):
     helpers.check_htp(run, read, tmp_path, golden_dir, extra)
 
 
+def test_htp_output_on_chromosome_x(tmp_path, golden_dir):
+    import helpers
+    helpers.check_htp_chrx(run, read, tmp_path)
+    helpers.check_htp_bgen_chrx(run, read, tmp_path, golden_dir)
+
+
 @pytest.mark.parametrize("bt", [False, True])
 def test_htp_output_on_dosages(tmp_path, golden_dir, bt):
     import helpers
