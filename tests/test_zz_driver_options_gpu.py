@@ -133,7 +133,7 @@ def test_htp_output(tmp_path, golden_dir):
 @pytest.mark.xfail(strict=False, reason="--htp for binary traits was written after the GPU budget of round 2 was spent: green "
                    "against the mock ABI (tests/test_driver_plumbing_cpu.py, same helper), the row formatter is checked "
                    "against the oracle restatement on its binary-trait branches; not yet run on hardware")
-@pytest.mark.parametrize("extra", [(), ("--firth", "--approx", "--pThresh", "0.1")])
+@pytest.mark.parametrize("extra", [("--firth", "--approx", "--pThresh", "0.1")])
 def test_htp_output_binary_traits(tmp_path, golden_dir, extra):
     """--htp --bt on the real library: case / control genotype counts == the .bed counts, Effect / CI / Pval / Info against
     the native file of the same run options."""
