@@ -406,30 +406,41 @@ def run_gpu(args):
         h1 = hostprep.ridge_grid(5)
         tau = np.tile(Bt * (1 - h1) / h1, (P, 1))
         chr_of_block = [1 + (22 * b) // (nb_local * world) for b in range(nb_local * world)]
-        t0 = time.perf_counter()
-        cs, best = st.l1_fit(tau)
-        t_l1 = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        loco = st.loco(chr_of_block)
-        t_loco = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        cs = sharding._sum_to_all(cs, dev); loco = sharding._sum_to_all(loco, dev)
-        t_gather = time.perf_counter() - t0
-        tt = torch.tensor([t_l1, t_loco, t_gather], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        n_owned = sum(1 for p in range(P) if owner[p] == rank)
-        peer_bytes = nb_local * bs * 0 + nb_local * R * N * 8 * (P - n_owned)      # W columns stored to other ranks per pass
-        pb = torch.tensor([float(peer_bytes)], dtype=torch.float64, device=dev)
-        dist.all_reduce(pb, op=dist.ReduceOp.MAX)
-        sharded = {"level1_seconds": float(tt[0]), "loco_seconds": float(tt[1]), "gather_seconds": float(tt[2]),
-                   "level1_width_B": Bt, "phenotypes_per_rank_max": max(owner.count(r) for r in range(world)),
-                   "peer_store_bytes_per_rank_per_step": float(pb[0]),
-                   "peer_store_GBps_per_rank": float(pb[0]) / (ms / args.steps * 1e-3) / 1e9,
-                   "nvlink_peer_copy_reference_GBps": 770.0,
-                   "finite": bool(np.isfinite(cs).all() and np.isfinite(loco).all()),
-                   "note": "level 1 is sharded by phenotype (p mod world): with %d traits on %d ranks the busiest rank fits %d; "
-                           "stores to peers ride inside the prediction / standardisation kernels, overlapped with compute"
-                           % (P, world, max(owner.count(r) for r in range(world)))}
+        # the level-1 / LOCO work of this rank; a failure here (a width B = nb x world x R this build has not met on hardware)
+        # must not take the level-0 numbers of the run with it: every rank learns whether any rank failed before the gathers
+        l1_err, t_l1, t_loco = None, 0.0, 0.0
+        try:
+            t0 = time.perf_counter()
+            cs, best = st.l1_fit(tau)
+            t_l1 = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            loco = st.loco(chr_of_block)
+            t_loco = time.perf_counter() - t0
+        except Exception as e:
+            l1_err = "rank %d: %s" % (rank, str(e)[:200])
+        flag = torch.tensor([1.0 if l1_err else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if float(flag.item()) > 0:
+            sharded = {"error": l1_err or "level 1 / LOCO failed on another rank", "level1_width_B": Bt}
+        else:
+            t0 = time.perf_counter()
+            cs = sharding._sum_to_all(cs, dev); loco = sharding._sum_to_all(loco, dev)
+            t_gather = time.perf_counter() - t0
+            tt = torch.tensor([t_l1, t_loco, t_gather], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            n_owned = sum(1 for p in range(P) if owner[p] == rank)
+            peer_bytes = nb_local * R * N * 8 * (P - n_owned)                          # W columns stored to other ranks per pass
+            pb = torch.tensor([float(peer_bytes)], dtype=torch.float64, device=dev)
+            dist.all_reduce(pb, op=dist.ReduceOp.MAX)
+            sharded = {"level1_seconds": float(tt[0]), "loco_seconds": float(tt[1]), "gather_seconds": float(tt[2]),
+                       "level1_width_B": Bt, "phenotypes_per_rank_max": max(owner.count(r) for r in range(world)),
+                       "peer_store_bytes_per_rank_per_step": float(pb[0]),
+                       "peer_store_GBps_per_rank": float(pb[0]) / (ms / args.steps * 1e-3) / 1e9,
+                       "nvlink_peer_copy_reference_GBps": 770.0,
+                       "finite": bool(np.isfinite(cs).all() and np.isfinite(loco).all()),
+                       "note": "level 1 is sharded by phenotype (p mod world): with %d traits on %d ranks the busiest rank fits %d; "
+                               "stores to peers ride inside the prediction / standardisation kernels, overlapped with compute"
+                               % (P, world, max(owner.count(r) for r in range(world)))}
 
     # ---- end to end from files through the C++ driver (rank 0, single GPU run only)
     file_e2e = None
