@@ -1525,7 +1525,7 @@ void run_step2_bt(const Params& p, Log& log) {
   std::vector<double> info1[2];
   std::vector<long> d_rr[2], d_aa[2];
   if (use_info1) for (int k = 0; k < 2; ++k) { info1[k].resize(bsz); d_rr[k].resize(bsz); d_aa[k].resize(bsz); }
-  const bool pgen_dev = !use_bgen && gb.pg && pgen_on_device() && !p.no_split && p.test_type == 0 && !hc;
+  const bool pgen_dev = !use_bgen && gb.pg && pgen_on_device() && !p.no_split && !p.htp && p.test_type == 0 && !hc;   // --htp counts on host rows
   if (pgen_dev) log << " * pgen records are decoded on the GPU\n";
   PgenBatch pbatch[2];
   std::future<void> pending;

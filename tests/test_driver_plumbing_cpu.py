@@ -232,6 +232,22 @@ def test_htp_output(tmp_path, golden_dir, extra):
     helpers.check_htp(run, read, tmp_path, golden_dir, extra)
 
 
+@pytest.mark.parametrize("bt", [False, True])
+def test_htp_output_on_pgen_equals_bed(tmp_path, golden_dir, bt):
+    """--htp needs the 2-bit rows on the host for the genotype counts: with .pgen input the records are decoded by the host
+    reader (not on the device) and the rows must be those of the .bed twin of the reference's fixture pair."""
+    d = golden_dir
+    base = ["--step", "2", "--phenoFile", d + ("/phenotype_bin.txt" if bt else "/phenotype.txt"), "--covarFile", d + "/covariates.txt",
+            "--bsize", "100", "--ignore-pred", "--htp", "C"] + (["--bt", "--firth", "--approx"] if bt else [])
+    run(base + ["--bed", d + "/example", "--out", str(tmp_path / "b")])
+    log = run(base + ["--pgen", d + "/example", "--out", str(tmp_path / "p")])
+    assert "decoded on the GPU" not in log
+    for nm in ("Y1", "Y2"):
+        a, b = read(str(tmp_path / "b") + "_%s.regenie" % nm), read(str(tmp_path / "p") + "_%s.regenie" % nm)
+        assert a == b and len(a.splitlines()) > 900
+        assert sum(int(l.split("\t")[13]) for l in a.splitlines()[1:]) > 0
+
+
 def test_htp_output_on_chromosome_x(tmp_path, golden_dir):
     import helpers
     helpers.check_htp_chrx(run, read, tmp_path)
